@@ -1,0 +1,85 @@
+/* ppd_b200.h — C ABI of libppd_b200.so, the B200 (sm_100a) implementation of
+ * proof-protocol-decoder's hot path.
+ *
+ * The reference has no FFI of its own for this path: its boundary is the Rust
+ * method `BlockTrace::into_txn_proof_gen_ir` (protocol_decoder/src/processed_block_trace.rs:38-45).
+ * Each entry point below names the reference interface it stands in for; the
+ * Rust shim that binds them (extern "C" block + build.rs) is in INTEGRATION.md.
+ *
+ * Conventions: plain pointers and sizes only; inputs are caller-owned and only
+ * borrowed for the call; outputs returned through `uint8_t** out` are allocated
+ * by the library and released with ppd_free(); every call returns a ppd_status
+ * (include/ppd_status.h) and never unwinds or aborts across the boundary.  A
+ * context is bound to one CUDA device and is not thread-safe; use one context
+ * per (thread, device).  There is NO CPU fallback: if no CUDA device is usable
+ * ppd_ctx_create fails with PPD_ERR_CUDA.
+ *
+ * Wire formats (FlatBlock, IrDump, PreImageDump): include/ppd_flat.h.
+ */
+#ifndef PPD_B200_H
+#define PPD_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#include "ppd_flat.h"
+#include "ppd_status.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ppd_ctx ppd_ctx;
+
+/* Work counters of the last call on a context. */
+typedef struct ppd_stats {
+  uint64_t nodes_hashed;       /* Keccak invocations over trie-node encodings (HashedPartialTrie::hash work) */
+  uint64_t node_permutations;  /* keccak-f[1600] permutations spent on them */
+  uint64_t key_hashes;         /* utils::hash calls: addresses, slots, code */
+  uint64_t key_permutations;
+  uint64_t arena_nodes;        /* node records resident in HBM */
+  uint64_t levels;             /* level launches */
+  double gpu_ms;               /* device time of the kernels of the call (CUDA events) */
+  double h2d_bytes, d2h_bytes;
+  uint64_t kernel_launches;
+} ppd_stats;
+
+int ppd_ctx_create(int device, ppd_ctx** out);
+void ppd_ctx_destroy(ppd_ctx* ctx);
+/* message of the last non-OK status on this context ("" if none) */
+const char* ppd_last_error(const ppd_ctx* ctx);
+void ppd_last_stats(const ppd_ctx* ctx, ppd_stats* out);
+void ppd_free(void* p);
+
+/* utils::hash (protocol_decoder/src/utils.rs:11-13) over a batch: message i is
+ * data[offsets[i] .. offsets[i+1]); out32n receives n x 32 bytes.  Host buffers. */
+int ppd_keccak256_batch(ppd_ctx* ctx, const uint8_t* data, const uint64_t* offsets, size_t n, uint8_t* out32n);
+
+/* process_compact_prestate_debug (compact/compact_prestate_processing.rs:1262-1281) plus the root
+ * of every resulting trie (HashedPartialTrie::hash): TrieCompact bytes -> PreImageDump. */
+int ppd_compact_decode(ppd_ctx* ctx, const uint8_t* witness, size_t len, uint8_t** out, size_t* out_len);
+
+/* BlockTrace::into_txn_proof_gen_ir (processed_block_trace.rs:38-50 -> decoding.rs:80-177):
+ * FlatBlock -> IrDump (one GenerationInputs per txn, plus dummies / the withdrawal entry). */
+int ppd_block_decode(ppd_ctx* ctx, const uint8_t* flat_block, size_t len, uint8_t** out, size_t* out_len);
+
+/* The same over n independent blocks: their version DAGs are hashed in one level-synchronous
+ * sweep.  statuses[i] is the status of block i; outs[i] is NULL for a failed block. */
+int ppd_blocks_decode_batch(ppd_ctx* ctx, const uint8_t* const* flat_blocks, const size_t* lens, size_t n, uint8_t** outs,
+                            size_t* out_lens, int* statuses);
+
+/* HashedPartialTrie::hash of the trie holding n leaves with 32-byte keys, given sorted by key
+ * (the state-trie rehash of config 5).  value i = vals[val_off[i] .. val_off[i+1]) is stored as
+ * given (it is the already-RLP-encoded leaf payload).  Host buffers. */
+int ppd_trie_root_sorted_leaves(ppd_ctx* ctx, const uint8_t* keys32, const uint64_t* val_off, const uint8_t* vals, size_t n,
+                                uint8_t root_out[32]);
+
+/* Device-resident variant for measurement: pointers are DEVICE pointers (cudaMalloc'ed by the
+ * caller, e.g. torch tensors); only the 32-byte root is copied back. */
+int ppd_trie_root_sorted_leaves_dev(ppd_ctx* ctx, const uint8_t* d_keys32, const uint64_t* d_val_off, const uint8_t* d_vals,
+                                    size_t n, size_t vals_bytes, uint8_t root_out[32]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,302 @@
+// host_arena.h — host-side construction of the node arena: persistent (path-copying) Merkle
+// Patricia tries whose every version stays addressable, so that ALL versions of ALL tries of a
+// block (or of a batch of blocks) are hashed by one level-synchronous GPU sweep.
+//
+// Replaces eth_trie_utils' insert / delete / get / create_trie_subset marking (SURVEY.md rows
+// a12, a13, a19; call sites decoding.rs:185-209, 239-289, 414-424 and
+// compact_to_partial_trie.rs:105,125).  The host only shapes the tries — which needs no hash —
+// and never computes a Keccak: every node hash, key hash and root comes from the CUDA kernels.
+//
+// Nibble strings are never materialised: a node refers to a range [nib_start, nib_start+nib_len)
+// of a full key stored once in key_pool, with ABSOLUTE positions (a leaf reached at depth d has
+// nib_start == d), so splitting and merging paths is index arithmetic.
+#pragma once
+#include <cstdint>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/ppd_status.h"
+#include "arena.h"
+
+namespace ppd {
+
+struct Fail {
+  int code;
+  std::string msg;
+};
+[[noreturn]] inline void fail(int code, const char* msg) { throw Fail{code, msg}; }
+
+static const uint32_t UNCHANGED = 0xfffffffeu;
+
+struct HostArena {
+  std::vector<NodeRec> nodes;
+  std::vector<uint16_t> level;
+  std::vector<uint8_t> key_pool, val_pool, hash_pool;
+  std::vector<uint32_t> child_pool;
+  std::vector<AccountRec> accounts;
+
+  void clear() {
+    nodes.clear(), level.clear(), key_pool.clear(), val_pool.clear(), hash_pool.clear(), child_pool.clear(), accounts.clear();
+  }
+
+  // ---- pools -------------------------------------------------------------------------------
+  uint32_t add_key_nibbles(const uint8_t* nib, uint32_t n) {
+    uint32_t off = (uint32_t)key_pool.size();
+    key_pool.resize(off + (n + 1) / 2 + 1, 0);  // one slack byte: the device reads key[(j>>1)+1] when j is odd
+    for (uint32_t i = 0; i < n; i++) key_pool[off + (i >> 1)] |= (i & 1) ? nib[i] : (uint8_t)(nib[i] << 4);
+    return off;
+  }
+  uint32_t add_key_bytes(const uint8_t* bytes, uint32_t nbytes) {
+    uint32_t off = (uint32_t)key_pool.size();
+    key_pool.insert(key_pool.end(), bytes, bytes + nbytes);
+    key_pool.push_back(0);
+    return off;
+  }
+  uint32_t add_val(const uint8_t* p, uint32_t n) {
+    uint32_t off = (uint32_t)((val_pool.size() + 3) & ~(size_t)3);
+    val_pool.resize(off + n);
+    if (n) memcpy(val_pool.data() + off, p, n);
+    return off;
+  }
+  uint32_t add_hash(const uint8_t* h) {
+    uint32_t idx = (uint32_t)(hash_pool.size() / 32);
+    hash_pool.insert(hash_pool.end(), h, h + 32);
+    return idx;
+  }
+  uint32_t key_nib(uint32_t koff, uint32_t i) const {
+    uint8_t b = key_pool[koff + (i >> 1)];
+    return (i & 1) ? (b & 15u) : (uint32_t)(b >> 4);
+  }
+
+  // ---- node accessors ----------------------------------------------------------------------
+  uint32_t kind(uint32_t n) const { return nodes[n].w0 & 0xff; }
+  uint32_t nstart(uint32_t n) const { return (nodes[n].w0 >> 8) & 0xff; }
+  uint32_t nlen(uint32_t n) const { return (nodes[n].w0 >> 16) & 0xff; }
+  bool is_leaf(uint32_t n) const { return kind(n) == NK_LEAF || kind(n) == NK_LEAF_ACCOUNT; }
+  bool is_opaque(uint32_t n) const { return kind(n) == NK_HASH || kind(n) == NK_ROOT; }  // Node::Hash
+  // a key that runs through this node (for the nibbles leading to it)
+  uint32_t rep_key(uint32_t n) const { return (kind(n) == NK_BRANCH || kind(n) == NK_HASH) ? nodes[n].a2 : nodes[n].a0; }
+  uint32_t child_at(uint32_t br, uint32_t nib) const {
+    uint32_t mask = nodes[br].a1, bit = 1u << nib;
+    if (!(mask & bit)) return NODE_EMPTY;
+    return child_pool[nodes[br].a0 + __builtin_popcount(mask & (bit - 1))];
+  }
+  uint16_t lvl(uint32_t n) const { return n == NODE_EMPTY ? 0 : level[n]; }
+
+  // ---- constructors ------------------------------------------------------------------------
+  uint32_t push(const NodeRec& r, uint32_t lv) {
+    if (lv > 0xffff) fail(PPD_ERR_BAD_ARGUMENT, "trie deeper than 65535 levels");
+    nodes.push_back(r);
+    level.push_back((uint16_t)lv);
+    return (uint32_t)nodes.size() - 1;
+  }
+  uint32_t new_hash(uint32_t hash_idx, uint32_t rep_koff) { return push({node_w0(NK_HASH, 0, 0), hash_idx, 0, rep_koff}, 0); }
+  uint32_t new_leaf(uint32_t koff, uint32_t start, uint32_t len, uint32_t val_off, uint32_t val_len) {
+    return push({node_w0(NK_LEAF, start, len), koff, val_off, val_len}, 0);
+  }
+  uint32_t new_account_leaf(uint32_t koff, uint32_t start, uint32_t len, uint32_t rec) {
+    uint32_t src = accounts[rec].storage_src;
+    return push({node_w0(NK_LEAF_ACCOUNT, start, len), koff, rec, 0}, src == NODE_EMPTY ? 0 : lvl(src) + 1u);
+  }
+  // the same leaf payload under a different key range
+  uint32_t releaf(uint32_t leaf, uint32_t koff, uint32_t start, uint32_t len) {
+    NodeRec r = nodes[leaf];
+    r.w0 = node_w0(r.w0 & 0xff, start, len);
+    r.a0 = koff;
+    return push(r, level[leaf]);
+  }
+  uint32_t new_ext(uint32_t koff, uint32_t start, uint32_t len, uint32_t child) {
+    return push({node_w0(NK_EXT, start, len), koff, child, 0}, lvl(child) + 1u);
+  }
+  uint32_t new_root(uint32_t child) { return push({node_w0(NK_ROOT, 0, 0), 0, child, 0}, child == NODE_EMPTY ? 0 : lvl(child) + 1u); }
+  uint32_t new_branch(uint32_t mask, const uint32_t* kids, uint32_t rep_koff) {
+    uint32_t base = (uint32_t)child_pool.size(), lv = 0;
+    uint32_t k = (uint32_t)__builtin_popcount(mask);
+    for (uint32_t i = 0; i < k; i++) {
+      child_pool.push_back(kids[i]);
+      if (level[kids[i]] > lv) lv = level[kids[i]];
+    }
+    return push({node_w0(NK_BRANCH, 0, 0), base, mask, rep_koff}, lv + 1u);
+  }
+  // copy of branch `br` with slot `nib` set to `child` (NODE_EMPTY removes it)
+  uint32_t branch_with(uint32_t br, uint32_t nib, uint32_t child) {
+    uint32_t kids[16], k = 0, nmask = 0;
+    for (uint32_t i = 0; i < 16; i++) {
+      uint32_t c = (i == nib) ? child : child_at(br, i);
+      if (c != NODE_EMPTY) kids[k++] = c, nmask |= 1u << i;
+    }
+    return new_branch(nmask, kids, rep_key(kids[0]));  // the representative key stays inside the subtree
+  }
+
+  // ---- persistent operations; keys are (koff, klen) full keys in key_pool --------------------
+  uint32_t common_prefix(uint32_t koff_a, uint32_t start_a, uint32_t len_a, uint32_t koff_b, uint32_t start_b, uint32_t len_b) const {
+    uint32_t m = len_a < len_b ? len_a : len_b, i = 0;
+    while (i < m && key_nib(koff_a, start_a + i) == key_nib(koff_b, start_b + i)) i++;
+    return i;
+  }
+
+  struct Payload {  // what a new leaf holds
+    bool account;
+    uint32_t a1, a2;  // LEAF: val_off, val_len; LEAF_ACCOUNT: record
+  };
+  uint32_t make_leaf(uint32_t koff, uint32_t start, uint32_t len, const Payload& p) {
+    return p.account ? new_account_leaf(koff, start, len, p.a1) : new_leaf(koff, start, len, p.a1, p.a2);
+  }
+  uint32_t split(uint32_t koff, uint32_t klen, uint32_t pos, uint32_t cp, uint32_t existing_nib, uint32_t existing, const Payload& p) {
+    // branch at depth pos+cp holding `existing` and a new leaf for the key; extension above for the cp common nibbles
+    uint32_t at = pos + cp;
+    if (at >= klen) fail(PPD_PANIC_KEY_IS_PREFIX_OF_KEY, "inserted key is a prefix of an existing key");
+    uint32_t new_nib = key_nib(koff, at);
+    uint32_t leaf = make_leaf(koff, at + 1, klen - at - 1, p);
+    uint32_t kids[2], mask = (1u << existing_nib) | (1u << new_nib);
+    if (existing_nib < new_nib)
+      kids[0] = existing, kids[1] = leaf;
+    else
+      kids[0] = leaf, kids[1] = existing;
+    uint32_t br = new_branch(mask, kids, koff);
+    return cp == 0 ? br : new_ext(koff, pos, cp, br);
+  }
+
+  uint32_t insert(uint32_t node, uint32_t koff, uint32_t klen, uint32_t pos, const Payload& p) {
+    if (node == NODE_EMPTY) return make_leaf(koff, pos, klen - pos, p);
+    switch (kind(node)) {
+      case NK_HASH:
+      case NK_ROOT:
+        fail(PPD_PANIC_INSERT_INTO_HASH_NODE, "insert traversed a hashed-out node");
+      case NK_BRANCH: {
+        if (pos >= klen) fail(PPD_PANIC_KEY_IS_PREFIX_OF_KEY, "inserted key ends at a branch");
+        uint32_t nib = key_nib(koff, pos);
+        uint32_t nc = insert(child_at(node, nib), koff, klen, pos + 1, p);
+        return branch_with(node, nib, nc);
+      }
+      case NK_EXT: {
+        uint32_t ek = nodes[node].a0, es = nstart(node), el = nlen(node), child = nodes[node].a1;
+        uint32_t cp = common_prefix(ek, es, el, koff, pos, klen - pos);
+        if (cp == el) return new_ext(ek, es, el, insert(child, koff, klen, pos + el, p));
+        uint32_t rem = el - cp - 1;
+        uint32_t existing = rem == 0 ? child : new_ext(ek, es + cp + 1, rem, child);
+        return split(koff, klen, pos, cp, key_nib(ek, es + cp), existing, p);
+      }
+      default: {  // leaves
+        uint32_t lk = nodes[node].a0, ls = nstart(node), ll = nlen(node);
+        uint32_t cp = common_prefix(lk, ls, ll, koff, pos, klen - pos);
+        if (cp == ll && ll == klen - pos) return make_leaf(koff, pos, klen - pos, p);  // overwrite
+        if (cp == ll) fail(PPD_PANIC_KEY_IS_PREFIX_OF_KEY, "existing key is a prefix of the inserted key");
+        uint32_t existing = releaf(node, lk, ls + cp + 1, ll - cp - 1);
+        return split(koff, klen, pos, cp, key_nib(lk, ls + cp), existing, p);
+      }
+    }
+  }
+
+  // an extension (ek, es, el) over `child`, merged into the child when that is a leaf / extension
+  uint32_t collapse_ext(uint32_t ek, uint32_t es, uint32_t el, uint32_t child) {
+    switch (kind(child)) {
+      case NK_EXT:
+        return new_ext(nodes[child].a0, nstart(child) - el, nlen(child) + el, nodes[child].a1);
+      case NK_LEAF:
+      case NK_LEAF_ACCOUNT:
+        return releaf(child, nodes[child].a0, nstart(child) - el, nlen(child) + el);
+      default:  // branch, hashed-out node
+        return new_ext(ek, es, el, child);
+    }
+  }
+  // returns UNCHANGED when the key is absent
+  uint32_t remove(uint32_t node, uint32_t koff, uint32_t klen, uint32_t pos) {
+    if (node == NODE_EMPTY) return UNCHANGED;
+    switch (kind(node)) {
+      case NK_HASH:
+      case NK_ROOT:
+        return UNCHANGED;
+      case NK_EXT: {
+        uint32_t ek = nodes[node].a0, es = nstart(node), el = nlen(node);
+        if (klen - pos < el || common_prefix(ek, es, el, koff, pos, el) != el) return UNCHANGED;
+        uint32_t r = remove(nodes[node].a1, koff, klen, pos + el);
+        if (r == UNCHANGED) return UNCHANGED;
+        if (r == NODE_EMPTY) return NODE_EMPTY;
+        return collapse_ext(rep_key(r), es, el, r);
+      }
+      case NK_BRANCH: {
+        if (pos >= klen) return UNCHANGED;
+        uint32_t nib = key_nib(koff, pos);
+        uint32_t r = remove(child_at(node, nib), koff, klen, pos + 1);
+        if (r == UNCHANGED) return UNCHANGED;
+        if (r != NODE_EMPTY) return branch_with(node, nib, r);
+        uint32_t left = nodes[node].a1 & ~(1u << nib);
+        int cnt = __builtin_popcount(left);
+        if (cnt >= 2) return branch_with(node, nib, NODE_EMPTY);
+        if (cnt == 0) return NODE_EMPTY;
+        uint32_t other_nib = (uint32_t)__builtin_ctz(left);
+        uint32_t other = child_at(node, other_nib);
+        return collapse_ext(rep_key(other), pos, 1, other);
+      }
+      default: {
+        uint32_t lk = nodes[node].a0, ls = nstart(node), ll = nlen(node);
+        if (ll == klen - pos && common_prefix(lk, ls, ll, koff, pos, ll) == ll) return NODE_EMPTY;
+        return UNCHANGED;
+      }
+    }
+  }
+
+  // node holding the value of the key, or NODE_EMPTY
+  uint32_t get(uint32_t node, uint32_t koff, uint32_t klen) const {
+    uint32_t pos = 0;
+    while (node != NODE_EMPTY) {
+      switch (kind(node)) {
+        case NK_HASH:
+        case NK_ROOT:
+          return NODE_EMPTY;
+        case NK_BRANCH:
+          if (pos >= klen) return NODE_EMPTY;
+          node = child_at(node, key_nib(koff, pos));
+          pos++;
+          break;
+        case NK_EXT: {
+          uint32_t el = nlen(node);
+          if (klen - pos < el || common_prefix(nodes[node].a0, nstart(node), el, koff, pos, el) != el) return NODE_EMPTY;
+          pos += el;
+          node = nodes[node].a1;
+          break;
+        }
+        default: {
+          uint32_t ll = nlen(node);
+          if (ll == klen - pos && common_prefix(nodes[node].a0, nstart(node), ll, koff, pos, ll) == ll) return node;
+          return NODE_EMPTY;
+        }
+      }
+    }
+    return NODE_EMPTY;
+  }
+
+  // create_trie_subset's marking pass (trie_subsets.rs mark_nodes_that_are_needed)
+  void mark(uint32_t node, uint32_t koff, uint32_t klen, std::vector<uint32_t>& touched) const {
+    uint32_t pos = 0;
+    while (node != NODE_EMPTY) {
+      touched.push_back(node);
+      switch (kind(node)) {
+        case NK_HASH:
+        case NK_ROOT:
+          if (pos < klen) fail(PPD_ERR_MISSING_KEYS_CREATING_SUB_PARTIAL_TRIE, "subset key runs into a hashed-out node");
+          return;
+        case NK_BRANCH:
+          if (pos >= klen) return;
+          node = child_at(node, key_nib(koff, pos));
+          pos++;
+          break;
+        case NK_EXT: {
+          uint32_t el = nlen(node), avail = klen - pos;
+          uint32_t m = avail < el ? avail : el;
+          if (common_prefix(nodes[node].a0, nstart(node), m, koff, pos, m) != m) return;
+          if (avail < el) return;
+          pos += el;
+          node = nodes[node].a1;
+          break;
+        }
+        default:
+          return;
+      }
+    }
+  }
+};
+
+}  // namespace ppd

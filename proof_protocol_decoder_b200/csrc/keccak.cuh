@@ -1,0 +1,201 @@
+// keccak.cuh — Keccak-256 for sm_100a, thread-per-sponge.
+//
+// Replaces: keccak-hash 0.10.0 -> tiny-keccak 2.0.2 as called through
+// protocol_decoder/src/utils.rs:11-13 (`hash`) and, for trie nodes, eth_trie_utils'
+// `hash_bytes_if_large_enough`.
+//
+// Layout: the 25 x 64-bit state lives in registers as 32-bit halves.  Per round on the 32-bit
+// ISA: theta = 20 LOP3 (5-input column parities) + 10 SHF (rotl1) + 50 LOP3 (3-input XOR applying
+// D), rho = 48 SHF, pi = register renaming, chi = 50 LOP3 (a ^ (~b & c)), iota <= 2: ~180
+// ALU-pipe instructions per round, 4 320 per permutation (DESIGN.md "Keccak roofline").
+#pragma once
+#include <cstdint>
+
+namespace ppd {
+
+__constant__ uint64_t KECCAK_RC[24] = {
+    0x0000000000000001ULL, 0x0000000000008082ULL, 0x800000000000808aULL, 0x8000000080008000ULL,
+    0x000000000000808bULL, 0x0000000080000001ULL, 0x8000000080008081ULL, 0x8000000000008009ULL,
+    0x000000000000008aULL, 0x0000000000000088ULL, 0x0000000080008009ULL, 0x000000008000000aULL,
+    0x000000008000808bULL, 0x800000000000008bULL, 0x8000000000008089ULL, 0x8000000000008003ULL,
+    0x8000000000008002ULL, 0x8000000000000080ULL, 0x000000000000800aULL, 0x800000008000000aULL,
+    0x8000000080008081ULL, 0x8000000000008080ULL, 0x0000000080000001ULL, 0x8000000080008008ULL};
+
+// 64-bit rotate-left by a compile-time amount as two funnel shifts on the halves
+template <int K>
+__device__ __forceinline__ uint64_t rotl64(uint64_t x) {
+  static_assert(K > 0 && K < 64, "rotation amount");
+  uint32_t lo = (uint32_t)x, hi = (uint32_t)(x >> 32);
+  uint32_t nlo, nhi;
+  if (K < 32) {
+    nhi = __funnelshift_l(lo, hi, (uint32_t)K);
+    nlo = __funnelshift_l(hi, lo, (uint32_t)K);
+  } else if (K == 32) {
+    nhi = lo;
+    nlo = hi;
+  } else {
+    nhi = __funnelshift_l(hi, lo, (uint32_t)(K - 32));
+    nlo = __funnelshift_l(lo, hi, (uint32_t)(K - 32));
+  }
+  return ((uint64_t)nhi << 32) | nlo;
+}
+
+__device__ __forceinline__ uint64_t xor3(uint64_t a, uint64_t b, uint64_t c) {
+  uint32_t lo, hi;
+  asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(lo) : "r"((uint32_t)a), "r"((uint32_t)b), "r"((uint32_t)c));
+  asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(hi) : "r"((uint32_t)(a >> 32)), "r"((uint32_t)(b >> 32)), "r"((uint32_t)(c >> 32)));
+  return ((uint64_t)hi << 32) | lo;
+}
+// a ^ (~b & c)
+__device__ __forceinline__ uint64_t chi1(uint64_t a, uint64_t b, uint64_t c) {
+  uint32_t lo, hi;
+  asm("lop3.b32 %0, %1, %2, %3, 0xD2;" : "=r"(lo) : "r"((uint32_t)a), "r"((uint32_t)b), "r"((uint32_t)c));
+  asm("lop3.b32 %0, %1, %2, %3, 0xD2;" : "=r"(hi) : "r"((uint32_t)(a >> 32)), "r"((uint32_t)(b >> 32)), "r"((uint32_t)(c >> 32)));
+  return ((uint64_t)hi << 32) | lo;
+}
+
+// One round.  Reads a[], writes a[] (through a register-renamed b[]).
+__device__ __forceinline__ void keccak_round(uint64_t (&a)[25], uint64_t rc) {
+  uint64_t c0 = xor3(xor3(a[0], a[5], a[10]), a[15], a[20]);
+  uint64_t c1 = xor3(xor3(a[1], a[6], a[11]), a[16], a[21]);
+  uint64_t c2 = xor3(xor3(a[2], a[7], a[12]), a[17], a[22]);
+  uint64_t c3 = xor3(xor3(a[3], a[8], a[13]), a[18], a[23]);
+  uint64_t c4 = xor3(xor3(a[4], a[9], a[14]), a[19], a[24]);
+  uint64_t r0 = rotl64<1>(c0), r1 = rotl64<1>(c1), r2 = rotl64<1>(c2), r3 = rotl64<1>(c3), r4 = rotl64<1>(c4);
+  // theta folded into the rho/pi gather: t = a ^ c[x-1] ^ rotl1(c[x+1]) is one LOP3 per half
+  uint64_t b[25];
+#define TH(i, x) xor3(a[i], (x == 0 ? c4 : x == 1 ? c0 : x == 2 ? c1 : x == 3 ? c2 : c3), (x == 0 ? r1 : x == 1 ? r2 : x == 2 ? r3 : x == 3 ? r4 : r0))
+  b[0] = TH(0, 0);
+  b[10] = rotl64<1>(TH(1, 1));
+  b[20] = rotl64<62>(TH(2, 2));
+  b[5] = rotl64<28>(TH(3, 3));
+  b[15] = rotl64<27>(TH(4, 4));
+  b[16] = rotl64<36>(TH(5, 0));
+  b[1] = rotl64<44>(TH(6, 1));
+  b[11] = rotl64<6>(TH(7, 2));
+  b[21] = rotl64<55>(TH(8, 3));
+  b[6] = rotl64<20>(TH(9, 4));
+  b[7] = rotl64<3>(TH(10, 0));
+  b[17] = rotl64<10>(TH(11, 1));
+  b[2] = rotl64<43>(TH(12, 2));
+  b[12] = rotl64<25>(TH(13, 3));
+  b[22] = rotl64<39>(TH(14, 4));
+  b[23] = rotl64<41>(TH(15, 0));
+  b[8] = rotl64<45>(TH(16, 1));
+  b[18] = rotl64<15>(TH(17, 2));
+  b[3] = rotl64<21>(TH(18, 3));
+  b[13] = rotl64<8>(TH(19, 4));
+  b[14] = rotl64<18>(TH(20, 0));
+  b[24] = rotl64<2>(TH(21, 1));
+  b[9] = rotl64<61>(TH(22, 2));
+  b[19] = rotl64<56>(TH(23, 3));
+  b[4] = rotl64<14>(TH(24, 4));
+#undef TH
+#pragma unroll
+  for (int y = 0; y < 25; y += 5) {
+    a[y + 0] = chi1(b[y + 0], b[y + 1], b[y + 2]);
+    a[y + 1] = chi1(b[y + 1], b[y + 2], b[y + 3]);
+    a[y + 2] = chi1(b[y + 2], b[y + 3], b[y + 4]);
+    a[y + 3] = chi1(b[y + 3], b[y + 4], b[y + 0]);
+    a[y + 4] = chi1(b[y + 4], b[y + 0], b[y + 1]);
+  }
+  a[0] ^= rc;
+}
+
+#ifndef PPD_KECCAK_UNROLL
+#define PPD_KECCAK_UNROLL 24
+#endif
+#define PPD_PRAGMA_(x) _Pragma(#x)
+#define PPD_PRAGMA_UNROLL(n) PPD_PRAGMA_(unroll n)
+
+__device__ __forceinline__ void keccak_f1600(uint64_t (&a)[25]) {
+  PPD_PRAGMA_UNROLL(PPD_KECCAK_UNROLL)
+  for (int r = 0; r < 24; r++) keccak_round(a, KECCAK_RC[r]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Block staging for a byte stream that a thread produces piecewise (RLP headers, child refs,
+// values).  Pull model: a thread appends whole segments (each <= 48 bytes) to its stage until at
+// least one 136-byte rate block is complete, then ALL lanes of the warp that still have blocks run
+// the one keccak_f1600 site convergently; the up-to-47 overflow bytes are moved to the front.
+//
+// The stage is PPD_STAGE_WORDS 32-bit words per thread in shared memory, word-interleaved
+// (word w of thread t at stage[w * BLOCK + t]): the bank depends on t only, so every access pattern
+// of a warp is conflict-free no matter how far each lane has advanced.
+// ---------------------------------------------------------------------------------------------
+#define PPD_STAGE_WORDS 46
+
+template <int BLOCK>
+struct Stage {
+  uint32_t* w;    // &smem[threadIdx.x]
+  uint32_t acc;   // pending bytes of word `widx` (low `sh` bits valid)
+  uint32_t sh;    // 0, 8, 16, 24
+  uint32_t widx;  // complete words staged
+
+  __device__ __forceinline__ void init(uint32_t* smem) {
+    w = smem + threadIdx.x;
+    acc = 0;
+    sh = 0;
+    widx = 0;
+  }
+  __device__ __forceinline__ uint32_t bytes() const { return 4 * widx + (sh >> 3); }
+  __device__ __forceinline__ void put_word(uint32_t x) {
+    uint64_t t = (uint64_t)acc | ((uint64_t)x << sh);
+    w[widx * BLOCK] = (uint32_t)t;
+    widx++;
+    acc = (uint32_t)(t >> 32);
+  }
+  __device__ __forceinline__ void put_byte(uint32_t b) {
+    acc |= b << sh;
+    sh += 8;
+    if (sh == 32) {
+      w[widx * BLOCK] = acc;
+      widx++;
+      acc = 0;
+      sh = 0;
+    }
+  }
+  // append the low n bytes of x (n = 0..4)
+  __device__ __forceinline__ void put_partial(uint32_t x, uint32_t n) {
+    if (n == 0) return;
+    if (n < 4) x &= (1u << (8 * n)) - 1;
+    uint64_t t = (uint64_t)acc | ((uint64_t)x << sh);
+    uint32_t nsh = sh + 8 * n;
+    if (nsh >= 32) {
+      w[widx * BLOCK] = (uint32_t)t;
+      widx++;
+      acc = (uint32_t)(t >> 32);
+      sh = nsh - 32;
+    } else {
+      acc = (uint32_t)t;
+      sh = nsh;
+    }
+  }
+  // Keccak padding 0x01 .. 0x80 (original Keccak, as tiny-keccak's Keccak::v256).  Needs bytes() < 136.
+  __device__ __forceinline__ void pad() {
+    w[widx * BLOCK] = acc | (0x01u << sh);
+    for (uint32_t i = widx + 1; i < 34; i++) w[i * BLOCK] = 0;
+    w[33 * BLOCK] |= 0x80000000u;
+  }
+  // after a block was absorbed: move the overflow words to the front
+  __device__ __forceinline__ void consume_block() {
+    uint32_t over = widx - 34;
+    for (uint32_t i = 0; i < over; i++) w[i * BLOCK] = w[(34 + i) * BLOCK];
+    widx = over;
+  }
+  // make the partial word visible in shared memory (for the inline < 32-byte case)
+  __device__ __forceinline__ void flush_partial() {
+    if (sh) w[widx * BLOCK] = acc;
+  }
+};
+
+template <int BLOCK>
+__device__ __forceinline__ void absorb_stage(uint64_t (&a)[25], const uint32_t* w) {
+#pragma unroll
+  for (int i = 0; i < 17; i++) {
+    uint32_t lo = w[(2 * i) * BLOCK], hi = w[(2 * i + 1) * BLOCK];
+    a[i] ^= ((uint64_t)hi << 32) | lo;
+  }
+}
+
+}  // namespace ppd

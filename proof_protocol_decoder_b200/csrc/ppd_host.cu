@@ -1,0 +1,1578 @@
+// ppd_host.cu — host side of libppd_b200.so: the C ABI (include/ppd_b200.h), the context that
+// owns the stream and the HBM buffers, and the block pipeline
+//
+//   FlatBlock ─► parse witness (compact_prestate_processing.rs:683-875, 387-668)
+//             ─► batch-hash every address / slot / code on the GPU      (utils.rs:11-13 call sites)
+//             ─► shape all versions of all tries as one persistent DAG   (host_arena.h; no hashing)
+//             ─► ONE level-synchronous GPU sweep over the DAG            (ppd_kernels.cu)
+//             ─► serialise Vec<GenerationInputs> as an IrDump            (decoding.rs:131-145)
+//
+// The host never computes a Keccak or a node encoding.  If the CUDA device or the kernels are not
+// usable every entry point fails with PPD_ERR_CUDA: there is no CPU fallback.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/ppd_b200.h"
+#include "arena.h"
+#include "host_arena.h"
+#include "ppd_kernels.h"
+
+using namespace ppd;
+
+#define CUDA_OK(expr)                                                                          \
+  do {                                                                                         \
+    cudaError_t e_ = (expr);                                                                   \
+    if (e_ != cudaSuccess) {                                                                   \
+      throw Fail{PPD_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_)};            \
+    }                                                                                          \
+  } while (0)
+
+namespace {
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  void reserve(size_t n) {
+    if (n <= cap) return;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = n + n / 4 + 256;
+    CUDA_OK(cudaMalloc(&p, want));
+    cap = want;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <class T>
+  T* as() const {
+    return reinterpret_cast<T*>(p);
+  }
+};
+
+struct H256 {
+  uint8_t b[32];
+  bool operator==(const H256& o) const { return memcmp(b, o.b, 32) == 0; }
+  bool operator<(const H256& o) const { return memcmp(b, o.b, 32) < 0; }
+};
+struct H256Hasher {
+  size_t operator()(const H256& h) const {
+    size_t v;
+    memcpy(&v, h.b + 8, sizeof v);
+    return v;
+  }
+};
+
+const uint8_t EMPTY_CODE_HASH[32] = {0xc5, 0xd2, 0x46, 0x01, 0x86, 0xf7, 0x23, 0x3c, 0x92, 0x7e, 0x7d, 0xb2, 0xdc, 0xc7, 0x03, 0xc0,
+                                     0xe5, 0x00, 0xb6, 0x53, 0xca, 0x82, 0x27, 0x3b, 0x7b, 0xfa, 0xd8, 0x04, 0x5d, 0x85, 0xa4, 0x70};
+const uint8_t EMPTY_TRIE_HASH[32] = {0x56, 0xe8, 0x1f, 0x17, 0x1b, 0xcc, 0x55, 0xa6, 0xff, 0x83, 0x45, 0xe6, 0x92, 0xc0, 0xf8, 0x6e,
+                                     0x5b, 0x48, 0xe0, 0x1b, 0x99, 0x6c, 0xad, 0xc0, 0x01, 0x62, 0x2f, 0xb5, 0xe3, 0x63, 0xb4, 0x21};
+
+}  // namespace
+
+struct ppd_ctx {
+  int device = 0;
+  cudaStream_t st = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::string err;
+  ppd_stats stats{};
+  // HBM buffers, grown on demand and reused across calls
+  DevBuf d_nodes, d_order, d_keys, d_vals, d_hashes, d_children, d_accounts, d_ref, d_ref_len, d_counters;
+  DevBuf d_msg, d_msg_off, d_digest;
+  DevBuf d_build[12];
+};
+
+namespace {
+
+void stats_reset(ppd_ctx* c) { c->stats = ppd_stats{}; }
+
+// ============================================================================================
+// Phase I: batched Keccak-256 of byte strings (addresses, slots, code)
+// ============================================================================================
+struct KeyHasher {
+  std::vector<uint8_t> data;
+  std::vector<uint64_t> off{0};
+  std::vector<H256> digest;
+  uint32_t add(const uint8_t* p, size_t n) {
+    data.insert(data.end(), p, p + n);
+    // keep every message 4-byte aligned so the kernel's word loads start aligned
+    while (data.size() & 3) data.push_back(0);
+    uint32_t idx = (uint32_t)lens.size();
+    lens.push_back(n);
+    off.push_back(data.size());
+    return idx;
+  }
+  std::vector<uint64_t> lens;
+  void run(ppd_ctx* c) {
+    size_t n = lens.size();
+    digest.resize(n);
+    if (!n) return;
+    // messages are padded to 4-byte boundaries, so pass explicit (begin, end) pairs
+    std::vector<uint64_t> se(2 * n);
+    for (size_t i = 0; i < n; i++) se[2 * i] = off[i], se[2 * i + 1] = off[i] + lens[i];
+    c->d_msg.reserve(data.size() + 16);
+    c->d_msg_off.reserve(se.size() * 8);
+    c->d_digest.reserve(n * 32);
+    CUDA_OK(cudaMemcpyAsync(c->d_msg.p, data.data(), data.size(), cudaMemcpyHostToDevice, c->st));
+    CUDA_OK(cudaMemcpyAsync(c->d_msg_off.p, se.data(), se.size() * 8, cudaMemcpyHostToDevice, c->st));
+    launch_keccak256_ranges(c->d_msg.as<uint8_t>(), c->d_msg_off.as<uint64_t>(), (uint32_t)n, c->d_digest.as<uint8_t>(), c->st);
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaMemcpyAsync(digest.data(), c->d_digest.p, n * 32, cudaMemcpyDeviceToHost, c->st));
+    CUDA_OK(cudaStreamSynchronize(c->st));
+    c->stats.key_hashes += n;
+    for (size_t i = 0; i < n; i++) c->stats.key_permutations += lens[i] / 136 + 1;
+    c->stats.h2d_bytes += (double)(data.size() + se.size() * 8);
+    c->stats.d2h_bytes += (double)(n * 32);
+    c->stats.kernel_launches += 1;
+  }
+};
+
+// ============================================================================================
+// Compact witness -> instruction tree (compact_prestate_processing.rs:683-875, 387-668)
+// ============================================================================================
+struct Span {
+  const uint8_t* p = nullptr;
+  uint32_t n = 0;
+};
+struct WInstr {
+  uint8_t op;
+  bool has_code = false, has_storage = false;
+  uint32_t mask = 0;
+  Span key;           // compact key bytes (leaf / extension / account leaf)
+  Span value;         // leaf value / code bytes
+  const uint8_t* hash = nullptr;
+  uint64_t nonce = 0;
+  Span balance;       // big-endian, <= 32 bytes
+  // tree links filled by the stack machine
+  int32_t first_child = -1, next_sibling = -1;  // branch children (ascending nibble order) / extension child
+  int32_t storage_node = -1, code_node = -1;    // account leaf
+};
+
+struct WCursor {
+  const uint8_t* p;
+  size_t n, pos = 0;
+  uint8_t read_byte() {
+    if (pos >= n) fail(PPD_ERR_UNEXPECTED_END_OF_STREAM, "read_byte at end of stream");
+    return p[pos++];
+  }
+  bool cbor_head(uint8_t& major, uint64_t& arg) {
+    if (pos >= n) return false;
+    uint8_t b = p[pos++];
+    major = b >> 5;
+    uint8_t ai = b & 31;
+    if (ai < 24) {
+      arg = ai;
+      return true;
+    }
+    if (ai > 27) return false;
+    size_t w = (size_t)1 << (ai - 24);
+    if (n - pos < w) return false;
+    arg = 0;
+    for (size_t i = 0; i < w; i++) arg = (arg << 8) | p[pos++];
+    return true;
+  }
+  Span cbor_bytes(int err) {
+    uint8_t major;
+    uint64_t len;
+    if (!cbor_head(major, len) || major != 2 || len > n - pos) fail(err, "bad CBOR byte string");
+    Span s{p + pos, (uint32_t)len};
+    pos += len;
+    return s;
+  }
+  uint64_t cbor_uint(uint64_t max) {
+    uint8_t major;
+    uint64_t v;
+    if (!cbor_head(major, v) || major != 0 || v > max) fail(PPD_ERR_INVALID_BYTES_FOR_TYPE, "bad CBOR unsigned integer");
+    return v;
+  }
+};
+
+// key_bytes_to_nibbles (compact_prestate_processing.rs:1338-1390); appends to `out`, returns count
+uint32_t compact_key_nibbles(Span k, uint8_t* out) {
+  if (k.n == 0) return 0;
+  uint32_t c = 0;
+  if (k.n == 1) {
+    out[c++] = k.p[0] & 15;
+    return c;
+  }
+  bool odd = k.p[0] & 1;
+  uint32_t m = k.n - 1;
+  if (2 * m > 64 + 1) fail(PPD_ERR_KEY_ERROR, "compact key longer than 64 nibbles");
+  for (uint32_t i = 0; i + 1 < m; i++) {
+    out[c++] = k.p[1 + i] >> 4;
+    out[c++] = k.p[1 + i] & 15;
+  }
+  out[c++] = k.p[m] >> 4;
+  if (!odd) out[c++] = k.p[m] & 15;
+  return c;
+}
+
+struct Witness {
+  uint8_t version = 0;
+  std::vector<WInstr> ins;
+  int32_t root = -1;  // -1: header only
+};
+
+void parse_witness(const uint8_t* w, size_t n, Witness& out) {
+  if (n == 0) fail(PPD_ERR_MISSING_HEADER, "missing header");
+  WCursor c{w, n};
+  out.version = c.read_byte();
+  std::vector<int32_t> stack;
+  while (c.pos < c.n) {
+    WInstr in;
+    in.op = c.read_byte();
+    switch (in.op) {
+      case PPD_OP_LEAF:
+        in.key = c.cbor_bytes(PPD_ERR_INVALID_BYTE_VECTOR);
+        in.value = c.cbor_bytes(PPD_ERR_INVALID_BYTE_VECTOR);
+        break;
+      case PPD_OP_EXTENSION:
+        in.key = c.cbor_bytes(PPD_ERR_INVALID_BYTE_VECTOR);
+        break;
+      case PPD_OP_BRANCH:
+        in.mask = (uint32_t)c.cbor_uint(0xffffffffull);
+        break;
+      case PPD_OP_HASH:
+        if (c.n - c.pos < 32) fail(PPD_ERR_INVALID_BYTES_FOR_TYPE, "short raw hash");
+        in.hash = c.p + c.pos;
+        c.pos += 32;
+        break;
+      case PPD_OP_CODE:
+        in.value = c.cbor_bytes(PPD_ERR_INVALID_BYTES_FOR_TYPE);
+        break;
+      case PPD_OP_ACCOUNT_LEAF: {
+        in.key = c.cbor_bytes(PPD_ERR_INVALID_BYTE_VECTOR);
+        uint8_t flags = c.read_byte();
+        in.has_code = flags & 1;
+        in.has_storage = flags & 2;
+        if (flags & 4) in.nonce = c.cbor_uint(~0ull);
+        if (flags & 8) {
+          in.balance = c.cbor_bytes(PPD_ERR_INVALID_BYTE_VECTOR);
+          if (in.balance.n > 32) fail(PPD_ERR_INVALID_BYTE_VECTOR, "balance wider than 256 bits");
+        }
+        if (flags & 1) (void)c.cbor_uint(~0ull);
+        break;
+      }
+      case PPD_OP_EMPTY_ROOT:
+        break;
+      default:
+        fail(PPD_ERR_INVALID_OPERATOR, "invalid opcode");
+    }
+    out.ins.push_back(in);
+  }
+  // stack machine: instructions arrive in post-order
+  for (int32_t i = 0; i < (int32_t)out.ins.size(); i++) {
+    WInstr& in = out.ins[i];
+    switch (in.op) {
+      case PPD_OP_EXTENSION:
+        if (stack.empty()) fail(PPD_ERR_INVALID_WITNESS_FORMAT, "extension with no preceding node");
+        in.first_child = stack.back();
+        stack.pop_back();
+        break;
+      case PPD_OP_BRANCH: {
+        size_t expected = (size_t)__builtin_popcount(in.mask);
+        if (stack.size() < expected) fail(PPD_ERR_INCORRECT_NUMBER_OF_NODES_PRECEDING_BRANCH, "branch mask wants more nodes than precede it");
+        if (in.mask >> 16) fail(PPD_ERR_MISSING_EXPECTED_NODES_PRECEDING_BRANCH, "branch mask has bits above 15");
+        size_t base = stack.size() - expected;
+        for (size_t k = 0; k < expected; k++) {  // lowest set bit <-> oldest pushed
+          if (k == 0)
+            in.first_child = stack[base];
+          else
+            out.ins[stack[base + k - 1]].next_sibling = stack[base + k];
+        }
+        if (expected) out.ins[stack[base + expected - 1]].next_sibling = -1;
+        stack.resize(base);
+        break;
+      }
+      case PPD_OP_ACCOUNT_LEAF:
+        if (in.has_storage) {
+          if (stack.empty() || out.ins[stack.back()].op == PPD_OP_CODE) fail(PPD_ERR_INVALID_WITNESS_FORMAT, "account leaf: no storage node");
+          in.storage_node = stack.back();
+          stack.pop_back();
+        }
+        if (in.has_code) {
+          if (stack.empty() || (out.ins[stack.back()].op != PPD_OP_CODE && out.ins[stack.back()].op != PPD_OP_HASH))
+            fail(PPD_ERR_INVALID_WITNESS_FORMAT, "account leaf: no code node");
+          in.code_node = stack.back();
+          stack.pop_back();
+        }
+        break;
+      default:
+        break;
+    }
+    stack.push_back(i);
+  }
+  if (stack.size() > 1) fail(PPD_ERR_NON_SINGLE_ENTRY_AFTER_PROCESSING, "more than one entry left");
+  out.root = stack.empty() ? -1 : stack[0];
+}
+
+// ============================================================================================
+// Items of one trie (what HashedPartialTrie::items() would list) and the canonical build
+// ============================================================================================
+struct TrieItem {
+  uint32_t koff, klen;
+  uint8_t kind;  // 0 value leaf, 1 account leaf, 2 hashed-out subtree
+  uint32_t a1, a2;
+};
+
+// Canonical trie over sorted, prefix-free items [lo, hi) whose keys agree on the first `depth`
+// nibbles.  Equals what inserting them one by one produces (compact_to_partial_trie.rs:105,125).
+uint32_t build_range(HostArena& A, const std::vector<TrieItem>& it, size_t lo, size_t hi, uint32_t depth) {
+  if (lo == hi) return NODE_EMPTY;
+  if (hi - lo == 1) {
+    const TrieItem& x = it[lo];
+    if (x.kind == 2) {
+      uint32_t h = A.new_hash(x.a1, x.koff);
+      return x.klen == depth ? h : A.new_ext(x.koff, depth, x.klen - depth, h);
+    }
+    if (x.kind == 1) return A.new_account_leaf(x.koff, depth, x.klen - depth, x.a1);
+    return A.new_leaf(x.koff, depth, x.klen - depth, x.a1, x.a2);
+  }
+  const TrieItem& f = it[lo];
+  const TrieItem& l = it[hi - 1];
+  uint32_t cp = A.common_prefix(f.koff, depth, f.klen - depth, l.koff, depth, l.klen - depth);
+  uint32_t at = depth + cp;
+  uint32_t kids[16], mask = 0, k = 0;
+  size_t i = lo;
+  while (i < hi) {
+    if (it[i].klen <= at) fail(PPD_PANIC_KEY_IS_PREFIX_OF_KEY, "a key is a prefix of another key");
+    uint32_t nib = A.key_nib(it[i].koff, at);
+    size_t j = i + 1;
+    while (j < hi && it[j].klen > at && A.key_nib(it[j].koff, at) == nib) j++;
+    if (mask & (1u << nib)) fail(PPD_ERR_UNSORTED_KEYS, "trie items are not sorted");
+    kids[k++] = build_range(A, it, i, j, at + 1);
+    mask |= 1u << nib;
+    i = j;
+  }
+  uint32_t br = A.new_branch(mask, kids, f.koff);
+  return cp == 0 ? br : A.new_ext(f.koff, depth, cp, br);
+}
+
+// ============================================================================================
+// One block being decoded
+// ============================================================================================
+struct TraceV {
+  const uint8_t* addr;
+  uint8_t flags;
+  const uint8_t *balance = nullptr, *nonce = nullptr;
+  uint32_t n_reads = 0, n_writes = 0;
+  const uint8_t *reads = nullptr, *writes = nullptr;
+  const uint8_t* code_read = nullptr;
+  Span code_write;
+  // message indices into the key hasher
+  uint32_t m_addr = 0, m_reads = 0, m_writes_full = 0, m_writes_min = 0, m_code = 0;
+};
+struct TxnV {
+  std::vector<TraceV> traces;
+  Span byte_code, new_txn_node, new_receipt_node;
+  uint64_t gas_used = 0;
+};
+struct FlatReader {
+  const uint8_t* p;
+  size_t n, pos = 0;
+  void need(size_t k) {
+    if (n - pos < k) fail(PPD_ERR_BAD_FLAT_INPUT, "flat block truncated");
+  }
+  uint8_t u8() {
+    need(1);
+    return p[pos++];
+  }
+  uint32_t u32() {
+    need(4);
+    uint32_t v;
+    memcpy(&v, p + pos, 4);
+    pos += 4;
+    return v;
+  }
+  uint64_t u64() {
+    need(8);
+    uint64_t v;
+    memcpy(&v, p + pos, 8);
+    pos += 8;
+    return v;
+  }
+  const uint8_t* raw(size_t k) {
+    need(k);
+    const uint8_t* r = p + pos;
+    pos += k;
+    return r;
+  }
+  Span bytes() {
+    uint32_t k = u32();
+    return Span{raw(k), k};
+  }
+};
+
+struct IrPlan {
+  uint64_t txn_before = 0, gas_before = 0, gas_after = 0;
+  bool has_signed_txn = false;
+  Span signed_txn;
+  bool has_withdrawals = false;
+  uint32_t state_sub = NODE_EMPTY, txn_sub = NODE_EMPTY, receipt_sub = NODE_EMPTY;  // roots of the tries the subsets are cut from
+  std::vector<std::pair<H256, uint32_t>> storage_subs;
+  std::vector<uint32_t> touched;
+  uint32_t root_state = 0, root_txn = 0, root_receipt = 0;  // NK_ROOT nodes
+  std::map<H256, Span> code;
+};
+
+struct BlockJob {
+  // input views
+  Span compact;
+  std::vector<TxnV> txns;
+  std::unordered_map<H256, Span, H256Hasher> resolved_code;
+  std::vector<std::pair<const uint8_t*, const uint8_t*>> withdrawals;
+  std::vector<uint32_t> m_withdrawal_addr;
+  const uint8_t* checkpoint = nullptr;
+  Span b_meta, b_hashes;
+  // decoded witness
+  Witness wit;
+  std::vector<uint32_t> m_inline_code;  // per instruction: message index of an inline Code node, or ~0
+  std::map<H256, Span> pre_code;        // WitnessOutput.code
+  // tries
+  uint32_t state_root = NODE_EMPTY;
+  std::unordered_map<H256, uint32_t, H256Hasher> storage;  // hashed address -> root node
+  struct PreAccount {
+    H256 haddr;
+    uint32_t rec;
+    bool storage_nonempty;
+  };
+  std::vector<PreAccount> pre_accounts;
+  std::unordered_map<H256, uint32_t, H256Hasher> pre_with_storage;  // accounts whose storage root != EMPTY_TRIE_HASH -> record
+  std::unordered_map<uint32_t, uint32_t> root_of;                   // trie root node -> its NK_ROOT node
+  std::vector<IrPlan> irs;
+  int status = PPD_OK;
+  std::string err;
+};
+
+void read_flat_block(const uint8_t* p, size_t n, BlockJob& b) {
+  FlatReader r{p, n};
+  if (r.u32() != PPD_FLAT_BLOCK_MAGIC || r.u32() != 1) fail(PPD_ERR_BAD_FLAT_INPUT, "bad magic/version");
+  if (r.u32() != 0) fail(PPD_PANIC_UNIMPLEMENTED_PRE_IMAGE, "only Combined{compact} pre-images are implemented by the reference");
+  b.compact = r.bytes();
+  uint32_t nt = r.u32();
+  b.txns.resize(nt);
+  for (uint32_t t = 0; t < nt; t++) {
+    TxnV& tx = b.txns[t];
+    uint32_t ntr = r.u32();
+    tx.traces.resize(ntr);
+    for (uint32_t i = 0; i < ntr; i++) {
+      TraceV& tr = tx.traces[i];
+      tr.addr = r.raw(20);
+      tr.flags = r.u8();
+      if (tr.flags & PPD_TR_BALANCE) tr.balance = r.raw(32);
+      if (tr.flags & PPD_TR_NONCE) tr.nonce = r.raw(32);
+      if (tr.flags & PPD_TR_STORAGE_READ) {
+        tr.n_reads = r.u32();
+        tr.reads = r.raw(32ull * tr.n_reads);
+      }
+      if (tr.flags & PPD_TR_STORAGE_WRITTEN) {
+        tr.n_writes = r.u32();
+        tr.writes = r.raw(64ull * tr.n_writes);
+      }
+      if (tr.flags & PPD_TR_CODE_READ) tr.code_read = r.raw(32);
+      if (tr.flags & PPD_TR_CODE_WRITE) tr.code_write = r.bytes();
+    }
+    tx.byte_code = r.bytes();
+    tx.new_txn_node = r.bytes();
+    tx.new_receipt_node = r.bytes();
+    tx.gas_used = r.u64();
+  }
+  uint32_t nc = r.u32();
+  for (uint32_t i = 0; i < nc; i++) {
+    H256 h;
+    memcpy(h.b, r.raw(32), 32);
+    b.resolved_code[h] = r.bytes();
+  }
+  uint32_t nw = r.u32();
+  for (uint32_t i = 0; i < nw; i++) {
+    const uint8_t* a = r.raw(20);
+    const uint8_t* v = r.raw(32);
+    b.withdrawals.push_back({a, v});
+  }
+  b.checkpoint = r.raw(32);
+  b.b_meta = r.bytes();
+  b.b_hashes = r.bytes();
+}
+
+// ---- minimal RLP helpers (structure only; no hashing) -----------------------------------------
+uint32_t u256_sig(const uint8_t* be) {
+  uint32_t i = 0;
+  while (i < 32 && be[i] == 0) i++;
+  return 32 - i;
+}
+void rlp_str(std::vector<uint8_t>& out, const uint8_t* p, size_t n) {
+  if (n == 1 && p[0] < 0x80) {
+    out.push_back(p[0]);
+    return;
+  }
+  if (n < 56) {
+    out.push_back((uint8_t)(0x80 + n));
+  } else {
+    uint8_t tmp[8];
+    int k = 0;
+    for (size_t v = n; v; v >>= 8) tmp[k++] = (uint8_t)v;
+    out.push_back((uint8_t)(0xb7 + k));
+    while (k) out.push_back(tmp[--k]);
+  }
+  out.insert(out.end(), p, p + n);
+}
+void rlp_u256(std::vector<uint8_t>& out, const uint8_t* be) {
+  uint32_t s = u256_sig(be);
+  rlp_str(out, be + 32 - s, s);
+}
+struct RlpItem {
+  bool is_list;
+  const uint8_t* payload;
+  size_t payload_len, total_len;
+};
+bool rlp_item(const uint8_t* p, size_t n, RlpItem& it) {
+  if (n == 0) return false;
+  uint8_t b = p[0];
+  if (b < 0x80) {
+    it = {false, p, 1, 1};
+    return true;
+  }
+  bool is_list = b >= 0xc0;
+  uint8_t sb = is_list ? 0xc0 : 0x80, lb = is_list ? 0xf7 : 0xb7;
+  size_t hdr, len;
+  if (b <= lb) {
+    hdr = 1;
+    len = b - sb;
+    if (!is_list && len == 1) {
+      if (n < 2 || p[1] < 0x80) return false;
+    }
+  } else {
+    size_t ll = b - lb;
+    if (ll > 8 || n < 1 + ll || p[1] == 0) return false;
+    len = 0;
+    for (size_t i = 0; i < ll; i++) len = (len << 8) | p[1 + i];
+    if (len < 56) return false;
+    hdr = 1 + ll;
+  }
+  if (len > n - hdr) return false;
+  it = {is_list, p + hdr, len, hdr + len};
+  return true;
+}
+bool rlp_is_u256(const uint8_t*& q, size_t& m) {
+  RlpItem it;
+  if (!rlp_item(q, m, it) || it.is_list || it.payload_len > 32) return false;
+  if (it.payload_len && it.payload[0] == 0) return false;
+  q += it.total_len, m -= it.total_len;
+  return true;
+}
+// plonky2_evm LegacyReceiptRlp {status: bool, cum_gas_used: U256, bloom: Bytes, logs: Vec<LogRlp>}
+bool is_legacy_receipt(const uint8_t* p, size_t n) {
+  RlpItem top, it;
+  if (!rlp_item(p, n, top) || !top.is_list) return false;
+  const uint8_t* q = top.payload;
+  size_t m = top.payload_len;
+  if (!rlp_item(q, m, it) || it.is_list || it.payload_len > 1) return false;
+  if (it.payload_len == 1 && (it.payload[0] == 0 || it.payload[0] > 1)) return false;
+  q += it.total_len, m -= it.total_len;
+  if (!rlp_is_u256(q, m)) return false;
+  if (!rlp_item(q, m, it) || it.is_list) return false;
+  q += it.total_len, m -= it.total_len;
+  if (!rlp_item(q, m, it) || !it.is_list) return false;
+  const uint8_t* lq = it.payload;
+  size_t lm = it.payload_len;
+  while (lm) {
+    RlpItem log, x;
+    if (!rlp_item(lq, lm, log) || !log.is_list) return false;
+    const uint8_t* f = log.payload;
+    size_t fm = log.payload_len;
+    if (!rlp_item(f, fm, x) || x.is_list || x.payload_len != 20) return false;
+    f += x.total_len, fm -= x.total_len;
+    if (!rlp_item(f, fm, x) || !x.is_list) return false;
+    const uint8_t* tq = x.payload;
+    size_t tm = x.payload_len;
+    while (tm) {
+      RlpItem t;
+      if (!rlp_item(tq, tm, t) || t.is_list || t.payload_len != 32) return false;
+      tq += t.total_len, tm -= t.total_len;
+    }
+    f += x.total_len, fm -= x.total_len;
+    if (!rlp_item(f, fm, x) || x.is_list) return false;
+    lq += log.total_len, lm -= log.total_len;
+  }
+  return true;
+}
+
+// ============================================================================================
+// Job = a batch of blocks sharing one arena, one key-hash launch and one sweep
+// ============================================================================================
+struct Job {
+  HostArena A;
+  KeyHasher kh;
+  std::vector<BlockJob> blocks;
+  std::vector<uint8_t> ref, ref_len;  // after the sweep
+  std::vector<uint32_t> stamp;
+  uint32_t serial = 0;
+};
+
+// ---- step 1: parse, collect every byte string that must be hashed ----------------------------
+void collect_messages(Job& J, BlockJob& b) {
+  parse_witness(b.compact.p, b.compact.n, b.wit);
+  if (b.wit.version != 1) fail(PPD_PANIC_INCOMPATIBLE_HEADER_VERSION, "compact header version is not 1");
+  b.m_inline_code.assign(b.wit.ins.size(), ~0u);
+  for (size_t i = 0; i < b.wit.ins.size(); i++)
+    if (b.wit.ins[i].op == PPD_OP_CODE) b.m_inline_code[i] = J.kh.add(b.wit.ins[i].value.p, b.wit.ins[i].value.n);
+  for (TxnV& tx : b.txns)
+    for (TraceV& tr : tx.traces) {
+      tr.m_addr = J.kh.add(tr.addr, 20);
+      tr.m_reads = (uint32_t)J.kh.lens.size();
+      for (uint32_t k = 0; k < tr.n_reads; k++) J.kh.add(tr.reads + 32 * k, 32);
+      tr.m_writes_full = (uint32_t)J.kh.lens.size();
+      for (uint32_t k = 0; k < tr.n_writes; k++) J.kh.add(tr.writes + 64 * k, 32);
+      // decoding.rs:235 hashes Nibbles::bytes_be() of the raw slot key, which drops leading zero bytes
+      tr.m_writes_min = (uint32_t)J.kh.lens.size();
+      for (uint32_t k = 0; k < tr.n_writes; k++) {
+        const uint8_t* key = tr.writes + 64 * k;
+        uint32_t z = 0;
+        while (z < 32 && key[z] == 0) z++;
+        J.kh.add(key + z, 32 - z);
+      }
+      if (tr.flags & PPD_TR_CODE_WRITE) tr.m_code = J.kh.add(tr.code_write.p, tr.code_write.n);
+    }
+  for (auto& w : b.withdrawals) b.m_withdrawal_addr.push_back(J.kh.add(w.first, 20));
+}
+
+// ---- step 2: pre-image tries -------------------------------------------------------------------
+struct TreeWalker {
+  Job& J;
+  BlockJob& b;
+  std::vector<TrieItem>* items;
+  uint8_t path[160];
+
+  // compact_to_partial_trie.rs:49-139: DFS with an accumulated key
+  void walk(int32_t idx, uint32_t depth) {
+    const WInstr& in = b.wit.ins[idx];
+    switch (in.op) {
+      case PPD_OP_BRANCH: {
+        uint32_t m = in.mask;
+        for (int32_t c = in.first_child; c >= 0; c = b.wit.ins[c].next_sibling) {
+          uint32_t nib = (uint32_t)__builtin_ctz(m);
+          m &= m - 1;
+          if (depth >= 64) fail(PPD_ERR_KEY_ERROR, "key longer than 64 nibbles");
+          path[depth] = (uint8_t)nib;
+          walk(c, depth + 1);
+        }
+        return;
+      }
+      case PPD_OP_CODE: {
+        H256 h = J.kh.digest[b.m_inline_code[idx]];
+        b.pre_code[h] = in.value;
+        return;
+      }
+      case PPD_OP_EMPTY_ROOT:
+        return;
+      case PPD_OP_HASH: {
+        uint32_t koff = J.A.add_key_nibbles(path, depth);
+        items->push_back({koff, depth, 2, J.A.add_hash(in.hash), 0});
+        return;
+      }
+      case PPD_OP_EXTENSION: {
+        uint32_t n = compact_key_nibbles(in.key, path + depth);
+        if (depth + n > 64) fail(PPD_ERR_KEY_ERROR, "key longer than 64 nibbles");
+        walk(in.first_child, depth + n);
+        return;
+      }
+      case PPD_OP_LEAF: {
+        uint32_t n = compact_key_nibbles(in.key, path + depth);
+        if (depth + n > 64) fail(PPD_ERR_KEY_ERROR, "key longer than 64 nibbles");
+        uint32_t koff = J.A.add_key_nibbles(path, depth + n);
+        std::vector<uint8_t> v;
+        rlp_str(v, in.value.p, in.value.n);
+        items->push_back({koff, depth + n, 0, J.A.add_val(v.data(), (uint32_t)v.size()), (uint32_t)v.size()});
+        return;
+      }
+      case PPD_OP_ACCOUNT_LEAF: {
+        uint32_t n = compact_key_nibbles(in.key, path + depth);
+        if (depth + n > 64) fail(PPD_ERR_KEY_ERROR, "key longer than 64 nibbles");
+        uint32_t koff = J.A.add_key_nibbles(path, depth + n);
+        items->push_back({koff, depth + n, 1, (uint32_t)idx /* resolved to a record later */, 0});
+        return;
+      }
+    }
+  }
+};
+
+uint32_t root_node_for(Job& J, BlockJob& b, uint32_t trie_root) {
+  auto f = b.root_of.find(trie_root);
+  if (f != b.root_of.end()) return f->second;
+  uint32_t r = J.A.new_root(trie_root);
+  b.root_of[trie_root] = r;
+  return r;
+}
+
+bool trie_root_is_empty_hash(const Job& J, uint32_t root) {
+  if (root == NODE_EMPTY) return true;
+  if (J.A.kind(root) == NK_HASH) return memcmp(J.A.hash_pool.data() + 32ull * J.A.nodes[root].a0, EMPTY_TRIE_HASH, 32) == 0;
+  return false;
+}
+
+void build_pre_image(Job& J, BlockJob& b) {
+  HostArena& A = J.A;
+  const Witness& W = b.wit;
+  if (W.root < 0) return;
+  // storage tries, in stream order (compact_prestate_processing.rs:608-625)
+  std::unordered_map<int32_t, uint32_t> storage_root_of_instr;
+  bool have_empty_form = false;
+  uint32_t empty_form = NODE_EMPTY;
+  std::vector<TrieItem> items;
+  for (int32_t i = 0; i < (int32_t)W.ins.size(); i++) {
+    const WInstr& in = W.ins[i];
+    if (in.op != PPD_OP_ACCOUNT_LEAF || !in.has_storage) continue;
+    items.clear();
+    TreeWalker tw{J, b, &items, {}};
+    std::map<H256, Span> saved = b.pre_code;  // code found inside a storage subtree is dropped by the reference
+    tw.walk(in.storage_node, 0);
+    b.pre_code = saved;
+    for (TrieItem& x : items)
+      if (x.kind == 1) fail(PPD_ERR_INVALID_WITNESS_FORMAT, "account leaf inside a storage trie");
+    uint32_t root = build_range(A, items, 0, items.size(), 0);
+    storage_root_of_instr[i] = root;
+    if (trie_root_is_empty_hash(J, root)) have_empty_form = true, empty_form = root;
+  }
+  // state trie
+  items.clear();
+  TreeWalker tw{J, b, &items, {}};
+  tw.walk(W.root, 0);
+  for (TrieItem& x : items) {
+    if (x.kind == 0) fail(PPD_PANIC_PRE_IMAGE_ACCOUNT_DECODE, "state leaf is not an account");
+    if (x.kind != 1) continue;
+    int32_t idx = (int32_t)x.a1;
+    const WInstr& in = W.ins[idx];
+    AccountRec rec;
+    memset(&rec, 0, sizeof rec);
+    for (int k = 0; k < 8; k++) rec.nonce[31 - k] = (uint8_t)(in.nonce >> (8 * k));
+    if (in.balance.n) memcpy(rec.balance + 32 - in.balance.n, in.balance.p, in.balance.n);
+    memcpy(rec.storage_root, EMPTY_TRIE_HASH, 32);
+    rec.storage_src = NODE_EMPTY;
+    uint32_t sroot = NODE_EMPTY;
+    bool has_trie = false, nonempty = false;
+    if (in.has_storage) {
+      sroot = storage_root_of_instr[idx];
+      nonempty = !trie_root_is_empty_hash(J, sroot);
+      has_trie = true;
+      if (nonempty) rec.storage_src = root_node_for(J, b, sroot);
+    }
+    // the reference joins accounts to storage tries by ROOT HASH (compact_to_partial_trie.rs:167-190):
+    // every account whose root is EMPTY_TRIE_HASH gets the last witnessed empty-rooted trie, if any
+    if (!nonempty) {
+      has_trie = have_empty_form;
+      sroot = empty_form;
+    }
+    if (in.has_code) {
+      const WInstr& c = W.ins[in.code_node];
+      if (c.op == PPD_OP_CODE) {
+        H256 h = J.kh.digest[b.m_inline_code[in.code_node]];
+        memcpy(rec.code_hash, h.b, 32);
+        b.pre_code[h] = c.value;
+      } else {
+        memcpy(rec.code_hash, c.hash, 32);
+      }
+    } else {
+      memcpy(rec.code_hash, EMPTY_CODE_HASH, 32);
+    }
+    uint32_t r = (uint32_t)A.accounts.size();
+    A.accounts.push_back(rec);
+    x.a1 = r;
+    // hashed address = the leaf's full key, left-padded (utils.rs:49-59)
+    // (value-minimal bytes_be, then left-padded to 32 bytes == the nibbles right-aligned)
+    H256 haddr;
+    memset(haddr.b, 0, 32);
+    for (uint32_t k = 0; k < x.klen; k++) {
+      uint32_t posn = 64 - x.klen + k;
+      haddr.b[posn >> 1] |= (uint8_t)((posn & 1) ? A.key_nib(x.koff, k) : (A.key_nib(x.koff, k) << 4));
+    }
+    if (has_trie) b.storage[haddr] = sroot;
+    b.pre_accounts.push_back({haddr, r, nonempty});
+    if (nonempty) b.pre_with_storage[haddr] = r;
+  }
+  b.state_root = build_range(A, items, 0, items.size(), 0);
+}
+
+// ---- step 3: the txn loop (decoding.rs:80-177), shaping only ------------------------------------
+uint32_t key_from_digest(Job& J, const H256& h) { return J.A.add_key_bytes(h.b, 32); }
+
+uint32_t txn_index_key(Job& J, size_t idx, uint32_t& klen) {
+  // Nibbles::from_bytes_be(rlp::encode(&txn_idx)), decoding.rs:190
+  uint8_t be[32];
+  memset(be, 0, 32);
+  for (int k = 0; k < 8; k++) be[31 - k] = (uint8_t)((uint64_t)idx >> (8 * k));
+  std::vector<uint8_t> enc;
+  rlp_u256(enc, be);
+  klen = (uint32_t)enc.size() * 2;
+  return J.A.add_key_bytes(enc.data(), (uint32_t)enc.size());
+}
+
+void u256_add(uint8_t a[32], const uint8_t b[32]) {
+  unsigned carry = 0;
+  for (int i = 31; i >= 0; i--) {
+    unsigned s = (unsigned)a[i] + b[i] + carry;
+    a[i] = (uint8_t)s;
+    carry = s >> 8;
+  }
+}
+
+void dummy_plan(Job& J, BlockJob& b, IrPlan& p, uint32_t state_root, uint32_t txn_root, uint32_t receipt_root,
+                const std::unordered_map<H256, uint32_t, H256Hasher>& storage, uint64_t txn_number, uint64_t gas_used) {
+  // create_dummy_gen_input (decoding.rs:484-549): every trie cut with the key 0_u64, which converts
+  // to zero nibbles: the root is the only marked node
+  p.txn_before = txn_number;
+  p.gas_before = p.gas_after = gas_used;
+  p.state_sub = state_root, p.txn_sub = txn_root, p.receipt_sub = receipt_root;
+  if (state_root != NODE_EMPTY) p.touched.push_back(state_root);
+  if (txn_root != NODE_EMPTY) p.touched.push_back(txn_root);
+  if (receipt_root != NODE_EMPTY) p.touched.push_back(receipt_root);
+  for (const auto& s : storage) {
+    p.storage_subs.push_back({s.first, s.second});
+    if (s.second != NODE_EMPTY) p.touched.push_back(s.second);
+  }
+  p.root_state = root_node_for(J, b, state_root);
+  p.root_txn = root_node_for(J, b, txn_root);
+  p.root_receipt = root_node_for(J, b, receipt_root);
+}
+
+void apply_withdrawals(Job& J, BlockJob& b, uint32_t& state_root) {
+  HostArena& A = J.A;
+  for (size_t i = 0; i < b.withdrawals.size(); i++) {
+    const H256& h = J.kh.digest[b.m_withdrawal_addr[i]];
+    uint32_t koff = key_from_digest(J, h);
+    uint32_t leaf = A.get(state_root, koff, 64);
+    if (leaf == NODE_EMPTY) fail(PPD_ERR_MISSING_WITHDRAWAL_ACCOUNT, "withdrawal to an account that is not in the state trie");
+    if (A.kind(leaf) != NK_LEAF_ACCOUNT) fail(PPD_ERR_ACCOUNT_DECODE, "withdrawal account does not decode");
+    AccountRec rec = A.accounts[A.nodes[leaf].a1];
+    u256_add(rec.balance, b.withdrawals[i].second);
+    uint32_t r = (uint32_t)A.accounts.size();
+    A.accounts.push_back(rec);
+    state_root = A.insert(state_root, koff, 64, 0, HostArena::Payload{true, r, 0});
+  }
+}
+
+void shape_block(Job& J, BlockJob& b) {
+  HostArena& A = J.A;
+  build_pre_image(J, b);
+  const uint32_t initial_state = b.state_root;
+  const auto initial_storage = b.storage;
+  uint32_t state = b.state_root, txn_trie = NODE_EMPTY, receipt_trie = NODE_EMPTY;
+  uint64_t txn_before = 0, gas_before = 0, gas_after = 0;
+
+  for (size_t ti = 0; ti < b.txns.size(); ti++) {
+    TxnV& tx = b.txns[ti];
+    IrPlan p;
+    // ---- into_processed_txn_info (processed_block_trace.rs:209-333): code map, receipt bytes ----
+    {
+      H256 e;
+      memcpy(e.b, EMPTY_CODE_HASH, 32);
+      p.code[e] = Span{};
+    }
+    for (TraceV& tr : tx.traces) {
+      if (tr.flags & PPD_TR_CODE_READ) {
+        H256 h;
+        memcpy(h.b, tr.code_read, 32);
+        if (!p.code.count(h)) {
+          auto f = b.pre_code.find(h);
+          if (f != b.pre_code.end()) {
+            p.code[h] = f->second;
+          } else {
+            auto g = b.resolved_code.find(h);
+            if (g == b.resolved_code.end()) fail(PPD_ERR_UNRESOLVED_CODE_HASH, "code hash not resolvable");
+            p.code[h] = g->second;
+          }
+        }
+      } else if (tr.flags & PPD_TR_CODE_WRITE) {
+        p.code[J.kh.digest[tr.m_code]] = tr.code_write;
+      }
+    }
+    Span receipt = tx.new_receipt_node;
+    if (!is_legacy_receipt(receipt.p, receipt.n)) {
+      RlpItem it;
+      if (!rlp_item(receipt.p, receipt.n, it) || it.is_list) fail(PPD_PANIC_RECEIPT_DECODE, "receipt is neither legacy nor a byte string");
+      receipt = Span{it.payload, (uint32_t)it.payload_len};
+    }
+
+    // ---- create_minimal_partial_tries_needed_by_txn (decoding.rs:179-217) ----
+    uint32_t tk_len = 0;
+    uint32_t tk = txn_index_key(J, ti, tk_len);
+    p.state_sub = state, p.txn_sub = txn_trie, p.receipt_sub = receipt_trie;
+    std::vector<uint32_t> haddr_key(tx.traces.size());
+    for (size_t i = 0; i < tx.traces.size(); i++) {
+      haddr_key[i] = key_from_digest(J, J.kh.digest[tx.traces[i].m_addr]);
+      A.mark(state, haddr_key[i], 64, p.touched);
+    }
+    A.mark(txn_trie, tk, tk_len, p.touched);
+    A.mark(receipt_trie, tk, tk_len, p.touched);
+    for (size_t i = 0; i < tx.traces.size(); i++) {
+      TraceV& tr = tx.traces[i];
+      const H256& haddr = J.kh.digest[tr.m_addr];
+      if (haddr.b[0] == 0) fail(PPD_PANIC_H256_FROM_SLICE, "H256::from_slice on a short bytes_be()");
+      auto f = b.storage.find(haddr);
+      if (f == b.storage.end()) {
+        // missing storage trie: Hash(pre-image storage root) when the account had storage in the pre-image
+        // and this txn does not access its slots, else an empty trie (decoding.rs:572-582)
+        uint32_t t = NODE_EMPTY;
+        auto g = b.pre_with_storage.find(haddr);
+        if (g != b.pre_with_storage.end() && tr.n_reads + tr.n_writes == 0) t = A.accounts[g->second].storage_src;
+        f = b.storage.insert({haddr, t}).first;
+      }
+      uint32_t sroot = f->second;
+      for (uint32_t k = 0; k < tr.n_reads; k++) A.mark(sroot, key_from_digest(J, J.kh.digest[tr.m_reads + k]), 64, p.touched);
+      for (uint32_t k = 0; k < tr.n_writes; k++) A.mark(sroot, key_from_digest(J, J.kh.digest[tr.m_writes_full + k]), 64, p.touched);
+      p.storage_subs.push_back({haddr, sroot});
+    }
+    gas_after += tx.gas_used;
+
+    // ---- apply_deltas_to_trie_state (decoding.rs:219-292) ----
+    for (TraceV& tr : tx.traces) {
+      const H256& haddr = J.kh.digest[tr.m_addr];
+      auto f = b.storage.find(haddr);
+      if (f == b.storage.end()) fail(PPD_ERR_MISSING_ACCOUNT_STORAGE_TRIE, "no storage trie for a written account");
+      for (uint32_t k = 0; k < tr.n_writes; k++) {
+        const uint8_t* val = tr.writes + 64 * k + 32;
+        uint32_t koff = key_from_digest(J, J.kh.digest[tr.m_writes_min + k]);
+        uint32_t sig = u256_sig(val);
+        if (sig == 0) {  // rlp(0) == [0x80]: a delete
+          uint32_t r = A.remove(f->second, koff, 64, 0);
+          if (r != UNCHANGED) f->second = r;
+        } else {
+          std::vector<uint8_t> enc;
+          rlp_str(enc, val + 32 - sig, sig);
+          uint32_t voff = A.add_val(enc.data(), (uint32_t)enc.size());
+          f->second = A.insert(f->second, koff, 64, 0, HostArena::Payload{false, voff, (uint32_t)enc.size()});
+        }
+      }
+    }
+    for (size_t i = 0; i < tx.traces.size(); i++) {
+      TraceV& tr = tx.traces[i];
+      bool storage_change = tr.n_writes != 0;
+      bool code_change = tr.flags & (PPD_TR_CODE_READ | PPD_TR_CODE_WRITE);
+      if (!((tr.flags & (PPD_TR_BALANCE | PPD_TR_NONCE)) || storage_change || code_change)) continue;
+      const H256& haddr = J.kh.digest[tr.m_addr];
+      uint32_t leaf = A.get(state, haddr_key[i], 64);
+      AccountRec rec;
+      if (leaf == NODE_EMPTY) {
+        memset(&rec, 0, sizeof rec);
+        memcpy(rec.storage_root, EMPTY_TRIE_HASH, 32);
+        memcpy(rec.code_hash, EMPTY_CODE_HASH, 32);
+        rec.storage_src = NODE_EMPTY;
+      } else {
+        if (A.kind(leaf) != NK_LEAF_ACCOUNT) fail(PPD_ERR_ACCOUNT_DECODE, "state leaf is not an account");
+        rec = A.accounts[A.nodes[leaf].a1];
+      }
+      if (storage_change) {
+        auto f = b.storage.find(haddr);
+        if (f == b.storage.end()) fail(PPD_ERR_MISSING_ACCOUNT_STORAGE_TRIE, "no storage trie for a changed account");
+        rec.storage_src = root_node_for(J, b, f->second);
+      }
+      if (tr.flags & PPD_TR_BALANCE) memcpy(rec.balance, tr.balance, 32);
+      if (tr.flags & PPD_TR_NONCE) memcpy(rec.nonce, tr.nonce, 32);
+      if (tr.flags & PPD_TR_CODE_READ) memcpy(rec.code_hash, tr.code_read, 32);
+      if (tr.flags & PPD_TR_CODE_WRITE) memcpy(rec.code_hash, J.kh.digest[tr.m_code].b, 32);
+      uint32_t r = (uint32_t)A.accounts.size();
+      A.accounts.push_back(rec);
+      state = A.insert(state, haddr_key[i], 64, 0, HostArena::Payload{true, r, 0});
+    }
+    for (size_t i = 0; i < tx.traces.size(); i++) {
+      if (!(tx.traces[i].flags & PPD_TR_SELF_DESTRUCTED)) continue;
+      const H256& haddr = J.kh.digest[tx.traces[i].m_addr];
+      if (!b.storage.erase(haddr)) fail(PPD_ERR_MISSING_ACCOUNT_STORAGE_TRIE, "self-destructed account has no storage trie");
+      uint32_t r = A.remove(state, haddr_key[i], 64, 0);
+      if (r != UNCHANGED) state = r;
+    }
+    {
+      uint32_t voff = A.add_val(tx.byte_code.p, tx.byte_code.n);
+      txn_trie = A.insert(txn_trie, tk, tk_len, 0, HostArena::Payload{false, voff, tx.byte_code.n});
+      uint32_t roff = A.add_val(receipt.p, receipt.n);
+      receipt_trie = A.insert(receipt_trie, tk, tk_len, 0, HostArena::Payload{false, roff, receipt.n});
+    }
+    // ---- calculate_trie_input_hashes + GenerationInputs (decoding.rs:130-145) ----
+    p.root_state = root_node_for(J, b, state);
+    p.root_txn = root_node_for(J, b, txn_trie);
+    p.root_receipt = root_node_for(J, b, receipt_trie);
+    p.txn_before = txn_before;
+    p.gas_before = gas_before;
+    p.gas_after = gas_after;
+    p.has_signed_txn = tx.byte_code.n != 0;
+    p.signed_txn = tx.byte_code;
+    txn_before += 1;
+    gas_before = gas_after;
+    b.irs.push_back(std::move(p));
+  }
+
+  // ---- pad_gen_inputs_with_dummy_inputs_if_needed (decoding.rs:304-347) ----
+  bool has_wd = !b.withdrawals.empty(), dummies = false;
+  if (b.irs.empty()) {
+    for (int k = 0; k < 2; k++) {
+      IrPlan d;
+      dummy_plan(J, b, d, initial_state, NODE_EMPTY, NODE_EMPTY, initial_storage, txn_before, gas_before);
+      b.irs.push_back(std::move(d));
+    }
+    dummies = true;
+  } else if (b.irs.size() == 1) {
+    IrPlan d;
+    if (!has_wd) {
+      dummy_plan(J, b, d, initial_state, NODE_EMPTY, NODE_EMPTY, initial_storage, txn_before, gas_before);
+      b.irs.insert(b.irs.begin(), std::move(d));
+    } else {
+      dummy_plan(J, b, d, state, txn_trie, receipt_trie, b.storage, txn_before, gas_before);
+      b.irs.push_back(std::move(d));
+    }
+    dummies = true;
+  }
+  // ---- add_withdrawals_to_txns (decoding.rs:356-402) ----
+  if (has_wd) {
+    if (!dummies) {
+      IrPlan d;
+      dummy_plan(J, b, d, state, txn_trie, receipt_trie, b.storage, txn_before, gas_before);
+      apply_withdrawals(J, b, state);
+      d.has_withdrawals = true;
+      d.root_state = root_node_for(J, b, state);
+      b.irs.push_back(std::move(d));
+    } else {
+      apply_withdrawals(J, b, state);
+      b.irs[1].has_withdrawals = true;
+      b.irs[1].root_state = root_node_for(J, b, state);
+    }
+  }
+  b.state_root = state;
+}
+
+// ---- step 4: the sweep ---------------------------------------------------------------------------
+void sweep(ppd_ctx* c, Job& J) {
+  HostArena& A = J.A;
+  uint32_t n = (uint32_t)A.nodes.size();
+  J.ref.assign(32ull * n, 0);
+  J.ref_len.assign(n, 0);
+  if (!n) return;
+  // counting sort of node ids by level
+  uint32_t n_levels = 0;
+  for (uint32_t i = 0; i < n; i++) n_levels = std::max<uint32_t>(n_levels, A.level[i] + 1u);
+  std::vector<uint32_t> level_start(n_levels + 1, 0), order(n);
+  for (uint32_t i = 0; i < n; i++) level_start[A.level[i] + 1]++;
+  for (uint32_t l = 0; l < n_levels; l++) level_start[l + 1] += level_start[l];
+  {
+    std::vector<uint32_t> cur(level_start.begin(), level_start.end() - 1);
+    for (uint32_t i = 0; i < n; i++) order[cur[A.level[i]]++] = i;
+  }
+  c->d_nodes.reserve(16ull * n);
+  c->d_order.reserve(4ull * n);
+  c->d_keys.reserve(A.key_pool.size() + 16);
+  c->d_vals.reserve(A.val_pool.size() + 16);
+  c->d_hashes.reserve(A.hash_pool.size() + 32);
+  c->d_children.reserve(4ull * A.child_pool.size() + 16);
+  c->d_accounts.reserve(sizeof(AccountRec) * A.accounts.size() + 16);
+  c->d_ref.reserve(32ull * n);
+  c->d_ref_len.reserve(n);
+  c->d_counters.reserve(16);
+  auto up = [&](DevBuf& d, const void* src, size_t bytes) {
+    if (!bytes) return;
+    CUDA_OK(cudaMemcpyAsync(d.p, src, bytes, cudaMemcpyHostToDevice, c->st));
+    c->stats.h2d_bytes += (double)bytes;
+  };
+  up(c->d_nodes, A.nodes.data(), 16ull * n);
+  up(c->d_order, order.data(), 4ull * n);
+  up(c->d_keys, A.key_pool.data(), A.key_pool.size());
+  up(c->d_vals, A.val_pool.data(), A.val_pool.size());
+  up(c->d_hashes, A.hash_pool.data(), A.hash_pool.size());
+  up(c->d_children, A.child_pool.data(), 4ull * A.child_pool.size());
+  up(c->d_accounts, A.accounts.data(), sizeof(AccountRec) * A.accounts.size());
+  CUDA_OK(cudaMemsetAsync(c->d_counters.p, 0, 16, c->st));
+  ArenaView V;
+  V.nodes = c->d_nodes.as<NodeRec>();
+  V.key_pool = c->d_keys.as<uint8_t>();
+  V.val_pool = c->d_vals.as<uint8_t>();
+  V.hash_pool = c->d_hashes.as<uint8_t>();
+  V.child_pool = c->d_children.as<uint32_t>();
+  V.accounts = c->d_accounts.as<AccountRec>();
+  V.ref = c->d_ref.as<uint8_t>();
+  V.ref_len = c->d_ref_len.as<uint8_t>();
+  V.counters = c->d_counters.as<unsigned long long>();
+  CUDA_OK(cudaEventRecord(c->ev0, c->st));
+  for (uint32_t l = 0; l < n_levels; l++) {
+    launch_hash_level(V, c->d_order.as<uint32_t>(), level_start[l], level_start[l + 1], c->st);
+    c->stats.kernel_launches++;
+  }
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(cudaEventRecord(c->ev1, c->st));
+  unsigned long long counters[2] = {0, 0};
+  CUDA_OK(cudaMemcpyAsync(J.ref.data(), c->d_ref.p, 32ull * n, cudaMemcpyDeviceToHost, c->st));
+  CUDA_OK(cudaMemcpyAsync(J.ref_len.data(), c->d_ref_len.p, n, cudaMemcpyDeviceToHost, c->st));
+  CUDA_OK(cudaMemcpyAsync(counters, c->d_counters.p, 16, cudaMemcpyDeviceToHost, c->st));
+  CUDA_OK(cudaStreamSynchronize(c->st));
+  float ms = 0;
+  CUDA_OK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+  c->stats.gpu_ms += ms;
+  c->stats.nodes_hashed += counters[0];
+  c->stats.node_permutations += counters[1];
+  c->stats.arena_nodes += n;
+  c->stats.levels += n_levels;
+  c->stats.d2h_bytes += 33.0 * n;
+}
+
+// ---- step 5: IrDump ------------------------------------------------------------------------------
+struct Out {
+  std::vector<uint8_t> b;
+  void u8(uint8_t v) { b.push_back(v); }
+  void u32(uint32_t v) {
+    uint8_t t[4];
+    memcpy(t, &v, 4);
+    b.insert(b.end(), t, t + 4);
+  }
+  void u64(uint64_t v) {
+    uint8_t t[8];
+    memcpy(t, &v, 8);
+    b.insert(b.end(), t, t + 8);
+  }
+  void raw(const uint8_t* p, size_t n) { b.insert(b.end(), p, p + n); }
+  void span(Span s) {
+    u32(s.n);
+    raw(s.p, s.n);
+  }
+  void u256(uint64_t v) {
+    uint8_t be[32];
+    memset(be, 0, 32);
+    for (int i = 0; i < 8; i++) be[31 - i] = (uint8_t)(v >> (8 * i));
+    raw(be, 32);
+  }
+};
+
+void account_rlp(const Job& J, const AccountRec& rec, std::vector<uint8_t>& out) {
+  std::vector<uint8_t> pl;
+  rlp_u256(pl, rec.nonce);
+  rlp_u256(pl, rec.balance);
+  const uint8_t* sr = rec.storage_src == NODE_EMPTY ? rec.storage_root : J.ref.data() + 32ull * rec.storage_src;
+  rlp_str(pl, sr, 32);
+  rlp_str(pl, rec.code_hash, 32);
+  out.clear();
+  out.push_back(0xf8);
+  out.push_back((uint8_t)pl.size());
+  out.insert(out.end(), pl.begin(), pl.end());
+}
+
+void dump_nibbles(const Job& J, Out& o, uint32_t node) {
+  uint32_t k = J.A.nodes[node].a0, s = J.A.nstart(node), n = J.A.nlen(node);
+  o.u8((uint8_t)n);
+  for (uint32_t i = 0; i < n; i++) o.u8((uint8_t)J.A.key_nib(k, s + i));
+}
+
+// create_partial_trie_subset_from_tracked_trie (trie_subsets.rs): untouched nodes whose encoding is
+// at least 32 bytes become Hash nodes; smaller ones are kept as they are
+void dump_subset(const Job& J, Out& o, uint32_t node) {
+  const HostArena& A = J.A;
+  if (node == NODE_EMPTY) {
+    o.u8(PPD_NODE_EMPTY);
+    return;
+  }
+  bool touched = J.stamp[node] == J.serial;
+  if ((!touched && J.ref_len[node] == 32) || A.is_opaque(node)) {
+    o.u8(PPD_NODE_HASH);
+    o.raw(J.ref.data() + 32ull * node, 32);
+    return;
+  }
+  switch (A.kind(node)) {
+    case NK_LEAF:
+      o.u8(PPD_NODE_LEAF);
+      dump_nibbles(J, o, node);
+      o.u32(A.nodes[node].a2);
+      o.raw(A.val_pool.data() + A.nodes[node].a1, A.nodes[node].a2);
+      return;
+    case NK_LEAF_ACCOUNT: {
+      o.u8(PPD_NODE_LEAF);
+      dump_nibbles(J, o, node);
+      std::vector<uint8_t> v;
+      account_rlp(J, A.accounts[A.nodes[node].a1], v);
+      o.u32((uint32_t)v.size());
+      o.raw(v.data(), v.size());
+      return;
+    }
+    case NK_EXT:
+      o.u8(PPD_NODE_EXTENSION);
+      dump_nibbles(J, o, node);
+      dump_subset(J, o, A.nodes[node].a1);
+      return;
+    case NK_BRANCH:
+      o.u8(PPD_NODE_BRANCH);
+      for (uint32_t i = 0; i < 16; i++) dump_subset(J, o, A.child_at(node, i));
+      o.u32(0);
+      return;
+  }
+}
+
+void dump_block(Job& J, BlockJob& b, Out& o) {
+  o.u32(PPD_IR_DUMP_MAGIC);
+  o.u32((uint32_t)b.irs.size());
+  for (IrPlan& p : b.irs) {
+    J.serial++;
+    for (uint32_t t : p.touched) J.stamp[t] = J.serial;
+    o.u256(p.txn_before);
+    o.u256(p.gas_before);
+    o.u256(p.gas_after);
+    o.u8(p.has_signed_txn);
+    o.span(p.has_signed_txn ? p.signed_txn : Span{});
+    if (p.has_withdrawals) {
+      o.u32((uint32_t)b.withdrawals.size());
+      for (auto& w : b.withdrawals) {
+        o.raw(w.first, 20);
+        o.raw(w.second, 32);
+      }
+    } else {
+      o.u32(0);
+    }
+    dump_subset(J, o, p.state_sub);
+    dump_subset(J, o, p.txn_sub);
+    dump_subset(J, o, p.receipt_sub);
+    std::stable_sort(p.storage_subs.begin(), p.storage_subs.end(), [](const auto& x, const auto& y) { return x.first < y.first; });
+    o.u32((uint32_t)p.storage_subs.size());
+    for (auto& s : p.storage_subs) {
+      o.raw(s.first.b, 32);
+      dump_subset(J, o, s.second);
+    }
+    o.raw(J.ref.data() + 32ull * p.root_state, 32);
+    o.raw(J.ref.data() + 32ull * p.root_txn, 32);
+    o.raw(J.ref.data() + 32ull * p.root_receipt, 32);
+    o.raw(b.checkpoint, 32);
+    o.u32((uint32_t)p.code.size());
+    for (auto& cd : p.code) {
+      o.raw(cd.first.b, 32);
+      o.span(cd.second);
+    }
+    o.span(b.b_meta);
+    o.span(b.b_hashes);
+  }
+}
+
+uint8_t* to_malloc(const std::vector<uint8_t>& v, size_t* n) {
+  uint8_t* p = (uint8_t*)malloc(v.size() ? v.size() : 1);
+  if (v.size()) memcpy(p, v.data(), v.size());
+  *n = v.size();
+  return p;
+}
+
+template <class F>
+int guarded(ppd_ctx* c, F f) {
+  if (!c) return PPD_ERR_BAD_ARGUMENT;
+  try {
+    CUDA_OK(cudaSetDevice(c->device));
+    f();
+    return PPD_OK;
+  } catch (const Fail& e) {
+    c->err = e.msg;
+    return e.code;
+  } catch (const std::exception& e) {
+    c->err = e.what();
+    return PPD_ERR_BAD_ARGUMENT;
+  }
+}
+
+void decode_blocks(ppd_ctx* c, const uint8_t* const* flats, const size_t* lens, size_t n, uint8_t** outs, size_t* out_lens, int* statuses) {
+  stats_reset(c);
+  Job J;
+  J.blocks.resize(n);
+  auto guard_block = [&](size_t i, auto fn) {
+    BlockJob& b = J.blocks[i];
+    if (b.status != PPD_OK) return;
+    try {
+      fn(b);
+    } catch (const Fail& e) {
+      if (e.code == PPD_ERR_CUDA) throw;
+      b.status = e.code;
+      b.err = e.msg;
+    }
+  };
+  for (size_t i = 0; i < n; i++)
+    guard_block(i, [&](BlockJob& b) {
+      read_flat_block(flats[i], lens[i], b);
+      collect_messages(J, b);
+    });
+  J.kh.run(c);
+  for (size_t i = 0; i < n; i++) guard_block(i, [&](BlockJob& b) { shape_block(J, b); });
+  sweep(c, J);
+  J.stamp.assign(J.A.nodes.size(), 0);
+  for (size_t i = 0; i < n; i++) {
+    outs[i] = nullptr;
+    out_lens[i] = 0;
+    guard_block(i, [&](BlockJob& b) {
+      Out o;
+      dump_block(J, b, o);
+      outs[i] = to_malloc(o.b, &out_lens[i]);
+    });
+    statuses[i] = J.blocks[i].status;
+    if (J.blocks[i].status != PPD_OK) c->err = J.blocks[i].err;
+  }
+}
+
+}  // namespace
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+extern "C" {
+
+int ppd_ctx_create(int device, ppd_ctx** out) {
+  if (!out) return PPD_ERR_BAD_ARGUMENT;
+  *out = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) return PPD_ERR_CUDA;
+  ppd_ctx* c = new ppd_ctx();
+  c->device = device;
+  if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess) {
+    delete c;
+    return PPD_ERR_CUDA;
+  }
+  *out = c;
+  return PPD_OK;
+}
+
+void ppd_ctx_destroy(ppd_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  DevBuf* bufs[] = {&c->d_nodes, &c->d_order,  &c->d_keys,     &c->d_vals, &c->d_hashes,  &c->d_children, &c->d_accounts,
+                    &c->d_ref,   &c->d_ref_len, &c->d_counters, &c->d_msg,  &c->d_msg_off, &c->d_digest};
+  for (DevBuf* b : bufs) b->release();
+  for (DevBuf& b : c->d_build) b.release();
+  if (c->ev0) cudaEventDestroy(c->ev0);
+  if (c->ev1) cudaEventDestroy(c->ev1);
+  if (c->st) cudaStreamDestroy(c->st);
+  delete c;
+}
+
+const char* ppd_last_error(const ppd_ctx* c) { return c ? c->err.c_str() : "null context"; }
+void ppd_last_stats(const ppd_ctx* c, ppd_stats* out) {
+  if (c && out) *out = c->stats;
+}
+void ppd_free(void* p) { free(p); }
+
+int ppd_keccak256_batch(ppd_ctx* c, const uint8_t* data, const uint64_t* offsets, size_t n, uint8_t* out32n) {
+  return guarded(c, [&] {
+    stats_reset(c);
+    if (!n) return;
+    size_t bytes = offsets[n];
+    c->d_msg.reserve(bytes + 16);
+    c->d_msg_off.reserve((n + 1) * 8);
+    c->d_digest.reserve(n * 32);
+    CUDA_OK(cudaMemcpyAsync(c->d_msg.p, data, bytes, cudaMemcpyHostToDevice, c->st));
+    CUDA_OK(cudaMemcpyAsync(c->d_msg_off.p, offsets, (n + 1) * 8, cudaMemcpyHostToDevice, c->st));
+    CUDA_OK(cudaEventRecord(c->ev0, c->st));
+    launch_keccak256_batch(c->d_msg.as<uint8_t>(), c->d_msg_off.as<uint64_t>(), (uint32_t)n, c->d_digest.as<uint8_t>(), c->st);
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaEventRecord(c->ev1, c->st));
+    CUDA_OK(cudaMemcpyAsync(out32n, c->d_digest.p, n * 32, cudaMemcpyDeviceToHost, c->st));
+    CUDA_OK(cudaStreamSynchronize(c->st));
+    float ms = 0;
+    CUDA_OK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    c->stats.gpu_ms = ms;
+    c->stats.key_hashes = n;
+    for (size_t i = 0; i < n; i++) c->stats.key_permutations += (offsets[i + 1] - offsets[i]) / 136 + 1;
+    c->stats.h2d_bytes = (double)(bytes + (n + 1) * 8);
+    c->stats.d2h_bytes = (double)(n * 32);
+    c->stats.kernel_launches = 1;
+  });
+}
+
+int ppd_compact_decode(ppd_ctx* c, const uint8_t* witness, size_t len, uint8_t** out, size_t* out_len) {
+  return guarded(c, [&] {
+    stats_reset(c);
+    Job J;
+    J.blocks.resize(1);
+    BlockJob& b = J.blocks[0];
+    b.compact = Span{witness, (uint32_t)len};
+    parse_witness(witness, len, b.wit);
+    b.m_inline_code.assign(b.wit.ins.size(), ~0u);
+    for (size_t i = 0; i < b.wit.ins.size(); i++)
+      if (b.wit.ins[i].op == PPD_OP_CODE) b.m_inline_code[i] = J.kh.add(b.wit.ins[i].value.p, b.wit.ins[i].value.n);
+    J.kh.run(c);
+    build_pre_image(J, b);
+    uint32_t sr = root_node_for(J, b, b.state_root);
+    std::map<H256, uint32_t> storage_roots;
+    for (auto& s : b.storage) storage_roots[s.first] = root_node_for(J, b, s.second);
+    sweep(c, J);
+    Out o;
+    o.u32(PPD_PRE_IMAGE_MAGIC);
+    o.u8(b.wit.version);
+    o.raw(J.ref.data() + 32ull * sr, 32);
+    o.u32((uint32_t)storage_roots.size());
+    for (auto& s : storage_roots) {
+      o.raw(s.first.b, 32);
+      o.raw(J.ref.data() + 32ull * s.second, 32);
+    }
+    o.u32((uint32_t)b.pre_code.size());
+    for (auto& cd : b.pre_code) {
+      o.raw(cd.first.b, 32);
+      o.u32(cd.second.n);
+    }
+    o.u64(c->stats.nodes_hashed);
+    o.u64(c->stats.node_permutations);
+    *out = to_malloc(o.b, out_len);
+  });
+}
+
+int ppd_blocks_decode_batch(ppd_ctx* c, const uint8_t* const* flats, const size_t* lens, size_t n, uint8_t** outs, size_t* out_lens,
+                            int* statuses) {
+  return guarded(c, [&] { decode_blocks(c, flats, lens, n, outs, out_lens, statuses); });
+}
+
+int ppd_block_decode(ppd_ctx* c, const uint8_t* flat, size_t len, uint8_t** out, size_t* out_len) {
+  int status = PPD_OK;
+  int rc = guarded(c, [&] { decode_blocks(c, &flat, &len, 1, out, out_len, &status); });
+  return rc != PPD_OK ? rc : status;
+}
+
+}  // extern "C"
+
+// ---- trie root over sorted leaves: structure built and hashed on the GPU (ppd_build.cu) ----------
+namespace {
+
+void trie_root_sorted_dev(ppd_ctx* c, const uint8_t* d_keys, const uint64_t* d_val_off, const uint8_t* d_vals, size_t n_, uint8_t root_out[32]) {
+  if (n_ == 0) {
+    memcpy(root_out, EMPTY_TRIE_HASH, 32);  // HashedPartialTrie::default().hash(): keccak(0x80), types.rs:30-34
+    return;
+  }
+  if (n_ >= 0x7fffffffull) fail(PPD_ERR_BAD_ARGUMENT, "at most 2^31 - 2 leaves per call");
+  const uint32_t n = (uint32_t)n_;
+  cudaStream_t st = c->st;
+  const uint32_t n1 = (n + 1 + 63) / 64, n2 = (n1 + 63) / 64, n3 = (n2 + 63) / 64;
+  enum { B_L, B_M, B_LINKA, B_LINKB, B_BIDX, B_TMP, B_SMALL, B_DEPTH, B_REP, B_CHILD, B_ORDER, B_UNUSED };
+  DevBuf* D = c->d_build;
+  D[B_L].reserve((size_t)n + 1 + 64);
+  D[B_M].reserve((size_t)n1 + n2 + n3 + 192);
+  D[B_LINKA].reserve(4ull * (n + 1));
+  D[B_LINKB].reserve(4ull * (n + 1));
+  D[B_BIDX].reserve(4ull * (n + 1));
+  D[B_TMP].reserve(4ull * scan_tmp_words((size_t)n + 1));
+  D[B_SMALL].reserve(1024);
+  int8_t* L = D[B_L].as<int8_t>();
+  int8_t* m1 = D[B_M].as<int8_t>();
+  int8_t* m2 = m1 + ((n1 + 63) & ~63u);
+  int8_t* m3 = m2 + ((n2 + 63) & ~63u);
+  uint32_t* small = D[B_SMALL].as<uint32_t>();  // [0] error flags, [1] root id, [2..3] counters(u64), [8..15] root, [16..79] hist, [80..143] cursor
+  CUDA_OK(cudaMemsetAsync(small, 0, 1024, st));
+  CUDA_OK(cudaEventRecord(c->ev0, st));
+  launch_lcp(d_keys, n, L, small + 0, st);
+  launch_min64(L, n + 1, m1, n1, st);
+  launch_min64(m1, n1, m2, n2, st);
+  launch_min64(m2, n2, m3, n3, st);
+  uint32_t* leader = D[B_LINKA].as<uint32_t>();
+  uint32_t* flag = D[B_LINKB].as<uint32_t>();
+  launch_leaders(L, m1, m2, m3, n, leader, flag, flag, st);
+  uint32_t* bidx = D[B_BIDX].as<uint32_t>();
+  exclusive_scan_u32(flag, bidx, n + 1, D[B_TMP].as<uint32_t>(), st);
+  CUDA_OK(cudaGetLastError());
+  uint32_t h_flags = 0, nb = 0;
+  CUDA_OK(cudaMemcpyAsync(&h_flags, small, 4, cudaMemcpyDeviceToHost, st));
+  CUDA_OK(cudaMemcpyAsync(&nb, bidx + n, 4, cudaMemcpyDeviceToHost, st));
+  CUDA_OK(cudaStreamSynchronize(st));
+  if (h_flags & 1) fail(PPD_ERR_UNSORTED_KEYS, "keys are not strictly ascending");
+  c->stats.kernel_launches += 11 + 3;
+
+  D[B_DEPTH].reserve(2ull * nb + 64);
+  D[B_REP].reserve(4ull * nb + 64);
+  D[B_CHILD].reserve(64ull * nb + 64);
+  D[B_ORDER].reserve(4ull * nb + 64);
+  c->d_ref.reserve(32ull * ((size_t)n + nb));
+  c->d_ref_len.reserve((size_t)n + nb);
+  BuildView V;
+  V.keys = d_keys;
+  V.val_off = d_val_off;
+  V.vals = d_vals;
+  V.n = n;
+  V.P = Pyramid{L, m1, m2, m3};
+  V.leader = leader;
+  V.bidx = bidx;
+  V.depth = D[B_DEPTH].as<uint8_t>();
+  V.ext_start = V.depth + nb + 32;
+  V.rep = D[B_REP].as<uint32_t>();
+  V.child = D[B_CHILD].as<uint32_t>();
+  V.root_id = small + 1;
+  V.ref = c->d_ref.as<uint8_t>();
+  V.ref_len = c->d_ref_len.as<uint8_t>();
+  V.root_out = reinterpret_cast<uint8_t*>(small + 8);
+  V.counters = reinterpret_cast<unsigned long long*>(small + 2);
+  if (nb) CUDA_OK(cudaMemsetAsync(V.child, 0xff, 64ull * nb, st));
+  launch_branch_info(V, st);
+  launch_depth_hist(V.depth, nb, small + 16, st);
+  uint32_t hist[64], cursor[64], start[65];
+  CUDA_OK(cudaMemcpyAsync(hist, small + 16, 256, cudaMemcpyDeviceToHost, st));
+  CUDA_OK(cudaStreamSynchronize(st));
+  // deepest level first
+  uint32_t acc = 0;
+  for (int d = 63; d >= 0; d--) {
+    cursor[d] = start[d] = acc;
+    acc += hist[d];
+  }
+  if (acc != nb) fail(PPD_ERR_CUDA, "branch histogram does not add up");
+  CUDA_OK(cudaMemcpyAsync(small + 80, cursor, 256, cudaMemcpyHostToDevice, st));
+  uint32_t* order = D[B_ORDER].as<uint32_t>();
+  launch_branch_scatter(V.depth, nb, small + 80, order, st);
+  launch_hash_sorted_leaves(V, st);
+  c->stats.kernel_launches += 4;
+  uint32_t levels = 1;
+  for (int d = 63; d >= 0; d--)
+    if (hist[d]) {
+      launch_hash_branch_level(V, order, start[d], start[d] + hist[d], st);
+      c->stats.kernel_launches++;
+      levels++;
+    }
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(cudaEventRecord(c->ev1, st));
+  uint32_t out[16];
+  CUDA_OK(cudaMemcpyAsync(out, small, 64, cudaMemcpyDeviceToHost, st));
+  CUDA_OK(cudaStreamSynchronize(st));
+  memcpy(root_out, out + 8, 32);
+  float ms = 0;
+  CUDA_OK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+  unsigned long long cnt[2];
+  memcpy(cnt, out + 2, 16);
+  c->stats.gpu_ms += ms;
+  c->stats.nodes_hashed += cnt[0];
+  c->stats.node_permutations += cnt[1];
+  c->stats.arena_nodes += (uint64_t)n + nb;
+  c->stats.levels += levels;
+  c->stats.d2h_bytes += 64 + 256 + 8;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ppd_trie_root_sorted_leaves_dev(ppd_ctx* c, const uint8_t* d_keys32, const uint64_t* d_val_off, const uint8_t* d_vals, size_t n,
+                                    size_t vals_bytes, uint8_t root_out[32]) {
+  (void)vals_bytes;
+  return guarded(c, [&] {
+    stats_reset(c);
+    trie_root_sorted_dev(c, d_keys32, d_val_off, d_vals, n, root_out);
+  });
+}
+
+int ppd_trie_root_sorted_leaves(ppd_ctx* c, const uint8_t* keys32, const uint64_t* val_off, const uint8_t* vals, size_t n,
+                                uint8_t root_out[32]) {
+  return guarded(c, [&] {
+    stats_reset(c);
+    if (!n) {
+      trie_root_sorted_dev(c, nullptr, nullptr, nullptr, 0, root_out);
+      return;
+    }
+    size_t vb = val_off[n];
+    c->d_keys.reserve(32 * n);
+    c->d_msg_off.reserve(8 * (n + 1));
+    c->d_vals.reserve(vb + 64);
+    CUDA_OK(cudaMemcpyAsync(c->d_keys.p, keys32, 32 * n, cudaMemcpyHostToDevice, c->st));
+    CUDA_OK(cudaMemcpyAsync(c->d_msg_off.p, val_off, 8 * (n + 1), cudaMemcpyHostToDevice, c->st));
+    CUDA_OK(cudaMemcpyAsync(c->d_vals.p, vals, vb, cudaMemcpyHostToDevice, c->st));
+    c->stats.h2d_bytes += (double)(32 * n + 8 * (n + 1) + vb);
+    trie_root_sorted_dev(c, c->d_keys.as<uint8_t>(), c->d_msg_off.as<uint64_t>(), c->d_vals.as<uint8_t>(), n, root_out);
+  });
+}
+
+}  // extern "C"

@@ -1,0 +1,54 @@
+// ppd_kernels.h — launchers of the sm_100a kernels (ppd_kernels.cu, ppd_build.cu)
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "arena.h"
+
+namespace ppd {
+
+void launch_keccak256_batch(const uint8_t* data, const uint64_t* offsets, uint32_t n, uint8_t* out, cudaStream_t st);
+void launch_keccak256_ranges(const uint8_t* data, const uint64_t* begin_end, uint32_t n, uint8_t* out, cudaStream_t st);
+void launch_hash_level(const ArenaView& A, const uint32_t* order, uint32_t begin, uint32_t end, cudaStream_t st);
+
+
+// ---- ppd_build.cu: trie construction from sorted leaves ----
+struct Pyramid {
+  const int8_t *L, *m1, *m2, *m3;
+};
+
+struct BuildView {
+  const uint8_t* keys;       // [N][32]
+  const uint64_t* val_off;   // [N+1]
+  const uint8_t* vals;
+  uint32_t n;
+  Pyramid P;
+  const uint32_t* leader;    // [N+1]
+  const uint32_t* bidx;      // [N+1] exclusive scan of leader flags
+  // branches
+  uint8_t* depth;            // [B]
+  uint8_t* ext_start;        // [B]  first nibble of the extension above the branch (== depth when none)
+  uint32_t* rep;             // [B]  an item below the branch
+  uint32_t* child;           // [B][16]
+  uint32_t* root_id;         // id of the root node (leaf or branch)
+  // results
+  uint8_t* ref;              // [N + B][32]
+  uint8_t* ref_len;          // [N + B]
+  uint8_t* root_out;         // [32]
+  unsigned long long* counters;
+};
+
+size_t scan_tmp_words(size_t n);
+void exclusive_scan_u32(const uint32_t* in, uint32_t* out, uint32_t n, uint32_t* tmp, cudaStream_t st);
+void launch_lcp(const uint8_t* keys, uint32_t n, int8_t* L, uint32_t* flags, cudaStream_t st);
+void launch_min64(const int8_t* in, uint32_t n_in, int8_t* out, uint32_t n_out, cudaStream_t st);
+void launch_leaders(const int8_t* L, const int8_t* m1, const int8_t* m2, const int8_t* m3, uint32_t n, uint32_t* link_a, uint32_t* link_b,
+                    uint32_t* flag, cudaStream_t st);
+void launch_branch_info(const BuildView& V, cudaStream_t st);
+void launch_depth_hist(const uint8_t* depth, uint32_t nb, uint32_t* hist, cudaStream_t st);
+void launch_branch_scatter(const uint8_t* depth, uint32_t nb, uint32_t* cursor, uint32_t* order, cudaStream_t st);
+void launch_hash_sorted_leaves(const BuildView& V, cudaStream_t st);
+void launch_hash_branch_level(const BuildView& V, const uint32_t* order, uint32_t begin, uint32_t end, cudaStream_t st);
+
+}  // namespace ppd

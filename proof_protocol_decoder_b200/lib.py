@@ -1,0 +1,218 @@
+"""ctypes binding of libppd_b200.so (include/ppd_b200.h)."""
+import ctypes
+import os
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(HERE, "libppd_b200.so")
+CSRC = os.path.join(HERE, "csrc")
+
+STATUS_NAMES = {
+    0: "OK",
+    1: "MissingHeader",
+    2: "InvalidOperator",
+    3: "UnexpectedEndOfStream",
+    4: "InvalidByteVector",
+    5: "InvalidBytesForType",
+    6: "InvalidWitnessFormat",
+    7: "NonSingleEntryAfterProcessing",
+    8: "IncorrectNumberOfNodesPrecedingBranch",
+    9: "MissingExpectedNodesPrecedingBranch",
+    10: "PrecedingNonNodeEntryFoundWhenProcessingRule",
+    11: "KeyError",
+    21: "AccountDecode",
+    22: "MissingAccountStorageTrie",
+    23: "NonExistentTrieEntry",
+    24: "MissingKeysCreatingSubPartialTrie",
+    25: "MissingWithdrawalAccount",
+    40: "panic: incompatible header version",
+    41: "panic: insert into hash node",
+    42: "panic: H256::from_slice",
+    43: "panic: receipt decode",
+    44: "panic: pre-image account decode",
+    45: "panic: unimplemented pre-image variant",
+    46: "panic: key is a prefix of another key",
+    60: "bad flat input",
+    61: "unresolved code hash",
+    62: "bad argument",
+    63: "unsorted keys",
+    100: "CUDA error",
+}
+
+
+class PpdError(Exception):
+    """A non-OK ppd_status.  Codes 1-11 are CompactParsingError variants, 21-25 TraceParsingError
+    variants (decoding.rs:31-49), 40-46 places where the reference panics."""
+
+    def __init__(self, code, msg=""):
+        super().__init__(f"ppd status {code} ({STATUS_NAMES.get(code, '?')}): {msg}")
+        self.code = code
+
+
+class PpdStats(ctypes.Structure):
+    _fields_ = [
+        ("nodes_hashed", ctypes.c_uint64),
+        ("node_permutations", ctypes.c_uint64),
+        ("key_hashes", ctypes.c_uint64),
+        ("key_permutations", ctypes.c_uint64),
+        ("arena_nodes", ctypes.c_uint64),
+        ("levels", ctypes.c_uint64),
+        ("gpu_ms", ctypes.c_double),
+        ("h2d_bytes", ctypes.c_double),
+        ("d2h_bytes", ctypes.c_double),
+        ("kernel_launches", ctypes.c_uint64),
+    ]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+EXPORTS = [
+    "ppd_ctx_create",
+    "ppd_ctx_destroy",
+    "ppd_last_error",
+    "ppd_last_stats",
+    "ppd_free",
+    "ppd_keccak256_batch",
+    "ppd_compact_decode",
+    "ppd_block_decode",
+    "ppd_blocks_decode_batch",
+    "ppd_trie_root_sorted_leaves",
+    "ppd_trie_root_sorted_leaves_dev",
+]
+
+
+def build_extension(verbose=False):
+    """Compile every CUDA source for sm_100a into libppd_b200.so, in-tree (nvcc cross-compiles without a GPU)."""
+    res = subprocess.run(["make", "-C", CSRC], capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("building libppd_b200.so failed:\n" + res.stdout + res.stderr)
+    if verbose:
+        print(res.stdout)
+    return SO_PATH
+
+
+class PpdLibrary:
+    def __init__(self, path=SO_PATH):
+        if not os.path.exists(path):
+            raise RuntimeError(f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` (there is no CPU fallback)")
+        L = ctypes.CDLL(path)
+        self.L = L
+        u8pp = ctypes.POINTER(ctypes.POINTER(ctypes.c_uint8))
+        szp = ctypes.POINTER(ctypes.c_size_t)
+        L.ppd_ctx_create.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)]
+        L.ppd_ctx_destroy.argtypes = [ctypes.c_void_p]
+        L.ppd_last_error.argtypes = [ctypes.c_void_p]
+        L.ppd_last_error.restype = ctypes.c_char_p
+        L.ppd_last_stats.argtypes = [ctypes.c_void_p, ctypes.POINTER(PpdStats)]
+        L.ppd_free.argtypes = [ctypes.c_void_p]
+        L.ppd_keccak256_batch.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]
+        L.ppd_compact_decode.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, u8pp, szp]
+        L.ppd_block_decode.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, u8pp, szp]
+        L.ppd_blocks_decode_batch.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+        L.ppd_trie_root_sorted_leaves.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_char_p]
+        L.ppd_trie_root_sorted_leaves_dev.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_char_p]
+
+    def exported(self):
+        return [name for name in EXPORTS if hasattr(self.L, name)]
+
+
+class Context:
+    """One ppd_ctx: a stream plus reusable HBM buffers on one CUDA device.  Not thread-safe."""
+
+    def __init__(self, device=0, lib=None):
+        self.lib = lib or load_library()
+        self.h = ctypes.c_void_p()
+        rc = self.lib.L.ppd_ctx_create(device, ctypes.byref(self.h))
+        if rc != 0:
+            raise PpdError(rc, "ppd_ctx_create failed: no usable CUDA device (there is no CPU fallback)")
+
+    def close(self):
+        if self.h:
+            self.lib.L.ppd_ctx_destroy(self.h)
+            self.h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise PpdError(rc, self.lib.L.ppd_last_error(self.h).decode(errors="replace"))
+
+    def stats(self):
+        s = PpdStats()
+        self.lib.L.ppd_last_stats(self.h, ctypes.byref(s))
+        return s.as_dict()
+
+    def _take(self, out, n):
+        data = ctypes.string_at(out, n.value)
+        self.lib.L.ppd_free(out)
+        return data
+
+    def keccak256_batch(self, data, offsets):
+        import numpy as np
+
+        data = np.ascontiguousarray(data, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        n = len(offsets) - 1
+        out = np.empty((n, 32), dtype=np.uint8)
+        self._check(self.lib.L.ppd_keccak256_batch(self.h, data.ctypes.data, offsets.ctypes.data, n, out.ctypes.data))
+        return out
+
+    def compact_decode(self, witness: bytes) -> bytes:
+        out, n = ctypes.POINTER(ctypes.c_uint8)(), ctypes.c_size_t()
+        buf = ctypes.create_string_buffer(bytes(witness), len(witness)) if len(witness) else ctypes.create_string_buffer(1)
+        self._check(self.lib.L.ppd_compact_decode(self.h, buf, len(witness), ctypes.byref(out), ctypes.byref(n)))
+        return self._take(out, n)
+
+    def block_decode(self, flat: bytes) -> bytes:
+        out, n = ctypes.POINTER(ctypes.c_uint8)(), ctypes.c_size_t()
+        buf = (ctypes.c_uint8 * len(flat)).from_buffer_copy(flat)
+        self._check(self.lib.L.ppd_block_decode(self.h, buf, len(flat), ctypes.byref(out), ctypes.byref(n)))
+        return self._take(out, n)
+
+    def blocks_decode_batch(self, flats):
+        n = len(flats)
+        bufs = [(ctypes.c_uint8 * len(f)).from_buffer_copy(f) for f in flats]
+        ptrs = (ctypes.c_void_p * n)(*[ctypes.addressof(b) for b in bufs])
+        lens = (ctypes.c_size_t * n)(*[len(f) for f in flats])
+        outs = (ctypes.POINTER(ctypes.c_uint8) * n)()
+        out_lens = (ctypes.c_size_t * n)()
+        statuses = (ctypes.c_int * n)()
+        self._check(self.lib.L.ppd_blocks_decode_batch(self.h, ptrs, lens, n, outs, out_lens, statuses))
+        res = []
+        for i in range(n):
+            if statuses[i] == 0:
+                res.append(ctypes.string_at(outs[i], out_lens[i]))
+                self.lib.L.ppd_free(outs[i])
+            else:
+                res.append(PpdError(statuses[i], "block %d" % i))
+        return res
+
+    def trie_root_sorted_leaves(self, keys, val_off, vals) -> bytes:
+        import numpy as np
+
+        keys = np.ascontiguousarray(keys, dtype=np.uint8)
+        val_off = np.ascontiguousarray(val_off, dtype=np.uint64)
+        vals = np.ascontiguousarray(vals, dtype=np.uint8)
+        out = ctypes.create_string_buffer(32)
+        self._check(self.lib.L.ppd_trie_root_sorted_leaves(self.h, keys.ctypes.data, val_off.ctypes.data, vals.ctypes.data, len(val_off) - 1, out))
+        return out.raw
+
+    def trie_root_sorted_leaves_dev(self, d_keys_ptr, d_val_off_ptr, d_vals_ptr, n, vals_bytes) -> bytes:
+        out = ctypes.create_string_buffer(32)
+        self._check(self.lib.L.ppd_trie_root_sorted_leaves_dev(self.h, d_keys_ptr, d_val_off_ptr, d_vals_ptr, n, vals_bytes, out))
+        return out.raw
+
+
+_lib = None
+
+
+def load_library():
+    global _lib
+    if _lib is None:
+        _lib = PpdLibrary()
+    return _lib

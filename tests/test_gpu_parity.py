@@ -1,0 +1,193 @@
+"""Parity of the CUDA path (through the C ABI) with the CPU oracle and the reference goldens.
+Run on the B200 box: python -m pytest tests -m gpu"""
+import numpy as np
+import pytest
+
+from ppd_oracle_lib import OracleError, parse_pre_image_dump
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from proof_protocol_decoder_b200.lib import Context
+
+    c = Context(0)
+    yield c
+    c.close()
+
+
+def _batch(msgs):
+    data = np.frombuffer(b"".join(msgs), dtype=np.uint8) if msgs else np.zeros(0, np.uint8)
+    off = np.zeros(len(msgs) + 1, dtype=np.uint64)
+    np.cumsum([len(m) for m in msgs], out=off[1:])
+    return data, off
+
+
+def test_keccak_batch_edges(ctx, oracle, goldens):
+    rng = np.random.default_rng(0)
+    lens = [0, 1, 20, 32, 55, 56, 134, 135, 136, 137, 271, 272, 273, 407, 408, 409, 1000, 4096]
+    msgs = [rng.bytes(n) for n in lens] + [b"\x80"]
+    data, off = _batch(msgs)
+    got = ctx.keccak256_batch(data, off)
+    want = oracle.keccak256_batch(data, off)
+    assert (got == want).all()
+    assert got[0].tobytes().hex() == goldens["constants"]["EMPTY_CODE_HASH"]
+    assert got[-1].tobytes().hex() == goldens["constants"]["EMPTY_TRIE_HASH"]
+
+
+def test_keccak_batch_random_lengths(ctx, oracle):
+    rng = np.random.default_rng(1)
+    lens = rng.integers(0, 4097, size=3000)
+    msgs = [rng.bytes(int(n)) for n in lens]
+    data, off = _batch(msgs)
+    assert (ctx.keccak256_batch(data, off) == oracle.keccak256_batch(data, off)).all()
+
+
+def test_keccak_batch_addresses_and_slots(ctx, oracle):
+    rng = np.random.default_rng(2)
+    for width in (20, 32):
+        n = 100_000
+        data = np.frombuffer(rng.bytes(width * n), dtype=np.uint8)
+        off = (np.arange(n + 1, dtype=np.uint64) * width).astype(np.uint64)
+        assert (ctx.keccak256_batch(data, off) == oracle.keccak256_batch(data, off)).all()
+
+
+@pytest.mark.parametrize("idx", range(6))
+def test_golden_state_roots_on_gpu(ctx, oracle, goldens, idx):
+    from proof_protocol_decoder_b200 import flat
+
+    g = goldens["compact_goldens"][idx]
+    w = bytes.fromhex(g["witness_hex"])
+    d = flat.parse_pre_image_dump(ctx.compact_decode(w))
+    assert d["version"] == 1
+    assert d["state_root"].hex() == g["state_root"]
+    o = parse_pre_image_dump(oracle.compact_decode(w))
+    assert d["storage"] == o["storage"]
+    assert d["code"] == o["code"]
+
+
+def test_header_only_and_simple_payload(ctx, oracle, goldens):
+    from proof_protocol_decoder_b200 import flat
+
+    d = flat.parse_pre_image_dump(ctx.compact_decode(b"\x01"))
+    assert d["state_root"].hex() == goldens["constants"]["EMPTY_TRIE_HASH"]
+
+
+@pytest.mark.parametrize(
+    "witness",
+    [b"", b"\x01\x07", b"\x01\x05\x41\x10", b"\x01\x00\x58", b"\x01\x03\x00", b"\x01\x06\x06", b"\x01\x06\x02\x03", b"\x01\x06\x02\x1a\x00\x01\x00\x00"],
+)
+def test_compact_error_variants_match_oracle(ctx, oracle, witness):
+    from proof_protocol_decoder_b200 import PpdError
+
+    with pytest.raises(OracleError) as eo:
+        oracle.compact_decode(witness)
+    with pytest.raises(PpdError) as eg:
+        ctx.compact_decode(witness)
+    assert eg.value.code == eo.value.code
+
+
+def _check_block(ctx, oracle, blk):
+    f = blk.flat
+    want = oracle.block_decode(f)
+    got = ctx.block_decode(f)
+    if got != want:
+        from proof_protocol_decoder_b200 import flat
+
+        a, b = flat.parse_ir_dump(got), flat.parse_ir_dump(want)
+        assert len(a) == len(b)
+        for i, (x, y) in enumerate(zip(a, b)):
+            for k in x:
+                assert x[k] == y[k], f"IR {i} field {k} differs"
+    assert got == want
+    return got
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3, 4, 5])
+def test_c1_blocks_bit_exact(ctx, oracle, seed):
+    from proof_protocol_decoder_b200 import synth
+
+    _check_block(ctx, oracle, synth.gen_block(seed, n_accounts=1000, n_txns=10, n_withdrawals=seed % 3))
+
+
+@pytest.mark.parametrize("n_txns,n_wd", [(0, 0), (0, 2), (1, 0), (1, 2), (2, 0), (2, 3)])
+def test_dummy_padding_and_withdrawals(ctx, oracle, n_txns, n_wd):
+    from proof_protocol_decoder_b200 import synth
+
+    _check_block(ctx, oracle, synth.gen_block(100 + n_txns * 10 + n_wd, n_accounts=120, n_txns=n_txns, n_withdrawals=n_wd))
+
+
+def test_tiny_states(ctx, oracle):
+    from proof_protocol_decoder_b200 import synth
+
+    for n in (0, 1, 2, 3):
+        _check_block(ctx, oracle, synth.gen_block(200 + n, n_accounts=n, n_txns=2, allow_self_destruct=False))
+
+
+def test_mainnet_shaped_block_scaled(ctx, oracle):
+    from proof_protocol_decoder_b200 import synth
+
+    blk = synth.gen_block(
+        2, n_accounts=2000, n_txns=20, contract_frac=0.15, slots_hi=512, virtual_depth=5, virtual_accounts_log16=5,
+        accounts_per_txn=(40, 60), slot_reads=(0, 3), slot_writes=(0, 3), allow_new_accounts=False, allow_self_destruct=False,
+    )
+    _check_block(ctx, oracle, blk)
+
+
+def test_blocks_batch_matches_single(ctx, oracle):
+    from proof_protocol_decoder_b200 import synth
+
+    blks = [synth.gen_block(300 + i, n_accounts=150, n_txns=3, n_withdrawals=i % 2) for i in range(6)]
+    outs = ctx.blocks_decode_batch([b.flat for b in blks])
+    for b, o in zip(blks, outs):
+        assert o == oracle.block_decode(b.flat)
+
+
+def test_reference_interface_mirror(ctx, oracle):
+    from proof_protocol_decoder_b200 import flat, synth
+
+    blk = synth.gen_block(11, n_accounts=100, n_txns=3, n_withdrawals=1)
+    bt, meta, other = blk.to_block_trace()
+    irs = bt.into_txn_proof_gen_ir(meta, other, ctx=ctx)
+    want = flat.parse_ir_dump(oracle.block_decode(bt.to_flat(meta, other)))
+    assert irs == want
+    assert len(irs) == 4  # 3 txns + the withdrawal dummy (decoding.rs:367-387)
+    assert irs[-1]["withdrawals"] and irs[-1]["signed_txn"] is None
+
+
+@pytest.mark.parametrize("n", [0, 1, 2, 3, 17, 1000, 50_000])
+def test_sorted_leaves_root(ctx, oracle, n):
+    from proof_protocol_decoder_b200 import synth
+
+    keys, val_off, vals = synth.gen_sorted_leaves(n, seed=n + 1)
+    assert ctx.trie_root_sorted_leaves(keys, val_off, vals) == oracle.trie_root_from_leaves(keys, val_off, vals)
+
+
+def test_sorted_leaves_shared_prefixes_and_small_values(ctx, oracle):
+    # long shared prefixes force extension nodes; tiny values force nodes shorter than 32 bytes (inlined refs)
+    rng = np.random.default_rng(3)
+    n = 4000
+    keys = np.zeros((n, 32), dtype=np.uint8)
+    keys[:, :28] = np.frombuffer(rng.bytes(28), dtype=np.uint8)
+    keys[:, 28:] = np.frombuffer(rng.bytes(4 * n), dtype=np.uint8).reshape(n, 4)
+    keys[: n // 2, 5] ^= 0x10
+    keys = np.unique(keys, axis=0)
+    be = keys.view(">u8")
+    keys = np.ascontiguousarray(keys[np.lexsort((be[:, 3], be[:, 2], be[:, 1], be[:, 0]))])
+    n = len(keys)
+    lens = rng.integers(1, 4, size=n).astype(np.uint64)
+    val_off = np.zeros(n + 1, dtype=np.uint64)
+    np.cumsum(lens, out=val_off[1:])
+    vals = np.frombuffer(rng.bytes(int(val_off[-1])), dtype=np.uint8)
+    assert ctx.trie_root_sorted_leaves(keys, val_off, vals) == oracle.trie_root_from_leaves(keys, val_off, vals)
+
+
+def test_unsorted_keys_are_rejected(ctx):
+    from proof_protocol_decoder_b200 import PpdError, synth
+
+    keys, val_off, vals = synth.gen_sorted_leaves(100, seed=9)
+    keys = keys[::-1].copy()
+    with pytest.raises(PpdError) as e:
+        ctx.trie_root_sorted_leaves(keys, val_off, vals)
+    assert e.value.code == 63
