@@ -1,0 +1,401 @@
+#!/usr/bin/env python3
+"""bench.py — headline benchmark of the hot path (BASELINE.json metric: MPT nodes keccak-hashed/sec
+and blocks decoded/sec).
+
+  python bench.py --gpus N --steps K --warmup W            this repo's CUDA path, one rank per GPU
+  python bench.py --impl reference --gpus N --steps K ...   the reference's CPU algorithm (oracle port)
+                                                            on the host cores, same metric and config
+
+Workload (config.workload): C2, the mainnet-shaped block of BASELINE.json configs[1] — ~20k touched
+accounts embedded in a virtual 16^7-account state, 200 txns — one block per GPU per step (weak
+scaling: rank r decodes the block of seed 2 + r).  A step = every Keccak of the block: all
+addresses / slots / code plus every node of every version of the state, storage, txn and receipt
+tries, hashed level-synchronously.
+  value  nodes/s with the block's arena and key messages already resident in HBM (device time,
+         CUDA events on the library's stream, L2 flushed between steps)
+  e2e    the same metric through the C ABI (ppd_block_decode) with HOST buffers: FlatBlock in,
+         IrDump out, every host<->device copy and all host work inside the timed region
+One JSON line on stdout (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ALU_OPS_PER_PERM = 4354  # 24 rounds x ~180 LOP3/SHF + 34 to absorb a rate block
+ALU_LANES_PER_SM_CLK = 64
+N_SM = 148
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "sm_max_mhz": d.get("sm_max_mhz", 1965.0), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0, "source": "fallback"}
+
+
+class ClockSampler:
+    FIELDS = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index):
+        self.gpu = str(gpu_index)
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100", "-i", self.gpu],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True,
+            )
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) >= 8:
+                self.rows.append(parts)
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = sorted(float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit())
+        mx = [float(r[2]) for r in self.rows if r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows for i in range(4) if r[4 + i].lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(self.rows)}
+
+
+def c2_block(seed, scale):
+    from proof_protocol_decoder_b200 import synth
+
+    cache = f"/tmp/ppd_c2_seed{seed}_scale{scale}.flat"
+    if os.path.exists(cache):
+        return open(cache, "rb").read()
+    blk = synth.gen_block(
+        seed,
+        n_accounts=max(10, int(20000 * scale)),
+        n_txns=max(2, int(200 * scale)),
+        contract_frac=0.15,
+        slots_lo=1,
+        slots_hi=256,
+        virtual_depth=7,
+        virtual_accounts_log16=7,
+        accounts_per_txn=(80, 120) if scale >= 0.5 else (max(2, int(80 * scale * 4)), max(4, int(120 * scale * 4))),
+        slot_reads=(0, 3),
+        slot_writes=(0, 3),
+        allow_new_accounts=False,
+        allow_self_destruct=False,
+        inline_code_frac=0.02,
+    )
+    f = blk.flat
+    try:
+        open(cache, "wb").write(f)
+    except OSError:
+        pass
+    return f
+
+
+def oracle_time_block(flat_bytes, repeats, threads):
+    """Decode `flat_bytes` `repeats` times on each of `threads` host threads (ctypes releases the GIL).
+    Returns (wall seconds, stats of one decode)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import ppd_oracle_lib
+
+    oracle = ppd_oracle_lib.load()
+    stats = {}
+
+    def work():
+        for _ in range(repeats):
+            oracle.block_decode(flat_bytes)
+        stats.update(oracle.last_stats())
+
+    ts = [threading.Thread(target=work) for _ in range(threads)]
+    t0 = time.perf_counter()
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    return time.perf_counter() - t0, stats
+
+
+def run_reference(args, rank, world):
+    """The reference's CPU algorithm for the path (the oracle: a C++ port of the reference's Rust,
+    which cannot be compiled here) on all host cores; each step decodes one bounded sample block per
+    core.  Rank 0 alone works."""
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    sample_scale = args.ref_scale
+    flat_bytes = c2_block(2, sample_scale)
+    for _ in range(max(1, min(args.warmup, 1))):
+        oracle_time_block(flat_bytes, 1, cores)
+    t_total, st = 0.0, {}
+    for _ in range(args.steps):
+        t, st = oracle_time_block(flat_bytes, 1, cores)
+        t_total += t
+    nodes = st["nodes_hashed"] * cores * args.steps
+    value = nodes / t_total
+    line = {
+        "impl": "reference",
+        "metric": "mpt_nodes_keccak_hashed_per_sec",
+        "value": value,
+        "unit": "nodes/s",
+        "n_gpus": args.gpus,
+        "steps": args.steps,
+        "warmup": args.warmup,
+        "ms_per_step": 1e3 * t_total / args.steps,
+        "higher_is_better": True,
+        "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": "u64",
+        "data": "synthetic",
+        "config": {"workload": "C2 mainnet-shaped block (BASELINE.json configs[1])", "sample": f"{sample_scale:g}x-scale C2 block per core per step", "l2": "n/a (CPU)"},
+        "blocks_per_sec": cores * args.steps / t_total,
+        "cpu_baseline": {
+            "value": value, "unit": "nodes/s", "cores": cores, "kind": "port",
+            "sample": f"one {sample_scale:g}x-scale C2 block ({st['nodes_hashed']} node hashes) per core per step; C++ restatement of the reference algorithm (the Rust reference cannot be built in this image)",
+        },
+        "e2e": {"value": value, "unit": "nodes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def c5_sweep(ctx, sizes, peaks, sm_mhz):
+    """Config 5: state-trie rehash over sorted leaves already resident in HBM (structure built and
+    hashed on the GPU).  Reported beside the headline to show the hashing kernels at scale."""
+    import torch
+
+    out = []
+    for n in sizes:
+        try:
+            g = torch.Generator(device="cuda")
+            g.manual_seed(5)
+            keys = torch.randint(0, 256, (n, 32), dtype=torch.uint8, device="cuda", generator=g)
+            hi = keys[:, :8].to(torch.int64)
+            k64 = torch.zeros(n, dtype=torch.int64, device="cuda")
+            for b in range(8):
+                k64 = (k64 << 8) | hi[:, b]
+            order = torch.argsort((k64 >> 1) & 0x7FFFFFFFFFFFFFFF)  # top 63 bits, unsigned order
+            del hi, k64
+            keys = keys[order].contiguous()
+            del order
+            lens = torch.randint(70, 81, (n,), dtype=torch.int64, device="cuda", generator=g)
+            val_off = torch.zeros(n + 1, dtype=torch.int64, device="cuda")
+            val_off[1:] = torch.cumsum(lens, 0)
+            vb = int(val_off[-1].item())
+            vals = torch.randint(0, 256, (vb,), dtype=torch.uint8, device="cuda", generator=g)
+            torch.cuda.synchronize()
+            best = None
+            for _ in range(3):
+                ctx.trie_root_sorted_leaves_dev(keys.data_ptr(), val_off.data_ptr(), vals.data_ptr(), n, vb)
+                st = ctx.stats()
+                if best is None or st["gpu_ms"] < best["gpu_ms"]:
+                    best = st
+            sec = best["gpu_ms"] / 1e3
+            alu_peak = ALU_LANES_PER_SM_CLK * N_SM * (sm_mhz or peaks["sm_max_mhz"]) * 1e6
+            out.append({
+                "leaves": n, "nodes_hashed": best["nodes_hashed"], "permutations": best["node_permutations"], "gpu_ms": best["gpu_ms"],
+                "nodes_per_sec": best["nodes_hashed"] / sec, "perms_per_sec": best["node_permutations"] / sec,
+                "alu_frac": best["node_permutations"] * ALU_OPS_PER_PERM / sec / alu_peak,
+                "hbm_frac": (best["node_bytes"] + 32 * best["nodes_hashed"]) / sec / 1e9 / peaks["hbm_gbs"],
+                "note": "includes building the trie structure on the GPU (LCP, branch discovery, counting sort)",
+            })
+            del keys, vals, val_off, lens
+            torch.cuda.empty_cache()
+        except Exception as e:  # noqa: BLE001 — the sweep is supplementary; never lose the headline line
+            out.append({"leaves": n, "error": str(e)[:200]})
+            break
+    return out
+
+
+def run_b200(args, rank, world, local_rank):
+    import torch
+
+    from proof_protocol_decoder_b200.lib import Context
+
+    peaks = load_peaks()
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+
+        dist = dist_mod
+        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    ctx = Context(local_rank)
+    flat_bytes = c2_block(2 + rank, args.scale)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+
+    # ---- warm-up (also leaves the arena resident for the device-resident measurement) ----
+    for _ in range(max(3, args.warmup)):
+        ir = ctx.block_decode(flat_bytes)
+    st = ctx.stats()
+    for _ in range(max(3, args.warmup)):
+        ctx.replay_last_hashing()
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    # ---- device-resident: every kernel of the block on the arena already in HBM ----
+    barrier()
+    dev_ms = 0.0
+    for _ in range(args.steps):
+        flush.zero_()
+        torch.cuda.synchronize()
+        dev_ms += ctx.replay_last_hashing()
+    barrier()
+    dev_ms = max_over_ranks(dev_ms)
+    # ---- end to end through the C ABI with host buffers ----
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ir = ctx.block_decode(flat_bytes)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    barrier()
+    e2e_s = max_over_ranks(e2e_s)
+    clocks = sampler.stop()
+    st = ctx.stats()
+
+    nodes_all = sum_over_ranks(float(st["nodes_hashed"]))
+    perms_all = sum_over_ranks(float(st["node_permutations"] + st["key_permutations"]))
+    keys_all = sum_over_ranks(float(st["key_hashes"]))
+    dev_s_per_step = dev_ms / 1e3 / args.steps
+    e2e_s_per_step = e2e_s / args.steps
+    sm_mhz = clocks.get("sm_mhz")
+    alu_peak = ALU_LANES_PER_SM_CLK * N_SM * (sm_mhz or peaks["sm_max_mhz"]) * 1e6  # instr/s on one GPU
+    algo_bytes = st["node_bytes"] + 32 * st["nodes_hashed"]  # L + 32 per hashed node (this rank)
+    achieved_gbs = algo_bytes / dev_s_per_step / 1e9
+    line = {
+        "metric": "mpt_nodes_keccak_hashed_per_sec",
+        "value": nodes_all / dev_s_per_step,
+        "unit": "nodes/s",
+        "n_gpus": world,
+        "steps": args.steps,
+        "warmup": max(3, args.warmup),
+        "ms_per_step": 1e3 * dev_s_per_step,
+        "higher_is_better": True,
+        "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": "u64",
+        "data": "synthetic",
+        "config": {
+            "workload": "C2 mainnet-shaped block (BASELINE.json configs[1]): 20k touched accounts in a virtual 16^7-account state, 200 txns; one block per GPU per step",
+            "scale": args.scale,
+            "flat_block_bytes": len(flat_bytes),
+            "ir_dump_bytes": len(ir),
+            "arena_nodes": st["arena_nodes"],
+            "levels": st["levels"],
+            "l2": "flushed between timed device-resident steps (256 MiB write)",
+            "parallelism": f"blocks sharded over {world} GPU(s), no data-path collective",
+        },
+        "blocks_per_sec": world / dev_s_per_step,
+        "permutations_per_sec": perms_all / dev_s_per_step,
+        "nodes_hashed_per_step": nodes_all,
+        "key_hashes_per_step": keys_all,
+        "e2e": {
+            "value": nodes_all / e2e_s_per_step,
+            "unit": "nodes/s",
+            "blocks_per_sec": world / e2e_s_per_step,
+            "ms_per_step": 1e3 * e2e_s_per_step,
+            "h2d_bytes_per_step": st["h2d_bytes"],
+            "d2h_bytes_per_step": st["d2h_bytes"],
+            "note": "ppd_block_decode: FlatBlock (host) -> IrDump (host); includes witness parse, trie shaping and IR serialisation on the host",
+        },
+        "gpu_launches": int(st["kernel_launches"]) * args.steps,
+        "clocks": clocks,
+        "roofline": {
+            "bound": "hbm",
+            "kernel": "hash_level_kernel (all level launches of one block)",
+            "achieved": achieved_gbs,
+            "peak": peaks["hbm_gbs"],
+            "unit": "GB/s",
+            "frac": achieved_gbs / peaks["hbm_gbs"],
+            "traffic": None,
+            "peak_source": peaks["source"],
+            "note": "Keccak is bound by the integer ALU pipe, not HBM (SURVEY.md 8d): see roofline_alu",
+        },
+        "roofline_alu": {
+            "bound": "alu-pipe (LOP3/SHF)",
+            "achieved": (st["node_permutations"] + st["key_permutations"]) * ALU_OPS_PER_PERM / dev_s_per_step / 1e12,
+            "peak": alu_peak / 1e12,
+            "unit": "Tinstr/s",
+            "frac": (st["node_permutations"] + st["key_permutations"]) * ALU_OPS_PER_PERM / dev_s_per_step / alu_peak,
+            "model": f"{ALU_OPS_PER_PERM} ALU instr per permutation; peak = {ALU_LANES_PER_SM_CLK} lanes/clk/SM x {N_SM} SMs x SM clock under load",
+        },
+    }
+    if rank == 0 and world == 1:
+        sample = c2_block(2, args.ref_scale)
+        t, ost = oracle_time_block(sample, 1, 1)
+        line["cpu_baseline"] = {
+            "value": ost["nodes_hashed"] / t,
+            "unit": "nodes/s",
+            "cores": 1,
+            "kind": "port",
+            "blocks_per_sec_at_sample_scale": 1.0 / t,
+            "sample": f"one {args.ref_scale:g}x-scale C2 block ({ost['nodes_hashed']} node hashes, {t:.2f} s) on 1 core; C++ restatement of the reference algorithm (the Rust reference cannot be built in this image)",
+        }
+        if not args.no_sweep:
+            line["c5_sweep"] = c5_sweep(ctx, [int(x) for x in args.sweep.split(",") if x], peaks, sm_mhz)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--scale", type=float, default=1.0, help="fraction of the C2 block size (1.0 = the named config)")
+    ap.add_argument("--ref-scale", type=float, default=0.1, help="size of the bounded CPU sample block")
+    ap.add_argument("--sweep", default="1000000,10000000", help="config-5 leaf counts measured beside the headline at N=1")
+    ap.add_argument("--no-sweep", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    run_b200(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

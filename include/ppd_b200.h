@@ -37,6 +37,7 @@ typedef struct ppd_stats {
   uint64_t node_permutations;  /* keccak-f[1600] permutations spent on them */
   uint64_t key_hashes;         /* utils::hash calls: addresses, slots, code */
   uint64_t key_permutations;
+  uint64_t node_bytes;         /* bytes of RLP absorbed by those invocations */
   uint64_t arena_nodes;        /* node records resident in HBM */
   uint64_t levels;             /* level launches */
   double gpu_ms;               /* device time of the kernels of the call (CUDA events) */
@@ -67,6 +68,10 @@ int ppd_block_decode(ppd_ctx* ctx, const uint8_t* flat_block, size_t len, uint8_
  * sweep.  statuses[i] is the status of block i; outs[i] is NULL for a failed block. */
 int ppd_blocks_decode_batch(ppd_ctx* ctx, const uint8_t* const* flat_blocks, const size_t* lens, size_t n, uint8_t** outs,
                             size_t* out_lens, int* statuses);
+
+/* Measurement hook: re-run every kernel of the last ppd_block_decode / ppd_blocks_decode_batch on
+ * the arena still resident in HBM (no host work, no copies); returns the device time (CUDA events). */
+int ppd_replay_last_hashing(ppd_ctx* ctx, double* gpu_ms_out);
 
 /* HashedPartialTrie::hash of the trie holding n leaves with 32-byte keys, given sorted by key
  * (the state-trie rehash of config 5).  value i = vals[val_off[i] .. val_off[i+1]) is stored as

@@ -455,7 +455,8 @@ struct Node {
   mutable int8_t ref_len = -1;  // cache: -1 unknown, 0..31 raw encoding inlined, 32 hashed
   mutable uint8_t ref[32];
 };
-static NodeP EMPTY_NODE = std::make_shared<Node>();
+// per thread: a process-wide singleton would make every branch copy contend on one reference count
+static thread_local NodeP EMPTY_NODE = std::make_shared<Node>();
 static NodeP mk_hash(const H256& h) {
   auto n = std::make_shared<Node>();
   n->kind = HASH;

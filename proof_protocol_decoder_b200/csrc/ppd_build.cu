@@ -359,7 +359,7 @@ template <int B>
 __global__ void __launch_bounds__(B) hash_sorted_leaves_kernel(BuildView V) {
   __shared__ uint32_t smem[PPD_STAGE_WORDS * B];
   uint32_t i = blockIdx.x * B + threadIdx.x;
-  uint32_t hashed = 0, perms = 0;
+  uint32_t hashed = 0, perms = 0, enc_bytes = 0;
   if (i < V.n) {
     const Pyramid& P = V.P;
     int dl = P.L[i], dr = P.L[i + 1];
@@ -432,6 +432,7 @@ __global__ void __launch_bounds__(B) hash_sorted_leaves_kernel(BuildView V) {
       o[0] = x, o[1] = y;
       V.ref_len[i] = 32;
       hashed = 1;
+      enc_bytes = total;
       if (is_root) {
         uint4* ro = reinterpret_cast<uint4*>(V.root_out);
         ro[0] = x, ro[1] = y;
@@ -442,10 +443,12 @@ __global__ void __launch_bounds__(B) hash_sorted_leaves_kernel(BuildView V) {
     for (int off = 16; off > 0; off >>= 1) {
       hashed += __shfl_down_sync(0xffffffffu, hashed, off);
       perms += __shfl_down_sync(0xffffffffu, perms, off);
+      enc_bytes += __shfl_down_sync(0xffffffffu, enc_bytes, off);
     }
     if ((threadIdx.x & 31) == 0 && hashed) {
       atomicAdd(V.counters + 0, (unsigned long long)hashed);
       atomicAdd(V.counters + 1, (unsigned long long)perms);
+      atomicAdd(V.counters + 2, (unsigned long long)enc_bytes);
     }
   }
 }
@@ -455,7 +458,7 @@ template <int B>
 __global__ void __launch_bounds__(B) hash_branch_level_kernel(BuildView V, const uint32_t* __restrict__ order, uint32_t begin, uint32_t end) {
   __shared__ uint32_t smem[PPD_STAGE_WORDS * B];
   uint32_t slot = begin + blockIdx.x * B + threadIdx.x;
-  uint32_t hashed = 0, perms = 0;
+  uint32_t hashed = 0, perms = 0, enc_bytes = 0;
   if (slot < end) {
     const uint32_t bi = __ldg(order + slot);
     const uint32_t id = V.n + bi;
@@ -526,6 +529,7 @@ __global__ void __launch_bounds__(B) hash_branch_level_kernel(BuildView V, const
         for (int k = 0; k < 4; k++) rw[2 * k] = (uint32_t)a[k], rw[2 * k + 1] = (uint32_t)(a[k] >> 32);
         rlen = 32;
         hashed++;
+        enc_bytes += total;
       } else {
         s.flush_partial();
         uint32_t nw = (total + 3) >> 2;
@@ -560,10 +564,12 @@ __global__ void __launch_bounds__(B) hash_branch_level_kernel(BuildView V, const
     for (int off = 16; off > 0; off >>= 1) {
       hashed += __shfl_down_sync(0xffffffffu, hashed, off);
       perms += __shfl_down_sync(0xffffffffu, perms, off);
+      enc_bytes += __shfl_down_sync(0xffffffffu, enc_bytes, off);
     }
     if ((threadIdx.x & 31) == 0 && hashed) {
       atomicAdd(V.counters + 0, (unsigned long long)hashed);
       atomicAdd(V.counters + 1, (unsigned long long)perms);
+      atomicAdd(V.counters + 2, (unsigned long long)enc_bytes);
     }
   }
 }

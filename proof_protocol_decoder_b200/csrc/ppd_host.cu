@@ -90,6 +90,11 @@ struct ppd_ctx {
   DevBuf d_nodes, d_order, d_keys, d_vals, d_hashes, d_children, d_accounts, d_ref, d_ref_len, d_counters;
   DevBuf d_msg, d_msg_off, d_digest;
   DevBuf d_build[12];
+  // the arena of the last block job stays resident so that its hashing can be re-run for measurement
+  bool has_last = false;
+  ArenaView last_view{};
+  std::vector<uint32_t> last_level_start;
+  uint32_t last_n_msgs = 0;
 };
 
 namespace {
@@ -1074,7 +1079,7 @@ void sweep(ppd_ctx* c, Job& J) {
   c->d_accounts.reserve(sizeof(AccountRec) * A.accounts.size() + 16);
   c->d_ref.reserve(32ull * n);
   c->d_ref_len.reserve(n);
-  c->d_counters.reserve(16);
+  c->d_counters.reserve(32);
   auto up = [&](DevBuf& d, const void* src, size_t bytes) {
     if (!bytes) return;
     CUDA_OK(cudaMemcpyAsync(d.p, src, bytes, cudaMemcpyHostToDevice, c->st));
@@ -1087,7 +1092,7 @@ void sweep(ppd_ctx* c, Job& J) {
   up(c->d_hashes, A.hash_pool.data(), A.hash_pool.size());
   up(c->d_children, A.child_pool.data(), 4ull * A.child_pool.size());
   up(c->d_accounts, A.accounts.data(), sizeof(AccountRec) * A.accounts.size());
-  CUDA_OK(cudaMemsetAsync(c->d_counters.p, 0, 16, c->st));
+  CUDA_OK(cudaMemsetAsync(c->d_counters.p, 0, 32, c->st));
   ArenaView V;
   V.nodes = c->d_nodes.as<NodeRec>();
   V.key_pool = c->d_keys.as<uint8_t>();
@@ -1105,16 +1110,21 @@ void sweep(ppd_ctx* c, Job& J) {
   }
   CUDA_OK(cudaGetLastError());
   CUDA_OK(cudaEventRecord(c->ev1, c->st));
-  unsigned long long counters[2] = {0, 0};
+  unsigned long long counters[3] = {0, 0, 0};
+  c->has_last = true;
+  c->last_view = V;
+  c->last_level_start = level_start;
+  c->last_n_msgs = (uint32_t)J.kh.lens.size();
   CUDA_OK(cudaMemcpyAsync(J.ref.data(), c->d_ref.p, 32ull * n, cudaMemcpyDeviceToHost, c->st));
   CUDA_OK(cudaMemcpyAsync(J.ref_len.data(), c->d_ref_len.p, n, cudaMemcpyDeviceToHost, c->st));
-  CUDA_OK(cudaMemcpyAsync(counters, c->d_counters.p, 16, cudaMemcpyDeviceToHost, c->st));
+  CUDA_OK(cudaMemcpyAsync(counters, c->d_counters.p, 24, cudaMemcpyDeviceToHost, c->st));
   CUDA_OK(cudaStreamSynchronize(c->st));
   float ms = 0;
   CUDA_OK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
   c->stats.gpu_ms += ms;
   c->stats.nodes_hashed += counters[0];
   c->stats.node_permutations += counters[1];
+  c->stats.node_bytes += counters[2];
   c->stats.arena_nodes += n;
   c->stats.levels += n_levels;
   c->stats.d2h_bytes += 33.0 * n;
@@ -1381,6 +1391,26 @@ int ppd_keccak256_batch(ppd_ctx* c, const uint8_t* data, const uint64_t* offsets
   });
 }
 
+// Re-run every kernel of the last ppd_block_decode / ppd_blocks_decode_batch call on the arena and
+// key messages that are still resident in HBM (no host work, no copies) and return its device time.
+int ppd_replay_last_hashing(ppd_ctx* c, double* gpu_ms_out) {
+  return guarded(c, [&] {
+    if (!c->has_last) fail(PPD_ERR_BAD_ARGUMENT, "no block job is resident");
+    CUDA_OK(cudaMemsetAsync(c->d_counters.p, 0, 32, c->st));
+    CUDA_OK(cudaEventRecord(c->ev0, c->st));
+    launch_keccak256_ranges(c->d_msg.as<uint8_t>(), c->d_msg_off.as<uint64_t>(), c->last_n_msgs, c->d_digest.as<uint8_t>(), c->st);
+    size_t nl = c->last_level_start.size() - 1;
+    for (size_t l = 0; l < nl; l++)
+      launch_hash_level(c->last_view, c->d_order.as<uint32_t>(), c->last_level_start[l], c->last_level_start[l + 1], c->st);
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaEventRecord(c->ev1, c->st));
+    CUDA_OK(cudaStreamSynchronize(c->st));
+    float ms = 0;
+    CUDA_OK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    if (gpu_ms_out) *gpu_ms_out = ms;
+  });
+}
+
 int ppd_compact_decode(ppd_ctx* c, const uint8_t* witness, size_t len, uint8_t** out, size_t* out_len) {
   return guarded(c, [&] {
     stats_reset(c);
@@ -1532,11 +1562,12 @@ void trie_root_sorted_dev(ppd_ctx* c, const uint8_t* d_keys, const uint64_t* d_v
   memcpy(root_out, out + 8, 32);
   float ms = 0;
   CUDA_OK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
-  unsigned long long cnt[2];
-  memcpy(cnt, out + 2, 16);
+  unsigned long long cnt[3];
+  memcpy(cnt, out + 2, 24);
   c->stats.gpu_ms += ms;
   c->stats.nodes_hashed += cnt[0];
   c->stats.node_permutations += cnt[1];
+  c->stats.node_bytes += cnt[2];
   c->stats.arena_nodes += (uint64_t)n + nb;
   c->stats.levels += levels;
   c->stats.d2h_bytes += 64 + 256 + 8;

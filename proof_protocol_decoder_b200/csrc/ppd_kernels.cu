@@ -178,7 +178,7 @@ template <int B>
 __global__ void __launch_bounds__(B) hash_level_kernel(ArenaView A, const uint32_t* __restrict__ order, uint32_t begin, uint32_t end) {
   __shared__ uint32_t smem[PPD_STAGE_WORDS * B];
   uint32_t slot = begin + blockIdx.x * B + threadIdx.x;
-  uint32_t hashed = 0, perms = 0;
+  uint32_t hashed = 0, perms = 0, enc_bytes = 0;
   if (slot < end) {
     uint32_t id = order ? __ldg(order + slot) : slot;
     uint4 rec = __ldg(reinterpret_cast<const uint4*>(A.nodes) + id);
@@ -362,6 +362,7 @@ __global__ void __launch_bounds__(B) hash_level_kernel(ArenaView A, const uint32
         store_digest(my_ref, a);
         A.ref_len[id] = 32;
         hashed = 1;
+        enc_bytes = kind == NK_ROOT ? (rec.z == NODE_EMPTY ? 1u : (uint32_t)A.ref_len[rec.z]) : total;
       }
     }
   }
@@ -370,10 +371,12 @@ __global__ void __launch_bounds__(B) hash_level_kernel(ArenaView A, const uint32
     for (int off = 16; off > 0; off >>= 1) {
       hashed += __shfl_down_sync(0xffffffffu, hashed, off);
       perms += __shfl_down_sync(0xffffffffu, perms, off);
+      enc_bytes += __shfl_down_sync(0xffffffffu, enc_bytes, off);
     }
     if ((threadIdx.x & 31) == 0 && hashed) {
       atomicAdd(A.counters + 0, (unsigned long long)hashed);
       atomicAdd(A.counters + 1, (unsigned long long)perms);
+      atomicAdd(A.counters + 2, (unsigned long long)enc_bytes);
     }
   }
 }

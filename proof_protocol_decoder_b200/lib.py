@@ -55,6 +55,7 @@ class PpdStats(ctypes.Structure):
         ("node_permutations", ctypes.c_uint64),
         ("key_hashes", ctypes.c_uint64),
         ("key_permutations", ctypes.c_uint64),
+        ("node_bytes", ctypes.c_uint64),
         ("arena_nodes", ctypes.c_uint64),
         ("levels", ctypes.c_uint64),
         ("gpu_ms", ctypes.c_double),
@@ -79,6 +80,7 @@ EXPORTS = [
     "ppd_blocks_decode_batch",
     "ppd_trie_root_sorted_leaves",
     "ppd_trie_root_sorted_leaves_dev",
+    "ppd_replay_last_hashing",
 ]
 
 
@@ -111,6 +113,7 @@ class PpdLibrary:
         L.ppd_block_decode.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, u8pp, szp]
         L.ppd_blocks_decode_batch.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
         L.ppd_trie_root_sorted_leaves.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_char_p]
+        L.ppd_replay_last_hashing.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_double)]
         L.ppd_trie_root_sorted_leaves_dev.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_char_p]
 
     def exported(self):
@@ -191,6 +194,11 @@ class Context:
             else:
                 res.append(PpdError(statuses[i], "block %d" % i))
         return res
+
+    def replay_last_hashing(self) -> float:
+        ms = ctypes.c_double()
+        self._check(self.lib.L.ppd_replay_last_hashing(self.h, ctypes.byref(ms)))
+        return ms.value
 
     def trie_root_sorted_leaves(self, keys, val_off, vals) -> bytes:
         import numpy as np

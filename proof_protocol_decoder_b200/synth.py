@@ -238,6 +238,23 @@ def _rand_slot_keys(rng, n):
     return [r.tobytes() for r in raw], [h.tobytes() for h in keccak256_fixed(raw)]
 
 
+class _SlotPool:
+    """pre-hashed slot keys, generated in large batches"""
+
+    def __init__(self, rng, chunk=4096):
+        self.rng, self.chunk = rng, chunk
+        self.raw, self.hashed = [], []
+
+    def take(self, n):
+        while len(self.raw) < n:
+            r, h = _rand_slot_keys(self.rng, max(self.chunk, n))
+            self.raw.extend(r)
+            self.hashed.extend(h)
+        r, h = self.raw[:n], self.hashed[:n]
+        del self.raw[:n], self.hashed[:n]
+        return r, h
+
+
 class SynthBlock:
     """A generated block: `flat` (FlatBlock bytes) plus the pieces it was made of."""
 
@@ -272,7 +289,7 @@ class SynthBlock:
             infos.append(TxnInfo(traces, TxnMeta(tx["byte_code"], tx["new_txn_trie_node_byte"], tx["new_receipt_trie_node_byte"], tx["gas_used"])))
         bt = BlockTrace({"combined": {"compact": self.compact}}, infos)
         code = dict(self.resolved_code)
-        meta = ProcessingMeta(lambda h: code[h])
+        meta = ProcessingMeta(lambda h: code.get(h))  # None: the witness carries that code
         other = OtherBlockData(BlockLevelData(self.b_meta, self.b_hashes, list(self.withdrawals)), self.checkpoint)
         return bt, meta, other
 
@@ -300,6 +317,7 @@ def gen_block(
     random Hash opcodes with the occupancy of a uniform trie (so paths look like mainnet proofs)."""
     rng = np.random.default_rng(seed)
     blk = SynthBlock()
+    pool = _SlotPool(rng)
     addrs, haddrs = _rand_addr(rng, n_accounts)
     order = sorted(range(n_accounts), key=lambda i: haddrs[i])
     accounts = []
@@ -316,7 +334,7 @@ def gen_block(
         if acc["contract"]:
             n_slots = int(np.exp(rng.uniform(np.log(slots_lo), np.log(slots_hi + 1))))
             n_slots = max(slots_lo, min(slots_hi, n_slots))
-            raw, hashed = _rand_slot_keys(rng, n_slots)
+            raw, hashed = pool.take(n_slots)
             for rk, hk in zip(raw, hashed):
                 vlen = int(rng.integers(1, 33))
                 v = int.from_bytes(rng.bytes(vlen), "big") | 1
@@ -404,7 +422,7 @@ def gen_block(
                     if existing and rng.random() < 0.85:
                         reads.append(existing[int(rng.integers(0, len(existing)))])
                     else:
-                        reads.append(_rand_slot_keys(rng, 1)[0][0])  # a slot that does not exist
+                        reads.append(pool.take(1)[0][0])  # a slot that does not exist
                 if reads or rng.random() < 0.3:
                     tr["storage_read"] = reads
                 nw = int(rng.integers(slot_writes[0], slot_writes[1] + 1))
@@ -418,7 +436,7 @@ def gen_block(
                         kx = existing[int(rng.integers(0, len(existing)))]
                         writes[kx] = int.from_bytes(rng.bytes(int(rng.integers(1, 33))), "big") | 1
                     else:
-                        raw, hashed = _rand_slot_keys(rng, 1)
+                        raw, hashed = pool.take(1)
                         writes[raw[0]] = int.from_bytes(rng.bytes(int(rng.integers(1, 33))), "big") | 1
                         acc["slots"][raw[0]] = (hashed[0], writes[raw[0]])
                 for kx, v in writes.items():
@@ -432,6 +450,8 @@ def gen_block(
                     tr["code_read"] = acc["code_hash"]
                     if acc["code"] is None:
                         code_table.setdefault(acc["code_hash"], rng.bytes(int(rng.integers(1, 400))))
+                    elif ai >= n_accounts:  # created in this block: its code is not carried by the witness
+                        code_table.setdefault(acc["code_hash"], acc["code"])
                 if allow_self_destruct and pos > 0 and rng.random() < 0.03:
                     tr["self_destructed"] = True
                     acc["alive"] = False
@@ -448,7 +468,7 @@ def gen_block(
                 tr["code_write"] = code
                 tr["nonce"] = 1
                 acc["nonce"] = 1
-                raw, hashed = _rand_slot_keys(rng, int(rng.integers(1, 5)))
+                raw, hashed = pool.take(int(rng.integers(1, 5)))
                 w = []
                 for rk, hk in zip(raw, hashed):
                     v = int.from_bytes(rng.bytes(int(rng.integers(1, 33))), "big") | 1

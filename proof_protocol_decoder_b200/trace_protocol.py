@@ -119,7 +119,9 @@ class BlockTrace:
         for h in wanted:
             if h not in seen:
                 seen.add(h)
-                resolved.append((h, p_meta.resolve_code_hash_fn(h)))
+                code = p_meta.resolve_code_hash_fn(h)
+                if code is not None:  # None: the caller knows the witness carries this code
+                    resolved.append((h, code))
         return flat.encode_flat_block(
             compact, txns, resolved, other_data.b_data.withdrawals, other_data.checkpoint_state_trie_root, other_data.b_data.b_meta, other_data.b_data.b_hashes
         )
