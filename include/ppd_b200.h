@@ -73,6 +73,12 @@ int ppd_blocks_decode_batch(ppd_ctx* ctx, const uint8_t* const* flat_blocks, con
  * the arena still resident in HBM (no host work, no copies); returns the device time (CUDA events). */
 int ppd_replay_last_hashing(ppd_ctx* ctx, double* gpu_ms_out);
 
+/* Measurement hook: ceilings of the Keccak roofline (csrc/ppd_microbench.cu).  variant 0: issue rate of
+ * dependent-free LOP3/SHF (units = ALU instructions); variants 1..: keccak-f[1600] on a register-resident
+ * state with different unroll factors / ALU-vs-FMA-pipe rotation splits (units = permutations). */
+int ppd_microbench(ppd_ctx* ctx, int variant, uint32_t blocks_per_sm, uint32_t iters, double* gpu_ms_out, double* units_out,
+                   uint32_t* digest_out);
+
 /* HashedPartialTrie::hash of the trie holding n leaves with 32-byte keys, given sorted by key
  * (the state-trie rehash of config 5).  value i = vals[val_off[i] .. val_off[i+1]) is stored as
  * given (it is the already-RLP-encoded leaf payload).  Host buffers. */

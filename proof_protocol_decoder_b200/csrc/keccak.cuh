@@ -21,6 +21,36 @@ __constant__ uint64_t KECCAK_RC[24] = {
     0x8000000000008002ULL, 0x8000000000000080ULL, 0x000000000000800aULL, 0x800000008000000aULL,
     0x8000000080008081ULL, 0x8000000000008080ULL, 0x0000000080000001ULL, 0x8000000080008008ULL};
 
+// Multipliers 2^k in constant memory: ptxas cannot strength-reduce a multiply by c[bank] into a
+// shift, so rotl64_mad below really issues on the FMA pipe (IMAD.WIDE) instead of the ALU pipe.
+__constant__ uint32_t KECCAK_POW2[32] = {1u << 0,  1u << 1,  1u << 2,  1u << 3,  1u << 4,  1u << 5,  1u << 6,  1u << 7,
+                                         1u << 8,  1u << 9,  1u << 10, 1u << 11, 1u << 12, 1u << 13, 1u << 14, 1u << 15,
+                                         1u << 16, 1u << 17, 1u << 18, 1u << 19, 1u << 20, 1u << 21, 1u << 22, 1u << 23,
+                                         1u << 24, 1u << 25, 1u << 26, 1u << 27, 1u << 28, 1u << 29, 1u << 30, 1u << 31};
+
+// 64-bit rotate-left entirely on the FMA pipe (no LOP3/SHF):
+//   t = lo * 2^k  (IMAD.WIDE)  -> t.hi = lo >> (32-k)        new_hi = hi * 2^k + t.hi   (IMAD)
+//   u = hi * 2^k  (IMAD.WIDE)  -> u.hi = hi >> (32-k)        new_lo = lo * 2^k + u.hi   (IMAD)
+// (the two addends never overlap, so + is |).  4 FMA-pipe instructions instead of 2 ALU-pipe ones.
+template <int K>
+__device__ __forceinline__ uint64_t rotl64_mad(uint64_t x) {
+  static_assert(K > 0 && K < 64 && K != 32, "rotation amount");
+  uint32_t lo = (uint32_t)x, hi = (uint32_t)(x >> 32);
+  if (K > 32) {
+    uint32_t t = lo;
+    lo = hi;
+    hi = t;
+  }
+  const uint32_t m = KECCAK_POW2[K & 31];
+  uint64_t t, u;
+  uint32_t nlo, nhi;
+  asm("mul.wide.u32 %0, %1, %2;" : "=l"(t) : "r"(lo), "r"(m));
+  asm("mul.wide.u32 %0, %1, %2;" : "=l"(u) : "r"(hi), "r"(m));
+  asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(nhi) : "r"(hi), "r"(m), "r"((uint32_t)(t >> 32)));
+  asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(nlo) : "r"(lo), "r"(m), "r"((uint32_t)(u >> 32)));
+  return ((uint64_t)nhi << 32) | nlo;
+}
+
 // 64-bit rotate-left by a compile-time amount as two funnel shifts on the halves
 template <int K>
 __device__ __forceinline__ uint64_t rotl64(uint64_t x) {
@@ -54,7 +84,17 @@ __device__ __forceinline__ uint64_t chi1(uint64_t a, uint64_t b, uint64_t c) {
   return ((uint64_t)hi << 32) | lo;
 }
 
+// rho rotation of lane I: on the FMA pipe for the lanes selected by MAD_MASK, else on the ALU pipe
+template <int K, int I, uint32_t MAD_MASK>
+__device__ __forceinline__ uint64_t rho(uint64_t x) {
+  if constexpr (((MAD_MASK >> I) & 1u) != 0 && K != 32)
+    return rotl64_mad<K>(x);
+  else
+    return rotl64<K>(x);
+}
+
 // One round.  Reads a[], writes a[] (through a register-renamed b[]).
+template <uint32_t MAD_MASK>
 __device__ __forceinline__ void keccak_round(uint64_t (&a)[25], uint64_t rc) {
   uint64_t c0 = xor3(xor3(a[0], a[5], a[10]), a[15], a[20]);
   uint64_t c1 = xor3(xor3(a[1], a[6], a[11]), a[16], a[21]);
@@ -66,30 +106,30 @@ __device__ __forceinline__ void keccak_round(uint64_t (&a)[25], uint64_t rc) {
   uint64_t b[25];
 #define TH(i, x) xor3(a[i], (x == 0 ? c4 : x == 1 ? c0 : x == 2 ? c1 : x == 3 ? c2 : c3), (x == 0 ? r1 : x == 1 ? r2 : x == 2 ? r3 : x == 3 ? r4 : r0))
   b[0] = TH(0, 0);
-  b[10] = rotl64<1>(TH(1, 1));
-  b[20] = rotl64<62>(TH(2, 2));
-  b[5] = rotl64<28>(TH(3, 3));
-  b[15] = rotl64<27>(TH(4, 4));
-  b[16] = rotl64<36>(TH(5, 0));
-  b[1] = rotl64<44>(TH(6, 1));
-  b[11] = rotl64<6>(TH(7, 2));
-  b[21] = rotl64<55>(TH(8, 3));
-  b[6] = rotl64<20>(TH(9, 4));
-  b[7] = rotl64<3>(TH(10, 0));
-  b[17] = rotl64<10>(TH(11, 1));
-  b[2] = rotl64<43>(TH(12, 2));
-  b[12] = rotl64<25>(TH(13, 3));
-  b[22] = rotl64<39>(TH(14, 4));
-  b[23] = rotl64<41>(TH(15, 0));
-  b[8] = rotl64<45>(TH(16, 1));
-  b[18] = rotl64<15>(TH(17, 2));
-  b[3] = rotl64<21>(TH(18, 3));
-  b[13] = rotl64<8>(TH(19, 4));
-  b[14] = rotl64<18>(TH(20, 0));
-  b[24] = rotl64<2>(TH(21, 1));
-  b[9] = rotl64<61>(TH(22, 2));
-  b[19] = rotl64<56>(TH(23, 3));
-  b[4] = rotl64<14>(TH(24, 4));
+  b[10] = rho<1, 1, MAD_MASK>(TH(1, 1));
+  b[20] = rho<62, 2, MAD_MASK>(TH(2, 2));
+  b[5] = rho<28, 3, MAD_MASK>(TH(3, 3));
+  b[15] = rho<27, 4, MAD_MASK>(TH(4, 4));
+  b[16] = rho<36, 5, MAD_MASK>(TH(5, 0));
+  b[1] = rho<44, 6, MAD_MASK>(TH(6, 1));
+  b[11] = rho<6, 7, MAD_MASK>(TH(7, 2));
+  b[21] = rho<55, 8, MAD_MASK>(TH(8, 3));
+  b[6] = rho<20, 9, MAD_MASK>(TH(9, 4));
+  b[7] = rho<3, 10, MAD_MASK>(TH(10, 0));
+  b[17] = rho<10, 11, MAD_MASK>(TH(11, 1));
+  b[2] = rho<43, 12, MAD_MASK>(TH(12, 2));
+  b[12] = rho<25, 13, MAD_MASK>(TH(13, 3));
+  b[22] = rho<39, 14, MAD_MASK>(TH(14, 4));
+  b[23] = rho<41, 15, MAD_MASK>(TH(15, 0));
+  b[8] = rho<45, 16, MAD_MASK>(TH(16, 1));
+  b[18] = rho<15, 17, MAD_MASK>(TH(17, 2));
+  b[3] = rho<21, 18, MAD_MASK>(TH(18, 3));
+  b[13] = rho<8, 19, MAD_MASK>(TH(19, 4));
+  b[14] = rho<18, 20, MAD_MASK>(TH(20, 0));
+  b[24] = rho<2, 21, MAD_MASK>(TH(21, 1));
+  b[9] = rho<61, 22, MAD_MASK>(TH(22, 2));
+  b[19] = rho<56, 23, MAD_MASK>(TH(23, 3));
+  b[4] = rho<14, 24, MAD_MASK>(TH(24, 4));
 #undef TH
 #pragma unroll
   for (int y = 0; y < 25; y += 5) {
@@ -103,15 +143,26 @@ __device__ __forceinline__ void keccak_round(uint64_t (&a)[25], uint64_t rc) {
 }
 
 #ifndef PPD_KECCAK_UNROLL
-#define PPD_KECCAK_UNROLL 24
+#define PPD_KECCAK_UNROLL 2
 #endif
 #define PPD_PRAGMA_(x) _Pragma(#x)
 #define PPD_PRAGMA_UNROLL(n) PPD_PRAGMA_(unroll n)
 
-__device__ __forceinline__ void keccak_f1600(uint64_t (&a)[25]) {
-  PPD_PRAGMA_UNROLL(PPD_KECCAK_UNROLL)
-  for (int r = 0; r < 24; r++) keccak_round(a, KECCAK_RC[r]);
+#ifndef PPD_KECCAK_MAD_MASK
+#define PPD_KECCAK_MAD_MASK 0u
+#endif
+
+template <int UNROLL, uint32_t MAD_MASK>
+__device__ __forceinline__ void keccak_f1600_t(uint64_t (&a)[25]) {
+  if constexpr (UNROLL >= 24) {
+#pragma unroll
+    for (int r = 0; r < 24; r++) keccak_round<MAD_MASK>(a, KECCAK_RC[r]);
+  } else {
+#pragma unroll UNROLL
+    for (int r = 0; r < 24; r++) keccak_round<MAD_MASK>(a, KECCAK_RC[r]);
+  }
 }
+__device__ __forceinline__ void keccak_f1600(uint64_t (&a)[25]) { keccak_f1600_t<PPD_KECCAK_UNROLL, PPD_KECCAK_MAD_MASK>(a); }
 
 // ---------------------------------------------------------------------------------------------
 // Block staging for a byte stream that a thread produces piecewise (RLP headers, child refs,

@@ -12,6 +12,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -1285,8 +1286,20 @@ int guarded(ppd_ctx* c, F f) {
   }
 }
 
+struct PhaseTimer {
+  bool on = getenv("PPD_TIMING") != nullptr;
+  std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
+  void lap(const char* what) {
+    if (!on) return;
+    auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "[ppd] %-10s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t).count());
+    t = now;
+  }
+};
+
 void decode_blocks(ppd_ctx* c, const uint8_t* const* flats, const size_t* lens, size_t n, uint8_t** outs, size_t* out_lens, int* statuses) {
   stats_reset(c);
+  PhaseTimer pt;
   Job J;
   J.blocks.resize(n);
   auto guard_block = [&](size_t i, auto fn) {
@@ -1305,9 +1318,13 @@ void decode_blocks(ppd_ctx* c, const uint8_t* const* flats, const size_t* lens, 
       read_flat_block(flats[i], lens[i], b);
       collect_messages(J, b);
     });
+  pt.lap("parse");
   J.kh.run(c);
+  pt.lap("keyhash");
   for (size_t i = 0; i < n; i++) guard_block(i, [&](BlockJob& b) { shape_block(J, b); });
+  pt.lap("shape");
   sweep(c, J);
+  pt.lap("sweep");
   J.stamp.assign(J.A.nodes.size(), 0);
   for (size_t i = 0; i < n; i++) {
     outs[i] = nullptr;
@@ -1320,6 +1337,7 @@ void decode_blocks(ppd_ctx* c, const uint8_t* const* flats, const size_t* lens, 
     statuses[i] = J.blocks[i].status;
     if (J.blocks[i].status != PPD_OK) c->err = J.blocks[i].err;
   }
+  pt.lap("dump");
 }
 
 }  // namespace
@@ -1408,6 +1426,31 @@ int ppd_replay_last_hashing(ppd_ctx* c, double* gpu_ms_out) {
     float ms = 0;
     CUDA_OK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
     if (gpu_ms_out) *gpu_ms_out = ms;
+  });
+}
+
+// Measurement hook (ppd_microbench.cu): variant 0 = dependent-free LOP3/SHF issue rate, 1.. = register
+// resident keccak-f variants.  units_out = ALU instructions (variant 0) or permutations executed.
+int ppd_microbench(ppd_ctx* c, int variant, uint32_t blocks_per_sm, uint32_t iters, double* gpu_ms_out, double* units_out, uint32_t* digest_out) {
+  return guarded(c, [&] {
+    c->d_counters.reserve(64);
+    CUDA_OK(cudaMemsetAsync(c->d_counters.p, 0, 64, c->st));
+    uint32_t bt = 0;
+    double per = 0;
+    // warm-up launch, then the timed one
+    if (!launch_microbench(variant, c->d_counters.as<uint32_t>(), blocks_per_sm, iters, &bt, &per, c->st)) fail(PPD_ERR_BAD_ARGUMENT, "unknown microbench variant");
+    CUDA_OK(cudaEventRecord(c->ev0, c->st));
+    launch_microbench(variant, c->d_counters.as<uint32_t>(), blocks_per_sm, iters, &bt, &per, c->st);
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaEventRecord(c->ev1, c->st));
+    uint32_t out[4];
+    CUDA_OK(cudaMemcpyAsync(out, c->d_counters.p, 16, cudaMemcpyDeviceToHost, c->st));
+    CUDA_OK(cudaStreamSynchronize(c->st));
+    float ms = 0;
+    CUDA_OK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    if (gpu_ms_out) *gpu_ms_out = ms;
+    if (units_out) *units_out = per * (double)iters * (double)bt * 148.0 * (double)blocks_per_sm;
+    if (digest_out) digest_out[0] = out[2], digest_out[1] = out[3];
   });
 }
 

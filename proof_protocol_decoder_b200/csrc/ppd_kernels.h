@@ -51,4 +51,8 @@ void launch_branch_scatter(const uint8_t* depth, uint32_t nb, uint32_t* cursor, 
 void launch_hash_sorted_leaves(const BuildView& V, cudaStream_t st);
 void launch_hash_branch_level(const BuildView& V, const uint32_t* order, uint32_t begin, uint32_t end, cudaStream_t st);
 
+// ---- ppd_microbench.cu ----
+bool launch_microbench(int variant, uint32_t* out, uint32_t blocks_per_sm, uint32_t iters, uint32_t* block_threads, double* units_per_thread_iter,
+                       cudaStream_t st);
+
 }  // namespace ppd

@@ -81,6 +81,7 @@ EXPORTS = [
     "ppd_trie_root_sorted_leaves",
     "ppd_trie_root_sorted_leaves_dev",
     "ppd_replay_last_hashing",
+    "ppd_microbench",
 ]
 
 
@@ -114,6 +115,7 @@ class PpdLibrary:
         L.ppd_blocks_decode_batch.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
         L.ppd_trie_root_sorted_leaves.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_char_p]
         L.ppd_replay_last_hashing.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_double)]
+        L.ppd_microbench.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_uint32, ctypes.c_uint32, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_uint32)]
         L.ppd_trie_root_sorted_leaves_dev.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_char_p]
 
     def exported(self):
@@ -199,6 +201,12 @@ class Context:
         ms = ctypes.c_double()
         self._check(self.lib.L.ppd_replay_last_hashing(self.h, ctypes.byref(ms)))
         return ms.value
+
+    def microbench(self, variant, blocks_per_sm=8, iters=2000):
+        ms, units = ctypes.c_double(), ctypes.c_double()
+        dig = (ctypes.c_uint32 * 2)()
+        self._check(self.lib.L.ppd_microbench(self.h, variant, blocks_per_sm, iters, ctypes.byref(ms), ctypes.byref(units), dig))
+        return ms.value, units.value, (dig[0], dig[1])
 
     def trie_root_sorted_leaves(self, keys, val_off, vals) -> bytes:
         import numpy as np
