@@ -166,42 +166,53 @@ __device__ __forceinline__ void keccak_f1600(uint64_t (&a)[25]) { keccak_f1600_t
 
 // ---------------------------------------------------------------------------------------------
 // Block staging for a byte stream that a thread produces piecewise (RLP headers, child refs,
-// values).  Pull model: a thread appends whole segments (each <= 48 bytes) to its stage until at
-// least one 136-byte rate block is complete, then ALL lanes of the warp that still have blocks run
-// the one keccak_f1600 site convergently; the up-to-47 overflow bytes are moved to the front.
+// values).  Pull model: a thread appends whole units (each <= 136 bytes) to its stage until at
+// least one 136-byte rate block is complete, then the WHOLE warp runs the one keccak_f1600 site
+// convergently (callers loop warp-uniformly, see ppd_kernels.cu).
 //
-// The stage is PPD_STAGE_WORDS 32-bit words per thread in shared memory, word-interleaved
-// (word w of thread t at stage[w * BLOCK + t]): the bank depends on t only, so every access pattern
-// of a warp is conflict-free no matter how far each lane has advanced.
+// The stage is a ring of 2 x 34 32-bit words per thread in shared memory, word-interleaved (word w
+// of thread t at stage[w * BLOCK + t]): the bank depends on t only, so every access pattern of a
+// warp is conflict-free no matter how far each lane has advanced.  A rate block is exactly one half
+// of the ring, so the bytes that overflow a block already sit where the next block starts:
+// consuming a block moves no data.
 // ---------------------------------------------------------------------------------------------
-#define PPD_STAGE_WORDS 46
+#define PPD_STAGE_WORDS 68
 
 template <int BLOCK>
 struct Stage {
-  uint32_t* w;    // &smem[threadIdx.x]
-  uint32_t acc;   // pending bytes of word `widx` (low `sh` bits valid)
-  uint32_t sh;    // 0, 8, 16, 24
-  uint32_t widx;  // complete words staged
+  uint32_t* w;     // &smem[threadIdx.x]
+  uint32_t acc;    // pending bytes of the word being assembled (low `sh` bits valid)
+  uint32_t sh;     // 0, 8, 16, 24
+  uint32_t widx;   // complete words staged since the start of the current block
+  uint32_t base;   // ring position of the current block: 0 or 34
+  uint32_t wpos;   // ring position of the next word
 
   __device__ __forceinline__ void init(uint32_t* smem) {
     w = smem + threadIdx.x;
     acc = 0;
     sh = 0;
     widx = 0;
+    base = 0;
+    wpos = 0;
   }
   __device__ __forceinline__ uint32_t bytes() const { return 4 * widx + (sh >> 3); }
-  __device__ __forceinline__ void put_word(uint32_t x) {
-    uint64_t t = (uint64_t)acc | ((uint64_t)x << sh);
-    w[widx * BLOCK] = (uint32_t)t;
+  __device__ __forceinline__ void push_word(uint32_t x) {
+    w[wpos * BLOCK] = x;
+    wpos = (wpos == PPD_STAGE_WORDS - 1) ? 0u : wpos + 1;
     widx++;
-    acc = (uint32_t)(t >> 32);
+  }
+  __device__ __forceinline__ void put_word(uint32_t x) {
+    // acc holds sh valid bits
+    uint32_t lo = acc | (x << sh);
+    uint32_t hi = sh ? (x >> (32 - sh)) : 0u;
+    push_word(lo);
+    acc = hi;
   }
   __device__ __forceinline__ void put_byte(uint32_t b) {
     acc |= b << sh;
     sh += 8;
     if (sh == 32) {
-      w[widx * BLOCK] = acc;
-      widx++;
+      push_word(acc);
       acc = 0;
       sh = 0;
     }
@@ -210,41 +221,44 @@ struct Stage {
   __device__ __forceinline__ void put_partial(uint32_t x, uint32_t n) {
     if (n == 0) return;
     if (n < 4) x &= (1u << (8 * n)) - 1;
-    uint64_t t = (uint64_t)acc | ((uint64_t)x << sh);
+    uint32_t lo = acc | (x << sh);
+    uint32_t hi = sh ? (x >> (32 - sh)) : 0u;
     uint32_t nsh = sh + 8 * n;
     if (nsh >= 32) {
-      w[widx * BLOCK] = (uint32_t)t;
-      widx++;
-      acc = (uint32_t)(t >> 32);
+      push_word(lo);
+      acc = hi;
       sh = nsh - 32;
     } else {
-      acc = (uint32_t)t;
+      acc = lo;
       sh = nsh;
     }
   }
   // Keccak padding 0x01 .. 0x80 (original Keccak, as tiny-keccak's Keccak::v256).  Needs bytes() < 136.
   __device__ __forceinline__ void pad() {
-    w[widx * BLOCK] = acc | (0x01u << sh);
-    for (uint32_t i = widx + 1; i < 34; i++) w[i * BLOCK] = 0;
-    w[33 * BLOCK] |= 0x80000000u;
+    uint32_t* blk = w + base * BLOCK;
+    blk[widx * BLOCK] = acc | (0x01u << sh);
+    for (uint32_t i = widx + 1; i < 34; i++) blk[i * BLOCK] = 0;
+    blk[33 * BLOCK] |= 0x80000000u;
   }
-  // after a block was absorbed: move the overflow words to the front
+  // after a block was absorbed: the overflow words are already at the start of the other half
   __device__ __forceinline__ void consume_block() {
-    uint32_t over = widx - 34;
-    for (uint32_t i = 0; i < over; i++) w[i * BLOCK] = w[(34 + i) * BLOCK];
-    widx = over;
+    widx -= 34;
+    base = 34 - base;
   }
   // make the partial word visible in shared memory (for the inline < 32-byte case)
   __device__ __forceinline__ void flush_partial() {
-    if (sh) w[widx * BLOCK] = acc;
+    if (sh) w[wpos * BLOCK] = acc;
   }
+  // word i of the current block
+  __device__ __forceinline__ uint32_t word(uint32_t i) const { return w[(base + i) * BLOCK]; }
 };
 
 template <int BLOCK>
-__device__ __forceinline__ void absorb_stage(uint64_t (&a)[25], const uint32_t* w) {
+__device__ __forceinline__ void absorb_stage(uint64_t (&a)[25], const Stage<BLOCK>& s) {
+  const uint32_t* blk = s.w + s.base * BLOCK;
 #pragma unroll
   for (int i = 0; i < 17; i++) {
-    uint32_t lo = w[(2 * i) * BLOCK], hi = w[(2 * i + 1) * BLOCK];
+    uint32_t lo = blk[(2 * i) * BLOCK], hi = blk[(2 * i + 1) * BLOCK];
     a[i] ^= ((uint64_t)hi << 32) | lo;
   }
 }

@@ -25,94 +25,14 @@
 #include <cstdint>
 
 #include "arena.h"
+#include "encode.cuh"
 #include "keccak.cuh"
 #include "ppd_kernels.h"
 
 namespace ppd {
 
-// ------------------------------------------------------------------ helpers (as ppd_kernels.cu)
-namespace b {
-
-template <int B>
-__device__ __forceinline__ void emit_len_prefix(Stage<B>& s, uint32_t len, uint32_t short_base, uint32_t long_base) {
-  if (len < 56) {
-    s.put_byte(short_base + len);
-  } else if (len < 256) {
-    s.put_byte(long_base + 1);
-    s.put_byte(len);
-  } else if (len < 65536) {
-    s.put_byte(long_base + 2);
-    s.put_byte(len >> 8);
-    s.put_byte(len & 255);
-  } else {
-    s.put_byte(long_base + 3);
-    s.put_byte(len >> 16);
-    s.put_byte((len >> 8) & 255);
-    s.put_byte(len & 255);
-  }
-}
-__device__ __forceinline__ uint32_t len_prefix_size(uint32_t len) { return len < 56 ? 1 : len < 256 ? 2 : len < 65536 ? 3 : 4; }
-__device__ __forceinline__ uint32_t hex_prefix_str_size(uint32_t n) { return n < 2 ? 1 : 2 + (n >> 1); }
-
-// rlp_str(hex_prefix(nibbles [start, start+n) of a 32-byte key held in 8 big-endian-packed words))
-template <int B>
-__device__ __forceinline__ void emit_hex_prefix_str(Stage<B>& s, const uint8_t* key, uint32_t start, uint32_t n, uint32_t is_leaf) {
-  if (n >= 2) s.put_byte(0x80 + 1 + (n >> 1));
-  uint32_t flag = (is_leaf ? 2u : 0u) + (n & 1);
-  uint32_t j = start, end = start + n;
-  if (n & 1) {
-    uint32_t bb = __ldg(key + (j >> 1));
-    s.put_byte((flag << 4) | ((j & 1) ? (bb & 15) : (bb >> 4)));
-    j++;
-  } else {
-    s.put_byte(flag << 4);
-  }
-  if ((j & 1) == 0) {
-    for (; j < end; j += 2) s.put_byte(__ldg(key + (j >> 1)));
-  } else {
-    uint32_t prev = __ldg(key + (j >> 1));
-    for (; j < end; j += 2) {
-      uint32_t next = __ldg(key + (j >> 1) + 1);
-      s.put_byte(((prev & 15) << 4) | (next >> 4));
-      prev = next;
-    }
-  }
-}
-
-// up to 32 bytes from any global address
-template <int B>
-__device__ __forceinline__ void emit_chunk(Stage<B>& s, const uint8_t* p, uint32_t len) {
-  if ((reinterpret_cast<uintptr_t>(p) & 3) == 0) {
-    const uint32_t* w = reinterpret_cast<const uint32_t*>(p);
-    uint32_t nw = len >> 2;
-    for (uint32_t i = 0; i < nw; i++) s.put_word(__ldg(w + i));
-    uint32_t rem = len & 3;
-    if (rem) {
-      uint32_t x = 0;
-      for (uint32_t k = 0; k < rem; k++) x |= (uint32_t)__ldg(p + 4 * nw + k) << (8 * k);
-      s.put_partial(x, rem);
-    }
-  } else {
-    for (uint32_t i = 0; i < len; i++) s.put_byte(__ldg(p + i));
-  }
-}
-
-template <int B>
-__device__ __forceinline__ void emit_ref_words(Stage<B>& s, const uint32_t (&w)[8], uint32_t len) {
-  if (len == 32) {
-    s.put_byte(0xa0);
-#pragma unroll
-    for (int i = 0; i < 8; i++) s.put_word(w[i]);
-  } else {
-#pragma unroll
-    for (int i = 0; i < 8; i++) {
-      uint32_t take = len > 4u * i ? min(4u, len - 4u * i) : 0u;
-      s.put_partial(w[i], take);
-    }
-  }
-}
-
-}  // namespace b
+using namespace enc;
+static constexpr uint32_t FULL = 0xffffffffu;
 
 // ------------------------------------------------------------------ structure kernels ---------
 
@@ -324,48 +244,70 @@ __global__ void branch_info_kernel(BuildView V) {
   }
 }
 
-// hist[d] = number of branches at depth d (block-local histogram, one global atomic per bin and block)
-__global__ void depth_hist_kernel(const uint8_t* __restrict__ depth, uint32_t nb, uint32_t* __restrict__ hist_out) {
-  __shared__ uint32_t hist[64];
-  if (threadIdx.x < 64) hist[threadIdx.x] = 0;
-  __syncthreads();
-  uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b < nb) atomicAdd(&hist[depth[b]], 1u);
-  __syncthreads();
-  if (threadIdx.x < 64 && hist[threadIdx.x]) atomicAdd(hist_out + threadIdx.x, hist[threadIdx.x]);
+// nchild[b] = number of children of branch b, minus one: every position of the branch's run whose L
+// equals the branch depth separates two children
+__global__ void child_count_kernel(const uint32_t* __restrict__ leader, const uint32_t* __restrict__ bidx, uint32_t n, uint32_t* __restrict__ nchild) {
+  uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q == 0 || q >= n) return;
+  atomicAdd(nchild + bidx[leader[q]], 1u);
 }
 
-// counting sort of the branches by depth: order[level_start[d] + k] = b
-__global__ void branch_scatter_kernel(const uint8_t* __restrict__ depth, uint32_t nb, uint32_t* __restrict__ cursor,
-                                      uint32_t* __restrict__ order) {
-  __shared__ uint32_t hist[64], base[64];
-  if (threadIdx.x < 64) hist[threadIdx.x] = 0;
+// Sort key of a branch: depth * 4 + permutation class.  A branch with k hashed children encodes to
+// 33 k + (16 - k) + 1 payload bytes: 1 rate block up to k = 3, 2 up to 7, 3 up to 12, else 4.
+__device__ __forceinline__ uint32_t branch_sort_key(uint32_t depth, uint32_t nchild_minus_1) {
+  uint32_t k = nchild_minus_1 + 1;
+  uint32_t cls = k <= 3 ? 0u : k <= 7 ? 1u : k <= 12 ? 2u : 3u;
+  return depth * 4 + cls;
+}
+
+// hist[key] = number of branches with that key (block-local histogram, one global atomic per bin and block)
+__global__ void depth_hist_kernel(const uint8_t* __restrict__ depth, const uint32_t* __restrict__ nchild, uint32_t nb, uint32_t* __restrict__ hist_out) {
+  __shared__ uint32_t hist[256];
+  hist[threadIdx.x] = 0;
   __syncthreads();
   uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-  uint32_t d = 0, rank = 0;
+  if (b < nb) atomicAdd(&hist[branch_sort_key(depth[b], nchild[b])], 1u);
+  __syncthreads();
+  if (hist[threadIdx.x]) atomicAdd(hist_out + threadIdx.x, hist[threadIdx.x]);
+}
+
+// counting sort of the branches by key: order[start[key] + k] = b
+__global__ void branch_scatter_kernel(const uint8_t* __restrict__ depth, const uint32_t* __restrict__ nchild, uint32_t nb, uint32_t* __restrict__ cursor,
+                                      uint32_t* __restrict__ order) {
+  __shared__ uint32_t hist[256], base[256];
+  hist[threadIdx.x] = 0;
+  __syncthreads();
+  uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t key = 0, rank = 0;
   if (b < nb) {
-    d = depth[b];
-    rank = atomicAdd(&hist[d], 1u);
+    key = branch_sort_key(depth[b], nchild[b]);
+    rank = atomicAdd(&hist[key], 1u);
   }
   __syncthreads();
-  if (threadIdx.x < 64 && hist[threadIdx.x]) base[threadIdx.x] = atomicAdd(cursor + threadIdx.x, hist[threadIdx.x]);
+  if (hist[threadIdx.x]) base[threadIdx.x] = atomicAdd(cursor + threadIdx.x, hist[threadIdx.x]);
   __syncthreads();
-  if (b < nb) order[base[d] + rank] = b;
+  if (b < nb) order[base[key] + rank] = b;
 }
 
 // ------------------------------------------------------------------ hashing kernels -----------
+// Both kernels loop warp-uniformly: lanes fill their stage (cheap, may diverge), then the whole warp
+// runs the single keccak_f1600 site converged; the loop ends when no lane has a block left.
 
 template <int B>
-__global__ void __launch_bounds__(B) hash_sorted_leaves_kernel(BuildView V) {
+__global__ void __launch_bounds__(B, 4) hash_sorted_leaves_kernel(BuildView V) {
   __shared__ uint32_t smem[PPD_STAGE_WORDS * B];
-  uint32_t i = blockIdx.x * B + threadIdx.x;
+  const uint32_t i = blockIdx.x * B + threadIdx.x;
   uint32_t hashed = 0, perms = 0, enc_bytes = 0;
-  if (i < V.n) {
+  bool busy = i < V.n, is_root = false;
+  const uint8_t* key = nullptr;
+  const uint8_t* val = nullptr;
+  uint32_t nib_start = 0, nib_len = 0, vlen = 0, vhdr = 0, payload = 0, total = 0, nunit = 0, unit = 0;
+  if (busy) {
     const Pyramid& P = V.P;
     int dl = P.L[i], dr = P.L[i + 1];
     int dp = max(dl, dr);
-    const uint8_t* key = V.keys + 32ull * i;
-    const bool is_root = dp < 0;
+    key = V.keys + 32ull * i;
+    is_root = dp < 0;
     if (is_root) {
       *V.root_id = i;
     } else {
@@ -375,203 +317,202 @@ __global__ void __launch_bounds__(B) hash_sorted_leaves_kernel(BuildView V) {
       uint32_t nib = (dp & 1) ? (kb & 15u) : (kb >> 4);
       V.child[16ull * pb + nib] = i;
     }
-    const uint32_t nib_start = (uint32_t)(dp + 1), nib_len = 64 - nib_start;
+    nib_start = (uint32_t)(dp + 1), nib_len = 64 - nib_start;
     const uint64_t vo = V.val_off[i];
-    const uint8_t* val = V.vals + vo;
-    const uint32_t vlen = (uint32_t)(V.val_off[i + 1] - vo);
-    const uint32_t vhdr = (vlen == 1 && __ldg(val) < 0x80) ? 0 : b::len_prefix_size(vlen);
-    const uint32_t payload = b::hex_prefix_str_size(nib_len) + vhdr + vlen;
-    const uint32_t total = b::len_prefix_size(payload) + payload;
-    const uint32_t nseg = 2 + ((vlen + 31) >> 5);
-    const bool inline_ref = !is_root && total < 32;
-    Stage<B> s;
-    s.init(smem);
-    uint64_t a[25];
+    val = V.vals + vo;
+    vlen = (uint32_t)(V.val_off[i + 1] - vo);
+    vhdr = (vlen == 1 && __ldg(val) < 0x80) ? 0 : len_prefix_size(vlen);
+    payload = hex_prefix_str_size(nib_len) + vhdr + vlen;
+    total = len_prefix_size(payload) + payload;
+    nunit = 1 + ((vlen + 127) >> 7);
+  }
+  const bool inline_ref = !is_root && total < 32;
+  Stage<B> s;
+  s.init(smem);
+  uint64_t a[25];
 #pragma unroll
-    for (int k = 0; k < 25; k++) a[k] = 0;
-    uint32_t seg = 0;
-    bool done = false;
-    while (!done) {
-      while (s.bytes() < 136 && seg < nseg) {
-        if (seg == 0) {
-          b::emit_len_prefix(s, payload, 0xc0, 0xf7);
-          b::emit_hex_prefix_str(s, key, nib_start, nib_len, 1);
-        } else if (seg == 1) {
-          if (vhdr) b::emit_len_prefix(s, vlen, 0x80, 0xb7);
+  for (int k = 0; k < 25; k++) a[k] = 0;
+  for (;;) {
+    bool permute = false, last = false;
+    if (busy) {
+      while (s.bytes() < 136 && unit < nunit) {
+        if (unit == 0) {
+          emit_len_prefix(s, payload, 0xc0, 0xf7);
+          emit_hex_prefix_str(s, key, nib_start, nib_len, 1);
+          if (vhdr) emit_len_prefix(s, vlen, 0x80, 0xb7);
         } else {
-          uint32_t off = (seg - 2) << 5;
-          b::emit_chunk(s, val + off, min(32u, vlen - off));
+          uint32_t off = (unit - 1) << 7;
+          emit_bytes(s, val + off, min(128u, vlen - off));
         }
-        seg++;
+        unit++;
       }
-      if (inline_ref) break;
-      if (s.bytes() < 136) {
-        s.pad();
-        done = true;
+      if (inline_ref) {
+        uint4 x, y;
+        inline_ref_words(s, total, x, y);
+        uint4* o = reinterpret_cast<uint4*>(V.ref + 32ull * i);
+        o[0] = x, o[1] = y;
+        V.ref_len[i] = (uint8_t)total;
+        busy = false;
+      } else {
+        last = s.bytes() < 136;
+        if (last) s.pad();
+        absorb_stage<B>(a, s);
+        permute = true;
       }
-      absorb_stage<B>(a, s.w);
-      keccak_f1600(a);
+    }
+    if (!__any_sync(FULL, permute)) break;
+    keccak_f1600(a);
+    if (permute) {
       perms++;
-      if (!done) s.consume_block();
-    }
-    uint4* o = reinterpret_cast<uint4*>(V.ref + 32ull * i);
-    if (inline_ref) {
-      s.flush_partial();
-      uint32_t nw = (total + 3) >> 2;
-      uint32_t h[8];
-#pragma unroll
-      for (int k = 0; k < 8; k++) h[k] = (uint32_t)k < nw ? s.w[k * B] : 0u;
-      uint32_t tail = total & 3;
-      if (tail) h[nw - 1] &= (1u << (8 * tail)) - 1;
-      o[0] = make_uint4(h[0], h[1], h[2], h[3]);
-      o[1] = make_uint4(h[4], h[5], h[6], h[7]);
-      V.ref_len[i] = (uint8_t)total;
-    } else {
-      uint4 x = make_uint4((uint32_t)a[0], (uint32_t)(a[0] >> 32), (uint32_t)a[1], (uint32_t)(a[1] >> 32));
-      uint4 y = make_uint4((uint32_t)a[2], (uint32_t)(a[2] >> 32), (uint32_t)a[3], (uint32_t)(a[3] >> 32));
-      o[0] = x, o[1] = y;
-      V.ref_len[i] = 32;
-      hashed = 1;
-      enc_bytes = total;
-      if (is_root) {
-        uint4* ro = reinterpret_cast<uint4*>(V.root_out);
-        ro[0] = x, ro[1] = y;
+      if (last) {
+        uint4 x, y;
+        digest_words(a, x, y);
+        uint4* o = reinterpret_cast<uint4*>(V.ref + 32ull * i);
+        o[0] = x, o[1] = y;
+        V.ref_len[i] = 32;
+        hashed = 1;
+        enc_bytes = total;
+        if (is_root) {
+          uint4* ro = reinterpret_cast<uint4*>(V.root_out);
+          ro[0] = x, ro[1] = y;
+        }
+        busy = false;
+      } else {
+        s.consume_block();
       }
     }
   }
-  if (V.counters) {
-    for (int off = 16; off > 0; off >>= 1) {
-      hashed += __shfl_down_sync(0xffffffffu, hashed, off);
-      perms += __shfl_down_sync(0xffffffffu, perms, off);
-      enc_bytes += __shfl_down_sync(0xffffffffu, enc_bytes, off);
-    }
-    if ((threadIdx.x & 31) == 0 && hashed) {
-      atomicAdd(V.counters + 0, (unsigned long long)hashed);
-      atomicAdd(V.counters + 1, (unsigned long long)perms);
-      atomicAdd(V.counters + 2, (unsigned long long)enc_bytes);
-    }
-  }
+  add_counters(V.counters, hashed, perms, enc_bytes);
 }
 
 // One level of branches (all at the same depth), each followed by its extension node if it has one.
+// Units of the branch message: 0 = list header, 1..4 = four child slots each (4 also carries the
+// empty value).  The extension message (header, hex-prefix nibbles, the branch's ref) is one unit.
 template <int B>
-__global__ void __launch_bounds__(B) hash_branch_level_kernel(BuildView V, const uint32_t* __restrict__ order, uint32_t begin, uint32_t end) {
+__global__ void __launch_bounds__(B, 4) hash_branch_level_kernel(BuildView V, const uint32_t* __restrict__ order, uint32_t begin, uint32_t end) {
   __shared__ uint32_t smem[PPD_STAGE_WORDS * B];
-  uint32_t slot = begin + blockIdx.x * B + threadIdx.x;
+  const uint32_t slot = begin + blockIdx.x * B + threadIdx.x;
   uint32_t hashed = 0, perms = 0, enc_bytes = 0;
-  if (slot < end) {
-    const uint32_t bi = __ldg(order + slot);
-    const uint32_t id = V.n + bi;
-    const uint32_t d = V.depth[bi], es = V.ext_start[bi];
-    const uint32_t ext_len = d - es;
-    const bool is_root = (*V.root_id == id);
+  bool busy = slot < end, is_root = false;
+  uint32_t bi = 0, id = 0, es = 0, ext_len = 0, payload = 1, total = 0, unit = 0, phase = 0;
+  uint32_t clen_packed[4] = {0, 0, 0, 0};
+  if (busy) {
+    bi = __ldg(order + slot);
+    id = V.n + bi;
+    const uint32_t d = V.depth[bi];
+    es = V.ext_start[bi];
+    ext_len = d - es;
+    is_root = (*V.root_id == id);
     uint32_t kid[16];
-    {
-      const uint4* ct = reinterpret_cast<const uint4*>(V.child + 16ull * bi);
+    const uint4* ct = reinterpret_cast<const uint4*>(V.child + 16ull * bi);
 #pragma unroll
-      for (int k = 0; k < 4; k++) {
-        uint4 t = __ldcg(ct + k);
-        kid[4 * k] = t.x, kid[4 * k + 1] = t.y, kid[4 * k + 2] = t.z, kid[4 * k + 3] = t.w;
-      }
+    for (int k = 0; k < 4; k++) {
+      uint4 t = __ldg(ct + k);
+      kid[4 * k] = t.x, kid[4 * k + 1] = t.y, kid[4 * k + 2] = t.z, kid[4 * k + 3] = t.w;
     }
-    uint32_t payload = 1;  // the empty branch value
 #pragma unroll
-    for (int k = 0; k < 16; k++) {
+    for (int k = 0; k < 16; k++) {  // sixteen independent byte loads
       uint32_t cl = kid[k] == NODE_EMPTY ? 0u : (uint32_t)V.ref_len[kid[k]];
+      clen_packed[k >> 2] |= cl << (8 * (k & 3));
       payload += kid[k] == NODE_EMPTY ? 1u : (cl == 32 ? 33u : cl);
     }
-    uint32_t total = b::len_prefix_size(payload) + payload;
-    Stage<B> s;
-    s.init(smem);
-    uint64_t a[25];
+    total = len_prefix_size(payload) + payload;
+  }
+  Stage<B> s;
+  s.init(smem);
+  uint64_t a[25];
 #pragma unroll
-    for (int k = 0; k < 25; k++) a[k] = 0;
-    uint32_t seg = 0, nseg = 18, phase = 0;
-    uint32_t rw[8];  // ref of the message just finished
-    uint32_t rlen = 0;
-    for (;;) {
+  for (int k = 0; k < 25; k++) a[k] = 0;
+  uint4 rx = make_uint4(0, 0, 0, 0), ry = rx;  // ref of the message just finished
+  uint32_t rlen = 0;
+  for (;;) {
+    bool permute = false, last = false;
+    if (busy) {
       if (phase == 0) {
-        while (s.bytes() < 136 && seg < nseg) {
-          if (seg == 0) {
-            b::emit_len_prefix(s, payload, 0xc0, 0xf7);
-          } else if (seg == 17) {
-            s.put_byte(0x80);
+        while (s.bytes() < 136 && unit < 5) {
+          if (unit == 0) {
+            emit_len_prefix(s, payload, 0xc0, 0xf7);
           } else {
-            uint32_t c = kid[0];
+            const uint32_t g = unit - 1;
+            const uint32_t lens = g == 0 ? clen_packed[0] : g == 1 ? clen_packed[1] : g == 2 ? clen_packed[2] : clen_packed[3];
+            // the child table was written by earlier launches: re-read the four ids (L1 / L2 hit)
+            const uint4 cc = __ldg(reinterpret_cast<const uint4*>(V.child + 16ull * bi) + g);
+            const uint32_t c[4] = {cc.x, cc.y, cc.z, cc.w};
+            uint4 x[4], y[4];
 #pragma unroll
-            for (int k = 1; k < 16; k++) c = (seg - 1 == (uint32_t)k) ? kid[k] : c;
-            if (c == NODE_EMPTY) {
-              s.put_byte(0x80);
-            } else {
-              const uint4* q = reinterpret_cast<const uint4*>(V.ref + 32ull * c);
-              uint4 x = __ldcg(q), y = __ldcg(q + 1);
-              uint32_t w[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
-              b::emit_ref_words(s, w, V.ref_len[c]);
+            for (int k = 0; k < 4; k++) {
+              if (c[k] != NODE_EMPTY) {
+                const uint4* q = reinterpret_cast<const uint4*>(V.ref + 32ull * c[k]);
+                x[k] = __ldcg(q), y[k] = __ldcg(q + 1);
+              }
             }
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+              if (c[k] != NODE_EMPTY)
+                emit_ref(s, x[k], y[k], (lens >> (8 * k)) & 0xff);
+              else
+                s.put_byte(0x80);
+            }
+            if (g == 3) s.put_byte(0x80);
           }
-          seg++;
+          unit++;
         }
       }
       const bool final_msg = (phase == 1) || ext_len == 0;
-      const bool want_inline = total < 32 && !(final_msg && is_root);
-      bool last = true;
-      if (!want_inline) {
+      if (total < 32 && !(final_msg && is_root)) {
+        inline_ref_words(s, total, rx, ry);
+        rlen = total;
+      } else {
         last = s.bytes() < 136;
         if (last) s.pad();
-        absorb_stage<B>(a, s.w);
-        keccak_f1600(a);
-        perms++;
-        if (!last) {
-          s.consume_block();
-          continue;
-        }
-#pragma unroll
-        for (int k = 0; k < 4; k++) rw[2 * k] = (uint32_t)a[k], rw[2 * k + 1] = (uint32_t)(a[k] >> 32);
-        rlen = 32;
-        hashed++;
-        enc_bytes += total;
-      } else {
-        s.flush_partial();
-        uint32_t nw = (total + 3) >> 2;
-#pragma unroll
-        for (int k = 0; k < 8; k++) rw[k] = (uint32_t)k < nw ? s.w[k * B] : 0u;
-        uint32_t tail = total & 3;
-        if (tail) rw[nw - 1] &= (1u << (8 * tail)) - 1;
-        rlen = total;
+        absorb_stage<B>(a, s);
+        permute = true;
       }
-      if (final_msg) break;
-      // the extension node above this branch: rlp[ hex_prefix(nibbles, false), ref ]
-      phase = 1;
-#pragma unroll
-      for (int k = 0; k < 25; k++) a[k] = 0;
-      s.init(smem);
-      payload = b::hex_prefix_str_size(ext_len) + (rlen == 32 ? 33u : rlen);
-      total = b::len_prefix_size(payload) + payload;
-      b::emit_len_prefix(s, payload, 0xc0, 0xf7);
-      b::emit_hex_prefix_str(s, V.keys + 32ull * V.rep[bi], es, ext_len, 0);
-      b::emit_ref_words(s, rw, rlen);
     }
+    if (!__any_sync(FULL, busy)) break;
+    if (__any_sync(FULL, permute)) keccak_f1600(a);
+    if (busy) {
+      bool msg_done = !permute;
+      if (permute) {
+        perms++;
+        if (last) {
+          digest_words(a, rx, ry);
+          rlen = 32;
+          hashed++;
+          enc_bytes += total;
+          msg_done = true;
+        } else {
+          s.consume_block();
+        }
+      }
+      if (msg_done) {
+        if (phase == 1 || ext_len == 0) {
+          busy = false;
+        } else {
+          // the extension node above this branch: rlp[ hex_prefix(nibbles, false), ref ]
+          phase = 1;
+#pragma unroll
+          for (int k = 0; k < 25; k++) a[k] = 0;
+          s.init(smem);
+          payload = hex_prefix_str_size(ext_len) + (rlen == 32 ? 33u : rlen);
+          total = len_prefix_size(payload) + payload;
+          emit_len_prefix(s, payload, 0xc0, 0xf7);
+          emit_hex_prefix_str(s, V.keys + 32ull * V.rep[bi], es, ext_len, 0);
+          emit_ref(s, rx, ry, rlen);
+        }
+      }
+    }
+  }
+  if (slot < end) {
     uint4* o = reinterpret_cast<uint4*>(V.ref + 32ull * id);
-    uint4 x = make_uint4(rw[0], rw[1], rw[2], rw[3]), y = make_uint4(rw[4], rw[5], rw[6], rw[7]);
-    o[0] = x, o[1] = y;
+    o[0] = rx, o[1] = ry;
     V.ref_len[id] = (uint8_t)rlen;
     if (is_root) {
       uint4* ro = reinterpret_cast<uint4*>(V.root_out);
-      ro[0] = x, ro[1] = y;
+      ro[0] = rx, ro[1] = ry;
     }
   }
-  if (V.counters) {
-    for (int off = 16; off > 0; off >>= 1) {
-      hashed += __shfl_down_sync(0xffffffffu, hashed, off);
-      perms += __shfl_down_sync(0xffffffffu, perms, off);
-      enc_bytes += __shfl_down_sync(0xffffffffu, enc_bytes, off);
-    }
-    if ((threadIdx.x & 31) == 0 && hashed) {
-      atomicAdd(V.counters + 0, (unsigned long long)hashed);
-      atomicAdd(V.counters + 1, (unsigned long long)perms);
-      atomicAdd(V.counters + 2, (unsigned long long)enc_bytes);
-    }
-  }
+  add_counters(V.counters, hashed, perms, enc_bytes);
 }
 
 // ------------------------------------------------------------------ launchers -----------------
@@ -601,13 +542,18 @@ void launch_branch_info(const BuildView& V, cudaStream_t st) {
   if (V.n < 2) return;
   branch_info_kernel<<<cdiv(V.n, 256), 256, 0, st>>>(V);
 }
-void launch_depth_hist(const uint8_t* depth, uint32_t nb, uint32_t* hist, cudaStream_t st) {
-  if (!nb) return;
-  depth_hist_kernel<<<cdiv(nb, 256), 256, 0, st>>>(depth, nb, hist);
+void launch_child_count(const uint32_t* leader, const uint32_t* bidx, uint32_t n, uint32_t* nchild, cudaStream_t st) {
+  if (n < 2) return;
+  child_count_kernel<<<cdiv(n, 256), 256, 0, st>>>(leader, bidx, n, nchild);
 }
-void launch_branch_scatter(const uint8_t* depth, uint32_t nb, uint32_t* cursor, uint32_t* order, cudaStream_t st) {
+// both use 256-thread blocks: one thread per histogram bin
+void launch_depth_hist(const uint8_t* depth, const uint32_t* nchild, uint32_t nb, uint32_t* hist, cudaStream_t st) {
   if (!nb) return;
-  branch_scatter_kernel<<<cdiv(nb, 256), 256, 0, st>>>(depth, nb, cursor, order);
+  depth_hist_kernel<<<cdiv(nb, 256), 256, 0, st>>>(depth, nchild, nb, hist);
+}
+void launch_branch_scatter(const uint8_t* depth, const uint32_t* nchild, uint32_t nb, uint32_t* cursor, uint32_t* order, cudaStream_t st) {
+  if (!nb) return;
+  branch_scatter_kernel<<<cdiv(nb, 256), 256, 0, st>>>(depth, nchild, nb, cursor, order);
 }
 void launch_hash_sorted_leaves(const BuildView& V, cudaStream_t st) {
   if (!V.n) return;

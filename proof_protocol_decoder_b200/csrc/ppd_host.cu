@@ -1061,15 +1061,33 @@ void sweep(ppd_ctx* c, Job& J) {
   J.ref.assign(32ull * n, 0);
   J.ref_len.assign(n, 0);
   if (!n) return;
-  // counting sort of node ids by level
+  // counting sort of node ids by (level, class): inside a level, nodes of one kind and one
+  // permutation count are adjacent, so the lanes of a warp do the same work
+  auto node_class = [&](uint32_t i) -> uint32_t {
+    const NodeRec& r = A.nodes[i];
+    uint32_t kind = r.w0 & 0xff, perms = 1;
+    if (kind == NK_LEAF) {
+      uint32_t nl = (r.w0 >> 16) & 0xff;
+      perms = ((nl < 2 ? 1 : 2 + (nl >> 1)) + r.a2 + 6) / 136 + 1;  // header bytes over-estimated by at most 3
+    } else if (kind == NK_BRANCH) {
+      uint32_t k = (uint32_t)__builtin_popcount(r.a1 & 0xffff);
+      perms = (17 - k + 33 * k + 3) / 136 + 1;
+    }
+    return kind * 8 + (perms > 8 ? 7 : perms - 1);
+  };
   uint32_t n_levels = 0;
   for (uint32_t i = 0; i < n; i++) n_levels = std::max<uint32_t>(n_levels, A.level[i] + 1u);
   std::vector<uint32_t> level_start(n_levels + 1, 0), order(n);
-  for (uint32_t i = 0; i < n; i++) level_start[A.level[i] + 1]++;
-  for (uint32_t l = 0; l < n_levels; l++) level_start[l + 1] += level_start[l];
   {
-    std::vector<uint32_t> cur(level_start.begin(), level_start.end() - 1);
-    for (uint32_t i = 0; i < n; i++) order[cur[A.level[i]]++] = i;
+    std::vector<uint8_t> cls(n);
+    std::vector<uint32_t> bucket((size_t)n_levels * 64 + 1, 0);
+    for (uint32_t i = 0; i < n; i++) {
+      cls[i] = (uint8_t)node_class(i);
+      bucket[(size_t)A.level[i] * 64 + cls[i] + 1]++;
+    }
+    for (size_t k = 0; k + 1 < bucket.size(); k++) bucket[k + 1] += bucket[k];
+    for (uint32_t l = 0; l <= n_levels; l++) level_start[l] = bucket[(size_t)l * 64];
+    for (uint32_t i = 0; i < n; i++) order[bucket[(size_t)A.level[i] * 64 + cls[i]]++] = i;
   }
   c->d_nodes.reserve(16ull * n);
   c->d_order.reserve(4ull * n);
@@ -1516,7 +1534,7 @@ void trie_root_sorted_dev(ppd_ctx* c, const uint8_t* d_keys, const uint64_t* d_v
   const uint32_t n = (uint32_t)n_;
   cudaStream_t st = c->st;
   const uint32_t n1 = (n + 1 + 63) / 64, n2 = (n1 + 63) / 64, n3 = (n2 + 63) / 64;
-  enum { B_L, B_M, B_LINKA, B_LINKB, B_BIDX, B_TMP, B_SMALL, B_DEPTH, B_REP, B_CHILD, B_ORDER, B_UNUSED };
+  enum { B_L, B_M, B_LINKA, B_LINKB, B_BIDX, B_TMP, B_SMALL, B_DEPTH, B_REP, B_CHILD, B_ORDER, B_NCHILD };
   DevBuf* D = c->d_build;
   D[B_L].reserve((size_t)n + 1 + 64);
   D[B_M].reserve((size_t)n1 + n2 + n3 + 192);
@@ -1524,13 +1542,13 @@ void trie_root_sorted_dev(ppd_ctx* c, const uint8_t* d_keys, const uint64_t* d_v
   D[B_LINKB].reserve(4ull * (n + 1));
   D[B_BIDX].reserve(4ull * (n + 1));
   D[B_TMP].reserve(4ull * scan_tmp_words((size_t)n + 1));
-  D[B_SMALL].reserve(1024);
+  D[B_SMALL].reserve(4096);
   int8_t* L = D[B_L].as<int8_t>();
   int8_t* m1 = D[B_M].as<int8_t>();
   int8_t* m2 = m1 + ((n1 + 63) & ~63u);
   int8_t* m3 = m2 + ((n2 + 63) & ~63u);
-  uint32_t* small = D[B_SMALL].as<uint32_t>();  // [0] error flags, [1] root id, [2..3] counters(u64), [8..15] root, [16..79] hist, [80..143] cursor
-  CUDA_OK(cudaMemsetAsync(small, 0, 1024, st));
+  uint32_t* small = D[B_SMALL].as<uint32_t>();  // [0] error flags, [1] root id, [2..7] counters(u64 x 3), [8..15] root, [64..319] hist, [320..575] cursor
+  CUDA_OK(cudaMemsetAsync(small, 0, 4096, st));
   CUDA_OK(cudaEventRecord(c->ev0, st));
   launch_lcp(d_keys, n, L, small + 0, st);
   launch_min64(L, n + 1, m1, n1, st);
@@ -1572,31 +1590,39 @@ void trie_root_sorted_dev(ppd_ctx* c, const uint8_t* d_keys, const uint64_t* d_v
   V.ref_len = c->d_ref_len.as<uint8_t>();
   V.root_out = reinterpret_cast<uint8_t*>(small + 8);
   V.counters = reinterpret_cast<unsigned long long*>(small + 2);
+  D[B_NCHILD].reserve(4ull * nb + 64);
+  uint32_t* nchild = D[B_NCHILD].as<uint32_t>();
   if (nb) CUDA_OK(cudaMemsetAsync(V.child, 0xff, 64ull * nb, st));
+  if (nb) CUDA_OK(cudaMemsetAsync(nchild, 0, 4ull * nb, st));
   launch_branch_info(V, st);
-  launch_depth_hist(V.depth, nb, small + 16, st);
-  uint32_t hist[64], cursor[64], start[65];
-  CUDA_OK(cudaMemcpyAsync(hist, small + 16, 256, cudaMemcpyDeviceToHost, st));
+  launch_child_count(leader, bidx, n, nchild, st);
+  // counting sort by (depth, permutation class): the lanes of a warp run the same number of permutations
+  launch_depth_hist(V.depth, nchild, nb, small + 64, st);
+  uint32_t hist[256], cursor[256], start[256];
+  CUDA_OK(cudaMemcpyAsync(hist, small + 64, 1024, cudaMemcpyDeviceToHost, st));
   CUDA_OK(cudaStreamSynchronize(st));
-  // deepest level first
+  // deepest level first; inside a depth, classes ascending
   uint32_t acc = 0;
-  for (int d = 63; d >= 0; d--) {
-    cursor[d] = start[d] = acc;
-    acc += hist[d];
-  }
-  if (acc != nb) fail(PPD_ERR_CUDA, "branch histogram does not add up");
-  CUDA_OK(cudaMemcpyAsync(small + 80, cursor, 256, cudaMemcpyHostToDevice, st));
-  uint32_t* order = D[B_ORDER].as<uint32_t>();
-  launch_branch_scatter(V.depth, nb, small + 80, order, st);
-  launch_hash_sorted_leaves(V, st);
-  c->stats.kernel_launches += 4;
-  uint32_t levels = 1;
   for (int d = 63; d >= 0; d--)
-    if (hist[d]) {
-      launch_hash_branch_level(V, order, start[d], start[d] + hist[d], st);
+    for (int k = 0; k < 4; k++) {
+      cursor[4 * d + k] = start[4 * d + k] = acc;
+      acc += hist[4 * d + k];
+    }
+  if (acc != nb) fail(PPD_ERR_CUDA, "branch histogram does not add up");
+  CUDA_OK(cudaMemcpyAsync(small + 320, cursor, 1024, cudaMemcpyHostToDevice, st));
+  uint32_t* order = D[B_ORDER].as<uint32_t>();
+  launch_branch_scatter(V.depth, nchild, nb, small + 320, order, st);
+  launch_hash_sorted_leaves(V, st);
+  c->stats.kernel_launches += 5;
+  uint32_t levels = 1;
+  for (int d = 63; d >= 0; d--) {
+    uint32_t cnt = hist[4 * d] + hist[4 * d + 1] + hist[4 * d + 2] + hist[4 * d + 3];
+    if (cnt) {
+      launch_hash_branch_level(V, order, start[4 * d], start[4 * d] + cnt, st);
       c->stats.kernel_launches++;
       levels++;
     }
+  }
   CUDA_OK(cudaGetLastError());
   CUDA_OK(cudaEventRecord(c->ev1, st));
   uint32_t out[16];
@@ -1613,7 +1639,7 @@ void trie_root_sorted_dev(ppd_ctx* c, const uint8_t* d_keys, const uint64_t* d_v
   c->stats.node_bytes += cnt[2];
   c->stats.arena_nodes += (uint64_t)n + nb;
   c->stats.levels += levels;
-  c->stats.d2h_bytes += 64 + 256 + 8;
+  c->stats.d2h_bytes += 64 + 1024 + 8;
 }
 
 }  // namespace

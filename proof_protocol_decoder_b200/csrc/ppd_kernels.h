@@ -46,8 +46,9 @@ void launch_min64(const int8_t* in, uint32_t n_in, int8_t* out, uint32_t n_out, 
 void launch_leaders(const int8_t* L, const int8_t* m1, const int8_t* m2, const int8_t* m3, uint32_t n, uint32_t* link_a, uint32_t* link_b,
                     uint32_t* flag, cudaStream_t st);
 void launch_branch_info(const BuildView& V, cudaStream_t st);
-void launch_depth_hist(const uint8_t* depth, uint32_t nb, uint32_t* hist, cudaStream_t st);
-void launch_branch_scatter(const uint8_t* depth, uint32_t nb, uint32_t* cursor, uint32_t* order, cudaStream_t st);
+void launch_child_count(const uint32_t* leader, const uint32_t* bidx, uint32_t n, uint32_t* nchild, cudaStream_t st);
+void launch_depth_hist(const uint8_t* depth, const uint32_t* nchild, uint32_t nb, uint32_t* hist, cudaStream_t st);
+void launch_branch_scatter(const uint8_t* depth, const uint32_t* nchild, uint32_t nb, uint32_t* cursor, uint32_t* order, cudaStream_t st);
 void launch_hash_sorted_leaves(const BuildView& V, cudaStream_t st);
 void launch_hash_branch_level(const BuildView& V, const uint32_t* order, uint32_t begin, uint32_t end, cudaStream_t st);
 
