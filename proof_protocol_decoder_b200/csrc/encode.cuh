@@ -167,18 +167,24 @@ template <int B>
 __device__ __forceinline__ void inline_ref_words(Stage<B>& s, uint32_t total, uint4& x, uint4& y) {
   s.flush_partial();
   uint32_t nw = (total + 3) >> 2;
-  uint32_t h[8];
-#pragma unroll
-  for (int k = 0; k < 8; k++) h[k] = (uint32_t)k < nw ? s.word(k) : 0u;
+  uint32_t h[8] = {s.template word<0>(), s.template word<1>(), s.template word<2>(), s.template word<3>(),
+                   s.template word<4>(), s.template word<5>(), s.template word<6>(), s.template word<7>()};
   uint32_t tail = total & 3;
-  if (tail) {
-    uint32_t keep = (1u << (8 * tail)) - 1;
+  uint32_t keep = tail ? (1u << (8 * tail)) - 1 : 0xffffffffu;
 #pragma unroll
-    for (int k = 0; k < 8; k++)
-      if ((uint32_t)k == nw - 1) h[k] &= keep;
-  }
+  for (int k = 0; k < 8; k++) h[k] = (uint32_t)k < nw ? ((uint32_t)k == nw - 1 ? h[k] & keep : h[k]) : 0u;
   x = make_uint4(h[0], h[1], h[2], h[3]);
   y = make_uint4(h[4], h[5], h[6], h[7]);
+}
+
+// g bytes of 0x80 (empty branch slots / the empty branch value), g <= 17
+template <int B>
+__device__ __forceinline__ void emit_empty_run(Stage<B>& s, uint32_t g) {
+  while (g >= 4) {
+    s.put_word(0x80808080u);
+    g -= 4;
+  }
+  s.put_partial(0x80808080u, g);
 }
 
 // per-warp accumulation of the work counters: one atomic triple per warp

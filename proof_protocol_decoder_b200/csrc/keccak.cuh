@@ -175,92 +175,107 @@ __device__ __forceinline__ void keccak_f1600(uint64_t (&a)[25]) { keccak_f1600_t
 // warp is conflict-free no matter how far each lane has advanced.  A rate block is exactly one half
 // of the ring, so the bytes that overflow a block already sit where the next block starts:
 // consuming a block moves no data.
+//
+// Appending a word costs one funnel shift, one store and the ring-pointer update: the bytes that do
+// not yet fill a word are kept in the TOP `sh` bits of `carry`, so the word to store is
+// funnelshift_l(carry, x, sh) and the new carry is x itself.  All addresses are 32-bit shared-window
+// addresses (explicit ld/st.shared), never generic pointers.
 // ---------------------------------------------------------------------------------------------
 #define PPD_STAGE_WORDS 68
 
+__device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+template <int OFF>
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(v) : "r"(addr), "n"(OFF) : "memory");
+  return v;
+}
+
 template <int BLOCK>
 struct Stage {
-  uint32_t* w;     // &smem[threadIdx.x]
-  uint32_t acc;    // pending bytes of the word being assembled (low `sh` bits valid)
+  static constexpr uint32_t STRIDE = 4u * BLOCK;                 // bytes between consecutive words of one thread
+  static constexpr uint32_t HALF = 34u * STRIDE, RING = 68u * STRIDE;
+  uint32_t lo;     // shared address of this thread's word 0
+  uint32_t addr;   // shared address of the next word slot
+  uint32_t blk;    // shared address of word 0 of the current block: lo or lo + HALF
+  uint32_t carry;  // pending bytes of the word being assembled, in the top `sh` bits
   uint32_t sh;     // 0, 8, 16, 24
-  uint32_t widx;   // complete words staged since the start of the current block
-  uint32_t base;   // ring position of the current block: 0 or 34
-  uint32_t wpos;   // ring position of the next word
 
   __device__ __forceinline__ void init(uint32_t* smem) {
-    w = smem + threadIdx.x;
-    acc = 0;
+    lo = (uint32_t)__cvta_generic_to_shared(smem) + 4u * threadIdx.x;
+    addr = lo;
+    blk = lo;
+    carry = 0;
     sh = 0;
-    widx = 0;
-    base = 0;
-    wpos = 0;
   }
-  __device__ __forceinline__ uint32_t bytes() const { return 4 * widx + (sh >> 3); }
+  // complete words staged since the start of the current block
+  __device__ __forceinline__ uint32_t words() const {
+    uint32_t d = addr - blk;
+    if ((int32_t)d < 0) d += RING;
+    return d / STRIDE;
+  }
+  __device__ __forceinline__ uint32_t bytes() const { return 4 * words() + (sh >> 3); }
   __device__ __forceinline__ void push_word(uint32_t x) {
-    w[wpos * BLOCK] = x;
-    wpos = (wpos == PPD_STAGE_WORDS - 1) ? 0u : wpos + 1;
-    widx++;
+    sts32(addr, x);
+    addr += STRIDE;
+    if (addr == lo + RING) addr = lo;
   }
   __device__ __forceinline__ void put_word(uint32_t x) {
-    // acc holds sh valid bits
-    uint32_t lo = acc | (x << sh);
-    uint32_t hi = sh ? (x >> (32 - sh)) : 0u;
-    push_word(lo);
-    acc = hi;
+    push_word(__funnelshift_l(carry, x, sh));
+    carry = x;
   }
   __device__ __forceinline__ void put_byte(uint32_t b) {
-    acc |= b << sh;
+    carry = __funnelshift_r(carry, b, 8);
     sh += 8;
     if (sh == 32) {
-      push_word(acc);
-      acc = 0;
+      push_word(carry);
       sh = 0;
     }
   }
   // append the low n bytes of x (n = 0..4)
   __device__ __forceinline__ void put_partial(uint32_t x, uint32_t n) {
     if (n == 0) return;
-    if (n < 4) x &= (1u << (8 * n)) - 1;
-    uint32_t lo = acc | (x << sh);
-    uint32_t hi = sh ? (x >> (32 - sh)) : 0u;
     uint32_t nsh = sh + 8 * n;
     if (nsh >= 32) {
-      push_word(lo);
-      acc = hi;
-      sh = nsh - 32;
-    } else {
-      acc = lo;
-      sh = nsh;
+      push_word(__funnelshift_l(carry, x, sh));
+      nsh -= 32;
     }
+    carry = __funnelshift_rc(carry, x, 8 * n);
+    sh = nsh;
   }
+  // the pending bytes, low-aligned
+  __device__ __forceinline__ uint32_t pending() const { return sh ? carry >> (32 - sh) : 0u; }
   // Keccak padding 0x01 .. 0x80 (original Keccak, as tiny-keccak's Keccak::v256).  Needs bytes() < 136.
   __device__ __forceinline__ void pad() {
-    uint32_t* blk = w + base * BLOCK;
-    blk[widx * BLOCK] = acc | (0x01u << sh);
-    for (uint32_t i = widx + 1; i < 34; i++) blk[i * BLOCK] = 0;
-    blk[33 * BLOCK] |= 0x80000000u;
+    const uint32_t last = blk + 33u * STRIDE;
+    uint32_t v = pending() | (0x01u << sh);
+    uint32_t p = addr;  // words() < 34: the slot of the partial word, inside the current half
+    while (p != last) {
+      sts32(p, v);
+      v = 0;
+      p += STRIDE;
+    }
+    sts32(last, v | 0x80000000u);
   }
   // after a block was absorbed: the overflow words are already at the start of the other half
-  __device__ __forceinline__ void consume_block() {
-    widx -= 34;
-    base = 34 - base;
+  __device__ __forceinline__ void consume_block() { blk = (blk == lo) ? lo + HALF : lo; }
+  // word K of the current block; flush_partial() first if the last word may be incomplete
+  template <int K>
+  __device__ __forceinline__ uint32_t word() const {
+    return lds32<K * (int)STRIDE>(blk);
   }
   // make the partial word visible in shared memory (for the inline < 32-byte case)
   __device__ __forceinline__ void flush_partial() {
-    if (sh) w[wpos * BLOCK] = acc;
+    if (sh) sts32(addr, pending());
   }
-  // word i of the current block
-  __device__ __forceinline__ uint32_t word(uint32_t i) const { return w[(base + i) * BLOCK]; }
 };
 
 template <int BLOCK>
 __device__ __forceinline__ void absorb_stage(uint64_t (&a)[25], const Stage<BLOCK>& s) {
-  const uint32_t* blk = s.w + s.base * BLOCK;
-#pragma unroll
-  for (int i = 0; i < 17; i++) {
-    uint32_t lo = blk[(2 * i) * BLOCK], hi = blk[(2 * i + 1) * BLOCK];
-    a[i] ^= ((uint64_t)hi << 32) | lo;
-  }
+#define PPD_ABSORB(i) a[i] ^= ((uint64_t)s.template word<2 * (i) + 1>() << 32) | s.template word<2 * (i)>();
+  PPD_ABSORB(0) PPD_ABSORB(1) PPD_ABSORB(2) PPD_ABSORB(3) PPD_ABSORB(4) PPD_ABSORB(5) PPD_ABSORB(6) PPD_ABSORB(7) PPD_ABSORB(8)
+  PPD_ABSORB(9) PPD_ABSORB(10) PPD_ABSORB(11) PPD_ABSORB(12) PPD_ABSORB(13) PPD_ABSORB(14) PPD_ABSORB(15) PPD_ABSORB(16)
+#undef PPD_ABSORB
 }
 
 }  // namespace ppd

@@ -395,7 +395,7 @@ __global__ void __launch_bounds__(B, 4) hash_branch_level_kernel(BuildView V, co
   uint32_t hashed = 0, perms = 0, enc_bytes = 0;
   bool busy = slot < end, is_root = false;
   uint32_t bi = 0, id = 0, es = 0, ext_len = 0, payload = 1, total = 0, unit = 0, phase = 0;
-  uint32_t clen_packed[4] = {0, 0, 0, 0};
+  uint32_t rem = 0, hmask = 0, next_slot = 0, nunit = 0;  // slots still to emit; slots referenced by hash
   if (busy) {
     bi = __ldg(order + slot);
     id = V.n + bi;
@@ -413,9 +413,11 @@ __global__ void __launch_bounds__(B, 4) hash_branch_level_kernel(BuildView V, co
 #pragma unroll
     for (int k = 0; k < 16; k++) {  // sixteen independent byte loads
       uint32_t cl = kid[k] == NODE_EMPTY ? 0u : (uint32_t)V.ref_len[kid[k]];
-      clen_packed[k >> 2] |= cl << (8 * (k & 3));
+      rem |= (kid[k] == NODE_EMPTY ? 0u : 1u) << k;
+      hmask |= (cl == 32 ? 1u : 0u) << k;
       payload += kid[k] == NODE_EMPTY ? 1u : (cl == 32 ? 33u : cl);
     }
+    nunit = 1 + ((uint32_t)__popc(rem) + 2) / 3;
     total = len_prefix_size(payload) + payload;
   }
   Stage<B> s;
@@ -429,31 +431,37 @@ __global__ void __launch_bounds__(B, 4) hash_branch_level_kernel(BuildView V, co
     bool permute = false, last = false;
     if (busy) {
       if (phase == 0) {
-        while (s.bytes() < 136 && unit < 5) {
+        while (s.bytes() < 136 && unit < nunit) {
           if (unit == 0) {
             emit_len_prefix(s, payload, 0xc0, 0xf7);
           } else {
-            const uint32_t g = unit - 1;
-            const uint32_t lens = g == 0 ? clen_packed[0] : g == 1 ? clen_packed[1] : g == 2 ? clen_packed[2] : clen_packed[3];
-            // the child table was written by earlier launches: re-read the four ids (L1 / L2 hit)
-            const uint4 cc = __ldg(reinterpret_cast<const uint4*>(V.child + 16ull * bi) + g);
-            const uint32_t c[4] = {cc.x, cc.y, cc.z, cc.w};
-            uint4 x[4], y[4];
+            // three children per unit, walked in compact order so that the lanes of a warp emit their
+            // j-th child together whatever slots the children sit in.  The child table was written by
+            // earlier launches: re-reading an id is an L1 / L2 hit.
+            uint32_t nib[3], cid[3];
+            uint4 x[3], y[3];
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
-              if (c[k] != NODE_EMPTY) {
-                const uint4* q = reinterpret_cast<const uint4*>(V.ref + 32ull * c[k]);
-                x[k] = __ldcg(q), y[k] = __ldcg(q + 1);
+            for (int t = 0; t < 3; t++) {
+              nib[t] = rem ? (uint32_t)__ffs(rem) - 1 : 16u;
+              rem &= rem - 1;
+              cid[t] = nib[t] < 16 ? __ldg(V.child + 16ull * bi + nib[t]) : 0u;
+            }
+#pragma unroll
+            for (int t = 0; t < 3; t++) {
+              if (nib[t] < 16) {
+                const uint4* q = reinterpret_cast<const uint4*>(V.ref + 32ull * cid[t]);
+                x[t] = __ldcg(q), y[t] = __ldcg(q + 1);
               }
             }
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
-              if (c[k] != NODE_EMPTY)
-                emit_ref(s, x[k], y[k], (lens >> (8 * k)) & 0xff);
-              else
-                s.put_byte(0x80);
+            for (int t = 0; t < 3; t++) {
+              if (nib[t] < 16) {
+                emit_empty_run(s, nib[t] - next_slot);
+                emit_ref(s, x[t], y[t], ((hmask >> nib[t]) & 1) ? 32u : (uint32_t)V.ref_len[cid[t]]);
+                next_slot = nib[t] + 1;
+              }
             }
-            if (g == 3) s.put_byte(0x80);
+            if (rem == 0) emit_empty_run(s, 17 - next_slot);  // trailing empty slots and the empty value
           }
           unit++;
         }

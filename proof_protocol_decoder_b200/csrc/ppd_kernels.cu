@@ -84,7 +84,8 @@ __global__ void __launch_bounds__(B) keccak256_batch_kernel(const uint8_t* __res
 //   LEAF_ACCOUNT  0: list header, hex-prefix key, string + list headers, nonce
 //                 1: balance, storage root, code hash
 //   EXT           0: list header, hex-prefix key, child ref
-//   BRANCH        0: list header   1..4: four child slots each (unit 4 also carries the empty value)
+//   BRANCH        0: list header   1..: three children each with the empty slots before them (the last
+//                 unit also carries the trailing empty slots and the empty value)
 //   ROOT          0: the child's raw RLP (only when it is shorter than 32 bytes) or 0x80
 
 template <int B>
@@ -98,8 +99,8 @@ __global__ void __launch_bounds__(B, 4) hash_level_kernel(ArenaView A, const uin
   uint32_t id = 0;
   uint4 rec = make_uint4(NK_HASH, 0, 0, 0);
   uint32_t payload = 0, nunit = 0, total = 0, unit = 0;
-  uint32_t v0 = 0, v1 = 0;                 // LEAF: vlen, vhdr   LEAF_ACCOUNT: vlen, nn | nb << 8 | apayload << 16
-  uint32_t clen_packed[4] = {0, 0, 0, 0};  // BRANCH: ref_len of the child in slot i at byte i
+  // LEAF: vlen, vhdr   LEAF_ACCOUNT: vlen, nn | nb << 8 | apayload << 16   BRANCH: slots left, walk state
+  uint32_t v0 = 0, v1 = 0;
 #define KIND (rec.x & 0xff)
 #define NIB_START ((rec.x >> 8) & 0xff)
 #define NIB_LEN ((rec.x >> 16) & 0xff)
@@ -142,21 +143,22 @@ __global__ void __launch_bounds__(B, 4) hash_level_kernel(ArenaView A, const uin
       case NK_BRANCH: {
         const uint32_t* ch = A.child_pool + rec.y;
         const uint32_t mask = rec.z & 0xffff;
+        const uint32_t k = __popc(mask);
         // all child ids, then all lengths: two batches of independent loads
         uint32_t cid[16];
 #pragma unroll
-        for (int k = 0; k < 16; k++) {
-          uint32_t bit = 1u << k;
-          cid[k] = (mask & bit) ? __ldg(ch + __popc(mask & (bit - 1))) : NODE_EMPTY;
-        }
-        payload = 1;  // the empty value
+        for (int j = 0; j < 16; j++) cid[j] = (uint32_t)j < k ? __ldg(ch + j) : NODE_EMPTY;
+        payload = 17 - k;  // empty slots and the empty value
+        uint32_t hashed_kids = 0;  // bit j: compact child j is referenced by hash
 #pragma unroll
-        for (int k = 0; k < 16; k++) {
-          uint32_t cl = cid[k] == NODE_EMPTY ? 0u : (uint32_t)A.ref_len[cid[k]];
-          clen_packed[k >> 2] |= cl << (8 * (k & 3));
-          payload += cid[k] == NODE_EMPTY ? 1u : (cl == 32 ? 33u : cl);
+        for (int j = 0; j < 16; j++) {
+          uint32_t cl = cid[j] == NODE_EMPTY ? 0u : (uint32_t)A.ref_len[cid[j]];
+          payload += cl == 32 ? 33u : cl;
+          hashed_kids |= (cl == 32 ? 1u : 0u) << j;
         }
-        nunit = 5;
+        v0 = mask;               // slots still to emit
+        v1 = hashed_kids << 16;  // | compact index of the next child << 8 | next slot
+        nunit = 1 + (k + 2) / 3;
         break;
       }
       case NK_ROOT: {
@@ -229,29 +231,35 @@ __global__ void __launch_bounds__(B, 4) hash_level_kernel(ArenaView A, const uin
             if (unit == 0) {
               emit_len_prefix(s, payload, 0xc0, 0xf7);
             } else {
+              // three children per unit, walked in compact order so that the lanes of a warp emit
+              // their j-th child together whatever slots the children sit in
               const uint32_t* ch = A.child_pool + rec.y;
-              const uint32_t mask = rec.z & 0xffff;
-              const uint32_t g = unit - 1;
-              const uint32_t lens = g == 0 ? clen_packed[0] : g == 1 ? clen_packed[1] : g == 2 ? clen_packed[2] : clen_packed[3];
-              uint4 x[4], y[4];
+              uint32_t j0 = (v1 >> 8) & 0xff, next_slot = v1 & 0xff;
+              uint32_t nib[3], cid[3];
+              uint4 x[3], y[3];
 #pragma unroll
-              for (int k = 0; k < 4; k++) {  // the four refs: independent loads, issued together
-                uint32_t bit = 1u << (4 * g + k);
-                if (mask & bit) {
-                  uint32_t c = __ldg(ch + __popc(mask & (bit - 1)));
-                  const uint4* q = reinterpret_cast<const uint4*>(A.ref + 32ull * c);
-                  x[k] = __ldcg(q), y[k] = __ldcg(q + 1);
+              for (int t = 0; t < 3; t++) {
+                nib[t] = v0 ? (uint32_t)__ffs(v0) - 1 : 16u;
+                v0 &= v0 - 1;
+                cid[t] = nib[t] < 16 ? __ldg(ch + j0 + t) : 0u;
+              }
+#pragma unroll
+              for (int t = 0; t < 3; t++) {  // the refs: independent loads, issued together
+                if (nib[t] < 16) {
+                  const uint4* q = reinterpret_cast<const uint4*>(A.ref + 32ull * cid[t]);
+                  x[t] = __ldcg(q), y[t] = __ldcg(q + 1);
                 }
               }
 #pragma unroll
-              for (int k = 0; k < 4; k++) {
-                uint32_t bit = 1u << (4 * g + k);
-                if (mask & bit)
-                  emit_ref(s, x[k], y[k], (lens >> (8 * k)) & 0xff);
-                else
-                  s.put_byte(0x80);
+              for (int t = 0; t < 3; t++) {
+                if (nib[t] < 16) {
+                  emit_empty_run(s, nib[t] - next_slot);
+                  emit_ref(s, x[t], y[t], ((v1 >> (16 + j0 + t)) & 1) ? 32u : (uint32_t)A.ref_len[cid[t]]);
+                  next_slot = nib[t] + 1;
+                }
               }
-              if (g == 3) s.put_byte(0x80);
+              if (v0 == 0) emit_empty_run(s, 17 - next_slot);  // trailing empty slots and the empty value
+              v1 = (v1 & 0xffff0000u) | ((j0 + 3) << 8) | next_slot;
             }
             break;
           default:  // NK_ROOT over Node::Empty or over a node whose encoding is < 32 bytes
