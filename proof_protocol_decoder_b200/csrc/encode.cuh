@@ -40,71 +40,66 @@ __device__ __forceinline__ uint32_t ld_bytes(const uint8_t* p, uint32_t cnt) {
   return __funnelshift_r(lo, hi, ofs * 8);
 }
 
-// n bytes from any global address
+// n bytes from any global address.  Branch-free in the alignment (lanes of a warp read values at
+// different alignments): always the funnel-shift path, with the look-ahead load predicated on the
+// word still holding a requested byte.
 template <int B>
 __device__ __forceinline__ void emit_bytes(Stage<B>& s, const uint8_t* p, uint32_t n) {
   if (n == 0) return;
   uintptr_t a = reinterpret_cast<uintptr_t>(p);
   const uint32_t* q = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
   const uint32_t ofs = (uint32_t)(a & 3), sh = ofs * 8;
+  const uint32_t nwords = (ofs + n + 3) >> 2;  // aligned words that hold a requested byte
   const uint32_t full = n >> 2, rem = n & 3;
   uint32_t cur = __ldg(q);
-  if (ofs == 0) {
-    for (uint32_t i = 0; i < full; i++) {
-      s.put_word(cur);
-      if (i + 1 < full || rem) cur = __ldg(q + i + 1);
-    }
-    if (rem) s.put_partial(cur, rem);
-  } else {
-    for (uint32_t i = 0; i < full; i++) {
-      uint32_t nxt = __ldg(q + i + 1);
-      s.put_word(__funnelshift_r(cur, nxt, sh));
-      cur = nxt;
-    }
-    if (rem) {
-      uint32_t nxt = (ofs + rem > 4) ? __ldg(q + full + 1) : 0u;
-      s.put_partial(__funnelshift_r(cur, nxt, sh), rem);
-    }
+  for (uint32_t i = 0; i < full; i++) {
+    uint32_t nxt = (i + 1 < nwords) ? __ldg(q + i + 1) : 0u;
+    s.put_word(__funnelshift_r(cur, nxt, sh));
+    cur = nxt;
+  }
+  if (rem) {
+    uint32_t nxt = (full + 1 < nwords) ? __ldg(q + full + 1) : 0u;
+    s.put_partial(__funnelshift_r(cur, nxt, sh), rem);
   }
 }
 
-// m bytes out[k] = (in[k] & 15) << 4 | in[k + 1] >> 4 with in = p[0 .. m]: a packed nibble string
-// that starts at the LOW nibble of p[0]
+// m bytes of a packed nibble string that starts at the high (odd == 0) or the low (odd == 1)
+// nibble of p[0]:  odd == 0: out[k] = in[k];  odd == 1: out[k] = (in[k] & 15) << 4 | in[k + 1] >> 4.
+// Branch-free in `odd` (lanes of a warp sit at depths of both parities).
 template <int B>
-__device__ __forceinline__ void emit_bytes_shift4(Stage<B>& s, const uint8_t* p, uint32_t m) {
+__device__ __forceinline__ void emit_nibble_bytes(Stage<B>& s, const uint8_t* p, uint32_t m, uint32_t odd) {
+  const uint32_t avail = m + odd;  // bytes readable from p
   uint32_t k = 0;
-  uint32_t W = ld_bytes(p, min(4u, m + 1));
+  uint32_t W = ld_bytes(p, min(4u, avail));
   while (m - k >= 4) {
-    uint32_t left = m + 1 - (k + 4);  // >= 1 bytes readable from p + k + 4
-    uint32_t Wn = ld_bytes(p + k + 4, min(4u, left));
+    uint32_t left = avail - (k + 4);
+    uint32_t Wn = left ? ld_bytes(p + k + 4, min(4u, left)) : 0u;
     uint32_t W1 = __funnelshift_r(W, Wn, 8);
-    s.put_word(((W & 0x0f0f0f0fu) << 4) | ((W1 >> 4) & 0x0f0f0f0fu));
+    uint32_t shifted = ((W & 0x0f0f0f0fu) << 4) | ((W1 >> 4) & 0x0f0f0f0fu);
+    s.put_word(odd ? shifted : W);
     W = Wn;
     k += 4;
   }
   uint32_t r = m - k;
-  if (r) s.put_partial(((W & 0x0f0f0f0fu) << 4) | ((W >> 12) & 0x0f0f0f0fu), r);
+  if (r) {
+    uint32_t shifted = ((W & 0x0f0f0f0fu) << 4) | ((W >> 12) & 0x0f0f0f0fu);
+    s.put_partial(odd ? shifted : W, r);
+  }
 }
 
 // rlp_str(hex_prefix(nibbles [start, start + n) of the packed key, is_leaf)): at most 34 bytes
 template <int B>
 __device__ __forceinline__ void emit_hex_prefix_str(Stage<B>& s, const uint8_t* key, uint32_t start, uint32_t n, uint32_t is_leaf) {
   if (n >= 2) s.put_byte(0x80 + 1 + (n >> 1));
-  uint32_t flag = (is_leaf ? 2u : 0u) + (n & 1);
-  uint32_t j = start;
+  const uint32_t flag = (is_leaf ? 2u : 0u) + (n & 1);
+  uint32_t first = flag << 4;
   if (n & 1) {
-    uint32_t b = __ldg(key + (j >> 1));
-    s.put_byte((flag << 4) | ((j & 1) ? (b & 15) : (b >> 4)));
-    j++;
-  } else {
-    s.put_byte(flag << 4);
+    uint32_t b = __ldg(key + (start >> 1));
+    first |= (start & 1) ? (b & 15) : (b >> 4);
   }
-  uint32_t m = n >> 1;
-  if (m == 0) return;
-  if ((j & 1) == 0)
-    emit_bytes(s, key + (j >> 1), m);
-  else
-    emit_bytes_shift4(s, key + (j >> 1), m);
+  s.put_byte(first);
+  const uint32_t j = start + (n & 1), m = n >> 1;
+  if (m) emit_nibble_bytes(s, key + (j >> 1), m, j & 1);
 }
 
 // a child reference inside a parent: 0xa0 || hash, or the child's raw RLP when shorter than 32 bytes

@@ -252,30 +252,29 @@ __global__ void child_count_kernel(const uint32_t* __restrict__ leader, const ui
   atomicAdd(nchild + bidx[leader[q]], 1u);
 }
 
-// Sort key of a branch: depth * 4 + permutation class.  A branch with k hashed children encodes to
-// 33 k + (16 - k) + 1 payload bytes: 1 rate block up to k = 3, 2 up to 7, 3 up to 12, else 4.
-__device__ __forceinline__ uint32_t branch_sort_key(uint32_t depth, uint32_t nchild_minus_1) {
-  uint32_t k = nchild_minus_1 + 1;
-  uint32_t cls = k <= 3 ? 0u : k <= 7 ? 1u : k <= 12 ? 2u : 3u;
-  return depth * 4 + cls;
-}
+// Sort key of a branch: depth * 16 + (number of children - 1).  Lanes of a warp then walk the same
+// number of children and run the same number of permutations (a branch with k hashed children
+// encodes to 33 k + (16 - k) + 1 payload bytes: 1 rate block up to k = 3, 2 up to 7, 3 up to 12, else 4).
+static constexpr int SORT_KEYS = 1024;
+__device__ __forceinline__ uint32_t branch_sort_key(uint32_t depth, uint32_t nchild_minus_1) { return depth * 16 + min(nchild_minus_1, 15u); }
 
 // hist[key] = number of branches with that key (block-local histogram, one global atomic per bin and block)
 __global__ void depth_hist_kernel(const uint8_t* __restrict__ depth, const uint32_t* __restrict__ nchild, uint32_t nb, uint32_t* __restrict__ hist_out) {
-  __shared__ uint32_t hist[256];
-  hist[threadIdx.x] = 0;
+  __shared__ uint32_t hist[SORT_KEYS];
+  for (int k = threadIdx.x; k < SORT_KEYS; k += blockDim.x) hist[k] = 0;
   __syncthreads();
   uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b < nb) atomicAdd(&hist[branch_sort_key(depth[b], nchild[b])], 1u);
   __syncthreads();
-  if (hist[threadIdx.x]) atomicAdd(hist_out + threadIdx.x, hist[threadIdx.x]);
+  for (int k = threadIdx.x; k < SORT_KEYS; k += blockDim.x)
+    if (hist[k]) atomicAdd(hist_out + k, hist[k]);
 }
 
 // counting sort of the branches by key: order[start[key] + k] = b
 __global__ void branch_scatter_kernel(const uint8_t* __restrict__ depth, const uint32_t* __restrict__ nchild, uint32_t nb, uint32_t* __restrict__ cursor,
                                       uint32_t* __restrict__ order) {
-  __shared__ uint32_t hist[256], base[256];
-  hist[threadIdx.x] = 0;
+  __shared__ uint32_t hist[SORT_KEYS], base[SORT_KEYS];
+  for (int k = threadIdx.x; k < SORT_KEYS; k += blockDim.x) hist[k] = 0;
   __syncthreads();
   uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
   uint32_t key = 0, rank = 0;
@@ -284,7 +283,8 @@ __global__ void branch_scatter_kernel(const uint8_t* __restrict__ depth, const u
     rank = atomicAdd(&hist[key], 1u);
   }
   __syncthreads();
-  if (hist[threadIdx.x]) base[threadIdx.x] = atomicAdd(cursor + threadIdx.x, hist[threadIdx.x]);
+  for (int k = threadIdx.x; k < SORT_KEYS; k += blockDim.x)
+    if (hist[k]) base[k] = atomicAdd(cursor + k, hist[k]);
   __syncthreads();
   if (b < nb) order[base[key] + rank] = b;
 }
@@ -554,14 +554,13 @@ void launch_child_count(const uint32_t* leader, const uint32_t* bidx, uint32_t n
   if (n < 2) return;
   child_count_kernel<<<cdiv(n, 256), 256, 0, st>>>(leader, bidx, n, nchild);
 }
-// both use 256-thread blocks: one thread per histogram bin
 void launch_depth_hist(const uint8_t* depth, const uint32_t* nchild, uint32_t nb, uint32_t* hist, cudaStream_t st) {
   if (!nb) return;
-  depth_hist_kernel<<<cdiv(nb, 256), 256, 0, st>>>(depth, nchild, nb, hist);
+  depth_hist_kernel<<<cdiv(nb, 1024), 1024, 0, st>>>(depth, nchild, nb, hist);
 }
 void launch_branch_scatter(const uint8_t* depth, const uint32_t* nchild, uint32_t nb, uint32_t* cursor, uint32_t* order, cudaStream_t st) {
   if (!nb) return;
-  branch_scatter_kernel<<<cdiv(nb, 256), 256, 0, st>>>(depth, nchild, nb, cursor, order);
+  branch_scatter_kernel<<<cdiv(nb, 1024), 1024, 0, st>>>(depth, nchild, nb, cursor, order);
 }
 void launch_hash_sorted_leaves(const BuildView& V, cudaStream_t st) {
   if (!V.n) return;

@@ -1065,13 +1065,13 @@ void sweep(ppd_ctx* c, Job& J) {
   // permutation count are adjacent, so the lanes of a warp do the same work
   auto node_class = [&](uint32_t i) -> uint32_t {
     const NodeRec& r = A.nodes[i];
-    uint32_t kind = r.w0 & 0xff, perms = 1;
+    uint32_t kind = r.w0 & 0xff;
+    if (kind == NK_BRANCH) return 40 + ((uint32_t)__builtin_popcount(r.a1 & 0xffff) - 1 & 15);  // by child count
+    if (kind == NK_ROOT) return 56;
+    uint32_t perms = 1;
     if (kind == NK_LEAF) {
       uint32_t nl = (r.w0 >> 16) & 0xff;
       perms = ((nl < 2 ? 1 : 2 + (nl >> 1)) + r.a2 + 6) / 136 + 1;  // header bytes over-estimated by at most 3
-    } else if (kind == NK_BRANCH) {
-      uint32_t k = (uint32_t)__builtin_popcount(r.a1 & 0xffff);
-      perms = (17 - k + 33 * k + 3) / 136 + 1;
     }
     return kind * 8 + (perms > 8 ? 7 : perms - 1);
   };
@@ -1542,13 +1542,13 @@ void trie_root_sorted_dev(ppd_ctx* c, const uint8_t* d_keys, const uint64_t* d_v
   D[B_LINKB].reserve(4ull * (n + 1));
   D[B_BIDX].reserve(4ull * (n + 1));
   D[B_TMP].reserve(4ull * scan_tmp_words((size_t)n + 1));
-  D[B_SMALL].reserve(4096);
+  D[B_SMALL].reserve(16384);
   int8_t* L = D[B_L].as<int8_t>();
   int8_t* m1 = D[B_M].as<int8_t>();
   int8_t* m2 = m1 + ((n1 + 63) & ~63u);
   int8_t* m3 = m2 + ((n2 + 63) & ~63u);
-  uint32_t* small = D[B_SMALL].as<uint32_t>();  // [0] error flags, [1] root id, [2..7] counters(u64 x 3), [8..15] root, [64..319] hist, [320..575] cursor
-  CUDA_OK(cudaMemsetAsync(small, 0, 4096, st));
+  uint32_t* small = D[B_SMALL].as<uint32_t>();  // [0] error flags, [1] root id, [2..7] counters(u64 x 3), [8..15] root, [1024..2047] hist, [2048..3071] cursor
+  CUDA_OK(cudaMemsetAsync(small, 0, 16384, st));
   CUDA_OK(cudaEventRecord(c->ev0, st));
   launch_lcp(d_keys, n, L, small + 0, st);
   launch_min64(L, n + 1, m1, n1, st);
@@ -1596,29 +1596,31 @@ void trie_root_sorted_dev(ppd_ctx* c, const uint8_t* d_keys, const uint64_t* d_v
   if (nb) CUDA_OK(cudaMemsetAsync(nchild, 0, 4ull * nb, st));
   launch_branch_info(V, st);
   launch_child_count(leader, bidx, n, nchild, st);
-  // counting sort by (depth, permutation class): the lanes of a warp run the same number of permutations
-  launch_depth_hist(V.depth, nchild, nb, small + 64, st);
-  uint32_t hist[256], cursor[256], start[256];
-  CUDA_OK(cudaMemcpyAsync(hist, small + 64, 1024, cudaMemcpyDeviceToHost, st));
+  // counting sort by (depth, number of children): the lanes of a warp walk the same number of children
+  // and run the same number of permutations
+  launch_depth_hist(V.depth, nchild, nb, small + 1024, st);
+  std::vector<uint32_t> hist(1024), cursor(1024), start(1024);
+  CUDA_OK(cudaMemcpyAsync(hist.data(), small + 1024, 4096, cudaMemcpyDeviceToHost, st));
   CUDA_OK(cudaStreamSynchronize(st));
-  // deepest level first; inside a depth, classes ascending
+  // deepest level first; inside a depth, child counts ascending
   uint32_t acc = 0;
   for (int d = 63; d >= 0; d--)
-    for (int k = 0; k < 4; k++) {
-      cursor[4 * d + k] = start[4 * d + k] = acc;
-      acc += hist[4 * d + k];
+    for (int k = 0; k < 16; k++) {
+      cursor[16 * d + k] = start[16 * d + k] = acc;
+      acc += hist[16 * d + k];
     }
   if (acc != nb) fail(PPD_ERR_CUDA, "branch histogram does not add up");
-  CUDA_OK(cudaMemcpyAsync(small + 320, cursor, 1024, cudaMemcpyHostToDevice, st));
+  CUDA_OK(cudaMemcpyAsync(small + 2048, cursor.data(), 4096, cudaMemcpyHostToDevice, st));
   uint32_t* order = D[B_ORDER].as<uint32_t>();
-  launch_branch_scatter(V.depth, nchild, nb, small + 320, order, st);
+  launch_branch_scatter(V.depth, nchild, nb, small + 2048, order, st);
   launch_hash_sorted_leaves(V, st);
   c->stats.kernel_launches += 5;
   uint32_t levels = 1;
   for (int d = 63; d >= 0; d--) {
-    uint32_t cnt = hist[4 * d] + hist[4 * d + 1] + hist[4 * d + 2] + hist[4 * d + 3];
+    uint32_t cnt = 0;
+    for (int k = 0; k < 16; k++) cnt += hist[16 * d + k];
     if (cnt) {
-      launch_hash_branch_level(V, order, start[4 * d], start[4 * d] + cnt, st);
+      launch_hash_branch_level(V, order, start[16 * d], start[16 * d] + cnt, st);
       c->stats.kernel_launches++;
       levels++;
     }
@@ -1639,7 +1641,7 @@ void trie_root_sorted_dev(ppd_ctx* c, const uint8_t* d_keys, const uint64_t* d_v
   c->stats.node_bytes += cnt[2];
   c->stats.arena_nodes += (uint64_t)n + nb;
   c->stats.levels += levels;
-  c->stats.d2h_bytes += 64 + 1024 + 8;
+  c->stats.d2h_bytes += 64 + 4096 + 8;
 }
 
 }  // namespace
