@@ -12,7 +12,7 @@
 namespace ppd {
 
 enum NodeKind : uint32_t {
-  NK_HASH = 0,          // a0 = index into hash_pool                       (Node::Hash)
+  NK_HASH = 0,          // never stored: a hashed-out subtree is the id HASH_ID_BASE + index into hash_pool (Node::Hash)
   NK_LEAF = 1,          // a0 = key byte offset, a1 = value offset, a2 = value length   (Node::Leaf)
   NK_LEAF_ACCOUNT = 2,  // a0 = key byte offset, a1 = account record index (Node::Leaf holding rlp(AccountRlp))
   NK_EXT = 3,           // a0 = key byte offset, a1 = child node           (Node::Extension)

@@ -28,28 +28,94 @@ struct Fail {
 [[noreturn]] inline void fail(int code, const char* msg) { throw Fail{code, msg}; }
 
 static const uint32_t UNCHANGED = 0xfffffffeu;
+// Hashed-out subtrees (Node::Hash) are not arena nodes: their id is HASH_ID_BASE + index into hash_pool,
+// their ref IS the pool entry, and nothing has to be computed for them.
+static const uint32_t HASH_ID_BASE = 0x80000000u, HASH_ID_END = 0xf0000000u;
+static inline bool is_hash_id(uint32_t n) { return n >= HASH_ID_BASE && n < HASH_ID_END; }
+
+// Growable array of trivially copyable elements whose storage survives clear() and may come from a
+// caller-supplied allocator (page-locked host memory for everything that is copied to or from the
+// device: the context keeps these buffers across calls, so steady state allocates nothing and the
+// copies run at full PCIe rate).  resize() does not initialise new elements.
+typedef void* (*PvecAlloc)(size_t);
+typedef void (*PvecFree)(void*);
+template <class T>
+struct PVec {
+  T* d = nullptr;
+  size_t n = 0, cap = 0;
+  PvecAlloc alloc_fn = nullptr;
+  PvecFree free_fn = nullptr;
+  PVec() {}
+  PVec(const PVec&) = delete;
+  PVec& operator=(const PVec&) = delete;
+  ~PVec() { release(); }
+  void release() {
+    if (d) (free_fn ? free_fn : ::free)(d);
+    d = nullptr, n = cap = 0;
+  }
+  void reserve(size_t want) {
+    if (want <= cap) return;
+    size_t nc = cap ? cap * 2 : 1024;
+    if (nc < want) nc = want;
+    T* nd = (T*)(alloc_fn ? alloc_fn : ::malloc)(nc * sizeof(T));
+    if (!nd) fail(PPD_ERR_BAD_ARGUMENT, "out of host memory");
+    if (n) memcpy(nd, d, n * sizeof(T));
+    if (d) (free_fn ? free_fn : ::free)(d);
+    d = nd, cap = nc;
+  }
+  size_t size() const { return n; }
+  bool empty() const { return n == 0; }
+  T* data() { return d; }
+  const T* data() const { return d; }
+  T& operator[](size_t i) { return d[i]; }
+  const T& operator[](size_t i) const { return d[i]; }
+  T& back() { return d[n - 1]; }
+  void clear() { n = 0; }
+  void resize(size_t m) {
+    reserve(m);
+    n = m;
+  }
+  void push_back(const T& v) {
+    if (n == cap) reserve(n + 1);
+    d[n++] = v;
+  }
+  void append(const T* p, size_t k) {
+    reserve(n + k);
+    memcpy(d + n, p, k * sizeof(T));
+    n += k;
+  }
+};
 
 struct HostArena {
-  std::vector<NodeRec> nodes;
-  std::vector<uint16_t> level;
-  std::vector<uint8_t> key_pool, val_pool, hash_pool;
-  std::vector<uint32_t> child_pool;
-  std::vector<AccountRec> accounts;
+  PVec<NodeRec> nodes;
+  PVec<uint16_t> level;
+  PVec<uint8_t> key_pool, val_pool, hash_pool;
+  PVec<uint32_t> child_pool;
+  PVec<AccountRec> accounts;
+  PVec<uint32_t> hash_rep;  // per hash_pool entry: a key that runs through the hashed-out node
+  void set_allocator(PvecAlloc a, PvecFree f) {
+    nodes.alloc_fn = key_pool.alloc_fn = val_pool.alloc_fn = hash_pool.alloc_fn = a;
+    nodes.free_fn = key_pool.free_fn = val_pool.free_fn = hash_pool.free_fn = f;
+    child_pool.alloc_fn = a, child_pool.free_fn = f;
+    accounts.alloc_fn = a, accounts.free_fn = f;
+  }
 
   void clear() {
     nodes.clear(), level.clear(), key_pool.clear(), val_pool.clear(), hash_pool.clear(), child_pool.clear(), accounts.clear();
+    hash_rep.clear();
   }
 
   // ---- pools -------------------------------------------------------------------------------
   uint32_t add_key_nibbles(const uint8_t* nib, uint32_t n) {
     uint32_t off = (uint32_t)key_pool.size();
-    key_pool.resize(off + (n + 1) / 2 + 1, 0);  // one slack byte: the device reads key[(j>>1)+1] when j is odd
+    key_pool.resize(off + (n + 1) / 2 + 1);  // one slack byte
+    memset(key_pool.data() + off, 0, (n + 1) / 2 + 1);
     for (uint32_t i = 0; i < n; i++) key_pool[off + (i >> 1)] |= (i & 1) ? nib[i] : (uint8_t)(nib[i] << 4);
     return off;
   }
   uint32_t add_key_bytes(const uint8_t* bytes, uint32_t nbytes) {
     uint32_t off = (uint32_t)key_pool.size();
-    key_pool.insert(key_pool.end(), bytes, bytes + nbytes);
+    key_pool.append(bytes, nbytes);
     key_pool.push_back(0);
     return off;
   }
@@ -61,7 +127,7 @@ struct HostArena {
   }
   uint32_t add_hash(const uint8_t* h) {
     uint32_t idx = (uint32_t)(hash_pool.size() / 32);
-    hash_pool.insert(hash_pool.end(), h, h + 32);
+    hash_pool.append(h, 32);
     return idx;
   }
   uint32_t key_nib(uint32_t koff, uint32_t i) const {
@@ -70,28 +136,38 @@ struct HostArena {
   }
 
   // ---- node accessors ----------------------------------------------------------------------
-  uint32_t kind(uint32_t n) const { return nodes[n].w0 & 0xff; }
+  uint32_t kind(uint32_t n) const { return is_hash_id(n) ? (uint32_t)NK_HASH : nodes[n].w0 & 0xff; }
   uint32_t nstart(uint32_t n) const { return (nodes[n].w0 >> 8) & 0xff; }
   uint32_t nlen(uint32_t n) const { return (nodes[n].w0 >> 16) & 0xff; }
   bool is_leaf(uint32_t n) const { return kind(n) == NK_LEAF || kind(n) == NK_LEAF_ACCOUNT; }
   bool is_opaque(uint32_t n) const { return kind(n) == NK_HASH || kind(n) == NK_ROOT; }  // Node::Hash
   // a key that runs through this node (for the nibbles leading to it)
-  uint32_t rep_key(uint32_t n) const { return (kind(n) == NK_BRANCH || kind(n) == NK_HASH) ? nodes[n].a2 : nodes[n].a0; }
+  uint32_t rep_key(uint32_t n) const {
+    if (is_hash_id(n)) return hash_rep[n - HASH_ID_BASE];
+    return kind(n) == NK_BRANCH ? nodes[n].a2 : nodes[n].a0;
+  }
+  const uint8_t* hash_of(uint32_t n) const { return hash_pool.data() + 32ull * (n - HASH_ID_BASE); }
   uint32_t child_at(uint32_t br, uint32_t nib) const {
     uint32_t mask = nodes[br].a1, bit = 1u << nib;
     if (!(mask & bit)) return NODE_EMPTY;
     return child_pool[nodes[br].a0 + __builtin_popcount(mask & (bit - 1))];
   }
-  uint16_t lvl(uint32_t n) const { return n == NODE_EMPTY ? 0 : level[n]; }
+  uint16_t lvl(uint32_t n) const { return (n == NODE_EMPTY || is_hash_id(n)) ? 0 : level[n]; }
 
   // ---- constructors ------------------------------------------------------------------------
   uint32_t push(const NodeRec& r, uint32_t lv) {
     if (lv > 0xffff) fail(PPD_ERR_BAD_ARGUMENT, "trie deeper than 65535 levels");
+    if (nodes.size() >= HASH_ID_BASE - 1) fail(PPD_ERR_BAD_ARGUMENT, "arena holds at most 2^31 nodes");
     nodes.push_back(r);
     level.push_back((uint16_t)lv);
     return (uint32_t)nodes.size() - 1;
   }
-  uint32_t new_hash(uint32_t hash_idx, uint32_t rep_koff) { return push({node_w0(NK_HASH, 0, 0), hash_idx, 0, rep_koff}, 0); }
+  uint32_t new_hash(uint32_t hash_idx, uint32_t rep_koff) {
+    if (hash_idx >= HASH_ID_END - HASH_ID_BASE) fail(PPD_ERR_BAD_ARGUMENT, "too many hashed-out nodes");
+    if (hash_rep.size() <= hash_idx) hash_rep.resize(hash_idx + 1);
+    hash_rep[hash_idx] = rep_koff;
+    return HASH_ID_BASE + hash_idx;
+  }
   uint32_t new_leaf(uint32_t koff, uint32_t start, uint32_t len, uint32_t val_off, uint32_t val_len) {
     return push({node_w0(NK_LEAF, start, len), koff, val_off, val_len}, 0);
   }
@@ -115,7 +191,7 @@ struct HostArena {
     uint32_t k = (uint32_t)__builtin_popcount(mask);
     for (uint32_t i = 0; i < k; i++) {
       child_pool.push_back(kids[i]);
-      if (level[kids[i]] > lv) lv = level[kids[i]];
+      if (lvl(kids[i]) > lv) lv = lvl(kids[i]);
     }
     return push({node_w0(NK_BRANCH, 0, 0), base, mask, rep_koff}, lv + 1u);
   }

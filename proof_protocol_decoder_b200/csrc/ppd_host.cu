@@ -16,7 +16,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
 #include <map>
+#include <mutex>
+#include <thread>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -25,6 +28,9 @@
 #include "arena.h"
 #include "host_arena.h"
 #include "ppd_kernels.h"
+#ifdef PPD_HOSTPROF
+#include "hostprof_stub.h"  // development-only host profiler build (tools/hostprof); never defined for libppd_b200.so
+#endif
 
 using namespace ppd;
 
@@ -81,8 +87,24 @@ const uint8_t EMPTY_TRIE_HASH[32] = {0x56, 0xe8, 0x1f, 0x17, 0x1b, 0xcc, 0x55, 0
 
 }  // namespace
 
+namespace {
+struct Job;
+void job_delete(Job*);
+#ifdef PPD_HOSTPROF
+void* pinned_alloc(size_t n) { return malloc(n); }
+void pinned_free(void* p) { free(p); }
+#else
+void* pinned_alloc(size_t n) {
+  void* p = nullptr;
+  return cudaHostAlloc(&p, n, cudaHostAllocDefault) == cudaSuccess ? p : nullptr;
+}
+void pinned_free(void* p) { cudaFreeHost(p); }
+#endif
+}  // namespace
+
 struct ppd_ctx {
   int device = 0;
+  Job* job = nullptr;  // host-side scratch of the block pipeline (page-locked pools), kept across calls
   cudaStream_t st = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   std::string err;
@@ -106,25 +128,40 @@ void stats_reset(ppd_ctx* c) { c->stats = ppd_stats{}; }
 // Phase I: batched Keccak-256 of byte strings (addresses, slots, code)
 // ============================================================================================
 struct KeyHasher {
-  std::vector<uint8_t> data;
+  PVec<uint8_t> data;
   std::vector<uint64_t> off{0};
-  std::vector<H256> digest;
+  PVec<H256> digest;
+  std::vector<uint64_t> lens;
+  PVec<uint64_t> se;  // (begin, end) pairs
+  KeyHasher() {
+    data.alloc_fn = pinned_alloc, data.free_fn = pinned_free;
+    digest.alloc_fn = pinned_alloc, digest.free_fn = pinned_free;
+    se.alloc_fn = pinned_alloc, se.free_fn = pinned_free;
+  }
+  void reset() {
+    data.clear(), digest.clear(), lens.clear(), se.clear();
+    off.assign(1, 0);
+  }
   uint32_t add(const uint8_t* p, size_t n) {
-    data.insert(data.end(), p, p + n);
-    // keep every message 4-byte aligned so the kernel's word loads start aligned
-    while (data.size() & 3) data.push_back(0);
+    size_t at = data.size(), padded = (n + 3) & ~(size_t)3;
+    data.resize(at + padded);  // every message starts 4-byte aligned
+    memcpy(data.data() + at, p, n);
+    memset(data.data() + at + n, 0, padded - n);
     uint32_t idx = (uint32_t)lens.size();
     lens.push_back(n);
     off.push_back(data.size());
     return idx;
   }
-  std::vector<uint64_t> lens;
   void run(ppd_ctx* c) {
     size_t n = lens.size();
     digest.resize(n);
     if (!n) return;
+#ifdef PPD_HOSTPROF
+    for (size_t i = 0; i < n; i++) hostprof::keccak256(data.data() + off[i], lens[i], digest[i].b);
+    return;
+#endif
     // messages are padded to 4-byte boundaries, so pass explicit (begin, end) pairs
-    std::vector<uint64_t> se(2 * n);
+    se.resize(2 * n);
     for (size_t i = 0; i < n; i++) se[2 * i] = off[i], se[2 * i + 1] = off[i] + lens[i];
     c->d_msg.reserve(data.size() + 16);
     c->d_msg_off.reserve(se.size() * 8);
@@ -150,18 +187,16 @@ struct Span {
   const uint8_t* p = nullptr;
   uint32_t n = 0;
 };
-struct WInstr {
-  uint8_t op;
-  bool has_code = false, has_storage = false;
-  uint32_t mask = 0;
-  Span key;           // compact key bytes (leaf / extension / account leaf)
-  Span value;         // leaf value / code bytes
-  const uint8_t* hash = nullptr;
-  uint64_t nonce = 0;
-  Span balance;       // big-endian, <= 32 bytes
+// One instruction of the witness, 20 bytes.  Operands are not copied: `pos` points at the first operand
+// byte and the (already validated) CBOR heads are re-read when the instruction is used.
+struct WNode {
+  uint32_t pos;
+  uint8_t op, flags;     // flags: the account leaf's flag byte (bit0 code, bit1 storage, bit2 nonce, bit3 balance)
+  uint16_t unused = 0;
   // tree links filled by the stack machine
-  int32_t first_child = -1, next_sibling = -1;  // branch children (ascending nibble order) / extension child
-  int32_t storage_node = -1, code_node = -1;    // account leaf
+  int32_t first_child;   // branch: first child (ascending nibble order); extension: child; account leaf: storage node
+  int32_t next_sibling;  // next child of the same branch
+  uint32_t aux;          // branch: the 32-bit mask; account leaf: code node (or ~0)
 };
 
 struct WCursor {
@@ -224,49 +259,76 @@ uint32_t compact_key_nibbles(Span k, uint8_t* out) {
 }
 
 struct Witness {
+  const uint8_t* bytes = nullptr;
+  size_t len = 0;
   uint8_t version = 0;
-  std::vector<WInstr> ins;
+  std::vector<WNode> ins;
   int32_t root = -1;  // -1: header only
+
+  // operand views (the stream was validated by parse_witness)
+  Span key(const WNode& x) const {
+    WCursor c{bytes, len, x.pos};
+    return c.cbor_bytes(PPD_ERR_INVALID_BYTE_VECTOR);
+  }
+  Span leaf_value(const WNode& x) const {
+    WCursor c{bytes, len, x.pos};
+    c.cbor_bytes(PPD_ERR_INVALID_BYTE_VECTOR);
+    return c.cbor_bytes(PPD_ERR_INVALID_BYTE_VECTOR);
+  }
+  Span code(const WNode& x) const { return key(x); }
+  const uint8_t* hash(const WNode& x) const { return bytes + x.pos; }
+  void account(const WNode& x, Span& key_out, uint64_t& nonce, Span& balance) const {
+    WCursor c{bytes, len, x.pos};
+    key_out = c.cbor_bytes(PPD_ERR_INVALID_BYTE_VECTOR);
+    c.pos++;  // flags
+    nonce = (x.flags & 4) ? c.cbor_uint(~0ull) : 0;
+    balance = (x.flags & 8) ? c.cbor_bytes(PPD_ERR_INVALID_BYTE_VECTOR) : Span{};
+  }
 };
 
 void parse_witness(const uint8_t* w, size_t n, Witness& out) {
   if (n == 0) fail(PPD_ERR_MISSING_HEADER, "missing header");
+  if (n >= 0xffffffffull) fail(PPD_ERR_BAD_ARGUMENT, "witness larger than 4 GiB");
   WCursor c{w, n};
+  out.bytes = w, out.len = n;
   out.version = c.read_byte();
-  std::vector<int32_t> stack;
+  out.ins.clear();
+  out.ins.reserve(n / 30 + 16);
+  // pass 1: instruction boundaries (compact_prestate_processing.rs:683-875)
   while (c.pos < c.n) {
-    WInstr in;
+    WNode in;
     in.op = c.read_byte();
+    in.pos = (uint32_t)c.pos;
+    in.flags = 0;
+    in.first_child = in.next_sibling = -1;
+    in.aux = ~0u;
     switch (in.op) {
       case PPD_OP_LEAF:
-        in.key = c.cbor_bytes(PPD_ERR_INVALID_BYTE_VECTOR);
-        in.value = c.cbor_bytes(PPD_ERR_INVALID_BYTE_VECTOR);
+        c.cbor_bytes(PPD_ERR_INVALID_BYTE_VECTOR);
+        c.cbor_bytes(PPD_ERR_INVALID_BYTE_VECTOR);
         break;
       case PPD_OP_EXTENSION:
-        in.key = c.cbor_bytes(PPD_ERR_INVALID_BYTE_VECTOR);
+        c.cbor_bytes(PPD_ERR_INVALID_BYTE_VECTOR);
         break;
       case PPD_OP_BRANCH:
-        in.mask = (uint32_t)c.cbor_uint(0xffffffffull);
+        in.aux = (uint32_t)c.cbor_uint(0xffffffffull);
         break;
       case PPD_OP_HASH:
         if (c.n - c.pos < 32) fail(PPD_ERR_INVALID_BYTES_FOR_TYPE, "short raw hash");
-        in.hash = c.p + c.pos;
         c.pos += 32;
         break;
       case PPD_OP_CODE:
-        in.value = c.cbor_bytes(PPD_ERR_INVALID_BYTES_FOR_TYPE);
+        c.cbor_bytes(PPD_ERR_INVALID_BYTES_FOR_TYPE);
         break;
       case PPD_OP_ACCOUNT_LEAF: {
-        in.key = c.cbor_bytes(PPD_ERR_INVALID_BYTE_VECTOR);
-        uint8_t flags = c.read_byte();
-        in.has_code = flags & 1;
-        in.has_storage = flags & 2;
-        if (flags & 4) in.nonce = c.cbor_uint(~0ull);
-        if (flags & 8) {
-          in.balance = c.cbor_bytes(PPD_ERR_INVALID_BYTE_VECTOR);
-          if (in.balance.n > 32) fail(PPD_ERR_INVALID_BYTE_VECTOR, "balance wider than 256 bits");
+        c.cbor_bytes(PPD_ERR_INVALID_BYTE_VECTOR);
+        in.flags = c.read_byte();
+        if (in.flags & 4) c.cbor_uint(~0ull);
+        if (in.flags & 8) {
+          Span bal = c.cbor_bytes(PPD_ERR_INVALID_BYTE_VECTOR);
+          if (bal.n > 32) fail(PPD_ERR_INVALID_BYTE_VECTOR, "balance wider than 256 bits");
         }
-        if (flags & 1) (void)c.cbor_uint(~0ull);
+        if (in.flags & 1) (void)c.cbor_uint(~0ull);
         break;
       }
       case PPD_OP_EMPTY_ROOT:
@@ -276,9 +338,12 @@ void parse_witness(const uint8_t* w, size_t n, Witness& out) {
     }
     out.ins.push_back(in);
   }
-  // stack machine: instructions arrive in post-order
+  // pass 2: the stack machine (compact_prestate_processing.rs:387-668): instructions arrive in post-order
+  std::vector<int32_t> stack;
+  stack.reserve(256);
+  WNode* ins = out.ins.data();
   for (int32_t i = 0; i < (int32_t)out.ins.size(); i++) {
-    WInstr& in = out.ins[i];
+    WNode& in = ins[i];
     switch (in.op) {
       case PPD_OP_EXTENSION:
         if (stack.empty()) fail(PPD_ERR_INVALID_WITNESS_FORMAT, "extension with no preceding node");
@@ -286,30 +351,30 @@ void parse_witness(const uint8_t* w, size_t n, Witness& out) {
         stack.pop_back();
         break;
       case PPD_OP_BRANCH: {
-        size_t expected = (size_t)__builtin_popcount(in.mask);
+        size_t expected = (size_t)__builtin_popcount(in.aux);
         if (stack.size() < expected) fail(PPD_ERR_INCORRECT_NUMBER_OF_NODES_PRECEDING_BRANCH, "branch mask wants more nodes than precede it");
-        if (in.mask >> 16) fail(PPD_ERR_MISSING_EXPECTED_NODES_PRECEDING_BRANCH, "branch mask has bits above 15");
+        if (in.aux >> 16) fail(PPD_ERR_MISSING_EXPECTED_NODES_PRECEDING_BRANCH, "branch mask has bits above 15");
         size_t base = stack.size() - expected;
         for (size_t k = 0; k < expected; k++) {  // lowest set bit <-> oldest pushed
           if (k == 0)
             in.first_child = stack[base];
           else
-            out.ins[stack[base + k - 1]].next_sibling = stack[base + k];
+            ins[stack[base + k - 1]].next_sibling = stack[base + k];
         }
-        if (expected) out.ins[stack[base + expected - 1]].next_sibling = -1;
+        if (expected) ins[stack[base + expected - 1]].next_sibling = -1;
         stack.resize(base);
         break;
       }
       case PPD_OP_ACCOUNT_LEAF:
-        if (in.has_storage) {
-          if (stack.empty() || out.ins[stack.back()].op == PPD_OP_CODE) fail(PPD_ERR_INVALID_WITNESS_FORMAT, "account leaf: no storage node");
-          in.storage_node = stack.back();
+        if (in.flags & 2) {
+          if (stack.empty() || ins[stack.back()].op == PPD_OP_CODE) fail(PPD_ERR_INVALID_WITNESS_FORMAT, "account leaf: no storage node");
+          in.first_child = stack.back();
           stack.pop_back();
         }
-        if (in.has_code) {
-          if (stack.empty() || (out.ins[stack.back()].op != PPD_OP_CODE && out.ins[stack.back()].op != PPD_OP_HASH))
+        if (in.flags & 1) {
+          if (stack.empty() || (ins[stack.back()].op != PPD_OP_CODE && ins[stack.back()].op != PPD_OP_HASH))
             fail(PPD_ERR_INVALID_WITNESS_FORMAT, "account leaf: no code node");
-          in.code_node = stack.back();
+          in.aux = (uint32_t)stack.back();
           stack.pop_back();
         }
         break;
@@ -455,6 +520,9 @@ struct BlockJob {
   std::vector<PreAccount> pre_accounts;
   std::unordered_map<H256, uint32_t, H256Hasher> pre_with_storage;  // accounts whose storage root != EMPTY_TRIE_HASH -> record
   std::unordered_map<uint32_t, uint32_t> root_of;                   // trie root node -> its NK_ROOT node
+  std::unordered_map<int32_t, uint32_t> storage_root_of_instr;      // account leaf instruction -> root of its witnessed storage trie
+  bool have_empty_form = false;                                     // a witnessed storage trie whose root is EMPTY_TRIE_HASH
+  uint32_t empty_form = NODE_EMPTY;
   std::vector<IrPlan> irs;
   int status = PPD_OK;
   std::string err;
@@ -620,18 +688,48 @@ struct Job {
   HostArena A;
   KeyHasher kh;
   std::vector<BlockJob> blocks;
-  std::vector<uint8_t> ref, ref_len;  // after the sweep
+  PVec<uint8_t> ref, ref_len;  // after the sweep
+  PVec<uint32_t> order;
   std::vector<uint32_t> stamp;
   uint32_t serial = 0;
+  Job() {
+    A.set_allocator(pinned_alloc, pinned_free);
+    ref.alloc_fn = ref_len.alloc_fn = pinned_alloc, ref.free_fn = ref_len.free_fn = pinned_free;
+    order.alloc_fn = pinned_alloc, order.free_fn = pinned_free;
+  }
+  void reset(size_t n_blocks) {
+    A.clear();
+    kh.reset();
+    blocks.clear();
+    blocks.resize(n_blocks);
+    ref.clear(), ref_len.clear(), order.clear();
+    serial = 0;
+  }
 };
+void job_delete(Job* j) { delete j; }
+Job& job_of(ppd_ctx* c, size_t n_blocks) {
+  if (!c->job) c->job = new Job();
+  c->job->reset(n_blocks);
+  return *c->job;
+}
 
 // ---- step 1: parse, collect every byte string that must be hashed ----------------------------
+void collect_witness_messages(Job& J, BlockJob& b) {
+  b.m_inline_code.clear();
+  const std::vector<WNode>& ins = b.wit.ins;
+  bool any = false;
+  for (size_t i = 0; i < ins.size(); i++)
+    if (ins[i].op == PPD_OP_CODE) {
+      if (!any) b.m_inline_code.assign(ins.size(), ~0u), any = true;
+      Span code = b.wit.code(ins[i]);
+      b.m_inline_code[i] = J.kh.add(code.p, code.n);
+    }
+}
+
 void collect_messages(Job& J, BlockJob& b) {
   parse_witness(b.compact.p, b.compact.n, b.wit);
   if (b.wit.version != 1) fail(PPD_PANIC_INCOMPATIBLE_HEADER_VERSION, "compact header version is not 1");
-  b.m_inline_code.assign(b.wit.ins.size(), ~0u);
-  for (size_t i = 0; i < b.wit.ins.size(); i++)
-    if (b.wit.ins[i].op == PPD_OP_CODE) b.m_inline_code[i] = J.kh.add(b.wit.ins[i].value.p, b.wit.ins[i].value.n);
+  collect_witness_messages(J, b);
   for (TxnV& tx : b.txns)
     for (TraceV& tr : tx.traces) {
       tr.m_addr = J.kh.add(tr.addr, 20);
@@ -653,62 +751,200 @@ void collect_messages(Job& J, BlockJob& b) {
 }
 
 // ---- step 2: pre-image tries -------------------------------------------------------------------
-struct TreeWalker {
+// The reference turns the witness tree into a trie by re-inserting every leaf and hashed-out subtree
+// with its full key (compact_to_partial_trie.rs:49-139), so the result is the canonical trie of those
+// items whatever shape the witness had.  WitnessTrie does the same in two ways:
+//   * convert(): one DFS that maps witness nodes to arena nodes directly.  That is only the canonical
+//     trie when every branch keeps at least two non-empty children and every extension has a non-empty
+//     key over a branch or a hashed-out node; the DFS checks exactly that (`canonical`).
+//   * items + build_range(): the general path, used for a trie whose witness is not canonical.
+struct WitnessTrie {
   Job& J;
   BlockJob& b;
-  std::vector<TrieItem>* items;
-  uint8_t path[160];
+  bool is_storage;
+  bool canonical = true;
+  bool wrong_leaf_kind = false;  // a value leaf in the state trie / an account leaf in a storage trie
+  uint8_t path[160];    // nibbles
+  uint8_t packed[84];   // the same path packed two nibbles per byte, maintained incrementally
+  std::vector<TrieItem>* items = nullptr;
+  // resolves an account leaf instruction to its record (state trie only)
+  uint32_t (*account_record)(Job&, BlockJob&, int32_t idx, const uint8_t* path, uint32_t klen) = nullptr;
 
-  // compact_to_partial_trie.rs:49-139: DFS with an accumulated key
-  void walk(int32_t idx, uint32_t depth) {
-    const WInstr& in = b.wit.ins[idx];
+  void set_nibble(uint32_t d, uint32_t nib) {
+    path[d] = (uint8_t)nib;
+    packed[d >> 1] = (d & 1) ? (uint8_t)((packed[d >> 1] & 0xf0) | nib) : (uint8_t)(nib << 4);
+  }
+  uint32_t push_key_nibbles(Span k, uint32_t depth) {  // key_bytes_to_nibbles appended at `depth`; returns the new depth
+    uint8_t tmp[72];
+    uint32_t n = compact_key_nibbles(k, tmp);
+    if (depth + n > 64) fail(PPD_ERR_KEY_ERROR, "key longer than 64 nibbles");
+    for (uint32_t i = 0; i < n; i++) set_nibble(depth + i, tmp[i]);
+    return depth + n;
+  }
+  uint32_t add_packed_key(uint32_t n) {  // the current path of n nibbles as a key in the pool
+    HostArena& A = J.A;
+    uint32_t off = (uint32_t)A.key_pool.size(), nb = (n + 1) / 2;
+    A.key_pool.resize(off + nb + 1);  // one slack byte (the device may read key[(j >> 1) + 1])
+    uint8_t* d = A.key_pool.data() + off;
+    memcpy(d, packed, nb);
+    if (n & 1) d[nb - 1] &= 0xf0;
+    d[nb] = 0;
+    return off;
+  }
+  uint32_t add_leaf_value(Span v) {  // rlp_str(value), compact_to_partial_trie.rs:119
+    HostArena& A = J.A;
+    uint8_t hdr[9];
+    uint32_t hl = 0;
+    if (!(v.n == 1 && v.p[0] < 0x80)) {
+      if (v.n < 56) {
+        hdr[hl++] = (uint8_t)(0x80 + v.n);
+      } else {
+        uint8_t tmp[8];
+        int k = 0;
+        for (size_t x = v.n; x; x >>= 8) tmp[k++] = (uint8_t)x;
+        hdr[hl++] = (uint8_t)(0xb7 + k);
+        while (k) hdr[hl++] = tmp[--k];
+      }
+    }
+    uint32_t off = (uint32_t)((A.val_pool.size() + 3) & ~(size_t)3);
+    A.val_pool.resize(off + hl + v.n);
+    memcpy(A.val_pool.data() + off, hdr, hl);
+    if (v.n) memcpy(A.val_pool.data() + off + hl, v.p, v.n);
+    last_val_len = hl + v.n;
+    return off;
+  }
+  uint32_t last_val_len = 0;
+
+  // ---- the direct conversion ----
+  uint32_t convert(int32_t idx, uint32_t depth) {
+    HostArena& A = J.A;
+    const WNode& in = b.wit.ins[idx];
     switch (in.op) {
       case PPD_OP_BRANCH: {
-        uint32_t m = in.mask;
+        uint32_t m = in.aux, kids[16], mask = 0, k = 0, rep = 0;
         for (int32_t c = in.first_child; c >= 0; c = b.wit.ins[c].next_sibling) {
           uint32_t nib = (uint32_t)__builtin_ctz(m);
           m &= m - 1;
           if (depth >= 64) fail(PPD_ERR_KEY_ERROR, "key longer than 64 nibbles");
-          path[depth] = (uint8_t)nib;
+          set_nibble(depth, nib);
+          uint32_t r = convert(c, depth + 1);
+          if (r != NODE_EMPTY) {
+            if (k == 0) rep = A.rep_key(r);
+            kids[k++] = r, mask |= 1u << nib;
+          }
+        }
+        if (k == 0) return NODE_EMPTY;
+        if (k < 2) canonical = false;
+        return A.new_branch(mask, kids, rep);
+      }
+      case PPD_OP_CODE: {
+        if (!is_storage) {  // code found inside a storage subtree is dropped by the reference
+          H256 h = J.kh.digest[b.m_inline_code[idx]];
+          b.pre_code[h] = b.wit.code(in);
+        }
+        return NODE_EMPTY;
+      }
+      case PPD_OP_EMPTY_ROOT:
+        return NODE_EMPTY;
+      case PPD_OP_HASH: {
+        uint32_t koff = add_packed_key(depth);
+        return A.new_hash(A.add_hash(b.wit.hash(in)), koff);
+      }
+      case PPD_OP_EXTENSION: {
+        uint32_t nd = push_key_nibbles(b.wit.key(in), depth);
+        uint32_t r = convert(in.first_child, nd);
+        if (r == NODE_EMPTY) return NODE_EMPTY;
+        uint32_t kd = A.kind(r);
+        if (nd == depth || !(kd == NK_BRANCH || kd == NK_HASH)) canonical = false;
+        return A.new_ext(A.rep_key(r), depth, nd - depth, r);
+      }
+      case PPD_OP_LEAF: {
+        uint32_t nd = push_key_nibbles(b.wit.key(in), depth);
+        uint32_t koff = add_packed_key(nd);
+        uint32_t voff = add_leaf_value(b.wit.leaf_value(in));
+        if (!is_storage) wrong_leaf_kind = true;  // reported after the walk, as the general path does
+        return A.new_leaf(koff, depth, nd - depth, voff, last_val_len);
+      }
+      case PPD_OP_ACCOUNT_LEAF: {
+        Span key, bal;
+        uint64_t nonce;
+        b.wit.account(in, key, nonce, bal);
+        uint32_t nd = push_key_nibbles(key, depth);
+        uint32_t koff = add_packed_key(nd);
+        if (is_storage) {
+          wrong_leaf_kind = true;
+          return A.new_leaf(koff, depth, nd - depth, 0, 0);
+        }
+        uint32_t rec = account_record(J, b, idx, path, nd);
+        return A.new_account_leaf(koff, depth, nd - depth, rec);
+      }
+    }
+    fail(PPD_ERR_INVALID_OPERATOR, "invalid opcode");
+  }
+
+  // ---- the general path: compact_to_partial_trie.rs:49-139 as a DFS with an accumulated key ----
+  void walk(int32_t idx, uint32_t depth) {
+    const WNode& in = b.wit.ins[idx];
+    switch (in.op) {
+      case PPD_OP_BRANCH: {
+        uint32_t m = in.aux;
+        for (int32_t c = in.first_child; c >= 0; c = b.wit.ins[c].next_sibling) {
+          uint32_t nib = (uint32_t)__builtin_ctz(m);
+          m &= m - 1;
+          if (depth >= 64) fail(PPD_ERR_KEY_ERROR, "key longer than 64 nibbles");
+          set_nibble(depth, nib);
           walk(c, depth + 1);
         }
         return;
       }
       case PPD_OP_CODE: {
-        H256 h = J.kh.digest[b.m_inline_code[idx]];
-        b.pre_code[h] = in.value;
+        if (!is_storage) {
+          H256 h = J.kh.digest[b.m_inline_code[idx]];
+          b.pre_code[h] = b.wit.code(in);
+        }
         return;
       }
       case PPD_OP_EMPTY_ROOT:
         return;
       case PPD_OP_HASH: {
-        uint32_t koff = J.A.add_key_nibbles(path, depth);
-        items->push_back({koff, depth, 2, J.A.add_hash(in.hash), 0});
+        uint32_t koff = add_packed_key(depth);
+        items->push_back({koff, depth, 2, J.A.add_hash(b.wit.hash(in)), 0});
         return;
       }
       case PPD_OP_EXTENSION: {
-        uint32_t n = compact_key_nibbles(in.key, path + depth);
-        if (depth + n > 64) fail(PPD_ERR_KEY_ERROR, "key longer than 64 nibbles");
-        walk(in.first_child, depth + n);
+        uint32_t nd = push_key_nibbles(b.wit.key(in), depth);
+        walk(in.first_child, nd);
         return;
       }
       case PPD_OP_LEAF: {
-        uint32_t n = compact_key_nibbles(in.key, path + depth);
-        if (depth + n > 64) fail(PPD_ERR_KEY_ERROR, "key longer than 64 nibbles");
-        uint32_t koff = J.A.add_key_nibbles(path, depth + n);
-        std::vector<uint8_t> v;
-        rlp_str(v, in.value.p, in.value.n);
-        items->push_back({koff, depth + n, 0, J.A.add_val(v.data(), (uint32_t)v.size()), (uint32_t)v.size()});
+        uint32_t nd = push_key_nibbles(b.wit.key(in), depth);
+        uint32_t koff = add_packed_key(nd);
+        uint32_t voff = add_leaf_value(b.wit.leaf_value(in));
+        items->push_back({koff, nd, 0, voff, last_val_len});
         return;
       }
       case PPD_OP_ACCOUNT_LEAF: {
-        uint32_t n = compact_key_nibbles(in.key, path + depth);
-        if (depth + n > 64) fail(PPD_ERR_KEY_ERROR, "key longer than 64 nibbles");
-        uint32_t koff = J.A.add_key_nibbles(path, depth + n);
-        items->push_back({koff, depth + n, 1, (uint32_t)idx /* resolved to a record later */, 0});
+        Span key, bal;
+        uint64_t nonce;
+        b.wit.account(in, key, nonce, bal);
+        uint32_t nd = push_key_nibbles(key, depth);
+        uint32_t koff = add_packed_key(nd);
+        items->push_back({koff, nd, 1, (uint32_t)idx /* resolved to a record later */, 0});
         return;
       }
     }
+  }
+};
+
+struct ArenaMark {
+  size_t nodes, keys, vals, hashes, children, accounts;
+  static ArenaMark take(const HostArena& A) {
+    return {A.nodes.size(), A.key_pool.size(), A.val_pool.size(), A.hash_pool.size(), A.child_pool.size(), A.accounts.size()};
+  }
+  void rewind(HostArena& A) const {
+    A.nodes.resize(nodes), A.level.resize(nodes), A.key_pool.resize(keys), A.val_pool.resize(vals), A.hash_pool.resize(hashes);
+    A.child_pool.resize(children), A.accounts.resize(accounts);
+    if (A.hash_rep.size() > hashes / 32) A.hash_rep.resize(hashes / 32);
   }
 };
 
@@ -722,90 +958,123 @@ uint32_t root_node_for(Job& J, BlockJob& b, uint32_t trie_root) {
 
 bool trie_root_is_empty_hash(const Job& J, uint32_t root) {
   if (root == NODE_EMPTY) return true;
-  if (J.A.kind(root) == NK_HASH) return memcmp(J.A.hash_pool.data() + 32ull * J.A.nodes[root].a0, EMPTY_TRIE_HASH, 32) == 0;
+  if (is_hash_id(root)) return memcmp(J.A.hash_of(root), EMPTY_TRIE_HASH, 32) == 0;
   return false;
 }
 
-void build_pre_image(Job& J, BlockJob& b) {
+// The account record of an account leaf instruction and the block's per-account tables
+// (compact_to_partial_trie.rs:141-190).  `path` holds the klen nibbles of the leaf's full key.
+uint32_t make_account_record(Job& J, BlockJob& b, int32_t idx, const uint8_t* path, uint32_t klen) {
   HostArena& A = J.A;
+  const Witness& W = b.wit;
+  const WNode& in = W.ins[idx];
+  Span key, balance;
+  uint64_t nonce;
+  W.account(in, key, nonce, balance);
+  AccountRec rec;
+  memset(&rec, 0, sizeof rec);
+  for (int k = 0; k < 8; k++) rec.nonce[31 - k] = (uint8_t)(nonce >> (8 * k));
+  if (balance.n) memcpy(rec.balance + 32 - balance.n, balance.p, balance.n);
+  memcpy(rec.storage_root, EMPTY_TRIE_HASH, 32);
+  rec.storage_src = NODE_EMPTY;
+  uint32_t sroot = NODE_EMPTY;
+  bool has_trie = false, nonempty = false;
+  if (in.flags & 2) {
+    sroot = b.storage_root_of_instr[idx];
+    nonempty = !trie_root_is_empty_hash(J, sroot);
+    has_trie = true;
+    if (nonempty) rec.storage_src = root_node_for(J, b, sroot);
+  }
+  // the reference joins accounts to storage tries by ROOT HASH (compact_to_partial_trie.rs:167-190):
+  // every account whose root is EMPTY_TRIE_HASH gets the last witnessed empty-rooted trie, if any
+  if (!nonempty) {
+    has_trie = b.have_empty_form;
+    sroot = b.empty_form;
+  }
+  if (in.flags & 1) {
+    const WNode& c = W.ins[in.aux];
+    if (c.op == PPD_OP_CODE) {
+      H256 h = J.kh.digest[b.m_inline_code[in.aux]];
+      memcpy(rec.code_hash, h.b, 32);
+      b.pre_code[h] = W.code(c);
+    } else {
+      memcpy(rec.code_hash, W.hash(c), 32);
+    }
+  } else {
+    memcpy(rec.code_hash, EMPTY_CODE_HASH, 32);
+  }
+  uint32_t r = (uint32_t)A.accounts.size();
+  A.accounts.push_back(rec);
+  // hashed address = the leaf's full key, left-padded (utils.rs:49-59)
+  // (value-minimal bytes_be, then left-padded to 32 bytes == the nibbles right-aligned)
+  H256 haddr;
+  memset(haddr.b, 0, 32);
+  for (uint32_t k = 0; k < klen; k++) {
+    uint32_t posn = 64 - klen + k;
+    haddr.b[posn >> 1] |= (uint8_t)((posn & 1) ? path[k] : (path[k] << 4));
+  }
+  if (has_trie) b.storage[haddr] = sroot;
+  b.pre_accounts.push_back({haddr, r, nonempty});
+  if (nonempty) b.pre_with_storage[haddr] = r;
+  return r;
+}
+
+// one trie of the pre-image: the direct conversion, or the general path when the witness is not canonical
+uint32_t build_witness_trie(Job& J, BlockJob& b, int32_t root_idx, bool is_storage) {
+  HostArena& A = J.A;
+  {
+    ArenaMark mark = ArenaMark::take(A);
+    size_t n_pre_accounts = b.pre_accounts.size();
+    WitnessTrie wt{J, b, is_storage};
+    wt.account_record = make_account_record;
+    uint32_t root = wt.convert(root_idx, 0);
+    if (wt.wrong_leaf_kind) {
+      if (is_storage) fail(PPD_ERR_INVALID_WITNESS_FORMAT, "account leaf inside a storage trie");
+      fail(PPD_PANIC_PRE_IMAGE_ACCOUNT_DECODE, "state leaf is not an account");
+    }
+    if (wt.canonical) return root;
+    // not canonical: undo and rebuild from the items
+    mark.rewind(A);
+    for (size_t i = n_pre_accounts; i < b.pre_accounts.size(); i++) {
+      b.storage.erase(b.pre_accounts[i].haddr);
+      b.pre_with_storage.erase(b.pre_accounts[i].haddr);
+    }
+    b.pre_accounts.resize(n_pre_accounts);
+    for (auto it = b.root_of.begin(); it != b.root_of.end();)
+      it = (it->second >= mark.nodes || (is_hash_id(it->first) ? it->first - HASH_ID_BASE >= mark.hashes / 32 : (it->first != NODE_EMPTY && it->first >= mark.nodes)))
+               ? b.root_of.erase(it)
+               : std::next(it);
+  }
+  std::vector<TrieItem> items;
+  WitnessTrie wt{J, b, is_storage};
+  wt.items = &items;
+  wt.walk(root_idx, 0);
+  for (TrieItem& x : items) {
+    if (is_storage && x.kind == 1) fail(PPD_ERR_INVALID_WITNESS_FORMAT, "account leaf inside a storage trie");
+    if (!is_storage && x.kind == 0) fail(PPD_PANIC_PRE_IMAGE_ACCOUNT_DECODE, "state leaf is not an account");
+    if (x.kind != 1) continue;
+    uint8_t nib[64];
+    for (uint32_t k = 0; k < x.klen; k++) nib[k] = (uint8_t)A.key_nib(x.koff, k);
+    x.a1 = make_account_record(J, b, (int32_t)x.a1, nib, x.klen);
+  }
+  return build_range(A, items, 0, items.size(), 0);
+}
+
+void build_pre_image(Job& J, BlockJob& b) {
   const Witness& W = b.wit;
   if (W.root < 0) return;
   // storage tries, in stream order (compact_prestate_processing.rs:608-625)
-  std::unordered_map<int32_t, uint32_t> storage_root_of_instr;
-  bool have_empty_form = false;
-  uint32_t empty_form = NODE_EMPTY;
-  std::vector<TrieItem> items;
+  b.storage_root_of_instr.clear();
+  b.have_empty_form = false;
+  b.empty_form = NODE_EMPTY;
   for (int32_t i = 0; i < (int32_t)W.ins.size(); i++) {
-    const WInstr& in = W.ins[i];
-    if (in.op != PPD_OP_ACCOUNT_LEAF || !in.has_storage) continue;
-    items.clear();
-    TreeWalker tw{J, b, &items, {}};
-    std::map<H256, Span> saved = b.pre_code;  // code found inside a storage subtree is dropped by the reference
-    tw.walk(in.storage_node, 0);
-    b.pre_code = saved;
-    for (TrieItem& x : items)
-      if (x.kind == 1) fail(PPD_ERR_INVALID_WITNESS_FORMAT, "account leaf inside a storage trie");
-    uint32_t root = build_range(A, items, 0, items.size(), 0);
-    storage_root_of_instr[i] = root;
-    if (trie_root_is_empty_hash(J, root)) have_empty_form = true, empty_form = root;
+    const WNode& in = W.ins[i];
+    if (in.op != PPD_OP_ACCOUNT_LEAF || !(in.flags & 2)) continue;
+    uint32_t root = build_witness_trie(J, b, in.first_child, true);
+    b.storage_root_of_instr[i] = root;
+    if (trie_root_is_empty_hash(J, root)) b.have_empty_form = true, b.empty_form = root;
   }
-  // state trie
-  items.clear();
-  TreeWalker tw{J, b, &items, {}};
-  tw.walk(W.root, 0);
-  for (TrieItem& x : items) {
-    if (x.kind == 0) fail(PPD_PANIC_PRE_IMAGE_ACCOUNT_DECODE, "state leaf is not an account");
-    if (x.kind != 1) continue;
-    int32_t idx = (int32_t)x.a1;
-    const WInstr& in = W.ins[idx];
-    AccountRec rec;
-    memset(&rec, 0, sizeof rec);
-    for (int k = 0; k < 8; k++) rec.nonce[31 - k] = (uint8_t)(in.nonce >> (8 * k));
-    if (in.balance.n) memcpy(rec.balance + 32 - in.balance.n, in.balance.p, in.balance.n);
-    memcpy(rec.storage_root, EMPTY_TRIE_HASH, 32);
-    rec.storage_src = NODE_EMPTY;
-    uint32_t sroot = NODE_EMPTY;
-    bool has_trie = false, nonempty = false;
-    if (in.has_storage) {
-      sroot = storage_root_of_instr[idx];
-      nonempty = !trie_root_is_empty_hash(J, sroot);
-      has_trie = true;
-      if (nonempty) rec.storage_src = root_node_for(J, b, sroot);
-    }
-    // the reference joins accounts to storage tries by ROOT HASH (compact_to_partial_trie.rs:167-190):
-    // every account whose root is EMPTY_TRIE_HASH gets the last witnessed empty-rooted trie, if any
-    if (!nonempty) {
-      has_trie = have_empty_form;
-      sroot = empty_form;
-    }
-    if (in.has_code) {
-      const WInstr& c = W.ins[in.code_node];
-      if (c.op == PPD_OP_CODE) {
-        H256 h = J.kh.digest[b.m_inline_code[in.code_node]];
-        memcpy(rec.code_hash, h.b, 32);
-        b.pre_code[h] = c.value;
-      } else {
-        memcpy(rec.code_hash, c.hash, 32);
-      }
-    } else {
-      memcpy(rec.code_hash, EMPTY_CODE_HASH, 32);
-    }
-    uint32_t r = (uint32_t)A.accounts.size();
-    A.accounts.push_back(rec);
-    x.a1 = r;
-    // hashed address = the leaf's full key, left-padded (utils.rs:49-59)
-    // (value-minimal bytes_be, then left-padded to 32 bytes == the nibbles right-aligned)
-    H256 haddr;
-    memset(haddr.b, 0, 32);
-    for (uint32_t k = 0; k < x.klen; k++) {
-      uint32_t posn = 64 - x.klen + k;
-      haddr.b[posn >> 1] |= (uint8_t)((posn & 1) ? A.key_nib(x.koff, k) : (A.key_nib(x.koff, k) << 4));
-    }
-    if (has_trie) b.storage[haddr] = sroot;
-    b.pre_accounts.push_back({haddr, r, nonempty});
-    if (nonempty) b.pre_with_storage[haddr] = r;
-  }
-  b.state_root = build_range(A, items, 0, items.size(), 0);
+  b.state_root = build_witness_trie(J, b, W.root, false);
 }
 
 // ---- step 3: the txn loop (decoding.rs:80-177), shaping only ------------------------------------
@@ -1058,9 +1327,14 @@ void shape_block(Job& J, BlockJob& b) {
 void sweep(ppd_ctx* c, Job& J) {
   HostArena& A = J.A;
   uint32_t n = (uint32_t)A.nodes.size();
-  J.ref.assign(32ull * n, 0);
-  J.ref_len.assign(n, 0);
+  J.ref.resize(32ull * n);
+  J.ref_len.resize(n);
   if (!n) return;
+#ifdef PPD_HOSTPROF
+  memset(J.ref.data(), 0, 32ull * n);
+  memset(J.ref_len.data(), 32, n);
+  return;
+#endif
   // counting sort of node ids by (level, class): inside a level, nodes of one kind and one
   // permutation count are adjacent, so the lanes of a warp do the same work
   auto node_class = [&](uint32_t i) -> uint32_t {
@@ -1077,7 +1351,9 @@ void sweep(ppd_ctx* c, Job& J) {
   };
   uint32_t n_levels = 0;
   for (uint32_t i = 0; i < n; i++) n_levels = std::max<uint32_t>(n_levels, A.level[i] + 1u);
-  std::vector<uint32_t> level_start(n_levels + 1, 0), order(n);
+  std::vector<uint32_t> level_start(n_levels + 1, 0);
+  PVec<uint32_t>& order = J.order;
+  order.resize(n);
   {
     std::vector<uint8_t> cls(n);
     std::vector<uint32_t> bucket((size_t)n_levels * 64 + 1, 0);
@@ -1150,63 +1426,127 @@ void sweep(ppd_ctx* c, Job& J) {
 }
 
 // ---- step 5: IrDump ------------------------------------------------------------------------------
+// Growable byte buffer with unchecked-after-need() writes; give() hands the malloc'ed storage to the caller.
 struct Out {
-  std::vector<uint8_t> b;
-  void u8(uint8_t v) { b.push_back(v); }
+  uint8_t* p = nullptr;
+  size_t n = 0, cap = 0;
+  Out() {}
+  Out(const Out&) = delete;
+  Out& operator=(const Out&) = delete;
+  Out(Out&& o) noexcept : p(o.p), n(o.n), cap(o.cap) { o.p = nullptr, o.n = o.cap = 0; }
+  ~Out() { free(p); }
+  void need(size_t k) {
+    if (n + k <= cap) return;
+    size_t nc = cap ? cap * 2 : 4096;
+    while (nc < n + k) nc *= 2;
+    uint8_t* q = (uint8_t*)realloc(p, nc);
+    if (!q) fail(PPD_ERR_BAD_ARGUMENT, "out of host memory");
+    p = q, cap = nc;
+  }
+  void u8(uint8_t v) {
+    need(1);
+    p[n++] = v;
+  }
   void u32(uint32_t v) {
-    uint8_t t[4];
-    memcpy(t, &v, 4);
-    b.insert(b.end(), t, t + 4);
+    need(4);
+    memcpy(p + n, &v, 4);
+    n += 4;
   }
   void u64(uint64_t v) {
-    uint8_t t[8];
-    memcpy(t, &v, 8);
-    b.insert(b.end(), t, t + 8);
+    need(8);
+    memcpy(p + n, &v, 8);
+    n += 8;
   }
-  void raw(const uint8_t* p, size_t n) { b.insert(b.end(), p, p + n); }
+  void raw(const uint8_t* q, size_t k) {
+    need(k);
+    if (k) memcpy(p + n, q, k);
+    n += k;
+  }
   void span(Span s) {
     u32(s.n);
     raw(s.p, s.n);
   }
   void u256(uint64_t v) {
-    uint8_t be[32];
-    memset(be, 0, 32);
-    for (int i = 0; i < 8; i++) be[31 - i] = (uint8_t)(v >> (8 * i));
-    raw(be, 32);
+    need(32);
+    memset(p + n, 0, 24);
+    for (int i = 0; i < 8; i++) p[n + 31 - i] = (uint8_t)(v >> (8 * i));
+    n += 32;
+  }
+  uint8_t* give(size_t* len) {
+    uint8_t* r = p ? p : (uint8_t*)malloc(1);
+    *len = n;
+    p = nullptr, n = cap = 0;
+    return r;
   }
 };
 
-void account_rlp(const Job& J, const AccountRec& rec, std::vector<uint8_t>& out) {
-  std::vector<uint8_t> pl;
-  rlp_u256(pl, rec.nonce);
-  rlp_u256(pl, rec.balance);
+// per-thread marks of the nodes a subset keeps expanded
+struct Stamp {
+  std::vector<uint32_t> v;
+  uint32_t serial = 0;
+};
+
+void account_rlp(const Job& J, const AccountRec& rec, Out& o) {
+  // rlp([nonce, balance, storage_root, code_hash]) preceded by its length (u32)
+  uint32_t nn = u256_sig(rec.nonce), nb = u256_sig(rec.balance);
+  auto str_size = [](const uint8_t* be, uint32_t sig) -> uint32_t { return sig == 0 ? 1 : (sig == 1 && be[31] < 0x80) ? 1 : 1 + sig; };
+  uint32_t payload = str_size(rec.nonce, nn) + str_size(rec.balance, nb) + 66;
+  o.u32(2 + payload);
+  o.need(2 + payload);
+  uint8_t* q = o.p + o.n;
+  *q++ = 0xf8;
+  *q++ = (uint8_t)payload;
+  auto put_u256 = [&](const uint8_t* be, uint32_t sig) {
+    if (sig == 0) {
+      *q++ = 0x80;
+      return;
+    }
+    if (!(sig == 1 && be[31] < 0x80)) *q++ = (uint8_t)(0x80 + sig);
+    memcpy(q, be + 32 - sig, sig);
+    q += sig;
+  };
+  put_u256(rec.nonce, nn);
+  put_u256(rec.balance, nb);
   const uint8_t* sr = rec.storage_src == NODE_EMPTY ? rec.storage_root : J.ref.data() + 32ull * rec.storage_src;
-  rlp_str(pl, sr, 32);
-  rlp_str(pl, rec.code_hash, 32);
-  out.clear();
-  out.push_back(0xf8);
-  out.push_back((uint8_t)pl.size());
-  out.insert(out.end(), pl.begin(), pl.end());
+  *q++ = 0xa0;
+  memcpy(q, sr, 32);
+  q += 32;
+  *q++ = 0xa0;
+  memcpy(q, rec.code_hash, 32);
+  q += 32;
+  o.n += 2 + payload;
 }
 
 void dump_nibbles(const Job& J, Out& o, uint32_t node) {
   uint32_t k = J.A.nodes[node].a0, s = J.A.nstart(node), n = J.A.nlen(node);
-  o.u8((uint8_t)n);
-  for (uint32_t i = 0; i < n; i++) o.u8((uint8_t)J.A.key_nib(k, s + i));
+  o.need(1 + n);
+  uint8_t* q = o.p + o.n;
+  *q++ = (uint8_t)n;
+  for (uint32_t i = 0; i < n; i++) *q++ = (uint8_t)J.A.key_nib(k, s + i);
+  o.n += 1 + n;
 }
 
 // create_partial_trie_subset_from_tracked_trie (trie_subsets.rs): untouched nodes whose encoding is
 // at least 32 bytes become Hash nodes; smaller ones are kept as they are
-void dump_subset(const Job& J, Out& o, uint32_t node) {
+void dump_subset(const Job& J, const Stamp& st, Out& o, uint32_t node) {
   const HostArena& A = J.A;
   if (node == NODE_EMPTY) {
     o.u8(PPD_NODE_EMPTY);
     return;
   }
-  bool touched = J.stamp[node] == J.serial;
+  if (is_hash_id(node)) {
+    o.need(33);
+    o.p[o.n] = PPD_NODE_HASH;
+    memcpy(o.p + o.n + 1, A.hash_of(node), 32);
+    o.n += 33;
+    return;
+  }
+  bool touched = st.v[node] == st.serial;
   if ((!touched && J.ref_len[node] == 32) || A.is_opaque(node)) {
-    o.u8(PPD_NODE_HASH);
-    o.raw(J.ref.data() + 32ull * node, 32);
+    o.need(33);
+    o.p[o.n] = PPD_NODE_HASH;
+    memcpy(o.p + o.n + 1, J.ref.data() + 32ull * node, 32);
+    o.n += 33;
     return;
   }
   switch (A.kind(node)) {
@@ -1216,83 +1556,176 @@ void dump_subset(const Job& J, Out& o, uint32_t node) {
       o.u32(A.nodes[node].a2);
       o.raw(A.val_pool.data() + A.nodes[node].a1, A.nodes[node].a2);
       return;
-    case NK_LEAF_ACCOUNT: {
+    case NK_LEAF_ACCOUNT:
       o.u8(PPD_NODE_LEAF);
       dump_nibbles(J, o, node);
-      std::vector<uint8_t> v;
-      account_rlp(J, A.accounts[A.nodes[node].a1], v);
-      o.u32((uint32_t)v.size());
-      o.raw(v.data(), v.size());
+      account_rlp(J, A.accounts[A.nodes[node].a1], o);
       return;
-    }
     case NK_EXT:
       o.u8(PPD_NODE_EXTENSION);
       dump_nibbles(J, o, node);
-      dump_subset(J, o, A.nodes[node].a1);
+      dump_subset(J, st, o, A.nodes[node].a1);
       return;
-    case NK_BRANCH:
+    case NK_BRANCH: {
       o.u8(PPD_NODE_BRANCH);
-      for (uint32_t i = 0; i < 16; i++) dump_subset(J, o, A.child_at(node, i));
+      // the children's refs and records are scattered: start all the misses before the first use
+      const uint32_t mask = A.nodes[node].a1 & 0xffff, k = (uint32_t)__builtin_popcount(mask);
+      const uint32_t* ch = A.child_pool.data() + A.nodes[node].a0;
+      for (uint32_t j = 0; j < k; j++) {
+        uint32_t c = ch[j];
+        if (is_hash_id(c)) {
+          __builtin_prefetch(A.hash_of(c));
+        } else {
+          __builtin_prefetch(&st.v[c]);
+          __builtin_prefetch(&A.nodes[c]);
+          __builtin_prefetch(J.ref.data() + 32ull * c);
+        }
+      }
+      o.need(16 * 33 + 8);
+      for (uint32_t i = 0, j = 0; i < 16; i++) {
+        if (mask & (1u << i))
+          dump_subset(J, st, o, ch[j++]);
+        else
+          o.p[o.n++] = PPD_NODE_EMPTY;
+      }
       o.u32(0);
       return;
+    }
   }
 }
 
-void dump_block(Job& J, BlockJob& b, Out& o) {
-  o.u32(PPD_IR_DUMP_MAGIC);
-  o.u32((uint32_t)b.irs.size());
-  for (IrPlan& p : b.irs) {
-    J.serial++;
-    for (uint32_t t : p.touched) J.stamp[t] = J.serial;
-    o.u256(p.txn_before);
-    o.u256(p.gas_before);
-    o.u256(p.gas_after);
-    o.u8(p.has_signed_txn);
-    o.span(p.has_signed_txn ? p.signed_txn : Span{});
-    if (p.has_withdrawals) {
-      o.u32((uint32_t)b.withdrawals.size());
-      for (auto& w : b.withdrawals) {
-        o.raw(w.first, 20);
-        o.raw(w.second, 32);
+void dump_ir(const Job& J, const BlockJob& b, IrPlan& p, Stamp& st, Out& o) {
+  st.serial++;
+  for (uint32_t t : p.touched)
+    if (!is_hash_id(t)) st.v[t] = st.serial;
+  o.u256(p.txn_before);
+  o.u256(p.gas_before);
+  o.u256(p.gas_after);
+  o.u8(p.has_signed_txn);
+  o.span(p.has_signed_txn ? p.signed_txn : Span{});
+  if (p.has_withdrawals) {
+    o.u32((uint32_t)b.withdrawals.size());
+    for (auto& w : b.withdrawals) {
+      o.raw(w.first, 20);
+      o.raw(w.second, 32);
+    }
+  } else {
+    o.u32(0);
+  }
+  dump_subset(J, st, o, p.state_sub);
+  dump_subset(J, st, o, p.txn_sub);
+  dump_subset(J, st, o, p.receipt_sub);
+  std::stable_sort(p.storage_subs.begin(), p.storage_subs.end(), [](const auto& x, const auto& y) { return x.first < y.first; });
+  o.u32((uint32_t)p.storage_subs.size());
+  for (auto& s : p.storage_subs) {
+    o.raw(s.first.b, 32);
+    dump_subset(J, st, o, s.second);
+  }
+  o.raw(J.ref.data() + 32ull * p.root_state, 32);
+  o.raw(J.ref.data() + 32ull * p.root_txn, 32);
+  o.raw(J.ref.data() + 32ull * p.root_receipt, 32);
+  o.raw(b.checkpoint, 32);
+  o.u32((uint32_t)p.code.size());
+  for (auto& cd : p.code) {
+    o.raw(cd.first.b, 32);
+    o.span(cd.second);
+  }
+  o.span(b.b_meta);
+  o.span(b.b_hashes);
+}
+
+// Runs f(item, worker) for every item in [0, n) on up to `workers` threads (the caller's included).
+template <class F>
+void parallel_for(size_t n, unsigned workers, F f) {
+  if (workers > n) workers = (unsigned)n;
+  if (workers <= 1) {
+    for (size_t i = 0; i < n; i++) f(i, 0u);
+    return;
+  }
+  std::atomic<size_t> next{0};
+  std::atomic<bool> failed{false};
+  Fail first{PPD_OK, ""};
+  std::mutex mu;
+  auto body = [&](unsigned w) {
+    for (;;) {
+      size_t i = next.fetch_add(1);
+      if (i >= n || failed.load()) return;
+      try {
+        f(i, w);
+      } catch (const Fail& e) {
+        std::lock_guard<std::mutex> g(mu);
+        if (!failed.exchange(true)) first = e;
       }
-    } else {
-      o.u32(0);
     }
-    dump_subset(J, o, p.state_sub);
-    dump_subset(J, o, p.txn_sub);
-    dump_subset(J, o, p.receipt_sub);
-    std::stable_sort(p.storage_subs.begin(), p.storage_subs.end(), [](const auto& x, const auto& y) { return x.first < y.first; });
-    o.u32((uint32_t)p.storage_subs.size());
-    for (auto& s : p.storage_subs) {
-      o.raw(s.first.b, 32);
-      dump_subset(J, o, s.second);
-    }
-    o.raw(J.ref.data() + 32ull * p.root_state, 32);
-    o.raw(J.ref.data() + 32ull * p.root_txn, 32);
-    o.raw(J.ref.data() + 32ull * p.root_receipt, 32);
-    o.raw(b.checkpoint, 32);
-    o.u32((uint32_t)p.code.size());
-    for (auto& cd : p.code) {
-      o.raw(cd.first.b, 32);
-      o.span(cd.second);
-    }
-    o.span(b.b_meta);
-    o.span(b.b_hashes);
-  }
+  };
+  std::vector<std::thread> th;
+  for (unsigned w = 1; w < workers; w++) th.emplace_back(body, w);
+  body(0);
+  for (auto& t : th) t.join();
+  if (failed.load()) throw first;
 }
 
-uint8_t* to_malloc(const std::vector<uint8_t>& v, size_t* n) {
-  uint8_t* p = (uint8_t*)malloc(v.size() ? v.size() : 1);
-  if (v.size()) memcpy(p, v.data(), v.size());
-  *n = v.size();
-  return p;
+unsigned host_threads() {
+  static unsigned n = [] {
+    if (const char* e = getenv("PPD_HOST_THREADS")) {
+      int v = atoi(e);
+      if (v >= 1) return (unsigned)std::min(v, 64);
+    }
+    unsigned h = std::thread::hardware_concurrency();
+    return h == 0 ? 1u : std::min(h, 16u);
+  }();
+  return n;
+}
+
+// Every IR of every block of the job: IRs are serialised independently on the host threads (each
+// with its own marks), then copied to their place in the block's output buffer.
+void dump_blocks(Job& J, uint8_t** outs, size_t* out_lens) {
+  struct Item {
+    uint32_t block, ir;
+  };
+  std::vector<Item> items;
+  for (size_t i = 0; i < J.blocks.size(); i++) {
+    outs[i] = nullptr, out_lens[i] = 0;
+    if (J.blocks[i].status != PPD_OK) continue;
+    for (size_t k = 0; k < J.blocks[i].irs.size(); k++) items.push_back({(uint32_t)i, (uint32_t)k});
+  }
+  const unsigned workers = std::max(1u, std::min<unsigned>(host_threads(), (unsigned)items.size()));
+  std::vector<Stamp> stamps(workers);
+  std::vector<Out> parts(items.size());
+  const size_t n_nodes = J.A.nodes.size();
+  parallel_for(items.size(), workers, [&](size_t i, unsigned w) {
+    Stamp& st = stamps[w];
+    if (st.v.size() != n_nodes) st.v.assign(n_nodes, 0), st.serial = 0;
+    BlockJob& b = J.blocks[items[i].block];
+    parts[i].need(256 << 10);
+    dump_ir(J, b, b.irs[items[i].ir], st, parts[i]);
+  });
+  if (getenv("PPD_TIMING")) fprintf(stderr, "[ppd]   dump: serialise done\n");
+  // offsets, then parallel copy
+  std::vector<size_t> at(items.size());
+  for (size_t i = 0, k = 0; i < J.blocks.size(); i++) {
+    if (J.blocks[i].status != PPD_OK) continue;
+    size_t total = 8;
+    for (size_t q = 0; q < J.blocks[i].irs.size(); q++, k++) {
+      at[k] = total;
+      total += parts[k].n;
+    }
+    uint8_t* buf = (uint8_t*)malloc(total);
+    if (!buf) fail(PPD_ERR_BAD_ARGUMENT, "out of host memory");
+    uint32_t hdr[2] = {PPD_IR_DUMP_MAGIC, (uint32_t)J.blocks[i].irs.size()};
+    memcpy(buf, hdr, 8);
+    outs[i] = buf, out_lens[i] = total;
+  }
+  parallel_for(items.size(), workers, [&](size_t i, unsigned) { memcpy(outs[items[i].block] + at[i], parts[i].p, parts[i].n); });
 }
 
 template <class F>
 int guarded(ppd_ctx* c, F f) {
   if (!c) return PPD_ERR_BAD_ARGUMENT;
   try {
+#ifndef PPD_HOSTPROF
     CUDA_OK(cudaSetDevice(c->device));
+#endif
     f();
     return PPD_OK;
   } catch (const Fail& e) {
@@ -1318,8 +1751,7 @@ struct PhaseTimer {
 void decode_blocks(ppd_ctx* c, const uint8_t* const* flats, const size_t* lens, size_t n, uint8_t** outs, size_t* out_lens, int* statuses) {
   stats_reset(c);
   PhaseTimer pt;
-  Job J;
-  J.blocks.resize(n);
+  Job& J = job_of(c, n);
   auto guard_block = [&](size_t i, auto fn) {
     BlockJob& b = J.blocks[i];
     if (b.status != PPD_OK) return;
@@ -1343,15 +1775,8 @@ void decode_blocks(ppd_ctx* c, const uint8_t* const* flats, const size_t* lens, 
   pt.lap("shape");
   sweep(c, J);
   pt.lap("sweep");
-  J.stamp.assign(J.A.nodes.size(), 0);
+  dump_blocks(J, outs, out_lens);
   for (size_t i = 0; i < n; i++) {
-    outs[i] = nullptr;
-    out_lens[i] = 0;
-    guard_block(i, [&](BlockJob& b) {
-      Out o;
-      dump_block(J, b, o);
-      outs[i] = to_malloc(o.b, &out_lens[i]);
-    });
     statuses[i] = J.blocks[i].status;
     if (J.blocks[i].status != PPD_OK) c->err = J.blocks[i].err;
   }
@@ -1368,6 +1793,10 @@ extern "C" {
 int ppd_ctx_create(int device, ppd_ctx** out) {
   if (!out) return PPD_ERR_BAD_ARGUMENT;
   *out = nullptr;
+#ifdef PPD_HOSTPROF
+  *out = new ppd_ctx();
+  return PPD_OK;
+#endif
   int count = 0;
   if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) return PPD_ERR_CUDA;
   ppd_ctx* c = new ppd_ctx();
@@ -1383,6 +1812,11 @@ int ppd_ctx_create(int device, ppd_ctx** out) {
 
 void ppd_ctx_destroy(ppd_ctx* c) {
   if (!c) return;
+#ifdef PPD_HOSTPROF
+  if (c->job) job_delete(c->job);
+  delete c;
+  return;
+#endif
   cudaSetDevice(c->device);
   DevBuf* bufs[] = {&c->d_nodes, &c->d_order,  &c->d_keys,     &c->d_vals, &c->d_hashes,  &c->d_children, &c->d_accounts,
                     &c->d_ref,   &c->d_ref_len, &c->d_counters, &c->d_msg,  &c->d_msg_off, &c->d_digest};
@@ -1391,6 +1825,7 @@ void ppd_ctx_destroy(ppd_ctx* c) {
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   if (c->st) cudaStreamDestroy(c->st);
+  if (c->job) job_delete(c->job);
   delete c;
 }
 
@@ -1475,14 +1910,11 @@ int ppd_microbench(ppd_ctx* c, int variant, uint32_t blocks_per_sm, uint32_t ite
 int ppd_compact_decode(ppd_ctx* c, const uint8_t* witness, size_t len, uint8_t** out, size_t* out_len) {
   return guarded(c, [&] {
     stats_reset(c);
-    Job J;
-    J.blocks.resize(1);
+    Job& J = job_of(c, 1);
     BlockJob& b = J.blocks[0];
     b.compact = Span{witness, (uint32_t)len};
     parse_witness(witness, len, b.wit);
-    b.m_inline_code.assign(b.wit.ins.size(), ~0u);
-    for (size_t i = 0; i < b.wit.ins.size(); i++)
-      if (b.wit.ins[i].op == PPD_OP_CODE) b.m_inline_code[i] = J.kh.add(b.wit.ins[i].value.p, b.wit.ins[i].value.n);
+    collect_witness_messages(J, b);
     J.kh.run(c);
     build_pre_image(J, b);
     uint32_t sr = root_node_for(J, b, b.state_root);
@@ -1505,7 +1937,7 @@ int ppd_compact_decode(ppd_ctx* c, const uint8_t* witness, size_t len, uint8_t**
     }
     o.u64(c->stats.nodes_hashed);
     o.u64(c->stats.node_permutations);
-    *out = to_malloc(o.b, out_len);
+    *out = o.give(out_len);
   });
 }
 

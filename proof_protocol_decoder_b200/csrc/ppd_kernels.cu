@@ -24,6 +24,14 @@ using namespace enc;
 
 static constexpr uint32_t FULL = 0xffffffffu;
 
+// A child id is an arena node or, from HASH_ID_BASE up, an entry of hash_pool (a hashed-out subtree of
+// the witness: its ref is the 32 bytes themselves, nothing is computed for it).
+static constexpr uint32_t HASH_ID_BASE = 0x80000000u;
+__device__ __forceinline__ const uint8_t* ref_ptr(const ArenaView& A, uint32_t id) {
+  return id >= HASH_ID_BASE ? A.hash_pool + 32ull * (id - HASH_ID_BASE) : A.ref + 32ull * id;
+}
+__device__ __forceinline__ uint32_t ref_len_of(const ArenaView& A, uint32_t id) { return id >= HASH_ID_BASE ? 32u : (uint32_t)A.ref_len[id]; }
+
 // ------------------------------------------------------------------ keccak batch -------------
 // Message i = data[offsets[i * stride] .. offsets[i * stride + 1]): stride 1 for a packed batch
 // (n + 1 offsets), stride 2 for explicit (begin, end) pairs.  Unit = 128 bytes of the message.
@@ -112,9 +120,6 @@ __global__ void __launch_bounds__(B, 4) hash_level_kernel(ArenaView A, const uin
     const uint8_t* copy_src = nullptr;
     busy = true;
     switch (KIND) {
-      case NK_HASH:
-        copy_src = A.hash_pool + 32ull * rec.y;
-        break;
       case NK_LEAF: {
         const uint8_t* val = A.val_pool + rec.z;
         v0 = rec.w;
@@ -135,7 +140,7 @@ __global__ void __launch_bounds__(B, 4) hash_level_kernel(ArenaView A, const uin
         break;
       }
       case NK_EXT: {
-        uint32_t clen = A.ref_len[rec.z];
+        uint32_t clen = ref_len_of(A, rec.z);
         payload = hex_prefix_str_size(NIB_LEN) + (clen == 32 ? 33 : clen);
         nunit = 1;
         break;
@@ -152,7 +157,7 @@ __global__ void __launch_bounds__(B, 4) hash_level_kernel(ArenaView A, const uin
         uint32_t hashed_kids = 0;  // bit j: compact child j is referenced by hash
 #pragma unroll
         for (int j = 0; j < 16; j++) {
-          uint32_t cl = cid[j] == NODE_EMPTY ? 0u : (uint32_t)A.ref_len[cid[j]];
+          uint32_t cl = cid[j] == NODE_EMPTY ? 0u : ref_len_of(A, cid[j]);
           payload += cl == 32 ? 33u : cl;
           hashed_kids |= (cl == 32 ? 1u : 0u) << j;
         }
@@ -163,7 +168,7 @@ __global__ void __launch_bounds__(B, 4) hash_level_kernel(ArenaView A, const uin
       }
       case NK_ROOT: {
         force_hash = true;
-        if (rec.z != NODE_EMPTY && A.ref_len[rec.z] == 32) copy_src = A.ref + 32ull * rec.z;
+        if (rec.z != NODE_EMPTY && ref_len_of(A, rec.z) == 32) copy_src = ref_ptr(A, rec.z);
         nunit = 1;
         break;
       }
@@ -225,7 +230,7 @@ __global__ void __launch_bounds__(B, 4) hash_level_kernel(ArenaView A, const uin
           case NK_EXT:
             emit_len_prefix(s, payload, 0xc0, 0xf7);
             emit_hex_prefix_str(s, A.key_pool + rec.y, NIB_START, NIB_LEN, 0);
-            emit_ref_at(s, A.ref + 32ull * rec.z, A.ref_len[rec.z]);
+            emit_ref_at(s, ref_ptr(A, rec.z), ref_len_of(A, rec.z));
             break;
           case NK_BRANCH:
             if (unit == 0) {
@@ -246,7 +251,7 @@ __global__ void __launch_bounds__(B, 4) hash_level_kernel(ArenaView A, const uin
 #pragma unroll
               for (int t = 0; t < 3; t++) {  // the refs: independent loads, issued together
                 if (nib[t] < 16) {
-                  const uint4* q = reinterpret_cast<const uint4*>(A.ref + 32ull * cid[t]);
+                  const uint4* q = reinterpret_cast<const uint4*>(ref_ptr(A, cid[t]));
                   x[t] = __ldcg(q), y[t] = __ldcg(q + 1);
                 }
               }
@@ -254,7 +259,7 @@ __global__ void __launch_bounds__(B, 4) hash_level_kernel(ArenaView A, const uin
               for (int t = 0; t < 3; t++) {
                 if (nib[t] < 16) {
                   emit_empty_run(s, nib[t] - next_slot);
-                  emit_ref(s, x[t], y[t], ((v1 >> (16 + j0 + t)) & 1) ? 32u : (uint32_t)A.ref_len[cid[t]]);
+                  emit_ref(s, x[t], y[t], ((v1 >> (16 + j0 + t)) & 1) ? 32u : ref_len_of(A, cid[t]));
                   next_slot = nib[t] + 1;
                 }
               }
@@ -266,7 +271,7 @@ __global__ void __launch_bounds__(B, 4) hash_level_kernel(ArenaView A, const uin
             if (rec.z == NODE_EMPTY)
               s.put_byte(0x80);
             else
-              emit_ref_at(s, A.ref + 32ull * rec.z, A.ref_len[rec.z]);
+              emit_ref_at(s, ref_ptr(A, rec.z), ref_len_of(A, rec.z));
             break;
         }
         unit++;
@@ -297,7 +302,7 @@ __global__ void __launch_bounds__(B, 4) hash_level_kernel(ArenaView A, const uin
         o[0] = x, o[1] = y;
         A.ref_len[id] = 32;
         hashed = 1;
-        enc_bytes = KIND == NK_ROOT ? (rec.z == NODE_EMPTY ? 1u : (uint32_t)A.ref_len[rec.z]) : total;
+        enc_bytes = KIND == NK_ROOT ? (rec.z == NODE_EMPTY ? 1u : ref_len_of(A, rec.z)) : total;
         busy = false;
       } else {
         s.consume_block();

@@ -122,6 +122,32 @@ class PpdLibrary:
         return [name for name in EXPORTS if hasattr(self.L, name)]
 
 
+class OwnedBuffer:
+    """A buffer allocated by the library (released with ppd_free), exposed without copying."""
+
+    def __init__(self, lib, ptr, n):
+        self._lib, self._ptr, self.nbytes = lib, ptr, n
+        self.view = memoryview((ctypes.c_uint8 * n).from_address(ctypes.addressof(ptr.contents))).cast("B") if n else memoryview(b"")
+
+    def close(self):
+        if self._ptr is not None:
+            self.view = None
+            self._lib.L.ppd_free(self._ptr)
+            self._ptr = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class Context:
     """One ppd_ctx: a stream plus reusable HBM buffers on one CUDA device.  Not thread-safe."""
 
@@ -174,10 +200,20 @@ class Context:
         return self._take(out, n)
 
     def block_decode(self, flat: bytes) -> bytes:
+        with self.block_decode_view(flat) as v:
+            return bytes(v.view)
+
+    def block_decode_view(self, flat) -> "OwnedBuffer":
+        """ppd_block_decode without any copy on the Python side: `flat` (bytes or a C-contiguous uint8
+        numpy array) is passed by address and the library-allocated IrDump is returned as an
+        OwnedBuffer (memoryview + ppd_free on close)."""
         out, n = ctypes.POINTER(ctypes.c_uint8)(), ctypes.c_size_t()
-        buf = (ctypes.c_uint8 * len(flat)).from_buffer_copy(flat)
-        self._check(self.lib.L.ppd_block_decode(self.h, buf, len(flat), ctypes.byref(out), ctypes.byref(n)))
-        return self._take(out, n)
+        if isinstance(flat, (bytes, bytearray)):
+            ptr, ln = ctypes.cast(ctypes.c_char_p(bytes(flat) if isinstance(flat, bytearray) else flat), ctypes.c_void_p), len(flat)
+        else:
+            ptr, ln = ctypes.c_void_p(flat.ctypes.data), flat.nbytes
+        self._check(self.lib.L.ppd_block_decode(self.h, ptr, ln, ctypes.byref(out), ctypes.byref(n)))
+        return OwnedBuffer(self.lib, out, n.value)
 
     def blocks_decode_batch(self, flats):
         n = len(flats)
