@@ -78,7 +78,12 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(self.rows)}
 
 
+C2_PARAMS = dict(contract_frac=0.15, slots_lo=1, slots_hi=256, virtual_depth=7, virtual_accounts_log16=7, slot_reads=(0, 3), slot_writes=(0, 3),
+                 allow_new_accounts=False, allow_self_destruct=False, inline_code_frac=0.02)
+
+
 def c2_block(seed, scale):
+    """One synthetic C2 block as a FlatBlock; cached under /tmp."""
     from proof_protocol_decoder_b200 import synth
 
     cache = f"/tmp/ppd_c2_seed{seed}_scale{scale}.flat"
@@ -88,24 +93,34 @@ def c2_block(seed, scale):
         seed,
         n_accounts=max(10, int(20000 * scale)),
         n_txns=max(2, int(200 * scale)),
-        contract_frac=0.15,
-        slots_lo=1,
-        slots_hi=256,
-        virtual_depth=7,
-        virtual_accounts_log16=7,
         accounts_per_txn=(80, 120) if scale >= 0.5 else (max(2, int(80 * scale * 4)), max(4, int(120 * scale * 4))),
-        slot_reads=(0, 3),
-        slot_writes=(0, 3),
-        allow_new_accounts=False,
-        allow_self_destruct=False,
-        inline_code_frac=0.02,
+        **C2_PARAMS,
     )
     f = blk.flat
     try:
-        open(cache, "wb").write(f)
+        tmp = cache + f".{os.getpid()}.tmp"
+        open(tmp, "wb").write(f)
+        os.replace(tmp, cache)
     except OSError:
         pass
     return f
+
+
+def _c2_block_job(a):
+    c2_block(*a)
+    return 0
+
+
+def c2_blocks(seeds, scale, procs):
+    """The blocks of the given seeds; missing ones are generated in parallel worker processes (the
+    generator is pure Python: ~10 s per full-size block)."""
+    missing = [s for s in seeds if not os.path.exists(f"/tmp/ppd_c2_seed{s}_scale{scale}.flat")]
+    if len(missing) > 1 and procs > 1:
+        import multiprocessing as mp
+
+        with mp.get_context("fork").Pool(min(procs, len(missing))) as pool:
+            pool.map(_c2_block_job, [(s, scale) for s in missing])
+    return [c2_block(s, scale) for s in seeds]
 
 
 def oracle_time_block(flat_bytes, repeats, threads):
@@ -223,6 +238,17 @@ def c5_sweep(ctx, sizes, peaks, sm_mhz):
 
 
 def run_b200(args, rank, world, local_rank):
+    # host threads: this rank's share of the box's cores; one block per host thread per step
+    cores = os.cpu_count() or 1
+    threads = max(1, min(16, cores // world))
+    os.environ.setdefault("PPD_HOST_THREADS", str(threads))
+    threads = int(os.environ["PPD_HOST_THREADS"])
+    n_blocks = args.blocks_per_step or threads
+    seeds = [2 + rank * n_blocks + j for j in range(n_blocks)]
+    # generated before CUDA is touched (worker processes are forked); ranks generate their own blocks
+    flats = c2_blocks(seeds, args.scale, max(1, cores // world))
+    flat_total = sum(len(f) for f in flats)
+
     import torch
 
     from proof_protocol_decoder_b200.lib import Context
@@ -257,19 +283,28 @@ def run_b200(args, rank, world, local_rank):
         return float(t.item())
 
     ctx = Context(local_rank)
-    flat_bytes = c2_block(2 + rank, args.scale)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
 
-    # ---- warm-up (also leaves the arena resident for the device-resident measurement) ----
+    def decode_step():
+        outs = ctx.blocks_decode_batch_view(flats)
+        total = 0
+        for o in outs:
+            if isinstance(o, Exception):
+                raise o
+            total += o.nbytes + o.view[0] + o.view[o.nbytes - 1]  # read the result
+            o.close()
+        return total
+
+    # ---- warm-up (also leaves the arenas resident for the device-resident measurement) ----
     for _ in range(max(3, args.warmup)):
-        ir = ctx.block_decode(flat_bytes)
+        ir_len = decode_step()
     st = ctx.stats()
     for _ in range(max(3, args.warmup)):
         ctx.replay_last_hashing()
 
     sampler = ClockSampler(local_rank)
     sampler.start()
-    # ---- device-resident: every kernel of the block on the arena already in HBM ----
+    # ---- device-resident: every kernel of the batch on the arenas already in HBM ----
     barrier()
     dev_ms = 0.0
     for _ in range(args.steps):
@@ -282,15 +317,20 @@ def run_b200(args, rank, world, local_rank):
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        with ctx.block_decode_view(flat_bytes) as v:  # host FlatBlock in, host IrDump out; read the result's first and last bytes
-            ir_len = v.nbytes
-            _ = v.view[0] + v.view[ir_len - 1]
+        ir_len = decode_step()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     barrier()
     e2e_s = max_over_ranks(e2e_s)
     clocks = sampler.stop()
     st = ctx.stats()
+    # latency of one block alone (all host threads on its IR dump)
+    single = []
+    for _ in range(3):
+        t1 = time.perf_counter()
+        with ctx.block_decode_view(flats[0]) as v:
+            _ = v.view[0]
+        single.append(time.perf_counter() - t1)
 
     nodes_all = sum_over_ranks(float(st["nodes_hashed"]))
     perms_all = sum_over_ranks(float(st["node_permutations"] + st["key_permutations"]))
@@ -315,33 +355,36 @@ def run_b200(args, rank, world, local_rank):
         "dtype": "u64",
         "data": "synthetic",
         "config": {
-            "workload": "C2 mainnet-shaped block (BASELINE.json configs[1]): 20k touched accounts in a virtual 16^7-account state, 200 txns; one block per GPU per step",
+            "workload": f"C2 mainnet-shaped blocks (BASELINE.json configs[1]): 20k touched accounts in a virtual 16^7-account state, 200 txns each; a batch of {n_blocks} independent blocks per GPU per step, one block per host thread",
             "scale": args.scale,
-            "flat_block_bytes": len(flat_bytes),
-            "ir_dump_bytes": ir_len,
+            "blocks_per_step_per_gpu": n_blocks,
+            "host_threads_per_gpu": threads,
+            "flat_block_bytes_per_step": flat_total,
+            "ir_dump_bytes_per_step": ir_len,
             "arena_nodes": st["arena_nodes"],
             "levels": st["levels"],
             "l2": "flushed between timed device-resident steps (256 MiB write)",
             "parallelism": f"blocks sharded over {world} GPU(s), no data-path collective",
         },
-        "blocks_per_sec": world / dev_s_per_step,
+        "blocks_per_sec": world * n_blocks / dev_s_per_step,
         "permutations_per_sec": perms_all / dev_s_per_step,
         "nodes_hashed_per_step": nodes_all,
         "key_hashes_per_step": keys_all,
         "e2e": {
             "value": nodes_all / e2e_s_per_step,
             "unit": "nodes/s",
-            "blocks_per_sec": world / e2e_s_per_step,
+            "blocks_per_sec": world * n_blocks / e2e_s_per_step,
             "ms_per_step": 1e3 * e2e_s_per_step,
+            "single_block_latency_ms": 1e3 * min(single),
             "h2d_bytes_per_step": st["h2d_bytes"],
             "d2h_bytes_per_step": st["d2h_bytes"],
-            "note": "ppd_block_decode: FlatBlock (host) -> IrDump (host); includes witness parse, trie shaping and IR serialisation on the host",
+            "note": "ppd_blocks_decode_batch: FlatBlocks (host) -> IrDumps (host); includes witness parse, trie shaping and IR serialisation on the host threads and every host<->device copy",
         },
         "gpu_launches": int(st["kernel_launches"]) * args.steps,
         "clocks": clocks,
         "roofline": {
             "bound": "hbm",
-            "kernel": "hash_level_kernel (all level launches of one block)",
+            "kernel": "hash_level_kernel (all level launches of the batch, lanes concurrent)",
             "achieved": achieved_gbs,
             "peak": peaks["hbm_gbs"],
             "unit": "GB/s",
@@ -386,6 +429,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--scale", type=float, default=1.0, help="fraction of the C2 block size (1.0 = the named config)")
+    ap.add_argument("--blocks-per-step", type=int, default=0, help="blocks per GPU per step (default: one per host thread)")
     ap.add_argument("--ref-scale", type=float, default=0.1, help="size of the bounded CPU sample block")
     ap.add_argument("--sweep", default="1000000,10000000", help="config-5 leaf counts measured beside the headline at N=1")
     ap.add_argument("--no-sweep", action="store_true")

@@ -18,6 +18,7 @@
 #include <cstring>
 #include <atomic>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <thread>
 #include <string>
@@ -102,22 +103,36 @@ void pinned_free(void* p) { cudaFreeHost(p); }
 #endif
 }  // namespace
 
-struct ppd_ctx {
-  int device = 0;
-  Job* job = nullptr;  // host-side scratch of the block pipeline (page-locked pools), kept across calls
+// One lane of the block pipeline: a stream, its HBM buffers and the host-side scratch of one block.
+// Blocks of a batch are decoded concurrently, one lane per host thread; the lanes' kernels and copies
+// overlap on the device.
+struct Lane {
   cudaStream_t st = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  std::string err;
   ppd_stats stats{};
-  // HBM buffers, grown on demand and reused across calls
   DevBuf d_nodes, d_order, d_keys, d_vals, d_hashes, d_children, d_accounts, d_ref, d_ref_len, d_counters;
   DevBuf d_msg, d_msg_off, d_digest;
-  DevBuf d_build[12];
-  // the arena of the last block job stays resident so that its hashing can be re-run for measurement
+  Job* job = nullptr;  // page-locked pools, kept across calls
+  // the arena of the lane's last block stays resident so that its hashing can be re-run for measurement
   bool has_last = false;
   ArenaView last_view{};
   std::vector<uint32_t> last_level_start;
   uint32_t last_n_msgs = 0;
+};
+
+struct ppd_ctx {
+  int device = 0;
+  cudaStream_t st = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::string err;
+  std::mutex err_mu;
+  ppd_stats stats{};
+  std::vector<Lane*> lanes;
+  size_t last_lanes_used = 0;  // lanes holding a resident block of the last decode call
+  // HBM buffers of the non-block entry points, grown on demand and reused across calls
+  DevBuf d_keys, d_vals, d_ref, d_ref_len, d_counters;
+  DevBuf d_msg, d_msg_off, d_digest;
+  DevBuf d_build[12];
 };
 
 namespace {
@@ -152,7 +167,7 @@ struct KeyHasher {
     off.push_back(data.size());
     return idx;
   }
-  void run(ppd_ctx* c) {
+  void run(Lane* c) {
     size_t n = lens.size();
     digest.resize(n);
     if (!n) return;
@@ -707,10 +722,35 @@ struct Job {
   }
 };
 void job_delete(Job* j) { delete j; }
-Job& job_of(ppd_ctx* c, size_t n_blocks) {
-  if (!c->job) c->job = new Job();
-  c->job->reset(n_blocks);
-  return *c->job;
+Job& job_of(Lane* l, size_t n_blocks) {
+  if (!l->job) l->job = new Job();
+  l->job->reset(n_blocks);
+  return *l->job;
+}
+
+Lane* lane_of(ppd_ctx* c, size_t w) {
+  while (c->lanes.size() <= w) {
+    std::unique_ptr<Lane> l(new Lane());
+#ifndef PPD_HOSTPROF
+    CUDA_OK(cudaStreamCreateWithFlags(&l->st, cudaStreamNonBlocking));
+    CUDA_OK(cudaEventCreate(&l->ev0));
+    CUDA_OK(cudaEventCreate(&l->ev1));
+#endif
+    c->lanes.push_back(l.release());
+  }
+  return c->lanes[w];
+}
+void lane_delete(Lane* l) {
+#ifndef PPD_HOSTPROF
+  DevBuf* bufs[] = {&l->d_nodes, &l->d_order,  &l->d_keys,     &l->d_vals, &l->d_hashes,  &l->d_children, &l->d_accounts,
+                    &l->d_ref,   &l->d_ref_len, &l->d_counters, &l->d_msg,  &l->d_msg_off, &l->d_digest};
+  for (DevBuf* b : bufs) b->release();
+  if (l->ev0) cudaEventDestroy(l->ev0);
+  if (l->ev1) cudaEventDestroy(l->ev1);
+  if (l->st) cudaStreamDestroy(l->st);
+#endif
+  if (l->job) job_delete(l->job);
+  delete l;
 }
 
 // ---- step 1: parse, collect every byte string that must be hashed ----------------------------
@@ -1324,7 +1364,7 @@ void shape_block(Job& J, BlockJob& b) {
 }
 
 // ---- step 4: the sweep ---------------------------------------------------------------------------
-void sweep(ppd_ctx* c, Job& J) {
+void sweep(Lane* c, Job& J) {
   HostArena& A = J.A;
   uint32_t n = (uint32_t)A.nodes.size();
   J.ref.resize(32ull * n);
@@ -1679,7 +1719,7 @@ unsigned host_threads() {
 
 // Every IR of every block of the job: IRs are serialised independently on the host threads (each
 // with its own marks), then copied to their place in the block's output buffer.
-void dump_blocks(Job& J, uint8_t** outs, size_t* out_lens) {
+void dump_blocks(Job& J, uint8_t** outs, size_t* out_lens, unsigned max_workers) {
   struct Item {
     uint32_t block, ir;
   };
@@ -1689,13 +1729,13 @@ void dump_blocks(Job& J, uint8_t** outs, size_t* out_lens) {
     if (J.blocks[i].status != PPD_OK) continue;
     for (size_t k = 0; k < J.blocks[i].irs.size(); k++) items.push_back({(uint32_t)i, (uint32_t)k});
   }
-  const unsigned workers = std::max(1u, std::min<unsigned>(host_threads(), (unsigned)items.size()));
+  const unsigned workers = std::max(1u, std::min<unsigned>(max_workers, (unsigned)items.size()));
   std::vector<Stamp> stamps(workers);
   std::vector<Out> parts(items.size());
   const size_t n_nodes = J.A.nodes.size();
   parallel_for(items.size(), workers, [&](size_t i, unsigned w) {
     Stamp& st = stamps[w];
-    if (st.v.size() != n_nodes) st.v.assign(n_nodes, 0), st.serial = 0;
+    if (st.v.size() != n_nodes) st.v.assign(n_nodes, 0), st.serial = 0;  // first item of this worker
     BlockJob& b = J.blocks[items[i].block];
     parts[i].need(256 << 10);
     dump_ir(J, b, b.irs[items[i].ir], st, parts[i]);
@@ -1748,39 +1788,64 @@ struct PhaseTimer {
   }
 };
 
+// One block on one lane: parse, key hashes, shaping, sweep, dump.  A failure that is the block's own
+// (bad input, a reference panic site) is reported through *status; a CUDA failure is thrown.
+void decode_one(ppd_ctx* c, Lane* L, const uint8_t* flat, size_t len, uint8_t** out, size_t* out_len, int* status, unsigned dump_workers) {
+  PhaseTimer pt;
+  Job& J = job_of(L, 1);
+  BlockJob& b = J.blocks[0];
+  *out = nullptr, *out_len = 0;
+  try {
+    read_flat_block(flat, len, b);
+    collect_messages(J, b);
+    pt.lap("parse");
+    J.kh.run(L);
+    pt.lap("keyhash");
+    shape_block(J, b);
+    pt.lap("shape");
+  } catch (const Fail& e) {
+    if (e.code == PPD_ERR_CUDA) throw;
+    *status = e.code;
+    std::lock_guard<std::mutex> g(c->err_mu);
+    c->err = e.msg;
+    return;
+  }
+  sweep(L, J);
+  pt.lap("sweep");
+  dump_blocks(J, out, out_len, dump_workers);
+  *status = PPD_OK;
+  pt.lap("dump");
+}
+
+void add_stats(ppd_stats& a, const ppd_stats& b) {
+  a.nodes_hashed += b.nodes_hashed, a.node_permutations += b.node_permutations, a.key_hashes += b.key_hashes;
+  a.key_permutations += b.key_permutations, a.node_bytes += b.node_bytes, a.arena_nodes += b.arena_nodes;
+  a.levels = std::max(a.levels, b.levels);
+  a.gpu_ms += b.gpu_ms, a.h2d_bytes += b.h2d_bytes, a.d2h_bytes += b.d2h_bytes, a.kernel_launches += b.kernel_launches;
+}
+
+// Blocks are independent (each BlockTrace carries its own pre-image, trace_protocol.rs:40-48): every
+// host thread takes blocks on its own lane, so parsing / shaping of one block overlaps the copies and
+// kernels of the others.
 void decode_blocks(ppd_ctx* c, const uint8_t* const* flats, const size_t* lens, size_t n, uint8_t** outs, size_t* out_lens, int* statuses) {
   stats_reset(c);
-  PhaseTimer pt;
-  Job& J = job_of(c, n);
-  auto guard_block = [&](size_t i, auto fn) {
-    BlockJob& b = J.blocks[i];
-    if (b.status != PPD_OK) return;
-    try {
-      fn(b);
-    } catch (const Fail& e) {
-      if (e.code == PPD_ERR_CUDA) throw;
-      b.status = e.code;
-      b.err = e.msg;
-    }
-  };
-  for (size_t i = 0; i < n; i++)
-    guard_block(i, [&](BlockJob& b) {
-      read_flat_block(flats[i], lens[i], b);
-      collect_messages(J, b);
-    });
-  pt.lap("parse");
-  J.kh.run(c);
-  pt.lap("keyhash");
-  for (size_t i = 0; i < n; i++) guard_block(i, [&](BlockJob& b) { shape_block(J, b); });
-  pt.lap("shape");
-  sweep(c, J);
-  pt.lap("sweep");
-  dump_blocks(J, outs, out_lens);
-  for (size_t i = 0; i < n; i++) {
-    statuses[i] = J.blocks[i].status;
-    if (J.blocks[i].status != PPD_OK) c->err = J.blocks[i].err;
+  if (!n) return;
+  const unsigned workers = (unsigned)std::min<size_t>(host_threads(), n);
+  for (unsigned w = 0; w < workers; w++) {
+    Lane* L = lane_of(c, w);
+    L->stats = ppd_stats{};
+    L->has_last = false;
   }
-  pt.lap("dump");
+  const unsigned dump_workers = std::max(1u, host_threads() / workers);
+  for (size_t i = 0; i < n; i++) outs[i] = nullptr, out_lens[i] = 0, statuses[i] = PPD_OK;
+  parallel_for(n, workers, [&](size_t i, unsigned w) {
+#ifndef PPD_HOSTPROF
+    CUDA_OK(cudaSetDevice(c->device));
+#endif
+    decode_one(c, c->lanes[w], flats[i], lens[i], &outs[i], &out_lens[i], &statuses[i], dump_workers);
+  });
+  c->last_lanes_used = workers;
+  for (unsigned w = 0; w < workers; w++) add_stats(c->stats, c->lanes[w]->stats);
 }
 
 }  // namespace
@@ -1813,19 +1878,18 @@ int ppd_ctx_create(int device, ppd_ctx** out) {
 void ppd_ctx_destroy(ppd_ctx* c) {
   if (!c) return;
 #ifdef PPD_HOSTPROF
-  if (c->job) job_delete(c->job);
+  for (Lane* l : c->lanes) lane_delete(l);
   delete c;
   return;
 #endif
   cudaSetDevice(c->device);
-  DevBuf* bufs[] = {&c->d_nodes, &c->d_order,  &c->d_keys,     &c->d_vals, &c->d_hashes,  &c->d_children, &c->d_accounts,
-                    &c->d_ref,   &c->d_ref_len, &c->d_counters, &c->d_msg,  &c->d_msg_off, &c->d_digest};
+  for (Lane* l : c->lanes) lane_delete(l);
+  DevBuf* bufs[] = {&c->d_keys, &c->d_vals, &c->d_ref, &c->d_ref_len, &c->d_counters, &c->d_msg, &c->d_msg_off, &c->d_digest};
   for (DevBuf* b : bufs) b->release();
   for (DevBuf& b : c->d_build) b.release();
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   if (c->st) cudaStreamDestroy(c->st);
-  if (c->job) job_delete(c->job);
   delete c;
 }
 
@@ -1866,14 +1930,24 @@ int ppd_keccak256_batch(ppd_ctx* c, const uint8_t* data, const uint64_t* offsets
 // key messages that are still resident in HBM (no host work, no copies) and return its device time.
 int ppd_replay_last_hashing(ppd_ctx* c, double* gpu_ms_out) {
   return guarded(c, [&] {
-    if (!c->has_last) fail(PPD_ERR_BAD_ARGUMENT, "no block job is resident");
-    CUDA_OK(cudaMemsetAsync(c->d_counters.p, 0, 32, c->st));
+    size_t used = 0;
+    for (size_t w = 0; w < c->last_lanes_used && w < c->lanes.size(); w++) used += c->lanes[w]->has_last;
+    if (!used) fail(PPD_ERR_BAD_ARGUMENT, "no block job is resident");
+    // all lanes start after ev0 on the main stream; the main stream then waits for every lane
     CUDA_OK(cudaEventRecord(c->ev0, c->st));
-    launch_keccak256_ranges(c->d_msg.as<uint8_t>(), c->d_msg_off.as<uint64_t>(), c->last_n_msgs, c->d_digest.as<uint8_t>(), c->st);
-    size_t nl = c->last_level_start.size() - 1;
-    for (size_t l = 0; l < nl; l++)
-      launch_hash_level(c->last_view, c->d_order.as<uint32_t>(), c->last_level_start[l], c->last_level_start[l + 1], c->st);
-    CUDA_OK(cudaGetLastError());
+    for (size_t w = 0; w < c->last_lanes_used; w++) {
+      Lane* L = c->lanes[w];
+      if (!L->has_last) continue;
+      CUDA_OK(cudaStreamWaitEvent(L->st, c->ev0, 0));
+      CUDA_OK(cudaMemsetAsync(L->d_counters.p, 0, 32, L->st));
+      launch_keccak256_ranges(L->d_msg.as<uint8_t>(), L->d_msg_off.as<uint64_t>(), L->last_n_msgs, L->d_digest.as<uint8_t>(), L->st);
+      size_t nl = L->last_level_start.size() - 1;
+      for (size_t l = 0; l < nl; l++)
+        launch_hash_level(L->last_view, L->d_order.as<uint32_t>(), L->last_level_start[l], L->last_level_start[l + 1], L->st);
+      CUDA_OK(cudaGetLastError());
+      CUDA_OK(cudaEventRecord(L->ev1, L->st));
+      CUDA_OK(cudaStreamWaitEvent(c->st, L->ev1, 0));
+    }
     CUDA_OK(cudaEventRecord(c->ev1, c->st));
     CUDA_OK(cudaStreamSynchronize(c->st));
     float ms = 0;
@@ -1910,17 +1984,20 @@ int ppd_microbench(ppd_ctx* c, int variant, uint32_t blocks_per_sm, uint32_t ite
 int ppd_compact_decode(ppd_ctx* c, const uint8_t* witness, size_t len, uint8_t** out, size_t* out_len) {
   return guarded(c, [&] {
     stats_reset(c);
-    Job& J = job_of(c, 1);
+    Lane* L = lane_of(c, 0);
+    L->stats = ppd_stats{};
+    Job& J = job_of(L, 1);
     BlockJob& b = J.blocks[0];
     b.compact = Span{witness, (uint32_t)len};
     parse_witness(witness, len, b.wit);
     collect_witness_messages(J, b);
-    J.kh.run(c);
+    J.kh.run(L);
     build_pre_image(J, b);
     uint32_t sr = root_node_for(J, b, b.state_root);
     std::map<H256, uint32_t> storage_roots;
     for (auto& s : b.storage) storage_roots[s.first] = root_node_for(J, b, s.second);
-    sweep(c, J);
+    sweep(L, J);
+    c->stats = L->stats;
     Out o;
     o.u32(PPD_PRE_IMAGE_MAGIC);
     o.u8(b.wit.version);

@@ -216,10 +216,23 @@ class Context:
         return OwnedBuffer(self.lib, out, n.value)
 
     def blocks_decode_batch(self, flats):
+        res = []
+        for v in self.blocks_decode_batch_view(flats):
+            if isinstance(v, PpdError):
+                res.append(v)
+            else:
+                with v:
+                    res.append(bytes(v.view))
+        return res
+
+    def blocks_decode_batch_view(self, flats):
+        """ppd_blocks_decode_batch without copies on the Python side: inputs by address, outputs as
+        OwnedBuffer (or PpdError for a block that failed on its own)."""
         n = len(flats)
-        bufs = [(ctypes.c_uint8 * len(f)).from_buffer_copy(f) for f in flats]
-        ptrs = (ctypes.c_void_p * n)(*[ctypes.addressof(b) for b in bufs])
-        lens = (ctypes.c_size_t * n)(*[len(f) for f in flats])
+        keep = [bytes(f) if isinstance(f, bytearray) else f for f in flats]
+        addr = [ctypes.cast(ctypes.c_char_p(f), ctypes.c_void_p).value if isinstance(f, bytes) else f.ctypes.data for f in keep]
+        ptrs = (ctypes.c_void_p * n)(*addr)
+        lens = (ctypes.c_size_t * n)(*[len(f) if isinstance(f, bytes) else f.nbytes for f in keep])
         outs = (ctypes.POINTER(ctypes.c_uint8) * n)()
         out_lens = (ctypes.c_size_t * n)()
         statuses = (ctypes.c_int * n)()
@@ -227,8 +240,7 @@ class Context:
         res = []
         for i in range(n):
             if statuses[i] == 0:
-                res.append(ctypes.string_at(outs[i], out_lens[i]))
-                self.lib.L.ppd_free(outs[i])
+                res.append(OwnedBuffer(self.lib, ctypes.cast(outs[i], ctypes.POINTER(ctypes.c_uint8)), out_lens[i]))
             else:
                 res.append(PpdError(statuses[i], "block %d" % i))
         return res
