@@ -1731,6 +1731,24 @@ void dump_blocks(Job& J, uint8_t** outs, size_t* out_lens, unsigned max_workers)
   }
   const unsigned workers = std::max(1u, std::min<unsigned>(max_workers, (unsigned)items.size()));
   std::vector<Stamp> stamps(workers);
+  if (workers == 1) {
+    // one thread (a lane of a batch): every IR of a block straight into the block's output buffer
+    Stamp& st = stamps[0];
+    st.v.assign(J.A.nodes.size(), 0);
+    for (size_t i = 0; i < J.blocks.size(); i++) {
+      BlockJob& b = J.blocks[i];
+      if (b.status != PPD_OK) continue;
+      size_t touched = 0;
+      for (IrPlan& p : b.irs) touched += p.touched.size();
+      Out o;
+      o.need(4096 + 600 * touched);
+      o.u32(PPD_IR_DUMP_MAGIC);
+      o.u32((uint32_t)b.irs.size());
+      for (IrPlan& p : b.irs) dump_ir(J, b, p, st, o);
+      outs[i] = o.give(&out_lens[i]);
+    }
+    return;
+  }
   std::vector<Out> parts(items.size());
   const size_t n_nodes = J.A.nodes.size();
   parallel_for(items.size(), workers, [&](size_t i, unsigned w) {

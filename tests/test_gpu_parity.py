@@ -191,3 +191,59 @@ def test_unsorted_keys_are_rejected(ctx):
     with pytest.raises(PpdError) as e:
         ctx.trie_root_sorted_leaves(keys, val_off, vals)
     assert e.value.code == 63
+
+
+def test_sorted_leaves_root_one_million(ctx, oracle):
+    # config 5 at 1 % of its full size: the largest the CPU oracle finishes in seconds
+    from proof_protocol_decoder_b200 import synth
+
+    keys, val_off, vals = synth.gen_sorted_leaves(1_000_000, seed=5)
+    assert ctx.trie_root_sorted_leaves(keys, val_off, vals) == oracle.trie_root_from_leaves(keys, val_off, vals)
+
+
+def test_sorted_leaves_structure_independent_of_launch_shape(ctx):
+    # size-independent property usable at full scale: the root of N leaves does not change when the
+    # values move (different alignments / offsets in the value pool), and changes when one byte of
+    # one value changes
+    from proof_protocol_decoder_b200 import synth
+
+    keys, val_off, vals = synth.gen_sorted_leaves(300_000, seed=8)
+    r0 = ctx.trie_root_sorted_leaves(keys, val_off, vals)
+    # insert a 3-byte gap in front of every value: same leaves, different alignment
+    lens = np.diff(val_off).astype(np.int64)
+    off2 = np.zeros(len(lens) + 1, dtype=np.uint64)
+    off2[1:] = np.cumsum(lens)
+    vals_shifted = np.concatenate([np.zeros(1, np.uint8), vals])
+    r1 = ctx.trie_root_sorted_leaves(keys, off2 + np.uint64(0), vals)
+    assert r1 == r0
+    vals2 = vals.copy()
+    vals2[int(val_off[123456])] ^= 1
+    assert ctx.trie_root_sorted_leaves(keys, val_off, vals2) != r0
+    del vals_shifted
+
+
+def test_storage_heavy_tries_sharded(ctx, oracle):
+    # config 3 in miniature through the sharding layer (world size 1 here; two ranks: test_sharding_gloo.py)
+    from proof_protocol_decoder_b200 import shard, synth
+
+    sizes = [50_000, 50_000, 20_000, 7, 1]
+    tries = [synth.gen_sorted_leaves(n, seed=70 + i, val_lo=1, val_hi=33) for i, n in enumerate(sizes)]
+    got = shard.sharded_trie_roots(lambda i: ctx.trie_root_sorted_leaves(*tries[i]), sizes)
+    assert got == [oracle.trie_root_from_leaves(*t) for t in tries]
+
+
+def test_batch_larger_than_lane_count_with_a_bad_block(ctx, oracle):
+    from proof_protocol_decoder_b200 import PpdError, synth
+
+    blks = [synth.gen_block(400 + i, n_accounts=80 + 5 * i, n_txns=i % 4, n_withdrawals=i % 3) for i in range(24)]
+    flats = [b.flat for b in blks]
+    bad = bytearray(flats[7])
+    # corrupt the compact header version (first byte of the witness, after magic/version/kind/len)
+    bad[16] = 2
+    flats[7] = bytes(bad)
+    outs = ctx.blocks_decode_batch(flats)
+    for i, (f, o) in enumerate(zip(flats, outs)):
+        if i == 7:
+            assert isinstance(o, PpdError) and o.code == 40
+        else:
+            assert o == oracle.block_decode(f), f"block {i}"
