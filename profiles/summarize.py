@@ -1,0 +1,110 @@
+#!/usr/bin/env python3
+"""Turn the ncu captures of profiles/capture.sh (gpurun_out/<tag>_*) into the tracked summaries under
+profiles/:  python profiles/summarize.py r01"""
+import collections
+import csv
+import json
+import os
+import subprocess
+import sys
+
+TAG = sys.argv[1] if len(sys.argv) > 1 else "r01"
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SRC = os.path.join(ROOT, "gpurun_out")
+DST = os.path.join(ROOT, "profiles")
+
+
+def launches(path):
+    rows = [r for r in csv.reader(open(path, errors="replace")) if len(r) > 10]
+    hdr = rows[0]
+    L = collections.OrderedDict()
+    for r in rows[1:]:
+        d = dict(zip(hdr, r))
+        e = L.setdefault(d["ID"], {"kernel": d["Kernel Name"].split("(")[0].replace("void ", "").replace("ppd::", ""), "grid": d["Grid Size"], "stream": d["Stream"]})
+        try:
+            e[d["Metric Name"]] = float(d["Metric Value"].replace(",", ""))
+        except ValueError:
+            pass
+    return list(L.values())
+
+
+def kernel_table(items, title):
+    agg = collections.OrderedDict()
+    for o in items:
+        a = agg.setdefault(o["kernel"], [0, 0.0, 0.0])
+        a[0] += 1
+        a[1] += o.get("gpu__time_duration.sum", 0.0)
+        a[2] += o.get("dram__bytes_read.sum", 0.0) + o.get("dram__bytes_write.sum", 0.0)
+    tot = sum(a[1] for a in agg.values()) or 1.0
+    out = [title, f"{'kernel':60s} {'launches':>8s} {'time us':>12s} {'share':>7s} {'dram MB':>10s}"]
+    for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        out.append(f"{k[:60]:60s} {a[0]:8d} {a[1] / 1e3:12.1f} {100 * a[1] / tot:6.1f}% {a[2] / 1e6:10.1f}")
+    return "\n".join(out)
+
+
+def raw_page(rep, metrics):
+    txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(txt.splitlines()))
+    hdr = rows[0]
+    idx = {h: i for i, h in enumerate(hdr)}
+    out = []
+    for r in rows[2:]:
+        out.append({m: r[idx[m]] for m in ["Kernel Name", "Grid Size"] + metrics if m in idx})
+    return out
+
+
+FULL = ["gpu__time_duration.sum", "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+        "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum", "smsp__thread_inst_executed_per_inst_executed.ratio",
+        "launch__registers_per_thread", "dram__bytes_read.sum", "dram__bytes_write.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+        "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio", "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio"]
+SHORT = ["time", "alu_pipe%", "issue%", "warps%", "warp_inst", "thr/inst", "regs", "dram_rd", "dram_wr", "smem_conflicts", "stall_math_throttle", "stall_long_sb"]
+
+
+def full_table(rep, title):
+    rows = raw_page(rep, FULL)
+    out = [title, "kernel | grid | " + " | ".join(SHORT)]
+    for r in rows:
+        out.append(f"{r['Kernel Name'].split('(')[0].replace('void ', '')[:34]:34s} | {r['Grid Size']:14s} | " + " | ".join(str(r.get(m, ''))[:11] for m in FULL))
+    return "\n".join(out), rows
+
+
+def main():
+    # ---- config 2 launch list ----
+    p = os.path.join(SRC, f"{TAG}_launches_c2.csv")
+    if os.path.exists(p):
+        items = launches(p)
+        open(os.path.join(DST, f"{TAG}_launches_c2_summary.txt"), "w").write(
+            "ncu launch list of `python bench.py --steps 2 --warmup 3 --no-sweep` (16 blocks per step; --metrics gpu__time_duration.sum,dram__bytes_*;\n"
+            "--clock-control none).  Launches are serialised and cold-cache under ncu: read SHARES, not absolutes.\n\n"
+            + kernel_table(items, f"all {len(items)} launches") + "\n\n"
+            + kernel_table([o for o in items if "at::" not in o["kernel"] and "native" not in o["kernel"]], "this library's kernels only") + "\n")
+        ours = [o for o in items if o["kernel"].startswith(("hash_level", "keccak256_batch"))]
+        hl = [o for o in ours if o["kernel"].startswith("hash_level")]
+        traffic = sum(o.get("dram__bytes_read.sum", 0) + o.get("dram__bytes_write.sum", 0) for o in hl) / max(1, len(hl))
+        json.dump({"kernel": "hash_level_kernel", "launches_in_capture": len(hl), "dram_bytes_per_launch_mean": traffic,
+                   "time_ns_per_launch_mean_under_ncu": sum(o.get("gpu__time_duration.sum", 0) for o in hl) / max(1, len(hl)),
+                   "source": f"gpurun_out/{TAG}_launches_c2.csv (ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum, all hash_level_kernel launches of the bench command)"},
+                  open(os.path.join(DST, f"{TAG}_traffic.json"), "w"), indent=1)
+    # ---- full capture of the level kernel (one block) ----
+    rep = os.path.join(SRC, f"{TAG}_hash_level_full.ncu-rep")
+    if os.path.exists(rep):
+        t, _ = full_table(rep, "ncu --set full, hash_level_kernel, the 17 level launches of one device-resident replay of one C2 block\n(PPD_HOST_THREADS=1, --blocks-per-step 1; --launch-skip 102 --launch-count 17)")
+        open(os.path.join(DST, f"{TAG}_hash_level_full.txt"), "w").write(t + "\n")
+    # ---- config 5 ----
+    p = os.path.join(SRC, f"{TAG}_launches_c5.csv")
+    if os.path.exists(p):
+        items = [o for o in launches(p) if "at::" not in o["kernel"] and "native" not in o["kernel"] and "at_cuda" not in o["kernel"]]
+        txt = "ncu launch list of `python profiles/run_c5.py 10000000 1` (sorted leaves resident in HBM -> root), this library's kernels:\n\n" + kernel_table(items, "")
+        txt += "\n\nper launch:\n" + "\n".join(f"{o['kernel'][:40]:40s} {o['grid']:16s} {o.get('gpu__time_duration.sum', 0) / 1e3:10.1f} us  dram {(o.get('dram__bytes_read.sum', 0) + o.get('dram__bytes_write.sum', 0)) / 1e6:9.1f} MB" for o in items)
+        open(os.path.join(DST, f"{TAG}_launches_c5_summary.txt"), "w").write(txt + "\n")
+    rep = os.path.join(SRC, f"{TAG}_c5_full.ncu-rep")
+    if os.path.exists(rep):
+        t, _ = full_table(rep, "ncu --set full, the hashing kernels of config 5 at 10M leaves (first 14 hash_* launches)")
+        open(os.path.join(DST, f"{TAG}_c5_full.txt"), "w").write(t + "\n")
+    for f in (f"{TAG}_bench_plain.log", f"{TAG}_c5_plain.log"):
+        if os.path.exists(os.path.join(SRC, f)):
+            open(os.path.join(DST, f), "w").write(open(os.path.join(SRC, f)).read())
+
+
+if __name__ == "__main__":
+    main()

@@ -201,25 +201,20 @@ def test_sorted_leaves_root_one_million(ctx, oracle):
     assert ctx.trie_root_sorted_leaves(keys, val_off, vals) == oracle.trie_root_from_leaves(keys, val_off, vals)
 
 
-def test_sorted_leaves_structure_independent_of_launch_shape(ctx):
+def test_sorted_leaves_root_independent_of_value_alignment(ctx):
     # size-independent property usable at full scale: the root of N leaves does not change when the
-    # values move (different alignments / offsets in the value pool), and changes when one byte of
-    # one value changes
+    # value pool is shifted by 1..3 bytes (every value at a different alignment), and does change
+    # when one bit of one value changes
     from proof_protocol_decoder_b200 import synth
 
     keys, val_off, vals = synth.gen_sorted_leaves(300_000, seed=8)
     r0 = ctx.trie_root_sorted_leaves(keys, val_off, vals)
-    # insert a 3-byte gap in front of every value: same leaves, different alignment
-    lens = np.diff(val_off).astype(np.int64)
-    off2 = np.zeros(len(lens) + 1, dtype=np.uint64)
-    off2[1:] = np.cumsum(lens)
-    vals_shifted = np.concatenate([np.zeros(1, np.uint8), vals])
-    r1 = ctx.trie_root_sorted_leaves(keys, off2 + np.uint64(0), vals)
-    assert r1 == r0
+    for k in (1, 2, 3):
+        shifted = np.concatenate([np.full(k, 0xEE, np.uint8), vals])
+        assert ctx.trie_root_sorted_leaves(keys, val_off + np.uint64(k), shifted) == r0
     vals2 = vals.copy()
     vals2[int(val_off[123456])] ^= 1
     assert ctx.trie_root_sorted_leaves(keys, val_off, vals2) != r0
-    del vals_shifted
 
 
 def test_storage_heavy_tries_sharded(ctx, oracle):
