@@ -33,6 +33,17 @@ ALU_LANES_PER_SM_CLK = 64
 N_SM = 148
 
 
+def load_traffic():
+    """Mean DRAM bytes per hash_level_kernel launch from the latest committed ncu launch list (profiles/rNN_traffic.json)."""
+    import glob
+
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_traffic.json")))
+    if not files:
+        return None, None
+    d = json.load(open(files[-1]))
+    return d.get("dram_bytes_per_launch_mean"), os.path.relpath(files[-1], ROOT)
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -341,6 +352,8 @@ def run_b200(args, rank, world, local_rank):
     alu_peak = ALU_LANES_PER_SM_CLK * N_SM * (sm_mhz or peaks["sm_max_mhz"]) * 1e6  # instr/s on one GPU
     algo_bytes = st["node_bytes"] + 32 * st["nodes_hashed"]  # L + 32 per hashed node (this rank)
     achieved_gbs = algo_bytes / dev_s_per_step / 1e9
+    traffic, traffic_src = load_traffic()
+    level_launches = max(1, int(st["kernel_launches"]) - n_blocks)  # all but the key-hash launches
     line = {
         "metric": "mpt_nodes_keccak_hashed_per_sec",
         "value": nodes_all / dev_s_per_step,
@@ -389,9 +402,12 @@ def run_b200(args, rank, world, local_rank):
             "peak": peaks["hbm_gbs"],
             "unit": "GB/s",
             "frac": achieved_gbs / peaks["hbm_gbs"],
-            "traffic": None,
+            "traffic": traffic,
+            "traffic_source": traffic_src,
+            "algorithmic_bytes_per_launch": algo_bytes / level_launches,
+            "launches_per_step": level_launches,
             "peak_source": peaks["source"],
-            "note": "Keccak is bound by the integer ALU pipe, not HBM (SURVEY.md 8d): see roofline_alu",
+            "note": "achieved = sum over the step's level launches of (L + 32) bytes per hashed node / device time of the step (lanes run concurrently, so a per-launch duration does not exist); traffic = mean DRAM bytes per hash_level_kernel launch under ncu. Keccak is bound by the integer ALU pipe, not HBM (SURVEY.md 8d): see roofline_alu",
         },
         "roofline_alu": {
             "bound": "alu-pipe (LOP3/SHF)",

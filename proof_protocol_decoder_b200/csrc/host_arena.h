@@ -92,7 +92,6 @@ struct HostArena {
   PVec<uint8_t> key_pool, val_pool, hash_pool;
   PVec<uint32_t> child_pool;
   PVec<AccountRec> accounts;
-  PVec<uint32_t> hash_rep;  // per hash_pool entry: a key that runs through the hashed-out node
   void set_allocator(PvecAlloc a, PvecFree f) {
     nodes.alloc_fn = key_pool.alloc_fn = val_pool.alloc_fn = hash_pool.alloc_fn = a;
     nodes.free_fn = key_pool.free_fn = val_pool.free_fn = hash_pool.free_fn = f;
@@ -102,7 +101,6 @@ struct HostArena {
 
   void clear() {
     nodes.clear(), level.clear(), key_pool.clear(), val_pool.clear(), hash_pool.clear(), child_pool.clear(), accounts.clear();
-    hash_rep.clear();
   }
 
   // ---- pools -------------------------------------------------------------------------------
@@ -141,11 +139,6 @@ struct HostArena {
   uint32_t nlen(uint32_t n) const { return (nodes[n].w0 >> 16) & 0xff; }
   bool is_leaf(uint32_t n) const { return kind(n) == NK_LEAF || kind(n) == NK_LEAF_ACCOUNT; }
   bool is_opaque(uint32_t n) const { return kind(n) == NK_HASH || kind(n) == NK_ROOT; }  // Node::Hash
-  // a key that runs through this node (for the nibbles leading to it)
-  uint32_t rep_key(uint32_t n) const {
-    if (is_hash_id(n)) return hash_rep[n - HASH_ID_BASE];
-    return kind(n) == NK_BRANCH ? nodes[n].a2 : nodes[n].a0;
-  }
   const uint8_t* hash_of(uint32_t n) const { return hash_pool.data() + 32ull * (n - HASH_ID_BASE); }
   uint32_t child_at(uint32_t br, uint32_t nib) const {
     uint32_t mask = nodes[br].a1, bit = 1u << nib;
@@ -162,10 +155,8 @@ struct HostArena {
     level.push_back((uint16_t)lv);
     return (uint32_t)nodes.size() - 1;
   }
-  uint32_t new_hash(uint32_t hash_idx, uint32_t rep_koff) {
+  uint32_t new_hash(uint32_t hash_idx) {
     if (hash_idx >= HASH_ID_END - HASH_ID_BASE) fail(PPD_ERR_BAD_ARGUMENT, "too many hashed-out nodes");
-    if (hash_rep.size() <= hash_idx) hash_rep.resize(hash_idx + 1);
-    hash_rep[hash_idx] = rep_koff;
     return HASH_ID_BASE + hash_idx;
   }
   uint32_t new_leaf(uint32_t koff, uint32_t start, uint32_t len, uint32_t val_off, uint32_t val_len) {
@@ -186,14 +177,14 @@ struct HostArena {
     return push({node_w0(NK_EXT, start, len), koff, child, 0}, lvl(child) + 1u);
   }
   uint32_t new_root(uint32_t child) { return push({node_w0(NK_ROOT, 0, 0), 0, child, 0}, child == NODE_EMPTY ? 0 : lvl(child) + 1u); }
-  uint32_t new_branch(uint32_t mask, const uint32_t* kids, uint32_t rep_koff) {
+  uint32_t new_branch(uint32_t mask, const uint32_t* kids) {
     uint32_t base = (uint32_t)child_pool.size(), lv = 0;
     uint32_t k = (uint32_t)__builtin_popcount(mask);
     for (uint32_t i = 0; i < k; i++) {
       child_pool.push_back(kids[i]);
       if (lvl(kids[i]) > lv) lv = lvl(kids[i]);
     }
-    return push({node_w0(NK_BRANCH, 0, 0), base, mask, rep_koff}, lv + 1u);
+    return push({node_w0(NK_BRANCH, 0, 0), base, mask, 0}, lv + 1u);
   }
   // copy of branch `br` with slot `nib` set to `child` (NODE_EMPTY removes it)
   uint32_t branch_with(uint32_t br, uint32_t nib, uint32_t child) {
@@ -202,7 +193,7 @@ struct HostArena {
       uint32_t c = (i == nib) ? child : child_at(br, i);
       if (c != NODE_EMPTY) kids[k++] = c, nmask |= 1u << i;
     }
-    return new_branch(nmask, kids, rep_key(kids[0]));  // the representative key stays inside the subtree
+    return new_branch(nmask, kids);
   }
 
   // ---- persistent operations; keys are (koff, klen) full keys in key_pool --------------------
@@ -230,7 +221,7 @@ struct HostArena {
       kids[0] = existing, kids[1] = leaf;
     else
       kids[0] = leaf, kids[1] = existing;
-    uint32_t br = new_branch(mask, kids, koff);
+    uint32_t br = new_branch(mask, kids);
     return cp == 0 ? br : new_ext(koff, pos, cp, br);
   }
 
@@ -290,7 +281,7 @@ struct HostArena {
         uint32_t r = remove(nodes[node].a1, koff, klen, pos + el);
         if (r == UNCHANGED) return UNCHANGED;
         if (r == NODE_EMPTY) return NODE_EMPTY;
-        return collapse_ext(rep_key(r), es, el, r);
+        return collapse_ext(ek, es, el, r);  // the extension's own key spells its nibbles
       }
       case NK_BRANCH: {
         if (pos >= klen) return UNCHANGED;
@@ -304,7 +295,14 @@ struct HostArena {
         if (cnt == 0) return NODE_EMPTY;
         uint32_t other_nib = (uint32_t)__builtin_ctz(left);
         uint32_t other = child_at(node, other_nib);
-        return collapse_ext(rep_key(other), pos, 1, other);
+        // a key that runs through the surviving child: the removed key's first `pos` nibbles, then its slot
+        uint32_t pk = (uint32_t)key_pool.size();
+        key_pool.resize(pk + pos / 2 + 2);
+        memcpy(key_pool.data() + pk, key_pool.data() + koff, pos / 2 + 1);
+        uint8_t* last = key_pool.data() + pk + pos / 2;
+        *last = (pos & 1) ? (uint8_t)((*last & 0xf0) | other_nib) : (uint8_t)(other_nib << 4);
+        key_pool[pk + pos / 2 + 1] = 0;
+        return collapse_ext(pk, pos, 1, other);
       }
       default: {
         uint32_t lk = nodes[node].a0, ls = nstart(node), ll = nlen(node);

@@ -418,7 +418,7 @@ uint32_t build_range(HostArena& A, const std::vector<TrieItem>& it, size_t lo, s
   if (hi - lo == 1) {
     const TrieItem& x = it[lo];
     if (x.kind == 2) {
-      uint32_t h = A.new_hash(x.a1, x.koff);
+      uint32_t h = A.new_hash(x.a1);
       return x.klen == depth ? h : A.new_ext(x.koff, depth, x.klen - depth, h);
     }
     if (x.kind == 1) return A.new_account_leaf(x.koff, depth, x.klen - depth, x.a1);
@@ -440,7 +440,7 @@ uint32_t build_range(HostArena& A, const std::vector<TrieItem>& it, size_t lo, s
     mask |= 1u << nib;
     i = j;
   }
-  uint32_t br = A.new_branch(mask, kids, f.koff);
+  uint32_t br = A.new_branch(mask, kids);
   return cp == 0 ? br : A.new_ext(f.koff, depth, cp, br);
 }
 
@@ -861,21 +861,18 @@ struct WitnessTrie {
     const WNode& in = b.wit.ins[idx];
     switch (in.op) {
       case PPD_OP_BRANCH: {
-        uint32_t m = in.aux, kids[16], mask = 0, k = 0, rep = 0;
+        uint32_t m = in.aux, kids[16], mask = 0, k = 0;
         for (int32_t c = in.first_child; c >= 0; c = b.wit.ins[c].next_sibling) {
           uint32_t nib = (uint32_t)__builtin_ctz(m);
           m &= m - 1;
           if (depth >= 64) fail(PPD_ERR_KEY_ERROR, "key longer than 64 nibbles");
           set_nibble(depth, nib);
           uint32_t r = convert(c, depth + 1);
-          if (r != NODE_EMPTY) {
-            if (k == 0) rep = A.rep_key(r);
-            kids[k++] = r, mask |= 1u << nib;
-          }
+          if (r != NODE_EMPTY) kids[k++] = r, mask |= 1u << nib;
         }
         if (k == 0) return NODE_EMPTY;
         if (k < 2) canonical = false;
-        return A.new_branch(mask, kids, rep);
+        return A.new_branch(mask, kids);
       }
       case PPD_OP_CODE: {
         if (!is_storage) {  // code found inside a storage subtree is dropped by the reference
@@ -886,17 +883,15 @@ struct WitnessTrie {
       }
       case PPD_OP_EMPTY_ROOT:
         return NODE_EMPTY;
-      case PPD_OP_HASH: {
-        uint32_t koff = add_packed_key(depth);
-        return A.new_hash(A.add_hash(b.wit.hash(in)), koff);
-      }
+      case PPD_OP_HASH:
+        return A.new_hash(A.add_hash(b.wit.hash(in)));
       case PPD_OP_EXTENSION: {
         uint32_t nd = push_key_nibbles(b.wit.key(in), depth);
         uint32_t r = convert(in.first_child, nd);
         if (r == NODE_EMPTY) return NODE_EMPTY;
         uint32_t kd = A.kind(r);
         if (nd == depth || !(kd == NK_BRANCH || kd == NK_HASH)) canonical = false;
-        return A.new_ext(A.rep_key(r), depth, nd - depth, r);
+        return A.new_ext(add_packed_key(nd), depth, nd - depth, r);
       }
       case PPD_OP_LEAF: {
         uint32_t nd = push_key_nibbles(b.wit.key(in), depth);
@@ -984,7 +979,6 @@ struct ArenaMark {
   void rewind(HostArena& A) const {
     A.nodes.resize(nodes), A.level.resize(nodes), A.key_pool.resize(keys), A.val_pool.resize(vals), A.hash_pool.resize(hashes);
     A.child_pool.resize(children), A.accounts.resize(accounts);
-    if (A.hash_rep.size() > hashes / 32) A.hash_rep.resize(hashes / 32);
   }
 };
 
@@ -1105,6 +1099,15 @@ void build_pre_image(Job& J, BlockJob& b) {
   if (W.root < 0) return;
   // storage tries, in stream order (compact_prestate_processing.rs:608-625)
   b.storage_root_of_instr.clear();
+  {
+    size_t n_acct = 0, n_storage = 0;
+    for (const WNode& x : W.ins) n_acct += x.op == PPD_OP_ACCOUNT_LEAF, n_storage += (x.op == PPD_OP_ACCOUNT_LEAF && (x.flags & 2));
+    b.storage.reserve(n_acct);
+    b.pre_accounts.reserve(n_acct);
+    b.pre_with_storage.reserve(n_storage);
+    b.storage_root_of_instr.reserve(n_storage);
+    b.root_of.reserve(2 * n_storage + 1024);
+  }
   b.have_empty_form = false;
   b.empty_form = NODE_EMPTY;
   for (int32_t i = 0; i < (int32_t)W.ins.size(); i++) {
@@ -1116,6 +1119,36 @@ void build_pre_image(Job& J, BlockJob& b) {
   }
   b.state_root = build_witness_trie(J, b, W.root, false);
 }
+
+struct PhaseTimer {
+  bool on = getenv("PPD_TIMING") != nullptr;
+  std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
+  void lap(const char* what) {
+    if (!on) return;
+    auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "[ppd] %-10s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t).count());
+    t = now;
+  }
+};
+// accumulating timer for the sections of the txn loop (PPD_TIMING only)
+struct SectionTimer {
+  bool on = getenv("PPD_TIMING") != nullptr;
+  double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  std::chrono::steady_clock::time_point t;
+  void start() {
+    if (on) t = std::chrono::steady_clock::now();
+  }
+  void stop(int k) {
+    if (!on) return;
+    auto now = std::chrono::steady_clock::now();
+    acc[k] += std::chrono::duration<double, std::milli>(now - t).count();
+    t = now;
+  }
+  void report(const char* const* names, int n) {
+    if (!on) return;
+    for (int k = 0; k < n; k++) fprintf(stderr, "[ppd]   %-12s %8.3f ms\n", names[k], acc[k]);
+  }
+};
 
 // ---- step 3: the txn loop (decoding.rs:80-177), shaping only ------------------------------------
 uint32_t key_from_digest(Job& J, const H256& h) { return J.A.add_key_bytes(h.b, 32); }
@@ -1177,7 +1210,10 @@ void apply_withdrawals(Job& J, BlockJob& b, uint32_t& state_root) {
 
 void shape_block(Job& J, BlockJob& b) {
   HostArena& A = J.A;
+  SectionTimer sec;
+  sec.start();
   build_pre_image(J, b);
+  sec.stop(0);
   const uint32_t initial_state = b.state_root;
   const auto initial_storage = b.storage;
   uint32_t state = b.state_root, txn_trie = NODE_EMPTY, receipt_trie = NODE_EMPTY;
@@ -1217,6 +1253,7 @@ void shape_block(Job& J, BlockJob& b) {
       receipt = Span{it.payload, (uint32_t)it.payload_len};
     }
 
+    sec.stop(1);
     // ---- create_minimal_partial_tries_needed_by_txn (decoding.rs:179-217) ----
     uint32_t tk_len = 0;
     uint32_t tk = txn_index_key(J, ti, tk_len);
@@ -1247,6 +1284,7 @@ void shape_block(Job& J, BlockJob& b) {
       p.storage_subs.push_back({haddr, sroot});
     }
     gas_after += tx.gas_used;
+    sec.stop(2);
 
     // ---- apply_deltas_to_trie_state (decoding.rs:219-292) ----
     for (TraceV& tr : tx.traces) {
@@ -1268,6 +1306,7 @@ void shape_block(Job& J, BlockJob& b) {
         }
       }
     }
+    sec.stop(3);
     for (size_t i = 0; i < tx.traces.size(); i++) {
       TraceV& tr = tx.traces[i];
       bool storage_change = tr.n_writes != 0;
@@ -1298,6 +1337,7 @@ void shape_block(Job& J, BlockJob& b) {
       A.accounts.push_back(rec);
       state = A.insert(state, haddr_key[i], 64, 0, HostArena::Payload{true, r, 0});
     }
+    sec.stop(4);
     for (size_t i = 0; i < tx.traces.size(); i++) {
       if (!(tx.traces[i].flags & PPD_TR_SELF_DESTRUCTED)) continue;
       const H256& haddr = J.kh.digest[tx.traces[i].m_addr];
@@ -1323,6 +1363,11 @@ void shape_block(Job& J, BlockJob& b) {
     txn_before += 1;
     gas_before = gas_after;
     b.irs.push_back(std::move(p));
+    sec.stop(5);
+  }
+  {
+    static const char* const names[] = {"pre-image", "code/receipt", "marks", "storage-wr", "state-wr", "rest"};
+    sec.report(names, 6);
   }
 
   // ---- pad_gen_inputs_with_dummy_inputs_if_needed (decoding.rs:304-347) ----
@@ -1794,17 +1839,6 @@ int guarded(ppd_ctx* c, F f) {
     return PPD_ERR_BAD_ARGUMENT;
   }
 }
-
-struct PhaseTimer {
-  bool on = getenv("PPD_TIMING") != nullptr;
-  std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
-  void lap(const char* what) {
-    if (!on) return;
-    auto now = std::chrono::steady_clock::now();
-    fprintf(stderr, "[ppd] %-10s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t).count());
-    t = now;
-  }
-};
 
 // One block on one lane: parse, key hashes, shaping, sweep, dump.  A failure that is the block's own
 // (bad input, a reference panic site) is reported through *status; a CUDA failure is thrown.
