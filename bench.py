@@ -254,7 +254,7 @@ def run_b200(args, rank, world, local_rank):
     threads = max(1, min(16, cores // world))
     os.environ.setdefault("PPD_HOST_THREADS", str(threads))
     threads = int(os.environ["PPD_HOST_THREADS"])
-    n_blocks = args.blocks_per_step or threads
+    n_blocks = args.blocks_per_step or 16  # per GPU, whatever the world size (weak scaling)
     seeds = [2 + rank * n_blocks + j for j in range(n_blocks)]
     # generated before CUDA is touched (worker processes are forked); ranks generate their own blocks
     flats = c2_blocks(seeds, args.scale, max(1, cores // world))
@@ -368,7 +368,7 @@ def run_b200(args, rank, world, local_rank):
         "dtype": "u64",
         "data": "synthetic",
         "config": {
-            "workload": f"C2 mainnet-shaped blocks (BASELINE.json configs[1]): 20k touched accounts in a virtual 16^7-account state, 200 txns each; a batch of {n_blocks} independent blocks per GPU per step, one block per host thread",
+            "workload": f"C2 mainnet-shaped blocks (BASELINE.json configs[1]): 20k touched accounts in a virtual 16^7-account state, 200 txns each; a batch of {n_blocks} independent blocks per GPU per step, one lane (stream + pools) per block, {threads} host thread(s) per GPU",
             "scale": args.scale,
             "blocks_per_step_per_gpu": n_blocks,
             "host_threads_per_gpu": threads,
@@ -445,7 +445,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--scale", type=float, default=1.0, help="fraction of the C2 block size (1.0 = the named config)")
-    ap.add_argument("--blocks-per-step", type=int, default=0, help="blocks per GPU per step (default: one per host thread)")
+    ap.add_argument("--blocks-per-step", type=int, default=0, help="blocks per GPU per step (default 16)")
     ap.add_argument("--ref-scale", type=float, default=0.1, help="size of the bounded CPU sample block")
     ap.add_argument("--sweep", default="1000000,10000000", help="config-5 leaf counts measured beside the headline at N=1")
     ap.add_argument("--no-sweep", action="store_true")

@@ -1879,25 +1879,30 @@ void add_stats(ppd_stats& a, const ppd_stats& b) {
 // Blocks are independent (each BlockTrace carries its own pre-image, trace_protocol.rs:40-48): every
 // host thread takes blocks on its own lane, so parsing / shaping of one block overlaps the copies and
 // kernels of the others.
+static const size_t MAX_LANES = 32;
+
 void decode_blocks(ppd_ctx* c, const uint8_t* const* flats, const size_t* lens, size_t n, uint8_t** outs, size_t* out_lens, int* statuses) {
   stats_reset(c);
   if (!n) return;
-  const unsigned workers = (unsigned)std::min<size_t>(host_threads(), n);
-  for (unsigned w = 0; w < workers; w++) {
+  // block i runs on lane i mod n_lanes; a host thread takes whole lanes, so a lane never runs two
+  // blocks at once and the last block of every lane stays resident in HBM (ppd_replay_last_hashing)
+  const size_t n_lanes = std::min(n, MAX_LANES);
+  const unsigned workers = (unsigned)std::min<size_t>(host_threads(), n_lanes);
+  for (size_t w = 0; w < n_lanes; w++) {
     Lane* L = lane_of(c, w);
     L->stats = ppd_stats{};
     L->has_last = false;
   }
   const unsigned dump_workers = std::max(1u, host_threads() / workers);
   for (size_t i = 0; i < n; i++) outs[i] = nullptr, out_lens[i] = 0, statuses[i] = PPD_OK;
-  parallel_for(n, workers, [&](size_t i, unsigned w) {
+  parallel_for(n_lanes, workers, [&](size_t lane, unsigned) {
 #ifndef PPD_HOSTPROF
     CUDA_OK(cudaSetDevice(c->device));
 #endif
-    decode_one(c, c->lanes[w], flats[i], lens[i], &outs[i], &out_lens[i], &statuses[i], dump_workers);
+    for (size_t i = lane; i < n; i += n_lanes) decode_one(c, c->lanes[lane], flats[i], lens[i], &outs[i], &out_lens[i], &statuses[i], dump_workers);
   });
-  c->last_lanes_used = workers;
-  for (unsigned w = 0; w < workers; w++) add_stats(c->stats, c->lanes[w]->stats);
+  c->last_lanes_used = n_lanes;
+  for (size_t w = 0; w < n_lanes; w++) add_stats(c->stats, c->lanes[w]->stats);
 }
 
 }  // namespace
