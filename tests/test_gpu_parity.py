@@ -242,3 +242,62 @@ def test_batch_larger_than_lane_count_with_a_bad_block(ctx, oracle):
             assert isinstance(o, PpdError) and o.code == 40
         else:
             assert o == oracle.block_decode(f), f"block {i}"
+
+
+def _mutations(w: bytes, rng, n):
+    out = []
+    for _ in range(n):
+        b = bytearray(w)
+        kind = rng.integers(0, 6)
+        if kind == 0 and len(b) > 2:  # flip one byte
+            i = int(rng.integers(1, len(b)))
+            b[i] ^= 1 << int(rng.integers(0, 8))
+        elif kind == 1 and len(b) > 2:  # truncate
+            b = b[: int(rng.integers(1, len(b)))]
+        elif kind == 2:  # insert a random byte
+            i = int(rng.integers(1, len(b) + 1))
+            b[i:i] = bytes([int(rng.integers(0, 256))])
+        elif kind == 3 and len(b) > 4:  # delete a short slice
+            i = int(rng.integers(1, len(b) - 1))
+            del b[i : i + int(rng.integers(1, 4))]
+        elif kind == 4 and len(b) > 8:  # duplicate a slice
+            i = int(rng.integers(1, len(b) - 4))
+            k = int(rng.integers(1, 40))
+            b[i:i] = b[i : i + k]
+        else:  # overwrite an opcode-looking byte
+            i = int(rng.integers(1, len(b)))
+            b[i] = int(rng.integers(0, 8))
+        out.append(bytes(b))
+    return out
+
+
+def test_mutated_witnesses_same_status_or_same_result(ctx, oracle, goldens):
+    # robustness parity: corrupt witnesses must fail with the same status as the oracle,
+    # and the ones that still decode must decode to the same tries
+    from proof_protocol_decoder_b200 import PpdError, flat, synth
+
+    rng = np.random.default_rng(2024)
+    seeds = [bytes.fromhex(g["witness_hex"]) for g in goldens["compact_goldens"]]
+    blk = synth.gen_block(31, n_accounts=40, n_txns=1, virtual_depth=3, virtual_accounts_log16=3, contract_frac=0.3)
+    bt, _, _ = blk.to_block_trace()
+    seeds.append(bytes(bt.trie_pre_images["combined"]["compact"]))
+    n_err = n_ok = 0
+    for w in seeds:
+        for m in _mutations(w, rng, 120):
+            try:
+                want = parse_pre_image_dump(oracle.compact_decode(m))
+                want_code = 0
+            except OracleError as e:
+                want, want_code = None, e.code
+            try:
+                got = flat.parse_pre_image_dump(ctx.compact_decode(m))
+                got_code = 0
+            except PpdError as e:
+                got, got_code = None, e.code
+            assert got_code == want_code, f"status {got_code} vs oracle {want_code} for witness {m.hex()}"
+            if want is not None:
+                assert got["state_root"] == want["state_root"] and got["storage"] == want["storage"] and got["code"] == want["code"], m.hex()
+                n_ok += 1
+            else:
+                n_err += 1
+    assert n_err > 100 and n_ok > 20
