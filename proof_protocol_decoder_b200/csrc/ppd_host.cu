@@ -273,6 +273,12 @@ uint32_t compact_key_nibbles(Span k, uint8_t* out) {
   return c;
 }
 
+// key_bytes_to_nibbles runs while the instructions are read (compact_prestate_processing.rs:787-835), so
+// a key of more than 64 nibbles is reported in stream order, before any later parse error
+void check_key_length(Span k) {
+  if (k.n >= 2 && 2 * (k.n - 1) > 64 + 1) fail(PPD_ERR_KEY_ERROR, "compact key longer than 64 nibbles");
+}
+
 struct Witness {
   const uint8_t* bytes = nullptr;
   size_t len = 0;
@@ -319,11 +325,11 @@ void parse_witness(const uint8_t* w, size_t n, Witness& out) {
     in.aux = ~0u;
     switch (in.op) {
       case PPD_OP_LEAF:
-        c.cbor_bytes(PPD_ERR_INVALID_BYTE_VECTOR);
+        check_key_length(c.cbor_bytes(PPD_ERR_INVALID_BYTE_VECTOR));
         c.cbor_bytes(PPD_ERR_INVALID_BYTE_VECTOR);
         break;
       case PPD_OP_EXTENSION:
-        c.cbor_bytes(PPD_ERR_INVALID_BYTE_VECTOR);
+        check_key_length(c.cbor_bytes(PPD_ERR_INVALID_BYTE_VECTOR));
         break;
       case PPD_OP_BRANCH:
         in.aux = (uint32_t)c.cbor_uint(0xffffffffull);
@@ -336,7 +342,7 @@ void parse_witness(const uint8_t* w, size_t n, Witness& out) {
         c.cbor_bytes(PPD_ERR_INVALID_BYTES_FOR_TYPE);
         break;
       case PPD_OP_ACCOUNT_LEAF: {
-        c.cbor_bytes(PPD_ERR_INVALID_BYTE_VECTOR);
+        check_key_length(c.cbor_bytes(PPD_ERR_INVALID_BYTE_VECTOR));
         in.flags = c.read_byte();
         if (in.flags & 4) c.cbor_uint(~0ull);
         if (in.flags & 8) {

@@ -301,3 +301,66 @@ def test_mutated_witnesses_same_status_or_same_result(ctx, oracle, goldens):
             else:
                 n_err += 1
     assert n_err > 100 and n_ok > 20
+
+
+def _error_cases():
+    """(name, FlatBlock) pairs that must fail: each is a valid synthetic block with one thing broken."""
+    import copy
+    import struct
+
+    from proof_protocol_decoder_b200 import synth
+
+    def base(**kw):
+        return synth.gen_block(55, n_accounts=80, n_txns=3, n_withdrawals=1, **kw)
+
+    cases = []
+    b = base()
+    b.withdrawals = [(bytes(range(20)), 5)]  # an account that is not in the state trie
+    cases.append(("withdrawal_to_missing_account", b.flat))
+
+    b = base(virtual_depth=3, virtual_accounts_log16=3)
+    b.txns = copy.deepcopy(b.txns)
+    b.txns[0]["traces"].append((bytes([7] * 20), {"balance": 1}))  # its path runs into a hashed-out subtree
+    cases.append(("touched_account_behind_hash_node", b.flat))
+
+    b = base()
+    b.txns = copy.deepcopy(b.txns)
+    addr, tr = b.txns[1]["traces"][0]
+    tr = dict(tr)
+    tr.pop("code_write", None)
+    tr["code_read"] = bytes([0xAB] * 32)  # nobody can resolve this hash
+    b.txns[1]["traces"][0] = (addr, tr)
+    cases.append(("unresolvable_code_hash", b.flat))
+
+    b = base()
+    b.txns = copy.deepcopy(b.txns)
+    b.txns[2]["new_receipt_trie_node_byte"] = b"\xc1\x80"  # a list that is not a legacy receipt
+    cases.append(("receipt_neither_legacy_nor_string", b.flat))
+
+    b = base()
+    f = bytearray(b.flat)
+    cases.append(("truncated_flat_block", bytes(f[: len(f) // 2])))
+    f2 = bytearray(b.flat)
+    struct.pack_into("<I", f2, 8, 1)  # pre_image_kind = Separate: todo!() in the reference
+    cases.append(("unimplemented_pre_image_kind", bytes(f2)))
+
+    b = base()
+    b.compact = b"\x02" + b.compact[1:]  # header version 2: assert at processed_block_trace.rs:175
+    cases.append(("incompatible_header_version", b.flat))
+    return cases
+
+
+@pytest.mark.parametrize("name,flat_block", _error_cases(), ids=[c[0] for c in _error_cases()])
+def test_block_error_statuses_match_oracle(ctx, oracle, name, flat_block):
+    from proof_protocol_decoder_b200 import PpdError
+
+    with pytest.raises(OracleError) as eo:
+        oracle.block_decode(flat_block)
+    with pytest.raises(PpdError) as eg:
+        ctx.block_decode(flat_block)
+    assert eg.value.code == eo.value.code, f"{name}: {eg.value} vs {eo.value}"
+    # the context stays usable after a failed block
+    from proof_protocol_decoder_b200 import synth
+
+    ok = synth.gen_block(56, n_accounts=30, n_txns=1).flat
+    assert ctx.block_decode(ok) == oracle.block_decode(ok)
