@@ -10,6 +10,7 @@
 // The host never computes a Keccak or a node encoding.  If the CUDA device or the kernels are not
 // usable every entry point fails with PPD_ERR_CUDA: there is no CPU fallback.
 #include <cuda_runtime.h>
+#include <sys/mman.h>
 
 #include <algorithm>
 #include <chrono>
@@ -1530,7 +1531,20 @@ struct Out {
     if (n + k <= cap) return;
     size_t nc = cap ? cap * 2 : 4096;
     while (nc < n + k) nc *= 2;
-    uint8_t* q = (uint8_t*)realloc(p, nc);
+    uint8_t* q;
+    if (nc >= (8u << 20)) {
+      // large output buffers: 2 MiB-aligned and advised for transparent huge pages, so that first-touch
+      // costs a few dozen page faults instead of thousands (free() releases it like any malloc block)
+      nc = (nc + (2u << 20) - 1) & ~(size_t)((2u << 20) - 1);
+      q = (uint8_t*)aligned_alloc(2u << 20, nc);
+      if (q) {
+        madvise(q, nc, MADV_HUGEPAGE);
+        if (n) memcpy(q, p, n);
+        free(p);
+      }
+    } else {
+      q = (uint8_t*)realloc(p, nc);
+    }
     if (!q) fail(PPD_ERR_BAD_ARGUMENT, "out of host memory");
     p = q, cap = nc;
   }
@@ -1672,13 +1686,32 @@ void dump_subset(const Job& J, const Stamp& st, Out& o, uint32_t node) {
           __builtin_prefetch(J.ref.data() + 32ull * c);
         }
       }
+      // hashed-out and untouched children are written inline (33 bytes each); only expanded children recurse
       o.need(16 * 33 + 8);
+      uint8_t* q = o.p + o.n;
       for (uint32_t i = 0, j = 0; i < 16; i++) {
-        if (mask & (1u << i))
-          dump_subset(J, st, o, ch[j++]);
-        else
-          o.p[o.n++] = PPD_NODE_EMPTY;
+        if (!(mask & (1u << i))) {
+          *q++ = PPD_NODE_EMPTY;
+          continue;
+        }
+        const uint32_t c = ch[j++];
+        const uint8_t* h = nullptr;
+        if (is_hash_id(c))
+          h = A.hash_of(c);
+        else if ((st.v[c] != st.serial && J.ref_len[c] == 32) || A.is_opaque(c))
+          h = J.ref.data() + 32ull * c;
+        if (h) {
+          *q++ = PPD_NODE_HASH;
+          memcpy(q, h, 32);
+          q += 32;
+        } else {
+          o.n = (size_t)(q - o.p);
+          dump_subset(J, st, o, c);
+          o.need((16 - i) * 33 + 8);
+          q = o.p + o.n;
+        }
       }
+      o.n = (size_t)(q - o.p);
       o.u32(0);
       return;
     }
