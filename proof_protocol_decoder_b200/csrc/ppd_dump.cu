@@ -1,0 +1,398 @@
+// ppd_dump.cu — serialising the per-txn sub-tries (IrDump "Trie" blobs, include/ppd_flat.h) ON THE GPU.
+//
+// Replaces the host walk that cut every txn's minimal sub-tries out of the hashed arena
+// (create_trie_subset, decoding.rs:551-602: keep every node on the path of an accessed key, replace
+// every untouched subtree by Hash(subtree hash)).  After the sweep the arena, the witness hashes and
+// every ref are resident in HBM, so cutting a subset is a gather: the host only uploads, per IR, the
+// ids of the nodes its keys touched and the order of its tries; the device
+//   1. ir_size_kernel  (one CTA per IR): de-duplicates the touched ids in a shared-memory hash set,
+//      computes every touched node's serialised size bottom-up (children that are touched are looked
+//      up in the set, all others are 1 byte (empty) or 33 bytes (hash)), lays the IR's segments
+//      (host literals and tries) out, and assigns every touched node its byte offset top-down;
+//   2. ir_emit_kernel  (one CTA per IR): every touched node writes its own bytes at its offset.
+// The IR's literal bytes (counters, signed txn, code map ...) are written by the host into the holes.
+// An IR the kernels cannot lay out (more unique touched nodes than the set holds, a node shared by two
+// tries of the IR, an untouched child whose encoding is shorter than 32 bytes, which the subset keeps
+// expanded) is flagged and serialised by the host instead.
+#include <cstdint>
+
+#include "../../include/ppd_flat.h"
+#include "arena.h"
+#include "ppd_kernels.h"
+
+namespace ppd {
+
+namespace {
+
+constexpr uint32_t HASH_ID_BASE = 0x80000000u;
+constexpr uint32_t SET_CAP = 8192, MAX_UNIQ = 4096, NOT_FOUND = 0xffffffffu, UNSET = 0xffffffffu;
+constexpr int DUMP_THREADS = 256;
+
+struct Shared {
+  uint32_t key[SET_CAP];   // node id or NODE_EMPTY
+  uint16_t slot[SET_CAP];  // index into the u_* arrays
+  uint32_t u_node[MAX_UNIQ], u_size[MAX_UNIQ], u_off[MAX_UNIQ];
+  uint32_t n_uniq, n_done, flag;
+};
+
+__device__ __forceinline__ uint32_t hash_slot(uint32_t id) { return (id * 2654435761u) >> 19; }  // 13 bits
+
+__device__ __forceinline__ uint32_t set_find(const Shared& s, uint32_t id) {
+  uint32_t h = hash_slot(id);
+  for (;;) {
+    uint32_t k = s.key[h];
+    if (k == id) return s.slot[h];
+    if (k == NODE_EMPTY) return NOT_FOUND;
+    h = (h + 1) & (SET_CAP - 1);
+  }
+}
+
+__device__ __forceinline__ bool is_hash_id(uint32_t id) { return id >= HASH_ID_BASE && id != NODE_EMPTY; }
+__device__ __forceinline__ uint32_t node_kind(const ArenaView& A, uint32_t id) { return A.nodes[id].w0 & 0xff; }
+
+__device__ __forceinline__ uint32_t u256_sig(const uint8_t* be) {
+  uint32_t i = 0;
+  while (i < 32 && be[i] == 0) i++;
+  return 32 - i;
+}
+__device__ __forceinline__ uint32_t u256_str_len(const uint8_t* be, uint32_t sig) { return sig == 0 ? 1u : (sig == 1 && be[31] < 0x80) ? 1u : 1u + sig; }
+// rlp([nonce, balance, storage_root, code_hash]): always a long list (payload >= 68)
+__device__ __forceinline__ uint32_t account_rlp_len(const AccountRec& r) {
+  return 2 + u256_str_len(r.nonce, u256_sig(r.nonce)) + u256_str_len(r.balance, u256_sig(r.balance)) + 66;
+}
+
+// serialised size of child `c` of a touched node: 1 (empty), 33 (hash), its own size when it is touched
+// itself (UNSET while that is not known yet).  Sets *flag for an untouched child kept expanded (< 32 bytes).
+__device__ __forceinline__ uint32_t child_size(const ArenaView& A, const Shared& s, uint32_t c, uint32_t* flag) {
+  if (c == NODE_EMPTY) return 1;
+  if (is_hash_id(c)) return 33;
+  uint32_t k = set_find(s, c);
+  if (k != NOT_FOUND) return s.u_size[k];
+  if (A.ref_len[c] != 32 && node_kind(A, c) != NK_ROOT) *flag = 1;
+  return 33;
+}
+
+// size of node u given its children's sizes, or UNSET when a touched child is not sized yet
+__device__ uint32_t node_size(const ArenaView& A, const Shared& s, uint32_t u, uint32_t* flag) {
+  const NodeRec r = A.nodes[u];
+  const uint32_t kind = r.w0 & 0xff, nlen = (r.w0 >> 16) & 0xff;
+  switch (kind) {
+    case NK_LEAF:
+      return 1 + 1 + nlen + 4 + r.a2;
+    case NK_LEAF_ACCOUNT:
+      return 1 + 1 + nlen + 4 + account_rlp_len(A.accounts[r.a1]);
+    case NK_EXT: {
+      uint32_t cs = child_size(A, s, r.a1, flag);
+      return cs == UNSET ? UNSET : 1 + 1 + nlen + cs;
+    }
+    case NK_BRANCH: {
+      const uint32_t mask = r.a1 & 0xffff, k = __popc(mask);
+      uint32_t total = 1 + (16 - k) + 4;
+      for (uint32_t j = 0; j < k; j++) {
+        uint32_t cs = child_size(A, s, A.child_pool[r.a0 + j], flag);
+        if (cs == UNSET) return UNSET;
+        total += cs;
+      }
+      return total;
+    }
+    default:  // NK_ROOT is never inserted
+      *flag = 1;
+      return 33;
+  }
+}
+
+__device__ void build_set(Shared& s, const uint32_t* ids, uint32_t n, const ArenaView& A, bool dedupe) {
+  for (uint32_t i = threadIdx.x; i < SET_CAP; i += blockDim.x) s.key[i] = NODE_EMPTY;
+  if (threadIdx.x == 0) s.n_uniq = 0, s.n_done = 0, s.flag = 0;
+  __syncthreads();
+  for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+    uint32_t id = ids[i];
+    if (id == NODE_EMPTY || is_hash_id(id)) continue;
+    if (dedupe && node_kind(A, id) == NK_ROOT) continue;  // opaque: always emitted as a hash by its parent
+    uint32_t h = hash_slot(id);
+    for (;;) {
+      uint32_t prev = atomicCAS(&s.key[h], NODE_EMPTY, id);
+      if (prev == NODE_EMPTY) {
+        uint32_t k = dedupe ? atomicAdd(&s.n_uniq, 1u) : i;
+        if (k < MAX_UNIQ) {
+          s.slot[h] = (uint16_t)k;
+          s.u_node[k] = id;
+        } else {
+          s.flag = 1;
+          s.slot[h] = 0;
+        }
+        break;
+      }
+      if (prev == id) break;
+      h = (h + 1) & (SET_CAP - 1);
+    }
+  }
+  __syncthreads();
+}
+
+}  // namespace
+
+// One CTA per IR.  Outputs: ir_size, ir_flag, ir_nuniq, and at [touched_begin[ir] + k] the k-th unique
+// touched node, its size and its offset inside the IR; seg_off[s] for every segment.
+__global__ void __launch_bounds__(DUMP_THREADS) ir_size_kernel(ArenaView A, IrDumpPlanView P) {
+  extern __shared__ uint8_t smem_raw[];
+  Shared& s = *reinterpret_cast<Shared*>(smem_raw);
+  const uint32_t ir = blockIdx.x;
+  const uint32_t tb = P.touched_begin[ir], tn = P.touched_begin[ir + 1] - tb;
+  build_set(s, P.touched + tb, tn, A, true);
+  const uint32_t nu = min(s.n_uniq, MAX_UNIQ);
+  for (uint32_t k = threadIdx.x; k < nu; k += blockDim.x) s.u_size[k] = UNSET, s.u_off[k] = UNSET;
+  __syncthreads();
+  // ---- sizes, bottom-up: a node is sized once all its touched children are ----
+  for (int round = 0; round < 80; round++) {
+    __syncthreads();
+    if (s.n_done >= nu) break;  // uniform: nothing writes between the barrier and this read
+    __syncthreads();
+    uint32_t local_flag = 0;
+    for (uint32_t k = threadIdx.x; k < nu; k += blockDim.x) {
+      if (s.u_size[k] != UNSET) continue;
+      uint32_t sz = node_size(A, s, s.u_node[k], &local_flag);
+      if (sz != UNSET) {
+        s.u_size[k] = sz;  // racy readers see UNSET or the final value
+        atomicAdd(&s.n_done, 1u);
+      }
+    }
+    if (local_flag) s.flag = 1;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && s.n_done < nu) s.flag = 1;
+  __syncthreads();
+  // ---- segments: literals and tries in output order ----
+  if (threadIdx.x == 0) {
+    uint32_t off = 0;
+    const uint32_t sb = P.seg_begin[ir], se = P.seg_begin[ir + 1];
+    for (uint32_t q = sb; q < se; q++) {
+      P.seg_off[q] = off;
+      const uint32_t a = P.seg_a[q], b = P.seg_b[q];
+      if (b == IR_SEG_LITERAL || b == IR_SEG_REF) {
+        off += b == IR_SEG_REF ? 32u : a;
+        continue;
+      }
+      uint32_t sz = 33;
+      if (b == NODE_EMPTY) {
+        sz = 1;
+      } else if (!is_hash_id(b)) {
+        uint32_t k = set_find(s, b);
+        if (k != NOT_FOUND) {
+          if (s.u_off[k] != UNSET) s.flag = 1;  // a node that roots two tries of one IR
+          s.u_off[k] = off;
+          sz = s.u_size[k];
+        } else if (A.ref_len[b] != 32 && node_kind(A, b) != NK_ROOT) {
+          s.flag = 1;
+        }
+      }
+      off += sz;
+    }
+    P.ir_size[ir] = off;
+    s.n_done = 0;
+  }
+  __syncthreads();
+  // ---- offsets, top-down: a node with an offset places its touched children ----
+  // u_size's top bit marks "children placed"
+  for (int round = 0; round < 80; round++) {
+    __syncthreads();
+    if (s.flag || s.n_done >= nu) break;  // uniform: nothing writes between the barrier and this read
+    __syncthreads();
+    for (uint32_t k = threadIdx.x; k < nu; k += blockDim.x) {
+      if (s.u_off[k] == UNSET || (s.u_size[k] & 0x80000000u)) continue;
+      const NodeRec r = A.nodes[s.u_node[k]];
+      const uint32_t kind = r.w0 & 0xff, nlen = (r.w0 >> 16) & 0xff;
+      uint32_t dummy = 0;
+      if (kind == NK_EXT) {
+        uint32_t c = is_hash_id(r.a1) ? NOT_FOUND : set_find(s, r.a1);
+        if (c != NOT_FOUND) {
+          if (s.u_off[c] != UNSET) s.flag = 1;
+          s.u_off[c] = s.u_off[k] + 2 + nlen;
+        }
+      } else if (kind == NK_BRANCH) {
+        const uint32_t mask = r.a1 & 0xffff;
+        uint32_t off = s.u_off[k] + 1;
+        for (uint32_t i = 0, j = 0; i < 16; i++) {
+          if (!(mask & (1u << i))) {
+            off += 1;
+            continue;
+          }
+          uint32_t cid = A.child_pool[r.a0 + j++];
+          uint32_t c = is_hash_id(cid) ? NOT_FOUND : set_find(s, cid);
+          if (c != NOT_FOUND) {
+            if (s.u_off[c] != UNSET) s.flag = 1;
+            s.u_off[c] = off;
+            off += s.u_size[c] & 0x7fffffffu;
+          } else {
+            off += child_size(A, s, cid, &dummy);
+          }
+        }
+      }
+      s.u_size[k] |= 0x80000000u;
+      atomicAdd(&s.n_done, 1u);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (s.n_done < nu) s.flag = 1;  // a touched node no trie of the IR reaches
+    P.ir_flag[ir] = s.flag;
+    P.ir_nuniq[ir] = nu;
+  }
+  for (uint32_t k = threadIdx.x; k < nu; k += blockDim.x) {
+    P.u_node[tb + k] = s.u_node[k];
+    P.u_size[tb + k] = s.u_size[k] & 0x7fffffffu;
+    P.u_off[tb + k] = s.u_off[k];
+  }
+}
+
+namespace {
+
+__device__ __forceinline__ uint8_t* put_hash(uint8_t* q, const uint8_t* h32) {
+  *q++ = PPD_NODE_HASH;
+  const uint4* src = reinterpret_cast<const uint4*>(h32);
+  uint4 x = __ldg(src), y = __ldg(src + 1);
+  const uint32_t w[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    q[4 * i] = (uint8_t)w[i], q[4 * i + 1] = (uint8_t)(w[i] >> 8), q[4 * i + 2] = (uint8_t)(w[i] >> 16), q[4 * i + 3] = (uint8_t)(w[i] >> 24);
+  }
+  return q + 32;
+}
+__device__ __forceinline__ uint8_t* put_u32(uint8_t* q, uint32_t v) {
+  q[0] = (uint8_t)v, q[1] = (uint8_t)(v >> 8), q[2] = (uint8_t)(v >> 16), q[3] = (uint8_t)(v >> 24);
+  return q + 4;
+}
+__device__ __forceinline__ uint8_t* put_nibbles(uint8_t* q, const ArenaView& A, const NodeRec& r) {
+  const uint32_t start = (r.w0 >> 8) & 0xff, n = (r.w0 >> 16) & 0xff;
+  const uint8_t* key = A.key_pool + r.a0;
+  *q++ = (uint8_t)n;
+  for (uint32_t i = 0; i < n; i++) {
+    uint32_t b = key[(start + i) >> 1];
+    *q++ = (uint8_t)(((start + i) & 1) ? (b & 15) : (b >> 4));
+  }
+  return q;
+}
+__device__ __forceinline__ uint8_t* put_u256_str(uint8_t* q, const uint8_t* be) {
+  uint32_t sig = u256_sig(be);
+  if (sig == 0) {
+    *q++ = 0x80;
+    return q;
+  }
+  if (!(sig == 1 && be[31] < 0x80)) *q++ = (uint8_t)(0x80 + sig);
+  for (uint32_t i = 32 - sig; i < 32; i++) *q++ = be[i];
+  return q;
+}
+// the child of a touched node: skipped when it is touched itself (it writes its own bytes)
+__device__ __forceinline__ uint8_t* put_child(uint8_t* q, const ArenaView& A, const Shared& s, uint32_t c) {
+  if (c == NODE_EMPTY) {
+    *q++ = PPD_NODE_EMPTY;
+    return q;
+  }
+  if (is_hash_id(c)) return put_hash(q, A.hash_pool + 32ull * (c - HASH_ID_BASE));
+  uint32_t k = set_find(s, c);
+  if (k != NOT_FOUND) return q + s.u_size[k];
+  return put_hash(q, A.ref + 32ull * c);
+}
+
+}  // namespace
+
+// One CTA per IR: every unique touched node writes its own bytes at out + ir_base[ir] + its offset.
+__global__ void __launch_bounds__(DUMP_THREADS) ir_emit_kernel(ArenaView A, IrDumpPlanView P, uint8_t* __restrict__ out) {
+  extern __shared__ uint8_t smem_raw[];
+  Shared& s = *reinterpret_cast<Shared*>(smem_raw);
+  const uint32_t ir = blockIdx.x;
+  if (P.ir_flag[ir]) return;  // serialised by the host
+  const uint32_t tb = P.touched_begin[ir], nu = P.ir_nuniq[ir];
+  build_set(s, P.u_node + tb, nu, A, false);
+  for (uint32_t k = threadIdx.x; k < nu; k += blockDim.x) s.u_size[k] = P.u_size[tb + k], s.u_off[k] = P.u_off[tb + k];
+  __syncthreads();
+  uint8_t* base = out + P.ir_base[ir];
+  for (uint32_t k = threadIdx.x; k < nu; k += blockDim.x) {
+    const uint32_t u = s.u_node[k];
+    const NodeRec r = A.nodes[u];
+    uint8_t* q = base + s.u_off[k];
+    switch (r.w0 & 0xff) {
+      case NK_LEAF: {
+        *q++ = PPD_NODE_LEAF;
+        q = put_nibbles(q, A, r);
+        q = put_u32(q, r.a2);
+        const uint8_t* v = A.val_pool + r.a1;
+        for (uint32_t i = 0; i < r.a2; i++) q[i] = v[i];
+        break;
+      }
+      case NK_LEAF_ACCOUNT: {
+        const AccountRec& acc = A.accounts[r.a1];
+        *q++ = PPD_NODE_LEAF;
+        q = put_nibbles(q, A, r);
+        uint32_t len = account_rlp_len(acc);
+        q = put_u32(q, len);
+        *q++ = 0xf8;
+        *q++ = (uint8_t)(len - 2);
+        q = put_u256_str(q, acc.nonce);
+        q = put_u256_str(q, acc.balance);
+        const uint8_t* sr = acc.storage_src == NODE_EMPTY ? acc.storage_root : A.ref + 32ull * acc.storage_src;
+        *q++ = 0xa0;
+        for (int i = 0; i < 32; i++) *q++ = sr[i];
+        *q++ = 0xa0;
+        for (int i = 0; i < 32; i++) *q++ = acc.code_hash[i];
+        break;
+      }
+      case NK_EXT:
+        *q++ = PPD_NODE_EXTENSION;
+        q = put_nibbles(q, A, r);
+        put_child(q, A, s, r.a1);
+        break;
+      case NK_BRANCH: {
+        *q++ = PPD_NODE_BRANCH;
+        const uint32_t mask = r.a1 & 0xffff;
+        for (uint32_t i = 0, j = 0; i < 16; i++) {
+          if (mask & (1u << i))
+            q = put_child(q, A, s, A.child_pool[r.a0 + j++]);
+          else
+            *q++ = PPD_NODE_EMPTY;
+        }
+        put_u32(q, 0);
+        break;
+      }
+      default:
+        break;
+    }
+  }
+  // untouched tries of the IR (a storage trie nobody reads: its root as a hash, or empty)
+  const uint32_t sb = P.seg_begin[ir], se = P.seg_begin[ir + 1];
+  for (uint32_t qi = sb + threadIdx.x; qi < se; qi += blockDim.x) {
+    const uint32_t b = P.seg_b[qi];
+    if (b == IR_SEG_LITERAL) continue;
+    uint8_t* q = base + P.seg_off[qi];
+    if (b == IR_SEG_REF) {
+      const uint8_t* r = A.ref + 32ull * P.seg_a[qi];
+      for (int i = 0; i < 32; i++) q[i] = r[i];
+      continue;
+    }
+    if (b == NODE_EMPTY)
+      *q = PPD_NODE_EMPTY;
+    else if (is_hash_id(b))
+      put_hash(q, A.hash_pool + 32ull * (b - HASH_ID_BASE));
+    else if (set_find(s, b) == NOT_FOUND)
+      put_hash(q, A.ref + 32ull * b);
+  }
+}
+
+size_t ir_dump_smem_bytes() { return sizeof(Shared); }
+
+void launch_ir_size(const ArenaView& A, const IrDumpPlanView& P, uint32_t n_ir, cudaStream_t st) {
+  if (!n_ir) return;
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(ir_size_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Shared));
+    cudaFuncSetAttribute(ir_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Shared));
+    attr = true;
+  }
+  ir_size_kernel<<<n_ir, DUMP_THREADS, sizeof(Shared), st>>>(A, P);
+}
+void launch_ir_emit(const ArenaView& A, const IrDumpPlanView& P, uint32_t n_ir, uint8_t* out, cudaStream_t st) {
+  if (!n_ir) return;
+  ir_emit_kernel<<<n_ir, DUMP_THREADS, sizeof(Shared), st>>>(A, P, out);
+}
+
+}  // namespace ppd

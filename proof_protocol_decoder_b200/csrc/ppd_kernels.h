@@ -52,6 +52,29 @@ void launch_branch_scatter(const uint8_t* depth, const uint32_t* nchild, uint32_
 void launch_hash_sorted_leaves(const BuildView& V, cudaStream_t st);
 void launch_hash_branch_level(const BuildView& V, const uint32_t* order, uint32_t begin, uint32_t end, cudaStream_t st);
 
+// ---- ppd_dump.cu: the per-txn sub-tries serialised on the GPU ----
+static const uint32_t IR_SEG_LITERAL = 0xfffffffeu;  // seg_b of a literal segment (seg_a = its length); else seg_b = root of a trie
+static const uint32_t IR_SEG_REF = 0xfffffffdu;      // seg_b of a "32 bytes of ref[seg_a]" segment (a trie root after the txn)
+struct IrDumpPlanView {
+  // inputs (per block): touched node ids of every IR, and every IR's segments in output order
+  const uint32_t* touched;        // concatenated
+  const uint32_t* touched_begin;  // [n_ir + 1]
+  const uint32_t* seg_a;
+  const uint32_t* seg_b;
+  const uint32_t* seg_begin;      // [n_ir + 1]
+  const uint64_t* ir_base;        // [n_ir] byte offset of the IR in the output (emit only)
+  // outputs of ir_size_kernel
+  uint32_t* seg_off;              // offset of every segment inside its IR
+  uint32_t* ir_size;
+  uint32_t* ir_flag;              // 1: the host must serialise this IR
+  uint32_t* ir_nuniq;
+  uint32_t* u_node;               // [touched_begin[ir] + k]: k-th unique touched node of the IR, its size, its offset
+  uint32_t* u_size;
+  uint32_t* u_off;
+};
+void launch_ir_size(const ArenaView& A, const IrDumpPlanView& P, uint32_t n_ir, cudaStream_t st);
+void launch_ir_emit(const ArenaView& A, const IrDumpPlanView& P, uint32_t n_ir, uint8_t* out, cudaStream_t st);
+
 // ---- ppd_microbench.cu ----
 bool launch_microbench(int variant, uint32_t* out, uint32_t blocks_per_sm, uint32_t iters, uint32_t* block_threads, double* units_per_thread_iter,
                        cudaStream_t st);
