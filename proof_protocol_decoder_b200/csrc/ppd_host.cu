@@ -1910,6 +1910,74 @@ int guarded(ppd_ctx* c, F f) {
   }
 }
 
+// ---- page-locked output buffers ---------------------------------------------------------------------
+// The IrDump of a block is ~50 MB that the caller owns until ppd_free().  Handing out page-locked
+// buffers from a process-wide pool lets the device write the result straight into the caller's buffer
+// (no bounce copy, no first-touch page faults); ppd_free() returns the buffer to the pool.  The pool is
+// capped (PPD_PINNED_OUT_MB, default 4096): beyond the cap outputs are ordinary malloc blocks.
+struct OutPool {
+  struct Entry {
+    uint8_t* p;
+    size_t cap;
+    bool in_use;
+  };
+  std::mutex mu;
+  std::vector<Entry> entries;
+  size_t total = 0;
+  size_t limit() {
+    static size_t v = [] {
+      const char* e = getenv("PPD_PINNED_OUT_MB");
+      return (size_t)(e ? atoll(e) : 4096) << 20;
+    }();
+    return v;
+  }
+  uint8_t* take(size_t n) {
+#ifdef PPD_HOSTPROF
+    return nullptr;
+#else
+    std::lock_guard<std::mutex> g(mu);
+    Entry* best = nullptr;
+    for (Entry& e : entries)
+      if (!e.in_use && e.cap >= n && (!best || e.cap < best->cap)) best = &e;
+    if (best) {
+      best->in_use = true;
+      return best->p;
+    }
+    size_t cap = (n + (n >> 3) + (8u << 20) - 1) & ~(size_t)((8u << 20) - 1);
+    if (total + cap > limit()) {
+      // make room by releasing idle buffers that were too small
+      for (size_t i = 0; i < entries.size() && total + cap > limit();)
+        if (!entries[i].in_use) {
+          cudaFreeHost(entries[i].p);
+          total -= entries[i].cap;
+          entries.erase(entries.begin() + i);
+        } else {
+          i++;
+        }
+      if (total + cap > limit()) return nullptr;
+    }
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, cap, cudaHostAllocPortable) != cudaSuccess) return nullptr;
+    entries.push_back({(uint8_t*)p, cap, true});
+    total += cap;
+    return (uint8_t*)p;
+#endif
+  }
+  bool give_back(void* p) {
+    std::lock_guard<std::mutex> g(mu);
+    for (Entry& e : entries)
+      if (e.p == p) {
+        e.in_use = false;
+        return true;
+      }
+    return false;
+  }
+};
+OutPool& out_pool() {
+  static OutPool* p = new OutPool();  // never destroyed: buffers may outlive every context
+  return *p;
+}
+
 // ---- step 5 on the GPU (ppd_dump.cu): the host lays out each IR as literals and tries; the device sizes,
 // places and writes every trie; the host fills the literals in.  IRs the device flags are serialised by
 // dump_ir.  Returns false when the block has to take the host path altogether.
@@ -2060,15 +2128,26 @@ bool gpu_dump_block(ppd_ctx* c, Lane* L, Job& J, uint8_t** out, size_t* out_len)
   }
   // ---- emit, copy back, fill the literals in ----
   Out o;
-  o.need(total);
+  uint8_t* pinned = out_pool().take(total);
+  if (!pinned) o.need(total);
+  uint8_t* dst = pinned ? pinned : o.p;
   L->d_out.reserve(total + 64);
   CUDA_OK(cudaMemcpyAsync(d + o_base, h + o_base, 8 * (size_t)n_ir, cudaMemcpyHostToDevice, L->st));
   launch_ir_emit(L->last_view, P, n_ir, L->d_out.as<uint8_t>(), L->st);
   CUDA_OK(cudaGetLastError());
-  // The output is pageable memory the caller will own: land the copy in a page-locked buffer in chunks
-  // (full-rate, truly asynchronous DMA) and move each chunk on while the next one is in flight.
-  J.out_stage.resize(total);
-  {
+  if (pinned) {
+    // straight into the caller's (page-locked) buffer
+    cudaError_t e = cudaMemcpyAsync(dst, L->d_out.p, total, cudaMemcpyDeviceToHost, L->st);
+    if (e == cudaSuccess) e = cudaEventRecord(L->ev_sync, L->st);
+    if (e == cudaSuccess) e = cudaEventSynchronize(L->ev_sync);
+    if (e != cudaSuccess) {
+      out_pool().give_back(pinned);
+      throw Fail{PPD_ERR_CUDA, std::string("IR dump copy: ") + cudaGetErrorString(e)};
+    }
+  } else {
+    // The output is pageable memory: land the copy in a page-locked buffer in chunks (full-rate,
+    // truly asynchronous DMA) and move each chunk on while the next one is in flight.
+    J.out_stage.resize(total);
     const size_t CH = 8u << 20;
     size_t n_ch = (total + CH - 1) / CH;
     std::vector<cudaEvent_t> evs(n_ch);
@@ -2093,9 +2172,9 @@ bool gpu_dump_block(ppd_ctx* c, Lane* L, Job& J, uint8_t** out, size_t* out_len)
   o.n = total;
   pt.lap("  d:emit+copy");
   uint32_t hdr[2] = {PPD_IR_DUMP_MAGIC, n_ir};
-  memcpy(o.p, hdr, 8);
+  memcpy(dst, hdr, 8);
   for (uint32_t i = 0; i < n_ir; i++) {
-    uint8_t* base = o.p + ir_base[i];
+    uint8_t* base = dst + ir_base[i];
     if (ir_flag[i]) {
       memcpy(base, host_parts[i].p, host_parts[i].n);
       continue;
@@ -2109,17 +2188,22 @@ bool gpu_dump_block(ppd_ctx* c, Lane* L, Job& J, uint8_t** out, size_t* out_len)
     size_t want_len = 0;
     fetch_refs(L, J);
     dump_blocks(J, &want, &want_len, 1);
-    bool same = want_len == o.n && memcmp(want, o.p, o.n) == 0;
+    bool same = want_len == o.n && memcmp(want, dst, o.n) == 0;
     size_t at = 0;
     if (!same)
-      while (at < want_len && at < o.n && want[at] == o.p[at]) at++;
+      while (at < want_len && at < o.n && want[at] == dst[at]) at++;
     free(want);
     if (!same) {
+      if (pinned) out_pool().give_back(pinned);
       std::lock_guard<std::mutex> g(c->err_mu);
       throw Fail{PPD_ERR_CUDA, "GPU IR dump differs from the host dump at byte " + std::to_string(at) + " (sizes " + std::to_string(o.n) + " / " + std::to_string(want_len) + ")"};
     }
   }
-  *out = o.give(out_len);
+  if (pinned) {
+    *out = pinned, *out_len = total;
+  } else {
+    *out = o.give(out_len);
+  }
   return true;
 #endif
 }
@@ -2241,7 +2325,9 @@ const char* ppd_last_error(const ppd_ctx* c) { return c ? c->err.c_str() : "null
 void ppd_last_stats(const ppd_ctx* c, ppd_stats* out) {
   if (c && out) *out = c->stats;
 }
-void ppd_free(void* p) { free(p); }
+void ppd_free(void* p) {
+  if (p && !out_pool().give_back(p)) free(p);
+}
 
 int ppd_keccak256_batch(ppd_ctx* c, const uint8_t* data, const uint64_t* offsets, size_t n, uint8_t* out32n) {
   return guarded(c, [&] {
