@@ -28,6 +28,7 @@
 #include "encode.cuh"
 #include "keccak.cuh"
 #include "ppd_kernels.h"
+#include "pyramid.cuh"
 
 namespace ppd {
 
@@ -78,55 +79,6 @@ __global__ void min64_kernel(const int8_t* __restrict__ in, uint32_t n_in, int8_
   uint64_t base = 64ull * j;
   for (uint32_t k = 0; k < 64 && base + k < n_in; k++) m = min(m, (int)in[base + k]);
   out[j] = (int8_t)m;
-}
-
-// largest p < q with L[p] < thr (thr >= 0; L[0] = -1 guarantees termination)
-__device__ __forceinline__ uint32_t scan_left(const Pyramid& P, uint32_t q, int thr) {
-  uint32_t p = q - 1;
-  for (;;) {
-    if ((p & 63u) == 63u) {
-      if ((p & 4095u) == 4095u) {
-        if ((p & 262143u) == 262143u && P.m3[p >> 18] >= thr) {
-          p -= 262144u;
-          continue;
-        }
-        if (P.m2[p >> 12] >= thr) {
-          p -= 4096u;
-          continue;
-        }
-      }
-      if (P.m1[p >> 6] >= thr) {
-        p -= 64u;
-        continue;
-      }
-    }
-    if (P.L[p] < thr) return p;
-    p--;
-  }
-}
-// smallest r > q with L[r] < thr (L[N] = -1 guarantees termination)
-__device__ __forceinline__ uint32_t scan_right(const Pyramid& P, uint32_t q, int thr) {
-  uint32_t p = q + 1;
-  for (;;) {
-    if ((p & 63u) == 0u) {
-      if ((p & 4095u) == 0u) {
-        if ((p & 262143u) == 0u && P.m3[p >> 18] >= thr) {
-          p += 262144u;
-          continue;
-        }
-        if (P.m2[p >> 12] >= thr) {
-          p += 4096u;
-          continue;
-        }
-      }
-      if (P.m1[p >> 6] >= thr) {
-        p += 64u;
-        continue;
-      }
-    }
-    if (P.L[p] < thr) return p;
-    p++;
-  }
 }
 
 // link[q] = nearest position to the left in the same branch run with the same depth, else q

@@ -28,6 +28,7 @@
 
 #include "../../include/ppd_b200.h"
 #include "arena.h"
+#include "devbuf.h"
 #include "host_arena.h"
 #include "ppd_kernels.h"
 #ifdef PPD_HOSTPROF
@@ -36,38 +37,7 @@
 
 using namespace ppd;
 
-#define CUDA_OK(expr)                                                                          \
-  do {                                                                                         \
-    cudaError_t e_ = (expr);                                                                   \
-    if (e_ != cudaSuccess) {                                                                   \
-      throw Fail{PPD_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_)};            \
-    }                                                                                          \
-  } while (0)
-
 namespace {
-
-struct DevBuf {
-  void* p = nullptr;
-  size_t cap = 0;
-  void reserve(size_t n) {
-    if (n <= cap) return;
-    if (p) cudaFree(p);
-    p = nullptr;
-    cap = 0;
-    size_t want = n + n / 4 + 256;
-    CUDA_OK(cudaMalloc(&p, want));
-    cap = want;
-  }
-  void release() {
-    if (p) cudaFree(p);
-    p = nullptr;
-    cap = 0;
-  }
-  template <class T>
-  T* as() const {
-    return reinterpret_cast<T*>(p);
-  }
-};
 
 struct H256 {
   uint8_t b[32];
