@@ -295,6 +295,9 @@ def run_b200(args, rank, world, local_rank):
 
     ctx = Context(local_rank)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+    # the step's inputs live in page-locked host memory (ppd_alloc_pinned), as a caller that serialises its
+    # BlockTrace for the library would place them; every step copies them to the device again
+    flats = [ctx.pinned_copy(f) for f in flats]
 
     def decode_step():
         outs = ctx.blocks_decode_batch_view(flats)

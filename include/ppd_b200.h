@@ -43,6 +43,10 @@ typedef struct ppd_stats {
   double gpu_ms;               /* device time of the kernels of the call (CUDA events) */
   double h2d_bytes, d2h_bytes;
   uint64_t kernel_launches;
+  uint64_t witnesses_on_gpu;      /* compact witnesses whose parse and pre-image arena were built by the GPU (ppd_parse.cu) */
+  uint64_t witness_instructions;  /* instructions of those witnesses */
+  uint64_t witness_bytes;         /* bytes of those witnesses */
+  double parse_gpu_ms;            /* device time of their parse / arena kernels (CUDA events) */
 } ppd_stats;
 
 int ppd_ctx_create(int device, ppd_ctx** out);
@@ -51,6 +55,11 @@ void ppd_ctx_destroy(ppd_ctx* ctx);
 const char* ppd_last_error(const ppd_ctx* ctx);
 void ppd_last_stats(const ppd_ctx* ctx, ppd_stats* out);
 void ppd_free(void* p);
+/* A page-locked host buffer of n bytes from the library's pool (an ordinary malloc block once the pool's
+ * cap is reached); release with ppd_free.  Inputs placed in such a buffer (the Rust shim serialises the
+ * BlockTrace of processed_block_trace.rs:38-45 straight into one) are read by the GPU's copy engine
+ * directly; any other host pointer is accepted too and staged through page-locked memory by the library. */
+void* ppd_alloc_pinned(size_t n);
 
 /* utils::hash (protocol_decoder/src/utils.rs:11-13) over a batch: message i is
  * data[offsets[i] .. offsets[i+1]); out32n receives n x 32 bytes.  Host buffers. */

@@ -85,6 +85,8 @@ struct Lane {
   DevBuf d_nodes, d_order, d_keys, d_vals, d_hashes, d_children, d_accounts, d_ref, d_ref_len, d_counters;
   DevBuf d_msg, d_msg_off, d_digest;
   DevBuf d_plan, d_out;  // IR dump plan and the serialised IrDump
+  DevBuf d_wit, d_pa, d_pb, d_pc;  // witness bytes and the scratch of the three parse phases (ppd_parse.cu)
+  uint32_t* h_parse = nullptr;     // page-locked landing area of the parse result words
   Job* job = nullptr;  // page-locked pools, kept across calls
   // the arena of the lane's last block stays resident so that its hashing can be re-run for measurement
   bool has_last = false;
@@ -522,6 +524,7 @@ struct BlockJob {
   std::unordered_map<uint32_t, uint32_t> root_of;                   // trie root node -> its NK_ROOT node
   std::unordered_map<int32_t, uint32_t> storage_root_of_instr;      // account leaf instruction -> root of its witnessed storage trie
   bool have_empty_form = false;                                     // a witnessed storage trie whose root is EMPTY_TRIE_HASH
+  bool pre_image_on_gpu = false;                                    // gpu_pre_image built the pre-image tries
   uint32_t empty_form = NODE_EMPTY;
   std::vector<IrPlan> irs;
   int status = PPD_OK;
@@ -693,6 +696,16 @@ struct Job {
   PVec<uint32_t> plan;  // IR dump plan (inputs, then the outputs read back)
   PVec<uint8_t> out_stage;  // page-locked landing buffer of the serialised IrDump
   bool refs_on_host = false;
+  // When the pre-image was built on the GPU (gpu_pre_image) the leading part of every pool is already in
+  // the lane's device buffers: the sweep uploads only what the txn loop appended.  The value and hash
+  // pools of that part are not copied to the host unless a host-side dump needs them (fetch_pools).
+  struct Resident {
+    size_t nodes = 0, keys = 0, vals = 0, hashes = 0, children = 0, accounts = 0;
+  } dev;
+  bool pools_on_host = true;
+  PVec<uint32_t> acct_list, code_list;
+  PVec<uint8_t> wit_stage;  // page-locked staging of a pageable witness
+  PVec<H256> code_digest;
   std::vector<uint32_t> stamp;
   uint32_t serial = 0;
   Job() {
@@ -701,8 +714,14 @@ struct Job {
     A.set_allocator(pinned_alloc, pinned_free);
     ref.alloc_fn = ref_len.alloc_fn = pinned_alloc, ref.free_fn = ref_len.free_fn = pinned_free;
     order.alloc_fn = pinned_alloc, order.free_fn = pinned_free;
+    A.level.alloc_fn = pinned_alloc, A.level.free_fn = pinned_free;
+    acct_list.alloc_fn = code_list.alloc_fn = pinned_alloc, acct_list.free_fn = code_list.free_fn = pinned_free;
+    code_digest.alloc_fn = pinned_alloc, code_digest.free_fn = pinned_free;
+    wit_stage.alloc_fn = pinned_alloc, wit_stage.free_fn = pinned_free;
   }
   void reset(size_t n_blocks) {
+    dev = Resident{};
+    pools_on_host = true;
     A.clear();
     kh.reset();
     blocks.clear();
@@ -735,8 +754,9 @@ void lane_delete(Lane* l) {
 #ifndef PPD_HOSTPROF
   DevBuf* bufs[] = {&l->d_nodes, &l->d_order,  &l->d_keys,     &l->d_vals, &l->d_hashes,  &l->d_children, &l->d_accounts,
                     &l->d_ref,   &l->d_ref_len, &l->d_counters, &l->d_msg,  &l->d_msg_off, &l->d_digest,
-                    &l->d_plan,  &l->d_out};
+                    &l->d_plan,  &l->d_out,     &l->d_wit,      &l->d_pa,   &l->d_pb,      &l->d_pc};
   for (DevBuf* b : bufs) b->release();
+  if (l->h_parse) pinned_free(l->h_parse);
   if (l->ev0) cudaEventDestroy(l->ev0);
   if (l->ev1) cudaEventDestroy(l->ev1);
   if (l->ev_sync) cudaEventDestroy(l->ev_sync);
@@ -760,9 +780,11 @@ void collect_witness_messages(Job& J, BlockJob& b) {
 }
 
 void collect_messages(Job& J, BlockJob& b) {
-  parse_witness(b.compact.p, b.compact.n, b.wit);
-  if (b.wit.version != 1) fail(PPD_PANIC_INCOMPATIBLE_HEADER_VERSION, "compact header version is not 1");
-  collect_witness_messages(J, b);
+  if (!b.pre_image_on_gpu) {
+    parse_witness(b.compact.p, b.compact.n, b.wit);
+    if (b.wit.version != 1) fail(PPD_PANIC_INCOMPATIBLE_HEADER_VERSION, "compact header version is not 1");
+    collect_witness_messages(J, b);
+  }
   for (TxnV& tx : b.txns)
     for (TraceV& tr : tx.traces) {
       tr.m_addr = J.kh.add(tr.addr, 20);
@@ -1113,6 +1135,362 @@ void build_pre_image(Job& J, BlockJob& b) {
   b.state_root = build_witness_trie(J, b, W.root, false);
 }
 
+// ---- step 2 on the GPU (ppd_parse.cu): witness bytes -> instruction list -> tree links -> arena ------
+// Three device phases with one small read-back each (instruction count; flags and pool sizes; the
+// structural half of the arena).  The host keeps only what the txn loop walks (node records, keys,
+// child lists, account records, levels); leaf values and the hashed-out subtrees stay in HBM.
+// Returns false when the witness is not a well-formed canonical one: the host builder then takes it
+// from the start and reports the reference's error, if any.
+void verify_gpu_pre_image(Lane* L, Job& J, BlockJob& b);
+void fetch_pools(Lane* c, Job& J);
+bool gpu_parse_enabled() {
+#ifdef PPD_HOSTPROF
+  return false;
+#else
+  return getenv("PPD_HOST_PARSE") == nullptr;  // read per call: the tests compare both builders in one process
+#endif
+}
+
+struct Carve {
+  uint8_t* base;
+  size_t off = 0;
+  template <class T>
+  T* take(size_t count) {
+    off = (off + 255) & ~(size_t)255;
+    T* r = reinterpret_cast<T*>(base + off);
+    off += count * sizeof(T);
+    return r;
+  }
+};
+
+bool gpu_pre_image(Lane* L, Job& J, BlockJob& b, bool check_version = true) {
+#ifdef PPD_HOSTPROF
+  return false;
+#else
+  const uint8_t* w = b.compact.p;
+  const size_t n = b.compact.n;
+  if (n < 2 || n >= 0xfff00000ull) return false;
+  HostArena& A = J.A;
+  cudaStream_t st = L->st;
+  if (!L->h_parse) {
+    L->h_parse = (uint32_t*)pinned_alloc(4 * PARSE_R_WORDS);
+    if (!L->h_parse) fail(PPD_ERR_BAD_ARGUMENT, "out of page-locked memory");
+  }
+  uint32_t* hr = L->h_parse;
+  // ---- phase A: instruction boundaries ----
+  L->d_wit.reserve(n + 64);
+  {
+    // A page-locked caller buffer (ppd_alloc_pinned, cudaHostRegister) is read by the copy engine directly.
+    // A pageable one is staged through the lane's page-locked buffer in chunks: concurrent pageable
+    // cudaMemcpyAsync calls serialise inside the driver, a plain memcpy per lane does not.
+    cudaPointerAttributes at{};
+    bool pinned = cudaPointerGetAttributes(&at, w) == cudaSuccess && at.type == cudaMemoryTypeHost;
+    if (!pinned) cudaGetLastError();
+    if (pinned) {
+      CUDA_OK(cudaMemcpyAsync(L->d_wit.p, w, n, cudaMemcpyHostToDevice, st));
+    } else {
+      J.wit_stage.resize(n);
+      const size_t CH = 4u << 20;
+      for (size_t at0 = 0; at0 < n; at0 += CH) {
+        size_t len = std::min(CH, n - at0);
+        memcpy(J.wit_stage.data() + at0, w + at0, len);
+        CUDA_OK(cudaMemcpyAsync(L->d_wit.as<uint8_t>() + at0, J.wit_stage.data() + at0, len, cudaMemcpyHostToDevice, st));
+      }
+    }
+  }
+  CUDA_OK(cudaMemsetAsync(L->d_wit.as<uint8_t>() + n, 0, 64, st));
+  L->stats.h2d_bytes += (double)n;
+  ParseBounds B{};
+  B.wit = L->d_wit.as<uint8_t>();
+  B.n = (uint32_t)n;
+  B.n_tiles = (uint32_t)((n + PARSE_TILE - 1) / PARSE_TILE);
+  B.group_tiles = 8;
+  while (B.group_tiles < 1024 && (uint64_t)B.group_tiles * B.group_tiles < B.n_tiles) B.group_tiles *= 2;
+  B.n_groups = (B.n_tiles + B.group_tiles - 1) / B.group_tiles;
+  auto layout_a = [&](Carve& c) {
+    B.result = c.take<uint32_t>(PARSE_R_WORDS);
+    B.exit1 = c.take<uint32_t>(n);
+    B.exit2 = c.take<uint32_t>((size_t)B.n_groups * PARSE_TILE);
+    B.group_entry = c.take<uint32_t>(B.n_groups);
+    B.tile_entry = c.take<uint32_t>(B.n_tiles);
+    B.bitmap = c.take<uint32_t>((size_t)B.n_tiles * (PARSE_TILE / 32));
+    B.tile_count = c.take<uint32_t>(B.n_tiles + 1);
+    B.tile_base = c.take<uint32_t>(B.n_tiles + 1);
+    B.scan_tmp = c.take<uint32_t>(parse_scan_tmp_words(B.n_tiles + 1, 1));
+  };
+  {
+    Carve sz{nullptr};
+    layout_a(sz);
+    L->d_pa.reserve(sz.off + 256);
+    Carve c{L->d_pa.as<uint8_t>()};
+    layout_a(c);
+  }
+  auto phase_ms = [&] {
+    float ms = 0;
+    CUDA_OK(cudaEventElapsedTime(&ms, L->ev0, L->ev1));
+    L->stats.parse_gpu_ms += ms;
+  };
+  CUDA_OK(cudaMemsetAsync(B.result, 0, 4 * PARSE_R_WORDS, st));
+  CUDA_OK(cudaEventRecord(L->ev0, st));
+  launch_parse_bounds(B, st);
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(cudaEventRecord(L->ev1, st));
+  CUDA_OK(cudaMemcpyAsync(hr, B.result, 4 * PARSE_R_WORDS, cudaMemcpyDeviceToHost, st));
+  lane_sync(L);
+  phase_ms();
+  L->stats.kernel_launches += parse_bounds_launches();
+  if (hr[PARSE_R_END] != (uint32_t)n) return false;  // a parse error: the host parser reports it
+  const uint32_t n_ins = hr[PARSE_R_NINS];
+  if (n_ins == 0 || n_ins > n) return false;
+  // ---- phase B: tree links, depths, sizes ----
+  ParseTree T{};
+  T.wit = B.wit, T.n = B.n, T.n_ins = n_ins, T.result = B.result;
+  T.cnt_stride = ((size_t)n_ins + 1 + 3) & ~(size_t)3;
+  uint32_t* ins_pos = nullptr;
+  auto layout_b = [&](Carve& c) {
+    const size_t n1 = (size_t)n_ins + 1;
+    const size_t n_m1 = (n1 + 63) / 64, n_m2 = (n_m1 + 63) / 64, n_m3 = (n_m2 + 63) / 64;
+    ins_pos = c.take<uint32_t>(n_ins);
+    T.meta = c.take<uint32_t>(n_ins);
+    T.knib = c.take<uint8_t>(n_ins);
+    T.delta = c.take<uint32_t>(n1);
+    T.hb = c.take<uint32_t>(n1);
+    T.h16 = c.take<int16_t>(n1);
+    T.m1 = c.take<int16_t>(n_m1);
+    T.m2 = c.take<int16_t>(n_m2);
+    T.m3 = c.take<int16_t>(n_m3);
+    T.parent = c.take<uint32_t>(n_ins);
+    T.info = c.take<uint32_t>(n_ins);
+    T.aux0 = c.take<uint32_t>(n_ins);
+    T.pending = c.take<uint32_t>(n_ins);
+    T.lvlmax = c.take<uint32_t>(n_ins);
+    T.cnt = c.take<uint32_t>(PARSE_N_CNT * T.cnt_stride);
+    T.scn = c.take<uint32_t>(PARSE_N_CNT * T.cnt_stride);
+    T.scan_tmp = c.take<uint32_t>(parse_scan_tmp_words(n1, PARSE_N_CNT));
+  };
+  {
+    Carve sz{nullptr};
+    layout_b(sz);
+    L->d_pb.reserve(sz.off + 256);
+    Carve c{L->d_pb.as<uint8_t>()};
+    layout_b(c);
+  }
+  T.ins_pos = ins_pos;
+  CUDA_OK(cudaEventRecord(L->ev0, st));
+  launch_parse_scatter(B, ins_pos, st);
+  launch_parse_tree(T, st);
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(cudaEventRecord(L->ev1, st));
+  CUDA_OK(cudaMemcpyAsync(hr, B.result, 4 * PARSE_R_WORDS, cudaMemcpyDeviceToHost, st));
+  lane_sync(L);
+  phase_ms();
+  L->stats.kernel_launches += 16;
+  if (hr[PARSE_R_FLAG] != 0 || hr[PARSE_R_HEIGHT] != 1) return false;
+  if (check_version && w[0] != 1) fail(PPD_PANIC_INCOMPATIBLE_HEADER_VERSION, "compact header version is not 1");
+  const uint32_t* tot = hr + PARSE_R_TOTALS;
+  const size_t n_nodes = tot[PARSE_C_NODE], n_hash = tot[PARSE_C_HASH], key_bytes = tot[PARSE_C_KEY], val_bytes = tot[PARSE_C_VAL],
+               n_child = tot[PARSE_C_CHILD], n_acct = tot[PARSE_C_ACCT], n_code = tot[PARSE_C_CODE];
+  const uint32_t root_ins = hr[PARSE_R_ROOT];
+  if (root_ins >= n_ins || n_hash >= HASH_ID_END - HASH_ID_BASE) return false;
+  // ---- phase C: emit the arena into the lane's buffers ----
+  ParseEmit E{};
+  E.T = T;
+  uint16_t* d_level = nullptr;
+  uint8_t* d_code_digest = nullptr;
+  auto layout_c = [&](Carve& c) {
+    d_level = c.take<uint16_t>(n_nodes + 1);
+    E.acct_list = c.take<uint32_t>(5 * n_acct + 1);
+    E.code_se = c.take<uint64_t>(2 * n_code + 1);
+    E.code_list = c.take<uint32_t>(2 * n_code + 1);
+    d_code_digest = c.take<uint8_t>(32 * n_code + 32);
+  };
+  {
+    Carve sz{nullptr};
+    layout_c(sz);
+    L->d_pc.reserve(sz.off + 256);
+    Carve c{L->d_pc.as<uint8_t>()};
+    layout_c(c);
+  }
+  // room for what the txn loop appends, so that the sweep does not have to move the resident part
+  L->d_nodes.reserve(16 * (n_nodes + n_nodes / 2) + 4096);
+  L->d_keys.reserve(2 * key_bytes + 65536);
+  L->d_vals.reserve(2 * val_bytes + 65536);
+  L->d_hashes.reserve(32 * n_hash + 32);
+  L->d_children.reserve(4 * (n_child + n_child / 2) + 4096);
+  L->d_accounts.reserve(sizeof(AccountRec) * (2 * n_acct + 64));
+  E.nodes = L->d_nodes.as<NodeRec>();
+  E.level = d_level;
+  E.key_pool = L->d_keys.as<uint8_t>();
+  E.val_pool = L->d_vals.as<uint8_t>();
+  E.hash_pool = L->d_hashes.as<uint8_t>();
+  E.child_pool = L->d_children.as<uint32_t>();
+  E.accounts = L->d_accounts.as<AccountRec>();
+  E.code_digest = d_code_digest;
+  CUDA_OK(cudaEventRecord(L->ev0, st));
+  if (n_code) {
+    launch_parse_code_list(E, st);
+    launch_keccak256_ranges(B.wit, E.code_se, (uint32_t)n_code, d_code_digest, st);
+    L->stats.kernel_launches += 2;
+    L->stats.key_hashes += n_code;
+  }
+  if (val_bytes) CUDA_OK(cudaMemsetAsync(E.val_pool, 0, val_bytes, st));
+  launch_parse_emit(E, st);
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(cudaEventRecord(L->ev1, st));
+  L->stats.kernel_launches += 2;
+  A.nodes.resize(n_nodes), A.level.resize(n_nodes), A.key_pool.resize(key_bytes), A.child_pool.resize(n_child), A.accounts.resize(n_acct);
+  A.val_pool.resize(val_bytes), A.hash_pool.resize(32 * n_hash);  // contents stay on the device (fetch_pools)
+  J.acct_list.resize(5 * n_acct), J.code_list.resize(2 * n_code), J.code_digest.resize(n_code);
+  auto down = [&](void* dst, const void* src, size_t bytes) {
+    if (!bytes) return;
+    CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st));
+    L->stats.d2h_bytes += (double)bytes;
+  };
+  down(A.nodes.data(), E.nodes, 16 * n_nodes);
+  down(A.level.data(), d_level, 2 * n_nodes);
+  down(A.key_pool.data(), E.key_pool, key_bytes);
+  down(A.child_pool.data(), E.child_pool, 4 * n_child);
+  down(A.accounts.data(), E.accounts, sizeof(AccountRec) * n_acct);
+  down(J.acct_list.data(), E.acct_list, 20 * n_acct);
+  down(J.code_list.data(), E.code_list, 8 * n_code);
+  down(J.code_digest.data(), d_code_digest, 32 * n_code);
+  down(hr, B.result, 4 * PARSE_R_WORDS);
+  lane_sync(L);
+  phase_ms();
+  for (size_t k = 0; k < n_code; k++) {
+    L->stats.key_permutations += J.code_list[2 * k + 1] / 136 + 1;
+    b.pre_code[J.code_digest[k]] = Span{w + J.code_list[2 * k], J.code_list[2 * k + 1]};
+  }
+  J.dev.nodes = n_nodes, J.dev.keys = key_bytes, J.dev.vals = val_bytes, J.dev.hashes = 32 * n_hash, J.dev.children = n_child, J.dev.accounts = n_acct;
+  J.pools_on_host = false;
+  // ---- the block's per-account tables (compact_to_partial_trie.rs:167-190), as make_account_record builds them ----
+  b.wit.version = w[0];
+  b.state_root = hr[PARSE_R_ROOT_ID];
+  b.storage.reserve(n_acct), b.pre_accounts.reserve(n_acct), b.root_of.reserve(2 * n_acct + 1024);
+  b.have_empty_form = false, b.empty_form = NODE_EMPTY;
+  const uint32_t* al = J.acct_list.data();
+  for (size_t a = 0; a < n_acct; a++)
+    if ((al[5 * a + 3] & 1u) && !(al[5 * a + 3] & 2u)) b.have_empty_form = true, b.empty_form = al[5 * a + 1];
+  for (size_t a = 0; a < n_acct; a++) {
+    const uint32_t leaf = al[5 * a], flags = al[5 * a + 3];
+    const bool nonempty = flags & 2u;
+    bool has_trie = flags & 1u;
+    uint32_t sroot = al[5 * a + 1];
+    if (!nonempty) has_trie = b.have_empty_form, sroot = b.empty_form;
+    const NodeRec& nr = A.nodes[leaf];
+    const uint32_t klen = ((nr.w0 >> 8) & 0xff) + ((nr.w0 >> 16) & 0xff);
+    H256 haddr;
+    if (klen == 64) {
+      memcpy(haddr.b, A.key_pool.data() + nr.a0, 32);
+    } else {  // utils.rs:49-59: the nibbles right-aligned in 32 bytes
+      memset(haddr.b, 0, 32);
+      for (uint32_t k = 0; k < klen; k++) {
+        uint32_t posn = 64 - klen + k, nib = A.key_nib(nr.a0, k);
+        haddr.b[posn >> 1] |= (uint8_t)((posn & 1) ? nib : (nib << 4));
+      }
+    }
+    if (has_trie) b.storage[haddr] = sroot;
+    b.pre_accounts.push_back({haddr, (uint32_t)a, nonempty});
+    if (nonempty) {
+      b.pre_with_storage[haddr] = (uint32_t)a;
+      b.root_of[al[5 * a + 1]] = al[5 * a + 2];
+    }
+  }
+  b.pre_image_on_gpu = true;
+  L->stats.witnesses_on_gpu += 1, L->stats.witness_instructions += n_ins, L->stats.witness_bytes += n;
+  if (getenv("PPD_VERIFY_GPU_PARSE")) verify_gpu_pre_image(L, J, b);
+  return true;
+#endif
+}
+
+// ---- PPD_VERIFY_GPU_PARSE: the GPU-built pre-image against the host builder's, node by node ----------
+struct TrieCmp {
+  const HostArena &X, &Y;
+  std::string why;
+  bool no(const char* what, uint32_t x, uint32_t y) {
+    if (why.empty()) why = std::string(what) + " (gpu node " + std::to_string(x) + ", host node " + std::to_string(y) + ")";
+    return false;
+  }
+  bool nibs_eq(uint32_t x, uint32_t y) {
+    if (X.nstart(x) != Y.nstart(y) || X.nlen(x) != Y.nlen(y)) return false;
+    for (uint32_t k = 0; k < X.nstart(x) + X.nlen(x); k++)  // the whole key up to the end of the node's range
+      if (X.key_nib(X.nodes[x].a0, k) != Y.key_nib(Y.nodes[y].a0, k)) return false;
+    return true;
+  }
+  bool eq(uint32_t x, uint32_t y) {
+    if (x == NODE_EMPTY || y == NODE_EMPTY) return x == y ? true : no("empty vs non-empty", x, y);
+    uint32_t kx = X.kind(x), ky = Y.kind(y);
+    if (kx != ky) return no("node kinds differ", x, y);
+    if (kx == NK_HASH) return memcmp(X.hash_of(x), Y.hash_of(y), 32) == 0 ? true : no("hashed-out nodes differ", x, y);
+    if (X.lvl(x) != Y.lvl(y)) return no("levels differ", x, y);
+    const NodeRec &a = X.nodes[x], &b = Y.nodes[y];
+    switch (kx) {
+      case NK_LEAF:
+        if (!nibs_eq(x, y)) return no("leaf keys differ", x, y);
+        if (a.a2 != b.a2 || memcmp(X.val_pool.data() + a.a1, Y.val_pool.data() + b.a1, a.a2) != 0) return no("leaf values differ", x, y);
+        return true;
+      case NK_LEAF_ACCOUNT: {
+        if (!nibs_eq(x, y)) return no("account keys differ", x, y);
+        const AccountRec &ra = X.accounts[a.a1], &rb = Y.accounts[b.a1];
+        if (memcmp(&ra, &rb, 128) != 0) return no("account records differ", x, y);
+        if ((ra.storage_src == NODE_EMPTY) != (rb.storage_src == NODE_EMPTY)) return no("account storage sources differ", x, y);
+        return ra.storage_src == NODE_EMPTY ? true : eq(ra.storage_src, rb.storage_src);
+      }
+      case NK_EXT:
+        if (!nibs_eq(x, y)) return no("extension keys differ", x, y);
+        return eq(a.a1, b.a1);
+      case NK_ROOT:
+        return eq(a.a1, b.a1);
+      case NK_BRANCH: {
+        if ((a.a1 & 0xffff) != (b.a1 & 0xffff)) return no("branch masks differ", x, y);
+        uint32_t k = (uint32_t)__builtin_popcount(a.a1 & 0xffff);
+        for (uint32_t i = 0; i < k; i++)
+          if (!eq(X.child_pool[a.a0 + i], Y.child_pool[b.a0 + i])) return false;
+        return true;
+      }
+    }
+    return no("unknown node kind", x, y);
+  }
+};
+
+void verify_gpu_pre_image(Lane* L, Job& J, BlockJob& b) {
+  fetch_pools(L, J);
+  std::unique_ptr<Job> J2(new Job());
+  J2->reset(1);
+  BlockJob& b2 = J2->blocks[0];
+  b2.compact = b.compact;
+  parse_witness(b.compact.p, b.compact.n, b2.wit);
+  collect_witness_messages(*J2, b2);
+  J2->kh.run(L);
+  build_pre_image(*J2, b2);
+  auto bad = [&](const std::string& m) { throw Fail{PPD_ERR_CUDA, "GPU pre-image differs from the host builder's: " + m}; };
+  TrieCmp cmp{J.A, J2->A};
+  if (!cmp.eq(b.state_root, b2.state_root)) bad("state trie: " + cmp.why);
+  if (b.storage.size() != b2.storage.size()) bad("storage map sizes " + std::to_string(b.storage.size()) + " / " + std::to_string(b2.storage.size()));
+  for (auto& s2 : b2.storage) {
+    auto f = b.storage.find(s2.first);
+    if (f == b.storage.end()) bad("storage trie missing for an account");
+    if (!cmp.eq(f->second, s2.second)) bad("storage trie: " + cmp.why);
+  }
+  if (b.pre_accounts.size() != b2.pre_accounts.size()) bad("pre-image account counts");
+  for (size_t i = 0; i < b.pre_accounts.size(); i++) {
+    const auto &p = b.pre_accounts[i], &q = b2.pre_accounts[i];
+    if (!(p.haddr == q.haddr) || p.storage_nonempty != q.storage_nonempty || memcmp(&J.A.accounts[p.rec], &J2->A.accounts[q.rec], 128) != 0)
+      bad("pre-image account " + std::to_string(i));
+  }
+  if (b.pre_with_storage.size() != b2.pre_with_storage.size()) bad("accounts with storage");
+  for (auto& s2 : b2.pre_with_storage)
+    if (!b.pre_with_storage.count(s2.first)) bad("account with storage missing");
+  if (b.pre_code.size() != b2.pre_code.size()) bad("code map sizes");
+  for (auto& c2 : b2.pre_code) {
+    auto f = b.pre_code.find(c2.first);
+    if (f == b.pre_code.end() || f->second.p != c2.second.p || f->second.n != c2.second.n) bad("code map entry");
+  }
+  for (auto& r : b.root_of) {
+    if (r.second >= J.A.nodes.size() || J.A.kind(r.second) != NK_ROOT || J.A.nodes[r.second].a1 != r.first) bad("root_of entry");
+  }
+}
+
 struct PhaseTimer {
   bool on = getenv("PPD_TIMING") != nullptr;
   std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
@@ -1205,7 +1583,7 @@ void shape_block(Job& J, BlockJob& b) {
   HostArena& A = J.A;
   SectionTimer sec;
   sec.start();
-  build_pre_image(J, b);
+  if (!b.pre_image_on_gpu) build_pre_image(J, b);
   sec.stop(0);
   const uint32_t initial_state = b.state_root;
   const auto initial_storage = b.storage;
@@ -1444,28 +1822,30 @@ void sweep(Lane* c, Job& J, bool refs_to_host = true) {
     for (uint32_t l = 0; l <= n_levels; l++) level_start[l] = bucket[(size_t)l * 64];
     for (uint32_t i = 0; i < n; i++) order[bucket[(size_t)A.level[i] * 64 + cls[i]]++] = i;
   }
-  c->d_nodes.reserve(16ull * n);
+  // the part of every pool that gpu_pre_image left in the lane's buffers stays where it is
+  const Job::Resident& R = J.dev;
+  c->d_nodes.reserve_keep(16ull * n, 16ull * R.nodes, c->st);
   c->d_order.reserve(4ull * n);
-  c->d_keys.reserve(A.key_pool.size() + 16);
-  c->d_vals.reserve(A.val_pool.size() + 16);
-  c->d_hashes.reserve(A.hash_pool.size() + 32);
-  c->d_children.reserve(4ull * A.child_pool.size() + 16);
-  c->d_accounts.reserve(sizeof(AccountRec) * A.accounts.size() + 16);
+  c->d_keys.reserve_keep(A.key_pool.size() + 16, R.keys, c->st);
+  c->d_vals.reserve_keep(A.val_pool.size() + 16, R.vals, c->st);
+  c->d_hashes.reserve_keep(A.hash_pool.size() + 32, R.hashes, c->st);
+  c->d_children.reserve_keep(4ull * A.child_pool.size() + 16, 4ull * R.children, c->st);
+  c->d_accounts.reserve_keep(sizeof(AccountRec) * A.accounts.size() + 16, sizeof(AccountRec) * R.accounts, c->st);
   c->d_ref.reserve(32ull * n);
   c->d_ref_len.reserve(n);
   c->d_counters.reserve(32);
-  auto up = [&](DevBuf& d, const void* src, size_t bytes) {
-    if (!bytes) return;
-    CUDA_OK(cudaMemcpyAsync(d.p, src, bytes, cudaMemcpyHostToDevice, c->st));
-    c->stats.h2d_bytes += (double)bytes;
+  auto up = [&](DevBuf& d, const void* src, size_t bytes, size_t resident = 0) {
+    if (bytes <= resident) return;
+    CUDA_OK(cudaMemcpyAsync(d.as<uint8_t>() + resident, (const uint8_t*)src + resident, bytes - resident, cudaMemcpyHostToDevice, c->st));
+    c->stats.h2d_bytes += (double)(bytes - resident);
   };
-  up(c->d_nodes, A.nodes.data(), 16ull * n);
+  up(c->d_nodes, A.nodes.data(), 16ull * n, 16ull * R.nodes);
   up(c->d_order, order.data(), 4ull * n);
-  up(c->d_keys, A.key_pool.data(), A.key_pool.size());
-  up(c->d_vals, A.val_pool.data(), A.val_pool.size());
-  up(c->d_hashes, A.hash_pool.data(), A.hash_pool.size());
-  up(c->d_children, A.child_pool.data(), 4ull * A.child_pool.size());
-  up(c->d_accounts, A.accounts.data(), sizeof(AccountRec) * A.accounts.size());
+  up(c->d_keys, A.key_pool.data(), A.key_pool.size(), R.keys);
+  up(c->d_vals, A.val_pool.data(), A.val_pool.size(), R.vals);
+  up(c->d_hashes, A.hash_pool.data(), A.hash_pool.size(), R.hashes);
+  up(c->d_children, A.child_pool.data(), 4ull * A.child_pool.size(), 4ull * R.children);
+  up(c->d_accounts, A.accounts.data(), sizeof(AccountRec) * A.accounts.size(), sizeof(AccountRec) * R.accounts);
   CUDA_OK(cudaMemsetAsync(c->d_counters.p, 0, 32, c->st));
   ArenaView V;
   V.nodes = c->d_nodes.as<NodeRec>();
@@ -1516,6 +1896,16 @@ void fetch_refs(Lane* c, Job& J) {
   lane_sync(c);
   c->stats.d2h_bytes += 33.0 * n;
   J.refs_on_host = true;
+}
+
+// the value and hash pools of a GPU-built pre-image, for the host paths that read them (host IR serialisation)
+void fetch_pools(Lane* c, Job& J) {
+  if (J.pools_on_host) return;
+  if (J.dev.vals) CUDA_OK(cudaMemcpyAsync(J.A.val_pool.data(), c->d_vals.p, J.dev.vals, cudaMemcpyDeviceToHost, c->st));
+  if (J.dev.hashes) CUDA_OK(cudaMemcpyAsync(J.A.hash_pool.data(), c->d_hashes.p, J.dev.hashes, cudaMemcpyDeviceToHost, c->st));
+  lane_sync(c);
+  c->stats.d2h_bytes += (double)(J.dev.vals + J.dev.hashes);
+  J.pools_on_host = true;
 }
 
 // ---- step 5: IrDump ------------------------------------------------------------------------------
@@ -2090,6 +2480,7 @@ bool gpu_dump_block(ppd_ctx* c, Lane* L, Job& J, uint8_t** out, size_t* out_len)
     if (ir_flag[i]) {
       if (st.v.empty()) st.v.assign(J.A.nodes.size(), 0);
       fetch_refs(L, J);
+      fetch_pools(L, J);
       dump_ir(J, b, b.irs[i], st, host_parts[i]);
       total += host_parts[i].n;
     } else {
@@ -2157,6 +2548,7 @@ bool gpu_dump_block(ppd_ctx* c, Lane* L, Job& J, uint8_t** out, size_t* out_len)
     uint8_t* want = nullptr;
     size_t want_len = 0;
     fetch_refs(L, J);
+    fetch_pools(L, J);
     dump_blocks(J, &want, &want_len, 1);
     bool same = want_len == o.n && memcmp(want, dst, o.n) == 0;
     size_t at = 0;
@@ -2187,6 +2579,7 @@ void decode_one(ppd_ctx* c, Lane* L, const uint8_t* flat, size_t len, uint8_t** 
   *out = nullptr, *out_len = 0;
   try {
     read_flat_block(flat, len, b);
+    if (gpu_parse_enabled()) gpu_pre_image(L, J, b);
     collect_messages(J, b);
     pt.lap("parse");
     J.kh.run(L);
@@ -2204,6 +2597,7 @@ void decode_one(ppd_ctx* c, Lane* L, const uint8_t* flat, size_t len, uint8_t** 
   pt.lap("sweep");
   if (!gpu_dump_block(c, L, J, out, out_len)) {
     fetch_refs(L, J);
+    fetch_pools(L, J);
     dump_blocks(J, out, out_len, dump_workers);
   }
   *status = PPD_OK;
@@ -2215,6 +2609,8 @@ void add_stats(ppd_stats& a, const ppd_stats& b) {
   a.key_permutations += b.key_permutations, a.node_bytes += b.node_bytes, a.arena_nodes += b.arena_nodes;
   a.levels = std::max(a.levels, b.levels);
   a.gpu_ms += b.gpu_ms, a.h2d_bytes += b.h2d_bytes, a.d2h_bytes += b.d2h_bytes, a.kernel_launches += b.kernel_launches;
+  a.witnesses_on_gpu += b.witnesses_on_gpu, a.witness_instructions += b.witness_instructions, a.witness_bytes += b.witness_bytes;
+  a.parse_gpu_ms += b.parse_gpu_ms;
 }
 
 // Blocks are independent (each BlockTrace carries its own pre-image, trace_protocol.rs:40-48): every
@@ -2297,6 +2693,10 @@ void ppd_last_stats(const ppd_ctx* c, ppd_stats* out) {
 }
 void ppd_free(void* p) {
   if (p && !out_pool().give_back(p)) free(p);
+}
+void* ppd_alloc_pinned(size_t n) {
+  void* p = out_pool().take(n ? n : 1);
+  return p ? p : malloc(n ? n : 1);
 }
 
 int ppd_keccak256_batch(ppd_ctx* c, const uint8_t* data, const uint64_t* offsets, size_t n, uint8_t* out32n) {
@@ -2388,11 +2788,14 @@ int ppd_compact_decode(ppd_ctx* c, const uint8_t* witness, size_t len, uint8_t**
     L->stats = ppd_stats{};
     Job& J = job_of(L, 1);
     BlockJob& b = J.blocks[0];
+    if (len >= 0xffffffffull) fail(PPD_ERR_BAD_ARGUMENT, "witness larger than 4 GiB");
     b.compact = Span{witness, (uint32_t)len};
-    parse_witness(witness, len, b.wit);
-    collect_witness_messages(J, b);
-    J.kh.run(L);
-    build_pre_image(J, b);
+    if (!(gpu_parse_enabled() && gpu_pre_image(L, J, b, /*check_version=*/false))) {
+      parse_witness(witness, len, b.wit);
+      collect_witness_messages(J, b);
+      J.kh.run(L);
+      build_pre_image(J, b);
+    }
     uint32_t sr = root_node_for(J, b, b.state_root);
     std::map<H256, uint32_t> storage_roots;
     for (auto& s : b.storage) storage_roots[s.first] = root_node_for(J, b, s.second);

@@ -75,6 +75,86 @@ struct IrDumpPlanView {
 void launch_ir_size(const ArenaView& A, const IrDumpPlanView& P, uint32_t n_ir, cudaStream_t st);
 void launch_ir_emit(const ArenaView& A, const IrDumpPlanView& P, uint32_t n_ir, uint8_t* out, cudaStream_t st);
 
+// ---- ppd_parse.cu: compact witness -> instruction list -> tree links -> node arena ----
+static const uint32_t PARSE_TILE = 4096;           // bytes per tile of the boundary search
+static const uint32_t PARSE_ERR = 0xffffff00u;     // chain values >= PARSE_ERR: PARSE_ERR | PPD_ERR_* of the failing instruction
+enum {  // words of ParseBounds::result / ParseTree::result (one 16-word device array)
+  PARSE_R_END = 0,     // where the instruction chain from byte 0 ends: n, or PARSE_ERR | code
+  PARSE_R_NINS = 1,    // number of instructions
+  PARSE_R_FLAG = 2,    // 0, or the first PARSE_WHY_* raised: the host builder must take this witness
+  PARSE_R_HEIGHT = 3,  // entries left on the stack (1 for a well-formed witness)
+  PARSE_R_ROOT = 4,    // the instruction left on the stack
+  PARSE_R_ROOT_ID = 5, // its arena id (written by the emit kernel)
+  PARSE_R_TOTALS = 8,  // PARSE_N_CNT totals of the size counters
+  PARSE_R_WORDS = 16
+};
+enum { PARSE_WHY_DECODE = 1, PARSE_WHY_STACK = 2, PARSE_WHY_NOT_CANONICAL = 3, PARSE_WHY_LEAF_KIND = 4, PARSE_WHY_KEY = 5 };
+enum {  // per-instruction size counters, scanned together
+  PARSE_C_NODE = 0,   // arena nodes (an account leaf with a non-empty storage trie also owns that trie's NK_ROOT node)
+  PARSE_C_HASH = 1,   // hash_pool entries
+  PARSE_C_KEY = 2,    // key_pool bytes
+  PARSE_C_VAL = 3,    // val_pool bytes (4-byte aligned values)
+  PARSE_C_CHILD = 4,  // child_pool slots
+  PARSE_C_ACCT = 5,   // account records
+  PARSE_C_CODE = 6,   // inline code strings
+  PARSE_C_SPARE = 7,
+  PARSE_N_CNT = 8
+};
+struct Pyramid16 {
+  const int16_t *L, *m1, *m2, *m3;
+};
+struct ParseBounds {
+  const uint8_t* wit;     // witness bytes (readable up to n + 16)
+  uint32_t n;
+  uint32_t n_tiles, group_tiles, n_groups;
+  uint32_t* exit1;        // [n]
+  uint32_t* exit2;        // [n_groups * PARSE_TILE]
+  uint32_t* group_entry;  // [n_groups]
+  uint32_t* tile_entry;   // [n_tiles]
+  uint32_t* bitmap;       // [n_tiles * PARSE_TILE / 32]
+  uint32_t* tile_count;   // [n_tiles + 1]
+  uint32_t* tile_base;    // [n_tiles + 1]
+  uint32_t* scan_tmp;     // parse_scan_tmp_words(n_tiles + 1, 1)
+  uint32_t* result;       // [PARSE_R_WORDS]
+};
+struct ParseTree {
+  const uint8_t* wit;
+  uint32_t n, n_ins;
+  const uint32_t* ins_pos;  // [n_ins]
+  uint32_t* meta;           // [n_ins]
+  uint8_t* knib;            // [n_ins]
+  uint32_t* delta;          // [n_ins + 1]
+  uint32_t* hb;             // [n_ins + 1]
+  int16_t *h16, *m1, *m2, *m3;
+  uint32_t* parent;         // [n_ins]
+  uint32_t* info;           // [n_ins]
+  uint32_t* aux0;           // [n_ins]
+  uint32_t *pending, *lvlmax;
+  uint32_t *cnt, *scn;      // [PARSE_N_CNT][cnt_stride]
+  size_t cnt_stride;        // >= n_ins + 1
+  uint32_t* scan_tmp;       // parse_scan_tmp_words(n_ins + 1, PARSE_N_CNT)
+  uint32_t* result;
+};
+struct ParseEmit {
+  ParseTree T;
+  NodeRec* nodes;
+  uint16_t* level;
+  uint8_t *key_pool, *val_pool, *hash_pool;
+  uint32_t* child_pool;
+  AccountRec* accounts;
+  uint32_t* acct_list;         // [n_accounts][5]: leaf node, storage trie root id, its NK_ROOT node, flags (1 storage flag, 2 non-empty), code index
+  uint64_t* code_se;           // [n_code][2] (begin, end) into the witness
+  uint32_t* code_list;         // [n_code][2] (pos, len)
+  const uint8_t* code_digest;  // [n_code][32]
+};
+size_t parse_scan_tmp_words(size_t n, uint32_t K);
+void launch_parse_bounds(const ParseBounds& B, cudaStream_t st);
+uint32_t parse_bounds_launches();
+void launch_parse_scatter(const ParseBounds& B, uint32_t* ins_pos, cudaStream_t st);
+void launch_parse_tree(const ParseTree& T, cudaStream_t st);
+void launch_parse_code_list(const ParseEmit& E, cudaStream_t st);
+void launch_parse_emit(const ParseEmit& E, cudaStream_t st);
+
 // ---- ppd_microbench.cu ----
 bool launch_microbench(int variant, uint32_t* out, uint32_t blocks_per_sm, uint32_t iters, uint32_t* block_threads, double* units_per_thread_iter,
                        cudaStream_t st);

@@ -1,0 +1,812 @@
+// ppd_parse.cu — the compact witness on the GPU: byte stream -> instruction list -> tree links ->
+// node arena (north-star items 1 and 2).
+//
+// Replaces, for a well-formed canonical witness, the reference's
+//   WitnessBytes::process_into_instructions_and_header  compact_prestate_processing.rs:683-875
+//   ParserState::parse (the rule engine == a stack machine) compact_prestate_processing.rs:325-668
+//   create_partial_trie_from_compact_node_rec              compact_to_partial_trie.rs:37-139
+//   convert_account_node_data_to_rlp_bytes...              compact_to_partial_trie.rs:141-165
+// Anything else (a parse or stack error, a witness whose tree is not the canonical trie of its items,
+// a leaf of the wrong kind) is only DETECTED here (`result[R_FLAG]`); the caller then takes the host
+// builder, which reproduces the reference's error order exactly.
+//
+// Phase A: instruction boundaries.  The stream is serial (an instruction's length is known only after
+//   its CBOR heads are read), so every byte position is decoded speculatively: nxt[p] = where the
+//   instruction that would start at p ends.  Per 4 KiB tile the chain p -> nxt[p] is pointer-doubled in
+//   shared memory into exit1[p] = the first position outside the tile that the chain from p reaches.
+//   Tiles are grouped (about sqrt(#tiles) per group); every position of a group's first tile walks
+//   exit1 to the end of the group (exit2); one thread then hops group to group from position 0, the
+//   groups' true entries are walked back down to tile entries, and one warp lane per tile marks the true
+//   instruction starts in a bitmap.  Counts are scanned and the starts scattered into ins_pos[].
+// Phase B: the stack machine in closed form.  Every instruction pushes one entry and pops `pops`;
+//   height_after = inclusive scan of (1 - pops).  The parent of instruction i is the next instruction
+//   whose height_after is not larger (nearest-smaller-value query on a min-pyramid), and i is its
+//   (height_after(i) - height_after(parent))-th popped entry: the k-th set bit of a branch mask, or the
+//   code / storage slot of an account leaf.  Depths and trie membership come from walking the parent
+//   chain (<= 64 steps); eight per-instruction size counters are scanned together.
+// Phase C: emit.  Every instruction writes its own arena records (node, key, value, hash, child slot,
+//   account record, storage ROOT node); levels are computed by climbing from the leaves with a
+//   pending-children counter per inner node (the last child to arrive continues upwards).
+#include <cstdint>
+
+#include "../../include/ppd_flat.h"
+#include "../../include/ppd_status.h"
+#include "arena.h"
+#include "ppd_kernels.h"
+#include "pyramid.cuh"
+
+namespace ppd {
+
+namespace {
+
+constexpr uint32_t TILE = PARSE_TILE;
+constexpr uint32_t PERR = PARSE_ERR;
+constexpr uint32_t NONE = 0xffffffffu;
+constexpr uint32_t HASH_BASE = 0x80000000u;
+
+__constant__ uint8_t C_EMPTY_TRIE_HASH[32] = {0x56, 0xe8, 0x1f, 0x17, 0x1b, 0xcc, 0x55, 0xa6, 0xff, 0x83, 0x45, 0xe6, 0x92, 0xc0, 0xf8, 0x6e,
+                                              0x5b, 0x48, 0xe0, 0x1b, 0x99, 0x6c, 0xad, 0xc0, 0x01, 0x62, 0x2f, 0xb5, 0xe3, 0x63, 0xb4, 0x21};
+__constant__ uint8_t C_EMPTY_CODE_HASH[32] = {0xc5, 0xd2, 0x46, 0x01, 0x86, 0xf7, 0x23, 0x3c, 0x92, 0x7e, 0x7d, 0xb2, 0xdc, 0xc7, 0x03, 0xc0,
+                                              0xe5, 0x00, 0xb6, 0x53, 0xca, 0x82, 0x27, 0x3b, 0x7b, 0xfa, 0xd8, 0x04, 0x5d, 0x85, 0xa4, 0x70};
+
+// ---------------------------------------------------------------------------------------------
+// Instruction decode (the byte grammar of compact_prestate_processing.rs:744-875; same checks in the
+// same order as the host parser)
+// ---------------------------------------------------------------------------------------------
+struct Ins {
+  uint32_t op, next, flags, aux;
+  uint32_t key_pos, key_len, val_pos, val_len;  // val: leaf value / code bytes / balance bytes
+  uint64_t nonce;
+};
+
+__device__ __forceinline__ bool cbor_head(const uint8_t* __restrict__ w, uint32_t n, uint32_t& pos, uint32_t& major, uint64_t& arg) {
+  if (pos >= n) return false;
+  uint32_t b = __ldg(w + pos++);
+  major = b >> 5;
+  uint32_t ai = b & 31;
+  if (ai < 24) {
+    arg = ai;
+    return true;
+  }
+  if (ai > 27) return false;
+  uint32_t wd = 1u << (ai - 24);
+  if (n - pos < wd) return false;
+  arg = 0;
+  for (uint32_t i = 0; i < wd; i++) arg = (arg << 8) | __ldg(w + pos++);
+  return true;
+}
+__device__ __forceinline__ bool cbor_bytes(const uint8_t* __restrict__ w, uint32_t n, uint32_t& pos, uint32_t& at, uint32_t& len) {
+  uint32_t major;
+  uint64_t arg;
+  if (!cbor_head(w, n, pos, major, arg) || major != 2 || arg > (uint64_t)(n - pos)) return false;
+  at = pos, len = (uint32_t)arg;
+  pos += len;
+  return true;
+}
+__device__ __forceinline__ bool key_too_long(uint32_t key_len) { return key_len >= 2 && 2 * (key_len - 1) > 64 + 1; }
+
+// 0, or the PPD_ERR_* code the host parser reports for an instruction starting at p (p < n)
+__device__ __forceinline__ uint32_t decode_ins(const uint8_t* __restrict__ w, uint32_t n, uint32_t p, Ins& o) {
+  uint32_t pos = p + 1, major;
+  uint64_t arg;
+  o.op = __ldg(w + p);
+  o.flags = 0, o.aux = 0, o.key_pos = o.key_len = o.val_pos = o.val_len = 0, o.nonce = 0;
+  switch (o.op) {
+    case PPD_OP_LEAF:
+      if (!cbor_bytes(w, n, pos, o.key_pos, o.key_len)) return PPD_ERR_INVALID_BYTE_VECTOR;
+      if (key_too_long(o.key_len)) return PPD_ERR_KEY_ERROR;
+      if (!cbor_bytes(w, n, pos, o.val_pos, o.val_len)) return PPD_ERR_INVALID_BYTE_VECTOR;
+      break;
+    case PPD_OP_EXTENSION:
+      if (!cbor_bytes(w, n, pos, o.key_pos, o.key_len)) return PPD_ERR_INVALID_BYTE_VECTOR;
+      if (key_too_long(o.key_len)) return PPD_ERR_KEY_ERROR;
+      break;
+    case PPD_OP_BRANCH:
+      if (!cbor_head(w, n, pos, major, arg) || major != 0 || arg > 0xffffffffull) return PPD_ERR_INVALID_BYTES_FOR_TYPE;
+      o.aux = (uint32_t)arg;
+      break;
+    case PPD_OP_HASH:
+      if (n - pos < 32) return PPD_ERR_INVALID_BYTES_FOR_TYPE;
+      o.val_pos = pos, o.val_len = 32;
+      pos += 32;
+      break;
+    case PPD_OP_CODE:
+      if (!cbor_bytes(w, n, pos, o.val_pos, o.val_len)) return PPD_ERR_INVALID_BYTES_FOR_TYPE;
+      break;
+    case PPD_OP_ACCOUNT_LEAF:
+      if (!cbor_bytes(w, n, pos, o.key_pos, o.key_len)) return PPD_ERR_INVALID_BYTE_VECTOR;
+      if (key_too_long(o.key_len)) return PPD_ERR_KEY_ERROR;
+      if (pos >= n) return PPD_ERR_UNEXPECTED_END_OF_STREAM;
+      o.flags = __ldg(w + pos++);
+      if (o.flags & 4) {
+        if (!cbor_head(w, n, pos, major, arg) || major != 0) return PPD_ERR_INVALID_BYTES_FOR_TYPE;
+        o.nonce = arg;
+      }
+      if (o.flags & 8) {
+        if (!cbor_bytes(w, n, pos, o.val_pos, o.val_len) || o.val_len > 32) return PPD_ERR_INVALID_BYTE_VECTOR;
+      }
+      if (o.flags & 1) {
+        if (!cbor_head(w, n, pos, major, arg) || major != 0) return PPD_ERR_INVALID_BYTES_FOR_TYPE;
+      }
+      break;
+    case PPD_OP_EMPTY_ROOT:
+      break;
+    default:
+      return PPD_ERR_INVALID_OPERATOR;
+  }
+  o.next = pos;
+  return 0;
+}
+// where the instruction starting at p ends, or PERR | code
+__device__ __forceinline__ uint32_t decode_next(const uint8_t* __restrict__ w, uint32_t n, uint32_t p) {
+  Ins o;
+  uint32_t e = decode_ins(w, n, p, o);
+  return e ? (PERR | e) : o.next;
+}
+
+// key_bytes_to_nibbles (compact_prestate_processing.rs:1338-1390): number of nibbles of a compact key
+__device__ __forceinline__ uint32_t key_nibble_count(const uint8_t* __restrict__ w, uint32_t at, uint32_t len) {
+  if (len == 0) return 0;
+  if (len == 1) return 1;
+  return 2 * (len - 1) - (__ldg(w + at) & 1u);
+}
+__device__ __forceinline__ void set_nib(uint8_t* pk, uint32_t d, uint32_t nib) { pk[d >> 1] |= (uint8_t)((d & 1) ? nib : (nib << 4)); }
+// the key's nibbles written at nibble positions d, d+1, ... of the packed path (caller bounds d + count <= 64)
+__device__ __forceinline__ void put_key_nibbles(uint8_t* pk, uint32_t d, const uint8_t* __restrict__ w, uint32_t at, uint32_t len) {
+  if (len == 0) return;
+  if (len == 1) {
+    set_nib(pk, d, __ldg(w + at) & 15u);
+    return;
+  }
+  uint32_t cnt = 2 * (len - 1) - (__ldg(w + at) & 1u);
+  for (uint32_t i = 0; i < cnt; i++) {
+    uint32_t b = __ldg(w + at + 1 + (i >> 1));
+    set_nib(pk, d + i, (i & 1) ? (b & 15u) : (b >> 4));
+  }
+}
+__device__ __forceinline__ uint32_t nth_set_bit(uint32_t mask, uint32_t k) {
+  for (uint32_t i = 0; i < k; i++) mask &= mask - 1;
+  return mask ? (uint32_t)__ffs(mask) - 1 : 0u;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Phase A
+// ---------------------------------------------------------------------------------------------
+constexpr int TE_THREADS = 512, TE_PER = TILE / TE_THREADS;
+
+__global__ void __launch_bounds__(TE_THREADS) tile_exit_kernel(const uint8_t* __restrict__ w, uint32_t n, uint32_t* __restrict__ exit1) {
+  __shared__ uint32_t nxt[TILE];
+  const uint32_t base = blockIdx.x * TILE, end = min(base + TILE, n);
+#pragma unroll
+  for (int k = 0; k < TE_PER; k++) {
+    uint32_t o = threadIdx.x + k * TE_THREADS, p = base + o;
+    if (p < end) nxt[o] = p == 0 ? 1u : decode_next(w, n, p);  // byte 0 is the header: "ends" at 1
+  }
+  __syncthreads();
+  // pointer doubling; any intermediate value is a point of the same chain, so updating in place is safe
+  for (;;) {
+    bool moved = false;
+#pragma unroll
+    for (int k = 0; k < TE_PER; k++) {
+      uint32_t o = threadIdx.x + k * TE_THREADS, p = base + o;
+      if (p < end) {
+        uint32_t v = nxt[o];
+        if (v < end) {
+          nxt[o] = nxt[v - base];
+          moved = true;
+        }
+      }
+    }
+    if (!__syncthreads_or(moved)) break;
+  }
+#pragma unroll
+  for (int k = 0; k < TE_PER; k++) {
+    uint32_t o = threadIdx.x + k * TE_THREADS, p = base + o;
+    if (p < end) exit1[p] = nxt[o];
+  }
+}
+
+// exit2[g][c]: where the chain from position c of group g's first tile leaves the group
+__global__ void group_exit_kernel(const uint32_t* __restrict__ exit1, uint32_t n, uint32_t group_bytes, uint32_t* __restrict__ exit2) {
+  uint32_t g = blockIdx.y, c = blockIdx.x * blockDim.x + threadIdx.x;
+  uint64_t gb = (uint64_t)g * group_bytes;
+  uint32_t gend = (uint32_t)min((uint64_t)n, gb + group_bytes);
+  uint32_t p = (uint32_t)gb + c;
+  if (c >= TILE || p >= gend) return;
+  uint32_t v = p;
+  while (v < gend) v = __ldg(exit1 + v);
+  exit2[(size_t)g * TILE + c] = v;
+}
+
+// hop group to group from position 0; result[0] = n (clean end) or PERR | code
+__global__ void top_chain_kernel(const uint32_t* __restrict__ exit1, const uint32_t* __restrict__ exit2, uint32_t n, uint32_t group_bytes,
+                                 uint32_t* __restrict__ group_entry, uint32_t* __restrict__ result) {
+  if (blockIdx.x || threadIdx.x) return;
+  uint32_t cur = 0;
+  while (cur < n) {
+    uint32_t g = cur / group_bytes;
+    uint64_t gb = (uint64_t)g * group_bytes;
+    uint32_t gend = (uint32_t)min((uint64_t)n, gb + group_bytes);
+    group_entry[g] = cur;
+    uint32_t off = cur - (uint32_t)gb;
+    if (off < TILE) {
+      cur = exit2[(size_t)g * TILE + off];
+    } else {  // an instruction jumped over the group's first tile
+      while (cur < gend) cur = exit1[cur];
+    }
+  }
+  result[PARSE_R_END] = cur;
+}
+
+__global__ void tile_entry_kernel(const uint32_t* __restrict__ exit1, const uint32_t* __restrict__ group_entry, uint32_t n, uint32_t n_groups,
+                                  uint32_t group_bytes, uint32_t* __restrict__ tile_entry) {
+  uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n_groups) return;
+  uint32_t cur = group_entry[g];
+  if (cur == NONE) return;
+  uint32_t gend = (uint32_t)min((uint64_t)n, (uint64_t)g * group_bytes + group_bytes);
+  while (cur < gend) {
+    tile_entry[cur / TILE] = cur;
+    cur = __ldg(exit1 + cur);
+  }
+}
+
+// one warp per tile: lane 0 walks the true chain through the tile and marks instruction starts
+constexpr int TM_WARPS = 4;
+__global__ void __launch_bounds__(TM_WARPS * 32) tile_mark_kernel(const uint8_t* __restrict__ w, uint32_t n, uint32_t n_tiles,
+                                                                  const uint32_t* __restrict__ tile_entry, uint32_t* __restrict__ bitmap,
+                                                                  uint32_t* __restrict__ tile_count) {
+  __shared__ uint32_t bits[TM_WARPS][TILE / 32];
+  const uint32_t wi = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t t = blockIdx.x * TM_WARPS + wi;
+  if (t >= n_tiles) return;
+  for (uint32_t k = lane; k < TILE / 32; k += 32) bits[wi][k] = 0;
+  __syncwarp();
+  uint32_t count = 0;
+  if (lane == 0) {
+    uint32_t cur = tile_entry[t];
+    const uint32_t base = t * TILE, end = min(base + TILE, n);
+    if (cur != NONE) {
+      if (cur == 0) cur = 1;  // the header byte is not an instruction
+      while (cur < end) {
+        uint32_t o = cur - base;
+        bits[wi][o >> 5] |= 1u << (o & 31);
+        count++;
+        cur = decode_next(w, n, cur);
+      }
+    }
+    tile_count[t] = count;
+  }
+  __syncwarp();
+  for (uint32_t k = lane; k < TILE / 32; k += 32) bitmap[(size_t)t * (TILE / 32) + k] = bits[wi][k];
+}
+
+__global__ void __launch_bounds__(TILE / 32) ins_scatter_kernel(const uint32_t* __restrict__ bitmap, const uint32_t* __restrict__ tile_base,
+                                                                uint32_t* __restrict__ ins_pos) {
+  __shared__ uint32_t wsum[TILE / 32 / 32];
+  const uint32_t t = blockIdx.x, tid = threadIdx.x;
+  uint32_t word = bitmap[(size_t)t * (TILE / 32) + tid];
+  uint32_t c = __popc(word), incl = c;
+  for (int off = 1; off < 32; off <<= 1) {
+    uint32_t x = __shfl_up_sync(0xffffffffu, incl, off);
+    if ((tid & 31) >= (uint32_t)off) incl += x;
+  }
+  if ((tid & 31) == 31) wsum[tid >> 5] = incl;
+  __syncthreads();
+  uint32_t before = 0;
+  for (uint32_t k = 0; k < (tid >> 5); k++) before += wsum[k];
+  uint32_t at = tile_base[t] + before + incl - c;
+  const uint32_t p0 = t * TILE + tid * 32;
+  while (word) {
+    uint32_t b = (uint32_t)__ffs(word) - 1;
+    word &= word - 1;
+    ins_pos[at++] = p0 + b;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// multi-array exclusive scan: K arrays of n uint32 each, array k at in + k * stride
+// ---------------------------------------------------------------------------------------------
+constexpr int MS_B = 256, MS_ITEMS = 4, MS_ELEMS = MS_B * MS_ITEMS;
+
+__global__ void __launch_bounds__(MS_B) mscan_block_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, uint32_t n, size_t stride,
+                                                           uint32_t* __restrict__ block_sums, size_t sums_stride) {
+  __shared__ uint32_t warp_sums[MS_B / 32];
+  const uint32_t k = blockIdx.y;
+  in += k * stride, out += k * stride;
+  uint32_t base = blockIdx.x * MS_ELEMS + threadIdx.x * MS_ITEMS;
+  uint32_t v[MS_ITEMS], sum = 0;
+#pragma unroll
+  for (int q = 0; q < MS_ITEMS; q++) {
+    v[q] = base + q < n ? in[base + q] : 0u;
+    sum += v[q];
+  }
+  uint32_t incl = sum;
+  for (int off = 1; off < 32; off <<= 1) {
+    uint32_t t = __shfl_up_sync(0xffffffffu, incl, off);
+    if ((threadIdx.x & 31) >= (uint32_t)off) incl += t;
+  }
+  if ((threadIdx.x & 31) == 31) warp_sums[threadIdx.x >> 5] = incl;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    uint32_t ws = threadIdx.x < MS_B / 32 ? warp_sums[threadIdx.x] : 0u, wi = ws;
+    for (int off = 1; off < 32; off <<= 1) {
+      uint32_t t = __shfl_up_sync(0xffffffffu, wi, off);
+      if (threadIdx.x >= (uint32_t)off) wi += t;
+    }
+    if (threadIdx.x < MS_B / 32) warp_sums[threadIdx.x] = wi - ws;
+    if (threadIdx.x == MS_B / 32 - 1 && block_sums) block_sums[k * sums_stride + blockIdx.x] = wi;
+  }
+  __syncthreads();
+  uint32_t excl = incl - sum + warp_sums[threadIdx.x >> 5];
+#pragma unroll
+  for (int q = 0; q < MS_ITEMS; q++) {
+    if (base + q < n) out[base + q] = excl;
+    excl += v[q];
+  }
+}
+__global__ void __launch_bounds__(MS_B) mscan_add_kernel(uint32_t* __restrict__ out, uint32_t n, size_t stride, const uint32_t* __restrict__ block_offsets,
+                                                         size_t sums_stride) {
+  const uint32_t k = blockIdx.y;
+  out += k * stride;
+  uint32_t add = block_offsets[k * sums_stride + blockIdx.x];
+  uint32_t i = blockIdx.x * MS_ELEMS + threadIdx.x;
+#pragma unroll
+  for (int q = 0; q < MS_ITEMS; q++) {
+    uint32_t j = i + q * MS_B;
+    if (j < n) out[j] += add;
+  }
+}
+
+void mscan(const uint32_t* in, uint32_t* out, uint32_t n, size_t stride, uint32_t K, uint32_t* tmp, cudaStream_t st) {
+  if (!n) return;
+  uint32_t nb = (n + MS_ELEMS - 1) / MS_ELEMS;
+  size_t ss = (nb + 3) & ~(size_t)3;
+  mscan_block_kernel<<<dim3(nb, K), MS_B, 0, st>>>(in, out, n, stride, nb > 1 ? tmp : nullptr, ss);
+  if (nb > 1) {
+    mscan(tmp, tmp, nb, ss, K, tmp + K * ss, st);
+    mscan_add_kernel<<<dim3(nb, K), MS_B, 0, st>>>(out, n, stride, tmp, ss);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Phase B
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t dw0(uint32_t kind, uint32_t nib_start, uint32_t nib_len) { return kind | (nib_start << 8) | (nib_len << 16); }
+__device__ __forceinline__ void raise(uint32_t* result, uint32_t reason) { atomicCAS(result + PARSE_R_FLAG, 0u, reason); }
+
+__device__ __forceinline__ uint32_t pops_of(uint32_t meta) {
+  uint32_t op = meta & 7u;
+  if (op == PPD_OP_EXTENSION) return 1;
+  if (op == PPD_OP_BRANCH) return __popc(meta >> 16);
+  if (op == PPD_OP_ACCOUNT_LEAF) return ((meta >> 8) & 1u) + ((meta >> 9) & 1u);
+  return 0;
+}
+
+// meta = op | flags << 8 | (branch mask & 0xffff) << 16
+__global__ void ins_info_kernel(ParseTree T) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > T.n_ins) return;
+  if (i == T.n_ins) {
+    T.delta[i] = 0;
+    return;
+  }
+  Ins o;
+  uint32_t e = decode_ins(T.wit, T.n, T.ins_pos[i], o);
+  if (e || o.op > 6) {
+    raise(T.result, PARSE_WHY_DECODE);
+    o.op = PPD_OP_EMPTY_ROOT, o.flags = 0, o.aux = 0, o.key_len = 0;
+  }
+  if (o.op == PPD_OP_BRANCH && (o.aux >> 16)) raise(T.result, PARSE_WHY_STACK);
+  uint32_t meta = o.op | ((o.flags & 0xffu) << 8) | ((o.aux & 0xffffu) << 16);
+  T.meta[i] = meta;
+  uint32_t kn = key_nibble_count(T.wit, o.key_pos, o.key_len);
+  T.knib[i] = (uint8_t)min(kn, 255u);
+  uint32_t pops = pops_of(meta);
+  T.delta[i] = 1u - pops;
+  T.pending[i] = o.op == PPD_OP_ACCOUNT_LEAF ? ((o.flags >> 1) & 1u) : pops;
+  T.lvlmax[i] = 0;
+  T.aux0[i] = NONE;
+}
+
+// heights as int16 (+ sentinel), stack underflow check
+__global__ void heights_kernel(ParseTree T) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > T.n_ins) return;
+  if (i == T.n_ins) {
+    T.h16[i] = INT16_MIN;
+    T.result[PARSE_R_HEIGHT] = T.hb[i];
+    return;
+  }
+  int32_t hb = (int32_t)T.hb[i];
+  int32_t pops = (int32_t)pops_of(T.meta[i]);
+  if (hb < pops) raise(T.result, PARSE_WHY_STACK);
+  int32_t ha = hb + 1 - pops;
+  if (ha > 30000 || ha < 1) {
+    raise(T.result, PARSE_WHY_STACK);
+    ha = ha < 1 ? 1 : 30000;
+  }
+  T.h16[i] = (int16_t)ha;
+}
+
+__global__ void min64_i16_kernel(const int16_t* __restrict__ in, uint32_t n_in, int16_t* __restrict__ out, uint32_t n_out) {
+  uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n_out) return;
+  int m = INT16_MAX;
+  uint32_t lo = j * 64, hi = min(lo + 64, n_in);
+  for (uint32_t k = lo; k < hi; k++) m = min(m, (int)in[k]);
+  out[j] = (int16_t)m;
+}
+
+// info = slot (bits 0-3) | role (bits 4-5: 0 child of branch / extension, 1 account code, 2 account storage)
+//        | depth << 8 | in_storage << 16 | storage_nonempty << 17 (account leaves)
+__global__ void link_kernel16(ParseTree T) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= T.n_ins) return;
+  Pyramid16 P{T.h16, T.m1, T.m2, T.m3};
+  int ha = T.h16[i];
+  uint32_t j = scan_right(P, i, ha + 1);  // first j > i with height_after(j) <= height_after(i); n_ins when none
+  T.parent[i] = j;
+  uint32_t info = 0;
+  if (j < T.n_ins) {
+    uint32_t pm = T.meta[j], pop = pm & 7u, cop = T.meta[i] & 7u;
+    uint32_t k = (uint32_t)(ha - (int)T.h16[j]);
+    if (k >= pops_of(pm)) {
+      raise(T.result, PARSE_WHY_STACK);
+      k = 0;
+    }
+    uint32_t role = 0;
+    if (pop == PPD_OP_ACCOUNT_LEAF) {
+      bool has_code = (pm >> 8) & 1u;
+      role = (has_code && k == 0) ? 1u : 2u;
+      if (role == 1) {
+        if (cop != PPD_OP_CODE && cop != PPD_OP_HASH) raise(T.result, PARSE_WHY_STACK);
+        T.aux0[j] = i;
+      } else if (cop == PPD_OP_CODE) {
+        raise(T.result, PARSE_WHY_STACK);
+      }
+    } else if (cop == PPD_OP_CODE || cop == PPD_OP_EMPTY_ROOT) {
+      raise(T.result, PARSE_WHY_NOT_CANONICAL);  // an empty child of a branch / extension: the host rebuilds from the items
+    }
+    info = k | (role << 4);
+  } else {
+    uint32_t cop = T.meta[i] & 7u;
+    if (cop == PPD_OP_CODE || cop == PPD_OP_EMPTY_ROOT) raise(T.result, PARSE_WHY_NOT_CANONICAL);
+    T.result[PARSE_R_ROOT] = i;
+  }
+  T.info[i] = info;
+}
+
+// depth inside the own trie, trie membership, canonicity, per-instruction sizes
+__global__ void shape_kernel(ParseTree T) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > T.n_ins) return;
+  const size_t S = T.cnt_stride;
+  if (i == T.n_ins) {
+    for (int k = 0; k < PARSE_N_CNT; k++) T.cnt[k * S + i] = 0;
+    return;
+  }
+  const uint32_t meta = T.meta[i], op = meta & 7u;
+  uint32_t info = T.info[i];
+  uint32_t c_node = 0, c_hash = 0, c_key = 0, c_val = 0, c_child = 0, c_acct = 0, c_code = 0;
+  if (op == PPD_OP_HASH) {
+    c_hash = 1;
+  } else if (op == PPD_OP_CODE) {
+    c_code = 1;
+  } else if (op != PPD_OP_EMPTY_ROOT) {
+    // walk to the root of the own trie
+    uint32_t cur = i, d = 0, in_storage = 0;
+    for (uint32_t guard = 0; guard < 4096; guard++) {
+      uint32_t j = T.parent[cur];
+      if (j >= T.n_ins) break;
+      uint32_t pop = T.meta[j] & 7u;
+      if (pop == PPD_OP_BRANCH) {
+        d += 1;
+      } else if (pop == PPD_OP_EXTENSION) {
+        d += T.knib[j];
+      } else {
+        in_storage = ((T.info[cur] >> 4) & 3u) == 2u;
+        break;
+      }
+      if (d > 200) break;
+      cur = j;
+    }
+    const uint32_t kn = T.knib[i];
+    c_node = 1;
+    if (op == PPD_OP_BRANCH) {
+      if (d >= 64) raise(T.result, PARSE_WHY_KEY);
+      uint32_t k = __popc(meta >> 16);
+      if (k < 2) raise(T.result, PARSE_WHY_NOT_CANONICAL);
+      c_child = k;
+    } else {
+      if (d + kn > 64) raise(T.result, PARSE_WHY_KEY);
+      uint32_t nd = min(d + kn, 64u);
+      c_key = (nd + 1) / 2 + 1;
+      if (op == PPD_OP_EXTENSION) {
+        uint32_t cop = i ? (T.meta[i - 1] & 7u) : 7u;  // the child is the entry on top of the stack: the previous instruction
+        if (kn == 0 || !(cop == PPD_OP_BRANCH || cop == PPD_OP_HASH)) raise(T.result, PARSE_WHY_NOT_CANONICAL);
+      } else if (op == PPD_OP_LEAF) {
+        if (!in_storage) raise(T.result, PARSE_WHY_LEAF_KIND);
+        Ins o;
+        decode_ins(T.wit, T.n, T.ins_pos[i], o);
+        uint32_t vl = o.val_len, hl = 0;
+        if (!(vl == 1 && __ldg(T.wit + o.val_pos) < 0x80)) hl = vl < 56 ? 1 : vl < 256 ? 2 : vl < 65536 ? 3 : vl < (1u << 24) ? 4 : 5;
+        c_val = (hl + vl + 3) & ~3u;
+      } else {  // account leaf
+        if (in_storage) raise(T.result, PARSE_WHY_LEAF_KIND);
+        c_acct = 1;
+        uint32_t nonempty = 0;
+        if (meta & (2u << 8)) {
+          uint32_t sop = i ? (T.meta[i - 1] & 7u) : 7u;
+          if (sop == PPD_OP_HASH) {
+            const uint8_t* h = T.wit + T.ins_pos[i - 1] + 1;
+            for (int k = 0; k < 32; k++) nonempty |= (uint32_t)(__ldg(h + k) != C_EMPTY_TRIE_HASH[k]);
+          } else {
+            nonempty = sop != PPD_OP_EMPTY_ROOT;
+          }
+        }
+        c_node += nonempty;  // the NK_ROOT node of the storage trie
+        info |= nonempty << 17;
+      }
+    }
+    info |= (min(d, 255u) << 8) | (in_storage << 16);
+    T.info[i] = info;
+  }
+  T.cnt[PARSE_C_NODE * S + i] = c_node;
+  T.cnt[PARSE_C_HASH * S + i] = c_hash;
+  T.cnt[PARSE_C_KEY * S + i] = c_key;
+  T.cnt[PARSE_C_VAL * S + i] = c_val;
+  T.cnt[PARSE_C_CHILD * S + i] = c_child;
+  T.cnt[PARSE_C_ACCT * S + i] = c_acct;
+  T.cnt[PARSE_C_CODE * S + i] = c_code;
+  T.cnt[PARSE_C_SPARE * S + i] = 0;
+}
+
+__global__ void totals_kernel(ParseTree T) {
+  uint32_t k = threadIdx.x;
+  if (k < PARSE_N_CNT) T.result[PARSE_R_TOTALS + k] = T.scn[k * T.cnt_stride + T.n_ins];
+}
+
+// ---------------------------------------------------------------------------------------------
+// Phase C
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t id_of(const ParseTree& T, uint32_t i) {
+  uint32_t op = T.meta[i] & 7u;
+  if (op == PPD_OP_HASH) return HASH_BASE + T.scn[PARSE_C_HASH * T.cnt_stride + i];
+  if (op == PPD_OP_CODE || op == PPD_OP_EMPTY_ROOT) return NODE_EMPTY;
+  return T.scn[PARSE_C_NODE * T.cnt_stride + i];
+}
+
+// inline code: (begin, end) pairs for the keccak launch and (pos, len) for the host
+__global__ void code_list_kernel(ParseEmit E) {
+  const ParseTree& T = E.T;
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= T.n_ins || (T.meta[i] & 7u) != PPD_OP_CODE) return;
+  Ins o;
+  decode_ins(T.wit, T.n, T.ins_pos[i], o);
+  uint32_t c = T.scn[PARSE_C_CODE * T.cnt_stride + i];
+  E.code_se[2 * c] = o.val_pos, E.code_se[2 * c + 1] = (uint64_t)o.val_pos + o.val_len;
+  E.code_list[2 * c] = o.val_pos, E.code_list[2 * c + 1] = o.val_len;
+}
+
+__device__ __forceinline__ void copy_bytes(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src, uint32_t n) {
+  for (uint32_t k = 0; k < n; k++) dst[k] = __ldg(src + k);
+}
+
+__global__ void __launch_bounds__(128) emit_kernel(ParseEmit E) {
+  const ParseTree& T = E.T;
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= T.n_ins) return;
+  const size_t S = T.cnt_stride;
+  const uint32_t meta = T.meta[i], op = meta & 7u, info = T.info[i];
+  const uint32_t pos = T.ins_pos[i];
+  const uint32_t my_id = id_of(T, i);
+  // register with the parent branch
+  {
+    uint32_t j = T.parent[i];
+    if (j >= T.n_ins) T.result[PARSE_R_ROOT_ID] = my_id;
+    if (j < T.n_ins && (T.meta[j] & 7u) == PPD_OP_BRANCH) E.child_pool[T.scn[PARSE_C_CHILD * S + j] + (info & 15u)] = my_id;
+  }
+  if (op == PPD_OP_HASH) {
+    uint32_t* dst = reinterpret_cast<uint32_t*>(E.hash_pool + 32ull * (my_id - HASH_BASE));
+    const uint8_t* src = T.wit + pos + 1;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      uint32_t b0 = __ldg(src + 4 * k), b1 = __ldg(src + 4 * k + 1), b2 = __ldg(src + 4 * k + 2), b3 = __ldg(src + 4 * k + 3);
+      dst[k] = b0 | (b1 << 8) | (b2 << 16) | (b3 << 24);
+    }
+    return;
+  }
+  if (op == PPD_OP_CODE || op == PPD_OP_EMPTY_ROOT) return;
+  if (op == PPD_OP_BRANCH) {
+    E.nodes[my_id] = NodeRec{dw0(NK_BRANCH, 0, 0), T.scn[PARSE_C_CHILD * S + i], meta >> 16, 0};
+    return;
+  }
+  Ins o;
+  decode_ins(T.wit, T.n, pos, o);
+  const uint32_t d = (info >> 8) & 255u, kn = T.knib[i], nd = min(d + kn, 64u);
+  // the full path: own key nibbles, then every ancestor's contribution up to the root of the own trie
+  uint8_t pk[36];
+#pragma unroll
+  for (int k = 0; k < 36; k++) pk[k] = 0;
+  if (d + kn <= 64) put_key_nibbles(pk, d, T.wit, o.key_pos, o.key_len);
+  {
+    uint32_t cur = i;
+    for (uint32_t guard = 0; guard < 4096; guard++) {
+      uint32_t j = T.parent[cur];
+      if (j >= T.n_ins) break;
+      uint32_t pm = T.meta[j], pop = pm & 7u;
+      uint32_t pd = (T.info[j] >> 8) & 255u;
+      if (pop == PPD_OP_BRANCH) {
+        if (pd < 64) set_nib(pk, pd, nth_set_bit(pm >> 16, T.info[cur] & 15u));
+      } else if (pop == PPD_OP_EXTENSION) {
+        Ins e;
+        decode_ins(T.wit, T.n, T.ins_pos[j], e);
+        if (pd + T.knib[j] <= 64) put_key_nibbles(pk, pd, T.wit, e.key_pos, e.key_len);
+      } else {
+        break;
+      }
+      cur = j;
+    }
+  }
+  const uint32_t koff = T.scn[PARSE_C_KEY * S + i];
+  {
+    uint8_t* kd = E.key_pool + koff;
+    uint32_t nb = (nd + 1) / 2;
+    for (uint32_t k = 0; k < nb; k++) kd[k] = pk[k];
+    kd[nb] = 0;
+  }
+  if (op == PPD_OP_EXTENSION) {
+    E.nodes[my_id] = NodeRec{dw0(NK_EXT, d, kn), koff, i ? id_of(T, i - 1) : NODE_EMPTY, 0};
+    return;
+  }
+  if (op == PPD_OP_LEAF) {
+    // rlp_str(value), compact_to_partial_trie.rs:119
+    uint32_t voff = T.scn[PARSE_C_VAL * S + i], vl = o.val_len, hl = 0;
+    uint8_t* v = E.val_pool + voff;
+    if (!(vl == 1 && __ldg(T.wit + o.val_pos) < 0x80)) {
+      if (vl < 56) {
+        v[hl++] = (uint8_t)(0x80 + vl);
+      } else {
+        uint32_t k = vl < 256 ? 1 : vl < 65536 ? 2 : vl < (1u << 24) ? 3 : 4;
+        v[hl++] = (uint8_t)(0xb7 + k);
+        for (uint32_t q = k; q-- > 0;) v[hl++] = (uint8_t)(vl >> (8 * q));
+      }
+    }
+    copy_bytes(v + hl, T.wit + o.val_pos, vl);
+    E.nodes[my_id] = NodeRec{dw0(NK_LEAF, d, kn), koff, voff, hl + vl};
+    return;
+  }
+  // account leaf: the record (compact_to_partial_trie.rs:141-165), the storage trie's ROOT node, the host's list entry
+  const uint32_t a = T.scn[PARSE_C_ACCT * S + i];
+  const uint32_t nonempty = (info >> 17) & 1u;
+  uint32_t sroot = NODE_EMPTY, root_node = NODE_EMPTY;
+  if (meta & (2u << 8)) sroot = i ? id_of(T, i - 1) : NODE_EMPTY;
+  if (nonempty) {
+    root_node = my_id + 1;
+    E.nodes[root_node] = NodeRec{dw0(NK_ROOT, 0, 0), 0, sroot, 0};
+  }
+  {
+    uint32_t* r = reinterpret_cast<uint32_t*>(E.accounts + a);
+    uint8_t* rb = reinterpret_cast<uint8_t*>(r);
+    for (int k = 0; k < 36; k++) r[k] = 0;
+    for (int k = 0; k < 8; k++) rb[31 - k] = (uint8_t)(o.nonce >> (8 * k));
+    if (meta & (8u << 8)) copy_bytes(rb + 32 + 32 - o.val_len, T.wit + o.val_pos, o.val_len);
+    for (int k = 0; k < 32; k++) rb[64 + k] = C_EMPTY_TRIE_HASH[k];
+    uint32_t code_idx = NONE;
+    if (meta & (1u << 8)) {
+      uint32_t ci = T.aux0[i];
+      if (ci < T.n_ins) {
+        if ((T.meta[ci] & 7u) == PPD_OP_CODE) {
+          code_idx = T.scn[PARSE_C_CODE * S + ci];
+          const uint8_t* dg = E.code_digest + 32ull * code_idx;
+          for (int k = 0; k < 32; k++) rb[96 + k] = dg[k];
+        } else {
+          copy_bytes(rb + 96, T.wit + T.ins_pos[ci] + 1, 32);
+        }
+      }
+    } else {
+      for (int k = 0; k < 32; k++) rb[96 + k] = C_EMPTY_CODE_HASH[k];
+    }
+    r[32] = root_node;  // storage_src
+    uint32_t* L = E.acct_list + 5ull * a;
+    L[0] = my_id, L[1] = sroot, L[2] = root_node, L[3] = ((meta >> 9) & 1u) | (nonempty << 1), L[4] = code_idx;
+  }
+  E.nodes[my_id] = NodeRec{dw0(NK_LEAF_ACCOUNT, d, kn), koff, a, 0};
+}
+
+// levels: 1 + the maximum level of what a node reads (host_arena.h constructors), bottom-up
+__global__ void climb_kernel(ParseEmit E) {
+  const ParseTree& T = E.T;
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= T.n_ins) return;
+  const size_t S = T.cnt_stride;
+  const uint32_t meta = T.meta[i], op = meta & 7u;
+  const bool starter = op == PPD_OP_LEAF || op == PPD_OP_HASH || op == PPD_OP_EMPTY_ROOT || op == PPD_OP_CODE ||
+                       (op == PPD_OP_ACCOUNT_LEAF && !(meta & (2u << 8)));
+  if (!starter) return;
+  if (op == PPD_OP_LEAF || op == PPD_OP_ACCOUNT_LEAF) E.level[T.scn[PARSE_C_NODE * S + i]] = 0;
+  uint32_t cur = i, lv = 0;
+  for (uint32_t guard = 0; guard < 4096; guard++) {
+    uint32_t j = T.parent[cur];
+    if (j >= T.n_ins) break;
+    uint32_t pm = T.meta[j], pop = pm & 7u;
+    uint32_t nid = T.scn[PARSE_C_NODE * S + j];
+    if (pop == PPD_OP_ACCOUNT_LEAF) {
+      if (((T.info[cur] >> 4) & 3u) != 2u) break;  // the code child does not affect the level
+      uint32_t nonempty = (T.info[j] >> 17) & 1u;
+      if (nonempty) E.level[nid + 1] = (uint16_t)min(lv + 1, 65535u);
+      lv = nonempty ? lv + 2 : 0;
+    } else if (pop == PPD_OP_BRANCH || pop == PPD_OP_EXTENSION) {
+      atomicMax(T.lvlmax + j, lv);
+      __threadfence();
+      uint32_t old = atomicSub(T.pending + j, 1u);
+      if (old != 1u) break;
+      __threadfence();
+      lv = atomicMax(T.lvlmax + j, 0u) + 1;
+    } else {
+      break;
+    }
+    E.level[nid] = (uint16_t)min(lv, 65535u);
+    cur = j;
+  }
+}
+
+inline uint32_t cdiv(uint64_t a, uint32_t b) { return (uint32_t)((a + b - 1) / b); }
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------------------------
+size_t parse_scan_tmp_words(size_t n, uint32_t K) {
+  size_t total = 0;
+  while (n > 1) {
+    n = (n + MS_ELEMS - 1) / MS_ELEMS;
+    total += K * ((n + 3) & ~(size_t)3);
+  }
+  return total + 16;
+}
+
+void launch_parse_bounds(const ParseBounds& B, cudaStream_t st) {
+  const uint32_t group_bytes = B.group_tiles * TILE;
+  tile_exit_kernel<<<B.n_tiles, TE_THREADS, 0, st>>>(B.wit, B.n, B.exit1);
+  group_exit_kernel<<<dim3(TILE / 256, B.n_groups), 256, 0, st>>>(B.exit1, B.n, group_bytes, B.exit2);
+  cudaMemsetAsync(B.group_entry, 0xff, 4ull * B.n_groups, st);
+  cudaMemsetAsync(B.tile_entry, 0xff, 4ull * B.n_tiles, st);
+  top_chain_kernel<<<1, 32, 0, st>>>(B.exit1, B.exit2, B.n, group_bytes, B.group_entry, B.result);
+  tile_entry_kernel<<<cdiv(B.n_groups, 64), 64, 0, st>>>(B.exit1, B.group_entry, B.n, B.n_groups, group_bytes, B.tile_entry);
+  tile_mark_kernel<<<cdiv(B.n_tiles, TM_WARPS), TM_WARPS * 32, 0, st>>>(B.wit, B.n, B.n_tiles, B.tile_entry, B.bitmap, B.tile_count);
+  cudaMemsetAsync(B.tile_count + B.n_tiles, 0, 4, st);
+  mscan(B.tile_count, B.tile_base, B.n_tiles + 1, 0, 1, B.scan_tmp, st);
+  cudaMemcpyAsync(B.result + PARSE_R_NINS, B.tile_base + B.n_tiles, 4, cudaMemcpyDeviceToDevice, st);
+}
+uint32_t parse_bounds_launches() { return 9; }
+
+void launch_parse_scatter(const ParseBounds& B, uint32_t* ins_pos, cudaStream_t st) {
+  ins_scatter_kernel<<<B.n_tiles, TILE / 32, 0, st>>>(B.bitmap, B.tile_base, ins_pos);
+}
+
+void launch_parse_tree(const ParseTree& T, cudaStream_t st) {
+  const uint32_t n1 = T.n_ins + 1;
+  ins_info_kernel<<<cdiv(n1, 256), 256, 0, st>>>(T);
+  mscan(T.delta, T.hb, n1, 0, 1, T.scan_tmp, st);
+  heights_kernel<<<cdiv(n1, 256), 256, 0, st>>>(T);
+  const uint32_t n_m1 = cdiv(n1, 64), n_m2 = cdiv(n_m1, 64), n_m3 = cdiv(n_m2, 64);
+  min64_i16_kernel<<<cdiv(n_m1, 128), 128, 0, st>>>(T.h16, n1, T.m1, n_m1);
+  min64_i16_kernel<<<cdiv(n_m2, 128), 128, 0, st>>>(T.m1, n_m1, T.m2, n_m2);
+  min64_i16_kernel<<<cdiv(n_m3, 128), 128, 0, st>>>(T.m2, n_m2, T.m3, n_m3);
+  link_kernel16<<<cdiv(T.n_ins, 256), 256, 0, st>>>(T);
+  shape_kernel<<<cdiv(n1, 256), 256, 0, st>>>(T);
+  mscan(T.cnt, T.scn, n1, T.cnt_stride, PARSE_N_CNT, T.scan_tmp, st);
+  totals_kernel<<<1, 32, 0, st>>>(T);
+}
+
+void launch_parse_code_list(const ParseEmit& E, cudaStream_t st) { code_list_kernel<<<cdiv(E.T.n_ins, 256), 256, 0, st>>>(E); }
+
+void launch_parse_emit(const ParseEmit& E, cudaStream_t st) {
+  emit_kernel<<<cdiv(E.T.n_ins, 128), 128, 0, st>>>(E);
+  climb_kernel<<<cdiv(E.T.n_ins, 256), 256, 0, st>>>(E);
+}
+
+}  // namespace ppd

@@ -1,5 +1,6 @@
 """ctypes binding of libppd_b200.so (include/ppd_b200.h)."""
 import ctypes
+import weakref
 import os
 import subprocess
 
@@ -62,6 +63,10 @@ class PpdStats(ctypes.Structure):
         ("h2d_bytes", ctypes.c_double),
         ("d2h_bytes", ctypes.c_double),
         ("kernel_launches", ctypes.c_uint64),
+        ("witnesses_on_gpu", ctypes.c_uint64),
+        ("witness_instructions", ctypes.c_uint64),
+        ("witness_bytes", ctypes.c_uint64),
+        ("parse_gpu_ms", ctypes.c_double),
     ]
 
     def as_dict(self):
@@ -74,6 +79,7 @@ EXPORTS = [
     "ppd_last_error",
     "ppd_last_stats",
     "ppd_free",
+    "ppd_alloc_pinned",
     "ppd_keccak256_batch",
     "ppd_compact_decode",
     "ppd_block_decode",
@@ -109,6 +115,8 @@ class PpdLibrary:
         L.ppd_last_error.restype = ctypes.c_char_p
         L.ppd_last_stats.argtypes = [ctypes.c_void_p, ctypes.POINTER(PpdStats)]
         L.ppd_free.argtypes = [ctypes.c_void_p]
+        L.ppd_alloc_pinned.argtypes = [ctypes.c_size_t]
+        L.ppd_alloc_pinned.restype = ctypes.c_void_p
         L.ppd_keccak256_batch.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]
         L.ppd_compact_decode.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, u8pp, szp]
         L.ppd_block_decode.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, u8pp, szp]
@@ -192,6 +200,24 @@ class Context:
         out = np.empty((n, 32), dtype=np.uint8)
         self._check(self.lib.L.ppd_keccak256_batch(self.h, data.ctypes.data, offsets.ctypes.data, n, out.ctypes.data))
         return out
+
+    def pinned_copy(self, data):
+        """`data` (bytes or a uint8 numpy array) copied into a page-locked buffer from the library's pool
+        (ppd_alloc_pinned); returns a uint8 numpy array over it.  The buffer goes back to the pool when the
+        array (and every view of it) is garbage collected."""
+        import numpy as np
+
+        src = np.frombuffer(data, dtype=np.uint8) if isinstance(data, (bytes, bytearray, memoryview)) else np.ascontiguousarray(data, dtype=np.uint8)
+        n = int(src.nbytes)
+        p = self.lib.L.ppd_alloc_pinned(n)
+        if not p:
+            raise MemoryError("ppd_alloc_pinned")
+        raw = (ctypes.c_uint8 * max(n, 1)).from_address(p)
+        arr = np.frombuffer(raw, dtype=np.uint8, count=n)
+        arr[:] = src
+        lib = self.lib
+        weakref.finalize(raw, lib.L.ppd_free, ctypes.c_void_p(p))
+        return arr
 
     def compact_decode(self, witness: bytes) -> bytes:
         out, n = ctypes.POINTER(ctypes.c_uint8)(), ctypes.c_size_t()

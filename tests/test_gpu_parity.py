@@ -364,3 +364,64 @@ def test_block_error_statuses_match_oracle(ctx, oracle, name, flat_block):
 
     ok = synth.gen_block(56, n_accounts=30, n_txns=1).flat
     assert ctx.block_decode(ok) == oracle.block_decode(ok)
+
+
+# ---- the witness parse / pre-image arena on the GPU (ppd_parse.cu) against the host builder --------------
+def _both_builders(ctx, fn):
+    """fn() with the GPU witness parser, then with the host one (PPD_HOST_PARSE); returns both results and stats."""
+    import os
+
+    os.environ.pop("PPD_HOST_PARSE", None)
+    a = fn()
+    sa = ctx.stats()
+    os.environ["PPD_HOST_PARSE"] = "1"
+    try:
+        b = fn()
+        sb = ctx.stats()
+    finally:
+        os.environ.pop("PPD_HOST_PARSE", None)
+    return a, sa, b, sb
+
+
+@pytest.mark.parametrize("idx", range(6))
+def test_gpu_parse_goldens_match_host_builder(ctx, oracle, goldens, idx):
+    g = goldens["compact_goldens"][idx]
+    wit = bytes.fromhex(g["witness_hex"])
+    a, sa, b, sb = _both_builders(ctx, lambda: ctx.compact_decode(wit))
+    assert a == b
+    assert parse_pre_image_dump(a)["state_root"].hex() == g["state_root"]
+    assert sb["witnesses_on_gpu"] == 0
+    # every golden is a canonical witness (SURVEY 7): the GPU builder must have taken all of them
+    assert sa["witnesses_on_gpu"] == 1, "the GPU parser declined a canonical golden witness"
+    assert sa["nodes_hashed"] == sb["nodes_hashed"] and sa["node_permutations"] == sb["node_permutations"]
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_gpu_parse_blocks_match_host_builder(ctx, oracle, seed):
+    from proof_protocol_decoder_b200 import synth
+
+    blk = synth.gen_block(40 + seed, n_accounts=1500, n_txns=8, contract_frac=0.2, slots_hi=256, virtual_depth=4,
+                          virtual_accounts_log16=5, accounts_per_txn=(20, 40), slot_reads=(0, 3), slot_writes=(0, 3),
+                          allow_new_accounts=False, allow_self_destruct=False)
+    a, sa, b, sb = _both_builders(ctx, lambda: ctx.block_decode(blk.flat))
+    assert a == b == oracle.block_decode(blk.flat)
+    assert sa["witnesses_on_gpu"] == 1 and sb["witnesses_on_gpu"] == 0
+    assert sa["witness_instructions"] > 1500
+    assert sa["nodes_hashed"] == sb["nodes_hashed"] and sa["node_bytes"] == sb["node_bytes"]
+
+
+def test_gpu_parse_declines_non_canonical_and_malformed(ctx, oracle, goldens):
+    """Witnesses the GPU builder must hand to the host builder: results and statuses still match the oracle."""
+    import witness_shapes as ws
+
+    cases = [p[1] for p in ws.PAIRS]
+    for wit in cases:
+        try:
+            want = oracle.compact_decode(wit)
+        except OracleError as e:
+            with pytest.raises(Exception) as ei:
+                ctx.compact_decode(wit)
+            assert getattr(ei.value, "code", None) == e.code
+            continue
+        assert ctx.compact_decode(wit) == want
+        assert ctx.stats()["witnesses_on_gpu"] == 0
