@@ -1210,6 +1210,7 @@ bool gpu_pre_image(Lane* L, Job& J, BlockJob& b, bool check_version = true) {
   auto layout_a = [&](Carve& c) {
     B.result = c.take<uint32_t>(PARSE_R_WORDS);
     B.exit1 = c.take<uint32_t>(n);
+    B.step1 = c.take<uint16_t>((size_t)B.n_tiles * PARSE_TILE);
     B.exit2 = c.take<uint32_t>((size_t)B.n_groups * PARSE_TILE);
     B.group_entry = c.take<uint32_t>(B.n_groups);
     B.tile_entry = c.take<uint32_t>(B.n_tiles);

@@ -108,6 +108,7 @@ struct ParseBounds {
   uint32_t n;
   uint32_t n_tiles, group_tiles, n_groups;
   uint32_t* exit1;        // [n]
+  uint16_t* step1;        // [n_tiles * PARSE_TILE] single-step links inside each tile
   uint32_t* exit2;        // [n_groups * PARSE_TILE]
   uint32_t* group_entry;  // [n_groups]
   uint32_t* tile_entry;   // [n_tiles]

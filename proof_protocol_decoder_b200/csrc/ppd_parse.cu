@@ -59,9 +59,9 @@ struct Ins {
   uint64_t nonce;
 };
 
-__device__ __forceinline__ bool cbor_head(const uint8_t* __restrict__ w, uint32_t n, uint32_t& pos, uint32_t& major, uint64_t& arg) {
+__device__ __forceinline__ bool cbor_head(const uint8_t* w, uint32_t n, uint32_t& pos, uint32_t& major, uint64_t& arg) {
   if (pos >= n) return false;
-  uint32_t b = __ldg(w + pos++);
+  uint32_t b = w[pos++];
   major = b >> 5;
   uint32_t ai = b & 31;
   if (ai < 24) {
@@ -72,10 +72,10 @@ __device__ __forceinline__ bool cbor_head(const uint8_t* __restrict__ w, uint32_
   uint32_t wd = 1u << (ai - 24);
   if (n - pos < wd) return false;
   arg = 0;
-  for (uint32_t i = 0; i < wd; i++) arg = (arg << 8) | __ldg(w + pos++);
+  for (uint32_t i = 0; i < wd; i++) arg = (arg << 8) | w[pos++];
   return true;
 }
-__device__ __forceinline__ bool cbor_bytes(const uint8_t* __restrict__ w, uint32_t n, uint32_t& pos, uint32_t& at, uint32_t& len) {
+__device__ __forceinline__ bool cbor_bytes(const uint8_t* w, uint32_t n, uint32_t& pos, uint32_t& at, uint32_t& len) {
   uint32_t major;
   uint64_t arg;
   if (!cbor_head(w, n, pos, major, arg) || major != 2 || arg > (uint64_t)(n - pos)) return false;
@@ -86,10 +86,10 @@ __device__ __forceinline__ bool cbor_bytes(const uint8_t* __restrict__ w, uint32
 __device__ __forceinline__ bool key_too_long(uint32_t key_len) { return key_len >= 2 && 2 * (key_len - 1) > 64 + 1; }
 
 // 0, or the PPD_ERR_* code the host parser reports for an instruction starting at p (p < n)
-__device__ __forceinline__ uint32_t decode_ins(const uint8_t* __restrict__ w, uint32_t n, uint32_t p, Ins& o) {
+__device__ __forceinline__ uint32_t decode_ins(const uint8_t* w, uint32_t n, uint32_t p, Ins& o) {
   uint32_t pos = p + 1, major;
   uint64_t arg;
-  o.op = __ldg(w + p);
+  o.op = w[p];
   o.flags = 0, o.aux = 0, o.key_pos = o.key_len = o.val_pos = o.val_len = 0, o.nonce = 0;
   switch (o.op) {
     case PPD_OP_LEAF:
@@ -117,7 +117,7 @@ __device__ __forceinline__ uint32_t decode_ins(const uint8_t* __restrict__ w, ui
       if (!cbor_bytes(w, n, pos, o.key_pos, o.key_len)) return PPD_ERR_INVALID_BYTE_VECTOR;
       if (key_too_long(o.key_len)) return PPD_ERR_KEY_ERROR;
       if (pos >= n) return PPD_ERR_UNEXPECTED_END_OF_STREAM;
-      o.flags = __ldg(w + pos++);
+      o.flags = w[pos++];
       if (o.flags & 4) {
         if (!cbor_head(w, n, pos, major, arg) || major != 0) return PPD_ERR_INVALID_BYTES_FOR_TYPE;
         o.nonce = arg;
@@ -138,7 +138,22 @@ __device__ __forceinline__ uint32_t decode_ins(const uint8_t* __restrict__ w, ui
   return 0;
 }
 // where the instruction starting at p ends, or PERR | code
-__device__ __forceinline__ uint32_t decode_next(const uint8_t* __restrict__ w, uint32_t n, uint32_t p) {
+__device__ __forceinline__ uint32_t decode_next(const uint8_t* w, uint32_t n, uint32_t p) {
+  // the two cases that make up almost every position: not an opcode (97 % of the speculative decodes),
+  // and a hashed-out node (most true instructions)
+  uint32_t op = w[p];
+  if (op > PPD_OP_EMPTY_ROOT) return PERR | PPD_ERR_INVALID_OPERATOR;
+  if (op == PPD_OP_HASH) return n - (p + 1) < 32 ? (PERR | PPD_ERR_INVALID_BYTES_FOR_TYPE) : p + 33;
+  if (op == PPD_OP_EMPTY_ROOT) return p + 1;
+  {
+    // every other opcode starts with a CBOR head: a byte string (an unsigned integer for a branch mask).
+    // Rejecting a wrong head here keeps the long decode below off almost every garbage position; the
+    // code is the one decode_ins reports for the same failure.
+    const uint32_t e_head = (op == PPD_OP_BRANCH || op == PPD_OP_CODE) ? PPD_ERR_INVALID_BYTES_FOR_TYPE : PPD_ERR_INVALID_BYTE_VECTOR;
+    if (p + 1 >= n) return PERR | e_head;
+    const uint32_t b = w[p + 1];
+    if ((b >> 5) != (op == PPD_OP_BRANCH ? 0u : 2u) || (b & 31u) > 27u) return PERR | e_head;
+  }
   Ins o;
   uint32_t e = decode_ins(w, n, p, o);
   return e ? (PERR | e) : o.next;
@@ -173,28 +188,51 @@ __device__ __forceinline__ uint32_t nth_set_bit(uint32_t mask, uint32_t k) {
 // Phase A
 // ---------------------------------------------------------------------------------------------
 constexpr int TE_THREADS = 512, TE_PER = TILE / TE_THREADS;
+constexpr uint32_t HALO = 128;  // an instruction's CBOR heads lie within 103 bytes of its opcode
 
-__global__ void __launch_bounds__(TE_THREADS) tile_exit_kernel(const uint8_t* __restrict__ w, uint32_t n, uint32_t* __restrict__ exit1) {
+// the tile's bytes (plus halo) staged in shared memory with 128-bit loads; `sb - base` is then indexed by
+// absolute stream position exactly like the global witness
+__device__ __forceinline__ void stage_tile(uint8_t* sb, const uint8_t* __restrict__ w, uint32_t n, uint32_t base, uint32_t tid, uint32_t nthreads) {
+  // base is a multiple of TILE and the witness buffer is 256-byte aligned and readable (zeroed) up to n + 64
+  const uint4* src = reinterpret_cast<const uint4*>(w + base);
+  uint4* dst = reinterpret_cast<uint4*>(sb);
+  const uint32_t avail = ((uint64_t)base + TILE + HALO <= (uint64_t)n + 48) ? (TILE + HALO) / 16 : (n + 48 - base) / 16;
+  for (uint32_t k = tid; k < (TILE + HALO) / 16; k += nthreads) dst[k] = k < avail ? __ldg(src + k) : make_uint4(0, 0, 0, 0);
+}
+
+__global__ void __launch_bounds__(TE_THREADS) tile_exit_kernel(const uint8_t* __restrict__ w, uint32_t n, uint32_t* __restrict__ exit1,
+                                                               uint16_t* __restrict__ step1) {
   __shared__ uint32_t nxt[TILE];
+  __shared__ __align__(16) uint16_t step[TILE];  // single-step links inside the tile (0xffff: the instruction ends outside), for tile_mark_kernel
+  __shared__ uint16_t active[TILE];  // positions whose chain has not left the tile yet
+  __shared__ uint32_t n_active;
+  __shared__ __align__(16) uint8_t sb[TILE + HALO];
   const uint32_t base = blockIdx.x * TILE, end = min(base + TILE, n);
-#pragma unroll
+  stage_tile(sb, w, n, base, threadIdx.x, TE_THREADS);
+  if (threadIdx.x == 0) n_active = 0;
+  __syncthreads();
+  const uint8_t* ws = sb - base;
+#pragma unroll 1
   for (int k = 0; k < TE_PER; k++) {
     uint32_t o = threadIdx.x + k * TE_THREADS, p = base + o;
-    if (p < end) nxt[o] = p == 0 ? 1u : decode_next(w, n, p);  // byte 0 is the header: "ends" at 1
+    if (p < end) {
+      uint32_t v = p == 0 ? 1u : decode_next(ws, n, p);  // byte 0 is the header: "ends" at 1
+      nxt[o] = v;
+      step[o] = v < end ? (uint16_t)(v - base) : (uint16_t)0xffffu;
+      if (v < end) active[atomicAdd(&n_active, 1u)] = (uint16_t)o;
+    }
   }
   __syncthreads();
-  // pointer doubling; any intermediate value is a point of the same chain, so updating in place is safe
+  // pointer doubling over the few positions that decode to an instruction ending inside the tile; any
+  // intermediate value is a point of the same chain, so updating in place is safe
+  const uint32_t na = n_active;
   for (;;) {
     bool moved = false;
-#pragma unroll
-    for (int k = 0; k < TE_PER; k++) {
-      uint32_t o = threadIdx.x + k * TE_THREADS, p = base + o;
-      if (p < end) {
-        uint32_t v = nxt[o];
-        if (v < end) {
-          nxt[o] = nxt[v - base];
-          moved = true;
-        }
+    for (uint32_t a = threadIdx.x; a < na; a += TE_THREADS) {
+      uint32_t o = active[a], v = nxt[o];
+      if (v < end) {
+        nxt[o] = nxt[v - base];
+        moved = true;
       }
     }
     if (!__syncthreads_or(moved)) break;
@@ -204,6 +242,8 @@ __global__ void __launch_bounds__(TE_THREADS) tile_exit_kernel(const uint8_t* __
     uint32_t o = threadIdx.x + k * TE_THREADS, p = base + o;
     if (p < end) exit1[p] = nxt[o];
   }
+  // the whole 8 KiB link table of the tile (entries past the end of the stream are never followed)
+  reinterpret_cast<uint4*>(step1 + (size_t)base)[threadIdx.x] = reinterpret_cast<const uint4*>(step)[threadIdx.x];
 }
 
 // exit2[g][c]: where the chain from position c of group g's first tile leaves the group
@@ -251,29 +291,43 @@ __global__ void tile_entry_kernel(const uint32_t* __restrict__ exit1, const uint
   }
 }
 
-// one warp per tile: lane 0 walks the true chain through the tile and marks instruction starts
+// One warp per tile: the tile's single-step links (written by tile_exit_kernel) are staged in shared memory,
+// lane 0 follows them from the tile's true entry and marks the instruction starts.
 constexpr int TM_WARPS = 4;
-__global__ void __launch_bounds__(TM_WARPS * 32) tile_mark_kernel(const uint8_t* __restrict__ w, uint32_t n, uint32_t n_tiles,
+__global__ void __launch_bounds__(TM_WARPS * 32) tile_mark_kernel(const uint16_t* __restrict__ step1, uint32_t n, uint32_t n_tiles,
                                                                   const uint32_t* __restrict__ tile_entry, uint32_t* __restrict__ bitmap,
                                                                   uint32_t* __restrict__ tile_count) {
   __shared__ uint32_t bits[TM_WARPS][TILE / 32];
+  __shared__ __align__(16) uint16_t step[TM_WARPS][TILE];
   const uint32_t wi = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t t = blockIdx.x * TM_WARPS + wi;
   if (t >= n_tiles) return;
+  const uint32_t base = t * TILE;
+  const uint32_t cur = tile_entry[t];
   for (uint32_t k = lane; k < TILE / 32; k += 32) bits[wi][k] = 0;
+  if (cur != NONE) {
+    const uint4* src = reinterpret_cast<const uint4*>(step1 + (size_t)base);
+    uint4* dst = reinterpret_cast<uint4*>(step[wi]);
+#pragma unroll 4
+    for (uint32_t k = lane; k < TILE / 8; k += 32) dst[k] = __ldg(src + k);
+  }
   __syncwarp();
-  uint32_t count = 0;
   if (lane == 0) {
-    uint32_t cur = tile_entry[t];
-    const uint32_t base = t * TILE, end = min(base + TILE, n);
+    uint32_t count = 0;
     if (cur != NONE) {
-      if (cur == 0) cur = 1;  // the header byte is not an instruction
-      while (cur < end) {
-        uint32_t o = cur - base;
-        bits[wi][o >> 5] |= 1u << (o & 31);
+      uint32_t o = cur - base;
+      if (cur == 0) o = step[wi][0];  // the header byte is not an instruction
+      uint32_t word = o >> 5, acc = 0;  // starts are visited in increasing order
+      while (o != 0xffffu) {
+        if ((o >> 5) != word) {
+          bits[wi][word] = acc;
+          word = o >> 5, acc = 0;
+        }
+        acc |= 1u << (o & 31);
         count++;
-        cur = decode_next(w, n, cur);
+        o = step[wi][o];
       }
+      if (acc) bits[wi][word] = acc;
     }
     tile_count[t] = count;
   }
@@ -609,12 +663,17 @@ __global__ void __launch_bounds__(128) emit_kernel(ParseEmit E) {
   }
   if (op == PPD_OP_HASH) {
     uint32_t* dst = reinterpret_cast<uint32_t*>(E.hash_pool + 32ull * (my_id - HASH_BASE));
-    const uint8_t* src = T.wit + pos + 1;
+    // 32 bytes at an arbitrary alignment: nine aligned words re-aligned with funnel shifts (the witness
+    // buffer is readable past its end)
+    const uintptr_t a = reinterpret_cast<uintptr_t>(T.wit + pos + 1);
+    const uint32_t* q = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
+    const uint32_t sh = (uint32_t)(a & 3) * 8;
+    uint32_t x[9];
 #pragma unroll
-    for (int k = 0; k < 8; k++) {
-      uint32_t b0 = __ldg(src + 4 * k), b1 = __ldg(src + 4 * k + 1), b2 = __ldg(src + 4 * k + 2), b3 = __ldg(src + 4 * k + 3);
-      dst[k] = b0 | (b1 << 8) | (b2 << 16) | (b3 << 24);
-    }
+    for (int k = 0; k < 9; k++) x[k] = __ldg(q + k);
+    uint4 lo = make_uint4(__funnelshift_r(x[0], x[1], sh), __funnelshift_r(x[1], x[2], sh), __funnelshift_r(x[2], x[3], sh), __funnelshift_r(x[3], x[4], sh));
+    uint4 hi = make_uint4(__funnelshift_r(x[4], x[5], sh), __funnelshift_r(x[5], x[6], sh), __funnelshift_r(x[6], x[7], sh), __funnelshift_r(x[7], x[8], sh));
+    reinterpret_cast<uint4*>(dst)[0] = lo, reinterpret_cast<uint4*>(dst)[1] = hi;
     return;
   }
   if (op == PPD_OP_CODE || op == PPD_OP_EMPTY_ROOT) return;
@@ -770,13 +829,13 @@ size_t parse_scan_tmp_words(size_t n, uint32_t K) {
 
 void launch_parse_bounds(const ParseBounds& B, cudaStream_t st) {
   const uint32_t group_bytes = B.group_tiles * TILE;
-  tile_exit_kernel<<<B.n_tiles, TE_THREADS, 0, st>>>(B.wit, B.n, B.exit1);
+  tile_exit_kernel<<<B.n_tiles, TE_THREADS, 0, st>>>(B.wit, B.n, B.exit1, B.step1);
   group_exit_kernel<<<dim3(TILE / 256, B.n_groups), 256, 0, st>>>(B.exit1, B.n, group_bytes, B.exit2);
   cudaMemsetAsync(B.group_entry, 0xff, 4ull * B.n_groups, st);
   cudaMemsetAsync(B.tile_entry, 0xff, 4ull * B.n_tiles, st);
   top_chain_kernel<<<1, 32, 0, st>>>(B.exit1, B.exit2, B.n, group_bytes, B.group_entry, B.result);
   tile_entry_kernel<<<cdiv(B.n_groups, 64), 64, 0, st>>>(B.exit1, B.group_entry, B.n, B.n_groups, group_bytes, B.tile_entry);
-  tile_mark_kernel<<<cdiv(B.n_tiles, TM_WARPS), TM_WARPS * 32, 0, st>>>(B.wit, B.n, B.n_tiles, B.tile_entry, B.bitmap, B.tile_count);
+  tile_mark_kernel<<<cdiv(B.n_tiles, TM_WARPS), TM_WARPS * 32, 0, st>>>(B.step1, B.n, B.n_tiles, B.tile_entry, B.bitmap, B.tile_count);
   cudaMemsetAsync(B.tile_count + B.n_tiles, 0, 4, st);
   mscan(B.tile_count, B.tile_base, B.n_tiles + 1, 0, 1, B.scan_tmp, st);
   cudaMemcpyAsync(B.result + PARSE_R_NINS, B.tile_base + B.n_tiles, 4, cudaMemcpyDeviceToDevice, st);
