@@ -251,10 +251,11 @@ def c5_sweep(ctx, sizes, peaks, sm_mhz):
 def run_b200(args, rank, world, local_rank):
     # host threads: this rank's share of the box's cores; one block per host thread per step
     cores = os.cpu_count() or 1
-    threads = max(1, min(16, cores // world))
+    # two host threads per core of this rank's share: a thread sleeps while its lane's copies and kernels run
+    threads = max(1, min(32, 2 * cores // world))
     os.environ.setdefault("PPD_HOST_THREADS", str(threads))
     threads = int(os.environ["PPD_HOST_THREADS"])
-    n_blocks = args.blocks_per_step or 16  # per GPU, whatever the world size (weak scaling)
+    n_blocks = args.blocks_per_step or 32  # per GPU, whatever the world size (weak scaling)
     seeds = [2 + rank * n_blocks + j for j in range(n_blocks)]
     # generated before CUDA is touched (worker processes are forked); ranks generate their own blocks
     flats = c2_blocks(seeds, args.scale, max(1, cores // world))
@@ -327,6 +328,18 @@ def run_b200(args, rank, world, local_rank):
         dev_ms += ctx.replay_last_hashing()
     barrier()
     dev_ms = max_over_ranks(dev_ms)
+    # ---- the same for the witness parse / arena kernels (ppd_parse.cu), witnesses resident in HBM ----
+    parse_ms = 0.0
+    if st["witnesses_on_gpu"]:
+        for _ in range(max(3, args.warmup)):
+            ctx.replay_last_parse()
+        barrier()
+        for _ in range(args.steps):
+            flush.zero_()
+            torch.cuda.synchronize()
+            parse_ms += ctx.replay_last_parse()
+        barrier()
+        parse_ms = max_over_ranks(parse_ms)
     # ---- end to end through the C ABI with host buffers ----
     barrier()
     t0 = time.perf_counter()
@@ -356,7 +369,10 @@ def run_b200(args, rank, world, local_rank):
     algo_bytes = st["node_bytes"] + 32 * st["nodes_hashed"]  # L + 32 per hashed node (this rank)
     achieved_gbs = algo_bytes / dev_s_per_step / 1e9
     traffic, traffic_src = load_traffic()
-    level_launches = max(1, int(st["kernel_launches"]) - n_blocks)  # all but the key-hash launches
+    level_launches = max(1, int(st["level_launches"]))
+    parse_s_per_step = parse_ms / 1e3 / args.steps
+    wit_bytes_all = sum_over_ranks(float(st["witness_bytes"]))
+    wit_ins_all = sum_over_ranks(float(st["witness_instructions"]))
     line = {
         "metric": "mpt_nodes_keccak_hashed_per_sec",
         "value": nodes_all / dev_s_per_step,
@@ -382,7 +398,9 @@ def run_b200(args, rank, world, local_rank):
             "l2": "flushed between timed device-resident steps (256 MiB write)",
             "parallelism": f"blocks sharded over {world} GPU(s), no data-path collective",
         },
-        "blocks_per_sec": world * n_blocks / dev_s_per_step,
+        "blocks_per_sec": world * n_blocks / (dev_s_per_step + parse_s_per_step),
+        "blocks_per_sec_note": "device-resident: the blocks of a step / (device time of the witness parse + arena kernels, plus device time of the hashing kernels), each replayed with all lanes concurrent",
+        "blocks_per_sec_hashing_only": world * n_blocks / dev_s_per_step,
         "permutations_per_sec": perms_all / dev_s_per_step,
         "nodes_hashed_per_step": nodes_all,
         "key_hashes_per_step": keys_all,
@@ -411,6 +429,20 @@ def run_b200(args, rank, world, local_rank):
             "launches_per_step": level_launches,
             "peak_source": peaks["source"],
             "note": "achieved = sum over the step's level launches of (L + 32) bytes per hashed node / device time of the step (lanes run concurrently, so a per-launch duration does not exist); traffic = mean DRAM bytes per hash_level_kernel launch under ncu. Keccak is bound by the integer ALU pipe, not HBM (SURVEY.md 8d): see roofline_alu",
+        },
+        "parse": {
+            "kernels": "ppd_parse.cu: tile_exit / group_exit / top_chain / tile_entry / tile_mark / scans / link / shape / emit / climb (all lanes concurrent)",
+            "witnesses_on_gpu_per_step": int(sum_over_ranks(float(st["witnesses_on_gpu"]))),
+            "witness_bytes_per_step": wit_bytes_all,
+            "instructions_per_step": wit_ins_all,
+            "ms_per_step": 1e3 * parse_s_per_step,
+            "bound": "hbm",
+            "achieved": (7.0 * wit_bytes_all / world / parse_s_per_step / 1e9) if parse_s_per_step else None,
+            "peak": peaks["hbm_gbs"],
+            "unit": "GB/s",
+            "frac": (7.0 * wit_bytes_all / world / parse_s_per_step / 1e9 / peaks["hbm_gbs"]) if parse_s_per_step else None,
+            "instructions_per_sec": (wit_ins_all / parse_s_per_step) if parse_s_per_step else None,
+            "note": "algorithmic bytes = 7 per witness byte for the boundary search (read the byte, write and re-read its 4-byte exit link, write its 2-byte step link) -- the instruction-level arrays behind it are 30x smaller; the chain walks between tiles are latency-bound by construction (DESIGN.md 5)",
         },
         "roofline_alu": {
             "bound": "alu-pipe (LOP3/SHF)",
@@ -448,7 +480,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--scale", type=float, default=1.0, help="fraction of the C2 block size (1.0 = the named config)")
-    ap.add_argument("--blocks-per-step", type=int, default=0, help="blocks per GPU per step (default 16)")
+    ap.add_argument("--blocks-per-step", type=int, default=0, help="blocks per GPU per step (default 32)")
     ap.add_argument("--ref-scale", type=float, default=0.1, help="size of the bounded CPU sample block")
     ap.add_argument("--sweep", default="1000000,10000000", help="config-5 leaf counts measured beside the headline at N=1")
     ap.add_argument("--no-sweep", action="store_true")

@@ -47,6 +47,7 @@ typedef struct ppd_stats {
   uint64_t witness_instructions;  /* instructions of those witnesses */
   uint64_t witness_bytes;         /* bytes of those witnesses */
   double parse_gpu_ms;            /* device time of their parse / arena kernels (CUDA events) */
+  uint64_t level_launches;        /* launches of the level-hashing kernel (one per level per block) */
 } ppd_stats;
 
 int ppd_ctx_create(int device, ppd_ctx** out);
@@ -81,6 +82,9 @@ int ppd_blocks_decode_batch(ppd_ctx* ctx, const uint8_t* const* flat_blocks, con
 /* Measurement hook: re-run every kernel of the last ppd_block_decode / ppd_blocks_decode_batch on
  * the arena still resident in HBM (no host work, no copies); returns the device time (CUDA events). */
 int ppd_replay_last_hashing(ppd_ctx* ctx, double* gpu_ms_out);
+/* The same for the compact-witness kernels (instruction boundaries, stack machine, arena emit: the GPU form of
+ * compact_prestate_processing.rs:683-875, 325-668 and compact_to_partial_trie.rs:37-165) of the last call. */
+int ppd_replay_last_parse(ppd_ctx* ctx, double* gpu_ms_out);
 
 /* Measurement hook: ceilings of the Keccak roofline (csrc/ppd_microbench.cu).  variant 0: issue rate of
  * dependent-free LOP3/SHF (units = ALU instructions); variants 1..: keccak-f[1600] on a register-resident

@@ -186,14 +186,24 @@ struct HostArena {
     }
     return push({node_w0(NK_BRANCH, 0, 0), base, mask, 0}, lv + 1u);
   }
-  // copy of branch `br` with slot `nib` set to `child` (NODE_EMPTY removes it)
+  // copy of branch `br` with slot `nib` set to `child` (NODE_EMPTY removes it).  The compact child list is
+  // copied as a block.  The level is an upper bound (the old branch's level, or the new child's + 1): any
+  // level above those of everything a node reads is a valid place in the bottom-up sweep.
   uint32_t branch_with(uint32_t br, uint32_t nib, uint32_t child) {
-    uint32_t kids[16], k = 0, nmask = 0;
-    for (uint32_t i = 0; i < 16; i++) {
-      uint32_t c = (i == nib) ? child : child_at(br, i);
-      if (c != NODE_EMPTY) kids[k++] = c, nmask |= 1u << i;
-    }
-    return new_branch(nmask, kids);
+    const uint32_t mask = nodes[br].a1 & 0xffffu, src = nodes[br].a0, bit = 1u << nib;
+    const uint32_t k = (uint32_t)__builtin_popcount(mask), r = (uint32_t)__builtin_popcount(mask & (bit - 1));
+    const uint32_t has = (mask & bit) ? 1u : 0u, put = child != NODE_EMPTY ? 1u : 0u;
+    const uint32_t nk = k - has + put, nmask = (mask & ~bit) | (put ? bit : 0u);
+    const uint32_t base = (uint32_t)child_pool.size();
+    child_pool.resize(base + nk);
+    uint32_t* d = child_pool.data() + base;
+    const uint32_t* o = child_pool.data() + src;
+    for (uint32_t i = 0; i < r; i++) d[i] = o[i];
+    if (put) d[r] = child;
+    for (uint32_t i = r + has; i < k; i++) d[i - has + put] = o[i];
+    uint32_t lv = level[br];
+    if (put && lvl(child) + 1u > lv) lv = lvl(child) + 1u;
+    return push({node_w0(NK_BRANCH, 0, 0), base, nmask, 0}, lv);
   }
 
   // ---- persistent operations; keys are (koff, klen) full keys in key_pool --------------------
@@ -342,8 +352,84 @@ struct HostArena {
     return NODE_EMPTY;
   }
 
-  // create_trie_subset's marking pass (trie_subsets.rs mark_nodes_that_are_needed)
-  void mark(uint32_t node, uint32_t koff, uint32_t klen, std::vector<uint32_t>& touched) const {
+  // The marking walks of many keys at once (all the keys one txn touches).  The walks are independent and each
+  // step is two dependent cache misses (node record, then child slot), so G of them advance in lock step with
+  // the next record / slot of every walk prefetched before any of them is read.  Same result per key as mark().
+  struct MarkItem {
+    uint32_t root, koff, klen;
+    uint32_t leaf;  // out: the leaf holding the key, or NODE_EMPTY
+  };
+  void mark_many(MarkItem* items, size_t n, std::vector<uint32_t>& touched) const {
+    constexpr int G = 12;
+    for (size_t g = 0; g < n; g += G) {
+      const int m = (int)(n - g < (size_t)G ? n - g : G);
+      uint32_t node[G], pos[G];
+      const uint32_t* slot[G];
+      int live = 0;
+      for (int j = 0; j < m; j++) {
+        node[j] = items[g + j].root, pos[j] = 0, slot[j] = nullptr;
+        items[g + j].leaf = NODE_EMPTY;
+        if (node[j] != NODE_EMPTY) {
+          live++;
+          if (!is_hash_id(node[j])) __builtin_prefetch(&nodes[node[j]]);
+        }
+      }
+      while (live) {
+        for (int j = 0; j < m; j++) {
+          const uint32_t nd = node[j];
+          if (nd == NODE_EMPTY) continue;
+          MarkItem& it = items[g + j];
+          touched.push_back(nd);
+          uint32_t next = NODE_EMPTY;
+          switch (kind(nd)) {
+            case NK_HASH:
+            case NK_ROOT:
+              if (pos[j] < it.klen) fail(PPD_ERR_MISSING_KEYS_CREATING_SUB_PARTIAL_TRIE, "subset key runs into a hashed-out node");
+              break;
+            case NK_BRANCH: {
+              if (pos[j] >= it.klen) break;
+              const uint32_t mask = nodes[nd].a1, bit = 1u << key_nib(it.koff, pos[j]);
+              pos[j]++;
+              if (mask & bit) {
+                slot[j] = &child_pool[nodes[nd].a0 + __builtin_popcount(mask & (bit - 1))];
+                __builtin_prefetch(slot[j]);
+                continue;  // node[j] is read from the slot in the second half of the step
+              }
+              break;
+            }
+            case NK_EXT: {
+              uint32_t el = nlen(nd), avail = it.klen - pos[j];
+              uint32_t mm = avail < el ? avail : el;
+              if (common_prefix(nodes[nd].a0, nstart(nd), mm, it.koff, pos[j], mm) != mm || avail < el) break;
+              pos[j] += el;
+              next = nodes[nd].a1;
+              break;
+            }
+            default: {
+              uint32_t ll = nlen(nd);
+              if (ll == it.klen - pos[j] && common_prefix(nodes[nd].a0, nstart(nd), ll, it.koff, pos[j], ll) == ll) it.leaf = nd;
+              break;
+            }
+          }
+          node[j] = next;
+          if (next == NODE_EMPTY)
+            live--;
+          else if (!is_hash_id(next))
+            __builtin_prefetch(&nodes[next]);
+        }
+        for (int j = 0; j < m; j++) {
+          if (!slot[j]) continue;
+          node[j] = *slot[j];
+          slot[j] = nullptr;
+          if (!is_hash_id(node[j])) __builtin_prefetch(&nodes[node[j]]);  // a set mask bit never holds NODE_EMPTY
+        }
+      }
+    }
+  }
+
+  // create_trie_subset's marking pass (trie_subsets.rs mark_nodes_that_are_needed).  Returns what get() returns
+  // for the same key: the leaf holding it, or NODE_EMPTY.
+  uint32_t mark(uint32_t node, uint32_t koff, uint32_t klen, std::vector<uint32_t>& touched) const {
     uint32_t pos = 0;
     while (node != NODE_EMPTY) {
       touched.push_back(node);
@@ -351,25 +437,29 @@ struct HostArena {
         case NK_HASH:
         case NK_ROOT:
           if (pos < klen) fail(PPD_ERR_MISSING_KEYS_CREATING_SUB_PARTIAL_TRIE, "subset key runs into a hashed-out node");
-          return;
+          return NODE_EMPTY;
         case NK_BRANCH:
-          if (pos >= klen) return;
+          if (pos >= klen) return NODE_EMPTY;
           node = child_at(node, key_nib(koff, pos));
           pos++;
           break;
         case NK_EXT: {
           uint32_t el = nlen(node), avail = klen - pos;
           uint32_t m = avail < el ? avail : el;
-          if (common_prefix(nodes[node].a0, nstart(node), m, koff, pos, m) != m) return;
-          if (avail < el) return;
+          if (common_prefix(nodes[node].a0, nstart(node), m, koff, pos, m) != m) return NODE_EMPTY;
+          if (avail < el) return NODE_EMPTY;
           pos += el;
           node = nodes[node].a1;
           break;
         }
-        default:
-          return;
+        default: {
+          uint32_t ll = nlen(node);
+          if (ll == klen - pos && common_prefix(nodes[node].a0, nstart(node), ll, koff, pos, ll) == ll) return node;
+          return NODE_EMPTY;
+        }
       }
     }
+    return NODE_EMPTY;
   }
 };
 

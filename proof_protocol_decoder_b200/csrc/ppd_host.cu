@@ -14,6 +14,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -87,6 +88,13 @@ struct Lane {
   DevBuf d_plan, d_out;  // IR dump plan and the serialised IrDump
   DevBuf d_wit, d_pa, d_pb, d_pc;  // witness bytes and the scratch of the three parse phases (ppd_parse.cu)
   uint32_t* h_parse = nullptr;     // page-locked landing area of the parse result words
+  // the launch parameters of the lane's last GPU parse (the witness and all scratch stay resident), for ppd_replay_last_parse
+  bool has_last_parse = false;
+  ParseBounds last_bounds{};
+  ParseEmit last_emit{};
+  uint32_t* last_ins_pos = nullptr;
+  uint32_t last_n_code = 0;
+  size_t last_val_bytes = 0;
   Job* job = nullptr;  // page-locked pools, kept across calls
   // the arena of the lane's last block stays resident so that its hashing can be re-run for measurement
   bool has_last = false;
@@ -95,8 +103,49 @@ struct Lane {
   uint32_t last_n_msgs = 0;
 };
 
+// Counting semaphore: how many lanes may have their witness upload + parse in flight at once.  All lanes of a
+// batch start together; letting every one of them share the copy engine and the SMs makes all of them finish
+// their parse late and at the same time, after which all host threads shape their tries at once with the GPU
+// idle.  Admitting a few at a time staggers the lanes, so the parse, the host shaping and the IR dump of
+// different blocks overlap.
+struct Slots {
+  std::mutex mu;
+  std::condition_variable cv;
+  int free_slots;
+  explicit Slots(int n) : free_slots(n) {}
+  void acquire() {
+    std::unique_lock<std::mutex> g(mu);
+    cv.wait(g, [&] { return free_slots > 0; });
+    free_slots--;
+  }
+  void release() {
+    {
+      std::lock_guard<std::mutex> g(mu);
+      free_slots++;
+    }
+    cv.notify_one();
+  }
+};
+struct SlotGuard {
+  Slots* s;
+  explicit SlotGuard(Slots* s_) : s(s_) {
+    if (s) s->acquire();
+  }
+  void done() {
+    if (s) s->release();
+    s = nullptr;
+  }
+  ~SlotGuard() { done(); }
+};
+int parse_slots() {
+  const char* e = getenv("PPD_PARSE_SLOTS");
+  int v = e ? atoi(e) : 3;
+  return v < 1 ? 1 : v;
+}
+
 struct ppd_ctx {
   int device = 0;
+  Slots parse_slots_sem{parse_slots()};
   cudaStream_t st = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   std::string err;
@@ -705,6 +754,7 @@ struct Job {
   bool pools_on_host = true;
   PVec<uint32_t> acct_list, code_list;
   PVec<uint8_t> wit_stage;  // page-locked staging of a pageable witness
+  std::vector<HostArena::MarkItem> mark_items;  // scratch of the txn loop
   PVec<H256> code_digest;
   std::vector<uint32_t> stamp;
   uint32_t serial = 0;
@@ -1163,7 +1213,7 @@ struct Carve {
   }
 };
 
-bool gpu_pre_image(Lane* L, Job& J, BlockJob& b, bool check_version = true) {
+bool gpu_pre_image(Lane* L, Job& J, BlockJob& b, bool check_version = true, Slots* slots = nullptr) {
 #ifdef PPD_HOSTPROF
   return false;
 #else
@@ -1177,6 +1227,7 @@ bool gpu_pre_image(Lane* L, Job& J, BlockJob& b, bool check_version = true) {
     if (!L->h_parse) fail(PPD_ERR_BAD_ARGUMENT, "out of page-locked memory");
   }
   uint32_t* hr = L->h_parse;
+  SlotGuard slot(slots);
   // ---- phase A: instruction boundaries ----
   L->d_wit.reserve(n + 64);
   {
@@ -1357,6 +1408,7 @@ bool gpu_pre_image(Lane* L, Job& J, BlockJob& b, bool check_version = true) {
   down(J.code_digest.data(), d_code_digest, 32 * n_code);
   down(hr, B.result, 4 * PARSE_R_WORDS);
   lane_sync(L);
+  slot.done();
   phase_ms();
   for (size_t k = 0; k < n_code; k++) {
     L->stats.key_permutations += J.code_list[2 * k + 1] / 136 + 1;
@@ -1398,6 +1450,7 @@ bool gpu_pre_image(Lane* L, Job& J, BlockJob& b, bool check_version = true) {
     }
   }
   b.pre_image_on_gpu = true;
+  L->has_last_parse = true, L->last_bounds = B, L->last_emit = E, L->last_ins_pos = ins_pos, L->last_n_code = (uint32_t)n_code, L->last_val_bytes = val_bytes;
   L->stats.witnesses_on_gpu += 1, L->stats.witness_instructions += n_ins, L->stats.witness_bytes += n;
   if (getenv("PPD_VERIFY_GPU_PARSE")) verify_gpu_pre_image(L, J, b);
   return true;
@@ -1630,17 +1683,26 @@ void shape_block(Job& J, BlockJob& b) {
     uint32_t tk_len = 0;
     uint32_t tk = txn_index_key(J, ti, tk_len);
     p.state_sub = state, p.txn_sub = txn_trie, p.receipt_sub = receipt_trie;
-    std::vector<uint32_t> haddr_key(tx.traces.size());
+    // every key this txn touches is marked in one interleaved pass (HostArena::mark_many).  The marking walk of an
+    // address also finds its leaf in the pre-txn state: the state writes below read the account from it (other
+    // addresses' writes in between only path-copy branches; the leaf's payload stays).
+    std::vector<uint32_t> haddr_key(tx.traces.size()), haddr_leaf(tx.traces.size());
+    std::vector<HostArena::MarkItem>& marks = J.mark_items;
+    marks.clear();
     for (size_t i = 0; i < tx.traces.size(); i++) {
       haddr_key[i] = key_from_digest(J, J.kh.digest[tx.traces[i].m_addr]);
-      A.mark(state, haddr_key[i], 64, p.touched);
+      marks.push_back({state, haddr_key[i], 64, NODE_EMPTY});
     }
-    A.mark(txn_trie, tk, tk_len, p.touched);
-    A.mark(receipt_trie, tk, tk_len, p.touched);
+    marks.push_back({txn_trie, tk, tk_len, NODE_EMPTY});
+    marks.push_back({receipt_trie, tk, tk_len, NODE_EMPTY});
+    bool short_haddr = false;
     for (size_t i = 0; i < tx.traces.size(); i++) {
       TraceV& tr = tx.traces[i];
       const H256& haddr = J.kh.digest[tr.m_addr];
-      if (haddr.b[0] == 0) fail(PPD_PANIC_H256_FROM_SLICE, "H256::from_slice on a short bytes_be()");
+      if (haddr.b[0] == 0) {  // reported after the marks collected so far (they come first in the reference's order)
+        short_haddr = true;
+        break;
+      }
       auto f = b.storage.find(haddr);
       if (f == b.storage.end()) {
         // missing storage trie: Hash(pre-image storage root) when the account had storage in the pre-image
@@ -1651,10 +1713,13 @@ void shape_block(Job& J, BlockJob& b) {
         f = b.storage.insert({haddr, t}).first;
       }
       uint32_t sroot = f->second;
-      for (uint32_t k = 0; k < tr.n_reads; k++) A.mark(sroot, key_from_digest(J, J.kh.digest[tr.m_reads + k]), 64, p.touched);
-      for (uint32_t k = 0; k < tr.n_writes; k++) A.mark(sroot, key_from_digest(J, J.kh.digest[tr.m_writes_full + k]), 64, p.touched);
+      for (uint32_t k = 0; k < tr.n_reads; k++) marks.push_back({sroot, key_from_digest(J, J.kh.digest[tr.m_reads + k]), 64, NODE_EMPTY});
+      for (uint32_t k = 0; k < tr.n_writes; k++) marks.push_back({sroot, key_from_digest(J, J.kh.digest[tr.m_writes_full + k]), 64, NODE_EMPTY});
       p.storage_subs.push_back({haddr, sroot});
     }
+    A.mark_many(marks.data(), marks.size(), p.touched);
+    if (short_haddr) fail(PPD_PANIC_H256_FROM_SLICE, "H256::from_slice on a short bytes_be()");
+    for (size_t i = 0; i < tx.traces.size(); i++) haddr_leaf[i] = marks[i].leaf;
     gas_after += tx.gas_used;
     sec.stop(2);
 
@@ -1685,7 +1750,7 @@ void shape_block(Job& J, BlockJob& b) {
       bool code_change = tr.flags & (PPD_TR_CODE_READ | PPD_TR_CODE_WRITE);
       if (!((tr.flags & (PPD_TR_BALANCE | PPD_TR_NONCE)) || storage_change || code_change)) continue;
       const H256& haddr = J.kh.digest[tr.m_addr];
-      uint32_t leaf = A.get(state, haddr_key[i], 64);
+      uint32_t leaf = haddr_leaf[i];
       AccountRec rec;
       if (leaf == NODE_EMPTY) {
         memset(&rec, 0, sizeof rec);
@@ -1862,6 +1927,7 @@ void sweep(Lane* c, Job& J, bool refs_to_host = true) {
   for (uint32_t l = 0; l < n_levels; l++) {
     launch_hash_level(V, c->d_order.as<uint32_t>(), level_start[l], level_start[l + 1], c->st);
     c->stats.kernel_launches++;
+    c->stats.level_launches++;
   }
   CUDA_OK(cudaGetLastError());
   CUDA_OK(cudaEventRecord(c->ev1, c->st));
@@ -2580,7 +2646,7 @@ void decode_one(ppd_ctx* c, Lane* L, const uint8_t* flat, size_t len, uint8_t** 
   *out = nullptr, *out_len = 0;
   try {
     read_flat_block(flat, len, b);
-    if (gpu_parse_enabled()) gpu_pre_image(L, J, b);
+    if (gpu_parse_enabled()) gpu_pre_image(L, J, b, true, &c->parse_slots_sem);
     collect_messages(J, b);
     pt.lap("parse");
     J.kh.run(L);
@@ -2611,7 +2677,7 @@ void add_stats(ppd_stats& a, const ppd_stats& b) {
   a.levels = std::max(a.levels, b.levels);
   a.gpu_ms += b.gpu_ms, a.h2d_bytes += b.h2d_bytes, a.d2h_bytes += b.d2h_bytes, a.kernel_launches += b.kernel_launches;
   a.witnesses_on_gpu += b.witnesses_on_gpu, a.witness_instructions += b.witness_instructions, a.witness_bytes += b.witness_bytes;
-  a.parse_gpu_ms += b.parse_gpu_ms;
+  a.parse_gpu_ms += b.parse_gpu_ms, a.level_launches += b.level_launches;
 }
 
 // Blocks are independent (each BlockTrace carries its own pre-image, trace_protocol.rs:40-48): every
@@ -2630,6 +2696,7 @@ void decode_blocks(ppd_ctx* c, const uint8_t* const* flats, const size_t* lens, 
     Lane* L = lane_of(c, w);
     L->stats = ppd_stats{};
     L->has_last = false;
+    L->has_last_parse = false;
   }
   const unsigned dump_workers = std::max(1u, host_threads() / workers);
   for (size_t i = 0; i < n; i++) outs[i] = nullptr, out_lens[i] = 0, statuses[i] = PPD_OK;
@@ -2745,6 +2812,45 @@ int ppd_replay_last_hashing(ppd_ctx* c, double* gpu_ms_out) {
       size_t nl = L->last_level_start.size() - 1;
       for (size_t l = 0; l < nl; l++)
         launch_hash_level(L->last_view, L->d_order.as<uint32_t>(), L->last_level_start[l], L->last_level_start[l + 1], L->st);
+      CUDA_OK(cudaGetLastError());
+      CUDA_OK(cudaEventRecord(L->ev1, L->st));
+      CUDA_OK(cudaStreamWaitEvent(c->st, L->ev1, 0));
+    }
+    CUDA_OK(cudaEventRecord(c->ev1, c->st));
+    CUDA_OK(cudaStreamSynchronize(c->st));
+    float ms = 0;
+    CUDA_OK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    if (gpu_ms_out) *gpu_ms_out = ms;
+  });
+}
+
+// The same for the witness parse / pre-image arena kernels (ppd_parse.cu) of the last call: every lane replays
+// its three phases back to back on the witness still resident in HBM (the sizes the host read back between the
+// phases are those of the first run, so nothing is copied or synchronised in between).
+int ppd_replay_last_parse(ppd_ctx* c, double* gpu_ms_out) {
+  return guarded(c, [&] {
+    size_t used = 0;
+    for (size_t w = 0; w < c->last_lanes_used && w < c->lanes.size(); w++) used += c->lanes[w]->has_last_parse;
+    if (!used) fail(PPD_ERR_BAD_ARGUMENT, "no GPU-parsed witness is resident");
+    CUDA_OK(cudaEventRecord(c->ev0, c->st));
+    for (size_t w = 0; w < c->last_lanes_used; w++) {
+      Lane* L = c->lanes[w];
+      if (!L->has_last_parse) continue;
+      CUDA_OK(cudaStreamWaitEvent(L->st, c->ev0, 0));
+      ParseEmit E = L->last_emit;
+      // the sweep may have moved the pools to larger buffers since
+      E.nodes = L->d_nodes.as<NodeRec>(), E.key_pool = L->d_keys.as<uint8_t>(), E.val_pool = L->d_vals.as<uint8_t>();
+      E.hash_pool = L->d_hashes.as<uint8_t>(), E.child_pool = L->d_children.as<uint32_t>(), E.accounts = L->d_accounts.as<AccountRec>();
+      CUDA_OK(cudaMemsetAsync(L->last_bounds.result, 0, 4 * PARSE_R_WORDS, L->st));
+      launch_parse_bounds(L->last_bounds, L->st);
+      launch_parse_scatter(L->last_bounds, L->last_ins_pos, L->st);
+      launch_parse_tree(E.T, L->st);
+      if (L->last_n_code) {
+        launch_parse_code_list(E, L->st);
+        launch_keccak256_ranges(E.T.wit, E.code_se, L->last_n_code, const_cast<uint8_t*>(E.code_digest), L->st);
+      }
+      if (L->last_val_bytes) CUDA_OK(cudaMemsetAsync(E.val_pool, 0, L->last_val_bytes, L->st));
+      launch_parse_emit(E, L->st);
       CUDA_OK(cudaGetLastError());
       CUDA_OK(cudaEventRecord(L->ev1, L->st));
       CUDA_OK(cudaStreamWaitEvent(c->st, L->ev1, 0));

@@ -67,6 +67,7 @@ class PpdStats(ctypes.Structure):
         ("witness_instructions", ctypes.c_uint64),
         ("witness_bytes", ctypes.c_uint64),
         ("parse_gpu_ms", ctypes.c_double),
+        ("level_launches", ctypes.c_uint64),
     ]
 
     def as_dict(self):
@@ -87,6 +88,7 @@ EXPORTS = [
     "ppd_trie_root_sorted_leaves",
     "ppd_trie_root_sorted_leaves_dev",
     "ppd_replay_last_hashing",
+    "ppd_replay_last_parse",
     "ppd_microbench",
 ]
 
@@ -123,6 +125,7 @@ class PpdLibrary:
         L.ppd_blocks_decode_batch.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
         L.ppd_trie_root_sorted_leaves.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_char_p]
         L.ppd_replay_last_hashing.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_double)]
+        L.ppd_replay_last_parse.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_double)]
         L.ppd_microbench.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_uint32, ctypes.c_uint32, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_uint32)]
         L.ppd_trie_root_sorted_leaves_dev.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_char_p]
 
@@ -274,6 +277,11 @@ class Context:
     def replay_last_hashing(self) -> float:
         ms = ctypes.c_double()
         self._check(self.lib.L.ppd_replay_last_hashing(self.h, ctypes.byref(ms)))
+        return ms.value
+
+    def replay_last_parse(self) -> float:
+        ms = ctypes.c_double()
+        self._check(self.lib.L.ppd_replay_last_parse(self.h, ctypes.byref(ms)))
         return ms.value
 
     def microbench(self, variant, blocks_per_sm=8, iters=2000):
