@@ -425,3 +425,21 @@ def test_gpu_parse_declines_non_canonical_and_malformed(ctx, oracle, goldens):
             continue
         assert ctx.compact_decode(wit) == want
         assert ctx.stats()["witnesses_on_gpu"] == 0
+
+
+@pytest.mark.parametrize("sizes", [
+    [20000] * 8,                                  # every code string spans five tiles
+    [3000, 40000, 17, 24000, 33000, 1, 9000, 45000, 12000],  # mixed: some longer than a whole tile group's first tile
+    [70000, 70000],                               # longer than a tile group (8 tiles) of a small witness
+])
+def test_gpu_parse_long_code_strings_jump_tiles_and_groups(ctx, oracle, sizes):
+    import witness_shapes as ws
+
+    wit = ws.long_code_witness(sizes)
+    want = oracle.compact_decode(wit)
+    got = ctx.compact_decode(wit)
+    st = ctx.stats()
+    assert got == want
+    assert st["witnesses_on_gpu"] == 1
+    assert st["witness_instructions"] == 2 * len(sizes) + 1
+    assert len(parse_pre_image_dump(got)["code"]) == len(sizes)  # one code map entry per (distinct, random) code string

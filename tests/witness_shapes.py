@@ -89,3 +89,30 @@ PAIRS = [
         HDR + account_with_storage(nibs("1" + K62), leaf(nibs("49" + K62), b"\x2a")) + account(nibs(K62), balance=1) + branch((1 << 0) | (1 << 3)),
     ),
 ]
+
+
+def code(b):
+    return bytes([OP_CODE]) + cbor_bytes(b)
+
+
+def account_with_code(key_nibbles, code_stream, code_len, balance=7, storage_stream=None):
+    # stream order: code, then storage, then the leaf; the code size follows the balance (read and discarded)
+    flags = 1 | 8 | (2 if storage_stream is not None else 0)
+    return (code_stream + (storage_stream or b"") + bytes([OP_ACCOUNT]) + cbor_bytes(compact_key(key_nibbles)) + bytes([flags])
+            + cbor_bytes(bytes([balance])) + cbor_uint(code_len))
+
+
+def long_code_witness(code_sizes, seed=7):
+    """A canonical witness of len(code_sizes) <= 16 accounts under one branch, account i carrying code_sizes[i]
+    bytes of inline code: with sizes of several tiles (4 KiB) the instruction chain jumps over whole tiles, and
+    over the first tile of a tile group, in the GPU parser's boundary search."""
+    import random
+
+    rnd = random.Random(seed)
+    out = HDR
+    mask = 0
+    for i, size in enumerate(code_sizes):
+        body = bytes(rnd.getrandbits(8) for _ in range(size))
+        out += account_with_code(nibs(("%x" % ((i * 7 + 3) % 16)) * 63), code(body), size, balance=1 + i)
+        mask |= 1 << i
+    return out + branch(mask)
