@@ -1220,6 +1220,15 @@ bool gpu_pre_image(Lane* L, Job& J, BlockJob& b, bool check_version = true, Slot
   const uint8_t* w = b.compact.p;
   const size_t n = b.compact.n;
   if (n < 2 || n >= 0xfff00000ull) return false;
+  // The three phases cost three read-backs and about 45 launches whatever the size: below a few hundred KiB
+  // that latency exceeds what the host builder needs for the whole witness (config 4: 1024 blocks of 100 KB
+  // each decode at 7.1 k blocks/s with the host builder, 3.3 k with this one), at config-2 size (36 MB) it
+  // is 16x faster.  PPD_GPU_PARSE_MIN_BYTES moves the switch (the tests set it to 0).
+  {
+    const char* e = getenv("PPD_GPU_PARSE_MIN_BYTES");
+    const size_t min_bytes = e ? (size_t)atoll(e) : (size_t)512 << 10;
+    if (n < min_bytes) return false;
+  }
   HostArena& A = J.A;
   cudaStream_t st = L->st;
   if (!L->h_parse) {
@@ -1227,7 +1236,16 @@ bool gpu_pre_image(Lane* L, Job& J, BlockJob& b, bool check_version = true, Slot
     if (!L->h_parse) fail(PPD_ERR_BAD_ARGUMENT, "out of page-locked memory");
   }
   uint32_t* hr = L->h_parse;
+  static const bool timing = getenv("PPD_TIMING") != nullptr;
+  auto t_prev = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) {
+    if (!timing) return;
+    auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "[ppd]   %-12s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t_prev).count());
+    t_prev = now;
+  };
   SlotGuard slot(slots);
+  lap("p:slot-wait");
   // ---- phase A: instruction boundaries ----
   L->d_wit.reserve(n + 64);
   {
@@ -1260,7 +1278,7 @@ bool gpu_pre_image(Lane* L, Job& J, BlockJob& b, bool check_version = true, Slot
   B.n_groups = (B.n_tiles + B.group_tiles - 1) / B.group_tiles;
   auto layout_a = [&](Carve& c) {
     B.result = c.take<uint32_t>(PARSE_R_WORDS);
-    B.exit1 = c.take<uint32_t>(n);
+    B.exit1 = c.take<uint32_t>((size_t)B.n_tiles * PARSE_TILE);  // whole tiles: tile_exit_kernel stores 128-bit rows
     B.step1 = c.take<uint16_t>((size_t)B.n_tiles * PARSE_TILE);
     B.exit2 = c.take<uint32_t>((size_t)B.n_groups * PARSE_TILE);
     B.group_entry = c.take<uint32_t>(B.n_groups);
@@ -1290,6 +1308,7 @@ bool gpu_pre_image(Lane* L, Job& J, BlockJob& b, bool check_version = true, Slot
   CUDA_OK(cudaMemcpyAsync(hr, B.result, 4 * PARSE_R_WORDS, cudaMemcpyDeviceToHost, st));
   lane_sync(L);
   phase_ms();
+  lap("p:upload+A");
   L->stats.kernel_launches += parse_bounds_launches();
   if (hr[PARSE_R_END] != (uint32_t)n) return false;  // a parse error: the host parser reports it
   const uint32_t n_ins = hr[PARSE_R_NINS];
@@ -1336,6 +1355,7 @@ bool gpu_pre_image(Lane* L, Job& J, BlockJob& b, bool check_version = true, Slot
   CUDA_OK(cudaMemcpyAsync(hr, B.result, 4 * PARSE_R_WORDS, cudaMemcpyDeviceToHost, st));
   lane_sync(L);
   phase_ms();
+  lap("p:B");
   L->stats.kernel_launches += 16;
   if (hr[PARSE_R_FLAG] != 0 || hr[PARSE_R_HEIGHT] != 1) return false;
   if (check_version && w[0] != 1) fail(PPD_PANIC_INCOMPATIBLE_HEADER_VERSION, "compact header version is not 1");
@@ -1410,6 +1430,7 @@ bool gpu_pre_image(Lane* L, Job& J, BlockJob& b, bool check_version = true, Slot
   lane_sync(L);
   slot.done();
   phase_ms();
+  lap("p:C+download");
   for (size_t k = 0; k < n_code; k++) {
     L->stats.key_permutations += J.code_list[2 * k + 1] / 136 + 1;
     b.pre_code[J.code_digest[k]] = Span{w + J.code_list[2 * k], J.code_list[2 * k + 1]};
@@ -1449,6 +1470,7 @@ bool gpu_pre_image(Lane* L, Job& J, BlockJob& b, bool check_version = true, Slot
       b.root_of[al[5 * a + 1]] = al[5 * a + 2];
     }
   }
+  lap("p:tables");
   b.pre_image_on_gpu = true;
   L->has_last_parse = true, L->last_bounds = B, L->last_emit = E, L->last_ins_pos = ins_pos, L->last_n_code = (uint32_t)n_code, L->last_val_bytes = val_bytes;
   L->stats.witnesses_on_gpu += 1, L->stats.witness_instructions += n_ins, L->stats.witness_bytes += n;
@@ -2646,6 +2668,7 @@ void decode_one(ppd_ctx* c, Lane* L, const uint8_t* flat, size_t len, uint8_t** 
   *out = nullptr, *out_len = 0;
   try {
     read_flat_block(flat, len, b);
+    pt.lap("read-flat");
     if (gpu_parse_enabled()) gpu_pre_image(L, J, b, true, &c->parse_slots_sem);
     collect_messages(J, b);
     pt.lap("parse");

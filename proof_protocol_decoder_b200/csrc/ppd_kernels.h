@@ -97,8 +97,7 @@ enum {  // per-instruction size counters, scanned together
   PARSE_C_CHILD = 4,  // child_pool slots
   PARSE_C_ACCT = 5,   // account records
   PARSE_C_CODE = 6,   // inline code strings
-  PARSE_C_SPARE = 7,
-  PARSE_N_CNT = 8
+  PARSE_N_CNT = 7
 };
 struct Pyramid16 {
   const int16_t *L, *m1, *m2, *m3;
@@ -107,7 +106,7 @@ struct ParseBounds {
   const uint8_t* wit;     // witness bytes (readable up to n + 16)
   uint32_t n;
   uint32_t n_tiles, group_tiles, n_groups;
-  uint32_t* exit1;        // [n]
+  uint32_t* exit1;        // [n_tiles * PARSE_TILE]
   uint16_t* step1;        // [n_tiles * PARSE_TILE] single-step links inside each tile
   uint32_t* exit2;        // [n_groups * PARSE_TILE]
   uint32_t* group_entry;  // [n_groups]

@@ -200,26 +200,86 @@ __device__ __forceinline__ void stage_tile(uint8_t* sb, const uint8_t* __restric
   for (uint32_t k = tid; k < (TILE + HALO) / 16; k += nthreads) dst[k] = k < avail ? __ldg(src + k) : make_uint4(0, 0, 0, 0);
 }
 
-__global__ void __launch_bounds__(TE_THREADS) tile_exit_kernel(const uint8_t* __restrict__ w, uint32_t n, uint32_t* __restrict__ exit1,
-                                                               uint16_t* __restrict__ step1) {
-  __shared__ uint32_t nxt[TILE];
+// the long decode, kept out of line so that the four positions a thread classifies share one copy of it
+__device__ __noinline__ uint32_t decode_next_slow(const uint8_t* w, uint32_t n, uint32_t p) {
+  Ins o;
+  uint32_t e = decode_ins(w, n, p, o);
+  return e ? (PERR | e) : o.next;
+}
+
+__global__ void __launch_bounds__(TE_THREADS, 3) tile_exit_kernel(const uint8_t* __restrict__ w, uint32_t n, uint32_t* __restrict__ exit1,
+                                                                  uint16_t* __restrict__ step1) {
+  __shared__ __align__(16) uint32_t nxt[TILE];
   __shared__ __align__(16) uint16_t step[TILE];  // single-step links inside the tile (0xffff: the instruction ends outside), for tile_mark_kernel
-  __shared__ uint16_t active[TILE];  // positions whose chain has not left the tile yet
+  __shared__ uint16_t active[TILE];              // positions whose chain has not left the tile yet
   __shared__ uint32_t n_active;
   __shared__ __align__(16) uint8_t sb[TILE + HALO];
+  constexpr uint32_t SLOW = PERR | 0xfeu;
   const uint32_t base = blockIdx.x * TILE, end = min(base + TILE, n);
+  const uint32_t lane = threadIdx.x & 31;
   stage_tile(sb, w, n, base, threadIdx.x, TE_THREADS);
   if (threadIdx.x == 0) n_active = 0;
   __syncthreads();
   const uint8_t* ws = sb - base;
+  const uint32_t* sw = reinterpret_cast<const uint32_t*>(sb);
+  // Four consecutive positions per thread from one 32-bit load.  The classification is branch-free: not an
+  // opcode -> error; hashed-out node -> p + 33; empty root -> p + 1; any other opcode must be followed by a
+  // CBOR head of the right major type, else the error decode_ins reports for it; only what passes that
+  // goes through the long decode.  (Every 32-byte window of a witness holds a real opcode, so divergent
+  // single-lane paths here would set the kernel's instruction count.)
 #pragma unroll 1
-  for (int k = 0; k < TE_PER; k++) {
-    uint32_t o = threadIdx.x + k * TE_THREADS, p = base + o;
-    if (p < end) {
-      uint32_t v = p == 0 ? 1u : decode_next(ws, n, p);  // byte 0 is the header: "ends" at 1
-      nxt[o] = v;
-      step[o] = v < end ? (uint16_t)(v - base) : (uint16_t)0xffffu;
-      if (v < end) active[atomicAdd(&n_active, 1u)] = (uint16_t)o;
+  for (uint32_t it = 0; it < TILE / (4 * TE_THREADS); it++) {
+    const uint32_t o0 = it * 4 * TE_THREADS + 4 * threadIdx.x;
+    const uint32_t W0 = sw[o0 >> 2], W1 = sw[(o0 >> 2) + 1];
+    uint32_t v[4];
+    bool any_slow = false;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const uint32_t p = base + o0 + j;
+      const uint32_t op = (W0 >> (8 * j)) & 255u;
+      const uint32_t b1 = j < 3 ? (W0 >> (8 * j + 8)) & 255u : W1 & 255u;
+      const bool is_uint_head = op == PPD_OP_BRANCH;
+      const uint32_t e_head = (is_uint_head || op == PPD_OP_CODE) ? PPD_ERR_INVALID_BYTES_FOR_TYPE : PPD_ERR_INVALID_BYTE_VECTOR;
+      const bool head_ok = p + 1 < n && (b1 >> 5) == (is_uint_head ? 0u : 2u) && (b1 & 31u) <= 27u;
+      uint32_t r = head_ok ? SLOW : (PERR | e_head);
+      r = op == PPD_OP_HASH ? (n - (p + 1) < 32 ? (PERR | PPD_ERR_INVALID_BYTES_FOR_TYPE) : p + 33) : r;
+      r = op == PPD_OP_EMPTY_ROOT ? p + 1 : r;
+      r = op > PPD_OP_EMPTY_ROOT ? (PERR | PPD_ERR_INVALID_OPERATOR) : r;
+      r = p == 0 ? 1u : r;   // byte 0 is the header: "ends" at 1
+      r = p >= end ? PERR : r;  // past the end of the stream: never referenced
+      v[j] = r;
+      any_slow |= r == SLOW;
+    }
+    if (any_slow) {
+#pragma unroll
+      for (int j = 0; j < 4; j++)
+        if (v[j] == SLOW) v[j] = decode_next_slow(ws, n, base + o0 + j);
+    }
+    uint32_t cnt = 0;
+    uint32_t st[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const bool in_tile = v[j] < end;
+      st[j] = in_tile ? v[j] - base : 0xffffu;
+      cnt += in_tile;
+    }
+    *reinterpret_cast<uint4*>(&nxt[o0]) = make_uint4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<uint2*>(&step[o0]) = make_uint2(st[0] | (st[1] << 16), st[2] | (st[3] << 16));
+    // warp-aggregated append of the in-tile positions to the active list
+    uint32_t incl = cnt;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      uint32_t x = __shfl_up_sync(0xffffffffu, incl, off);
+      if (lane >= (uint32_t)off) incl += x;
+    }
+    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+    if (total) {
+      uint32_t at = 0;
+      if (lane == 31) at = atomicAdd(&n_active, total);
+      at = __shfl_sync(0xffffffffu, at, 31) + incl - cnt;
+#pragma unroll
+      for (int j = 0; j < 4; j++)
+        if (v[j] < end) active[at++] = (uint16_t)(o0 + j);
     }
   }
   __syncthreads();
@@ -229,18 +289,19 @@ __global__ void __launch_bounds__(TE_THREADS) tile_exit_kernel(const uint8_t* __
   for (;;) {
     bool moved = false;
     for (uint32_t a = threadIdx.x; a < na; a += TE_THREADS) {
-      uint32_t o = active[a], v = nxt[o];
-      if (v < end) {
-        nxt[o] = nxt[v - base];
+      uint32_t o = active[a], x = nxt[o];
+      if (x < end) {
+        nxt[o] = nxt[x - base];
         moved = true;
       }
     }
     if (!__syncthreads_or(moved)) break;
   }
+  {
+    const uint4* s4 = reinterpret_cast<const uint4*>(nxt);
+    uint4* d4 = reinterpret_cast<uint4*>(exit1 + base);  // the exit1 array is padded to whole tiles
 #pragma unroll
-  for (int k = 0; k < TE_PER; k++) {
-    uint32_t o = threadIdx.x + k * TE_THREADS, p = base + o;
-    if (p < end) exit1[p] = nxt[o];
+    for (uint32_t k = threadIdx.x; k < TILE / 4; k += TE_THREADS) d4[k] = s4[k];
   }
   // the whole 8 KiB link table of the tile (entries past the end of the stream are never followed)
   reinterpret_cast<uint4*>(step1 + (size_t)base)[threadIdx.x] = reinterpret_cast<const uint4*>(step)[threadIdx.x];
@@ -613,7 +674,6 @@ __global__ void shape_kernel(ParseTree T) {
   T.cnt[PARSE_C_CHILD * S + i] = c_child;
   T.cnt[PARSE_C_ACCT * S + i] = c_acct;
   T.cnt[PARSE_C_CODE * S + i] = c_code;
-  T.cnt[PARSE_C_SPARE * S + i] = 0;
 }
 
 __global__ void totals_kernel(ParseTree T) {

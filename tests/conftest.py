@@ -11,6 +11,11 @@ for _p in (ROOT, TESTS):
         sys.path.insert(0, _p)
 
 
+# The GPU witness parser (ppd_parse.cu) only takes witnesses above a size threshold in production (small ones are
+# latency-bound, the host builder is faster); the tests run every witness through it.
+os.environ.setdefault("PPD_GPU_PARSE_MIN_BYTES", "0")
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 

@@ -443,3 +443,21 @@ def test_gpu_parse_long_code_strings_jump_tiles_and_groups(ctx, oracle, sizes):
     assert st["witnesses_on_gpu"] == 1
     assert st["witness_instructions"] == 2 * len(sizes) + 1
     assert len(parse_pre_image_dump(got)["code"]) == len(sizes)  # one code map entry per (distinct, random) code string
+
+
+def test_gpu_parse_size_threshold(ctx, oracle):
+    """Production default: witnesses under 512 KiB take the host builder, larger ones the GPU parser; same bytes out."""
+    import os
+
+    import witness_shapes as ws
+
+    small = ws.long_code_witness([20000] * 4)      # 80 KB
+    big = ws.long_code_witness([60000] * 12)       # 720 KB
+    saved = os.environ.pop("PPD_GPU_PARSE_MIN_BYTES", None)
+    try:
+        for wit, on_gpu in ((small, 0), (big, 1)):
+            assert ctx.compact_decode(wit) == oracle.compact_decode(wit)
+            assert ctx.stats()["witnesses_on_gpu"] == on_gpu
+    finally:
+        if saved is not None:
+            os.environ["PPD_GPU_PARSE_MIN_BYTES"] = saved
