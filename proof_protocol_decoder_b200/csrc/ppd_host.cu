@@ -2477,6 +2477,13 @@ bool gpu_dump_block(ppd_ctx* c, Lane* L, Job& J, uint8_t** out, size_t* out_len)
   std::vector<uint32_t> seg_a, seg_b, seg_begin(1, 0), touched_begin(1, 0), lit_at;  // lit_at[seg]: offset into lit.b
   size_t n_touched = 0;
   for (IrPlan& p : b.irs) n_touched += p.touched.size();
+  {
+    // the two dump kernels cost two read-backs and about a millisecond of launch + CTA latency whatever the size;
+    // a small block (config 1: a few thousand touched nodes) is serialised faster by the host threads
+    const char* e = getenv("PPD_GPU_DUMP_MIN_TOUCHED");
+    const size_t min_touched = e ? (size_t)atoll(e) : 32768;
+    if (n_touched < min_touched) return false;
+  }
   auto add_lit_from = [&](size_t from) {  // the bytes appended to lit.b since `from` become (part of) a literal segment
     uint32_t len = (uint32_t)(lit.b.size() - from);
     if (!len) return;
@@ -2578,7 +2585,8 @@ bool gpu_dump_block(ppd_ctx* c, Lane* L, Job& J, uint8_t** out, size_t* out_len)
   }
   // ---- emit, copy back, fill the literals in ----
   Out o;
-  uint8_t* pinned = out_pool().take(total);
+  // pool buffers are 8 MiB-granular: a small IrDump (a config-1 block is 85 KB) lands in the lane's staging buffer instead
+  uint8_t* pinned = total >= ((size_t)1 << 20) ? out_pool().take(total) : nullptr;
   if (!pinned) o.need(total);
   uint8_t* dst = pinned ? pinned : o.p;
   L->d_out.reserve(total + 64);

@@ -14,6 +14,7 @@ for _p in (ROOT, TESTS):
 # The GPU witness parser (ppd_parse.cu) only takes witnesses above a size threshold in production (small ones are
 # latency-bound, the host builder is faster); the tests run every witness through it.
 os.environ.setdefault("PPD_GPU_PARSE_MIN_BYTES", "0")
+os.environ.setdefault("PPD_GPU_DUMP_MIN_TOUCHED", "0")  # likewise for the GPU IR dump
 
 
 def pytest_configure(config):
