@@ -10,8 +10,10 @@ import sys
 
 TAG = sys.argv[1] if len(sys.argv) > 1 else "r01"
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-SRC = os.path.join(ROOT, "gpurun_out")
-DST = os.path.join(ROOT, "profiles")
+SRC = os.environ.get("SRC", os.path.join(ROOT, "gpurun_out"))
+DST = os.environ.get("DST", os.path.join(ROOT, "profiles"))
+PARSE_KERNELS = ("tile_exit", "group_exit", "top_chain", "tile_entry", "tile_mark", "ins_scatter", "ins_info", "heights_kernel", "min64_i16",
+                 "link_kernel16", "shape_kernel", "mscan", "emit_kernel", "climb_kernel", "code_list", "totals_kernel")
 
 
 def launches(path):
@@ -74,10 +76,12 @@ def main():
     if os.path.exists(p):
         items = launches(p)
         open(os.path.join(DST, f"{TAG}_launches_c2_summary.txt"), "w").write(
-            "ncu launch list of `python bench.py --steps 2 --warmup 3 --no-sweep` (16 blocks per step; --metrics gpu__time_duration.sum,dram__bytes_*;\n"
+            "ncu launch list of `python bench.py --steps 2 --warmup 3 --no-sweep` (32 blocks per step; first 4000 launches; --metrics gpu__time_duration.sum,dram__bytes_*;\n"
             "--clock-control none).  Launches are serialised and cold-cache under ncu: read SHARES, not absolutes.\n\n"
             + kernel_table(items, f"all {len(items)} launches") + "\n\n"
             + kernel_table([o for o in items if "at::" not in o["kernel"] and "native" not in o["kernel"]], "this library's kernels only") + "\n")
+        for o in items:
+            o["kernel"] = o["kernel"].replace("<unnamed>::", "").replace("unnamed>::", "")
         ours = [o for o in items if o["kernel"].startswith(("hash_level", "keccak256_batch"))]
         hl = [o for o in ours if o["kernel"].startswith("hash_level")]
         traffic = sum(o.get("dram__bytes_read.sum", 0) + o.get("dram__bytes_write.sum", 0) for o in hl) / max(1, len(hl))
@@ -101,10 +105,50 @@ def main():
     if os.path.exists(rep):
         t, _ = full_table(rep, "ncu --set full, the hashing kernels of config 5 at 10M leaves (first 14 hash_* launches)")
         open(os.path.join(DST, f"{TAG}_c5_full.txt"), "w").write(t + "\n")
-    for f in (f"{TAG}_bench_plain.log", f"{TAG}_c5_plain.log"):
+    # ---- witness parse / arena kernels ----
+    p = os.path.join(SRC, f"{TAG}_launches_parse.csv")
+    if os.path.exists(p):
+        items = [o for o in launches(p) if "at::" not in o["kernel"] and "native" not in o["kernel"] and "at_cuda" not in o["kernel"]]
+        for o in items:
+            o["kernel"] = o["kernel"].replace("<unnamed>::", "").replace("unnamed>::", "")
+        last = max(i for i, o in enumerate(items) if o["kernel"].startswith("tile_exit"))
+        one = items[last:]
+        txt = ("ncu launch list of `python profiles/run_parse.py 2` (one config-2 block, 34.6 MB witness, 1.05 M instructions, one lane):\n"
+               "the kernels of the LAST decode, in launch order.  Serialised and cold-cache under ncu: read SHARES; the plain run's\n"
+               "CUDA-event time of the parse phases is in " + f"{TAG}_parse_plain.log.\n\n")
+        agg = collections.OrderedDict()
+        for o in one:
+            a = agg.setdefault(o["kernel"], [0, 0.0, 0.0, 0.0])
+            a[0] += 1
+            a[1] += o.get("gpu__time_duration.sum", 0.0)
+            a[2] += o.get("dram__bytes_read.sum", 0.0)
+            a[3] += o.get("dram__bytes_write.sum", 0.0)
+        tot = sum(a[1] for a in agg.values()) or 1.0
+        txt += f"{'kernel':44s} {'launches':>8s} {'time us':>10s} {'share':>7s} {'dram rd MB':>11s} {'dram wr MB':>11s}\n"
+        for k, a in agg.items():
+            txt += f"{k[:44]:44s} {a[0]:8d} {a[1] / 1e3:10.1f} {100 * a[1] / tot:6.1f}% {a[2] / 1e6:11.1f} {a[3] / 1e6:11.1f}\n"
+        txt += f"{'total':44s} {'':8s} {tot / 1e3:10.1f}\n"
+        open(os.path.join(DST, f"{TAG}_launches_parse_summary.txt"), "w").write(txt)
+    rep = os.path.join(SRC, f"{TAG}_parse_full.ncu-rep")
+    if os.path.exists(rep):
+        t, rows = full_table(rep, "ncu --set full, the witness parse / arena kernels of one config-2 block (both decodes of `profiles/run_parse.py 2`; the second one is warm)")
+        open(os.path.join(DST, f"{TAG}_parse_full.txt"), "w").write(t + "\n")
+    for f in (f"{TAG}_bench_plain.log", f"{TAG}_c5_plain.log", f"{TAG}_parse_plain.log"):
         if os.path.exists(os.path.join(SRC, f)):
             open(os.path.join(DST, f), "w").write(open(os.path.join(SRC, f)).read())
 
 
+def count_parse_kernels(path):
+    """number of ppd_parse.cu launches in one decode (the last one of the launch list)"""
+    items = launches(path)
+    for o in items:
+        o["kernel"] = o["kernel"].replace("<unnamed>::", "").replace("unnamed>::", "")
+    last = max(i for i, o in enumerate(items) if o["kernel"].startswith("tile_exit"))
+    return sum(1 for o in items[last:] if o["kernel"].startswith(PARSE_KERNELS))
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 2 and sys.argv[1] == "--count-parse-kernels":
+        print(count_parse_kernels(sys.argv[2]))
+    else:
+        main()

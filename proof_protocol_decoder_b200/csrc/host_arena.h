@@ -266,6 +266,56 @@ struct HostArena {
     }
   }
 
+  // Inserts of many distinct keys into one trie version (all the accounts one txn writes): items sorted by key,
+  // all of them sharing the first `pos` nibbles.  The result is the trie inserting them one by one gives (a
+  // Merkle-Patricia trie is canonical for its key set), but every node on the shared upper part of the paths is
+  // created once instead of once per key: the versions in between, which nobody observes (the reference hashes
+  // a trie once per txn, decoding.rs:458-464), are neither built nor hashed.
+  struct BatchItem {
+    uint32_t koff, klen;
+    Payload payload;
+  };
+  uint32_t insert_many(uint32_t node, const BatchItem* it, size_t lo, size_t hi, uint32_t pos) {
+    if (lo == hi) return node;
+    if (hi - lo == 1) return insert(node, it[lo].koff, it[lo].klen, pos, it[lo].payload);
+    const uint32_t k0 = node == NODE_EMPTY ? (uint32_t)NK_LEAF : kind(node);
+    if (k0 == NK_HASH || k0 == NK_ROOT) fail(PPD_PANIC_INSERT_INTO_HASH_NODE, "insert traversed a hashed-out node");
+    if (k0 == NK_EXT) {
+      const uint32_t ek = nodes[node].a0, es = nstart(node), el = nlen(node), child = nodes[node].a1;
+      // sorted keys: when the first and the last run through the whole extension, all of them do
+      if (common_prefix(ek, es, el, it[lo].koff, pos, it[lo].klen - pos) == el &&
+          common_prefix(ek, es, el, it[hi - 1].koff, pos, it[hi - 1].klen - pos) == el) {
+        uint32_t nc = insert_many(child, it, lo, hi, pos + el);
+        return new_ext(ek, es, el, nc);
+      }
+    }
+    if (k0 != NK_BRANCH) {  // an empty slot, a leaf, an extension that has to split: one by one
+      for (size_t i = lo; i < hi; i++) node = insert(node, it[i].koff, it[i].klen, pos, it[i].payload);
+      return node;
+    }
+    uint32_t kids[16];
+    {
+      const uint32_t mask = nodes[node].a1 & 0xffffu, base = nodes[node].a0;
+      uint32_t r = 0;
+      for (uint32_t nib = 0; nib < 16; nib++) kids[nib] = (mask >> nib) & 1u ? child_pool[base + r++] : NODE_EMPTY;
+    }
+    uint32_t lv = level[node];
+    for (size_t i = lo; i < hi;) {
+      if (pos >= it[i].klen) fail(PPD_PANIC_KEY_IS_PREFIX_OF_KEY, "inserted key ends at a branch");
+      const uint32_t nib = key_nib(it[i].koff, pos);
+      size_t j = i + 1;
+      while (j < hi && pos < it[j].klen && key_nib(it[j].koff, pos) == nib) j++;
+      kids[nib] = insert_many(kids[nib], it, i, j, pos + 1);  // (the arena may have been reallocated: nothing of `node` is held across this call)
+      if (lvl(kids[nib]) + 1u > lv) lv = lvl(kids[nib]) + 1u;
+      i = j;
+    }
+    const uint32_t base = (uint32_t)child_pool.size();
+    uint32_t nmask = 0;
+    for (uint32_t nib = 0; nib < 16; nib++)
+      if (kids[nib] != NODE_EMPTY) child_pool.push_back(kids[nib]), nmask |= 1u << nib;
+    return push({node_w0(NK_BRANCH, 0, 0), base, nmask, 0}, lv);
+  }
+
   // an extension (ek, es, el) over `child`, merged into the child when that is a leaf / extension
   uint32_t collapse_ext(uint32_t ek, uint32_t es, uint32_t el, uint32_t child) {
     switch (kind(child)) {

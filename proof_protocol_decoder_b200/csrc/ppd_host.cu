@@ -755,6 +755,7 @@ struct Job {
   PVec<uint32_t> acct_list, code_list;
   PVec<uint8_t> wit_stage;  // page-locked staging of a pageable witness
   std::vector<HostArena::MarkItem> mark_items;  // scratch of the txn loop
+  std::vector<HostArena::BatchItem> batch_items;
   PVec<H256> code_digest;
   std::vector<uint32_t> stamp;
   uint32_t serial = 0;
@@ -1766,6 +1767,8 @@ void shape_block(Job& J, BlockJob& b) {
       }
     }
     sec.stop(3);
+    std::vector<HostArena::BatchItem>& batch = J.batch_items;
+    batch.clear();
     for (size_t i = 0; i < tx.traces.size(); i++) {
       TraceV& tr = tx.traces[i];
       bool storage_change = tr.n_writes != 0;
@@ -1794,8 +1797,13 @@ void shape_block(Job& J, BlockJob& b) {
       if (tr.flags & PPD_TR_CODE_WRITE) memcpy(rec.code_hash, J.kh.digest[tr.m_code].b, 32);
       uint32_t r = (uint32_t)A.accounts.size();
       A.accounts.push_back(rec);
-      state = A.insert(state, haddr_key[i], 64, 0, HostArena::Payload{true, r, 0});
+      batch.push_back({haddr_key[i], 64, HostArena::Payload{true, r, 0}});
     }
+    // the txn's account writes in one descent (addresses are distinct: TxnInfo.traces is a map, trace_protocol.rs:118)
+    std::sort(batch.begin(), batch.end(), [&](const HostArena::BatchItem& x, const HostArena::BatchItem& y) {
+      return memcmp(A.key_pool.data() + x.koff, A.key_pool.data() + y.koff, 32) < 0;
+    });
+    state = A.insert_many(state, batch.data(), 0, batch.size(), 0);
     sec.stop(4);
     for (size_t i = 0; i < tx.traces.size(); i++) {
       if (!(tx.traces[i].flags & PPD_TR_SELF_DESTRUCTED)) continue;
