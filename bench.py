@@ -255,7 +255,7 @@ def run_b200(args, rank, world, local_rank):
     threads = max(1, min(32, 2 * cores // world))
     os.environ.setdefault("PPD_HOST_THREADS", str(threads))
     threads = int(os.environ["PPD_HOST_THREADS"])
-    n_blocks = args.blocks_per_step or 32  # per GPU, whatever the world size (weak scaling)
+    n_blocks = min(64, args.blocks_per_step or 64)  # per GPU, whatever the world size (weak scaling); the library keeps up to 64 lanes resident
     seeds = [2 + rank * n_blocks + j for j in range(n_blocks)]
     # generated before CUDA is touched (worker processes are forked); ranks generate their own blocks
     flats = c2_blocks(seeds, args.scale, max(1, cores // world))
@@ -480,7 +480,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--scale", type=float, default=1.0, help="fraction of the C2 block size (1.0 = the named config)")
-    ap.add_argument("--blocks-per-step", type=int, default=0, help="blocks per GPU per step (default 32)")
+    ap.add_argument("--blocks-per-step", type=int, default=0, help="blocks per GPU per step (default 64, at most 64)")
     ap.add_argument("--ref-scale", type=float, default=0.1, help="size of the bounded CPU sample block")
     ap.add_argument("--sweep", default="1000000,10000000", help="config-5 leaf counts measured beside the headline at N=1")
     ap.add_argument("--no-sweep", action="store_true")

@@ -2371,7 +2371,7 @@ int guarded(ppd_ctx* c, F f) {
 // The IrDump of a block is ~50 MB that the caller owns until ppd_free().  Handing out page-locked
 // buffers from a process-wide pool lets the device write the result straight into the caller's buffer
 // (no bounce copy, no first-touch page faults); ppd_free() returns the buffer to the pool.  The pool is
-// capped (PPD_PINNED_OUT_MB, default 4096): beyond the cap outputs are ordinary malloc blocks.
+// capped (PPD_PINNED_OUT_MB, default 12288): beyond the cap outputs are ordinary malloc blocks.
 struct OutPool {
   struct Entry {
     uint8_t* p;
@@ -2384,7 +2384,7 @@ struct OutPool {
   size_t limit() {
     static size_t v = [] {
       const char* e = getenv("PPD_PINNED_OUT_MB");
-      return (size_t)(e ? atoll(e) : 4096) << 20;
+      return (size_t)(e ? atoll(e) : 12288) << 20;
     }();
     return v;
   }
@@ -2722,7 +2722,7 @@ void add_stats(ppd_stats& a, const ppd_stats& b) {
 // Blocks are independent (each BlockTrace carries its own pre-image, trace_protocol.rs:40-48): every
 // host thread takes blocks on its own lane, so parsing / shaping of one block overlaps the copies and
 // kernels of the others.
-static const size_t MAX_LANES = 32;
+static const size_t MAX_LANES = 64;
 
 void decode_blocks(ppd_ctx* c, const uint8_t* const* flats, const size_t* lens, size_t n, uint8_t** outs, size_t* out_lens, int* statuses) {
   stats_reset(c);
