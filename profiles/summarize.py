@@ -76,7 +76,7 @@ def main():
     if os.path.exists(p):
         items = launches(p)
         open(os.path.join(DST, f"{TAG}_launches_c2_summary.txt"), "w").write(
-            "ncu launch list of `python bench.py --steps 2 --warmup 3 --no-sweep` (32 blocks per step; first 4000 launches; --metrics gpu__time_duration.sum,dram__bytes_*;\n"
+            "ncu launch list of `python bench.py --steps 2 --warmup 3 --no-sweep` (64 blocks per step; first 4000 launches; --metrics gpu__time_duration.sum,dram__bytes_*;\n"
             "--clock-control none).  Launches are serialised and cold-cache under ncu: read SHARES, not absolutes.\n\n"
             + kernel_table(items, f"all {len(items)} launches") + "\n\n"
             + kernel_table([o for o in items if "at::" not in o["kernel"] and "native" not in o["kernel"]], "this library's kernels only") + "\n")
