@@ -139,7 +139,7 @@ struct SlotGuard {
 };
 int parse_slots() {
   const char* e = getenv("PPD_PARSE_SLOTS");
-  int v = e ? atoi(e) : 3;
+  int v = e ? atoi(e) : 4;
   return v < 1 ? 1 : v;
 }
 
@@ -167,6 +167,18 @@ void stats_reset(ppd_ctx* c) { c->stats = ppd_stats{}; }
 void lane_sync(Lane* l) {
   CUDA_OK(cudaEventRecord(l->ev_sync, l->st));
   CUDA_OK(cudaEventSynchronize(l->ev_sync));
+}
+// The same by polling, for the short waits a lane makes while it holds a parse slot (at most PPD_PARSE_SLOTS
+// threads poll at a time): a sleeping thread is woken late when every core is busy shaping other blocks, and
+// everything queued behind the slot waits with it.
+void lane_sync_poll(Lane* l) {
+  CUDA_OK(cudaEventRecord(l->ev_sync, l->st));
+  for (unsigned spins = 0;; spins++) {
+    cudaError_t e = cudaEventQuery(l->ev_sync);
+    if (e == cudaSuccess) return;
+    if (e != cudaErrorNotReady) CUDA_OK(e);
+    if (spins > 200) std::this_thread::yield();
+  }
 }
 
 // ============================================================================================
@@ -1246,6 +1258,7 @@ bool gpu_pre_image(Lane* L, Job& J, BlockJob& b, bool check_version = true, Slot
     t_prev = now;
   };
   SlotGuard slot(slots);
+  auto sync_in_slot = [&] { slots ? lane_sync_poll(L) : lane_sync(L); };
   lap("p:slot-wait");
   // ---- phase A: instruction boundaries ----
   L->d_wit.reserve(n + 64);
@@ -1307,7 +1320,7 @@ bool gpu_pre_image(Lane* L, Job& J, BlockJob& b, bool check_version = true, Slot
   CUDA_OK(cudaGetLastError());
   CUDA_OK(cudaEventRecord(L->ev1, st));
   CUDA_OK(cudaMemcpyAsync(hr, B.result, 4 * PARSE_R_WORDS, cudaMemcpyDeviceToHost, st));
-  lane_sync(L);
+  sync_in_slot();
   phase_ms();
   lap("p:upload+A");
   L->stats.kernel_launches += parse_bounds_launches();
@@ -1354,7 +1367,7 @@ bool gpu_pre_image(Lane* L, Job& J, BlockJob& b, bool check_version = true, Slot
   CUDA_OK(cudaGetLastError());
   CUDA_OK(cudaEventRecord(L->ev1, st));
   CUDA_OK(cudaMemcpyAsync(hr, B.result, 4 * PARSE_R_WORDS, cudaMemcpyDeviceToHost, st));
-  lane_sync(L);
+  sync_in_slot();
   phase_ms();
   lap("p:B");
   L->stats.kernel_launches += 16;
@@ -1411,6 +1424,7 @@ bool gpu_pre_image(Lane* L, Job& J, BlockJob& b, bool check_version = true, Slot
   CUDA_OK(cudaGetLastError());
   CUDA_OK(cudaEventRecord(L->ev1, st));
   L->stats.kernel_launches += 2;
+  slot.done();  // the next lane may start its upload while this one's emit kernels and download run
   A.nodes.resize(n_nodes), A.level.resize(n_nodes), A.key_pool.resize(key_bytes), A.child_pool.resize(n_child), A.accounts.resize(n_acct);
   A.val_pool.resize(val_bytes), A.hash_pool.resize(32 * n_hash);  // contents stay on the device (fetch_pools)
   J.acct_list.resize(5 * n_acct), J.code_list.resize(2 * n_code), J.code_digest.resize(n_code);
@@ -1429,7 +1443,6 @@ bool gpu_pre_image(Lane* L, Job& J, BlockJob& b, bool check_version = true, Slot
   down(J.code_digest.data(), d_code_digest, 32 * n_code);
   down(hr, B.result, 4 * PARSE_R_WORDS);
   lane_sync(L);
-  slot.done();
   phase_ms();
   lap("p:C+download");
   for (size_t k = 0; k < n_code; k++) {
