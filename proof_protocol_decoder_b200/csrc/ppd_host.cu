@@ -1316,14 +1316,13 @@ bool gpu_pre_image(Lane* L, Job& J, BlockJob& b, bool check_version = true, Slot
   };
   CUDA_OK(cudaMemsetAsync(B.result, 0, 4 * PARSE_R_WORDS, st));
   CUDA_OK(cudaEventRecord(L->ev0, st));
-  launch_parse_bounds(B, st);
+  L->stats.kernel_launches += launch_parse_bounds(B, st);
   CUDA_OK(cudaGetLastError());
   CUDA_OK(cudaEventRecord(L->ev1, st));
   CUDA_OK(cudaMemcpyAsync(hr, B.result, 4 * PARSE_R_WORDS, cudaMemcpyDeviceToHost, st));
   sync_in_slot();
   phase_ms();
   lap("p:upload+A");
-  L->stats.kernel_launches += parse_bounds_launches();
   if (hr[PARSE_R_END] != (uint32_t)n) return false;  // a parse error: the host parser reports it
   const uint32_t n_ins = hr[PARSE_R_NINS];
   if (n_ins == 0 || n_ins > n) return false;
@@ -1363,14 +1362,13 @@ bool gpu_pre_image(Lane* L, Job& J, BlockJob& b, bool check_version = true, Slot
   T.ins_pos = ins_pos;
   CUDA_OK(cudaEventRecord(L->ev0, st));
   launch_parse_scatter(B, ins_pos, st);
-  launch_parse_tree(T, st);
+  L->stats.kernel_launches += 1 + launch_parse_tree(T, st);
   CUDA_OK(cudaGetLastError());
   CUDA_OK(cudaEventRecord(L->ev1, st));
   CUDA_OK(cudaMemcpyAsync(hr, B.result, 4 * PARSE_R_WORDS, cudaMemcpyDeviceToHost, st));
   sync_in_slot();
   phase_ms();
   lap("p:B");
-  L->stats.kernel_launches += 16;
   if (hr[PARSE_R_FLAG] != 0 || hr[PARSE_R_HEIGHT] != 1) return false;
   if (check_version && w[0] != 1) fail(PPD_PANIC_INCOMPATIBLE_HEADER_VERSION, "compact header version is not 1");
   const uint32_t* tot = hr + PARSE_R_TOTALS;

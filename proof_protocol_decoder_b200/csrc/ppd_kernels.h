@@ -148,10 +148,9 @@ struct ParseEmit {
   const uint8_t* code_digest;  // [n_code][32]
 };
 size_t parse_scan_tmp_words(size_t n, uint32_t K);
-void launch_parse_bounds(const ParseBounds& B, cudaStream_t st);
-uint32_t parse_bounds_launches();
+uint32_t launch_parse_bounds(const ParseBounds& B, cudaStream_t st);  // the launchers return the number of kernels launched
 void launch_parse_scatter(const ParseBounds& B, uint32_t* ins_pos, cudaStream_t st);
-void launch_parse_tree(const ParseTree& T, cudaStream_t st);
+uint32_t launch_parse_tree(const ParseTree& T, cudaStream_t st);
 void launch_parse_code_list(const ParseEmit& E, cudaStream_t st);
 void launch_parse_emit(const ParseEmit& E, cudaStream_t st);
 

@@ -473,15 +473,18 @@ __global__ void __launch_bounds__(MS_B) mscan_add_kernel(uint32_t* __restrict__ 
   }
 }
 
-void mscan(const uint32_t* in, uint32_t* out, uint32_t n, size_t stride, uint32_t K, uint32_t* tmp, cudaStream_t st) {
-  if (!n) return;
-  uint32_t nb = (n + MS_ELEMS - 1) / MS_ELEMS;
+// returns the number of kernels launched
+uint32_t mscan(const uint32_t* in, uint32_t* out, uint32_t n, size_t stride, uint32_t K, uint32_t* tmp, cudaStream_t st) {
+  if (!n) return 0;
+  uint32_t nb = (n + MS_ELEMS - 1) / MS_ELEMS, launches = 1;
   size_t ss = (nb + 3) & ~(size_t)3;
   mscan_block_kernel<<<dim3(nb, K), MS_B, 0, st>>>(in, out, n, stride, nb > 1 ? tmp : nullptr, ss);
   if (nb > 1) {
-    mscan(tmp, tmp, nb, ss, K, tmp + K * ss, st);
+    launches += mscan(tmp, tmp, nb, ss, K, tmp + K * ss, st);
     mscan_add_kernel<<<dim3(nb, K), MS_B, 0, st>>>(out, n, stride, tmp, ss);
+    launches++;
   }
+  return launches;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -887,7 +890,7 @@ size_t parse_scan_tmp_words(size_t n, uint32_t K) {
   return total + 16;
 }
 
-void launch_parse_bounds(const ParseBounds& B, cudaStream_t st) {
+uint32_t launch_parse_bounds(const ParseBounds& B, cudaStream_t st) {
   const uint32_t group_bytes = B.group_tiles * TILE;
   tile_exit_kernel<<<B.n_tiles, TE_THREADS, 0, st>>>(B.wit, B.n, B.exit1, B.step1);
   group_exit_kernel<<<dim3(TILE / 256, B.n_groups), 256, 0, st>>>(B.exit1, B.n, group_bytes, B.exit2);
@@ -897,19 +900,20 @@ void launch_parse_bounds(const ParseBounds& B, cudaStream_t st) {
   tile_entry_kernel<<<cdiv(B.n_groups, 64), 64, 0, st>>>(B.exit1, B.group_entry, B.n, B.n_groups, group_bytes, B.tile_entry);
   tile_mark_kernel<<<cdiv(B.n_tiles, TM_WARPS), TM_WARPS * 32, 0, st>>>(B.step1, B.n, B.n_tiles, B.tile_entry, B.bitmap, B.tile_count);
   cudaMemsetAsync(B.tile_count + B.n_tiles, 0, 4, st);
-  mscan(B.tile_count, B.tile_base, B.n_tiles + 1, 0, 1, B.scan_tmp, st);
+  uint32_t launches = 5 + mscan(B.tile_count, B.tile_base, B.n_tiles + 1, 0, 1, B.scan_tmp, st);
   cudaMemcpyAsync(B.result + PARSE_R_NINS, B.tile_base + B.n_tiles, 4, cudaMemcpyDeviceToDevice, st);
+  return launches;
 }
-uint32_t parse_bounds_launches() { return 9; }
 
 void launch_parse_scatter(const ParseBounds& B, uint32_t* ins_pos, cudaStream_t st) {
   ins_scatter_kernel<<<B.n_tiles, TILE / 32, 0, st>>>(B.bitmap, B.tile_base, ins_pos);
 }
 
-void launch_parse_tree(const ParseTree& T, cudaStream_t st) {
+uint32_t launch_parse_tree(const ParseTree& T, cudaStream_t st) {
   const uint32_t n1 = T.n_ins + 1;
   ins_info_kernel<<<cdiv(n1, 256), 256, 0, st>>>(T);
-  mscan(T.delta, T.hb, n1, 0, 1, T.scan_tmp, st);
+  uint32_t launches = 8;  // ins_info, heights, 3 x min64, link, shape, totals
+  launches += mscan(T.delta, T.hb, n1, 0, 1, T.scan_tmp, st);
   heights_kernel<<<cdiv(n1, 256), 256, 0, st>>>(T);
   const uint32_t n_m1 = cdiv(n1, 64), n_m2 = cdiv(n_m1, 64), n_m3 = cdiv(n_m2, 64);
   min64_i16_kernel<<<cdiv(n_m1, 128), 128, 0, st>>>(T.h16, n1, T.m1, n_m1);
@@ -917,8 +921,9 @@ void launch_parse_tree(const ParseTree& T, cudaStream_t st) {
   min64_i16_kernel<<<cdiv(n_m3, 128), 128, 0, st>>>(T.m2, n_m2, T.m3, n_m3);
   link_kernel16<<<cdiv(T.n_ins, 256), 256, 0, st>>>(T);
   shape_kernel<<<cdiv(n1, 256), 256, 0, st>>>(T);
-  mscan(T.cnt, T.scn, n1, T.cnt_stride, PARSE_N_CNT, T.scan_tmp, st);
+  launches += mscan(T.cnt, T.scn, n1, T.cnt_stride, PARSE_N_CNT, T.scan_tmp, st);
   totals_kernel<<<1, 32, 0, st>>>(T);
+  return launches;
 }
 
 void launch_parse_code_list(const ParseEmit& E, cudaStream_t st) { code_list_kernel<<<cdiv(E.T.n_ins, 256), 256, 0, st>>>(E); }

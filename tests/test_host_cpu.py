@@ -111,3 +111,16 @@ def test_oracle_error_codes(oracle):
     with pytest.raises(OracleError) as e:
         oracle.block_decode(blk.flat)
     assert e.value.code == 40  # assert on the header version, processed_block_trace.rs:175
+
+
+def test_host_arena_batched_operations_match_one_by_one(tmp_path):
+    """csrc/host_arena.h on the CPU (tests/cpp/host_arena_check.cpp, g++ only): insert_many == sequential inserts,
+    mark_many == mark, branch_with == a rebuilt branch, removals unaffected, levels above their children's."""
+    import subprocess
+
+    exe = tmp_path / "host_arena_check"
+    src = os.path.join(ROOT, "tests", "cpp", "host_arena_check.cpp")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-Wall", "-Werror", "-o", str(exe), src])
+    out = subprocess.run([str(exe), "60"], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "60 rounds ok" in out.stdout
