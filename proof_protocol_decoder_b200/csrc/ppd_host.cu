@@ -87,6 +87,7 @@ struct Lane {
   DevBuf d_msg, d_msg_off, d_digest;
   DevBuf d_plan, d_out;  // IR dump plan and the serialised IrDump
   DevBuf d_wit, d_pa, d_pb, d_pc;  // witness bytes and the scratch of the three parse phases (ppd_parse.cu)
+  DevBuf d_level, d_okeys, d_obins;  // node levels, and the scratch of the (level, class) ordering on the device
   uint32_t* h_parse = nullptr;     // page-locked landing area of the parse result words
   // the launch parameters of the lane's last GPU parse (the witness and all scratch stay resident), for ppd_replay_last_parse
   bool has_last_parse = false;
@@ -817,7 +818,8 @@ void lane_delete(Lane* l) {
 #ifndef PPD_HOSTPROF
   DevBuf* bufs[] = {&l->d_nodes, &l->d_order,  &l->d_keys,     &l->d_vals, &l->d_hashes,  &l->d_children, &l->d_accounts,
                     &l->d_ref,   &l->d_ref_len, &l->d_counters, &l->d_msg,  &l->d_msg_off, &l->d_digest,
-                    &l->d_plan,  &l->d_out,     &l->d_wit,      &l->d_pa,   &l->d_pb,      &l->d_pc};
+                    &l->d_plan,  &l->d_out,     &l->d_wit,      &l->d_pa,   &l->d_pb,      &l->d_pc,
+                    &l->d_level, &l->d_okeys,   &l->d_obins};
   for (DevBuf* b : bufs) b->release();
   if (l->h_parse) pinned_free(l->h_parse);
   if (l->ev0) cudaEventDestroy(l->ev0);
@@ -1382,7 +1384,6 @@ bool gpu_pre_image(Lane* L, Job& J, BlockJob& b, bool check_version = true, Slot
   uint16_t* d_level = nullptr;
   uint8_t* d_code_digest = nullptr;
   auto layout_c = [&](Carve& c) {
-    d_level = c.take<uint16_t>(n_nodes + 1);
     E.acct_list = c.take<uint32_t>(5 * n_acct + 1);
     E.code_se = c.take<uint64_t>(2 * n_code + 1);
     E.code_list = c.take<uint32_t>(2 * n_code + 1);
@@ -1397,6 +1398,8 @@ bool gpu_pre_image(Lane* L, Job& J, BlockJob& b, bool check_version = true, Slot
   }
   // room for what the txn loop appends, so that the sweep does not have to move the resident part
   L->d_nodes.reserve(16 * (n_nodes + n_nodes / 2) + 4096);
+  L->d_level.reserve(2 * (n_nodes + n_nodes / 2) + 4096);
+  d_level = L->d_level.as<uint16_t>();
   L->d_keys.reserve(2 * key_bytes + 65536);
   L->d_vals.reserve(2 * val_bytes + 65536);
   L->d_hashes.reserve(32 * n_hash + 32);
@@ -1899,26 +1902,30 @@ void sweep(Lane* c, Job& J, bool refs_to_host = true) {
   memset(J.ref_len.data(), 32, n);
   return;
 #endif
-  // counting sort of node ids by (level, class): inside a level, nodes of one kind and one
-  // permutation count are adjacent, so the lanes of a warp do the same work
-  auto node_class = [&](uint32_t i) -> uint32_t {
-    const NodeRec& r = A.nodes[i];
-    uint32_t kind = r.w0 & 0xff;
-    if (kind == NK_BRANCH) return 40 + ((uint32_t)__builtin_popcount(r.a1 & 0xffff) - 1 & 15);  // by child count
-    if (kind == NK_ROOT) return 56;
-    uint32_t perms = 1;
-    if (kind == NK_LEAF) {
-      uint32_t nl = (r.w0 >> 16) & 0xff;
-      perms = ((nl < 2 ? 1 : 2 + (nl >> 1)) + r.a2 + 6) / 136 + 1;  // header bytes over-estimated by at most 3
-    }
-    return kind * 8 + (perms > 8 ? 7 : perms - 1);
-  };
+  // node ids counting-sorted by (level, class): inside a level, nodes of one kind and one permutation count are
+  // adjacent, so the lanes of a warp do the same work.  The sort itself runs on the device (ppd_kernels.cu:
+  // launch_order_by_level_class); the host only needs where every level starts.
   uint32_t n_levels = 0;
   for (uint32_t i = 0; i < n; i++) n_levels = std::max<uint32_t>(n_levels, A.level[i] + 1u);
   std::vector<uint32_t> level_start(n_levels + 1, 0);
+  for (uint32_t i = 0; i < n; i++) level_start[A.level[i] + 1u]++;
+  for (uint32_t l = 0; l < n_levels; l++) level_start[l + 1] += level_start[l];
+  const bool device_order = 64u * n_levels <= ORDER_MAX_BINS;
   PVec<uint32_t>& order = J.order;
-  order.resize(n);
-  {
+  if (!device_order) {  // a trie deeper than 64 levels: the same sort on the host
+    auto node_class = [&](uint32_t i) -> uint32_t {
+      const NodeRec& r = A.nodes[i];
+      uint32_t kind = r.w0 & 0xff;
+      if (kind == NK_BRANCH) return 40 + ((uint32_t)__builtin_popcount(r.a1 & 0xffff) - 1 & 15);  // by child count
+      if (kind == NK_ROOT) return 56;
+      uint32_t perms = 1;
+      if (kind == NK_LEAF) {
+        uint32_t nl = (r.w0 >> 16) & 0xff;
+        perms = ((nl < 2 ? 1 : 2 + (nl >> 1)) + r.a2 + 6) / 136 + 1;  // header bytes over-estimated by at most 3
+      }
+      return kind * 8 + (perms > 8 ? 7 : perms - 1);
+    };
+    order.resize(n);
     std::vector<uint8_t> cls(n);
     std::vector<uint32_t> bucket((size_t)n_levels * 64 + 1, 0);
     for (uint32_t i = 0; i < n; i++) {
@@ -1926,7 +1933,6 @@ void sweep(Lane* c, Job& J, bool refs_to_host = true) {
       bucket[(size_t)A.level[i] * 64 + cls[i] + 1]++;
     }
     for (size_t k = 0; k + 1 < bucket.size(); k++) bucket[k + 1] += bucket[k];
-    for (uint32_t l = 0; l <= n_levels; l++) level_start[l] = bucket[(size_t)l * 64];
     for (uint32_t i = 0; i < n; i++) order[bucket[(size_t)A.level[i] * 64 + cls[i]]++] = i;
   }
   // the part of every pool that gpu_pre_image left in the lane's buffers stays where it is
@@ -1947,7 +1953,18 @@ void sweep(Lane* c, Job& J, bool refs_to_host = true) {
     c->stats.h2d_bytes += (double)(bytes - resident);
   };
   up(c->d_nodes, A.nodes.data(), 16ull * n, 16ull * R.nodes);
-  up(c->d_order, order.data(), 4ull * n);
+  if (device_order) {
+    c->d_level.reserve_keep(2ull * n + 16, 2ull * R.nodes, c->st);
+    c->d_okeys.reserve(2ull * n + 16);
+    c->d_obins.reserve(4ull * ORDER_MAX_BINS);
+    up(c->d_level, A.level.data(), 2ull * n, 2ull * R.nodes);
+    CUDA_OK(cudaMemsetAsync(c->d_obins.p, 0, 4ull * 64 * n_levels, c->st));
+    launch_order_by_level_class(c->d_nodes.as<NodeRec>(), c->d_level.as<uint16_t>(), n, 64 * n_levels, c->d_okeys.as<uint16_t>(),
+                                c->d_obins.as<uint32_t>(), c->d_order.as<uint32_t>(), c->st);
+    c->stats.kernel_launches += 3;
+  } else {
+    up(c->d_order, order.data(), 4ull * n);
+  }
   up(c->d_keys, A.key_pool.data(), A.key_pool.size(), R.keys);
   up(c->d_vals, A.val_pool.data(), A.val_pool.size(), R.vals);
   up(c->d_hashes, A.hash_pool.data(), A.hash_pool.size(), R.hashes);

@@ -328,6 +328,112 @@ void launch_keccak256_ranges(const uint8_t* data, const uint64_t* begin_end, uin
   if (!n) return;
   keccak256_batch_kernel<KB><<<(n + KB - 1) / KB, KB, 0, st>>>(data, begin_end, 2, n, out);
 }
+// ------------------------------------------------------------------ level / class ordering ----
+// order[] = node ids counting-sorted by (level, class): inside a level, nodes of one kind and one permutation
+// count are adjacent, so the lanes of a warp do the same work.  Three launches: per-CTA shared-memory
+// histograms flushed to bins[], an exclusive scan of the bins, and a scatter in which every CTA reserves one
+// range per key it holds.  The order inside a bucket is whatever the atomics give (hashing does not care).
+static constexpr int OS_THREADS = 256, OS_PER = 8;  // nodes per CTA = 2048
+
+__device__ __forceinline__ uint32_t node_class(const NodeRec& r) {
+  const uint32_t kind = r.w0 & 0xff;
+  if (kind == NK_BRANCH) return 40 + ((__popc(r.a1 & 0xffff) - 1) & 15);  // by child count
+  if (kind == NK_ROOT) return 56;
+  uint32_t perms = 1;
+  if (kind == NK_LEAF) {
+    const uint32_t nl = (r.w0 >> 16) & 0xff;
+    perms = ((nl < 2 ? 1 : 2 + (nl >> 1)) + r.a2 + 6) / 136 + 1;  // header bytes over-estimated by at most 3
+  }
+  return kind * 8 + (perms > 8 ? 7 : perms - 1);
+}
+
+__global__ void __launch_bounds__(OS_THREADS) order_hist_kernel(const NodeRec* __restrict__ nodes, const uint16_t* __restrict__ level, uint32_t n,
+                                                                uint32_t n_bins, uint16_t* __restrict__ keys, uint32_t* __restrict__ bins) {
+  extern __shared__ uint32_t sh[];
+  for (uint32_t k = threadIdx.x; k < n_bins; k += OS_THREADS) sh[k] = 0;
+  __syncthreads();
+  const uint32_t base = blockIdx.x * (OS_THREADS * OS_PER);
+#pragma unroll
+  for (int q = 0; q < OS_PER; q++) {
+    const uint32_t i = base + q * OS_THREADS + threadIdx.x;
+    if (i < n) {
+      const uint32_t key = min((uint32_t)level[i] * 64u + node_class(nodes[i]), n_bins - 1);
+      keys[i] = (uint16_t)key;
+      atomicAdd(&sh[key], 1u);
+    }
+  }
+  __syncthreads();
+  for (uint32_t k = threadIdx.x; k < n_bins; k += OS_THREADS)
+    if (sh[k]) atomicAdd(&bins[k], sh[k]);
+}
+
+// exclusive scan of bins[0 .. n_bins) in place, one CTA (n_bins <= 4096)
+__global__ void __launch_bounds__(1024) order_scan_kernel(uint32_t* __restrict__ bins, uint32_t n_bins) {
+  __shared__ uint32_t warp_sums[32];
+  __shared__ uint32_t carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (uint32_t base = 0; base < n_bins; base += 1024) {
+    const uint32_t i = base + threadIdx.x;
+    const uint32_t v = i < n_bins ? bins[i] : 0u;
+    uint32_t incl = v;
+    for (int off = 1; off < 32; off <<= 1) {
+      uint32_t t = __shfl_up_sync(0xffffffffu, incl, off);
+      if ((threadIdx.x & 31) >= (uint32_t)off) incl += t;
+    }
+    if ((threadIdx.x & 31) == 31) warp_sums[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      uint32_t ws = warp_sums[threadIdx.x], wi = ws;
+      for (int off = 1; off < 32; off <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, wi, off);
+        if (threadIdx.x >= (uint32_t)off) wi += t;
+      }
+      warp_sums[threadIdx.x] = wi - ws;
+    }
+    __syncthreads();
+    const uint32_t excl = carry + warp_sums[threadIdx.x >> 5] + incl - v;
+    if (i < n_bins) bins[i] = excl;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry = excl + v;
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(OS_THREADS) order_scatter_kernel(const uint16_t* __restrict__ keys, uint32_t n, uint32_t n_bins,
+                                                                   uint32_t* __restrict__ cursor, uint32_t* __restrict__ order) {
+  extern __shared__ uint32_t sh[];  // [n_bins] counts, then this CTA's base per key
+  for (uint32_t k = threadIdx.x; k < n_bins; k += OS_THREADS) sh[k] = 0;
+  __syncthreads();
+  const uint32_t base = blockIdx.x * (OS_THREADS * OS_PER);
+  uint32_t key[OS_PER], rank[OS_PER];
+#pragma unroll
+  for (int q = 0; q < OS_PER; q++) {
+    const uint32_t i = base + q * OS_THREADS + threadIdx.x;
+    key[q] = i < n ? keys[i] : 0xffffffffu;
+    rank[q] = i < n ? atomicAdd(&sh[key[q]], 1u) : 0u;
+  }
+  __syncthreads();
+  for (uint32_t k = threadIdx.x; k < n_bins; k += OS_THREADS)
+    if (sh[k]) sh[k] = atomicAdd(&cursor[k], sh[k]);
+  __syncthreads();
+#pragma unroll
+  for (int q = 0; q < OS_PER; q++) {
+    const uint32_t i = base + q * OS_THREADS + threadIdx.x;
+    if (i < n) order[sh[key[q]] + rank[q]] = i;
+  }
+}
+
+// bins: [n_bins] zeroed by the caller; on return bins[k] = end of bucket k (the scatter advances the cursors)
+void launch_order_by_level_class(const NodeRec* nodes, const uint16_t* level, uint32_t n, uint32_t n_bins, uint16_t* keys, uint32_t* bins,
+                                 uint32_t* order, cudaStream_t st) {
+  if (!n) return;
+  const uint32_t blocks = (n + OS_THREADS * OS_PER - 1) / (OS_THREADS * OS_PER);
+  order_hist_kernel<<<blocks, OS_THREADS, 4 * n_bins, st>>>(nodes, level, n, n_bins, keys, bins);
+  order_scan_kernel<<<1, 1024, 0, st>>>(bins, n_bins);
+  order_scatter_kernel<<<blocks, OS_THREADS, 4 * n_bins, st>>>(keys, n, n_bins, bins, order);
+}
+
 void launch_hash_level(const ArenaView& A, const uint32_t* order, uint32_t begin, uint32_t end, cudaStream_t st) {
   if (end <= begin) return;
   uint32_t n = end - begin;
