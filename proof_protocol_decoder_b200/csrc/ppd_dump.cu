@@ -247,16 +247,30 @@ __global__ void __launch_bounds__(DUMP_THREADS) ir_size_kernel(ArenaView A, IrDu
 
 namespace {
 
+// PPD_NODE_HASH || 32 bytes at an arbitrary destination alignment: the 33 bytes are laid out as nine little-endian
+// words, the bytes up to the first 4-byte boundary and after the last one are stored one by one, everything in
+// between as aligned words re-aligned with funnel shifts (8 word stores instead of 33 byte stores; hashed-out
+// children are most of an IR's bytes).
 __device__ __forceinline__ uint8_t* put_hash(uint8_t* q, const uint8_t* h32) {
-  *q++ = PPD_NODE_HASH;
   const uint4* src = reinterpret_cast<const uint4*>(h32);
-  uint4 x = __ldg(src), y = __ldg(src + 1);
+  const uint4 x = __ldg(src), y = __ldg(src + 1);
   const uint32_t w[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
+  uint32_t S[10];
+  S[0] = (uint32_t)PPD_NODE_HASH | (w[0] << 8);
 #pragma unroll
-  for (int i = 0; i < 8; i++) {
-    q[4 * i] = (uint8_t)w[i], q[4 * i + 1] = (uint8_t)(w[i] >> 8), q[4 * i + 2] = (uint8_t)(w[i] >> 16), q[4 * i + 3] = (uint8_t)(w[i] >> 24);
-  }
-  return q + 32;
+  for (int k = 1; k < 8; k++) S[k] = __funnelshift_r(w[k - 1], w[k], 24);
+  S[8] = w[7] >> 24;
+  S[9] = 0;
+  const uint32_t head = (4u - (uint32_t)(reinterpret_cast<uintptr_t>(q) & 3u)) & 3u;  // bytes before the first aligned word
+  for (uint32_t i = 0; i < head; i++) q[i] = (uint8_t)(S[0] >> (8 * i));
+  uint32_t* qw = reinterpret_cast<uint32_t*>(q + head);
+  const uint32_t sh = 8 * head, nwords = (33u - head) >> 2;  // 8 when head == 0 or 1 ... 7 when head == 2 or 3 (then 2 or 1 tail bytes)
+#pragma unroll
+  for (int j = 0; j < 8; j++)
+    if ((uint32_t)j < nwords) qw[j] = __funnelshift_r(S[j], S[j + 1], sh);
+  const uint32_t done = head + 4 * nwords;
+  for (uint32_t i = done; i < 33; i++) q[i] = (uint8_t)(S[i >> 2] >> (8 * (i & 3)));
+  return q + 33;
 }
 __device__ __forceinline__ uint8_t* put_u32(uint8_t* q, uint32_t v) {
   q[0] = (uint8_t)v, q[1] = (uint8_t)(v >> 8), q[2] = (uint8_t)(v >> 16), q[3] = (uint8_t)(v >> 24);
