@@ -1328,6 +1328,10 @@ bool gpu_pre_image(Lane* L, Job& J, BlockJob& b, bool check_version = true, Slot
   if (hr[PARSE_R_END] != (uint32_t)n) return false;  // a parse error: the host parser reports it
   const uint32_t n_ins = hr[PARSE_R_NINS];
   if (n_ins == 0 || n_ins > n) return false;
+  // phase B keeps about 100 bytes per instruction: a stream of one- and two-byte instructions (no real witness:
+  // a node that can be a child is at least an opcode and a CBOR head) would ask for more memory than the witness
+  // justifies; the host builder takes it
+  if ((uint64_t)n_ins * 4 > (uint64_t)n + 256) return false;
   // ---- phase B: tree links, depths, sizes ----
   ParseTree T{};
   T.wit = B.wit, T.n = B.n, T.n_ins = n_ins, T.result = B.result;

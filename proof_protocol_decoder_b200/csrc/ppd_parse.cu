@@ -236,16 +236,18 @@ __global__ void __launch_bounds__(TE_THREADS, 3) tile_exit_kernel(const uint8_t*
 #pragma unroll
     for (int j = 0; j < 4; j++) {
       const uint32_t p = base + o0 + j;
-      const uint32_t op = (W0 >> (8 * j)) & 255u;
-      const uint32_t b1 = j < 3 ? (W0 >> (8 * j + 8)) & 255u : W1 & 255u;
+      const uint32_t op = __byte_perm(W0, 0, 0x4440 + j);               // byte j of W0
+      const uint32_t b1 = j < 3 ? __byte_perm(W0, 0, 0x4440 + j + 1) : (W1 & 255u);  // the byte after it
+      // opcodes 0 1 2 4 5 start with a CBOR head: an unsigned integer (major 0) for a branch mask, else a byte
+      // string (major 2); additional info above 27 is not accepted.  Error code per opcode from a nibble table.
       const bool is_uint_head = op == PPD_OP_BRANCH;
-      const uint32_t e_head = (is_uint_head || op == PPD_OP_CODE) ? PPD_ERR_INVALID_BYTES_FOR_TYPE : PPD_ERR_INVALID_BYTE_VECTOR;
-      const bool head_ok = p + 1 < n && (b1 >> 5) == (is_uint_head ? 0u : 2u) && (b1 & 31u) <= 27u;
+      const uint32_t e_head = (((uint32_t)PPD_ERR_INVALID_BYTE_VECTOR * 0x00100011u + (uint32_t)PPD_ERR_INVALID_BYTES_FOR_TYPE * 0x00010100u) >> (4 * (op & 7u))) & 15u;
+      const bool head_ok = p + 1 < n && (b1 - (is_uint_head ? 0u : 0x40u)) <= 0x1bu;
       uint32_t r = head_ok ? SLOW : (PERR | e_head);
       r = op == PPD_OP_HASH ? (n - (p + 1) < 32 ? (PERR | PPD_ERR_INVALID_BYTES_FOR_TYPE) : p + 33) : r;
       r = op == PPD_OP_EMPTY_ROOT ? p + 1 : r;
       r = op > PPD_OP_EMPTY_ROOT ? (PERR | PPD_ERR_INVALID_OPERATOR) : r;
-      r = p == 0 ? 1u : r;   // byte 0 is the header: "ends" at 1
+      r = p == 0 ? 1u : r;      // byte 0 is the header: "ends" at 1
       r = p >= end ? PERR : r;  // past the end of the stream: never referenced
       v[j] = r;
       any_slow |= r == SLOW;
