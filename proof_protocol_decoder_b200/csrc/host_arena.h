@@ -410,7 +410,7 @@ struct HostArena {
     uint32_t leaf;  // out: the leaf holding the key, or NODE_EMPTY
   };
   void mark_many(MarkItem* items, size_t n, std::vector<uint32_t>& touched) const {
-    constexpr int G = 12;
+    constexpr int G = 32;
     for (size_t g = 0; g < n; g += G) {
       const int m = (int)(n - g < (size_t)G ? n - g : G);
       uint32_t node[G], pos[G];

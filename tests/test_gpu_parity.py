@@ -487,3 +487,28 @@ def test_gpu_parse_random_shapes_verified_against_host_builder(ctx, oracle, seed
         os.environ.pop("PPD_VERIFY_GPU_PARSE", None)
     assert ctx.stats()["witnesses_on_gpu"] == 1
     assert got == oracle.block_decode(blk.flat)
+
+
+def test_full_size_config2_block_bit_exact(ctx, oracle):
+    """BASELINE.json configs[1] at full size (20k touched accounts in a virtual 16^7-account state, 200 txns: a 36 MB
+    witness, 1.05 M instructions, 52 MB of IR): the bench's own block, decoded with production thresholds (GPU witness
+    parser, GPU IR dump), byte for byte against the CPU oracle."""
+    import os
+    import sys
+
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+
+    flat = bench.c2_block(2, 1.0)
+    saved = {k: os.environ.pop(k, None) for k in ("PPD_GPU_PARSE_MIN_BYTES", "PPD_GPU_DUMP_MIN_TOUCHED")}
+    try:
+        got = ctx.block_decode(flat)
+        st = ctx.stats()
+    finally:
+        for k, v in saved.items():
+            if v is not None:
+                os.environ[k] = v
+    assert st["witnesses_on_gpu"] == 1 and st["witness_instructions"] > 1_000_000
+    want = oracle.block_decode(flat)
+    assert len(got) == len(want) > 50_000_000
+    assert got == want
