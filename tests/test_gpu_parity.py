@@ -512,3 +512,46 @@ def test_full_size_config2_block_bit_exact(ctx, oracle):
     want = oracle.block_decode(flat)
     assert len(got) == len(want) > 50_000_000
     assert got == want
+
+
+def test_gpu_parse_leaf_value_lengths(ctx, oracle):
+    """rlp_str(value) of a storage leaf (compact_to_partial_trie.rs:119) as the GPU emitter writes it: the single byte
+    below 0x80 that is its own encoding, short strings, and every width of the long-string header."""
+    import witness_shapes as ws
+
+    for n in (1, 2, 31, 32, 55, 56, 57, 255, 256, 257, 65535, 65536, 70001):
+        for first in (0x05, 0x80):
+            val = bytes([first]) + bytes((7 * i + n) & 255 for i in range(n - 1))
+            storage = ws.leaf(ws.nibs("3" * 64), val)
+            wit = ws.HDR + ws.account_with_storage(ws.nibs("a" * 63), storage) + ws.account(ws.nibs("b" * 63), balance=9) + ws.branch((1 << 10) | (1 << 11))
+            want = oracle.compact_decode(wit)
+            assert ctx.compact_decode(wit) == want, f"value of {n} bytes starting with {first:#x}"
+            assert ctx.stats()["witnesses_on_gpu"] == 1
+
+
+def test_gpu_parse_stream_lengths_around_tile_boundaries(ctx, oracle):
+    """Witness lengths of exactly k tiles (4 KiB), one byte less and one byte more, and a last instruction that ends
+    exactly on a tile boundary: the boundary search's end-of-stream handling."""
+    import witness_shapes as ws
+
+    def witness(code_len):
+        body = bytes((i * 31 + 7) & 255 for i in range(code_len))
+        return (ws.HDR + ws.account_with_code(ws.nibs("1" * 63), ws.code(body), code_len) + ws.account(ws.nibs("2" * 63), balance=3)
+                + ws.branch((1 << 1) | (1 << 2)))
+
+    base = len(witness(1000)) - 1000
+    seen = set()
+    for tiles in (1, 2, 3, 8, 9, 16):
+        for delta in (-2, -1, 0, 1, 2):
+            target = tiles * 4096 + delta
+            code_len = target - base
+            wit = witness(code_len)
+            for fix in range(4):  # the CBOR heads grow with the length: step until the total matches
+                if len(wit) == target:
+                    break
+                code_len += target - len(wit)
+                wit = witness(code_len)
+            seen.add(len(wit) % 4096)
+            assert ctx.compact_decode(wit) == oracle.compact_decode(wit), f"witness of {len(wit)} bytes"
+            assert ctx.stats()["witnesses_on_gpu"] == 1
+    assert {0, 1, 2, 4094, 4095} <= seen
