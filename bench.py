@@ -410,8 +410,8 @@ def run_b200(args, rank, world, local_rank):
             "blocks_per_sec": world * n_blocks / e2e_s_per_step,
             "ms_per_step": 1e3 * e2e_s_per_step,
             "single_block_latency_ms": 1e3 * min(single),
-            "h2d_bytes_per_step": st["h2d_bytes"],
-            "d2h_bytes_per_step": st["d2h_bytes"],
+            "h2d_bytes_per_step": sum_over_ranks(float(st["h2d_bytes"])),
+            "d2h_bytes_per_step": sum_over_ranks(float(st["d2h_bytes"])),
             "note": "ppd_blocks_decode_batch: FlatBlocks (host) -> IrDumps (host); includes witness parse, trie shaping and IR serialisation on the host threads and every host<->device copy",
         },
         "gpu_launches": int(st["kernel_launches"]) * args.steps,
