@@ -12,18 +12,19 @@
 //
 // Phase A: instruction boundaries.  The stream is serial (an instruction's length is known only after
 //   its CBOR heads are read), so every byte position is decoded speculatively: nxt[p] = where the
-//   instruction that would start at p ends.  Per 4 KiB tile the chain p -> nxt[p] is pointer-doubled in
-//   shared memory into exit1[p] = the first position outside the tile that the chain from p reaches.
-//   Tiles are grouped (about sqrt(#tiles) per group); every position of a group's first tile walks
-//   exit1 to the end of the group (exit2); one thread then hops group to group from position 0, the
-//   groups' true entries are walked back down to tile entries, and one warp lane per tile marks the true
+//   instruction that would start at p ends.  Per 4 KiB tile (staged in shared memory) the chain
+//   p -> nxt[p] is pointer-doubled into exit1[p] = the first position outside the tile that the chain
+//   from p reaches; the single-step links are kept too (step1).  Tiles are grouped (about sqrt(#tiles)
+//   per group); every position of a group's first tile walks exit1 to the end of the group (exit2); one
+//   thread then hops group to group from position 0, the groups' true entries are walked back down to
+//   tile entries, and one warp lane per tile follows step1 from the tile's entry and marks the true
 //   instruction starts in a bitmap.  Counts are scanned and the starts scattered into ins_pos[].
 // Phase B: the stack machine in closed form.  Every instruction pushes one entry and pops `pops`;
 //   height_after = inclusive scan of (1 - pops).  The parent of instruction i is the next instruction
 //   whose height_after is not larger (nearest-smaller-value query on a min-pyramid), and i is its
 //   (height_after(i) - height_after(parent))-th popped entry: the k-th set bit of a branch mask, or the
 //   code / storage slot of an account leaf.  Depths and trie membership come from walking the parent
-//   chain (<= 64 steps); eight per-instruction size counters are scanned together.
+//   chain (<= 64 steps); seven per-instruction size counters are scanned together.
 // Phase C: emit.  Every instruction writes its own arena records (node, key, value, hash, child slot,
 //   account record, storage ROOT node); levels are computed by climbing from the leaves with a
 //   pending-children counter per inner node (the last child to arrive continues upwards).
@@ -137,28 +138,6 @@ __device__ __forceinline__ uint32_t decode_ins(const uint8_t* w, uint32_t n, uin
   o.next = pos;
   return 0;
 }
-// where the instruction starting at p ends, or PERR | code
-__device__ __forceinline__ uint32_t decode_next(const uint8_t* w, uint32_t n, uint32_t p) {
-  // the two cases that make up almost every position: not an opcode (97 % of the speculative decodes),
-  // and a hashed-out node (most true instructions)
-  uint32_t op = w[p];
-  if (op > PPD_OP_EMPTY_ROOT) return PERR | PPD_ERR_INVALID_OPERATOR;
-  if (op == PPD_OP_HASH) return n - (p + 1) < 32 ? (PERR | PPD_ERR_INVALID_BYTES_FOR_TYPE) : p + 33;
-  if (op == PPD_OP_EMPTY_ROOT) return p + 1;
-  {
-    // every other opcode starts with a CBOR head: a byte string (an unsigned integer for a branch mask).
-    // Rejecting a wrong head here keeps the long decode below off almost every garbage position; the
-    // code is the one decode_ins reports for the same failure.
-    const uint32_t e_head = (op == PPD_OP_BRANCH || op == PPD_OP_CODE) ? PPD_ERR_INVALID_BYTES_FOR_TYPE : PPD_ERR_INVALID_BYTE_VECTOR;
-    if (p + 1 >= n) return PERR | e_head;
-    const uint32_t b = w[p + 1];
-    if ((b >> 5) != (op == PPD_OP_BRANCH ? 0u : 2u) || (b & 31u) > 27u) return PERR | e_head;
-  }
-  Ins o;
-  uint32_t e = decode_ins(w, n, p, o);
-  return e ? (PERR | e) : o.next;
-}
-
 // key_bytes_to_nibbles (compact_prestate_processing.rs:1338-1390): number of nibbles of a compact key
 __device__ __forceinline__ uint32_t key_nibble_count(const uint8_t* __restrict__ w, uint32_t at, uint32_t len) {
   if (len == 0) return 0;
@@ -187,7 +166,7 @@ __device__ __forceinline__ uint32_t nth_set_bit(uint32_t mask, uint32_t k) {
 // ---------------------------------------------------------------------------------------------
 // Phase A
 // ---------------------------------------------------------------------------------------------
-constexpr int TE_THREADS = 512, TE_PER = TILE / TE_THREADS;
+constexpr int TE_THREADS = 512;
 constexpr uint32_t HALO = 128;  // an instruction's CBOR heads lie within 103 bytes of its opcode
 
 // the tile's bytes (plus halo) staged in shared memory with 128-bit loads; `sb - base` is then indexed by
