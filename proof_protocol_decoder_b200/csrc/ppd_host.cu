@@ -548,6 +548,68 @@ struct FlatReader {
   }
 };
 
+// uint32 -> uint32 map without a heap allocation per entry (open addressing, linear probing).  The txn loop asks for
+// the NK_ROOT node of about a hundred new trie versions per txn; with node-based maps that is one malloc each, on
+// every host thread at once.
+struct FlatMapU32 {
+  static constexpr uint64_t EMPTY_SLOT = ~0ull;  // (key 0xffffffff, value 0xffffffff): values are node ids, never 0xffffffff
+  std::vector<uint64_t> slots;
+  size_t count = 0;
+  static size_t hash(uint32_t k) { return (size_t)(k * 0x9E3779B1u); }
+  void clear() {
+    slots.clear();
+    count = 0;
+  }
+  void rehash(size_t cap) {  // cap: a power of two
+    std::vector<uint64_t> old;
+    old.swap(slots);
+    slots.assign(cap, EMPTY_SLOT);
+    count = 0;
+    for (uint64_t e : old)
+      if (e != EMPTY_SLOT) put((uint32_t)(e >> 32), (uint32_t)e);
+  }
+  void reserve(size_t n) {
+    size_t cap = 64;
+    while (cap < 2 * n) cap <<= 1;
+    if (cap > slots.size()) rehash(cap);
+  }
+  const uint32_t* find(uint32_t key) const {
+    if (slots.empty()) return nullptr;
+    const size_t m = slots.size() - 1;
+    for (size_t i = hash(key) & m;; i = (i + 1) & m) {
+      const uint64_t e = slots[i];
+      if (e == EMPTY_SLOT) return nullptr;
+      if ((uint32_t)(e >> 32) == key) return reinterpret_cast<const uint32_t*>(&slots[i]);  // little-endian: the value is the low word
+    }
+  }
+  void put(uint32_t key, uint32_t val) {
+    if (2 * (count + 1) > slots.size()) rehash(slots.empty() ? 64 : slots.size() * 2);
+    const size_t m = slots.size() - 1;
+    for (size_t i = hash(key) & m;; i = (i + 1) & m) {
+      const uint64_t e = slots[i];
+      if (e == EMPTY_SLOT || (uint32_t)(e >> 32) == key) {
+        count += e == EMPTY_SLOT;
+        slots[i] = ((uint64_t)key << 32) | val;
+        return;
+      }
+    }
+  }
+  template <class Pred>
+  void erase_if(Pred pred) {  // rare (a witness rebuilt from its items): rebuild without the matching entries
+    std::vector<uint64_t> old;
+    old.swap(slots);
+    slots.assign(old.size(), EMPTY_SLOT);
+    count = 0;
+    for (uint64_t e : old)
+      if (e != EMPTY_SLOT && !pred((uint32_t)(e >> 32), (uint32_t)e)) put((uint32_t)(e >> 32), (uint32_t)e);
+  }
+  template <class F>
+  void for_each(F f) const {
+    for (uint64_t e : slots)
+      if (e != EMPTY_SLOT) f((uint32_t)(e >> 32), (uint32_t)e);
+  }
+};
+
 struct IrPlan {
   uint64_t txn_before = 0, gas_before = 0, gas_after = 0;
   bool has_signed_txn = false;
@@ -583,7 +645,7 @@ struct BlockJob {
   };
   std::vector<PreAccount> pre_accounts;
   std::unordered_map<H256, uint32_t, H256Hasher> pre_with_storage;  // accounts whose storage root != EMPTY_TRIE_HASH -> record
-  std::unordered_map<uint32_t, uint32_t> root_of;                   // trie root node -> its NK_ROOT node
+  FlatMapU32 root_of;                                               // trie root node -> its NK_ROOT node
   std::unordered_map<int32_t, uint32_t> storage_root_of_instr;      // account leaf instruction -> root of its witnessed storage trie
   bool have_empty_form = false;                                     // a witnessed storage trie whose root is EMPTY_TRIE_HASH
   bool pre_image_on_gpu = false;                                    // gpu_pre_image built the pre-image tries
@@ -1063,10 +1125,9 @@ struct ArenaMark {
 };
 
 uint32_t root_node_for(Job& J, BlockJob& b, uint32_t trie_root) {
-  auto f = b.root_of.find(trie_root);
-  if (f != b.root_of.end()) return f->second;
+  if (const uint32_t* f = b.root_of.find(trie_root)) return *f;
   uint32_t r = J.A.new_root(trie_root);
-  b.root_of[trie_root] = r;
+  b.root_of.put(trie_root, r);
   return r;
 }
 
@@ -1154,10 +1215,9 @@ uint32_t build_witness_trie(Job& J, BlockJob& b, int32_t root_idx, bool is_stora
       b.pre_with_storage.erase(b.pre_accounts[i].haddr);
     }
     b.pre_accounts.resize(n_pre_accounts);
-    for (auto it = b.root_of.begin(); it != b.root_of.end();)
-      it = (it->second >= mark.nodes || (is_hash_id(it->first) ? it->first - HASH_ID_BASE >= mark.hashes / 32 : (it->first != NODE_EMPTY && it->first >= mark.nodes)))
-               ? b.root_of.erase(it)
-               : std::next(it);
+    b.root_of.erase_if([&](uint32_t root, uint32_t root_node) {
+      return root_node >= mark.nodes || (is_hash_id(root) ? root - HASH_ID_BASE >= mark.hashes / 32 : (root != NODE_EMPTY && root >= mark.nodes));
+    });
   }
   std::vector<TrieItem> items;
   WitnessTrie wt{J, b, is_storage};
@@ -1486,7 +1546,7 @@ bool gpu_pre_image(Lane* L, Job& J, BlockJob& b, bool check_version = true, Slot
     b.pre_accounts.push_back({haddr, (uint32_t)a, nonempty});
     if (nonempty) {
       b.pre_with_storage[haddr] = (uint32_t)a;
-      b.root_of[al[5 * a + 1]] = al[5 * a + 2];
+      b.root_of.put(al[5 * a + 1], al[5 * a + 2]);
     }
   }
   lap("p:tables");
@@ -1581,9 +1641,9 @@ void verify_gpu_pre_image(Lane* L, Job& J, BlockJob& b) {
     auto f = b.pre_code.find(c2.first);
     if (f == b.pre_code.end() || f->second.p != c2.second.p || f->second.n != c2.second.n) bad("code map entry");
   }
-  for (auto& r : b.root_of) {
-    if (r.second >= J.A.nodes.size() || J.A.kind(r.second) != NK_ROOT || J.A.nodes[r.second].a1 != r.first) bad("root_of entry");
-  }
+  b.root_of.for_each([&](uint32_t root, uint32_t root_node) {
+    if (root_node >= J.A.nodes.size() || J.A.kind(root_node) != NK_ROOT || J.A.nodes[root_node].a1 != root) bad("root_of entry");
+  });
 }
 
 struct PhaseTimer {
@@ -1681,7 +1741,9 @@ void shape_block(Job& J, BlockJob& b) {
   if (!b.pre_image_on_gpu) build_pre_image(J, b);
   sec.stop(0);
   const uint32_t initial_state = b.state_root;
-  const auto initial_storage = b.storage;
+  // the storage tries before the first txn: only the dummy IRs of a block with at most one txn read them (decoding.rs:304-347)
+  std::unordered_map<H256, uint32_t, H256Hasher> initial_storage;
+  if (b.txns.size() <= 1) initial_storage = b.storage;
   uint32_t state = b.state_root, txn_trie = NODE_EMPTY, receipt_trie = NODE_EMPTY;
   uint64_t txn_before = 0, gas_before = 0, gas_after = 0;
 
@@ -1736,6 +1798,7 @@ void shape_block(Job& J, BlockJob& b) {
     }
     marks.push_back({txn_trie, tk, tk_len, NODE_EMPTY});
     marks.push_back({receipt_trie, tk, tk_len, NODE_EMPTY});
+    p.storage_subs.reserve(tx.traces.size());
     bool short_haddr = false;
     for (size_t i = 0; i < tx.traces.size(); i++) {
       TraceV& tr = tx.traces[i];
@@ -1758,6 +1821,7 @@ void shape_block(Job& J, BlockJob& b) {
       for (uint32_t k = 0; k < tr.n_writes; k++) marks.push_back({sroot, key_from_digest(J, J.kh.digest[tr.m_writes_full + k]), 64, NODE_EMPTY});
       p.storage_subs.push_back({haddr, sroot});
     }
+    p.touched.reserve(marks.size() * 10);
     A.mark_many(marks.data(), marks.size(), p.touched);
     if (short_haddr) fail(PPD_PANIC_H256_FROM_SLICE, "H256::from_slice on a short bytes_be()");
     for (size_t i = 0; i < tx.traces.size(); i++) haddr_leaf[i] = marks[i].leaf;
@@ -1777,10 +1841,17 @@ void shape_block(Job& J, BlockJob& b) {
           uint32_t r = A.remove(f->second, koff, 64, 0);
           if (r != UNCHANGED) f->second = r;
         } else {
-          std::vector<uint8_t> enc;
-          rlp_str(enc, val + 32 - sig, sig);
-          uint32_t voff = A.add_val(enc.data(), (uint32_t)enc.size());
-          f->second = A.insert(f->second, koff, 64, 0, HostArena::Payload{false, voff, (uint32_t)enc.size()});
+          uint8_t enc[34];  // rlp(U256): the byte itself below 0x80, else 0x80 + length and the significant bytes
+          uint32_t el = 0;
+          if (sig == 1 && val[31] < 0x80) {
+            enc[el++] = val[31];
+          } else {
+            enc[el++] = (uint8_t)(0x80 + sig);
+            memcpy(enc + el, val + 32 - sig, sig);
+            el += sig;
+          }
+          uint32_t voff = A.add_val(enc, el);
+          f->second = A.insert(f->second, koff, 64, 0, HostArena::Payload{false, voff, el});
         }
       }
     }
