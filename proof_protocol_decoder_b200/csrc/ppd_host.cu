@@ -610,6 +610,76 @@ struct FlatMapU32 {
   }
 };
 
+// H256 -> uint32 map with inline keys (open addressing, linear probing, tombstones).  Keys are Keccak digests, so
+// their first eight bytes are the hash.  find() / end() / insert() / erase() / operator[] follow std::unordered_map
+// closely enough for the call sites; iteration goes through for_each().
+struct H256Map {
+  struct Entry {
+    H256 first;
+    uint32_t second;
+    uint32_t state;  // 0 empty, 1 full, 2 deleted
+  };
+  std::vector<Entry> slots;
+  size_t n_full = 0, n_used = 0;  // n_used counts deleted slots too
+  static size_t hash(const H256& k) {
+    uint64_t h;
+    memcpy(&h, k.b, 8);
+    return (size_t)(h * 0x9E3779B97F4A7C15ull >> 17);
+  }
+  size_t size() const { return n_full; }
+  Entry* end() const { return nullptr; }
+  void rehash(size_t cap) {
+    std::vector<Entry> old;
+    old.swap(slots);
+    slots.assign(cap, Entry{H256{}, 0, 0});
+    n_full = n_used = 0;
+    for (const Entry& e : old)
+      if (e.state == 1) insert({e.first, e.second});
+  }
+  void reserve(size_t n) {
+    size_t cap = 64;
+    while (cap < 2 * n) cap <<= 1;
+    if (cap > slots.size()) rehash(cap);
+  }
+  Entry* find(const H256& k) const {
+    if (slots.empty()) return nullptr;
+    const size_t m = slots.size() - 1;
+    for (size_t i = hash(k) & m;; i = (i + 1) & m) {
+      const Entry& e = slots[i];
+      if (e.state == 0) return nullptr;
+      if (e.state == 1 && e.first == k) return const_cast<Entry*>(&e);
+    }
+  }
+  size_t count(const H256& k) const { return find(k) ? 1 : 0; }
+  std::pair<Entry*, bool> insert(const std::pair<H256, uint32_t>& kv) {
+    if (Entry* f = find(kv.first)) return {f, false};
+    if (2 * (n_used + 1) > slots.size()) rehash(slots.empty() ? 64 : (n_full * 4 > slots.size() ? slots.size() * 2 : slots.size()));
+    const size_t m = slots.size() - 1;
+    for (size_t i = hash(kv.first) & m;; i = (i + 1) & m) {
+      Entry& e = slots[i];
+      if (e.state != 1) {
+        n_used += e.state == 0;
+        e.first = kv.first, e.second = kv.second, e.state = 1;
+        n_full++;
+        return {&e, true};
+      }
+    }
+  }
+  uint32_t& operator[](const H256& k) { return insert({k, 0u}).first->second; }
+  size_t erase(const H256& k) {
+    Entry* f = find(k);
+    if (!f) return 0;
+    f->state = 2;
+    n_full--;
+    return 1;
+  }
+  template <class F>
+  void for_each(F f) const {
+    for (const Entry& e : slots)
+      if (e.state == 1) f(e);
+  }
+};
+
 struct IrPlan {
   uint64_t txn_before = 0, gas_before = 0, gas_after = 0;
   bool has_signed_txn = false;
@@ -637,14 +707,14 @@ struct BlockJob {
   std::map<H256, Span> pre_code;        // WitnessOutput.code
   // tries
   uint32_t state_root = NODE_EMPTY;
-  std::unordered_map<H256, uint32_t, H256Hasher> storage;  // hashed address -> root node
+  H256Map storage;  // hashed address -> root node
   struct PreAccount {
     H256 haddr;
     uint32_t rec;
     bool storage_nonempty;
   };
   std::vector<PreAccount> pre_accounts;
-  std::unordered_map<H256, uint32_t, H256Hasher> pre_with_storage;  // accounts whose storage root != EMPTY_TRIE_HASH -> record
+  H256Map pre_with_storage;  // accounts whose storage root != EMPTY_TRIE_HASH -> record
   FlatMapU32 root_of;                                               // trie root node -> its NK_ROOT node
   std::unordered_map<int32_t, uint32_t> storage_root_of_instr;      // account leaf instruction -> root of its witnessed storage trie
   bool have_empty_form = false;                                     // a witnessed storage trie whose root is EMPTY_TRIE_HASH
@@ -1622,11 +1692,11 @@ void verify_gpu_pre_image(Lane* L, Job& J, BlockJob& b) {
   TrieCmp cmp{J.A, J2->A};
   if (!cmp.eq(b.state_root, b2.state_root)) bad("state trie: " + cmp.why);
   if (b.storage.size() != b2.storage.size()) bad("storage map sizes " + std::to_string(b.storage.size()) + " / " + std::to_string(b2.storage.size()));
-  for (auto& s2 : b2.storage) {
+  b2.storage.for_each([&](const H256Map::Entry& s2) {
     auto f = b.storage.find(s2.first);
     if (f == b.storage.end()) bad("storage trie missing for an account");
     if (!cmp.eq(f->second, s2.second)) bad("storage trie: " + cmp.why);
-  }
+  });
   if (b.pre_accounts.size() != b2.pre_accounts.size()) bad("pre-image account counts");
   for (size_t i = 0; i < b.pre_accounts.size(); i++) {
     const auto &p = b.pre_accounts[i], &q = b2.pre_accounts[i];
@@ -1634,8 +1704,9 @@ void verify_gpu_pre_image(Lane* L, Job& J, BlockJob& b) {
       bad("pre-image account " + std::to_string(i));
   }
   if (b.pre_with_storage.size() != b2.pre_with_storage.size()) bad("accounts with storage");
-  for (auto& s2 : b2.pre_with_storage)
+  b2.pre_with_storage.for_each([&](const H256Map::Entry& s2) {
     if (!b.pre_with_storage.count(s2.first)) bad("account with storage missing");
+  });
   if (b.pre_code.size() != b2.pre_code.size()) bad("code map sizes");
   for (auto& c2 : b2.pre_code) {
     auto f = b.pre_code.find(c2.first);
@@ -1700,7 +1771,7 @@ void u256_add(uint8_t a[32], const uint8_t b[32]) {
 }
 
 void dummy_plan(Job& J, BlockJob& b, IrPlan& p, uint32_t state_root, uint32_t txn_root, uint32_t receipt_root,
-                const std::unordered_map<H256, uint32_t, H256Hasher>& storage, uint64_t txn_number, uint64_t gas_used) {
+                const H256Map& storage, uint64_t txn_number, uint64_t gas_used) {
   // create_dummy_gen_input (decoding.rs:484-549): every trie cut with the key 0_u64, which converts
   // to zero nibbles: the root is the only marked node
   p.txn_before = txn_number;
@@ -1709,10 +1780,10 @@ void dummy_plan(Job& J, BlockJob& b, IrPlan& p, uint32_t state_root, uint32_t tx
   if (state_root != NODE_EMPTY) p.touched.push_back(state_root);
   if (txn_root != NODE_EMPTY) p.touched.push_back(txn_root);
   if (receipt_root != NODE_EMPTY) p.touched.push_back(receipt_root);
-  for (const auto& s : storage) {
+  storage.for_each([&](const H256Map::Entry& s) {
     p.storage_subs.push_back({s.first, s.second});
     if (s.second != NODE_EMPTY) p.touched.push_back(s.second);
-  }
+  });
   p.root_state = root_node_for(J, b, state_root);
   p.root_txn = root_node_for(J, b, txn_root);
   p.root_receipt = root_node_for(J, b, receipt_root);
@@ -1742,7 +1813,7 @@ void shape_block(Job& J, BlockJob& b) {
   sec.stop(0);
   const uint32_t initial_state = b.state_root;
   // the storage tries before the first txn: only the dummy IRs of a block with at most one txn read them (decoding.rs:304-347)
-  std::unordered_map<H256, uint32_t, H256Hasher> initial_storage;
+  H256Map initial_storage;
   if (b.txns.size() <= 1) initial_storage = b.storage;
   uint32_t state = b.state_root, txn_trie = NODE_EMPTY, receipt_trie = NODE_EMPTY;
   uint64_t txn_before = 0, gas_before = 0, gas_after = 0;
@@ -3047,7 +3118,7 @@ int ppd_compact_decode(ppd_ctx* c, const uint8_t* witness, size_t len, uint8_t**
     }
     uint32_t sr = root_node_for(J, b, b.state_root);
     std::map<H256, uint32_t> storage_roots;
-    for (auto& s : b.storage) storage_roots[s.first] = root_node_for(J, b, s.second);
+    b.storage.for_each([&](const H256Map::Entry& s) { storage_roots[s.first] = root_node_for(J, b, s.second); });
     sweep(L, J);
     c->stats = L->stats;
     Out o;
