@@ -48,6 +48,7 @@ typedef struct ppd_stats {
   uint64_t witness_bytes;         /* bytes of those witnesses */
   double parse_gpu_ms;            /* device time of their parse / arena kernels (CUDA events) */
   uint64_t level_launches;        /* launches of the level-hashing kernel (one per level per block) */
+  uint64_t marks_on_gpu;          /* create_trie_subset marking walks (one per accessed key per txn) done by the device */
 } ppd_stats;
 
 int ppd_ctx_create(int device, ppd_ctx** out);

@@ -688,6 +688,7 @@ struct IrPlan {
   uint32_t state_sub = NODE_EMPTY, txn_sub = NODE_EMPTY, receipt_sub = NODE_EMPTY;  // roots of the tries the subsets are cut from
   std::vector<std::pair<H256, uint32_t>> storage_subs;
   std::vector<uint32_t> touched;
+  std::vector<HostArena::MarkItem> items;  // marking walks left to the device (launch_mark_walk); materialize_touched() runs them on the host
   uint32_t root_state = 0, root_txn = 0, root_receipt = 0;  // NK_ROOT nodes
   std::map<H256, Span> code;
 };
@@ -715,6 +716,7 @@ struct BlockJob {
   };
   std::vector<PreAccount> pre_accounts;
   H256Map pre_with_storage;  // accounts whose storage root != EMPTY_TRIE_HASH -> record
+  H256Map acct_rec;          // hashed address -> the account's current record (what state.get() + rlp::decode gives, decoding.rs:251-254)
   FlatMapU32 root_of;                                               // trie root node -> its NK_ROOT node
   std::unordered_map<int32_t, uint32_t> storage_root_of_instr;      // account leaf instruction -> root of its witnessed storage trie
   bool have_empty_form = false;                                     // a witnessed storage trie whose root is EMPTY_TRIE_HASH
@@ -901,6 +903,8 @@ struct Job {
   PVec<uint8_t> wit_stage;  // page-locked staging of a pageable witness
   std::vector<HostArena::MarkItem> mark_items;  // scratch of the txn loop
   std::vector<HostArena::BatchItem> batch_items;
+  std::vector<uint32_t> haddr_keys, haddr_leaves;
+  bool device_marks = false;  // this block's subset marking walks run on the device (decode_one decides)
   PVec<H256> code_digest;
   std::vector<uint32_t> stamp;
   uint32_t serial = 0;
@@ -918,6 +922,7 @@ struct Job {
   void reset(size_t n_blocks) {
     dev = Resident{};
     pools_on_host = true;
+    device_marks = false;
     A.clear();
     kh.reset();
     blocks.clear();
@@ -1260,6 +1265,7 @@ uint32_t make_account_record(Job& J, BlockJob& b, int32_t idx, const uint8_t* pa
   }
   if (has_trie) b.storage[haddr] = sroot;
   b.pre_accounts.push_back({haddr, r, nonempty});
+  if (J.device_marks) b.acct_rec[haddr] = r;
   if (nonempty) b.pre_with_storage[haddr] = r;
   return r;
 }
@@ -1283,6 +1289,7 @@ uint32_t build_witness_trie(Job& J, BlockJob& b, int32_t root_idx, bool is_stora
     for (size_t i = n_pre_accounts; i < b.pre_accounts.size(); i++) {
       b.storage.erase(b.pre_accounts[i].haddr);
       b.pre_with_storage.erase(b.pre_accounts[i].haddr);
+      b.acct_rec.erase(b.pre_accounts[i].haddr);
     }
     b.pre_accounts.resize(n_pre_accounts);
     b.root_of.erase_if([&](uint32_t root, uint32_t root_node) {
@@ -1590,6 +1597,7 @@ bool gpu_pre_image(Lane* L, Job& J, BlockJob& b, bool check_version = true, Slot
   b.wit.version = w[0];
   b.state_root = hr[PARSE_R_ROOT_ID];
   b.storage.reserve(n_acct), b.pre_accounts.reserve(n_acct), b.root_of.reserve(2 * n_acct + 1024);
+  if (J.device_marks) b.acct_rec.reserve(n_acct + n_acct / 4);
   b.have_empty_form = false, b.empty_form = NODE_EMPTY;
   const uint32_t* al = J.acct_list.data();
   for (size_t a = 0; a < n_acct; a++)
@@ -1614,6 +1622,7 @@ bool gpu_pre_image(Lane* L, Job& J, BlockJob& b, bool check_version = true, Slot
     }
     if (has_trie) b.storage[haddr] = sroot;
     b.pre_accounts.push_back({haddr, (uint32_t)a, nonempty});
+    if (J.device_marks) b.acct_rec.insert({haddr, (uint32_t)a});
     if (nonempty) {
       b.pre_with_storage[haddr] = (uint32_t)a;
       b.root_of.put(al[5 * a + 1], al[5 * a + 2]);
@@ -1857,10 +1866,10 @@ void shape_block(Job& J, BlockJob& b) {
     uint32_t tk_len = 0;
     uint32_t tk = txn_index_key(J, ti, tk_len);
     p.state_sub = state, p.txn_sub = txn_trie, p.receipt_sub = receipt_trie;
-    // every key this txn touches is marked in one interleaved pass (HostArena::mark_many).  The marking walk of an
-    // address also finds its leaf in the pre-txn state: the state writes below read the account from it (other
-    // addresses' writes in between only path-copy branches; the leaf's payload stays).
-    std::vector<uint32_t> haddr_key(tx.traces.size()), haddr_leaf(tx.traces.size());
+    // every key this txn touches: marked on the device after the sweep's upload (mark_walk_kernel), or here in one
+    // interleaved pass (HostArena::mark_many) when the block is dumped by the host or is being redone for its error
+    std::vector<uint32_t>&haddr_key = J.haddr_keys, &haddr_leaf = J.haddr_leaves;
+    haddr_key.resize(tx.traces.size()), haddr_leaf.resize(tx.traces.size());
     std::vector<HostArena::MarkItem>& marks = J.mark_items;
     marks.clear();
     for (size_t i = 0; i < tx.traces.size(); i++) {
@@ -1892,10 +1901,16 @@ void shape_block(Job& J, BlockJob& b) {
       for (uint32_t k = 0; k < tr.n_writes; k++) marks.push_back({sroot, key_from_digest(J, J.kh.digest[tr.m_writes_full + k]), 64, NODE_EMPTY});
       p.storage_subs.push_back({haddr, sroot});
     }
-    p.touched.reserve(marks.size() * 10);
-    A.mark_many(marks.data(), marks.size(), p.touched);
+    if (J.device_marks) {
+      p.items.assign(marks.begin(), marks.end());  // walked by mark_walk_kernel once the arena is resident
+    } else {
+      p.touched.reserve(marks.size() * 10);
+      A.mark_many(marks.data(), marks.size(), p.touched);
+      // the marking walk of an address also finds its leaf in the pre-txn state: the state writes below read the account
+      // from it (other addresses' writes in between only path-copy branches; the leaf's payload stays)
+      for (size_t i = 0; i < tx.traces.size() && i < marks.size(); i++) haddr_leaf[i] = marks[i].leaf;
+    }
     if (short_haddr) fail(PPD_PANIC_H256_FROM_SLICE, "H256::from_slice on a short bytes_be()");
-    for (size_t i = 0; i < tx.traces.size(); i++) haddr_leaf[i] = marks[i].leaf;
     gas_after += tx.gas_used;
     sec.stop(2);
 
@@ -1935,16 +1950,21 @@ void shape_block(Job& J, BlockJob& b) {
       bool code_change = tr.flags & (PPD_TR_CODE_READ | PPD_TR_CODE_WRITE);
       if (!((tr.flags & (PPD_TR_BALANCE | PPD_TR_NONCE)) || storage_change || code_change)) continue;
       const H256& haddr = J.kh.digest[tr.m_addr];
-      uint32_t leaf = haddr_leaf[i];
+      // the account as state.get() would give it (decoding.rs:251-254): the leaf the host's marking walk found, or, when
+      // the marking walks are left to the device, the record tracked per hashed address
       AccountRec rec;
-      if (leaf == NODE_EMPTY) {
+      const H256Map::Entry* cur = J.device_marks ? b.acct_rec.find(haddr) : nullptr;
+      const uint32_t leaf = J.device_marks ? NODE_EMPTY : haddr_leaf[i];
+      if (cur) {
+        rec = A.accounts[cur->second];
+      } else if (leaf != NODE_EMPTY) {
+        if (A.kind(leaf) != NK_LEAF_ACCOUNT) fail(PPD_ERR_ACCOUNT_DECODE, "state leaf is not an account");
+        rec = A.accounts[A.nodes[leaf].a1];
+      } else {
         memset(&rec, 0, sizeof rec);
         memcpy(rec.storage_root, EMPTY_TRIE_HASH, 32);
         memcpy(rec.code_hash, EMPTY_CODE_HASH, 32);
         rec.storage_src = NODE_EMPTY;
-      } else {
-        if (A.kind(leaf) != NK_LEAF_ACCOUNT) fail(PPD_ERR_ACCOUNT_DECODE, "state leaf is not an account");
-        rec = A.accounts[A.nodes[leaf].a1];
       }
       if (storage_change) {
         auto f = b.storage.find(haddr);
@@ -1957,6 +1977,7 @@ void shape_block(Job& J, BlockJob& b) {
       if (tr.flags & PPD_TR_CODE_WRITE) memcpy(rec.code_hash, J.kh.digest[tr.m_code].b, 32);
       uint32_t r = (uint32_t)A.accounts.size();
       A.accounts.push_back(rec);
+      if (J.device_marks) b.acct_rec[haddr] = r;
       batch.push_back({haddr_key[i], 64, HostArena::Payload{true, r, 0}});
     }
     // the txn's account writes in one descent (addresses are distinct: TxnInfo.traces is a map, trace_protocol.rs:118)
@@ -1969,6 +1990,7 @@ void shape_block(Job& J, BlockJob& b) {
       if (!(tx.traces[i].flags & PPD_TR_SELF_DESTRUCTED)) continue;
       const H256& haddr = J.kh.digest[tx.traces[i].m_addr];
       if (!b.storage.erase(haddr)) fail(PPD_ERR_MISSING_ACCOUNT_STORAGE_TRIE, "self-destructed account has no storage trie");
+      if (J.device_marks) b.acct_rec.erase(haddr);
       uint32_t r = A.remove(state, haddr_key[i], 64, 0);
       if (r != UNCHANGED) state = r;
     }
@@ -2380,7 +2402,16 @@ void dump_subset(const Job& J, const Stamp& st, Out& o, uint32_t node) {
   }
 }
 
+// the marking walks of an IR that were left to the device, run on the host instead (host serialisation of the IR)
+void materialize_touched(const Job& J, IrPlan& p) {
+  if (p.items.empty()) return;
+  p.touched.reserve(p.touched.size() + p.items.size() * 10);
+  J.A.mark_many(p.items.data(), p.items.size(), p.touched);
+  p.items.clear();
+}
+
 void dump_ir(const Job& J, const BlockJob& b, IrPlan& p, Stamp& st, Out& o) {
+  materialize_touched(J, p);
   st.serial++;
   for (uint32_t t : p.touched)
     if (!is_hash_id(t)) st.v[t] = st.serial;
@@ -2470,6 +2501,9 @@ void dump_blocks(Job& J, uint8_t** outs, size_t* out_lens, unsigned max_workers)
     uint32_t block, ir;
   };
   std::vector<Item> items;
+  for (BlockJob& b : J.blocks)
+    if (b.status == PPD_OK)
+      for (IrPlan& p : b.irs) materialize_touched(J, p);  // (throws what the reference's marking pass reports)
   for (size_t i = 0; i < J.blocks.size(); i++) {
     outs[i] = nullptr, out_lens[i] = 0;
     if (J.blocks[i].status != PPD_OK) continue;
@@ -2644,27 +2678,28 @@ bool gpu_dump_enabled() {
 #endif
 }
 
-bool gpu_dump_block(ppd_ctx* c, Lane* L, Job& J, uint8_t** out, size_t* out_len) {
+enum { DUMP_ON_HOST = 0, DUMP_DONE = 1, DUMP_REDO_HOST_MARKS = 2 };
+int gpu_dump_block(ppd_ctx* c, Lane* L, Job& J, uint8_t** out, size_t* out_len) {
 #ifdef PPD_HOSTPROF
-  return false;
+  return DUMP_ON_HOST;
 #else
   const bool disabled = !gpu_dump_enabled();
   static const bool verify = getenv("PPD_VERIFY_GPU_DUMP") != nullptr;
   BlockJob& b = J.blocks[0];
   const uint32_t n_ir = (uint32_t)b.irs.size();
-  if (disabled || !L->has_last || n_ir == 0 || J.A.nodes.size() == 0) return false;
+  if (disabled || !L->has_last || n_ir == 0 || J.A.nodes.size() == 0) return DUMP_ON_HOST;
   PhaseTimer pt;
   // ---- plan ----
   LitPool lit;
   std::vector<uint32_t> seg_a, seg_b, seg_begin(1, 0), touched_begin(1, 0), lit_at;  // lit_at[seg]: offset into lit.b
-  size_t n_touched = 0;
-  for (IrPlan& p : b.irs) n_touched += p.touched.size();
+  size_t n_touched = 0, n_items = 0;
+  for (IrPlan& p : b.irs) n_touched += p.touched.size() + MARK_SLOTS * p.items.size(), n_items += p.items.size();
   {
     // the two dump kernels cost two read-backs and about a millisecond of launch + CTA latency whatever the size;
     // a small block (config 1: a few thousand touched nodes) is serialised faster by the host threads
     const char* e = getenv("PPD_GPU_DUMP_MIN_TOUCHED");
     const size_t min_touched = e ? (size_t)atoll(e) : 32768;
-    if (n_touched < min_touched) return false;
+    if (n_touched - (MARK_SLOTS - 8) * n_items < min_touched) return DUMP_ON_HOST;  // a marking walk touches about eight nodes
   }
   auto add_lit_from = [&](size_t from) {  // the bytes appended to lit.b since `from` become (part of) a literal segment
     uint32_t len = (uint32_t)(lit.b.size() - from);
@@ -2709,23 +2744,33 @@ bool gpu_dump_block(ppd_ctx* c, Lane* L, Job& J, uint8_t** out, size_t* out_len)
     lit.span(b.b_hashes);
     add_lit_from(from);
     seg_begin.push_back((uint32_t)seg_a.size());
-    touched_begin.push_back((uint32_t)(touched_begin.back() + p.touched.size()));
+    touched_begin.push_back((uint32_t)(touched_begin.back() + p.touched.size() + MARK_SLOTS * p.items.size()));
   }
   const uint32_t n_seg = (uint32_t)seg_a.size();
   // one pinned buffer / one device buffer: [touched | touched_begin | seg_a | seg_b | seg_begin | ir_base(u64) |
   //                                        seg_off | ir_size | ir_flag | ir_nuniq | u_node | u_size | u_off]
   auto al = [](size_t x) { return (x + 3) & ~(size_t)3; };  // keep the u64 array 8-byte aligned (counts in u32 words)
+  // (items4: the marking walks left to the device, 4 words each; mark_flags: [n_ir + 1] written by mark_walk_kernel)
   const size_t o_touched = 0, o_tb = al(o_touched + n_touched), o_sa = al(o_tb + n_ir + 1), o_sb = al(o_sa + n_seg), o_sg = al(o_sb + n_seg),
-               o_base = al(o_sg + n_ir + 1), o_in_end = al(o_base + 2 * (size_t)n_ir);
-  const size_t o_soff = o_in_end, o_isz = al(o_soff + n_seg), o_ifl = al(o_isz + n_ir), o_inu = al(o_ifl + n_ir), o_un = al(o_inu + n_ir),
-               o_us = al(o_un + n_touched), o_uo = al(o_us + n_touched), o_end = al(o_uo + n_touched);
+               o_it = al(o_sg + n_ir + 1), o_base = al(o_it + 4 * n_items), o_in_end = al(o_base + 2 * (size_t)n_ir);
+  const size_t o_soff = o_in_end, o_isz = al(o_soff + n_seg), o_ifl = al(o_isz + n_ir), o_mf = al(o_ifl + n_ir), o_inu = al(o_mf + n_ir + 1),
+               o_un = al(o_inu + n_ir), o_us = al(o_un + n_touched), o_uo = al(o_us + n_touched), o_end = al(o_uo + n_touched);
   J.plan.resize(o_end);
   uint32_t* h = J.plan.data();
   {
     uint32_t* t = h + o_touched;
-    for (IrPlan& p : b.irs) {
+    uint32_t* it4 = h + o_it;
+    for (uint32_t ir = 0; ir < n_ir; ir++) {
+      IrPlan& p = b.irs[ir];
       if (!p.touched.empty()) memcpy(t, p.touched.data(), 4 * p.touched.size());
       t += p.touched.size();
+      if (!p.items.empty()) {
+        memset(t, 0xff, 4 * MARK_SLOTS * p.items.size());  // NODE_EMPTY: slots a walk does not reach
+        for (const HostArena::MarkItem& m : p.items) {
+          it4[0] = m.root, it4[1] = m.koff, it4[2] = (m.klen & 0xffu) | (ir << 8), it4[3] = (uint32_t)(t - (h + o_touched));
+          it4 += 4, t += MARK_SLOTS;
+        }
+      }
     }
   }
   memcpy(h + o_tb, touched_begin.data(), 4 * (n_ir + 1));
@@ -2741,6 +2786,12 @@ bool gpu_dump_block(ppd_ctx* c, Lane* L, Job& J, uint8_t** out, size_t* out_len)
   P.seg_off = d + o_soff, P.ir_size = d + o_isz, P.ir_flag = d + o_ifl, P.ir_nuniq = d + o_inu;
   P.u_node = d + o_un, P.u_size = d + o_us, P.u_off = d + o_uo;
   pt.lap("  d:plan");
+  if (n_items) {
+    CUDA_OK(cudaMemsetAsync(d + o_mf, 0, 4 * (n_ir + 1), L->st));
+    launch_mark_walk(L->last_view, d + o_it, (uint32_t)n_items, n_ir, d + o_touched, d + o_mf, L->st);
+    L->stats.kernel_launches += 1;
+    L->stats.marks_on_gpu += n_items;
+  }
   launch_ir_size(L->last_view, P, n_ir, L->st);
   CUDA_OK(cudaGetLastError());
   CUDA_OK(cudaMemcpyAsync(h + o_soff, d + o_soff, 4 * (o_inu - o_soff), cudaMemcpyDeviceToHost, L->st));  // seg_off, ir_size, ir_flag
@@ -2748,7 +2799,15 @@ bool gpu_dump_block(ppd_ctx* c, Lane* L, Job& J, uint8_t** out, size_t* out_len)
   L->stats.h2d_bytes += 4.0 * o_base, L->stats.d2h_bytes += 4.0 * (o_inu - o_soff), L->stats.kernel_launches += 1;
   pt.lap("  d:size");
   // ---- IRs the device could not lay out: host serialisation ----
-  const uint32_t *seg_off = h + o_soff, *ir_size = h + o_isz, *ir_flag = h + o_ifl;
+  const uint32_t *seg_off = h + o_soff, *ir_size = h + o_isz;
+  uint32_t* ir_flag = h + o_ifl;
+  if (n_items) {
+    const uint32_t* mark_flags = h + o_mf;
+    // a key ran into a hashed-out node: the reference reports MissingKeysCreatingSubPartialTrie, possibly after other
+    // errors of earlier txns; the block is redone with the host's marking pass, which keeps the reference's order
+    if (mark_flags[n_ir]) return DUMP_REDO_HOST_MARKS;
+    for (uint32_t i = 0; i < n_ir; i++) ir_flag[i] |= mark_flags[i];  // a walk longer than its slots: the host serialises that IR
+  }
   std::vector<Out> host_parts(n_ir);
   Stamp st;
   uint64_t* ir_base = reinterpret_cast<uint64_t*>(h + o_base);
@@ -2845,43 +2904,80 @@ bool gpu_dump_block(ppd_ctx* c, Lane* L, Job& J, uint8_t** out, size_t* out_len)
   } else {
     *out = o.give(out_len);
   }
-  return true;
+  return DUMP_DONE;
 #endif
 }
 
 // One block on one lane: parse, key hashes, shaping, sweep, dump.  A failure that is the block's own
 // (bad input, a reference panic site) is reported through *status; a CUDA failure is thrown.
+// Whether the block's subset marking walks are left to the device: only when the device also serialises the IRs (same
+// threshold as gpu_dump_block; a marking walk touches about eight nodes).
+bool device_marks_wanted(const BlockJob& b) {
+  // Opt-in (PPD_DEVICE_MARKS): measured on the 16-core box the host's own marking pass is the better choice today,
+  // because its interleaved, prefetched walks are what brings the paths into the cache that the inserts of the same
+  // txn then copy; without it the inserts take those misses one by one (state writes 7 -> 28 ms per block, 410 -> 296
+  // blocks/s).  It pays once the inserts themselves run on the device.
+  if (!gpu_dump_enabled() || !getenv("PPD_DEVICE_MARKS")) return false;
+  size_t n_marks = 0;
+  for (const TxnV& tx : b.txns) {
+    n_marks += 2;
+    for (const TraceV& tr : tx.traces) n_marks += 1 + tr.n_reads + tr.n_writes;
+  }
+  const char* e = getenv("PPD_GPU_DUMP_MIN_TOUCHED");
+  const size_t min_touched = e ? (size_t)atoll(e) : 32768;
+  return n_marks > 0 && 8 * n_marks >= min_touched;
+}
+
 void decode_one(ppd_ctx* c, Lane* L, const uint8_t* flat, size_t len, uint8_t** out, size_t* out_len, int* status, unsigned dump_workers) {
-  PhaseTimer pt;
-  Job& J = job_of(L, 1);
-  BlockJob& b = J.blocks[0];
   *out = nullptr, *out_len = 0;
-  try {
-    read_flat_block(flat, len, b);
-    pt.lap("read-flat");
-    if (gpu_parse_enabled()) gpu_pre_image(L, J, b, true, &c->parse_slots_sem);
-    collect_messages(J, b);
-    pt.lap("parse");
-    J.kh.run(L);
-    pt.lap("keyhash");
-    shape_block(J, b);
-    pt.lap("shape");
-  } catch (const Fail& e) {
-    if (e.code == PPD_ERR_CUDA) throw;
-    *status = e.code;
-    std::lock_guard<std::mutex> g(c->err_mu);
-    c->err = e.msg;
-    return;
+  const ppd_stats stats0 = L->stats;
+  // Second attempt: only after a first one with device-side marking walks that met an error.  With the marks
+  // deferred to the device the host cannot tell whether an earlier txn's marking pass would have failed first, so the
+  // block is redone with the host's own marking pass, which reports errors in the reference's order.
+  for (int attempt = 0; attempt < 2; attempt++) {
+    PhaseTimer pt;
+    Job& J = job_of(L, 1);
+    BlockJob& b = J.blocks[0];
+    bool redo = false;
+    try {
+      read_flat_block(flat, len, b);
+      J.device_marks = attempt == 0 && device_marks_wanted(b);
+      pt.lap("read-flat");
+      if (gpu_parse_enabled()) gpu_pre_image(L, J, b, true, &c->parse_slots_sem);
+      collect_messages(J, b);
+      pt.lap("parse");
+      J.kh.run(L);
+      pt.lap("keyhash");
+      shape_block(J, b);
+      pt.lap("shape");
+      sweep(L, J, /*refs_to_host=*/!gpu_dump_enabled());
+      pt.lap("sweep");
+      const int r = gpu_dump_block(c, L, J, out, out_len);
+      if (r == DUMP_REDO_HOST_MARKS) {
+        redo = true;
+      } else if (r == DUMP_ON_HOST) {
+        fetch_refs(L, J);
+        fetch_pools(L, J);
+        dump_blocks(J, out, out_len, dump_workers);
+      }
+      pt.lap("dump");
+    } catch (const Fail& e) {
+      if (e.code == PPD_ERR_CUDA) throw;
+      if (J.device_marks) {
+        redo = true;
+      } else {
+        *status = e.code;
+        std::lock_guard<std::mutex> g(c->err_mu);
+        c->err = e.msg;
+        return;
+      }
+    }
+    if (!redo) {
+      *status = PPD_OK;
+      return;
+    }
+    L->stats = stats0;
   }
-  sweep(L, J, /*refs_to_host=*/!gpu_dump_enabled());
-  pt.lap("sweep");
-  if (!gpu_dump_block(c, L, J, out, out_len)) {
-    fetch_refs(L, J);
-    fetch_pools(L, J);
-    dump_blocks(J, out, out_len, dump_workers);
-  }
-  *status = PPD_OK;
-  pt.lap("dump");
 }
 
 void add_stats(ppd_stats& a, const ppd_stats& b) {
@@ -2890,7 +2986,7 @@ void add_stats(ppd_stats& a, const ppd_stats& b) {
   a.levels = std::max(a.levels, b.levels);
   a.gpu_ms += b.gpu_ms, a.h2d_bytes += b.h2d_bytes, a.d2h_bytes += b.d2h_bytes, a.kernel_launches += b.kernel_launches;
   a.witnesses_on_gpu += b.witnesses_on_gpu, a.witness_instructions += b.witness_instructions, a.witness_bytes += b.witness_bytes;
-  a.parse_gpu_ms += b.parse_gpu_ms, a.level_launches += b.level_launches;
+  a.parse_gpu_ms += b.parse_gpu_ms, a.level_launches += b.level_launches, a.marks_on_gpu += b.marks_on_gpu;
 }
 
 // Blocks are independent (each BlockTrace carries its own pre-image, trace_protocol.rs:40-48): every

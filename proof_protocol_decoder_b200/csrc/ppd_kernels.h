@@ -77,6 +77,10 @@ struct IrDumpPlanView {
   uint32_t* u_off;
 };
 void launch_ir_size(const ArenaView& A, const IrDumpPlanView& P, uint32_t n_ir, cudaStream_t st);
+// the subset marking walks on the device: items4 = n_items x (root, key offset, key nibbles | ir << 8, first slot in touched[]);
+// every item owns MARK_SLOTS slots of touched[]; flags[0 .. n_ir) = slot overflow per IR, flags[n_ir] = a key ran into a hashed-out node
+static const uint32_t MARK_SLOTS = 16;
+void launch_mark_walk(const ArenaView& A, const uint32_t* items4, uint32_t n_items, uint32_t n_ir, uint32_t* touched, uint32_t* flags, cudaStream_t st);
 void launch_ir_emit(const ArenaView& A, const IrDumpPlanView& P, uint32_t n_ir, uint8_t* out, cudaStream_t st);
 
 // ---- ppd_parse.cu: compact witness -> instruction list -> tree links -> node arena ----

@@ -68,6 +68,7 @@ class PpdStats(ctypes.Structure):
         ("witness_bytes", ctypes.c_uint64),
         ("parse_gpu_ms", ctypes.c_double),
         ("level_launches", ctypes.c_uint64),
+        ("marks_on_gpu", ctypes.c_uint64),
     ]
 
     def as_dict(self):
