@@ -84,6 +84,18 @@ class BlockTrace:
     trie_pre_images: dict
     txn_info: List[TxnInfo] = field(default_factory=list)
 
+    @classmethod
+    def from_json(cls, src) -> "BlockTrace":
+        """The reference's serde JSON form (trace_protocol.rs:40-205, deserializers.rs:8-79): text or a parsed value."""
+        from . import wire
+
+        return wire.block_trace_from_json(src)
+
+    def to_json(self) -> str:
+        from . import wire
+
+        return wire.block_trace_dumps(self)
+
     def to_flat(self, p_meta: ProcessingMeta, other_data: OtherBlockData) -> bytes:
         pre = self.trie_pre_images
         if "combined" not in pre:
