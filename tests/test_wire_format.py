@@ -113,3 +113,28 @@ def test_enum_tags_and_missing_fields():
     with pytest.raises(PpdError) as ei:
         sep.to_flat(ProcessingMeta(lambda h: b""), OtherBlockData())
     assert ei.value.code == 45
+
+
+def test_random_traces_round_trip():
+    """hypothesis: any TxnTrace / TxnMeta the dataclasses can hold survives to_json -> from_json unchanged."""
+    from hypothesis import given, settings
+    from hypothesis import strategies as st
+
+    h256 = st.binary(min_size=32, max_size=32)
+    u256 = st.integers(min_value=0, max_value=(1 << 256) - 1)
+    usage = st.one_of(st.builds(lambda h: ContractCodeUsage(read=h), h256), st.builds(lambda b: ContractCodeUsage(write=b), st.binary(max_size=64)))
+    trace = st.builds(
+        TxnTrace, balance=st.none() | u256, nonce=st.none() | u256, storage_read=st.none() | st.lists(h256, max_size=4),
+        storage_written=st.none() | st.dictionaries(h256, u256, max_size=4), code_usage=st.none() | usage, self_destructed=st.none() | st.booleans(),
+    )
+    meta = st.builds(TxnMeta, byte_code=st.binary(max_size=80), new_txn_trie_node_byte=st.binary(max_size=80),
+                     new_receipt_trie_node_byte=st.binary(max_size=80), gas_used=st.integers(min_value=0, max_value=(1 << 64) - 1))
+    info = st.builds(TxnInfo, traces=st.dictionaries(st.binary(min_size=20, max_size=20), trace, max_size=4), meta=meta)
+
+    @settings(max_examples=150, deadline=None)
+    @given(st.binary(min_size=1, max_size=200), st.lists(info, max_size=3))
+    def check(compact, infos):
+        bt = BlockTrace(trie_pre_images={"combined": {"compact": compact}}, txn_info=infos)
+        assert BlockTrace.from_json(bt.to_json()) == bt
+
+    check()
