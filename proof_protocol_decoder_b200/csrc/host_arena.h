@@ -300,6 +300,13 @@ struct HostArena {
       for (uint32_t nib = 0; nib < 16; nib++) kids[nib] = (mask >> nib) & 1u ? child_pool[base + r++] : NODE_EMPTY;
     }
     uint32_t lv = level[node];
+    if (hi - lo >= 3) {  // the children the groups below descend into: fetched while the first group is being worked on
+      for (size_t i = lo; i < hi; i++) {
+        if (pos >= it[i].klen) break;
+        const uint32_t c = kids[key_nib(it[i].koff, pos)];
+        if (c != NODE_EMPTY && !is_hash_id(c)) __builtin_prefetch(&nodes[c]);
+      }
+    }
     for (size_t i = lo; i < hi;) {
       if (pos >= it[i].klen) fail(PPD_PANIC_KEY_IS_PREFIX_OF_KEY, "inserted key ends at a branch");
       const uint32_t nib = key_nib(it[i].koff, pos);
