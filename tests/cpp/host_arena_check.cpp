@@ -3,7 +3,8 @@
 //   insert_many(sorted keys)  ==  insert, key by key (same canonical trie, node for node)
 //   mark_many                 ==  mark, key by key (same touched nodes, same leaves)
 //   branch_with               ==  rebuilding the branch from its 16 slots
-// Built and run by tests/test_host_cpu.py with g++ (no CUDA needed: the header only shapes tries).
+//   flat_maps.h               ==  std::map under a random mix of operations
+// Built and run by tests/test_host_cpu.py with g++ (no CUDA needed: the headers only shape tries).
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -11,7 +12,9 @@
 #include <random>
 #include <vector>
 
+#include "../../proof_protocol_decoder_b200/csrc/flat_maps.h"
 #include "../../proof_protocol_decoder_b200/csrc/host_arena.h"
+#include <map>
 
 using namespace ppd;
 
@@ -176,6 +179,74 @@ int main(int argc, char** argv) {
       if (b != UNCHANGED) r2 = b;
     }
     CHECK(same(A, r1, r2), "round %d: tries differ after removals", round);
+  }
+  // ---- flat_maps.h against std::map under a random mix of inserts, overwrites, erasures and look-ups ----
+  for (int round = 0; round < rounds; round++) {
+    FlatMapU32 fm;
+    std::map<uint32_t, uint32_t> ref;
+    H256Map hm;
+    std::map<std::vector<uint8_t>, uint32_t> href;
+    if (round & 1) fm.reserve(100), hm.reserve(100);
+    const size_t ops = 200 + rng() % 20000;
+    auto key_of = [&](uint32_t i) {
+      H256 k;
+      uint64_t x = i * 0x9E3779B97F4A7C15ull + 1;
+      for (int w = 0; w < 4; w++) {
+        x ^= x >> 29, x *= 0xBF58476D1CE4E5B9ull;
+        memcpy(k.b + 8 * w, &x, 8);
+      }
+      if (i % 7 == 0) memset(k.b, 0, 8);  // colliding hash prefixes
+      return k;
+    };
+    for (size_t op = 0; op < ops; op++) {
+      const uint32_t k = (uint32_t)(rng() % 3000), v = (uint32_t)(rng() % 1000000);
+      const uint32_t key32 = (k % 11 == 0) ? 0xffffffffu - (k % 5) : k;  // NODE_EMPTY and its neighbours are valid keys
+      const H256 hk = key_of(k);
+      const std::vector<uint8_t> hv(hk.b, hk.b + 32);
+      switch (rng() % 4) {
+        case 0:
+          fm.put(key32, v), ref[key32] = v;
+          hm[hk] = v, href[hv] = v;
+          break;
+        case 1: {
+          auto ins = hm.insert({hk, v});
+          auto rins = href.insert({hv, v});
+          CHECK(ins.second == rins.second && ins.first->second == rins.first->second, "H256Map::insert");
+          break;
+        }
+        case 2:
+          CHECK(hm.erase(hk) == href.erase(hv), "H256Map::erase");
+          break;
+        default: {
+          const uint32_t* f = fm.find(key32);
+          auto r = ref.find(key32);
+          CHECK((f != nullptr) == (r != ref.end()) && (!f || *f == r->second), "FlatMapU32::find");
+          auto hf = hm.find(hk);
+          auto hr = href.find(hv);
+          CHECK((hf != hm.end()) == (hr != href.end()) && (hf == hm.end() || hf->second == hr->second), "H256Map::find");
+        }
+      }
+    }
+    CHECK(fm.count == ref.size(), "FlatMapU32 size %zu / %zu", fm.count, ref.size());
+    CHECK(hm.size() == href.size(), "H256Map size %zu / %zu", hm.size(), href.size());
+    size_t seen = 0;
+    hm.for_each([&](const H256Map::Entry& e) {
+      seen++;
+      auto hr = href.find(std::vector<uint8_t>(e.first.b, e.first.b + 32));
+      CHECK(hr != href.end() && hr->second == e.second, "H256Map::for_each entry");
+    });
+    CHECK(seen == href.size(), "H256Map::for_each count");
+    fm.erase_if([&](uint32_t key, uint32_t) { return key % 2 == 0; });
+    for (auto it = ref.begin(); it != ref.end();) it = it->first % 2 == 0 ? ref.erase(it) : std::next(it);
+    size_t left = 0;
+    fm.for_each([&](uint32_t key, uint32_t val) {
+      left++;
+      CHECK(ref.count(key) && ref[key] == val, "FlatMapU32 after erase_if");
+    });
+    CHECK(left == ref.size(), "FlatMapU32::erase_if count");
+    H256Map copy = hm;  // the storage-map snapshot a dummy IR reads
+    hm.erase(key_of(1));
+    CHECK(copy.size() == href.size(), "H256Map copy is independent");
   }
   if (failures) {
     fprintf(stderr, "%d check(s) failed\n", failures);
