@@ -3006,6 +3006,7 @@ int ppd_replay_last_parse(ppd_ctx* c, double* gpu_ms_out) {
       // the sweep may have moved the pools to larger buffers since
       E.nodes = L->d_nodes.as<NodeRec>(), E.key_pool = L->d_keys.as<uint8_t>(), E.val_pool = L->d_vals.as<uint8_t>();
       E.hash_pool = L->d_hashes.as<uint8_t>(), E.child_pool = L->d_children.as<uint32_t>(), E.accounts = L->d_accounts.as<AccountRec>();
+      E.level = L->d_level.as<uint16_t>();
       CUDA_OK(cudaMemsetAsync(L->last_bounds.result, 0, 4 * PARSE_R_WORDS, L->st));
       launch_parse_bounds(L->last_bounds, L->st);
       launch_parse_scatter(L->last_bounds, L->last_ins_pos, L->st);
