@@ -40,6 +40,15 @@ struct AccountRec {
   uint32_t pad[3];
 };
 
+// IrDump plan segments (ppd_dump.cu): seg_b is the root of a trie to cut and serialise (a node id, a hashed-out id or
+// NODE_EMPTY), or one of these kinds
+static const uint32_t IR_SEG_LITERAL = 0xfffffffeu;  // seg_a bytes the HOST writes after the copy back (host-shaped blocks)
+static const uint32_t IR_SEG_REF = 0xfffffffdu;      // 32 bytes of ref[seg_a] (a trie root after the txn)
+static const uint32_t IR_SEG_FLAT = 0xfffffffcu;     // seg_a bytes of the FlatBlock resident in HBM, from offset seg_c
+static const uint32_t IR_SEG_KEY32 = 0xfffffffbu;    // 32 bytes of key_pool at seg_a (a hashed address)
+static const uint32_t IR_SEG_LIT_DEV = 0xfffffffau;  // seg_a bytes of the uploaded literal pool, from offset seg_c
+static const uint32_t IR_SEG_KIND_MIN = 0xfffffffau;
+
 // Device-side view of one arena (all pointers are device pointers).
 struct ArenaView {
   const NodeRec* nodes;

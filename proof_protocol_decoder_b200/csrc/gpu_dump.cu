@@ -139,7 +139,7 @@ int gpu_dump_block(ppd_ctx* c, Lane* L, Job& J, uint8_t** out, size_t* out_len) 
   L->d_plan.reserve(4 * o_end);
   uint32_t* d = L->d_plan.as<uint32_t>();
   CUDA_OK(cudaMemcpyAsync(d, h, 4 * o_base, cudaMemcpyHostToDevice, L->st));
-  IrDumpPlanView P;
+  IrDumpPlanView P{};
   P.touched = d + o_touched, P.touched_begin = d + o_tb, P.seg_a = d + o_sa, P.seg_b = d + o_sb, P.seg_begin = d + o_sg;
   P.ir_base = reinterpret_cast<const uint64_t*>(d + o_base);
   P.seg_off = d + o_soff, P.ir_size = d + o_isz, P.ir_flag = d + o_ifl, P.ir_nuniq = d + o_inu;

@@ -162,34 +162,58 @@ __global__ void __launch_bounds__(DUMP_THREADS) ir_size_kernel(ArenaView A, IrDu
   __syncthreads();
   if (threadIdx.x == 0 && s.n_done < nu) s.flag = 1;
   __syncthreads();
-  // ---- segments: literals and tries in output order ----
-  if (threadIdx.x == 0) {
-    uint32_t off = 0;
+  // ---- segments: literals and tries in output order.  Every segment's size in parallel, then a block-wide
+  // exclusive scan in chunks of DUMP_THREADS (an IR of a mainnet-shaped block has ~250 segments) ----
+  {
+    __shared__ uint32_t scan_warp[DUMP_THREADS / 32];
+    __shared__ uint32_t scan_carry;
+    if (threadIdx.x == 0) scan_carry = 0;
+    __syncthreads();
     const uint32_t sb = P.seg_begin[ir], se = P.seg_begin[ir + 1];
-    for (uint32_t q = sb; q < se; q++) {
-      P.seg_off[q] = off;
-      const uint32_t a = P.seg_a[q], b = P.seg_b[q];
-      if (b == IR_SEG_LITERAL || b == IR_SEG_REF) {
-        off += b == IR_SEG_REF ? 32u : a;
-        continue;
-      }
-      uint32_t sz = 33;
-      if (b == NODE_EMPTY) {
-        sz = 1;
-      } else if (!is_hash_id(b)) {
-        uint32_t k = set_find(s, b);
-        if (k != NOT_FOUND) {
-          if (s.u_off[k] != UNSET) s.flag = 1;  // a node that roots two tries of one IR
-          s.u_off[k] = off;
-          sz = s.u_size[k];
-        } else if (A.ref_len[b] != 32 && node_kind(A, b) != NK_ROOT) {
-          s.flag = 1;
+    for (uint32_t q0 = sb; q0 < se; q0 += DUMP_THREADS) {
+      const uint32_t q = q0 + threadIdx.x;
+      uint32_t sz = 0, trie_slot = NOT_FOUND;
+      if (q < se) {
+        const uint32_t a = P.seg_a[q], b = P.seg_b[q];
+        if (b == NODE_EMPTY) {
+          sz = 1;
+        } else if (b >= IR_SEG_KIND_MIN) {
+          sz = (b == IR_SEG_REF || b == IR_SEG_KEY32) ? 32u : a;
+        } else if (is_hash_id(b)) {
+          sz = 33;
+        } else {
+          sz = 33;
+          const uint32_t k = set_find(s, b);
+          if (k != NOT_FOUND) {
+            trie_slot = k;
+            sz = s.u_size[k];
+          } else if (A.ref_len[b] != 32 && node_kind(A, b) != NK_ROOT) {
+            s.flag = 1;
+          }
         }
       }
-      off += sz;
+      uint32_t incl = sz;
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if ((threadIdx.x & 31) >= (uint32_t)o) incl += t;
+      }
+      if ((threadIdx.x & 31) == 31) scan_warp[threadIdx.x >> 5] = incl;
+      __syncthreads();
+      uint32_t before = scan_carry;
+      for (uint32_t w = 0; w < (threadIdx.x >> 5); w++) before += scan_warp[w];
+      const uint32_t off = before + incl - sz;
+      if (q < se) {
+        P.seg_off[q] = off;
+        if (trie_slot != NOT_FOUND && atomicCAS(&s.u_off[trie_slot], UNSET, off) != UNSET) s.flag = 1;  // a node that roots two tries of one IR
+      }
+      __syncthreads();
+      if (threadIdx.x == DUMP_THREADS - 1) scan_carry = off + sz;
+      __syncthreads();
     }
-    P.ir_size[ir] = off;
-    s.n_done = 0;
+    if (threadIdx.x == 0) {
+      P.ir_size[ir] = scan_carry;
+      s.n_done = 0;
+    }
   }
   __syncthreads();
   // ---- offsets, top-down: a node with an offset places its touched children ----
@@ -372,15 +396,23 @@ __global__ void __launch_bounds__(DUMP_THREADS) ir_emit_kernel(ArenaView A, IrDu
         break;
     }
   }
-  // untouched tries of the IR (a storage trie nobody reads: its root as a hash, or empty)
+  // the other segments: untouched tries (a storage trie nobody reads: its root as a hash, or empty), roots, hashed
+  // addresses, and the literal bytes that are resident in HBM (FlatBlock ranges, the uploaded literal pool)
   const uint32_t sb = P.seg_begin[ir], se = P.seg_begin[ir + 1];
   for (uint32_t qi = sb + threadIdx.x; qi < se; qi += blockDim.x) {
     const uint32_t b = P.seg_b[qi];
     if (b == IR_SEG_LITERAL) continue;
     uint8_t* q = base + P.seg_off[qi];
-    if (b == IR_SEG_REF) {
-      const uint8_t* r = A.ref + 32ull * P.seg_a[qi];
+    if (b == IR_SEG_REF || b == IR_SEG_KEY32) {
+      const uint8_t* r = b == IR_SEG_REF ? A.ref + 32ull * P.seg_a[qi] : A.key_pool + P.seg_a[qi];
       for (int i = 0; i < 32; i++) q[i] = r[i];
+      continue;
+    }
+    if (b == IR_SEG_FLAT || b == IR_SEG_LIT_DEV) {
+      const uint32_t len = P.seg_a[qi];
+      if (len > 96) continue;  // long ones: the whole block copies them below
+      const uint8_t* src = (b == IR_SEG_FLAT ? P.flat : P.lit) + P.seg_c[qi];
+      for (uint32_t i = 0; i < len; i++) q[i] = src[i];
       continue;
     }
     if (b == NODE_EMPTY)
@@ -389,6 +421,17 @@ __global__ void __launch_bounds__(DUMP_THREADS) ir_emit_kernel(ArenaView A, IrDu
       put_hash(q, A.hash_pool + 32ull * (b - HASH_ID_BASE));
     else if (set_find(s, b) == NOT_FOUND)
       put_hash(q, A.ref + 32ull * b);
+  }
+  if (P.seg_c) {
+    for (uint32_t qi = sb; qi < se; qi++) {
+      const uint32_t b = P.seg_b[qi];
+      if (b != IR_SEG_FLAT && b != IR_SEG_LIT_DEV) continue;
+      const uint32_t len = P.seg_a[qi];
+      if (len <= 96) continue;
+      const uint8_t* src = (b == IR_SEG_FLAT ? P.flat : P.lit) + P.seg_c[qi];
+      uint8_t* q = base + P.seg_off[qi];
+      for (uint32_t i = threadIdx.x; i < len; i += blockDim.x) q[i] = src[i];
+    }
   }
 }
 

@@ -57,8 +57,7 @@ void launch_hash_sorted_leaves(const BuildView& V, cudaStream_t st);
 void launch_hash_branch_level(const BuildView& V, const uint32_t* order, uint32_t begin, uint32_t end, cudaStream_t st);
 
 // ---- ppd_dump.cu: the per-txn sub-tries serialised on the GPU ----
-static const uint32_t IR_SEG_LITERAL = 0xfffffffeu;  // seg_b of a literal segment (seg_a = its length); else seg_b = root of a trie
-static const uint32_t IR_SEG_REF = 0xfffffffdu;      // seg_b of a "32 bytes of ref[seg_a]" segment (a trie root after the txn)
+// segment kinds IR_SEG_* (seg_b): arena.h
 struct IrDumpPlanView {
   // inputs (per block): touched node ids of every IR, and every IR's segments in output order
   const uint32_t* touched;        // concatenated
@@ -66,6 +65,9 @@ struct IrDumpPlanView {
   const uint32_t* seg_a;
   const uint32_t* seg_b;
   const uint32_t* seg_begin;      // [n_ir + 1]
+  const uint32_t* seg_c;          // source offset of IR_SEG_FLAT / IR_SEG_LIT_DEV segments (nullptr: the plan has none)
+  const uint8_t* flat;            // the FlatBlock resident in HBM
+  const uint8_t* lit;             // the uploaded literal pool
   const uint64_t* ir_base;        // [n_ir] byte offset of the IR in the output (emit only)
   // outputs of ir_size_kernel
   uint32_t* seg_off;              // offset of every segment inside its IR

@@ -1,0 +1,959 @@
+// txn_core.h — the txn loop of decoding.rs:80-177 on the node arena, written once for the device and for a CPU
+// check harness (tests/cpp/txn_core_check.cpp emulates the thread block phase by phase; the product only ever
+// runs the __device__ instantiation, ppd_txn.cu).
+//
+// What it replaces: per txn
+//   create_minimal_partial_tries_needed_by_txn  decoding.rs:179-217, 551-602  -> marking walks (mark_item)
+//   apply_deltas_to_trie_state                  decoding.rs:219-292, 431-456  -> two batched trie updates (Batch)
+//   eth_trie_utils insert / delete / get                       -> path copies on the arena in HBM
+//
+// Design.  The shape of a trie never depends on a hash, so every version of every trie of a block is built
+// before anything is hashed, as new records appended to the arena (nodes are immutable, old versions stay
+// addressable, unchanged subtrees are shared).  One thread block runs the whole txn loop of one block; the txns
+// are sequential, the keys of one txn are parallel:
+//   * every key walks the current version from the root and records the nodes it passes (its path) and where
+//     it ends (its terminal: an empty slot, a leaf, a hashed-out node, or the middle of an extension);
+//   * keys are sorted per trie (op_rank) with the LCP of neighbours (op_lcp), so "the keys that pass through
+//     the node at depth d on my path" is a contiguous range and its first key, the OWNER, is the one whose LCP
+//     with its predecessor is < d;
+//   * terminals are resolved by their owners (a new leaf, an overwrite, a split, a removal);
+//   * path nodes are re-assembled bottom-up, one barrier per depth: the owner of a branch gathers the results
+//     of the children its range touched, creates the new version once (not once per key), and collapses a
+//     branch left with one child exactly as delete does.
+// The result of a batch is the trie the reference reaches by applying the same writes one by one (a Merkle
+// Patricia trie is canonical for its items, hashed-out subtrees counting as items), without the versions in
+// between, which nobody observes (the reference hashes a trie once per txn, decoding.rs:458-464).
+// Anything the reference would report as an error (an insert through a hashed-out node, a subset key running
+// into one, a key that is a prefix of another ...) raises a flag; the block is then redone by the host path
+// (host_txn.cu), which reports errors in the reference's order.
+#pragma once
+#include <cstdint>
+
+#include "../../include/ppd_flat.h"
+#include "arena.h"
+
+#if defined(__CUDACC__)
+#define PPD_HD __host__ __device__
+#else
+#define PPD_HD
+#endif
+
+namespace ppd {
+namespace txn {
+
+static const uint32_t T_UNCHANGED = 0xfffffffeu;  // batch result: the subtree did not change
+static const uint32_t ST_ABSENT = 0xfffffffeu;    // AcctState::storage: no entry in the storage map (decoding.rs:572-582)
+static const uint32_t NONE = 0xfffffffdu;
+static const uint32_t HASH_BASE = 0x80000000u, HASH_END = 0xf0000000u;
+static const uint32_t MARK_SLOTS_T = 16;  // == MARK_SLOTS (ppd_kernels.h)
+static const uint32_t PATH_CAP = 24;      // nodes a batched key may pass before its terminal
+static const uint32_t OWNER_TXN_TRIE = 0xffffff01u, OWNER_RECEIPT_TRIE = 0xffffff02u, OWNER_STATE_TRIE = 0xffffff03u;
+static const uint32_t TRF_STATE_WRITE = 0x100u;   // TxnTrace::flags: the trace changes the account (processed_block_trace.rs:238-256)
+static const uint32_t TRF_MIN_KEYS = 0x200u;      // a written slot key has a leading zero byte: decoding.rs:235 hashes the shortened key
+
+enum : uint32_t {
+  TXF_OK = 0,
+  TXF_INSERT_INTO_HASH = 1,  // PPD_PANIC_INSERT_INTO_HASH_NODE in the reference
+  TXF_KEY_PREFIX = 2,        // PPD_PANIC_KEY_IS_PREFIX_OF_KEY
+  TXF_MARK_INTO_HASH = 3,    // PPD_ERR_MISSING_KEYS_CREATING_SUB_PARTIAL_TRIE
+  TXF_MARK_SLOTS = 4,        // a marking walk longer than its slots
+  TXF_PATH_DEPTH = 5,        // a batched key passes more than PATH_CAP nodes
+  TXF_NODES_FULL = 6,
+  TXF_CHILDREN_FULL = 7,
+  TXF_KEYS_FULL = 8,
+  TXF_NOT_ACCOUNT = 9,       // PPD_ERR_ACCOUNT_DECODE
+  TXF_DUP_KEY = 10,          // the same key twice in one batch (only a malformed FlatBlock has that)
+  TXF_SHORT_HADDR = 11,      // PPD_PANIC_H256_FROM_SLICE
+  TXF_LEVELS = 12,
+  TXF_WITHDRAWAL = 13,       // PPD_ERR_MISSING_WITHDRAWAL_ACCOUNT / account decode
+  TXF_STACK = 14,
+};
+
+enum : uint8_t { OP_DEL = 0, OP_PUT_LEAF = 1, OP_PUT_ACCOUNT = 2 };
+enum : uint8_t { TK_EMPTY = 0, TK_LEAF_SAME = 1, TK_LEAF_OTHER = 2, TK_HASH = 3, TK_DIVERGE = 4, TK_BAD = 5 };
+
+// One write of a batch, in sorted order.
+struct SOp {
+  uint32_t koff;   // key in key_pool
+  uint32_t a1, a2; // PUT_LEAF: value offset, length; PUT_ACCOUNT: account record
+  uint32_t owner;  // trace whose storage trie it writes, or OWNER_*
+  uint8_t klen;    // nibbles
+  int8_t lcp;      // common prefix (nibbles) with the previous op of the same trie; -1 for the first
+  uint8_t kind;
+  uint8_t pad;
+};
+
+// One TxnTrace (trace_protocol.rs:152-183) as the host lays it out for the device.  Offsets are into the FlatBlock.
+struct TxnTrace {
+  uint32_t flags, txn;
+  uint32_t off_addr, off_balance, off_nonce;
+  uint32_t off_reads, n_reads, off_writes, n_writes;
+  uint32_t code_off, code_len;
+  uint32_t m_reads, m_wfull, m_wmin, m_code;  // digest indices (the address digest of trace t is digest t)
+  uint32_t op0;    // first round-1 op of the trace (n_writes of them)
+  uint32_t item0;  // first storage marking walk, relative to the txn's first walk
+  uint32_t rec;    // account record its state write fills
+  uint32_t val0;   // val_pool offset of its first written value (36 bytes apart)
+  uint32_t acct;   // (device) account table slot
+  uint32_t rank;   // (device) position among the txn's traces sorted by hashed address
+  uint32_t pad;
+};
+
+struct TxnDesc {
+  uint32_t trace_begin, trace_end;
+  uint32_t touched_base;  // first slot of the IR's touched list
+  uint32_t seg_tries;     // plan segments: +0 state, +1 transactions, +2 receipts sub-trie
+  uint32_t seg_storage;   // +2r: hashed address of the r-th account in sorted order, +2r+1: its storage sub-trie
+  uint32_t seg_roots;     // +0 state, +1 transactions, +2 receipts root after the txn
+  uint32_t key_off, key_nibs;  // Nibbles::from_bytes_be(rlp(txn_idx)), decoding.rs:190
+  uint32_t off_txn_bytes, len_txn_bytes, off_receipt, len_receipt;  // FlatBlock offsets
+  uint32_t val_txn, val_receipt;                                    // val_pool offsets
+  uint32_t op1_begin, op1_end;  // round 1: storage writes of every trace, then the txn / receipt inserts
+  uint32_t op2_begin, op2_end;  // round 2: state writes and self-destructs
+};
+
+struct AcctState {
+  uint32_t storage;    // root of the account's storage trie in PartialTrieState, NODE_EMPTY, or ST_ABSENT
+  uint32_t root_node;  // NK_ROOT node over `storage`, or NONE
+  uint32_t pre_rec;    // the account's record in the pre-image, or NONE
+  uint32_t owner;      // (table) first trace that claimed the slot, or 0xffffffff
+};
+
+struct Cursors {
+  uint32_t n_nodes, n_children, key_bytes;  // allocation cursors
+  uint32_t flag, flag_txn;                  // first TXF_* raised and where
+  uint32_t state_root, txn_root, receipt_root;
+  uint32_t max_level;
+  uint32_t pad[7];
+};
+
+// Everything the loop touches.  All pointers are device pointers (host pointers in the CPU harness).
+struct View {
+  // arena (mutable: the loop appends)
+  NodeRec* nodes;
+  uint16_t* level;
+  uint8_t* key_pool;
+  uint8_t* val_pool;
+  const uint8_t* hash_pool;
+  uint32_t* child_pool;
+  AccountRec* accounts;
+  uint32_t cap_nodes, cap_children, cap_keys;
+  // inputs
+  const uint8_t* flat;
+  TxnTrace* traces;
+  const TxnDesc* txns;
+  uint32_t n_txns, n_traces;
+  uint32_t dig_base;         // key_pool offset of digest 0 (32 bytes each)
+  AcctState* acct;           // account table
+  const uint8_t* pre_flags;  // per pre-image account: bit0 storage root != EMPTY_TRIE_HASH
+  SOp* ops1;
+  SOp* ops2;
+  // plan (outputs)
+  uint32_t* touched;
+  uint32_t* seg_a;
+  uint32_t* seg_b;
+  // scratch, sized for the largest batch of the block
+  uint32_t* path_node;  // [max_ops][PATH_CAP]
+  uint8_t* path_depth;  // [max_ops][PATH_CAP]
+  uint8_t* plen;        // [max_ops]
+  uint8_t* top;         // [max_ops]
+  uint32_t* tnode;      // [max_ops] terminal node
+  uint8_t* tdepth;      // [max_ops]
+  uint8_t* tkind;       // [max_ops]
+  uint32_t* res;        // [max_ops]
+  uint32_t* acct_leaf;  // [max traces per txn] state leaf of the trace's address before the txn
+  Cursors* cur;
+};
+
+PPD_HD inline bool is_hash_id(uint32_t n) { return n >= HASH_BASE && n < HASH_END; }
+
+// ---- the execution context: how threads of the block see shared counters ------------------------------------
+// Device: a thread block.  Harness: one "thread" at a time.
+struct Ctx {
+  View v;
+  uint32_t tid, nthreads;
+  uint32_t* sh_dmax;  // shared: deepest entry of the running batch
+};
+
+#if defined(__CUDA_ARCH__)
+#define PPD_ATOMIC_ADD(p, x) atomicAdd((p), (x))
+#define PPD_ATOMIC_MAX(p, x) atomicMax((p), (x))
+#define PPD_ATOMIC_CAS(p, c, x) atomicCAS((p), (c), (x))
+#else
+PPD_HD inline uint32_t host_atomic_add(uint32_t* p, uint32_t x) {
+  uint32_t o = *p;
+  *p = o + x;
+  return o;
+}
+PPD_HD inline uint32_t host_atomic_max(uint32_t* p, uint32_t x) {
+  uint32_t o = *p;
+  if (x > o) *p = x;
+  return o;
+}
+PPD_HD inline uint32_t host_atomic_cas(uint32_t* p, uint32_t c, uint32_t x) {
+  uint32_t o = *p;
+  if (o == c) *p = x;
+  return o;
+}
+#define PPD_ATOMIC_ADD(p, x) ppd::txn::host_atomic_add((p), (x))
+#define PPD_ATOMIC_MAX(p, x) ppd::txn::host_atomic_max((p), (x))
+#define PPD_ATOMIC_CAS(p, c, x) ppd::txn::host_atomic_cas((p), (c), (x))
+#endif
+
+PPD_HD inline void raise(const View& v, uint32_t why, uint32_t txn) {
+  if (PPD_ATOMIC_CAS(&v.cur->flag, 0u, why) == 0u) v.cur->flag_txn = txn;
+}
+
+// ---- arena primitives (the device form of host_arena.h) -------------------------------------------------------
+PPD_HD inline uint32_t key_nib(const View& v, uint32_t koff, uint32_t i) {
+  const uint32_t b = v.key_pool[koff + (i >> 1)];
+  return (i & 1) ? (b & 15u) : (b >> 4);
+}
+PPD_HD inline uint32_t lvl(const View& v, uint32_t n) { return (n == NODE_EMPTY || n >= HASH_BASE) ? 0u : (uint32_t)v.level[n]; }
+PPD_HD inline uint32_t kind_of(const View& v, uint32_t n) { return is_hash_id(n) ? (uint32_t)NK_HASH : (v.nodes[n].w0 & 0xffu); }
+PPD_HD inline uint32_t w0(uint32_t kind, uint32_t start, uint32_t len) { return kind | (start << 8) | (len << 16); }
+
+PPD_HD inline uint32_t push_node(const View& v, const NodeRec& r, uint32_t lv) {
+  uint32_t id = PPD_ATOMIC_ADD(&v.cur->n_nodes, 1u);
+  if (id >= v.cap_nodes) {
+    raise(v, TXF_NODES_FULL, 0);
+    id = v.cap_nodes - 1;  // a sink slot: the block is redone anyway
+  }
+  if (lv > 0xfff0u) raise(v, TXF_LEVELS, 0), lv = 0xfff0u;
+  v.nodes[id] = r;
+  v.level[id] = (uint16_t)lv;
+  PPD_ATOMIC_MAX(&v.cur->max_level, lv);
+  return id;
+}
+PPD_HD inline uint32_t alloc_children(const View& v, uint32_t k) {
+  uint32_t at = PPD_ATOMIC_ADD(&v.cur->n_children, k);
+  if (at + k > v.cap_children) {
+    raise(v, TXF_CHILDREN_FULL, 0);
+    at = v.cap_children - 16;
+  }
+  return at;
+}
+PPD_HD inline uint32_t common_prefix(const View& v, uint32_t ka, uint32_t sa, uint32_t kb, uint32_t sb, uint32_t m) {
+  uint32_t i = 0;
+  while (i < m && key_nib(v, ka, sa + i) == key_nib(v, kb, sb + i)) i++;
+  return i;
+}
+PPD_HD inline uint32_t child_at(const View& v, const NodeRec& br, uint32_t nib) {
+  const uint32_t mask = br.a1 & 0xffffu, bit = 1u << nib;
+  if (!(mask & bit)) return NODE_EMPTY;
+#if defined(__CUDA_ARCH__)
+  return v.child_pool[br.a0 + __popc(mask & (bit - 1))];
+#else
+  return v.child_pool[br.a0 + __builtin_popcount(mask & (bit - 1))];
+#endif
+}
+PPD_HD inline uint32_t popc16(uint32_t m) {
+#if defined(__CUDA_ARCH__)
+  return __popc(m & 0xffffu);
+#else
+  return (uint32_t)__builtin_popcount(m & 0xffffu);
+#endif
+}
+
+PPD_HD inline uint32_t new_leaf_for(const View& v, const SOp& o, uint32_t start) {
+  const uint32_t len = o.klen - start;
+  if (o.kind == OP_PUT_ACCOUNT) {
+    const uint32_t src = v.accounts[o.a1].storage_src;
+    return push_node(v, NodeRec{w0(NK_LEAF_ACCOUNT, start, len), o.koff, o.a1, 0}, src == NODE_EMPTY ? 0u : lvl(v, src) + 1u);
+  }
+  return push_node(v, NodeRec{w0(NK_LEAF, start, len), o.koff, o.a1, o.a2}, 0);
+}
+PPD_HD inline uint32_t new_ext(const View& v, uint32_t koff, uint32_t start, uint32_t len, uint32_t child) {
+  return push_node(v, NodeRec{w0(NK_EXT, start, len), koff, child, 0}, lvl(v, child) + 1u);
+}
+PPD_HD inline uint32_t new_root(const View& v, uint32_t child) {
+  return push_node(v, NodeRec{w0(NK_ROOT, 0, 0), 0, child, 0}, child == NODE_EMPTY ? 0u : lvl(v, child) + 1u);
+}
+// the same leaf payload under a different key range
+PPD_HD inline uint32_t releaf(const View& v, uint32_t leaf, uint32_t koff, uint32_t start, uint32_t len) {
+  NodeRec r = v.nodes[leaf];
+  r.w0 = w0(r.w0 & 0xffu, start, len);
+  r.a0 = koff;
+  return push_node(v, r, v.level[leaf]);
+}
+// branch from 16 slots (NODE_EMPTY = none); at least two are set
+PPD_HD inline uint32_t new_branch16(const View& v, const uint32_t* kids, uint32_t min_level) {
+  uint32_t mask = 0, k = 0, lv = min_level;
+  for (uint32_t i = 0; i < 16; i++)
+    if (kids[i] != NODE_EMPTY) mask |= 1u << i, k++;
+  const uint32_t base = alloc_children(v, k);
+  for (uint32_t i = 0, j = 0; i < 16; i++)
+    if (kids[i] != NODE_EMPTY) {
+      v.child_pool[base + j++] = kids[i];
+      const uint32_t l = lvl(v, kids[i]) + 1u;
+      if (l > lv) lv = l;
+    }
+  return push_node(v, NodeRec{w0(NK_BRANCH, 0, 0), base, mask, 0}, lv);
+}
+// copy of branch `br` with slot `nib` set to `child` (never NODE_EMPTY here)
+PPD_HD inline uint32_t branch_with(const View& v, uint32_t br, uint32_t nib, uint32_t child) {
+  const NodeRec r = v.nodes[br];
+  const uint32_t mask = r.a1 & 0xffffu, bit = 1u << nib;
+  const uint32_t k = popc16(mask), rk = popc16(mask & (bit - 1)), has = (mask & bit) ? 1u : 0u;
+  const uint32_t nk = k - has + 1u, base = alloc_children(v, nk);
+  for (uint32_t i = 0; i < rk; i++) v.child_pool[base + i] = v.child_pool[r.a0 + i];
+  v.child_pool[base + rk] = child;
+  for (uint32_t i = rk + has; i < k; i++) v.child_pool[base + i - has + 1u] = v.child_pool[r.a0 + i];
+  uint32_t lv = v.level[br];
+  if (lvl(v, child) + 1u > lv) lv = lvl(v, child) + 1u;
+  return push_node(v, NodeRec{w0(NK_BRANCH, 0, 0), base, mask | bit, 0}, lv);
+}
+// an extension (ek, es, el) over `child`, merged into the child when that is a leaf / an extension (delete's collapse)
+PPD_HD inline uint32_t collapse_ext(const View& v, uint32_t ek, uint32_t es, uint32_t el, uint32_t child) {
+  const uint32_t k = kind_of(v, child);
+  if (k == NK_EXT) {
+    const NodeRec c = v.nodes[child];
+    return new_ext(v, c.a0, ((c.w0 >> 8) & 0xffu) - el, ((c.w0 >> 16) & 0xffu) + el, c.a1);
+  }
+  if (k == NK_LEAF || k == NK_LEAF_ACCOUNT) {
+    const NodeRec c = v.nodes[child];
+    return releaf(v, child, c.a0, ((c.w0 >> 8) & 0xffu) - el, ((c.w0 >> 16) & 0xffu) + el);
+  }
+  return new_ext(v, ek, es, el, child);
+}
+// the single child left in slot `nib` of a branch at depth `pos` on the path of key `koff`
+PPD_HD inline uint32_t collapse_branch(const View& v, uint32_t koff, uint32_t pos, uint32_t nib, uint32_t other) {
+  const uint32_t k = kind_of(v, other);
+  if (k == NK_EXT || k == NK_LEAF || k == NK_LEAF_ACCOUNT) return collapse_ext(v, 0, pos, 1, other);  // their own keys spell the nibble
+  // a key that runs through the surviving child: the path's first `pos` nibbles, then its slot
+  const uint32_t nb = pos / 2 + 2;
+  uint32_t pk = PPD_ATOMIC_ADD(&v.cur->key_bytes, nb);
+  if (pk + nb > v.cap_keys) {
+    raise(v, TXF_KEYS_FULL, 0);
+    pk = v.cap_keys - 40;
+  }
+  for (uint32_t i = 0; i <= pos / 2; i++) v.key_pool[pk + i] = v.key_pool[koff + i];
+  uint8_t* last = v.key_pool + pk + pos / 2;
+  *last = (pos & 1) ? (uint8_t)((*last & 0xf0u) | nib) : (uint8_t)(nib << 4);
+  v.key_pool[pk + pos / 2 + 1] = 0;
+  return new_ext(v, pk, pos, 1, other);
+}
+
+// ---- insert of one key below `base`, which sits at depth `depth` on the key's path (HostArena::insert, iterative) ----
+PPD_HD inline uint32_t split_at(const View& v, const SOp& o, uint32_t pos, uint32_t cp, uint32_t existing_nib, uint32_t existing, uint32_t txn) {
+  const uint32_t at = pos + cp;
+  if (at >= o.klen) {
+    raise(v, TXF_KEY_PREFIX, txn);
+    return existing;
+  }
+  const uint32_t new_nib = key_nib(v, o.koff, at);
+  uint32_t kids[16];
+  for (int i = 0; i < 16; i++) kids[i] = NODE_EMPTY;
+  kids[existing_nib] = existing;
+  kids[new_nib] = new_leaf_for(v, o, at + 1);
+  const uint32_t br = new_branch16(v, kids, 0);
+  return cp == 0 ? br : new_ext(v, o.koff, pos, cp, br);
+}
+PPD_HD inline uint32_t insert_one(const View& v, uint32_t base, uint32_t depth, const SOp& o, uint32_t txn) {
+  uint32_t st_node[PATH_CAP];
+  uint8_t st_nib[PATH_CAP];  // 0..15: branch slot; 0xff: extension
+  uint32_t sp = 0, node = base, pos = depth, result;
+  for (;;) {
+    if (node == NODE_EMPTY) {
+      result = new_leaf_for(v, o, pos);
+      break;
+    }
+    const uint32_t k = kind_of(v, node);
+    if (k == NK_HASH || k == NK_ROOT) {
+      raise(v, TXF_INSERT_INTO_HASH, txn);
+      return base;
+    }
+    const NodeRec r = v.nodes[node];
+    const uint32_t ns = (r.w0 >> 8) & 0xffu, nl = (r.w0 >> 16) & 0xffu;
+    if (k == NK_BRANCH) {
+      if (pos >= o.klen || sp == PATH_CAP) {
+        raise(v, pos >= o.klen ? TXF_KEY_PREFIX : TXF_STACK, txn);
+        return base;
+      }
+      const uint32_t nib = key_nib(v, o.koff, pos);
+      st_node[sp] = node, st_nib[sp] = (uint8_t)nib, sp++;
+      node = child_at(v, r, nib);
+      pos++;
+    } else if (k == NK_EXT) {
+      const uint32_t avail = o.klen - pos, m = avail < nl ? avail : nl;
+      const uint32_t cp = common_prefix(v, r.a0, ns, o.koff, pos, m);
+      if (cp == nl) {
+        if (sp == PATH_CAP) {
+          raise(v, TXF_STACK, txn);
+          return base;
+        }
+        st_node[sp] = node, st_nib[sp] = 0xff, sp++;
+        node = r.a1;
+        pos += nl;
+      } else {
+        const uint32_t rem = nl - cp - 1;
+        const uint32_t existing = rem == 0 ? r.a1 : new_ext(v, r.a0, ns + cp + 1, rem, r.a1);
+        result = split_at(v, o, pos, cp, key_nib(v, r.a0, ns + cp), existing, txn);
+        break;
+      }
+    } else {  // leaves
+      const uint32_t avail = o.klen - pos, m = avail < nl ? avail : nl;
+      const uint32_t cp = common_prefix(v, r.a0, ns, o.koff, pos, m);
+      if (cp == nl && nl == avail) {
+        result = new_leaf_for(v, o, pos);  // overwrite
+      } else if (cp == nl) {
+        raise(v, TXF_KEY_PREFIX, txn);
+        return base;
+      } else {
+        const uint32_t existing = releaf(v, node, r.a0, ns + cp + 1, nl - cp - 1);
+        result = split_at(v, o, pos, cp, key_nib(v, r.a0, ns + cp), existing, txn);
+      }
+      break;
+    }
+  }
+  while (sp) {
+    sp--;
+    if (st_nib[sp] == 0xff) {
+      const NodeRec r = v.nodes[st_node[sp]];
+      result = new_ext(v, r.a0, (r.w0 >> 8) & 0xffu, (r.w0 >> 16) & 0xffu, result);
+    } else {
+      result = branch_with(v, st_node[sp], st_nib[sp], result);
+    }
+  }
+  return result;
+}
+
+// ---- marking walk (create_trie_subset's mark_nodes_that_are_needed); returns the leaf holding the key or NODE_EMPTY ----
+PPD_HD inline uint32_t mark_item(const View& v, uint32_t root, uint32_t koff, uint32_t klen, uint32_t* out, uint32_t txn) {
+  uint32_t node = root, pos = 0, cnt = 0;
+  while (node != NODE_EMPTY) {
+    if (cnt == MARK_SLOTS_T) {
+      raise(v, TXF_MARK_SLOTS, txn);
+      break;
+    }
+    out[cnt++] = node;
+    if (is_hash_id(node)) {
+      if (pos < klen) raise(v, TXF_MARK_INTO_HASH, txn);
+      break;
+    }
+    const NodeRec r = v.nodes[node];
+    const uint32_t kind = r.w0 & 0xffu;
+    if (kind == NK_ROOT) {
+      if (pos < klen) raise(v, TXF_MARK_INTO_HASH, txn);
+      break;
+    }
+    if (kind == NK_BRANCH) {
+      if (pos >= klen) break;
+      node = child_at(v, r, key_nib(v, koff, pos));
+      pos++;
+    } else if (kind == NK_EXT) {
+      const uint32_t es = (r.w0 >> 8) & 0xffu, el = (r.w0 >> 16) & 0xffu, avail = klen - pos, m = avail < el ? avail : el;
+      if (common_prefix(v, r.a0, es, koff, pos, m) != m || avail < el) break;
+      pos += el;
+      node = r.a1;
+    } else {
+      const uint32_t ls = (r.w0 >> 8) & 0xffu, ll = (r.w0 >> 16) & 0xffu;
+      if (ll == klen - pos && common_prefix(v, r.a0, ls, koff, pos, ll) == ll) return node;
+      break;
+    }
+  }
+  return NODE_EMPTY;
+}
+
+// ---- one batched update: ops[0 .. n) sorted by (trie, key) ----------------------------------------------------
+struct Batch {
+  const SOp* ops;
+  uint32_t n;
+  uint32_t txn;
+};
+
+PPD_HD inline uint32_t trie_root_of(const View& v, uint32_t owner) {
+  if (owner == OWNER_STATE_TRIE) return v.cur->state_root;
+  if (owner == OWNER_TXN_TRIE) return v.cur->txn_root;
+  if (owner == OWNER_RECEIPT_TRIE) return v.cur->receipt_root;
+  return v.acct[v.traces[owner].acct].storage;
+}
+
+// phase 1: the walk of op i
+PPD_HD inline void batch_walk(const Ctx& c, const Batch& b, uint32_t i) {
+  const View& v = c.v;
+  const SOp o = b.ops[i];
+  uint32_t node = trie_root_of(v, o.owner), pos = 0, pl = 0, deepest = 0;
+  uint32_t* pn = v.path_node + (size_t)i * PATH_CAP;
+  uint8_t* pd = v.path_depth + (size_t)i * PATH_CAP;
+  uint32_t tk = TK_EMPTY, tn = NODE_EMPTY, td = 0;
+  const bool put = o.kind != OP_DEL;
+  for (;;) {
+    if (node == NODE_EMPTY) {
+      tk = TK_EMPTY, td = pos;
+      break;
+    }
+    const uint32_t k = kind_of(v, node);
+    if (k == NK_HASH || k == NK_ROOT) {
+      tk = TK_HASH, tn = node, td = pos;
+      if (put) raise(v, TXF_INSERT_INTO_HASH, b.txn);
+      break;
+    }
+    const NodeRec r = v.nodes[node];
+    const uint32_t ns = (r.w0 >> 8) & 0xffu, nl = (r.w0 >> 16) & 0xffu;
+    if (k == NK_BRANCH) {
+      if (pos >= o.klen || pl == PATH_CAP) {
+        if (pos >= o.klen) {
+          if (put) raise(v, TXF_KEY_PREFIX, b.txn);
+        } else {
+          raise(v, TXF_PATH_DEPTH, b.txn);
+        }
+        tk = TK_BAD, tn = node, td = pos;
+        break;
+      }
+      pn[pl] = node, pd[pl] = (uint8_t)pos, pl++;
+      deepest = pos;
+      node = child_at(v, r, key_nib(v, o.koff, pos));
+      pos++;
+    } else if (k == NK_EXT) {
+      const uint32_t avail = o.klen - pos, m = avail < nl ? avail : nl;
+      const uint32_t cp = common_prefix(v, r.a0, ns, o.koff, pos, m);
+      if (cp == nl) {
+        if (pl == PATH_CAP) {
+          raise(v, TXF_PATH_DEPTH, b.txn);
+          tk = TK_BAD, tn = node, td = pos;
+          break;
+        }
+        pn[pl] = node, pd[pl] = (uint8_t)pos, pl++;
+        deepest = pos;
+        node = r.a1;
+        pos += nl;
+      } else {
+        if (cp == avail && put) raise(v, TXF_KEY_PREFIX, b.txn);
+        tk = TK_DIVERGE, tn = node, td = pos;
+        deepest = pos;
+        break;
+      }
+    } else {
+      const uint32_t avail = o.klen - pos, m = avail < nl ? avail : nl;
+      const uint32_t cp = common_prefix(v, r.a0, ns, o.koff, pos, m);
+      const bool same = cp == nl && nl == avail;
+      if (!same && (cp == nl || cp == avail) && put) raise(v, TXF_KEY_PREFIX, b.txn);
+      tk = same ? TK_LEAF_SAME : TK_LEAF_OTHER, tn = node, td = pos;
+      break;
+    }
+  }
+  v.plen[i] = (uint8_t)pl, v.top[i] = (uint8_t)pl;
+  v.tnode[i] = tn, v.tdepth[i] = (uint8_t)td, v.tkind[i] = (uint8_t)tk;
+  v.res[i] = T_UNCHANGED;
+  if (pl || tk == TK_DIVERGE) PPD_ATOMIC_MAX(c.sh_dmax, deepest + 1u);  // (depth + 1: 0 means no entry anywhere)
+}
+
+// phase 2: terminals resolved by their owners (the first key of the group that ends at the same place)
+PPD_HD inline void batch_terminal(const Ctx& c, const Batch& b, uint32_t i) {
+  const View& v = c.v;
+  const uint32_t tk = v.tkind[i], td = v.tdepth[i];
+  if (tk == TK_DIVERGE || tk == TK_HASH || tk == TK_BAD) return;  // the extension is handled with the path nodes
+  if ((int)b.ops[i].lcp >= (int)td) return;                       // shares the terminal with its predecessor
+  uint32_t base = tk == TK_EMPTY ? NODE_EMPTY : v.tnode[i];
+  bool changed = false;
+  // a delete of the leaf's own key first, then the inserts (the order of distinct keys does not matter)
+  for (uint32_t j = i; j < b.n && (j == i || (int)b.ops[j].lcp >= (int)td); j++)
+    if (b.ops[j].kind == OP_DEL && v.tkind[j] == TK_LEAF_SAME) base = NODE_EMPTY, changed = true;
+  for (uint32_t j = i; j < b.n && (j == i || (int)b.ops[j].lcp >= (int)td); j++)
+    if (b.ops[j].kind != OP_DEL) base = insert_one(v, base, td, b.ops[j], b.txn), changed = true;
+  v.res[i] = changed ? base : T_UNCHANGED;
+}
+
+// phase 3, once per depth d from the deepest entry up to 0: the owner of the path node that starts at depth d
+// creates its new version from the results of the children its range touched
+PPD_HD inline void batch_assemble(const Ctx& c, const Batch& b, uint32_t i, uint32_t d) {
+  const View& v = c.v;
+  uint32_t node;
+  const uint32_t t = v.top[i];
+  if (t > 0 && v.path_depth[(size_t)i * PATH_CAP + t - 1] == d) {
+    node = v.path_node[(size_t)i * PATH_CAP + t - 1];
+    v.top[i] = (uint8_t)(t - 1);
+  } else if (v.tkind[i] == TK_DIVERGE && v.tdepth[i] == d) {
+    node = v.tnode[i];
+  } else {
+    return;
+  }
+  if ((int)b.ops[i].lcp >= (int)d) return;  // not the owner
+  const NodeRec r = v.nodes[node];
+  const uint32_t koff = b.ops[i].koff;
+  if ((r.w0 & 0xffu) == NK_BRANCH) {
+    uint32_t kids[16];
+    {
+      const uint32_t mask = r.a1 & 0xffffu;
+      uint32_t q = 0;
+      for (uint32_t nib = 0; nib < 16; nib++) kids[nib] = (mask >> nib) & 1u ? v.child_pool[r.a0 + q++] : NODE_EMPTY;
+    }
+    bool changed = false;
+    uint32_t lv = v.level[node];
+    for (uint32_t j = i; j < b.n && (j == i || (int)b.ops[j].lcp >= (int)d); j++) {
+      if (j != i && (int)b.ops[j].lcp > (int)d) continue;  // same child as its predecessor
+      const uint32_t rj = v.res[j];
+      if (rj == T_UNCHANGED) continue;
+      kids[key_nib(v, b.ops[j].koff, d)] = rj;
+      changed = true;
+    }
+    if (!changed) {
+      v.res[i] = T_UNCHANGED;
+      return;
+    }
+    uint32_t nk = 0, last = 0;
+    for (uint32_t nib = 0; nib < 16; nib++)
+      if (kids[nib] != NODE_EMPTY) nk++, last = nib;
+    if (nk >= 2)
+      v.res[i] = new_branch16(v, kids, lv);
+    else if (nk == 1)
+      v.res[i] = collapse_branch(v, koff, d, last, kids[last]);
+    else
+      v.res[i] = NODE_EMPTY;
+    return;
+  }
+  // an extension: the keys that run through it changed its child; the ones that leave it half way split it
+  const uint32_t es = (r.w0 >> 8) & 0xffu, el = (r.w0 >> 16) & 0xffu;
+  uint32_t base = node;
+  bool changed = false;
+  for (uint32_t j = i; j < b.n && (j == i || (int)b.ops[j].lcp >= (int)d); j++) {
+    if (v.tkind[j] == TK_DIVERGE && v.tdepth[j] == d) continue;
+    // the first key that runs through owns the child's result (every earlier key of the range leaves inside the extension)
+    const uint32_t rj = v.res[j];
+    if (rj == NODE_EMPTY)
+      base = NODE_EMPTY, changed = true;
+    else if (rj != T_UNCHANGED)
+      base = collapse_ext(v, r.a0, es, el, rj), changed = true;
+    break;
+  }
+  for (uint32_t j = i; j < b.n && (j == i || (int)b.ops[j].lcp >= (int)d); j++)
+    if (v.tkind[j] == TK_DIVERGE && v.tdepth[j] == d && b.ops[j].kind != OP_DEL) base = insert_one(v, base, d, b.ops[j], b.txn), changed = true;
+  v.res[i] = changed ? base : T_UNCHANGED;
+}
+
+// ---- op preparation (all txns at once, before the loop) -----------------------------------------------------
+// 32-byte keys compare as big-endian numbers == bytewise
+PPD_HD inline int cmp32(const uint8_t* a, const uint8_t* b) {
+  for (int i = 0; i < 32; i++)
+    if (a[i] != b[i]) return a[i] < b[i] ? -1 : 1;
+  return 0;
+}
+PPD_HD inline int lcp_nibbles(const View& v, uint32_t ka, uint32_t na, uint32_t kb, uint32_t nb) {
+  const uint32_t m = na < nb ? na : nb;
+  uint32_t i = 0;
+  while (i < m && key_nib(v, ka, i) == key_nib(v, kb, i)) i++;
+  return (int)i;
+}
+PPD_HD inline const uint8_t* digest(const View& v, uint32_t m) { return v.key_pool + v.dig_base + 32ull * m; }
+
+// per trace t: the byte ranges of the FlatBlock whose Keccak-256 the loop needs (utils.rs:11-13 call sites
+// processed_block_trace.rs:219,234,277 and decoding.rs:235), as (begin, end) pairs indexed like the digests
+PPD_HD inline void prep_msgs(const View& v, uint32_t t, uint64_t* se) {
+  const TxnTrace& tr = v.traces[t];
+  se[2 * t] = tr.off_addr, se[2 * t + 1] = tr.off_addr + 20ull;
+  for (uint32_t k = 0; k < tr.n_reads; k++) se[2 * (tr.m_reads + k)] = tr.off_reads + 32ull * k, se[2 * (tr.m_reads + k) + 1] = tr.off_reads + 32ull * k + 32;
+  for (uint32_t k = 0; k < tr.n_writes; k++) {
+    const uint64_t key = tr.off_writes + 64ull * k;
+    se[2 * (tr.m_wfull + k)] = key, se[2 * (tr.m_wfull + k) + 1] = key + 32;
+    if (tr.flags & TRF_MIN_KEYS) {  // Nibbles::bytes_be() drops leading zero bytes (decoding.rs:235)
+      uint32_t z = 0;
+      while (z < 32 && v.flat[key + z] == 0) z++;
+      se[2 * (tr.m_wmin + k)] = key + z, se[2 * (tr.m_wmin + k) + 1] = key + 32;
+    }
+  }
+  if ((tr.flags & PPD_TR_CODE_WRITE) && !(tr.flags & PPD_TR_CODE_READ)) se[2 * tr.m_code] = tr.code_off, se[2 * tr.m_code + 1] = (uint64_t)tr.code_off + tr.code_len;
+}
+
+// per trace t: its rank among the traces of its txn by hashed address, and its state op
+PPD_HD inline void prep_trace(const View& v, uint32_t t) {
+  TxnTrace& tr = v.traces[t];
+  const TxnDesc& tx = v.txns[tr.txn];
+  const uint8_t* me = digest(v, t);
+  const bool state_op = (tr.flags & (TRF_STATE_WRITE | PPD_TR_SELF_DESTRUCTED)) != 0;
+  uint32_t rank = 0, srank = 0;
+  for (uint32_t u = tx.trace_begin; u < tx.trace_end; u++) {
+    if (u == t) continue;
+    const int c = cmp32(digest(v, u), me);
+    if (c == 0) raise(v, TXF_DUP_KEY, tr.txn);
+    if (c < 0 || (c == 0 && u < t)) {
+      rank++;
+      if (v.traces[u].flags & (TRF_STATE_WRITE | PPD_TR_SELF_DESTRUCTED)) srank++;
+    }
+  }
+  tr.rank = rank;
+  if (me[0] == 0) raise(v, TXF_SHORT_HADDR, tr.txn);  // H256::from_slice(&nibbles.bytes_be()), decoding.rs:202
+  if (state_op) {
+    SOp o;
+    o.koff = v.dig_base + 32u * t, o.klen = 64, o.lcp = -1, o.pad = 0;
+    o.kind = (tr.flags & PPD_TR_SELF_DESTRUCTED) ? OP_DEL : OP_PUT_ACCOUNT;
+    o.a1 = tr.rec, o.a2 = 0, o.owner = OWNER_STATE_TRIE;
+    v.ops2[tx.op2_begin + srank] = o;
+  }
+}
+// per written slot (trace t, write w): rlp(U256 value) into val_pool, its rank among the trace's writes, its op
+PPD_HD inline void prep_write(const View& v, uint32_t t, uint32_t w) {
+  const TxnTrace& tr = v.traces[t];
+  const uint8_t* me = digest(v, tr.m_wmin + w);
+  uint32_t rank = 0;
+  for (uint32_t u = 0; u < tr.n_writes; u++) {
+    if (u == w) continue;
+    const int c = cmp32(digest(v, tr.m_wmin + u), me);
+    if (c == 0) raise(v, TXF_DUP_KEY, tr.txn);
+    if (c < 0 || (c == 0 && u < w)) rank++;
+  }
+  const uint8_t* val = v.flat + tr.off_writes + 64ull * w + 32;
+  uint32_t z = 0;
+  while (z < 32 && val[z] == 0) z++;
+  const uint32_t sig = 32 - z;
+  SOp o;
+  o.koff = v.dig_base + 32u * (tr.m_wmin + w), o.klen = 64, o.lcp = -1, o.pad = 0, o.owner = t;
+  if (sig == 0) {  // rlp(0) == [0x80]: a delete (decoding.rs:238-243)
+    o.kind = OP_DEL, o.a1 = o.a2 = 0;
+  } else {
+    uint8_t* dst = v.val_pool + tr.val0 + 36u * w;
+    uint32_t el = 0;
+    if (sig == 1 && val[31] < 0x80) {
+      dst[el++] = val[31];
+    } else {
+      dst[el++] = (uint8_t)(0x80 + sig);
+      for (uint32_t k = 0; k < sig; k++) dst[el++] = val[z + k];
+    }
+    o.kind = OP_PUT_LEAF, o.a1 = tr.val0 + 36u * w, o.a2 = el;
+  }
+  v.ops1[tr.op0 + rank] = o;
+}
+// per txn: the inserts into the transactions and receipts tries (decoding.rs:284-289), after the storage ops
+PPD_HD inline void prep_txn(const View& v, uint32_t ti) {
+  const TxnDesc& tx = v.txns[ti];
+  SOp o;
+  o.koff = tx.key_off, o.klen = (uint8_t)tx.key_nibs, o.lcp = -1, o.pad = 0, o.kind = OP_PUT_LEAF;
+  o.a1 = tx.val_txn, o.a2 = tx.len_txn_bytes, o.owner = OWNER_TXN_TRIE;
+  v.ops1[tx.op1_end - 2] = o;
+  o.a1 = tx.val_receipt, o.a2 = tx.len_receipt, o.owner = OWNER_RECEIPT_TRIE;
+  v.ops1[tx.op1_end - 1] = o;
+  for (uint32_t k = 0; k < tx.len_txn_bytes; k++) v.val_pool[tx.val_txn + k] = v.flat[tx.off_txn_bytes + k];
+  for (uint32_t k = 0; k < tx.len_receipt; k++) v.val_pool[tx.val_receipt + k] = v.flat[tx.off_receipt + k];
+}
+// per sorted op: the LCP with its predecessor in the same trie
+PPD_HD inline void prep_lcp(const View& v, SOp* ops, uint32_t i, uint32_t seg_first) {
+  if (i == seg_first || ops[i - 1].owner != ops[i].owner) {
+    ops[i].lcp = -1;
+    return;
+  }
+  const int l = lcp_nibbles(v, ops[i - 1].koff, ops[i - 1].klen, ops[i].koff, ops[i].klen);
+  if (l >= (int)ops[i].klen || l >= (int)ops[i - 1].klen) raise(v, TXF_DUP_KEY, 0);
+  ops[i].lcp = (int8_t)l;
+}
+
+// ---- the account table: slot of every trace's address, initial PartialTrieState entry of every account --------
+struct AcctInit {
+  uint32_t table_mask;           // slots - 1
+  uint32_t state_root;           // root of the pre-image state trie
+  const uint32_t* join_storage;  // per pre-image account: root of the storage trie the by-root join gives it, or ST_ABSENT
+  const uint32_t* join_root;     // its NK_ROOT node, or NONE
+};
+PPD_HD inline uint32_t get_leaf(const View& v, uint32_t root, uint32_t koff, uint32_t klen) {
+  uint32_t node = root, pos = 0;
+  while (node != NODE_EMPTY) {
+    if (is_hash_id(node)) return NODE_EMPTY;
+    const NodeRec r = v.nodes[node];
+    const uint32_t kind = r.w0 & 0xffu, ns = (r.w0 >> 8) & 0xffu, nl = (r.w0 >> 16) & 0xffu;
+    if (kind == NK_ROOT) return NODE_EMPTY;
+    if (kind == NK_BRANCH) {
+      if (pos >= klen) return NODE_EMPTY;
+      node = child_at(v, r, key_nib(v, koff, pos));
+      pos++;
+    } else if (kind == NK_EXT) {
+      if (klen - pos < nl || common_prefix(v, r.a0, ns, koff, pos, nl) != nl) return NODE_EMPTY;
+      pos += nl;
+      node = r.a1;
+    } else {
+      return (nl == klen - pos && common_prefix(v, r.a0, ns, koff, pos, nl) == nl) ? node : NODE_EMPTY;
+    }
+  }
+  return NODE_EMPTY;
+}
+PPD_HD inline void acct_claim(const View& v, const AcctInit& a, uint32_t t) {
+  const uint8_t* me = digest(v, t);
+  uint32_t h = ((uint32_t)me[4] | ((uint32_t)me[5] << 8) | ((uint32_t)me[6] << 16) | ((uint32_t)me[7] << 24)) & a.table_mask;
+  for (;;) {
+    const uint32_t prev = PPD_ATOMIC_CAS(&v.acct[h].owner, 0xffffffffu, t);
+    if (prev == 0xffffffffu) {
+      // first trace of this address: the account's entry in the initial PartialTrieState
+      AcctState s;
+      s.owner = t, s.storage = ST_ABSENT, s.root_node = NONE, s.pre_rec = NONE;
+      const uint32_t leaf = get_leaf(v, a.state_root, v.dig_base + 32u * t, 64);
+      if (leaf != NODE_EMPTY && (v.nodes[leaf].w0 & 0xffu) == NK_LEAF_ACCOUNT) {
+        const uint32_t r = v.nodes[leaf].a1;
+        s.pre_rec = r, s.storage = a.join_storage[r], s.root_node = a.join_root[r];
+      }
+      v.acct[h].storage = s.storage, v.acct[h].root_node = s.root_node, v.acct[h].pre_rec = s.pre_rec;
+      v.traces[t].acct = h;
+      return;
+    }
+    if (prev == t || cmp32(digest(v, prev), me) == 0) {
+      v.traces[t].acct = h;
+      return;
+    }
+    h = (h + 1) & a.table_mask;
+  }
+}
+
+// ---- the loop itself: one thread block per block of txns (the harness runs it as a block of one thread) ------
+#if defined(__CUDA_ARCH__)
+#define PPD_BLOCK_SYNC() __syncthreads()
+#else
+#define PPD_BLOCK_SYNC() ((void)0)
+#endif
+
+PPD_HD inline void run_batch(const Ctx& c, const Batch& b) {
+  const View& v = c.v;
+  if (c.tid == 0) *c.sh_dmax = 0;
+  PPD_BLOCK_SYNC();
+  for (uint32_t i = c.tid; i < b.n; i += c.nthreads) batch_walk(c, b, i);
+  PPD_BLOCK_SYNC();
+  for (uint32_t i = c.tid; i < b.n; i += c.nthreads) batch_terminal(c, b, i);
+  PPD_BLOCK_SYNC();
+  const uint32_t dmax = *c.sh_dmax;
+  for (uint32_t d = dmax; d-- > 0;) {
+    for (uint32_t i = c.tid; i < b.n; i += c.nthreads) batch_assemble(c, b, i, d);
+    PPD_BLOCK_SYNC();
+  }
+  // the first op of every trie holds the trie's new root
+  for (uint32_t i = c.tid; i < b.n; i += c.nthreads) {
+    if (b.ops[i].lcp != -1) continue;
+    const uint32_t r = v.res[i];
+    if (r == T_UNCHANGED) continue;
+    const uint32_t owner = b.ops[i].owner;
+    if (owner == OWNER_STATE_TRIE) {
+      v.cur->state_root = r;
+    } else if (owner == OWNER_TXN_TRIE) {
+      v.cur->txn_root = r;
+    } else if (owner == OWNER_RECEIPT_TRIE) {
+      v.cur->receipt_root = r;
+    } else {
+      AcctState& a = v.acct[v.traces[owner].acct];
+      a.storage = r, a.root_node = NONE;
+    }
+  }
+  PPD_BLOCK_SYNC();
+}
+
+// the trace that owns the k-th storage marking walk of the txn (item0 ascends with the trace index)
+PPD_HD inline uint32_t trace_of_item(const View& v, const TxnDesc& tx, uint32_t k) {
+  uint32_t lo = tx.trace_begin, hi = tx.trace_end;  // last trace with item0 <= k
+  while (hi - lo > 1) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (v.traces[mid].item0 <= k)
+      lo = mid;
+    else
+      hi = mid;
+  }
+  return lo;
+}
+
+PPD_HD inline void copy32(uint8_t* d, const uint8_t* s) {
+  for (int i = 0; i < 32; i++) d[i] = s[i];
+}
+
+PPD_HD inline void run_txn(const Ctx& c, uint32_t ti, const uint8_t* empty_trie_hash, const uint8_t* empty_code_hash) {
+  const View& v = c.v;
+  const TxnDesc tx = v.txns[ti];
+  const uint32_t ntr = tx.trace_end - tx.trace_begin;
+  // ---- the tries the subsets are cut from (decoding.rs:179-217): roots before the txn ----
+  if (c.tid == 0) {
+    v.seg_b[tx.seg_tries + 0] = v.cur->state_root;
+    v.seg_b[tx.seg_tries + 1] = v.cur->txn_root;
+    v.seg_b[tx.seg_tries + 2] = v.cur->receipt_root;
+  }
+  for (uint32_t k = c.tid; k < ntr; k += c.nthreads) {
+    const uint32_t t = tx.trace_begin + k;
+    const TxnTrace& tr = v.traces[t];
+    AcctState& a = v.acct[tr.acct];
+    if (a.storage == ST_ABSENT) {
+      // a missing storage trie: Hash(pre-image storage root) when the account had storage in the pre-image and this txn
+      // does not access its slots, else an empty trie (decoding.rs:572-582); it stays in the live state
+      uint32_t s = NODE_EMPTY;
+      if (a.pre_rec != NONE && (v.pre_flags[a.pre_rec] & 1u) && tr.n_reads + tr.n_writes == 0) s = v.accounts[a.pre_rec].storage_src;
+      a.storage = s, a.root_node = NONE;
+    }
+    v.seg_a[tx.seg_storage + 2 * tr.rank] = v.dig_base + 32u * t;
+    v.seg_b[tx.seg_storage + 2 * tr.rank] = IR_SEG_KEY32;
+    v.seg_a[tx.seg_storage + 2 * tr.rank + 1] = 0;
+    v.seg_b[tx.seg_storage + 2 * tr.rank + 1] = a.storage;
+  }
+  PPD_BLOCK_SYNC();
+  // ---- marking walks: every accessed key on the tries before the txn ----
+  {
+    uint32_t n_storage_items = 0;
+    if (ntr) {
+      const TxnTrace& last = v.traces[tx.trace_end - 1];
+      n_storage_items = last.item0 + last.n_reads + last.n_writes;
+    }
+    const uint32_t n_items = ntr + 2 + n_storage_items;
+    for (uint32_t k = c.tid; k < n_items; k += c.nthreads) {
+      uint32_t* out = v.touched + tx.touched_base + MARK_SLOTS_T * k;
+      if (k < ntr) {
+        const uint32_t t = tx.trace_begin + k;
+        v.acct_leaf[k] = mark_item(v, v.cur->state_root, v.dig_base + 32u * t, 64, out, ti);
+      } else if (k == ntr) {
+        mark_item(v, v.cur->txn_root, tx.key_off, tx.key_nibs, out, ti);
+      } else if (k == ntr + 1) {
+        mark_item(v, v.cur->receipt_root, tx.key_off, tx.key_nibs, out, ti);
+      } else {
+        const uint32_t q = k - ntr - 2, t = trace_of_item(v, tx, q);
+        const TxnTrace& tr = v.traces[t];
+        const uint32_t j = q - tr.item0;
+        const uint32_t m = j < tr.n_reads ? tr.m_reads + j : tr.m_wfull + (j - tr.n_reads);
+        mark_item(v, v.acct[tr.acct].storage, v.dig_base + 32u * m, 64, out, ti);
+      }
+    }
+  }
+  PPD_BLOCK_SYNC();
+  // ---- apply_deltas_to_trie_state (decoding.rs:219-292): storage writes, the txn and receipt inserts ----
+  run_batch(c, Batch{v.ops1 + tx.op1_begin, tx.op1_end - tx.op1_begin, ti});
+  // ---- the accounts after the txn: storage_root = the storage trie's hash after the writes (late-bound: an NK_ROOT node) ----
+  for (uint32_t k = c.tid; k < ntr; k += c.nthreads) {
+    const uint32_t t = tx.trace_begin + k;
+    const TxnTrace& tr = v.traces[t];
+    if (!(tr.flags & TRF_STATE_WRITE)) continue;
+    AccountRec rec;
+    const uint32_t leaf = v.acct_leaf[k];
+    if (leaf != NODE_EMPTY) {
+      if ((v.nodes[leaf].w0 & 0xffu) != NK_LEAF_ACCOUNT) {
+        raise(v, TXF_NOT_ACCOUNT, ti);
+        continue;
+      }
+      rec = v.accounts[v.nodes[leaf].a1];
+    } else {  // EMPTY_ACCOUNT_BYTES_RLPED, decoding.rs:251-254
+      for (int i = 0; i < 32; i++) rec.nonce[i] = 0, rec.balance[i] = 0;
+      copy32(rec.storage_root, empty_trie_hash);
+      copy32(rec.code_hash, empty_code_hash);
+      rec.storage_src = NODE_EMPTY;
+      rec.pad[0] = rec.pad[1] = rec.pad[2] = 0;
+    }
+    if (tr.n_writes) {
+      AcctState& a = v.acct[tr.acct];
+      if (a.root_node == NONE) a.root_node = new_root(v, a.storage);
+      rec.storage_src = a.root_node;
+    }
+    if (tr.flags & PPD_TR_BALANCE) copy32(rec.balance, v.flat + tr.off_balance);
+    if (tr.flags & PPD_TR_NONCE) copy32(rec.nonce, v.flat + tr.off_nonce);
+    if (tr.flags & PPD_TR_CODE_READ)
+      copy32(rec.code_hash, v.flat + tr.code_off);
+    else if (tr.flags & PPD_TR_CODE_WRITE)
+      copy32(rec.code_hash, digest(v, tr.m_code));
+    v.accounts[tr.rec] = rec;
+  }
+  PPD_BLOCK_SYNC();
+  // ---- state writes and self-destructs in one descent ----
+  run_batch(c, Batch{v.ops2 + tx.op2_begin, tx.op2_end - tx.op2_begin, ti});
+  for (uint32_t k = c.tid; k < ntr; k += c.nthreads) {
+    const TxnTrace& tr = v.traces[tx.trace_begin + k];
+    if (tr.flags & PPD_TR_SELF_DESTRUCTED) {  // trie_state.storage.remove(hashed_addr), decoding.rs:271-282
+      AcctState& a = v.acct[tr.acct];
+      a.storage = ST_ABSENT, a.root_node = NONE;
+    }
+  }
+  // ---- calculate_trie_input_hashes (decoding.rs:458-464): three NK_ROOT nodes, read by the dump as refs ----
+  if (c.tid == 0) {
+    v.seg_a[tx.seg_roots + 0] = new_root(v, v.cur->state_root);
+    v.seg_a[tx.seg_roots + 1] = new_root(v, v.cur->txn_root);
+    v.seg_a[tx.seg_roots + 2] = new_root(v, v.cur->receipt_root);
+  }
+  PPD_BLOCK_SYNC();
+}
+
+}  // namespace txn
+}  // namespace ppd
