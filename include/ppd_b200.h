@@ -49,6 +49,9 @@ typedef struct ppd_stats {
   double parse_gpu_ms;            /* device time of their parse / arena kernels (CUDA events) */
   uint64_t level_launches;        /* launches of the level-hashing kernel (one per level per block) */
   uint64_t marks_on_gpu;          /* create_trie_subset marking walks (one per accessed key per txn) done by the device */
+  uint64_t txn_loops_on_gpu;      /* blocks whose txn loop (decoding.rs:80-177: deltas, subsets, roots) ran on the device (ppd_txn.cu) */
+  double txn_gpu_ms;              /* device time of those loops (CUDA events) */
+  double dump_gpu_ms;             /* device time of the IrDump kernels (ppd_dump.cu) */
 } ppd_stats;
 
 int ppd_ctx_create(int device, ppd_ctx** out);

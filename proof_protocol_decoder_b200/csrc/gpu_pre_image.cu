@@ -29,7 +29,27 @@ struct Carve {
   }
 };
 
-bool gpu_pre_image(Lane* L, Job& J, BlockJob& b, bool check_version, Slots* slots) {
+// Host bytes to the device on the lane's stream.  A page-locked caller buffer (ppd_alloc_pinned, cudaHostRegister) is
+// read by the copy engine directly.  A pageable one is staged through the lane's page-locked buffer in chunks:
+// concurrent pageable cudaMemcpyAsync calls serialise inside the driver, a plain memcpy per lane does not.
+void upload_bytes(Lane* L, Job& J, uint8_t* dst, const uint8_t* src, size_t n) {
+  cudaPointerAttributes at{};
+  bool pinned = cudaPointerGetAttributes(&at, src) == cudaSuccess && at.type == cudaMemoryTypeHost;
+  if (!pinned) cudaGetLastError();
+  if (pinned) {
+    CUDA_OK(cudaMemcpyAsync(dst, src, n, cudaMemcpyHostToDevice, L->st));
+    return;
+  }
+  J.wit_stage.resize(n);
+  const size_t CH = 4u << 20;
+  for (size_t at0 = 0; at0 < n; at0 += CH) {
+    size_t len = std::min(CH, n - at0);
+    memcpy(J.wit_stage.data() + at0, src + at0, len);
+    CUDA_OK(cudaMemcpyAsync(dst + at0, J.wit_stage.data() + at0, len, cudaMemcpyHostToDevice, L->st));
+  }
+}
+
+bool gpu_pre_image(Lane* L, Job& J, BlockJob& b, bool check_version, Slots* slots, const PreImageDeviceOnly* dev_only) {
 #ifdef PPD_HOSTPROF
   return false;
 #else
@@ -64,30 +84,16 @@ bool gpu_pre_image(Lane* L, Job& J, BlockJob& b, bool check_version, Slots* slot
   auto sync_in_slot = [&] { slots ? lane_sync_poll(L) : lane_sync(L); };
   lap("p:slot-wait");
   // ---- phase A: instruction boundaries ----
-  L->d_wit.reserve(n + 64);
-  {
-    // A page-locked caller buffer (ppd_alloc_pinned, cudaHostRegister) is read by the copy engine directly.
-    // A pageable one is staged through the lane's page-locked buffer in chunks: concurrent pageable
-    // cudaMemcpyAsync calls serialise inside the driver, a plain memcpy per lane does not.
-    cudaPointerAttributes at{};
-    bool pinned = cudaPointerGetAttributes(&at, w) == cudaSuccess && at.type == cudaMemoryTypeHost;
-    if (!pinned) cudaGetLastError();
-    if (pinned) {
-      CUDA_OK(cudaMemcpyAsync(L->d_wit.p, w, n, cudaMemcpyHostToDevice, st));
-    } else {
-      J.wit_stage.resize(n);
-      const size_t CH = 4u << 20;
-      for (size_t at0 = 0; at0 < n; at0 += CH) {
-        size_t len = std::min(CH, n - at0);
-        memcpy(J.wit_stage.data() + at0, w + at0, len);
-        CUDA_OK(cudaMemcpyAsync(L->d_wit.as<uint8_t>() + at0, J.wit_stage.data() + at0, len, cudaMemcpyHostToDevice, st));
-      }
-    }
+  if (dev_only) {
+    // the whole FlatBlock is resident (gpu_txn.cu uploaded it; the 64 bytes after it are zero)
+  } else {
+    L->d_wit.reserve(n + 64);
+    upload_bytes(L, J, L->d_wit.as<uint8_t>(), w, n);
+    CUDA_OK(cudaMemsetAsync(L->d_wit.as<uint8_t>() + n, 0, 64, st));
+    L->stats.h2d_bytes += (double)n;
   }
-  CUDA_OK(cudaMemsetAsync(L->d_wit.as<uint8_t>() + n, 0, 64, st));
-  L->stats.h2d_bytes += (double)n;
   ParseBounds B{};
-  B.wit = L->d_wit.as<uint8_t>();
+  B.wit = dev_only ? dev_only->d_witness : L->d_wit.as<uint8_t>();
   B.n = (uint32_t)n;
   B.n_tiles = (uint32_t)((n + PARSE_TILE - 1) / PARSE_TILE);
   B.group_tiles = 8;
@@ -202,14 +208,24 @@ bool gpu_pre_image(Lane* L, Job& J, BlockJob& b, bool check_version, Slots* slot
     layout_c(c);
   }
   // room for what the txn loop appends, so that the sweep does not have to move the resident part
-  L->d_nodes.reserve(16 * (n_nodes + n_nodes / 2) + 4096);
-  L->d_level.reserve(2 * (n_nodes + n_nodes / 2) + 4096);
+  if (dev_only) {
+    const PreImageDeviceOnly& X = *dev_only;
+    L->d_nodes.reserve(16 * (n_nodes + X.extra_nodes) + 4096);
+    L->d_level.reserve(2 * (n_nodes + X.extra_nodes) + 4096);
+    L->d_keys.reserve(key_bytes + X.extra_keys + 65536);
+    L->d_vals.reserve(val_bytes + X.extra_vals + 65536);
+    L->d_children.reserve(4 * (n_child + X.extra_children) + 4096);
+    L->d_accounts.reserve(sizeof(AccountRec) * (n_acct + X.extra_accounts + 64));
+  } else {
+    L->d_nodes.reserve(16 * (n_nodes + n_nodes / 2) + 4096);
+    L->d_level.reserve(2 * (n_nodes + n_nodes / 2) + 4096);
+    L->d_keys.reserve(2 * key_bytes + 65536);
+    L->d_vals.reserve(2 * val_bytes + 65536);
+    L->d_children.reserve(4 * (n_child + n_child / 2) + 4096);
+    L->d_accounts.reserve(sizeof(AccountRec) * (2 * n_acct + 64));
+  }
   d_level = L->d_level.as<uint16_t>();
-  L->d_keys.reserve(2 * key_bytes + 65536);
-  L->d_vals.reserve(2 * val_bytes + 65536);
   L->d_hashes.reserve(32 * n_hash + 32);
-  L->d_children.reserve(4 * (n_child + n_child / 2) + 4096);
-  L->d_accounts.reserve(sizeof(AccountRec) * (2 * n_acct + 64));
   E.nodes = L->d_nodes.as<NodeRec>();
   E.level = d_level;
   E.key_pool = L->d_keys.as<uint8_t>();
@@ -231,23 +247,28 @@ bool gpu_pre_image(Lane* L, Job& J, BlockJob& b, bool check_version, Slots* slot
   CUDA_OK(cudaEventRecord(L->ev1, st));
   L->stats.kernel_launches += 2;
   slot.done();  // the next lane may start its upload while this one's emit kernels and download run
-  A.nodes.resize(n_nodes), A.level.resize(n_nodes), A.key_pool.resize(key_bytes), A.child_pool.resize(n_child), A.accounts.resize(n_acct);
-  A.val_pool.resize(val_bytes), A.hash_pool.resize(32 * n_hash);  // contents stay on the device (fetch_pools)
-  J.acct_list.resize(5 * n_acct), J.code_list.resize(2 * n_code), J.code_digest.resize(n_code);
   auto down = [&](void* dst, const void* src, size_t bytes) {
     if (!bytes) return;
     CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st));
     L->stats.d2h_bytes += (double)bytes;
   };
-  down(A.nodes.data(), E.nodes, 16 * n_nodes);
-  down(A.level.data(), d_level, 2 * n_nodes);
-  down(A.key_pool.data(), E.key_pool, key_bytes);
-  down(A.child_pool.data(), E.child_pool, 4 * n_child);
-  down(A.accounts.data(), E.accounts, sizeof(AccountRec) * n_acct);
-  down(J.acct_list.data(), E.acct_list, 20 * n_acct);
+  J.code_list.resize(2 * n_code), J.code_digest.resize(n_code);
+  if (!dev_only) {
+    A.nodes.resize(n_nodes), A.level.resize(n_nodes), A.key_pool.resize(key_bytes), A.child_pool.resize(n_child), A.accounts.resize(n_acct);
+    A.val_pool.resize(val_bytes), A.hash_pool.resize(32 * n_hash);  // contents stay on the device (fetch_pools)
+    J.acct_list.resize(5 * n_acct);
+    down(A.nodes.data(), E.nodes, 16 * n_nodes);
+    down(A.level.data(), d_level, 2 * n_nodes);
+    down(A.key_pool.data(), E.key_pool, key_bytes);
+    down(A.child_pool.data(), E.child_pool, 4 * n_child);
+    down(A.accounts.data(), E.accounts, sizeof(AccountRec) * n_acct);
+    down(J.acct_list.data(), E.acct_list, 20 * n_acct);
+  }
   down(J.code_list.data(), E.code_list, 8 * n_code);
   down(J.code_digest.data(), d_code_digest, 32 * n_code);
   down(hr, B.result, 4 * PARSE_R_WORDS);
+  J.dev.nodes = n_nodes, J.dev.keys = key_bytes, J.dev.vals = val_bytes, J.dev.hashes = 32 * n_hash, J.dev.children = n_child, J.dev.accounts = n_acct;
+  if (dev_only && dev_only->after_launch) dev_only->after_launch(dev_only->arg, E);  // queued behind the emit kernels, before the wait below
   lane_sync(L);
   phase_ms();
   lap("p:C+download");
@@ -255,11 +276,16 @@ bool gpu_pre_image(Lane* L, Job& J, BlockJob& b, bool check_version, Slots* slot
     L->stats.key_permutations += J.code_list[2 * k + 1] / 136 + 1;
     b.pre_code[J.code_digest[k]] = Span{w + J.code_list[2 * k], J.code_list[2 * k + 1]};
   }
-  J.dev.nodes = n_nodes, J.dev.keys = key_bytes, J.dev.vals = val_bytes, J.dev.hashes = 32 * n_hash, J.dev.children = n_child, J.dev.accounts = n_acct;
   J.pools_on_host = false;
   // ---- the block's per-account tables (compact_to_partial_trie.rs:167-190), as make_account_record builds them ----
   b.wit.version = w[0];
   b.state_root = hr[PARSE_R_ROOT_ID];
+  if (dev_only) {  // the per-account tables are built on the device (ppd_txn.cu: join_*_kernel, acct_claim_kernel)
+    b.pre_image_on_gpu = true;
+    L->has_last_parse = true, L->last_bounds = B, L->last_emit = E, L->last_ins_pos = ins_pos, L->last_n_code = (uint32_t)n_code, L->last_val_bytes = val_bytes;
+    L->stats.witnesses_on_gpu += 1, L->stats.witness_instructions += n_ins, L->stats.witness_bytes += n;
+    return true;
+  }
   b.storage.reserve(n_acct), b.pre_accounts.reserve(n_acct), b.root_of.reserve(2 * n_acct + 1024);
   if (J.device_marks) b.acct_rec.reserve(n_acct + n_acct / 4);
   b.have_empty_form = false, b.empty_form = NODE_EMPTY;

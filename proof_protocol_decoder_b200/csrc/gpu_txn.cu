@@ -1,0 +1,434 @@
+// gpu_txn.cu — one block decoded with everything after the flat input on the device:
+//
+//   FlatBlock (host) ─H2D─► witness parse + pre-image arena        ppd_parse.cu   (gpu_pre_image, device-only mode)
+//                         ► Keccak of addresses / slot keys / code  ppd_kernels.cu (ranges of the resident FlatBlock)
+//                         ► pre-image hashed level by level         ppd_kernels.cu (the storage roots feed the by-root join)
+//                         ► account join, op sort, THE TXN LOOP     ppd_txn.cu / txn_core.h
+//                         ► the loop's new nodes hashed level by level
+//                         ► every IR sized, laid out and written    ppd_dump.cu    ─D2H─► IrDump (host)
+//
+// The host reads the flat input, lays out descriptors and literals (txn_tables.cu) and launches; it shapes no trie,
+// keeps no arena and copies nothing of the arena back.  Per block it waits five times for a few words (instruction
+// count; pool sizes; code digests + level histogram; the loop's flag + cursors; IR sizes) and once for the output.
+// A block the loop flags (an error the reference would report, or a capacity limit) is redone by the host path
+// (decode_one in ppd_host.cu), which reports errors in the reference's order.
+#include "host_pipeline.h"
+#include "txn_tables.h"
+
+namespace ppd {
+
+bool gpu_txn_enabled() {
+#ifdef PPD_HOSTPROF
+  return false;
+#else
+  return gpu_parse_enabled() && gpu_dump_enabled() && getenv("PPD_HOST_TXN") == nullptr;  // read per call: the tests compare both paths
+#endif
+}
+
+#ifndef PPD_HOSTPROF
+namespace {
+
+struct Carve2 {
+  uint8_t* base;
+  size_t off = 0;
+  template <class T>
+  T* take(size_t count) {
+    off = (off + 255) & ~(size_t)255;
+    T* r = reinterpret_cast<T*>(base + off);
+    off += count * sizeof(T);
+    return r;
+  }
+};
+
+// what the hook queued behind the emit kernels needs, and what it leaves for the rest of the pipeline
+struct HookState {
+  Lane* L;
+  Job* J;
+  TxnTables* T;
+  const uint8_t* d_flat;
+  size_t n_txns;
+  // out
+  TxnBases B{};
+  txn::View v{};
+  txn::JoinView j{};
+  txn::AcctInit ai{};
+  uint32_t table_slots = 0, n_pre_nodes = 0, cap_tail = 0;
+  uint64_t* se = nullptr;
+  uint32_t *bins_pre = nullptr, *bins_tail = nullptr;
+  uint16_t* okeys = nullptr;
+  uint32_t* h_bins = nullptr;   // page-locked: [4096] pre-image bins, [4096] tail bins, then Cursors
+  uint8_t* h_code_digests = nullptr;
+};
+
+void after_emit(void* arg, const ParseEmit& E) {
+  HookState& H = *(HookState*)arg;
+  Lane* L = H.L;
+  Job& J = *H.J;
+  TxnTables& T = *H.T;
+  cudaStream_t st = L->st;
+  const size_t n_nodes = J.dev.nodes, n_acct = J.dev.accounts, n_traces = T.traces.size();
+  H.n_pre_nodes = (uint32_t)n_nodes;
+  H.cap_tail = (uint32_t)T.est_nodes;
+  // ---- where the loop's additions go in the pools ----
+  TxnBases& B = H.B;
+  B.dig_base = (uint32_t)((J.dev.keys + 31) & ~(size_t)31);
+  B.txn_key_base = B.dig_base + 32u * T.n_msgs;
+  B.key_cursor = B.txn_key_base + 12u * (uint32_t)H.n_txns;
+  B.val_base = (uint32_t)((J.dev.vals + 3) & ~(size_t)3);
+  B.rec_base = (uint32_t)n_acct;
+  // ---- device memory of the loop ----
+  uint32_t table = 64;
+  while (table < 2 * n_traces) table <<= 1;
+  uint32_t jtable = 64;
+  while (jtable < 2 * n_acct) jtable <<= 1;
+  H.table_slots = table;
+  txn::View& v = H.v;
+  txn::JoinView& j = H.j;
+  const size_t n_sorted = std::max<size_t>(n_nodes, T.est_nodes);
+  auto layout = [&](Carve2& c) {
+    v.traces = c.take<txn::TxnTrace>(n_traces + 1);
+    H.se = c.take<uint64_t>(2ull * T.n_msgs + 2);
+    v.ops1 = c.take<txn::SOp>(T.n_ops1 + 1);
+    v.ops2 = c.take<txn::SOp>(T.n_ops2 + 1);
+    v.acct = c.take<txn::AcctState>(table);
+    j.slot_owner = c.take<uint32_t>(jtable);
+    j.slot_best = c.take<uint32_t>(jtable);
+    j.join_storage = c.take<uint32_t>(n_acct + 1);
+    j.join_root = c.take<uint32_t>(n_acct + 1);
+    j.pre_flags = c.take<uint8_t>(n_acct + 1);
+    v.path_node = c.take<uint32_t>((size_t)T.max_ops * txn::PATH_CAP + 1);
+    v.path_depth = c.take<uint8_t>((size_t)T.max_ops * txn::PATH_CAP + 1);
+    v.plen = c.take<uint8_t>(T.max_ops + 1);
+    v.top = c.take<uint8_t>(T.max_ops + 1);
+    v.tnode = c.take<uint32_t>(T.max_ops + 1);
+    v.tdepth = c.take<uint8_t>(T.max_ops + 1);
+    v.tkind = c.take<uint8_t>(T.max_ops + 1);
+    v.res = c.take<uint32_t>(T.max_ops + 1);
+    v.acct_leaf = c.take<uint32_t>(T.max_traces + 1);
+    v.cur = c.take<txn::Cursors>(1);
+    H.bins_pre = c.take<uint32_t>(ORDER_MAX_BINS);
+    H.bins_tail = c.take<uint32_t>(ORDER_MAX_BINS);
+    H.okeys = c.take<uint16_t>(n_sorted + 16);
+  };
+  {
+    Carve2 sz{nullptr};
+    layout(sz);
+    L->d_txn.reserve(sz.off + 256);
+    Carve2 c{L->d_txn.as<uint8_t>()};
+    layout(c);
+  }
+  v.nodes = E.nodes, v.level = E.level, v.key_pool = E.key_pool, v.val_pool = E.val_pool, v.hash_pool = E.hash_pool;
+  v.child_pool = E.child_pool, v.accounts = E.accounts;
+  v.cap_nodes = (uint32_t)(n_nodes + T.est_nodes), v.cap_children = (uint32_t)(J.dev.children + T.est_children);
+  v.cap_keys = (uint32_t)std::min<size_t>(L->d_keys.cap, 0xfffffff0u);
+  v.flat = H.d_flat, v.n_txns = (uint32_t)H.n_txns, v.n_traces = (uint32_t)n_traces, v.dig_base = B.dig_base;
+  v.pre_flags = j.pre_flags;
+  j.acct_list = E.acct_list, j.n_acct = (uint32_t)n_acct, j.table_mask = jtable - 1;
+  // ---- the byte strings to hash: straight out of the resident FlatBlock ----
+  CUDA_OK(cudaMemcpyAsync(v.traces, T.traces.data(), sizeof(txn::TxnTrace) * n_traces, cudaMemcpyHostToDevice, st));
+  L->stats.h2d_bytes += (double)(sizeof(txn::TxnTrace) * n_traces);
+  launch_txn_msgs(v, H.se, st);
+  launch_keccak256_ranges(H.d_flat, H.se, T.n_msgs, E.key_pool + B.dig_base, st);
+  L->stats.kernel_launches += 2, L->stats.key_hashes += T.n_msgs;
+  // the digests of written code are keys of the IRs' code maps, which the host sorts
+  for (size_t k = 0; k < T.code_write_traces.size(); k++) {
+    const uint32_t m = T.traces[T.code_write_traces[k]].m_code;
+    CUDA_OK(cudaMemcpyAsync(H.h_code_digests + 32 * k, E.key_pool + B.dig_base + 32ull * m, 32, cudaMemcpyDeviceToHost, st));
+  }
+  // ---- pre-image nodes sorted by (level, class); the host needs where every level starts ----
+  L->d_order.reserve(4ull * n_nodes + 16);
+  CUDA_OK(cudaMemsetAsync(H.bins_pre, 0, 4ull * ORDER_MAX_BINS, st));
+  launch_order_by_level_class(E.nodes, E.level, (uint32_t)n_nodes, ORDER_MAX_BINS, H.okeys, H.bins_pre, L->d_order.as<uint32_t>(), st);
+  CUDA_OK(cudaMemcpyAsync(H.h_bins, H.bins_pre, 4ull * ORDER_MAX_BINS, cudaMemcpyDeviceToHost, st));
+  L->stats.kernel_launches += 3, L->stats.d2h_bytes += 4.0 * ORDER_MAX_BINS;
+}
+
+// level_start[] from the bins the scatter left behind (bins[k] = end of bucket k; 64 buckets per level)
+void levels_from_bins(const uint32_t* bins, uint32_t n, std::vector<uint32_t>& level_start) {
+  level_start.assign(1, 0);
+  for (uint32_t l = 0; l < ORDER_MAX_BINS / 64; l++) {
+    const uint32_t end = bins[64 * l + 63];
+    level_start.push_back(end);
+    if (end >= n) break;
+  }
+}
+
+}  // namespace
+#endif
+
+int gpu_block(ppd_ctx* c, Lane* L, Job& J, const uint8_t* flat, size_t len, uint8_t** out, size_t* out_len) {
+#ifdef PPD_HOSTPROF
+  return GPU_BLOCK_DECLINED;
+#else
+  BlockJob& b = J.blocks[0];
+  if (!gpu_txn_enabled()) return GPU_BLOCK_DECLINED;
+  {
+    const char* e = getenv("PPD_GPU_PARSE_MIN_BYTES");
+    const size_t min_bytes = e ? (size_t)atoll(e) : (size_t)512 << 10;
+    if (b.compact.n < min_bytes || b.compact.n < 2) return GPU_BLOCK_DECLINED;
+  }
+  TxnTables& T = J.txn;
+  PhaseTimer pt;
+  if (!txn_tables_phase1(b, flat, len, T)) return GPU_BLOCK_DECLINED;
+  pt.lap("t:tables1");
+  cudaStream_t st = L->st;
+  const ppd_stats stats0 = L->stats;
+  // ---- the FlatBlock to the device; the witness inside it lands 256-byte aligned ----
+  const size_t wit_off = (size_t)(b.compact.p - flat);
+  const size_t lead = (256 - (wit_off & 255)) & 255;
+  L->d_flat.reserve(lead + len + 512);
+  uint8_t* d_flat = L->d_flat.as<uint8_t>() + lead;
+  upload_bytes(L, J, d_flat, flat, len);
+  CUDA_OK(cudaMemsetAsync(d_flat + len, 0, 256, st));
+  L->stats.h2d_bytes += (double)len;
+  // page-locked landing areas
+  const size_t h_words = 2 * ORDER_MAX_BINS + sizeof(txn::Cursors) / 4 + 64;
+  J.txn_host.resize(h_words + 8 * T.code_write_traces.size() + 8);
+  HookState H;
+  H.L = L, H.J = &J, H.T = &T, H.d_flat = d_flat, H.n_txns = b.txns.size();
+  H.h_bins = J.txn_host.data();
+  H.h_code_digests = reinterpret_cast<uint8_t*>(J.txn_host.data() + h_words);
+  PreImageDeviceOnly X{};
+  X.d_witness = d_flat + wit_off;
+  X.extra_nodes = T.est_nodes, X.extra_children = T.est_children;
+  X.extra_keys = 64 + 32ull * T.n_msgs + 12ull * b.txns.size() + 40ull * (T.n_ops1 + T.n_ops2) + 4096;
+  X.extra_vals = 64 + T.val_writes + 8ull * b.txns.size();
+  for (const TxnV& tx : b.txns) X.extra_vals += tx.byte_code.n + tx.new_receipt_node.n;
+  X.extra_accounts = T.n_recs + 1;
+  X.after_launch = after_emit, X.arg = &H;
+  if (!gpu_pre_image(L, J, b, true, &c->parse_slots_sem, &X)) {
+    L->stats = stats0;
+    return GPU_BLOCK_DECLINED;  // a witness the host builder takes (malformed, not canonical)
+  }
+  pt.lap("t:pre-image");
+  // ---- plan of every IR (needs the witness's code strings and the digests of written code) ----
+  struct CD {
+    HookState* H;
+    TxnTables* T;
+    std::vector<uint32_t> slot_of;  // trace -> index into h_code_digests
+  } cd{&H, &T, {}};
+  if (!T.code_write_traces.empty()) {
+    cd.slot_of.assign(T.traces.size(), 0);
+    for (size_t k = 0; k < T.code_write_traces.size(); k++) cd.slot_of[T.code_write_traces[k]] = (uint32_t)k;
+  }
+  auto code_digest = [](void* arg, uint32_t t) -> const uint8_t* {
+    CD* x = (CD*)arg;
+    return x->H->h_code_digests + 32ull * x->slot_of[t];
+  };
+  if (!txn_tables_phase2(b, flat, H.B, code_digest, &cd, T)) {
+    L->stats = stats0;
+    return GPU_BLOCK_DECLINED;
+  }
+  pt.lap("t:tables2");
+  txn::View& v = H.v;
+  const uint32_t n_ir = T.n_ir, n_seg = (uint32_t)T.seg_a.size(), n_touched = T.touched_begin[n_ir];
+  const uint32_t n_pre = H.n_pre_nodes;
+  // ---- the plan on the device: [txns | seg_a | seg_b | seg_c | seg_begin | touched_begin | lit | ir_base | touched |
+  //                              seg_off | ir_size, ir_flag | ir_nuniq | u_node | u_size | u_off] ----
+  IrDumpPlanView P{};
+  uint32_t *d_seg_a, *d_seg_b, *d_seg_c, *d_seg_begin, *d_touched_begin, *d_touched, *d_ir_size;
+  uint64_t* d_ir_base;
+  uint8_t* d_lit;
+  txn::TxnDesc* d_txns;
+  auto plan_layout = [&](Carve2& cv) {
+    d_txns = cv.take<txn::TxnDesc>(n_ir + 1);
+    d_seg_a = cv.take<uint32_t>(n_seg + 1), d_seg_b = cv.take<uint32_t>(n_seg + 1), d_seg_c = cv.take<uint32_t>(n_seg + 1);
+    d_seg_begin = cv.take<uint32_t>(n_ir + 1), d_touched_begin = cv.take<uint32_t>(n_ir + 1);
+    d_lit = cv.take<uint8_t>(T.lit.size() + 16);
+    d_ir_base = cv.take<uint64_t>(n_ir + 1);
+    d_touched = cv.take<uint32_t>((size_t)n_touched + 16);
+    P.seg_off = cv.take<uint32_t>(n_seg + 1);
+    d_ir_size = cv.take<uint32_t>(2ull * n_ir + 2);  // ir_size, then ir_flag: read back together
+    P.ir_nuniq = cv.take<uint32_t>(n_ir + 1);
+    P.u_node = cv.take<uint32_t>((size_t)n_touched + 16), P.u_size = cv.take<uint32_t>((size_t)n_touched + 16), P.u_off = cv.take<uint32_t>((size_t)n_touched + 16);
+  };
+  {
+    Carve2 sz{nullptr};
+    plan_layout(sz);
+    L->d_plan.reserve(sz.off + 256);
+    Carve2 cv{L->d_plan.as<uint8_t>()};
+    plan_layout(cv);
+  }
+  P.ir_size = d_ir_size, P.ir_flag = d_ir_size + n_ir;
+  P.touched = d_touched, P.touched_begin = d_touched_begin, P.seg_a = d_seg_a, P.seg_b = d_seg_b, P.seg_c = d_seg_c, P.seg_begin = d_seg_begin;
+  P.flat = d_flat, P.lit = d_lit, P.ir_base = d_ir_base;
+  auto up = [&](void* dst, const void* src, size_t bytes) {
+    if (!bytes) return;
+    CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st));
+    L->stats.h2d_bytes += (double)bytes;
+  };
+  up(d_txns, T.txns.data(), sizeof(txn::TxnDesc) * n_ir);
+  up(d_seg_a, T.seg_a.data(), 4ull * n_seg), up(d_seg_b, T.seg_b.data(), 4ull * n_seg), up(d_seg_c, T.seg_c.data(), 4ull * n_seg);
+  up(d_seg_begin, T.seg_begin.data(), 4ull * (n_ir + 1)), up(d_touched_begin, T.touched_begin.data(), 4ull * (n_ir + 1));
+  up(d_lit, T.lit.data(), T.lit.size());
+  up(v.key_pool + H.B.txn_key_base, T.txn_keys.data(), T.txn_keys.size());
+  up(v.traces, T.traces.data(), sizeof(txn::TxnTrace) * T.traces.size());  // (phase 2 rebased the record and value offsets)
+  CUDA_OK(cudaMemsetAsync(d_touched, 0xff, 4ull * n_touched, st));
+  v.txns = d_txns, v.touched = d_touched, v.seg_a = d_seg_a, v.seg_b = d_seg_b;
+  // ---- the pre-image hashed: the storage roots decide which trie an account gets (the by-root join) ----
+  std::vector<uint32_t> level_pre, level_tail;
+  levels_from_bins(H.h_bins, n_pre, level_pre);
+  L->d_ref.reserve(32ull * v.cap_nodes);
+  L->d_ref_len.reserve(v.cap_nodes);
+  L->d_counters.reserve(32);
+  CUDA_OK(cudaMemsetAsync(L->d_counters.p, 0, 32, st));
+  ArenaView V;
+  V.nodes = v.nodes, V.key_pool = v.key_pool, V.val_pool = v.val_pool, V.hash_pool = v.hash_pool, V.child_pool = v.child_pool;
+  V.accounts = v.accounts, V.ref = L->d_ref.as<uint8_t>(), V.ref_len = L->d_ref_len.as<uint8_t>();
+  V.counters = L->d_counters.as<unsigned long long>();
+  CUDA_OK(cudaEventRecord(L->ev0, st));
+  for (size_t l = 0; l + 1 < level_pre.size(); l++) {
+    launch_hash_level(V, L->d_order.as<uint32_t>(), level_pre[l], level_pre[l + 1], st);
+    L->stats.kernel_launches++, L->stats.level_launches++;
+  }
+  CUDA_OK(cudaEventRecord(L->ev1, st));
+  // ---- join, account table, sorted ops, the loop ----
+  H.j.ref = V.ref;
+  CUDA_OK(cudaMemsetAsync(H.j.slot_owner, 0xff, 4ull * (H.j.table_mask + 1), st));
+  CUDA_OK(cudaMemsetAsync(H.j.slot_best, 0, 4ull * (H.j.table_mask + 1), st));
+  launch_join(H.j, st);
+  txn::Cursors init;
+  memset(&init, 0, sizeof init);
+  init.n_nodes = n_pre, init.n_children = (uint32_t)J.dev.children, init.key_bytes = H.B.key_cursor;
+  init.state_root = b.state_root, init.txn_root = NODE_EMPTY, init.receipt_root = NODE_EMPTY;
+  launch_txn_init(v, init, H.table_slots, st);
+  H.ai = txn::AcctInit{H.table_slots - 1, b.state_root, H.j.join_storage, H.j.join_root};
+  uint32_t max_writes = 0;
+  for (size_t t = 0; t < T.traces.size(); t++) max_writes = std::max(max_writes, T.traces[t].n_writes);
+  L->stats.kernel_launches += 3 + launch_txn_prep(v, H.ai, T.n_ops1, T.n_ops2, max_writes, st);
+  CUDA_OK(cudaEventRecord(L->ev_loop0, st));
+  launch_txn_loop(v, st);
+  CUDA_OK(cudaEventRecord(L->ev_loop1, st));
+  L->stats.kernel_launches += 1;
+  // ---- the loop's nodes sorted by (level, class) ----
+  L->d_order2.reserve(4ull * H.cap_tail + 16);
+  CUDA_OK(cudaMemsetAsync(H.bins_tail, 0, 4ull * ORDER_MAX_BINS, st));
+  launch_order_by_level_class(v.nodes, v.level, H.cap_tail, ORDER_MAX_BINS, H.okeys, H.bins_tail, L->d_order2.as<uint32_t>(), st, n_pre, &v.cur->n_nodes);
+  CUDA_OK(cudaGetLastError());
+  txn::Cursors* h_cur = reinterpret_cast<txn::Cursors*>(H.h_bins + 2 * ORDER_MAX_BINS);
+  CUDA_OK(cudaMemcpyAsync(H.h_bins + ORDER_MAX_BINS, H.bins_tail, 4ull * ORDER_MAX_BINS, cudaMemcpyDeviceToHost, st));
+  CUDA_OK(cudaMemcpyAsync(h_cur, v.cur, sizeof(txn::Cursors), cudaMemcpyDeviceToHost, st));
+  L->stats.kernel_launches += 3, L->stats.d2h_bytes += 4.0 * ORDER_MAX_BINS + sizeof(txn::Cursors);
+  lane_sync(L);
+  pt.lap("t:loop");
+  {
+    float ms = 0;
+    CUDA_OK(cudaEventElapsedTime(&ms, L->ev0, L->ev1));
+    L->stats.gpu_ms += ms;
+    CUDA_OK(cudaEventElapsedTime(&ms, L->ev_loop0, L->ev_loop1));
+    L->stats.txn_gpu_ms += ms;
+  }
+  if (h_cur->flag || h_cur->max_level >= ORDER_MAX_BINS / 64) {
+    if (getenv("PPD_TIMING")) fprintf(stderr, "[ppd] device txn loop flag %u at txn %u (max level %u): host path\n", h_cur->flag, h_cur->flag_txn, h_cur->max_level);
+    L->stats = stats0;
+    L->has_last_parse = false;
+    return GPU_BLOCK_DECLINED;
+  }
+  const uint32_t n_total = h_cur->n_nodes, n_tail = n_total - n_pre;
+  levels_from_bins(H.h_bins + ORDER_MAX_BINS, n_tail, level_tail);
+  CUDA_OK(cudaEventRecord(L->ev0, st));
+  for (size_t l = 0; l + 1 < level_tail.size(); l++) {
+    launch_hash_level(V, L->d_order2.as<uint32_t>(), level_tail[l], level_tail[l + 1], st);
+    L->stats.kernel_launches++, L->stats.level_launches++;
+  }
+  CUDA_OK(cudaEventRecord(L->ev1, st));
+  // ---- every IR sized and laid out ----
+  CUDA_OK(cudaEventRecord(L->ev_loop0, st));
+  launch_ir_size(V, P, n_ir, st);
+  CUDA_OK(cudaEventRecord(L->ev_loop1, st));
+  CUDA_OK(cudaGetLastError());
+  J.plan.resize(2ull * n_ir + 8);
+  uint32_t* h_sizes = J.plan.data();
+  unsigned long long* h_counters = reinterpret_cast<unsigned long long*>(H.h_bins);  // (the pre-image bins are consumed)
+  CUDA_OK(cudaMemcpyAsync(h_sizes, d_ir_size, 8ull * n_ir, cudaMemcpyDeviceToHost, st));
+  CUDA_OK(cudaMemcpyAsync(h_counters, L->d_counters.p, 24, cudaMemcpyDeviceToHost, st));
+  L->stats.kernel_launches += 1, L->stats.d2h_bytes += 8.0 * n_ir + 24;
+  lane_sync(L);
+  pt.lap("t:sweep+size");
+  {
+    float ms = 0;
+    CUDA_OK(cudaEventElapsedTime(&ms, L->ev0, L->ev1));
+    L->stats.gpu_ms += ms;
+    CUDA_OK(cudaEventElapsedTime(&ms, L->ev_loop0, L->ev_loop1));
+    L->stats.dump_gpu_ms += ms;
+  }
+  L->stats.nodes_hashed += h_counters[0], L->stats.node_permutations += h_counters[1], L->stats.node_bytes += h_counters[2];
+  L->stats.arena_nodes += n_total;
+  L->stats.levels += level_pre.size() + level_tail.size() - 2;
+  for (size_t m = 0; m < T.traces.size(); m++) {
+    const txn::TxnTrace& tr = T.traces[m];
+    L->stats.key_permutations += 1 + tr.n_reads + tr.n_writes + ((tr.flags & txn::TRF_MIN_KEYS) ? tr.n_writes : 0);
+    if ((tr.flags & PPD_TR_CODE_WRITE) && !(tr.flags & PPD_TR_CODE_READ)) L->stats.key_permutations += tr.code_len / 136 + 1;
+  }
+  L->stats.marks_on_gpu += T.n_items;
+  L->stats.txn_loops_on_gpu += 1;
+  L->has_last = true, L->last_view = V;
+  L->last_level_start = level_pre, L->last_level_start2 = level_tail, L->last_n_msgs = T.n_msgs;
+  L->last_msg_data = d_flat, L->last_msg_se = H.se, L->last_digest_out = v.key_pool + H.B.dig_base;
+  L->last_txn = H.v, L->last_join = H.j, L->last_ai = H.ai, L->last_init = init, L->last_table_slots = H.table_slots;
+  L->last_n_ops1 = T.n_ops1, L->last_n_ops2 = T.n_ops2, L->last_max_writes = max_writes, L->last_n_touched = n_touched;
+  L->last_plan = P, L->last_n_ir = n_ir, L->has_last_txn = true;
+  L->last_cap_tail = H.cap_tail, L->last_bins_tail = H.bins_tail, L->last_okeys = H.okeys;
+  // an IR the dump kernels cannot lay out (an untouched node shorter than 32 bytes that the subset keeps expanded, more
+  // touched nodes than a thread block's set holds): the host path serialises such blocks
+  uint64_t total = 8;
+  PVec<uint64_t>& ir_base = J.ir_base;
+  ir_base.resize(n_ir);
+  for (uint32_t i = 0; i < n_ir; i++) {
+    if (h_sizes[n_ir + i]) {
+      if (getenv("PPD_TIMING")) fprintf(stderr, "[ppd] IR %u cannot be laid out on the device: host path\n", i);
+      L->stats = stats0;
+      L->has_last = L->has_last_parse = L->has_last_txn = false;
+      return GPU_BLOCK_DECLINED;
+    }
+    ir_base[i] = total;
+    total += h_sizes[i];
+  }
+  // ---- written on the device, copied back once ----
+  Out o;
+  uint8_t* pinned = total >= ((size_t)1 << 20) ? out_pool().take(total) : nullptr;
+  if (!pinned) o.need(total);
+  uint8_t* dst = pinned ? pinned : o.p;
+  L->d_out.reserve(total + 64);
+  L->last_out_bytes = total;
+  up(d_ir_base, ir_base.data(), 8ull * n_ir);
+  const uint32_t hdr[2] = {PPD_IR_DUMP_MAGIC, n_ir};
+  up(L->d_out.p, hdr, 8);
+  CUDA_OK(cudaEventRecord(L->ev0, st));
+  launch_ir_emit(V, P, n_ir, L->d_out.as<uint8_t>(), st);
+  CUDA_OK(cudaEventRecord(L->ev1, st));
+  CUDA_OK(cudaGetLastError());
+  L->stats.kernel_launches += 1;
+  if (pinned) {
+    cudaError_t e = cudaMemcpyAsync(dst, L->d_out.p, total, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaEventRecord(L->ev_sync, st);
+    if (e == cudaSuccess) e = cudaEventSynchronize(L->ev_sync);
+    if (e != cudaSuccess) {
+      out_pool().give_back(pinned);
+      throw Fail{PPD_ERR_CUDA, std::string("IR dump copy: ") + cudaGetErrorString(e)};
+    }
+  } else {
+    // pageable output: land the copy in the lane's page-locked buffer, then move it on
+    J.out_stage.resize(total);
+    CUDA_OK(cudaMemcpyAsync(J.out_stage.data(), L->d_out.p, total, cudaMemcpyDeviceToHost, st));
+    lane_sync(L);
+    memcpy(o.p, J.out_stage.data(), total);
+    o.n = total;
+  }
+  L->stats.d2h_bytes += (double)total;
+  {
+    float ms = 0;
+    CUDA_OK(cudaEventElapsedTime(&ms, L->ev0, L->ev1));
+    L->stats.dump_gpu_ms += ms;
+  }
+  pt.lap("t:emit+copy");
+  if (pinned) {
+    *out = pinned, *out_len = total;
+  } else {
+    *out = o.give(out_len);
+  }
+  return GPU_BLOCK_DONE;
+#endif
+}
+
+}  // namespace ppd

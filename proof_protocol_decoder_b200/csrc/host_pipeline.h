@@ -34,6 +34,7 @@
 #include "flat_maps.h"
 #include "host_arena.h"
 #include "ppd_kernels.h"
+#include "txn_tables.h"
 
 namespace ppd {
 
@@ -60,6 +61,8 @@ struct Lane {
   DevBuf d_plan, d_out;  // IR dump plan and the serialised IrDump
   DevBuf d_wit, d_pa, d_pb, d_pc;  // witness bytes and the scratch of the three parse phases (ppd_parse.cu)
   DevBuf d_level, d_okeys, d_obins;  // node levels, and the scratch of the (level, class) ordering on the device
+  DevBuf d_flat, d_txn, d_order2;    // the device txn loop (gpu_txn.cu): the resident FlatBlock, its tables and scratch, the order of its nodes
+  cudaEvent_t ev_loop0 = nullptr, ev_loop1 = nullptr;
   uint32_t* h_parse = nullptr;     // page-locked landing area of the parse result words
   // the launch parameters of the lane's last GPU parse (the witness and all scratch stay resident), for ppd_replay_last_parse
   bool has_last_parse = false;
@@ -72,8 +75,22 @@ struct Lane {
   // the arena of the lane's last block stays resident so that its hashing can be re-run for measurement
   bool has_last = false;
   ArenaView last_view{};
-  std::vector<uint32_t> last_level_start;
+  std::vector<uint32_t> last_level_start, last_level_start2;  // (second sweep: the nodes the device txn loop appended, in d_order2)
   uint32_t last_n_msgs = 0;
+  const uint8_t* last_msg_data = nullptr;  // null: the key messages are in d_msg / d_msg_off / d_digest
+  const uint64_t* last_msg_se = nullptr;
+  uint8_t* last_digest_out = nullptr;
+  // the launch parameters of the lane's last device txn loop and IR dump, for ppd_replay_last_txn / ppd_replay_last_dump
+  bool has_last_txn = false;
+  txn::View last_txn{};
+  txn::JoinView last_join{};
+  txn::AcctInit last_ai{};
+  txn::Cursors last_init{};
+  uint32_t last_table_slots = 0, last_n_ops1 = 0, last_n_ops2 = 0, last_max_writes = 0, last_n_touched = 0, last_n_ir = 0, last_cap_tail = 0;
+  uint32_t* last_bins_tail = nullptr;
+  uint16_t* last_okeys = nullptr;
+  IrDumpPlanView last_plan{};
+  size_t last_out_bytes = 0;
 };
 
 // Counting semaphore: how many lanes may have their witness upload + parse in flight at once.  All lanes of a
@@ -431,6 +448,9 @@ struct Job {
   std::vector<uint32_t> haddr_keys, haddr_leaves;
   bool device_marks = false;  // this block's subset marking walks run on the device (decode_one decides)
   PVec<H256> code_digest;
+  TxnTables txn;              // tables of the device txn loop (gpu_txn.cu)
+  PVec<uint32_t> txn_host;    // page-locked landing area of its read-backs
+  PVec<uint64_t> ir_base;
   std::vector<uint32_t> stamp;
   uint32_t serial = 0;
   Job() {
@@ -443,6 +463,9 @@ struct Job {
     acct_list.alloc_fn = code_list.alloc_fn = pinned_alloc, acct_list.free_fn = code_list.free_fn = pinned_free;
     code_digest.alloc_fn = pinned_alloc, code_digest.free_fn = pinned_free;
     wit_stage.alloc_fn = pinned_alloc, wit_stage.free_fn = pinned_free;
+    txn.set_allocator(pinned_alloc, pinned_free);
+    txn_host.alloc_fn = pinned_alloc, txn_host.free_fn = pinned_free;
+    ir_base.alloc_fn = pinned_alloc, ir_base.free_fn = pinned_free;
   }
   void reset(size_t n_blocks) {
     dev = Resident{};
@@ -465,7 +488,17 @@ void collect_messages(Job& J, BlockJob& b);
 uint32_t root_node_for(Job& J, BlockJob& b, uint32_t trie_root);
 void build_pre_image(Job& J, BlockJob& b);
 bool gpu_parse_enabled();
-bool gpu_pre_image(Lane* L, Job& J, BlockJob& b, bool check_version = true, Slots* slots = nullptr);
+// dev_only: the txn loop runs on the device too (gpu_txn.cu), so nothing of the arena is copied back: the witness is
+// already resident (inside the uploaded FlatBlock), the pools get room for what the loop appends, and `after_launch`
+// queues more work behind the emit kernels before the final wait
+struct PreImageDeviceOnly {
+  const uint8_t* d_witness;
+  size_t extra_nodes, extra_children, extra_keys, extra_vals, extra_accounts;
+  void (*after_launch)(void* arg, const ParseEmit& E);
+  void* arg;
+};
+bool gpu_pre_image(Lane* L, Job& J, BlockJob& b, bool check_version = true, Slots* slots = nullptr, const PreImageDeviceOnly* dev_only = nullptr);
+void upload_bytes(Lane* L, Job& J, uint8_t* dst, const uint8_t* src, size_t n);
 void verify_gpu_pre_image(Lane* L, Job& J, BlockJob& b);
 void shape_block(Job& J, BlockJob& b);
 void sweep(Lane* c, Job& J, bool refs_to_host = true);
@@ -676,6 +709,10 @@ struct OutPool {
 };
 OutPool& out_pool();
 
+bool gpu_txn_enabled();
+enum { GPU_BLOCK_DECLINED = 0, GPU_BLOCK_DONE = 1 };
+// the whole block on the device (gpu_txn.cu); DECLINED: nothing was produced, the host path decodes the block
+int gpu_block(ppd_ctx* c, Lane* L, Job& J, const uint8_t* flat, size_t len, uint8_t** out, size_t* out_len);
 bool gpu_dump_enabled();
 enum { DUMP_ON_HOST = 0, DUMP_DONE = 1, DUMP_REDO_HOST_MARKS = 2 };
 int gpu_dump_block(ppd_ctx* c, Lane* L, Job& J, uint8_t** out, size_t* out_len);

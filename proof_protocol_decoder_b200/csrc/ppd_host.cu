@@ -91,6 +91,8 @@ Lane* lane_of(ppd_ctx* c, size_t w) {
     CUDA_OK(cudaEventCreate(&l->ev0));
     CUDA_OK(cudaEventCreate(&l->ev1));
     CUDA_OK(cudaEventCreateWithFlags(&l->ev_sync, cudaEventBlockingSync | cudaEventDisableTiming));
+    CUDA_OK(cudaEventCreate(&l->ev_loop0));
+    CUDA_OK(cudaEventCreate(&l->ev_loop1));
 #endif
     c->lanes.push_back(l.release());
   }
@@ -101,12 +103,14 @@ void lane_delete(Lane* l) {
   DevBuf* bufs[] = {&l->d_nodes, &l->d_order,  &l->d_keys,     &l->d_vals, &l->d_hashes,  &l->d_children, &l->d_accounts,
                     &l->d_ref,   &l->d_ref_len, &l->d_counters, &l->d_msg,  &l->d_msg_off, &l->d_digest,
                     &l->d_plan,  &l->d_out,     &l->d_wit,      &l->d_pa,   &l->d_pb,      &l->d_pc,
-                    &l->d_level, &l->d_okeys,   &l->d_obins};
+                    &l->d_level, &l->d_okeys,   &l->d_obins,    &l->d_flat, &l->d_txn,     &l->d_order2};
   for (DevBuf* b : bufs) b->release();
   if (l->h_parse) pinned_free(l->h_parse);
   if (l->ev0) cudaEventDestroy(l->ev0);
   if (l->ev1) cudaEventDestroy(l->ev1);
   if (l->ev_sync) cudaEventDestroy(l->ev_sync);
+  if (l->ev_loop0) cudaEventDestroy(l->ev_loop0);
+  if (l->ev_loop1) cudaEventDestroy(l->ev_loop1);
   if (l->st) cudaStreamDestroy(l->st);
 #endif
   if (l->job) job_delete(l->job);
@@ -217,6 +221,9 @@ void sweep(Lane* c, Job& J, bool refs_to_host) {
   c->has_last = true;
   c->last_view = V;
   c->last_level_start = level_start;
+  c->last_level_start2.clear();
+  c->last_msg_data = nullptr;
+  c->has_last_txn = false;
   c->last_n_msgs = (uint32_t)J.kh.lens.size();
   J.refs_on_host = refs_to_host;
   if (refs_to_host) {
@@ -316,6 +323,7 @@ void decode_one(ppd_ctx* c, Lane* L, const uint8_t* flat, size_t len, uint8_t** 
   // Second attempt: only after a first one with device-side marking walks that met an error.  With the marks
   // deferred to the device the host cannot tell whether an earlier txn's marking pass would have failed first, so the
   // block is redone with the host's own marking pass, which reports errors in the reference's order.
+  bool try_device = gpu_txn_enabled();
   for (int attempt = 0; attempt < 2; attempt++) {
     PhaseTimer pt;
     Job& J = job_of(L, 1);
@@ -323,8 +331,18 @@ void decode_one(ppd_ctx* c, Lane* L, const uint8_t* flat, size_t len, uint8_t** 
     bool redo = false;
     try {
       read_flat_block(flat, len, b);
-      J.device_marks = attempt == 0 && device_marks_wanted(b);
       pt.lap("read-flat");
+      if (try_device) {
+        // everything after the flat input on the device (gpu_txn.cu); a block it declines starts over on the host path
+        try_device = false;
+        if (gpu_block(c, L, J, flat, len, out, out_len) == GPU_BLOCK_DONE) {
+          *status = PPD_OK;
+          return;
+        }
+        attempt--;
+        continue;
+      }
+      J.device_marks = attempt == 0 && device_marks_wanted(b);
       if (gpu_parse_enabled()) gpu_pre_image(L, J, b, true, &c->parse_slots_sem);
       collect_messages(J, b);
       pt.lap("parse");
@@ -369,6 +387,7 @@ void add_stats(ppd_stats& a, const ppd_stats& b) {
   a.gpu_ms += b.gpu_ms, a.h2d_bytes += b.h2d_bytes, a.d2h_bytes += b.d2h_bytes, a.kernel_launches += b.kernel_launches;
   a.witnesses_on_gpu += b.witnesses_on_gpu, a.witness_instructions += b.witness_instructions, a.witness_bytes += b.witness_bytes;
   a.parse_gpu_ms += b.parse_gpu_ms, a.level_launches += b.level_launches, a.marks_on_gpu += b.marks_on_gpu;
+  a.txn_loops_on_gpu += b.txn_loops_on_gpu, a.txn_gpu_ms += b.txn_gpu_ms, a.dump_gpu_ms += b.dump_gpu_ms;
 }
 
 // Blocks are independent (each BlockTrace carries its own pre-image, trace_protocol.rs:40-48): every
@@ -388,6 +407,7 @@ void decode_blocks(ppd_ctx* c, const uint8_t* const* flats, const size_t* lens, 
     L->stats = ppd_stats{};
     L->has_last = false;
     L->has_last_parse = false;
+    L->has_last_txn = false;
   }
   const unsigned dump_workers = std::max(1u, host_threads() / workers);
   for (size_t i = 0; i < n; i++) outs[i] = nullptr, out_lens[i] = 0, statuses[i] = PPD_OK;
@@ -499,10 +519,16 @@ int ppd_replay_last_hashing(ppd_ctx* c, double* gpu_ms_out) {
       if (!L->has_last) continue;
       CUDA_OK(cudaStreamWaitEvent(L->st, c->ev0, 0));
       CUDA_OK(cudaMemsetAsync(L->d_counters.p, 0, 32, L->st));
-      launch_keccak256_ranges(L->d_msg.as<uint8_t>(), L->d_msg_off.as<uint64_t>(), L->last_n_msgs, L->d_digest.as<uint8_t>(), L->st);
+      if (L->last_msg_data)
+        launch_keccak256_ranges(L->last_msg_data, L->last_msg_se, L->last_n_msgs, L->last_digest_out, L->st);
+      else
+        launch_keccak256_ranges(L->d_msg.as<uint8_t>(), L->d_msg_off.as<uint64_t>(), L->last_n_msgs, L->d_digest.as<uint8_t>(), L->st);
       size_t nl = L->last_level_start.size() - 1;
       for (size_t l = 0; l < nl; l++)
         launch_hash_level(L->last_view, L->d_order.as<uint32_t>(), L->last_level_start[l], L->last_level_start[l + 1], L->st);
+      // the nodes the device txn loop appended (gpu_txn.cu) are a second sweep over their own order
+      for (size_t l = 0; l + 1 < L->last_level_start2.size(); l++)
+        launch_hash_level(L->last_view, L->d_order2.as<uint32_t>(), L->last_level_start2[l], L->last_level_start2[l + 1], L->st);
       CUDA_OK(cudaGetLastError());
       CUDA_OK(cudaEventRecord(L->ev1, L->st));
       CUDA_OK(cudaStreamWaitEvent(c->st, L->ev1, 0));

@@ -347,9 +347,14 @@ __device__ __forceinline__ uint32_t node_class(const NodeRec& r) {
   return kind * 8 + (perms > 8 ? 7 : perms - 1);
 }
 
+// The nodes sorted are first .. first + n (n read from *n_dev - first when n_dev is given: the txn loop's node count is
+// only known on the device); keys[] and order[] are indexed from 0, order[] holds node ids.
 __global__ void __launch_bounds__(OS_THREADS) order_hist_kernel(const NodeRec* __restrict__ nodes, const uint16_t* __restrict__ level, uint32_t n,
-                                                                uint32_t n_bins, uint16_t* __restrict__ keys, uint32_t* __restrict__ bins) {
+                                                                uint32_t n_bins, uint16_t* __restrict__ keys, uint32_t* __restrict__ bins,
+                                                                uint32_t first, const uint32_t* __restrict__ n_dev) {
   extern __shared__ uint32_t sh[];
+  if (n_dev) n = min(n, *n_dev - first);
+  if (blockIdx.x * (OS_THREADS * OS_PER) >= n) return;
   for (uint32_t k = threadIdx.x; k < n_bins; k += OS_THREADS) sh[k] = 0;
   __syncthreads();
   const uint32_t base = blockIdx.x * (OS_THREADS * OS_PER);
@@ -357,7 +362,7 @@ __global__ void __launch_bounds__(OS_THREADS) order_hist_kernel(const NodeRec* _
   for (int q = 0; q < OS_PER; q++) {
     const uint32_t i = base + q * OS_THREADS + threadIdx.x;
     if (i < n) {
-      const uint32_t key = min((uint32_t)level[i] * 64u + node_class(nodes[i]), n_bins - 1);
+      const uint32_t key = min((uint32_t)level[first + i] * 64u + node_class(nodes[first + i]), n_bins - 1);
       keys[i] = (uint16_t)key;
       atomicAdd(&sh[key], 1u);
     }
@@ -401,8 +406,11 @@ __global__ void __launch_bounds__(1024) order_scan_kernel(uint32_t* __restrict__
 }
 
 __global__ void __launch_bounds__(OS_THREADS) order_scatter_kernel(const uint16_t* __restrict__ keys, uint32_t n, uint32_t n_bins,
-                                                                   uint32_t* __restrict__ cursor, uint32_t* __restrict__ order) {
+                                                                   uint32_t* __restrict__ cursor, uint32_t* __restrict__ order, uint32_t first,
+                                                                   const uint32_t* __restrict__ n_dev) {
   extern __shared__ uint32_t sh[];  // [n_bins] counts, then this CTA's base per key
+  if (n_dev) n = min(n, *n_dev - first);
+  if (blockIdx.x * (OS_THREADS * OS_PER) >= n) return;
   for (uint32_t k = threadIdx.x; k < n_bins; k += OS_THREADS) sh[k] = 0;
   __syncthreads();
   const uint32_t base = blockIdx.x * (OS_THREADS * OS_PER);
@@ -420,18 +428,18 @@ __global__ void __launch_bounds__(OS_THREADS) order_scatter_kernel(const uint16_
 #pragma unroll
   for (int q = 0; q < OS_PER; q++) {
     const uint32_t i = base + q * OS_THREADS + threadIdx.x;
-    if (i < n) order[sh[key[q]] + rank[q]] = i;
+    if (i < n) order[sh[key[q]] + rank[q]] = first + i;
   }
 }
 
 // bins: [n_bins] zeroed by the caller; on return bins[k] = end of bucket k (the scatter advances the cursors)
 void launch_order_by_level_class(const NodeRec* nodes, const uint16_t* level, uint32_t n, uint32_t n_bins, uint16_t* keys, uint32_t* bins,
-                                 uint32_t* order, cudaStream_t st) {
+                                 uint32_t* order, cudaStream_t st, uint32_t first, const uint32_t* n_dev) {
   if (!n) return;
   const uint32_t blocks = (n + OS_THREADS * OS_PER - 1) / (OS_THREADS * OS_PER);
-  order_hist_kernel<<<blocks, OS_THREADS, 4 * n_bins, st>>>(nodes, level, n, n_bins, keys, bins);
+  order_hist_kernel<<<blocks, OS_THREADS, 4 * n_bins, st>>>(nodes, level, n, n_bins, keys, bins, first, n_dev);
   order_scan_kernel<<<1, 1024, 0, st>>>(bins, n_bins);
-  order_scatter_kernel<<<blocks, OS_THREADS, 4 * n_bins, st>>>(keys, n, n_bins, bins, order);
+  order_scatter_kernel<<<blocks, OS_THREADS, 4 * n_bins, st>>>(keys, n, n_bins, bins, order, first, n_dev);
 }
 
 void launch_hash_level(const ArenaView& A, const uint32_t* order, uint32_t begin, uint32_t end, cudaStream_t st) {

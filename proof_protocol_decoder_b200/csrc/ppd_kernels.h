@@ -5,6 +5,7 @@
 #include <cstdint>
 
 #include "arena.h"
+#include "txn_core.h"
 
 namespace ppd {
 
@@ -13,8 +14,9 @@ void launch_keccak256_ranges(const uint8_t* data, const uint64_t* begin_end, uin
 void launch_hash_level(const ArenaView& A, const uint32_t* order, uint32_t begin, uint32_t end, cudaStream_t st);
 // order[] = node ids counting-sorted by (level, class) on the device; n_bins = 64 * levels (<= 4096), bins zeroed by the caller
 static const uint32_t ORDER_MAX_BINS = 4096;
+// sorts the nodes first .. first + n (n clipped to *n_dev - first when n_dev, a device pointer, is given)
 void launch_order_by_level_class(const NodeRec* nodes, const uint16_t* level, uint32_t n, uint32_t n_bins, uint16_t* keys, uint32_t* bins,
-                                 uint32_t* order, cudaStream_t st);
+                                 uint32_t* order, cudaStream_t st, uint32_t first = 0, const uint32_t* n_dev = nullptr);
 
 
 // ---- ppd_build.cu: trie construction from sorted leaves ----
@@ -163,6 +165,13 @@ void launch_parse_scatter(const ParseBounds& B, uint32_t* ins_pos, cudaStream_t 
 uint32_t launch_parse_tree(const ParseTree& T, cudaStream_t st);
 void launch_parse_code_list(const ParseEmit& E, cudaStream_t st);
 void launch_parse_emit(const ParseEmit& E, cudaStream_t st);
+
+// ---- ppd_txn.cu: the txn loop on the GPU (txn_core.h) ----
+void launch_txn_msgs(const txn::View& v, uint64_t* se, cudaStream_t st);
+void launch_txn_init(const txn::View& v, const txn::Cursors& init, uint32_t table_slots, cudaStream_t st);
+void launch_join(const txn::JoinView& j, cudaStream_t st);
+uint32_t launch_txn_prep(const txn::View& v, const txn::AcctInit& a, uint32_t n_ops1, uint32_t n_ops2, uint32_t max_writes, cudaStream_t st);
+void launch_txn_loop(const txn::View& v, cudaStream_t st);
 
 // ---- ppd_microbench.cu ----
 bool launch_microbench(int variant, uint32_t* out, uint32_t blocks_per_sm, uint32_t iters, uint32_t* block_threads, double* units_per_thread_iter,

@@ -1,0 +1,160 @@
+// ppd_txn.cu — the txn loop on the GPU: kernels around txn_core.h.
+//
+//   txn_msgs_kernel      byte ranges of the FlatBlock to hash (addresses, slot keys, written code), one thread per trace
+//   join_*_kernel        convert_storage_trie_root_keyed_hashmap_to_account_addr_keyed (compact_to_partial_trie.rs:167-190):
+//                        accounts get the storage trie witnessed LAST under their storage root, whoever witnessed it
+//   acct_claim_kernel    one table slot per distinct address; the account's entry in the initial PartialTrieState
+//   prep_*_kernel        ops of every txn sorted per trie (rank sort: batches are tens of keys, O(n^2) is parallel and tiny),
+//                        written values RLP-encoded into val_pool, LCPs of neighbours
+//   txn_loop_kernel      ONE thread block runs the whole txn loop of a block (decoding.rs:80-177): txns are sequential,
+//                        the keys of a txn parallel; blocks of a batch run concurrently, one lane each
+// All of it is pointer chasing over the arena: latency bound by construction (a walk is ~2 dependent loads per trie
+// level), which is why a block's loop is one resident CTA that other lanes' kernels overlap, not a grid.
+#include <cstdint>
+
+#include "ppd_kernels.h"
+#include "txn_core.h"
+
+namespace ppd {
+
+using namespace txn;
+
+namespace {
+
+__constant__ uint8_t C_EMPTY_TRIE[32] = {0x56, 0xe8, 0x1f, 0x17, 0x1b, 0xcc, 0x55, 0xa6, 0xff, 0x83, 0x45, 0xe6, 0x92, 0xc0, 0xf8, 0x6e,
+                                         0x5b, 0x48, 0xe0, 0x1b, 0x99, 0x6c, 0xad, 0xc0, 0x01, 0x62, 0x2f, 0xb5, 0xe3, 0x63, 0xb4, 0x21};
+__constant__ uint8_t C_EMPTY_CODE[32] = {0xc5, 0xd2, 0x46, 0x01, 0x86, 0xf7, 0x23, 0x3c, 0x92, 0x7e, 0x7d, 0xb2, 0xdc, 0xc7, 0x03, 0xc0,
+                                         0xe5, 0x00, 0xb6, 0x53, 0xca, 0x82, 0x27, 0x3b, 0x7b, 0xfa, 0xd8, 0x04, 0x5d, 0x85, 0xa4, 0x70};
+
+__global__ void txn_msgs_kernel(View v, uint64_t* __restrict__ se) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < v.n_traces) prep_msgs(v, t, se);
+}
+
+__global__ void txn_init_kernel(View v, Cursors init, uint32_t table_slots) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) *v.cur = init;
+  if (i < table_slots) v.acct[i] = AcctState{ST_ABSENT, NONE, NONE, 0xffffffffu};
+}
+
+// ---- the by-root join ------------------------------------------------------------------------------------
+__device__ __forceinline__ const uint8_t* storage_root_of(const JoinView& j, uint32_t r) {
+  const uint32_t flags = j.acct_list[5ull * r + 3];
+  return (flags & 2u) ? j.ref + 32ull * j.acct_list[5ull * r + 2] : C_EMPTY_TRIE;
+}
+__device__ __forceinline__ bool same32(const uint8_t* a, const uint8_t* b) {
+  bool same = true;
+  for (int i = 0; i < 32; i++) same &= a[i] == b[i];
+  return same;
+}
+__device__ __forceinline__ uint32_t root_slot_hash(const uint8_t* k, uint32_t mask) {
+  return ((uint32_t)k[8] | ((uint32_t)k[9] << 8) | ((uint32_t)k[10] << 16) | ((uint32_t)k[11] << 24)) & mask;
+}
+// every account that witnesses a storage node: the table entry of its root keeps the LAST such account
+__global__ void join_insert_kernel(JoinView j) {
+  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= j.n_acct) return;
+  if (!(j.acct_list[5ull * r + 3] & 1u)) return;
+  const uint8_t* key = storage_root_of(j, r);
+  uint32_t h = root_slot_hash(key, j.table_mask);
+  for (;;) {
+    const uint32_t prev = atomicCAS(&j.slot_owner[h], 0xffffffffu, r);
+    if (prev == 0xffffffffu || prev == r || same32(storage_root_of(j, prev), key)) {
+      atomicMax(&j.slot_best[h], r + 1u);
+      return;
+    }
+    h = (h + 1) & j.table_mask;
+  }
+}
+__global__ void join_resolve_kernel(JoinView j) {
+  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= j.n_acct) return;
+  const uint8_t* key = storage_root_of(j, r);
+  j.pre_flags[r] = (uint8_t)((j.acct_list[5ull * r + 3] >> 1) & 1u);
+  uint32_t h = root_slot_hash(key, j.table_mask), storage = ST_ABSENT, root = NONE;
+  for (;;) {
+    const uint32_t own = j.slot_owner[h];
+    if (own == 0xffffffffu) break;
+    if (same32(storage_root_of(j, own), key)) {
+      const uint32_t best = j.slot_best[h] - 1u;
+      storage = j.acct_list[5ull * best + 1];
+      root = j.acct_list[5ull * best + 2];
+      if (root == NODE_EMPTY) root = NONE;
+      break;
+    }
+    h = (h + 1) & j.table_mask;
+  }
+  j.join_storage[r] = storage, j.join_root[r] = root;
+}
+
+__global__ void acct_claim_kernel(View v, AcctInit a) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < v.n_traces) acct_claim(v, a, t);
+}
+__global__ void prep_trace_kernel(View v) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < v.n_traces) prep_trace(v, t);
+}
+// grid (trace, chunk of its writes)
+__global__ void prep_write_kernel(View v) {
+  const uint32_t t = blockIdx.x, w = blockIdx.y * blockDim.x + threadIdx.x;
+  if (w < v.traces[t].n_writes) prep_write(v, t, w);
+}
+__global__ void prep_txn_kernel(View v) {
+  const uint32_t ti = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ti < v.n_txns) prep_txn(v, ti);
+}
+__global__ void prep_lcp_kernel(View v, uint32_t n1, uint32_t n2) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n1)
+    prep_lcp(v, v.ops1, i);
+  else if (i < n1 + n2)
+    prep_lcp(v, v.ops2, i - n1);
+}
+
+constexpr int LOOP_THREADS = 256;
+__global__ void __launch_bounds__(LOOP_THREADS, 1) txn_loop_kernel(View v) {
+  __shared__ uint32_t sh_dmax, sh_stop;
+  Ctx c{v, threadIdx.x, blockDim.x, &sh_dmax};
+  for (uint32_t ti = 0; ti < v.n_txns; ti++) {
+    run_txn(c, ti, C_EMPTY_TRIE, C_EMPTY_CODE);
+    // a raised flag ends the loop (the host path redoes the block); one thread reads it so that the decision is uniform
+    if (threadIdx.x == 0) sh_stop = *reinterpret_cast<volatile uint32_t*>(&v.cur->flag);
+    __syncthreads();
+    if (sh_stop) break;
+    __syncthreads();
+  }
+}
+
+}  // namespace
+
+static inline uint32_t cdiv(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
+
+void launch_txn_msgs(const View& v, uint64_t* se, cudaStream_t st) {
+  if (v.n_traces) txn_msgs_kernel<<<cdiv(v.n_traces, 128), 128, 0, st>>>(v, se);
+}
+void launch_txn_init(const View& v, const Cursors& init, uint32_t table_slots, cudaStream_t st) {
+  txn_init_kernel<<<cdiv(table_slots, 256), 256, 0, st>>>(v, init, table_slots);
+}
+void launch_join(const JoinView& j, cudaStream_t st) {
+  if (!j.n_acct) return;
+  join_insert_kernel<<<cdiv(j.n_acct, 128), 128, 0, st>>>(j);
+  join_resolve_kernel<<<cdiv(j.n_acct, 128), 128, 0, st>>>(j);
+}
+uint32_t launch_txn_prep(const View& v, const AcctInit& a, uint32_t n_ops1, uint32_t n_ops2, uint32_t max_writes, cudaStream_t st) {
+  if (!v.n_traces) return 0;
+  acct_claim_kernel<<<cdiv(v.n_traces, 128), 128, 0, st>>>(v, a);
+  prep_trace_kernel<<<cdiv(v.n_traces, 128), 128, 0, st>>>(v);
+  uint32_t launches = 4;
+  if (max_writes) {
+    const uint32_t threads = max_writes >= 64 ? 128 : 32;
+    prep_write_kernel<<<dim3(v.n_traces, cdiv(max_writes, threads)), threads, 0, st>>>(v);
+    launches++;
+  }
+  prep_txn_kernel<<<cdiv(v.n_txns, 64), 64, 0, st>>>(v);
+  prep_lcp_kernel<<<cdiv(n_ops1 + n_ops2, 128), 128, 0, st>>>(v, n_ops1, n_ops2);
+  return launches;
+}
+void launch_txn_loop(const View& v, cudaStream_t st) { txn_loop_kernel<<<1, LOOP_THREADS, 0, st>>>(v); }
+
+}  // namespace ppd

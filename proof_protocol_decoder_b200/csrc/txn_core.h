@@ -165,6 +165,19 @@ struct View {
   Cursors* cur;
 };
 
+// the by-root join of accounts to witnessed storage tries (compact_to_partial_trie.rs:167-190), ppd_txn.cu
+struct JoinView {
+  const uint32_t* acct_list;  // [n_acct][5] as ParseEmit writes it: leaf, storage trie root, its NK_ROOT node, flags, code index
+  uint32_t n_acct;
+  const uint8_t* ref;         // refs of the pre-image nodes (the storage roots are hashed before the loop)
+  uint32_t* slot_owner;       // [table_mask + 1], 0xffffffff = free
+  uint32_t* slot_best;        // [table_mask + 1], 1 + the last account that witnesses a trie with this root
+  uint32_t table_mask;
+  uint32_t* join_storage;     // [n_acct] out
+  uint32_t* join_root;        // [n_acct] out
+  uint8_t* pre_flags;         // [n_acct] out
+};
+
 PPD_HD inline bool is_hash_id(uint32_t n) { return n >= HASH_BASE && n < HASH_END; }
 
 // ---- the execution context: how threads of the block see shared counters ------------------------------------
@@ -677,7 +690,7 @@ PPD_HD inline void prep_trace(const View& v, uint32_t t) {
     SOp o;
     o.koff = v.dig_base + 32u * t, o.klen = 64, o.lcp = -1, o.pad = 0;
     o.kind = (tr.flags & PPD_TR_SELF_DESTRUCTED) ? OP_DEL : OP_PUT_ACCOUNT;
-    o.a1 = tr.rec, o.a2 = 0, o.owner = OWNER_STATE_TRIE;
+    o.a1 = tr.rec, o.a2 = tr.txn, o.owner = OWNER_STATE_TRIE;
     v.ops2[tx.op2_begin + srank] = o;
   }
 }
@@ -725,9 +738,11 @@ PPD_HD inline void prep_txn(const View& v, uint32_t ti) {
   for (uint32_t k = 0; k < tx.len_txn_bytes; k++) v.val_pool[tx.val_txn + k] = v.flat[tx.off_txn_bytes + k];
   for (uint32_t k = 0; k < tx.len_receipt; k++) v.val_pool[tx.val_receipt + k] = v.flat[tx.off_receipt + k];
 }
-// per sorted op: the LCP with its predecessor in the same trie
-PPD_HD inline void prep_lcp(const View& v, SOp* ops, uint32_t i, uint32_t seg_first) {
-  if (i == seg_first || ops[i - 1].owner != ops[i].owner) {
+// per sorted op: the LCP with its predecessor in the same trie (state ops carry their txn in a2: one state trie
+// version per txn)
+PPD_HD inline void prep_lcp(const View& v, SOp* ops, uint32_t i) {
+  const bool first = i == 0 || ops[i - 1].owner != ops[i].owner || (ops[i].owner == OWNER_STATE_TRIE && ops[i - 1].a2 != ops[i].a2);
+  if (first) {
     ops[i].lcp = -1;
     return;
   }

@@ -69,6 +69,9 @@ class PpdStats(ctypes.Structure):
         ("parse_gpu_ms", ctypes.c_double),
         ("level_launches", ctypes.c_uint64),
         ("marks_on_gpu", ctypes.c_uint64),
+        ("txn_loops_on_gpu", ctypes.c_uint64),
+        ("txn_gpu_ms", ctypes.c_double),
+        ("dump_gpu_ms", ctypes.c_double),
     ]
 
     def as_dict(self):

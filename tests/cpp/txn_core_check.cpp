@@ -200,11 +200,8 @@ int check_block(const std::vector<uint8_t>& flatv, const char* name) {
   for (uint32_t t = 0; t < n_traces; t++)
     for (uint32_t w = 0; w < T.traces[t].n_writes; w++) txn::prep_write(v, t, w);
   for (uint32_t ti = 0; ti < v.n_txns; ti++) txn::prep_txn(v, ti);
-  for (uint32_t ti = 0; ti < v.n_txns; ti++) {
-    const txn::TxnDesc& tx = T.txns[ti];
-    for (uint32_t i = tx.op1_begin; i < tx.op1_end; i++) txn::prep_lcp(v, v.ops1, i, tx.op1_begin);
-    for (uint32_t i = tx.op2_begin; i < tx.op2_end; i++) txn::prep_lcp(v, v.ops2, i, tx.op2_begin);
-  }
+  for (uint32_t i = 0; i < T.n_ops1; i++) txn::prep_lcp(v, v.ops1, i);
+  for (uint32_t i = 0; i < T.n_ops2; i++) txn::prep_lcp(v, v.ops2, i);
   uint32_t sh_dmax = 0;
   txn::Ctx c{v, 0, 1, &sh_dmax};
   for (uint32_t ti = 0; ti < v.n_txns && !cur.flag; ti++) txn::run_txn(c, ti, EMPTY_TRIE_HASH, EMPTY_CODE_HASH);
