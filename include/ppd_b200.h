@@ -78,15 +78,27 @@ int ppd_compact_decode(ppd_ctx* ctx, const uint8_t* witness, size_t len, uint8_t
  * FlatBlock -> IrDump (one GenerationInputs per txn, plus dummies / the withdrawal entry). */
 int ppd_block_decode(ppd_ctx* ctx, const uint8_t* flat_block, size_t len, uint8_t** out, size_t* out_len);
 
-/* The same over n independent blocks: their version DAGs are hashed in one level-synchronous
- * sweep.  statuses[i] is the status of block i; outs[i] is NULL for a failed block. */
+/* The same over n independent blocks, decoded concurrently (up to 64 resident at a time, each on its own stream and
+ * HBM pools; every block's tries are hashed by level-synchronous sweeps of its own).  statuses[i] is the status of
+ * block i; outs[i] is NULL for a failed block.  On a non-OK return (a CUDA failure) no output is handed out: every
+ * outs[i] is NULL. */
 int ppd_blocks_decode_batch(ppd_ctx* ctx, const uint8_t* const* flat_blocks, const size_t* lens, size_t n, uint8_t** outs,
                             size_t* out_lens, int* statuses);
 
-/* Measurement hook: re-run every kernel of the last ppd_block_decode / ppd_blocks_decode_batch on
- * the arena still resident in HBM (no host work, no copies); returns the device time (CUDA events). */
+/* Measurement hook: re-run kernels of the last ppd_block_decode / ppd_blocks_decode_batch on what is still resident
+ * in HBM (no host work, no copies); returns the device time (CUDA events).  `what` selects the stages, which every
+ * lane runs in pipeline order, lanes concurrently: the witness parse + pre-image arena (ppd_parse.cu), key hashing and
+ * the level sweeps (ppd_kernels.cu), the txn loop with its join / account table / op sort (ppd_txn.cu), IR sizing and
+ * emit (ppd_dump.cu).  TXN and DUMP apply to blocks whose txn loop ran on the device. */
+#define PPD_REPLAY_PARSE 1u
+#define PPD_REPLAY_HASH 2u
+#define PPD_REPLAY_TXN 4u
+#define PPD_REPLAY_DUMP 8u
+#define PPD_REPLAY_ALL 15u
+int ppd_replay_last(ppd_ctx* ctx, unsigned what, double* gpu_ms_out);
+/* = ppd_replay_last(ctx, PPD_REPLAY_HASH, ...) */
 int ppd_replay_last_hashing(ppd_ctx* ctx, double* gpu_ms_out);
-/* The same for the compact-witness kernels (instruction boundaries, stack machine, arena emit: the GPU form of
+/* = ppd_replay_last(ctx, PPD_REPLAY_PARSE, ...): the compact-witness kernels (instruction boundaries, stack machine, arena emit: the GPU form of
  * compact_prestate_processing.rs:683-875, 325-668 and compact_to_partial_trie.rs:37-165) of the last call. */
 int ppd_replay_last_parse(ppd_ctx* ctx, double* gpu_ms_out);
 

@@ -634,6 +634,9 @@ void parallel_for(size_t n, unsigned workers, F f) {
       } catch (const Fail& e) {
         std::lock_guard<std::mutex> g(mu);
         if (!failed.exchange(true)) first = e;
+      } catch (const std::exception& e) {  // (an exception leaving a std::thread would terminate the process)
+        std::lock_guard<std::mutex> g(mu);
+        if (!failed.exchange(true)) first = Fail{PPD_ERR_BAD_ARGUMENT, e.what()};
       }
     }
   };

@@ -11,11 +11,15 @@ void read_flat_block(const uint8_t* p, size_t n, BlockJob& b) {
   if (r.u32() != PPD_FLAT_BLOCK_MAGIC || r.u32() != 1) fail(PPD_ERR_BAD_FLAT_INPUT, "bad magic/version");
   if (r.u32() != 0) fail(PPD_PANIC_UNIMPLEMENTED_PRE_IMAGE, "only Combined{compact} pre-images are implemented by the reference");
   b.compact = r.bytes();
+  // counts are checked against the bytes that are left before anything is sized by them (a txn is at least 24 bytes,
+  // a trace 21, a resolved-code entry 36, a withdrawal 52)
   uint32_t nt = r.u32();
+  if ((uint64_t)nt * 24 > r.n - r.pos) fail(PPD_ERR_BAD_FLAT_INPUT, "txn count exceeds the input");
   b.txns.resize(nt);
   for (uint32_t t = 0; t < nt; t++) {
     TxnV& tx = b.txns[t];
     uint32_t ntr = r.u32();
+    if ((uint64_t)ntr * 21 > r.n - r.pos) fail(PPD_ERR_BAD_FLAT_INPUT, "trace count exceeds the input");
     tx.traces.resize(ntr);
     for (uint32_t i = 0; i < ntr; i++) {
       TraceV& tr = tx.traces[i];
@@ -40,12 +44,14 @@ void read_flat_block(const uint8_t* p, size_t n, BlockJob& b) {
     tx.gas_used = r.u64();
   }
   uint32_t nc = r.u32();
+  if ((uint64_t)nc * 36 > r.n - r.pos) fail(PPD_ERR_BAD_FLAT_INPUT, "code count exceeds the input");
   for (uint32_t i = 0; i < nc; i++) {
     H256 h;
     memcpy(h.b, r.raw(32), 32);
     b.resolved_code[h] = r.bytes();
   }
   uint32_t nw = r.u32();
+  if ((uint64_t)nw * 52 > r.n - r.pos) fail(PPD_ERR_BAD_FLAT_INPUT, "withdrawal count exceeds the input");
   for (uint32_t i = 0; i < nw; i++) {
     const uint8_t* a = r.raw(20);
     const uint8_t* v = r.raw(32);

@@ -361,6 +361,11 @@ void decode_one(ppd_ctx* c, Lane* L, const uint8_t* flat, size_t len, uint8_t** 
         dump_blocks(J, out, out_len, dump_workers);
       }
       pt.lap("dump");
+    } catch (const std::bad_alloc&) {
+      *status = PPD_ERR_BAD_FLAT_INPUT;  // sizes taken from the input that no memory can hold
+      std::lock_guard<std::mutex> g(c->err_mu);
+      c->err = "out of memory while reading the block";
+      return;
     } catch (const Fail& e) {
       if (e.code == PPD_ERR_CUDA) throw;
       if (J.device_marks) {
@@ -505,31 +510,82 @@ int ppd_keccak256_batch(ppd_ctx* c, const uint8_t* data, const uint64_t* offsets
   });
 }
 
-// Re-run every kernel of the last ppd_block_decode / ppd_blocks_decode_batch call on the arena and
-// key messages that are still resident in HBM (no host work, no copies) and return its device time.
-int ppd_replay_last_hashing(ppd_ctx* c, double* gpu_ms_out) {
+// Measurement hooks: re-run kernels of the last ppd_block_decode / ppd_blocks_decode_batch call on what is still
+// resident in HBM (no host work, no copies) and return the device time.  Every lane replays the selected stages in
+// pipeline order on its own stream, lanes concurrently, as in the call itself:
+//   PPD_REPLAY_PARSE  witness parse + pre-image arena (ppd_parse.cu)
+//   PPD_REPLAY_HASH   key hashing and the level sweeps (ppd_kernels.cu); with TXN, the loop runs between the two sweeps
+//   PPD_REPLAY_TXN    by-root join, account table, op sort, the txn loop, the order of its nodes (ppd_txn.cu)
+//   PPD_REPLAY_DUMP   IR sizing and emit (ppd_dump.cu)
+// TXN and DUMP exist for lanes whose block took the device txn loop (gpu_txn.cu).
+static void replay_lane(Lane* L, unsigned what) {
+  cudaStream_t st = L->st;
+  if ((what & PPD_REPLAY_PARSE) && L->has_last_parse) {
+    ParseEmit E = L->last_emit;
+    // the sweep may have moved the pools to larger buffers since
+    E.nodes = L->d_nodes.as<NodeRec>(), E.key_pool = L->d_keys.as<uint8_t>(), E.val_pool = L->d_vals.as<uint8_t>();
+    E.hash_pool = L->d_hashes.as<uint8_t>(), E.child_pool = L->d_children.as<uint32_t>(), E.accounts = L->d_accounts.as<AccountRec>();
+    E.level = L->d_level.as<uint16_t>();
+    CUDA_OK(cudaMemsetAsync(L->last_bounds.result, 0, 4 * PARSE_R_WORDS, st));
+    launch_parse_bounds(L->last_bounds, st);
+    launch_parse_scatter(L->last_bounds, L->last_ins_pos, st);
+    launch_parse_tree(E.T, st);
+    if (L->last_n_code) {
+      launch_parse_code_list(E, st);
+      launch_keccak256_ranges(E.T.wit, E.code_se, L->last_n_code, const_cast<uint8_t*>(E.code_digest), st);
+    }
+    if (L->last_val_bytes) CUDA_OK(cudaMemsetAsync(E.val_pool, 0, L->last_val_bytes, st));
+    launch_parse_emit(E, st);
+  }
+  if ((what & PPD_REPLAY_HASH) && L->has_last) {
+    CUDA_OK(cudaMemsetAsync(L->d_counters.p, 0, 32, st));
+    if (L->last_msg_data)
+      launch_keccak256_ranges(L->last_msg_data, L->last_msg_se, L->last_n_msgs, L->last_digest_out, st);
+    else
+      launch_keccak256_ranges(L->d_msg.as<uint8_t>(), L->d_msg_off.as<uint64_t>(), L->last_n_msgs, L->d_digest.as<uint8_t>(), st);
+    for (size_t l = 0; l + 1 < L->last_level_start.size(); l++)
+      launch_hash_level(L->last_view, L->d_order.as<uint32_t>(), L->last_level_start[l], L->last_level_start[l + 1], st);
+  }
+  if ((what & PPD_REPLAY_TXN) && L->has_last_txn) {
+    const txn::View& v = L->last_txn;
+    CUDA_OK(cudaMemsetAsync(v.touched, 0xff, 4ull * L->last_n_touched, st));
+    CUDA_OK(cudaMemsetAsync(L->last_join.slot_owner, 0xff, 4ull * (L->last_join.table_mask + 1), st));
+    CUDA_OK(cudaMemsetAsync(L->last_join.slot_best, 0, 4ull * (L->last_join.table_mask + 1), st));
+    launch_join(L->last_join, st);
+    launch_txn_init(v, L->last_init, L->last_table_slots, st);
+    launch_txn_prep(v, L->last_ai, L->last_n_ops1, L->last_n_ops2, L->last_max_writes, st);
+    launch_txn_loop(v, st);
+    CUDA_OK(cudaMemsetAsync(L->last_bins_tail, 0, 4ull * ORDER_MAX_BINS, st));
+    launch_order_by_level_class(v.nodes, v.level, L->last_cap_tail, ORDER_MAX_BINS, L->last_okeys, L->last_bins_tail, L->d_order2.as<uint32_t>(), st,
+                                L->last_init.n_nodes, &v.cur->n_nodes);
+  }
+  if ((what & PPD_REPLAY_HASH) && L->has_last) {
+    // the nodes the device txn loop appended (gpu_txn.cu) are a second sweep over their own order
+    for (size_t l = 0; l + 1 < L->last_level_start2.size(); l++)
+      launch_hash_level(L->last_view, L->d_order2.as<uint32_t>(), L->last_level_start2[l], L->last_level_start2[l + 1], st);
+  }
+  if ((what & PPD_REPLAY_DUMP) && L->has_last_txn) {
+    launch_ir_size(L->last_view, L->last_plan, L->last_n_ir, st);
+    launch_ir_emit(L->last_view, L->last_plan, L->last_n_ir, L->d_out.as<uint8_t>(), st);
+  }
+  CUDA_OK(cudaGetLastError());
+}
+
+int ppd_replay_last(ppd_ctx* c, unsigned what, double* gpu_ms_out) {
   return guarded(c, [&] {
     size_t used = 0;
-    for (size_t w = 0; w < c->last_lanes_used && w < c->lanes.size(); w++) used += c->lanes[w]->has_last;
-    if (!used) fail(PPD_ERR_BAD_ARGUMENT, "no block job is resident");
+    for (size_t w = 0; w < c->last_lanes_used && w < c->lanes.size(); w++) {
+      const Lane* L = c->lanes[w];
+      used += ((what & PPD_REPLAY_PARSE) && L->has_last_parse) || ((what & PPD_REPLAY_HASH) && L->has_last) ||
+              ((what & (PPD_REPLAY_TXN | PPD_REPLAY_DUMP)) && L->has_last_txn);
+    }
+    if (!used) fail(PPD_ERR_BAD_ARGUMENT, "nothing of the requested kind is resident");
     // all lanes start after ev0 on the main stream; the main stream then waits for every lane
     CUDA_OK(cudaEventRecord(c->ev0, c->st));
     for (size_t w = 0; w < c->last_lanes_used; w++) {
       Lane* L = c->lanes[w];
-      if (!L->has_last) continue;
       CUDA_OK(cudaStreamWaitEvent(L->st, c->ev0, 0));
-      CUDA_OK(cudaMemsetAsync(L->d_counters.p, 0, 32, L->st));
-      if (L->last_msg_data)
-        launch_keccak256_ranges(L->last_msg_data, L->last_msg_se, L->last_n_msgs, L->last_digest_out, L->st);
-      else
-        launch_keccak256_ranges(L->d_msg.as<uint8_t>(), L->d_msg_off.as<uint64_t>(), L->last_n_msgs, L->d_digest.as<uint8_t>(), L->st);
-      size_t nl = L->last_level_start.size() - 1;
-      for (size_t l = 0; l < nl; l++)
-        launch_hash_level(L->last_view, L->d_order.as<uint32_t>(), L->last_level_start[l], L->last_level_start[l + 1], L->st);
-      // the nodes the device txn loop appended (gpu_txn.cu) are a second sweep over their own order
-      for (size_t l = 0; l + 1 < L->last_level_start2.size(); l++)
-        launch_hash_level(L->last_view, L->d_order2.as<uint32_t>(), L->last_level_start2[l], L->last_level_start2[l + 1], L->st);
-      CUDA_OK(cudaGetLastError());
+      replay_lane(L, what);
       CUDA_OK(cudaEventRecord(L->ev1, L->st));
       CUDA_OK(cudaStreamWaitEvent(c->st, L->ev1, 0));
     }
@@ -540,46 +596,8 @@ int ppd_replay_last_hashing(ppd_ctx* c, double* gpu_ms_out) {
     if (gpu_ms_out) *gpu_ms_out = ms;
   });
 }
-
-// The same for the witness parse / pre-image arena kernels (ppd_parse.cu) of the last call: every lane replays
-// its three phases back to back on the witness still resident in HBM (the sizes the host read back between the
-// phases are those of the first run, so nothing is copied or synchronised in between).
-int ppd_replay_last_parse(ppd_ctx* c, double* gpu_ms_out) {
-  return guarded(c, [&] {
-    size_t used = 0;
-    for (size_t w = 0; w < c->last_lanes_used && w < c->lanes.size(); w++) used += c->lanes[w]->has_last_parse;
-    if (!used) fail(PPD_ERR_BAD_ARGUMENT, "no GPU-parsed witness is resident");
-    CUDA_OK(cudaEventRecord(c->ev0, c->st));
-    for (size_t w = 0; w < c->last_lanes_used; w++) {
-      Lane* L = c->lanes[w];
-      if (!L->has_last_parse) continue;
-      CUDA_OK(cudaStreamWaitEvent(L->st, c->ev0, 0));
-      ParseEmit E = L->last_emit;
-      // the sweep may have moved the pools to larger buffers since
-      E.nodes = L->d_nodes.as<NodeRec>(), E.key_pool = L->d_keys.as<uint8_t>(), E.val_pool = L->d_vals.as<uint8_t>();
-      E.hash_pool = L->d_hashes.as<uint8_t>(), E.child_pool = L->d_children.as<uint32_t>(), E.accounts = L->d_accounts.as<AccountRec>();
-      E.level = L->d_level.as<uint16_t>();
-      CUDA_OK(cudaMemsetAsync(L->last_bounds.result, 0, 4 * PARSE_R_WORDS, L->st));
-      launch_parse_bounds(L->last_bounds, L->st);
-      launch_parse_scatter(L->last_bounds, L->last_ins_pos, L->st);
-      launch_parse_tree(E.T, L->st);
-      if (L->last_n_code) {
-        launch_parse_code_list(E, L->st);
-        launch_keccak256_ranges(E.T.wit, E.code_se, L->last_n_code, const_cast<uint8_t*>(E.code_digest), L->st);
-      }
-      if (L->last_val_bytes) CUDA_OK(cudaMemsetAsync(E.val_pool, 0, L->last_val_bytes, L->st));
-      launch_parse_emit(E, L->st);
-      CUDA_OK(cudaGetLastError());
-      CUDA_OK(cudaEventRecord(L->ev1, L->st));
-      CUDA_OK(cudaStreamWaitEvent(c->st, L->ev1, 0));
-    }
-    CUDA_OK(cudaEventRecord(c->ev1, c->st));
-    CUDA_OK(cudaStreamSynchronize(c->st));
-    float ms = 0;
-    CUDA_OK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
-    if (gpu_ms_out) *gpu_ms_out = ms;
-  });
-}
+int ppd_replay_last_hashing(ppd_ctx* c, double* gpu_ms_out) { return ppd_replay_last(c, PPD_REPLAY_HASH, gpu_ms_out); }
+int ppd_replay_last_parse(ppd_ctx* c, double* gpu_ms_out) { return ppd_replay_last(c, PPD_REPLAY_PARSE, gpu_ms_out); }
 
 // Measurement hook (ppd_microbench.cu): variant 0 = dependent-free LOP3/SHF issue rate, 1.. = register
 // resident keccak-f variants.  units_out = ALU instructions (variant 0) or permutations executed.
@@ -648,12 +666,23 @@ int ppd_compact_decode(ppd_ctx* c, const uint8_t* witness, size_t len, uint8_t**
 
 int ppd_blocks_decode_batch(ppd_ctx* c, const uint8_t* const* flats, const size_t* lens, size_t n, uint8_t** outs, size_t* out_lens,
                             int* statuses) {
-  return guarded(c, [&] { decode_blocks(c, flats, lens, n, outs, out_lens, statuses); });
+  int rc = guarded(c, [&] { decode_blocks(c, flats, lens, n, outs, out_lens, statuses); });
+  if (rc != PPD_OK && outs)  // a CUDA failure: no output is handed out (page-locked buffers go back to the pool)
+    for (size_t i = 0; i < n; i++) {
+      if (outs[i]) ppd_free(outs[i]);
+      outs[i] = nullptr;
+      if (out_lens) out_lens[i] = 0;
+    }
+  return rc;
 }
 
 int ppd_block_decode(ppd_ctx* c, const uint8_t* flat, size_t len, uint8_t** out, size_t* out_len) {
   int status = PPD_OK;
   int rc = guarded(c, [&] { decode_blocks(c, &flat, &len, 1, out, out_len, &status); });
+  if (rc != PPD_OK && out && *out) {
+    ppd_free(*out);
+    *out = nullptr;
+  }
   return rc != PPD_OK ? rc : status;
 }
 

@@ -91,6 +91,7 @@ EXPORTS = [
     "ppd_blocks_decode_batch",
     "ppd_trie_root_sorted_leaves",
     "ppd_trie_root_sorted_leaves_dev",
+    "ppd_replay_last",
     "ppd_replay_last_hashing",
     "ppd_replay_last_parse",
     "ppd_microbench",
@@ -128,6 +129,7 @@ class PpdLibrary:
         L.ppd_block_decode.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, u8pp, szp]
         L.ppd_blocks_decode_batch.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
         L.ppd_trie_root_sorted_leaves.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_char_p]
+        L.ppd_replay_last.argtypes = [ctypes.c_void_p, ctypes.c_uint, ctypes.POINTER(ctypes.c_double)]
         L.ppd_replay_last_hashing.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_double)]
         L.ppd_replay_last_parse.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_double)]
         L.ppd_microbench.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_uint32, ctypes.c_uint32, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_uint32)]
@@ -277,6 +279,14 @@ class Context:
             else:
                 res.append(PpdError(statuses[i], "block %d" % i))
         return res
+
+    REPLAY_PARSE, REPLAY_HASH, REPLAY_TXN, REPLAY_DUMP, REPLAY_ALL = 1, 2, 4, 8, 15
+
+    def replay_last(self, what=15) -> float:
+        """Device time (ms) of the selected stages of the last decode call, re-run on what is resident in HBM."""
+        ms = ctypes.c_double()
+        self._check(self.lib.L.ppd_replay_last(self.h, what, ctypes.byref(ms)))
+        return ms.value
 
     def replay_last_hashing(self) -> float:
         ms = ctypes.c_double()
