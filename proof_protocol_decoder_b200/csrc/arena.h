@@ -47,7 +47,8 @@ static const uint32_t IR_SEG_REF = 0xfffffffdu;      // 32 bytes of ref[seg_a] (
 static const uint32_t IR_SEG_FLAT = 0xfffffffcu;     // seg_a bytes of the FlatBlock resident in HBM, from offset seg_c
 static const uint32_t IR_SEG_KEY32 = 0xfffffffbu;    // 32 bytes of key_pool at seg_a (a hashed address)
 static const uint32_t IR_SEG_LIT_DEV = 0xfffffffau;  // seg_a bytes of the uploaded literal pool, from offset seg_c
-static const uint32_t IR_SEG_KIND_MIN = 0xfffffffau;
+static const uint32_t IR_SEG_ROOT_ONLY = 0xfffffff9u;  // the trie rooted at seg_a with only its root kept (a dummy entry's tries)
+static const uint32_t IR_SEG_KIND_MIN = 0xfffffff9u;
 
 // Device-side view of one arena (all pointers are device pointers).
 struct ArenaView {

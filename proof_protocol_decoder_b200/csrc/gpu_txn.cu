@@ -56,6 +56,8 @@ struct HookState {
   uint64_t* se = nullptr;
   uint32_t *bins_pre = nullptr, *bins_tail = nullptr;
   uint16_t* okeys = nullptr;
+  txn::Withdrawal* d_withdrawals = nullptr;
+  txn::AcctExport* d_export = nullptr;
   uint32_t* h_bins = nullptr;   // page-locked: [4096] pre-image bins, [4096] tail bins, then Cursors
   uint8_t* h_code_digests = nullptr;
 };
@@ -96,6 +98,9 @@ void after_emit(void* arg, const ParseEmit& E) {
     j.join_storage = c.take<uint32_t>(n_acct + 1);
     j.join_root = c.take<uint32_t>(n_acct + 1);
     j.pre_flags = c.take<uint8_t>(n_acct + 1);
+    v.pre_slot = c.take<uint32_t>(n_acct + 1);
+    H.d_withdrawals = c.take<txn::Withdrawal>(T.withdrawals.size() + 1);
+    H.d_export = c.take<txn::AcctExport>(T.needs_dummies() ? n_acct + 1 : 1);
     v.path_node = c.take<uint32_t>((size_t)T.max_ops * txn::PATH_CAP + 1);
     v.path_depth = c.take<uint8_t>((size_t)T.max_ops * txn::PATH_CAP + 1);
     v.plen = c.take<uint8_t>(T.max_ops + 1);
@@ -123,6 +128,8 @@ void after_emit(void* arg, const ParseEmit& E) {
   v.cap_keys = (uint32_t)std::min<size_t>(L->d_keys.cap, 0xfffffff0u);
   v.flat = H.d_flat, v.n_txns = (uint32_t)H.n_txns, v.n_traces = (uint32_t)n_traces, v.dig_base = B.dig_base;
   v.pre_flags = j.pre_flags;
+  v.withdrawals = H.d_withdrawals, v.n_withdrawals = (uint32_t)T.withdrawals.size();
+  if (v.n_withdrawals) CUDA_OK(cudaMemcpyAsync(H.d_withdrawals, T.withdrawals.data(), sizeof(txn::Withdrawal) * v.n_withdrawals, cudaMemcpyHostToDevice, st));
   j.acct_list = E.acct_list, j.n_acct = (uint32_t)n_acct, j.table_mask = jtable - 1;
   // ---- the byte strings to hash: straight out of the resident FlatBlock ----
   CUDA_OK(cudaMemcpyAsync(v.traces, T.traces.data(), sizeof(txn::TxnTrace) * n_traces, cudaMemcpyHostToDevice, st));
@@ -223,21 +230,25 @@ int gpu_block(ppd_ctx* c, Lane* L, Job& J, const uint8_t* flat, size_t len, uint
   txn::View& v = H.v;
   const uint32_t n_ir = T.n_ir, n_seg = (uint32_t)T.seg_a.size(), n_touched = T.touched_begin[n_ir];
   const uint32_t n_pre = H.n_pre_nodes;
+  // dummy entries list every storage trie of the state: their segments are appended after the loop (txn_tables_dummies)
+  const int n_dummies = (T.dummy_initial[0] >= 0) + (T.dummy_initial[1] >= 0) + (T.dummy_final >= 0);
+  const size_t dummy_entries = J.dev.accounts + T.traces.size();
+  const size_t seg_cap = n_seg + (size_t)n_dummies * (2 * dummy_entries + 32), lit_cap = T.lit.size() + (size_t)n_dummies * (36 * dummy_entries + 512);
   // ---- the plan on the device: [txns | seg_a | seg_b | seg_c | seg_begin | touched_begin | lit | ir_base | touched |
   //                              seg_off | ir_size, ir_flag | ir_nuniq | u_node | u_size | u_off] ----
   IrDumpPlanView P{};
-  uint32_t *d_seg_a, *d_seg_b, *d_seg_c, *d_seg_begin, *d_touched_begin, *d_touched, *d_ir_size;
+  uint32_t *d_seg_a, *d_seg_b, *d_seg_c, *d_seg_begin, *d_seg_end, *d_touched_begin, *d_touched, *d_ir_size;
   uint64_t* d_ir_base;
   uint8_t* d_lit;
   txn::TxnDesc* d_txns;
   auto plan_layout = [&](Carve2& cv) {
     d_txns = cv.take<txn::TxnDesc>(n_ir + 1);
-    d_seg_a = cv.take<uint32_t>(n_seg + 1), d_seg_b = cv.take<uint32_t>(n_seg + 1), d_seg_c = cv.take<uint32_t>(n_seg + 1);
-    d_seg_begin = cv.take<uint32_t>(n_ir + 1), d_touched_begin = cv.take<uint32_t>(n_ir + 1);
-    d_lit = cv.take<uint8_t>(T.lit.size() + 16);
+    d_seg_a = cv.take<uint32_t>(seg_cap + 1), d_seg_b = cv.take<uint32_t>(seg_cap + 1), d_seg_c = cv.take<uint32_t>(seg_cap + 1);
+    d_seg_begin = cv.take<uint32_t>(n_ir + 1), d_seg_end = cv.take<uint32_t>(n_ir + 1), d_touched_begin = cv.take<uint32_t>(n_ir + 1);
+    d_lit = cv.take<uint8_t>(lit_cap + 16);
     d_ir_base = cv.take<uint64_t>(n_ir + 1);
     d_touched = cv.take<uint32_t>((size_t)n_touched + 16);
-    P.seg_off = cv.take<uint32_t>(n_seg + 1);
+    P.seg_off = cv.take<uint32_t>(seg_cap + 1);
     d_ir_size = cv.take<uint32_t>(2ull * n_ir + 2);  // ir_size, then ir_flag: read back together
     P.ir_nuniq = cv.take<uint32_t>(n_ir + 1);
     P.u_node = cv.take<uint32_t>((size_t)n_touched + 16), P.u_size = cv.take<uint32_t>((size_t)n_touched + 16), P.u_off = cv.take<uint32_t>((size_t)n_touched + 16);
@@ -251,15 +262,18 @@ int gpu_block(ppd_ctx* c, Lane* L, Job& J, const uint8_t* flat, size_t len, uint
   }
   P.ir_size = d_ir_size, P.ir_flag = d_ir_size + n_ir;
   P.touched = d_touched, P.touched_begin = d_touched_begin, P.seg_a = d_seg_a, P.seg_b = d_seg_b, P.seg_c = d_seg_c, P.seg_begin = d_seg_begin;
+  P.seg_end = d_seg_end;
   P.flat = d_flat, P.lit = d_lit, P.ir_base = d_ir_base;
   auto up = [&](void* dst, const void* src, size_t bytes) {
     if (!bytes) return;
     CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st));
     L->stats.h2d_bytes += (double)bytes;
   };
-  up(d_txns, T.txns.data(), sizeof(txn::TxnDesc) * n_ir);
+  up(d_txns, T.txns.data(), sizeof(txn::TxnDesc) * T.txns.size());
   up(d_seg_a, T.seg_a.data(), 4ull * n_seg), up(d_seg_b, T.seg_b.data(), 4ull * n_seg), up(d_seg_c, T.seg_c.data(), 4ull * n_seg);
-  up(d_seg_begin, T.seg_begin.data(), 4ull * (n_ir + 1)), up(d_touched_begin, T.touched_begin.data(), 4ull * (n_ir + 1));
+  up(d_touched_begin, T.touched_begin.data(), 4ull * (n_ir + 1));
+  if (!n_dummies) up(d_seg_begin, T.seg_begin.data(), 4ull * (n_ir + 1)), up(d_seg_end, T.seg_end.data(), 4ull * (n_ir + 1));
+  if (v.n_withdrawals) up(H.d_withdrawals, T.withdrawals.data(), sizeof(txn::Withdrawal) * v.n_withdrawals);  // (phase 2 rebased the records)
   up(d_lit, T.lit.data(), T.lit.size());
   up(v.key_pool + H.B.txn_key_base, T.txn_keys.data(), T.txn_keys.size());
   up(v.traces, T.traces.data(), sizeof(txn::TxnTrace) * T.traces.size());  // (phase 2 rebased the record and value offsets)
@@ -286,6 +300,7 @@ int gpu_block(ppd_ctx* c, Lane* L, Job& J, const uint8_t* flat, size_t len, uint
   H.j.ref = V.ref;
   CUDA_OK(cudaMemsetAsync(H.j.slot_owner, 0xff, 4ull * (H.j.table_mask + 1), st));
   CUDA_OK(cudaMemsetAsync(H.j.slot_best, 0, 4ull * (H.j.table_mask + 1), st));
+  CUDA_OK(cudaMemsetAsync(v.pre_slot, 0xff, 4ull * (H.j.n_acct + 1), st));
   launch_join(H.j, st);
   txn::Cursors init;
   memset(&init, 0, sizeof init);
@@ -297,7 +312,7 @@ int gpu_block(ppd_ctx* c, Lane* L, Job& J, const uint8_t* flat, size_t len, uint
   for (size_t t = 0; t < T.traces.size(); t++) max_writes = std::max(max_writes, T.traces[t].n_writes);
   L->stats.kernel_launches += 3 + launch_txn_prep(v, H.ai, T.n_ops1, T.n_ops2, max_writes, st);
   CUDA_OK(cudaEventRecord(L->ev_loop0, st));
-  launch_txn_loop(v, st);
+  launch_txn_loop(v, b.state_root, st);
   CUDA_OK(cudaEventRecord(L->ev_loop1, st));
   L->stats.kernel_launches += 1;
   // ---- the loop's nodes sorted by (level, class) ----
@@ -323,6 +338,30 @@ int gpu_block(ppd_ctx* c, Lane* L, Job& J, const uint8_t* flat, size_t len, uint
     L->stats = stats0;
     L->has_last_parse = false;
     return GPU_BLOCK_DECLINED;
+  }
+  if (n_dummies) {
+    // the storage map as it was before the first and is after the last txn, then the dummies' segments
+    const size_t n_acct = J.dev.accounts, n_tr = T.traces.size();
+    const size_t w_export = (sizeof(txn::AcctExport) * (n_acct + 1) + 3) / 4, w_table = (sizeof(txn::AcctState) * H.table_slots + 3) / 4, w_dig = 8 * (n_tr + 1);
+    J.txn_export.resize(w_export + w_table + w_dig + 16);
+    txn::AcctExport* h_export = reinterpret_cast<txn::AcctExport*>(J.txn_export.data());
+    txn::AcctState* h_table = reinterpret_cast<txn::AcctState*>(J.txn_export.data() + w_export);
+    uint8_t* h_dig = reinterpret_cast<uint8_t*>(J.txn_export.data() + w_export + w_table);
+    launch_acct_export(v, H.j, H.d_export, st);
+    CUDA_OK(cudaGetLastError());
+    if (n_acct) CUDA_OK(cudaMemcpyAsync(h_export, H.d_export, sizeof(txn::AcctExport) * n_acct, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaMemcpyAsync(h_table, v.acct, sizeof(txn::AcctState) * H.table_slots, cudaMemcpyDeviceToHost, st));
+    if (n_tr) CUDA_OK(cudaMemcpyAsync(h_dig, v.key_pool + H.B.dig_base, 32ull * n_tr, cudaMemcpyDeviceToHost, st));
+    L->stats.kernel_launches += 1, L->stats.d2h_bytes += (double)(sizeof(txn::AcctExport) * n_acct + sizeof(txn::AcctState) * H.table_slots + 32ull * n_tr);
+    lane_sync(L);
+    const size_t seg0 = T.seg_a.size(), lit0 = T.lit.size();
+    txn_tables_dummies(b, flat, *h_cur, h_export, (uint32_t)n_acct, h_table, H.table_slots, h_dig, T);
+    if (T.seg_a.size() > seg_cap || T.lit.size() > lit_cap) fail(PPD_ERR_BAD_ARGUMENT, "dummy entries exceed their plan space");
+    up(d_seg_a + seg0, T.seg_a.data() + seg0, 4ull * (T.seg_a.size() - seg0)), up(d_seg_b + seg0, T.seg_b.data() + seg0, 4ull * (T.seg_b.size() - seg0));
+    up(d_seg_c + seg0, T.seg_c.data() + seg0, 4ull * (T.seg_c.size() - seg0));
+    up(d_lit + lit0, T.lit.data() + lit0, T.lit.size() - lit0);
+    up(d_seg_begin, T.seg_begin.data(), 4ull * (n_ir + 1)), up(d_seg_end, T.seg_end.data(), 4ull * (n_ir + 1));
+    pt.lap("t:dummies");
   }
   const uint32_t n_total = h_cur->n_nodes, n_tail = n_total - n_pre;
   levels_from_bins(H.h_bins + ORDER_MAX_BINS, n_tail, level_tail);

@@ -450,6 +450,7 @@ struct Job {
   PVec<H256> code_digest;
   TxnTables txn;              // tables of the device txn loop (gpu_txn.cu)
   PVec<uint32_t> txn_host;    // page-locked landing area of its read-backs
+  PVec<uint32_t> txn_export;  // ... and of the storage map a block with dummy entries reads back
   PVec<uint64_t> ir_base;
   std::vector<uint32_t> stamp;
   uint32_t serial = 0;
@@ -465,6 +466,7 @@ struct Job {
     wit_stage.alloc_fn = pinned_alloc, wit_stage.free_fn = pinned_free;
     txn.set_allocator(pinned_alloc, pinned_free);
     txn_host.alloc_fn = pinned_alloc, txn_host.free_fn = pinned_free;
+    txn_export.alloc_fn = pinned_alloc, txn_export.free_fn = pinned_free;
     ir_base.alloc_fn = pinned_alloc, ir_base.free_fn = pinned_free;
   }
   void reset(size_t n_blocks) {

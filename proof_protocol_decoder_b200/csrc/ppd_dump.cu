@@ -169,7 +169,7 @@ __global__ void __launch_bounds__(DUMP_THREADS) ir_size_kernel(ArenaView A, IrDu
     __shared__ uint32_t scan_carry;
     if (threadIdx.x == 0) scan_carry = 0;
     __syncthreads();
-    const uint32_t sb = P.seg_begin[ir], se = P.seg_begin[ir + 1];
+    const uint32_t sb = P.seg_begin[ir], se = P.seg_end ? P.seg_end[ir] : P.seg_begin[ir + 1];
     for (uint32_t q0 = sb; q0 < se; q0 += DUMP_THREADS) {
       const uint32_t q = q0 + threadIdx.x;
       uint32_t sz = 0, trie_slot = NOT_FOUND;
@@ -177,6 +177,17 @@ __global__ void __launch_bounds__(DUMP_THREADS) ir_size_kernel(ArenaView A, IrDu
         const uint32_t a = P.seg_a[q], b = P.seg_b[q];
         if (b == NODE_EMPTY) {
           sz = 1;
+        } else if (b == IR_SEG_ROOT_ONLY) {
+          // a trie of which only the root is kept (create_trie_subset with the key 0_u64, decoding.rs:466-471)
+          if (a == NODE_EMPTY) {
+            sz = 1;
+          } else if (is_hash_id(a) || node_kind(A, a) == NK_ROOT) {
+            sz = 33;
+          } else {
+            uint32_t fl = 0;
+            sz = node_size(A, s, a, &fl);
+            if (fl) s.flag = 1;
+          }
         } else if (b >= IR_SEG_KIND_MIN) {
           sz = (b == IR_SEG_REF || b == IR_SEG_KEY32) ? 32u : a;
         } else if (is_hash_id(b)) {
@@ -334,6 +345,57 @@ __device__ __forceinline__ uint8_t* put_child(uint8_t* q, const ArenaView& A, co
 
 }  // namespace
 
+// the bytes of node u at q: its own fields, and every child that is not touched itself (touched ones write themselves)
+__device__ void emit_node(const ArenaView& A, const Shared& s, uint32_t u, uint8_t* q) {
+  const NodeRec r = A.nodes[u];
+  switch (r.w0 & 0xff) {
+    case NK_LEAF: {
+      *q++ = PPD_NODE_LEAF;
+      q = put_nibbles(q, A, r);
+      q = put_u32(q, r.a2);
+      const uint8_t* v = A.val_pool + r.a1;
+      for (uint32_t i = 0; i < r.a2; i++) q[i] = v[i];
+      break;
+    }
+    case NK_LEAF_ACCOUNT: {
+      const AccountRec& acc = A.accounts[r.a1];
+      *q++ = PPD_NODE_LEAF;
+      q = put_nibbles(q, A, r);
+      uint32_t len = account_rlp_len(acc);
+      q = put_u32(q, len);
+      *q++ = 0xf8;
+      *q++ = (uint8_t)(len - 2);
+      q = put_u256_str(q, acc.nonce);
+      q = put_u256_str(q, acc.balance);
+      const uint8_t* sr = acc.storage_src == NODE_EMPTY ? acc.storage_root : A.ref + 32ull * acc.storage_src;
+      *q++ = 0xa0;
+      for (int i = 0; i < 32; i++) *q++ = sr[i];
+      *q++ = 0xa0;
+      for (int i = 0; i < 32; i++) *q++ = acc.code_hash[i];
+      break;
+    }
+    case NK_EXT:
+      *q++ = PPD_NODE_EXTENSION;
+      q = put_nibbles(q, A, r);
+      put_child(q, A, s, r.a1);
+      break;
+    case NK_BRANCH: {
+      *q++ = PPD_NODE_BRANCH;
+      const uint32_t mask = r.a1 & 0xffff;
+      for (uint32_t i = 0, j = 0; i < 16; i++) {
+        if (mask & (1u << i))
+          q = put_child(q, A, s, A.child_pool[r.a0 + j++]);
+        else
+          *q++ = PPD_NODE_EMPTY;
+      }
+      put_u32(q, 0);
+      break;
+    }
+    default:
+      break;
+  }
+}
+
 // One CTA per IR: every unique touched node writes its own bytes at out + ir_base[ir] + its offset.
 __global__ void __launch_bounds__(DUMP_THREADS) ir_emit_kernel(ArenaView A, IrDumpPlanView P, uint8_t* __restrict__ out) {
   extern __shared__ uint8_t smem_raw[];
@@ -345,60 +407,10 @@ __global__ void __launch_bounds__(DUMP_THREADS) ir_emit_kernel(ArenaView A, IrDu
   for (uint32_t k = threadIdx.x; k < nu; k += blockDim.x) s.u_size[k] = P.u_size[tb + k], s.u_off[k] = P.u_off[tb + k];
   __syncthreads();
   uint8_t* base = out + P.ir_base[ir];
-  for (uint32_t k = threadIdx.x; k < nu; k += blockDim.x) {
-    const uint32_t u = s.u_node[k];
-    const NodeRec r = A.nodes[u];
-    uint8_t* q = base + s.u_off[k];
-    switch (r.w0 & 0xff) {
-      case NK_LEAF: {
-        *q++ = PPD_NODE_LEAF;
-        q = put_nibbles(q, A, r);
-        q = put_u32(q, r.a2);
-        const uint8_t* v = A.val_pool + r.a1;
-        for (uint32_t i = 0; i < r.a2; i++) q[i] = v[i];
-        break;
-      }
-      case NK_LEAF_ACCOUNT: {
-        const AccountRec& acc = A.accounts[r.a1];
-        *q++ = PPD_NODE_LEAF;
-        q = put_nibbles(q, A, r);
-        uint32_t len = account_rlp_len(acc);
-        q = put_u32(q, len);
-        *q++ = 0xf8;
-        *q++ = (uint8_t)(len - 2);
-        q = put_u256_str(q, acc.nonce);
-        q = put_u256_str(q, acc.balance);
-        const uint8_t* sr = acc.storage_src == NODE_EMPTY ? acc.storage_root : A.ref + 32ull * acc.storage_src;
-        *q++ = 0xa0;
-        for (int i = 0; i < 32; i++) *q++ = sr[i];
-        *q++ = 0xa0;
-        for (int i = 0; i < 32; i++) *q++ = acc.code_hash[i];
-        break;
-      }
-      case NK_EXT:
-        *q++ = PPD_NODE_EXTENSION;
-        q = put_nibbles(q, A, r);
-        put_child(q, A, s, r.a1);
-        break;
-      case NK_BRANCH: {
-        *q++ = PPD_NODE_BRANCH;
-        const uint32_t mask = r.a1 & 0xffff;
-        for (uint32_t i = 0, j = 0; i < 16; i++) {
-          if (mask & (1u << i))
-            q = put_child(q, A, s, A.child_pool[r.a0 + j++]);
-          else
-            *q++ = PPD_NODE_EMPTY;
-        }
-        put_u32(q, 0);
-        break;
-      }
-      default:
-        break;
-    }
-  }
+  for (uint32_t k = threadIdx.x; k < nu; k += blockDim.x) emit_node(A, s, s.u_node[k], base + s.u_off[k]);
   // the other segments: untouched tries (a storage trie nobody reads: its root as a hash, or empty), roots, hashed
   // addresses, and the literal bytes that are resident in HBM (FlatBlock ranges, the uploaded literal pool)
-  const uint32_t sb = P.seg_begin[ir], se = P.seg_begin[ir + 1];
+  const uint32_t sb = P.seg_begin[ir], se = P.seg_end ? P.seg_end[ir] : P.seg_begin[ir + 1];
   for (uint32_t qi = sb + threadIdx.x; qi < se; qi += blockDim.x) {
     const uint32_t b = P.seg_b[qi];
     if (b == IR_SEG_LITERAL) continue;
@@ -406,6 +418,18 @@ __global__ void __launch_bounds__(DUMP_THREADS) ir_emit_kernel(ArenaView A, IrDu
     if (b == IR_SEG_REF || b == IR_SEG_KEY32) {
       const uint8_t* r = b == IR_SEG_REF ? A.ref + 32ull * P.seg_a[qi] : A.key_pool + P.seg_a[qi];
       for (int i = 0; i < 32; i++) q[i] = r[i];
+      continue;
+    }
+    if (b == IR_SEG_ROOT_ONLY) {
+      const uint32_t a = P.seg_a[qi];
+      if (a == NODE_EMPTY)
+        *q = PPD_NODE_EMPTY;
+      else if (is_hash_id(a))
+        put_hash(q, A.hash_pool + 32ull * (a - HASH_ID_BASE));
+      else if (node_kind(A, a) == NK_ROOT)
+        put_hash(q, A.ref + 32ull * a);
+      else
+        emit_node(A, s, a, q);
       continue;
     }
     if (b == IR_SEG_FLAT || b == IR_SEG_LIT_DEV) {

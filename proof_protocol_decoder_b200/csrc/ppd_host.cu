@@ -551,10 +551,11 @@ static void replay_lane(Lane* L, unsigned what) {
     CUDA_OK(cudaMemsetAsync(v.touched, 0xff, 4ull * L->last_n_touched, st));
     CUDA_OK(cudaMemsetAsync(L->last_join.slot_owner, 0xff, 4ull * (L->last_join.table_mask + 1), st));
     CUDA_OK(cudaMemsetAsync(L->last_join.slot_best, 0, 4ull * (L->last_join.table_mask + 1), st));
+    CUDA_OK(cudaMemsetAsync(v.pre_slot, 0xff, 4ull * (L->last_join.n_acct + 1), st));
     launch_join(L->last_join, st);
     launch_txn_init(v, L->last_init, L->last_table_slots, st);
     launch_txn_prep(v, L->last_ai, L->last_n_ops1, L->last_n_ops2, L->last_max_writes, st);
-    launch_txn_loop(v, st);
+    launch_txn_loop(v, L->last_init.state_root, st);
     CUDA_OK(cudaMemsetAsync(L->last_bins_tail, 0, 4ull * ORDER_MAX_BINS, st));
     launch_order_by_level_class(v.nodes, v.level, L->last_cap_tail, ORDER_MAX_BINS, L->last_okeys, L->last_bins_tail, L->d_order2.as<uint32_t>(), st,
                                 L->last_init.n_nodes, &v.cur->n_nodes);

@@ -67,6 +67,7 @@ struct IrDumpPlanView {
   const uint32_t* seg_a;
   const uint32_t* seg_b;
   const uint32_t* seg_begin;      // [n_ir + 1]
+  const uint32_t* seg_end;        // [n_ir], or nullptr: IR i ends where IR i + 1 begins
   const uint32_t* seg_c;          // source offset of IR_SEG_FLAT / IR_SEG_LIT_DEV segments (nullptr: the plan has none)
   const uint8_t* flat;            // the FlatBlock resident in HBM
   const uint8_t* lit;             // the uploaded literal pool
@@ -171,7 +172,8 @@ void launch_txn_msgs(const txn::View& v, uint64_t* se, cudaStream_t st);
 void launch_txn_init(const txn::View& v, const txn::Cursors& init, uint32_t table_slots, cudaStream_t st);
 void launch_join(const txn::JoinView& j, cudaStream_t st);
 uint32_t launch_txn_prep(const txn::View& v, const txn::AcctInit& a, uint32_t n_ops1, uint32_t n_ops2, uint32_t max_writes, cudaStream_t st);
-void launch_txn_loop(const txn::View& v, cudaStream_t st);
+void launch_txn_loop(const txn::View& v, uint32_t initial_state, cudaStream_t st);
+void launch_acct_export(const txn::View& v, const txn::JoinView& j, txn::AcctExport* out, cudaStream_t st);
 
 // ---- ppd_microbench.cu ----
 bool launch_microbench(int variant, uint32_t* out, uint32_t blocks_per_sm, uint32_t iters, uint32_t* block_threads, double* units_per_thread_iter,

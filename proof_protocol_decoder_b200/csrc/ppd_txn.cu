@@ -29,12 +29,14 @@ __constant__ uint8_t C_EMPTY_CODE[32] = {0xc5, 0xd2, 0x46, 0x01, 0x86, 0xf7, 0x2
 __global__ void txn_msgs_kernel(View v, uint64_t* __restrict__ se) {
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t < v.n_traces) prep_msgs(v, t, se);
+  if (t < v.n_withdrawals) prep_withdrawal_msg(v, t, se);
 }
 
 __global__ void txn_init_kernel(View v, Cursors init, uint32_t table_slots) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i == 0) *v.cur = init;
   if (i < table_slots) v.acct[i] = AcctState{ST_ABSENT, NONE, NONE, 0xffffffffu};
+  // (pre_slot[] is reset by the launcher's memset)
 }
 
 // ---- the by-root join ------------------------------------------------------------------------------------
@@ -112,8 +114,14 @@ __global__ void prep_lcp_kernel(View v, uint32_t n1, uint32_t n2) {
     prep_lcp(v, v.ops2, i - n1);
 }
 
+__global__ void acct_export_kernel(View v, const uint32_t* __restrict__ acct_list, const uint32_t* __restrict__ join_storage, uint32_t n_acct,
+                                   AcctExport* __restrict__ out) {
+  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < n_acct) export_account(v, acct_list, join_storage, r, out);
+}
+
 constexpr int LOOP_THREADS = 256;
-__global__ void __launch_bounds__(LOOP_THREADS, 1) txn_loop_kernel(View v) {
+__global__ void __launch_bounds__(LOOP_THREADS, 1) txn_loop_kernel(View v, uint32_t initial_state) {
   __shared__ uint32_t sh_dmax, sh_stop;
   Ctx c{v, threadIdx.x, blockDim.x, &sh_dmax};
   for (uint32_t ti = 0; ti < v.n_txns; ti++) {
@@ -124,6 +132,7 @@ __global__ void __launch_bounds__(LOOP_THREADS, 1) txn_loop_kernel(View v) {
     if (sh_stop) break;
     __syncthreads();
   }
+  run_finish(c, initial_state);
 }
 
 }  // namespace
@@ -131,7 +140,8 @@ __global__ void __launch_bounds__(LOOP_THREADS, 1) txn_loop_kernel(View v) {
 static inline uint32_t cdiv(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
 
 void launch_txn_msgs(const View& v, uint64_t* se, cudaStream_t st) {
-  if (v.n_traces) txn_msgs_kernel<<<cdiv(v.n_traces, 128), 128, 0, st>>>(v, se);
+  const uint32_t n = v.n_traces > v.n_withdrawals ? v.n_traces : v.n_withdrawals;
+  if (n) txn_msgs_kernel<<<cdiv(n, 128), 128, 0, st>>>(v, se);
 }
 void launch_txn_init(const View& v, const Cursors& init, uint32_t table_slots, cudaStream_t st) {
   txn_init_kernel<<<cdiv(table_slots, 256), 256, 0, st>>>(v, init, table_slots);
@@ -142,19 +152,27 @@ void launch_join(const JoinView& j, cudaStream_t st) {
   join_resolve_kernel<<<cdiv(j.n_acct, 128), 128, 0, st>>>(j);
 }
 uint32_t launch_txn_prep(const View& v, const AcctInit& a, uint32_t n_ops1, uint32_t n_ops2, uint32_t max_writes, cudaStream_t st) {
-  if (!v.n_traces) return 0;
-  acct_claim_kernel<<<cdiv(v.n_traces, 128), 128, 0, st>>>(v, a);
-  prep_trace_kernel<<<cdiv(v.n_traces, 128), 128, 0, st>>>(v);
-  uint32_t launches = 4;
-  if (max_writes) {
-    const uint32_t threads = max_writes >= 64 ? 128 : 32;
-    prep_write_kernel<<<dim3(v.n_traces, cdiv(max_writes, threads)), threads, 0, st>>>(v);
-    launches++;
+  uint32_t launches = 0;
+  if (v.n_traces) {
+    acct_claim_kernel<<<cdiv(v.n_traces, 128), 128, 0, st>>>(v, a);
+    prep_trace_kernel<<<cdiv(v.n_traces, 128), 128, 0, st>>>(v);
+    launches += 2;
+    if (max_writes) {
+      const uint32_t threads = max_writes >= 64 ? 128 : 32;
+      prep_write_kernel<<<dim3(v.n_traces, cdiv(max_writes, threads)), threads, 0, st>>>(v);
+      launches++;
+    }
   }
-  prep_txn_kernel<<<cdiv(v.n_txns, 64), 64, 0, st>>>(v);
-  prep_lcp_kernel<<<cdiv(n_ops1 + n_ops2, 128), 128, 0, st>>>(v, n_ops1, n_ops2);
+  if (v.n_txns) {
+    prep_txn_kernel<<<cdiv(v.n_txns, 64), 64, 0, st>>>(v);
+    prep_lcp_kernel<<<cdiv(n_ops1 + n_ops2, 128), 128, 0, st>>>(v, n_ops1, n_ops2);
+    launches += 2;
+  }
   return launches;
 }
-void launch_txn_loop(const View& v, cudaStream_t st) { txn_loop_kernel<<<1, LOOP_THREADS, 0, st>>>(v); }
+void launch_txn_loop(const View& v, uint32_t initial_state, cudaStream_t st) { txn_loop_kernel<<<1, LOOP_THREADS, 0, st>>>(v, initial_state); }
+void launch_acct_export(const View& v, const JoinView& j, AcctExport* out, cudaStream_t st) {
+  if (j.n_acct) acct_export_kernel<<<cdiv(j.n_acct, 128), 128, 0, st>>>(v, j.acct_list, j.join_storage, j.n_acct, out);
+}
 
 }  // namespace ppd

@@ -119,12 +119,22 @@ struct AcctState {
   uint32_t owner;      // (table) first trace that claimed the slot, or 0xffffffff
 };
 
+enum { XR_INITIAL_STATE = 0, XR_EMPTY = 1, XR_FINAL_STATE = 2, XR_FINAL_TXN = 3, XR_FINAL_RECEIPT = 4, XR_AFTER_WITHDRAWALS = 5 };
 struct Cursors {
   uint32_t n_nodes, n_children, key_bytes;  // allocation cursors
   uint32_t flag, flag_txn;                  // first TXF_* raised and where
   uint32_t state_root, txn_root, receipt_root;
   uint32_t max_level;
-  uint32_t pad[7];
+  uint32_t roots[6];  // NK_ROOT nodes the dummy entries refer to (XR_*), created when the loop ends
+  uint32_t state_before_withdrawals;
+};
+
+// One withdrawal (decoding.rs:404-428): balance += amount on the account of the hashed address
+struct Withdrawal {
+  uint32_t m_addr;      // digest index of the address
+  uint32_t off_amount;  // FlatBlock offset of the 32-byte amount
+  uint32_t rec;         // account record the updated account fills
+  uint32_t pad;
 };
 
 // Everything the loop touches.  All pointers are device pointers (host pointers in the CPU harness).
@@ -145,6 +155,9 @@ struct View {
   uint32_t n_txns, n_traces;
   uint32_t dig_base;         // key_pool offset of digest 0 (32 bytes each)
   AcctState* acct;           // account table
+  uint32_t* pre_slot;        // per pre-image account: its slot of the account table once a trace touched it (else >= NONE)
+  const Withdrawal* withdrawals;
+  uint32_t n_withdrawals;
   const uint8_t* pre_flags;  // per pre-image account: bit0 storage root != EMPTY_TRIE_HASH
   SOp* ops1;
   SOp* ops2;
@@ -668,6 +681,11 @@ PPD_HD inline void prep_msgs(const View& v, uint32_t t, uint64_t* se) {
   if ((tr.flags & PPD_TR_CODE_WRITE) && !(tr.flags & PPD_TR_CODE_READ)) se[2 * tr.m_code] = tr.code_off, se[2 * tr.m_code + 1] = (uint64_t)tr.code_off + tr.code_len;
 }
 
+PPD_HD inline void prep_withdrawal_msg(const View& v, uint32_t w, uint64_t* se) {  // the address precedes the amount
+  const Withdrawal wd = v.withdrawals[w];
+  se[2 * wd.m_addr] = wd.off_amount - 20ull, se[2 * wd.m_addr + 1] = wd.off_amount;
+}
+
 // per trace t: its rank among the traces of its txn by hashed address, and its state op
 PPD_HD inline void prep_trace(const View& v, uint32_t t) {
   TxnTrace& tr = v.traces[t];
@@ -792,6 +810,7 @@ PPD_HD inline void acct_claim(const View& v, const AcctInit& a, uint32_t t) {
       if (leaf != NODE_EMPTY && (v.nodes[leaf].w0 & 0xffu) == NK_LEAF_ACCOUNT) {
         const uint32_t r = v.nodes[leaf].a1;
         s.pre_rec = r, s.storage = a.join_storage[r], s.root_node = a.join_root[r];
+        v.pre_slot[r] = h;
       }
       v.acct[h].storage = s.storage, v.acct[h].root_node = s.root_node, v.acct[h].pre_rec = s.pre_rec;
       v.traces[t].acct = h;
@@ -968,6 +987,67 @@ PPD_HD inline void run_txn(const Ctx& c, uint32_t ti, const uint8_t* empty_trie_
     v.seg_a[tx.seg_roots + 2] = new_root(v, v.cur->receipt_root);
   }
   PPD_BLOCK_SYNC();
+}
+
+// ---- after the last txn: the NK_ROOT nodes dummy entries refer to, and the withdrawals (decoding.rs:356-428) ----
+PPD_HD inline void u256_add(uint8_t* a, const uint8_t* b) {
+  uint32_t carry = 0;
+  for (int i = 31; i >= 0; i--) {
+    const uint32_t x = (uint32_t)a[i] + b[i] + carry;
+    a[i] = (uint8_t)x;
+    carry = x >> 8;
+  }
+}
+PPD_HD inline void run_finish(const Ctx& c, uint32_t initial_state) {
+  const View& v = c.v;
+  if (c.tid == 0 && !v.cur->flag) {
+    Cursors& cur = *v.cur;
+    cur.roots[XR_INITIAL_STATE] = new_root(v, initial_state);
+    cur.roots[XR_EMPTY] = new_root(v, NODE_EMPTY);
+    cur.roots[XR_FINAL_STATE] = new_root(v, cur.state_root);
+    cur.roots[XR_FINAL_TXN] = new_root(v, cur.txn_root);
+    cur.roots[XR_FINAL_RECEIPT] = new_root(v, cur.receipt_root);
+    cur.state_before_withdrawals = cur.state_root;
+    // one after the other, as the reference does: a later withdrawal to the same address sees the earlier one
+    for (uint32_t w = 0; w < v.n_withdrawals && !cur.flag; w++) {
+      const Withdrawal wd = v.withdrawals[w];
+      const uint32_t koff = v.dig_base + 32u * wd.m_addr;
+      const uint32_t leaf = get_leaf(v, cur.state_root, koff, 64);
+      if (leaf == NODE_EMPTY || (v.nodes[leaf].w0 & 0xffu) != NK_LEAF_ACCOUNT) {
+        raise(v, TXF_WITHDRAWAL, 0xffffffffu);
+        break;
+      }
+      AccountRec rec = v.accounts[v.nodes[leaf].a1];
+      u256_add(rec.balance, v.flat + wd.off_amount);
+      v.accounts[wd.rec] = rec;
+      SOp o;
+      o.koff = koff, o.klen = 64, o.lcp = -1, o.kind = OP_PUT_ACCOUNT, o.pad = 0, o.a1 = wd.rec, o.a2 = 0, o.owner = OWNER_STATE_TRIE;
+      cur.state_root = insert_one(v, cur.state_root, 0, o, 0xffffffffu);
+    }
+    cur.roots[XR_AFTER_WITHDRAWALS] = new_root(v, cur.state_root);
+  }
+  PPD_BLOCK_SYNC();
+}
+
+// ---- the storage map for dummy entries (decoding.rs:531-549 lists EVERY storage trie): per pre-image account its
+// hashed address and the root of its trie before the first and after the last txn ----
+struct AcctExport {
+  uint8_t haddr[32];
+  uint32_t initial, final_;  // node id, NODE_EMPTY, or ST_ABSENT
+};
+PPD_HD inline void export_account(const View& v, const uint32_t* acct_list, const uint32_t* join_storage, uint32_t r, AcctExport* out) {
+  const NodeRec nr = v.nodes[acct_list[5ull * r]];
+  const uint32_t ns = (nr.w0 >> 8) & 0xffu, nl = (nr.w0 >> 16) & 0xffu, klen = ns + nl;
+  AcctExport e;
+  for (int i = 0; i < 32; i++) e.haddr[i] = 0;
+  for (uint32_t k = 0; k < klen && k < 64; k++) {  // utils.rs:49-59: the nibbles right-aligned in 32 bytes
+    const uint32_t posn = 64 - klen + k, nib = key_nib(v, nr.a0, k);
+    e.haddr[posn >> 1] |= (uint8_t)((posn & 1) ? nib : (nib << 4));
+  }
+  e.initial = join_storage[r];
+  const uint32_t slot = v.pre_slot[r];
+  e.final_ = slot < NONE ? v.acct[slot].storage : e.initial;
+  out[r] = e;
 }
 
 }  // namespace txn

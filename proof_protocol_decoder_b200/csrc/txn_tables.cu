@@ -9,8 +9,6 @@ using txn::TxnTrace;
 
 bool txn_tables_phase1(const BlockJob& b, const uint8_t* flat, size_t flat_len, TxnTables& T) {
   T.clear();
-  // blocks that need dummy entries or withdrawals (decoding.rs:304-428) are shaped by the host path
-  if (b.txns.size() < 2 || !b.withdrawals.empty()) return false;
   if (flat_len >= 0xfff00000ull) return false;
   size_t n_traces = 0;
   for (const TxnV& tx : b.txns) n_traces += tx.traces.size();
@@ -62,9 +60,27 @@ bool txn_tables_phase1(const BlockJob& b, const uint8_t* flat, size_t flat_len, 
     n_items += tx.traces.size() + 2 + item;
   }
   if (n_items * txn::MARK_SLOTS_T >= (1ull << 31)) return false;
+  // withdrawals (decoding.rs:404-428): the hashed address of each, and the record the updated account fills
+  T.withdrawals.resize(b.withdrawals.size());
+  for (size_t w = 0; w < b.withdrawals.size(); w++) T.withdrawals[w] = txn::Withdrawal{m++, (uint32_t)(b.withdrawals[w].second - flat), rec++, 0};
+  // the entries of the IrDump (pad_gen_inputs_with_dummy_inputs_if_needed, decoding.rs:304-347; add_withdrawals_to_txns, :356-402)
+  {
+    const size_t n = b.txns.size();
+    const bool wd = !b.withdrawals.empty();
+    if (n == 0) {
+      T.dummy_initial[0] = 0, T.dummy_initial[1] = 1, T.first_txn_ir = 2, T.n_ir = 2;
+    } else if (n == 1 && !wd) {
+      T.dummy_initial[0] = 0, T.first_txn_ir = 1, T.n_ir = 2;
+    } else if (wd) {
+      T.first_txn_ir = 0, T.dummy_final = (int)n, T.n_ir = (uint32_t)n + 1;
+    } else {
+      T.first_txn_ir = 0, T.n_ir = (uint32_t)n;
+    }
+  }
   T.n_msgs = m, T.n_ops1 = op, T.n_recs = rec, T.n_items = (uint32_t)n_items, T.val_writes = val, T.val_extra = 0;
-  T.est_nodes = 16ull * (T.n_ops1 + T.n_ops2) + 16ull * b.txns.size() + 1024;
-  T.est_children = 48ull * T.n_ops1 + 128ull * T.n_ops2 + 64ull * b.txns.size() + 4096;
+  T.est_nodes = 0;
+  T.est_nodes = 16ull * (T.n_ops1 + T.n_ops2) + 16ull * b.txns.size() + 80ull * b.withdrawals.size() + 1024;
+  T.est_children = 48ull * T.n_ops1 + 128ull * T.n_ops2 + 64ull * b.txns.size() + 1100ull * b.withdrawals.size() + 4096;
   return true;
 }
 
@@ -112,7 +128,10 @@ bool txn_tables_phase2(const BlockJob& b, const uint8_t* flat, const TxnBases& B
   T.txns.resize(b.txns.size());
   T.txn_keys.resize(12 * b.txns.size());
   memset(T.txn_keys.data(), 0, T.txn_keys.size());
-  T.seg_a.clear(), T.seg_b.clear(), T.seg_c.clear(), T.seg_begin.clear(), T.touched_begin.clear(), T.lit.clear();
+  T.seg_a.clear(), T.seg_b.clear(), T.seg_c.clear(), T.lit.clear();
+  T.seg_begin.resize(T.n_ir + 1), T.seg_end.resize(T.n_ir + 1), T.touched_begin.resize(T.n_ir + 1);
+  for (uint32_t i = 0; i <= T.n_ir; i++) T.seg_begin[i] = T.seg_end[i] = 0, T.touched_begin[i] = 0;
+  for (size_t w = 0; w < T.withdrawals.size(); w++) T.withdrawals[w].rec += B.rec_base;
   uint32_t t = 0, op = 0, op2 = 0, val = B.val_base + T.val_writes;
   uint64_t touched = 0, gas_before = 0;
   PlanWriter W(T);
@@ -196,8 +215,9 @@ bool txn_tables_phase2(const BlockJob& b, const uint8_t* flat, const TxnBases& B
     d.op1_end = op;
     d.op2_begin = op2, op2 += ops2, d.op2_end = op2;
     // ---- the IrDump entry (include/ppd_flat.h) as segments ----
-    T.seg_begin.push_back((uint32_t)T.seg_a.size());
-    T.touched_begin.push_back((uint32_t)touched);
+    const uint32_t ir = T.first_txn_ir + (uint32_t)ti;
+    T.seg_begin[ir] = (uint32_t)T.seg_a.size();
+    T.touched_begin[ir] = (uint32_t)touched;
     d.touched_base = (uint32_t)touched;
     touched += (uint64_t)txn::MARK_SLOTS_T * (ntr + 2 + items);
     const uint64_t gas_after = gas_before + tx.gas_used;
@@ -219,14 +239,79 @@ bool txn_tables_phase2(const BlockJob& b, const uint8_t* flat, const TxnBases& B
     // u32 b_meta_len, bytes, u32 b_hashes_len, bytes: the same bytes as in the FlatBlock
     W.flat((uint32_t)(b.b_meta.p - 4 - flat), 4 + b.b_meta.n + 4 + b.b_hashes.n);
     W.flush();
+    T.seg_end[ir] = (uint32_t)T.seg_a.size();
     gas_before = gas_after;
     T.txns[ti] = d;
   }
-  T.seg_begin.push_back((uint32_t)T.seg_a.size());
-  T.touched_begin.push_back((uint32_t)touched);
-  T.n_ir = (uint32_t)b.txns.size();
+  // dummy entries touch nothing (their tries keep only their roots): empty ranges of the touched list
+  for (uint32_t i = 0; i <= T.n_ir; i++)
+    if (i < T.first_txn_ir || i >= T.first_txn_ir + b.txns.size()) T.touched_begin[i] = i < T.first_txn_ir ? 0 : (uint32_t)touched;
   T.val_extra = val - B.val_base;
   return true;
+}
+
+// ---- dummy entries (create_dummy_gen_input, decoding.rs:484-549): every trie cut with the key 0_u64, which converts to
+// zero nibbles, so only the root of every trie is kept; EVERY storage trie of the state is listed ----
+void txn_tables_dummies(const BlockJob& b, const uint8_t* flat, const txn::Cursors& cur, const txn::AcctExport* accounts, uint32_t n_accounts,
+                        const txn::AcctState* table, uint32_t table_slots, const uint8_t* digests, TxnTables& T) {
+  struct Entry {
+    H256 haddr;
+    uint32_t root;
+  };
+  std::vector<Entry> initial, final_;
+  for (uint32_t r = 0; r < n_accounts; r++) {
+    H256 h;
+    memcpy(h.b, accounts[r].haddr, 32);
+    if (accounts[r].initial != txn::ST_ABSENT) initial.push_back({h, accounts[r].initial});
+    if (accounts[r].final_ != txn::ST_ABSENT) final_.push_back({h, accounts[r].final_});
+  }
+  for (uint32_t k = 0; k < table_slots; k++) {  // accounts the txns created
+    const txn::AcctState& a = table[k];
+    if (a.owner == 0xffffffffu || a.pre_rec != txn::NONE || a.storage == txn::ST_ABSENT) continue;
+    H256 h;
+    memcpy(h.b, digests + 32ull * a.owner, 32);
+    final_.push_back({h, a.storage});
+  }
+  auto by_addr = [](const Entry& x, const Entry& y) { return x.haddr < y.haddr; };
+  std::sort(initial.begin(), initial.end(), by_addr);
+  std::sort(final_.begin(), final_.end(), by_addr);
+  uint64_t gas = 0;
+  for (const TxnV& tx : b.txns) gas += tx.gas_used;
+  PlanWriter W(T);
+  auto emit = [&](int ir, bool on_final, bool with_withdrawals) {
+    T.seg_begin[ir] = (uint32_t)T.seg_a.size();
+    W.u256(b.txns.size()), W.u256(gas), W.u256(gas);
+    W.u8(0), W.u32(0);  // no signed txn
+    if (with_withdrawals)
+      W.flat((uint32_t)(b.withdrawals[0].first - 4 - flat), 4 + 52 * (uint32_t)b.withdrawals.size());  // u32 count + (address, amount) pairs, as in the FlatBlock
+    else
+      W.u32(0);
+    W.flush();
+    W.seg(on_final ? cur.state_before_withdrawals : b.state_root, IR_SEG_ROOT_ONLY, 0);
+    W.seg(on_final ? cur.txn_root : NODE_EMPTY, IR_SEG_ROOT_ONLY, 0);
+    W.seg(on_final ? cur.receipt_root : NODE_EMPTY, IR_SEG_ROOT_ONLY, 0);
+    const std::vector<Entry>& storage = on_final ? final_ : initial;
+    W.u32((uint32_t)storage.size());
+    for (const Entry& e : storage) {
+      W.raw(e.haddr.b, 32);
+      W.flush();
+      W.seg(e.root, IR_SEG_ROOT_ONLY, 0);
+    }
+    W.flush();
+    const uint32_t r_state = with_withdrawals ? cur.roots[txn::XR_AFTER_WITHDRAWALS] : on_final ? cur.roots[txn::XR_FINAL_STATE] : cur.roots[txn::XR_INITIAL_STATE];
+    W.seg(r_state, IR_SEG_REF, 0);
+    W.seg(on_final ? cur.roots[txn::XR_FINAL_TXN] : cur.roots[txn::XR_EMPTY], IR_SEG_REF, 0);
+    W.seg(on_final ? cur.roots[txn::XR_FINAL_RECEIPT] : cur.roots[txn::XR_EMPTY], IR_SEG_REF, 0);
+    W.flat((uint32_t)(b.checkpoint - flat), 32);
+    W.u32(0);  // a dummy carries no contract code
+    W.flat((uint32_t)(b.b_meta.p - 4 - flat), 4 + b.b_meta.n + 4 + b.b_hashes.n);
+    W.flush();
+    T.seg_end[ir] = (uint32_t)T.seg_a.size();
+  };
+  const bool wd = !b.withdrawals.empty();
+  if (T.dummy_initial[0] >= 0) emit(T.dummy_initial[0], false, false);
+  if (T.dummy_initial[1] >= 0) emit(T.dummy_initial[1], false, wd);  // no txns: the second dummy carries the withdrawals
+  if (T.dummy_final >= 0) emit(T.dummy_final, true, wd);
 }
 
 }  // namespace ppd

@@ -19,24 +19,31 @@ struct BlockJob;
 struct TxnTables {
   PVec<txn::TxnTrace> traces;
   PVec<txn::TxnDesc> txns;
-  PVec<uint32_t> seg_a, seg_b, seg_c, seg_begin, touched_begin;
+  PVec<txn::Withdrawal> withdrawals;
+  PVec<uint32_t> seg_a, seg_b, seg_c, seg_begin, seg_end, touched_begin;
   PVec<uint8_t> lit, txn_keys;
   std::vector<uint32_t> code_write_traces;  // traces with a code write: the code maps need their digests
   // counts
   uint32_t n_msgs = 0, n_ops1 = 0, n_ops2 = 0, max_ops = 0, max_traces = 0, n_items = 0, n_recs = 0, n_ir = 0;
+  // IrDump entries: txn i is entry first_txn_ir + i; the dummies of decoding.rs:304-347 / 356-402 (-1: none)
+  uint32_t first_txn_ir = 0;
+  int dummy_initial[2] = {-1, -1}, dummy_final = -1;
+  bool needs_dummies() const { return dummy_initial[0] >= 0 || dummy_final >= 0; }
   uint32_t val_writes = 0;  // val_pool bytes of the written slot values (36 each)
   uint32_t val_extra = 0;   // val_pool bytes the loop writes in all (written values, txn bytes, receipts), from val_base (phase 2)
   uint64_t est_nodes = 0, est_children = 0;
   void set_allocator(PvecAlloc a, PvecFree f) {
     traces.alloc_fn = a, traces.free_fn = f, txns.alloc_fn = a, txns.free_fn = f;
-    PVec<uint32_t>* u[] = {&seg_a, &seg_b, &seg_c, &seg_begin, &touched_begin};
+    PVec<uint32_t>* u[] = {&seg_a, &seg_b, &seg_c, &seg_begin, &seg_end, &touched_begin};
+    withdrawals.alloc_fn = a, withdrawals.free_fn = f;
     for (auto* x : u) x->alloc_fn = a, x->free_fn = f;
     lit.alloc_fn = a, lit.free_fn = f, txn_keys.alloc_fn = a, txn_keys.free_fn = f;
   }
   void clear() {
-    traces.clear(), txns.clear(), seg_a.clear(), seg_b.clear(), seg_c.clear(), seg_begin.clear(), touched_begin.clear();
+    traces.clear(), txns.clear(), withdrawals.clear(), seg_a.clear(), seg_b.clear(), seg_c.clear(), seg_begin.clear(), seg_end.clear(), touched_begin.clear();
     lit.clear(), txn_keys.clear(), code_write_traces.clear();
     n_msgs = n_ops1 = n_ops2 = max_ops = max_traces = n_items = n_recs = n_ir = 0;
+    first_txn_ir = 0, dummy_initial[0] = dummy_initial[1] = dummy_final = -1;
     val_writes = val_extra = 0, est_nodes = est_children = 0;
   }
 };
@@ -58,5 +65,10 @@ bool txn_tables_phase1(const BlockJob& b, const uint8_t* flat, size_t flat_len, 
 // code_digest(trace) returns the Keccak-256 of the code the trace writes.  Returns false: the host path reports the error.
 bool txn_tables_phase2(const BlockJob& b, const uint8_t* flat, const TxnBases& B, const uint8_t* (*code_digest)(void*, uint32_t), void* cd_arg,
                        TxnTables& T);
+
+// phase 3, only for a block with dummy entries (at most one txn, or withdrawals), after the loop: their segments, from
+// the storage map the device exported.  `table` / `digests`: the account table and the address digest of every trace.
+void txn_tables_dummies(const BlockJob& b, const uint8_t* flat, const txn::Cursors& cur, const txn::AcctExport* accounts, uint32_t n_accounts,
+                        const txn::AcctState* table, uint32_t table_slots, const uint8_t* digests, TxnTables& T);
 
 }  // namespace ppd

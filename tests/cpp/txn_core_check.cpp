@@ -113,7 +113,7 @@ int check_block(const std::vector<uint8_t>& flatv, const char* name) {
   HostArena& A = J2.A;
   TxnTables T;
   if (!txn_tables_phase1(b2, flat, flatv.size(), T)) {
-    printf("%s: not a block the device loop takes (fewer than two txns, or withdrawals): skipped\n", name);
+    printf("%s: not a block the device loop takes: skipped\n", name);
     return 0;
   }
   const uint32_t n_traces = (uint32_t)T.traces.size();
@@ -141,9 +141,11 @@ int check_block(const std::vector<uint8_t>& flatv, const char* name) {
   v.child_pool = children.data(), v.accounts = accounts.data();
   v.cap_nodes = (uint32_t)nodes.size(), v.cap_children = (uint32_t)children.size(), v.cap_keys = (uint32_t)keys.size();
   v.flat = flat, v.traces = T.traces.data(), v.n_txns = (uint32_t)b2.txns.size(), v.n_traces = n_traces, v.dig_base = B.dig_base;
+  v.withdrawals = T.withdrawals.data(), v.n_withdrawals = (uint32_t)T.withdrawals.size();
   // digests (the device runs keccak256_batch_kernel over the same (begin, end) table)
   std::vector<uint64_t> se(2ull * T.n_msgs);
   for (uint32_t t = 0; t < n_traces; t++) txn::prep_msgs(v, t, se.data());
+  for (uint32_t w = 0; w < v.n_withdrawals; w++) txn::prep_withdrawal_msg(v, w, se.data());
   for (uint32_t m = 0; m < T.n_msgs; m++) hostprof::keccak256(flat + se[2 * m], se[2 * m + 1] - se[2 * m], keys.data() + B.dig_base + 32ull * m);
   struct CD {
     txn::View* v;
@@ -175,6 +177,8 @@ int check_block(const std::vector<uint8_t>& flatv, const char* name) {
     pre_flags[pa.rec] = pa.storage_nonempty ? 1 : 0;
   }
   v.pre_flags = pre_flags.data();
+  std::vector<uint32_t> pre_slot(n_pre_acct + 1, 0xffffffffu);
+  v.pre_slot = pre_slot.data();
   uint32_t table = 64;
   while (table < 2 * n_traces) table <<= 1;
   std::vector<txn::AcctState> acct(table);
@@ -205,9 +209,24 @@ int check_block(const std::vector<uint8_t>& flatv, const char* name) {
   uint32_t sh_dmax = 0;
   txn::Ctx c{v, 0, 1, &sh_dmax};
   for (uint32_t ti = 0; ti < v.n_txns && !cur.flag; ti++) txn::run_txn(c, ti, EMPTY_TRIE_HASH, EMPTY_CODE_HASH);
+  txn::run_finish(c, b2.state_root);
   if (cur.flag) {
     printf("%s: the loop raised flag %u at txn %u (the host path would redo the block)\n", name, cur.flag, cur.flag_txn);
     return 2;
+  }
+  if (T.needs_dummies()) {
+    // the storage map as the device exports it (ppd_txn.cu: acct_export_kernel)
+    std::vector<txn::AcctExport> ex(n_pre_acct + 1);
+    for (const BlockJob::PreAccount& pa : b2.pre_accounts) {
+      txn::AcctExport e;
+      memcpy(e.haddr, pa.haddr.b, 32);
+      e.initial = join_storage[pa.rec];
+      const uint32_t slot = pre_slot[pa.rec];
+      e.final_ = slot < txn::NONE ? acct[slot].storage : e.initial;
+      ex[pa.rec] = e;
+    }
+    txn_tables_dummies(b2, flat, cur, ex.data(), n_pre_acct, acct.data(), table, keys.data() + B.dig_base, T);
+    v.seg_a = T.seg_a.data(), v.seg_b = T.seg_b.data();
   }
   // ---- compare ----
   ArenaRO R1{J1.A.nodes.data(), J1.A.key_pool.data(), J1.A.val_pool.data(), J1.A.hash_pool.data(), J1.A.child_pool.data(), J1.A.accounts.data(), {}};
@@ -216,8 +235,46 @@ int check_block(const std::vector<uint8_t>& flatv, const char* name) {
   auto expect = [&](bool ok, uint32_t ti, const char* what) {
     if (!ok && bad++ < 10) printf("%s: txn %u: %s differs\n", name, ti, what);
   };
+  expect(b1.irs.size() == T.n_ir, 0, "number of IrDump entries");
+  // dummy entries: the tries (roots only), every storage trie in hashed-address order, the roots after
+  auto check_dummy = [&](int ir) {
+    if (ir < 0 || (size_t)ir >= b1.irs.size()) return;
+    IrPlan& p = b1.irs[ir];
+    uint32_t q = T.seg_begin[ir];
+    auto next_kind = [&](uint32_t kind) {
+      while (q < T.seg_end[ir] && v.seg_b[q] != kind) q++;
+      return q < T.seg_end[ir] ? q++ : 0xffffffffu;
+    };
+    uint32_t s0 = next_kind(IR_SEG_ROOT_ONLY), s1 = next_kind(IR_SEG_ROOT_ONLY), s2 = next_kind(IR_SEG_ROOT_ONLY);
+    expect(s0 != 0xffffffffu && s2 != 0xffffffffu, ir, "dummy: trie segments");
+    if (s2 == 0xffffffffu) return;
+    expect(R1.fp(p.state_sub) == R2.fp(v.seg_a[s0]), ir, "dummy: state trie");
+    expect(R1.fp(p.txn_sub) == R2.fp(v.seg_a[s1]), ir, "dummy: transactions trie");
+    expect(R1.fp(p.receipt_sub) == R2.fp(v.seg_a[s2]), ir, "dummy: receipts trie");
+    std::stable_sort(p.storage_subs.begin(), p.storage_subs.end(), [](const auto& x, const auto& y) { return x.first < y.first; });
+    for (size_t k = 0; k < p.storage_subs.size(); k++) {
+      uint32_t sq = next_kind(IR_SEG_ROOT_ONLY);
+      expect(sq != 0xffffffffu, ir, "dummy: number of storage tries");
+      if (sq == 0xffffffffu) return;
+      // the hashed address is the tail of the literal segment before it
+      const uint32_t lq = sq - 1;
+      expect(v.seg_b[lq] == IR_SEG_LIT_DEV && memcmp(T.lit.data() + T.seg_c[lq] + v.seg_a[lq] - 32, p.storage_subs[k].first.b, 32) == 0, ir, "dummy: hashed address order");
+      expect(R1.fp(p.storage_subs[k].second) == R2.fp(v.seg_a[sq]), ir, "dummy: a storage trie");
+    }
+    uint32_t r0 = next_kind(IR_SEG_REF), r1 = next_kind(IR_SEG_REF), r2 = next_kind(IR_SEG_REF);
+    expect(r2 != 0xffffffffu, ir, "dummy: root segments");
+    if (r2 == 0xffffffffu) return;
+    expect(R1.fp(p.root_state) == R2.fp(v.seg_a[r0]), ir, "dummy: state root after");
+    expect(R1.fp(p.root_txn) == R2.fp(v.seg_a[r1]), ir, "dummy: transactions root after");
+    expect(R1.fp(p.root_receipt) == R2.fp(v.seg_a[r2]), ir, "dummy: receipts root after");
+    bool has_wd_seg = false;
+    for (uint32_t k = T.seg_begin[ir]; k < T.seg_end[ir]; k++)
+      has_wd_seg |= v.seg_b[k] == IR_SEG_FLAT && !b2.withdrawals.empty() && T.seg_c[k] == (uint32_t)(b2.withdrawals[0].first - 4 - flat);
+    expect(has_wd_seg == p.has_withdrawals, ir, "dummy: withdrawals");
+  };
+  check_dummy(T.dummy_initial[0]), check_dummy(T.dummy_initial[1]), check_dummy(T.dummy_final);
   for (uint32_t ti = 0; ti < v.n_txns; ti++) {
-    IrPlan& p = b1.irs[ti];
+    IrPlan& p = b1.irs[T.first_txn_ir + ti];
     const txn::TxnDesc& tx = T.txns[ti];
     expect(R1.fp(p.state_sub) == R2.fp(v.seg_b[tx.seg_tries]), ti, "state trie before the txn");
     expect(R1.fp(p.txn_sub) == R2.fp(v.seg_b[tx.seg_tries + 1]), ti, "transactions trie before the txn");
@@ -235,7 +292,7 @@ int check_block(const std::vector<uint8_t>& flatv, const char* name) {
     expect(R1.fp(p.root_receipt) == R2.fp(v.seg_a[tx.seg_roots + 2]), ti, "receipts trie after the txn");
     std::set<uint64_t> t1, t2;
     for (uint32_t n : p.touched) t1.insert(R1.fp(n));
-    for (uint32_t k = T.touched_begin[ti]; k < T.touched_begin[ti + 1]; k++)
+    for (uint32_t k = T.touched_begin[T.first_txn_ir + ti]; k < T.touched_begin[T.first_txn_ir + ti + 1]; k++)
       if (touched[k] != NODE_EMPTY) t2.insert(R2.fp(touched[k]));
     expect(t1 == t2, ti, "set of touched nodes");
   }
