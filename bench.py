@@ -89,15 +89,22 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(self.rows)}
 
 
-C2_PARAMS = dict(contract_frac=0.15, slots_lo=1, slots_hi=256, virtual_depth=7, virtual_accounts_log16=7, slot_reads=(0, 3), slot_writes=(0, 3),
-                 allow_new_accounts=False, allow_self_destruct=False, inline_code_frac=0.02)
+# SURVEY.md 8d's C2: 20k touched accounts in a virtual 16^7-account state, 15 % contracts, 200 txns, ~100 accounts and
+# ~150 slot accesses per txn (15 contracts x (0..10 reads + 0..10 writes)), self-destructs.  Departures, stated in
+# config.departures: storage tries are witnessed in full (the generator has no hashed-out siblings inside storage tries),
+# so slots per contract are log-uniform 1..256 instead of 1..4096; no accounts are created (in a virtual state a new
+# address lands on a hashed-out sibling, which the reference rejects).
+C2_PARAMS = dict(contract_frac=0.15, slots_lo=1, slots_hi=256, virtual_depth=7, virtual_accounts_log16=7, slot_reads=(0, 10), slot_writes=(0, 10),
+                 allow_new_accounts=False, allow_self_destruct=True, inline_code_frac=0.02)
+C2_TAG = "r2"  # cache key of the generated blocks: bump when C2_PARAMS change
+C2_DEPARTURES = "slots per contract log-uniform 1..256 with storage tries witnessed in full (spec: 1..4096 with hashed siblings); no new accounts"
 
 
 def c2_block(seed, scale):
     """One synthetic C2 block as a FlatBlock; cached under /tmp."""
     from proof_protocol_decoder_b200 import synth
 
-    cache = f"/tmp/ppd_c2_seed{seed}_scale{scale}.flat"
+    cache = f"/tmp/ppd_c2{C2_TAG}_seed{seed}_scale{scale}.flat"
     if os.path.exists(cache):
         return open(cache, "rb").read()
     blk = synth.gen_block(
@@ -125,7 +132,7 @@ def _c2_block_job(a):
 def c2_blocks(seeds, scale, procs):
     """The blocks of the given seeds; missing ones are generated in parallel worker processes (the
     generator is pure Python: ~10 s per full-size block)."""
-    missing = [s for s in seeds if not os.path.exists(f"/tmp/ppd_c2_seed{s}_scale{scale}.flat")]
+    missing = [s for s in seeds if not os.path.exists(f"/tmp/ppd_c2{C2_TAG}_seed{s}_scale{scale}.flat")]
     if len(missing) > 1 and procs > 1:
         import multiprocessing as mp
 
@@ -158,9 +165,9 @@ def oracle_time_block(flat_bytes, repeats, threads):
 
 
 def run_reference(args, rank, world):
-    """The reference's CPU algorithm for the path (the oracle: a C++ port of the reference's Rust,
-    which cannot be compiled here) on all host cores; each step decodes one bounded sample block per
-    core.  Rank 0 alone works."""
+    """The reference's CPU algorithm for the path (the oracle: a C++ port of the reference's Rust, which cannot be
+    compiled here) on all host cores, on the SAME config as the b200 arm: every step decodes one full-size C2 block
+    per core (about 10 s per block per core; the warm-up is one step).  Rank 0 alone works."""
     if rank != 0:
         return
     cores = os.cpu_count() or 1
@@ -174,6 +181,7 @@ def run_reference(args, rank, world):
         t_total += t
     nodes = st["nodes_hashed"] * cores * args.steps
     value = nodes / t_total
+    workload = "C2 mainnet-shaped block (BASELINE.json configs[1])" + ("" if sample_scale == 1.0 else f" at {sample_scale:g}x scale")
     line = {
         "impl": "reference",
         "metric": "mpt_nodes_keccak_hashed_per_sec",
@@ -181,15 +189,17 @@ def run_reference(args, rank, world):
         "unit": "nodes/s",
         "n_gpus": args.gpus,
         "steps": args.steps,
-        "warmup": args.warmup,
+        "warmup": max(1, min(args.warmup, 1)),
         "ms_per_step": 1e3 * t_total / args.steps,
         "higher_is_better": True,
         "scaling": "weak",
         "vs_baseline": None,
         "dtype": "u64",
         "data": "synthetic",
-        "config": {"workload": "C2 mainnet-shaped block (BASELINE.json configs[1])", "sample": f"{sample_scale:g}x-scale C2 block per core per step", "l2": "n/a (CPU)"},
+        "config": {"workload": workload, "scale": sample_scale, "departures": C2_DEPARTURES,
+                   "sample": f"one {sample_scale:g}x-scale C2 block (seed 2) per core per step, {cores} cores", "l2": "n/a (CPU)"},
         "blocks_per_sec": cores * args.steps / t_total,
+        "nodes_hashed_per_block": st["nodes_hashed"],
         "cpu_baseline": {
             "value": value, "unit": "nodes/s", "cores": cores, "kind": "port",
             "sample": f"one {sample_scale:g}x-scale C2 block ({st['nodes_hashed']} node hashes) per core per step; C++ restatement of the reference algorithm (the Rust reference cannot be built in this image)",
@@ -248,14 +258,38 @@ def c5_sweep(ctx, sizes, peaks, sm_mhz):
     return out
 
 
+def measure_pcie(torch, mb=256):
+    """Pinned-memory copy bandwidth of this GPU's link, both directions at once (GB/s each): what bounds a pipeline
+    that streams FlatBlocks in and IrDumps out."""
+    n = mb << 20
+    h_in = torch.empty(n, dtype=torch.uint8).pin_memory()
+    h_out = torch.empty(n, dtype=torch.uint8).pin_memory()
+    d_in = torch.empty(n, dtype=torch.uint8, device="cuda")
+    d_out = torch.empty(n, dtype=torch.uint8, device="cuda")
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    best = None
+    for _ in range(3):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        with torch.cuda.stream(s1):
+            d_in.copy_(h_in, non_blocking=True)
+        with torch.cuda.stream(s2):
+            h_out.copy_(d_out, non_blocking=True)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return n / best / 1e9
+
+
+N1_CACHE = "/tmp/ppd_bench_n1.json"  # the N=1 run leaves its e2e blocks/s and the oracle's node count here for the N>1 runs of the same box
+
+
 def run_b200(args, rank, world, local_rank):
-    # host threads: this rank's share of the box's cores; one block per host thread per step
     cores = os.cpu_count() or 1
-    # two host threads per core of this rank's share: a thread sleeps while its lane's copies and kernels run
-    threads = max(1, min(32, 2 * cores // world))
-    os.environ.setdefault("PPD_HOST_THREADS", str(threads))
-    threads = int(os.environ["PPD_HOST_THREADS"])
     n_blocks = min(64, args.blocks_per_step or 64)  # per GPU, whatever the world size (weak scaling); the library keeps up to 64 lanes resident
+    # one host thread per resident block: with the txn loop on the device a block's thread mostly waits for its lane
+    os.environ.setdefault("PPD_HOST_THREADS", str(n_blocks))
+    threads = int(os.environ["PPD_HOST_THREADS"])
     seeds = [2 + rank * n_blocks + j for j in range(n_blocks)]
     # generated before CUDA is touched (worker processes are forked); ranks generate their own blocks
     flats = c2_blocks(seeds, args.scale, max(1, cores // world))
@@ -273,6 +307,13 @@ def run_b200(args, rank, world, local_rank):
 
         dist = dist_mod
         dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
+        # this rank's threads on its share of the host cores (the ranks of a box share them)
+        try:
+            avail = sorted(os.sched_getaffinity(0))
+            share = max(1, len(avail) // world)
+            os.sched_setaffinity(0, set(avail[local_rank * share:(local_rank + 1) * share] or avail))
+        except (AttributeError, OSError):
+            pass
 
     def barrier():
         torch.cuda.synchronize()
@@ -295,6 +336,7 @@ def run_b200(args, rank, world, local_rank):
         return float(t.item())
 
     ctx = Context(local_rank)
+    pcie_gbs = measure_pcie(torch)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
     # the step's inputs live in page-locked host memory (ppd_alloc_pinned), as a caller that serialises its
     # BlockTrace for the library would place them; every step copies them to the device again
@@ -310,36 +352,32 @@ def run_b200(args, rank, world, local_rank):
             o.close()
         return total
 
-    # ---- warm-up (also leaves the arenas resident for the device-resident measurement) ----
+    # ---- warm-up (also leaves the arenas resident for the device-resident measurements) ----
     for _ in range(max(3, args.warmup)):
         ir_len = decode_step()
     st = ctx.stats()
-    for _ in range(max(3, args.warmup)):
-        ctx.replay_last_hashing()
+    on_device = int(st["txn_loops_on_gpu"])
 
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    # ---- device-resident: every kernel of the batch on the arenas already in HBM ----
-    barrier()
-    dev_ms = 0.0
-    for _ in range(args.steps):
-        flush.zero_()
-        torch.cuda.synchronize()
-        dev_ms += ctx.replay_last_hashing()
-    barrier()
-    dev_ms = max_over_ranks(dev_ms)
-    # ---- the same for the witness parse / arena kernels (ppd_parse.cu), witnesses resident in HBM ----
-    parse_ms = 0.0
-    if st["witnesses_on_gpu"]:
+    def replay(what):
+        """device time per step of the selected stages, every lane replaying them concurrently on resident data"""
         for _ in range(max(3, args.warmup)):
-            ctx.replay_last_parse()
+            ctx.replay_last(what)
         barrier()
+        ms = 0.0
         for _ in range(args.steps):
             flush.zero_()
             torch.cuda.synchronize()
-            parse_ms += ctx.replay_last_parse()
+            ms += ctx.replay_last(what)
         barrier()
-        parse_ms = max_over_ranks(parse_ms)
+        return max_over_ranks(ms) / args.steps
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    hash_ms = replay(ctx.REPLAY_HASH)
+    parse_ms = replay(ctx.REPLAY_PARSE) if st["witnesses_on_gpu"] else 0.0
+    txn_ms = replay(ctx.REPLAY_TXN) if on_device else 0.0
+    dump_ms = replay(ctx.REPLAY_DUMP) if on_device else 0.0
+    all_ms = replay(ctx.REPLAY_ALL)
     # ---- end to end through the C ABI with host buffers ----
     barrier()
     t0 = time.perf_counter()
@@ -351,18 +389,20 @@ def run_b200(args, rank, world, local_rank):
     e2e_s = max_over_ranks(e2e_s)
     clocks = sampler.stop()
     st = ctx.stats()
-    # latency of one block alone (all host threads on its IR dump)
+    # latency of one block alone, and the node count of the seed-2 block (rank 0) for the normalisation below
     single = []
     for _ in range(3):
         t1 = time.perf_counter()
         with ctx.block_decode_view(flats[0]) as v:
             _ = v.view[0]
         single.append(time.perf_counter() - t1)
+    own_nodes_block0 = ctx.stats()["nodes_hashed"]
 
     nodes_all = sum_over_ranks(float(st["nodes_hashed"]))
     perms_all = sum_over_ranks(float(st["node_permutations"] + st["key_permutations"]))
     keys_all = sum_over_ranks(float(st["key_hashes"]))
-    dev_s_per_step = dev_ms / 1e3 / args.steps
+    host_busy_all = sum_over_ranks(float(st["host_busy_ms"]))
+    dev_s_per_step = hash_ms / 1e3
     e2e_s_per_step = e2e_s / args.steps
     sm_mhz = clocks.get("sm_mhz")
     alu_peak = ALU_LANES_PER_SM_CLK * N_SM * (sm_mhz or peaks["sm_max_mhz"]) * 1e6  # instr/s on one GPU
@@ -370,12 +410,56 @@ def run_b200(args, rank, world, local_rank):
     achieved_gbs = algo_bytes / dev_s_per_step / 1e9
     traffic, traffic_src = load_traffic()
     level_launches = max(1, int(st["level_launches"]))
-    parse_s_per_step = parse_ms / 1e3 / args.steps
     wit_bytes_all = sum_over_ranks(float(st["witness_bytes"]))
     wit_ins_all = sum_over_ranks(float(st["witness_instructions"]))
+    blocks_all = world * n_blocks
+    h2d_all, d2h_all = sum_over_ranks(float(st["h2d_bytes"])), sum_over_ranks(float(st["d2h_bytes"]))
+    e2e_bps = blocks_all / e2e_s_per_step
+    # ---- the reference's node count for the same block (its hashing work is the unit both arms are quoted in) ----
+    cpu_baseline, oracle_nodes = None, None
+    if rank == 0 and world == 1:
+        sample = c2_block(2, args.ref_scale)
+        t, ost = oracle_time_block(sample, 1, 1)
+        cpu_baseline = {
+            "value": ost["nodes_hashed"] / t,
+            "unit": "nodes/s",
+            "cores": 1,
+            "kind": "port",
+            "blocks_per_sec": 1.0 / t,
+            "nodes_hashed_per_block": ost["nodes_hashed"],
+            "sample": f"one {args.ref_scale:g}x-scale C2 block (seed 2: {ost['nodes_hashed']} node hashes, {t:.2f} s) on 1 core; C++ restatement of the reference algorithm (the Rust reference cannot be built in this image)",
+        }
+        if args.ref_scale == args.scale:
+            oracle_nodes = ost["nodes_hashed"]
+    n1 = {}
+    if world == 1 and rank == 0:
+        n1 = {"e2e_blocks_per_sec": e2e_bps, "oracle_nodes_block0": oracle_nodes, "own_nodes_block0": own_nodes_block0, "scale": args.scale, "tag": C2_TAG}
+        try:
+            json.dump(n1, open(N1_CACHE, "w"))
+        except OSError:
+            pass
+    elif os.path.exists(N1_CACHE):
+        try:
+            n1 = json.load(open(N1_CACHE))
+            if n1.get("scale") != args.scale or n1.get("tag") != C2_TAG:
+                n1 = {}
+        except (OSError, ValueError):
+            n1 = {}
+    norm = 1.0
+    if n1.get("oracle_nodes_block0") and n1.get("own_nodes_block0"):
+        norm = n1["oracle_nodes_block0"] / n1["own_nodes_block0"]
+    # ---- what bounds end-to-end blocks/s ----
+    per_block_host_ms = host_busy_all / blocks_all
+    per_block_h2d, per_block_d2h = h2d_all / blocks_all, d2h_all / blocks_all
+    bounds = {
+        "device_pipeline": blocks_all / (all_ms / 1e3),
+        "pcie": world * pcie_gbs * 1e9 / max(per_block_h2d, per_block_d2h),
+        "host_cores": cores / (per_block_host_ms / 1e3) if per_block_host_ms else None,
+    }
+    limiter = min((k for k in bounds if bounds[k]), key=lambda k: bounds[k])
     line = {
         "metric": "mpt_nodes_keccak_hashed_per_sec",
-        "value": nodes_all / dev_s_per_step,
+        "value": norm * nodes_all / dev_s_per_step,
         "unit": "nodes/s",
         "n_gpus": world,
         "steps": args.steps,
@@ -389,83 +473,111 @@ def run_b200(args, rank, world, local_rank):
         "config": {
             "workload": f"C2 mainnet-shaped blocks (BASELINE.json configs[1]): 20k touched accounts in a virtual 16^7-account state, 200 txns each; a batch of {n_blocks} independent blocks per GPU per step, one lane (stream + pools) per block, {threads} host thread(s) per GPU",
             "scale": args.scale,
+            "departures": C2_DEPARTURES,
             "blocks_per_step_per_gpu": n_blocks,
             "host_threads_per_gpu": threads,
+            "host_cores": cores,
             "flat_block_bytes_per_step": flat_total,
             "ir_dump_bytes_per_step": ir_len,
             "arena_nodes": st["arena_nodes"],
             "levels": st["levels"],
+            "txn_loops_on_device_per_step": on_device,
             "l2": "flushed between timed device-resident steps (256 MiB write)",
             "parallelism": f"blocks sharded over {world} GPU(s), no data-path collective",
         },
-        "blocks_per_sec": world * n_blocks / (dev_s_per_step + parse_s_per_step),
-        "blocks_per_sec_note": "device-resident: the blocks of a step / (device time of the witness parse + arena kernels, plus device time of the hashing kernels), each replayed with all lanes concurrent",
-        "blocks_per_sec_hashing_only": world * n_blocks / dev_s_per_step,
+        "value_note": "node hashes per second of the hashing kernels (key hashing + both level sweeps of every block, lanes concurrent) on arenas resident in HBM, in units of the REFERENCE's node hashes for the same block (nodes_normalisation)",
+        "nodes_normalisation": {"factor": norm, "oracle_nodes_block0": n1.get("oracle_nodes_block0"), "own_nodes_block0": n1.get("own_nodes_block0"),
+                                "note": "the library hashes every node of every trie version it builds; the reference hashes a few per cent fewer or more (it never builds unobserved versions, but hashes per-txn subsets): throughputs are quoted in the reference's count"},
+        "blocks_per_sec": blocks_all / (all_ms / 1e3),
+        "blocks_per_sec_note": "device-resident: the blocks of a step / device time of the WHOLE pipeline replayed on resident data (witness parse, key hashing, pre-image sweep, by-root join, txn loop, second sweep, IR sizing and emit), every lane in pipeline order, lanes concurrent",
+        "device_ms_per_step": {"hashing": hash_ms, "parse": parse_ms, "txn_loop": txn_ms, "dump": dump_ms, "whole_pipeline": all_ms,
+                               "note": "each stage replayed alone with all lanes concurrent, then all of them together"},
+        "blocks_per_sec_hashing_only": blocks_all / dev_s_per_step,
         "permutations_per_sec": perms_all / dev_s_per_step,
         "nodes_hashed_per_step": nodes_all,
         "key_hashes_per_step": keys_all,
         "e2e": {
-            "value": nodes_all / e2e_s_per_step,
+            "value": norm * nodes_all / e2e_s_per_step,
             "unit": "nodes/s",
-            "blocks_per_sec": world * n_blocks / e2e_s_per_step,
+            "blocks_per_sec": e2e_bps,
             "ms_per_step": 1e3 * e2e_s_per_step,
             "single_block_latency_ms": 1e3 * min(single),
-            "h2d_bytes_per_step": sum_over_ranks(float(st["h2d_bytes"])),
-            "d2h_bytes_per_step": sum_over_ranks(float(st["d2h_bytes"])),
-            "note": "ppd_blocks_decode_batch: FlatBlocks (host) -> IrDumps (host); includes witness parse, trie shaping and IR serialisation on the host threads and every host<->device copy",
+            "h2d_bytes_per_step": h2d_all,
+            "d2h_bytes_per_step": d2h_all,
+            "boundary_bytes_per_step": {"flat_blocks": flat_total * world, "ir_dumps": ir_len * world},
+            "host_busy_ms_per_block": per_block_host_ms,
+            "note": "ppd_blocks_decode_batch: FlatBlocks (page-locked host memory) -> IrDumps (host); every host<->device copy and all host work (flat input reading, descriptor tables, launches) inside the timed region",
+        },
+        "e2e_blocks_per_sec": e2e_bps,
+        "e2e_efficiency_vs_n1": (e2e_bps / (world * n1["e2e_blocks_per_sec"])) if n1.get("e2e_blocks_per_sec") else None,
+        "limiter": {
+            "name": limiter,
+            "bounds_blocks_per_sec": bounds,
+            "pcie_gbs_per_direction": pcie_gbs,
+            "pcie_bytes_per_block": {"h2d": per_block_h2d, "d2h": per_block_d2h},
+            "host_busy_ms_per_block": per_block_host_ms,
+            "note": "upper bounds on end-to-end blocks/s: the device pipeline replayed on resident data; each GPU's PCIe link at the measured pinned-copy rate (both directions busy) over the bytes a block moves in the busier direction; the box's cores over the host time a block costs outside waits for the device",
         },
         "gpu_launches": int(st["kernel_launches"]) * args.steps,
         "clocks": clocks,
         "roofline": {
+            "bound": "alu",
+            "kernel": "hash_level_kernel + keccak256_batch_kernel (all level launches of the batch, lanes concurrent)",
+            "achieved": (st["node_permutations"] + st["key_permutations"]) * ALU_OPS_PER_PERM / dev_s_per_step / 1e12,
+            "peak": alu_peak / 1e12,
+            "unit": "Tinstr/s",
+            "frac": (st["node_permutations"] + st["key_permutations"]) * ALU_OPS_PER_PERM / dev_s_per_step / alu_peak,
+            "traffic": traffic,
+            "traffic_source": traffic_src,
+            "model": f"{ALU_OPS_PER_PERM} ALU-pipe (LOP3/SHF) instructions per keccak-f[1600] permutation (SURVEY.md 8d); peak = {ALU_LANES_PER_SM_CLK} lanes/clk/SM x {N_SM} SMs x SM clock sampled under load",
+            "peak_source": "profiles/r02_microbench.txt: dependent-free LOP3/SHF issue measured at 64 lanes/clk/SM (MEASURED_PEAKS.json has no integer peak)",
+            "launches_per_step": level_launches,
+            "note": "Keccak is bound by the integer ALU pipe, not HBM (SURVEY.md 8d); the HBM view is in roofline_hbm",
+        },
+        "roofline_hbm": {
             "bound": "hbm",
-            "kernel": "hash_level_kernel (all level launches of the batch, lanes concurrent)",
             "achieved": achieved_gbs,
             "peak": peaks["hbm_gbs"],
             "unit": "GB/s",
             "frac": achieved_gbs / peaks["hbm_gbs"],
-            "traffic": traffic,
-            "traffic_source": traffic_src,
             "algorithmic_bytes_per_launch": algo_bytes / level_launches,
-            "launches_per_step": level_launches,
             "peak_source": peaks["source"],
-            "note": "achieved = sum over the step's level launches of (L + 32) bytes per hashed node / device time of the step (lanes run concurrently, so a per-launch duration does not exist); traffic = mean DRAM bytes per hash_level_kernel launch under ncu. Keccak is bound by the integer ALU pipe, not HBM (SURVEY.md 8d): see roofline_alu",
+            "note": "achieved = sum over the step's level launches of (L + 32) bytes per hashed node / device time of the step",
         },
         "parse": {
             "kernels": "ppd_parse.cu: tile_exit / group_exit / top_chain / tile_entry / tile_mark / scans / link / shape / emit / climb (all lanes concurrent)",
             "witnesses_on_gpu_per_step": int(sum_over_ranks(float(st["witnesses_on_gpu"]))),
             "witness_bytes_per_step": wit_bytes_all,
             "instructions_per_step": wit_ins_all,
-            "ms_per_step": 1e3 * parse_s_per_step,
+            "ms_per_step": parse_ms,
             "bound": "hbm",
-            "achieved": (7.0 * wit_bytes_all / world / parse_s_per_step / 1e9) if parse_s_per_step else None,
+            "achieved": (7.0 * wit_bytes_all / world / (parse_ms / 1e3) / 1e9) if parse_ms else None,
             "peak": peaks["hbm_gbs"],
             "unit": "GB/s",
-            "frac": (7.0 * wit_bytes_all / world / parse_s_per_step / 1e9 / peaks["hbm_gbs"]) if parse_s_per_step else None,
-            "instructions_per_sec": (wit_ins_all / parse_s_per_step) if parse_s_per_step else None,
-            "note": "algorithmic bytes = 7 per witness byte for the boundary search (read the byte, write and re-read its 4-byte exit link, write its 2-byte step link) -- the instruction-level arrays behind it are 30x smaller; the chain walks between tiles are latency-bound by construction (DESIGN.md 5)",
+            "frac": (7.0 * wit_bytes_all / world / (parse_ms / 1e3) / 1e9 / peaks["hbm_gbs"]) if parse_ms else None,
+            "instructions_per_sec": (wit_ins_all / (parse_ms / 1e3)) if parse_ms else None,
+            "note": "algorithmic bytes = 7 per witness byte for the boundary search (read the byte, write and re-read its 4-byte exit link, write its 2-byte step link)",
         },
-        "roofline_alu": {
-            "bound": "alu-pipe (LOP3/SHF)",
-            "achieved": (st["node_permutations"] + st["key_permutations"]) * ALU_OPS_PER_PERM / dev_s_per_step / 1e12,
-            "peak": alu_peak / 1e12,
-            "unit": "Tinstr/s",
-            "frac": (st["node_permutations"] + st["key_permutations"]) * ALU_OPS_PER_PERM / dev_s_per_step / alu_peak,
-            "model": f"{ALU_OPS_PER_PERM} ALU instr per permutation; peak = {ALU_LANES_PER_SM_CLK} lanes/clk/SM x {N_SM} SMs x SM clock under load",
+        "txn_loop": {
+            "kernels": "ppd_txn.cu: join / acct_claim / prep_* / txn_loop_kernel (one thread block per block of txns; lanes concurrent)",
+            "ms_per_step": txn_ms,
+            "blocks_per_sec": (blocks_all / (txn_ms / 1e3)) if txn_ms else None,
+            "bound": "latency (dependent loads down the tries; one resident CTA per block)",
+        },
+        "dump": {
+            "kernels": "ppd_dump.cu: ir_size_kernel + ir_emit_kernel (one thread block per IR)",
+            "ms_per_step": dump_ms,
+            "bytes_per_step": ir_len * world,
+            "achieved": (ir_len / (dump_ms / 1e3) / 1e9) if dump_ms else None,
+            "unit": "GB/s written",
+            "frac_of_hbm": (ir_len / (dump_ms / 1e3) / 1e9 / peaks["hbm_gbs"]) if dump_ms else None,
+            "frac_of_pcie": (ir_len / (dump_ms / 1e3) / 1e9 / pcie_gbs) if dump_ms else None,
         },
     }
-    if rank == 0 and world == 1:
-        sample = c2_block(2, args.ref_scale)
-        t, ost = oracle_time_block(sample, 1, 1)
-        line["cpu_baseline"] = {
-            "value": ost["nodes_hashed"] / t,
-            "unit": "nodes/s",
-            "cores": 1,
-            "kind": "port",
-            "blocks_per_sec_at_sample_scale": 1.0 / t,
-            "sample": f"one {args.ref_scale:g}x-scale C2 block ({ost['nodes_hashed']} node hashes, {t:.2f} s) on 1 core; C++ restatement of the reference algorithm (the Rust reference cannot be built in this image)",
-        }
-        if not args.no_sweep:
-            line["c5_sweep"] = c5_sweep(ctx, [int(x) for x in args.sweep.split(",") if x], peaks, sm_mhz)
+    if cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline
+    if rank == 0 and world == 1 and not args.no_sweep:
+        line["c5_sweep"] = c5_sweep(ctx, [int(x) for x in args.sweep.split(",") if x], peaks, sm_mhz)
     if rank == 0:
         print(json.dumps(line), flush=True)
     if dist is not None:
@@ -481,7 +593,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--scale", type=float, default=1.0, help="fraction of the C2 block size (1.0 = the named config)")
     ap.add_argument("--blocks-per-step", type=int, default=0, help="blocks per GPU per step (default 64, at most 64)")
-    ap.add_argument("--ref-scale", type=float, default=0.1, help="size of the bounded CPU sample block")
+    ap.add_argument("--ref-scale", type=float, default=1.0, help="size of the CPU arm's block (1.0 = the same config as the b200 arm)")
     ap.add_argument("--sweep", default="1000000,10000000", help="config-5 leaf counts measured beside the headline at N=1")
     ap.add_argument("--no-sweep", action="store_true")
     args = ap.parse_args()

@@ -52,6 +52,8 @@ typedef struct ppd_stats {
   uint64_t txn_loops_on_gpu;      /* blocks whose txn loop (decoding.rs:80-177: deltas, subsets, roots) ran on the device (ppd_txn.cu) */
   double txn_gpu_ms;              /* device time of those loops (CUDA events) */
   double dump_gpu_ms;             /* device time of the IrDump kernels (ppd_dump.cu) */
+  double host_busy_ms;            /* host time of the blocks' threads outside waits for the device, summed over blocks */
+  double host_wait_ms;            /* ... and their time waiting for the device */
 } ppd_stats;
 
 int ppd_ctx_create(int device, ppd_ctx** out);

@@ -311,7 +311,7 @@ bool gpu_pre_image(Lane* L, Job& J, BlockJob& b, bool check_version, Slots* slot
       }
     }
     if (has_trie) b.storage[haddr] = sroot;
-    b.pre_accounts.push_back({haddr, (uint32_t)a, nonempty});
+    b.pre_accounts.push_back({haddr, (uint32_t)a, nonempty, (flags & 1u) != 0, al[5 * a + 1]});
     if (J.device_marks) b.acct_rec.insert({haddr, (uint32_t)a});
     if (nonempty) {
       b.pre_with_storage[haddr] = (uint32_t)a;
@@ -319,7 +319,8 @@ bool gpu_pre_image(Lane* L, Job& J, BlockJob& b, bool check_version, Slots* slot
     }
   }
   lap("p:tables");
-  b.pre_image_on_gpu = true;
+  b.pre_image_on_gpu = true, b.pre_image_built = true;
+  b.storage_partial = true;  // (not known without a pass over the arena: the join by root is always resolved)
   L->has_last_parse = true, L->last_bounds = B, L->last_emit = E, L->last_ins_pos = ins_pos, L->last_n_code = (uint32_t)n_code, L->last_val_bytes = val_bytes;
   L->stats.witnesses_on_gpu += 1, L->stats.witness_instructions += n_ins, L->stats.witness_bytes += n;
   if (getenv("PPD_VERIFY_GPU_PARSE")) verify_gpu_pre_image(L, J, b);

@@ -395,7 +395,14 @@ struct BlockJob {
     H256 haddr;
     uint32_t rec;
     bool storage_nonempty;
+    bool witnesses_storage = false;  // its account leaf carries a storage node (flag bit 1)
+    uint32_t own_root = NODE_EMPTY;  // root of the trie that node converts to
   };
+  // a storage trie is witnessed only in part (it holds a hashed-out node): two accounts with the same storage root may
+  // then be witnessed differently, and the reference's join by root hash (compact_to_partial_trie.rs:167-190) gives
+  // both the trie witnessed last: resolved with the hashed roots before the txn loop (join_storage_by_root)
+  bool storage_partial = false;
+  bool pre_image_built = false;
   std::vector<PreAccount> pre_accounts;
   H256Map pre_with_storage;  // accounts whose storage root != EMPTY_TRIE_HASH -> record
   H256Map acct_rec;          // hashed address -> the account's current record (what state.get() + rlp::decode gives, decoding.rs:251-254)
@@ -489,6 +496,7 @@ void collect_witness_messages(Job& J, BlockJob& b);
 void collect_messages(Job& J, BlockJob& b);
 uint32_t root_node_for(Job& J, BlockJob& b, uint32_t trie_root);
 void build_pre_image(Job& J, BlockJob& b);
+void join_storage_by_root(Lane* L, Job& J, BlockJob& b);
 bool gpu_parse_enabled();
 // dev_only: the txn loop runs on the device too (gpu_txn.cu), so nothing of the arena is copied back: the witness is
 // already resident (inside the uploaded FlatBlock), the pools get room for what the loop appends, and `after_launch`

@@ -261,7 +261,7 @@ void shape_block(Job& J, BlockJob& b) {
   HostArena& A = J.A;
   SectionTimer sec;
   sec.start();
-  if (!b.pre_image_on_gpu) build_pre_image(J, b);
+  if (!b.pre_image_built) build_pre_image(J, b);
   sec.stop(0);
   const uint32_t initial_state = b.state_root;
   // the storage tries before the first txn: only the dummy IRs of a block with at most one txn read them (decoding.rs:304-347)

@@ -238,6 +238,7 @@ struct WitnessTrie {
       case PPD_OP_EMPTY_ROOT:
         return NODE_EMPTY;
       case PPD_OP_HASH:
+        if (is_storage) b.storage_partial = true;
         return A.new_hash(A.add_hash(b.wit.hash(in)));
       case PPD_OP_EXTENSION: {
         uint32_t nd = push_key_nibbles(b.wit.key(in), depth);
@@ -296,6 +297,7 @@ struct WitnessTrie {
       case PPD_OP_EMPTY_ROOT:
         return;
       case PPD_OP_HASH: {
+        if (is_storage) b.storage_partial = true;
         uint32_t koff = add_packed_key(depth);
         items->push_back({koff, depth, 2, J.A.add_hash(b.wit.hash(in)), 0});
         return;
@@ -401,7 +403,7 @@ uint32_t make_account_record(Job& J, BlockJob& b, int32_t idx, const uint8_t* pa
     haddr.b[posn >> 1] |= (uint8_t)((posn & 1) ? path[k] : (path[k] << 4));
   }
   if (has_trie) b.storage[haddr] = sroot;
-  b.pre_accounts.push_back({haddr, r, nonempty});
+  b.pre_accounts.push_back({haddr, r, nonempty, (in.flags & 2) != 0, (in.flags & 2) ? b.storage_root_of_instr[idx] : NODE_EMPTY});
   if (J.device_marks) b.acct_rec[haddr] = r;
   if (nonempty) b.pre_with_storage[haddr] = r;
   return r;
@@ -472,6 +474,43 @@ void build_pre_image(Job& J, BlockJob& b) {
     if (trie_root_is_empty_hash(J, root)) b.have_empty_form = true, b.empty_form = root;
   }
   b.state_root = build_witness_trie(J, b, W.root, false);
+  b.pre_image_built = true;
+}
+
+// convert_storage_trie_root_keyed_hashmap_to_account_addr_keyed (compact_to_partial_trie.rs:167-190) with the roots in
+// hand: every storage trie was hashed and stored under its ROOT HASH while the witness was processed (a later trie
+// with the same root replacing an earlier one, compact_prestate_processing.rs:617-619), then every account takes the
+// trie stored under its storage root.  The builders above give an account its own witnessed trie, which is the same
+// thing unless two accounts with one root are witnessed differently (expanded / hashed-out, or expanded in different
+// places); this pass hashes the pre-image on the GPU and re-joins by root.
+void join_storage_by_root(Lane* L, Job& J, BlockJob& b) {
+#ifndef PPD_HOSTPROF
+  bool any = false;
+  for (const BlockJob::PreAccount& pa : b.pre_accounts) any |= pa.witnesses_storage;
+  if (!any) return;
+  const ppd_stats keep = L->stats;
+  sweep(L, J, /*refs_to_host=*/true);
+  L->stats = keep;  // (the block's own sweep counts these nodes)
+  auto root_hash = [&](const BlockJob::PreAccount& pa) {
+    H256 h;
+    const uint32_t src = J.A.accounts[pa.rec].storage_src;
+    memcpy(h.b, src == NODE_EMPTY ? EMPTY_TRIE_HASH : J.ref.data() + 32ull * src, 32);
+    return h;
+  };
+  std::unordered_map<H256, size_t, H256Hasher> last;  // root hash -> the last account that witnesses a trie with it
+  for (size_t i = 0; i < b.pre_accounts.size(); i++)
+    if (b.pre_accounts[i].witnesses_storage) last[root_hash(b.pre_accounts[i])] = i;
+  for (const BlockJob::PreAccount& pa : b.pre_accounts) {
+    auto f = last.find(root_hash(pa));
+    if (f == last.end())
+      b.storage.erase(pa.haddr);
+    else
+      b.storage[pa.haddr] = b.pre_accounts[f->second].own_root;
+  }
+  J.refs_on_host = false;
+#else
+  (void)L, (void)J, (void)b;
+#endif
 }
 
 }  // namespace ppd

@@ -33,17 +33,23 @@ void stats_reset(ppd_ctx* c) { c->stats = ppd_stats{}; }
 
 // wait for everything queued on the lane's stream without spinning (lanes may outnumber cores)
 void lane_sync(Lane* l) {
+  const auto t0 = std::chrono::steady_clock::now();
   CUDA_OK(cudaEventRecord(l->ev_sync, l->st));
   CUDA_OK(cudaEventSynchronize(l->ev_sync));
+  l->stats.host_wait_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
 }
 // The same by polling, for the short waits a lane makes while it holds a parse slot (at most PPD_PARSE_SLOTS
 // threads poll at a time): a sleeping thread is woken late when every core is busy shaping other blocks, and
 // everything queued behind the slot waits with it.
 void lane_sync_poll(Lane* l) {
+  const auto t0 = std::chrono::steady_clock::now();
   CUDA_OK(cudaEventRecord(l->ev_sync, l->st));
   for (unsigned spins = 0;; spins++) {
     cudaError_t e = cudaEventQuery(l->ev_sync);
-    if (e == cudaSuccess) return;
+    if (e == cudaSuccess) {
+      l->stats.host_wait_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+      return;
+    }
     if (e != cudaErrorNotReady) CUDA_OK(e);
     if (spins > 200) std::this_thread::yield();
   }
@@ -317,7 +323,17 @@ bool device_marks_wanted(const BlockJob& b) {
   return n_marks > 0 && 8 * n_marks >= min_touched;
 }
 
+void decode_one_inner(ppd_ctx* c, Lane* L, const uint8_t* flat, size_t len, uint8_t** out, size_t* out_len, int* status, unsigned dump_workers);
+// host_busy_ms: what the block cost its host thread apart from waiting for the device (the quantity that bounds
+// blocks/s when several GPUs share the host's cores)
 void decode_one(ppd_ctx* c, Lane* L, const uint8_t* flat, size_t len, uint8_t** out, size_t* out_len, int* status, unsigned dump_workers) {
+  const auto t0 = std::chrono::steady_clock::now();
+  const double wait0 = L->stats.host_wait_ms;
+  decode_one_inner(c, L, flat, len, out, out_len, status, dump_workers);
+  const double total = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  L->stats.host_busy_ms += total - (L->stats.host_wait_ms - wait0);
+}
+void decode_one_inner(ppd_ctx* c, Lane* L, const uint8_t* flat, size_t len, uint8_t** out, size_t* out_len, int* status, unsigned dump_workers) {
   *out = nullptr, *out_len = 0;
   const ppd_stats stats0 = L->stats;
   // Second attempt: only after a first one with device-side marking walks that met an error.  With the marks
@@ -348,6 +364,8 @@ void decode_one(ppd_ctx* c, Lane* L, const uint8_t* flat, size_t len, uint8_t** 
       pt.lap("parse");
       J.kh.run(L);
       pt.lap("keyhash");
+      if (!b.pre_image_built) build_pre_image(J, b);
+      if (b.storage_partial) join_storage_by_root(L, J, b);
       shape_block(J, b);
       pt.lap("shape");
       sweep(L, J, /*refs_to_host=*/!gpu_dump_enabled());
@@ -393,6 +411,7 @@ void add_stats(ppd_stats& a, const ppd_stats& b) {
   a.witnesses_on_gpu += b.witnesses_on_gpu, a.witness_instructions += b.witness_instructions, a.witness_bytes += b.witness_bytes;
   a.parse_gpu_ms += b.parse_gpu_ms, a.level_launches += b.level_launches, a.marks_on_gpu += b.marks_on_gpu;
   a.txn_loops_on_gpu += b.txn_loops_on_gpu, a.txn_gpu_ms += b.txn_gpu_ms, a.dump_gpu_ms += b.dump_gpu_ms;
+  a.host_busy_ms += b.host_busy_ms, a.host_wait_ms += b.host_wait_ms;
 }
 
 // Blocks are independent (each BlockTrace carries its own pre-image, trace_protocol.rs:40-48): every

@@ -72,6 +72,8 @@ class PpdStats(ctypes.Structure):
         ("txn_loops_on_gpu", ctypes.c_uint64),
         ("txn_gpu_ms", ctypes.c_double),
         ("dump_gpu_ms", ctypes.c_double),
+        ("host_busy_ms", ctypes.c_double),
+        ("host_wait_ms", ctypes.c_double),
     ]
 
     def as_dict(self):

@@ -1,0 +1,96 @@
+"""The device txn loop (csrc/txn_core.h: the code ppd_txn.cu's txn_loop_kernel instantiates) checked on the CPU.
+
+tests/cpp/txn_core_check.cpp runs it as a thread block of one thread on host memory and compares, txn by txn and
+structurally, with the host form of the same loop (csrc/host_txn.cu), which the GPU parity tests pin to the oracle:
+the tries every subset is cut from, every storage trie in hashed-address order, the set of nodes the marking walks
+touch, the tries after the txn, and the dummy / withdrawal entries.  Test infrastructure only: the binary is built with
+-DPPD_HOSTPROF (no GPU, no node hashing) and is not part of libppd_b200.so."""
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CSRC = os.path.join(ROOT, "proof_protocol_decoder_b200", "csrc")
+
+
+@pytest.fixture(scope="module")
+def txncheck():
+    if shutil.which("nvcc") is None:
+        pytest.skip("nvcc is needed to build the check harness")
+    res = subprocess.run(["make", "-C", CSRC, "txncheck"], capture_output=True, text=True)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    return os.path.join(CSRC, "build", "txncheck")
+
+
+def _run(binary, tmp_path, blocks):
+    paths = []
+    for i, blk in enumerate(blocks):
+        p = tmp_path / f"b{i}.flat"
+        p.write_bytes(blk.flat)
+        paths.append(str(p))
+    res = subprocess.run([binary] + paths, capture_output=True, text=True)
+    lines = [ln for ln in res.stdout.splitlines() if ln.strip()]
+    assert res.returncode == 0, "\n".join(lines[-20:]) + res.stderr[-2000:]
+    assert len(lines) == len(blocks) and all(ln.endswith("identical") for ln in lines), "\n".join(lines[-20:])
+
+
+def test_device_txn_loop_matches_host_loop_on_random_blocks(txncheck, tmp_path):
+    from proof_protocol_decoder_b200 import synth
+
+    rng = np.random.default_rng(11)
+    blocks = []
+    for i in range(40):
+        vd = 0 if i % 3 else int(rng.integers(1, 4))  # a virtual state (hashed-out siblings) every third block
+        blocks.append(
+            synth.gen_block(
+                2000 + i,
+                n_accounts=int(rng.integers(2, 60)),
+                n_txns=int(rng.integers(2, 25)),
+                contract_frac=float(rng.uniform(0.2, 1.0)),
+                slots_hi=int(rng.integers(1, 30)),
+                accounts_per_txn=(1, int(rng.integers(2, 20))),
+                slot_reads=(0, int(rng.integers(1, 10))),
+                slot_writes=(0, int(rng.integers(1, 16))),
+                zero_write_frac=float(rng.uniform(0, 0.7)),  # deletes: branches collapse, extensions merge
+                virtual_depth=vd,
+                allow_new_accounts=(vd == 0),
+            )
+        )
+    _run(txncheck, tmp_path, blocks)
+
+
+def test_device_txn_loop_dummies_and_withdrawals(txncheck, tmp_path):
+    """pad_gen_inputs_with_dummy_inputs_if_needed / add_withdrawals_to_txns (decoding.rs:304-402): every combination
+    of 0 / 1 / 2 / 5 txns with 0 / 1 / 3 withdrawals."""
+    from proof_protocol_decoder_b200 import synth
+
+    rng = np.random.default_rng(12)
+    blocks = []
+    for n_txns in (0, 1, 2, 5):
+        for wd in (0, 1, 3):
+            for _ in range(2):
+                blocks.append(
+                    synth.gen_block(
+                        3000 + len(blocks),
+                        n_accounts=int(rng.integers(2, 60)),
+                        n_txns=n_txns,
+                        contract_frac=float(rng.uniform(0.2, 1.0)),
+                        slots_hi=int(rng.integers(1, 30)),
+                        accounts_per_txn=(1, int(rng.integers(2, 20))),
+                        slot_writes=(0, int(rng.integers(1, 16))),
+                        zero_write_frac=float(rng.uniform(0, 0.7)),
+                        n_withdrawals=wd,
+                    )
+                )
+    _run(txncheck, tmp_path, blocks)
+
+
+def test_device_txn_loop_mainnet_shaped(txncheck, tmp_path):
+    from proof_protocol_decoder_b200 import synth
+
+    blk = synth.gen_block(4, n_accounts=2000, n_txns=20, contract_frac=0.15, slots_hi=256, virtual_depth=7, accounts_per_txn=(30, 60),
+                          slot_reads=(0, 3), slot_writes=(0, 3), allow_new_accounts=False, allow_self_destruct=False, inline_code_frac=0.02)
+    _run(txncheck, tmp_path, [blk, synth.gen_block(1, n_accounts=1000, n_txns=10, n_withdrawals=2)])
