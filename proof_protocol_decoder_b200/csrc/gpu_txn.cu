@@ -128,6 +128,7 @@ void after_emit(void* arg, const ParseEmit& E) {
   v.cap_keys = (uint32_t)std::min<size_t>(L->d_keys.cap, 0xfffffff0u);
   v.flat = H.d_flat, v.n_txns = (uint32_t)H.n_txns, v.n_traces = (uint32_t)n_traces, v.dig_base = B.dig_base;
   v.pre_flags = j.pre_flags;
+  v.a_nodes = &v.cur->n_nodes, v.a_children = &v.cur->n_children, v.a_keys = &v.cur->key_bytes, v.a_max_level = &v.cur->max_level;
   v.withdrawals = H.d_withdrawals, v.n_withdrawals = (uint32_t)T.withdrawals.size();
   if (v.n_withdrawals) CUDA_OK(cudaMemcpyAsync(H.d_withdrawals, T.withdrawals.data(), sizeof(txn::Withdrawal) * v.n_withdrawals, cudaMemcpyHostToDevice, st));
   j.acct_list = E.acct_list, j.n_acct = (uint32_t)n_acct, j.table_mask = jtable - 1;
@@ -236,7 +237,23 @@ int gpu_block(ppd_ctx* c, Lane* L, Job& J, const uint8_t* flat, size_t len, uint
   const size_t seg_cap = n_seg + (size_t)n_dummies * (2 * dummy_entries + 32), lit_cap = T.lit.size() + (size_t)n_dummies * (36 * dummy_entries + 512);
   // ---- the plan on the device: [txns | seg_a | seg_b | seg_c | seg_begin | touched_begin | lit | ir_base | touched |
   //                              seg_off | ir_size, ir_flag | ir_nuniq | u_node | u_size | u_off] ----
+  // IRs whose touched list may hold more distinct nodes than a thread block's shared-memory set: their sets live in HBM
+  PVec<uint64_t>& big_off = J.big_off;
+  PVec<uint32_t>& big_cap = J.big_cap;
+  big_off.resize(n_ir + 1), big_cap.resize(n_ir + 1);
+  size_t big_words = 0;
+  for (uint32_t i = 0; i < n_ir; i++) {
+    const uint32_t tn = T.touched_begin[i + 1] - T.touched_begin[i];
+    big_off[i] = ~0ull, big_cap[i] = 0;
+    if (tn <= 2 * IR_SET_MAX_UNIQ) continue;
+    uint32_t cap = 1u << 14;
+    while (cap < 2 * tn) cap <<= 1;
+    big_off[i] = big_words, big_cap[i] = cap;
+    big_words += 2ull * cap;
+  }
   IrDumpPlanView P{};
+  uint64_t* d_big_off;
+  uint32_t* d_big_cap;
   uint32_t *d_seg_a, *d_seg_b, *d_seg_c, *d_seg_begin, *d_seg_end, *d_touched_begin, *d_touched, *d_ir_size;
   uint64_t* d_ir_base;
   uint8_t* d_lit;
@@ -251,6 +268,8 @@ int gpu_block(ppd_ctx* c, Lane* L, Job& J, const uint8_t* flat, size_t len, uint
     P.seg_off = cv.take<uint32_t>(seg_cap + 1);
     d_ir_size = cv.take<uint32_t>(2ull * n_ir + 2);  // ir_size, then ir_flag: read back together
     P.ir_nuniq = cv.take<uint32_t>(n_ir + 1);
+    d_big_off = cv.take<uint64_t>(n_ir + 1), d_big_cap = cv.take<uint32_t>(n_ir + 1);
+    P.big_scratch = cv.take<uint32_t>(big_words + 16);
     P.u_node = cv.take<uint32_t>((size_t)n_touched + 16), P.u_size = cv.take<uint32_t>((size_t)n_touched + 16), P.u_off = cv.take<uint32_t>((size_t)n_touched + 16);
   };
   {
@@ -263,6 +282,7 @@ int gpu_block(ppd_ctx* c, Lane* L, Job& J, const uint8_t* flat, size_t len, uint
   P.ir_size = d_ir_size, P.ir_flag = d_ir_size + n_ir;
   P.touched = d_touched, P.touched_begin = d_touched_begin, P.seg_a = d_seg_a, P.seg_b = d_seg_b, P.seg_c = d_seg_c, P.seg_begin = d_seg_begin;
   P.seg_end = d_seg_end;
+  P.big_off = d_big_off, P.big_cap = d_big_cap;
   P.flat = d_flat, P.lit = d_lit, P.ir_base = d_ir_base;
   auto up = [&](void* dst, const void* src, size_t bytes) {
     if (!bytes) return;
@@ -275,6 +295,7 @@ int gpu_block(ppd_ctx* c, Lane* L, Job& J, const uint8_t* flat, size_t len, uint
   if (!n_dummies) up(d_seg_begin, T.seg_begin.data(), 4ull * (n_ir + 1)), up(d_seg_end, T.seg_end.data(), 4ull * (n_ir + 1));
   if (v.n_withdrawals) up(H.d_withdrawals, T.withdrawals.data(), sizeof(txn::Withdrawal) * v.n_withdrawals);  // (phase 2 rebased the records)
   up(d_lit, T.lit.data(), T.lit.size());
+  up(d_big_off, big_off.data(), 8ull * n_ir), up(d_big_cap, big_cap.data(), 4ull * n_ir);
   up(v.key_pool + H.B.txn_key_base, T.txn_keys.data(), T.txn_keys.size());
   up(v.traces, T.traces.data(), sizeof(txn::TxnTrace) * T.traces.size());  // (phase 2 rebased the record and value offsets)
   CUDA_OK(cudaMemsetAsync(d_touched, 0xff, 4ull * n_touched, st));

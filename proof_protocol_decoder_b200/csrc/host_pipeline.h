@@ -458,7 +458,8 @@ struct Job {
   TxnTables txn;              // tables of the device txn loop (gpu_txn.cu)
   PVec<uint32_t> txn_host;    // page-locked landing area of its read-backs
   PVec<uint32_t> txn_export;  // ... and of the storage map a block with dummy entries reads back
-  PVec<uint64_t> ir_base;
+  PVec<uint64_t> ir_base, big_off;
+  PVec<uint32_t> big_cap;
   std::vector<uint32_t> stamp;
   uint32_t serial = 0;
   Job() {
@@ -475,6 +476,7 @@ struct Job {
     txn_host.alloc_fn = pinned_alloc, txn_host.free_fn = pinned_free;
     txn_export.alloc_fn = pinned_alloc, txn_export.free_fn = pinned_free;
     ir_base.alloc_fn = pinned_alloc, ir_base.free_fn = pinned_free;
+    big_off.alloc_fn = pinned_alloc, big_off.free_fn = pinned_free, big_cap.alloc_fn = pinned_alloc, big_cap.free_fn = pinned_free;
   }
   void reset(size_t n_blocks) {
     dev = Resident{};

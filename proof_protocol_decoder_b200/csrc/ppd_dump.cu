@@ -28,23 +28,47 @@ constexpr uint32_t HASH_ID_BASE = 0x80000000u;
 constexpr uint32_t SET_CAP = 8192, MAX_UNIQ = 4096, NOT_FOUND = 0xffffffffu, UNSET = 0xffffffffu;
 constexpr int DUMP_THREADS = 256;
 
-struct Shared {
+// The set of an IR's touched nodes.  For an ordinary IR (at most MAX_UNIQ distinct touched nodes) everything lives in
+// shared memory; for a big one (a txn that writes tens of thousands of slots: config 3) the table and the per-node
+// arrays are in HBM (table: the block's scratch; arrays: the plan's u_node / u_size / u_off themselves).
+struct SharedSet {
   uint32_t key[SET_CAP];   // node id or NODE_EMPTY
-  uint16_t slot[SET_CAP];  // index into the u_* arrays
+  uint32_t slot[SET_CAP];  // index into the u_* arrays
   uint32_t u_node[MAX_UNIQ], u_size[MAX_UNIQ], u_off[MAX_UNIQ];
-  uint32_t n_uniq, n_done, flag;
+};
+struct Set {
+  uint32_t *key, *slot, *u_node, *u_size, *u_off;
+  uint32_t shift, mask, max_uniq;
+  uint32_t n_uniq, n_done, flag;  // (this struct lives in shared memory)
 };
 
-__device__ __forceinline__ uint32_t hash_slot(uint32_t id) { return (id * 2654435761u) >> 19; }  // 13 bits
+__device__ __forceinline__ uint32_t hash_slot(const Set& s, uint32_t id) { return (id * 2654435761u) >> s.shift; }
 
-__device__ __forceinline__ uint32_t set_find(const Shared& s, uint32_t id) {
-  uint32_t h = hash_slot(id);
+__device__ __forceinline__ uint32_t set_find(const Set& s, uint32_t id) {
+  uint32_t h = hash_slot(s, id);
   for (;;) {
     uint32_t k = s.key[h];
     if (k == id) return s.slot[h];
     if (k == NODE_EMPTY) return NOT_FOUND;
-    h = (h + 1) & (SET_CAP - 1);
+    h = (h + 1) & s.mask;
   }
+}
+
+// points the set at shared memory, or at the IR's region of the big-IR scratch
+__device__ void set_bind(Set& s, SharedSet& sm, const IrDumpPlanView& P, uint32_t ir, uint32_t tb) {
+  if (threadIdx.x == 0) {
+    const uint64_t big = P.big_off ? P.big_off[ir] : ~0ull;
+    if (big == ~0ull) {
+      s.key = sm.key, s.slot = sm.slot, s.u_node = sm.u_node, s.u_size = sm.u_size, s.u_off = sm.u_off;
+      s.mask = SET_CAP - 1, s.shift = 19, s.max_uniq = MAX_UNIQ;
+    } else {
+      const uint32_t cap = P.big_cap[ir];  // a power of two >= 2 x the IR's touched slots
+      s.key = P.big_scratch + big, s.slot = s.key + cap;
+      s.u_node = P.u_node + tb, s.u_size = P.u_size + tb, s.u_off = P.u_off + tb;
+      s.mask = cap - 1, s.shift = 32 - (31 - __clz(cap)), s.max_uniq = cap / 2;
+    }
+  }
+  __syncthreads();
 }
 
 __device__ __forceinline__ bool is_hash_id(uint32_t id) { return id >= HASH_ID_BASE && id != NODE_EMPTY; }
@@ -63,7 +87,7 @@ __device__ __forceinline__ uint32_t account_rlp_len(const AccountRec& r) {
 
 // serialised size of child `c` of a touched node: 1 (empty), 33 (hash), its own size when it is touched
 // itself (UNSET while that is not known yet).  Sets *flag for an untouched child kept expanded (< 32 bytes).
-__device__ __forceinline__ uint32_t child_size(const ArenaView& A, const Shared& s, uint32_t c, uint32_t* flag) {
+__device__ __forceinline__ uint32_t child_size(const ArenaView& A, const Set& s, uint32_t c, uint32_t* flag) {
   if (c == NODE_EMPTY) return 1;
   if (is_hash_id(c)) return 33;
   uint32_t k = set_find(s, c);
@@ -73,7 +97,7 @@ __device__ __forceinline__ uint32_t child_size(const ArenaView& A, const Shared&
 }
 
 // size of node u given its children's sizes, or UNSET when a touched child is not sized yet
-__device__ uint32_t node_size(const ArenaView& A, const Shared& s, uint32_t u, uint32_t* flag) {
+__device__ uint32_t node_size(const ArenaView& A, const Set& s, uint32_t u, uint32_t* flag) {
   const NodeRec r = A.nodes[u];
   const uint32_t kind = r.w0 & 0xff, nlen = (r.w0 >> 16) & 0xff;
   switch (kind) {
@@ -101,21 +125,21 @@ __device__ uint32_t node_size(const ArenaView& A, const Shared& s, uint32_t u, u
   }
 }
 
-__device__ void build_set(Shared& s, const uint32_t* ids, uint32_t n, const ArenaView& A, bool dedupe) {
-  for (uint32_t i = threadIdx.x; i < SET_CAP; i += blockDim.x) s.key[i] = NODE_EMPTY;
+__device__ void build_set(Set& s, const uint32_t* ids, uint32_t n, const ArenaView& A, bool dedupe) {
+  for (uint32_t i = threadIdx.x; i <= s.mask; i += blockDim.x) s.key[i] = NODE_EMPTY;
   if (threadIdx.x == 0) s.n_uniq = 0, s.n_done = 0, s.flag = 0;
   __syncthreads();
   for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
     uint32_t id = ids[i];
     if (id == NODE_EMPTY || is_hash_id(id)) continue;
     if (dedupe && node_kind(A, id) == NK_ROOT) continue;  // opaque: always emitted as a hash by its parent
-    uint32_t h = hash_slot(id);
+    uint32_t h = hash_slot(s, id);
     for (;;) {
       uint32_t prev = atomicCAS(&s.key[h], NODE_EMPTY, id);
       if (prev == NODE_EMPTY) {
         uint32_t k = dedupe ? atomicAdd(&s.n_uniq, 1u) : i;
-        if (k < MAX_UNIQ) {
-          s.slot[h] = (uint16_t)k;
+        if (k < s.max_uniq) {
+          s.slot[h] = k;
           s.u_node[k] = id;
         } else {
           s.flag = 1;
@@ -124,7 +148,7 @@ __device__ void build_set(Shared& s, const uint32_t* ids, uint32_t n, const Aren
         break;
       }
       if (prev == id) break;
-      h = (h + 1) & (SET_CAP - 1);
+      h = (h + 1) & s.mask;
     }
   }
   __syncthreads();
@@ -136,11 +160,12 @@ __device__ void build_set(Shared& s, const uint32_t* ids, uint32_t n, const Aren
 // touched node, its size and its offset inside the IR; seg_off[s] for every segment.
 __global__ void __launch_bounds__(DUMP_THREADS) ir_size_kernel(ArenaView A, IrDumpPlanView P) {
   extern __shared__ uint8_t smem_raw[];
-  Shared& s = *reinterpret_cast<Shared*>(smem_raw);
+  __shared__ Set s;
   const uint32_t ir = blockIdx.x;
   const uint32_t tb = P.touched_begin[ir], tn = P.touched_begin[ir + 1] - tb;
+  set_bind(s, *reinterpret_cast<SharedSet*>(smem_raw), P, ir, tb);
   build_set(s, P.touched + tb, tn, A, true);
-  const uint32_t nu = min(s.n_uniq, MAX_UNIQ);
+  const uint32_t nu = min(s.n_uniq, s.max_uniq);
   for (uint32_t k = threadIdx.x; k < nu; k += blockDim.x) s.u_size[k] = UNSET, s.u_off[k] = UNSET;
   __syncthreads();
   // ---- sizes, bottom-up: a node is sized once all its touched children are ----
@@ -274,9 +299,10 @@ __global__ void __launch_bounds__(DUMP_THREADS) ir_size_kernel(ArenaView A, IrDu
     P.ir_nuniq[ir] = nu;
   }
   for (uint32_t k = threadIdx.x; k < nu; k += blockDim.x) {
-    P.u_node[tb + k] = s.u_node[k];
-    P.u_size[tb + k] = s.u_size[k] & 0x7fffffffu;
-    P.u_off[tb + k] = s.u_off[k];
+    const uint32_t node = s.u_node[k], size = s.u_size[k] & 0x7fffffffu, off = s.u_off[k];  // (a big IR's arrays ARE the plan's)
+    P.u_node[tb + k] = node;
+    P.u_size[tb + k] = size;
+    P.u_off[tb + k] = off;
   }
 }
 
@@ -332,7 +358,7 @@ __device__ __forceinline__ uint8_t* put_u256_str(uint8_t* q, const uint8_t* be) 
   return q;
 }
 // the child of a touched node: skipped when it is touched itself (it writes its own bytes)
-__device__ __forceinline__ uint8_t* put_child(uint8_t* q, const ArenaView& A, const Shared& s, uint32_t c) {
+__device__ __forceinline__ uint8_t* put_child(uint8_t* q, const ArenaView& A, const Set& s, uint32_t c) {
   if (c == NODE_EMPTY) {
     *q++ = PPD_NODE_EMPTY;
     return q;
@@ -346,7 +372,7 @@ __device__ __forceinline__ uint8_t* put_child(uint8_t* q, const ArenaView& A, co
 }  // namespace
 
 // the bytes of node u at q: its own fields, and every child that is not touched itself (touched ones write themselves)
-__device__ void emit_node(const ArenaView& A, const Shared& s, uint32_t u, uint8_t* q) {
+__device__ void emit_node(const ArenaView& A, const Set& s, uint32_t u, uint8_t* q) {
   const NodeRec r = A.nodes[u];
   switch (r.w0 & 0xff) {
     case NK_LEAF: {
@@ -399,12 +425,15 @@ __device__ void emit_node(const ArenaView& A, const Shared& s, uint32_t u, uint8
 // One CTA per IR: every unique touched node writes its own bytes at out + ir_base[ir] + its offset.
 __global__ void __launch_bounds__(DUMP_THREADS) ir_emit_kernel(ArenaView A, IrDumpPlanView P, uint8_t* __restrict__ out) {
   extern __shared__ uint8_t smem_raw[];
-  Shared& s = *reinterpret_cast<Shared*>(smem_raw);
+  __shared__ Set s;
   const uint32_t ir = blockIdx.x;
   if (P.ir_flag[ir]) return;  // serialised by the host
   const uint32_t tb = P.touched_begin[ir], nu = P.ir_nuniq[ir];
-  build_set(s, P.u_node + tb, nu, A, false);
-  for (uint32_t k = threadIdx.x; k < nu; k += blockDim.x) s.u_size[k] = P.u_size[tb + k], s.u_off[k] = P.u_off[tb + k];
+  set_bind(s, *reinterpret_cast<SharedSet*>(smem_raw), P, ir, tb);
+  if (s.u_node != P.u_node + tb) {  // an ordinary IR: the set again in shared memory (a big IR's table is still in HBM)
+    build_set(s, P.u_node + tb, nu, A, false);
+    for (uint32_t k = threadIdx.x; k < nu; k += blockDim.x) s.u_size[k] = P.u_size[tb + k], s.u_off[k] = P.u_off[tb + k];
+  }
   __syncthreads();
   uint8_t* base = out + P.ir_base[ir];
   for (uint32_t k = threadIdx.x; k < nu; k += blockDim.x) emit_node(A, s, s.u_node[k], base + s.u_off[k]);
@@ -512,17 +541,17 @@ __global__ void __launch_bounds__(128) mark_walk_kernel(ArenaView A, const uint4
   }
 }
 
-size_t ir_dump_smem_bytes() { return sizeof(Shared); }
+size_t ir_dump_smem_bytes() { return sizeof(SharedSet); }
 
 void launch_ir_size(const ArenaView& A, const IrDumpPlanView& P, uint32_t n_ir, cudaStream_t st) {
   if (!n_ir) return;
   static bool attr = false;
   if (!attr) {
-    cudaFuncSetAttribute(ir_size_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Shared));
-    cudaFuncSetAttribute(ir_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Shared));
+    cudaFuncSetAttribute(ir_size_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SharedSet));
+    cudaFuncSetAttribute(ir_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SharedSet));
     attr = true;
   }
-  ir_size_kernel<<<n_ir, DUMP_THREADS, sizeof(Shared), st>>>(A, P);
+  ir_size_kernel<<<n_ir, DUMP_THREADS, sizeof(SharedSet), st>>>(A, P);
 }
 void launch_mark_walk(const ArenaView& A, const uint32_t* items4, uint32_t n_items, uint32_t n_ir, uint32_t* touched, uint32_t* flags, cudaStream_t st) {
   if (!n_items) return;
@@ -530,7 +559,7 @@ void launch_mark_walk(const ArenaView& A, const uint32_t* items4, uint32_t n_ite
 }
 void launch_ir_emit(const ArenaView& A, const IrDumpPlanView& P, uint32_t n_ir, uint8_t* out, cudaStream_t st) {
   if (!n_ir) return;
-  ir_emit_kernel<<<n_ir, DUMP_THREADS, sizeof(Shared), st>>>(A, P, out);
+  ir_emit_kernel<<<n_ir, DUMP_THREADS, sizeof(SharedSet), st>>>(A, P, out);
 }
 
 }  // namespace ppd

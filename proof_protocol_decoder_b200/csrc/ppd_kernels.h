@@ -72,6 +72,11 @@ struct IrDumpPlanView {
   const uint8_t* flat;            // the FlatBlock resident in HBM
   const uint8_t* lit;             // the uploaded literal pool
   const uint64_t* ir_base;        // [n_ir] byte offset of the IR in the output (emit only)
+  // IRs with more touched slots than a thread block's shared-memory set holds keep their set in HBM: big_off[ir] = word
+  // offset of the IR's table in big_scratch (~0: an ordinary IR), big_cap[ir] = its capacity (a power of two); or nullptr
+  const uint64_t* big_off;
+  const uint32_t* big_cap;
+  uint32_t* big_scratch;
   // outputs of ir_size_kernel
   uint32_t* seg_off;              // offset of every segment inside its IR
   uint32_t* ir_size;
@@ -85,6 +90,7 @@ void launch_ir_size(const ArenaView& A, const IrDumpPlanView& P, uint32_t n_ir, 
 // the subset marking walks on the device: items4 = n_items x (root, key offset, key nibbles | ir << 8, first slot in touched[]);
 // every item owns MARK_SLOTS slots of touched[]; flags[0 .. n_ir) = slot overflow per IR, flags[n_ir] = a key ran into a hashed-out node
 static const uint32_t MARK_SLOTS = 16;
+static const uint32_t IR_SET_MAX_UNIQ = 4096;  // distinct touched nodes an ordinary IR may have (ppd_dump.cu: MAX_UNIQ)
 void launch_mark_walk(const ArenaView& A, const uint32_t* items4, uint32_t n_items, uint32_t n_ir, uint32_t* touched, uint32_t* flags, cudaStream_t st);
 void launch_ir_emit(const ArenaView& A, const IrDumpPlanView& P, uint32_t n_ir, uint8_t* out, cudaStream_t st);
 

@@ -122,7 +122,10 @@ __global__ void acct_export_kernel(View v, const uint32_t* __restrict__ acct_lis
 
 constexpr int LOOP_THREADS = 256;
 __global__ void __launch_bounds__(LOOP_THREADS, 1) txn_loop_kernel(View v, uint32_t initial_state) {
-  __shared__ uint32_t sh_dmax, sh_stop;
+  __shared__ uint32_t sh_dmax, sh_stop, sh_cursor[4];
+  if (threadIdx.x == 0) sh_cursor[0] = v.cur->n_nodes, sh_cursor[1] = v.cur->n_children, sh_cursor[2] = v.cur->key_bytes, sh_cursor[3] = v.cur->max_level;
+  v.a_nodes = &sh_cursor[0], v.a_children = &sh_cursor[1], v.a_keys = &sh_cursor[2], v.a_max_level = &sh_cursor[3];
+  __syncthreads();
   Ctx c{v, threadIdx.x, blockDim.x, &sh_dmax};
   for (uint32_t ti = 0; ti < v.n_txns; ti++) {
     run_txn(c, ti, C_EMPTY_TRIE, C_EMPTY_CODE);
@@ -133,6 +136,7 @@ __global__ void __launch_bounds__(LOOP_THREADS, 1) txn_loop_kernel(View v, uint3
     __syncthreads();
   }
   run_finish(c, initial_state);
+  if (threadIdx.x == 0) v.cur->n_nodes = sh_cursor[0], v.cur->n_children = sh_cursor[1], v.cur->key_bytes = sh_cursor[2], v.cur->max_level = sh_cursor[3];
 }
 
 }  // namespace

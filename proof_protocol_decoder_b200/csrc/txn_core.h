@@ -148,6 +148,9 @@ struct View {
   uint32_t* child_pool;
   AccountRec* accounts;
   uint32_t cap_nodes, cap_children, cap_keys;
+  // allocation cursors: &cur->n_nodes ..., or shared-memory copies of them while the loop kernel runs (an allocation is
+  // then a shared-memory atomic instead of a round trip to L2)
+  uint32_t *a_nodes, *a_children, *a_keys, *a_max_level;
   // inputs
   const uint8_t* flat;
   TxnTrace* traces;
@@ -240,7 +243,7 @@ PPD_HD inline uint32_t kind_of(const View& v, uint32_t n) { return is_hash_id(n)
 PPD_HD inline uint32_t w0(uint32_t kind, uint32_t start, uint32_t len) { return kind | (start << 8) | (len << 16); }
 
 PPD_HD inline uint32_t push_node(const View& v, const NodeRec& r, uint32_t lv) {
-  uint32_t id = PPD_ATOMIC_ADD(&v.cur->n_nodes, 1u);
+  uint32_t id = PPD_ATOMIC_ADD(v.a_nodes, 1u);
   if (id >= v.cap_nodes) {
     raise(v, TXF_NODES_FULL, 0);
     id = v.cap_nodes - 1;  // a sink slot: the block is redone anyway
@@ -248,11 +251,11 @@ PPD_HD inline uint32_t push_node(const View& v, const NodeRec& r, uint32_t lv) {
   if (lv > 0xfff0u) raise(v, TXF_LEVELS, 0), lv = 0xfff0u;
   v.nodes[id] = r;
   v.level[id] = (uint16_t)lv;
-  PPD_ATOMIC_MAX(&v.cur->max_level, lv);
+  PPD_ATOMIC_MAX(v.a_max_level, lv);
   return id;
 }
 PPD_HD inline uint32_t alloc_children(const View& v, uint32_t k) {
-  uint32_t at = PPD_ATOMIC_ADD(&v.cur->n_children, k);
+  uint32_t at = PPD_ATOMIC_ADD(v.a_children, k);
   if (at + k > v.cap_children) {
     raise(v, TXF_CHILDREN_FULL, 0);
     at = v.cap_children - 16;
@@ -348,7 +351,7 @@ PPD_HD inline uint32_t collapse_branch(const View& v, uint32_t koff, uint32_t po
   if (k == NK_EXT || k == NK_LEAF || k == NK_LEAF_ACCOUNT) return collapse_ext(v, 0, pos, 1, other);  // their own keys spell the nibble
   // a key that runs through the surviving child: the path's first `pos` nibbles, then its slot
   const uint32_t nb = pos / 2 + 2;
-  uint32_t pk = PPD_ATOMIC_ADD(&v.cur->key_bytes, nb);
+  uint32_t pk = PPD_ATOMIC_ADD(v.a_keys, nb);
   if (pk + nb > v.cap_keys) {
     raise(v, TXF_KEYS_FULL, 0);
     pk = v.cap_keys - 40;

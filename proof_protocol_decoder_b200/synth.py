@@ -509,6 +509,128 @@ def gen_block(
     return blk
 
 
+# ------------------------------------------------------------------------------------------------
+# config 3: a storage-heavy block (few contracts with very large storage tries)
+# ------------------------------------------------------------------------------------------------
+_NIB = {c: i for i, c in enumerate(_HEX)}
+
+
+def emit_full_trie(keys, leaf_bytes):
+    """Witness stream (post-order, as compact_prestate_processing.rs:387-668 consumes it) of the FULL trie over
+    `keys` (uint8 [n, 32], strictly ascending); leaf_bytes(i, key_suffix_hex) returns the leaf's instruction bytes.
+    Iterative (one pass over the leaves with a stack of open branches): a million leaves take seconds."""
+    n = len(keys)
+    out = []
+    if n == 0:
+        return [b"\x06"]
+    hexs = [k.tobytes().hex() for k in keys]
+    if n == 1:
+        return [leaf_bytes(0, hexs[0])]
+    diff = keys[1:] != keys[:-1]
+    first = diff.argmax(axis=1)
+    assert diff.any(axis=1).all(), "keys must be distinct"
+    x = keys[1:][np.arange(n - 1), first] ^ keys[:-1][np.arange(n - 1), first]
+    lcp = (2 * first + (x < 16)).astype(np.int64)
+    L = [-1] + lcp.tolist() + [-1]
+    stack = []  # open branches: [depth, mask]
+    for i in range(n):
+        lc, ln = L[i], L[i + 1]
+        hx = hexs[i]
+        s = (lc if lc > ln else ln) + 1
+        out.append(leaf_bytes(i, hx[s:]))
+        if ln > lc:
+            stack.append([ln, 1 << _NIB[hx[ln]]])
+            continue
+        stack[-1][1] |= 1 << _NIB[hx[lc]]
+        while stack and stack[-1][0] > ln:
+            d, mask = stack.pop()
+            out.append(b"\x02" + cbor_uint(mask))
+            parent = stack[-1][0] if stack else -1
+            p = parent if parent > ln else ln
+            if p < d - 1:
+                ext = hx[p + 1 : d]
+                out.append(b"\x01" + cbor_bytes(bytes([0x02 | (len(ext) & 1)]) + bytes.fromhex(ext + ("0" if len(ext) & 1 else ""))))
+            if p < 0:
+                break
+            if stack and p == parent:
+                stack[-1][1] |= 1 << _NIB[hx[p]]
+            else:
+                stack.append([p, 1 << _NIB[hx[p]]])
+                break
+    return out
+
+
+def gen_c3_block(seed=3, n_contracts=4, slots=1_000_000, n_plain=1000, writes_per_contract=10_000, reads_per_contract=100):
+    """BASELINE.json configs[2] / SURVEY.md 8d C3: `n_contracts` contracts with `slots` storage slots each (full leaves,
+    values 1..32 bytes) plus `n_plain` plain accounts; ONE txn that writes `writes_per_contract` slots of every contract
+    (60 % overwrite an existing slot, 10 % delete one, 30 % create a new one) and reads a few.  Only the slots the txn
+    overwrites / deletes / reads need a known pre-image; the other leaves' keys are random 32-byte strings."""
+    rng = np.random.default_rng(seed)
+    blk = SynthBlock()
+    n_acc = n_contracts + n_plain
+    addrs, haddrs = _rand_addr(rng, n_acc)
+    order = sorted(range(n_acc), key=lambda i: haddrs[i])
+    contracts = list(range(n_contracts))
+    known = min(slots, writes_per_contract + reads_per_contract)
+    storage_streams, known_raw = {}, {}
+    for c in contracts:
+        raw, hashed = _rand_slot_keys(rng, known)
+        rest = np.frombuffer(rng.bytes(32 * (slots - known)), dtype=np.uint8).reshape(-1, 32)
+        keys = np.concatenate([np.frombuffer(b"".join(hashed), dtype=np.uint8).reshape(-1, 32), rest]) if known else rest
+        be = keys.view(">u8")
+        idx = np.lexsort((be[:, 3], be[:, 2], be[:, 1], be[:, 0]))
+        keys = np.ascontiguousarray(keys[idx])
+        vlen = rng.integers(1, 33, size=slots)
+        vraw = rng.bytes(32 * slots)
+
+        def leaf_bytes(i, suffix, vlen=vlen, vraw=vraw):
+            v = bytes([vraw[32 * i] | 1]) + vraw[32 * i + 1 : 32 * i + int(vlen[i])]  # no leading zero byte
+            k = bytes([0x02 | (len(suffix) & 1)]) + bytes.fromhex(suffix + ("0" if len(suffix) & 1 else "")) if suffix else b""
+            return b"\x00" + cbor_bytes(k) + cbor_bytes(v)
+
+        storage_streams[c] = emit_full_trie(keys, leaf_bytes)
+        known_raw[c] = raw
+    accounts = [{"addr": addrs[i], "nonce": int(rng.integers(0, 1 << 16)), "balance": int.from_bytes(rng.bytes(12), "big") | 1, "code_hash": rng.bytes(32)} for i in range(n_acc)]
+    em = _Emitter(rng)
+    keys_hex = [haddrs[i].hex() + "0" for i in order]
+
+    def account_leaf_fn(i, depth):
+        ai = order[i]
+        acc = accounts[ai]
+        flags = 4 | 8
+        if ai < n_contracts:
+            flags |= 1 | 2
+            em.out.append(b"\x03" + acc["code_hash"])
+            em.out.extend(storage_streams[ai])
+        body = cbor_uint(acc["nonce"] or 1) + cbor_bytes(acc["balance"].to_bytes((acc["balance"].bit_length() + 7) // 8, "big"))
+        if flags & 1:
+            body += cbor_uint(1234)
+        nib = [int(ch, 16) for ch in keys_hex[i][depth:64]]
+        em.out.append(b"\x05" + cbor_bytes(compact_key(nib)) + bytes([flags]) + body)
+
+    em.out.append(b"\x01")
+    em.emit(keys_hex, 0, n_acc, 0, account_leaf_fn)
+    blk.compact = b"".join(em.out)
+    # ---- the txn ----
+    sender = n_contracts  # a plain account
+    traces = [(addrs[sender], {"nonce": accounts[sender]["nonce"] + 1, "balance": 12345})]
+    for c in contracts:
+        raw = known_raw[c]
+        n_over, n_del = int(0.6 * writes_per_contract), int(0.1 * writes_per_contract)
+        n_over, n_del = min(n_over, len(raw)), min(n_del, max(0, len(raw) - int(0.6 * writes_per_contract)))
+        n_new = writes_per_contract - n_over - n_del
+        new_raw, _ = _rand_slot_keys(rng, n_new)
+        written = [(k, int.from_bytes(rng.bytes(int(rng.integers(1, 33))), "big") | 1) for k in raw[:n_over]]
+        written += [(k, 0) for k in raw[n_over : n_over + n_del]]
+        written += [(k, int.from_bytes(rng.bytes(int(rng.integers(1, 33))), "big") | 1) for k in new_raw]
+        reads = raw[n_over + n_del : n_over + n_del + reads_per_contract]
+        traces.append((addrs[c], {"balance": 777 + c, "storage_read": list(reads), "storage_written": written}))
+    rec = legacy_receipt(1, 4_000_000, 2, rng)
+    blk.txns.append({"traces": traces, "byte_code": rng.bytes(200), "new_txn_trie_node_byte": b"", "new_receipt_trie_node_byte": rec, "gas_used": 4_000_000})
+    blk.stats = {"contracts": n_contracts, "slots": slots, "plain": n_plain, "writes_per_contract": writes_per_contract}
+    return blk
+
+
 def gen_config(name, seed=None):
     """The named BASELINE.json configs (scaled variants via kwargs of gen_block)."""
     if name == "C1":
@@ -529,6 +651,8 @@ def gen_config(name, seed=None):
             allow_self_destruct=False,
             inline_code_frac=0.02,
         )
+    if name == "C3":
+        return gen_c3_block(3 if seed is None else seed)
     raise ValueError(name)
 
 

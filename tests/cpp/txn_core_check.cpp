@@ -197,6 +197,7 @@ int check_block(const std::vector<uint8_t>& flatv, const char* name) {
   cur.n_nodes = n_pre_nodes, cur.n_children = (uint32_t)A.child_pool.size(), cur.key_bytes = B.key_cursor;
   cur.state_root = b2.state_root, cur.txn_root = NODE_EMPTY, cur.receipt_root = NODE_EMPTY;
   v.cur = &cur;
+  v.a_nodes = &cur.n_nodes, v.a_children = &cur.n_children, v.a_keys = &cur.key_bytes, v.a_max_level = &cur.max_level;
   // ---- the kernels, in launch order ----
   txn::AcctInit ai{table - 1, b2.state_root, join_storage.data(), join_root.data()};
   for (uint32_t t = 0; t < n_traces; t++) txn::acct_claim(v, ai, t);
