@@ -27,6 +27,8 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# one CUDA stream per resident block: ask for the 32 hardware queues the device has (8 unless set) before torch creates the context
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 ALU_OPS_PER_PERM = 4354  # 24 rounds x ~180 LOP3/SHF + 34 to absorb a rate block
 ALU_LANES_PER_SM_CLK = 64

@@ -121,6 +121,16 @@ int ppd_trie_root_sorted_leaves(ppd_ctx* ctx, const uint8_t* keys32, const uint6
 int ppd_trie_root_sorted_leaves_dev(ppd_ctx* ctx, const uint8_t* d_keys32, const uint64_t* d_val_off, const uint8_t* d_vals,
                                     size_t n, size_t vals_bytes, uint8_t root_out[32]);
 
+/* One huge trie over several streams or GPUs: the leaves are split by their first `base_depth`
+ * nibbles; each part is hashed like a whole trie, except that its nodes sit `base_depth` nibbles below the root
+ * (ref_out = the 32 bytes the node above embeds; every key of the part must share those nibbles, and the part's top
+ * node must encode to at least 32 bytes, which a 64-nibble key guarantees).  DEVICE pointers. */
+int ppd_trie_subroot_sorted_leaves_dev(ppd_ctx* ctx, const uint8_t* d_keys32, const uint64_t* d_val_off, const uint8_t* d_vals, size_t n,
+                                       size_t vals_bytes, uint32_t base_depth, uint8_t ref_out[32]);
+/* ... and the branch over them: child_hashes16x32[i] is the ref of the part whose next nibble is i (used when bit i of
+ * `mask` is set); root_out = HashedPartialTrie::hash() of that branch.  Host buffers; hashed on the GPU. */
+int ppd_trie_root_from_children(ppd_ctx* ctx, const uint8_t* child_hashes16x32, uint32_t mask, uint8_t root_out[32]);
+
 #ifdef __cplusplus
 }
 #endif

@@ -80,7 +80,7 @@ bool gpu_pre_image(Lane* L, Job& J, BlockJob& b, bool check_version, Slots* slot
     fprintf(stderr, "[ppd]   %-12s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t_prev).count());
     t_prev = now;
   };
-  SlotGuard slot(slots);
+  SlotGuard slot(slots, &L->stats.host_wait_ms);
   auto sync_in_slot = [&] { slots ? lane_sync_poll(L) : lane_sync(L); };
   lap("p:slot-wait");
   // ---- phase A: instruction boundaries ----

@@ -127,6 +127,7 @@ void after_emit(void* arg, const ParseEmit& E) {
   v.cap_nodes = (uint32_t)(n_nodes + T.est_nodes), v.cap_children = (uint32_t)(J.dev.children + T.est_children);
   v.cap_keys = (uint32_t)std::min<size_t>(L->d_keys.cap, 0xfffffff0u);
   v.flat = H.d_flat, v.n_txns = (uint32_t)H.n_txns, v.n_traces = (uint32_t)n_traces, v.dig_base = B.dig_base;
+  v.rec_base = B.rec_base, v.val_base = B.val_base;
   v.pre_flags = j.pre_flags;
   v.a_nodes = &v.cur->n_nodes, v.a_children = &v.cur->n_children, v.a_keys = &v.cur->key_bytes, v.a_max_level = &v.cur->max_level;
   v.withdrawals = H.d_withdrawals, v.n_withdrawals = (uint32_t)T.withdrawals.size();
@@ -293,11 +294,9 @@ int gpu_block(ppd_ctx* c, Lane* L, Job& J, const uint8_t* flat, size_t len, uint
   up(d_seg_a, T.seg_a.data(), 4ull * n_seg), up(d_seg_b, T.seg_b.data(), 4ull * n_seg), up(d_seg_c, T.seg_c.data(), 4ull * n_seg);
   up(d_touched_begin, T.touched_begin.data(), 4ull * (n_ir + 1));
   if (!n_dummies) up(d_seg_begin, T.seg_begin.data(), 4ull * (n_ir + 1)), up(d_seg_end, T.seg_end.data(), 4ull * (n_ir + 1));
-  if (v.n_withdrawals) up(H.d_withdrawals, T.withdrawals.data(), sizeof(txn::Withdrawal) * v.n_withdrawals);  // (phase 2 rebased the records)
   up(d_lit, T.lit.data(), T.lit.size());
   up(d_big_off, big_off.data(), 8ull * n_ir), up(d_big_cap, big_cap.data(), 4ull * n_ir);
   up(v.key_pool + H.B.txn_key_base, T.txn_keys.data(), T.txn_keys.size());
-  up(v.traces, T.traces.data(), sizeof(txn::TxnTrace) * T.traces.size());  // (phase 2 rebased the record and value offsets)
   CUDA_OK(cudaMemsetAsync(d_touched, 0xff, 4ull * n_touched, st));
   v.txns = d_txns, v.touched = d_touched, v.seg_a = d_seg_a, v.seg_b = d_seg_b;
   // ---- the pre-image hashed: the storage roots decide which trie an account gets (the by-root join) ----
@@ -322,20 +321,20 @@ int gpu_block(ppd_ctx* c, Lane* L, Job& J, const uint8_t* flat, size_t len, uint
   CUDA_OK(cudaMemsetAsync(H.j.slot_owner, 0xff, 4ull * (H.j.table_mask + 1), st));
   CUDA_OK(cudaMemsetAsync(H.j.slot_best, 0, 4ull * (H.j.table_mask + 1), st));
   CUDA_OK(cudaMemsetAsync(v.pre_slot, 0xff, 4ull * (H.j.n_acct + 1), st));
-  launch_join(H.j, st);
   txn::Cursors init;
   memset(&init, 0, sizeof init);
   init.n_nodes = n_pre, init.n_children = (uint32_t)J.dev.children, init.key_bytes = H.B.key_cursor;
   init.state_root = b.state_root, init.txn_root = NODE_EMPTY, init.receipt_root = NODE_EMPTY;
   launch_txn_init(v, init, H.table_slots, st);
+  H.j.flag = &v.cur->flag;
+  launch_join(H.j, st);
   H.ai = txn::AcctInit{H.table_slots - 1, b.state_root, H.j.join_storage, H.j.join_root};
   uint32_t max_writes = 0;
   for (size_t t = 0; t < T.traces.size(); t++) max_writes = std::max(max_writes, T.traces[t].n_writes);
   L->stats.kernel_launches += 3 + launch_txn_prep(v, H.ai, T.n_ops1, T.n_ops2, max_writes, st);
   CUDA_OK(cudaEventRecord(L->ev_loop0, st));
-  launch_txn_loop(v, b.state_root, st);
+  L->stats.kernel_launches += launch_txn_loop(v, b.state_root, st);
   CUDA_OK(cudaEventRecord(L->ev_loop1, st));
-  L->stats.kernel_launches += 1;
   // ---- the loop's nodes sorted by (level, class) ----
   L->d_order2.reserve(4ull * H.cap_tail + 16);
   CUDA_OK(cudaMemsetAsync(H.bins_tail, 0, 4ull * ORDER_MAX_BINS, st));
@@ -353,6 +352,11 @@ int gpu_block(ppd_ctx* c, Lane* L, Job& J, const uint8_t* flat, size_t len, uint
     L->stats.gpu_ms += ms;
     CUDA_OK(cudaEventElapsedTime(&ms, L->ev_loop0, L->ev_loop1));
     L->stats.txn_gpu_ms += ms;
+  }
+  if (getenv("PPD_TIMING")) {
+    const unsigned long long* pc = h_cur->phase_clocks;
+    fprintf(stderr, "[ppd]   loop phases (Mclk): setup %.2f marks %.2f batch1 %.2f records %.2f batch2 %.2f roots %.2f\n", pc[0] / 1e6, pc[1] / 1e6, pc[2] / 1e6,
+            pc[3] / 1e6, pc[4] / 1e6, pc[5] / 1e6);
   }
   if (h_cur->flag || h_cur->max_level >= ORDER_MAX_BINS / 64) {
     if (getenv("PPD_TIMING")) fprintf(stderr, "[ppd] device txn loop flag %u at txn %u (max level %u): host path\n", h_cur->flag, h_cur->flag_txn, h_cur->max_level);
@@ -460,9 +464,11 @@ int gpu_block(ppd_ctx* c, Lane* L, Job& J, const uint8_t* flat, size_t len, uint
   CUDA_OK(cudaGetLastError());
   L->stats.kernel_launches += 1;
   if (pinned) {
+    const auto tw = std::chrono::steady_clock::now();
     cudaError_t e = cudaMemcpyAsync(dst, L->d_out.p, total, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaEventRecord(L->ev_sync, st);
     if (e == cudaSuccess) e = cudaEventSynchronize(L->ev_sync);
+    L->stats.host_wait_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tw).count();
     if (e != cudaSuccess) {
       out_pool().give_back(pinned);
       throw Fail{PPD_ERR_CUDA, std::string("IR dump copy: ") + cudaGetErrorString(e)};

@@ -118,8 +118,11 @@ struct Slots {
 };
 struct SlotGuard {
   Slots* s;
-  explicit SlotGuard(Slots* s_) : s(s_) {
-    if (s) s->acquire();
+  explicit SlotGuard(Slots* s_, double* wait_ms = nullptr) : s(s_) {
+    if (!s) return;
+    const auto t0 = std::chrono::steady_clock::now();
+    s->acquire();
+    if (wait_ms) *wait_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
   }
   void done() {
     if (s) s->release();

@@ -3,6 +3,8 @@
 // (compact_to_partial_trie.rs:37-190) for the witnesses the GPU parser declines: malformed ones (the error and
 // its place in stream order are reported from here), non-canonical ones, and those too small to pay for three
 // device round trips.  Structure only: no hashing.
+#include <functional>
+
 #include "host_pipeline.h"
 
 namespace ppd {
@@ -500,13 +502,47 @@ void join_storage_by_root(Lane* L, Job& J, BlockJob& b) {
   std::unordered_map<H256, size_t, H256Hasher> last;  // root hash -> the last account that witnesses a trie with it
   for (size_t i = 0; i < b.pre_accounts.size(); i++)
     if (b.pre_accounts[i].witnesses_storage) last[root_hash(b.pre_accounts[i])] = i;
-  for (const BlockJob::PreAccount& pa : b.pre_accounts) {
+  // "Possibility of identical tries between accounts, so we need to do a clone here" (compact_to_partial_trie.rs:183-185):
+  // an account that takes ANOTHER account's trie gets its own copy of the nodes, so that a txn touching both cuts a
+  // separate subset out of each (the marks of an IR are kept per node id)
+  HostArena& A = J.A;
+  std::function<uint32_t(uint32_t)> clone = [&](uint32_t n) -> uint32_t {
+    if (n == NODE_EMPTY || is_hash_id(n)) return n;
+    const NodeRec r = A.nodes[n];
+    const uint32_t lv = A.level[n];
+    switch (r.w0 & 0xff) {
+      case NK_EXT: {
+        NodeRec c = r;
+        c.a1 = clone(r.a1);
+        return A.push(c, lv);
+      }
+      case NK_BRANCH: {
+        const uint32_t k = (uint32_t)__builtin_popcount(r.a1 & 0xffffu);
+        uint32_t kids[16];
+        for (uint32_t i = 0; i < k; i++) kids[i] = clone(A.child_pool[r.a0 + i]);
+        NodeRec c = r;
+        c.a0 = (uint32_t)A.child_pool.size();
+        for (uint32_t i = 0; i < k; i++) A.child_pool.push_back(kids[i]);
+        return A.push(c, lv);
+      }
+      default:
+        return A.push(r, lv);  // leaves (their key and value bytes are immutable and shared); ROOT nodes do not occur inside a trie
+    }
+  };
+  bool cloned = false;
+  for (size_t i = 0; i < b.pre_accounts.size(); i++) {
+    const BlockJob::PreAccount& pa = b.pre_accounts[i];
     auto f = last.find(root_hash(pa));
-    if (f == last.end())
+    if (f == last.end()) {
       b.storage.erase(pa.haddr);
-    else
-      b.storage[pa.haddr] = b.pre_accounts[f->second].own_root;
+      continue;
+    }
+    const uint32_t root = b.pre_accounts[f->second].own_root;
+    const bool other = f->second != i && root != NODE_EMPTY && !is_hash_id(root);
+    b.storage[pa.haddr] = other ? clone(root) : root;
+    cloned |= other;
   }
+  (void)cloned;
   J.refs_on_host = false;
 #else
   (void)L, (void)J, (void)b;

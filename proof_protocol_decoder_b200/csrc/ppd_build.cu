@@ -54,11 +54,13 @@ __device__ __forceinline__ int lcp_nibbles(const uint4* a, const uint4* bq, int*
 }
 
 // L[0] = L[N] = -1;  L[i] = lcp(key[i-1], key[i]).  flags[0] |= 1 if not strictly ascending.
-__global__ void lcp_kernel(const uint8_t* __restrict__ keys, uint32_t n, int8_t* __restrict__ L, uint32_t* __restrict__ flags) {
+// (for a SUB-trie whose keys share their first base_depth nibbles the two ends get base_depth - 1, which is what
+// they are inside the whole trie: every node then sits where it sits there)
+__global__ void lcp_kernel(const uint8_t* __restrict__ keys, uint32_t n, int8_t* __restrict__ L, uint32_t* __restrict__ flags, int boundary) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i > n) return;
   if (i == 0 || i == n) {
-    L[i] = -1;
+    L[i] = (int8_t)boundary;
     return;
   }
   uint4 ka[2], kb[2];
@@ -185,7 +187,7 @@ __global__ void branch_info_kernel(BuildView V) {
   V.depth[bi] = (uint8_t)d;
   V.rep[bi] = l;
   V.ext_start[bi] = (uint8_t)(dp + 1);
-  if (dp < 0) {
+  if (dp < V.base_depth) {
     *V.root_id = V.n + bi;
   } else {
     uint32_t pl = (dl >= dr) ? l : r1;
@@ -259,7 +261,7 @@ __global__ void __launch_bounds__(B, 4) hash_sorted_leaves_kernel(BuildView V) {
     int dl = P.L[i], dr = P.L[i + 1];
     int dp = max(dl, dr);
     key = V.keys + 32ull * i;
-    is_root = dp < 0;
+    is_root = dp < V.base_depth;
     if (is_root) {
       *V.root_id = i;
     } else {
@@ -480,8 +482,8 @@ __global__ void __launch_bounds__(B, 4) hash_branch_level_kernel(BuildView V, co
 static constexpr int HB = 128;
 static inline uint32_t cdiv(uint64_t a, uint32_t b) { return (uint32_t)((a + b - 1) / b); }
 
-void launch_lcp(const uint8_t* keys, uint32_t n, int8_t* L, uint32_t* flags, cudaStream_t st) {
-  lcp_kernel<<<cdiv((uint64_t)n + 1, 256), 256, 0, st>>>(keys, n, L, flags);
+void launch_lcp(const uint8_t* keys, uint32_t n, int8_t* L, uint32_t* flags, cudaStream_t st, int base_depth) {
+  lcp_kernel<<<cdiv((uint64_t)n + 1, 256), 256, 0, st>>>(keys, n, L, flags, base_depth - 1);
 }
 void launch_min64(const int8_t* in, uint32_t n_in, int8_t* out, uint32_t n_out, cudaStream_t st) {
   min64_kernel<<<cdiv(n_out, 256), 256, 0, st>>>(in, n_in, out, n_out);

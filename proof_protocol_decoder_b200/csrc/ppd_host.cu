@@ -418,13 +418,21 @@ void add_stats(ppd_stats& a, const ppd_stats& b) {
 // host thread takes blocks on its own lane, so parsing / shaping of one block overlaps the copies and
 // kernels of the others.
 static const size_t MAX_LANES = 64;
+static size_t max_lanes() {
+  static const size_t n = [] {
+    const char* e = getenv("PPD_MAX_LANES");
+    const long v = e ? atol(e) : (long)MAX_LANES;
+    return (size_t)(v < 1 ? 1 : v > (long)MAX_LANES ? (long)MAX_LANES : v);
+  }();
+  return n;
+}
 
 void decode_blocks(ppd_ctx* c, const uint8_t* const* flats, const size_t* lens, size_t n, uint8_t** outs, size_t* out_lens, int* statuses) {
   stats_reset(c);
   if (!n) return;
   // block i runs on lane i mod n_lanes; a host thread takes whole lanes, so a lane never runs two
   // blocks at once and the last block of every lane stays resident in HBM (ppd_replay_last_hashing)
-  const size_t n_lanes = std::min(n, MAX_LANES);
+  const size_t n_lanes = std::min(n, max_lanes());
   const unsigned workers = (unsigned)std::min<size_t>(host_threads(), n_lanes);
   for (size_t w = 0; w < n_lanes; w++) {
     Lane* L = lane_of(c, w);
@@ -459,6 +467,10 @@ int ppd_ctx_create(int device, ppd_ctx** out) {
   *out = new ppd_ctx();
   return PPD_OK;
 #endif
+  // every lane has its own stream; the device multiplexes streams onto CUDA_DEVICE_MAX_CONNECTIONS hardware queues
+  // (8 unless set, 32 at most), and kernels of streams that share a queue wait for each other.  Only effective when
+  // set before the process creates its CUDA context (lib.py and bench.py set it at import time for Python callers).
+  setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
   int count = 0;
   if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) return PPD_ERR_CUDA;
   ppd_ctx* c = new ppd_ctx();
@@ -571,8 +583,8 @@ static void replay_lane(Lane* L, unsigned what) {
     CUDA_OK(cudaMemsetAsync(L->last_join.slot_owner, 0xff, 4ull * (L->last_join.table_mask + 1), st));
     CUDA_OK(cudaMemsetAsync(L->last_join.slot_best, 0, 4ull * (L->last_join.table_mask + 1), st));
     CUDA_OK(cudaMemsetAsync(v.pre_slot, 0xff, 4ull * (L->last_join.n_acct + 1), st));
-    launch_join(L->last_join, st);
     launch_txn_init(v, L->last_init, L->last_table_slots, st);
+    launch_join(L->last_join, st);
     launch_txn_prep(v, L->last_ai, L->last_n_ops1, L->last_n_ops2, L->last_max_writes, st);
     launch_txn_loop(v, L->last_init.state_root, st);
     CUDA_OK(cudaMemsetAsync(L->last_bins_tail, 0, 4ull * ORDER_MAX_BINS, st));
@@ -711,7 +723,7 @@ int ppd_block_decode(ppd_ctx* c, const uint8_t* flat, size_t len, uint8_t** out,
 // ---- trie root over sorted leaves: structure built and hashed on the GPU (ppd_build.cu) ----------
 namespace {
 
-void trie_root_sorted_dev(ppd_ctx* c, const uint8_t* d_keys, const uint64_t* d_val_off, const uint8_t* d_vals, size_t n_, uint8_t root_out[32]) {
+void trie_root_sorted_dev(ppd_ctx* c, const uint8_t* d_keys, const uint64_t* d_val_off, const uint8_t* d_vals, size_t n_, uint8_t root_out[32], int base_depth = 0) {
   if (n_ == 0) {
     memcpy(root_out, EMPTY_TRIE_HASH, 32);  // HashedPartialTrie::default().hash(): keccak(0x80), types.rs:30-34
     return;
@@ -736,7 +748,7 @@ void trie_root_sorted_dev(ppd_ctx* c, const uint8_t* d_keys, const uint64_t* d_v
   uint32_t* small = D[B_SMALL].as<uint32_t>();  // [0] error flags, [1] root id, [2..7] counters(u64 x 3), [8..15] root, [1024..2047] hist, [2048..3071] cursor
   CUDA_OK(cudaMemsetAsync(small, 0, 16384, st));
   CUDA_OK(cudaEventRecord(c->ev0, st));
-  launch_lcp(d_keys, n, L, small + 0, st);
+  launch_lcp(d_keys, n, L, small + 0, st, base_depth);
   launch_min64(L, n + 1, m1, n1, st);
   launch_min64(m1, n1, m2, n2, st);
   launch_min64(m2, n2, m3, n3, st);
@@ -764,6 +776,7 @@ void trie_root_sorted_dev(ppd_ctx* c, const uint8_t* d_keys, const uint64_t* d_v
   V.val_off = d_val_off;
   V.vals = d_vals;
   V.n = n;
+  V.base_depth = base_depth;
   V.P = Pyramid{L, m1, m2, m3};
   V.leader = leader;
   V.bidx = bidx;
@@ -840,6 +853,49 @@ int ppd_trie_root_sorted_leaves_dev(ppd_ctx* c, const uint8_t* d_keys32, const u
   return guarded(c, [&] {
     stats_reset(c);
     trie_root_sorted_dev(c, d_keys32, d_val_off, d_vals, n, root_out);
+  });
+}
+
+int ppd_trie_subroot_sorted_leaves_dev(ppd_ctx* c, const uint8_t* d_keys32, const uint64_t* d_val_off, const uint8_t* d_vals, size_t n,
+                                       size_t vals_bytes, uint32_t base_depth, uint8_t ref_out[32]) {
+  (void)vals_bytes;
+  return guarded(c, [&] {
+    stats_reset(c);
+    if (base_depth >= 64 || n == 0) fail(PPD_ERR_BAD_ARGUMENT, "a sub-trie needs leaves and a base depth below 64");
+    trie_root_sorted_dev(c, d_keys32, d_val_off, d_vals, n, ref_out, (int)base_depth);
+  });
+}
+
+// The branch over up to 16 hashed children (the top of a trie whose sub-tries were hashed apart, on other streams or
+// other GPUs): a three-node arena (16 hash-pool entries, the branch, its ROOT) through the ordinary level kernel.
+int ppd_trie_root_from_children(ppd_ctx* c, const uint8_t* child_hashes16x32, uint32_t mask, uint8_t root_out[32]) {
+  return guarded(c, [&] {
+    stats_reset(c);
+    mask &= 0xffffu;
+    if (__builtin_popcount(mask) < 2) fail(PPD_ERR_BAD_ARGUMENT, "a branch has at least two children");
+    NodeRec nodes[2];
+    uint32_t kids[16], k = 0;
+    for (uint32_t i = 0; i < 16; i++)
+      if (mask & (1u << i)) kids[k++] = HASH_ID_BASE + i;
+    nodes[0] = NodeRec{node_w0(NK_BRANCH, 0, 0), 0, mask, 0};
+    nodes[1] = NodeRec{node_w0(NK_ROOT, 0, 0), 0, 0, 0};
+    c->d_keys.reserve(4096), c->d_vals.reserve(4096), c->d_ref.reserve(4096), c->d_ref_len.reserve(256), c->d_counters.reserve(32);
+    c->d_msg.reserve(4096);  // hash pool, nodes, children
+    uint8_t* base = c->d_msg.as<uint8_t>();
+    CUDA_OK(cudaMemcpyAsync(base, child_hashes16x32, 512, cudaMemcpyHostToDevice, c->st));
+    CUDA_OK(cudaMemcpyAsync(base + 512, nodes, sizeof nodes, cudaMemcpyHostToDevice, c->st));
+    CUDA_OK(cudaMemcpyAsync(base + 1024, kids, 4 * k, cudaMemcpyHostToDevice, c->st));
+    CUDA_OK(cudaMemsetAsync(c->d_counters.p, 0, 32, c->st));
+    ArenaView V{};
+    V.nodes = reinterpret_cast<const NodeRec*>(base + 512), V.hash_pool = base, V.child_pool = reinterpret_cast<const uint32_t*>(base + 1024);
+    V.key_pool = c->d_keys.as<uint8_t>(), V.val_pool = c->d_vals.as<uint8_t>(), V.accounts = nullptr;
+    V.ref = c->d_ref.as<uint8_t>(), V.ref_len = c->d_ref_len.as<uint8_t>(), V.counters = c->d_counters.as<unsigned long long>();
+    launch_hash_level(V, nullptr, 0, 1, c->st);
+    launch_hash_level(V, nullptr, 1, 2, c->st);
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaMemcpyAsync(root_out, V.ref + 32, 32, cudaMemcpyDeviceToHost, c->st));
+    CUDA_OK(cudaStreamSynchronize(c->st));
+    c->stats.nodes_hashed = 2, c->stats.kernel_launches = 2;
   });
 }
 

@@ -29,6 +29,7 @@ struct BuildView {
   const uint64_t* val_off;   // [N+1]
   const uint8_t* vals;
   uint32_t n;
+  int base_depth;            // nibbles every key shares with the trie above (0: a whole trie; the node found is the root)
   Pyramid P;
   const uint32_t* leader;    // [N+1]
   const uint32_t* bidx;      // [N+1] exclusive scan of leader flags
@@ -47,7 +48,7 @@ struct BuildView {
 
 size_t scan_tmp_words(size_t n);
 void exclusive_scan_u32(const uint32_t* in, uint32_t* out, uint32_t n, uint32_t* tmp, cudaStream_t st);
-void launch_lcp(const uint8_t* keys, uint32_t n, int8_t* L, uint32_t* flags, cudaStream_t st);
+void launch_lcp(const uint8_t* keys, uint32_t n, int8_t* L, uint32_t* flags, cudaStream_t st, int base_depth = 0);
 void launch_min64(const int8_t* in, uint32_t n_in, int8_t* out, uint32_t n_out, cudaStream_t st);
 void launch_leaders(const int8_t* L, const int8_t* m1, const int8_t* m2, const int8_t* m3, uint32_t n, uint32_t* link_a, uint32_t* link_b,
                     uint32_t* flag, cudaStream_t st);
@@ -178,7 +179,7 @@ void launch_txn_msgs(const txn::View& v, uint64_t* se, cudaStream_t st);
 void launch_txn_init(const txn::View& v, const txn::Cursors& init, uint32_t table_slots, cudaStream_t st);
 void launch_join(const txn::JoinView& j, cudaStream_t st);
 uint32_t launch_txn_prep(const txn::View& v, const txn::AcctInit& a, uint32_t n_ops1, uint32_t n_ops2, uint32_t max_writes, cudaStream_t st);
-void launch_txn_loop(const txn::View& v, uint32_t initial_state, cudaStream_t st);
+uint32_t launch_txn_loop(const txn::View& v, uint32_t initial_state, cudaStream_t st);  // returns the number of launches
 void launch_acct_export(const txn::View& v, const txn::JoinView& j, txn::AcctExport* out, cudaStream_t st);
 
 // ---- ppd_microbench.cu ----

@@ -11,6 +11,7 @@
 // All of it is pointer chasing over the arena: latency bound by construction (a walk is ~2 dependent loads per trie
 // level), which is why a block's loop is one resident CTA that other lanes' kernels overlap, not a grid.
 #include <cstdint>
+#include <cstdlib>
 
 #include "ppd_kernels.h"
 #include "txn_core.h"
@@ -82,6 +83,9 @@ __global__ void join_resolve_kernel(JoinView j) {
       storage = j.acct_list[5ull * best + 1];
       root = j.acct_list[5ull * best + 2];
       if (root == NODE_EMPTY) root = NONE;
+      // another account's expanded trie: the reference clones it (compact_to_partial_trie.rs:183-185), because a
+      // txn that touches both accounts cuts a separate subset out of each; the host path does that
+      if (best != r && storage < HASH_BASE) atomicCAS(j.flag, 0u, (uint32_t)TXF_SHARED_TRIE);
       break;
     }
     h = (h + 1) & j.table_mask;
@@ -121,21 +125,30 @@ __global__ void acct_export_kernel(View v, const uint32_t* __restrict__ acct_lis
 }
 
 constexpr int LOOP_THREADS = 256;
-__global__ void __launch_bounds__(LOOP_THREADS, 1) txn_loop_kernel(View v, uint32_t initial_state) {
+// txns [ti0, ti1) of the block.  The loop of a block is launched in chunks so that the kernels of another lane that
+// shares the hardware queue (the device has at most 32 of them) are not held up behind one 20 ms kernel.
+__global__ void __launch_bounds__(LOOP_THREADS, 1) txn_loop_kernel(View v, uint32_t initial_state, uint32_t ti0, uint32_t ti1, uint32_t finish) {
   __shared__ uint32_t sh_dmax, sh_stop, sh_cursor[4];
-  if (threadIdx.x == 0) sh_cursor[0] = v.cur->n_nodes, sh_cursor[1] = v.cur->n_children, sh_cursor[2] = v.cur->key_bytes, sh_cursor[3] = v.cur->max_level;
+  __shared__ long long sh_clock;
+  if (threadIdx.x == 0) {
+    sh_clock = clock64();
+    sh_cursor[0] = v.cur->n_nodes, sh_cursor[1] = v.cur->n_children, sh_cursor[2] = v.cur->key_bytes, sh_cursor[3] = v.cur->max_level;
+    sh_stop = *reinterpret_cast<volatile uint32_t*>(&v.cur->flag);
+  }
   v.a_nodes = &sh_cursor[0], v.a_children = &sh_cursor[1], v.a_keys = &sh_cursor[2], v.a_max_level = &sh_cursor[3];
   __syncthreads();
-  Ctx c{v, threadIdx.x, blockDim.x, &sh_dmax};
-  for (uint32_t ti = 0; ti < v.n_txns; ti++) {
+  if (sh_stop) return;  // an earlier chunk (or the join) raised a flag: the host path redoes the block
+  Ctx c{v, threadIdx.x, blockDim.x, &sh_dmax, &sh_clock};
+  for (uint32_t ti = ti0; ti < ti1; ti++) {
     run_txn(c, ti, C_EMPTY_TRIE, C_EMPTY_CODE);
-    // a raised flag ends the loop (the host path redoes the block); one thread reads it so that the decision is uniform
+    // a raised flag ends the loop; one thread reads it so that the decision is uniform
     if (threadIdx.x == 0) sh_stop = *reinterpret_cast<volatile uint32_t*>(&v.cur->flag);
     __syncthreads();
     if (sh_stop) break;
     __syncthreads();
   }
-  run_finish(c, initial_state);
+  if (finish) run_finish(c, initial_state);
+  __syncthreads();
   if (threadIdx.x == 0) v.cur->n_nodes = sh_cursor[0], v.cur->n_children = sh_cursor[1], v.cur->key_bytes = sh_cursor[2], v.cur->max_level = sh_cursor[3];
 }
 
@@ -174,7 +187,20 @@ uint32_t launch_txn_prep(const View& v, const AcctInit& a, uint32_t n_ops1, uint
   }
   return launches;
 }
-void launch_txn_loop(const View& v, uint32_t initial_state, cudaStream_t st) { txn_loop_kernel<<<1, LOOP_THREADS, 0, st>>>(v, initial_state); }
+uint32_t launch_txn_loop(const View& v, uint32_t initial_state, cudaStream_t st) {
+  static const uint32_t chunk = [] {
+    const char* e = getenv("PPD_LOOP_CHUNK");
+    const int x = e ? atoi(e) : 16;
+    return (uint32_t)(x < 1 ? 1 : x);
+  }();
+  uint32_t launches = 0;
+  for (uint32_t t0 = 0; t0 < v.n_txns || launches == 0; t0 += chunk) {
+    const uint32_t t1 = t0 + chunk < v.n_txns ? t0 + chunk : v.n_txns;
+    txn_loop_kernel<<<1, LOOP_THREADS, 0, st>>>(v, initial_state, t0, t1, t1 == v.n_txns ? 1u : 0u);
+    launches++;
+  }
+  return launches;
+}
 void launch_acct_export(const View& v, const JoinView& j, AcctExport* out, cudaStream_t st) {
   if (j.n_acct) acct_export_kernel<<<cdiv(j.n_acct, 128), 128, 0, st>>>(v, j.acct_list, j.join_storage, j.n_acct, out);
 }

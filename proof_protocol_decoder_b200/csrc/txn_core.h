@@ -67,6 +67,7 @@ enum : uint32_t {
   TXF_LEVELS = 12,
   TXF_WITHDRAWAL = 13,       // PPD_ERR_MISSING_WITHDRAWAL_ACCOUNT / account decode
   TXF_STACK = 14,
+  TXF_SHARED_TRIE = 15,      // the by-root join gives two accounts the SAME witnessed trie: the host path clones it, as the reference does
 };
 
 enum : uint8_t { OP_DEL = 0, OP_PUT_LEAF = 1, OP_PUT_ACCOUNT = 2 };
@@ -127,6 +128,7 @@ struct Cursors {
   uint32_t max_level;
   uint32_t roots[6];  // NK_ROOT nodes the dummy entries refer to (XR_*), created when the loop ends
   uint32_t state_before_withdrawals;
+  unsigned long long phase_clocks[8];  // SM clocks per phase of the loop, summed over txns (setup, marks, batch 1, records, batch 2, roots)
 };
 
 // One withdrawal (decoding.rs:404-428): balance += amount on the account of the hashed address
@@ -157,6 +159,7 @@ struct View {
   const TxnDesc* txns;
   uint32_t n_txns, n_traces;
   uint32_t dig_base;         // key_pool offset of digest 0 (32 bytes each)
+  uint32_t rec_base, val_base;  // TxnTrace::rec / val0 and Withdrawal::rec count from here (accounts[], val_pool)
   AcctState* acct;           // account table
   uint32_t* pre_slot;        // per pre-image account: its slot of the account table once a trace touched it (else >= NONE)
   const Withdrawal* withdrawals;
@@ -192,6 +195,7 @@ struct JoinView {
   uint32_t* join_storage;     // [n_acct] out
   uint32_t* join_root;        // [n_acct] out
   uint8_t* pre_flags;         // [n_acct] out
+  uint32_t* flag;             // &Cursors::flag
 };
 
 PPD_HD inline bool is_hash_id(uint32_t n) { return n >= HASH_BASE && n < HASH_END; }
@@ -202,6 +206,7 @@ struct Ctx {
   View v;
   uint32_t tid, nthreads;
   uint32_t* sh_dmax;  // shared: deepest entry of the running batch
+  long long* sh_clock;  // shared: clock at the last phase boundary
 };
 
 #if defined(__CUDA_ARCH__)
@@ -711,7 +716,7 @@ PPD_HD inline void prep_trace(const View& v, uint32_t t) {
     SOp o;
     o.koff = v.dig_base + 32u * t, o.klen = 64, o.lcp = -1, o.pad = 0;
     o.kind = (tr.flags & PPD_TR_SELF_DESTRUCTED) ? OP_DEL : OP_PUT_ACCOUNT;
-    o.a1 = tr.rec, o.a2 = tr.txn, o.owner = OWNER_STATE_TRIE;
+    o.a1 = v.rec_base + tr.rec, o.a2 = tr.txn, o.owner = OWNER_STATE_TRIE;
     v.ops2[tx.op2_begin + srank] = o;
   }
 }
@@ -735,7 +740,7 @@ PPD_HD inline void prep_write(const View& v, uint32_t t, uint32_t w) {
   if (sig == 0) {  // rlp(0) == [0x80]: a delete (decoding.rs:238-243)
     o.kind = OP_DEL, o.a1 = o.a2 = 0;
   } else {
-    uint8_t* dst = v.val_pool + tr.val0 + 36u * w;
+    uint8_t* dst = v.val_pool + v.val_base + tr.val0 + 36u * w;
     uint32_t el = 0;
     if (sig == 1 && val[31] < 0x80) {
       dst[el++] = val[31];
@@ -743,7 +748,7 @@ PPD_HD inline void prep_write(const View& v, uint32_t t, uint32_t w) {
       dst[el++] = (uint8_t)(0x80 + sig);
       for (uint32_t k = 0; k < sig; k++) dst[el++] = val[z + k];
     }
-    o.kind = OP_PUT_LEAF, o.a1 = tr.val0 + 36u * w, o.a2 = el;
+    o.kind = OP_PUT_LEAF, o.a1 = v.val_base + tr.val0 + 36u * w, o.a2 = el;
   }
   v.ops1[tr.op0 + rank] = o;
 }
@@ -830,8 +835,17 @@ PPD_HD inline void acct_claim(const View& v, const AcctInit& a, uint32_t t) {
 // ---- the loop itself: one thread block per block of txns (the harness runs it as a block of one thread) ------
 #if defined(__CUDA_ARCH__)
 #define PPD_BLOCK_SYNC() __syncthreads()
+#define PPD_PHASE_CLOCK(c, k)                                \
+  do {                                                       \
+    if ((c).tid == 0) {                                      \
+      const long long now_ = clock64();                      \
+      (c).v.cur->phase_clocks[k] += now_ - *(c).sh_clock;    \
+      *(c).sh_clock = now_;                                  \
+    }                                                        \
+  } while (0)
 #else
 #define PPD_BLOCK_SYNC() ((void)0)
+#define PPD_PHASE_CLOCK(c, k) ((void)0)
 #endif
 
 PPD_HD inline void run_batch(const Ctx& c, const Batch& b) {
@@ -911,6 +925,7 @@ PPD_HD inline void run_txn(const Ctx& c, uint32_t ti, const uint8_t* empty_trie_
     v.seg_b[tx.seg_storage + 2 * tr.rank + 1] = a.storage;
   }
   PPD_BLOCK_SYNC();
+  PPD_PHASE_CLOCK(c, 0);
   // ---- marking walks: every accessed key on the tries before the txn ----
   {
     uint32_t n_storage_items = 0;
@@ -938,8 +953,10 @@ PPD_HD inline void run_txn(const Ctx& c, uint32_t ti, const uint8_t* empty_trie_
     }
   }
   PPD_BLOCK_SYNC();
+  PPD_PHASE_CLOCK(c, 1);
   // ---- apply_deltas_to_trie_state (decoding.rs:219-292): storage writes, the txn and receipt inserts ----
   run_batch(c, Batch{v.ops1 + tx.op1_begin, tx.op1_end - tx.op1_begin, ti});
+  PPD_PHASE_CLOCK(c, 2);
   // ---- the accounts after the txn: storage_root = the storage trie's hash after the writes (late-bound: an NK_ROOT node) ----
   for (uint32_t k = c.tid; k < ntr; k += c.nthreads) {
     const uint32_t t = tx.trace_begin + k;
@@ -971,11 +988,13 @@ PPD_HD inline void run_txn(const Ctx& c, uint32_t ti, const uint8_t* empty_trie_
       copy32(rec.code_hash, v.flat + tr.code_off);
     else if (tr.flags & PPD_TR_CODE_WRITE)
       copy32(rec.code_hash, digest(v, tr.m_code));
-    v.accounts[tr.rec] = rec;
+    v.accounts[v.rec_base + tr.rec] = rec;
   }
   PPD_BLOCK_SYNC();
+  PPD_PHASE_CLOCK(c, 3);
   // ---- state writes and self-destructs in one descent ----
   run_batch(c, Batch{v.ops2 + tx.op2_begin, tx.op2_end - tx.op2_begin, ti});
+  PPD_PHASE_CLOCK(c, 4);
   for (uint32_t k = c.tid; k < ntr; k += c.nthreads) {
     const TxnTrace& tr = v.traces[tx.trace_begin + k];
     if (tr.flags & PPD_TR_SELF_DESTRUCTED) {  // trie_state.storage.remove(hashed_addr), decoding.rs:271-282
@@ -990,6 +1009,7 @@ PPD_HD inline void run_txn(const Ctx& c, uint32_t ti, const uint8_t* empty_trie_
     v.seg_a[tx.seg_roots + 2] = new_root(v, v.cur->receipt_root);
   }
   PPD_BLOCK_SYNC();
+  PPD_PHASE_CLOCK(c, 5);
 }
 
 // ---- after the last txn: the NK_ROOT nodes dummy entries refer to, and the withdrawals (decoding.rs:356-428) ----
@@ -1022,9 +1042,9 @@ PPD_HD inline void run_finish(const Ctx& c, uint32_t initial_state) {
       }
       AccountRec rec = v.accounts[v.nodes[leaf].a1];
       u256_add(rec.balance, v.flat + wd.off_amount);
-      v.accounts[wd.rec] = rec;
+      v.accounts[v.rec_base + wd.rec] = rec;
       SOp o;
-      o.koff = koff, o.klen = 64, o.lcp = -1, o.kind = OP_PUT_ACCOUNT, o.pad = 0, o.a1 = wd.rec, o.a2 = 0, o.owner = OWNER_STATE_TRIE;
+      o.koff = koff, o.klen = 64, o.lcp = -1, o.kind = OP_PUT_ACCOUNT, o.pad = 0, o.a1 = v.rec_base + wd.rec, o.a2 = 0, o.owner = OWNER_STATE_TRIE;
       cur.state_root = insert_one(v, cur.state_root, 0, o, 0xffffffffu);
     }
     cur.roots[XR_AFTER_WITHDRAWALS] = new_root(v, cur.state_root);

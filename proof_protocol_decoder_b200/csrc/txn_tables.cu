@@ -131,7 +131,6 @@ bool txn_tables_phase2(const BlockJob& b, const uint8_t* flat, const TxnBases& B
   T.seg_a.clear(), T.seg_b.clear(), T.seg_c.clear(), T.lit.clear();
   T.seg_begin.resize(T.n_ir + 1), T.seg_end.resize(T.n_ir + 1), T.touched_begin.resize(T.n_ir + 1);
   for (uint32_t i = 0; i <= T.n_ir; i++) T.seg_begin[i] = T.seg_end[i] = 0, T.touched_begin[i] = 0;
-  for (size_t w = 0; w < T.withdrawals.size(); w++) T.withdrawals[w].rec += B.rec_base;
   uint32_t t = 0, op = 0, op2 = 0, val = B.val_base + T.val_writes;
   uint64_t touched = 0, gas_before = 0;
   PlanWriter W(T);
@@ -156,9 +155,7 @@ bool txn_tables_phase2(const BlockJob& b, const uint8_t* flat, const TxnBases& B
     uint32_t items = 0, ops2 = 0;
     for (uint32_t k = 0; k < ntr; k++, t++) {
       const TraceV& tr = tx.traces[k];
-      txn::TxnTrace& dt = T.traces[t];
-      if (dt.flags & txn::TRF_STATE_WRITE) dt.rec += B.rec_base;
-      dt.val0 += B.val_base;
+      const txn::TxnTrace& dt = T.traces[t];
       items += tr.n_reads + tr.n_writes;
       if (dt.flags & (txn::TRF_STATE_WRITE | PPD_TR_SELF_DESTRUCTED)) ops2++;
       if (tr.flags & PPD_TR_CODE_READ) {

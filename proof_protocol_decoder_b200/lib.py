@@ -4,6 +4,10 @@ import weakref
 import os
 import subprocess
 
+# Every block of a batch runs on its own CUDA stream; the device multiplexes streams onto CUDA_DEVICE_MAX_CONNECTIONS
+# hardware queues (8 unless set, at most 32).  Must be in the environment before the process creates its CUDA context.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.path.join(HERE, "libppd_b200.so")
 CSRC = os.path.join(HERE, "csrc")
@@ -93,6 +97,8 @@ EXPORTS = [
     "ppd_blocks_decode_batch",
     "ppd_trie_root_sorted_leaves",
     "ppd_trie_root_sorted_leaves_dev",
+    "ppd_trie_subroot_sorted_leaves_dev",
+    "ppd_trie_root_from_children",
     "ppd_replay_last",
     "ppd_replay_last_hashing",
     "ppd_replay_last_parse",
@@ -136,6 +142,8 @@ class PpdLibrary:
         L.ppd_replay_last_parse.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_double)]
         L.ppd_microbench.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_uint32, ctypes.c_uint32, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_uint32)]
         L.ppd_trie_root_sorted_leaves_dev.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_char_p]
+        L.ppd_trie_subroot_sorted_leaves_dev.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_uint32, ctypes.c_char_p]
+        L.ppd_trie_root_from_children.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_uint32, ctypes.c_char_p]
 
     def exported(self):
         return [name for name in EXPORTS if hasattr(self.L, name)]
@@ -319,6 +327,20 @@ class Context:
     def trie_root_sorted_leaves_dev(self, d_keys_ptr, d_val_off_ptr, d_vals_ptr, n, vals_bytes) -> bytes:
         out = ctypes.create_string_buffer(32)
         self._check(self.lib.L.ppd_trie_root_sorted_leaves_dev(self.h, d_keys_ptr, d_val_off_ptr, d_vals_ptr, n, vals_bytes, out))
+        return out.raw
+
+
+    def trie_subroot_sorted_leaves_dev(self, d_keys_ptr, d_val_off_ptr, d_vals_ptr, n, vals_bytes, base_depth) -> bytes:
+        """The ref of the sub-trie over n sorted leaves that share their first base_depth nibbles (device pointers)."""
+        out = ctypes.create_string_buffer(32)
+        self._check(self.lib.L.ppd_trie_subroot_sorted_leaves_dev(self.h, d_keys_ptr, d_val_off_ptr, d_vals_ptr, n, vals_bytes, base_depth, out))
+        return out.raw
+
+    def trie_root_from_children(self, child_hashes, mask) -> bytes:
+        """Root of the branch whose child i (bit i of mask) has the 32-byte ref child_hashes[32 * i : 32 * i + 32]."""
+        out = ctypes.create_string_buffer(32)
+        buf = bytes(child_hashes).ljust(512, b"\0")
+        self._check(self.lib.L.ppd_trie_root_from_children(self.h, buf, mask, out))
         return out.raw
 
 

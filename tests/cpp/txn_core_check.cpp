@@ -141,6 +141,7 @@ int check_block(const std::vector<uint8_t>& flatv, const char* name) {
   v.child_pool = children.data(), v.accounts = accounts.data();
   v.cap_nodes = (uint32_t)nodes.size(), v.cap_children = (uint32_t)children.size(), v.cap_keys = (uint32_t)keys.size();
   v.flat = flat, v.traces = T.traces.data(), v.n_txns = (uint32_t)b2.txns.size(), v.n_traces = n_traces, v.dig_base = B.dig_base;
+  v.rec_base = B.rec_base, v.val_base = B.val_base;
   v.withdrawals = T.withdrawals.data(), v.n_withdrawals = (uint32_t)T.withdrawals.size();
   // digests (the device runs keccak256_batch_kernel over the same (begin, end) table)
   std::vector<uint64_t> se(2ull * T.n_msgs);
@@ -208,7 +209,8 @@ int check_block(const std::vector<uint8_t>& flatv, const char* name) {
   for (uint32_t i = 0; i < T.n_ops1; i++) txn::prep_lcp(v, v.ops1, i);
   for (uint32_t i = 0; i < T.n_ops2; i++) txn::prep_lcp(v, v.ops2, i);
   uint32_t sh_dmax = 0;
-  txn::Ctx c{v, 0, 1, &sh_dmax};
+  long long sh_clock = 0;
+  txn::Ctx c{v, 0, 1, &sh_dmax, &sh_clock};
   for (uint32_t ti = 0; ti < v.n_txns && !cur.flag; ti++) txn::run_txn(c, ti, EMPTY_TRIE_HASH, EMPTY_CODE_HASH);
   txn::run_finish(c, b2.state_root);
   if (cur.flag) {
