@@ -407,7 +407,10 @@ def test_gpu_parse_blocks_match_host_builder(ctx, oracle, seed):
     assert a == b == oracle.block_decode(blk.flat)
     assert sa["witnesses_on_gpu"] == 1 and sb["witnesses_on_gpu"] == 0
     assert sa["witness_instructions"] > 1500
-    assert sa["nodes_hashed"] == sb["nodes_hashed"] and sa["node_bytes"] == sb["node_bytes"]
+    # (with the witness parsed on the GPU the txn loop runs there too and builds fewer unobserved trie versions than the
+    # host loop, which the host-parsed block takes: the node counts of the two differ, the outputs do not)
+    assert sa["txn_loops_on_gpu"] == 1 and sb["txn_loops_on_gpu"] == 0
+    assert sa["nodes_hashed"] <= sb["nodes_hashed"]
 
 
 def test_gpu_parse_declines_non_canonical_and_malformed(ctx, oracle, goldens):
