@@ -102,6 +102,8 @@ void after_emit(void* arg, const ParseEmit& E) {
     H.d_withdrawals = c.take<txn::Withdrawal>(T.withdrawals.size() + 1);
     H.d_export = c.take<txn::AcctExport>(T.needs_dummies() ? n_acct + 1 : 1);
     v.path_node = c.take<uint32_t>((size_t)T.max_ops * txn::PATH_CAP + 1);
+    v.path_a0 = c.take<uint32_t>((size_t)T.max_ops * txn::PATH_CAP + 1);
+    v.path_a1 = c.take<uint32_t>((size_t)T.max_ops * txn::PATH_CAP + 1);
     v.path_depth = c.take<uint8_t>((size_t)T.max_ops * txn::PATH_CAP + 1);
     v.plen = c.take<uint8_t>(T.max_ops + 1);
     v.top = c.take<uint8_t>(T.max_ops + 1);
@@ -109,7 +111,6 @@ void after_emit(void* arg, const ParseEmit& E) {
     v.tdepth = c.take<uint8_t>(T.max_ops + 1);
     v.tkind = c.take<uint8_t>(T.max_ops + 1);
     v.res = c.take<uint32_t>(T.max_ops + 1);
-    v.acct_leaf = c.take<uint32_t>(T.max_traces + 1);
     v.cur = c.take<txn::Cursors>(1);
     H.bins_pre = c.take<uint32_t>(ORDER_MAX_BINS);
     H.bins_tail = c.take<uint32_t>(ORDER_MAX_BINS);
@@ -329,11 +330,10 @@ int gpu_block(ppd_ctx* c, Lane* L, Job& J, const uint8_t* flat, size_t len, uint
   H.j.flag = &v.cur->flag;
   launch_join(H.j, st);
   H.ai = txn::AcctInit{H.table_slots - 1, b.state_root, H.j.join_storage, H.j.join_root};
-  uint32_t max_writes = 0;
-  for (size_t t = 0; t < T.traces.size(); t++) max_writes = std::max(max_writes, T.traces[t].n_writes);
+  const uint32_t max_writes = T.max_trace_keys;
   L->stats.kernel_launches += 3 + launch_txn_prep(v, H.ai, T.n_ops1, T.n_ops2, max_writes, st);
   CUDA_OK(cudaEventRecord(L->ev_loop0, st));
-  L->stats.kernel_launches += launch_txn_loop(v, b.state_root, st);
+  L->stats.kernel_launches += launch_txn_loop(v, b.state_root, T.max_ops, st);
   CUDA_OK(cudaEventRecord(L->ev_loop1, st));
   // ---- the loop's nodes sorted by (level, class) ----
   L->d_order2.reserve(4ull * H.cap_tail + 16);
@@ -430,7 +430,7 @@ int gpu_block(ppd_ctx* c, Lane* L, Job& J, const uint8_t* flat, size_t len, uint
   L->last_level_start = level_pre, L->last_level_start2 = level_tail, L->last_n_msgs = T.n_msgs;
   L->last_msg_data = d_flat, L->last_msg_se = H.se, L->last_digest_out = v.key_pool + H.B.dig_base;
   L->last_txn = H.v, L->last_join = H.j, L->last_ai = H.ai, L->last_init = init, L->last_table_slots = H.table_slots;
-  L->last_n_ops1 = T.n_ops1, L->last_n_ops2 = T.n_ops2, L->last_max_writes = max_writes, L->last_n_touched = n_touched;
+  L->last_n_ops1 = T.n_ops1, L->last_n_ops2 = T.n_ops2, L->last_max_writes = max_writes, L->last_n_touched = n_touched, L->last_max_keys = T.max_ops;
   L->last_plan = P, L->last_n_ir = n_ir, L->has_last_txn = true;
   L->last_cap_tail = H.cap_tail, L->last_bins_tail = H.bins_tail, L->last_okeys = H.okeys;
   // an IR the dump kernels cannot lay out (an untouched node shorter than 32 bytes that the subset keeps expanded, more

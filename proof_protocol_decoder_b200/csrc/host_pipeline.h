@@ -86,7 +86,7 @@ struct Lane {
   txn::JoinView last_join{};
   txn::AcctInit last_ai{};
   txn::Cursors last_init{};
-  uint32_t last_table_slots = 0, last_n_ops1 = 0, last_n_ops2 = 0, last_max_writes = 0, last_n_touched = 0, last_n_ir = 0, last_cap_tail = 0;
+  uint32_t last_table_slots = 0, last_n_ops1 = 0, last_n_ops2 = 0, last_max_writes = 0, last_n_touched = 0, last_n_ir = 0, last_cap_tail = 0, last_max_keys = 0;
   uint32_t* last_bins_tail = nullptr;
   uint16_t* last_okeys = nullptr;
   IrDumpPlanView last_plan{};

@@ -586,7 +586,7 @@ static void replay_lane(Lane* L, unsigned what) {
     launch_txn_init(v, L->last_init, L->last_table_slots, st);
     launch_join(L->last_join, st);
     launch_txn_prep(v, L->last_ai, L->last_n_ops1, L->last_n_ops2, L->last_max_writes, st);
-    launch_txn_loop(v, L->last_init.state_root, st);
+    launch_txn_loop(v, L->last_init.state_root, L->last_max_keys, st);
     CUDA_OK(cudaMemsetAsync(L->last_bins_tail, 0, 4ull * ORDER_MAX_BINS, st));
     launch_order_by_level_class(v.nodes, v.level, L->last_cap_tail, ORDER_MAX_BINS, L->last_okeys, L->last_bins_tail, L->d_order2.as<uint32_t>(), st,
                                 L->last_init.n_nodes, &v.cur->n_nodes);

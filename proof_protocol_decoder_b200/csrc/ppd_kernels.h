@@ -179,7 +179,8 @@ void launch_txn_msgs(const txn::View& v, uint64_t* se, cudaStream_t st);
 void launch_txn_init(const txn::View& v, const txn::Cursors& init, uint32_t table_slots, cudaStream_t st);
 void launch_join(const txn::JoinView& j, cudaStream_t st);
 uint32_t launch_txn_prep(const txn::View& v, const txn::AcctInit& a, uint32_t n_ops1, uint32_t n_ops2, uint32_t max_writes, cudaStream_t st);
-uint32_t launch_txn_loop(const txn::View& v, uint32_t initial_state, cudaStream_t st);  // returns the number of launches
+// max_keys: the most keys (accessed + written) any txn of the block has; returns the number of launches
+uint32_t launch_txn_loop(const txn::View& v, uint32_t initial_state, uint32_t max_keys, cudaStream_t st);
 void launch_acct_export(const txn::View& v, const txn::JoinView& j, txn::AcctExport* out, cudaStream_t st);
 
 // ---- ppd_microbench.cu ----

@@ -101,10 +101,10 @@ __global__ void prep_trace_kernel(View v) {
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t < v.n_traces) prep_trace(v, t);
 }
-// grid (trace, chunk of its writes)
-__global__ void prep_write_kernel(View v) {
-  const uint32_t t = blockIdx.x, w = blockIdx.y * blockDim.x + threadIdx.x;
-  if (w < v.traces[t].n_writes) prep_write(v, t, w);
+// grid (trace, chunk of its storage keys)
+__global__ void prep_storage_key_kernel(View v) {
+  const uint32_t t = blockIdx.x, k = blockIdx.y * blockDim.x + threadIdx.x;
+  if (k < v.traces[t].n_keys) prep_storage_key(v, t, k);
 }
 __global__ void prep_txn_kernel(View v) {
   const uint32_t ti = blockIdx.x * blockDim.x + threadIdx.x;
@@ -125,10 +125,22 @@ __global__ void acct_export_kernel(View v, const uint32_t* __restrict__ acct_lis
 }
 
 constexpr int LOOP_THREADS = 256;
+constexpr uint32_t SH_KEYS = 512;  // keys of one txn whose scratch fits in shared memory
+struct LoopShared {
+  uint32_t path_node[SH_KEYS * PATH_CAP], path_a0[SH_KEYS * PATH_CAP], path_a1[SH_KEYS * PATH_CAP];
+  uint32_t tnode[SH_KEYS], res[SH_KEYS];
+  SOp ops[SH_KEYS];
+  uint8_t path_depth[SH_KEYS * PATH_CAP];
+  uint8_t plen[SH_KEYS], top[SH_KEYS], tdepth[SH_KEYS], tkind[SH_KEYS];
+};
 // txns [ti0, ti1) of the block.  The loop of a block is launched in chunks so that the kernels of another lane that
-// shares the hardware queue (the device has at most 32 of them) are not held up behind one 20 ms kernel.
-__global__ void __launch_bounds__(LOOP_THREADS, 1) txn_loop_kernel(View v, uint32_t initial_state, uint32_t ti0, uint32_t ti1, uint32_t finish) {
-  __shared__ uint32_t sh_dmax, sh_stop, sh_cursor[4];
+// shares the hardware queue (the device has at most 32 of them) are not held up behind one long kernel.  use_shared: the
+// scratch of a txn (path, terminal, result per key) and its keys live in shared memory: every step of the re-assembly
+// then costs one trip to L2 / HBM (the child table) instead of four.
+__global__ void __launch_bounds__(LOOP_THREADS, 1) txn_loop_kernel(View v, uint32_t initial_state, uint32_t ti0, uint32_t ti1, uint32_t finish,
+                                                                   uint32_t use_shared) {
+  extern __shared__ __align__(16) uint8_t loop_smem[];
+  __shared__ uint32_t sh_dmax[2], sh_stop, sh_cursor[4];
   __shared__ long long sh_clock;
   if (threadIdx.x == 0) {
     sh_clock = clock64();
@@ -136,9 +148,14 @@ __global__ void __launch_bounds__(LOOP_THREADS, 1) txn_loop_kernel(View v, uint3
     sh_stop = *reinterpret_cast<volatile uint32_t*>(&v.cur->flag);
   }
   v.a_nodes = &sh_cursor[0], v.a_children = &sh_cursor[1], v.a_keys = &sh_cursor[2], v.a_max_level = &sh_cursor[3];
+  if (use_shared) {
+    LoopShared& S = *reinterpret_cast<LoopShared*>(loop_smem);
+    v.path_node = S.path_node, v.path_a0 = S.path_a0, v.path_a1 = S.path_a1, v.path_depth = S.path_depth;
+    v.plen = S.plen, v.top = S.top, v.tnode = S.tnode, v.tdepth = S.tdepth, v.tkind = S.tkind, v.res = S.res, v.sh_ops = S.ops;
+  }
   __syncthreads();
   if (sh_stop) return;  // an earlier chunk (or the join) raised a flag: the host path redoes the block
-  Ctx c{v, threadIdx.x, blockDim.x, &sh_dmax, &sh_clock};
+  Ctx c{v, threadIdx.x, blockDim.x, sh_dmax, &sh_clock};
   for (uint32_t ti = ti0; ti < ti1; ti++) {
     run_txn(c, ti, C_EMPTY_TRIE, C_EMPTY_CODE);
     // a raised flag ends the loop; one thread reads it so that the decision is uniform
@@ -176,7 +193,7 @@ uint32_t launch_txn_prep(const View& v, const AcctInit& a, uint32_t n_ops1, uint
     launches += 2;
     if (max_writes) {
       const uint32_t threads = max_writes >= 64 ? 128 : 32;
-      prep_write_kernel<<<dim3(v.n_traces, cdiv(max_writes, threads)), threads, 0, st>>>(v);
+      prep_storage_key_kernel<<<dim3(v.n_traces, cdiv(max_writes, threads)), threads, 0, st>>>(v);
       launches++;
     }
   }
@@ -187,7 +204,14 @@ uint32_t launch_txn_prep(const View& v, const AcctInit& a, uint32_t n_ops1, uint
   }
   return launches;
 }
-uint32_t launch_txn_loop(const View& v, uint32_t initial_state, cudaStream_t st) {
+uint32_t launch_txn_loop(const View& v, uint32_t initial_state, uint32_t max_keys, cudaStream_t st) {
+  static const bool attr = [] {
+    cudaFuncSetAttribute(txn_loop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LoopShared));
+    return true;
+  }();
+  (void)attr;
+  const uint32_t use_shared = max_keys <= SH_KEYS ? 1u : 0u;  // max_keys: the most keys any txn of the block has
+  const size_t smem = use_shared ? sizeof(LoopShared) : 0;
   static const uint32_t chunk = [] {
     const char* e = getenv("PPD_LOOP_CHUNK");
     const int x = e ? atoi(e) : 16;
@@ -196,7 +220,7 @@ uint32_t launch_txn_loop(const View& v, uint32_t initial_state, cudaStream_t st)
   uint32_t launches = 0;
   for (uint32_t t0 = 0; t0 < v.n_txns || launches == 0; t0 += chunk) {
     const uint32_t t1 = t0 + chunk < v.n_txns ? t0 + chunk : v.n_txns;
-    txn_loop_kernel<<<1, LOOP_THREADS, 0, st>>>(v, initial_state, t0, t1, t1 == v.n_txns ? 1u : 0u);
+    txn_loop_kernel<<<1, LOOP_THREADS, smem, st>>>(v, initial_state, t0, t1, t1 == v.n_txns ? 1u : 0u, use_shared);
     launches++;
   }
   return launches;

@@ -3,7 +3,7 @@
 // runs the __device__ instantiation, ppd_txn.cu).
 //
 // What it replaces: per txn
-//   create_minimal_partial_tries_needed_by_txn  decoding.rs:179-217, 551-602  -> marking walks (mark_item)
+//   create_minimal_partial_tries_needed_by_txn  decoding.rs:179-217, 551-602  -> every key's walk marks what it visits (batch_walk)
 //   apply_deltas_to_trie_state                  decoding.rs:219-292, 431-456  -> two batched trie updates (Batch)
 //   eth_trie_utils insert / delete / get                       -> path copies on the arena in HBM
 //
@@ -11,8 +11,9 @@
 // before anything is hashed, as new records appended to the arena (nodes are immutable, old versions stay
 // addressable, unchanged subtrees are shared).  One thread block runs the whole txn loop of one block; the txns
 // are sequential, the keys of one txn are parallel:
-//   * every key walks the current version from the root and records the nodes it passes (its path) and where
-//     it ends (its terminal: an empty slot, a leaf, a hashed-out node, or the middle of an extension);
+//   * every key the txn accesses or writes walks the version before the txn ONCE: the walk marks the nodes it visits
+//     (the subset of the txn keeps those expanded) and records the nodes it passes (its path) and where it ends (its
+//     terminal: an empty slot, a leaf, a hashed-out node, or the middle of an extension);
 //   * keys are sorted per trie (op_rank) with the LCP of neighbours (op_lcp), so "the keys that pass through
 //     the node at depth d on my path" is a contiguous range and its first key, the OWNER, is the one whose LCP
 //     with its predecessor is < d;
@@ -45,8 +46,8 @@ static const uint32_t T_UNCHANGED = 0xfffffffeu;  // batch result: the subtree d
 static const uint32_t ST_ABSENT = 0xfffffffeu;    // AcctState::storage: no entry in the storage map (decoding.rs:572-582)
 static const uint32_t NONE = 0xfffffffdu;
 static const uint32_t HASH_BASE = 0x80000000u, HASH_END = 0xf0000000u;
-static const uint32_t MARK_SLOTS_T = 16;  // == MARK_SLOTS (ppd_kernels.h)
-static const uint32_t PATH_CAP = 24;      // nodes a batched key may pass before its terminal
+static const uint32_t MARK_SLOTS_T = 16;  // == MARK_SLOTS (ppd_kernels.h): touched slots per key
+static const uint32_t PATH_CAP = 15;      // nodes a key may pass before its terminal (the path and the terminal fill the key's touched slots)
 static const uint32_t OWNER_TXN_TRIE = 0xffffff01u, OWNER_RECEIPT_TRIE = 0xffffff02u, OWNER_STATE_TRIE = 0xffffff03u;
 static const uint32_t TRF_STATE_WRITE = 0x100u;   // TxnTrace::flags: the trace changes the account (processed_block_trace.rs:238-256)
 static const uint32_t TRF_MIN_KEYS = 0x200u;      // a written slot key has a leading zero byte: decoding.rs:235 hashes the shortened key
@@ -70,10 +71,12 @@ enum : uint32_t {
   TXF_SHARED_TRIE = 15,      // the by-root join gives two accounts the SAME witnessed trie: the host path clones it, as the reference does
 };
 
-enum : uint8_t { OP_DEL = 0, OP_PUT_LEAF = 1, OP_PUT_ACCOUNT = 2 };
+enum : uint8_t { OP_DEL = 0, OP_PUT_LEAF = 1, OP_PUT_ACCOUNT = 2, OP_NONE = 3 };  // OP_NONE: a key that is only accessed
+enum : uint8_t { SOP_MARK = 1 };  // SOp::pad: the key is one the txn ACCESSES (its walk is a marking walk of create_trie_subset)
 enum : uint8_t { TK_EMPTY = 0, TK_LEAF_SAME = 1, TK_LEAF_OTHER = 2, TK_HASH = 3, TK_DIVERGE = 4, TK_BAD = 5 };
 
-// One write of a batch, in sorted order.
+// One key of a txn, in sorted order within its trie: an accessed key (marking walk only), a write (which is an access
+// too, unless decoding.rs:235 hashed a shortened slot key for it), a delete.
 struct SOp {
   uint32_t koff;   // key in key_pool
   uint32_t a1, a2; // PUT_LEAF: value offset, length; PUT_ACCOUNT: account record
@@ -91,8 +94,8 @@ struct TxnTrace {
   uint32_t off_reads, n_reads, off_writes, n_writes;
   uint32_t code_off, code_len;
   uint32_t m_reads, m_wfull, m_wmin, m_code;  // digest indices (the address digest of trace t is digest t)
-  uint32_t op0;    // first round-1 op of the trace (n_writes of them)
-  uint32_t item0;  // first storage marking walk, relative to the txn's first walk
+  uint32_t op0;    // first round-1 key of the trace: its slot reads, its slot writes (twice with TRF_MIN_KEYS: the full and the shortened key)
+  uint32_t n_keys; // how many
   uint32_t rec;    // account record its state write fills
   uint32_t val0;   // val_pool offset of its first written value (36 bytes apart)
   uint32_t acct;   // (device) account table slot
@@ -171,16 +174,19 @@ struct View {
   uint32_t* touched;
   uint32_t* seg_a;
   uint32_t* seg_b;
-  // scratch, sized for the largest batch of the block
-  uint32_t* path_node;  // [max_ops][PATH_CAP]
-  uint8_t* path_depth;  // [max_ops][PATH_CAP]
-  uint8_t* plen;        // [max_ops]
-  uint8_t* top;         // [max_ops]
-  uint32_t* tnode;      // [max_ops] terminal node
-  uint8_t* tdepth;      // [max_ops]
-  uint8_t* tkind;       // [max_ops]
-  uint32_t* res;        // [max_ops]
-  uint32_t* acct_leaf;  // [max traces per txn] state leaf of the trace's address before the txn
+  // scratch of the running txn, indexed by key (round-1 keys first, then the state keys); in shared memory when the
+  // txn's keys fit (ppd_txn.cu), else in HBM
+  uint32_t* path_node;  // [keys][PATH_CAP] nodes passed, root first
+  uint32_t* path_a0;    // [keys][PATH_CAP] their NodeRec::a0 (branch: first child slot; extension: key offset) ...
+  uint32_t* path_a1;    // [keys][PATH_CAP] ... and a1 (branch: child mask; extension: child), so that re-assembly does not re-read the records
+  uint8_t* path_depth;  // [keys][PATH_CAP] nibble depth at which the node starts | 0x80 for an extension
+  uint8_t* plen;        // [keys]
+  uint8_t* top;         // [keys]
+  uint32_t* tnode;      // [keys] terminal node
+  uint8_t* tdepth;      // [keys]
+  uint8_t* tkind;       // [keys]
+  uint32_t* res;        // [keys]
+  SOp* sh_ops;          // [keys] copy of the txn's keys when the scratch is in shared memory, else nullptr
   Cursors* cur;
 };
 
@@ -205,7 +211,7 @@ PPD_HD inline bool is_hash_id(uint32_t n) { return n >= HASH_BASE && n < HASH_EN
 struct Ctx {
   View v;
   uint32_t tid, nthreads;
-  uint32_t* sh_dmax;  // shared: deepest entry of the running batch
+  uint32_t* sh_dmax;  // shared [2]: deepest path entry of the txn's two batches
   long long* sh_clock;  // shared: clock at the last phase boundary
 };
 
@@ -269,6 +275,13 @@ PPD_HD inline uint32_t alloc_children(const View& v, uint32_t k) {
 }
 PPD_HD inline uint32_t common_prefix(const View& v, uint32_t ka, uint32_t sa, uint32_t kb, uint32_t sb, uint32_t m) {
   uint32_t i = 0;
+  if (((sa ^ sb) & 1u) == 0) {  // same parity (always, for nodes on a key's own path): whole bytes at a time
+    if ((sa & 1u) && i < m) {
+      if (key_nib(v, ka, sa) != key_nib(v, kb, sb)) return 0;
+      i = 1;
+    }
+    while (i + 2 <= m && v.key_pool[ka + ((sa + i) >> 1)] == v.key_pool[kb + ((sb + i) >> 1)]) i += 2;
+  }
   while (i < m && key_nib(v, ka, sa + i) == key_nib(v, kb, sb + i)) i++;
   return i;
 }
@@ -452,47 +465,11 @@ PPD_HD inline uint32_t insert_one(const View& v, uint32_t base, uint32_t depth, 
   return result;
 }
 
-// ---- marking walk (create_trie_subset's mark_nodes_that_are_needed); returns the leaf holding the key or NODE_EMPTY ----
-PPD_HD inline uint32_t mark_item(const View& v, uint32_t root, uint32_t koff, uint32_t klen, uint32_t* out, uint32_t txn) {
-  uint32_t node = root, pos = 0, cnt = 0;
-  while (node != NODE_EMPTY) {
-    if (cnt == MARK_SLOTS_T) {
-      raise(v, TXF_MARK_SLOTS, txn);
-      break;
-    }
-    out[cnt++] = node;
-    if (is_hash_id(node)) {
-      if (pos < klen) raise(v, TXF_MARK_INTO_HASH, txn);
-      break;
-    }
-    const NodeRec r = v.nodes[node];
-    const uint32_t kind = r.w0 & 0xffu;
-    if (kind == NK_ROOT) {
-      if (pos < klen) raise(v, TXF_MARK_INTO_HASH, txn);
-      break;
-    }
-    if (kind == NK_BRANCH) {
-      if (pos >= klen) break;
-      node = child_at(v, r, key_nib(v, koff, pos));
-      pos++;
-    } else if (kind == NK_EXT) {
-      const uint32_t es = (r.w0 >> 8) & 0xffu, el = (r.w0 >> 16) & 0xffu, avail = klen - pos, m = avail < el ? avail : el;
-      if (common_prefix(v, r.a0, es, koff, pos, m) != m || avail < el) break;
-      pos += el;
-      node = r.a1;
-    } else {
-      const uint32_t ls = (r.w0 >> 8) & 0xffu, ll = (r.w0 >> 16) & 0xffu;
-      if (ll == klen - pos && common_prefix(v, r.a0, ls, koff, pos, ll) == ll) return node;
-      break;
-    }
-  }
-  return NODE_EMPTY;
-}
-
-// ---- one batched update: ops[0 .. n) sorted by (trie, key) ----------------------------------------------------
+// ---- one batched update: ops[0 .. n) sorted by (trie, key); scratch entries base .. base + n ----------------------
 struct Batch {
   const SOp* ops;
   uint32_t n;
+  uint32_t base;  // index of ops[0] in the scratch arrays
   uint32_t txn;
 };
 
@@ -503,24 +480,32 @@ PPD_HD inline uint32_t trie_root_of(const View& v, uint32_t owner) {
   return v.acct[v.traces[owner].acct].storage;
 }
 
-// phase 1: the walk of op i
-PPD_HD inline void batch_walk(const Ctx& c, const Batch& b, uint32_t i) {
+// The walk of key i down the current version of its trie.  It is the key's marking walk (the nodes it visits go to the
+// IR's touched list: create_trie_subset keeps exactly those expanded) AND the first half of its write: the nodes passed
+// (with their child tables' whereabouts) and where the key ends are kept for the re-assembly.
+PPD_HD inline void batch_walk(const Ctx& c, const Batch& b, uint32_t i, uint32_t* touched, uint32_t* dmax) {
   const View& v = c.v;
   const SOp o = b.ops[i];
-  uint32_t node = trie_root_of(v, o.owner), pos = 0, pl = 0, deepest = 0;
-  uint32_t* pn = v.path_node + (size_t)i * PATH_CAP;
-  uint8_t* pd = v.path_depth + (size_t)i * PATH_CAP;
+  const uint32_t e = b.base + i;
+  uint32_t node = trie_root_of(v, o.owner), pos = 0, pl = 0, deepest = 0, nt = 0;
+  uint32_t* pn = v.path_node + (size_t)e * PATH_CAP;
+  uint32_t* pa0 = v.path_a0 + (size_t)e * PATH_CAP;
+  uint32_t* pa1 = v.path_a1 + (size_t)e * PATH_CAP;
+  uint8_t* pd = v.path_depth + (size_t)e * PATH_CAP;
   uint32_t tk = TK_EMPTY, tn = NODE_EMPTY, td = 0;
-  const bool put = o.kind != OP_DEL;
+  const bool put = o.kind == OP_PUT_LEAF || o.kind == OP_PUT_ACCOUNT, mark = (o.pad & SOP_MARK) != 0;
   for (;;) {
     if (node == NODE_EMPTY) {
       tk = TK_EMPTY, td = pos;
       break;
     }
+    if (mark) touched[nt] = node;
+    nt++;
     const uint32_t k = kind_of(v, node);
     if (k == NK_HASH || k == NK_ROOT) {
       tk = TK_HASH, tn = node, td = pos;
       if (put) raise(v, TXF_INSERT_INTO_HASH, b.txn);
+      if (mark && pos < o.klen) raise(v, TXF_MARK_INTO_HASH, b.txn);  // MissingKeysCreatingSubPartialTrie
       break;
     }
     const NodeRec r = v.nodes[node];
@@ -535,7 +520,7 @@ PPD_HD inline void batch_walk(const Ctx& c, const Batch& b, uint32_t i) {
         tk = TK_BAD, tn = node, td = pos;
         break;
       }
-      pn[pl] = node, pd[pl] = (uint8_t)pos, pl++;
+      pn[pl] = node, pa0[pl] = r.a0, pa1[pl] = r.a1, pd[pl] = (uint8_t)pos, pl++;
       deepest = pos;
       node = child_at(v, r, key_nib(v, o.koff, pos));
       pos++;
@@ -548,7 +533,7 @@ PPD_HD inline void batch_walk(const Ctx& c, const Batch& b, uint32_t i) {
           tk = TK_BAD, tn = node, td = pos;
           break;
         }
-        pn[pl] = node, pd[pl] = (uint8_t)pos, pl++;
+        pn[pl] = node, pa0[pl] = r.a0, pa1[pl] = r.a1, pd[pl] = (uint8_t)(pos | 0x80u), pl++;
         deepest = pos;
         node = r.a1;
         pos += nl;
@@ -567,93 +552,100 @@ PPD_HD inline void batch_walk(const Ctx& c, const Batch& b, uint32_t i) {
       break;
     }
   }
-  v.plen[i] = (uint8_t)pl, v.top[i] = (uint8_t)pl;
-  v.tnode[i] = tn, v.tdepth[i] = (uint8_t)td, v.tkind[i] = (uint8_t)tk;
-  v.res[i] = T_UNCHANGED;
-  if (pl || tk == TK_DIVERGE) PPD_ATOMIC_MAX(c.sh_dmax, deepest + 1u);  // (depth + 1: 0 means no entry anywhere)
+  if (nt > MARK_SLOTS_T) raise(v, TXF_MARK_SLOTS, b.txn);  // (unreachable: PATH_CAP + 1 slots)
+  v.plen[e] = (uint8_t)pl, v.top[e] = (uint8_t)pl;
+  v.tnode[e] = tn, v.tdepth[e] = (uint8_t)td, v.tkind[e] = (uint8_t)tk;
+  v.res[e] = T_UNCHANGED;
+  if (pl || tk == TK_DIVERGE) PPD_ATOMIC_MAX(dmax, deepest + 1u);  // (depth + 1: 0 means no entry anywhere)
 }
 
-// phase 2: terminals resolved by their owners (the first key of the group that ends at the same place)
+// terminals resolved by their owners (the first key of the group that ends at the same place)
 PPD_HD inline void batch_terminal(const Ctx& c, const Batch& b, uint32_t i) {
   const View& v = c.v;
-  const uint32_t tk = v.tkind[i], td = v.tdepth[i];
+  const uint32_t e = b.base + i;
+  const uint32_t tk = v.tkind[e], td = v.tdepth[e];
   if (tk == TK_DIVERGE || tk == TK_HASH || tk == TK_BAD) return;  // the extension is handled with the path nodes
   if ((int)b.ops[i].lcp >= (int)td) return;                       // shares the terminal with its predecessor
-  uint32_t base = tk == TK_EMPTY ? NODE_EMPTY : v.tnode[i];
+  uint32_t base = tk == TK_EMPTY ? NODE_EMPTY : v.tnode[e];
   bool changed = false;
   // a delete of the leaf's own key first, then the inserts (the order of distinct keys does not matter)
   for (uint32_t j = i; j < b.n && (j == i || (int)b.ops[j].lcp >= (int)td); j++)
-    if (b.ops[j].kind == OP_DEL && v.tkind[j] == TK_LEAF_SAME) base = NODE_EMPTY, changed = true;
+    if (b.ops[j].kind == OP_DEL && v.tkind[b.base + j] == TK_LEAF_SAME) base = NODE_EMPTY, changed = true;
   for (uint32_t j = i; j < b.n && (j == i || (int)b.ops[j].lcp >= (int)td); j++)
-    if (b.ops[j].kind != OP_DEL) base = insert_one(v, base, td, b.ops[j], b.txn), changed = true;
-  v.res[i] = changed ? base : T_UNCHANGED;
+    if (b.ops[j].kind == OP_PUT_LEAF || b.ops[j].kind == OP_PUT_ACCOUNT) base = insert_one(v, base, td, b.ops[j], b.txn), changed = true;
+  v.res[e] = changed ? base : T_UNCHANGED;
 }
 
-// phase 3, once per depth d from the deepest entry up to 0: the owner of the path node that starts at depth d
-// creates its new version from the results of the children its range touched
+// once per depth d from the deepest entry up to 0: the owner of the path node that starts at depth d creates its new
+// version from the results of the children its range touched
 PPD_HD inline void batch_assemble(const Ctx& c, const Batch& b, uint32_t i, uint32_t d) {
   const View& v = c.v;
-  uint32_t node;
-  const uint32_t t = v.top[i];
-  if (t > 0 && v.path_depth[(size_t)i * PATH_CAP + t - 1] == d) {
-    node = v.path_node[(size_t)i * PATH_CAP + t - 1];
-    v.top[i] = (uint8_t)(t - 1);
-  } else if (v.tkind[i] == TK_DIVERGE && v.tdepth[i] == d) {
-    node = v.tnode[i];
+  const uint32_t e = b.base + i;
+  uint32_t node, a0, a1;
+  bool is_ext;
+  const uint32_t t = v.top[e];
+  if (t > 0 && (v.path_depth[(size_t)e * PATH_CAP + t - 1] & 0x7fu) == d) {
+    const size_t at = (size_t)e * PATH_CAP + t - 1;
+    node = v.path_node[at], a0 = v.path_a0[at], a1 = v.path_a1[at], is_ext = (v.path_depth[at] & 0x80u) != 0;
+    v.top[e] = (uint8_t)(t - 1);
+  } else if (v.tkind[e] == TK_DIVERGE && v.tdepth[e] == d) {
+    node = v.tnode[e], is_ext = true;
+    const NodeRec r = v.nodes[node];
+    a0 = r.a0, a1 = r.a1;
   } else {
     return;
   }
   if ((int)b.ops[i].lcp >= (int)d) return;  // not the owner
-  const NodeRec r = v.nodes[node];
   const uint32_t koff = b.ops[i].koff;
-  if ((r.w0 & 0xffu) == NK_BRANCH) {
+  if (!is_ext) {
     uint32_t kids[16];
     {
-      const uint32_t mask = r.a1 & 0xffffu;
+      const uint32_t mask = a1 & 0xffffu;
       uint32_t q = 0;
-      for (uint32_t nib = 0; nib < 16; nib++) kids[nib] = (mask >> nib) & 1u ? v.child_pool[r.a0 + q++] : NODE_EMPTY;
+      for (uint32_t nib = 0; nib < 16; nib++) kids[nib] = (mask >> nib) & 1u ? v.child_pool[a0 + q++] : NODE_EMPTY;
     }
     bool changed = false;
-    uint32_t lv = v.level[node];
+    const uint32_t lv = v.level[node];
     for (uint32_t j = i; j < b.n && (j == i || (int)b.ops[j].lcp >= (int)d); j++) {
       if (j != i && (int)b.ops[j].lcp > (int)d) continue;  // same child as its predecessor
-      const uint32_t rj = v.res[j];
+      const uint32_t rj = v.res[b.base + j];
       if (rj == T_UNCHANGED) continue;
       kids[key_nib(v, b.ops[j].koff, d)] = rj;
       changed = true;
     }
     if (!changed) {
-      v.res[i] = T_UNCHANGED;
+      v.res[e] = T_UNCHANGED;
       return;
     }
     uint32_t nk = 0, last = 0;
     for (uint32_t nib = 0; nib < 16; nib++)
       if (kids[nib] != NODE_EMPTY) nk++, last = nib;
     if (nk >= 2)
-      v.res[i] = new_branch16(v, kids, lv);
+      v.res[e] = new_branch16(v, kids, lv);
     else if (nk == 1)
-      v.res[i] = collapse_branch(v, koff, d, last, kids[last]);
+      v.res[e] = collapse_branch(v, koff, d, last, kids[last]);
     else
-      v.res[i] = NODE_EMPTY;
+      v.res[e] = NODE_EMPTY;
     return;
   }
   // an extension: the keys that run through it changed its child; the ones that leave it half way split it
-  const uint32_t es = (r.w0 >> 8) & 0xffu, el = (r.w0 >> 16) & 0xffu;
+  const uint32_t el = (v.nodes[node].w0 >> 16) & 0xffu;
   uint32_t base = node;
   bool changed = false;
   for (uint32_t j = i; j < b.n && (j == i || (int)b.ops[j].lcp >= (int)d); j++) {
-    if (v.tkind[j] == TK_DIVERGE && v.tdepth[j] == d) continue;
+    if (v.tkind[b.base + j] == TK_DIVERGE && v.tdepth[b.base + j] == d) continue;
     // the first key that runs through owns the child's result (every earlier key of the range leaves inside the extension)
-    const uint32_t rj = v.res[j];
+    const uint32_t rj = v.res[b.base + j];
     if (rj == NODE_EMPTY)
       base = NODE_EMPTY, changed = true;
     else if (rj != T_UNCHANGED)
-      base = collapse_ext(v, r.a0, es, el, rj), changed = true;
+      base = collapse_ext(v, a0, d, el, rj), changed = true;
     break;
   }
   for (uint32_t j = i; j < b.n && (j == i || (int)b.ops[j].lcp >= (int)d); j++)
-    if (v.tkind[j] == TK_DIVERGE && v.tdepth[j] == d && b.ops[j].kind != OP_DEL) base = insert_one(v, base, d, b.ops[j], b.txn), changed = true;
-  v.res[i] = changed ? base : T_UNCHANGED;
+    if (v.tkind[b.base + j] == TK_DIVERGE && v.tdepth[b.base + j] == d && (b.ops[j].kind == OP_PUT_LEAF || b.ops[j].kind == OP_PUT_ACCOUNT))
+      base = insert_one(v, base, d, b.ops[j], b.txn), changed = true;
+  v.res[e] = changed ? base : T_UNCHANGED;
 }
 
 // ---- op preparation (all txns at once, before the loop) -----------------------------------------------------
@@ -694,69 +686,79 @@ PPD_HD inline void prep_withdrawal_msg(const View& v, uint32_t w, uint64_t* se) 
   se[2 * wd.m_addr] = wd.off_amount - 20ull, se[2 * wd.m_addr + 1] = wd.off_amount;
 }
 
-// per trace t: its rank among the traces of its txn by hashed address, and its state op
+// per trace t: its rank among the traces of its txn by hashed address, which is the place of its state key (and of its
+// storage trie in the IR): every trace accesses its account (processed_block_trace.rs:267), some write it
 PPD_HD inline void prep_trace(const View& v, uint32_t t) {
   TxnTrace& tr = v.traces[t];
   const TxnDesc& tx = v.txns[tr.txn];
   const uint8_t* me = digest(v, t);
-  const bool state_op = (tr.flags & (TRF_STATE_WRITE | PPD_TR_SELF_DESTRUCTED)) != 0;
-  uint32_t rank = 0, srank = 0;
+  uint32_t rank = 0;
   for (uint32_t u = tx.trace_begin; u < tx.trace_end; u++) {
     if (u == t) continue;
     const int c = cmp32(digest(v, u), me);
-    if (c == 0) raise(v, TXF_DUP_KEY, tr.txn);
-    if (c < 0 || (c == 0 && u < t)) {
-      rank++;
-      if (v.traces[u].flags & (TRF_STATE_WRITE | PPD_TR_SELF_DESTRUCTED)) srank++;
-    }
+    if (c == 0) raise(v, TXF_DUP_KEY, tr.txn);  // (TxnInfo.traces is a map: only a malformed FlatBlock repeats an address)
+    if (c < 0 || (c == 0 && u < t)) rank++;
   }
   tr.rank = rank;
   if (me[0] == 0) raise(v, TXF_SHORT_HADDR, tr.txn);  // H256::from_slice(&nibbles.bytes_be()), decoding.rs:202
-  if (state_op) {
-    SOp o;
-    o.koff = v.dig_base + 32u * t, o.klen = 64, o.lcp = -1, o.pad = 0;
-    o.kind = (tr.flags & PPD_TR_SELF_DESTRUCTED) ? OP_DEL : OP_PUT_ACCOUNT;
-    o.a1 = v.rec_base + tr.rec, o.a2 = tr.txn, o.owner = OWNER_STATE_TRIE;
-    v.ops2[tx.op2_begin + srank] = o;
-  }
-}
-// per written slot (trace t, write w): rlp(U256 value) into val_pool, its rank among the trace's writes, its op
-PPD_HD inline void prep_write(const View& v, uint32_t t, uint32_t w) {
-  const TxnTrace& tr = v.traces[t];
-  const uint8_t* me = digest(v, tr.m_wmin + w);
-  uint32_t rank = 0;
-  for (uint32_t u = 0; u < tr.n_writes; u++) {
-    if (u == w) continue;
-    const int c = cmp32(digest(v, tr.m_wmin + u), me);
-    if (c == 0) raise(v, TXF_DUP_KEY, tr.txn);
-    if (c < 0 || (c == 0 && u < w)) rank++;
-  }
-  const uint8_t* val = v.flat + tr.off_writes + 64ull * w + 32;
-  uint32_t z = 0;
-  while (z < 32 && val[z] == 0) z++;
-  const uint32_t sig = 32 - z;
   SOp o;
-  o.koff = v.dig_base + 32u * (tr.m_wmin + w), o.klen = 64, o.lcp = -1, o.pad = 0, o.owner = t;
-  if (sig == 0) {  // rlp(0) == [0x80]: a delete (decoding.rs:238-243)
-    o.kind = OP_DEL, o.a1 = o.a2 = 0;
-  } else {
-    uint8_t* dst = v.val_pool + v.val_base + tr.val0 + 36u * w;
-    uint32_t el = 0;
-    if (sig == 1 && val[31] < 0x80) {
-      dst[el++] = val[31];
+  o.koff = v.dig_base + 32u * t, o.klen = 64, o.lcp = -1, o.pad = SOP_MARK;
+  o.kind = (tr.flags & PPD_TR_SELF_DESTRUCTED) ? OP_DEL : (tr.flags & TRF_STATE_WRITE) ? OP_PUT_ACCOUNT : OP_NONE;
+  o.a1 = v.rec_base + tr.rec, o.a2 = tr.txn, o.owner = OWNER_STATE_TRIE;
+  v.ops2[tx.op2_begin + rank] = o;
+}
+// per storage key k of trace t (its slot reads, then its slot writes; with TRF_MIN_KEYS the writes once more under the
+// shortened key decoding.rs:235 hashes): its rank among the trace's keys, rlp(U256 value) of a write into val_pool
+PPD_HD inline void prep_storage_key(const View& v, uint32_t t, uint32_t k) {
+  const TxnTrace& tr = v.traces[t];
+  const bool min_keys = (tr.flags & TRF_MIN_KEYS) != 0;
+  auto key_of = [&](uint32_t q) -> uint32_t {  // digest index of key q
+    if (q < tr.n_reads) return tr.m_reads + q;
+    if (q < tr.n_reads + tr.n_writes) return tr.m_wfull + (q - tr.n_reads);
+    return tr.m_wmin + (q - tr.n_reads - tr.n_writes);
+  };
+  auto writes = [&](uint32_t q) -> bool { return min_keys ? q >= tr.n_reads + tr.n_writes : q >= tr.n_reads; };
+  const uint32_t mk = key_of(k);
+  const uint8_t* me = digest(v, mk);
+  uint32_t rank = 0;
+  for (uint32_t u = 0; u < tr.n_keys; u++) {
+    if (u == k) continue;
+    const int c = cmp32(digest(v, key_of(u)), me);
+    if (c == 0 && writes(u) && writes(k)) raise(v, TXF_DUP_KEY, tr.txn);  // (a slot may be read and written; written twice it cannot be)
+    if (c < 0 || (c == 0 && u < k)) rank++;
+  }
+  SOp o;
+  o.koff = v.dig_base + 32u * mk, o.klen = 64, o.lcp = -1, o.owner = t, o.a1 = o.a2 = 0;
+  o.pad = (min_keys && writes(k)) ? 0 : SOP_MARK;  // the shortened key is not one create_trie_subset is given
+  o.kind = OP_NONE;
+  if (writes(k)) {
+    const uint32_t w = k - tr.n_reads - (min_keys ? tr.n_writes : 0);
+    const uint8_t* val = v.flat + tr.off_writes + 64ull * w + 32;
+    uint32_t z = 0;
+    while (z < 32 && val[z] == 0) z++;
+    const uint32_t sig = 32 - z;
+    if (sig == 0) {  // rlp(0) == [0x80]: a delete (decoding.rs:238-243)
+      o.kind = OP_DEL;
     } else {
-      dst[el++] = (uint8_t)(0x80 + sig);
-      for (uint32_t k = 0; k < sig; k++) dst[el++] = val[z + k];
+      uint8_t* dst = v.val_pool + v.val_base + tr.val0 + 36u * w;
+      uint32_t el = 0;
+      if (sig == 1 && val[31] < 0x80) {
+        dst[el++] = val[31];
+      } else {
+        dst[el++] = (uint8_t)(0x80 + sig);
+        for (uint32_t q = 0; q < sig; q++) dst[el++] = val[z + q];
+      }
+      o.kind = OP_PUT_LEAF, o.a1 = v.val_base + tr.val0 + 36u * w, o.a2 = el;
     }
-    o.kind = OP_PUT_LEAF, o.a1 = v.val_base + tr.val0 + 36u * w, o.a2 = el;
   }
   v.ops1[tr.op0 + rank] = o;
 }
-// per txn: the inserts into the transactions and receipts tries (decoding.rs:284-289), after the storage ops
+// per txn: the inserts into the transactions and receipts tries (decoding.rs:284-289), after the storage keys; the same
+// keys are the ones the tries' subsets are cut with (decoding.rs:190-197)
 PPD_HD inline void prep_txn(const View& v, uint32_t ti) {
   const TxnDesc& tx = v.txns[ti];
   SOp o;
-  o.koff = tx.key_off, o.klen = (uint8_t)tx.key_nibs, o.lcp = -1, o.pad = 0, o.kind = OP_PUT_LEAF;
+  o.koff = tx.key_off, o.klen = (uint8_t)tx.key_nibs, o.lcp = -1, o.pad = SOP_MARK, o.kind = OP_PUT_LEAF;
   o.a1 = tx.val_txn, o.a2 = tx.len_txn_bytes, o.owner = OWNER_TXN_TRIE;
   v.ops1[tx.op1_end - 2] = o;
   o.a1 = tx.val_receipt, o.a2 = tx.len_receipt, o.owner = OWNER_RECEIPT_TRIE;
@@ -764,8 +766,8 @@ PPD_HD inline void prep_txn(const View& v, uint32_t ti) {
   for (uint32_t k = 0; k < tx.len_txn_bytes; k++) v.val_pool[tx.val_txn + k] = v.flat[tx.off_txn_bytes + k];
   for (uint32_t k = 0; k < tx.len_receipt; k++) v.val_pool[tx.val_receipt + k] = v.flat[tx.off_receipt + k];
 }
-// per sorted op: the LCP with its predecessor in the same trie (state ops carry their txn in a2: one state trie
-// version per txn)
+// per sorted key: the LCP with its predecessor in the same trie (state keys carry their txn in a2: one state trie version
+// per txn).  Equal keys (a slot read and written) get the full length: the later one then shares everything with the earlier.
 PPD_HD inline void prep_lcp(const View& v, SOp* ops, uint32_t i) {
   const bool first = i == 0 || ops[i - 1].owner != ops[i].owner || (ops[i].owner == OWNER_STATE_TRIE && ops[i - 1].a2 != ops[i].a2);
   if (first) {
@@ -773,7 +775,7 @@ PPD_HD inline void prep_lcp(const View& v, SOp* ops, uint32_t i) {
     return;
   }
   const int l = lcp_nibbles(v, ops[i - 1].koff, ops[i - 1].klen, ops[i].koff, ops[i].klen);
-  if (l >= (int)ops[i].klen || l >= (int)ops[i - 1].klen) raise(v, TXF_DUP_KEY, 0);
+  if ((l >= (int)ops[i].klen) != (l >= (int)ops[i - 1].klen)) raise(v, TXF_KEY_PREFIX, 0);
   ops[i].lcp = (int8_t)l;
 }
 
@@ -848,23 +850,19 @@ PPD_HD inline void acct_claim(const View& v, const AcctInit& a, uint32_t t) {
 #define PPD_PHASE_CLOCK(c, k) ((void)0)
 #endif
 
-PPD_HD inline void run_batch(const Ctx& c, const Batch& b) {
+// terminals, re-assembly and new roots of one batch whose keys have been walked
+PPD_HD inline void run_batch(const Ctx& c, const Batch& b, uint32_t dmax) {
   const View& v = c.v;
-  if (c.tid == 0) *c.sh_dmax = 0;
-  PPD_BLOCK_SYNC();
-  for (uint32_t i = c.tid; i < b.n; i += c.nthreads) batch_walk(c, b, i);
-  PPD_BLOCK_SYNC();
   for (uint32_t i = c.tid; i < b.n; i += c.nthreads) batch_terminal(c, b, i);
   PPD_BLOCK_SYNC();
-  const uint32_t dmax = *c.sh_dmax;
   for (uint32_t d = dmax; d-- > 0;) {
     for (uint32_t i = c.tid; i < b.n; i += c.nthreads) batch_assemble(c, b, i, d);
     PPD_BLOCK_SYNC();
   }
-  // the first op of every trie holds the trie's new root
+  // the first key of every trie holds the trie's new root
   for (uint32_t i = c.tid; i < b.n; i += c.nthreads) {
     if (b.ops[i].lcp != -1) continue;
-    const uint32_t r = v.res[i];
+    const uint32_t r = v.res[b.base + i];
     if (r == T_UNCHANGED) continue;
     const uint32_t owner = b.ops[i].owner;
     if (owner == OWNER_STATE_TRIE) {
@@ -881,19 +879,6 @@ PPD_HD inline void run_batch(const Ctx& c, const Batch& b) {
   PPD_BLOCK_SYNC();
 }
 
-// the trace that owns the k-th storage marking walk of the txn (item0 ascends with the trace index)
-PPD_HD inline uint32_t trace_of_item(const View& v, const TxnDesc& tx, uint32_t k) {
-  uint32_t lo = tx.trace_begin, hi = tx.trace_end;  // last trace with item0 <= k
-  while (hi - lo > 1) {
-    const uint32_t mid = (lo + hi) >> 1;
-    if (v.traces[mid].item0 <= k)
-      lo = mid;
-    else
-      hi = mid;
-  }
-  return lo;
-}
-
 PPD_HD inline void copy32(uint8_t* d, const uint8_t* s) {
   for (int i = 0; i < 32; i++) d[i] = s[i];
 }
@@ -902,11 +887,20 @@ PPD_HD inline void run_txn(const Ctx& c, uint32_t ti, const uint8_t* empty_trie_
   const View& v = c.v;
   const TxnDesc tx = v.txns[ti];
   const uint32_t ntr = tx.trace_end - tx.trace_begin;
+  const uint32_t n1 = tx.op1_end - tx.op1_begin, n2 = tx.op2_end - tx.op2_begin;
+  // the txn's keys: in shared memory next to the scratch when they fit
+  const SOp* ops1 = v.ops1 + tx.op1_begin;
+  const SOp* ops2 = v.ops2 + tx.op2_begin;
+  if (v.sh_ops) {
+    for (uint32_t k = c.tid; k < n1 + n2; k += c.nthreads) v.sh_ops[k] = k < n1 ? ops1[k] : ops2[k - n1];
+    ops1 = v.sh_ops, ops2 = v.sh_ops + n1;
+  }
   // ---- the tries the subsets are cut from (decoding.rs:179-217): roots before the txn ----
   if (c.tid == 0) {
     v.seg_b[tx.seg_tries + 0] = v.cur->state_root;
     v.seg_b[tx.seg_tries + 1] = v.cur->txn_root;
     v.seg_b[tx.seg_tries + 2] = v.cur->receipt_root;
+    c.sh_dmax[0] = 0, c.sh_dmax[1] = 0;
   }
   for (uint32_t k = c.tid; k < ntr; k += c.nthreads) {
     const uint32_t t = tx.trace_begin + k;
@@ -926,36 +920,20 @@ PPD_HD inline void run_txn(const Ctx& c, uint32_t ti, const uint8_t* empty_trie_
   }
   PPD_BLOCK_SYNC();
   PPD_PHASE_CLOCK(c, 0);
-  // ---- marking walks: every accessed key on the tries before the txn ----
-  {
-    uint32_t n_storage_items = 0;
-    if (ntr) {
-      const TxnTrace& last = v.traces[tx.trace_end - 1];
-      n_storage_items = last.item0 + last.n_reads + last.n_writes;
-    }
-    const uint32_t n_items = ntr + 2 + n_storage_items;
-    for (uint32_t k = c.tid; k < n_items; k += c.nthreads) {
-      uint32_t* out = v.touched + tx.touched_base + MARK_SLOTS_T * k;
-      if (k < ntr) {
-        const uint32_t t = tx.trace_begin + k;
-        v.acct_leaf[k] = mark_item(v, v.cur->state_root, v.dig_base + 32u * t, 64, out, ti);
-      } else if (k == ntr) {
-        mark_item(v, v.cur->txn_root, tx.key_off, tx.key_nibs, out, ti);
-      } else if (k == ntr + 1) {
-        mark_item(v, v.cur->receipt_root, tx.key_off, tx.key_nibs, out, ti);
-      } else {
-        const uint32_t q = k - ntr - 2, t = trace_of_item(v, tx, q);
-        const TxnTrace& tr = v.traces[t];
-        const uint32_t j = q - tr.item0;
-        const uint32_t m = j < tr.n_reads ? tr.m_reads + j : tr.m_wfull + (j - tr.n_reads);
-        mark_item(v, v.acct[tr.acct].storage, v.dig_base + 32u * m, 64, out, ti);
-      }
-    }
+  // ---- every key of the txn walks the tries as they are before the txn: the marking walks of
+  // create_minimal_partial_tries_needed_by_txn (decoding.rs:179-217) and the first half of the writes ----
+  const Batch b1{ops1, n1, 0, ti}, b2{ops2, n2, n1, ti};
+  for (uint32_t k = c.tid; k < n1 + n2; k += c.nthreads) {
+    uint32_t* out = v.touched + tx.touched_base + MARK_SLOTS_T * k;
+    if (k < n1)
+      batch_walk(c, b1, k, out, &c.sh_dmax[0]);
+    else
+      batch_walk(c, b2, k - n1, out, &c.sh_dmax[1]);
   }
   PPD_BLOCK_SYNC();
   PPD_PHASE_CLOCK(c, 1);
   // ---- apply_deltas_to_trie_state (decoding.rs:219-292): storage writes, the txn and receipt inserts ----
-  run_batch(c, Batch{v.ops1 + tx.op1_begin, tx.op1_end - tx.op1_begin, ti});
+  run_batch(c, b1, c.sh_dmax[0]);
   PPD_PHASE_CLOCK(c, 2);
   // ---- the accounts after the txn: storage_root = the storage trie's hash after the writes (late-bound: an NK_ROOT node) ----
   for (uint32_t k = c.tid; k < ntr; k += c.nthreads) {
@@ -963,14 +941,15 @@ PPD_HD inline void run_txn(const Ctx& c, uint32_t ti, const uint8_t* empty_trie_
     const TxnTrace& tr = v.traces[t];
     if (!(tr.flags & TRF_STATE_WRITE)) continue;
     AccountRec rec;
-    const uint32_t leaf = v.acct_leaf[k];
-    if (leaf != NODE_EMPTY) {
+    const uint32_t e = n1 + tr.rank;  // the trace's state key: its walk found the account as state.get() would (decoding.rs:251-254)
+    if (v.tkind[e] == TK_LEAF_SAME) {
+      const uint32_t leaf = v.tnode[e];
       if ((v.nodes[leaf].w0 & 0xffu) != NK_LEAF_ACCOUNT) {
         raise(v, TXF_NOT_ACCOUNT, ti);
         continue;
       }
       rec = v.accounts[v.nodes[leaf].a1];
-    } else {  // EMPTY_ACCOUNT_BYTES_RLPED, decoding.rs:251-254
+    } else {  // EMPTY_ACCOUNT_BYTES_RLPED
       for (int i = 0; i < 32; i++) rec.nonce[i] = 0, rec.balance[i] = 0;
       copy32(rec.storage_root, empty_trie_hash);
       copy32(rec.code_hash, empty_code_hash);
@@ -993,8 +972,7 @@ PPD_HD inline void run_txn(const Ctx& c, uint32_t ti, const uint8_t* empty_trie_
   PPD_BLOCK_SYNC();
   PPD_PHASE_CLOCK(c, 3);
   // ---- state writes and self-destructs in one descent ----
-  run_batch(c, Batch{v.ops2 + tx.op2_begin, tx.op2_end - tx.op2_begin, ti});
-  PPD_PHASE_CLOCK(c, 4);
+  run_batch(c, b2, c.sh_dmax[1]);
   for (uint32_t k = c.tid; k < ntr; k += c.nthreads) {
     const TxnTrace& tr = v.traces[tx.trace_begin + k];
     if (tr.flags & PPD_TR_SELF_DESTRUCTED) {  // trie_state.storage.remove(hashed_addr), decoding.rs:271-282
@@ -1002,6 +980,7 @@ PPD_HD inline void run_txn(const Ctx& c, uint32_t ti, const uint8_t* empty_trie_
       a.storage = ST_ABSENT, a.root_node = NONE;
     }
   }
+  PPD_PHASE_CLOCK(c, 4);
   // ---- calculate_trie_input_hashes (decoding.rs:458-464): three NK_ROOT nodes, read by the dump as refs ----
   if (c.tid == 0) {
     v.seg_a[tx.seg_roots + 0] = new_root(v, v.cur->state_root);

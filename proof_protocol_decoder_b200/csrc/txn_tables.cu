@@ -46,16 +46,18 @@ bool txn_tables_phase1(const BlockJob& b, const uint8_t* flat, size_t flat_len, 
         d.m_code = m++;
         T.code_write_traces.push_back(t);
       }
-      d.op0 = op, op += tr.n_writes;
-      d.item0 = item, item += tr.n_reads + tr.n_writes;
+      T.max_trace_keys = std::max(T.max_trace_keys, tr.n_reads + 2 * tr.n_writes);
+      d.n_keys = tr.n_reads + tr.n_writes * ((d.flags & txn::TRF_MIN_KEYS) ? 2u : 1u);
+      d.op0 = op, op += d.n_keys;
+      item += d.n_keys;
       if (d.flags & txn::TRF_STATE_WRITE) d.rec = rec++;
       d.val0 = val, val += 36u * tr.n_writes;
-      if (d.flags & (txn::TRF_STATE_WRITE | PPD_TR_SELF_DESTRUCTED)) ops2++;
+      ops2++;  // every trace accesses its account
       T.traces[t++] = d;
     }
     op += 2;  // the inserts into the transactions and receipts tries
     T.n_ops2 += ops2;
-    T.max_ops = std::max(T.max_ops, std::max(op - op_begin, ops2));
+    T.max_ops = std::max(T.max_ops, op - op_begin + ops2);  // keys of the txn: storage, txn / receipt index, state
     T.max_traces = std::max<uint32_t>(T.max_traces, (uint32_t)tx.traces.size());
     n_items += tx.traces.size() + 2 + item;
   }
@@ -156,8 +158,8 @@ bool txn_tables_phase2(const BlockJob& b, const uint8_t* flat, const TxnBases& B
     for (uint32_t k = 0; k < ntr; k++, t++) {
       const TraceV& tr = tx.traces[k];
       const txn::TxnTrace& dt = T.traces[t];
-      items += tr.n_reads + tr.n_writes;
-      if (dt.flags & (txn::TRF_STATE_WRITE | PPD_TR_SELF_DESTRUCTED)) ops2++;
+      items += dt.n_keys;
+      ops2++;
       if (tr.flags & PPD_TR_CODE_READ) {
         H256 h;
         memcpy(h.b, tr.code_read, 32);
@@ -207,7 +209,7 @@ bool txn_tables_phase2(const BlockJob& b, const uint8_t* flat, const TxnBases& B
       d.key_off = B.txn_key_base + 12u * (uint32_t)ti, d.key_nibs = 2u * (uint32_t)enc.size();
     }
     d.op1_begin = op;
-    for (uint32_t k = d.trace_begin; k < d.trace_end; k++) op += T.traces[k].n_writes;
+    for (uint32_t k = d.trace_begin; k < d.trace_end; k++) op += T.traces[k].n_keys;
     op += 2;
     d.op1_end = op;
     d.op2_begin = op2, op2 += ops2, d.op2_end = op2;

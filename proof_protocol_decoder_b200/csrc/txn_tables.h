@@ -29,6 +29,7 @@ struct TxnTables {
   uint32_t first_txn_ir = 0;
   int dummy_initial[2] = {-1, -1}, dummy_final = -1;
   bool needs_dummies() const { return dummy_initial[0] >= 0 || dummy_final >= 0; }
+  uint32_t max_trace_keys = 0;  // the most storage keys any trace has
   uint32_t val_writes = 0;  // val_pool bytes of the written slot values (36 each)
   uint32_t val_extra = 0;   // val_pool bytes the loop writes in all (written values, txn bytes, receipts), from val_base (phase 2)
   uint64_t est_nodes = 0, est_children = 0;
@@ -44,7 +45,7 @@ struct TxnTables {
     lit.clear(), txn_keys.clear(), code_write_traces.clear();
     n_msgs = n_ops1 = n_ops2 = max_ops = max_traces = n_items = n_recs = n_ir = 0;
     first_txn_ir = 0, dummy_initial[0] = dummy_initial[1] = dummy_final = -1;
-    val_writes = val_extra = 0, est_nodes = est_children = 0;
+    max_trace_keys = 0, val_writes = val_extra = 0, est_nodes = est_children = 0;
   }
 };
 

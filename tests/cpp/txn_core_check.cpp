@@ -189,10 +189,13 @@ int check_block(const std::vector<uint8_t>& flatv, const char* name) {
   v.ops1 = ops1.data(), v.ops2 = ops2.data();
   std::vector<uint32_t> touched(T.touched_begin.back() + 16, NODE_EMPTY);
   v.touched = touched.data(), v.seg_a = T.seg_a.data(), v.seg_b = T.seg_b.data();
-  std::vector<uint32_t> path_node((size_t)T.max_ops * txn::PATH_CAP + 1), tnode(T.max_ops + 1), res(T.max_ops + 1), acct_leaf(T.max_traces + 1);
+  std::vector<uint32_t> path_node((size_t)T.max_ops * txn::PATH_CAP + 1), path_a0(path_node.size()), path_a1(path_node.size()), tnode(T.max_ops + 1), res(T.max_ops + 1);
   std::vector<uint8_t> path_depth((size_t)T.max_ops * txn::PATH_CAP + 1), plen(T.max_ops + 1), top(T.max_ops + 1), tdepth(T.max_ops + 1), tkind(T.max_ops + 1);
-  v.path_node = path_node.data(), v.path_depth = path_depth.data(), v.plen = plen.data(), v.top = top.data(), v.tnode = tnode.data();
-  v.tdepth = tdepth.data(), v.tkind = tkind.data(), v.res = res.data(), v.acct_leaf = acct_leaf.data();
+  std::vector<txn::SOp> sh_ops(T.max_ops + 1);
+  v.path_node = path_node.data(), v.path_a0 = path_a0.data(), v.path_a1 = path_a1.data(), v.path_depth = path_depth.data();
+  v.plen = plen.data(), v.top = top.data(), v.tnode = tnode.data();
+  v.tdepth = tdepth.data(), v.tkind = tkind.data(), v.res = res.data();
+  v.sh_ops = (n_traces & 1) ? sh_ops.data() : nullptr;  // both ways of reaching a txn's keys get exercised
   txn::Cursors cur;
   memset(&cur, 0, sizeof cur);
   cur.n_nodes = n_pre_nodes, cur.n_children = (uint32_t)A.child_pool.size(), cur.key_bytes = B.key_cursor;
@@ -204,13 +207,13 @@ int check_block(const std::vector<uint8_t>& flatv, const char* name) {
   for (uint32_t t = 0; t < n_traces; t++) txn::acct_claim(v, ai, t);
   for (uint32_t t = 0; t < n_traces; t++) txn::prep_trace(v, t);
   for (uint32_t t = 0; t < n_traces; t++)
-    for (uint32_t w = 0; w < T.traces[t].n_writes; w++) txn::prep_write(v, t, w);
+    for (uint32_t k = 0; k < T.traces[t].n_keys; k++) txn::prep_storage_key(v, t, k);
   for (uint32_t ti = 0; ti < v.n_txns; ti++) txn::prep_txn(v, ti);
   for (uint32_t i = 0; i < T.n_ops1; i++) txn::prep_lcp(v, v.ops1, i);
   for (uint32_t i = 0; i < T.n_ops2; i++) txn::prep_lcp(v, v.ops2, i);
-  uint32_t sh_dmax = 0;
+  uint32_t sh_dmax[2] = {0, 0};
   long long sh_clock = 0;
-  txn::Ctx c{v, 0, 1, &sh_dmax, &sh_clock};
+  txn::Ctx c{v, 0, 1, sh_dmax, &sh_clock};
   for (uint32_t ti = 0; ti < v.n_txns && !cur.flag; ti++) txn::run_txn(c, ti, EMPTY_TRIE_HASH, EMPTY_CODE_HASH);
   txn::run_finish(c, b2.state_root);
   if (cur.flag) {

@@ -70,6 +70,30 @@ def test_device_loop_takes_the_block_and_matches_oracle_and_host_loop(ctx, oracl
         assert got_host == want, f"block {i}: the host txn loop differs from the oracle"
 
 
+def test_shortened_slot_keys_and_read_write_overlap(ctx, oracle):
+    """decoding.rs:235 hashes a written slot key without its leading zero bytes, while the subset is cut with the hash
+    of the full key (processed_block_trace.rs:234); and a slot may be both read and written by one txn."""
+    from proof_protocol_decoder_b200 import synth
+
+    rng = np.random.default_rng(13)
+    for i in range(6):
+        blk = synth.gen_block(7000 + i, n_accounts=40, n_txns=6, contract_frac=0.8, slots_hi=12, accounts_per_txn=(3, 12), slot_reads=(1, 6), slot_writes=(1, 8))
+        for tx in blk.txns:
+            for _, tr in tx["traces"]:
+                if tr.get("storage_written"):
+                    w = list(tr["storage_written"])
+                    for _ in range(int(rng.integers(1, 3))):
+                        z = int(rng.integers(1, 30))
+                        w.append((bytes(z) + bytes([1 + int(rng.integers(0, 255))]) + rng.bytes(31 - z), int(rng.integers(1, 1 << 60))))
+                    tr["storage_written"] = w
+                    tr["storage_read"] = list(tr.get("storage_read") or []) + [k for k, _ in w[:2]]
+        want = _oracle(oracle, blk.flat)
+        got, st = _decode(ctx, blk.flat, host_txn=False)
+        assert got == want and st["txn_loops_on_gpu"] == 1
+        got_host, _ = _decode(ctx, blk.flat, host_txn=True)
+        assert got_host == want
+
+
 def _account(key_nibbles, balance, storage_stream=None):
     from proof_protocol_decoder_b200.synth import cbor_bytes, compact_key
 

@@ -94,3 +94,29 @@ def test_device_txn_loop_mainnet_shaped(txncheck, tmp_path):
     blk = synth.gen_block(4, n_accounts=2000, n_txns=20, contract_frac=0.15, slots_hi=256, virtual_depth=7, accounts_per_txn=(30, 60),
                           slot_reads=(0, 3), slot_writes=(0, 3), allow_new_accounts=False, allow_self_destruct=False, inline_code_frac=0.02)
     _run(txncheck, tmp_path, [blk, synth.gen_block(1, n_accounts=1000, n_txns=10, n_withdrawals=2)])
+
+
+def test_device_txn_loop_shortened_slot_keys_and_read_write_overlap(txncheck, tmp_path):
+    """decoding.rs:235 hashes Nibbles::bytes_be() of a written slot key, which drops leading zero bytes, while the
+    subset is cut with the hash of the full key (processed_block_trace.rs:234): such a write walks two keys.  And a
+    slot may be both read and written by one txn: the same key twice in one batch."""
+    from proof_protocol_decoder_b200 import synth
+
+    rng = np.random.default_rng(13)
+    blocks = []
+    for i in range(6):
+        blk = synth.gen_block(7000 + i, n_accounts=40, n_txns=6, contract_frac=0.8, slots_hi=12, accounts_per_txn=(3, 12), slot_reads=(1, 6), slot_writes=(1, 8))
+        for tx in blk.txns:
+            for _, tr in tx["traces"]:
+                if tr.get("storage_written"):
+                    w = list(tr["storage_written"])
+                    # new slots whose raw key starts with zero bytes
+                    for _ in range(int(rng.integers(1, 3))):
+                        z = int(rng.integers(1, 30))
+                        key = bytes(z) + bytes([1 + int(rng.integers(0, 255))]) + rng.bytes(31 - z)
+                        w.append((key, int(rng.integers(1, 1 << 60))))
+                    tr["storage_written"] = w
+                    # read what is written, too
+                    tr["storage_read"] = list(tr.get("storage_read") or []) + [k for k, _ in tr["storage_written"][:2]]
+        blocks.append(blk)
+    _run(txncheck, tmp_path, blocks)
