@@ -359,6 +359,8 @@ def run_b200(args, rank, world, local_rank):
         ir_len = decode_step()
     st = ctx.stats()
     on_device = int(st["txn_loops_on_gpu"])
+    # the blocks a replay covers: the last block of every lane is what stays resident in HBM
+    resident = min(n_blocks, int(os.environ.get("PPD_MAX_LANES", "64")))
 
     def replay(what):
         """device time per step of the selected stages, every lane replaying them concurrently on resident data"""
@@ -409,7 +411,7 @@ def run_b200(args, rank, world, local_rank):
     sm_mhz = clocks.get("sm_mhz")
     alu_peak = ALU_LANES_PER_SM_CLK * N_SM * (sm_mhz or peaks["sm_max_mhz"]) * 1e6  # instr/s on one GPU
     algo_bytes = st["node_bytes"] + 32 * st["nodes_hashed"]  # L + 32 per hashed node (this rank)
-    achieved_gbs = algo_bytes / dev_s_per_step / 1e9
+    achieved_gbs = algo_bytes * (resident / n_blocks) / dev_s_per_step / 1e9
     traffic, traffic_src = load_traffic()
     level_launches = max(1, int(st["level_launches"]))
     wit_bytes_all = sum_over_ranks(float(st["witness_bytes"]))
@@ -453,15 +455,16 @@ def run_b200(args, rank, world, local_rank):
     # ---- what bounds end-to-end blocks/s ----
     per_block_host_ms = host_busy_all / blocks_all
     per_block_h2d, per_block_d2h = h2d_all / blocks_all, d2h_all / blocks_all
+    blocks_replayed = world * resident
     bounds = {
-        "device_pipeline": blocks_all / (all_ms / 1e3),
+        "device_pipeline": blocks_replayed / (all_ms / 1e3),
         "pcie": world * pcie_gbs * 1e9 / max(per_block_h2d, per_block_d2h),
         "host_cores": cores / (per_block_host_ms / 1e3) if per_block_host_ms else None,
     }
     limiter = min((k for k in bounds if bounds[k]), key=lambda k: bounds[k])
     line = {
         "metric": "mpt_nodes_keccak_hashed_per_sec",
-        "value": norm * nodes_all / dev_s_per_step,
+        "value": norm * nodes_all * (resident / n_blocks) / dev_s_per_step,
         "unit": "nodes/s",
         "n_gpus": world,
         "steps": args.steps,
@@ -490,12 +493,12 @@ def run_b200(args, rank, world, local_rank):
         "value_note": "node hashes per second of the hashing kernels (key hashing + both level sweeps of every block, lanes concurrent) on arenas resident in HBM, in units of the REFERENCE's node hashes for the same block (nodes_normalisation)",
         "nodes_normalisation": {"factor": norm, "oracle_nodes_block0": n1.get("oracle_nodes_block0"), "own_nodes_block0": n1.get("own_nodes_block0"),
                                 "note": "the library hashes every node of every trie version it builds; the reference hashes a few per cent fewer or more (it never builds unobserved versions, but hashes per-txn subsets): throughputs are quoted in the reference's count"},
-        "blocks_per_sec": blocks_all / (all_ms / 1e3),
+        "blocks_per_sec": blocks_replayed / (all_ms / 1e3),
         "blocks_per_sec_note": "device-resident: the blocks of a step / device time of the WHOLE pipeline replayed on resident data (witness parse, key hashing, pre-image sweep, by-root join, txn loop, second sweep, IR sizing and emit), every lane in pipeline order, lanes concurrent",
-        "device_ms_per_step": {"hashing": hash_ms, "parse": parse_ms, "txn_loop": txn_ms, "dump": dump_ms, "whole_pipeline": all_ms,
-                               "note": "each stage replayed alone with all lanes concurrent, then all of them together"},
-        "blocks_per_sec_hashing_only": blocks_all / dev_s_per_step,
-        "permutations_per_sec": perms_all / dev_s_per_step,
+        "device_ms_per_step": {"hashing": hash_ms, "parse": parse_ms, "txn_loop": txn_ms, "dump": dump_ms, "whole_pipeline": all_ms, "blocks_replayed": blocks_replayed,
+                               "note": "each stage replayed alone with all lanes concurrent (the resident block of every lane), then all of them together"},
+        "blocks_per_sec_hashing_only": blocks_replayed / dev_s_per_step,
+        "permutations_per_sec": perms_all * (resident / n_blocks) / dev_s_per_step,
         "nodes_hashed_per_step": nodes_all,
         "key_hashes_per_step": keys_all,
         "e2e": {
@@ -525,10 +528,10 @@ def run_b200(args, rank, world, local_rank):
         "roofline": {
             "bound": "alu",
             "kernel": "hash_level_kernel + keccak256_batch_kernel (all level launches of the batch, lanes concurrent)",
-            "achieved": (st["node_permutations"] + st["key_permutations"]) * ALU_OPS_PER_PERM / dev_s_per_step / 1e12,
+            "achieved": (st["node_permutations"] + st["key_permutations"]) * (resident / n_blocks) * ALU_OPS_PER_PERM / dev_s_per_step / 1e12,
             "peak": alu_peak / 1e12,
             "unit": "Tinstr/s",
-            "frac": (st["node_permutations"] + st["key_permutations"]) * ALU_OPS_PER_PERM / dev_s_per_step / alu_peak,
+            "frac": (st["node_permutations"] + st["key_permutations"]) * (resident / n_blocks) * ALU_OPS_PER_PERM / dev_s_per_step / alu_peak,
             "traffic": traffic,
             "traffic_source": traffic_src,
             "model": f"{ALU_OPS_PER_PERM} ALU-pipe (LOP3/SHF) instructions per keccak-f[1600] permutation (SURVEY.md 8d); peak = {ALU_LANES_PER_SM_CLK} lanes/clk/SM x {N_SM} SMs x SM clock sampled under load",
@@ -553,27 +556,27 @@ def run_b200(args, rank, world, local_rank):
             "instructions_per_step": wit_ins_all,
             "ms_per_step": parse_ms,
             "bound": "hbm",
-            "achieved": (7.0 * wit_bytes_all / world / (parse_ms / 1e3) / 1e9) if parse_ms else None,
+            "achieved": (7.0 * wit_bytes_all * (resident / n_blocks) / world / (parse_ms / 1e3) / 1e9) if parse_ms else None,
             "peak": peaks["hbm_gbs"],
             "unit": "GB/s",
-            "frac": (7.0 * wit_bytes_all / world / (parse_ms / 1e3) / 1e9 / peaks["hbm_gbs"]) if parse_ms else None,
-            "instructions_per_sec": (wit_ins_all / (parse_ms / 1e3)) if parse_ms else None,
+            "frac": (7.0 * wit_bytes_all * (resident / n_blocks) / world / (parse_ms / 1e3) / 1e9 / peaks["hbm_gbs"]) if parse_ms else None,
+            "instructions_per_sec": (wit_ins_all * (resident / n_blocks) / (parse_ms / 1e3)) if parse_ms else None,
             "note": "algorithmic bytes = 7 per witness byte for the boundary search (read the byte, write and re-read its 4-byte exit link, write its 2-byte step link)",
         },
         "txn_loop": {
             "kernels": "ppd_txn.cu: join / acct_claim / prep_* / txn_loop_kernel (one thread block per block of txns; lanes concurrent)",
             "ms_per_step": txn_ms,
-            "blocks_per_sec": (blocks_all / (txn_ms / 1e3)) if txn_ms else None,
+            "blocks_per_sec": (blocks_replayed / (txn_ms / 1e3)) if txn_ms else None,
             "bound": "latency (dependent loads down the tries; one resident CTA per block)",
         },
         "dump": {
             "kernels": "ppd_dump.cu: ir_size_kernel + ir_emit_kernel (one thread block per IR)",
             "ms_per_step": dump_ms,
-            "bytes_per_step": ir_len * world,
-            "achieved": (ir_len / (dump_ms / 1e3) / 1e9) if dump_ms else None,
+            "bytes_replayed": ir_len * resident / n_blocks,
+            "achieved": (ir_len * (resident / n_blocks) / (dump_ms / 1e3) / 1e9) if dump_ms else None,
             "unit": "GB/s written",
-            "frac_of_hbm": (ir_len / (dump_ms / 1e3) / 1e9 / peaks["hbm_gbs"]) if dump_ms else None,
-            "frac_of_pcie": (ir_len / (dump_ms / 1e3) / 1e9 / pcie_gbs) if dump_ms else None,
+            "frac_of_hbm": (ir_len * (resident / n_blocks) / (dump_ms / 1e3) / 1e9 / peaks["hbm_gbs"]) if dump_ms else None,
+            "frac_of_pcie": (ir_len * (resident / n_blocks) / (dump_ms / 1e3) / 1e9 / pcie_gbs) if dump_ms else None,
         },
     }
     if cpu_baseline:

@@ -51,14 +51,14 @@ int gpu_dump_block(ppd_ctx* c, Lane* L, Job& J, uint8_t** out, size_t* out_len) 
   // ---- plan ----
   LitPool lit;
   std::vector<uint32_t> seg_a, seg_b, seg_begin(1, 0), touched_begin(1, 0), lit_at;  // lit_at[seg]: offset into lit.b
-  size_t n_touched = 0, n_items = 0;
-  for (IrPlan& p : b.irs) n_touched += p.touched.size() + MARK_SLOTS * p.items.size(), n_items += p.items.size();
+  size_t n_touched = 0;
+  for (IrPlan& p : b.irs) n_touched += p.touched.size();
   {
     // the two dump kernels cost two read-backs and about a millisecond of launch + CTA latency whatever the size;
     // a small block (config 1: a few thousand touched nodes) is serialised faster by the host threads
     const char* e = getenv("PPD_GPU_DUMP_MIN_TOUCHED");
     const size_t min_touched = e ? (size_t)atoll(e) : 32768;
-    if (n_touched - (MARK_SLOTS - 8) * n_items < min_touched) return DUMP_ON_HOST;  // a marking walk touches about eight nodes
+    if (n_touched < min_touched) return DUMP_ON_HOST;
   }
   auto add_lit_from = [&](size_t from) {  // the bytes appended to lit.b since `from` become (part of) a literal segment
     uint32_t len = (uint32_t)(lit.b.size() - from);
@@ -103,33 +103,24 @@ int gpu_dump_block(ppd_ctx* c, Lane* L, Job& J, uint8_t** out, size_t* out_len) 
     lit.span(b.b_hashes);
     add_lit_from(from);
     seg_begin.push_back((uint32_t)seg_a.size());
-    touched_begin.push_back((uint32_t)(touched_begin.back() + p.touched.size() + MARK_SLOTS * p.items.size()));
+    touched_begin.push_back((uint32_t)(touched_begin.back() + p.touched.size()));
   }
   const uint32_t n_seg = (uint32_t)seg_a.size();
   // one pinned buffer / one device buffer: [touched | touched_begin | seg_a | seg_b | seg_begin | ir_base(u64) |
   //                                        seg_off | ir_size | ir_flag | ir_nuniq | u_node | u_size | u_off]
   auto al = [](size_t x) { return (x + 3) & ~(size_t)3; };  // keep the u64 array 8-byte aligned (counts in u32 words)
-  // (items4: the marking walks left to the device, 4 words each; mark_flags: [n_ir + 1] written by mark_walk_kernel)
   const size_t o_touched = 0, o_tb = al(o_touched + n_touched), o_sa = al(o_tb + n_ir + 1), o_sb = al(o_sa + n_seg), o_sg = al(o_sb + n_seg),
-               o_it = al(o_sg + n_ir + 1), o_base = al(o_it + 4 * n_items), o_in_end = al(o_base + 2 * (size_t)n_ir);
-  const size_t o_soff = o_in_end, o_isz = al(o_soff + n_seg), o_ifl = al(o_isz + n_ir), o_mf = al(o_ifl + n_ir), o_inu = al(o_mf + n_ir + 1),
+               o_base = al(o_sg + n_ir + 1), o_in_end = al(o_base + 2 * (size_t)n_ir);
+  const size_t o_soff = o_in_end, o_isz = al(o_soff + n_seg), o_ifl = al(o_isz + n_ir), o_inu = al(o_ifl + n_ir),
                o_un = al(o_inu + n_ir), o_us = al(o_un + n_touched), o_uo = al(o_us + n_touched), o_end = al(o_uo + n_touched);
   J.plan.resize(o_end);
   uint32_t* h = J.plan.data();
   {
     uint32_t* t = h + o_touched;
-    uint32_t* it4 = h + o_it;
     for (uint32_t ir = 0; ir < n_ir; ir++) {
       IrPlan& p = b.irs[ir];
       if (!p.touched.empty()) memcpy(t, p.touched.data(), 4 * p.touched.size());
       t += p.touched.size();
-      if (!p.items.empty()) {
-        memset(t, 0xff, 4 * MARK_SLOTS * p.items.size());  // NODE_EMPTY: slots a walk does not reach
-        for (const HostArena::MarkItem& m : p.items) {
-          it4[0] = m.root, it4[1] = m.koff, it4[2] = (m.klen & 0xffu) | (ir << 8), it4[3] = (uint32_t)(t - (h + o_touched));
-          it4 += 4, t += MARK_SLOTS;
-        }
-      }
     }
   }
   memcpy(h + o_tb, touched_begin.data(), 4 * (n_ir + 1));
@@ -145,12 +136,6 @@ int gpu_dump_block(ppd_ctx* c, Lane* L, Job& J, uint8_t** out, size_t* out_len) 
   P.seg_off = d + o_soff, P.ir_size = d + o_isz, P.ir_flag = d + o_ifl, P.ir_nuniq = d + o_inu;
   P.u_node = d + o_un, P.u_size = d + o_us, P.u_off = d + o_uo;
   pt.lap("  d:plan");
-  if (n_items) {
-    CUDA_OK(cudaMemsetAsync(d + o_mf, 0, 4 * (n_ir + 1), L->st));
-    launch_mark_walk(L->last_view, d + o_it, (uint32_t)n_items, n_ir, d + o_touched, d + o_mf, L->st);
-    L->stats.kernel_launches += 1;
-    L->stats.marks_on_gpu += n_items;
-  }
   launch_ir_size(L->last_view, P, n_ir, L->st);
   CUDA_OK(cudaGetLastError());
   CUDA_OK(cudaMemcpyAsync(h + o_soff, d + o_soff, 4 * (o_inu - o_soff), cudaMemcpyDeviceToHost, L->st));  // seg_off, ir_size, ir_flag
@@ -160,13 +145,6 @@ int gpu_dump_block(ppd_ctx* c, Lane* L, Job& J, uint8_t** out, size_t* out_len) 
   // ---- IRs the device could not lay out: host serialisation ----
   const uint32_t *seg_off = h + o_soff, *ir_size = h + o_isz;
   uint32_t* ir_flag = h + o_ifl;
-  if (n_items) {
-    const uint32_t* mark_flags = h + o_mf;
-    // a key ran into a hashed-out node: the reference reports MissingKeysCreatingSubPartialTrie, possibly after other
-    // errors of earlier txns; the block is redone with the host's marking pass, which keeps the reference's order
-    if (mark_flags[n_ir]) return DUMP_REDO_HOST_MARKS;
-    for (uint32_t i = 0; i < n_ir; i++) ir_flag[i] |= mark_flags[i];  // a walk longer than its slots: the host serialises that IR
-  }
   std::vector<Out> host_parts(n_ir);
   Stamp st;
   uint64_t* ir_base = reinterpret_cast<uint64_t*>(h + o_base);

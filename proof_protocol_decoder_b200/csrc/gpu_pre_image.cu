@@ -287,7 +287,6 @@ bool gpu_pre_image(Lane* L, Job& J, BlockJob& b, bool check_version, Slots* slot
     return true;
   }
   b.storage.reserve(n_acct), b.pre_accounts.reserve(n_acct), b.root_of.reserve(2 * n_acct + 1024);
-  if (J.device_marks) b.acct_rec.reserve(n_acct + n_acct / 4);
   b.have_empty_form = false, b.empty_form = NODE_EMPTY;
   const uint32_t* al = J.acct_list.data();
   for (size_t a = 0; a < n_acct; a++)
@@ -312,7 +311,6 @@ bool gpu_pre_image(Lane* L, Job& J, BlockJob& b, bool check_version, Slots* slot
     }
     if (has_trie) b.storage[haddr] = sroot;
     b.pre_accounts.push_back({haddr, (uint32_t)a, nonempty, (flags & 1u) != 0, al[5 * a + 1]});
-    if (J.device_marks) b.acct_rec.insert({haddr, (uint32_t)a});
     if (nonempty) {
       b.pre_with_storage[haddr] = (uint32_t)a;
       b.root_of.put(al[5 * a + 1], al[5 * a + 2]);

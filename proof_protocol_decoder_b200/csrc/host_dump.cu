@@ -130,16 +130,7 @@ void dump_subset(const Job& J, const Stamp& st, Out& o, uint32_t node) {
   }
 }
 
-// the marking walks of an IR that were left to the device, run on the host instead (host serialisation of the IR)
-void materialize_touched(const Job& J, IrPlan& p) {
-  if (p.items.empty()) return;
-  p.touched.reserve(p.touched.size() + p.items.size() * 10);
-  J.A.mark_many(p.items.data(), p.items.size(), p.touched);
-  p.items.clear();
-}
-
 void dump_ir(const Job& J, const BlockJob& b, IrPlan& p, Stamp& st, Out& o) {
-  materialize_touched(J, p);
   st.serial++;
   for (uint32_t t : p.touched)
     if (!is_hash_id(t)) st.v[t] = st.serial;
@@ -198,9 +189,6 @@ void dump_blocks(Job& J, uint8_t** outs, size_t* out_lens, unsigned max_workers)
     uint32_t block, ir;
   };
   std::vector<Item> items;
-  for (BlockJob& b : J.blocks)
-    if (b.status == PPD_OK)
-      for (IrPlan& p : b.irs) materialize_touched(J, p);  // (throws what the reference's marking pass reports)
   for (size_t i = 0; i < J.blocks.size(); i++) {
     outs[i] = nullptr, out_lens[i] = 0;
     if (J.blocks[i].status != PPD_OK) continue;

@@ -373,7 +373,6 @@ struct IrPlan {
   uint32_t state_sub = NODE_EMPTY, txn_sub = NODE_EMPTY, receipt_sub = NODE_EMPTY;  // roots of the tries the subsets are cut from
   std::vector<std::pair<H256, uint32_t>> storage_subs;
   std::vector<uint32_t> touched;
-  std::vector<HostArena::MarkItem> items;  // marking walks left to the device (launch_mark_walk); materialize_touched() runs them on the host
   uint32_t root_state = 0, root_txn = 0, root_receipt = 0;  // NK_ROOT nodes
   std::map<H256, Span> code;
 };
@@ -408,7 +407,6 @@ struct BlockJob {
   bool pre_image_built = false;
   std::vector<PreAccount> pre_accounts;
   H256Map pre_with_storage;  // accounts whose storage root != EMPTY_TRIE_HASH -> record
-  H256Map acct_rec;          // hashed address -> the account's current record (what state.get() + rlp::decode gives, decoding.rs:251-254)
   FlatMapU32 root_of;                                               // trie root node -> its NK_ROOT node
   std::unordered_map<int32_t, uint32_t> storage_root_of_instr;      // account leaf instruction -> root of its witnessed storage trie
   bool have_empty_form = false;                                     // a witnessed storage trie whose root is EMPTY_TRIE_HASH
@@ -456,7 +454,6 @@ struct Job {
   std::vector<HostArena::MarkItem> mark_items;  // scratch of the txn loop
   std::vector<HostArena::BatchItem> batch_items;
   std::vector<uint32_t> haddr_keys, haddr_leaves;
-  bool device_marks = false;  // this block's subset marking walks run on the device (decode_one decides)
   PVec<H256> code_digest;
   TxnTables txn;              // tables of the device txn loop (gpu_txn.cu)
   PVec<uint32_t> txn_host;    // page-locked landing area of its read-backs
@@ -484,7 +481,6 @@ struct Job {
   void reset(size_t n_blocks) {
     dev = Resident{};
     pools_on_host = true;
-    device_marks = false;
     A.clear();
     kh.reset();
     blocks.clear();
@@ -732,7 +728,7 @@ enum { GPU_BLOCK_DECLINED = 0, GPU_BLOCK_DONE = 1 };
 // the whole block on the device (gpu_txn.cu); DECLINED: nothing was produced, the host path decodes the block
 int gpu_block(ppd_ctx* c, Lane* L, Job& J, const uint8_t* flat, size_t len, uint8_t** out, size_t* out_len);
 bool gpu_dump_enabled();
-enum { DUMP_ON_HOST = 0, DUMP_DONE = 1, DUMP_REDO_HOST_MARKS = 2 };
+enum { DUMP_ON_HOST = 0, DUMP_DONE = 1 };
 int gpu_dump_block(ppd_ctx* c, Lane* L, Job& J, uint8_t** out, size_t* out_len);
 
 }  // namespace ppd

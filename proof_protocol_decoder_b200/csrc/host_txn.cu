@@ -309,8 +309,7 @@ void shape_block(Job& J, BlockJob& b) {
     uint32_t tk_len = 0;
     uint32_t tk = txn_index_key(J, ti, tk_len);
     p.state_sub = state, p.txn_sub = txn_trie, p.receipt_sub = receipt_trie;
-    // every key this txn touches: marked on the device after the sweep's upload (mark_walk_kernel), or here in one
-    // interleaved pass (HostArena::mark_many) when the block is dumped by the host or is being redone for its error
+    // every key this txn touches, marked in one interleaved pass (HostArena::mark_many)
     std::vector<uint32_t>&haddr_key = J.haddr_keys, &haddr_leaf = J.haddr_leaves;
     haddr_key.resize(tx.traces.size()), haddr_leaf.resize(tx.traces.size());
     std::vector<HostArena::MarkItem>& marks = J.mark_items;
@@ -344,15 +343,11 @@ void shape_block(Job& J, BlockJob& b) {
       for (uint32_t k = 0; k < tr.n_writes; k++) marks.push_back({sroot, key_from_digest(J, J.kh.digest[tr.m_writes_full + k]), 64, NODE_EMPTY});
       p.storage_subs.push_back({haddr, sroot});
     }
-    if (J.device_marks) {
-      p.items.assign(marks.begin(), marks.end());  // walked by mark_walk_kernel once the arena is resident
-    } else {
-      p.touched.reserve(marks.size() * 10);
-      A.mark_many(marks.data(), marks.size(), p.touched);
-      // the marking walk of an address also finds its leaf in the pre-txn state: the state writes below read the account
-      // from it (other addresses' writes in between only path-copy branches; the leaf's payload stays)
-      for (size_t i = 0; i < tx.traces.size() && i < marks.size(); i++) haddr_leaf[i] = marks[i].leaf;
-    }
+    p.touched.reserve(marks.size() * 10);
+    A.mark_many(marks.data(), marks.size(), p.touched);
+    // the marking walk of an address also finds its leaf in the pre-txn state: the state writes below read the account
+    // from it (other addresses' writes in between only path-copy branches; the leaf's payload stays)
+    for (size_t i = 0; i < tx.traces.size() && i < marks.size(); i++) haddr_leaf[i] = marks[i].leaf;
     if (short_haddr) fail(PPD_PANIC_H256_FROM_SLICE, "H256::from_slice on a short bytes_be()");
     gas_after += tx.gas_used;
     sec.stop(2);
@@ -393,14 +388,10 @@ void shape_block(Job& J, BlockJob& b) {
       bool code_change = tr.flags & (PPD_TR_CODE_READ | PPD_TR_CODE_WRITE);
       if (!((tr.flags & (PPD_TR_BALANCE | PPD_TR_NONCE)) || storage_change || code_change)) continue;
       const H256& haddr = J.kh.digest[tr.m_addr];
-      // the account as state.get() would give it (decoding.rs:251-254): the leaf the host's marking walk found, or, when
-      // the marking walks are left to the device, the record tracked per hashed address
+      // the account as state.get() would give it (decoding.rs:251-254): the leaf the marking walk found
       AccountRec rec;
-      const H256Map::Entry* cur = J.device_marks ? b.acct_rec.find(haddr) : nullptr;
-      const uint32_t leaf = J.device_marks ? NODE_EMPTY : haddr_leaf[i];
-      if (cur) {
-        rec = A.accounts[cur->second];
-      } else if (leaf != NODE_EMPTY) {
+      const uint32_t leaf = haddr_leaf[i];
+      if (leaf != NODE_EMPTY) {
         if (A.kind(leaf) != NK_LEAF_ACCOUNT) fail(PPD_ERR_ACCOUNT_DECODE, "state leaf is not an account");
         rec = A.accounts[A.nodes[leaf].a1];
       } else {
@@ -420,7 +411,6 @@ void shape_block(Job& J, BlockJob& b) {
       if (tr.flags & PPD_TR_CODE_WRITE) memcpy(rec.code_hash, J.kh.digest[tr.m_code].b, 32);
       uint32_t r = (uint32_t)A.accounts.size();
       A.accounts.push_back(rec);
-      if (J.device_marks) b.acct_rec[haddr] = r;
       batch.push_back({haddr_key[i], 64, HostArena::Payload{true, r, 0}});
     }
     // the txn's account writes in one descent (addresses are distinct: TxnInfo.traces is a map, trace_protocol.rs:118)
@@ -433,7 +423,6 @@ void shape_block(Job& J, BlockJob& b) {
       if (!(tx.traces[i].flags & PPD_TR_SELF_DESTRUCTED)) continue;
       const H256& haddr = J.kh.digest[tx.traces[i].m_addr];
       if (!b.storage.erase(haddr)) fail(PPD_ERR_MISSING_ACCOUNT_STORAGE_TRIE, "self-destructed account has no storage trie");
-      if (J.device_marks) b.acct_rec.erase(haddr);
       uint32_t r = A.remove(state, haddr_key[i], 64, 0);
       if (r != UNCHANGED) state = r;
     }

@@ -406,7 +406,6 @@ uint32_t make_account_record(Job& J, BlockJob& b, int32_t idx, const uint8_t* pa
   }
   if (has_trie) b.storage[haddr] = sroot;
   b.pre_accounts.push_back({haddr, r, nonempty, (in.flags & 2) != 0, (in.flags & 2) ? b.storage_root_of_instr[idx] : NODE_EMPTY});
-  if (J.device_marks) b.acct_rec[haddr] = r;
   if (nonempty) b.pre_with_storage[haddr] = r;
   return r;
 }
@@ -430,7 +429,6 @@ uint32_t build_witness_trie(Job& J, BlockJob& b, int32_t root_idx, bool is_stora
     for (size_t i = n_pre_accounts; i < b.pre_accounts.size(); i++) {
       b.storage.erase(b.pre_accounts[i].haddr);
       b.pre_with_storage.erase(b.pre_accounts[i].haddr);
-      b.acct_rec.erase(b.pre_accounts[i].haddr);
     }
     b.pre_accounts.resize(n_pre_accounts);
     b.root_of.erase_if([&](uint32_t root, uint32_t root_node) {

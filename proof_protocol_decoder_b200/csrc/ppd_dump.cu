@@ -488,59 +488,6 @@ __global__ void __launch_bounds__(DUMP_THREADS) ir_emit_kernel(ArenaView A, IrDu
   }
 }
 
-// ---- create_trie_subset's marking pass (trie_subsets.rs mark_nodes_that_are_needed; decoding.rs:185-209) ----
-// One thread per (trie version, key): walks the resident arena exactly as HostArena::mark does and writes the
-// node ids it visits into the item's MARK_SLOTS slots of the IR's touched list (the host pre-fills them with
-// NODE_EMPTY).  flags[ir] = 1: an item of that IR visited more nodes than it has slots (the host serialises the
-// IR); flags[n_ir] = 1: a key ran into a hashed-out node, which is MissingKeysCreatingSubPartialTrie in the
-// reference (the host then redoes the block with its own marking pass to report errors in the reference's order).
-__device__ __forceinline__ uint32_t pool_nib(const uint8_t* __restrict__ keys, uint32_t koff, uint32_t i) {
-  const uint32_t b = keys[koff + (i >> 1)];
-  return (i & 1) ? (b & 15u) : (b >> 4);
-}
-__global__ void __launch_bounds__(128) mark_walk_kernel(ArenaView A, const uint4* __restrict__ items, uint32_t n_items, uint32_t n_ir,
-                                                        uint32_t* __restrict__ touched, uint32_t* __restrict__ flags) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_items) return;
-  const uint4 it = items[i];
-  const uint32_t koff = it.y, klen = it.z & 0xffu, ir = it.z >> 8;
-  uint32_t* out = touched + it.w;
-  uint32_t node = it.x, pos = 0, cnt = 0;
-  while (node != NODE_EMPTY) {
-    if (cnt == MARK_SLOTS) {
-      flags[ir] = 1;
-      break;
-    }
-    out[cnt++] = node;
-    if (is_hash_id(node)) {
-      if (pos < klen) flags[n_ir] = 1;
-      break;
-    }
-    const NodeRec r = A.nodes[node];
-    const uint32_t kind = r.w0 & 0xff;
-    if (kind == NK_ROOT) {
-      if (pos < klen) flags[n_ir] = 1;
-      break;
-    }
-    if (kind == NK_BRANCH) {
-      if (pos >= klen) break;
-      const uint32_t bit = 1u << pool_nib(A.key_pool, koff, pos);
-      if (!(r.a1 & bit)) break;
-      node = A.child_pool[r.a0 + __popc(r.a1 & 0xffffu & (bit - 1))];
-      pos++;
-    } else if (kind == NK_EXT) {
-      const uint32_t es = (r.w0 >> 8) & 0xff, el = (r.w0 >> 16) & 0xff, avail = klen - pos, m = min(avail, el);
-      bool same = true;
-      for (uint32_t k = 0; k < m && same; k++) same = pool_nib(A.key_pool, r.a0, es + k) == pool_nib(A.key_pool, koff, pos + k);
-      if (!same || avail < el) break;
-      pos += el;
-      node = r.a1;
-    } else {
-      break;  // a leaf ends the walk
-    }
-  }
-}
-
 size_t ir_dump_smem_bytes() { return sizeof(SharedSet); }
 
 void launch_ir_size(const ArenaView& A, const IrDumpPlanView& P, uint32_t n_ir, cudaStream_t st) {
@@ -552,10 +499,6 @@ void launch_ir_size(const ArenaView& A, const IrDumpPlanView& P, uint32_t n_ir, 
     attr = true;
   }
   ir_size_kernel<<<n_ir, DUMP_THREADS, sizeof(SharedSet), st>>>(A, P);
-}
-void launch_mark_walk(const ArenaView& A, const uint32_t* items4, uint32_t n_items, uint32_t n_ir, uint32_t* touched, uint32_t* flags, cudaStream_t st) {
-  if (!n_items) return;
-  mark_walk_kernel<<<(n_items + 127) / 128, 128, 0, st>>>(A, reinterpret_cast<const uint4*>(items4), n_items, n_ir, touched, flags);
 }
 void launch_ir_emit(const ArenaView& A, const IrDumpPlanView& P, uint32_t n_ir, uint8_t* out, cudaStream_t st) {
   if (!n_ir) return;

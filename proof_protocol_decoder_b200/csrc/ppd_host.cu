@@ -305,24 +305,6 @@ namespace {
 
 // One block on one lane: parse, key hashes, shaping, sweep, dump.  A failure that is the block's own
 // (bad input, a reference panic site) is reported through *status; a CUDA failure is thrown.
-// Whether the block's subset marking walks are left to the device: only when the device also serialises the IRs (same
-// threshold as gpu_dump_block; a marking walk touches about eight nodes).
-bool device_marks_wanted(const BlockJob& b) {
-  // Opt-in (PPD_DEVICE_MARKS): measured on the 16-core box the host's own marking pass is the better choice today,
-  // because its interleaved, prefetched walks are what brings the paths into the cache that the inserts of the same
-  // txn then copy; without it the inserts take those misses one by one (state writes 7 -> 28 ms per block, 410 -> 296
-  // blocks/s).  It pays once the inserts themselves run on the device.
-  if (!gpu_dump_enabled() || !getenv("PPD_DEVICE_MARKS")) return false;
-  size_t n_marks = 0;
-  for (const TxnV& tx : b.txns) {
-    n_marks += 2;
-    for (const TraceV& tr : tx.traces) n_marks += 1 + tr.n_reads + tr.n_writes;
-  }
-  const char* e = getenv("PPD_GPU_DUMP_MIN_TOUCHED");
-  const size_t min_touched = e ? (size_t)atoll(e) : 32768;
-  return n_marks > 0 && 8 * n_marks >= min_touched;
-}
-
 void decode_one_inner(ppd_ctx* c, Lane* L, const uint8_t* flat, size_t len, uint8_t** out, size_t* out_len, int* status, unsigned dump_workers);
 // host_busy_ms: what the block cost its host thread apart from waiting for the device (the quantity that bounds
 // blocks/s when several GPUs share the host's cores)
@@ -335,30 +317,23 @@ void decode_one(ppd_ctx* c, Lane* L, const uint8_t* flat, size_t len, uint8_t** 
 }
 void decode_one_inner(ppd_ctx* c, Lane* L, const uint8_t* flat, size_t len, uint8_t** out, size_t* out_len, int* status, unsigned dump_workers) {
   *out = nullptr, *out_len = 0;
-  const ppd_stats stats0 = L->stats;
-  // Second attempt: only after a first one with device-side marking walks that met an error.  With the marks
-  // deferred to the device the host cannot tell whether an earlier txn's marking pass would have failed first, so the
-  // block is redone with the host's own marking pass, which reports errors in the reference's order.
-  bool try_device = gpu_txn_enabled();
-  for (int attempt = 0; attempt < 2; attempt++) {
+  // First everything after the flat input on the device (gpu_txn.cu).  A block it declines (an error the reference
+  // would report, a witness the GPU parser hands to the host builder, a capacity limit) starts over on the host path:
+  // the host shapes the tries, in the reference's order of operations, and the device hashes and serialises them.
+  for (int on_device = gpu_txn_enabled() ? 1 : 0; on_device >= 0; on_device--) {
     PhaseTimer pt;
     Job& J = job_of(L, 1);
     BlockJob& b = J.blocks[0];
-    bool redo = false;
     try {
       read_flat_block(flat, len, b);
       pt.lap("read-flat");
-      if (try_device) {
-        // everything after the flat input on the device (gpu_txn.cu); a block it declines starts over on the host path
-        try_device = false;
+      if (on_device) {
         if (gpu_block(c, L, J, flat, len, out, out_len) == GPU_BLOCK_DONE) {
           *status = PPD_OK;
           return;
         }
-        attempt--;
         continue;
       }
-      J.device_marks = attempt == 0 && device_marks_wanted(b);
       if (gpu_parse_enabled()) gpu_pre_image(L, J, b, true, &c->parse_slots_sem);
       collect_messages(J, b);
       pt.lap("parse");
@@ -370,15 +345,14 @@ void decode_one_inner(ppd_ctx* c, Lane* L, const uint8_t* flat, size_t len, uint
       pt.lap("shape");
       sweep(L, J, /*refs_to_host=*/!gpu_dump_enabled());
       pt.lap("sweep");
-      const int r = gpu_dump_block(c, L, J, out, out_len);
-      if (r == DUMP_REDO_HOST_MARKS) {
-        redo = true;
-      } else if (r == DUMP_ON_HOST) {
+      if (gpu_dump_block(c, L, J, out, out_len) == DUMP_ON_HOST) {
         fetch_refs(L, J);
         fetch_pools(L, J);
         dump_blocks(J, out, out_len, dump_workers);
       }
       pt.lap("dump");
+      *status = PPD_OK;
+      return;
     } catch (const std::bad_alloc&) {
       *status = PPD_ERR_BAD_FLAT_INPUT;  // sizes taken from the input that no memory can hold
       std::lock_guard<std::mutex> g(c->err_mu);
@@ -386,20 +360,11 @@ void decode_one_inner(ppd_ctx* c, Lane* L, const uint8_t* flat, size_t len, uint
       return;
     } catch (const Fail& e) {
       if (e.code == PPD_ERR_CUDA) throw;
-      if (J.device_marks) {
-        redo = true;
-      } else {
-        *status = e.code;
-        std::lock_guard<std::mutex> g(c->err_mu);
-        c->err = e.msg;
-        return;
-      }
-    }
-    if (!redo) {
-      *status = PPD_OK;
+      *status = e.code;
+      std::lock_guard<std::mutex> g(c->err_mu);
+      c->err = e.msg;
       return;
     }
-    L->stats = stats0;
   }
 }
 

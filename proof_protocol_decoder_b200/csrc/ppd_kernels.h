@@ -88,11 +88,9 @@ struct IrDumpPlanView {
   uint32_t* u_off;
 };
 void launch_ir_size(const ArenaView& A, const IrDumpPlanView& P, uint32_t n_ir, cudaStream_t st);
-// the subset marking walks on the device: items4 = n_items x (root, key offset, key nibbles | ir << 8, first slot in touched[]);
-// every item owns MARK_SLOTS slots of touched[]; flags[0 .. n_ir) = slot overflow per IR, flags[n_ir] = a key ran into a hashed-out node
+// slots of the IR's touched list every key of a txn owns (the device txn loop's walks fill them, txn_core.h)
 static const uint32_t MARK_SLOTS = 16;
 static const uint32_t IR_SET_MAX_UNIQ = 4096;  // distinct touched nodes an ordinary IR may have (ppd_dump.cu: MAX_UNIQ)
-void launch_mark_walk(const ArenaView& A, const uint32_t* items4, uint32_t n_items, uint32_t n_ir, uint32_t* touched, uint32_t* flags, cudaStream_t st);
 void launch_ir_emit(const ArenaView& A, const IrDumpPlanView& P, uint32_t n_ir, uint8_t* out, cudaStream_t st);
 
 // ---- ppd_parse.cu: compact witness -> instruction list -> tree links -> node arena ----

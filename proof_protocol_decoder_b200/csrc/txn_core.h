@@ -131,7 +131,9 @@ struct Cursors {
   uint32_t max_level;
   uint32_t roots[6];  // NK_ROOT nodes the dummy entries refer to (XR_*), created when the loop ends
   uint32_t state_before_withdrawals;
-  unsigned long long phase_clocks[8];  // SM clocks per phase of the loop, summed over txns (setup, marks, batch 1, records, batch 2, roots)
+  // SM clocks per phase of the loop, summed over txns: setup, walks, batch 1 (terminals, re-assembly, roots), records,
+  // batch 2 (terminals, re-assembly, roots), root nodes
+  unsigned long long phase_clocks[10];
 };
 
 // One withdrawal (decoding.rs:404-428): balance += amount on the account of the hashed address
@@ -851,14 +853,16 @@ PPD_HD inline void acct_claim(const View& v, const AcctInit& a, uint32_t t) {
 #endif
 
 // terminals, re-assembly and new roots of one batch whose keys have been walked
-PPD_HD inline void run_batch(const Ctx& c, const Batch& b, uint32_t dmax) {
+PPD_HD inline void run_batch(const Ctx& c, const Batch& b, uint32_t dmax, int clock_slot) {
   const View& v = c.v;
   for (uint32_t i = c.tid; i < b.n; i += c.nthreads) batch_terminal(c, b, i);
   PPD_BLOCK_SYNC();
+  PPD_PHASE_CLOCK(c, clock_slot);
   for (uint32_t d = dmax; d-- > 0;) {
     for (uint32_t i = c.tid; i < b.n; i += c.nthreads) batch_assemble(c, b, i, d);
     PPD_BLOCK_SYNC();
   }
+  PPD_PHASE_CLOCK(c, clock_slot + 1);
   // the first key of every trie holds the trie's new root
   for (uint32_t i = c.tid; i < b.n; i += c.nthreads) {
     if (b.ops[i].lcp != -1) continue;
@@ -877,6 +881,7 @@ PPD_HD inline void run_batch(const Ctx& c, const Batch& b, uint32_t dmax) {
     }
   }
   PPD_BLOCK_SYNC();
+  PPD_PHASE_CLOCK(c, clock_slot + 2);
 }
 
 PPD_HD inline void copy32(uint8_t* d, const uint8_t* s) {
@@ -933,8 +938,7 @@ PPD_HD inline void run_txn(const Ctx& c, uint32_t ti, const uint8_t* empty_trie_
   PPD_BLOCK_SYNC();
   PPD_PHASE_CLOCK(c, 1);
   // ---- apply_deltas_to_trie_state (decoding.rs:219-292): storage writes, the txn and receipt inserts ----
-  run_batch(c, b1, c.sh_dmax[0]);
-  PPD_PHASE_CLOCK(c, 2);
+  run_batch(c, b1, c.sh_dmax[0], 2);
   // ---- the accounts after the txn: storage_root = the storage trie's hash after the writes (late-bound: an NK_ROOT node) ----
   for (uint32_t k = c.tid; k < ntr; k += c.nthreads) {
     const uint32_t t = tx.trace_begin + k;
@@ -970,9 +974,9 @@ PPD_HD inline void run_txn(const Ctx& c, uint32_t ti, const uint8_t* empty_trie_
     v.accounts[v.rec_base + tr.rec] = rec;
   }
   PPD_BLOCK_SYNC();
-  PPD_PHASE_CLOCK(c, 3);
+  PPD_PHASE_CLOCK(c, 5);
   // ---- state writes and self-destructs in one descent ----
-  run_batch(c, b2, c.sh_dmax[1]);
+  run_batch(c, b2, c.sh_dmax[1], 6);
   for (uint32_t k = c.tid; k < ntr; k += c.nthreads) {
     const TxnTrace& tr = v.traces[tx.trace_begin + k];
     if (tr.flags & PPD_TR_SELF_DESTRUCTED) {  // trie_state.storage.remove(hashed_addr), decoding.rs:271-282
@@ -980,7 +984,6 @@ PPD_HD inline void run_txn(const Ctx& c, uint32_t ti, const uint8_t* empty_trie_
       a.storage = ST_ABSENT, a.root_node = NONE;
     }
   }
-  PPD_PHASE_CLOCK(c, 4);
   // ---- calculate_trie_input_hashes (decoding.rs:458-464): three NK_ROOT nodes, read by the dump as refs ----
   if (c.tid == 0) {
     v.seg_a[tx.seg_roots + 0] = new_root(v, v.cur->state_root);
@@ -988,7 +991,7 @@ PPD_HD inline void run_txn(const Ctx& c, uint32_t ti, const uint8_t* empty_trie_
     v.seg_a[tx.seg_roots + 2] = new_root(v, v.cur->receipt_root);
   }
   PPD_BLOCK_SYNC();
-  PPD_PHASE_CLOCK(c, 5);
+  PPD_PHASE_CLOCK(c, 9);
 }
 
 // ---- after the last txn: the NK_ROOT nodes dummy entries refer to, and the withdrawals (decoding.rs:356-428) ----

@@ -560,44 +560,32 @@ def test_gpu_parse_stream_lengths_around_tile_boundaries(ctx, oracle):
     assert {0, 1, 2, 4094, 4095} <= seen
 
 
-def test_subset_marking_on_the_device_matches_host_marking(ctx, oracle):
-    """create_trie_subset's marking walks (decoding.rs:185-209) run on the device after the sweep's upload
-    (mark_walk_kernel) when PPD_DEVICE_MARKS is set; the host's interleaved pass is the default.  Same bytes either way, and the same status for a block
-    whose txn touches a key under a hashed-out node (MissingKeysCreatingSubPartialTrie, via the redo path)."""
-    import os
-
+def test_subset_marking_on_the_device_and_error_order(ctx, oracle):
+    """create_trie_subset's marking walks (decoding.rs:185-209) are the walks of the device txn loop (txn_core.h:
+    batch_walk).  A txn that touches a key under a hashed-out node is MissingKeysCreatingSubPartialTrie in the reference,
+    possibly after other errors of earlier txns: the device loop only flags it, the host path then redoes the block
+    and reports errors in the reference's order."""
     from proof_protocol_decoder_b200 import synth
 
     blk = synth.gen_block(77, n_accounts=1200, n_txns=12, contract_frac=0.3, slots_hi=64, virtual_depth=3, virtual_accounts_log16=5,
                           accounts_per_txn=(20, 40), slot_reads=(0, 4), slot_writes=(0, 4), allow_new_accounts=False, allow_self_destruct=False)
     want = oracle.block_decode(blk.flat)
-    saved = os.environ.pop("PPD_DEVICE_MARKS", None)
-    try:
-        assert ctx.block_decode(blk.flat) == want
-        assert ctx.stats()["marks_on_gpu"] == 0  # the host's marking pass is the default (ppd_host.cu: device_marks_wanted)
-    finally:
-        if saved is not None:
-            os.environ["PPD_DEVICE_MARKS"] = saved
+    assert ctx.block_decode(blk.flat) == want
+    st = ctx.stats()
+    assert st["txn_loops_on_gpu"] == 1 and st["marks_on_gpu"] > 12 * 20
+    for seed in (1, 2, 3):  # config-1 shaped blocks with new accounts, self-destructs, withdrawals
+        c1 = synth.gen_block(seed, n_accounts=1000, n_txns=10, n_withdrawals=seed % 3)
+        assert ctx.block_decode(c1.flat) == oracle.block_decode(c1.flat)
+        assert ctx.stats()["marks_on_gpu"] > 0
     # a new account in a state with hashed-out siblings: its key runs into a hash node
     bad = synth.gen_block(78, n_accounts=300, n_txns=4, virtual_depth=3, virtual_accounts_log16=5, accounts_per_txn=(5, 10),
                           allow_new_accounts=True, allow_self_destruct=False)
-    os.environ["PPD_DEVICE_MARKS"] = "1"
     try:
-        got = ctx.block_decode(blk.flat)
-        st = ctx.stats()
-        assert got == want
-        assert st["marks_on_gpu"] > 12 * 20
-        for seed in (1, 2, 3):  # config-1 shaped blocks with new accounts, self-destructs, withdrawals
-            c1 = synth.gen_block(seed, n_accounts=1000, n_txns=10, n_withdrawals=seed % 3)
-            assert ctx.block_decode(c1.flat) == oracle.block_decode(c1.flat)
-            assert ctx.stats()["marks_on_gpu"] > 0
-        try:
-            want_bad = oracle.block_decode(bad.flat)
-        except OracleError as e:
-            with pytest.raises(Exception) as ei:
-                ctx.block_decode(bad.flat)
-            assert getattr(ei.value, "code", None) == e.code
-        else:
-            assert ctx.block_decode(bad.flat) == want_bad
-    finally:
-        os.environ.pop("PPD_DEVICE_MARKS", None)
+        want_bad = oracle.block_decode(bad.flat)
+    except OracleError as e:
+        with pytest.raises(Exception) as ei:
+            ctx.block_decode(bad.flat)
+        assert getattr(ei.value, "code", None) == e.code
+        assert ctx.stats()["txn_loops_on_gpu"] == 0  # the host path reported it
+    else:
+        assert ctx.block_decode(bad.flat) == want_bad
