@@ -260,6 +260,147 @@ def c5_sweep(ctx, sizes, peaks, sm_mhz):
     return out
 
 
+def _unit_leaves(torch, n, seed, top_nibble, val_lo, val_hi):
+    """n sorted leaves on the device whose keys start with `top_nibble` (a deterministic function of the seed, so that
+    every world size hashes the same trie)."""
+    g = torch.Generator(device="cuda")
+    g.manual_seed(seed)
+    keys = torch.randint(0, 256, (n, 32), dtype=torch.uint8, device="cuda", generator=g)
+    keys[:, 0] = (keys[:, 0] & 15) | (top_nibble << 4)
+    k64 = torch.zeros(n, dtype=torch.int64, device="cuda")
+    for b in range(8):
+        k64 = (k64 << 8) | keys[:, b].to(torch.int64)
+    order = torch.argsort((k64 >> 1) & 0x7FFFFFFFFFFFFFFF)
+    keys = keys[order].contiguous()
+    del k64, order
+    lens = torch.randint(val_lo, val_hi + 1, (n,), dtype=torch.int64, device="cuda", generator=g)
+    val_off = torch.zeros(n + 1, dtype=torch.int64, device="cuda")
+    val_off[1:] = torch.cumsum(lens, 0)
+    vb = int(val_off[-1].item())
+    vals = torch.randint(1, 256, (vb,), dtype=torch.uint8, device="cuda", generator=g)
+    return keys, val_off, vals, vb
+
+
+def _gather_refs(torch, dist, local, n_units):
+    """{unit: 32-byte ref} of every rank -> all refs on every rank (one all-reduce: units are disjoint)."""
+    buf = torch.zeros(32 * n_units, dtype=torch.int32, device="cuda")
+    for u, r in local.items():
+        buf[32 * u: 32 * u + 32] = torch.frombuffer(bytearray(r), dtype=torch.uint8).to("cuda").to(torch.int32)
+    if dist is not None:
+        dist.all_reduce(buf, op=dist.ReduceOp.SUM)
+    raw = bytes(buf.to(torch.uint8).cpu().numpy().tobytes())
+    return [raw[32 * u: 32 * u + 32] for u in range(n_units)]
+
+
+def split_legs(ctx, torch, dist, rank, world, args, barrier, max_over_ranks, sum_over_ranks, n1):
+    """Config 5 (one huge trie) and the storage side of config 3 (a few 1 M-slot tries) over `world` GPUs:
+    tries are cut at their top nibble into 16 sub-tries, the units are dealt to the ranks, each rank hashes its units
+    (structure built and hashed on its GPU), one NCCL all-reduce gathers the 32-byte refs, rank 0 hashes the top
+    branches (and, for config 3, the state trie whose account leaves carry the gathered storage roots,
+    decoding.rs:438-447).  Strong scaling: the tries are the same for every world size, so are their roots."""
+    from proof_protocol_decoder_b200 import synth
+
+    out = {}
+    # ---------------- config 5 ----------------
+    total = args.c5_leaves
+    per = total // 16
+    mine = [i for i in range(16) if i % world == rank]
+    units = {i: _unit_leaves(torch, per, 5000 + i, i, 70, 80) for i in mine}
+    for _ in range(2):  # warm-up (buffers of the context grow to size)
+        for i in mine[:1]:
+            k, vo, v, vb = units[i]
+            ctx.trie_subroot_sorted_leaves_dev(k.data_ptr(), vo.data_ptr(), v.data_ptr(), per, vb, 1)
+    barrier()
+    t0 = time.perf_counter()
+    local, nodes, perms, dev_ms = {}, 0, 0, 0.0
+    for i in mine:
+        k, vo, v, vb = units[i]
+        local[i] = ctx.trie_subroot_sorted_leaves_dev(k.data_ptr(), vo.data_ptr(), v.data_ptr(), per, vb, 1)
+        st = ctx.stats()
+        nodes += st["nodes_hashed"]
+        perms += st["node_permutations"]
+        dev_ms += st["gpu_ms"]
+    refs = _gather_refs(torch, dist, local, 16)
+    root = ctx.trie_root_from_children(b"".join(refs), 0xFFFF) if rank == 0 else b""
+    torch.cuda.synchronize()
+    wall = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    nodes_all, perms_all, dev_ms_max = sum_over_ranks(float(nodes)), sum_over_ranks(float(perms)), max_over_ranks(dev_ms)
+    leg = {"leaves": per * 16, "ms": 1e3 * wall, "device_ms_max_over_ranks": dev_ms_max, "nodes_hashed": nodes_all + 1, "nodes_per_sec": (nodes_all + 1) / wall,
+           "permutations_per_sec": perms_all / wall, "root": root.hex() if rank == 0 else None, "units_per_rank": len(mine),
+           "note": "16 sub-tries by top nibble dealt to the ranks; refs gathered by one NCCL all-reduce of 512 bytes; top branch on rank 0; wall clock between barriers, max over ranks"}
+    if world == 1:
+        # the same trie hashed whole: the split must give its root
+        keys = torch.cat([units[i][0] for i in range(16)])
+        lens = torch.cat([units[i][1][1:] - units[i][1][:-1] for i in range(16)])
+        val_off = torch.zeros(per * 16 + 1, dtype=torch.int64, device="cuda")
+        val_off[1:] = torch.cumsum(lens, 0)
+        vals = torch.cat([units[i][2] for i in range(16)])
+        whole = ctx.trie_root_sorted_leaves_dev(keys.data_ptr(), val_off.data_ptr(), vals.data_ptr(), per * 16, int(val_off[-1].item()))
+        leg["whole_trie_ms"] = ctx.stats()["gpu_ms"]
+        leg["equals_whole_trie_root"] = whole == root
+        del keys, lens, val_off, vals
+    elif rank == 0 and n1.get("c5_split"):
+        leg["root_equals_n1_run"] = n1["c5_split"].get("root") == leg["root"]
+        leg["speedup_vs_n1"] = n1["c5_split"]["ms"] / leg["ms"]
+        leg["efficiency_vs_n1"] = leg["speedup_vs_n1"] / world
+    out["c5_split"] = leg
+    del units
+    torch.cuda.empty_cache()
+    # ---------------- config 3: storage tries sharded, roots joined into the account leaves ----------------
+    n_c, slots = 4, args.c3_slots
+    per = slots // 16
+    all_units = [(c, i) for c in range(n_c) for i in range(16)]
+    mine = [u for k, u in enumerate(all_units) if k % world == rank]
+    units = {u: _unit_leaves(torch, per, 3000 + 16 * u[0] + u[1], u[1], 1, 33) for u in mine}
+    barrier()
+    t0 = time.perf_counter()
+    local, nodes, perms = {}, 0, 0
+    for (c, i) in mine:
+        k, vo, v, vb = units[(c, i)]
+        local[16 * c + i] = ctx.trie_subroot_sorted_leaves_dev(k.data_ptr(), vo.data_ptr(), v.data_ptr(), per, vb, 1)
+        st = ctx.stats()
+        nodes += st["nodes_hashed"]
+        perms += st["node_permutations"]
+    refs = _gather_refs(torch, dist, local, 16 * n_c)
+    state_root = b""
+    if rank == 0:
+        storage_roots = [ctx.trie_root_from_children(b"".join(refs[16 * c: 16 * c + 16]), 0xFFFF) for c in range(n_c)]
+        # the state trie: 1 000 plain accounts + the contracts, whose leaves carry the storage roots just gathered
+        import numpy as np
+
+        rng = np.random.default_rng(3)
+        n_acc = 1000 + n_c
+        hk = rng.bytes(32 * n_acc)
+        items = []
+        for a in range(n_acc):
+            sroot = storage_roots[a] if a < n_c else bytes.fromhex("56e81f171bcc55a6ff8345e692c0f86e5b48e01b996cadc001622fb5e363b421")
+            rlp = synth.rlp_list([synth.rlp_int(a + 1), synth.rlp_int(10 ** 18 + a), synth.rlp_str(sroot), synth.rlp_str(hk[32 * a: 32 * a + 32][::-1])])
+            items.append((hk[32 * a: 32 * a + 32], rlp))
+        items.sort()
+        keys = np.frombuffer(b"".join(k for k, _ in items), dtype=np.uint8).reshape(-1, 32)
+        val_off = np.zeros(n_acc + 1, dtype=np.uint64)
+        val_off[1:] = np.cumsum([len(v) for _, v in items])
+        vals = np.frombuffer(b"".join(v for _, v in items), dtype=np.uint8)
+        state_root = ctx.trie_root_sorted_leaves(keys, val_off, vals)
+        nodes += ctx.stats()["nodes_hashed"] + n_c
+    torch.cuda.synchronize()
+    wall = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    nodes_all = sum_over_ranks(float(nodes))
+    leg = {"contracts": n_c, "slots_per_contract": per * 16, "plain_accounts": 1000, "ms": 1e3 * wall, "nodes_hashed": nodes_all, "nodes_per_sec": nodes_all / wall,
+           "state_root": state_root.hex() if rank == 0 else None, "units_per_rank": len(mine),
+           "note": "64 storage sub-tries (4 contracts x 16 top nibbles) dealt to the ranks; their refs gathered by one NCCL all-reduce; rank 0 hashes the 4 top branches and the state trie whose account leaves carry those storage roots"}
+    if world > 1 and rank == 0 and n1.get("c3_sharded"):
+        leg["state_root_equals_n1_run"] = n1["c3_sharded"].get("state_root") == leg["state_root"]
+        leg["speedup_vs_n1"] = n1["c3_sharded"]["ms"] / leg["ms"]
+        leg["efficiency_vs_n1"] = leg["speedup_vs_n1"] / world
+    out["c3_sharded"] = leg
+    del units
+    torch.cuda.empty_cache()
+    return out
+
+
 def measure_pcie(torch, mb=256):
     """Pinned-memory copy bandwidth of this GPU's link, both directions at once (GB/s each): what bounds a pipeline
     that streams FlatBlocks in and IrDumps out."""
@@ -579,6 +720,18 @@ def run_b200(args, rank, world, local_rank):
             "frac_of_pcie": (ir_len * (resident / n_blocks) / (dump_ms / 1e3) / 1e9 / pcie_gbs) if dump_ms else None,
         },
     }
+    if not args.no_split:
+        try:
+            legs = split_legs(ctx, torch, dist, rank, world, args, barrier, max_over_ranks, sum_over_ranks, n1)
+            line.update(legs)
+            if world == 1 and rank == 0:
+                n1.update({k: {"ms": v["ms"], "root": v.get("root"), "state_root": v.get("state_root")} for k, v in legs.items()})
+                try:
+                    json.dump(n1, open(N1_CACHE, "w"))
+                except OSError:
+                    pass
+        except Exception as e:  # noqa: BLE001 — supplementary legs never cost the headline line
+            line["split_legs_error"] = str(e)[:300]
     if cpu_baseline:
         line["cpu_baseline"] = cpu_baseline
     if rank == 0 and world == 1 and not args.no_sweep:
@@ -601,6 +754,9 @@ def main():
     ap.add_argument("--ref-scale", type=float, default=1.0, help="size of the CPU arm's block (1.0 = the same config as the b200 arm)")
     ap.add_argument("--sweep", default="1000000,10000000", help="config-5 leaf counts measured beside the headline at N=1")
     ap.add_argument("--no-sweep", action="store_true")
+    ap.add_argument("--c5-leaves", type=int, default=32_000_000, help="leaves of the config-5 trie that is split over the GPUs")
+    ap.add_argument("--c3-slots", type=int, default=1_000_000, help="slots of each of the four config-3 storage tries that are sharded over the GPUs")
+    ap.add_argument("--no-split", action="store_true", help="skip the c5_split / c3_sharded legs")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

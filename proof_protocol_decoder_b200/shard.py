@@ -7,7 +7,11 @@ its data model:
   * storage tries only meet at the account leaf's storage_root (decoding.rs:438-447,
     compact_prestate_processing.rs:617-621), so per-account tries are bin-packed over the ranks by
     size and only their 32-byte roots are exchanged.
-The single exchange step is an all-gather of 32-byte roots (NCCL on the GPUs, gloo in the CPU tests).
+  * one huge trie (config 5, or a 1 M-slot storage trie of config 3) splits at its top nibble into 16 sub-tries
+    whose keys share that nibble; each is hashed like a whole trie whose nodes sit one nibble below the root
+    (ppd_trie_subroot_sorted_leaves_dev), 16 refs are gathered and the top branch is hashed last
+    (ppd_trie_root_from_children).
+The single exchange step is an all-gather of 32-byte roots / refs (NCCL on the GPUs, gloo in the CPU tests).
 """
 from typing import Callable, Dict, List, Sequence
 
@@ -80,3 +84,48 @@ def sharded_block_roots(decode_fn: Callable[[int], Sequence[bytes]], n_blocks: i
             local[3 * i + k] = roots[k]
     flat = all_gather_roots(local, 3 * n_blocks, dist, device)
     return [flat[3 * i : 3 * i + 3] for i in range(n_blocks)]
+
+
+def top_nibble_ranges(torch, keys):
+    """[lo, hi) of the leaves whose key starts with nibble i, for i in 0..15 (keys: sorted uint8 [n, 32] on any device)."""
+    top = (keys[:, 0] >> 4).to(torch.int64)
+    bounds = torch.searchsorted(top, torch.arange(17, dtype=torch.int64, device=keys.device)).tolist()
+    return [(bounds[i], bounds[i + 1]) for i in range(16)]
+
+
+def split_trie_refs(ctx, torch, keys, val_off, vals, nibbles=None):
+    """The refs of the sub-tries below the top branch of the trie over the sorted leaves (device tensors), for the
+    top nibbles in `nibbles` (default: all 16).  Returns (refs: 16 x 32 bytes, zeros where absent or not asked for;
+    mask of the non-empty sub-tries among ALL 16; stats summed over the parts)."""
+    ranges = top_nibble_ranges(torch, keys)
+    refs = [bytes(32)] * 16
+    mask = 0
+    tot = {"nodes_hashed": 0, "node_permutations": 0, "node_bytes": 0, "gpu_ms": 0.0}
+    for i, (lo, hi) in enumerate(ranges):
+        if hi <= lo:
+            continue
+        mask |= 1 << i
+        if nibbles is not None and i not in nibbles:
+            continue
+        v0 = int(val_off[lo].item())
+        sub_off = (val_off[lo : hi + 1] - v0).contiguous()
+        sub_keys = keys[lo:hi]
+        refs[i] = ctx.trie_subroot_sorted_leaves_dev(sub_keys.data_ptr(), sub_off.data_ptr(), vals.data_ptr() + v0, hi - lo, int(sub_off[-1].item()), 1)
+        st = ctx.stats()
+        for k in tot:
+            tot[k] += st[k]
+    return refs, mask, tot
+
+
+def all_gather_refs(torch, local_refs, owned, dist=None):
+    """Every rank holds the refs of the top nibbles it owns; every rank gets all 16 (one NCCL all-reduce of 512 bytes:
+    the entries a rank does not own are zero)."""
+    buf = torch.zeros(512, dtype=torch.uint8, device="cuda" if torch.cuda.is_available() else "cpu")
+    for i in owned:
+        buf[32 * i : 32 * i + 32] = torch.frombuffer(bytearray(local_refs[i]), dtype=torch.uint8).to(buf.device)
+    if dist is not None and dist.is_initialized() and dist.get_world_size() > 1:
+        wide = buf.to(torch.int32)
+        dist.all_reduce(wide, op=dist.ReduceOp.SUM)
+        buf = wide.to(torch.uint8)
+    raw = bytes(buf.cpu().numpy().tobytes())
+    return [raw[32 * i : 32 * i + 32] for i in range(16)]
