@@ -111,6 +111,8 @@ void after_emit(void* arg, const ParseEmit& E) {
     v.tdepth = c.take<uint8_t>(T.max_ops + 1);
     v.tkind = c.take<uint8_t>(T.max_ops + 1);
     v.res = c.take<uint32_t>(T.max_ops + 1);
+    v.res_lv = c.take<uint16_t>(T.max_ops + 1);
+    v.key_hi = c.take<uint32_t>(T.max_ops + 1);
     v.cur = c.take<txn::Cursors>(1);
     H.bins_pre = c.take<uint32_t>(ORDER_MAX_BINS);
     H.bins_tail = c.take<uint32_t>(ORDER_MAX_BINS);

@@ -128,7 +128,8 @@ constexpr int LOOP_THREADS = 256;
 constexpr uint32_t SH_KEYS = 512;  // keys of one txn whose scratch fits in shared memory
 struct LoopShared {
   uint32_t path_node[SH_KEYS * PATH_CAP], path_a0[SH_KEYS * PATH_CAP], path_a1[SH_KEYS * PATH_CAP];
-  uint32_t tnode[SH_KEYS], res[SH_KEYS];
+  uint32_t tnode[SH_KEYS], res[SH_KEYS], key_hi[SH_KEYS];
+  uint16_t res_lv[SH_KEYS];
   SOp ops[SH_KEYS];
   uint8_t path_depth[SH_KEYS * PATH_CAP];
   uint8_t plen[SH_KEYS], top[SH_KEYS], tdepth[SH_KEYS], tkind[SH_KEYS];
@@ -151,7 +152,7 @@ __global__ void __launch_bounds__(LOOP_THREADS, 1) txn_loop_kernel(View v, uint3
   if (use_shared) {
     LoopShared& S = *reinterpret_cast<LoopShared*>(loop_smem);
     v.path_node = S.path_node, v.path_a0 = S.path_a0, v.path_a1 = S.path_a1, v.path_depth = S.path_depth;
-    v.plen = S.plen, v.top = S.top, v.tnode = S.tnode, v.tdepth = S.tdepth, v.tkind = S.tkind, v.res = S.res, v.sh_ops = S.ops;
+    v.plen = S.plen, v.top = S.top, v.tnode = S.tnode, v.tdepth = S.tdepth, v.tkind = S.tkind, v.res = S.res, v.res_lv = S.res_lv, v.key_hi = S.key_hi, v.sh_ops = S.ops;
   }
   __syncthreads();
   if (sh_stop) return;  // an earlier chunk (or the join) raised a flag: the host path redoes the block

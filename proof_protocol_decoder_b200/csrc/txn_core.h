@@ -187,7 +187,9 @@ struct View {
   uint32_t* tnode;      // [keys] terminal node
   uint8_t* tdepth;      // [keys]
   uint8_t* tkind;       // [keys]
-  uint32_t* res;        // [keys]
+  uint32_t* res;        // [keys] new version of the sub-trie the key is the first of, T_UNCHANGED, or NODE_EMPTY
+  uint16_t* res_lv;     // [keys] its level
+  uint32_t* key_hi;     // [keys] nibbles 0..7 of the key, most significant first (the re-assembly's child slots without a key load)
   SOp* sh_ops;          // [keys] copy of the txn's keys when the scratch is in shared memory, else nullptr
   Cursors* cur;
 };
@@ -304,70 +306,75 @@ PPD_HD inline uint32_t popc16(uint32_t m) {
 #endif
 }
 
-PPD_HD inline uint32_t new_leaf_for(const View& v, const SOp& o, uint32_t start) {
+// A node id with its level.  The level of a new node is 1 + the largest level of what it reads; the creators carry the
+// levels of what they have just made instead of reading them back (a read back is a trip to L2, and sixteen of them in
+// a row, one per child of a new branch, were most of the re-assembly's time).
+struct NL {
+  uint32_t id, lv;
+};
+PPD_HD inline NL new_leaf_for(const View& v, const SOp& o, uint32_t start) {
   const uint32_t len = o.klen - start;
   if (o.kind == OP_PUT_ACCOUNT) {
     const uint32_t src = v.accounts[o.a1].storage_src;
-    return push_node(v, NodeRec{w0(NK_LEAF_ACCOUNT, start, len), o.koff, o.a1, 0}, src == NODE_EMPTY ? 0u : lvl(v, src) + 1u);
+    const uint32_t lv = src == NODE_EMPTY ? 0u : lvl(v, src) + 1u;
+    return NL{push_node(v, NodeRec{w0(NK_LEAF_ACCOUNT, start, len), o.koff, o.a1, 0}, lv), lv};
   }
-  return push_node(v, NodeRec{w0(NK_LEAF, start, len), o.koff, o.a1, o.a2}, 0);
+  return NL{push_node(v, NodeRec{w0(NK_LEAF, start, len), o.koff, o.a1, o.a2}, 0), 0};
 }
-PPD_HD inline uint32_t new_ext(const View& v, uint32_t koff, uint32_t start, uint32_t len, uint32_t child) {
-  return push_node(v, NodeRec{w0(NK_EXT, start, len), koff, child, 0}, lvl(v, child) + 1u);
+PPD_HD inline NL new_ext(const View& v, uint32_t koff, uint32_t start, uint32_t len, NL child) {
+  return NL{push_node(v, NodeRec{w0(NK_EXT, start, len), koff, child.id, 0}, child.lv + 1u), child.lv + 1u};
 }
 PPD_HD inline uint32_t new_root(const View& v, uint32_t child) {
   return push_node(v, NodeRec{w0(NK_ROOT, 0, 0), 0, child, 0}, child == NODE_EMPTY ? 0u : lvl(v, child) + 1u);
 }
 // the same leaf payload under a different key range
-PPD_HD inline uint32_t releaf(const View& v, uint32_t leaf, uint32_t koff, uint32_t start, uint32_t len) {
+PPD_HD inline NL releaf(const View& v, uint32_t leaf, uint32_t leaf_lv, uint32_t koff, uint32_t start, uint32_t len) {
   NodeRec r = v.nodes[leaf];
   r.w0 = w0(r.w0 & 0xffu, start, len);
   r.a0 = koff;
-  return push_node(v, r, v.level[leaf]);
+  return NL{push_node(v, r, leaf_lv), leaf_lv};
 }
-// branch from 16 slots (NODE_EMPTY = none); at least two are set
-PPD_HD inline uint32_t new_branch16(const View& v, const uint32_t* kids, uint32_t min_level) {
-  uint32_t mask = 0, k = 0, lv = min_level;
+// branch of level lv from 16 slots (NODE_EMPTY = none); at least two are set
+PPD_HD inline NL new_branch16(const View& v, const uint32_t* kids, uint32_t lv) {
+  uint32_t mask = 0, k = 0;
   for (uint32_t i = 0; i < 16; i++)
     if (kids[i] != NODE_EMPTY) mask |= 1u << i, k++;
   const uint32_t base = alloc_children(v, k);
   for (uint32_t i = 0, j = 0; i < 16; i++)
-    if (kids[i] != NODE_EMPTY) {
-      v.child_pool[base + j++] = kids[i];
-      const uint32_t l = lvl(v, kids[i]) + 1u;
-      if (l > lv) lv = l;
-    }
-  return push_node(v, NodeRec{w0(NK_BRANCH, 0, 0), base, mask, 0}, lv);
+    if (kids[i] != NODE_EMPTY) v.child_pool[base + j++] = kids[i];
+  return NL{push_node(v, NodeRec{w0(NK_BRANCH, 0, 0), base, mask, 0}, lv), lv};
 }
 // copy of branch `br` with slot `nib` set to `child` (never NODE_EMPTY here)
-PPD_HD inline uint32_t branch_with(const View& v, uint32_t br, uint32_t nib, uint32_t child) {
+PPD_HD inline NL branch_with(const View& v, uint32_t br, uint32_t nib, NL child) {
   const NodeRec r = v.nodes[br];
+  uint32_t lv = v.level[br];
   const uint32_t mask = r.a1 & 0xffffu, bit = 1u << nib;
   const uint32_t k = popc16(mask), rk = popc16(mask & (bit - 1)), has = (mask & bit) ? 1u : 0u;
   const uint32_t nk = k - has + 1u, base = alloc_children(v, nk);
-  for (uint32_t i = 0; i < rk; i++) v.child_pool[base + i] = v.child_pool[r.a0 + i];
-  v.child_pool[base + rk] = child;
-  for (uint32_t i = rk + has; i < k; i++) v.child_pool[base + i - has + 1u] = v.child_pool[r.a0 + i];
-  uint32_t lv = v.level[br];
-  if (lvl(v, child) + 1u > lv) lv = lvl(v, child) + 1u;
-  return push_node(v, NodeRec{w0(NK_BRANCH, 0, 0), base, mask | bit, 0}, lv);
+  uint32_t old[16];
+  for (uint32_t i = 0; i < 16; i++) old[i] = i < k ? v.child_pool[r.a0 + i] : 0u;  // (all in flight together)
+  for (uint32_t i = 0; i < rk; i++) v.child_pool[base + i] = old[i];
+  v.child_pool[base + rk] = child.id;
+  for (uint32_t i = rk + has; i < k; i++) v.child_pool[base + i - has + 1u] = old[i];
+  if (child.lv + 1u > lv) lv = child.lv + 1u;
+  return NL{push_node(v, NodeRec{w0(NK_BRANCH, 0, 0), base, mask | bit, 0}, lv), lv};
 }
 // an extension (ek, es, el) over `child`, merged into the child when that is a leaf / an extension (delete's collapse)
-PPD_HD inline uint32_t collapse_ext(const View& v, uint32_t ek, uint32_t es, uint32_t el, uint32_t child) {
-  const uint32_t k = kind_of(v, child);
+PPD_HD inline NL collapse_ext(const View& v, uint32_t ek, uint32_t es, uint32_t el, NL child) {
+  const uint32_t k = kind_of(v, child.id);
   if (k == NK_EXT) {
-    const NodeRec c = v.nodes[child];
-    return new_ext(v, c.a0, ((c.w0 >> 8) & 0xffu) - el, ((c.w0 >> 16) & 0xffu) + el, c.a1);
+    const NodeRec c = v.nodes[child.id];  // (the merged extension reads what the child read: the child's level)
+    return NL{push_node(v, NodeRec{w0(NK_EXT, ((c.w0 >> 8) & 0xffu) - el, ((c.w0 >> 16) & 0xffu) + el), c.a0, c.a1, 0}, child.lv), child.lv};
   }
   if (k == NK_LEAF || k == NK_LEAF_ACCOUNT) {
-    const NodeRec c = v.nodes[child];
-    return releaf(v, child, c.a0, ((c.w0 >> 8) & 0xffu) - el, ((c.w0 >> 16) & 0xffu) + el);
+    const NodeRec c = v.nodes[child.id];
+    return releaf(v, child.id, child.lv, c.a0, ((c.w0 >> 8) & 0xffu) - el, ((c.w0 >> 16) & 0xffu) + el);
   }
   return new_ext(v, ek, es, el, child);
 }
 // the single child left in slot `nib` of a branch at depth `pos` on the path of key `koff`
-PPD_HD inline uint32_t collapse_branch(const View& v, uint32_t koff, uint32_t pos, uint32_t nib, uint32_t other) {
-  const uint32_t k = kind_of(v, other);
+PPD_HD inline NL collapse_branch(const View& v, uint32_t koff, uint32_t pos, uint32_t nib, NL other) {
+  const uint32_t k = kind_of(v, other.id);
   if (k == NK_EXT || k == NK_LEAF || k == NK_LEAF_ACCOUNT) return collapse_ext(v, 0, pos, 1, other);  // their own keys spell the nibble
   // a key that runs through the surviving child: the path's first `pos` nibbles, then its slot
   const uint32_t nb = pos / 2 + 2;
@@ -384,7 +391,7 @@ PPD_HD inline uint32_t collapse_branch(const View& v, uint32_t koff, uint32_t po
 }
 
 // ---- insert of one key below `base`, which sits at depth `depth` on the key's path (HostArena::insert, iterative) ----
-PPD_HD inline uint32_t split_at(const View& v, const SOp& o, uint32_t pos, uint32_t cp, uint32_t existing_nib, uint32_t existing, uint32_t txn) {
+PPD_HD inline NL split_at(const View& v, const SOp& o, uint32_t pos, uint32_t cp, uint32_t existing_nib, NL existing, uint32_t txn) {
   const uint32_t at = pos + cp;
   if (at >= o.klen) {
     raise(v, TXF_KEY_PREFIX, txn);
@@ -393,15 +400,17 @@ PPD_HD inline uint32_t split_at(const View& v, const SOp& o, uint32_t pos, uint3
   const uint32_t new_nib = key_nib(v, o.koff, at);
   uint32_t kids[16];
   for (int i = 0; i < 16; i++) kids[i] = NODE_EMPTY;
-  kids[existing_nib] = existing;
-  kids[new_nib] = new_leaf_for(v, o, at + 1);
-  const uint32_t br = new_branch16(v, kids, 0);
+  const NL leaf = new_leaf_for(v, o, at + 1);
+  kids[existing_nib] = existing.id;
+  kids[new_nib] = leaf.id;
+  const NL br = new_branch16(v, kids, (existing.lv > leaf.lv ? existing.lv : leaf.lv) + 1u);
   return cp == 0 ? br : new_ext(v, o.koff, pos, cp, br);
 }
-PPD_HD inline uint32_t insert_one(const View& v, uint32_t base, uint32_t depth, const SOp& o, uint32_t txn) {
-  uint32_t st_node[PATH_CAP];
-  uint8_t st_nib[PATH_CAP];  // 0..15: branch slot; 0xff: extension
-  uint32_t sp = 0, node = base, pos = depth, result;
+PPD_HD inline NL insert_one(const View& v, NL base, uint32_t depth, const SOp& o, uint32_t txn) {
+  uint32_t st_node[PATH_CAP + 1];
+  uint8_t st_nib[PATH_CAP + 1];  // 0..15: branch slot; 0xff: extension
+  uint32_t sp = 0, node = base.id, pos = depth;
+  NL result = base;
   for (;;) {
     if (node == NODE_EMPTY) {
       result = new_leaf_for(v, o, pos);
@@ -415,7 +424,7 @@ PPD_HD inline uint32_t insert_one(const View& v, uint32_t base, uint32_t depth, 
     const NodeRec r = v.nodes[node];
     const uint32_t ns = (r.w0 >> 8) & 0xffu, nl = (r.w0 >> 16) & 0xffu;
     if (k == NK_BRANCH) {
-      if (pos >= o.klen || sp == PATH_CAP) {
+      if (pos >= o.klen || sp == PATH_CAP + 1) {
         raise(v, pos >= o.klen ? TXF_KEY_PREFIX : TXF_STACK, txn);
         return base;
       }
@@ -427,7 +436,7 @@ PPD_HD inline uint32_t insert_one(const View& v, uint32_t base, uint32_t depth, 
       const uint32_t avail = o.klen - pos, m = avail < nl ? avail : nl;
       const uint32_t cp = common_prefix(v, r.a0, ns, o.koff, pos, m);
       if (cp == nl) {
-        if (sp == PATH_CAP) {
+        if (sp == PATH_CAP + 1) {
           raise(v, TXF_STACK, txn);
           return base;
         }
@@ -436,7 +445,8 @@ PPD_HD inline uint32_t insert_one(const View& v, uint32_t base, uint32_t depth, 
         pos += nl;
       } else {
         const uint32_t rem = nl - cp - 1;
-        const uint32_t existing = rem == 0 ? r.a1 : new_ext(v, r.a0, ns + cp + 1, rem, r.a1);
+        const NL child{r.a1, lvl(v, r.a1)};
+        const NL existing = rem == 0 ? child : new_ext(v, r.a0, ns + cp + 1, rem, child);
         result = split_at(v, o, pos, cp, key_nib(v, r.a0, ns + cp), existing, txn);
         break;
       }
@@ -449,7 +459,7 @@ PPD_HD inline uint32_t insert_one(const View& v, uint32_t base, uint32_t depth, 
         raise(v, TXF_KEY_PREFIX, txn);
         return base;
       } else {
-        const uint32_t existing = releaf(v, node, r.a0, ns + cp + 1, nl - cp - 1);
+        const NL existing = releaf(v, node, node == base.id ? base.lv : (uint32_t)v.level[node], r.a0, ns + cp + 1, nl - cp - 1);
         result = split_at(v, o, pos, cp, key_nib(v, r.a0, ns + cp), existing, txn);
       }
       break;
@@ -557,7 +567,11 @@ PPD_HD inline void batch_walk(const Ctx& c, const Batch& b, uint32_t i, uint32_t
   if (nt > MARK_SLOTS_T) raise(v, TXF_MARK_SLOTS, b.txn);  // (unreachable: PATH_CAP + 1 slots)
   v.plen[e] = (uint8_t)pl, v.top[e] = (uint8_t)pl;
   v.tnode[e] = tn, v.tdepth[e] = (uint8_t)td, v.tkind[e] = (uint8_t)tk;
-  v.res[e] = T_UNCHANGED;
+  v.res[e] = T_UNCHANGED, v.res_lv[e] = 0;
+  {
+    const uint8_t* kb = v.key_pool + o.koff;  // (every key has at least four bytes behind its offset: digests, padded txn keys)
+    v.key_hi[e] = ((uint32_t)kb[0] << 24) | ((uint32_t)kb[1] << 16) | ((uint32_t)kb[2] << 8) | kb[3];
+  }
   if (pl || tk == TK_DIVERGE) PPD_ATOMIC_MAX(dmax, deepest + 1u);  // (depth + 1: 0 means no entry anywhere)
 }
 
@@ -568,14 +582,19 @@ PPD_HD inline void batch_terminal(const Ctx& c, const Batch& b, uint32_t i) {
   const uint32_t tk = v.tkind[e], td = v.tdepth[e];
   if (tk == TK_DIVERGE || tk == TK_HASH || tk == TK_BAD) return;  // the extension is handled with the path nodes
   if ((int)b.ops[i].lcp >= (int)td) return;                       // shares the terminal with its predecessor
-  uint32_t base = tk == TK_EMPTY ? NODE_EMPTY : v.tnode[e];
+  // nothing to do for a group of accessed-only keys (most groups): decided before anything is loaded
+  bool any = false;
+  for (uint32_t j = i; j < b.n && (j == i || (int)b.ops[j].lcp >= (int)td); j++) any |= b.ops[j].kind != OP_NONE;
+  if (!any) return;
+  NL base{NODE_EMPTY, 0};
+  if (tk != TK_EMPTY) base = NL{v.tnode[e], (uint32_t)v.level[v.tnode[e]]};
   bool changed = false;
   // a delete of the leaf's own key first, then the inserts (the order of distinct keys does not matter)
   for (uint32_t j = i; j < b.n && (j == i || (int)b.ops[j].lcp >= (int)td); j++)
-    if (b.ops[j].kind == OP_DEL && v.tkind[b.base + j] == TK_LEAF_SAME) base = NODE_EMPTY, changed = true;
+    if (b.ops[j].kind == OP_DEL && v.tkind[b.base + j] == TK_LEAF_SAME) base = NL{NODE_EMPTY, 0}, changed = true;
   for (uint32_t j = i; j < b.n && (j == i || (int)b.ops[j].lcp >= (int)td); j++)
     if (b.ops[j].kind == OP_PUT_LEAF || b.ops[j].kind == OP_PUT_ACCOUNT) base = insert_one(v, base, td, b.ops[j], b.txn), changed = true;
-  v.res[e] = changed ? base : T_UNCHANGED;
+  if (changed) v.res[e] = base.id, v.res_lv[e] = (uint16_t)base.lv;
 }
 
 // once per depth d from the deepest entry up to 0: the owner of the path node that starts at depth d creates its new
@@ -607,12 +626,17 @@ PPD_HD inline void batch_assemble(const Ctx& c, const Batch& b, uint32_t i, uint
       for (uint32_t nib = 0; nib < 16; nib++) kids[nib] = (mask >> nib) & 1u ? v.child_pool[a0 + q++] : NODE_EMPTY;
     }
     bool changed = false;
-    const uint32_t lv = v.level[node];
+    uint32_t lv = v.level[node];  // (an upper bound of what the untouched children need; the changed ones are added below)
+    uint32_t last_changed = 16, last_changed_lv = 0;
     for (uint32_t j = i; j < b.n && (j == i || (int)b.ops[j].lcp >= (int)d); j++) {
       if (j != i && (int)b.ops[j].lcp > (int)d) continue;  // same child as its predecessor
       const uint32_t rj = v.res[b.base + j];
       if (rj == T_UNCHANGED) continue;
-      kids[key_nib(v, b.ops[j].koff, d)] = rj;
+      const uint32_t nib = d < 8 ? (v.key_hi[b.base + j] >> (28 - 4 * d)) & 15u : key_nib(v, b.ops[j].koff, d);
+      kids[nib] = rj;
+      const uint32_t l = (uint32_t)v.res_lv[b.base + j];
+      if (rj != NODE_EMPTY && l + 1u > lv) lv = l + 1u;
+      last_changed = nib, last_changed_lv = l;
       changed = true;
     }
     if (!changed) {
@@ -622,32 +646,35 @@ PPD_HD inline void batch_assemble(const Ctx& c, const Batch& b, uint32_t i, uint
     uint32_t nk = 0, last = 0;
     for (uint32_t nib = 0; nib < 16; nib++)
       if (kids[nib] != NODE_EMPTY) nk++, last = nib;
+    NL r{NODE_EMPTY, 0};
     if (nk >= 2)
-      v.res[e] = new_branch16(v, kids, lv);
+      r = new_branch16(v, kids, lv);
     else if (nk == 1)
-      v.res[e] = collapse_branch(v, koff, d, last, kids[last]);
-    else
-      v.res[e] = NODE_EMPTY;
+      r = collapse_branch(v, koff, d, last, NL{kids[last], last == last_changed ? last_changed_lv : lvl(v, kids[last])});
+    v.res[e] = r.id, v.res_lv[e] = (uint16_t)r.lv;
     return;
   }
   // an extension: the keys that run through it changed its child; the ones that leave it half way split it
   const uint32_t el = (v.nodes[node].w0 >> 16) & 0xffu;
-  uint32_t base = node;
+  NL base{node, (uint32_t)v.level[node]};
   bool changed = false;
   for (uint32_t j = i; j < b.n && (j == i || (int)b.ops[j].lcp >= (int)d); j++) {
     if (v.tkind[b.base + j] == TK_DIVERGE && v.tdepth[b.base + j] == d) continue;
     // the first key that runs through owns the child's result (every earlier key of the range leaves inside the extension)
     const uint32_t rj = v.res[b.base + j];
     if (rj == NODE_EMPTY)
-      base = NODE_EMPTY, changed = true;
+      base = NL{NODE_EMPTY, 0}, changed = true;
     else if (rj != T_UNCHANGED)
-      base = collapse_ext(v, a0, d, el, rj), changed = true;
+      base = collapse_ext(v, a0, d, el, NL{rj, (uint32_t)v.res_lv[b.base + j]}), changed = true;
     break;
   }
   for (uint32_t j = i; j < b.n && (j == i || (int)b.ops[j].lcp >= (int)d); j++)
     if (v.tkind[b.base + j] == TK_DIVERGE && v.tdepth[b.base + j] == d && (b.ops[j].kind == OP_PUT_LEAF || b.ops[j].kind == OP_PUT_ACCOUNT))
       base = insert_one(v, base, d, b.ops[j], b.txn), changed = true;
-  v.res[e] = changed ? base : T_UNCHANGED;
+  if (changed)
+    v.res[e] = base.id, v.res_lv[e] = (uint16_t)base.lv;
+  else
+    v.res[e] = T_UNCHANGED;
 }
 
 // ---- op preparation (all txns at once, before the loop) -----------------------------------------------------
@@ -1027,7 +1054,7 @@ PPD_HD inline void run_finish(const Ctx& c, uint32_t initial_state) {
       v.accounts[v.rec_base + wd.rec] = rec;
       SOp o;
       o.koff = koff, o.klen = 64, o.lcp = -1, o.kind = OP_PUT_ACCOUNT, o.pad = 0, o.a1 = v.rec_base + wd.rec, o.a2 = 0, o.owner = OWNER_STATE_TRIE;
-      cur.state_root = insert_one(v, cur.state_root, 0, o, 0xffffffffu);
+      cur.state_root = insert_one(v, NL{cur.state_root, lvl(v, cur.state_root)}, 0, o, 0xffffffffu).id;
     }
     cur.roots[XR_AFTER_WITHDRAWALS] = new_root(v, cur.state_root);
   }

@@ -194,7 +194,9 @@ int check_block(const std::vector<uint8_t>& flatv, const char* name) {
   std::vector<txn::SOp> sh_ops(T.max_ops + 1);
   v.path_node = path_node.data(), v.path_a0 = path_a0.data(), v.path_a1 = path_a1.data(), v.path_depth = path_depth.data();
   v.plen = plen.data(), v.top = top.data(), v.tnode = tnode.data();
-  v.tdepth = tdepth.data(), v.tkind = tkind.data(), v.res = res.data();
+  std::vector<uint16_t> res_lv(T.max_ops + 1);
+  std::vector<uint32_t> key_hi(T.max_ops + 1);
+  v.tdepth = tdepth.data(), v.tkind = tkind.data(), v.res = res.data(), v.res_lv = res_lv.data(), v.key_hi = key_hi.data();
   v.sh_ops = (n_traces & 1) ? sh_ops.data() : nullptr;  // both ways of reaching a txn's keys get exercised
   txn::Cursors cur;
   memset(&cur, 0, sizeof cur);
@@ -233,6 +235,23 @@ int check_block(const std::vector<uint8_t>& flatv, const char* name) {
     }
     txn_tables_dummies(b2, flat, cur, ex.data(), n_pre_acct, acct.data(), table, keys.data() + B.dig_base, T);
     v.seg_a = T.seg_a.data(), v.seg_b = T.seg_b.data();
+  }
+  // ---- the sweep's invariant: a node's level exceeds the level of everything it reads ----
+  {
+    auto lv = [&](uint32_t n) -> int { return (n == NODE_EMPTY || n >= 0x80000000u) ? -1 : (int)level[n]; };
+    for (uint32_t n = n_pre_nodes; n < cur.n_nodes; n++) {
+      const NodeRec r = nodes[n];
+      const uint32_t kind = r.w0 & 0xff;
+      int need = -1;
+      if (kind == NK_EXT || kind == NK_ROOT) need = lv(r.a1);
+      if (kind == NK_LEAF_ACCOUNT) need = lv(accounts[r.a1].storage_src);
+      if (kind == NK_BRANCH)
+        for (uint32_t j = 0; j < (uint32_t)__builtin_popcount(r.a1 & 0xffff); j++) need = std::max(need, lv(children[r.a0 + j]));
+      if ((int)level[n] <= need) {
+        printf("%s: node %u (kind %u) has level %u but reads a node of level %d\n", name, n, kind, level[n], need);
+        return 1;
+      }
+    }
   }
   // ---- compare ----
   ArenaRO R1{J1.A.nodes.data(), J1.A.key_pool.data(), J1.A.val_pool.data(), J1.A.hash_pool.data(), J1.A.child_pool.data(), J1.A.accounts.data(), {}};
