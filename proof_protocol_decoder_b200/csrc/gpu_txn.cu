@@ -87,6 +87,9 @@ void after_emit(void* arg, const ParseEmit& E) {
   txn::View& v = H.v;
   txn::JoinView& j = H.j;
   const size_t n_sorted = std::max<size_t>(n_nodes, T.est_nodes);
+  const size_t pc_slow_n = (size_t)T.max_ops * txn::PATH_CAP;  // (no txn has more path nodes than keys x path length)
+  size_t pc_map_n = 64;
+  while (pc_map_n < 2 * pc_slow_n) pc_map_n <<= 1;
   auto layout = [&](Carve2& c) {
     v.traces = c.take<txn::TxnTrace>(n_traces + 1);
     H.se = c.take<uint64_t>(2ull * T.n_msgs + 2);
@@ -102,17 +105,18 @@ void after_emit(void* arg, const ParseEmit& E) {
     H.d_withdrawals = c.take<txn::Withdrawal>(T.withdrawals.size() + 1);
     H.d_export = c.take<txn::AcctExport>(T.needs_dummies() ? n_acct + 1 : 1);
     v.path_node = c.take<uint32_t>((size_t)T.max_ops * txn::PATH_CAP + 1);
-    v.path_a0 = c.take<uint32_t>((size_t)T.max_ops * txn::PATH_CAP + 1);
-    v.path_a1 = c.take<uint32_t>((size_t)T.max_ops * txn::PATH_CAP + 1);
+    v.path_pc = c.take<uint32_t>((size_t)T.max_ops * txn::PATH_CAP + 1);
     v.path_depth = c.take<uint8_t>((size_t)T.max_ops * txn::PATH_CAP + 1);
     v.plen = c.take<uint8_t>(T.max_ops + 1);
-    v.top = c.take<uint8_t>(T.max_ops + 1);
     v.tnode = c.take<uint32_t>(T.max_ops + 1);
+    v.tpc = c.take<uint32_t>(T.max_ops + 1);
     v.tdepth = c.take<uint8_t>(T.max_ops + 1);
     v.tkind = c.take<uint8_t>(T.max_ops + 1);
-    v.res = c.take<uint32_t>(T.max_ops + 1);
-    v.res_lv = c.take<uint16_t>(T.max_ops + 1);
     v.key_hi = c.take<uint32_t>(T.max_ops + 1);
+    // the path-node table in HBM: everything for a txn whose keys do not fit in shared memory, the spill tier otherwise
+    v.pc_slow = c.take<txn::PathNode>(pc_slow_n + 1);
+    v.pc_map = c.take<uint32_t>(pc_map_n);
+    v.pc_map_key = c.take<uint32_t>(pc_map_n);
     v.cur = c.take<txn::Cursors>(1);
     H.bins_pre = c.take<uint32_t>(ORDER_MAX_BINS);
     H.bins_tail = c.take<uint32_t>(ORDER_MAX_BINS);
@@ -132,6 +136,8 @@ void after_emit(void* arg, const ParseEmit& E) {
   v.flat = H.d_flat, v.n_txns = (uint32_t)H.n_txns, v.n_traces = (uint32_t)n_traces, v.dig_base = B.dig_base;
   v.rec_base = B.rec_base, v.val_base = B.val_base;
   v.pre_flags = j.pre_flags;
+  v.pc_fast = nullptr, v.pc_n_fast = 0, v.pc_n_slow = (uint32_t)pc_slow_n, v.pc_map_mask = (uint32_t)pc_map_n - 1, v.pc_count = &v.cur->pc_count;
+  v.sh_ops = nullptr;
   v.a_nodes = &v.cur->n_nodes, v.a_children = &v.cur->n_children, v.a_keys = &v.cur->key_bytes, v.a_max_level = &v.cur->max_level;
   v.withdrawals = H.d_withdrawals, v.n_withdrawals = (uint32_t)T.withdrawals.size();
   if (v.n_withdrawals) CUDA_OK(cudaMemcpyAsync(H.d_withdrawals, T.withdrawals.data(), sizeof(txn::Withdrawal) * v.n_withdrawals, cudaMemcpyHostToDevice, st));
@@ -357,8 +363,8 @@ int gpu_block(ppd_ctx* c, Lane* L, Job& J, const uint8_t* flat, size_t len, uint
   }
   if (getenv("PPD_TIMING")) {
     const unsigned long long* pc = h_cur->phase_clocks;
-    fprintf(stderr, "[ppd]   loop phases (Mclk): setup %.2f walks %.2f | batch1 terminals %.2f assembly %.2f roots %.2f | records %.2f | batch2 terminals %.2f assembly %.2f roots %.2f | root nodes %.2f\n",
-            pc[0] / 1e6, pc[1] / 1e6, pc[2] / 1e6, pc[3] / 1e6, pc[4] / 1e6, pc[5] / 1e6, pc[6] / 1e6, pc[7] / 1e6, pc[8] / 1e6, pc[9] / 1e6);
+    fprintf(stderr, "[ppd]   loop phases (Mclk): setup %.2f | walks %.2f | announce %.2f | storage tries up %.2f | records %.2f | state trie up %.2f | root nodes %.2f\n",
+            pc[0] / 1e6, pc[1] / 1e6, pc[2] / 1e6, pc[3] / 1e6, pc[4] / 1e6, pc[5] / 1e6, pc[6] / 1e6);
   }
   if (h_cur->flag || h_cur->max_level >= ORDER_MAX_BINS / 64) {
     if (getenv("PPD_TIMING")) fprintf(stderr, "[ppd] device txn loop flag %u at txn %u (max level %u): host path\n", h_cur->flag, h_cur->flag_txn, h_cur->max_level);

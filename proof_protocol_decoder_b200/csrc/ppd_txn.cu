@@ -125,14 +125,17 @@ __global__ void acct_export_kernel(View v, const uint32_t* __restrict__ acct_lis
 }
 
 constexpr int LOOP_THREADS = 256;
-constexpr uint32_t SH_KEYS = 512;  // keys of one txn whose scratch fits in shared memory
+constexpr uint32_t SH_KEYS = 512;   // keys of one txn whose scratch fits in shared memory
+constexpr uint32_t SH_NODES = 640;  // path-node table entries in shared memory (the rest of a txn's spill to HBM)
+constexpr uint32_t SH_MAP = 4096;   // slots of the node id -> entry map
 struct LoopShared {
-  uint32_t path_node[SH_KEYS * PATH_CAP], path_a0[SH_KEYS * PATH_CAP], path_a1[SH_KEYS * PATH_CAP];
-  uint32_t tnode[SH_KEYS], res[SH_KEYS], key_hi[SH_KEYS];
-  uint16_t res_lv[SH_KEYS];
+  PathNode pc[SH_NODES];
+  uint32_t path_node[SH_KEYS * PATH_CAP], path_pc[SH_KEYS * PATH_CAP];
+  uint32_t pc_map[SH_MAP], pc_map_key[SH_MAP];
+  uint32_t tnode[SH_KEYS], tpc[SH_KEYS], key_hi[SH_KEYS];
   SOp ops[SH_KEYS];
   uint8_t path_depth[SH_KEYS * PATH_CAP];
-  uint8_t plen[SH_KEYS], top[SH_KEYS], tdepth[SH_KEYS], tkind[SH_KEYS];
+  uint8_t plen[SH_KEYS], tdepth[SH_KEYS], tkind[SH_KEYS];
 };
 // txns [ti0, ti1) of the block.  The loop of a block is launched in chunks so that the kernels of another lane that
 // shares the hardware queue (the device has at most 32 of them) are not held up behind one long kernel.  use_shared: the
@@ -141,7 +144,7 @@ struct LoopShared {
 __global__ void __launch_bounds__(LOOP_THREADS, 1) txn_loop_kernel(View v, uint32_t initial_state, uint32_t ti0, uint32_t ti1, uint32_t finish,
                                                                    uint32_t use_shared) {
   extern __shared__ __align__(16) uint8_t loop_smem[];
-  __shared__ uint32_t sh_dmax[2], sh_stop, sh_cursor[4];
+  __shared__ uint32_t sh_stop, sh_cursor[4], sh_pc_count;
   __shared__ long long sh_clock;
   if (threadIdx.x == 0) {
     sh_clock = clock64();
@@ -151,12 +154,16 @@ __global__ void __launch_bounds__(LOOP_THREADS, 1) txn_loop_kernel(View v, uint3
   v.a_nodes = &sh_cursor[0], v.a_children = &sh_cursor[1], v.a_keys = &sh_cursor[2], v.a_max_level = &sh_cursor[3];
   if (use_shared) {
     LoopShared& S = *reinterpret_cast<LoopShared*>(loop_smem);
-    v.path_node = S.path_node, v.path_a0 = S.path_a0, v.path_a1 = S.path_a1, v.path_depth = S.path_depth;
-    v.plen = S.plen, v.top = S.top, v.tnode = S.tnode, v.tdepth = S.tdepth, v.tkind = S.tkind, v.res = S.res, v.res_lv = S.res_lv, v.key_hi = S.key_hi, v.sh_ops = S.ops;
+    v.path_node = S.path_node, v.path_pc = S.path_pc, v.path_depth = S.path_depth;
+    v.plen = S.plen, v.tnode = S.tnode, v.tpc = S.tpc, v.tdepth = S.tdepth, v.tkind = S.tkind, v.key_hi = S.key_hi, v.sh_ops = S.ops;
+    v.pc_fast = S.pc, v.pc_n_fast = SH_NODES, v.pc_map = S.pc_map, v.pc_map_key = S.pc_map_key, v.pc_map_mask = SH_MAP - 1;
+    // (pc_slow / pc_n_slow: the HBM tier the host laid out; a txn with more path nodes than the map takes is flagged)
+    if (v.pc_n_slow > SH_MAP / 2 - SH_NODES) v.pc_n_slow = SH_MAP / 2 - SH_NODES;
   }
   __syncthreads();
   if (sh_stop) return;  // an earlier chunk (or the join) raised a flag: the host path redoes the block
-  Ctx c{v, threadIdx.x, blockDim.x, sh_dmax, &sh_clock};
+  v.pc_count = &sh_pc_count;
+  Ctx c{v, threadIdx.x, blockDim.x, &sh_clock};
   for (uint32_t ti = ti0; ti < ti1; ti++) {
     run_txn(c, ti, C_EMPTY_TRIE, C_EMPTY_CODE);
     // a raised flag ends the loop; one thread reads it so that the decision is uniform

@@ -68,7 +68,8 @@ enum : uint32_t {
   TXF_LEVELS = 12,
   TXF_WITHDRAWAL = 13,       // PPD_ERR_MISSING_WITHDRAWAL_ACCOUNT / account decode
   TXF_STACK = 14,
-  TXF_SHARED_TRIE = 15,      // the by-root join gives two accounts the SAME witnessed trie: the host path clones it, as the reference does
+  TXF_SHARED_TRIE = 15,
+  TXF_PATH_TABLE = 16,       // the path-node table of a txn is full      // the by-root join gives two accounts the SAME witnessed trie: the host path clones it, as the reference does
 };
 
 enum : uint8_t { OP_DEL = 0, OP_PUT_LEAF = 1, OP_PUT_ACCOUNT = 2, OP_NONE = 3 };  // OP_NONE: a key that is only accessed
@@ -131,9 +132,11 @@ struct Cursors {
   uint32_t max_level;
   uint32_t roots[6];  // NK_ROOT nodes the dummy entries refer to (XR_*), created when the loop ends
   uint32_t state_before_withdrawals;
-  // SM clocks per phase of the loop, summed over txns: setup, walks, batch 1 (terminals, re-assembly, roots), records,
-  // batch 2 (terminals, re-assembly, roots), root nodes
-  unsigned long long phase_clocks[10];
+  uint32_t pc_count;  // path-node table entries handed out (when the table is in HBM)
+  uint32_t pad0;
+  // SM clocks per phase of the loop, summed over txns: setup, walks, announce, storage / txn / receipt tries back up,
+  // account records, state trie back up, root nodes
+  unsigned long long phase_clocks[8];
 };
 
 // One withdrawal (decoding.rs:404-428): balance += amount on the account of the hashed address
@@ -142,6 +145,17 @@ struct Withdrawal {
   uint32_t off_amount;  // FlatBlock offset of the 32-byte amount
   uint32_t rec;         // account record the updated account fills
   uint32_t pad;
+};
+
+// A node on the path of some key of the running txn.
+struct PathNode {
+  uint32_t kids[16];  // a branch's children as they are before the txn, overwritten by the children that changed; an extension: [0] = its child's result
+  uint32_t node;      // the arena node
+  uint32_t lv;        // level the new version needs: the old node's, raised by changed children
+  uint32_t pending;   // children (groups of keys) that have not reported yet: the last one to report re-assembles the node
+  uint32_t owner;     // first key through the node (index into the batch)
+  uint32_t changed;
+  uint32_t pad[3];
 };
 
 // Everything the loop touches.  All pointers are device pointers (host pointers in the CPU harness).
@@ -179,18 +193,25 @@ struct View {
   // scratch of the running txn, indexed by key (round-1 keys first, then the state keys); in shared memory when the
   // txn's keys fit (ppd_txn.cu), else in HBM
   uint32_t* path_node;  // [keys][PATH_CAP] nodes passed, root first
-  uint32_t* path_a0;    // [keys][PATH_CAP] their NodeRec::a0 (branch: first child slot; extension: key offset) ...
-  uint32_t* path_a1;    // [keys][PATH_CAP] ... and a1 (branch: child mask; extension: child), so that re-assembly does not re-read the records
+  uint32_t* path_pc;    // [keys][PATH_CAP] the node's entry in the path-node table below, for the levels the key leads
   uint8_t* path_depth;  // [keys][PATH_CAP] nibble depth at which the node starts | 0x80 for an extension
   uint8_t* plen;        // [keys]
-  uint8_t* top;         // [keys]
   uint32_t* tnode;      // [keys] terminal node
+  uint32_t* tpc;        // [keys] its path-node entry when the key leaves an extension half way
   uint8_t* tdepth;      // [keys]
   uint8_t* tkind;       // [keys]
-  uint32_t* res;        // [keys] new version of the sub-trie the key is the first of, T_UNCHANGED, or NODE_EMPTY
-  uint16_t* res_lv;     // [keys] its level
-  uint32_t* key_hi;     // [keys] nibbles 0..7 of the key, most significant first (the re-assembly's child slots without a key load)
+  uint32_t* key_hi;     // [keys] nibbles 0..7 of the key, most significant first (child slots without a key load)
   SOp* sh_ops;          // [keys] copy of the txn's keys when the scratch is in shared memory, else nullptr
+  // the path-node table of the running txn: one entry per distinct node some key passes (or leaves half way), made by
+  // the node's OWNER (the first key through it) during the walk; children report to it on their way up.  The first
+  // pc_fast entries live in shared memory, the rest in HBM.
+  PathNode* pc_fast;
+  PathNode* pc_slow;
+  uint32_t pc_n_fast, pc_n_slow;
+  uint32_t* pc_count;   // entries handed out (reset per txn)
+  uint32_t* pc_map;     // [pc_map_mask + 1] node id -> entry + 1 (open addressing; 0 = free), reset per txn
+  uint32_t* pc_map_key;
+  uint32_t pc_map_mask;
   Cursors* cur;
 };
 
@@ -215,11 +236,12 @@ PPD_HD inline bool is_hash_id(uint32_t n) { return n >= HASH_BASE && n < HASH_EN
 struct Ctx {
   View v;
   uint32_t tid, nthreads;
-  uint32_t* sh_dmax;  // shared [2]: deepest path entry of the txn's two batches
   long long* sh_clock;  // shared: clock at the last phase boundary
 };
 
 #if defined(__CUDA_ARCH__)
+#define PPD_FENCE_BLOCK() __threadfence_block()
+#define PPD_ATOMIC_SUB(p, x) atomicSub((p), (x))
 #define PPD_ATOMIC_ADD(p, x) atomicAdd((p), (x))
 #define PPD_ATOMIC_MAX(p, x) atomicMax((p), (x))
 #define PPD_ATOMIC_CAS(p, c, x) atomicCAS((p), (c), (x))
@@ -239,6 +261,8 @@ PPD_HD inline uint32_t host_atomic_cas(uint32_t* p, uint32_t c, uint32_t x) {
   if (o == c) *p = x;
   return o;
 }
+#define PPD_FENCE_BLOCK() ((void)0)
+#define PPD_ATOMIC_SUB(p, x) ppd::txn::host_atomic_add((p), 0u - (x))
 #define PPD_ATOMIC_ADD(p, x) ppd::txn::host_atomic_add((p), (x))
 #define PPD_ATOMIC_MAX(p, x) ppd::txn::host_atomic_max((p), (x))
 #define PPD_ATOMIC_CAS(p, c, x) ppd::txn::host_atomic_cas((p), (c), (x))
@@ -492,19 +516,55 @@ PPD_HD inline uint32_t trie_root_of(const View& v, uint32_t owner) {
   return v.acct[v.traces[owner].acct].storage;
 }
 
+PPD_HD inline PathNode& pc_at(const View& v, uint32_t idx) { return idx < v.pc_n_fast ? v.pc_fast[idx] : v.pc_slow[idx - v.pc_n_fast]; }
+PPD_HD inline uint32_t pc_hash(uint32_t node) { return node * 2654435761u; }
+// the owner of a path node makes its table entry (children and level are loaded here, in the shadow of the walk's own
+// load of one of those children) and publishes it under the node id
+PPD_HD inline uint32_t pc_make(const View& v, uint32_t node, const NodeRec& r, bool is_branch, uint32_t owner, uint32_t txn) {
+  uint32_t idx = PPD_ATOMIC_ADD(v.pc_count, 1u);
+  if (idx >= v.pc_n_fast + v.pc_n_slow) {
+    raise(v, TXF_PATH_TABLE, txn);
+    return NONE;
+  }
+  PathNode& p = pc_at(v, idx);
+  if (is_branch) {
+    const uint32_t mask = r.a1 & 0xffffu;
+    uint32_t q = 0;
+    for (uint32_t nib = 0; nib < 16; nib++) p.kids[nib] = (mask >> nib) & 1u ? v.child_pool[r.a0 + q++] : NODE_EMPTY;
+  } else {
+    p.kids[0] = T_UNCHANGED;
+  }
+  p.node = node, p.lv = v.level[node], p.pending = 0, p.owner = owner, p.changed = 0;
+  uint32_t h = pc_hash(node) & v.pc_map_mask;
+  for (;;) {
+    const uint32_t prev = PPD_ATOMIC_CAS(&v.pc_map_key[h], 0xffffffffu, node);
+    if (prev == 0xffffffffu || prev == node) break;  // (a node has one owner: `prev == node` does not happen)
+    h = (h + 1) & v.pc_map_mask;
+  }
+  v.pc_map[h] = idx + 1u;
+  return idx;
+}
+PPD_HD inline uint32_t pc_find(const View& v, uint32_t node) {
+  uint32_t h = pc_hash(node) & v.pc_map_mask;
+  for (;;) {
+    const uint32_t k = v.pc_map_key[h];
+    if (k == node) return v.pc_map[h] - 1u;
+    if (k == 0xffffffffu) return NONE;
+    h = (h + 1) & v.pc_map_mask;
+  }
+}
+
 // The walk of key i down the current version of its trie.  It is the key's marking walk (the nodes it visits go to the
 // IR's touched list: create_trie_subset keeps exactly those expanded) AND the first half of its write: the nodes passed
-// (with their child tables' whereabouts) and where the key ends are kept for the re-assembly.
-PPD_HD inline void batch_walk(const Ctx& c, const Batch& b, uint32_t i, uint32_t* touched, uint32_t* dmax) {
+// and where the key ends are kept for the way back up.
+PPD_HD inline void batch_walk(const Ctx& c, const Batch& b, uint32_t i, uint32_t* touched) {
   const View& v = c.v;
   const SOp o = b.ops[i];
   const uint32_t e = b.base + i;
-  uint32_t node = trie_root_of(v, o.owner), pos = 0, pl = 0, deepest = 0, nt = 0;
+  uint32_t node = trie_root_of(v, o.owner), pos = 0, pl = 0, nt = 0;
   uint32_t* pn = v.path_node + (size_t)e * PATH_CAP;
-  uint32_t* pa0 = v.path_a0 + (size_t)e * PATH_CAP;
-  uint32_t* pa1 = v.path_a1 + (size_t)e * PATH_CAP;
   uint8_t* pd = v.path_depth + (size_t)e * PATH_CAP;
-  uint32_t tk = TK_EMPTY, tn = NODE_EMPTY, td = 0;
+  uint32_t tk = TK_EMPTY, tn = NODE_EMPTY, td = 0, tpc = NONE;
   const bool put = o.kind == OP_PUT_LEAF || o.kind == OP_PUT_ACCOUNT, mark = (o.pad & SOP_MARK) != 0;
   for (;;) {
     if (node == NODE_EMPTY) {
@@ -522,6 +582,7 @@ PPD_HD inline void batch_walk(const Ctx& c, const Batch& b, uint32_t i, uint32_t
     }
     const NodeRec r = v.nodes[node];
     const uint32_t ns = (r.w0 >> 8) & 0xffu, nl = (r.w0 >> 16) & 0xffu;
+    const bool owner = (int)o.lcp < (int)pos;  // the first key through this node
     if (k == NK_BRANCH) {
       if (pos >= o.klen || pl == PATH_CAP) {
         if (pos >= o.klen) {
@@ -532,27 +593,26 @@ PPD_HD inline void batch_walk(const Ctx& c, const Batch& b, uint32_t i, uint32_t
         tk = TK_BAD, tn = node, td = pos;
         break;
       }
-      pn[pl] = node, pa0[pl] = r.a0, pa1[pl] = r.a1, pd[pl] = (uint8_t)pos, pl++;
-      deepest = pos;
+      pn[pl] = node, pd[pl] = (uint8_t)pos, pl++;
+      if (owner) pc_make(v, node, r, true, i, b.txn);
       node = child_at(v, r, key_nib(v, o.koff, pos));
       pos++;
     } else if (k == NK_EXT) {
       const uint32_t avail = o.klen - pos, m = avail < nl ? avail : nl;
       const uint32_t cp = common_prefix(v, r.a0, ns, o.koff, pos, m);
+      if (owner) tpc = pc_make(v, node, r, false, i, b.txn);
       if (cp == nl) {
         if (pl == PATH_CAP) {
           raise(v, TXF_PATH_DEPTH, b.txn);
           tk = TK_BAD, tn = node, td = pos;
           break;
         }
-        pn[pl] = node, pa0[pl] = r.a0, pa1[pl] = r.a1, pd[pl] = (uint8_t)(pos | 0x80u), pl++;
-        deepest = pos;
+        pn[pl] = node, pd[pl] = (uint8_t)(pos | 0x80u), pl++;
         node = r.a1;
         pos += nl;
       } else {
         if (cp == avail && put) raise(v, TXF_KEY_PREFIX, b.txn);
         tk = TK_DIVERGE, tn = node, td = pos;
-        deepest = pos;
         break;
       }
     } else {
@@ -565,116 +625,157 @@ PPD_HD inline void batch_walk(const Ctx& c, const Batch& b, uint32_t i, uint32_t
     }
   }
   if (nt > MARK_SLOTS_T) raise(v, TXF_MARK_SLOTS, b.txn);  // (unreachable: PATH_CAP + 1 slots)
-  v.plen[e] = (uint8_t)pl, v.top[e] = (uint8_t)pl;
+  v.plen[e] = (uint8_t)pl;
   v.tnode[e] = tn, v.tdepth[e] = (uint8_t)td, v.tkind[e] = (uint8_t)tk;
-  v.res[e] = T_UNCHANGED, v.res_lv[e] = 0;
   {
     const uint8_t* kb = v.key_pool + o.koff;  // (every key has at least four bytes behind its offset: digests, padded txn keys)
     v.key_hi[e] = ((uint32_t)kb[0] << 24) | ((uint32_t)kb[1] << 16) | ((uint32_t)kb[2] << 8) | kb[3];
   }
-  if (pl || tk == TK_DIVERGE) PPD_ATOMIC_MAX(dmax, deepest + 1u);  // (depth + 1: 0 means no entry anywhere)
 }
 
-// terminals resolved by their owners (the first key of the group that ends at the same place)
-PPD_HD inline void batch_terminal(const Ctx& c, const Batch& b, uint32_t i) {
+// After every walk: a key looks up the table entry of every node on its path, and announces itself at the nodes whose
+// child it LEADS (it is the first key of the group that goes into that child): every leader will report there, and the
+// last report re-assembles the node.  A key leads the child of the branch at depth d when its LCP with its predecessor
+// is <= d; the one child of an extension that ends at depth d' when it is < d'.  A key that leaves an extension half
+// way announces itself there on its own account.
+PPD_HD inline void batch_announce(const Ctx& c, const Batch& b, uint32_t i) {
   const View& v = c.v;
   const uint32_t e = b.base + i;
-  const uint32_t tk = v.tkind[e], td = v.tdepth[e];
-  if (tk == TK_DIVERGE || tk == TK_HASH || tk == TK_BAD) return;  // the extension is handled with the path nodes
-  if ((int)b.ops[i].lcp >= (int)td) return;                       // shares the terminal with its predecessor
-  // nothing to do for a group of accessed-only keys (most groups): decided before anything is loaded
-  bool any = false;
-  for (uint32_t j = i; j < b.n && (j == i || (int)b.ops[j].lcp >= (int)td); j++) any |= b.ops[j].kind != OP_NONE;
-  if (!any) return;
-  NL base{NODE_EMPTY, 0};
-  if (tk != TK_EMPTY) base = NL{v.tnode[e], (uint32_t)v.level[v.tnode[e]]};
-  bool changed = false;
-  // a delete of the leaf's own key first, then the inserts (the order of distinct keys does not matter)
-  for (uint32_t j = i; j < b.n && (j == i || (int)b.ops[j].lcp >= (int)td); j++)
-    if (b.ops[j].kind == OP_DEL && v.tkind[b.base + j] == TK_LEAF_SAME) base = NL{NODE_EMPTY, 0}, changed = true;
-  for (uint32_t j = i; j < b.n && (j == i || (int)b.ops[j].lcp >= (int)td); j++)
-    if (b.ops[j].kind == OP_PUT_LEAF || b.ops[j].kind == OP_PUT_ACCOUNT) base = insert_one(v, base, td, b.ops[j], b.txn), changed = true;
-  if (changed) v.res[e] = base.id, v.res_lv[e] = (uint16_t)base.lv;
+  const int lcp = (int)b.ops[i].lcp;
+  const uint32_t pl = v.plen[e];
+  const uint32_t* pn = v.path_node + (size_t)e * PATH_CAP;
+  uint32_t* ppc = v.path_pc + (size_t)e * PATH_CAP;
+  const uint8_t* pd = v.path_depth + (size_t)e * PATH_CAP;
+  bool leads = true;
+  for (uint32_t t = pl; t-- > 0;) {
+    const uint32_t d = pd[t] & 0x7fu;
+    const uint32_t child_depth = (pd[t] & 0x80u) ? (t + 1 < pl ? (uint32_t)(pd[t + 1] & 0x7fu) : (uint32_t)v.tdepth[e]) : d + 1;
+    const uint32_t idx = pc_find(v, pn[t]);
+    ppc[t] = idx;
+    leads = leads && lcp < (int)child_depth;  // (once the predecessor goes into the same child it does so at every node above)
+    if (leads && idx != NONE) PPD_ATOMIC_ADD(&pc_at(v, idx).pending, 1u);
+  }
+  uint32_t tidx = NONE;
+  if (v.tkind[e] == TK_DIVERGE) {
+    tidx = pc_find(v, v.tnode[e]);
+    if (tidx != NONE) PPD_ATOMIC_ADD(&pc_at(v, tidx).pending, 1u);
+  }
+  v.tpc[e] = tidx;
 }
 
-// once per depth d from the deepest entry up to 0: the owner of the path node that starts at depth d creates its new
-// version from the results of the children its range touched
-PPD_HD inline void batch_assemble(const Ctx& c, const Batch& b, uint32_t i, uint32_t d) {
-  const View& v = c.v;
-  const uint32_t e = b.base + i;
-  uint32_t node, a0, a1;
-  bool is_ext;
-  const uint32_t t = v.top[e];
-  if (t > 0 && (v.path_depth[(size_t)e * PATH_CAP + t - 1] & 0x7fu) == d) {
-    const size_t at = (size_t)e * PATH_CAP + t - 1;
-    node = v.path_node[at], a0 = v.path_a0[at], a1 = v.path_a1[at], is_ext = (v.path_depth[at] & 0x80u) != 0;
-    v.top[e] = (uint8_t)(t - 1);
-  } else if (v.tkind[e] == TK_DIVERGE && v.tdepth[e] == d) {
-    node = v.tnode[e], is_ext = true;
-    const NodeRec r = v.nodes[node];
-    a0 = r.a0, a1 = r.a1;
-  } else {
-    return;
-  }
-  if ((int)b.ops[i].lcp >= (int)d) return;  // not the owner
-  const uint32_t koff = b.ops[i].koff;
-  if (!is_ext) {
-    uint32_t kids[16];
-    {
-      const uint32_t mask = a1 & 0xffffu;
-      uint32_t q = 0;
-      for (uint32_t nib = 0; nib < 16; nib++) kids[nib] = (mask >> nib) & 1u ? v.child_pool[a0 + q++] : NODE_EMPTY;
-    }
-    bool changed = false;
-    uint32_t lv = v.level[node];  // (an upper bound of what the untouched children need; the changed ones are added below)
-    uint32_t last_changed = 16, last_changed_lv = 0;
-    for (uint32_t j = i; j < b.n && (j == i || (int)b.ops[j].lcp >= (int)d); j++) {
-      if (j != i && (int)b.ops[j].lcp > (int)d) continue;  // same child as its predecessor
-      const uint32_t rj = v.res[b.base + j];
-      if (rj == T_UNCHANGED) continue;
-      const uint32_t nib = d < 8 ? (v.key_hi[b.base + j] >> (28 - 4 * d)) & 15u : key_nib(v, b.ops[j].koff, d);
-      kids[nib] = rj;
-      const uint32_t l = (uint32_t)v.res_lv[b.base + j];
-      if (rj != NODE_EMPTY && l + 1u > lv) lv = l + 1u;
-      last_changed = nib, last_changed_lv = l;
-      changed = true;
-    }
-    if (!changed) {
-      v.res[e] = T_UNCHANGED;
-      return;
-    }
-    uint32_t nk = 0, last = 0;
-    for (uint32_t nib = 0; nib < 16; nib++)
-      if (kids[nib] != NODE_EMPTY) nk++, last = nib;
-    NL r{NODE_EMPTY, 0};
-    if (nk >= 2)
-      r = new_branch16(v, kids, lv);
-    else if (nk == 1)
-      r = collapse_branch(v, koff, d, last, NL{kids[last], last == last_changed ? last_changed_lv : lvl(v, kids[last])});
-    v.res[e] = r.id, v.res_lv[e] = (uint16_t)r.lv;
-    return;
-  }
-  // an extension: the keys that run through it changed its child; the ones that leave it half way split it
-  const uint32_t el = (v.nodes[node].w0 >> 16) & 0xffu;
-  NL base{node, (uint32_t)v.level[node]};
+// new version of the branch behind table entry p (the children that changed have been written into p.kids); koff / d: a
+// key through the branch and the branch's depth
+PPD_HD inline NL assemble_branch(const View& v, PathNode& p, uint32_t koff, uint32_t d) {
+  uint32_t nk = 0, last = 0;
+  for (uint32_t nib = 0; nib < 16; nib++)
+    if (p.kids[nib] != NODE_EMPTY) nk++, last = nib;
+  if (nk >= 2) return new_branch16(v, p.kids, p.lv);
+  if (nk == 1) return collapse_branch(v, koff, d, last, NL{p.kids[last], lvl(v, p.kids[last])});  // (delete's collapse; rare)
+  return NL{NODE_EMPTY, 0};
+}
+// new version of the extension behind table entry p (its child's result is in p.kids[0], with its level in [1]); the keys
+// of its range that leave it half way split it
+PPD_HD inline NL assemble_ext(const View& v, const Batch& b, PathNode& p, uint32_t d) {
+  const NodeRec r = v.nodes[p.node];
+  const uint32_t el = (r.w0 >> 16) & 0xffu;
+  NL base{p.node, p.lv};
   bool changed = false;
-  for (uint32_t j = i; j < b.n && (j == i || (int)b.ops[j].lcp >= (int)d); j++) {
-    if (v.tkind[b.base + j] == TK_DIVERGE && v.tdepth[b.base + j] == d) continue;
-    // the first key that runs through owns the child's result (every earlier key of the range leaves inside the extension)
-    const uint32_t rj = v.res[b.base + j];
-    if (rj == NODE_EMPTY)
-      base = NL{NODE_EMPTY, 0}, changed = true;
-    else if (rj != T_UNCHANGED)
-      base = collapse_ext(v, a0, d, el, NL{rj, (uint32_t)v.res_lv[b.base + j]}), changed = true;
-    break;
-  }
-  for (uint32_t j = i; j < b.n && (j == i || (int)b.ops[j].lcp >= (int)d); j++)
+  const uint32_t rj = p.kids[0];
+  if (rj == NODE_EMPTY)
+    base = NL{NODE_EMPTY, 0}, changed = true;
+  else if (rj != T_UNCHANGED)
+    base = collapse_ext(v, r.a0, d, el, NL{rj, p.kids[1]}), changed = true;
+  for (uint32_t j = p.owner; j < b.n && (j == p.owner || (int)b.ops[j].lcp >= (int)d); j++)
     if (v.tkind[b.base + j] == TK_DIVERGE && v.tdepth[b.base + j] == d && (b.ops[j].kind == OP_PUT_LEAF || b.ops[j].kind == OP_PUT_ACCOUNT))
       base = insert_one(v, base, d, b.ops[j], b.txn), changed = true;
-  if (changed)
-    v.res[e] = base.id, v.res_lv[e] = (uint16_t)base.lv;
-  else
-    v.res[e] = T_UNCHANGED;
+  return changed ? base : NL{T_UNCHANGED, 0};
+}
+
+PPD_HD inline void set_trie_root(const View& v, uint32_t owner, uint32_t r) {
+  if (owner == OWNER_STATE_TRIE) {
+    v.cur->state_root = r;
+  } else if (owner == OWNER_TXN_TRIE) {
+    v.cur->txn_root = r;
+  } else if (owner == OWNER_RECEIPT_TRIE) {
+    v.cur->receipt_root = r;
+  } else {
+    AcctState& a = v.acct[v.traces[owner].acct];
+    a.storage = r, a.root_node = NONE;
+  }
+}
+
+// The way back up of key i.  Its terminal is resolved by the first key of the group that ends there (a new leaf, an
+// overwrite, a split, a removal).  That key reports the result to the node above; the LAST child to report to a node
+// re-assembles it (a branch left with one child collapses as delete does) and reports it to the node
+// above in turn, on behalf of the node's whole range (every key of the range has the same nodes above).  No barrier
+// and no scan of the range: a step is a handful of shared-memory operations plus the stores of the new node.  Whoever
+// re-assembles the topmost node installs the trie's new root.
+PPD_HD inline void batch_climb(const Ctx& c, const Batch& b, uint32_t i) {
+  const View& v = c.v;
+  const uint32_t e = b.base + i;
+  const SOp& o = b.ops[i];
+  const uint32_t tk = v.tkind[e], td = v.tdepth[e];
+  const uint32_t* ppc = v.path_pc + (size_t)e * PATH_CAP;
+  const uint8_t* pd = v.path_depth + (size_t)e * PATH_CAP;
+  NL cur{T_UNCHANGED, 0};
+  uint32_t t = v.plen[e];
+  if (tk == TK_DIVERGE) {
+    // one of the keys that leave the extension half way: it reports to the extension on its own account
+    const uint32_t idx = v.tpc[e];
+    if (idx == NONE) return;
+    PathNode& p = pc_at(v, idx);
+    PPD_FENCE_BLOCK();
+    if (PPD_ATOMIC_SUB(&p.pending, 1u) != 1u) return;
+    PPD_FENCE_BLOCK();
+    cur = assemble_ext(v, b, p, td);
+  } else {
+    if ((int)o.lcp >= (int)td) return;  // shares the terminal with its predecessor: the group's first key reports
+    if (tk == TK_EMPTY || tk == TK_LEAF_SAME || tk == TK_LEAF_OTHER) {
+      bool any = false;  // nothing to do for a group of accessed-only keys (most groups): decided before anything is loaded
+      for (uint32_t j = i; j < b.n && (j == i || (int)b.ops[j].lcp >= (int)td); j++) any |= b.ops[j].kind != OP_NONE;
+      if (any) {
+        NL base{NODE_EMPTY, 0};
+        if (tk != TK_EMPTY) base = NL{v.tnode[e], (uint32_t)v.level[v.tnode[e]]};
+        bool changed = false;
+        // a delete of the leaf's own key first, then the inserts (the order of distinct keys does not matter)
+        for (uint32_t j = i; j < b.n && (j == i || (int)b.ops[j].lcp >= (int)td); j++)
+          if (b.ops[j].kind == OP_DEL && v.tkind[b.base + j] == TK_LEAF_SAME) base = NL{NODE_EMPTY, 0}, changed = true;
+        for (uint32_t j = i; j < b.n && (j == i || (int)b.ops[j].lcp >= (int)td); j++)
+          if (b.ops[j].kind == OP_PUT_LEAF || b.ops[j].kind == OP_PUT_ACCOUNT) base = insert_one(v, base, td, b.ops[j], b.txn), changed = true;
+        if (changed) cur = base;
+      }
+    }
+  }
+  for (;;) {
+    if (t == 0) {  // what this key carries is the new version of the whole trie
+      if (cur.id != T_UNCHANGED) set_trie_root(v, o.owner, cur.id);
+      return;
+    }
+    t--;
+    const uint32_t d = pd[t] & 0x7fu;
+    const bool is_ext = (pd[t] & 0x80u) != 0;
+    const uint32_t idx = ppc[t];
+    if (idx == NONE) return;  // (the table was full: a flag is up)
+    PathNode& q = pc_at(v, idx);
+    if (cur.id != T_UNCHANGED) {
+      if (is_ext) {
+        q.kids[0] = cur.id, q.kids[1] = cur.lv;
+      } else {
+        q.kids[d < 8 ? (v.key_hi[e] >> (28 - 4 * d)) & 15u : key_nib(v, o.koff, d)] = cur.id;
+        if (cur.id != NODE_EMPTY) PPD_ATOMIC_MAX(&q.lv, cur.lv + 1u);
+      }
+      q.changed = 1;
+    }
+    PPD_FENCE_BLOCK();
+    if (PPD_ATOMIC_SUB(&q.pending, 1u) != 1u) return;  // others have yet to report: the last of them carries on
+    PPD_FENCE_BLOCK();
+    if (is_ext)
+      cur = assemble_ext(v, b, q, d);
+    else if (q.changed)
+      cur = assemble_branch(v, q, o.koff, d);
+    else
+      cur = NL{T_UNCHANGED, 0};
+  }
 }
 
 // ---- op preparation (all txns at once, before the loop) -----------------------------------------------------
@@ -879,38 +980,6 @@ PPD_HD inline void acct_claim(const View& v, const AcctInit& a, uint32_t t) {
 #define PPD_PHASE_CLOCK(c, k) ((void)0)
 #endif
 
-// terminals, re-assembly and new roots of one batch whose keys have been walked
-PPD_HD inline void run_batch(const Ctx& c, const Batch& b, uint32_t dmax, int clock_slot) {
-  const View& v = c.v;
-  for (uint32_t i = c.tid; i < b.n; i += c.nthreads) batch_terminal(c, b, i);
-  PPD_BLOCK_SYNC();
-  PPD_PHASE_CLOCK(c, clock_slot);
-  for (uint32_t d = dmax; d-- > 0;) {
-    for (uint32_t i = c.tid; i < b.n; i += c.nthreads) batch_assemble(c, b, i, d);
-    PPD_BLOCK_SYNC();
-  }
-  PPD_PHASE_CLOCK(c, clock_slot + 1);
-  // the first key of every trie holds the trie's new root
-  for (uint32_t i = c.tid; i < b.n; i += c.nthreads) {
-    if (b.ops[i].lcp != -1) continue;
-    const uint32_t r = v.res[b.base + i];
-    if (r == T_UNCHANGED) continue;
-    const uint32_t owner = b.ops[i].owner;
-    if (owner == OWNER_STATE_TRIE) {
-      v.cur->state_root = r;
-    } else if (owner == OWNER_TXN_TRIE) {
-      v.cur->txn_root = r;
-    } else if (owner == OWNER_RECEIPT_TRIE) {
-      v.cur->receipt_root = r;
-    } else {
-      AcctState& a = v.acct[v.traces[owner].acct];
-      a.storage = r, a.root_node = NONE;
-    }
-  }
-  PPD_BLOCK_SYNC();
-  PPD_PHASE_CLOCK(c, clock_slot + 2);
-}
-
 PPD_HD inline void copy32(uint8_t* d, const uint8_t* s) {
   for (int i = 0; i < 32; i++) d[i] = s[i];
 }
@@ -932,8 +1001,9 @@ PPD_HD inline void run_txn(const Ctx& c, uint32_t ti, const uint8_t* empty_trie_
     v.seg_b[tx.seg_tries + 0] = v.cur->state_root;
     v.seg_b[tx.seg_tries + 1] = v.cur->txn_root;
     v.seg_b[tx.seg_tries + 2] = v.cur->receipt_root;
-    c.sh_dmax[0] = 0, c.sh_dmax[1] = 0;
+    *v.pc_count = 0;
   }
+  for (uint32_t k = c.tid; k <= v.pc_map_mask; k += c.nthreads) v.pc_map_key[k] = 0xffffffffu;
   for (uint32_t k = c.tid; k < ntr; k += c.nthreads) {
     const uint32_t t = tx.trace_begin + k;
     const TxnTrace& tr = v.traces[t];
@@ -958,14 +1028,24 @@ PPD_HD inline void run_txn(const Ctx& c, uint32_t ti, const uint8_t* empty_trie_
   for (uint32_t k = c.tid; k < n1 + n2; k += c.nthreads) {
     uint32_t* out = v.touched + tx.touched_base + MARK_SLOTS_T * k;
     if (k < n1)
-      batch_walk(c, b1, k, out, &c.sh_dmax[0]);
+      batch_walk(c, b1, k, out);
     else
-      batch_walk(c, b2, k - n1, out, &c.sh_dmax[1]);
+      batch_walk(c, b2, k - n1, out);
   }
   PPD_BLOCK_SYNC();
   PPD_PHASE_CLOCK(c, 1);
+  for (uint32_t k = c.tid; k < n1 + n2; k += c.nthreads) {
+    if (k < n1)
+      batch_announce(c, b1, k);
+    else
+      batch_announce(c, b2, k - n1);
+  }
+  PPD_BLOCK_SYNC();
+  PPD_PHASE_CLOCK(c, 2);
   // ---- apply_deltas_to_trie_state (decoding.rs:219-292): storage writes, the txn and receipt inserts ----
-  run_batch(c, b1, c.sh_dmax[0], 2);
+  for (uint32_t k = c.tid; k < n1; k += c.nthreads) batch_climb(c, b1, k);
+  PPD_BLOCK_SYNC();
+  PPD_PHASE_CLOCK(c, 3);
   // ---- the accounts after the txn: storage_root = the storage trie's hash after the writes (late-bound: an NK_ROOT node) ----
   for (uint32_t k = c.tid; k < ntr; k += c.nthreads) {
     const uint32_t t = tx.trace_begin + k;
@@ -1001,9 +1081,11 @@ PPD_HD inline void run_txn(const Ctx& c, uint32_t ti, const uint8_t* empty_trie_
     v.accounts[v.rec_base + tr.rec] = rec;
   }
   PPD_BLOCK_SYNC();
-  PPD_PHASE_CLOCK(c, 5);
+  PPD_PHASE_CLOCK(c, 4);
   // ---- state writes and self-destructs in one descent ----
-  run_batch(c, b2, c.sh_dmax[1], 6);
+  for (uint32_t k = c.tid; k < n2; k += c.nthreads) batch_climb(c, b2, k);
+  PPD_BLOCK_SYNC();
+  PPD_PHASE_CLOCK(c, 5);
   for (uint32_t k = c.tid; k < ntr; k += c.nthreads) {
     const TxnTrace& tr = v.traces[tx.trace_begin + k];
     if (tr.flags & PPD_TR_SELF_DESTRUCTED) {  // trie_state.storage.remove(hashed_addr), decoding.rs:271-282
@@ -1018,7 +1100,7 @@ PPD_HD inline void run_txn(const Ctx& c, uint32_t ti, const uint8_t* empty_trie_
     v.seg_a[tx.seg_roots + 2] = new_root(v, v.cur->receipt_root);
   }
   PPD_BLOCK_SYNC();
-  PPD_PHASE_CLOCK(c, 9);
+  PPD_PHASE_CLOCK(c, 6);
 }
 
 // ---- after the last txn: the NK_ROOT nodes dummy entries refer to, and the withdrawals (decoding.rs:356-428) ----

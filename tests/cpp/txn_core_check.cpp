@@ -189,15 +189,21 @@ int check_block(const std::vector<uint8_t>& flatv, const char* name) {
   v.ops1 = ops1.data(), v.ops2 = ops2.data();
   std::vector<uint32_t> touched(T.touched_begin.back() + 16, NODE_EMPTY);
   v.touched = touched.data(), v.seg_a = T.seg_a.data(), v.seg_b = T.seg_b.data();
-  std::vector<uint32_t> path_node((size_t)T.max_ops * txn::PATH_CAP + 1), path_a0(path_node.size()), path_a1(path_node.size()), tnode(T.max_ops + 1), res(T.max_ops + 1);
-  std::vector<uint8_t> path_depth((size_t)T.max_ops * txn::PATH_CAP + 1), plen(T.max_ops + 1), top(T.max_ops + 1), tdepth(T.max_ops + 1), tkind(T.max_ops + 1);
+  const size_t np = (size_t)T.max_ops * txn::PATH_CAP + 1;
+  std::vector<uint32_t> path_node(np), path_pc(np), tnode(T.max_ops + 1), tpc(T.max_ops + 1), key_hi(T.max_ops + 1);
+  std::vector<uint8_t> path_depth(np), plen(T.max_ops + 1), tdepth(T.max_ops + 1), tkind(T.max_ops + 1);
   std::vector<txn::SOp> sh_ops(T.max_ops + 1);
-  v.path_node = path_node.data(), v.path_a0 = path_a0.data(), v.path_a1 = path_a1.data(), v.path_depth = path_depth.data();
-  v.plen = plen.data(), v.top = top.data(), v.tnode = tnode.data();
-  std::vector<uint16_t> res_lv(T.max_ops + 1);
-  std::vector<uint32_t> key_hi(T.max_ops + 1);
-  v.tdepth = tdepth.data(), v.tkind = tkind.data(), v.res = res.data(), v.res_lv = res_lv.data(), v.key_hi = key_hi.data();
+  v.path_node = path_node.data(), v.path_pc = path_pc.data(), v.path_depth = path_depth.data();
+  v.plen = plen.data(), v.tnode = tnode.data(), v.tpc = tpc.data(), v.tdepth = tdepth.data(), v.tkind = tkind.data(), v.key_hi = key_hi.data();
   v.sh_ops = (n_traces & 1) ? sh_ops.data() : nullptr;  // both ways of reaching a txn's keys get exercised
+  // the path-node table in two tiers, the first one tiny so that the spill tier is exercised
+  std::vector<txn::PathNode> pc_fast(5), pc_slow(np);
+  size_t map_n = 64;
+  while (map_n < 2 * np) map_n <<= 1;
+  std::vector<uint32_t> pc_map(map_n), pc_map_key(map_n);
+  uint32_t pc_count = 0;
+  v.pc_fast = pc_fast.data(), v.pc_n_fast = (uint32_t)pc_fast.size(), v.pc_slow = pc_slow.data(), v.pc_n_slow = (uint32_t)pc_slow.size();
+  v.pc_map = pc_map.data(), v.pc_map_key = pc_map_key.data(), v.pc_map_mask = (uint32_t)map_n - 1, v.pc_count = &pc_count;
   txn::Cursors cur;
   memset(&cur, 0, sizeof cur);
   cur.n_nodes = n_pre_nodes, cur.n_children = (uint32_t)A.child_pool.size(), cur.key_bytes = B.key_cursor;
@@ -213,9 +219,8 @@ int check_block(const std::vector<uint8_t>& flatv, const char* name) {
   for (uint32_t ti = 0; ti < v.n_txns; ti++) txn::prep_txn(v, ti);
   for (uint32_t i = 0; i < T.n_ops1; i++) txn::prep_lcp(v, v.ops1, i);
   for (uint32_t i = 0; i < T.n_ops2; i++) txn::prep_lcp(v, v.ops2, i);
-  uint32_t sh_dmax[2] = {0, 0};
   long long sh_clock = 0;
-  txn::Ctx c{v, 0, 1, sh_dmax, &sh_clock};
+  txn::Ctx c{v, 0, 1, &sh_clock};
   for (uint32_t ti = 0; ti < v.n_txns && !cur.flag; ti++) txn::run_txn(c, ti, EMPTY_TRIE_HASH, EMPTY_CODE_HASH);
   txn::run_finish(c, b2.state_root);
   if (cur.flag) {
