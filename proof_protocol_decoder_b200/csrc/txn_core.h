@@ -527,14 +527,36 @@ PPD_HD inline uint32_t pc_make(const View& v, uint32_t node, const NodeRec& r, b
     return NONE;
   }
   PathNode& p = pc_at(v, idx);
+  const uint32_t old_lv = v.level[node];
   if (is_branch) {
-    const uint32_t mask = r.a1 & 0xffffu;
+    // all loads first, then the stores: a store between two loads would make every load wait for the one before it
+    const uint32_t mask = r.a1 & 0xffffu, k = popc16(mask);
+    uint32_t c[16];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (uint32_t q = 0; q < 16; q++) c[q] = q < k ? v.child_pool[r.a0 + q] : NODE_EMPTY;
     uint32_t q = 0;
-    for (uint32_t nib = 0; nib < 16; nib++) p.kids[nib] = (mask >> nib) & 1u ? v.child_pool[r.a0 + q++] : NODE_EMPTY;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (uint32_t nib = 0; nib < 16; nib++) {
+      uint32_t x = NODE_EMPTY;
+      if ((mask >> nib) & 1u) {
+        // the q-th compact child: selected without indexing the register array dynamically
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (uint32_t z = 0; z < 16; z++)
+          if (z == q) x = c[z];
+        q++;
+      }
+      p.kids[nib] = x;
+    }
   } else {
     p.kids[0] = T_UNCHANGED;
   }
-  p.node = node, p.lv = v.level[node], p.pending = 0, p.owner = owner, p.changed = 0;
+  p.node = node, p.lv = old_lv, p.pending = 0, p.owner = owner, p.changed = 0;
   uint32_t h = pc_hash(node) & v.pc_map_mask;
   for (;;) {
     const uint32_t prev = PPD_ATOMIC_CAS(&v.pc_map_key[h], 0xffffffffu, node);
@@ -631,6 +653,101 @@ PPD_HD inline void batch_walk(const Ctx& c, const Batch& b, uint32_t i, uint32_t
     const uint8_t* kb = v.key_pool + o.koff;  // (every key has at least four bytes behind its offset: digests, padded txn keys)
     v.key_hi[e] = ((uint32_t)kb[0] << 24) | ((uint32_t)kb[1] << 16) | ((uint32_t)kb[2] << 8) | kb[3];
   }
+}
+
+// The canonical trie over a small group of sorted items that share their first `td` nibbles: the writes of one group
+// (keys that end at the same place) plus, possibly, the leaf that was there.  One pass with a stack of open branches
+// (no walk per item, no intermediate versions): what inserting the items one by one arrives at.  Returns false when the
+// group is not of the plain kind (too many items, keys of different lengths): the caller then inserts one by one.
+static const uint32_t GROUP_MAX = 12;
+PPD_HD inline bool build_group(const View& v, const Batch& b, uint32_t first, uint32_t end, uint32_t td, uint32_t old_leaf, bool keep_old, NL* out, uint32_t txn) {
+  // items: (key offset, op index or NONE for the old leaf), in key order, with the LCP (absolute) to the previous item
+  uint32_t ik[GROUP_MAX + 1], iop[GROUP_MAX + 1];
+  int il[GROUP_MAX + 2];
+  uint32_t m = 0;
+  NodeRec oldr{};
+  uint32_t old_koff = 0, old_lv = 0;
+  if (keep_old) {
+    oldr = v.nodes[old_leaf];
+    old_koff = oldr.a0;
+    old_lv = v.level[old_leaf];
+    if (((oldr.w0 >> 8) & 0xffu) + ((oldr.w0 >> 16) & 0xffu) != 64u) return false;
+  }
+  bool old_placed = !keep_old;
+  int run_min = 127, prev_cpx = -1;
+  for (uint32_t j = first; j < end; j++) {
+    if (j > first && (int)b.ops[j].lcp < run_min) run_min = b.ops[j].lcp;
+    const uint8_t kind = b.ops[j].kind;
+    if (kind != OP_PUT_LEAF && kind != OP_PUT_ACCOUNT) continue;
+    if (b.ops[j].klen != 64 || m + 2 > GROUP_MAX) return false;
+    int l_prev = m == 0 ? (int)td - 1 : run_min;  // LCP with the previous write (the minimum over the keys skipped in between)
+    if (!old_placed) {
+      const int cpx = (int)td + (int)common_prefix(v, old_koff, td, b.ops[j].koff, td, 64 - td);
+      if (cpx >= 64) return false;  // (an overwrite: the caller drops the old leaf)
+      if (key_nib(v, old_koff, (uint32_t)cpx) < key_nib(v, b.ops[j].koff, (uint32_t)cpx)) {
+        // the old leaf comes before this write
+        ik[m] = old_koff, iop[m] = NONE, il[m] = m == 0 ? (int)td - 1 : prev_cpx, m++;
+        old_placed = true;
+        l_prev = cpx;
+      } else {
+        prev_cpx = cpx;
+      }
+    }
+    ik[m] = b.ops[j].koff, iop[m] = j, il[m] = l_prev, m++;
+    run_min = 127;
+  }
+  if (!old_placed) ik[m] = old_koff, iop[m] = NONE, il[m] = m == 0 ? (int)td - 1 : prev_cpx, m++;
+  il[m] = (int)td - 1;
+  if (m == 0) {
+    *out = NL{NODE_EMPTY, 0};
+    return true;
+  }
+  // stack of open branches
+  uint32_t sd[GROUP_MAX + 1], slv[GROUP_MAX + 1], sk[GROUP_MAX + 1][16];
+  uint32_t sp = 0;
+  for (uint32_t k = 0; k < m; k++) {
+    const int lc = il[k], ln = il[k + 1];
+    const uint32_t s = (uint32_t)((lc > ln ? lc : ln) + 1);
+    NL cur = iop[k] == NONE ? releaf(v, old_leaf, old_lv, old_koff, s, 64 - s) : new_leaf_for(v, b.ops[iop[k]], s);
+    if (ln > lc) {  // a branch at depth ln opens with this leaf as its first child
+      sd[sp] = (uint32_t)ln, slv[sp] = cur.lv + 1u;
+      for (int z = 0; z < 16; z++) sk[sp][z] = NODE_EMPTY;
+      sk[sp][key_nib(v, ik[k], (uint32_t)ln)] = cur.id;
+      sp++;
+      continue;
+    }
+    if (sp == 0) {  // a single item
+      *out = cur;
+      return true;
+    }
+    sk[sp - 1][key_nib(v, ik[k], (uint32_t)lc)] = cur.id;
+    if (cur.lv + 1u > slv[sp - 1]) slv[sp - 1] = cur.lv + 1u;
+    while (sp && (int)sd[sp - 1] > ln) {
+      sp--;
+      const uint32_t d = sd[sp];
+      NL br = new_branch16(v, sk[sp], slv[sp]);
+      const int parent = sp ? (int)sd[sp - 1] : (int)td - 1;
+      const int p = parent > ln ? parent : ln;
+      if (p < (int)d - 1) br = new_ext(v, ik[k], (uint32_t)(p + 1), d - (uint32_t)(p + 1), br);
+      if (p < (int)td) {  // above the group: this is its top node
+        *out = br;
+        return true;
+      }
+      const uint32_t nib = key_nib(v, ik[k], (uint32_t)p);
+      if (sp && p == parent) {
+        sk[sp - 1][nib] = br.id;
+        if (br.lv + 1u > slv[sp - 1]) slv[sp - 1] = br.lv + 1u;
+      } else {
+        sd[sp] = (uint32_t)p, slv[sp] = br.lv + 1u;
+        for (int z = 0; z < 16; z++) sk[sp][z] = NODE_EMPTY;
+        sk[sp][nib] = br.id;
+        sp++;
+        break;
+      }
+    }
+  }
+  raise(v, TXF_STACK, txn);  // (unreachable: the last item closes every open branch)
+  return false;
 }
 
 // After every walk: a key looks up the table entry of every node on its path, and announces itself at the nodes whose
@@ -736,12 +853,24 @@ PPD_HD inline void batch_climb(const Ctx& c, const Batch& b, uint32_t i) {
       if (any) {
         NL base{NODE_EMPTY, 0};
         if (tk != TK_EMPTY) base = NL{v.tnode[e], (uint32_t)v.level[v.tnode[e]]};
-        bool changed = false;
-        // a delete of the leaf's own key first, then the inserts (the order of distinct keys does not matter)
-        for (uint32_t j = i; j < b.n && (j == i || (int)b.ops[j].lcp >= (int)td); j++)
-          if (b.ops[j].kind == OP_DEL && v.tkind[b.base + j] == TK_LEAF_SAME) base = NL{NODE_EMPTY, 0}, changed = true;
-        for (uint32_t j = i; j < b.n && (j == i || (int)b.ops[j].lcp >= (int)td); j++)
-          if (b.ops[j].kind == OP_PUT_LEAF || b.ops[j].kind == OP_PUT_ACCOUNT) base = insert_one(v, base, td, b.ops[j], b.txn), changed = true;
+        bool changed = false, keep_old = tk != TK_EMPTY;
+        uint32_t end = i, n_put = 0;
+        // the leaf that is there goes when its own key is deleted or overwritten; then the inserts (the order of distinct keys does not matter)
+        for (uint32_t j = i; j < b.n && (j == i || (int)b.ops[j].lcp >= (int)td); j++, end++) {
+          const uint8_t kind = b.ops[j].kind;
+          if (kind == OP_DEL && v.tkind[b.base + j] == TK_LEAF_SAME) base = NL{NODE_EMPTY, 0}, changed = true, keep_old = false;
+          if (kind == OP_PUT_LEAF || kind == OP_PUT_ACCOUNT) {
+            n_put++, changed = true;
+            if (v.tkind[b.base + j] == TK_LEAF_SAME) keep_old = false;
+          }
+        }
+        NL built;
+        if (n_put >= 2 && build_group(v, b, i, end, td, v.tnode[e], keep_old, &built, b.txn)) {
+          base = built;
+        } else {
+          for (uint32_t j = i; j < end; j++)
+            if (b.ops[j].kind == OP_PUT_LEAF || b.ops[j].kind == OP_PUT_ACCOUNT) base = insert_one(v, base, td, b.ops[j], b.txn);
+        }
         if (changed) cur = base;
       }
     }
