@@ -518,8 +518,8 @@ PPD_HD inline uint32_t trie_root_of(const View& v, uint32_t owner) {
 
 PPD_HD inline PathNode& pc_at(const View& v, uint32_t idx) { return idx < v.pc_n_fast ? v.pc_fast[idx] : v.pc_slow[idx - v.pc_n_fast]; }
 PPD_HD inline uint32_t pc_hash(uint32_t node) { return node * 2654435761u; }
-// the owner of a path node makes its table entry (children and level are loaded here, in the shadow of the walk's own
-// load of one of those children) and publishes it under the node id
+// the owner of a path node makes its table entry during the walk and publishes it under the node id; the node's child
+// table and level are loaded afterwards, all entries in parallel (pc_fill)
 PPD_HD inline uint32_t pc_make(const View& v, uint32_t node, const NodeRec& r, bool is_branch, uint32_t owner, uint32_t txn) {
   uint32_t idx = PPD_ATOMIC_ADD(v.pc_count, 1u);
   if (idx >= v.pc_n_fast + v.pc_n_slow) {
@@ -527,36 +527,8 @@ PPD_HD inline uint32_t pc_make(const View& v, uint32_t node, const NodeRec& r, b
     return NONE;
   }
   PathNode& p = pc_at(v, idx);
-  const uint32_t old_lv = v.level[node];
-  if (is_branch) {
-    // all loads first, then the stores: a store between two loads would make every load wait for the one before it
-    const uint32_t mask = r.a1 & 0xffffu, k = popc16(mask);
-    uint32_t c[16];
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-    for (uint32_t q = 0; q < 16; q++) c[q] = q < k ? v.child_pool[r.a0 + q] : NODE_EMPTY;
-    uint32_t q = 0;
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-    for (uint32_t nib = 0; nib < 16; nib++) {
-      uint32_t x = NODE_EMPTY;
-      if ((mask >> nib) & 1u) {
-        // the q-th compact child: selected without indexing the register array dynamically
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-        for (uint32_t z = 0; z < 16; z++)
-          if (z == q) x = c[z];
-        q++;
-      }
-      p.kids[nib] = x;
-    }
-  } else {
-    p.kids[0] = T_UNCHANGED;
-  }
-  p.node = node, p.lv = old_lv, p.pending = 0, p.owner = owner, p.changed = 0;
+  p.kids[0] = r.a0, p.kids[1] = is_branch ? (r.a1 & 0xffffu) : 0x10000u;  // (until pc_fill replaces them)
+  p.node = node, p.lv = 0, p.pending = 0, p.owner = owner, p.changed = 0;
   uint32_t h = pc_hash(node) & v.pc_map_mask;
   for (;;) {
     const uint32_t prev = PPD_ATOMIC_CAS(&v.pc_map_key[h], 0xffffffffu, node);
@@ -565,6 +537,39 @@ PPD_HD inline uint32_t pc_make(const View& v, uint32_t node, const NodeRec& r, b
   }
   v.pc_map[h] = idx + 1u;
   return idx;
+}
+// per table entry: the node's children as they are before the txn (sixteen independent loads), and its level
+PPD_HD inline void pc_fill(const View& v, uint32_t idx) {
+  PathNode& p = pc_at(v, idx);
+  const uint32_t a0 = p.kids[0], m = p.kids[1];
+  const uint32_t old_lv = v.level[p.node];
+  if (m & 0x10000u) {  // an extension: [0] will hold its child's result
+    p.kids[0] = T_UNCHANGED, p.kids[1] = 0;
+  } else {
+    const uint32_t mask = m & 0xffffu, k = popc16(mask);
+    uint32_t c[16];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (uint32_t q = 0; q < 16; q++) c[q] = q < k ? v.child_pool[a0 + q] : NODE_EMPTY;  // all in flight together
+    uint32_t q = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (uint32_t nib = 0; nib < 16; nib++) {
+      uint32_t x = NODE_EMPTY;
+      if ((mask >> nib) & 1u) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (uint32_t z = 0; z < 16; z++)
+          if (z == q) x = c[z];  // (the q-th compact child, without indexing the register array dynamically)
+        q++;
+      }
+      p.kids[nib] = x;
+    }
+  }
+  p.lv = old_lv;
 }
 PPD_HD inline uint32_t pc_find(const View& v, uint32_t node) {
   uint32_t h = pc_hash(node) & v.pc_map_mask;
@@ -1163,6 +1168,10 @@ PPD_HD inline void run_txn(const Ctx& c, uint32_t ti, const uint8_t* empty_trie_
   }
   PPD_BLOCK_SYNC();
   PPD_PHASE_CLOCK(c, 1);
+  {
+    const uint32_t n_pc = *v.pc_count < v.pc_n_fast + v.pc_n_slow ? *v.pc_count : v.pc_n_fast + v.pc_n_slow;
+    for (uint32_t k = c.tid; k < n_pc; k += c.nthreads) pc_fill(v, k);
+  }
   for (uint32_t k = c.tid; k < n1 + n2; k += c.nthreads) {
     if (k < n1)
       batch_announce(c, b1, k);
