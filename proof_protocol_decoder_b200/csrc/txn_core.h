@@ -33,10 +33,15 @@
 #include "../../include/ppd_flat.h"
 #include "arena.h"
 
+// Everything is force-inlined on the device: the View (a struct of ~60 pointers and sizes) must never be an object in
+// memory that some store through a uint32_t* might alias, or every use of a field becomes a reload behind every store
+// (measured: the sixteen child-table stores of one node took sixteen dependent round trips).
 #if defined(__CUDACC__)
-#define PPD_HD __host__ __device__
+#define PPD_HD __host__ __device__ __forceinline__
+#define PPD_INLINE
 #else
 #define PPD_HD
+#define PPD_INLINE inline
 #endif
 
 namespace ppd {
@@ -229,7 +234,7 @@ struct JoinView {
   uint32_t* flag;             // &Cursors::flag
 };
 
-PPD_HD inline bool is_hash_id(uint32_t n) { return n >= HASH_BASE && n < HASH_END; }
+PPD_HD PPD_INLINE bool is_hash_id(uint32_t n) { return n >= HASH_BASE && n < HASH_END; }
 
 // ---- the execution context: how threads of the block see shared counters ------------------------------------
 // Device: a thread block.  Harness: one "thread" at a time.
@@ -246,17 +251,17 @@ struct Ctx {
 #define PPD_ATOMIC_MAX(p, x) atomicMax((p), (x))
 #define PPD_ATOMIC_CAS(p, c, x) atomicCAS((p), (c), (x))
 #else
-PPD_HD inline uint32_t host_atomic_add(uint32_t* p, uint32_t x) {
+PPD_HD PPD_INLINE uint32_t host_atomic_add(uint32_t* p, uint32_t x) {
   uint32_t o = *p;
   *p = o + x;
   return o;
 }
-PPD_HD inline uint32_t host_atomic_max(uint32_t* p, uint32_t x) {
+PPD_HD PPD_INLINE uint32_t host_atomic_max(uint32_t* p, uint32_t x) {
   uint32_t o = *p;
   if (x > o) *p = x;
   return o;
 }
-PPD_HD inline uint32_t host_atomic_cas(uint32_t* p, uint32_t c, uint32_t x) {
+PPD_HD PPD_INLINE uint32_t host_atomic_cas(uint32_t* p, uint32_t c, uint32_t x) {
   uint32_t o = *p;
   if (o == c) *p = x;
   return o;
@@ -268,20 +273,20 @@ PPD_HD inline uint32_t host_atomic_cas(uint32_t* p, uint32_t c, uint32_t x) {
 #define PPD_ATOMIC_CAS(p, c, x) ppd::txn::host_atomic_cas((p), (c), (x))
 #endif
 
-PPD_HD inline void raise(const View& v, uint32_t why, uint32_t txn) {
+PPD_HD PPD_INLINE void raise(const View& v, uint32_t why, uint32_t txn) {
   if (PPD_ATOMIC_CAS(&v.cur->flag, 0u, why) == 0u) v.cur->flag_txn = txn;
 }
 
 // ---- arena primitives (the device form of host_arena.h) -------------------------------------------------------
-PPD_HD inline uint32_t key_nib(const View& v, uint32_t koff, uint32_t i) {
+PPD_HD PPD_INLINE uint32_t key_nib(const View& v, uint32_t koff, uint32_t i) {
   const uint32_t b = v.key_pool[koff + (i >> 1)];
   return (i & 1) ? (b & 15u) : (b >> 4);
 }
-PPD_HD inline uint32_t lvl(const View& v, uint32_t n) { return (n == NODE_EMPTY || n >= HASH_BASE) ? 0u : (uint32_t)v.level[n]; }
-PPD_HD inline uint32_t kind_of(const View& v, uint32_t n) { return is_hash_id(n) ? (uint32_t)NK_HASH : (v.nodes[n].w0 & 0xffu); }
-PPD_HD inline uint32_t w0(uint32_t kind, uint32_t start, uint32_t len) { return kind | (start << 8) | (len << 16); }
+PPD_HD PPD_INLINE uint32_t lvl(const View& v, uint32_t n) { return (n == NODE_EMPTY || n >= HASH_BASE) ? 0u : (uint32_t)v.level[n]; }
+PPD_HD PPD_INLINE uint32_t kind_of(const View& v, uint32_t n) { return is_hash_id(n) ? (uint32_t)NK_HASH : (v.nodes[n].w0 & 0xffu); }
+PPD_HD PPD_INLINE uint32_t w0(uint32_t kind, uint32_t start, uint32_t len) { return kind | (start << 8) | (len << 16); }
 
-PPD_HD inline uint32_t push_node(const View& v, const NodeRec& r, uint32_t lv) {
+PPD_HD PPD_INLINE uint32_t push_node(const View& v, const NodeRec& r, uint32_t lv) {
   uint32_t id = PPD_ATOMIC_ADD(v.a_nodes, 1u);
   if (id >= v.cap_nodes) {
     raise(v, TXF_NODES_FULL, 0);
@@ -293,7 +298,7 @@ PPD_HD inline uint32_t push_node(const View& v, const NodeRec& r, uint32_t lv) {
   PPD_ATOMIC_MAX(v.a_max_level, lv);
   return id;
 }
-PPD_HD inline uint32_t alloc_children(const View& v, uint32_t k) {
+PPD_HD PPD_INLINE uint32_t alloc_children(const View& v, uint32_t k) {
   uint32_t at = PPD_ATOMIC_ADD(v.a_children, k);
   if (at + k > v.cap_children) {
     raise(v, TXF_CHILDREN_FULL, 0);
@@ -301,7 +306,7 @@ PPD_HD inline uint32_t alloc_children(const View& v, uint32_t k) {
   }
   return at;
 }
-PPD_HD inline uint32_t common_prefix(const View& v, uint32_t ka, uint32_t sa, uint32_t kb, uint32_t sb, uint32_t m) {
+PPD_HD PPD_INLINE uint32_t common_prefix(const View& v, uint32_t ka, uint32_t sa, uint32_t kb, uint32_t sb, uint32_t m) {
   uint32_t i = 0;
   if (((sa ^ sb) & 1u) == 0) {  // same parity (always, for nodes on a key's own path): whole bytes at a time
     if ((sa & 1u) && i < m) {
@@ -313,7 +318,7 @@ PPD_HD inline uint32_t common_prefix(const View& v, uint32_t ka, uint32_t sa, ui
   while (i < m && key_nib(v, ka, sa + i) == key_nib(v, kb, sb + i)) i++;
   return i;
 }
-PPD_HD inline uint32_t child_at(const View& v, const NodeRec& br, uint32_t nib) {
+PPD_HD PPD_INLINE uint32_t child_at(const View& v, const NodeRec& br, uint32_t nib) {
   const uint32_t mask = br.a1 & 0xffffu, bit = 1u << nib;
   if (!(mask & bit)) return NODE_EMPTY;
 #if defined(__CUDA_ARCH__)
@@ -322,7 +327,7 @@ PPD_HD inline uint32_t child_at(const View& v, const NodeRec& br, uint32_t nib) 
   return v.child_pool[br.a0 + __builtin_popcount(mask & (bit - 1))];
 #endif
 }
-PPD_HD inline uint32_t popc16(uint32_t m) {
+PPD_HD PPD_INLINE uint32_t popc16(uint32_t m) {
 #if defined(__CUDA_ARCH__)
   return __popc(m & 0xffffu);
 #else
@@ -336,7 +341,7 @@ PPD_HD inline uint32_t popc16(uint32_t m) {
 struct NL {
   uint32_t id, lv;
 };
-PPD_HD inline NL new_leaf_for(const View& v, const SOp& o, uint32_t start) {
+PPD_HD PPD_INLINE NL new_leaf_for(const View& v, const SOp& o, uint32_t start) {
   const uint32_t len = o.klen - start;
   if (o.kind == OP_PUT_ACCOUNT) {
     const uint32_t src = v.accounts[o.a1].storage_src;
@@ -345,21 +350,21 @@ PPD_HD inline NL new_leaf_for(const View& v, const SOp& o, uint32_t start) {
   }
   return NL{push_node(v, NodeRec{w0(NK_LEAF, start, len), o.koff, o.a1, o.a2}, 0), 0};
 }
-PPD_HD inline NL new_ext(const View& v, uint32_t koff, uint32_t start, uint32_t len, NL child) {
+PPD_HD PPD_INLINE NL new_ext(const View& v, uint32_t koff, uint32_t start, uint32_t len, NL child) {
   return NL{push_node(v, NodeRec{w0(NK_EXT, start, len), koff, child.id, 0}, child.lv + 1u), child.lv + 1u};
 }
-PPD_HD inline uint32_t new_root(const View& v, uint32_t child) {
+PPD_HD PPD_INLINE uint32_t new_root(const View& v, uint32_t child) {
   return push_node(v, NodeRec{w0(NK_ROOT, 0, 0), 0, child, 0}, child == NODE_EMPTY ? 0u : lvl(v, child) + 1u);
 }
 // the same leaf payload under a different key range
-PPD_HD inline NL releaf(const View& v, uint32_t leaf, uint32_t leaf_lv, uint32_t koff, uint32_t start, uint32_t len) {
+PPD_HD PPD_INLINE NL releaf(const View& v, uint32_t leaf, uint32_t leaf_lv, uint32_t koff, uint32_t start, uint32_t len) {
   NodeRec r = v.nodes[leaf];
   r.w0 = w0(r.w0 & 0xffu, start, len);
   r.a0 = koff;
   return NL{push_node(v, r, leaf_lv), leaf_lv};
 }
 // branch of level lv from 16 slots (NODE_EMPTY = none); at least two are set
-PPD_HD inline NL new_branch16(const View& v, const uint32_t* kids, uint32_t lv) {
+PPD_HD PPD_INLINE NL new_branch16(const View& v, const uint32_t* kids, uint32_t lv) {
   uint32_t mask = 0, k = 0;
   for (uint32_t i = 0; i < 16; i++)
     if (kids[i] != NODE_EMPTY) mask |= 1u << i, k++;
@@ -369,7 +374,7 @@ PPD_HD inline NL new_branch16(const View& v, const uint32_t* kids, uint32_t lv) 
   return NL{push_node(v, NodeRec{w0(NK_BRANCH, 0, 0), base, mask, 0}, lv), lv};
 }
 // copy of branch `br` with slot `nib` set to `child` (never NODE_EMPTY here)
-PPD_HD inline NL branch_with(const View& v, uint32_t br, uint32_t nib, NL child) {
+PPD_HD PPD_INLINE NL branch_with(const View& v, uint32_t br, uint32_t nib, NL child) {
   const NodeRec r = v.nodes[br];
   uint32_t lv = v.level[br];
   const uint32_t mask = r.a1 & 0xffffu, bit = 1u << nib;
@@ -384,7 +389,7 @@ PPD_HD inline NL branch_with(const View& v, uint32_t br, uint32_t nib, NL child)
   return NL{push_node(v, NodeRec{w0(NK_BRANCH, 0, 0), base, mask | bit, 0}, lv), lv};
 }
 // an extension (ek, es, el) over `child`, merged into the child when that is a leaf / an extension (delete's collapse)
-PPD_HD inline NL collapse_ext(const View& v, uint32_t ek, uint32_t es, uint32_t el, NL child) {
+PPD_HD PPD_INLINE NL collapse_ext(const View& v, uint32_t ek, uint32_t es, uint32_t el, NL child) {
   const uint32_t k = kind_of(v, child.id);
   if (k == NK_EXT) {
     const NodeRec c = v.nodes[child.id];  // (the merged extension reads what the child read: the child's level)
@@ -397,7 +402,7 @@ PPD_HD inline NL collapse_ext(const View& v, uint32_t ek, uint32_t es, uint32_t 
   return new_ext(v, ek, es, el, child);
 }
 // the single child left in slot `nib` of a branch at depth `pos` on the path of key `koff`
-PPD_HD inline NL collapse_branch(const View& v, uint32_t koff, uint32_t pos, uint32_t nib, NL other) {
+PPD_HD PPD_INLINE NL collapse_branch(const View& v, uint32_t koff, uint32_t pos, uint32_t nib, NL other) {
   const uint32_t k = kind_of(v, other.id);
   if (k == NK_EXT || k == NK_LEAF || k == NK_LEAF_ACCOUNT) return collapse_ext(v, 0, pos, 1, other);  // their own keys spell the nibble
   // a key that runs through the surviving child: the path's first `pos` nibbles, then its slot
@@ -415,7 +420,7 @@ PPD_HD inline NL collapse_branch(const View& v, uint32_t koff, uint32_t pos, uin
 }
 
 // ---- insert of one key below `base`, which sits at depth `depth` on the key's path (HostArena::insert, iterative) ----
-PPD_HD inline NL split_at(const View& v, const SOp& o, uint32_t pos, uint32_t cp, uint32_t existing_nib, NL existing, uint32_t txn) {
+PPD_HD PPD_INLINE NL split_at(const View& v, const SOp& o, uint32_t pos, uint32_t cp, uint32_t existing_nib, NL existing, uint32_t txn) {
   const uint32_t at = pos + cp;
   if (at >= o.klen) {
     raise(v, TXF_KEY_PREFIX, txn);
@@ -430,7 +435,7 @@ PPD_HD inline NL split_at(const View& v, const SOp& o, uint32_t pos, uint32_t cp
   const NL br = new_branch16(v, kids, (existing.lv > leaf.lv ? existing.lv : leaf.lv) + 1u);
   return cp == 0 ? br : new_ext(v, o.koff, pos, cp, br);
 }
-PPD_HD inline NL insert_one(const View& v, NL base, uint32_t depth, const SOp& o, uint32_t txn) {
+PPD_HD PPD_INLINE NL insert_one(const View& v, NL base, uint32_t depth, const SOp& o, uint32_t txn) {
   uint32_t st_node[PATH_CAP + 1];
   uint8_t st_nib[PATH_CAP + 1];  // 0..15: branch slot; 0xff: extension
   uint32_t sp = 0, node = base.id, pos = depth;
@@ -509,18 +514,18 @@ struct Batch {
   uint32_t txn;
 };
 
-PPD_HD inline uint32_t trie_root_of(const View& v, uint32_t owner) {
+PPD_HD PPD_INLINE uint32_t trie_root_of(const View& v, uint32_t owner) {
   if (owner == OWNER_STATE_TRIE) return v.cur->state_root;
   if (owner == OWNER_TXN_TRIE) return v.cur->txn_root;
   if (owner == OWNER_RECEIPT_TRIE) return v.cur->receipt_root;
   return v.acct[v.traces[owner].acct].storage;
 }
 
-PPD_HD inline PathNode& pc_at(const View& v, uint32_t idx) { return idx < v.pc_n_fast ? v.pc_fast[idx] : v.pc_slow[idx - v.pc_n_fast]; }
-PPD_HD inline uint32_t pc_hash(uint32_t node) { return node * 2654435761u; }
+PPD_HD PPD_INLINE PathNode& pc_at(const View& v, uint32_t idx) { return idx < v.pc_n_fast ? v.pc_fast[idx] : v.pc_slow[idx - v.pc_n_fast]; }
+PPD_HD PPD_INLINE uint32_t pc_hash(uint32_t node) { return node * 2654435761u; }
 // the owner of a path node makes its table entry during the walk and publishes it under the node id; the node's child
 // table and level are loaded afterwards, all entries in parallel (pc_fill)
-PPD_HD inline uint32_t pc_make(const View& v, uint32_t node, const NodeRec& r, bool is_branch, uint32_t owner, uint32_t txn) {
+PPD_HD PPD_INLINE uint32_t pc_make(const View& v, uint32_t node, const NodeRec& r, bool is_branch, uint32_t owner, uint32_t txn) {
   uint32_t idx = PPD_ATOMIC_ADD(v.pc_count, 1u);
   if (idx >= v.pc_n_fast + v.pc_n_slow) {
     raise(v, TXF_PATH_TABLE, txn);
@@ -539,7 +544,7 @@ PPD_HD inline uint32_t pc_make(const View& v, uint32_t node, const NodeRec& r, b
   return idx;
 }
 // per table entry: the node's children as they are before the txn (sixteen independent loads), and its level
-PPD_HD inline void pc_fill(const View& v, uint32_t idx) {
+PPD_HD PPD_INLINE void pc_fill(const View& v, uint32_t idx) {
   PathNode& p = pc_at(v, idx);
   const uint32_t a0 = p.kids[0], m = p.kids[1];
   const uint32_t old_lv = v.level[p.node];
@@ -571,7 +576,7 @@ PPD_HD inline void pc_fill(const View& v, uint32_t idx) {
   }
   p.lv = old_lv;
 }
-PPD_HD inline uint32_t pc_find(const View& v, uint32_t node) {
+PPD_HD PPD_INLINE uint32_t pc_find(const View& v, uint32_t node) {
   uint32_t h = pc_hash(node) & v.pc_map_mask;
   for (;;) {
     const uint32_t k = v.pc_map_key[h];
@@ -584,7 +589,7 @@ PPD_HD inline uint32_t pc_find(const View& v, uint32_t node) {
 // The walk of key i down the current version of its trie.  It is the key's marking walk (the nodes it visits go to the
 // IR's touched list: create_trie_subset keeps exactly those expanded) AND the first half of its write: the nodes passed
 // and where the key ends are kept for the way back up.
-PPD_HD inline void batch_walk(const Ctx& c, const Batch& b, uint32_t i, uint32_t* touched) {
+PPD_HD PPD_INLINE void batch_walk(const Ctx& c, const Batch& b, uint32_t i, uint32_t* touched) {
   const View& v = c.v;
   const SOp o = b.ops[i];
   const uint32_t e = b.base + i;
@@ -665,7 +670,7 @@ PPD_HD inline void batch_walk(const Ctx& c, const Batch& b, uint32_t i, uint32_t
 // (no walk per item, no intermediate versions): what inserting the items one by one arrives at.  Returns false when the
 // group is not of the plain kind (too many items, keys of different lengths): the caller then inserts one by one.
 static const uint32_t GROUP_MAX = 12;
-PPD_HD inline bool build_group(const View& v, const Batch& b, uint32_t first, uint32_t end, uint32_t td, uint32_t old_leaf, bool keep_old, NL* out, uint32_t txn) {
+PPD_HD PPD_INLINE bool build_group(const View& v, const Batch& b, uint32_t first, uint32_t end, uint32_t td, uint32_t old_leaf, bool keep_old, NL* out, uint32_t txn) {
   // items: (key offset, op index or NONE for the old leaf), in key order, with the LCP (absolute) to the previous item
   uint32_t ik[GROUP_MAX + 1], iop[GROUP_MAX + 1];
   int il[GROUP_MAX + 2];
@@ -760,7 +765,7 @@ PPD_HD inline bool build_group(const View& v, const Batch& b, uint32_t first, ui
 // last report re-assembles the node.  A key leads the child of the branch at depth d when its LCP with its predecessor
 // is <= d; the one child of an extension that ends at depth d' when it is < d'.  A key that leaves an extension half
 // way announces itself there on its own account.
-PPD_HD inline void batch_announce(const Ctx& c, const Batch& b, uint32_t i) {
+PPD_HD PPD_INLINE void batch_announce(const Ctx& c, const Batch& b, uint32_t i) {
   const View& v = c.v;
   const uint32_t e = b.base + i;
   const int lcp = (int)b.ops[i].lcp;
@@ -787,7 +792,7 @@ PPD_HD inline void batch_announce(const Ctx& c, const Batch& b, uint32_t i) {
 
 // new version of the branch behind table entry p (the children that changed have been written into p.kids); koff / d: a
 // key through the branch and the branch's depth
-PPD_HD inline NL assemble_branch(const View& v, PathNode& p, uint32_t koff, uint32_t d) {
+PPD_HD PPD_INLINE NL assemble_branch(const View& v, PathNode& p, uint32_t koff, uint32_t d) {
   uint32_t nk = 0, last = 0;
   for (uint32_t nib = 0; nib < 16; nib++)
     if (p.kids[nib] != NODE_EMPTY) nk++, last = nib;
@@ -797,7 +802,7 @@ PPD_HD inline NL assemble_branch(const View& v, PathNode& p, uint32_t koff, uint
 }
 // new version of the extension behind table entry p (its child's result is in p.kids[0], with its level in [1]); the keys
 // of its range that leave it half way split it
-PPD_HD inline NL assemble_ext(const View& v, const Batch& b, PathNode& p, uint32_t d) {
+PPD_HD PPD_INLINE NL assemble_ext(const View& v, const Batch& b, PathNode& p, uint32_t d) {
   const NodeRec r = v.nodes[p.node];
   const uint32_t el = (r.w0 >> 16) & 0xffu;
   NL base{p.node, p.lv};
@@ -813,7 +818,7 @@ PPD_HD inline NL assemble_ext(const View& v, const Batch& b, PathNode& p, uint32
   return changed ? base : NL{T_UNCHANGED, 0};
 }
 
-PPD_HD inline void set_trie_root(const View& v, uint32_t owner, uint32_t r) {
+PPD_HD PPD_INLINE void set_trie_root(const View& v, uint32_t owner, uint32_t r) {
   if (owner == OWNER_STATE_TRIE) {
     v.cur->state_root = r;
   } else if (owner == OWNER_TXN_TRIE) {
@@ -832,7 +837,7 @@ PPD_HD inline void set_trie_root(const View& v, uint32_t owner, uint32_t r) {
 // above in turn, on behalf of the node's whole range (every key of the range has the same nodes above).  No barrier
 // and no scan of the range: a step is a handful of shared-memory operations plus the stores of the new node.  Whoever
 // re-assembles the topmost node installs the trie's new root.
-PPD_HD inline void batch_climb(const Ctx& c, const Batch& b, uint32_t i) {
+PPD_HD PPD_INLINE void batch_climb(const Ctx& c, const Batch& b, uint32_t i) {
   const View& v = c.v;
   const uint32_t e = b.base + i;
   const SOp& o = b.ops[i];
@@ -914,22 +919,22 @@ PPD_HD inline void batch_climb(const Ctx& c, const Batch& b, uint32_t i) {
 
 // ---- op preparation (all txns at once, before the loop) -----------------------------------------------------
 // 32-byte keys compare as big-endian numbers == bytewise
-PPD_HD inline int cmp32(const uint8_t* a, const uint8_t* b) {
+PPD_HD PPD_INLINE int cmp32(const uint8_t* a, const uint8_t* b) {
   for (int i = 0; i < 32; i++)
     if (a[i] != b[i]) return a[i] < b[i] ? -1 : 1;
   return 0;
 }
-PPD_HD inline int lcp_nibbles(const View& v, uint32_t ka, uint32_t na, uint32_t kb, uint32_t nb) {
+PPD_HD PPD_INLINE int lcp_nibbles(const View& v, uint32_t ka, uint32_t na, uint32_t kb, uint32_t nb) {
   const uint32_t m = na < nb ? na : nb;
   uint32_t i = 0;
   while (i < m && key_nib(v, ka, i) == key_nib(v, kb, i)) i++;
   return (int)i;
 }
-PPD_HD inline const uint8_t* digest(const View& v, uint32_t m) { return v.key_pool + v.dig_base + 32ull * m; }
+PPD_HD PPD_INLINE const uint8_t* digest(const View& v, uint32_t m) { return v.key_pool + v.dig_base + 32ull * m; }
 
 // per trace t: the byte ranges of the FlatBlock whose Keccak-256 the loop needs (utils.rs:11-13 call sites
 // processed_block_trace.rs:219,234,277 and decoding.rs:235), as (begin, end) pairs indexed like the digests
-PPD_HD inline void prep_msgs(const View& v, uint32_t t, uint64_t* se) {
+PPD_HD PPD_INLINE void prep_msgs(const View& v, uint32_t t, uint64_t* se) {
   const TxnTrace& tr = v.traces[t];
   se[2 * t] = tr.off_addr, se[2 * t + 1] = tr.off_addr + 20ull;
   for (uint32_t k = 0; k < tr.n_reads; k++) se[2 * (tr.m_reads + k)] = tr.off_reads + 32ull * k, se[2 * (tr.m_reads + k) + 1] = tr.off_reads + 32ull * k + 32;
@@ -945,14 +950,14 @@ PPD_HD inline void prep_msgs(const View& v, uint32_t t, uint64_t* se) {
   if ((tr.flags & PPD_TR_CODE_WRITE) && !(tr.flags & PPD_TR_CODE_READ)) se[2 * tr.m_code] = tr.code_off, se[2 * tr.m_code + 1] = (uint64_t)tr.code_off + tr.code_len;
 }
 
-PPD_HD inline void prep_withdrawal_msg(const View& v, uint32_t w, uint64_t* se) {  // the address precedes the amount
+PPD_HD PPD_INLINE void prep_withdrawal_msg(const View& v, uint32_t w, uint64_t* se) {  // the address precedes the amount
   const Withdrawal wd = v.withdrawals[w];
   se[2 * wd.m_addr] = wd.off_amount - 20ull, se[2 * wd.m_addr + 1] = wd.off_amount;
 }
 
 // per trace t: its rank among the traces of its txn by hashed address, which is the place of its state key (and of its
 // storage trie in the IR): every trace accesses its account (processed_block_trace.rs:267), some write it
-PPD_HD inline void prep_trace(const View& v, uint32_t t) {
+PPD_HD PPD_INLINE void prep_trace(const View& v, uint32_t t) {
   TxnTrace& tr = v.traces[t];
   const TxnDesc& tx = v.txns[tr.txn];
   const uint8_t* me = digest(v, t);
@@ -973,7 +978,7 @@ PPD_HD inline void prep_trace(const View& v, uint32_t t) {
 }
 // per storage key k of trace t (its slot reads, then its slot writes; with TRF_MIN_KEYS the writes once more under the
 // shortened key decoding.rs:235 hashes): its rank among the trace's keys, rlp(U256 value) of a write into val_pool
-PPD_HD inline void prep_storage_key(const View& v, uint32_t t, uint32_t k) {
+PPD_HD PPD_INLINE void prep_storage_key(const View& v, uint32_t t, uint32_t k) {
   const TxnTrace& tr = v.traces[t];
   const bool min_keys = (tr.flags & TRF_MIN_KEYS) != 0;
   auto key_of = [&](uint32_t q) -> uint32_t {  // digest index of key q
@@ -1019,7 +1024,7 @@ PPD_HD inline void prep_storage_key(const View& v, uint32_t t, uint32_t k) {
 }
 // per txn: the inserts into the transactions and receipts tries (decoding.rs:284-289), after the storage keys; the same
 // keys are the ones the tries' subsets are cut with (decoding.rs:190-197)
-PPD_HD inline void prep_txn(const View& v, uint32_t ti) {
+PPD_HD PPD_INLINE void prep_txn(const View& v, uint32_t ti) {
   const TxnDesc& tx = v.txns[ti];
   SOp o;
   o.koff = tx.key_off, o.klen = (uint8_t)tx.key_nibs, o.lcp = -1, o.pad = SOP_MARK, o.kind = OP_PUT_LEAF;
@@ -1032,7 +1037,7 @@ PPD_HD inline void prep_txn(const View& v, uint32_t ti) {
 }
 // per sorted key: the LCP with its predecessor in the same trie (state keys carry their txn in a2: one state trie version
 // per txn).  Equal keys (a slot read and written) get the full length: the later one then shares everything with the earlier.
-PPD_HD inline void prep_lcp(const View& v, SOp* ops, uint32_t i) {
+PPD_HD PPD_INLINE void prep_lcp(const View& v, SOp* ops, uint32_t i) {
   const bool first = i == 0 || ops[i - 1].owner != ops[i].owner || (ops[i].owner == OWNER_STATE_TRIE && ops[i - 1].a2 != ops[i].a2);
   if (first) {
     ops[i].lcp = -1;
@@ -1050,7 +1055,7 @@ struct AcctInit {
   const uint32_t* join_storage;  // per pre-image account: root of the storage trie the by-root join gives it, or ST_ABSENT
   const uint32_t* join_root;     // its NK_ROOT node, or NONE
 };
-PPD_HD inline uint32_t get_leaf(const View& v, uint32_t root, uint32_t koff, uint32_t klen) {
+PPD_HD PPD_INLINE uint32_t get_leaf(const View& v, uint32_t root, uint32_t koff, uint32_t klen) {
   uint32_t node = root, pos = 0;
   while (node != NODE_EMPTY) {
     if (is_hash_id(node)) return NODE_EMPTY;
@@ -1071,7 +1076,7 @@ PPD_HD inline uint32_t get_leaf(const View& v, uint32_t root, uint32_t koff, uin
   }
   return NODE_EMPTY;
 }
-PPD_HD inline void acct_claim(const View& v, const AcctInit& a, uint32_t t) {
+PPD_HD PPD_INLINE void acct_claim(const View& v, const AcctInit& a, uint32_t t) {
   const uint8_t* me = digest(v, t);
   uint32_t h = ((uint32_t)me[4] | ((uint32_t)me[5] << 8) | ((uint32_t)me[6] << 16) | ((uint32_t)me[7] << 24)) & a.table_mask;
   for (;;) {
@@ -1114,11 +1119,11 @@ PPD_HD inline void acct_claim(const View& v, const AcctInit& a, uint32_t t) {
 #define PPD_PHASE_CLOCK(c, k) ((void)0)
 #endif
 
-PPD_HD inline void copy32(uint8_t* d, const uint8_t* s) {
+PPD_HD PPD_INLINE void copy32(uint8_t* d, const uint8_t* s) {
   for (int i = 0; i < 32; i++) d[i] = s[i];
 }
 
-PPD_HD inline void run_txn(const Ctx& c, uint32_t ti, const uint8_t* empty_trie_hash, const uint8_t* empty_code_hash) {
+PPD_HD PPD_INLINE void run_txn(const Ctx& c, uint32_t ti, const uint8_t* empty_trie_hash, const uint8_t* empty_code_hash) {
   const View& v = c.v;
   const TxnDesc tx = v.txns[ti];
   const uint32_t ntr = tx.trace_end - tx.trace_begin;
@@ -1242,7 +1247,7 @@ PPD_HD inline void run_txn(const Ctx& c, uint32_t ti, const uint8_t* empty_trie_
 }
 
 // ---- after the last txn: the NK_ROOT nodes dummy entries refer to, and the withdrawals (decoding.rs:356-428) ----
-PPD_HD inline void u256_add(uint8_t* a, const uint8_t* b) {
+PPD_HD PPD_INLINE void u256_add(uint8_t* a, const uint8_t* b) {
   uint32_t carry = 0;
   for (int i = 31; i >= 0; i--) {
     const uint32_t x = (uint32_t)a[i] + b[i] + carry;
@@ -1250,7 +1255,7 @@ PPD_HD inline void u256_add(uint8_t* a, const uint8_t* b) {
     carry = x >> 8;
   }
 }
-PPD_HD inline void run_finish(const Ctx& c, uint32_t initial_state) {
+PPD_HD PPD_INLINE void run_finish(const Ctx& c, uint32_t initial_state) {
   const View& v = c.v;
   if (c.tid == 0 && !v.cur->flag) {
     Cursors& cur = *v.cur;
@@ -1287,7 +1292,7 @@ struct AcctExport {
   uint8_t haddr[32];
   uint32_t initial, final_;  // node id, NODE_EMPTY, or ST_ABSENT
 };
-PPD_HD inline void export_account(const View& v, const uint32_t* acct_list, const uint32_t* join_storage, uint32_t r, AcctExport* out) {
+PPD_HD PPD_INLINE void export_account(const View& v, const uint32_t* acct_list, const uint32_t* join_storage, uint32_t r, AcctExport* out) {
   const NodeRec nr = v.nodes[acct_list[5ull * r]];
   const uint32_t ns = (nr.w0 >> 8) & 0xffu, nl = (nr.w0 >> 16) & 0xffu, klen = ns + nl;
   AcctExport e;
