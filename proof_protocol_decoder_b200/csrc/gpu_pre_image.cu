@@ -83,6 +83,7 @@ bool gpu_pre_image(Lane* L, Job& J, BlockJob& b, bool check_version, Slots* slot
   SlotGuard slot(slots, &L->stats.host_wait_ms);
   auto sync_in_slot = [&] { slots ? lane_sync_poll(L) : lane_sync(L); };
   lap("p:slot-wait");
+  trace_mark(L, "slot");
   // ---- phase A: instruction boundaries ----
   if (dev_only) {
     // the whole FlatBlock is resident (gpu_txn.cu uploaded it; the 64 bytes after it are zero)
@@ -132,6 +133,7 @@ bool gpu_pre_image(Lane* L, Job& J, BlockJob& b, bool check_version, Slots* slot
   sync_in_slot();
   phase_ms();
   lap("p:upload+A");
+  trace_mark(L, "parse_a");
   if (hr[PARSE_R_END] != (uint32_t)n) return false;  // a parse error: the host parser reports it
   const uint32_t n_ins = hr[PARSE_R_NINS];
   if (n_ins == 0 || n_ins > n) return false;
@@ -182,6 +184,7 @@ bool gpu_pre_image(Lane* L, Job& J, BlockJob& b, bool check_version, Slots* slot
   sync_in_slot();
   phase_ms();
   lap("p:B");
+  trace_mark(L, "parse_b");
   if (hr[PARSE_R_FLAG] != 0 || hr[PARSE_R_HEIGHT] != 1) return false;
   if (check_version && w[0] != 1) fail(PPD_PANIC_INCOMPATIBLE_HEADER_VERSION, "compact header version is not 1");
   const uint32_t* tot = hr + PARSE_R_TOTALS;
@@ -272,6 +275,7 @@ bool gpu_pre_image(Lane* L, Job& J, BlockJob& b, bool check_version, Slots* slot
   lane_sync(L);
   phase_ms();
   lap("p:C+download");
+  trace_mark(L, "parse_c");
   for (size_t k = 0; k < n_code; k++) {
     L->stats.key_permutations += J.code_list[2 * k + 1] / 136 + 1;
     b.pre_code[J.code_digest[k]] = Span{w + J.code_list[2 * k], J.code_list[2 * k + 1]};

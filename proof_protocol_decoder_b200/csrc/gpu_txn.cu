@@ -196,7 +196,10 @@ int gpu_block(ppd_ctx* c, Lane* L, Job& J, const uint8_t* flat, size_t len, uint
   const size_t lead = (256 - (wit_off & 255)) & 255;
   L->d_flat.reserve(lead + len + 512);
   uint8_t* d_flat = L->d_flat.as<uint8_t>() + lead;
+  L->tr_n = 0;
+  trace_mark(L, "begin");
   upload_bytes(L, J, d_flat, flat, len);
+  trace_mark(L, "uploaded");
   CUDA_OK(cudaMemsetAsync(d_flat + len, 0, 256, st));
   L->stats.h2d_bytes += (double)len;
   // page-locked landing areas
@@ -219,6 +222,7 @@ int gpu_block(ppd_ctx* c, Lane* L, Job& J, const uint8_t* flat, size_t len, uint
     return GPU_BLOCK_DECLINED;  // a witness the host builder takes (malformed, not canonical)
   }
   pt.lap("t:pre-image");
+  trace_mark(L, "parsed");
   // ---- plan of every IR (needs the witness's code strings and the digests of written code) ----
   struct CD {
     HookState* H;
@@ -319,12 +323,14 @@ int gpu_block(ppd_ctx* c, Lane* L, Job& J, const uint8_t* flat, size_t len, uint
   V.nodes = v.nodes, V.key_pool = v.key_pool, V.val_pool = v.val_pool, V.hash_pool = v.hash_pool, V.child_pool = v.child_pool;
   V.accounts = v.accounts, V.ref = L->d_ref.as<uint8_t>(), V.ref_len = L->d_ref_len.as<uint8_t>();
   V.counters = L->d_counters.as<unsigned long long>();
+  trace_mark(L, "plan_up");
   CUDA_OK(cudaEventRecord(L->ev0, st));
   for (size_t l = 0; l + 1 < level_pre.size(); l++) {
     launch_hash_level(V, L->d_order.as<uint32_t>(), level_pre[l], level_pre[l + 1], st);
     L->stats.kernel_launches++, L->stats.level_launches++;
   }
   CUDA_OK(cudaEventRecord(L->ev1, st));
+  trace_mark(L, "pre_hashed");
   // ---- join, account table, sorted ops, the loop ----
   H.j.ref = V.ref;
   CUDA_OK(cudaMemsetAsync(H.j.slot_owner, 0xff, 4ull * (H.j.table_mask + 1), st));
@@ -340,9 +346,11 @@ int gpu_block(ppd_ctx* c, Lane* L, Job& J, const uint8_t* flat, size_t len, uint
   H.ai = txn::AcctInit{H.table_slots - 1, b.state_root, H.j.join_storage, H.j.join_root};
   const uint32_t max_writes = T.max_trace_keys;
   L->stats.kernel_launches += 3 + launch_txn_prep(v, H.ai, T.n_ops1, T.n_ops2, max_writes, st);
+  trace_mark(L, "prep");
   CUDA_OK(cudaEventRecord(L->ev_loop0, st));
   L->stats.kernel_launches += launch_txn_loop(v, b.state_root, T.max_ops, st);
   CUDA_OK(cudaEventRecord(L->ev_loop1, st));
+  trace_mark(L, "loop");
   // ---- the loop's nodes sorted by (level, class) ----
   L->d_order2.reserve(4ull * H.cap_tail + 16);
   CUDA_OK(cudaMemsetAsync(H.bins_tail, 0, 4ull * ORDER_MAX_BINS, st));
@@ -352,6 +360,7 @@ int gpu_block(ppd_ctx* c, Lane* L, Job& J, const uint8_t* flat, size_t len, uint
   CUDA_OK(cudaMemcpyAsync(H.h_bins + ORDER_MAX_BINS, H.bins_tail, 4ull * ORDER_MAX_BINS, cudaMemcpyDeviceToHost, st));
   CUDA_OK(cudaMemcpyAsync(h_cur, v.cur, sizeof(txn::Cursors), cudaMemcpyDeviceToHost, st));
   L->stats.kernel_launches += 3, L->stats.d2h_bytes += 4.0 * ORDER_MAX_BINS + sizeof(txn::Cursors);
+  trace_mark(L, "tail_order");
   lane_sync(L);
   pt.lap("t:loop");
   {
@@ -398,12 +407,14 @@ int gpu_block(ppd_ctx* c, Lane* L, Job& J, const uint8_t* flat, size_t len, uint
   }
   const uint32_t n_total = h_cur->n_nodes, n_tail = n_total - n_pre;
   levels_from_bins(H.h_bins + ORDER_MAX_BINS, n_tail, level_tail);
+  trace_mark(L, "host_resumed");
   CUDA_OK(cudaEventRecord(L->ev0, st));
   for (size_t l = 0; l + 1 < level_tail.size(); l++) {
     launch_hash_level(V, L->d_order2.as<uint32_t>(), level_tail[l], level_tail[l + 1], st);
     L->stats.kernel_launches++, L->stats.level_launches++;
   }
   CUDA_OK(cudaEventRecord(L->ev1, st));
+  trace_mark(L, "tail_hashed");
   // ---- every IR sized and laid out ----
   CUDA_OK(cudaEventRecord(L->ev_loop0, st));
   launch_ir_size(V, P, n_ir, st);
@@ -415,6 +426,7 @@ int gpu_block(ppd_ctx* c, Lane* L, Job& J, const uint8_t* flat, size_t len, uint
   CUDA_OK(cudaMemcpyAsync(h_sizes, d_ir_size, 8ull * n_ir, cudaMemcpyDeviceToHost, st));
   CUDA_OK(cudaMemcpyAsync(h_counters, L->d_counters.p, 24, cudaMemcpyDeviceToHost, st));
   L->stats.kernel_launches += 1, L->stats.d2h_bytes += 8.0 * n_ir + 24;
+  trace_mark(L, "ir_sized");
   lane_sync(L);
   pt.lap("t:sweep+size");
   {
@@ -466,14 +478,17 @@ int gpu_block(ppd_ctx* c, Lane* L, Job& J, const uint8_t* flat, size_t len, uint
   up(d_ir_base, ir_base.data(), 8ull * n_ir);
   const uint32_t hdr[2] = {PPD_IR_DUMP_MAGIC, n_ir};
   up(L->d_out.p, hdr, 8);
+  trace_mark(L, "host_resumed2");
   CUDA_OK(cudaEventRecord(L->ev0, st));
   launch_ir_emit(V, P, n_ir, L->d_out.as<uint8_t>(), st);
   CUDA_OK(cudaEventRecord(L->ev1, st));
+  trace_mark(L, "ir_emitted");
   CUDA_OK(cudaGetLastError());
   L->stats.kernel_launches += 1;
   if (pinned) {
     const auto tw = std::chrono::steady_clock::now();
     cudaError_t e = cudaMemcpyAsync(dst, L->d_out.p, total, cudaMemcpyDeviceToHost, st);
+    trace_mark(L, "downloaded");
     if (e == cudaSuccess) e = cudaEventRecord(L->ev_sync, st);
     if (e == cudaSuccess) e = cudaEventSynchronize(L->ev_sync);
     L->stats.host_wait_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tw).count();
@@ -496,6 +511,8 @@ int gpu_block(ppd_ctx* c, Lane* L, Job& J, const uint8_t* flat, size_t len, uint
     L->stats.dump_gpu_ms += ms;
   }
   pt.lap("t:emit+copy");
+  trace_mark(L, "end");
+  trace_flush(L);
   if (pinned) {
     *out = pinned, *out_len = total;
   } else {

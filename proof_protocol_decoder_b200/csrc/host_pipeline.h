@@ -91,6 +91,12 @@ struct Lane {
   uint16_t* last_okeys = nullptr;
   IrDumpPlanView last_plan{};
   size_t last_out_bytes = 0;
+  // PPD_TRACE: events recorded on the stream at stage boundaries, resolved into a timeline when the block is done
+  std::vector<cudaEvent_t> tr_ev;
+  std::vector<const char*> tr_label;
+  std::vector<double> tr_host_ms;
+  size_t tr_n = 0;
+  int id = 0;
 };
 
 // Counting semaphore: how many lanes may have their witness upload + parse in flight at once.  All lanes of a
@@ -159,6 +165,11 @@ namespace ppd {
 void stats_reset(ppd_ctx* c);
 void lane_sync(Lane* l);
 void lane_sync_poll(Lane* l);
+// PPD_TRACE=<file>: one row per stage boundary of every block (lane, block, label, device ms, host ms since the
+// context was made), for the pipeline timeline in profiles/.  Off: trace_mark costs one predictable branch.
+bool trace_on();
+void trace_mark(Lane* l, const char* label);
+void trace_flush(Lane* l);
 
 // ============================================================================================
 // Phase I: batched Keccak-256 of byte strings (addresses, slots, code)

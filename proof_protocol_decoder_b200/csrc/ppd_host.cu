@@ -55,6 +55,66 @@ void lane_sync_poll(Lane* l) {
   }
 }
 
+// ---- PPD_TRACE ----
+namespace {
+struct TraceState {
+  FILE* f = nullptr;
+  cudaEvent_t base = nullptr;
+  std::chrono::steady_clock::time_point host0;
+  std::mutex mu;
+  unsigned seq = 0;
+};
+TraceState& trace_state() {
+  static TraceState* t = [] {
+    TraceState* s = new TraceState;
+#ifndef PPD_HOSTPROF
+    const char* path = getenv("PPD_TRACE");
+    if (path && *path && (s->f = fopen(path, "w")) != nullptr) {
+      if (cudaEventCreate(&s->base) != cudaSuccess || cudaEventRecord(s->base, 0) != cudaSuccess || cudaEventSynchronize(s->base) != cudaSuccess) {
+        fclose(s->f);
+        s->f = nullptr;
+      }
+      s->host0 = std::chrono::steady_clock::now();
+      if (s->f) fprintf(s->f, "lane,block,label,device_ms,host_ms\n");
+    }
+#endif
+    return s;
+  }();
+  return *t;
+}
+}  // namespace
+bool trace_on() { return trace_state().f != nullptr; }
+void trace_mark(Lane* l, const char* label) {
+#ifndef PPD_HOSTPROF
+  TraceState& t = trace_state();
+  if (!t.f) return;
+  if (l->tr_n == l->tr_ev.size()) {
+    cudaEvent_t e;
+    CUDA_OK(cudaEventCreate(&e));
+    l->tr_ev.push_back(e), l->tr_label.push_back(label), l->tr_host_ms.push_back(0);
+  }
+  CUDA_OK(cudaEventRecord(l->tr_ev[l->tr_n], l->st));
+  l->tr_label[l->tr_n] = label;
+  l->tr_host_ms[l->tr_n] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t.host0).count();
+  l->tr_n++;
+#endif
+}
+void trace_flush(Lane* l) {
+#ifndef PPD_HOSTPROF
+  TraceState& t = trace_state();
+  if (!t.f || !l->tr_n) return;
+  std::lock_guard<std::mutex> g(t.mu);
+  const unsigned seq = t.seq++;
+  for (size_t k = 0; k < l->tr_n; k++) {
+    float ms = 0;
+    if (cudaEventSynchronize(l->tr_ev[k]) != cudaSuccess || cudaEventElapsedTime(&ms, t.base, l->tr_ev[k]) != cudaSuccess) ms = -1;
+    fprintf(t.f, "%d,%u,%s,%.4f,%.4f\n", l->id, seq, l->tr_label[k], ms, l->tr_host_ms[k]);
+  }
+  fflush(t.f);
+  l->tr_n = 0;
+#endif
+}
+
 void KeyHasher::run(Lane* c) {
   size_t n = lens.size();
   digest.resize(n);
@@ -92,6 +152,7 @@ Job& job_of(Lane* l, size_t n_blocks) {
 Lane* lane_of(ppd_ctx* c, size_t w) {
   while (c->lanes.size() <= w) {
     std::unique_ptr<Lane> l(new Lane());
+    l->id = (int)c->lanes.size();
 #ifndef PPD_HOSTPROF
     CUDA_OK(cudaStreamCreateWithFlags(&l->st, cudaStreamNonBlocking));
     CUDA_OK(cudaEventCreate(&l->ev0));
@@ -112,6 +173,7 @@ void lane_delete(Lane* l) {
                     &l->d_level, &l->d_okeys,   &l->d_obins,    &l->d_flat, &l->d_txn,     &l->d_order2};
   for (DevBuf* b : bufs) b->release();
   if (l->h_parse) pinned_free(l->h_parse);
+  for (cudaEvent_t e : l->tr_ev) cudaEventDestroy(e);
   if (l->ev0) cudaEventDestroy(l->ev0);
   if (l->ev1) cudaEventDestroy(l->ev1);
   if (l->ev_sync) cudaEventDestroy(l->ev_sync);
