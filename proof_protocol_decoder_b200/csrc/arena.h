@@ -24,7 +24,7 @@ static const uint32_t NODE_EMPTY = 0xffffffffu;  // Node::Empty as a child / as 
 
 // word0 = kind | nib_start << 8 | nib_len << 16 ; nibble i of a key is the high (i even) or low
 // (i odd) half of key_pool[key_off + i / 2]
-struct NodeRec {
+struct alignas(16) NodeRec {  // (one 128-bit load / store on the device)
   uint32_t w0, a0, a1, a2;
 };
 static inline uint32_t node_w0(uint32_t kind, uint32_t nib_start, uint32_t nib_len) { return kind | (nib_start << 8) | (nib_len << 16); }

@@ -82,6 +82,16 @@ bool gpu_pre_image(Lane* L, Job& J, BlockJob& b, bool check_version, Slots* slot
   };
   SlotGuard slot(slots, &L->stats.host_wait_ms);
   auto sync_in_slot = [&] { slots ? lane_sync_poll(L) : lane_sync(L); };
+  // the result words a host thread waits for: written into page-locked memory by a kernel when the whole block stays on
+  // the device (a copy engine would serve them behind every bulk upload other lanes have queued)
+  auto small_to_host = [&](void* dst, const void* src, size_t bytes) {
+    if (!bytes) return;
+    if (dev_only)
+      lane_copy(L, dst, src, bytes);
+    else
+      CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st));
+    L->stats.d2h_bytes += (double)bytes;
+  };
   lap("p:slot-wait");
   trace_mark(L, "slot");
   // ---- phase A: instruction boundaries ----
@@ -94,6 +104,7 @@ bool gpu_pre_image(Lane* L, Job& J, BlockJob& b, bool check_version, Slots* slot
     L->stats.h2d_bytes += (double)n;
   }
   ParseBounds B{};
+  auto result_to_host = [&] { small_to_host(hr, B.result, 4 * PARSE_R_WORDS); };
   B.wit = dev_only ? dev_only->d_witness : L->d_wit.as<uint8_t>();
   B.n = (uint32_t)n;
   B.n_tiles = (uint32_t)((n + PARSE_TILE - 1) / PARSE_TILE);
@@ -129,7 +140,7 @@ bool gpu_pre_image(Lane* L, Job& J, BlockJob& b, bool check_version, Slots* slot
   L->stats.kernel_launches += launch_parse_bounds(B, st);
   CUDA_OK(cudaGetLastError());
   CUDA_OK(cudaEventRecord(L->ev1, st));
-  CUDA_OK(cudaMemcpyAsync(hr, B.result, 4 * PARSE_R_WORDS, cudaMemcpyDeviceToHost, st));
+  result_to_host();
   sync_in_slot();
   phase_ms();
   lap("p:upload+A");
@@ -180,7 +191,7 @@ bool gpu_pre_image(Lane* L, Job& J, BlockJob& b, bool check_version, Slots* slot
   L->stats.kernel_launches += 1 + launch_parse_tree(T, st);
   CUDA_OK(cudaGetLastError());
   CUDA_OK(cudaEventRecord(L->ev1, st));
-  CUDA_OK(cudaMemcpyAsync(hr, B.result, 4 * PARSE_R_WORDS, cudaMemcpyDeviceToHost, st));
+  result_to_host();
   sync_in_slot();
   phase_ms();
   lap("p:B");
@@ -267,9 +278,10 @@ bool gpu_pre_image(Lane* L, Job& J, BlockJob& b, bool check_version, Slots* slot
     down(A.accounts.data(), E.accounts, sizeof(AccountRec) * n_acct);
     down(J.acct_list.data(), E.acct_list, 20 * n_acct);
   }
-  down(J.code_list.data(), E.code_list, 8 * n_code);
-  down(J.code_digest.data(), d_code_digest, 32 * n_code);
-  down(hr, B.result, 4 * PARSE_R_WORDS);
+  small_to_host(J.code_list.data(), E.code_list, 8 * n_code);
+  small_to_host(J.code_digest.data(), d_code_digest, 32 * n_code);
+  result_to_host();
+  lane_copy_flush(L);
   J.dev.nodes = n_nodes, J.dev.keys = key_bytes, J.dev.vals = val_bytes, J.dev.hashes = 32 * n_hash, J.dev.children = n_child, J.dev.accounts = n_acct;
   if (dev_only && dev_only->after_launch) dev_only->after_launch(dev_only->arg, E);  // queued behind the emit kernels, before the wait below
   lane_sync(L);

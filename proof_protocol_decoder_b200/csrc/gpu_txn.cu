@@ -140,10 +140,12 @@ void after_emit(void* arg, const ParseEmit& E) {
   v.sh_ops = nullptr;
   v.a_nodes = &v.cur->n_nodes, v.a_children = &v.cur->n_children, v.a_keys = &v.cur->key_bytes, v.a_max_level = &v.cur->max_level;
   v.withdrawals = H.d_withdrawals, v.n_withdrawals = (uint32_t)T.withdrawals.size();
-  if (v.n_withdrawals) CUDA_OK(cudaMemcpyAsync(H.d_withdrawals, T.withdrawals.data(), sizeof(txn::Withdrawal) * v.n_withdrawals, cudaMemcpyHostToDevice, st));
+  // (tables and read-backs go by kernel copy, lane_copy: the copy engines are left to the FlatBlock and the IrDump)
+  lane_copy(L, H.d_withdrawals, T.withdrawals.data(), sizeof(txn::Withdrawal) * v.n_withdrawals);
   j.acct_list = E.acct_list, j.n_acct = (uint32_t)n_acct, j.table_mask = jtable - 1;
   // ---- the byte strings to hash: straight out of the resident FlatBlock ----
-  CUDA_OK(cudaMemcpyAsync(v.traces, T.traces.data(), sizeof(txn::TxnTrace) * n_traces, cudaMemcpyHostToDevice, st));
+  lane_copy(L, v.traces, T.traces.data(), sizeof(txn::TxnTrace) * n_traces);
+  lane_copy_flush(L);
   L->stats.h2d_bytes += (double)(sizeof(txn::TxnTrace) * n_traces);
   launch_txn_msgs(v, H.se, st);
   launch_keccak256_ranges(H.d_flat, H.se, T.n_msgs, E.key_pool + B.dig_base, st);
@@ -151,13 +153,13 @@ void after_emit(void* arg, const ParseEmit& E) {
   // the digests of written code are keys of the IRs' code maps, which the host sorts
   for (size_t k = 0; k < T.code_write_traces.size(); k++) {
     const uint32_t m = T.traces[T.code_write_traces[k]].m_code;
-    CUDA_OK(cudaMemcpyAsync(H.h_code_digests + 32 * k, E.key_pool + B.dig_base + 32ull * m, 32, cudaMemcpyDeviceToHost, st));
+    lane_copy(L, H.h_code_digests + 32 * k, E.key_pool + B.dig_base + 32ull * m, 32);
   }
   // ---- pre-image nodes sorted by (level, class); the host needs where every level starts ----
   L->d_order.reserve(4ull * n_nodes + 16);
   CUDA_OK(cudaMemsetAsync(H.bins_pre, 0, 4ull * ORDER_MAX_BINS, st));
   launch_order_by_level_class(E.nodes, E.level, (uint32_t)n_nodes, ORDER_MAX_BINS, H.okeys, H.bins_pre, L->d_order.as<uint32_t>(), st);
-  CUDA_OK(cudaMemcpyAsync(H.h_bins, H.bins_pre, 4ull * ORDER_MAX_BINS, cudaMemcpyDeviceToHost, st));
+  lane_copy(L, H.h_bins, H.bins_pre, 4ull * ORDER_MAX_BINS);
   L->stats.kernel_launches += 3, L->stats.d2h_bytes += 4.0 * ORDER_MAX_BINS;
 }
 
@@ -300,7 +302,7 @@ int gpu_block(ppd_ctx* c, Lane* L, Job& J, const uint8_t* flat, size_t len, uint
   P.flat = d_flat, P.lit = d_lit, P.ir_base = d_ir_base;
   auto up = [&](void* dst, const void* src, size_t bytes) {
     if (!bytes) return;
-    CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st));
+    lane_copy(L, dst, src, bytes);
     L->stats.h2d_bytes += (double)bytes;
   };
   up(d_txns, T.txns.data(), sizeof(txn::TxnDesc) * T.txns.size());
@@ -310,6 +312,7 @@ int gpu_block(ppd_ctx* c, Lane* L, Job& J, const uint8_t* flat, size_t len, uint
   up(d_lit, T.lit.data(), T.lit.size());
   up(d_big_off, big_off.data(), 8ull * n_ir), up(d_big_cap, big_cap.data(), 4ull * n_ir);
   up(v.key_pool + H.B.txn_key_base, T.txn_keys.data(), T.txn_keys.size());
+  lane_copy_flush(L);
   CUDA_OK(cudaMemsetAsync(d_touched, 0xff, 4ull * n_touched, st));
   v.txns = d_txns, v.touched = d_touched, v.seg_a = d_seg_a, v.seg_b = d_seg_b;
   // ---- the pre-image hashed: the storage roots decide which trie an account gets (the by-root join) ----
@@ -346,6 +349,21 @@ int gpu_block(ppd_ctx* c, Lane* L, Job& J, const uint8_t* flat, size_t len, uint
   H.ai = txn::AcctInit{H.table_slots - 1, b.state_root, H.j.join_storage, H.j.join_root};
   const uint32_t max_writes = T.max_trace_keys;
   L->stats.kernel_launches += 3 + launch_txn_prep(v, H.ai, T.n_ops1, T.n_ops2, max_writes, st);
+#ifdef PPD_LOOP_PROF
+  // development builds: the per-thread event log of one txn (PPD_LOOP_EVLOG=<txn>:<file>)
+  static unsigned long long* d_evlog = nullptr;
+  static uint32_t* d_evcount = nullptr;
+  const uint32_t ev_cap = 1u << 16;
+  const char* ev_env = getenv("PPD_LOOP_EVLOG");
+  if (ev_env) {
+    if (!d_evlog) {
+      CUDA_OK(cudaMalloc(&d_evlog, 16ull * ev_cap));
+      CUDA_OK(cudaMalloc(&d_evcount, 4));
+    }
+    CUDA_OK(cudaMemsetAsync(d_evcount, 0, 4, st));
+    v.evlog = d_evlog, v.evcount = d_evcount, v.ev_txn = (uint32_t)atoi(ev_env), v.ev_cap = ev_cap;
+  }
+#endif
   trace_mark(L, "prep");
   CUDA_OK(cudaEventRecord(L->ev_loop0, st));
   L->stats.kernel_launches += launch_txn_loop(v, b.state_root, T.max_ops, st);
@@ -357,12 +375,26 @@ int gpu_block(ppd_ctx* c, Lane* L, Job& J, const uint8_t* flat, size_t len, uint
   launch_order_by_level_class(v.nodes, v.level, H.cap_tail, ORDER_MAX_BINS, H.okeys, H.bins_tail, L->d_order2.as<uint32_t>(), st, n_pre, &v.cur->n_nodes);
   CUDA_OK(cudaGetLastError());
   txn::Cursors* h_cur = reinterpret_cast<txn::Cursors*>(H.h_bins + 2 * ORDER_MAX_BINS);
-  CUDA_OK(cudaMemcpyAsync(H.h_bins + ORDER_MAX_BINS, H.bins_tail, 4ull * ORDER_MAX_BINS, cudaMemcpyDeviceToHost, st));
-  CUDA_OK(cudaMemcpyAsync(h_cur, v.cur, sizeof(txn::Cursors), cudaMemcpyDeviceToHost, st));
+  lane_copy(L, H.h_bins + ORDER_MAX_BINS, H.bins_tail, 4ull * ORDER_MAX_BINS);
+  lane_copy(L, h_cur, v.cur, sizeof(txn::Cursors));
   L->stats.kernel_launches += 3, L->stats.d2h_bytes += 4.0 * ORDER_MAX_BINS + sizeof(txn::Cursors);
   trace_mark(L, "tail_order");
   lane_sync(L);
   pt.lap("t:loop");
+#ifdef PPD_LOOP_PROF
+  if (ev_env && strchr(ev_env, ':')) {
+    uint32_t n_ev = 0;
+    CUDA_OK(cudaMemcpy(&n_ev, d_evcount, 4, cudaMemcpyDeviceToHost));
+    n_ev = std::min(n_ev, ev_cap);
+    std::vector<unsigned long long> ev(2ull * n_ev);
+    if (n_ev) CUDA_OK(cudaMemcpy(ev.data(), d_evlog, 16ull * n_ev, cudaMemcpyDeviceToHost));
+    if (FILE* f = fopen(strchr(ev_env, ':') + 1, "w")) {
+      fprintf(f, "clock,thread,event\n");
+      for (uint32_t k = 0; k < n_ev; k++) fprintf(f, "%llu,%llu,%llu\n", ev[2 * k], ev[2 * k + 1] >> 16, ev[2 * k + 1] & 0xffff);
+      fclose(f);
+    }
+  }
+#endif
   {
     float ms = 0;
     CUDA_OK(cudaEventElapsedTime(&ms, L->ev0, L->ev1));
@@ -391,9 +423,9 @@ int gpu_block(ppd_ctx* c, Lane* L, Job& J, const uint8_t* flat, size_t len, uint
     uint8_t* h_dig = reinterpret_cast<uint8_t*>(J.txn_export.data() + w_export + w_table);
     launch_acct_export(v, H.j, H.d_export, st);
     CUDA_OK(cudaGetLastError());
-    if (n_acct) CUDA_OK(cudaMemcpyAsync(h_export, H.d_export, sizeof(txn::AcctExport) * n_acct, cudaMemcpyDeviceToHost, st));
-    CUDA_OK(cudaMemcpyAsync(h_table, v.acct, sizeof(txn::AcctState) * H.table_slots, cudaMemcpyDeviceToHost, st));
-    if (n_tr) CUDA_OK(cudaMemcpyAsync(h_dig, v.key_pool + H.B.dig_base, 32ull * n_tr, cudaMemcpyDeviceToHost, st));
+    lane_copy(L, h_export, H.d_export, sizeof(txn::AcctExport) * n_acct);
+    lane_copy(L, h_table, v.acct, sizeof(txn::AcctState) * H.table_slots);
+    lane_copy(L, h_dig, v.key_pool + H.B.dig_base, 32ull * n_tr);
     L->stats.kernel_launches += 1, L->stats.d2h_bytes += (double)(sizeof(txn::AcctExport) * n_acct + sizeof(txn::AcctState) * H.table_slots + 32ull * n_tr);
     lane_sync(L);
     const size_t seg0 = T.seg_a.size(), lit0 = T.lit.size();
@@ -403,6 +435,7 @@ int gpu_block(ppd_ctx* c, Lane* L, Job& J, const uint8_t* flat, size_t len, uint
     up(d_seg_c + seg0, T.seg_c.data() + seg0, 4ull * (T.seg_c.size() - seg0));
     up(d_lit + lit0, T.lit.data() + lit0, T.lit.size() - lit0);
     up(d_seg_begin, T.seg_begin.data(), 4ull * (n_ir + 1)), up(d_seg_end, T.seg_end.data(), 4ull * (n_ir + 1));
+    lane_copy_flush(L);
     pt.lap("t:dummies");
   }
   const uint32_t n_total = h_cur->n_nodes, n_tail = n_total - n_pre;
@@ -423,8 +456,8 @@ int gpu_block(ppd_ctx* c, Lane* L, Job& J, const uint8_t* flat, size_t len, uint
   J.plan.resize(2ull * n_ir + 8);
   uint32_t* h_sizes = J.plan.data();
   unsigned long long* h_counters = reinterpret_cast<unsigned long long*>(H.h_bins);  // (the pre-image bins are consumed)
-  CUDA_OK(cudaMemcpyAsync(h_sizes, d_ir_size, 8ull * n_ir, cudaMemcpyDeviceToHost, st));
-  CUDA_OK(cudaMemcpyAsync(h_counters, L->d_counters.p, 24, cudaMemcpyDeviceToHost, st));
+  lane_copy(L, h_sizes, d_ir_size, 8ull * n_ir);
+  lane_copy(L, h_counters, L->d_counters.p, 24);
   L->stats.kernel_launches += 1, L->stats.d2h_bytes += 8.0 * n_ir + 24;
   trace_mark(L, "ir_sized");
   lane_sync(L);
@@ -476,8 +509,9 @@ int gpu_block(ppd_ctx* c, Lane* L, Job& J, const uint8_t* flat, size_t len, uint
   L->d_out.reserve(total + 64);
   L->last_out_bytes = total;
   up(d_ir_base, ir_base.data(), 8ull * n_ir);
-  const uint32_t hdr[2] = {PPD_IR_DUMP_MAGIC, n_ir};
-  up(L->d_out.p, hdr, 8);
+  launch_store_u32x2(L->d_out.as<uint32_t>(), PPD_IR_DUMP_MAGIC, n_ir, st);
+  L->stats.h2d_bytes += 8;
+  lane_copy_flush(L);
   trace_mark(L, "host_resumed2");
   CUDA_OK(cudaEventRecord(L->ev0, st));
   launch_ir_emit(V, P, n_ir, L->d_out.as<uint8_t>(), st);

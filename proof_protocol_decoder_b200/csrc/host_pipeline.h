@@ -97,6 +97,7 @@ struct Lane {
   std::vector<double> tr_host_ms;
   size_t tr_n = 0;
   int id = 0;
+  CopyBatch copies;  // lane_copy: queued until lane_copy_flush (every wait flushes)
 };
 
 // Counting semaphore: how many lanes may have their witness upload + parse in flight at once.  All lanes of a
@@ -167,6 +168,9 @@ void lane_sync(Lane* l);
 void lane_sync_poll(Lane* l);
 // PPD_TRACE=<file>: one row per stage boundary of every block (lane, block, label, device ms, host ms since the
 // context was made), for the pipeline timeline in profiles/.  Off: trace_mark costs one predictable branch.
+// copy by kernel (CopyBatch): queue, and launch what is queued.  Anything launched after a flush sees the copies.
+void lane_copy(Lane* l, void* dst, const void* src, size_t bytes);
+void lane_copy_flush(Lane* l);
 bool trace_on();
 void trace_mark(Lane* l, const char* label);
 void trace_flush(Lane* l);

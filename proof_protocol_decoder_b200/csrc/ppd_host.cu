@@ -31,8 +31,25 @@ void pinned_free(void* p) { cudaFreeHost(p); }
 
 void stats_reset(ppd_ctx* c) { c->stats = ppd_stats{}; }
 
+void lane_copy_flush(Lane* l) {
+#ifndef PPD_HOSTPROF
+  if (!l->copies.n) return;
+  launch_copy_segments(l->copies, l->st);
+  CUDA_OK(cudaGetLastError());
+  l->stats.kernel_launches += 1;
+  l->copies.n = 0;
+#endif
+}
+void lane_copy(Lane* l, void* dst, const void* src, size_t bytes) {
+  if (!bytes) return;
+  if (l->copies.n == CopyBatch::MAX) lane_copy_flush(l);
+  CopyBatch& b = l->copies;
+  b.dst[b.n] = dst, b.src[b.n] = src, b.bytes[b.n] = bytes, b.n++;
+}
+
 // wait for everything queued on the lane's stream without spinning (lanes may outnumber cores)
 void lane_sync(Lane* l) {
+  lane_copy_flush(l);
   const auto t0 = std::chrono::steady_clock::now();
   CUDA_OK(cudaEventRecord(l->ev_sync, l->st));
   CUDA_OK(cudaEventSynchronize(l->ev_sync));
@@ -42,6 +59,7 @@ void lane_sync(Lane* l) {
 // threads poll at a time): a sleeping thread is woken late when every core is busy shaping other blocks, and
 // everything queued behind the slot waits with it.
 void lane_sync_poll(Lane* l) {
+  lane_copy_flush(l);
   const auto t0 = std::chrono::steady_clock::now();
   CUDA_OK(cudaEventRecord(l->ev_sync, l->st));
   for (unsigned spins = 0;; spins++) {

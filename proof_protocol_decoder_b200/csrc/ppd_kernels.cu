@@ -432,6 +432,37 @@ __global__ void __launch_bounds__(OS_THREADS) order_scatter_kernel(const uint16_
   }
 }
 
+// ---- copies by kernel (see CopyBatch) ----
+__global__ void copy_segments_kernel(CopyBatch B) {
+  const uint32_t s = blockIdx.y;
+  uint8_t* d = reinterpret_cast<uint8_t*>(B.dst[s]);
+  const uint8_t* p = reinterpret_cast<const uint8_t*>(B.src[s]);
+  const unsigned long long n = B.bytes[s];
+  const unsigned long long tid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x, nt = (unsigned long long)gridDim.x * blockDim.x;
+  const uintptr_t both = reinterpret_cast<uintptr_t>(d) | reinterpret_cast<uintptr_t>(p);
+  unsigned long long done = 0;
+  if ((both & 15) == 0) {
+    const unsigned long long nv = n / 16;
+    for (unsigned long long i = tid; i < nv; i += nt) reinterpret_cast<uint4*>(d)[i] = reinterpret_cast<const uint4*>(p)[i];
+    done = nv * 16;
+  } else if ((both & 3) == 0) {
+    const unsigned long long nv = n / 4;
+    for (unsigned long long i = tid; i < nv; i += nt) reinterpret_cast<uint32_t*>(d)[i] = reinterpret_cast<const uint32_t*>(p)[i];
+    done = nv * 4;
+  }
+  for (unsigned long long i = done + tid; i < n; i += nt) d[i] = p[i];
+}
+void launch_copy_segments(const CopyBatch& B, cudaStream_t st) {
+  if (!B.n) return;
+  unsigned long long most = 0;
+  for (uint32_t k = 0; k < B.n; k++) most = B.bytes[k] > most ? B.bytes[k] : most;
+  uint32_t gx = (uint32_t)((most + 16 * 256 * 4 - 1) / (16 * 256 * 4));
+  gx = gx < 1 ? 1 : (gx > 32 ? 32 : gx);
+  copy_segments_kernel<<<dim3(gx, B.n), 256, 0, st>>>(B);
+}
+__global__ void store_u32x2_kernel(uint32_t* dst, uint32_t a, uint32_t b) { dst[0] = a, dst[1] = b; }
+void launch_store_u32x2(uint32_t* dst, uint32_t a, uint32_t b, cudaStream_t st) { store_u32x2_kernel<<<1, 1, 0, st>>>(dst, a, b); }
+
 // bins: [n_bins] zeroed by the caller; on return bins[k] = end of bucket k (the scatter advances the cursors)
 void launch_order_by_level_class(const NodeRec* nodes, const uint16_t* level, uint32_t n, uint32_t n_bins, uint16_t* keys, uint32_t* bins,
                                  uint32_t* order, cudaStream_t st, uint32_t first, const uint32_t* n_dev) {

@@ -18,6 +18,18 @@ static const uint32_t ORDER_MAX_BINS = 4096;
 void launch_order_by_level_class(const NodeRec* nodes, const uint16_t* level, uint32_t n, uint32_t n_bins, uint16_t* keys, uint32_t* bins,
                                  uint32_t* order, cudaStream_t st, uint32_t first = 0, const uint32_t* n_dev = nullptr);
 
+// Small and medium copies done by a kernel instead of the copy engines: either side may be page-locked host memory
+// (device-accessible under unified addressing).  A copy engine serves its queue in order, so a few words a lane's host
+// thread waits for would sit behind every bulk upload / download other lanes have queued; a kernel is not queued there.
+struct CopyBatch {
+  static const uint32_t MAX = 16;
+  void* dst[MAX];
+  const void* src[MAX];
+  unsigned long long bytes[MAX];
+  uint32_t n = 0;
+};
+void launch_copy_segments(const CopyBatch& B, cudaStream_t st);
+void launch_store_u32x2(uint32_t* dst, uint32_t a, uint32_t b, cudaStream_t st);
 
 // ---- ppd_build.cu: trie construction from sorted leaves ----
 struct Pyramid {

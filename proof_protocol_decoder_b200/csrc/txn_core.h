@@ -218,6 +218,10 @@ struct View {
   uint32_t* pc_map_key;
   uint32_t pc_map_mask;
   Cursors* cur;
+  // PPD_LOOP_PROF builds: per-thread event log of one txn (clock, thread << 16 | event)
+  unsigned long long* evlog;
+  uint32_t* evcount;
+  uint32_t ev_txn, ev_cap;
 };
 
 // the by-root join of accounts to witnessed storage tries (compact_to_partial_trie.rs:167-190), ppd_txn.cu
@@ -244,6 +248,17 @@ struct Ctx {
   long long* sh_clock;  // shared: clock at the last phase boundary
 };
 
+#if defined(__CUDA_ARCH__) && defined(PPD_LOOP_PROF)
+#define PPD_EV(v, txn, tid, id)                                                        \
+  do {                                                                                 \
+    if ((v).evlog && (txn) == (v).ev_txn) {                                            \
+      const uint32_t ev_i = atomicAdd((v).evcount, 1u);                                \
+      if (ev_i < (v).ev_cap) (v).evlog[2 * ev_i] = clock64(), (v).evlog[2 * ev_i + 1] = ((unsigned long long)(tid) << 16) | (id); \
+    }                                                                                  \
+  } while (0)
+#else
+#define PPD_EV(v, txn, tid, id) ((void)0)
+#endif
 #if defined(__CUDA_ARCH__)
 #define PPD_FENCE_BLOCK() __threadfence_block()
 #define PPD_ATOMIC_SUB(p, x) atomicSub((p), (x))
@@ -306,17 +321,68 @@ PPD_HD PPD_INLINE uint32_t alloc_children(const View& v, uint32_t k) {
   }
   return at;
 }
+// up to 32 bytes of the key pool from byte offset `off`, as 8 words in memory order (byte j of the string: word j / 4,
+// bits 8 * (j % 4)): aligned word loads, all in flight together, shifted into place.  Words past the first `nbytes` bytes
+// are zero.
+PPD_HD PPD_INLINE void load_key_words(const View& v, uint32_t off, uint32_t nbytes, uint32_t* w) {
+  const uint32_t* base = reinterpret_cast<const uint32_t*>(v.key_pool) + (off >> 2);
+  const uint32_t sh = 8u * (off & 3u), nw = (nbytes + (off & 3u) + 3u) >> 2;
+  uint32_t a[9];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (uint32_t j = 0; j < 9; j++) a[j] = j < nw ? base[j] : 0u;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (uint32_t j = 0; j < 8; j++) w[j] = sh ? (a[j] >> sh) | (a[j + 1] << (32u - sh)) : a[j];
+}
+PPD_HD PPD_INLINE uint32_t ctz32(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+  return (uint32_t)__ffs((int)x) - 1u;
+#else
+  return (uint32_t)__builtin_ctz(x);
+#endif
+}
+// the number of leading nibbles (at most m) that key a from nibble sa and key b from nibble sb have in common
 PPD_HD PPD_INLINE uint32_t common_prefix(const View& v, uint32_t ka, uint32_t sa, uint32_t kb, uint32_t sb, uint32_t m) {
-  uint32_t i = 0;
-  if (((sa ^ sb) & 1u) == 0) {  // same parity (always, for nodes on a key's own path): whole bytes at a time
-    if ((sa & 1u) && i < m) {
-      if (key_nib(v, ka, sa) != key_nib(v, kb, sb)) return 0;
-      i = 1;
+  if (m == 0) return 0;
+  if (((sa ^ sb) & 1u) == 0 && m <= 64u - (sa & 1u)) {
+    // same parity (always, for nodes on a key's own path): both strings loaded whole, one round trip, compared in registers
+    const uint32_t odd = sa & 1u, nb = (odd + m + 1u) >> 1;
+    uint32_t wa[8], wb[8];
+    load_key_words(v, ka + (sa >> 1), nb, wa);
+    load_key_words(v, kb + (sb >> 1), nb, wb);
+    uint32_t cp = 2u * nb;  // (in nibbles from the first byte; no difference found: everything loaded is equal)
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int j = 7; j >= 0; j--) {
+      uint32_t x = wa[j] ^ wb[j];
+      if (j == 0 && odd) x &= ~0xf0u;  // the first byte's high nibble is before the start
+      if (x) {
+        const uint32_t byte = ctz32(x) >> 3, bx = (x >> (8u * byte)) & 0xffu;
+        cp = 2u * (4u * (uint32_t)j + byte) + ((bx & 0xf0u) ? 0u : 1u);
+      }
     }
-    while (i + 2 <= m && v.key_pool[ka + ((sa + i) >> 1)] == v.key_pool[kb + ((sb + i) >> 1)]) i += 2;
+    cp -= odd;
+    return cp < m ? cp : m;
   }
+  uint32_t i = 0;
   while (i < m && key_nib(v, ka, sa + i) == key_nib(v, kb, sb + i)) i++;
   return i;
+}
+// nibble i of a key held in registers (load_key_words from the key's first byte)
+PPD_HD PPD_INLINE uint32_t nib_of_words(const uint32_t* w, uint32_t i) {
+  const uint32_t j = i >> 3;
+  uint32_t x = w[0];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (uint32_t z = 1; z < 8; z++)
+    if (j == z) x = w[z];
+  const uint32_t byte = (x >> (8u * ((i >> 1) & 3u))) & 0xffu;
+  return (i & 1u) ? (byte & 15u) : (byte >> 4);
 }
 PPD_HD PPD_INLINE uint32_t child_at(const View& v, const NodeRec& br, uint32_t nib) {
   const uint32_t mask = br.a1 & 0xffffu, bit = 1u << nib;
@@ -551,28 +617,17 @@ PPD_HD PPD_INLINE void pc_fill(const View& v, uint32_t idx) {
   if (m & 0x10000u) {  // an extension: [0] will hold its child's result
     p.kids[0] = T_UNCHANGED, p.kids[1] = 0;
   } else {
-    const uint32_t mask = m & 0xffffu, k = popc16(mask);
-    uint32_t c[16];
+    const uint32_t mask = m & 0xffffu;
+    // sixteen independent loads (the slot of a child in the compact table follows from the mask alone)
+    uint32_t x[16];
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-    for (uint32_t q = 0; q < 16; q++) c[q] = q < k ? v.child_pool[a0 + q] : NODE_EMPTY;  // all in flight together
-    uint32_t q = 0;
+    for (uint32_t nib = 0; nib < 16; nib++) x[nib] = ((mask >> nib) & 1u) ? v.child_pool[a0 + popc16(mask & ((1u << nib) - 1u))] : NODE_EMPTY;
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-    for (uint32_t nib = 0; nib < 16; nib++) {
-      uint32_t x = NODE_EMPTY;
-      if ((mask >> nib) & 1u) {
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-        for (uint32_t z = 0; z < 16; z++)
-          if (z == q) x = c[z];  // (the q-th compact child, without indexing the register array dynamically)
-        q++;
-      }
-      p.kids[nib] = x;
-    }
+    for (uint32_t nib = 0; nib < 16; nib++) p.kids[nib] = x[nib];
   }
   p.lv = old_lv;
 }
@@ -591,9 +646,12 @@ PPD_HD PPD_INLINE uint32_t pc_find(const View& v, uint32_t node) {
 // and where the key ends are kept for the way back up.
 PPD_HD PPD_INLINE void batch_walk(const Ctx& c, const Batch& b, uint32_t i, uint32_t* touched) {
   const View& v = c.v;
+  PPD_EV(v, b.txn, c.tid, 1);
   const SOp o = b.ops[i];
   const uint32_t e = b.base + i;
   uint32_t node = trie_root_of(v, o.owner), pos = 0, pl = 0, nt = 0;
+  uint32_t kw[8];  // the key, in registers: the nibble that picks a branch's child costs no load
+  load_key_words(v, o.koff, (o.klen + 1u) >> 1, kw);
   uint32_t* pn = v.path_node + (size_t)e * PATH_CAP;
   uint8_t* pd = v.path_depth + (size_t)e * PATH_CAP;
   uint32_t tk = TK_EMPTY, tn = NODE_EMPTY, td = 0, tpc = NONE;
@@ -605,14 +663,15 @@ PPD_HD PPD_INLINE void batch_walk(const Ctx& c, const Batch& b, uint32_t i, uint
     }
     if (mark) touched[nt] = node;
     nt++;
-    const uint32_t k = kind_of(v, node);
+    NodeRec r{NK_HASH, 0, 0, 0};
+    if (!is_hash_id(node)) r = v.nodes[node];
+    const uint32_t k = r.w0 & 0xffu;
     if (k == NK_HASH || k == NK_ROOT) {
       tk = TK_HASH, tn = node, td = pos;
       if (put) raise(v, TXF_INSERT_INTO_HASH, b.txn);
       if (mark && pos < o.klen) raise(v, TXF_MARK_INTO_HASH, b.txn);  // MissingKeysCreatingSubPartialTrie
       break;
     }
-    const NodeRec r = v.nodes[node];
     const uint32_t ns = (r.w0 >> 8) & 0xffu, nl = (r.w0 >> 16) & 0xffu;
     const bool owner = (int)o.lcp < (int)pos;  // the first key through this node
     if (k == NK_BRANCH) {
@@ -627,7 +686,7 @@ PPD_HD PPD_INLINE void batch_walk(const Ctx& c, const Batch& b, uint32_t i, uint
       }
       pn[pl] = node, pd[pl] = (uint8_t)pos, pl++;
       if (owner) pc_make(v, node, r, true, i, b.txn);
-      node = child_at(v, r, key_nib(v, o.koff, pos));
+      node = child_at(v, r, nib_of_words(kw, pos));
       pos++;
     } else if (k == NK_EXT) {
       const uint32_t avail = o.klen - pos, m = avail < nl ? avail : nl;
@@ -659,10 +718,9 @@ PPD_HD PPD_INLINE void batch_walk(const Ctx& c, const Batch& b, uint32_t i, uint
   if (nt > MARK_SLOTS_T) raise(v, TXF_MARK_SLOTS, b.txn);  // (unreachable: PATH_CAP + 1 slots)
   v.plen[e] = (uint8_t)pl;
   v.tnode[e] = tn, v.tdepth[e] = (uint8_t)td, v.tkind[e] = (uint8_t)tk;
-  {
-    const uint8_t* kb = v.key_pool + o.koff;  // (every key has at least four bytes behind its offset: digests, padded txn keys)
-    v.key_hi[e] = ((uint32_t)kb[0] << 24) | ((uint32_t)kb[1] << 16) | ((uint32_t)kb[2] << 8) | kb[3];
-  }
+  // the key's first eight nibbles, most significant first (short keys: zero nibbles after their end)
+  v.key_hi[e] = (kw[0] << 24) | ((kw[0] & 0xff00u) << 8) | ((kw[0] >> 8) & 0xff00u) | (kw[0] >> 24);
+  PPD_EV(v, b.txn, c.tid, 2);
 }
 
 // The canonical trie over a small group of sorted items that share their first `td` nibbles: the writes of one group
@@ -885,6 +943,7 @@ PPD_HD PPD_INLINE void batch_climb(const Ctx& c, const Batch& b, uint32_t i) {
       }
     }
   }
+  PPD_EV(v, b.txn, c.tid, 11);
   for (;;) {
     if (t == 0) {  // what this key carries is the new version of the whole trie
       if (cur.id != T_UNCHANGED) set_trie_root(v, o.owner, cur.id);
@@ -908,12 +967,14 @@ PPD_HD PPD_INLINE void batch_climb(const Ctx& c, const Batch& b, uint32_t i) {
     PPD_FENCE_BLOCK();
     if (PPD_ATOMIC_SUB(&q.pending, 1u) != 1u) return;  // others have yet to report: the last of them carries on
     PPD_FENCE_BLOCK();
+    PPD_EV(v, b.txn, c.tid, 12);
     if (is_ext)
       cur = assemble_ext(v, b, q, d);
     else if (q.changed)
       cur = assemble_branch(v, q, o.koff, d);
     else
       cur = NL{T_UNCHANGED, 0};
+    PPD_EV(v, b.txn, c.tid, 13);
   }
 }
 
@@ -1161,6 +1222,7 @@ PPD_HD PPD_INLINE void run_txn(const Ctx& c, uint32_t ti, const uint8_t* empty_t
   }
   PPD_BLOCK_SYNC();
   PPD_PHASE_CLOCK(c, 0);
+  if (c.tid == 0) PPD_EV(v, ti, 0, 100 + 0);
   // ---- every key of the txn walks the tries as they are before the txn: the marking walks of
   // create_minimal_partial_tries_needed_by_txn (decoding.rs:179-217) and the first half of the writes ----
   const Batch b1{ops1, n1, 0, ti}, b2{ops2, n2, n1, ti};
@@ -1173,24 +1235,38 @@ PPD_HD PPD_INLINE void run_txn(const Ctx& c, uint32_t ti, const uint8_t* empty_t
   }
   PPD_BLOCK_SYNC();
   PPD_PHASE_CLOCK(c, 1);
+  if (c.tid == 0) PPD_EV(v, ti, 0, 100 + 1);
   {
     const uint32_t n_pc = *v.pc_count < v.pc_n_fast + v.pc_n_slow ? *v.pc_count : v.pc_n_fast + v.pc_n_slow;
-    for (uint32_t k = c.tid; k < n_pc; k += c.nthreads) pc_fill(v, k);
+    for (uint32_t k = c.tid; k < n_pc; k += c.nthreads) {
+      PPD_EV(v, ti, c.tid, 3);
+      pc_fill(v, k);
+      PPD_EV(v, ti, c.tid, 4);
+    }
   }
   for (uint32_t k = c.tid; k < n1 + n2; k += c.nthreads) {
+    PPD_EV(v, ti, c.tid, 5);
     if (k < n1)
       batch_announce(c, b1, k);
     else
       batch_announce(c, b2, k - n1);
+    PPD_EV(v, ti, c.tid, 6);
   }
   PPD_BLOCK_SYNC();
   PPD_PHASE_CLOCK(c, 2);
+  if (c.tid == 0) PPD_EV(v, ti, 0, 100 + 2);
   // ---- apply_deltas_to_trie_state (decoding.rs:219-292): storage writes, the txn and receipt inserts ----
-  for (uint32_t k = c.tid; k < n1; k += c.nthreads) batch_climb(c, b1, k);
+  for (uint32_t k = c.tid; k < n1; k += c.nthreads) {
+    PPD_EV(v, ti, c.tid, 10);
+    batch_climb(c, b1, k);
+    PPD_EV(v, ti, c.tid, 14);
+  }
   PPD_BLOCK_SYNC();
   PPD_PHASE_CLOCK(c, 3);
+  if (c.tid == 0) PPD_EV(v, ti, 0, 100 + 3);
   // ---- the accounts after the txn: storage_root = the storage trie's hash after the writes (late-bound: an NK_ROOT node) ----
   for (uint32_t k = c.tid; k < ntr; k += c.nthreads) {
+    PPD_EV(v, ti, c.tid, 30);
     const uint32_t t = tx.trace_begin + k;
     const TxnTrace& tr = v.traces[t];
     if (!(tr.flags & TRF_STATE_WRITE)) continue;
@@ -1222,13 +1298,20 @@ PPD_HD PPD_INLINE void run_txn(const Ctx& c, uint32_t ti, const uint8_t* empty_t
     else if (tr.flags & PPD_TR_CODE_WRITE)
       copy32(rec.code_hash, digest(v, tr.m_code));
     v.accounts[v.rec_base + tr.rec] = rec;
+    PPD_EV(v, ti, c.tid, 31);
   }
   PPD_BLOCK_SYNC();
   PPD_PHASE_CLOCK(c, 4);
+  if (c.tid == 0) PPD_EV(v, ti, 0, 100 + 4);
   // ---- state writes and self-destructs in one descent ----
-  for (uint32_t k = c.tid; k < n2; k += c.nthreads) batch_climb(c, b2, k);
+  for (uint32_t k = c.tid; k < n2; k += c.nthreads) {
+    PPD_EV(v, ti, c.tid, 20);
+    batch_climb(c, b2, k);
+    PPD_EV(v, ti, c.tid, 24);
+  }
   PPD_BLOCK_SYNC();
   PPD_PHASE_CLOCK(c, 5);
+  if (c.tid == 0) PPD_EV(v, ti, 0, 100 + 5);
   for (uint32_t k = c.tid; k < ntr; k += c.nthreads) {
     const TxnTrace& tr = v.traces[tx.trace_begin + k];
     if (tr.flags & PPD_TR_SELF_DESTRUCTED) {  // trie_state.storage.remove(hashed_addr), decoding.rs:271-282
@@ -1244,6 +1327,7 @@ PPD_HD PPD_INLINE void run_txn(const Ctx& c, uint32_t ti, const uint8_t* empty_t
   }
   PPD_BLOCK_SYNC();
   PPD_PHASE_CLOCK(c, 6);
+  if (c.tid == 0) PPD_EV(v, ti, 0, 100 + 6);
 }
 
 // ---- after the last txn: the NK_ROOT nodes dummy entries refer to, and the withdrawals (decoding.rs:356-428) ----

@@ -9,7 +9,7 @@ import subprocess
 os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(HERE, "libppd_b200.so")
+SO_PATH = os.environ.get("PPD_LIB") or os.path.join(HERE, "libppd_b200.so")  # (PPD_LIB: a development build, csrc/Makefile "prof")
 CSRC = os.path.join(HERE, "csrc")
 
 STATUS_NAMES = {
