@@ -580,6 +580,13 @@ struct Batch {
   uint32_t txn;
 };
 
+// The nodes on the path of key i at depth <= shared_depth(b, i) are on the path of a neighbouring key as well (keys are
+// sorted: a node at depth d is shared with the predecessor / successor exactly when the LCP with it is >= d); the nodes
+// below are this key's alone.  -1: the key is alone in its trie.
+PPD_HD PPD_INLINE int shared_depth(const Batch& b, uint32_t i) {
+  const int prev = (int)b.ops[i].lcp, next = i + 1 < b.n ? (int)b.ops[i + 1].lcp : -1;
+  return prev > next ? prev : next;
+}
 PPD_HD PPD_INLINE uint32_t trie_root_of(const View& v, uint32_t owner) {
   if (owner == OWNER_STATE_TRIE) return v.cur->state_root;
   if (owner == OWNER_TXN_TRIE) return v.cur->txn_root;
@@ -656,6 +663,7 @@ PPD_HD PPD_INLINE void batch_walk(const Ctx& c, const Batch& b, uint32_t i, uint
   uint8_t* pd = v.path_depth + (size_t)e * PATH_CAP;
   uint32_t tk = TK_EMPTY, tn = NODE_EMPTY, td = 0, tpc = NONE;
   const bool put = o.kind == OP_PUT_LEAF || o.kind == OP_PUT_ACCOUNT, mark = (o.pad & SOP_MARK) != 0;
+  const int shared = shared_depth(b, i);
   for (;;) {
     if (node == NODE_EMPTY) {
       tk = TK_EMPTY, td = pos;
@@ -673,7 +681,7 @@ PPD_HD PPD_INLINE void batch_walk(const Ctx& c, const Batch& b, uint32_t i, uint
       break;
     }
     const uint32_t ns = (r.w0 >> 8) & 0xffu, nl = (r.w0 >> 16) & 0xffu;
-    const bool owner = (int)o.lcp < (int)pos;  // the first key through this node
+    const bool owner = (int)o.lcp < (int)pos && (int)pos <= shared;  // the first key through this node, when there are others
     if (k == NK_BRANCH) {
       if (pos >= o.klen || pl == PATH_CAP) {
         if (pos >= o.klen) {
@@ -831,9 +839,11 @@ PPD_HD PPD_INLINE void batch_announce(const Ctx& c, const Batch& b, uint32_t i) 
   const uint32_t* pn = v.path_node + (size_t)e * PATH_CAP;
   uint32_t* ppc = v.path_pc + (size_t)e * PATH_CAP;
   const uint8_t* pd = v.path_depth + (size_t)e * PATH_CAP;
+  const int shared = shared_depth(b, i);
   bool leads = true;
   for (uint32_t t = pl; t-- > 0;) {
     const uint32_t d = pd[t] & 0x7fu;
+    if ((int)d > shared) continue;  // this key's alone: no table entry (batch_climb rebuilds it in place)
     const uint32_t child_depth = (pd[t] & 0x80u) ? (t + 1 < pl ? (uint32_t)(pd[t + 1] & 0x7fu) : (uint32_t)v.tdepth[e]) : d + 1;
     const uint32_t idx = pc_find(v, pn[t]);
     ppc[t] = idx;
@@ -841,7 +851,7 @@ PPD_HD PPD_INLINE void batch_announce(const Ctx& c, const Batch& b, uint32_t i) 
     if (leads && idx != NONE) PPD_ATOMIC_ADD(&pc_at(v, idx).pending, 1u);
   }
   uint32_t tidx = NONE;
-  if (v.tkind[e] == TK_DIVERGE) {
+  if (v.tkind[e] == TK_DIVERGE && (int)v.tdepth[e] <= shared) {
     tidx = pc_find(v, v.tnode[e]);
     if (tidx != NONE) PPD_ATOMIC_ADD(&pc_at(v, tidx).pending, 1u);
   }
@@ -889,6 +899,35 @@ PPD_HD PPD_INLINE void set_trie_root(const View& v, uint32_t owner, uint32_t r) 
   }
 }
 
+// ---- the part of a path that is one key's alone: rebuilt by that key's thread, node by node, without the table ----
+// branch `node` at depth d with the child in slot `nib` replaced by the (changed) result `cur`; koff: a key through it
+PPD_HD PPD_INLINE NL private_branch(const View& v, uint32_t node, uint32_t d, uint32_t nib, NL cur, uint32_t koff) {
+  if (cur.id != NODE_EMPTY) return branch_with(v, node, nib, cur);
+  const NodeRec r = v.nodes[node];
+  const uint32_t lv = v.level[node];
+  const uint32_t mask = r.a1 & 0xffffu, bit = 1u << nib;
+  if (!(mask & bit)) return NL{T_UNCHANGED, 0};
+  const uint32_t left = mask & ~bit, nk = popc16(left);
+  if (nk >= 2) {  // the branch without the child
+    const uint32_t base = alloc_children(v, nk), gone = popc16(mask & (bit - 1u));
+    uint32_t old[16];
+    for (uint32_t i = 0; i < 16; i++) old[i] = i <= nk ? v.child_pool[r.a0 + i] : 0u;  // (all in flight together)
+    for (uint32_t i = 0; i < nk; i++) v.child_pool[base + i] = old[i < gone ? i : i + 1u];
+    return NL{push_node(v, NodeRec{w0(NK_BRANCH, 0, 0), base, left, 0}, lv), lv};
+  }
+  if (nk == 1) {  // delete's collapse
+    const uint32_t last = ctz32(left), kid = v.child_pool[r.a0 + popc16(mask & ((1u << last) - 1u))];
+    return collapse_branch(v, koff, d, last, NL{kid, lvl(v, kid)});
+  }
+  return NL{NODE_EMPTY, 0};
+}
+// extension `node` at depth d over the (changed) result `cur` of its child
+PPD_HD PPD_INLINE NL private_ext(const View& v, uint32_t node, uint32_t d, NL cur) {
+  if (cur.id == NODE_EMPTY) return cur;
+  const NodeRec r = v.nodes[node];
+  return collapse_ext(v, r.a0, d, (r.w0 >> 16) & 0xffu, cur);
+}
+
 // The way back up of key i.  Its terminal is resolved by the first key of the group that ends there (a new leaf, an
 // overwrite, a split, a removal).  That key reports the result to the node above; the LAST child to report to a node
 // re-assembles it (a branch left with one child collapses as delete does) and reports it to the node
@@ -904,7 +943,11 @@ PPD_HD PPD_INLINE void batch_climb(const Ctx& c, const Batch& b, uint32_t i) {
   const uint8_t* pd = v.path_depth + (size_t)e * PATH_CAP;
   NL cur{T_UNCHANGED, 0};
   uint32_t t = v.plen[e];
-  if (tk == TK_DIVERGE) {
+  const int shared = shared_depth(b, i);
+  if (tk == TK_DIVERGE && (int)td > shared) {
+    // the only key at this extension, which it leaves half way: the split, in place
+    if (o.kind == OP_PUT_LEAF || o.kind == OP_PUT_ACCOUNT) cur = insert_one(v, NL{v.tnode[e], (uint32_t)v.level[v.tnode[e]]}, td, o, b.txn);
+  } else if (tk == TK_DIVERGE) {
     // one of the keys that leave the extension half way: it reports to the extension on its own account
     const uint32_t idx = v.tpc[e];
     if (idx == NONE) return;
@@ -952,6 +995,13 @@ PPD_HD PPD_INLINE void batch_climb(const Ctx& c, const Batch& b, uint32_t i) {
     t--;
     const uint32_t d = pd[t] & 0x7fu;
     const bool is_ext = (pd[t] & 0x80u) != 0;
+    if ((int)d > shared) {  // this key's alone
+      if (cur.id != T_UNCHANGED) {
+        const uint32_t node = v.path_node[(size_t)e * PATH_CAP + t];
+        cur = is_ext ? private_ext(v, node, d, cur) : private_branch(v, node, d, d < 8 ? (v.key_hi[e] >> (28 - 4 * d)) & 15u : key_nib(v, o.koff, d), cur, o.koff);
+      }
+      continue;
+    }
     const uint32_t idx = ppc[t];
     if (idx == NONE) return;  // (the table was full: a flag is up)
     PathNode& q = pc_at(v, idx);
