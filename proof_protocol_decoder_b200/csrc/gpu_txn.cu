@@ -25,6 +25,152 @@ bool gpu_txn_enabled() {
 #endif
 }
 
+// ---- the txn loops of the blocks in flight, batched (host_pipeline.h: StreamPool) -------------------------------------
+// A lane whose block is ready for its loop hands the task over and gives its main stream back; a service thread takes
+// whatever tasks are waiting when a loop stream is free and launches them together, one thread block each.
+struct LoopBatcher {
+  static const int MAX_STREAMS = 16, BMAX = 16;
+  struct Req {
+    txn::LoopTask task;
+    uint32_t n_txns = 0;
+    cudaEvent_t ready = nullptr, start = nullptr, done = nullptr, done_blocking = nullptr;
+    bool launched = false;
+    uint32_t launches = 0;
+    cudaError_t err = cudaSuccess;
+  };
+  struct LoopStream {
+    cudaStream_t st = nullptr;
+    cudaEvent_t idle = nullptr;     // recorded after a batch: the stream (and its task array) is free again when it has passed
+    txn::LoopTask* tasks = nullptr;  // page-locked, BMAX entries: what the batch's launches read
+  };
+  int device = 0, n_streams = 0;
+  LoopStream ls[MAX_STREAMS];
+  std::mutex mu;
+  std::condition_variable cv_work, cv_launched;
+  std::deque<Req*> q;
+  bool stop = false;
+  std::thread th;
+
+  void serve() {
+#ifndef PPD_HOSTPROF
+    cudaSetDevice(device);
+    int next = 0;
+    for (;;) {
+      Req* batch[BMAX];
+      int n = 0;
+      {
+        std::unique_lock<std::mutex> g(mu);
+        cv_work.wait(g, [&] { return stop || !q.empty(); });
+        if (stop && q.empty()) return;
+      }
+      // a free loop stream: the first whose last batch has ended, else wait for the one used longest ago
+      int pick = -1;
+      for (int k = 0; k < n_streams && pick < 0; k++) {
+        const int s = (next + k) % n_streams;
+        if (cudaEventQuery(ls[s].idle) == cudaSuccess) pick = s;
+      }
+      if (pick < 0) {
+        pick = next;
+        cudaEventSynchronize(ls[pick].idle);  // (tasks keep arriving meanwhile: they make the next batch)
+      }
+      next = (pick + 1) % n_streams;
+      {
+        std::lock_guard<std::mutex> g(mu);
+        while (n < BMAX && !q.empty()) batch[n++] = q.front(), q.pop_front();
+      }
+      LoopStream& S = ls[pick];
+      uint32_t max_txns = 0;
+      bool any_shared = false;
+      cudaError_t err = cudaSuccess;
+      for (int k = 0; k < n; k++) {
+        S.tasks[k] = batch[k]->task;
+        max_txns = std::max(max_txns, batch[k]->n_txns);
+        any_shared |= batch[k]->task.use_shared != 0;
+        if (err == cudaSuccess) err = cudaStreamWaitEvent(S.st, batch[k]->ready, 0);
+      }
+      for (int k = 0; k < n && err == cudaSuccess; k++) err = cudaEventRecord(batch[k]->start, S.st);
+      uint32_t launches = 0;
+      if (err == cudaSuccess) {
+        launches = launch_txn_loops(S.tasks, (uint32_t)n, max_txns, any_shared, S.st);
+        err = cudaGetLastError();
+      }
+      for (int k = 0; k < n && err == cudaSuccess; k++) {
+        err = cudaEventRecord(batch[k]->done, S.st);
+        if (err == cudaSuccess) err = cudaEventRecord(batch[k]->done_blocking, S.st);
+      }
+      if (err == cudaSuccess) err = cudaEventRecord(S.idle, S.st);
+      {
+        std::lock_guard<std::mutex> g(mu);
+        for (int k = 0; k < n; k++) batch[k]->launched = true, batch[k]->launches = launches, batch[k]->err = err;
+      }
+      cv_launched.notify_all();
+    }
+#endif
+  }
+};
+
+LoopBatcher* loop_batcher_create(int device, int n_streams) {
+#ifdef PPD_HOSTPROF
+  return nullptr;
+#else
+  LoopBatcher* b = new LoopBatcher();
+  b->device = device;
+  b->n_streams = std::min(n_streams, (int)LoopBatcher::MAX_STREAMS);
+  for (int k = 0; k < b->n_streams; k++) {
+    LoopBatcher::LoopStream& S = b->ls[k];
+    S.tasks = (txn::LoopTask*)pinned_alloc(sizeof(txn::LoopTask) * LoopBatcher::BMAX);
+    if (!S.tasks || cudaStreamCreateWithFlags(&S.st, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&S.idle, cudaEventBlockingSync | cudaEventDisableTiming) != cudaSuccess || cudaEventRecord(S.idle, S.st) != cudaSuccess) {
+      b->n_streams = k + 1;
+      loop_batcher_destroy(b);
+      return nullptr;
+    }
+  }
+  b->th = std::thread([b] { b->serve(); });
+  return b;
+#endif
+}
+void loop_batcher_destroy(LoopBatcher* b) {
+#ifndef PPD_HOSTPROF
+  if (!b) return;
+  if (b->th.joinable()) {
+    {
+      std::lock_guard<std::mutex> g(b->mu);
+      b->stop = true;
+    }
+    b->cv_work.notify_all();
+    b->th.join();
+  }
+  for (int k = 0; k < b->n_streams; k++) {
+    if (b->ls[k].st) cudaStreamSynchronize(b->ls[k].st), cudaStreamDestroy(b->ls[k].st);
+    if (b->ls[k].idle) cudaEventDestroy(b->ls[k].idle);
+    if (b->ls[k].tasks) pinned_free(b->ls[k].tasks);
+  }
+  delete b;
+#endif
+}
+uint32_t loop_batcher_run(LoopBatcher* b, const txn::View& v, uint32_t initial_state, uint32_t max_keys, cudaEvent_t ready, cudaEvent_t start,
+                          cudaEvent_t done, cudaEvent_t done_blocking) {
+#ifdef PPD_HOSTPROF
+  return 0;
+#else
+  LoopBatcher::Req r;
+  r.task.v = v, r.task.initial_state = initial_state, r.task.use_shared = txn_loop_uses_shared(max_keys);
+  r.n_txns = v.n_txns, r.ready = ready, r.start = start, r.done = done, r.done_blocking = done_blocking;
+  {
+    std::lock_guard<std::mutex> g(b->mu);
+    b->q.push_back(&r);
+  }
+  b->cv_work.notify_one();
+  {
+    std::unique_lock<std::mutex> g(b->mu);
+    b->cv_launched.wait(g, [&] { return r.launched; });
+  }
+  CUDA_OK(r.err);
+  return r.launches;
+#endif
+}
+
 #ifndef PPD_HOSTPROF
 namespace {
 
@@ -365,9 +511,25 @@ int gpu_block(ppd_ctx* c, Lane* L, Job& J, const uint8_t* flat, size_t len, uint
   }
 #endif
   trace_mark(L, "prep");
-  CUDA_OK(cudaEventRecord(L->ev_loop0, st));
-  L->stats.kernel_launches += launch_txn_loop(v, b.state_root, T.max_ops, st);
-  CUDA_OK(cudaEventRecord(L->ev_loop1, st));
+  if (c->batcher && L->lease) {
+    // the loop runs on a loop stream, batched with the loops of other lanes that are due; this lane's main stream goes
+    // back to the pool meanwhile
+    lane_copy_flush(L);
+    CUDA_OK(cudaEventRecord(L->ev_ready, st));
+    L->lease->release();
+    L->stats.kernel_launches += loop_batcher_run(c->batcher, v, b.state_root, T.max_ops, L->ev_ready, L->ev_loop0, L->ev_loop1, L->ev_loop_done);
+    {
+      const auto tw = std::chrono::steady_clock::now();
+      CUDA_OK(cudaEventSynchronize(L->ev_loop_done));
+      L->stats.host_wait_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tw).count();
+    }
+    L->lease->acquire();
+    st = L->st;
+  } else {
+    CUDA_OK(cudaEventRecord(L->ev_loop0, st));
+    L->stats.kernel_launches += launch_txn_loop(L->h_task, v, b.state_root, T.max_ops, st);
+    CUDA_OK(cudaEventRecord(L->ev_loop1, st));
+  }
   trace_mark(L, "loop");
   // ---- the loop's nodes sorted by (level, class) ----
   L->d_order2.reserve(4ull * H.cap_tail + 16);
@@ -404,8 +566,8 @@ int gpu_block(ppd_ctx* c, Lane* L, Job& J, const uint8_t* flat, size_t len, uint
   }
   if (getenv("PPD_TIMING")) {
     const unsigned long long* pc = h_cur->phase_clocks;
-    fprintf(stderr, "[ppd]   loop phases (Mclk): setup %.2f | walks %.2f | announce %.2f | storage tries up %.2f | records %.2f | state trie up %.2f | root nodes %.2f\n",
-            pc[0] / 1e6, pc[1] / 1e6, pc[2] / 1e6, pc[3] / 1e6, pc[4] / 1e6, pc[5] / 1e6, pc[6] / 1e6);
+    fprintf(stderr, "[ppd]   loop phases (Mclk): setup %.2f | walks %.2f | announce %.2f | storage tries up %.2f | records + state trie up %.2f | root nodes %.2f\n",
+            pc[0] / 1e6, pc[1] / 1e6, pc[2] / 1e6, pc[3] / 1e6, pc[5] / 1e6, pc[6] / 1e6);
   }
   if (h_cur->flag || h_cur->max_level >= ORDER_MAX_BINS / 64) {
     if (getenv("PPD_TIMING")) fprintf(stderr, "[ppd] device txn loop flag %u at txn %u (max level %u): host path\n", h_cur->flag, h_cur->flag_txn, h_cur->max_level);

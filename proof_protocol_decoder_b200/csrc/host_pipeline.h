@@ -20,6 +20,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <deque>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -98,6 +99,11 @@ struct Lane {
   size_t tr_n = 0;
   int id = 0;
   CopyBatch copies;  // lane_copy: queued until lane_copy_flush (every wait flushes)
+  // the stream pool (StreamPool below): `st` is the lane's own stream unless a decode holds one of the pool's
+  cudaStream_t own_st = nullptr;
+  struct StreamLease* lease = nullptr;
+  txn::LoopTask* h_task = nullptr;  // page-locked: the kernel argument of a loop launched on the lane's own stream
+  cudaEvent_t ev_ready = nullptr, ev_loop_done = nullptr;  // (ev_loop_done: blocking-sync)
 };
 
 // Counting semaphore: how many lanes may have their witness upload + parse in flight at once.  All lanes of a
@@ -145,8 +151,77 @@ inline int parse_slots() {
 
 }  // namespace ppd
 
+namespace ppd {
+// The device runs at most CUDA_DEVICE_MAX_CONNECTIONS (32) streams side by side: more streams share hardware queues, and
+// a kernel waits for everything queued before it on ITS queue, whatever the stream.  So the lanes (one per block in
+// flight: HBM buffers, host scratch, a host thread) do not own the streams their work runs on:
+//   * a block holds one of the pool's main streams while it has short kernels and copies to queue (parse, hashing
+//     sweeps, IR dump), and gives it back while its txn loop runs;
+//   * the txn loops, the only long kernels (one resident thread block for milliseconds), run on a few loop streams,
+//     the loops that are due together as ONE launch (LoopBatcher, gpu_txn.cu).
+// Main + loop streams stay below 32, so nothing short ever queues behind a loop; blocks in flight are not limited by
+// the stream count.
+struct StreamPool {
+  std::mutex mu;
+  std::condition_variable cv;
+  std::vector<cudaStream_t> all, free_;
+  cudaStream_t acquire(double* wait_ms) {
+    const auto t0 = std::chrono::steady_clock::now();
+    std::unique_lock<std::mutex> g(mu);
+    cv.wait(g, [&] { return !free_.empty(); });
+    cudaStream_t s = free_.back();
+    free_.pop_back();
+    if (wait_ms) *wait_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    return s;
+  }
+  void release(cudaStream_t s) {
+    {
+      std::lock_guard<std::mutex> g(mu);
+      free_.push_back(s);
+    }
+    cv.notify_one();
+  }
+};
+// a decode's hold on a pool stream (no pool: the lane keeps its own stream throughout)
+struct StreamLease {
+  StreamPool* pool;
+  Lane* L;
+  bool held = false;
+  StreamLease(StreamPool* p, Lane* l) : pool(p), L(l) {
+    L->lease = this;
+    acquire();
+  }
+  void acquire() {
+    if (!pool || held) return;
+    L->st = pool->acquire(&L->stats.host_wait_ms);
+    held = true;
+  }
+  void release() {  // (everything queued on it stays queued: streams are in order, the next holder's work runs behind it)
+    if (!pool || !held) return;
+    lane_copy_flush_fwd(L);
+    pool->release(L->st);
+    L->st = L->own_st;
+    held = false;
+  }
+  ~StreamLease() {
+    release();
+    L->lease = nullptr;
+  }
+  static void lane_copy_flush_fwd(Lane* l);
+};
+struct LoopBatcher;
+LoopBatcher* loop_batcher_create(int device, int n_streams);
+void loop_batcher_destroy(LoopBatcher* b);
+// queues the loop behind `ready` (an event recorded on the stream that prepared it), returns once it is launched; the
+// caller then waits for `done`.  start / done: recorded on the loop stream around the launches.  Returns the launches.
+uint32_t loop_batcher_run(LoopBatcher* b, const txn::View& v, uint32_t initial_state, uint32_t max_keys, cudaEvent_t ready, cudaEvent_t start,
+                          cudaEvent_t done, cudaEvent_t done_blocking);
+}  // namespace ppd
+
 struct ppd_ctx {
   int device = 0;
+  ppd::StreamPool* pool = nullptr;      // null: every lane works on its own stream
+  ppd::LoopBatcher* batcher = nullptr;
   ppd::Slots parse_slots_sem{ppd::parse_slots()};
   cudaStream_t st = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;

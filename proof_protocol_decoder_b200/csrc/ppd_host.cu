@@ -31,6 +31,7 @@ void pinned_free(void* p) { cudaFreeHost(p); }
 
 void stats_reset(ppd_ctx* c) { c->stats = ppd_stats{}; }
 
+void StreamLease::lane_copy_flush_fwd(Lane* l) { lane_copy_flush(l); }
 void lane_copy_flush(Lane* l) {
 #ifndef PPD_HOSTPROF
   if (!l->copies.n) return;
@@ -173,6 +174,11 @@ Lane* lane_of(ppd_ctx* c, size_t w) {
     l->id = (int)c->lanes.size();
 #ifndef PPD_HOSTPROF
     CUDA_OK(cudaStreamCreateWithFlags(&l->st, cudaStreamNonBlocking));
+    l->own_st = l->st;
+    l->h_task = (txn::LoopTask*)pinned_alloc(sizeof(txn::LoopTask));
+    if (!l->h_task) fail(PPD_ERR_BAD_ARGUMENT, "out of page-locked memory");
+    CUDA_OK(cudaEventCreateWithFlags(&l->ev_ready, cudaEventDisableTiming));
+    CUDA_OK(cudaEventCreateWithFlags(&l->ev_loop_done, cudaEventBlockingSync | cudaEventDisableTiming));
     CUDA_OK(cudaEventCreate(&l->ev0));
     CUDA_OK(cudaEventCreate(&l->ev1));
     CUDA_OK(cudaEventCreateWithFlags(&l->ev_sync, cudaEventBlockingSync | cudaEventDisableTiming));
@@ -192,6 +198,9 @@ void lane_delete(Lane* l) {
   for (DevBuf* b : bufs) b->release();
   if (l->h_parse) pinned_free(l->h_parse);
   for (cudaEvent_t e : l->tr_ev) cudaEventDestroy(e);
+  if (l->h_task) pinned_free(l->h_task);
+  if (l->ev_ready) cudaEventDestroy(l->ev_ready);
+  if (l->ev_loop_done) cudaEventDestroy(l->ev_loop_done);
   if (l->ev0) cudaEventDestroy(l->ev0);
   if (l->ev1) cudaEventDestroy(l->ev1);
   if (l->ev_sync) cudaEventDestroy(l->ev_sync);
@@ -400,6 +409,7 @@ void decode_one_inner(ppd_ctx* c, Lane* L, const uint8_t* flat, size_t len, uint
   // First everything after the flat input on the device (gpu_txn.cu).  A block it declines (an error the reference
   // would report, a witness the GPU parser hands to the host builder, a capacity limit) starts over on the host path:
   // the host shapes the tries, in the reference's order of operations, and the device hashes and serialises them.
+  StreamLease lease(c->pool, L);
   for (int on_device = gpu_txn_enabled() ? 1 : 0; on_device >= 0; on_device--) {
     PhaseTimer pt;
     Job& J = job_of(L, 1);
@@ -525,6 +535,30 @@ int ppd_ctx_create(int device, ppd_ctx** out) {
     delete c;
     return PPD_ERR_CUDA;
   }
+  // the stream pool and the loop streams (host_pipeline.h: StreamPool): made first and together, so that they sit on
+  // hardware queues of their own; PPD_STREAM_POOL=0: every lane on its own stream, loops included
+  {
+    const char* e = getenv("PPD_STREAM_POOL");
+    const int n_main = e ? atoi(e) : 22;
+    const char* e2 = getenv("PPD_LOOP_STREAMS");
+    const int n_loop = e2 ? std::max(1, atoi(e2)) : 8;
+    if (n_main > 0) {
+      c->pool = new StreamPool();
+      for (int k = 0; k < n_main; k++) {
+        cudaStream_t s = nullptr;
+        if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) {
+          ppd_ctx_destroy(c);
+          return PPD_ERR_CUDA;
+        }
+        c->pool->all.push_back(s), c->pool->free_.push_back(s);
+      }
+      c->batcher = loop_batcher_create(device, n_loop);
+      if (!c->batcher) {
+        ppd_ctx_destroy(c);
+        return PPD_ERR_CUDA;
+      }
+    }
+  }
   *out = c;
   return PPD_OK;
 }
@@ -537,6 +571,11 @@ void ppd_ctx_destroy(ppd_ctx* c) {
   return;
 #endif
   cudaSetDevice(c->device);
+  if (c->batcher) loop_batcher_destroy(c->batcher);
+  if (c->pool) {
+    for (cudaStream_t s : c->pool->all) cudaStreamDestroy(s);
+    delete c->pool;
+  }
   for (Lane* l : c->lanes) lane_delete(l);
   DevBuf* bufs[] = {&c->d_keys, &c->d_vals, &c->d_ref, &c->d_ref_len, &c->d_counters, &c->d_msg, &c->d_msg_off, &c->d_digest};
   for (DevBuf* b : bufs) b->release();
@@ -631,7 +670,7 @@ static void replay_lane(Lane* L, unsigned what) {
     launch_txn_init(v, L->last_init, L->last_table_slots, st);
     launch_join(L->last_join, st);
     launch_txn_prep(v, L->last_ai, L->last_n_ops1, L->last_n_ops2, L->last_max_writes, st);
-    launch_txn_loop(v, L->last_init.state_root, L->last_max_keys, st);
+    launch_txn_loop(L->h_task, v, L->last_init.state_root, L->last_max_keys, st);
     CUDA_OK(cudaMemsetAsync(L->last_bins_tail, 0, 4ull * ORDER_MAX_BINS, st));
     launch_order_by_level_class(v.nodes, v.level, L->last_cap_tail, ORDER_MAX_BINS, L->last_okeys, L->last_bins_tail, L->d_order2.as<uint32_t>(), st,
                                 L->last_init.n_nodes, &v.cur->n_nodes);

@@ -190,7 +190,11 @@ void launch_txn_init(const txn::View& v, const txn::Cursors& init, uint32_t tabl
 void launch_join(const txn::JoinView& j, cudaStream_t st);
 uint32_t launch_txn_prep(const txn::View& v, const txn::AcctInit& a, uint32_t n_ops1, uint32_t n_ops2, uint32_t max_writes, cudaStream_t st);
 // max_keys: the most keys (accessed + written) any txn of the block has; returns the number of launches
-uint32_t launch_txn_loop(const txn::View& v, uint32_t initial_state, uint32_t max_keys, cudaStream_t st);
+// the loops of n blocks as one series of launches (one thread block per task; tasks: device-accessible, e.g. page-locked
+// host memory, untouched until the launches have run); max_txns: the most txns any of them has
+uint32_t launch_txn_loops(const txn::LoopTask* tasks, uint32_t n, uint32_t max_txns, bool any_shared, cudaStream_t st);
+uint32_t txn_loop_uses_shared(uint32_t max_keys);
+uint32_t launch_txn_loop(txn::LoopTask* slot, const txn::View& v, uint32_t initial_state, uint32_t max_keys, cudaStream_t st);
 void launch_acct_export(const txn::View& v, const txn::JoinView& j, txn::AcctExport* out, cudaStream_t st);
 
 // ---- ppd_microbench.cu ----

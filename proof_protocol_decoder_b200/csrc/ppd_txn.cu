@@ -126,8 +126,8 @@ __global__ void acct_export_kernel(View v, const uint32_t* __restrict__ acct_lis
 
 constexpr int LOOP_THREADS = 256;
 constexpr uint32_t SH_KEYS = 512;   // keys of one txn whose scratch fits in shared memory
-constexpr uint32_t SH_NODES = 640;  // path-node table entries in shared memory (the rest of a txn's spill to HBM)
-constexpr uint32_t SH_MAP = 4096;   // slots of the node id -> entry map
+constexpr uint32_t SH_NODES = 384;  // path-node table entries in shared memory (the rest of a txn's spill to HBM)
+constexpr uint32_t SH_MAP = 2048;   // slots of the node id -> entry map
 struct LoopShared {
   PathNode pc[SH_NODES];
   uint32_t path_node[SH_KEYS * PATH_CAP], path_pc[SH_KEYS * PATH_CAP];
@@ -141,11 +141,25 @@ struct LoopShared {
 // shares the hardware queue (the device has at most 32 of them) are not held up behind one long kernel.  use_shared: the
 // scratch of a txn (path, terminal, result per key) and its keys live in shared memory: every step of the re-assembly
 // then costs one trip to L2 / HBM (the child table) instead of four.
-__global__ void __launch_bounds__(LOOP_THREADS, 1) txn_loop_kernel(View v, uint32_t initial_state, uint32_t ti0, uint32_t ti1, uint32_t finish,
-                                                                   uint32_t use_shared) {
+// One thread block per task (= per block of the batch): blocks of different lanes whose loops are due together run as
+// one launch (gpu_txn.cu: LoopBatcher), so a loop does not hold a lane's stream (one of the device's 32 hardware queues)
+// for its whole length.  tasks: device-accessible (page-locked host memory), read once per launch.
+__global__ void __launch_bounds__(LOOP_THREADS, 1) txn_loop_kernel(const LoopTask* __restrict__ tasks, uint32_t ti0, uint32_t ti1) {
   extern __shared__ __align__(16) uint8_t loop_smem[];
   __shared__ uint32_t sh_stop, sh_cursor[4], sh_pc_count;
   __shared__ long long sh_clock;
+  __shared__ LoopTask sh_task;
+  {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(tasks + blockIdx.x);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(&sh_task);
+    for (uint32_t k = threadIdx.x; k < sizeof(LoopTask) / 4; k += blockDim.x) dst[k] = src[k];
+  }
+  __syncthreads();
+  View v = sh_task.v;
+  const uint32_t initial_state = sh_task.initial_state, use_shared = sh_task.use_shared;
+  if (ti1 > v.n_txns) ti1 = v.n_txns;
+  if (ti0 > ti1 || (ti0 == ti1 && ti0 != 0)) return;  // this block's txns ended in an earlier launch of the batch
+  const bool finish = ti1 == v.n_txns;
   if (threadIdx.x == 0) {
     sh_clock = clock64();
     sh_cursor[0] = v.cur->n_nodes, sh_cursor[1] = v.cur->n_children, sh_cursor[2] = v.cur->key_bytes, sh_cursor[3] = v.cur->max_level;
@@ -212,26 +226,29 @@ uint32_t launch_txn_prep(const View& v, const AcctInit& a, uint32_t n_ops1, uint
   }
   return launches;
 }
-uint32_t launch_txn_loop(const View& v, uint32_t initial_state, uint32_t max_keys, cudaStream_t st) {
+uint32_t txn_loop_uses_shared(uint32_t max_keys) { return max_keys <= SH_KEYS ? 1u : 0u; }  // max_keys: the most keys any txn of the block has
+uint32_t launch_txn_loops(const LoopTask* tasks, uint32_t n, uint32_t max_txns, bool any_shared, cudaStream_t st) {
   static const bool attr = [] {
     cudaFuncSetAttribute(txn_loop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LoopShared));
     return true;
   }();
   (void)attr;
-  const uint32_t use_shared = max_keys <= SH_KEYS ? 1u : 0u;  // max_keys: the most keys any txn of the block has
-  const size_t smem = use_shared ? sizeof(LoopShared) : 0;
+  const size_t smem = any_shared ? sizeof(LoopShared) : 0;
   static const uint32_t chunk = [] {
     const char* e = getenv("PPD_LOOP_CHUNK");
     const int x = e ? atoi(e) : 16;
     return (uint32_t)(x < 1 ? 1 : x);
   }();
   uint32_t launches = 0;
-  for (uint32_t t0 = 0; t0 < v.n_txns || launches == 0; t0 += chunk) {
-    const uint32_t t1 = t0 + chunk < v.n_txns ? t0 + chunk : v.n_txns;
-    txn_loop_kernel<<<1, LOOP_THREADS, smem, st>>>(v, initial_state, t0, t1, t1 == v.n_txns ? 1u : 0u, use_shared);
+  for (uint32_t t0 = 0; t0 < max_txns || launches == 0; t0 += chunk) {
+    txn_loop_kernel<<<n, LOOP_THREADS, smem, st>>>(tasks, t0, t0 + chunk);
     launches++;
   }
   return launches;
+}
+uint32_t launch_txn_loop(LoopTask* slot, const View& v, uint32_t initial_state, uint32_t max_keys, cudaStream_t st) {
+  slot->v = v, slot->initial_state = initial_state, slot->use_shared = txn_loop_uses_shared(max_keys);
+  return launch_txn_loops(slot, 1, v.n_txns, slot->use_shared != 0, st);
 }
 void launch_acct_export(const View& v, const JoinView& j, AcctExport* out, cudaStream_t st) {
   if (j.n_acct) acct_export_kernel<<<cdiv(j.n_acct, 128), 128, 0, st>>>(v, j.acct_list, j.join_storage, j.n_acct, out);

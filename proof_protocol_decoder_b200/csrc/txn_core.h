@@ -225,6 +225,12 @@ struct View {
 };
 
 // the by-root join of accounts to witnessed storage tries (compact_to_partial_trie.rs:167-190), ppd_txn.cu
+// one block's loop as the kernel takes it (ppd_txn.cu: txn_loop_kernel; an array of these per launch)
+struct LoopTask {
+  View v;
+  uint32_t initial_state, use_shared, pad[2];
+};
+
 struct JoinView {
   const uint32_t* acct_list;  // [n_acct][5] as ParseEmit writes it: leaf, storage trie root, its NK_ROOT node, flags, code index
   uint32_t n_acct;
@@ -260,6 +266,7 @@ struct Ctx {
 #define PPD_EV(v, txn, tid, id) ((void)0)
 #endif
 #if defined(__CUDA_ARCH__)
+#define PPD_PREFETCH(p) asm volatile("prefetch.global.L1 [%0];" ::"l"(p))
 #define PPD_FENCE_BLOCK() __threadfence_block()
 #define PPD_ATOMIC_SUB(p, x) atomicSub((p), (x))
 #define PPD_ATOMIC_ADD(p, x) atomicAdd((p), (x))
@@ -282,6 +289,7 @@ PPD_HD PPD_INLINE uint32_t host_atomic_cas(uint32_t* p, uint32_t c, uint32_t x) 
   return o;
 }
 #define PPD_FENCE_BLOCK() ((void)0)
+#define PPD_PREFETCH(p) ((void)0)
 #define PPD_ATOMIC_SUB(p, x) ppd::txn::host_atomic_add((p), 0u - (x))
 #define PPD_ATOMIC_ADD(p, x) ppd::txn::host_atomic_add((p), (x))
 #define PPD_ATOMIC_MAX(p, x) ppd::txn::host_atomic_max((p), (x))
@@ -693,6 +701,10 @@ PPD_HD PPD_INLINE void batch_walk(const Ctx& c, const Batch& b, uint32_t i, uint
         break;
       }
       pn[pl] = node, pd[pl] = (uint8_t)pos, pl++;
+      if (o.kind != OP_NONE) {  // a write comes back up through this branch: its level and whole child row will be read then
+        PPD_PREFETCH(v.level + node);
+        PPD_PREFETCH(v.child_pool + r.a0 + 8);
+      }
       if (owner) pc_make(v, node, r, true, i, b.txn);
       node = child_at(v, r, nib_of_words(kw, pos));
       pos++;
@@ -1350,10 +1362,8 @@ PPD_HD PPD_INLINE void run_txn(const Ctx& c, uint32_t ti, const uint8_t* empty_t
     v.accounts[v.rec_base + tr.rec] = rec;
     PPD_EV(v, ti, c.tid, 31);
   }
-  PPD_BLOCK_SYNC();
-  PPD_PHASE_CLOCK(c, 4);
-  if (c.tid == 0) PPD_EV(v, ti, 0, 100 + 4);
-  // ---- state writes and self-destructs in one descent ----
+  // ---- state writes and self-destructs in one descent (a new account leaf holds the INDEX of its record: nothing
+  // below reads what the records pass writes, so no barrier in between) ----
   for (uint32_t k = c.tid; k < n2; k += c.nthreads) {
     PPD_EV(v, ti, c.tid, 20);
     batch_climb(c, b2, k);
