@@ -566,8 +566,8 @@ int gpu_block(ppd_ctx* c, Lane* L, Job& J, const uint8_t* flat, size_t len, uint
   }
   if (getenv("PPD_TIMING")) {
     const unsigned long long* pc = h_cur->phase_clocks;
-    fprintf(stderr, "[ppd]   loop phases (Mclk): setup %.2f | walks %.2f | announce %.2f | storage tries up %.2f | records + state trie up %.2f | root nodes %.2f\n",
-            pc[0] / 1e6, pc[1] / 1e6, pc[2] / 1e6, pc[3] / 1e6, pc[5] / 1e6, pc[6] / 1e6);
+    fprintf(stderr, "[ppd]   loop phases (Mclk): setup %.2f | walks %.2f | announce %.2f | storage tries up %.2f | records %.2f | state trie up %.2f | root nodes %.2f\n",
+            pc[0] / 1e6, pc[1] / 1e6, pc[2] / 1e6, pc[3] / 1e6, pc[4] / 1e6, pc[5] / 1e6, pc[6] / 1e6);
   }
   if (h_cur->flag || h_cur->max_level >= ORDER_MAX_BINS / 64) {
     if (getenv("PPD_TIMING")) fprintf(stderr, "[ppd] device txn loop flag %u at txn %u (max level %u): host path\n", h_cur->flag, h_cur->flag_txn, h_cur->max_level);

@@ -701,10 +701,6 @@ PPD_HD PPD_INLINE void batch_walk(const Ctx& c, const Batch& b, uint32_t i, uint
         break;
       }
       pn[pl] = node, pd[pl] = (uint8_t)pos, pl++;
-      if (o.kind != OP_NONE) {  // a write comes back up through this branch: its level and whole child row will be read then
-        PPD_PREFETCH(v.level + node);
-        PPD_PREFETCH(v.child_pool + r.a0 + 8);
-      }
       if (owner) pc_make(v, node, r, true, i, b.txn);
       node = child_at(v, r, nib_of_words(kw, pos));
       pos++;
@@ -1362,8 +1358,10 @@ PPD_HD PPD_INLINE void run_txn(const Ctx& c, uint32_t ti, const uint8_t* empty_t
     v.accounts[v.rec_base + tr.rec] = rec;
     PPD_EV(v, ti, c.tid, 31);
   }
-  // ---- state writes and self-destructs in one descent (a new account leaf holds the INDEX of its record: nothing
-  // below reads what the records pass writes, so no barrier in between) ----
+  PPD_BLOCK_SYNC();  // (a new account leaf's level follows from its record's storage root node: new_leaf_for)
+  PPD_PHASE_CLOCK(c, 4);
+  if (c.tid == 0) PPD_EV(v, ti, 0, 100 + 4);
+  // ---- state writes and self-destructs in one descent ----
   for (uint32_t k = c.tid; k < n2; k += c.nthreads) {
     PPD_EV(v, ti, c.tid, 20);
     batch_climb(c, b2, k);
