@@ -472,12 +472,12 @@ void add_stats(ppd_stats& a, const ppd_stats& b) {
 // Blocks are independent (each BlockTrace carries its own pre-image, trace_protocol.rs:40-48): every
 // host thread takes blocks on its own lane, so parsing / shaping of one block overlaps the copies and
 // kernels of the others.
-static const size_t MAX_LANES = 64;
+static const size_t MAX_LANES = 64, LANES_CAP = 128;
 static size_t max_lanes() {
   static const size_t n = [] {
     const char* e = getenv("PPD_MAX_LANES");
     const long v = e ? atol(e) : (long)MAX_LANES;
-    return (size_t)(v < 1 ? 1 : v > (long)MAX_LANES ? (long)MAX_LANES : v);
+    return (size_t)(v < 1 ? 1 : v > (long)LANES_CAP ? (long)LANES_CAP : v);
   }();
   return n;
 }

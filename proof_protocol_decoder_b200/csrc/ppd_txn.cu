@@ -107,8 +107,7 @@ __global__ void prep_storage_key_kernel(View v) {
   if (k < v.traces[t].n_keys) prep_storage_key(v, t, k);
 }
 __global__ void prep_txn_kernel(View v) {
-  const uint32_t ti = blockIdx.x * blockDim.x + threadIdx.x;
-  if (ti < v.n_txns) prep_txn(v, ti);
+  prep_txn(v, blockIdx.x, threadIdx.x, blockDim.x);  // one thread block per txn
 }
 __global__ void prep_lcp_kernel(View v, uint32_t n1, uint32_t n2) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -126,8 +125,12 @@ __global__ void acct_export_kernel(View v, const uint32_t* __restrict__ acct_lis
 
 constexpr int LOOP_THREADS = 256;
 constexpr uint32_t SH_KEYS = 512;   // keys of one txn whose scratch fits in shared memory
-constexpr uint32_t SH_NODES = 384;  // path-node table entries in shared memory (the rest of a txn's spill to HBM)
-constexpr uint32_t SH_MAP = 2048;   // slots of the node id -> entry map
+#ifndef PPD_SH_NODES
+#define PPD_SH_NODES 384
+#define PPD_SH_MAP 2048
+#endif
+constexpr uint32_t SH_NODES = PPD_SH_NODES;  // path-node table entries in shared memory (the rest of a txn's spill to HBM)
+constexpr uint32_t SH_MAP = PPD_SH_MAP;   // slots of the node id -> entry map
 struct LoopShared {
   PathNode pc[SH_NODES];
   uint32_t path_node[SH_KEYS * PATH_CAP], path_pc[SH_KEYS * PATH_CAP];
@@ -220,7 +223,7 @@ uint32_t launch_txn_prep(const View& v, const AcctInit& a, uint32_t n_ops1, uint
     }
   }
   if (v.n_txns) {
-    prep_txn_kernel<<<cdiv(v.n_txns, 64), 64, 0, st>>>(v);
+    prep_txn_kernel<<<v.n_txns, 128, 0, st>>>(v);
     prep_lcp_kernel<<<cdiv(n_ops1 + n_ops2, 128), 128, 0, st>>>(v, n_ops1, n_ops2);
     launches += 2;
   }

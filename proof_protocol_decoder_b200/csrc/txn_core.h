@@ -1143,16 +1143,19 @@ PPD_HD PPD_INLINE void prep_storage_key(const View& v, uint32_t t, uint32_t k) {
 }
 // per txn: the inserts into the transactions and receipts tries (decoding.rs:284-289), after the storage keys; the same
 // keys are the ones the tries' subsets are cut with (decoding.rs:190-197)
-PPD_HD PPD_INLINE void prep_txn(const View& v, uint32_t ti) {
+// (a group of `nthreads` threads per txn: the txn's bytes and its receipt are copied by all of them)
+PPD_HD PPD_INLINE void prep_txn(const View& v, uint32_t ti, uint32_t tid = 0, uint32_t nthreads = 1) {
   const TxnDesc& tx = v.txns[ti];
-  SOp o;
-  o.koff = tx.key_off, o.klen = (uint8_t)tx.key_nibs, o.lcp = -1, o.pad = SOP_MARK, o.kind = OP_PUT_LEAF;
-  o.a1 = tx.val_txn, o.a2 = tx.len_txn_bytes, o.owner = OWNER_TXN_TRIE;
-  v.ops1[tx.op1_end - 2] = o;
-  o.a1 = tx.val_receipt, o.a2 = tx.len_receipt, o.owner = OWNER_RECEIPT_TRIE;
-  v.ops1[tx.op1_end - 1] = o;
-  for (uint32_t k = 0; k < tx.len_txn_bytes; k++) v.val_pool[tx.val_txn + k] = v.flat[tx.off_txn_bytes + k];
-  for (uint32_t k = 0; k < tx.len_receipt; k++) v.val_pool[tx.val_receipt + k] = v.flat[tx.off_receipt + k];
+  if (tid == 0) {
+    SOp o;
+    o.koff = tx.key_off, o.klen = (uint8_t)tx.key_nibs, o.lcp = -1, o.pad = SOP_MARK, o.kind = OP_PUT_LEAF;
+    o.a1 = tx.val_txn, o.a2 = tx.len_txn_bytes, o.owner = OWNER_TXN_TRIE;
+    v.ops1[tx.op1_end - 2] = o;
+    o.a1 = tx.val_receipt, o.a2 = tx.len_receipt, o.owner = OWNER_RECEIPT_TRIE;
+    v.ops1[tx.op1_end - 1] = o;
+  }
+  for (uint32_t k = tid; k < tx.len_txn_bytes; k += nthreads) v.val_pool[tx.val_txn + k] = v.flat[tx.off_txn_bytes + k];
+  for (uint32_t k = tid; k < tx.len_receipt; k += nthreads) v.val_pool[tx.val_receipt + k] = v.flat[tx.off_receipt + k];
 }
 // per sorted key: the LCP with its predecessor in the same trie (state keys carry their txn in a2: one state trie version
 // per txn).  Equal keys (a slot read and written) get the full length: the later one then shares everything with the earlier.
