@@ -29,7 +29,7 @@ bool gpu_txn_enabled() {
 // A lane whose block is ready for its loop hands the task over and gives its main stream back; a service thread takes
 // whatever tasks are waiting when a loop stream is free and launches them together, one thread block each.
 struct LoopBatcher {
-  static const int MAX_STREAMS = 16, BMAX = 16;
+  static const int MAX_STREAMS = 16, BMAX = (int)LOOP_BATCH_MAX;
   struct Req {
     txn::LoopTask task;
     uint32_t n_txns = 0;
@@ -250,19 +250,19 @@ void after_emit(void* arg, const ParseEmit& E) {
     v.pre_slot = c.take<uint32_t>(n_acct + 1);
     H.d_withdrawals = c.take<txn::Withdrawal>(T.withdrawals.size() + 1);
     H.d_export = c.take<txn::AcctExport>(T.needs_dummies() ? n_acct + 1 : 1);
-    v.path_node = c.take<uint32_t>((size_t)T.max_ops * txn::PATH_CAP + 1);
-    v.path_pc = c.take<uint32_t>((size_t)T.max_ops * txn::PATH_CAP + 1);
-    v.path_depth = c.take<uint8_t>((size_t)T.max_ops * txn::PATH_CAP + 1);
-    v.plen = c.take<uint8_t>(T.max_ops + 1);
-    v.tnode = c.take<uint32_t>(T.max_ops + 1);
-    v.tpc = c.take<uint32_t>(T.max_ops + 1);
-    v.tdepth = c.take<uint8_t>(T.max_ops + 1);
-    v.tkind = c.take<uint8_t>(T.max_ops + 1);
-    v.key_hi = c.take<uint32_t>(T.max_ops + 1);
+    v.s.path_node = c.take<uint32_t>((size_t)T.max_ops * txn::PATH_CAP + 1);
+    v.s.path_pc = c.take<uint32_t>((size_t)T.max_ops * txn::PATH_CAP + 1);
+    v.s.path_depth = c.take<uint8_t>((size_t)T.max_ops * txn::PATH_CAP + 1);
+    v.s.plen = c.take<uint8_t>(T.max_ops + 1);
+    v.s.tnode = c.take<uint32_t>(T.max_ops + 1);
+    v.s.tpc = c.take<uint32_t>(T.max_ops + 1);
+    v.s.tdepth = c.take<uint8_t>(T.max_ops + 1);
+    v.s.tkind = c.take<uint8_t>(T.max_ops + 1);
+    v.s.key_hi = c.take<uint32_t>(T.max_ops + 1);
     // the path-node table in HBM: everything for a txn whose keys do not fit in shared memory, the spill tier otherwise
-    v.pc_slow = c.take<txn::PathNode>(pc_slow_n + 1);
-    v.pc_map = c.take<uint32_t>(pc_map_n);
-    v.pc_map_key = c.take<uint32_t>(pc_map_n);
+    v.s.pc_slow = c.take<txn::PathNode>(pc_slow_n + 1);
+    v.s.pc_map = c.take<uint32_t>(pc_map_n);
+    v.s.pc_map_key = c.take<uint32_t>(pc_map_n);
     v.cur = c.take<txn::Cursors>(1);
     H.bins_pre = c.take<uint32_t>(ORDER_MAX_BINS);
     H.bins_tail = c.take<uint32_t>(ORDER_MAX_BINS);
@@ -282,9 +282,9 @@ void after_emit(void* arg, const ParseEmit& E) {
   v.flat = H.d_flat, v.n_txns = (uint32_t)H.n_txns, v.n_traces = (uint32_t)n_traces, v.dig_base = B.dig_base;
   v.rec_base = B.rec_base, v.val_base = B.val_base;
   v.pre_flags = j.pre_flags;
-  v.pc_fast = nullptr, v.pc_n_fast = 0, v.pc_n_slow = (uint32_t)pc_slow_n, v.pc_map_mask = (uint32_t)pc_map_n - 1, v.pc_count = &v.cur->pc_count;
-  v.sh_ops = nullptr;
-  v.a_nodes = &v.cur->n_nodes, v.a_children = &v.cur->n_children, v.a_keys = &v.cur->key_bytes, v.a_max_level = &v.cur->max_level;
+  v.s.pc_fast = nullptr, v.s.pc_n_fast = 0, v.s.pc_n_slow = (uint32_t)pc_slow_n, v.s.pc_map_mask = (uint32_t)pc_map_n - 1, v.s.pc_count = &v.cur->pc_count;
+  v.s.sh_ops = nullptr;
+  v.s.a_nodes = &v.cur->n_nodes, v.s.a_children = &v.cur->n_children, v.s.a_keys = &v.cur->key_bytes, v.s.a_max_level = &v.cur->max_level;
   v.withdrawals = H.d_withdrawals, v.n_withdrawals = (uint32_t)T.withdrawals.size();
   // (tables and read-backs go by kernel copy, lane_copy: the copy engines are left to the FlatBlock and the IrDump)
   lane_copy(L, H.d_withdrawals, T.withdrawals.data(), sizeof(txn::Withdrawal) * v.n_withdrawals);

@@ -192,6 +192,7 @@ uint32_t launch_txn_prep(const txn::View& v, const txn::AcctInit& a, uint32_t n_
 // max_keys: the most keys (accessed + written) any txn of the block has; returns the number of launches
 // the loops of n blocks as one series of launches (one thread block per task; tasks: device-accessible, e.g. page-locked
 // host memory, untouched until the launches have run); max_txns: the most txns any of them has
+static const uint32_t LOOP_BATCH_MAX = 12;  // loops per launch (their views travel as kernel parameters)
 uint32_t launch_txn_loops(const txn::LoopTask* tasks, uint32_t n, uint32_t max_txns, bool any_shared, cudaStream_t st);
 uint32_t txn_loop_uses_shared(uint32_t max_keys);
 uint32_t launch_txn_loop(txn::LoopTask* slot, const txn::View& v, uint32_t initial_state, uint32_t max_keys, cudaStream_t st);

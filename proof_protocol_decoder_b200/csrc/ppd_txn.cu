@@ -124,6 +124,7 @@ __global__ void acct_export_kernel(View v, const uint32_t* __restrict__ acct_lis
 }
 
 constexpr int LOOP_THREADS = 256;
+constexpr uint32_t LOOP_SCRATCH_BYTES = (sizeof(Scratch) + 15) & ~15u;
 constexpr uint32_t SH_KEYS = 512;   // keys of one txn whose scratch fits in shared memory
 #ifndef PPD_SH_NODES
 #define PPD_SH_NODES 384
@@ -144,22 +145,18 @@ struct LoopShared {
 // shares the hardware queue (the device has at most 32 of them) are not held up behind one long kernel.  use_shared: the
 // scratch of a txn (path, terminal, result per key) and its keys live in shared memory: every step of the re-assembly
 // then costs one trip to L2 / HBM (the child table) instead of four.
+struct LoopBatchArg {
+  LoopTask t[LOOP_BATCH_MAX];
+};
 // One thread block per task (= per block of the batch): blocks of different lanes whose loops are due together run as
 // one launch (gpu_txn.cu: LoopBatcher), so a loop does not hold a lane's stream (one of the device's 32 hardware queues)
 // for its whole length.  tasks: device-accessible (page-locked host memory), read once per launch.
-__global__ void __launch_bounds__(LOOP_THREADS, 1) txn_loop_kernel(const LoopTask* __restrict__ tasks, uint32_t ti0, uint32_t ti1) {
-  extern __shared__ __align__(16) uint8_t loop_smem[];
+__global__ void __launch_bounds__(LOOP_THREADS, 1) txn_loop_kernel(const __grid_constant__ LoopBatchArg A, uint32_t ti0, uint32_t ti1) {
+  extern __shared__ __align__(16) uint8_t loop_smem[];  // [Scratch | LoopShared when the txns' keys fit]
   __shared__ uint32_t sh_stop, sh_cursor[4], sh_pc_count;
   __shared__ long long sh_clock;
-  __shared__ LoopTask sh_task;
-  {
-    const uint32_t* src = reinterpret_cast<const uint32_t*>(tasks + blockIdx.x);
-    uint32_t* dst = reinterpret_cast<uint32_t*>(&sh_task);
-    for (uint32_t k = threadIdx.x; k < sizeof(LoopTask) / 4; k += blockDim.x) dst[k] = src[k];
-  }
-  __syncthreads();
-  View v = sh_task.v;
-  const uint32_t initial_state = sh_task.initial_state, use_shared = sh_task.use_shared;
+  const View& v = A.t[blockIdx.x].v;  // (kernel-parameter space: fields are read from the constant bank)
+  const uint32_t initial_state = A.t[blockIdx.x].initial_state, use_shared = A.t[blockIdx.x].use_shared;
   if (ti1 > v.n_txns) ti1 = v.n_txns;
   if (ti0 > ti1 || (ti0 == ti1 && ti0 != 0)) return;  // this block's txns ended in an earlier launch of the batch
   const bool finish = ti1 == v.n_txns;
@@ -167,19 +164,23 @@ __global__ void __launch_bounds__(LOOP_THREADS, 1) txn_loop_kernel(const LoopTas
     sh_clock = clock64();
     sh_cursor[0] = v.cur->n_nodes, sh_cursor[1] = v.cur->n_children, sh_cursor[2] = v.cur->key_bytes, sh_cursor[3] = v.cur->max_level;
     sh_stop = *reinterpret_cast<volatile uint32_t*>(&v.cur->flag);
-  }
-  v.a_nodes = &sh_cursor[0], v.a_children = &sh_cursor[1], v.a_keys = &sh_cursor[2], v.a_max_level = &sh_cursor[3];
-  if (use_shared) {
-    LoopShared& S = *reinterpret_cast<LoopShared*>(loop_smem);
-    v.path_node = S.path_node, v.path_pc = S.path_pc, v.path_depth = S.path_depth;
-    v.plen = S.plen, v.tnode = S.tnode, v.tpc = S.tpc, v.tdepth = S.tdepth, v.tkind = S.tkind, v.key_hi = S.key_hi, v.sh_ops = S.ops;
-    v.pc_fast = S.pc, v.pc_n_fast = SH_NODES, v.pc_map = S.pc_map, v.pc_map_key = S.pc_map_key, v.pc_map_mask = SH_MAP - 1;
-    // (pc_slow / pc_n_slow: the HBM tier the host laid out; a txn with more path nodes than the map takes is flagged)
-    if (v.pc_n_slow > SH_MAP / 2 - SH_NODES) v.pc_n_slow = SH_MAP / 2 - SH_NODES;
+    Scratch sc = v.s;
+    sc.a_nodes = &sh_cursor[0], sc.a_children = &sh_cursor[1], sc.a_keys = &sh_cursor[2], sc.a_max_level = &sh_cursor[3];
+    if (use_shared) {
+      LoopShared& S = *reinterpret_cast<LoopShared*>(loop_smem + LOOP_SCRATCH_BYTES);
+      sc.path_node = S.path_node, sc.path_pc = S.path_pc, sc.path_depth = S.path_depth;
+      sc.plen = S.plen, sc.tnode = S.tnode, sc.tpc = S.tpc, sc.tdepth = S.tdepth, sc.tkind = S.tkind, sc.key_hi = S.key_hi, sc.sh_ops = S.ops;
+      sc.pc_fast = S.pc, sc.pc_n_fast = SH_NODES, sc.pc_map = S.pc_map, sc.pc_map_key = S.pc_map_key, sc.pc_map_mask = SH_MAP - 1;
+      // (pc_slow / pc_n_slow: the HBM tier the host laid out; a txn with more path nodes than the map takes is flagged)
+      if (sc.pc_n_slow > SH_MAP / 2 - SH_NODES) sc.pc_n_slow = SH_MAP / 2 - SH_NODES;
+    }
+    sc.pc_count = &sh_pc_count;
+#if defined(__CUDA_ARCH__)
+    SCR(v) = sc;
+#endif
   }
   __syncthreads();
   if (sh_stop) return;  // an earlier chunk (or the join) raised a flag: the host path redoes the block
-  v.pc_count = &sh_pc_count;
   Ctx c{v, threadIdx.x, blockDim.x, &sh_clock};
   for (uint32_t ti = ti0; ti < ti1; ti++) {
     run_txn(c, ti, C_EMPTY_TRIE, C_EMPTY_CODE);
@@ -232,19 +233,22 @@ uint32_t launch_txn_prep(const View& v, const AcctInit& a, uint32_t n_ops1, uint
 uint32_t txn_loop_uses_shared(uint32_t max_keys) { return max_keys <= SH_KEYS ? 1u : 0u; }  // max_keys: the most keys any txn of the block has
 uint32_t launch_txn_loops(const LoopTask* tasks, uint32_t n, uint32_t max_txns, bool any_shared, cudaStream_t st) {
   static const bool attr = [] {
-    cudaFuncSetAttribute(txn_loop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LoopShared));
+    cudaFuncSetAttribute(txn_loop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(LOOP_SCRATCH_BYTES + sizeof(LoopShared)));
     return true;
   }();
   (void)attr;
-  const size_t smem = any_shared ? sizeof(LoopShared) : 0;
+  const size_t smem = LOOP_SCRATCH_BYTES + (any_shared ? sizeof(LoopShared) : 0);
   static const uint32_t chunk = [] {
     const char* e = getenv("PPD_LOOP_CHUNK");
     const int x = e ? atoi(e) : 16;
     return (uint32_t)(x < 1 ? 1 : x);
   }();
+  if (n > LOOP_BATCH_MAX) n = LOOP_BATCH_MAX;
+  static thread_local LoopBatchArg A;  // (copied into the launch: the caller's array is free again on return)
+  for (uint32_t k = 0; k < n; k++) A.t[k] = tasks[k];
   uint32_t launches = 0;
   for (uint32_t t0 = 0; t0 < max_txns || launches == 0; t0 += chunk) {
-    txn_loop_kernel<<<n, LOOP_THREADS, smem, st>>>(tasks, t0, t0 + chunk);
+    txn_loop_kernel<<<n, LOOP_THREADS, smem, st>>>(A, t0, t0 + chunk);
     launches++;
   }
   return launches;

@@ -164,37 +164,12 @@ struct PathNode {
 };
 
 // Everything the loop touches.  All pointers are device pointers (host pointers in the CPU harness).
-struct View {
-  // arena (mutable: the loop appends)
-  NodeRec* nodes;
-  uint16_t* level;
-  uint8_t* key_pool;
-  uint8_t* val_pool;
-  const uint8_t* hash_pool;
-  uint32_t* child_pool;
-  AccountRec* accounts;
-  uint32_t cap_nodes, cap_children, cap_keys;
+// The part of a view the loop kernel re-points: the cursors and the scratch of the running txn live in shared memory while
+// it runs (ppd_txn.cu); everything else of the view is read-only kernel-parameter space.  SCR(v) is how the loop reads it.
+struct Scratch {
   // allocation cursors: &cur->n_nodes ..., or shared-memory copies of them while the loop kernel runs (an allocation is
   // then a shared-memory atomic instead of a round trip to L2)
   uint32_t *a_nodes, *a_children, *a_keys, *a_max_level;
-  // inputs
-  const uint8_t* flat;
-  TxnTrace* traces;
-  const TxnDesc* txns;
-  uint32_t n_txns, n_traces;
-  uint32_t dig_base;         // key_pool offset of digest 0 (32 bytes each)
-  uint32_t rec_base, val_base;  // TxnTrace::rec / val0 and Withdrawal::rec count from here (accounts[], val_pool)
-  AcctState* acct;           // account table
-  uint32_t* pre_slot;        // per pre-image account: its slot of the account table once a trace touched it (else >= NONE)
-  const Withdrawal* withdrawals;
-  uint32_t n_withdrawals;
-  const uint8_t* pre_flags;  // per pre-image account: bit0 storage root != EMPTY_TRIE_HASH
-  SOp* ops1;
-  SOp* ops2;
-  // plan (outputs)
-  uint32_t* touched;
-  uint32_t* seg_a;
-  uint32_t* seg_b;
   // scratch of the running txn, indexed by key (round-1 keys first, then the state keys); in shared memory when the
   // txn's keys fit (ppd_txn.cu), else in HBM
   uint32_t* path_node;  // [keys][PATH_CAP] nodes passed, root first
@@ -217,12 +192,54 @@ struct View {
   uint32_t* pc_map;     // [pc_map_mask + 1] node id -> entry + 1 (open addressing; 0 = free), reset per txn
   uint32_t* pc_map_key;
   uint32_t pc_map_mask;
+};
+
+struct View {
+  // arena (mutable: the loop appends)
+  NodeRec* nodes;
+  uint16_t* level;
+  uint8_t* key_pool;
+  uint8_t* val_pool;
+  const uint8_t* hash_pool;
+  uint32_t* child_pool;
+  AccountRec* accounts;
+  uint32_t cap_nodes, cap_children, cap_keys;
+  // inputs
+  const uint8_t* flat;
+  TxnTrace* traces;
+  const TxnDesc* txns;
+  uint32_t n_txns, n_traces;
+  uint32_t dig_base;         // key_pool offset of digest 0 (32 bytes each)
+  uint32_t rec_base, val_base;  // TxnTrace::rec / val0 and Withdrawal::rec count from here (accounts[], val_pool)
+  AcctState* acct;           // account table
+  uint32_t* pre_slot;        // per pre-image account: its slot of the account table once a trace touched it (else >= NONE)
+  const Withdrawal* withdrawals;
+  uint32_t n_withdrawals;
+  const uint8_t* pre_flags;  // per pre-image account: bit0 storage root != EMPTY_TRIE_HASH
+  SOp* ops1;
+  SOp* ops2;
+  // plan (outputs)
+  uint32_t* touched;
+  uint32_t* seg_a;
+  uint32_t* seg_b;
+  Scratch s;  // what the loop kernel re-points to shared memory (SCR below)
   Cursors* cur;
   // PPD_LOOP_PROF builds: per-thread event log of one txn (clock, thread << 16 | event)
   unsigned long long* evlog;
   uint32_t* evcount;
   uint32_t ev_txn, ev_cap;
 };
+
+#if defined(__CUDA_ARCH__)
+// (the loop kernel keeps its Scratch at the start of its dynamic shared memory)
+__device__ __forceinline__ Scratch& scratch_of(const View&) {
+  extern __shared__ __align__(16) uint8_t ppd_loop_smem[];
+  return *reinterpret_cast<Scratch*>(ppd_loop_smem);
+}
+#define SCR(v) ppd::txn::scratch_of(v)
+#else
+#define SCR(v) ((v).s)
+#endif
 
 // the by-root join of accounts to witnessed storage tries (compact_to_partial_trie.rs:167-190), ppd_txn.cu
 // one block's loop as the kernel takes it (ppd_txn.cu: txn_loop_kernel; an array of these per launch)
@@ -249,7 +266,7 @@ PPD_HD PPD_INLINE bool is_hash_id(uint32_t n) { return n >= HASH_BASE && n < HAS
 // ---- the execution context: how threads of the block see shared counters ------------------------------------
 // Device: a thread block.  Harness: one "thread" at a time.
 struct Ctx {
-  View v;
+  const View& v;
   uint32_t tid, nthreads;
   long long* sh_clock;  // shared: clock at the last phase boundary
 };
@@ -310,7 +327,7 @@ PPD_HD PPD_INLINE uint32_t kind_of(const View& v, uint32_t n) { return is_hash_i
 PPD_HD PPD_INLINE uint32_t w0(uint32_t kind, uint32_t start, uint32_t len) { return kind | (start << 8) | (len << 16); }
 
 PPD_HD PPD_INLINE uint32_t push_node(const View& v, const NodeRec& r, uint32_t lv) {
-  uint32_t id = PPD_ATOMIC_ADD(v.a_nodes, 1u);
+  uint32_t id = PPD_ATOMIC_ADD(SCR(v).a_nodes, 1u);
   if (id >= v.cap_nodes) {
     raise(v, TXF_NODES_FULL, 0);
     id = v.cap_nodes - 1;  // a sink slot: the block is redone anyway
@@ -318,11 +335,11 @@ PPD_HD PPD_INLINE uint32_t push_node(const View& v, const NodeRec& r, uint32_t l
   if (lv > 0xfff0u) raise(v, TXF_LEVELS, 0), lv = 0xfff0u;
   v.nodes[id] = r;
   v.level[id] = (uint16_t)lv;
-  PPD_ATOMIC_MAX(v.a_max_level, lv);
+  PPD_ATOMIC_MAX(SCR(v).a_max_level, lv);
   return id;
 }
 PPD_HD PPD_INLINE uint32_t alloc_children(const View& v, uint32_t k) {
-  uint32_t at = PPD_ATOMIC_ADD(v.a_children, k);
+  uint32_t at = PPD_ATOMIC_ADD(SCR(v).a_children, k);
   if (at + k > v.cap_children) {
     raise(v, TXF_CHILDREN_FULL, 0);
     at = v.cap_children - 16;
@@ -481,7 +498,7 @@ PPD_HD PPD_INLINE NL collapse_branch(const View& v, uint32_t koff, uint32_t pos,
   if (k == NK_EXT || k == NK_LEAF || k == NK_LEAF_ACCOUNT) return collapse_ext(v, 0, pos, 1, other);  // their own keys spell the nibble
   // a key that runs through the surviving child: the path's first `pos` nibbles, then its slot
   const uint32_t nb = pos / 2 + 2;
-  uint32_t pk = PPD_ATOMIC_ADD(v.a_keys, nb);
+  uint32_t pk = PPD_ATOMIC_ADD(SCR(v).a_keys, nb);
   if (pk + nb > v.cap_keys) {
     raise(v, TXF_KEYS_FULL, 0);
     pk = v.cap_keys - 40;
@@ -602,26 +619,26 @@ PPD_HD PPD_INLINE uint32_t trie_root_of(const View& v, uint32_t owner) {
   return v.acct[v.traces[owner].acct].storage;
 }
 
-PPD_HD PPD_INLINE PathNode& pc_at(const View& v, uint32_t idx) { return idx < v.pc_n_fast ? v.pc_fast[idx] : v.pc_slow[idx - v.pc_n_fast]; }
+PPD_HD PPD_INLINE PathNode& pc_at(const View& v, uint32_t idx) { return idx < SCR(v).pc_n_fast ? SCR(v).pc_fast[idx] : SCR(v).pc_slow[idx - SCR(v).pc_n_fast]; }
 PPD_HD PPD_INLINE uint32_t pc_hash(uint32_t node) { return node * 2654435761u; }
 // the owner of a path node makes its table entry during the walk and publishes it under the node id; the node's child
 // table and level are loaded afterwards, all entries in parallel (pc_fill)
 PPD_HD PPD_INLINE uint32_t pc_make(const View& v, uint32_t node, const NodeRec& r, bool is_branch, uint32_t owner, uint32_t txn) {
-  uint32_t idx = PPD_ATOMIC_ADD(v.pc_count, 1u);
-  if (idx >= v.pc_n_fast + v.pc_n_slow) {
+  uint32_t idx = PPD_ATOMIC_ADD(SCR(v).pc_count, 1u);
+  if (idx >= SCR(v).pc_n_fast + SCR(v).pc_n_slow) {
     raise(v, TXF_PATH_TABLE, txn);
     return NONE;
   }
   PathNode& p = pc_at(v, idx);
   p.kids[0] = r.a0, p.kids[1] = is_branch ? (r.a1 & 0xffffu) : 0x10000u;  // (until pc_fill replaces them)
   p.node = node, p.lv = 0, p.pending = 0, p.owner = owner, p.changed = 0;
-  uint32_t h = pc_hash(node) & v.pc_map_mask;
+  uint32_t h = pc_hash(node) & SCR(v).pc_map_mask;
   for (;;) {
-    const uint32_t prev = PPD_ATOMIC_CAS(&v.pc_map_key[h], 0xffffffffu, node);
+    const uint32_t prev = PPD_ATOMIC_CAS(&SCR(v).pc_map_key[h], 0xffffffffu, node);
     if (prev == 0xffffffffu || prev == node) break;  // (a node has one owner: `prev == node` does not happen)
-    h = (h + 1) & v.pc_map_mask;
+    h = (h + 1) & SCR(v).pc_map_mask;
   }
-  v.pc_map[h] = idx + 1u;
+  SCR(v).pc_map[h] = idx + 1u;
   return idx;
 }
 // per table entry: the node's children as they are before the txn (sixteen independent loads), and its level
@@ -647,12 +664,12 @@ PPD_HD PPD_INLINE void pc_fill(const View& v, uint32_t idx) {
   p.lv = old_lv;
 }
 PPD_HD PPD_INLINE uint32_t pc_find(const View& v, uint32_t node) {
-  uint32_t h = pc_hash(node) & v.pc_map_mask;
+  uint32_t h = pc_hash(node) & SCR(v).pc_map_mask;
   for (;;) {
-    const uint32_t k = v.pc_map_key[h];
-    if (k == node) return v.pc_map[h] - 1u;
+    const uint32_t k = SCR(v).pc_map_key[h];
+    if (k == node) return SCR(v).pc_map[h] - 1u;
     if (k == 0xffffffffu) return NONE;
-    h = (h + 1) & v.pc_map_mask;
+    h = (h + 1) & SCR(v).pc_map_mask;
   }
 }
 
@@ -667,8 +684,8 @@ PPD_HD PPD_INLINE void batch_walk(const Ctx& c, const Batch& b, uint32_t i, uint
   uint32_t node = trie_root_of(v, o.owner), pos = 0, pl = 0, nt = 0;
   uint32_t kw[8];  // the key, in registers: the nibble that picks a branch's child costs no load
   load_key_words(v, o.koff, (o.klen + 1u) >> 1, kw);
-  uint32_t* pn = v.path_node + (size_t)e * PATH_CAP;
-  uint8_t* pd = v.path_depth + (size_t)e * PATH_CAP;
+  uint32_t* pn = SCR(v).path_node + (size_t)e * PATH_CAP;
+  uint8_t* pd = SCR(v).path_depth + (size_t)e * PATH_CAP;
   uint32_t tk = TK_EMPTY, tn = NODE_EMPTY, td = 0, tpc = NONE;
   const bool put = o.kind == OP_PUT_LEAF || o.kind == OP_PUT_ACCOUNT, mark = (o.pad & SOP_MARK) != 0;
   const int shared = shared_depth(b, i);
@@ -732,10 +749,10 @@ PPD_HD PPD_INLINE void batch_walk(const Ctx& c, const Batch& b, uint32_t i, uint
     }
   }
   if (nt > MARK_SLOTS_T) raise(v, TXF_MARK_SLOTS, b.txn);  // (unreachable: PATH_CAP + 1 slots)
-  v.plen[e] = (uint8_t)pl;
-  v.tnode[e] = tn, v.tdepth[e] = (uint8_t)td, v.tkind[e] = (uint8_t)tk;
+  SCR(v).plen[e] = (uint8_t)pl;
+  SCR(v).tnode[e] = tn, SCR(v).tdepth[e] = (uint8_t)td, SCR(v).tkind[e] = (uint8_t)tk;
   // the key's first eight nibbles, most significant first (short keys: zero nibbles after their end)
-  v.key_hi[e] = (kw[0] << 24) | ((kw[0] & 0xff00u) << 8) | ((kw[0] >> 8) & 0xff00u) | (kw[0] >> 24);
+  SCR(v).key_hi[e] = (kw[0] << 24) | ((kw[0] & 0xff00u) << 8) | ((kw[0] >> 8) & 0xff00u) | (kw[0] >> 24);
   PPD_EV(v, b.txn, c.tid, 2);
 }
 
@@ -843,27 +860,27 @@ PPD_HD PPD_INLINE void batch_announce(const Ctx& c, const Batch& b, uint32_t i) 
   const View& v = c.v;
   const uint32_t e = b.base + i;
   const int lcp = (int)b.ops[i].lcp;
-  const uint32_t pl = v.plen[e];
-  const uint32_t* pn = v.path_node + (size_t)e * PATH_CAP;
-  uint32_t* ppc = v.path_pc + (size_t)e * PATH_CAP;
-  const uint8_t* pd = v.path_depth + (size_t)e * PATH_CAP;
+  const uint32_t pl = SCR(v).plen[e];
+  const uint32_t* pn = SCR(v).path_node + (size_t)e * PATH_CAP;
+  uint32_t* ppc = SCR(v).path_pc + (size_t)e * PATH_CAP;
+  const uint8_t* pd = SCR(v).path_depth + (size_t)e * PATH_CAP;
   const int shared = shared_depth(b, i);
   bool leads = true;
   for (uint32_t t = pl; t-- > 0;) {
     const uint32_t d = pd[t] & 0x7fu;
     if ((int)d > shared) continue;  // this key's alone: no table entry (batch_climb rebuilds it in place)
-    const uint32_t child_depth = (pd[t] & 0x80u) ? (t + 1 < pl ? (uint32_t)(pd[t + 1] & 0x7fu) : (uint32_t)v.tdepth[e]) : d + 1;
+    const uint32_t child_depth = (pd[t] & 0x80u) ? (t + 1 < pl ? (uint32_t)(pd[t + 1] & 0x7fu) : (uint32_t)SCR(v).tdepth[e]) : d + 1;
     const uint32_t idx = pc_find(v, pn[t]);
     ppc[t] = idx;
     leads = leads && lcp < (int)child_depth;  // (once the predecessor goes into the same child it does so at every node above)
     if (leads && idx != NONE) PPD_ATOMIC_ADD(&pc_at(v, idx).pending, 1u);
   }
   uint32_t tidx = NONE;
-  if (v.tkind[e] == TK_DIVERGE && (int)v.tdepth[e] <= shared) {
-    tidx = pc_find(v, v.tnode[e]);
+  if (SCR(v).tkind[e] == TK_DIVERGE && (int)SCR(v).tdepth[e] <= shared) {
+    tidx = pc_find(v, SCR(v).tnode[e]);
     if (tidx != NONE) PPD_ATOMIC_ADD(&pc_at(v, tidx).pending, 1u);
   }
-  v.tpc[e] = tidx;
+  SCR(v).tpc[e] = tidx;
 }
 
 // new version of the branch behind table entry p (the children that changed have been written into p.kids); koff / d: a
@@ -889,7 +906,7 @@ PPD_HD PPD_INLINE NL assemble_ext(const View& v, const Batch& b, PathNode& p, ui
   else if (rj != T_UNCHANGED)
     base = collapse_ext(v, r.a0, d, el, NL{rj, p.kids[1]}), changed = true;
   for (uint32_t j = p.owner; j < b.n && (j == p.owner || (int)b.ops[j].lcp >= (int)d); j++)
-    if (v.tkind[b.base + j] == TK_DIVERGE && v.tdepth[b.base + j] == d && (b.ops[j].kind == OP_PUT_LEAF || b.ops[j].kind == OP_PUT_ACCOUNT))
+    if (SCR(v).tkind[b.base + j] == TK_DIVERGE && SCR(v).tdepth[b.base + j] == d && (b.ops[j].kind == OP_PUT_LEAF || b.ops[j].kind == OP_PUT_ACCOUNT))
       base = insert_one(v, base, d, b.ops[j], b.txn), changed = true;
   return changed ? base : NL{T_UNCHANGED, 0};
 }
@@ -946,18 +963,18 @@ PPD_HD PPD_INLINE void batch_climb(const Ctx& c, const Batch& b, uint32_t i) {
   const View& v = c.v;
   const uint32_t e = b.base + i;
   const SOp& o = b.ops[i];
-  const uint32_t tk = v.tkind[e], td = v.tdepth[e];
-  const uint32_t* ppc = v.path_pc + (size_t)e * PATH_CAP;
-  const uint8_t* pd = v.path_depth + (size_t)e * PATH_CAP;
+  const uint32_t tk = SCR(v).tkind[e], td = SCR(v).tdepth[e];
+  const uint32_t* ppc = SCR(v).path_pc + (size_t)e * PATH_CAP;
+  const uint8_t* pd = SCR(v).path_depth + (size_t)e * PATH_CAP;
   NL cur{T_UNCHANGED, 0};
-  uint32_t t = v.plen[e];
+  uint32_t t = SCR(v).plen[e];
   const int shared = shared_depth(b, i);
   if (tk == TK_DIVERGE && (int)td > shared) {
     // the only key at this extension, which it leaves half way: the split, in place
-    if (o.kind == OP_PUT_LEAF || o.kind == OP_PUT_ACCOUNT) cur = insert_one(v, NL{v.tnode[e], (uint32_t)v.level[v.tnode[e]]}, td, o, b.txn);
+    if (o.kind == OP_PUT_LEAF || o.kind == OP_PUT_ACCOUNT) cur = insert_one(v, NL{SCR(v).tnode[e], (uint32_t)v.level[SCR(v).tnode[e]]}, td, o, b.txn);
   } else if (tk == TK_DIVERGE) {
     // one of the keys that leave the extension half way: it reports to the extension on its own account
-    const uint32_t idx = v.tpc[e];
+    const uint32_t idx = SCR(v).tpc[e];
     if (idx == NONE) return;
     PathNode& p = pc_at(v, idx);
     PPD_FENCE_BLOCK();
@@ -971,20 +988,20 @@ PPD_HD PPD_INLINE void batch_climb(const Ctx& c, const Batch& b, uint32_t i) {
       for (uint32_t j = i; j < b.n && (j == i || (int)b.ops[j].lcp >= (int)td); j++) any |= b.ops[j].kind != OP_NONE;
       if (any) {
         NL base{NODE_EMPTY, 0};
-        if (tk != TK_EMPTY) base = NL{v.tnode[e], (uint32_t)v.level[v.tnode[e]]};
+        if (tk != TK_EMPTY) base = NL{SCR(v).tnode[e], (uint32_t)v.level[SCR(v).tnode[e]]};
         bool changed = false, keep_old = tk != TK_EMPTY;
         uint32_t end = i, n_put = 0;
         // the leaf that is there goes when its own key is deleted or overwritten; then the inserts (the order of distinct keys does not matter)
         for (uint32_t j = i; j < b.n && (j == i || (int)b.ops[j].lcp >= (int)td); j++, end++) {
           const uint8_t kind = b.ops[j].kind;
-          if (kind == OP_DEL && v.tkind[b.base + j] == TK_LEAF_SAME) base = NL{NODE_EMPTY, 0}, changed = true, keep_old = false;
+          if (kind == OP_DEL && SCR(v).tkind[b.base + j] == TK_LEAF_SAME) base = NL{NODE_EMPTY, 0}, changed = true, keep_old = false;
           if (kind == OP_PUT_LEAF || kind == OP_PUT_ACCOUNT) {
             n_put++, changed = true;
-            if (v.tkind[b.base + j] == TK_LEAF_SAME) keep_old = false;
+            if (SCR(v).tkind[b.base + j] == TK_LEAF_SAME) keep_old = false;
           }
         }
         NL built;
-        if (n_put >= 2 && build_group(v, b, i, end, td, v.tnode[e], keep_old, &built, b.txn)) {
+        if (n_put >= 2 && build_group(v, b, i, end, td, SCR(v).tnode[e], keep_old, &built, b.txn)) {
           base = built;
         } else {
           for (uint32_t j = i; j < end; j++)
@@ -1005,8 +1022,8 @@ PPD_HD PPD_INLINE void batch_climb(const Ctx& c, const Batch& b, uint32_t i) {
     const bool is_ext = (pd[t] & 0x80u) != 0;
     if ((int)d > shared) {  // this key's alone
       if (cur.id != T_UNCHANGED) {
-        const uint32_t node = v.path_node[(size_t)e * PATH_CAP + t];
-        cur = is_ext ? private_ext(v, node, d, cur) : private_branch(v, node, d, d < 8 ? (v.key_hi[e] >> (28 - 4 * d)) & 15u : key_nib(v, o.koff, d), cur, o.koff);
+        const uint32_t node = SCR(v).path_node[(size_t)e * PATH_CAP + t];
+        cur = is_ext ? private_ext(v, node, d, cur) : private_branch(v, node, d, d < 8 ? (SCR(v).key_hi[e] >> (28 - 4 * d)) & 15u : key_nib(v, o.koff, d), cur, o.koff);
       }
       continue;
     }
@@ -1017,7 +1034,7 @@ PPD_HD PPD_INLINE void batch_climb(const Ctx& c, const Batch& b, uint32_t i) {
       if (is_ext) {
         q.kids[0] = cur.id, q.kids[1] = cur.lv;
       } else {
-        q.kids[d < 8 ? (v.key_hi[e] >> (28 - 4 * d)) & 15u : key_nib(v, o.koff, d)] = cur.id;
+        q.kids[d < 8 ? (SCR(v).key_hi[e] >> (28 - 4 * d)) & 15u : key_nib(v, o.koff, d)] = cur.id;
         if (cur.id != NODE_EMPTY) PPD_ATOMIC_MAX(&q.lv, cur.lv + 1u);
       }
       q.changed = 1;
@@ -1253,18 +1270,18 @@ PPD_HD PPD_INLINE void run_txn(const Ctx& c, uint32_t ti, const uint8_t* empty_t
   // the txn's keys: in shared memory next to the scratch when they fit
   const SOp* ops1 = v.ops1 + tx.op1_begin;
   const SOp* ops2 = v.ops2 + tx.op2_begin;
-  if (v.sh_ops) {
-    for (uint32_t k = c.tid; k < n1 + n2; k += c.nthreads) v.sh_ops[k] = k < n1 ? ops1[k] : ops2[k - n1];
-    ops1 = v.sh_ops, ops2 = v.sh_ops + n1;
+  if (SCR(v).sh_ops) {
+    for (uint32_t k = c.tid; k < n1 + n2; k += c.nthreads) SCR(v).sh_ops[k] = k < n1 ? ops1[k] : ops2[k - n1];
+    ops1 = SCR(v).sh_ops, ops2 = SCR(v).sh_ops + n1;
   }
   // ---- the tries the subsets are cut from (decoding.rs:179-217): roots before the txn ----
   if (c.tid == 0) {
     v.seg_b[tx.seg_tries + 0] = v.cur->state_root;
     v.seg_b[tx.seg_tries + 1] = v.cur->txn_root;
     v.seg_b[tx.seg_tries + 2] = v.cur->receipt_root;
-    *v.pc_count = 0;
+    *SCR(v).pc_count = 0;
   }
-  for (uint32_t k = c.tid; k <= v.pc_map_mask; k += c.nthreads) v.pc_map_key[k] = 0xffffffffu;
+  for (uint32_t k = c.tid; k <= SCR(v).pc_map_mask; k += c.nthreads) SCR(v).pc_map_key[k] = 0xffffffffu;
   for (uint32_t k = c.tid; k < ntr; k += c.nthreads) {
     const uint32_t t = tx.trace_begin + k;
     const TxnTrace& tr = v.traces[t];
@@ -1298,7 +1315,7 @@ PPD_HD PPD_INLINE void run_txn(const Ctx& c, uint32_t ti, const uint8_t* empty_t
   PPD_PHASE_CLOCK(c, 1);
   if (c.tid == 0) PPD_EV(v, ti, 0, 100 + 1);
   {
-    const uint32_t n_pc = *v.pc_count < v.pc_n_fast + v.pc_n_slow ? *v.pc_count : v.pc_n_fast + v.pc_n_slow;
+    const uint32_t n_pc = *SCR(v).pc_count < SCR(v).pc_n_fast + SCR(v).pc_n_slow ? *SCR(v).pc_count : SCR(v).pc_n_fast + SCR(v).pc_n_slow;
     for (uint32_t k = c.tid; k < n_pc; k += c.nthreads) {
       PPD_EV(v, ti, c.tid, 3);
       pc_fill(v, k);
@@ -1333,8 +1350,8 @@ PPD_HD PPD_INLINE void run_txn(const Ctx& c, uint32_t ti, const uint8_t* empty_t
     if (!(tr.flags & TRF_STATE_WRITE)) continue;
     AccountRec rec;
     const uint32_t e = n1 + tr.rank;  // the trace's state key: its walk found the account as state.get() would (decoding.rs:251-254)
-    if (v.tkind[e] == TK_LEAF_SAME) {
-      const uint32_t leaf = v.tnode[e];
+    if (SCR(v).tkind[e] == TK_LEAF_SAME) {
+      const uint32_t leaf = SCR(v).tnode[e];
       if ((v.nodes[leaf].w0 & 0xffu) != NK_LEAF_ACCOUNT) {
         raise(v, TXF_NOT_ACCOUNT, ti);
         continue;

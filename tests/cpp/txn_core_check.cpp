@@ -193,23 +193,23 @@ int check_block(const std::vector<uint8_t>& flatv, const char* name) {
   std::vector<uint32_t> path_node(np), path_pc(np), tnode(T.max_ops + 1), tpc(T.max_ops + 1), key_hi(T.max_ops + 1);
   std::vector<uint8_t> path_depth(np), plen(T.max_ops + 1), tdepth(T.max_ops + 1), tkind(T.max_ops + 1);
   std::vector<txn::SOp> sh_ops(T.max_ops + 1);
-  v.path_node = path_node.data(), v.path_pc = path_pc.data(), v.path_depth = path_depth.data();
-  v.plen = plen.data(), v.tnode = tnode.data(), v.tpc = tpc.data(), v.tdepth = tdepth.data(), v.tkind = tkind.data(), v.key_hi = key_hi.data();
-  v.sh_ops = (n_traces & 1) ? sh_ops.data() : nullptr;  // both ways of reaching a txn's keys get exercised
+  v.s.path_node = path_node.data(), v.s.path_pc = path_pc.data(), v.s.path_depth = path_depth.data();
+  v.s.plen = plen.data(), v.s.tnode = tnode.data(), v.s.tpc = tpc.data(), v.s.tdepth = tdepth.data(), v.s.tkind = tkind.data(), v.s.key_hi = key_hi.data();
+  v.s.sh_ops = (n_traces & 1) ? sh_ops.data() : nullptr;  // both ways of reaching a txn's keys get exercised
   // the path-node table in two tiers, the first one tiny so that the spill tier is exercised
   std::vector<txn::PathNode> pc_fast(5), pc_slow(np);
   size_t map_n = 64;
   while (map_n < 2 * np) map_n <<= 1;
   std::vector<uint32_t> pc_map(map_n), pc_map_key(map_n);
   uint32_t pc_count = 0;
-  v.pc_fast = pc_fast.data(), v.pc_n_fast = (uint32_t)pc_fast.size(), v.pc_slow = pc_slow.data(), v.pc_n_slow = (uint32_t)pc_slow.size();
-  v.pc_map = pc_map.data(), v.pc_map_key = pc_map_key.data(), v.pc_map_mask = (uint32_t)map_n - 1, v.pc_count = &pc_count;
+  v.s.pc_fast = pc_fast.data(), v.s.pc_n_fast = (uint32_t)pc_fast.size(), v.s.pc_slow = pc_slow.data(), v.s.pc_n_slow = (uint32_t)pc_slow.size();
+  v.s.pc_map = pc_map.data(), v.s.pc_map_key = pc_map_key.data(), v.s.pc_map_mask = (uint32_t)map_n - 1, v.s.pc_count = &pc_count;
   txn::Cursors cur;
   memset(&cur, 0, sizeof cur);
   cur.n_nodes = n_pre_nodes, cur.n_children = (uint32_t)A.child_pool.size(), cur.key_bytes = B.key_cursor;
   cur.state_root = b2.state_root, cur.txn_root = NODE_EMPTY, cur.receipt_root = NODE_EMPTY;
   v.cur = &cur;
-  v.a_nodes = &cur.n_nodes, v.a_children = &cur.n_children, v.a_keys = &cur.key_bytes, v.a_max_level = &cur.max_level;
+  v.s.a_nodes = &cur.n_nodes, v.s.a_children = &cur.n_children, v.s.a_keys = &cur.key_bytes, v.s.a_max_level = &cur.max_level;
   // ---- the kernels, in launch order ----
   txn::AcctInit ai{table - 1, b2.state_root, join_storage.data(), join_root.data()};
   for (uint32_t t = 0; t < n_traces; t++) txn::acct_claim(v, ai, t);
