@@ -485,8 +485,12 @@ def run_b200(args, rank, world, local_rank):
     # BlockTrace for the library would place them; every step copies them to the device again
     flats = [ctx.pinned_copy(f) for f in flats]
 
-    def decode_step():
-        outs = ctx.blocks_decode_batch_view(flats)
+    # a timed end-to-end step decodes every block e2e_mult times in one call: the pipeline's ramp at both ends of a call
+    # is then a smaller share, as in a node that keeps feeding blocks
+    e2e_mult = max(1, args.e2e_mult)
+
+    def decode_step(mult=1):
+        outs = ctx.blocks_decode_batch_view(flats * mult)
         total = 0
         for o in outs:
             if isinstance(o, Exception):
@@ -501,7 +505,7 @@ def run_b200(args, rank, world, local_rank):
     st = ctx.stats()
     on_device = int(st["txn_loops_on_gpu"])
     # the blocks a replay covers: the last block of every lane is what stays resident in HBM
-    resident = min(n_blocks, int(os.environ.get("PPD_MAX_LANES", "64")))
+    resident = ctx.replay_lanes()
 
     def replay(what):
         """device time per step of the selected stages, every lane replaying them concurrently on resident data"""
@@ -527,7 +531,7 @@ def run_b200(args, rank, world, local_rank):
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        ir_len = decode_step()
+        ir_len = decode_step(e2e_mult)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     barrier()
@@ -547,17 +551,18 @@ def run_b200(args, rank, world, local_rank):
     perms_all = sum_over_ranks(float(st["node_permutations"] + st["key_permutations"]))
     keys_all = sum_over_ranks(float(st["key_hashes"]))
     host_busy_all = sum_over_ranks(float(st["host_busy_ms"]))
+    blocks_step = n_blocks * e2e_mult  # blocks of one end-to-end step on this GPU (the stats of the last call cover them)
     dev_s_per_step = hash_ms / 1e3
     e2e_s_per_step = e2e_s / args.steps
     sm_mhz = clocks.get("sm_mhz")
     alu_peak = ALU_LANES_PER_SM_CLK * N_SM * (sm_mhz or peaks["sm_max_mhz"]) * 1e6  # instr/s on one GPU
     algo_bytes = st["node_bytes"] + 32 * st["nodes_hashed"]  # L + 32 per hashed node (this rank)
-    achieved_gbs = algo_bytes * (resident / n_blocks) / dev_s_per_step / 1e9
+    achieved_gbs = algo_bytes * (resident / blocks_step) / dev_s_per_step / 1e9
     traffic, traffic_src = load_traffic()
     level_launches = max(1, int(st["level_launches"]))
     wit_bytes_all = sum_over_ranks(float(st["witness_bytes"]))
     wit_ins_all = sum_over_ranks(float(st["witness_instructions"]))
-    blocks_all = world * n_blocks
+    blocks_all = world * blocks_step
     h2d_all, d2h_all = sum_over_ranks(float(st["h2d_bytes"])), sum_over_ranks(float(st["d2h_bytes"]))
     e2e_bps = blocks_all / e2e_s_per_step
     # ---- the reference's node count for the same block (its hashing work is the unit both arms are quoted in) ----
@@ -598,14 +603,14 @@ def run_b200(args, rank, world, local_rank):
     per_block_h2d, per_block_d2h = h2d_all / blocks_all, d2h_all / blocks_all
     blocks_replayed = world * resident
     bounds = {
-        "device_pipeline": blocks_replayed / (all_ms / 1e3),
+        "device_pipeline": blocks_replayed / ((hash_ms + parse_ms + dump_ms) / 1e3),
         "pcie": world * pcie_gbs * 1e9 / max(per_block_h2d, per_block_d2h),
         "host_cores": cores / (per_block_host_ms / 1e3) if per_block_host_ms else None,
     }
     limiter = min((k for k in bounds if bounds[k]), key=lambda k: bounds[k])
     line = {
         "metric": "mpt_nodes_keccak_hashed_per_sec",
-        "value": norm * nodes_all * (resident / n_blocks) / dev_s_per_step,
+        "value": norm * nodes_all * (resident / blocks_step) / dev_s_per_step,
         "unit": "nodes/s",
         "n_gpus": world,
         "steps": args.steps,
@@ -620,14 +625,15 @@ def run_b200(args, rank, world, local_rank):
             "workload": f"C2 mainnet-shaped blocks (BASELINE.json configs[1]): 20k touched accounts in a virtual 16^7-account state, 200 txns each; a batch of {n_blocks} independent blocks per GPU per step, one lane (stream + pools) per block, {threads} host thread(s) per GPU",
             "scale": args.scale,
             "departures": C2_DEPARTURES,
-            "blocks_per_step_per_gpu": n_blocks,
+            "blocks_per_step_per_gpu": blocks_step,
+            "distinct_blocks_per_gpu": n_blocks,
             "host_threads_per_gpu": threads,
             "host_cores": cores,
-            "flat_block_bytes_per_step": flat_total,
+            "flat_block_bytes_per_step": flat_total * e2e_mult,
             "ir_dump_bytes_per_step": ir_len,
             "arena_nodes": st["arena_nodes"],
             "levels": st["levels"],
-            "txn_loops_on_device_per_step": on_device,
+            "txn_loops_on_device_per_step": int(st["txn_loops_on_gpu"]),
             "l2": "flushed between timed device-resident steps (256 MiB write)",
             "parallelism": f"blocks sharded over {world} GPU(s), no data-path collective",
         },
@@ -639,7 +645,7 @@ def run_b200(args, rank, world, local_rank):
         "device_ms_per_step": {"hashing": hash_ms, "parse": parse_ms, "txn_loop": txn_ms, "dump": dump_ms, "whole_pipeline": all_ms, "blocks_replayed": blocks_replayed,
                                "note": "each stage replayed alone with all lanes concurrent (the resident block of every lane), then all of them together"},
         "blocks_per_sec_hashing_only": blocks_replayed / dev_s_per_step,
-        "permutations_per_sec": perms_all * (resident / n_blocks) / dev_s_per_step,
+        "permutations_per_sec": perms_all * (resident / blocks_step) / dev_s_per_step,
         "nodes_hashed_per_step": nodes_all,
         "key_hashes_per_step": keys_all,
         "e2e": {
@@ -650,7 +656,7 @@ def run_b200(args, rank, world, local_rank):
             "single_block_latency_ms": 1e3 * min(single),
             "h2d_bytes_per_step": h2d_all,
             "d2h_bytes_per_step": d2h_all,
-            "boundary_bytes_per_step": {"flat_blocks": flat_total * world, "ir_dumps": ir_len * world},
+            "boundary_bytes_per_step": {"flat_blocks": flat_total * e2e_mult * world, "ir_dumps": ir_len * world},
             "host_busy_ms_per_block": per_block_host_ms,
             "note": "ppd_blocks_decode_batch: FlatBlocks (page-locked host memory) -> IrDumps (host); every host<->device copy and all host work (flat input reading, descriptor tables, launches) inside the timed region",
         },
@@ -662,17 +668,18 @@ def run_b200(args, rank, world, local_rank):
             "pcie_gbs_per_direction": pcie_gbs,
             "pcie_bytes_per_block": {"h2d": per_block_h2d, "d2h": per_block_d2h},
             "host_busy_ms_per_block": per_block_host_ms,
-            "note": "upper bounds on end-to-end blocks/s: the device pipeline replayed on resident data; each GPU's PCIe link at the measured pinned-copy rate (both directions busy) over the bytes a block moves in the busier direction; the box's cores over the host time a block costs outside waits for the device",
+            "device_pipeline_lockstep": blocks_replayed / (all_ms / 1e3),
+            "note": "upper bounds on end-to-end blocks/s: device_pipeline = the kernels that fill the device (witness parse, key hashing and both level sweeps, IR sizing and emit), each stage replayed by all resident lanes at once, times added; the txn loops run beside them, one SM each (device_pipeline_lockstep: every lane replaying its whole pipeline from the same instant, loops included: stages of different lanes do not overlap there as they do in a running pipeline); pcie = each GPU's link at the measured pinned-copy rate over the bytes a block moves in the busier direction; host_cores = the box's cores over the CPU time a block costs its host thread",
         },
         "gpu_launches": int(st["kernel_launches"]) * args.steps,
         "clocks": clocks,
         "roofline": {
             "bound": "alu",
             "kernel": "hash_level_kernel + keccak256_batch_kernel (all level launches of the batch, lanes concurrent)",
-            "achieved": (st["node_permutations"] + st["key_permutations"]) * (resident / n_blocks) * ALU_OPS_PER_PERM / dev_s_per_step / 1e12,
+            "achieved": (st["node_permutations"] + st["key_permutations"]) * (resident / blocks_step) * ALU_OPS_PER_PERM / dev_s_per_step / 1e12,
             "peak": alu_peak / 1e12,
             "unit": "Tinstr/s",
-            "frac": (st["node_permutations"] + st["key_permutations"]) * (resident / n_blocks) * ALU_OPS_PER_PERM / dev_s_per_step / alu_peak,
+            "frac": (st["node_permutations"] + st["key_permutations"]) * (resident / blocks_step) * ALU_OPS_PER_PERM / dev_s_per_step / alu_peak,
             "traffic": traffic,
             "traffic_source": traffic_src,
             "model": f"{ALU_OPS_PER_PERM} ALU-pipe (LOP3/SHF) instructions per keccak-f[1600] permutation (SURVEY.md 8d); peak = {ALU_LANES_PER_SM_CLK} lanes/clk/SM x {N_SM} SMs x SM clock sampled under load",
@@ -697,11 +704,11 @@ def run_b200(args, rank, world, local_rank):
             "instructions_per_step": wit_ins_all,
             "ms_per_step": parse_ms,
             "bound": "hbm",
-            "achieved": (7.0 * wit_bytes_all * (resident / n_blocks) / world / (parse_ms / 1e3) / 1e9) if parse_ms else None,
+            "achieved": (7.0 * wit_bytes_all * (resident / blocks_step) / world / (parse_ms / 1e3) / 1e9) if parse_ms else None,
             "peak": peaks["hbm_gbs"],
             "unit": "GB/s",
-            "frac": (7.0 * wit_bytes_all * (resident / n_blocks) / world / (parse_ms / 1e3) / 1e9 / peaks["hbm_gbs"]) if parse_ms else None,
-            "instructions_per_sec": (wit_ins_all * (resident / n_blocks) / (parse_ms / 1e3)) if parse_ms else None,
+            "frac": (7.0 * wit_bytes_all * (resident / blocks_step) / world / (parse_ms / 1e3) / 1e9 / peaks["hbm_gbs"]) if parse_ms else None,
+            "instructions_per_sec": (wit_ins_all * (resident / blocks_step) / (parse_ms / 1e3)) if parse_ms else None,
             "note": "algorithmic bytes = 7 per witness byte for the boundary search (read the byte, write and re-read its 4-byte exit link, write its 2-byte step link)",
         },
         "txn_loop": {
@@ -713,11 +720,11 @@ def run_b200(args, rank, world, local_rank):
         "dump": {
             "kernels": "ppd_dump.cu: ir_size_kernel + ir_emit_kernel (one thread block per IR)",
             "ms_per_step": dump_ms,
-            "bytes_replayed": ir_len * resident / n_blocks,
-            "achieved": (ir_len * (resident / n_blocks) / (dump_ms / 1e3) / 1e9) if dump_ms else None,
+            "bytes_replayed": ir_len * resident / blocks_step,
+            "achieved": (ir_len * (resident / blocks_step) / (dump_ms / 1e3) / 1e9) if dump_ms else None,
             "unit": "GB/s written",
-            "frac_of_hbm": (ir_len * (resident / n_blocks) / (dump_ms / 1e3) / 1e9 / peaks["hbm_gbs"]) if dump_ms else None,
-            "frac_of_pcie": (ir_len * (resident / n_blocks) / (dump_ms / 1e3) / 1e9 / pcie_gbs) if dump_ms else None,
+            "frac_of_hbm": (ir_len * (resident / blocks_step) / (dump_ms / 1e3) / 1e9 / peaks["hbm_gbs"]) if dump_ms else None,
+            "frac_of_pcie": (ir_len * (resident / blocks_step) / (dump_ms / 1e3) / 1e9 / pcie_gbs) if dump_ms else None,
         },
     }
     if not args.no_split:
@@ -751,6 +758,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--scale", type=float, default=1.0, help="fraction of the C2 block size (1.0 = the named config)")
     ap.add_argument("--blocks-per-step", type=int, default=0, help="blocks per GPU per step (default 64, at most 64)")
+    ap.add_argument("--e2e-mult", type=int, default=2, help="an end-to-end step decodes every block this many times in one call")
     ap.add_argument("--ref-scale", type=float, default=1.0, help="size of the CPU arm's block (1.0 = the same config as the b200 arm)")
     ap.add_argument("--sweep", default="1000000,10000000", help="config-5 leaf counts measured beside the headline at N=1")
     ap.add_argument("--no-sweep", action="store_true")

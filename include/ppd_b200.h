@@ -52,7 +52,7 @@ typedef struct ppd_stats {
   uint64_t txn_loops_on_gpu;      /* blocks whose txn loop (decoding.rs:80-177: deltas, subsets, roots) ran on the device (ppd_txn.cu) */
   double txn_gpu_ms;              /* device time of those loops (CUDA events) */
   double dump_gpu_ms;             /* device time of the IrDump kernels (ppd_dump.cu) */
-  double host_busy_ms;            /* host time of the blocks' threads outside waits for the device, summed over blocks */
+  double host_busy_ms;            /* CPU time of the blocks' host threads (thread CPU clock: sleeping for the device does not count), summed over blocks */
   double host_wait_ms;            /* ... and their time waiting for the device */
 } ppd_stats;
 
@@ -98,6 +98,9 @@ int ppd_blocks_decode_batch(ppd_ctx* ctx, const uint8_t* const* flat_blocks, con
 #define PPD_REPLAY_DUMP 8u
 #define PPD_REPLAY_ALL 15u
 int ppd_replay_last(ppd_ctx* ctx, unsigned what, double* gpu_ms_out);
+/* How many lanes (= blocks) a replay covers: the lanes of the last decode call that still hold a block, at most 30 (every
+ * lane replays on a stream of its own, and the device runs 32 streams side by side). */
+size_t ppd_replay_lanes(const ppd_ctx* ctx);
 /* = ppd_replay_last(ctx, PPD_REPLAY_HASH, ...) */
 int ppd_replay_last_hashing(ppd_ctx* ctx, double* gpu_ms_out);
 /* = ppd_replay_last(ctx, PPD_REPLAY_PARSE, ...): the compact-witness kernels (instruction boundaries, stack machine, arena emit: the GPU form of

@@ -9,6 +9,8 @@
 //
 // The host never computes a Keccak or a node encoding.  If the CUDA device or the kernels are not
 // usable every entry point fails with PPD_ERR_CUDA: there is no CPU fallback.
+#include <time.h>
+
 #include "host_pipeline.h"
 #ifdef PPD_HOSTPROF
 #include "../../tools/hostprof_stub.h"  // development-only host profiler build (tools/hostprof); never defined for libppd_b200.so
@@ -395,14 +397,17 @@ namespace {
 // One block on one lane: parse, key hashes, shaping, sweep, dump.  A failure that is the block's own
 // (bad input, a reference panic site) is reported through *status; a CUDA failure is thrown.
 void decode_one_inner(ppd_ctx* c, Lane* L, const uint8_t* flat, size_t len, uint8_t** out, size_t* out_len, int* status, unsigned dump_workers);
-// host_busy_ms: what the block cost its host thread apart from waiting for the device (the quantity that bounds
-// blocks/s when several GPUs share the host's cores)
+// host_busy_ms: the CPU time the block cost its host thread (CLOCK_THREAD_CPUTIME_ID: sleeping for the device or for a
+// stream does not count, polling does) — the quantity that bounds blocks/s when several GPUs share the host's cores
+static double thread_cpu_ms() {
+  timespec ts;
+  clock_gettime(CLOCK_THREAD_CPUTIME_ID, &ts);
+  return 1e3 * (double)ts.tv_sec + 1e-6 * (double)ts.tv_nsec;
+}
 void decode_one(ppd_ctx* c, Lane* L, const uint8_t* flat, size_t len, uint8_t** out, size_t* out_len, int* status, unsigned dump_workers) {
-  const auto t0 = std::chrono::steady_clock::now();
-  const double wait0 = L->stats.host_wait_ms;
+  const double t0 = thread_cpu_ms();
   decode_one_inner(c, L, flat, len, out, out_len, status, dump_workers);
-  const double total = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-  L->stats.host_busy_ms += total - (L->stats.host_wait_ms - wait0);
+  L->stats.host_busy_ms += thread_cpu_ms() - t0;
 }
 void decode_one_inner(ppd_ctx* c, Lane* L, const uint8_t* flat, size_t len, uint8_t** out, size_t* out_len, int* status, unsigned dump_workers) {
   *out = nullptr, *out_len = 0;
@@ -687,10 +692,13 @@ static void replay_lane(Lane* L, unsigned what) {
   CUDA_OK(cudaGetLastError());
 }
 
+static const size_t REPLAY_LANES_MAX = 30;
+size_t ppd_replay_lanes(const ppd_ctx* c) { return c ? std::min(std::min(c->last_lanes_used, c->lanes.size()), REPLAY_LANES_MAX) : 0; }
 int ppd_replay_last(ppd_ctx* c, unsigned what, double* gpu_ms_out) {
   return guarded(c, [&] {
     size_t used = 0;
-    for (size_t w = 0; w < c->last_lanes_used && w < c->lanes.size(); w++) {
+    const size_t n_lanes = ppd_replay_lanes(c);
+    for (size_t w = 0; w < n_lanes; w++) {
       const Lane* L = c->lanes[w];
       used += ((what & PPD_REPLAY_PARSE) && L->has_last_parse) || ((what & PPD_REPLAY_HASH) && L->has_last) ||
               ((what & (PPD_REPLAY_TXN | PPD_REPLAY_DUMP)) && L->has_last_txn);
@@ -698,7 +706,7 @@ int ppd_replay_last(ppd_ctx* c, unsigned what, double* gpu_ms_out) {
     if (!used) fail(PPD_ERR_BAD_ARGUMENT, "nothing of the requested kind is resident");
     // all lanes start after ev0 on the main stream; the main stream then waits for every lane
     CUDA_OK(cudaEventRecord(c->ev0, c->st));
-    for (size_t w = 0; w < c->last_lanes_used; w++) {
+    for (size_t w = 0; w < n_lanes; w++) {
       Lane* L = c->lanes[w];
       CUDA_OK(cudaStreamWaitEvent(L->st, c->ev0, 0));
       replay_lane(L, what);

@@ -100,6 +100,7 @@ EXPORTS = [
     "ppd_trie_subroot_sorted_leaves_dev",
     "ppd_trie_root_from_children",
     "ppd_replay_last",
+    "ppd_replay_lanes",
     "ppd_replay_last_hashing",
     "ppd_replay_last_parse",
     "ppd_microbench",
@@ -138,6 +139,8 @@ class PpdLibrary:
         L.ppd_blocks_decode_batch.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
         L.ppd_trie_root_sorted_leaves.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_char_p]
         L.ppd_replay_last.argtypes = [ctypes.c_void_p, ctypes.c_uint, ctypes.POINTER(ctypes.c_double)]
+        L.ppd_replay_lanes.argtypes = [ctypes.c_void_p]
+        L.ppd_replay_lanes.restype = ctypes.c_size_t
         L.ppd_replay_last_hashing.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_double)]
         L.ppd_replay_last_parse.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_double)]
         L.ppd_microbench.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_uint32, ctypes.c_uint32, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_uint32)]
@@ -297,6 +300,10 @@ class Context:
         ms = ctypes.c_double()
         self._check(self.lib.L.ppd_replay_last(self.h, what, ctypes.byref(ms)))
         return ms.value
+
+    def replay_lanes(self) -> int:
+        """How many lanes (= resident blocks) replay_last covers."""
+        return int(self.lib.L.ppd_replay_lanes(self.h))
 
     def replay_last_hashing(self) -> float:
         ms = ctypes.c_double()
