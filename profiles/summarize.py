@@ -76,7 +76,7 @@ def main():
     if os.path.exists(p):
         items = launches(p)
         open(os.path.join(DST, f"{TAG}_launches_c2_summary.txt"), "w").write(
-            "ncu launch list of `python bench.py --steps 2 --warmup 3 --no-sweep` (64 blocks per step; first 4000 launches; --metrics gpu__time_duration.sum,dram__bytes_*;\n"
+            "ncu launch list of the bench command (profiles/capture*.sh says which: r01 64 blocks per step, first 4000 launches; r02 4 blocks per step, all launches; --metrics gpu__time_duration.sum,dram__bytes_*;\n"
             "--clock-control none).  Launches are serialised and cold-cache under ncu: read SHARES, not absolutes.\n\n"
             + kernel_table(items, f"all {len(items)} launches") + "\n\n"
             + kernel_table([o for o in items if "at::" not in o["kernel"] and "native" not in o["kernel"]], "this library's kernels only") + "\n")
@@ -92,8 +92,20 @@ def main():
     # ---- full capture of the level kernel (one block) ----
     rep = os.path.join(SRC, f"{TAG}_hash_level_full.ncu-rep")
     if os.path.exists(rep):
-        t, _ = full_table(rep, "ncu --set full, hash_level_kernel, the 17 level launches of one device-resident replay of one C2 block\n(PPD_HOST_THREADS=1, --blocks-per-step 1; --launch-skip 102 --launch-count 17)")
+        t, _ = full_table(rep, "ncu --set full, hash_level_kernel, the level launches of one device-resident replay of one C2 block\n(PPD_HOST_THREADS=1, --blocks-per-step 1; launch-skip / launch-count as in profiles/capture*.sh)")
         open(os.path.join(DST, f"{TAG}_hash_level_full.txt"), "w").write(t + "\n")
+    rep = os.path.join(SRC, f"{TAG}_txn_loop_full.ncu-rep")
+    if os.path.exists(rep):
+        more = ["smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio", "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+                "smsp__warps_active.avg.per_cycle_active", "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum"]
+        rows = raw_page(rep, FULL + more)
+        out = ["ncu --set full, txn_loop_kernel: two launches (16 txns each) of one config-2 block's loop (one thread block of 256 threads)", ""]
+        for r in rows:
+            out.append(r["Kernel Name"].split("(")[0] + "  grid " + r["Grid Size"])
+            for m in FULL + more:
+                if m in r:
+                    out.append(f"  {m:95s} {r[m]}")
+        open(os.path.join(DST, f"{TAG}_txn_loop_full.txt"), "w").write("\n".join(out) + "\n")
     # ---- config 5 ----
     p = os.path.join(SRC, f"{TAG}_launches_c5.csv")
     if os.path.exists(p):
@@ -147,8 +159,26 @@ def count_parse_kernels(path):
     return sum(1 for o in items[last:] if o["kernel"].startswith(PARSE_KERNELS))
 
 
+def count_kernel(path, name, blocks):
+    """launches of kernel `name` per block decode: the launches before the first replay (3 warm-up decodes of `blocks`
+    blocks each would need the program's structure; simpler: the level launches between two consecutive tile_exit launches)"""
+    items = launches(path)
+    for o in items:
+        o["kernel"] = o["kernel"].replace("<unnamed>::", "").replace("unnamed>::", "")
+    # the last decode of the capture runs one lane at a time only when blocks == 1; count over the whole capture instead
+    firsts = [i for i, o in enumerate(items) if o["kernel"].startswith("tile_exit")]
+    n_decodes = len(firsts)
+    # decodes are followed by replays (no tile_exit in a HASH replay): count the launches up to the first replay, i.e.
+    # within the first blocks * 3 decodes there are blocks * 3 * per_block of them
+    upto = firsts[min(len(firsts) - 1, blocks * 3)] if n_decodes > blocks * 3 else len(items)
+    n = sum(1 for o in items[:upto] if o["kernel"].startswith(name))
+    return n // (blocks * 3)
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 2 and sys.argv[1] == "--count-parse-kernels":
         print(count_parse_kernels(sys.argv[2]))
+    elif len(sys.argv) > 4 and sys.argv[1] == "--count-kernel":
+        print(count_kernel(sys.argv[2], sys.argv[3], int(sys.argv[4])))
     else:
         main()
