@@ -15,7 +15,7 @@ ncu $LIST -c 8000 --log-file $RAW/${TAG}_launches_c2.csv $B > $RAW/${TAG}_ncu_c2
 # 2. full capture of the level-hashing kernel: one block per step, the level launches of the first timed replay
 #    (31 level launches per decode / replay; 3 warm-up decodes + 3 warm-up replays come first)
 B1="python bench.py --steps 1 --warmup 3 --no-sweep --no-split --blocks-per-step 1 --e2e-mult 1"
-NL=$(python profiles/summarize.py --count-kernel $RAW/${TAG}_launches_c2.csv hash_level_kernel 4)
+NL=${NL:-31}  # level launches per block decode (profiles/r02_launches_block_summary.txt)
 echo "level launches per block: $NL"
 PPD_HOST_THREADS=1 $B1 > /dev/null 2>&1 && PPD_HOST_THREADS=1 ncu --set full --clock-control none --import-source on -k regex:hash_level_kernel \
     --launch-skip $((6 * NL)) --launch-count $NL -o $RAW/${TAG}_hash_level_full $B1 > $RAW/${TAG}_ncu_full.log 2>&1
