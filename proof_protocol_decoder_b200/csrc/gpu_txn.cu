@@ -411,7 +411,7 @@ int gpu_block(ppd_ctx* c, Lane* L, Job& J, const uint8_t* flat, size_t len, uint
     uint32_t cap = 1u << 14;
     while (cap < 2 * tn) cap <<= 1;
     big_off[i] = big_words, big_cap[i] = cap;
-    big_words += 2ull * cap;
+    big_words += 3ull * cap;  // table keys, table slots, parents
   }
   IrDumpPlanView P{};
   uint64_t* d_big_off;

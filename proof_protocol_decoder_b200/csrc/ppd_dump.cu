@@ -14,6 +14,7 @@
 // An IR the kernels cannot lay out (more unique touched nodes than the set holds, a node shared by two
 // tries of the IR, an untouched child whose encoding is shorter than 32 bytes, which the subset keeps
 // expanded) is flagged and serialised by the host instead.
+#include <cstddef>
 #include <cstdint>
 
 #include "../../include/ppd_flat.h"
@@ -35,9 +36,10 @@ struct SharedSet {
   uint32_t key[SET_CAP];   // node id or NODE_EMPTY
   uint32_t slot[SET_CAP];  // index into the u_* arrays
   uint32_t u_node[MAX_UNIQ], u_size[MAX_UNIQ], u_off[MAX_UNIQ];
+  uint32_t u_par[MAX_UNIQ];  // index of the touched node's touched parent (ir_size_kernel)
 };
 struct Set {
-  uint32_t *key, *slot, *u_node, *u_size, *u_off;
+  uint32_t *key, *slot, *u_node, *u_size, *u_off, *u_par;
   uint32_t shift, mask, max_uniq;
   uint32_t n_uniq, n_done, flag;  // (this struct lives in shared memory)
 };
@@ -59,11 +61,11 @@ __device__ void set_bind(Set& s, SharedSet& sm, const IrDumpPlanView& P, uint32_
   if (threadIdx.x == 0) {
     const uint64_t big = P.big_off ? P.big_off[ir] : ~0ull;
     if (big == ~0ull) {
-      s.key = sm.key, s.slot = sm.slot, s.u_node = sm.u_node, s.u_size = sm.u_size, s.u_off = sm.u_off;
+      s.key = sm.key, s.slot = sm.slot, s.u_node = sm.u_node, s.u_size = sm.u_size, s.u_off = sm.u_off, s.u_par = sm.u_par;
       s.mask = SET_CAP - 1, s.shift = 19, s.max_uniq = MAX_UNIQ;
     } else {
       const uint32_t cap = P.big_cap[ir];  // a power of two >= 2 x the IR's touched slots
-      s.key = P.big_scratch + big, s.slot = s.key + cap;
+      s.key = P.big_scratch + big, s.slot = s.key + cap, s.u_par = s.slot + cap;  // (3 x cap words per big IR)
       s.u_node = P.u_node + tb, s.u_size = P.u_size + tb, s.u_off = P.u_off + tb;
       s.mask = cap - 1, s.shift = 32 - (31 - __clz(cap)), s.max_uniq = cap / 2;
     }
@@ -166,26 +168,85 @@ __global__ void __launch_bounds__(DUMP_THREADS) ir_size_kernel(ArenaView A, IrDu
   set_bind(s, *reinterpret_cast<SharedSet*>(smem_raw), P, ir, tb);
   build_set(s, P.touched + tb, tn, A, true);
   const uint32_t nu = min(s.n_uniq, s.max_uniq);
-  for (uint32_t k = threadIdx.x; k < nu; k += blockDim.x) s.u_size[k] = UNSET, s.u_off[k] = UNSET;
+  constexpr uint32_t PLACED = 0x80000000u;
+  for (uint32_t k = threadIdx.x; k < nu; k += blockDim.x) s.u_par[k] = UNSET;
   __syncthreads();
-  // ---- sizes, bottom-up: a node is sized once all its touched children are ----
-  for (int round = 0; round < 80; round++) {
-    __syncthreads();
-    if (s.n_done >= nu) break;  // uniform: nothing writes between the barrier and this read
-    __syncthreads();
+  // ---- pass 1 (the only one that waits for HBM): per touched node, the bytes that do not depend on other touched
+  // nodes (its own fields, its untouched children: 1 byte empty, 33 hashed), how many touched children it has, and
+  // every touched child's parent.  The touched nodes of a trie form a tree: sizes then flow up it in shared memory. ----
+  {
     uint32_t local_flag = 0;
     for (uint32_t k = threadIdx.x; k < nu; k += blockDim.x) {
-      if (s.u_size[k] != UNSET) continue;
-      uint32_t sz = node_size(A, s, s.u_node[k], &local_flag);
-      if (sz != UNSET) {
-        s.u_size[k] = sz;  // racy readers see UNSET or the final value
-        atomicAdd(&s.n_done, 1u);
+      const NodeRec r = A.nodes[s.u_node[k]];
+      const uint32_t kind = r.w0 & 0xff, nlen = (r.w0 >> 16) & 0xff;
+      uint32_t fixed = 0, pend = 0;
+      auto child = [&](uint32_t c) {
+        if (c == NODE_EMPTY) return 1u;
+        if (is_hash_id(c)) return 33u;
+        const uint32_t kc = set_find(s, c);
+        if (kc != NOT_FOUND) {
+          if (atomicCAS(&s.u_par[kc], UNSET, k) != UNSET) local_flag = 1;  // a node with two touched parents
+          pend++;
+          return 0u;
+        }
+        if (A.ref_len[c] != 32 && node_kind(A, c) != NK_ROOT) local_flag = 1;  // an untouched child the subset keeps expanded
+        return 33u;
+      };
+      switch (kind) {
+        case NK_LEAF:
+          fixed = 1 + 1 + nlen + 4 + r.a2;
+          break;
+        case NK_LEAF_ACCOUNT:
+          fixed = 1 + 1 + nlen + 4 + account_rlp_len(A.accounts[r.a1]);
+          break;
+        case NK_EXT:
+          fixed = 1 + 1 + nlen + child(r.a1);
+          break;
+        case NK_BRANCH: {
+          const uint32_t mask = r.a1 & 0xffff, nk = __popc(mask);
+          uint32_t cid[16];
+#pragma unroll
+          for (uint32_t j = 0; j < 16; j++) cid[j] = j < nk ? A.child_pool[r.a0 + j] : NODE_EMPTY;  // (all in flight together)
+          fixed = 1 + (16 - nk) + 4;
+#pragma unroll
+          for (uint32_t j = 0; j < 16; j++)
+            if (j < nk) fixed += child(cid[j]);
+          break;
+        }
+        default:  // NK_ROOT is never inserted
+          local_flag = 1;
+          fixed = 33;
       }
+      s.u_size[k] = fixed;
+      s.u_off[k] = pend;  // (until the segments are laid out: the touched children that have yet to report)
     }
     if (local_flag) s.flag = 1;
   }
   __syncthreads();
-  if (threadIdx.x == 0 && s.n_done < nu) s.flag = 1;
+  // ---- sizes flow up: a node without touched children is final; it adds its size to its parent's, and whoever
+  // reports last to a parent carries on from there ----
+  for (uint32_t k = threadIdx.x; k < nu; k += blockDim.x) {
+    if (s.u_off[k] != 0) continue;
+    uint32_t cur = k;
+    for (uint32_t guard = 0; guard < 128; guard++) {
+      const uint32_t p = s.u_par[cur];
+      if (p == UNSET) break;
+      atomicAdd(&s.u_size[p], *reinterpret_cast<volatile uint32_t*>(&s.u_size[cur]));
+      __threadfence_block();
+      if (atomicSub(&s.u_off[p], 1u) != 1u) break;
+      __threadfence_block();
+      cur = p;
+    }
+  }
+  __syncthreads();
+  {
+    uint32_t stuck = 0;
+    for (uint32_t k = threadIdx.x; k < nu; k += blockDim.x) {
+      stuck |= s.u_off[k];
+      s.u_off[k] = UNSET;
+    }
+    if (stuck) s.flag = 1;  // (a cycle of parents: not a trie)
+  }
   __syncthreads();
   // ---- segments: literals and tries in output order.  Every segment's size in parallel, then a block-wide
   // exclusive scan in chunks of DUMP_THREADS (an IR of a mainnet-shaped block has ~250 segments) ----
@@ -252,45 +313,70 @@ __global__ void __launch_bounds__(DUMP_THREADS) ir_size_kernel(ArenaView A, IrDu
     }
   }
   __syncthreads();
-  // ---- offsets, top-down: a node with an offset places its touched children ----
-  // u_size's top bit marks "children placed"
-  for (int round = 0; round < 80; round++) {
-    __syncthreads();
-    if (s.flag || s.n_done >= nu) break;  // uniform: nothing writes between the barrier and this read
-    __syncthreads();
+  // ---- offsets.  Pass 2 over the arena (warm): every touched node places its touched children RELATIVE to its own
+  // first byte; then the offsets flow down the tree in shared memory (a trie's root got its offset from its segment) ----
+  if (!s.flag) {
     for (uint32_t k = threadIdx.x; k < nu; k += blockDim.x) {
-      if (s.u_off[k] == UNSET || (s.u_size[k] & 0x80000000u)) continue;
       const NodeRec r = A.nodes[s.u_node[k]];
       const uint32_t kind = r.w0 & 0xff, nlen = (r.w0 >> 16) & 0xff;
-      uint32_t dummy = 0;
       if (kind == NK_EXT) {
-        uint32_t c = is_hash_id(r.a1) ? NOT_FOUND : set_find(s, r.a1);
+        const uint32_t c = is_hash_id(r.a1) ? NOT_FOUND : set_find(s, r.a1);
         if (c != NOT_FOUND) {
-          if (s.u_off[c] != UNSET) s.flag = 1;
-          s.u_off[c] = s.u_off[k] + 2 + nlen;
+          if (s.u_off[c] != UNSET) s.flag = 1;  // (also the root of a trie of this IR)
+          s.u_off[c] = 2 + nlen;
         }
       } else if (kind == NK_BRANCH) {
-        const uint32_t mask = r.a1 & 0xffff;
-        uint32_t off = s.u_off[k] + 1;
+        const uint32_t mask = r.a1 & 0xffff, nk = __popc(mask);
+        uint32_t cid[16];
+#pragma unroll
+        for (uint32_t j = 0; j < 16; j++) cid[j] = j < nk ? A.child_pool[r.a0 + j] : NODE_EMPTY;
+        uint32_t off = 1;
         for (uint32_t i = 0, j = 0; i < 16; i++) {
           if (!(mask & (1u << i))) {
             off += 1;
             continue;
           }
-          uint32_t cid = A.child_pool[r.a0 + j++];
-          uint32_t c = is_hash_id(cid) ? NOT_FOUND : set_find(s, cid);
+          uint32_t c_id = NODE_EMPTY;
+#pragma unroll
+          for (uint32_t z = 0; z < 16; z++)
+            if (z == j) c_id = cid[z];
+          j++;
+          const uint32_t c = is_hash_id(c_id) ? NOT_FOUND : set_find(s, c_id);
           if (c != NOT_FOUND) {
             if (s.u_off[c] != UNSET) s.flag = 1;
             s.u_off[c] = off;
-            off += s.u_size[c] & 0x7fffffffu;
+            off += s.u_size[c];
           } else {
-            off += child_size(A, s, cid, &dummy);
+            off += 33;
           }
         }
       }
-      s.u_size[k] |= 0x80000000u;
-      atomicAdd(&s.n_done, 1u);
     }
+  }
+  __syncthreads();
+  for (int round = 0; round < 130; round++) {
+    __syncthreads();
+    if (s.flag || s.n_done >= nu) break;  // uniform: nothing writes between the barrier and this read
+    __syncthreads();
+    uint32_t progressed = 0;
+    for (uint32_t k = threadIdx.x; k < nu; k += blockDim.x) {
+      if (*reinterpret_cast<volatile uint32_t*>(&s.u_size[k]) & PLACED) continue;
+      const uint32_t p = s.u_par[k];
+      uint32_t off = *reinterpret_cast<volatile uint32_t*>(&s.u_off[k]);
+      if (p != UNSET) {
+        if (!(*reinterpret_cast<volatile uint32_t*>(&s.u_size[p]) & PLACED)) continue;
+        __threadfence_block();
+        off += *reinterpret_cast<volatile uint32_t*>(&s.u_off[p]);
+      } else if (off == UNSET) {
+        s.flag = 1;  // a touched node no trie of the IR reaches
+        continue;
+      }
+      s.u_off[k] = off;
+      __threadfence_block();
+      atomicOr(&s.u_size[k], PLACED);
+      progressed++;
+    }
+    if (progressed) atomicAdd(&s.n_done, progressed);
   }
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -502,7 +588,7 @@ void launch_ir_size(const ArenaView& A, const IrDumpPlanView& P, uint32_t n_ir, 
 }
 void launch_ir_emit(const ArenaView& A, const IrDumpPlanView& P, uint32_t n_ir, uint8_t* out, cudaStream_t st) {
   if (!n_ir) return;
-  ir_emit_kernel<<<n_ir, DUMP_THREADS, sizeof(SharedSet), st>>>(A, P, out);
+  ir_emit_kernel<<<n_ir, DUMP_THREADS, offsetof(SharedSet, u_par), st>>>(A, P, out);  // (no parents there: two thread blocks per SM)
 }
 
 }  // namespace ppd
