@@ -168,7 +168,7 @@ __global__ void __launch_bounds__(DUMP_THREADS) ir_size_kernel(ArenaView A, IrDu
   set_bind(s, *reinterpret_cast<SharedSet*>(smem_raw), P, ir, tb);
   build_set(s, P.touched + tb, tn, A, true);
   const uint32_t nu = min(s.n_uniq, s.max_uniq);
-  constexpr uint32_t PLACED = 0x80000000u;
+  constexpr uint32_t PLACED = 0x80000000u, NO_KIDS = 0x40000000u;
   for (uint32_t k = threadIdx.x; k < nu; k += blockDim.x) s.u_par[k] = UNSET;
   __syncthreads();
   // ---- pass 1 (the only one that waits for HBM): per touched node, the bytes that do not depend on other touched
@@ -218,7 +218,7 @@ __global__ void __launch_bounds__(DUMP_THREADS) ir_size_kernel(ArenaView A, IrDu
           fixed = 33;
       }
       s.u_size[k] = fixed;
-      s.u_off[k] = pend;  // (until the segments are laid out: the touched children that have yet to report)
+      s.u_off[k] = pend ? pend : NO_KIDS;  // (until the segments are laid out: the touched children that have yet to report)
     }
     if (local_flag) s.flag = 1;
   }
@@ -226,7 +226,7 @@ __global__ void __launch_bounds__(DUMP_THREADS) ir_size_kernel(ArenaView A, IrDu
   // ---- sizes flow up: a node without touched children is final; it adds its size to its parent's, and whoever
   // reports last to a parent carries on from there ----
   for (uint32_t k = threadIdx.x; k < nu; k += blockDim.x) {
-    if (s.u_off[k] != 0) continue;
+    if (s.u_off[k] != NO_KIDS) continue;  // (a parent's count may reach 0 while this loop runs: it is carried on by its last child)
     uint32_t cur = k;
     for (uint32_t guard = 0; guard < 128; guard++) {
       const uint32_t p = s.u_par[cur];
@@ -242,7 +242,7 @@ __global__ void __launch_bounds__(DUMP_THREADS) ir_size_kernel(ArenaView A, IrDu
   {
     uint32_t stuck = 0;
     for (uint32_t k = threadIdx.x; k < nu; k += blockDim.x) {
-      stuck |= s.u_off[k];
+      stuck |= s.u_off[k] & ~NO_KIDS;
       s.u_off[k] = UNSET;
     }
     if (stuck) s.flag = 1;  // (a cycle of parents: not a trie)

@@ -512,6 +512,7 @@ def test_full_size_config2_block_bit_exact(ctx, oracle):
             if v is not None:
                 os.environ[k] = v
     assert st["witnesses_on_gpu"] == 1 and st["witness_instructions"] > 1_000_000
+    assert st["txn_loops_on_gpu"] == 1, "the bench's block fell back to the host path (a flag of the device txn loop or of the IR layout)"
     want = oracle.block_decode(flat)
     assert len(got) == len(want) > 50_000_000
     assert got == want
