@@ -398,9 +398,7 @@ namespace {
 // words, the bytes up to the first 4-byte boundary and after the last one are stored one by one, everything in
 // between as aligned words re-aligned with funnel shifts (8 word stores instead of 33 byte stores; hashed-out
 // children are most of an IR's bytes).
-__device__ __forceinline__ uint8_t* put_hash(uint8_t* q, const uint8_t* h32) {
-  const uint4* src = reinterpret_cast<const uint4*>(h32);
-  const uint4 x = __ldg(src), y = __ldg(src + 1);
+__device__ __forceinline__ uint8_t* put_hash_regs(uint8_t* q, const uint4 x, const uint4 y) {
   const uint32_t w[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
   uint32_t S[10];
   S[0] = (uint32_t)PPD_NODE_HASH | (w[0] << 8);
@@ -418,6 +416,10 @@ __device__ __forceinline__ uint8_t* put_hash(uint8_t* q, const uint8_t* h32) {
   const uint32_t done = head + 4 * nwords;
   for (uint32_t i = done; i < 33; i++) q[i] = (uint8_t)(S[i >> 2] >> (8 * (i & 3)));
   return q + 33;
+}
+__device__ __forceinline__ uint8_t* put_hash(uint8_t* q, const uint8_t* h32) {
+  const uint4* src = reinterpret_cast<const uint4*>(h32);
+  return put_hash_regs(q, __ldg(src), __ldg(src + 1));
 }
 __device__ __forceinline__ uint8_t* put_u32(uint8_t* q, uint32_t v) {
   q[0] = (uint8_t)v, q[1] = (uint8_t)(v >> 8), q[2] = (uint8_t)(v >> 16), q[3] = (uint8_t)(v >> 24);
@@ -492,14 +494,58 @@ __device__ void emit_node(const ArenaView& A, const Set& s, uint32_t u, uint8_t*
       put_child(q, A, s, r.a1);
       break;
     case NK_BRANCH: {
+      // Children that are not touched themselves are 33-byte hashes gathered from all over the ref / hash pools: the
+      // child ids are loaded together, then the hashes four children at a time (eight 16-byte loads in flight), so a
+      // branch costs six round trips to memory instead of two per child.
       *q++ = PPD_NODE_BRANCH;
-      const uint32_t mask = r.a1 & 0xffff;
-      for (uint32_t i = 0, j = 0; i < 16; i++) {
-        if (mask & (1u << i))
-          q = put_child(q, A, s, A.child_pool[r.a0 + j++]);
-        else
-          *q++ = PPD_NODE_EMPTY;
+      const uint32_t mask = r.a1 & 0xffff, nk = __popc(mask);
+      uint32_t cid[16];
+#pragma unroll
+      for (uint32_t j = 0; j < 16; j++) cid[j] = j < nk ? A.child_pool[r.a0 + j] : NODE_EMPTY;
+      uint32_t m = mask;
+      int prev_slot = -1;
+#pragma unroll
+      for (uint32_t g = 0; g < 16; g += 4) {
+        if (g >= nk) break;
+        const uint4* src[4];
+        uint32_t skip[4];
+        uint4 x[4], y[4];
+#pragma unroll
+        for (uint32_t z = 0; z < 4; z++) {
+          const uint32_t c = cid[g + z];
+          src[z] = nullptr, skip[z] = 0;
+          if (g + z >= nk) continue;
+          if (c == NODE_EMPTY) {
+            skip[z] = NOT_FOUND;  // (not in a compact child row; sized as one byte by ir_size_kernel)
+          } else if (is_hash_id(c)) {
+            src[z] = reinterpret_cast<const uint4*>(A.hash_pool + 32ull * (c - HASH_ID_BASE));
+          } else {
+            const uint32_t k = set_find(s, c);
+            if (k != NOT_FOUND)
+              skip[z] = s.u_size[k];  // touched itself: it writes its own bytes
+            else
+              src[z] = reinterpret_cast<const uint4*>(A.ref + 32ull * c);
+          }
+        }
+#pragma unroll
+        for (uint32_t z = 0; z < 4; z++)
+          if (src[z]) x[z] = __ldg(src[z]), y[z] = __ldg(src[z] + 1);
+#pragma unroll
+        for (uint32_t z = 0; z < 4; z++) {
+          if (g + z >= nk) continue;
+          const int slot = __ffs((int)m) - 1;
+          m &= m - 1;
+          for (int e = prev_slot + 1; e < slot; e++) *q++ = PPD_NODE_EMPTY;
+          prev_slot = slot;
+          if (src[z])
+            q = put_hash_regs(q, x[z], y[z]);
+          else if (skip[z] == NOT_FOUND)
+            *q++ = PPD_NODE_EMPTY;
+          else
+            q += skip[z];
+        }
       }
+      for (int e = prev_slot + 1; e < 16; e++) *q++ = PPD_NODE_EMPTY;
       put_u32(q, 0);
       break;
     }
