@@ -145,7 +145,7 @@ struct SlotGuard {
 };
 inline int parse_slots() {
   const char* e = getenv("PPD_PARSE_SLOTS");
-  int v = e ? atoi(e) : 4;
+  int v = e ? atoi(e) : 8;
   return v < 1 ? 1 : v;
 }
 
