@@ -81,7 +81,11 @@ bool gpu_pre_image(Lane* L, Job& J, BlockJob& b, bool check_version, Slots* slot
     t_prev = now;
   };
   SlotGuard slot(slots, &L->stats.host_wait_ms);
-  auto sync_in_slot = [&] { slots ? lane_sync_poll(L) : lane_sync(L); };
+  // (PPD_SLOT_POLL=1: poll instead of sleeping while a parse slot is held — round 1's host-heavy pipeline woke sleeping
+  // threads late; with the txn loop on the device the cores are mostly idle, and polling threads of several GPUs' ranks
+  // would take them from each other)
+  static const bool slot_poll = getenv("PPD_SLOT_POLL") != nullptr && atoi(getenv("PPD_SLOT_POLL")) != 0;
+  auto sync_in_slot = [&] { (slots && slot_poll) ? lane_sync_poll(L) : lane_sync(L); };
   // the result words a host thread waits for: written into page-locked memory by a kernel when the whole block stays on
   // the device (a copy engine would serve them behind every bulk upload other lanes have queued)
   auto small_to_host = [&](void* dst, const void* src, size_t bytes) {
