@@ -48,6 +48,7 @@ typedef enum ppd_status {
   PPD_PANIC_PRE_IMAGE_ACCOUNT_DECODE = 44,    /* processed_block_trace.rs:91, compact_to_partial_trie.rs:176 */
   PPD_PANIC_UNIMPLEMENTED_PRE_IMAGE = 45,     /* todo!() at processed_block_trace.rs:144,161,167 */
   PPD_PANIC_KEY_IS_PREFIX_OF_KEY = 46,        /* Nibbles::get_nibble(0) on an empty postfix */
+  PPD_PANIC_U256_FROM_BIG_ENDIAN = 47,        /* compact_prestate_processing.rs read_cbor_u256: U256::from_big_endian of more than 32 bytes (an account leaf's balance) */
 
   /* this library's own failures */
   PPD_ERR_BAD_FLAT_INPUT = 60,

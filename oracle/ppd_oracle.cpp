@@ -899,7 +899,7 @@ static uint8_t parse_instructions(const uint8_t* w, size_t n, std::vector<Instr>
         }
         if (flags & 8) {
           Bytes b = c.read_cbor_bytes(PPD_ERR_INVALID_BYTE_VECTOR, "account leaf balance");
-          if (b.size() > 32) fail(PPD_ERR_INVALID_BYTE_VECTOR, "balance wider than 256 bits");
+          if (b.size() > 32) fail(PPD_PANIC_U256_FROM_BIG_ENDIAN, "balance wider than 256 bits (U256::from_big_endian panics)");
           memcpy(in.balance + 32 - b.size(), b.data(), b.size());
         }
         if (flags & 1) (void)c.read_cbor_uint(~0ull, "code size");

@@ -49,7 +49,7 @@ void parse_witness(const uint8_t* w, size_t n, Witness& out) {
         if (in.flags & 4) c.cbor_uint(~0ull);
         if (in.flags & 8) {
           Span bal = c.cbor_bytes(PPD_ERR_INVALID_BYTE_VECTOR);
-          if (bal.n > 32) fail(PPD_ERR_INVALID_BYTE_VECTOR, "balance wider than 256 bits");
+          if (bal.n > 32) fail(PPD_PANIC_U256_FROM_BIG_ENDIAN, "balance wider than 256 bits (U256::from_big_endian panics)");
         }
         if (in.flags & 1) (void)c.cbor_uint(~0ull);
         break;

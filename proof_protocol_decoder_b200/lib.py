@@ -37,6 +37,7 @@ STATUS_NAMES = {
     44: "panic: pre-image account decode",
     45: "panic: unimplemented pre-image variant",
     46: "panic: key is a prefix of another key",
+    47: "panic: U256::from_big_endian of more than 32 bytes",
     60: "bad flat input",
     61: "unresolved code hash",
     62: "bad argument",
@@ -47,7 +48,7 @@ STATUS_NAMES = {
 
 class PpdError(Exception):
     """A non-OK ppd_status.  Codes 1-11 are CompactParsingError variants, 21-25 TraceParsingError
-    variants (decoding.rs:31-49), 40-46 places where the reference panics."""
+    variants (decoding.rs:31-49), 40-47 places where the reference panics."""
 
     def __init__(self, code, msg=""):
         super().__init__(f"ppd status {code} ({STATUS_NAMES.get(code, '?')}): {msg}")

@@ -267,6 +267,7 @@ class SynthBlock:
         self.b_meta = b""
         self.b_hashes = b""
         self.stats = {}
+        self.final_accounts = []
 
     @property
     def flat(self):
@@ -506,6 +507,7 @@ def gen_block(
     blk.b_meta = rng.bytes(64)
     blk.b_hashes = rng.bytes(96)
     blk.stats = {"accounts": n_accounts, "txns": n_txns, "witness_bytes": len(blk.compact)}
+    blk.final_accounts = accounts  # every account as the txns leave it (tests: an independent model of the final state)
     return blk
 
 

@@ -88,6 +88,20 @@ def test_compact_error_variants_match_oracle(ctx, oracle, witness):
     assert eg.value.code == eo.value.code
 
 
+def test_balance_wider_than_256_bits_is_the_u256_panic(ctx, oracle):
+    """read_cbor_u256 reads the byte vector and U256::from_big_endian panics on more than 32 bytes
+    (compact_prestate_processing.rs): a panic site (status 47), not CompactParsingError::InvalidByteVector."""
+    import witness_shapes as ws
+    from proof_protocol_decoder_b200 import PpdError
+
+    wide = ws.HDR + ws.account(ws.nibs("a" * 63), balance=1 << 263) + ws.account(ws.nibs("b" * 63), balance=9) + ws.branch((1 << 10) | (1 << 11))
+    with pytest.raises(OracleError) as eo:
+        oracle.compact_decode(wide)
+    with pytest.raises(PpdError) as eg:
+        ctx.compact_decode(wide)
+    assert eo.value.code == eg.value.code == 47
+
+
 def _check_block(ctx, oracle, blk):
     f = blk.flat
     want = oracle.block_decode(f)
@@ -112,7 +126,9 @@ def test_c1_blocks_bit_exact(ctx, oracle, seed):
 
 
 @pytest.mark.parametrize("n_txns,n_wd", [(0, 0), (0, 2), (1, 0), (1, 2), (2, 0), (2, 3)])
-def test_dummy_padding_and_withdrawals(ctx, oracle, n_txns, n_wd):
+def test_dummy_padding_and_withdrawals_unpinned(ctx, oracle, n_txns, n_wd):
+    """(unpinned: the dummy entries' subset key 0_u64 as zero nibbles is this repo's reading of eth_trie_utils, shared by the
+    oracle; no reference fixture covers it — DESIGN.md section 8)"""
     from proof_protocol_decoder_b200 import synth
 
     _check_block(ctx, oracle, synth.gen_block(100 + n_txns * 10 + n_wd, n_accounts=120, n_txns=n_txns, n_withdrawals=n_wd))
