@@ -346,27 +346,9 @@ int gpu_block(ppd_ctx* c, Lane* L, Job& J, const uint8_t* flat, size_t len, uint
   uint8_t* d_flat = L->d_flat.as<uint8_t>() + lead;
   L->tr_n = 0;
   trace_mark(L, "begin");
-  if (c->st_up && L->lease) {
-    // the upload queues for the copy engine on the context's upload stream; a main stream is taken once it is done
-    L->st = c->st_up;
-    upload_bytes(L, J, d_flat, flat, len);
-    CUDA_OK(cudaMemsetAsync(d_flat + len, 0, 256, c->st_up));
-    trace_mark(L, "uploaded");
-    L->st = L->own_st;
-    CUDA_OK(cudaEventRecord(L->ev_copy, c->st_up));
-    {
-      const auto tw = std::chrono::steady_clock::now();
-      CUDA_OK(cudaEventSynchronize(L->ev_copy));
-      L->stats.host_wait_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tw).count();
-    }
-    L->lease->acquire();
-    st = L->st;
-  } else {
-    if (L->lease) L->lease->acquire(), st = L->st;
-    upload_bytes(L, J, d_flat, flat, len);
-    trace_mark(L, "uploaded");
-    CUDA_OK(cudaMemsetAsync(d_flat + len, 0, 256, st));
-  }
+  upload_bytes(L, J, d_flat, flat, len);
+  trace_mark(L, "uploaded");
+  CUDA_OK(cudaMemsetAsync(d_flat + len, 0, 256, st));
   L->stats.h2d_bytes += (double)len;
   // page-locked landing areas
   const size_t h_words = 2 * ORDER_MAX_BINS + sizeof(txn::Cursors) / 4 + 64;
@@ -700,18 +682,10 @@ int gpu_block(ppd_ctx* c, Lane* L, Job& J, const uint8_t* flat, size_t len, uint
   CUDA_OK(cudaGetLastError());
   L->stats.kernel_launches += 1;
   if (pinned) {
-    cudaStream_t st_copy = st;
-    if (c->st_down && L->lease) {
-      // the emit is waited for, the main stream goes back to the pool, and the download queues for the copy engine on
-      // the context's download stream
-      lane_sync(L);
-      L->lease->release();
-      st_copy = c->st_down;
-    }
     const auto tw = std::chrono::steady_clock::now();
-    cudaError_t e = cudaMemcpyAsync(dst, L->d_out.p, total, cudaMemcpyDeviceToHost, st_copy);
-    if (st_copy == st) trace_mark(L, "downloaded");
-    if (e == cudaSuccess) e = cudaEventRecord(L->ev_sync, st_copy);
+    cudaError_t e = cudaMemcpyAsync(dst, L->d_out.p, total, cudaMemcpyDeviceToHost, st);
+    trace_mark(L, "downloaded");
+    if (e == cudaSuccess) e = cudaEventRecord(L->ev_sync, st);
     if (e == cudaSuccess) e = cudaEventSynchronize(L->ev_sync);
     L->stats.host_wait_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tw).count();
     if (e != cudaSuccess) {

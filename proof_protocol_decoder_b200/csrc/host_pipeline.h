@@ -104,7 +104,6 @@ struct Lane {
   struct StreamLease* lease = nullptr;
   txn::LoopTask* h_task = nullptr;  // page-locked: the kernel argument of a loop launched on the lane's own stream
   cudaEvent_t ev_ready = nullptr, ev_loop_done = nullptr;  // (ev_loop_done: blocking-sync)
-  cudaEvent_t ev_copy = nullptr;  // blocking-sync: the block's bulk upload / download on the context's copy streams
 };
 
 // Counting semaphore: how many lanes may have their witness upload + parse in flight at once.  All lanes of a
@@ -188,7 +187,10 @@ struct StreamLease {
   StreamPool* pool;
   Lane* L;
   bool held = false;
-  StreamLease(StreamPool* p, Lane* l) : pool(p), L(l) { L->lease = this; }  // (taken when the block first has something to queue)
+  StreamLease(StreamPool* p, Lane* l) : pool(p), L(l) {
+    L->lease = this;
+    acquire();
+  }
   void acquire() {
     if (!pool || held) return;
     L->st = pool->acquire(&L->stats.host_wait_ms);
@@ -220,9 +222,6 @@ struct ppd_ctx {
   int device = 0;
   ppd::StreamPool* pool = nullptr;      // null: every lane works on its own stream
   ppd::LoopBatcher* batcher = nullptr;
-  // with the pool: the FlatBlock uploads and the IrDump downloads of all lanes go through these two streams (a copy
-  // engine serves one copy at a time anyway), so that no main stream is held while a block queues for a copy engine
-  cudaStream_t st_up = nullptr, st_down = nullptr;
   ppd::Slots parse_slots_sem{ppd::parse_slots()};
   cudaStream_t st = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;

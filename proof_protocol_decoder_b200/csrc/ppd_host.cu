@@ -181,7 +181,6 @@ Lane* lane_of(ppd_ctx* c, size_t w) {
     if (!l->h_task) fail(PPD_ERR_BAD_ARGUMENT, "out of page-locked memory");
     CUDA_OK(cudaEventCreateWithFlags(&l->ev_ready, cudaEventDisableTiming));
     CUDA_OK(cudaEventCreateWithFlags(&l->ev_loop_done, cudaEventBlockingSync | cudaEventDisableTiming));
-    CUDA_OK(cudaEventCreateWithFlags(&l->ev_copy, cudaEventBlockingSync | cudaEventDisableTiming));
     CUDA_OK(cudaEventCreate(&l->ev0));
     CUDA_OK(cudaEventCreate(&l->ev1));
     CUDA_OK(cudaEventCreateWithFlags(&l->ev_sync, cudaEventBlockingSync | cudaEventDisableTiming));
@@ -204,7 +203,6 @@ void lane_delete(Lane* l) {
   if (l->h_task) pinned_free(l->h_task);
   if (l->ev_ready) cudaEventDestroy(l->ev_ready);
   if (l->ev_loop_done) cudaEventDestroy(l->ev_loop_done);
-  if (l->ev_copy) cudaEventDestroy(l->ev_copy);
   if (l->ev0) cudaEventDestroy(l->ev0);
   if (l->ev1) cudaEventDestroy(l->ev1);
   if (l->ev_sync) cudaEventDestroy(l->ev_sync);
@@ -424,7 +422,6 @@ void decode_one_inner(ppd_ctx* c, Lane* L, const uint8_t* flat, size_t len, uint
     try {
       read_flat_block(flat, len, b);
       pt.lap("read-flat");
-      if (!on_device) lease.acquire();  // (gpu_block takes its stream once the FlatBlock is on the device)
       if (on_device) {
         if (gpu_block(c, L, J, flat, len, out, out_len) == GPU_BLOCK_DONE) {
           *status = PPD_OK;
@@ -547,7 +544,7 @@ int ppd_ctx_create(int device, ppd_ctx** out) {
   // hardware queues of their own; PPD_STREAM_POOL=0: every lane on its own stream, loops included
   {
     const char* e = getenv("PPD_STREAM_POOL");
-    const int n_main = e ? atoi(e) : 20;
+    const int n_main = e ? atoi(e) : 22;
     const char* e2 = getenv("PPD_LOOP_STREAMS");
     const int n_loop = e2 ? std::max(1, atoi(e2)) : 8;
     if (n_main > 0) {
@@ -559,12 +556,6 @@ int ppd_ctx_create(int device, ppd_ctx** out) {
           return PPD_ERR_CUDA;
         }
         c->pool->all.push_back(s), c->pool->free_.push_back(s);
-      }
-      const char* e3 = getenv("PPD_COPY_STREAMS");
-      if ((!e3 || atoi(e3) != 0) &&
-          (cudaStreamCreateWithFlags(&c->st_up, cudaStreamNonBlocking) != cudaSuccess || cudaStreamCreateWithFlags(&c->st_down, cudaStreamNonBlocking) != cudaSuccess)) {
-        ppd_ctx_destroy(c);
-        return PPD_ERR_CUDA;
       }
       c->batcher = loop_batcher_create(device, n_loop);
       if (!c->batcher) {
@@ -590,8 +581,6 @@ void ppd_ctx_destroy(ppd_ctx* c) {
     for (cudaStream_t s : c->pool->all) cudaStreamDestroy(s);
     delete c->pool;
   }
-  if (c->st_up) cudaStreamDestroy(c->st_up);
-  if (c->st_down) cudaStreamDestroy(c->st_down);
   for (Lane* l : c->lanes) lane_delete(l);
   DevBuf* bufs[] = {&c->d_keys, &c->d_vals, &c->d_ref, &c->d_ref_len, &c->d_counters, &c->d_msg, &c->d_msg_off, &c->d_digest};
   for (DevBuf* b : bufs) b->release();
