@@ -27,7 +27,10 @@ namespace {
 
 constexpr uint32_t HASH_ID_BASE = 0x80000000u;
 constexpr uint32_t SET_CAP = 8192, MAX_UNIQ = 4096, NOT_FOUND = 0xffffffffu, UNSET = 0xffffffffu;
-constexpr int DUMP_THREADS = 256;
+#ifndef PPD_DUMP_THREADS
+#define PPD_DUMP_THREADS 1024
+#endif
+constexpr int DUMP_THREADS = PPD_DUMP_THREADS;
 
 // The set of an IR's touched nodes.  For an ordinary IR (at most MAX_UNIQ distinct touched nodes) everything lives in
 // shared memory; for a big one (a txn that writes tens of thousands of slots: config 3) the table and the per-node
