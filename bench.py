@@ -485,19 +485,24 @@ def run_b200(args, rank, world, local_rank):
     # BlockTrace for the library would place them; every step copies them to the device again
     flats = [ctx.pinned_copy(f) for f in flats]
 
-    # a timed end-to-end step decodes every block e2e_mult times in one call: the pipeline's ramp at both ends of a call
-    # is then a smaller share, as in a node that keeps feeding blocks
+    # a timed end-to-end step decodes every block e2e_mult times in one call (512 blocks by default): the pipeline's ramp
+    # at both ends of a call (one block's latency in flight, ~70 ms) is then a small share, as in a node that keeps feeding
+    # blocks; outputs are consumed as they finish, so only those in flight are held
     e2e_mult = max(1, args.e2e_mult)
 
     def decode_step(mult=1):
-        outs = ctx.blocks_decode_batch_view(flats * mult)
-        total = 0
-        for o in outs:
+        # ppd_blocks_decode_stream: every block's IrDump is handed over (and read, and released) as soon as it is done
+        got = []
+
+        def on_done(i, o):
             if isinstance(o, Exception):
                 raise o
-            total += o.nbytes + o.view[0] + o.view[o.nbytes - 1]  # read the result
+            got.append(o.nbytes + o.view[0] + o.view[o.nbytes - 1])  # read the result
             o.close()
-        return total
+
+        ctx.blocks_decode_stream(flats * mult, on_done)
+        assert len(got) == len(flats) * mult
+        return sum(got)
 
     # ---- warm-up (also leaves the arenas resident for the device-resident measurements) ----
     for _ in range(max(3, args.warmup)):
@@ -658,7 +663,7 @@ def run_b200(args, rank, world, local_rank):
             "d2h_bytes_per_step": d2h_all,
             "boundary_bytes_per_step": {"flat_blocks": flat_total * e2e_mult * world, "ir_dumps": ir_len * world},
             "host_busy_ms_per_block": per_block_host_ms,
-            "note": "ppd_blocks_decode_batch: FlatBlocks (page-locked host memory) -> IrDumps (host); every host<->device copy and all host work (flat input reading, descriptor tables, launches) inside the timed region",
+            "note": "ppd_blocks_decode_stream: FlatBlocks (page-locked host memory) -> IrDumps (page-locked host memory, read and released by the callback as each block finishes); every host<->device copy and all host work (flat input reading, descriptor tables, launches) inside the timed region",
         },
         "e2e_blocks_per_sec": e2e_bps,
         "e2e_efficiency_vs_n1": (e2e_bps / (world * n1["e2e_blocks_per_sec"])) if n1.get("e2e_blocks_per_sec") else None,
@@ -758,7 +763,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--scale", type=float, default=1.0, help="fraction of the C2 block size (1.0 = the named config)")
     ap.add_argument("--blocks-per-step", type=int, default=0, help="blocks per GPU per step (default 64, at most 64)")
-    ap.add_argument("--e2e-mult", type=int, default=2, help="an end-to-end step decodes every block this many times in one call")
+    ap.add_argument("--e2e-mult", type=int, default=8, help="an end-to-end step decodes every block this many times in one call")
     ap.add_argument("--ref-scale", type=float, default=1.0, help="size of the CPU arm's block (1.0 = the same config as the b200 arm)")
     ap.add_argument("--sweep", default="1000000,10000000", help="config-5 leaf counts measured beside the headline at N=1")
     ap.add_argument("--no-sweep", action="store_true")

@@ -87,6 +87,14 @@ int ppd_block_decode(ppd_ctx* ctx, const uint8_t* flat_block, size_t len, uint8_
 int ppd_blocks_decode_batch(ppd_ctx* ctx, const uint8_t* const* flat_blocks, const size_t* lens, size_t n, uint8_t** outs,
                             size_t* out_lens, int* statuses);
 
+/* The same for a caller that consumes blocks as they finish (a node that keeps feeding blocks: the pipeline never drains
+ * between calls' worth of blocks, and only the outputs in flight are held): `done` is called once per block, from one
+ * of the library's host threads, as soon as that block is decoded — in completion order, not input order; `out` (NULL
+ * for a failed block) is the callee's to release with ppd_free.  Calls of `done` may overlap on different threads.
+ * A non-OK return is a CUDA failure; blocks delivered before it stay delivered. */
+typedef void (*ppd_block_done_fn)(void* user, size_t index, int status, uint8_t* out, size_t out_len);
+int ppd_blocks_decode_stream(ppd_ctx* ctx, const uint8_t* const* flat_blocks, const size_t* lens, size_t n, ppd_block_done_fn done, void* user);
+
 /* Measurement hook: re-run kernels of the last ppd_block_decode / ppd_blocks_decode_batch on what is still resident
  * in HBM (no host work, no copies); returns the device time (CUDA events).  `what` selects the stages, which every
  * lane runs in pipeline order, lanes concurrently: the witness parse + pre-image arena (ppd_parse.cu), key hashing and

@@ -487,7 +487,8 @@ static size_t max_lanes() {
   return n;
 }
 
-void decode_blocks(ppd_ctx* c, const uint8_t* const* flats, const size_t* lens, size_t n, uint8_t** outs, size_t* out_lens, int* statuses) {
+void decode_blocks(ppd_ctx* c, const uint8_t* const* flats, const size_t* lens, size_t n, uint8_t** outs, size_t* out_lens, int* statuses,
+                   ppd_block_done_fn done = nullptr, void* user = nullptr) {
   stats_reset(c);
   if (!n) return;
   // block i runs on lane i mod n_lanes; a host thread takes whole lanes, so a lane never runs two
@@ -507,7 +508,14 @@ void decode_blocks(ppd_ctx* c, const uint8_t* const* flats, const size_t* lens, 
 #ifndef PPD_HOSTPROF
     CUDA_OK(cudaSetDevice(c->device));
 #endif
-    for (size_t i = lane; i < n; i += n_lanes) decode_one(c, c->lanes[lane], flats[i], lens[i], &outs[i], &out_lens[i], &statuses[i], dump_workers);
+    for (size_t i = lane; i < n; i += n_lanes) {
+      decode_one(c, c->lanes[lane], flats[i], lens[i], &outs[i], &out_lens[i], &statuses[i], dump_workers);
+      if (done) {  // streaming: the block's output goes to the caller now (and is the caller's to free)
+        uint8_t* o = outs[i];
+        outs[i] = nullptr;
+        done(user, i, statuses[i], o, out_lens[i]);
+      }
+    }
   });
   c->last_lanes_used = n_lanes;
   for (size_t w = 0; w < n_lanes; w++) add_stats(c->stats, c->lanes[w]->stats);
@@ -797,6 +805,17 @@ int ppd_blocks_decode_batch(ppd_ctx* c, const uint8_t* const* flats, const size_
       outs[i] = nullptr;
       if (out_lens) out_lens[i] = 0;
     }
+  return rc;
+}
+
+int ppd_blocks_decode_stream(ppd_ctx* c, const uint8_t* const* flats, const size_t* lens, size_t n, ppd_block_done_fn done, void* user) {
+  if (!done) return PPD_ERR_BAD_ARGUMENT;
+  std::vector<uint8_t*> outs(n, nullptr);
+  std::vector<size_t> out_lens(n, 0);
+  std::vector<int> statuses(n, PPD_OK);
+  int rc = guarded(c, [&] { decode_blocks(c, flats, lens, n, outs.data(), out_lens.data(), statuses.data(), done, user); });
+  for (size_t i = 0; i < n; i++)  // (only after a failure: an output that was never handed over)
+    if (outs[i]) ppd_free(outs[i]);
   return rc;
 }
 

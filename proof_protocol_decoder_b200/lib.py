@@ -85,6 +85,9 @@ class PpdStats(ctypes.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
+# void (*ppd_block_done_fn)(void* user, size_t index, int status, uint8_t* out, size_t out_len)
+BLOCK_DONE_FN = ctypes.CFUNCTYPE(None, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.POINTER(ctypes.c_uint8), ctypes.c_size_t)
+
 EXPORTS = [
     "ppd_ctx_create",
     "ppd_ctx_destroy",
@@ -100,6 +103,7 @@ EXPORTS = [
     "ppd_trie_root_sorted_leaves_dev",
     "ppd_trie_subroot_sorted_leaves_dev",
     "ppd_trie_root_from_children",
+    "ppd_blocks_decode_stream",
     "ppd_replay_last",
     "ppd_replay_lanes",
     "ppd_replay_last_hashing",
@@ -140,6 +144,7 @@ class PpdLibrary:
         L.ppd_blocks_decode_batch.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
         L.ppd_trie_root_sorted_leaves.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_char_p]
         L.ppd_replay_last.argtypes = [ctypes.c_void_p, ctypes.c_uint, ctypes.POINTER(ctypes.c_double)]
+        L.ppd_blocks_decode_stream.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, BLOCK_DONE_FN, ctypes.c_void_p]
         L.ppd_replay_lanes.argtypes = [ctypes.c_void_p]
         L.ppd_replay_lanes.restype = ctypes.c_size_t
         L.ppd_replay_last_hashing.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_double)]
@@ -293,6 +298,27 @@ class Context:
             else:
                 res.append(PpdError(statuses[i], "block %d" % i))
         return res
+
+    def blocks_decode_stream(self, flats, on_done):
+        """ppd_blocks_decode_stream: on_done(index, result) is called as each block finishes (from the library's host
+        threads, in completion order); result is an OwnedBuffer (close it when done) or a PpdError."""
+        n = len(flats)
+        keep = [bytes(f) if isinstance(f, bytearray) else f for f in flats]
+        addr = [ctypes.cast(ctypes.c_char_p(f), ctypes.c_void_p).value if isinstance(f, bytes) else f.ctypes.data for f in keep]
+        ptrs = (ctypes.c_void_p * n)(*addr)
+        lens = (ctypes.c_size_t * n)(*[len(f) if isinstance(f, bytes) else f.nbytes for f in keep])
+        failure = []
+
+        def tramp(_user, index, status, out, out_len):
+            try:
+                on_done(index, OwnedBuffer(self.lib, out, out_len) if status == 0 else PpdError(status, "block %d" % index))
+            except BaseException as e:  # noqa: BLE001 — raised again on the calling thread
+                failure.append(e)
+
+        cb = BLOCK_DONE_FN(tramp)
+        self._check(self.lib.L.ppd_blocks_decode_stream(self.h, ptrs, lens, n, cb, None))
+        if failure:
+            raise failure[0]
 
     REPLAY_PARSE, REPLAY_HASH, REPLAY_TXN, REPLAY_DUMP, REPLAY_ALL = 1, 2, 4, 8, 15
 

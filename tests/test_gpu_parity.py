@@ -88,6 +88,32 @@ def test_compact_error_variants_match_oracle(ctx, oracle, witness):
     assert eg.value.code == eo.value.code
 
 
+def test_blocks_stream_hands_every_block_over_once(ctx, oracle):
+    """ppd_blocks_decode_stream: the same bytes as ppd_blocks_decode_batch, each block delivered exactly once through the
+    callback (in completion order), a failing block with its status."""
+    from proof_protocol_decoder_b200 import PpdError, synth
+
+    blocks = [synth.gen_block(300 + i, n_accounts=60 + 10 * i, n_txns=3 + i % 3, n_withdrawals=i % 2) for i in range(9)]
+    bad = synth.gen_block(3, n_accounts=50, n_txns=1)
+    bad.withdrawals = [(b"\x11" * 20, 5)]  # not in the state trie: MissingWithdrawalAccount
+    flats = [b.flat for b in blocks] + [bad.flat]
+    got = {}
+
+    def on_done(i, o):
+        assert i not in got
+        if isinstance(o, Exception):
+            got[i] = o
+        else:
+            got[i] = bytes(o.view)
+            o.close()
+
+    ctx.blocks_decode_stream(flats, on_done)
+    assert sorted(got) == list(range(len(flats)))
+    for i, b in enumerate(blocks):
+        assert got[i] == oracle.block_decode(b.flat)
+    assert isinstance(got[len(blocks)], PpdError) and got[len(blocks)].code == 25
+
+
 def test_balance_wider_than_256_bits_is_the_u256_panic(ctx, oracle):
     """read_cbor_u256 reads the byte vector and U256::from_big_endian panics on more than 32 bytes
     (compact_prestate_processing.rs): a panic site (status 47), not CompactParsingError::InvalidByteVector."""
