@@ -140,6 +140,8 @@ def c2_blocks(seeds, scale, procs):
 
         with mp.get_context("fork").Pool(min(procs, len(missing))) as pool:
             pool.map(_c2_block_job, [(s, scale) for s in missing])
+    if missing:
+        os.sync()  # the cache files (gigabytes of dirty pages) are written back now, not under the timed steps
     return [c2_block(s, scale) for s in seeds]
 
 
