@@ -403,27 +403,37 @@ def split_legs(ctx, torch, dist, rank, world, args, barrier, max_over_ranks, sum
     return out
 
 
-def measure_pcie(torch, mb=256):
-    """Pinned-memory copy bandwidth of this GPU's link, both directions at once (GB/s each): what bounds a pipeline
-    that streams FlatBlocks in and IrDumps out."""
+def measure_pcie(torch, mb=64, secs=0.3, barrier=None):
+    """Pinned-memory copy bandwidth of this GPU's link, both directions at once (GB/s in the slower direction), measured
+    for `secs` on several streams while every other rank does the same (the ranks start together behind `barrier`): GPUs
+    of one box may share a PCIe switch or root port, and what bounds a pipeline that streams FlatBlocks in and IrDumps
+    out is what the link gives when all of them copy."""
     n = mb << 20
-    h_in = torch.empty(n, dtype=torch.uint8).pin_memory()
-    h_out = torch.empty(n, dtype=torch.uint8).pin_memory()
-    d_in = torch.empty(n, dtype=torch.uint8, device="cuda")
-    d_out = torch.empty(n, dtype=torch.uint8, device="cuda")
-    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
-    best = None
-    for _ in range(3):
+    k = 4
+    h_in = [torch.empty(n, dtype=torch.uint8).pin_memory() for _ in range(k)]
+    h_out = [torch.empty(n, dtype=torch.uint8).pin_memory() for _ in range(k)]
+    d_in = [torch.empty(n, dtype=torch.uint8, device="cuda") for _ in range(k)]
+    d_out = [torch.empty(n, dtype=torch.uint8, device="cuda") for _ in range(k)]
+    s_up = [torch.cuda.Stream() for _ in range(k)]
+    s_dn = [torch.cuda.Stream() for _ in range(k)]
+    for i in range(k):  # touch everything once
+        d_in[i].copy_(h_in[i], non_blocking=True)
+        h_out[i].copy_(d_out[i], non_blocking=True)
+    torch.cuda.synchronize()
+    if barrier is not None:
+        barrier()
+    t0 = time.perf_counter()
+    rounds = 0
+    while time.perf_counter() - t0 < secs:
+        for i in range(k):
+            with torch.cuda.stream(s_up[i]):
+                d_in[i].copy_(h_in[i], non_blocking=True)
+            with torch.cuda.stream(s_dn[i]):
+                h_out[i].copy_(d_out[i], non_blocking=True)
         torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        with torch.cuda.stream(s1):
-            d_in.copy_(h_in, non_blocking=True)
-        with torch.cuda.stream(s2):
-            h_out.copy_(d_out, non_blocking=True)
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        best = dt if best is None else min(best, dt)
-    return n / best / 1e9
+        rounds += 1
+    dt = time.perf_counter() - t0
+    return rounds * k * n / dt / 1e9
 
 
 N1_CACHE = "/tmp/ppd_bench_n1.json"  # the N=1 run leaves its e2e blocks/s and the oracle's node count here for the N>1 runs of the same box
@@ -481,7 +491,7 @@ def run_b200(args, rank, world, local_rank):
         return float(t.item())
 
     ctx = Context(local_rank)
-    pcie_gbs = measure_pcie(torch)
+    pcie_gbs = measure_pcie(torch, barrier=barrier)  # (all ranks at once)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
     # the step's inputs live in page-locked host memory (ppd_alloc_pinned), as a caller that serialises its
     # BlockTrace for the library would place them; every step copies them to the device again
@@ -611,7 +621,7 @@ def run_b200(args, rank, world, local_rank):
     blocks_replayed = world * resident
     bounds = {
         "device_pipeline": blocks_replayed / ((hash_ms + parse_ms + dump_ms) / 1e3),
-        "pcie": world * pcie_gbs * 1e9 / max(per_block_h2d, per_block_d2h),
+        "pcie": sum_over_ranks(pcie_gbs) * 1e9 / max(per_block_h2d, per_block_d2h),
         "host_cores": cores / (per_block_host_ms / 1e3) if per_block_host_ms else None,
     }
     limiter = min((k for k in bounds if bounds[k]), key=lambda k: bounds[k])
@@ -673,10 +683,11 @@ def run_b200(args, rank, world, local_rank):
             "name": limiter,
             "bounds_blocks_per_sec": bounds,
             "pcie_gbs_per_direction": pcie_gbs,
+            "pcie_gbs_per_direction_all_gpus": sum_over_ranks(pcie_gbs),
             "pcie_bytes_per_block": {"h2d": per_block_h2d, "d2h": per_block_d2h},
             "host_busy_ms_per_block": per_block_host_ms,
             "device_pipeline_lockstep": blocks_replayed / (all_ms / 1e3),
-            "note": "upper bounds on end-to-end blocks/s: device_pipeline = the kernels that fill the device (witness parse, key hashing and both level sweeps, IR sizing and emit), each stage replayed by all resident lanes at once, times added; the txn loops run beside them, one SM each (device_pipeline_lockstep: every lane replaying its whole pipeline from the same instant, loops included: stages of different lanes do not overlap there as they do in a running pipeline); pcie = each GPU's link at the measured pinned-copy rate over the bytes a block moves in the busier direction; host_cores = the box's cores over the CPU time a block costs its host thread",
+            "note": "upper bounds on end-to-end blocks/s: device_pipeline = the kernels that fill the device (witness parse, key hashing and both level sweeps, IR sizing and emit), each stage replayed by all resident lanes at once, times added; the txn loops run beside them, one SM each (device_pipeline_lockstep: every lane replaying its whole pipeline from the same instant, loops included: stages of different lanes do not overlap there as they do in a running pipeline); pcie = the pinned-copy rate of all GPUs' links measured while every rank copies in both directions at once (GPUs of a box may share a switch or root port), over the bytes a block moves in the busier direction; host_cores = the box's cores over the CPU time a block costs its host thread",
         },
         "gpu_launches": int(st["kernel_launches"]) * args.steps,
         "clocks": clocks,
