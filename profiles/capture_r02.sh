@@ -23,6 +23,8 @@ PPD_HOST_THREADS=1 $B1 > /dev/null 2>&1 && PPD_HOST_THREADS=1 ncu --set full --c
 PR="python profiles/run_parse.py"
 $PR 3 > $RAW/${TAG}_block_plain.log 2> $RAW/${TAG}_block_plain.err && \
   ncu --set full --clock-control none --import-source on -k regex:txn_loop_kernel --launch-skip 30 --launch-count 2 -o $RAW/${TAG}_txn_loop_full $PR 3 > $RAW/${TAG}_ncu_loop.log 2>&1
+# 3b. full capture of the IR sizing / emit kernels of the third decode
+ncu --set full --clock-control none --import-source on -k "regex:ir_size_kernel|ir_emit_kernel" --launch-skip 4 --launch-count 2 -o $RAW/${TAG}_dump_full $PR 3 > $RAW/${TAG}_ncu_dump.log 2>&1
 # 4. per-kernel launch list of one block decode (warm)
 ncu $LIST -c 3000 --log-file $RAW/${TAG}_launches_block.csv $PR 2 > /dev/null 2>&1
 python profiles/summarize_block.py $RAW/${TAG}_launches_block.csv 2 "one config-2 block (python profiles/run_parse.py 2, the second decode)" > $OUT/${TAG}_launches_block_summary.txt

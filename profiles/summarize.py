@@ -106,6 +106,10 @@ def main():
                 if m in r:
                     out.append(f"  {m:95s} {r[m]}")
         open(os.path.join(DST, f"{TAG}_txn_loop_full.txt"), "w").write("\n".join(out) + "\n")
+    rep = os.path.join(SRC, f"{TAG}_dump_full.ncu-rep")
+    if os.path.exists(rep):
+        t, _ = full_table(rep, "ncu --set full, ir_size_kernel + ir_emit_kernel of one config-2 block (200 IRs, one thread block of 1 024 threads each; the third decode of `profiles/run_parse.py 3`)")
+        open(os.path.join(DST, f"{TAG}_dump_full.txt"), "w").write(t + "\n")
     # ---- config 5 ----
     p = os.path.join(SRC, f"{TAG}_launches_c5.csv")
     if os.path.exists(p):
