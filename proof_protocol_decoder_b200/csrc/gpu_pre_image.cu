@@ -170,6 +170,7 @@ bool gpu_pre_image(Lane* L, Job& J, BlockJob& b, bool check_version, Slots* slot
     T.delta = c.take<uint32_t>(n1);
     T.hb = c.take<uint32_t>(n1);
     T.h16 = c.take<int16_t>(n1);
+    T.m0 = c.take<int16_t>(8 * n_m1);
     T.m1 = c.take<int16_t>(n_m1);
     T.m2 = c.take<int16_t>(n_m2);
     T.m3 = c.take<int16_t>(n_m3);

@@ -155,7 +155,7 @@ struct ParseTree {
   uint8_t* knib;            // [n_ins]
   uint32_t* delta;          // [n_ins + 1]
   uint32_t* hb;             // [n_ins + 1]
-  int16_t *h16, *m1, *m2, *m3;
+  int16_t *h16, *m0, *m1, *m2, *m3;  // heights after each instruction; minima over 8 / 64 / 4 096 / 262 144 of them
   uint32_t* parent;         // [n_ins]
   uint32_t* info;           // [n_ins]
   uint32_t* aux0;           // [n_ins]

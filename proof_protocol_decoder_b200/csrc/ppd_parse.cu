@@ -29,6 +29,7 @@
 //   account record, storage ROOT node); levels are computed by climbing from the leaves with a
 //   pending-children counter per inner node (the last child to arrive continues upwards).
 #include <cstdint>
+#include <cstdlib>
 
 #include "../../include/ppd_flat.h"
 #include "../../include/ppd_status.h"
@@ -186,7 +187,7 @@ __device__ __noinline__ uint32_t decode_next_slow(const uint8_t* w, uint32_t n, 
   return e ? (PERR | e) : o.next;
 }
 
-__global__ void __launch_bounds__(TE_THREADS, 3) tile_exit_kernel(const uint8_t* __restrict__ w, uint32_t n, uint32_t* __restrict__ exit1,
+__global__ void __launch_bounds__(TE_THREADS, 3) tile_exit_kernel_v1(const uint8_t* __restrict__ w, uint32_t n, uint32_t* __restrict__ exit1,
                                                                   uint16_t* __restrict__ step1) {
   __shared__ __align__(16) uint32_t nxt[TILE];
   __shared__ __align__(16) uint16_t step[TILE];  // single-step links inside the tile (0xffff: the instruction ends outside), for tile_mark_kernel
@@ -261,6 +262,134 @@ __global__ void __launch_bounds__(TE_THREADS, 3) tile_exit_kernel(const uint8_t*
 #pragma unroll
       for (int j = 0; j < 4; j++)
         if (v[j] < end) active[at++] = (uint16_t)(o0 + j);
+    }
+  }
+  __syncthreads();
+  // pointer doubling over the few positions that decode to an instruction ending inside the tile; any
+  // intermediate value is a point of the same chain, so updating in place is safe
+  const uint32_t na = n_active;
+  for (;;) {
+    bool moved = false;
+    for (uint32_t a = threadIdx.x; a < na; a += TE_THREADS) {
+      uint32_t o = active[a], x = nxt[o];
+      if (x < end) {
+        nxt[o] = nxt[x - base];
+        moved = true;
+      }
+    }
+    if (!__syncthreads_or(moved)) break;
+  }
+  {
+    const uint4* s4 = reinterpret_cast<const uint4*>(nxt);
+    uint4* d4 = reinterpret_cast<uint4*>(exit1 + base);  // the exit1 array is padded to whole tiles
+#pragma unroll
+    for (uint32_t k = threadIdx.x; k < TILE / 4; k += TE_THREADS) d4[k] = s4[k];
+  }
+  // the whole 8 KiB link table of the tile (entries past the end of the stream are never followed)
+  reinterpret_cast<uint4*>(step1 + (size_t)base)[threadIdx.x] = reinterpret_cast<const uint4*>(step)[threadIdx.x];
+}
+
+// Round 2, second form.  Only a byte below 7 can start an instruction, and 97 % of a witness is hash bytes, so the
+// kernel works on LISTS instead of classifying every position (round-1 capture: 15 k warp instructions per tile, most
+// of them single-lane calls of the long decode):
+//   pass 1  eight positions per thread: the link tables get their defaults ("not an opcode") with 128-bit stores, the
+//           bytes below 7 are found with one exact SIMD-in-register test per word and listed (about 230 per tile);
+//   pass 2  one listed position per thread: hashed-out node -> p + 33, empty root -> p + 1, any other opcode must be
+//           followed by a CBOR head of the right major type (else the error decode_ins reports); what passes is
+//           listed again (about 50 per tile);
+//   pass 3  decode_ins, one listed position per thread, so the warps that run the long decode are full;
+// then the pointer doubling over the positions whose instruction ends inside the tile, as before.
+constexpr uint32_t TE_SMEM_BYTES = 4 * TILE + 4 * 2 * TILE + (TILE + HALO) + 16;
+
+__global__ void __launch_bounds__(TE_THREADS, 3) tile_exit_kernel(const uint8_t* __restrict__ w, uint32_t n, uint32_t* __restrict__ exit1,
+                                                                  uint16_t* __restrict__ step1) {
+  extern __shared__ __align__(16) uint8_t te_smem[];
+  uint32_t* nxt = reinterpret_cast<uint32_t*>(te_smem);            // [TILE]
+  uint16_t* step = reinterpret_cast<uint16_t*>(te_smem + 4 * TILE);  // [TILE] single-step links inside the tile (0xffff: the instruction ends outside), for tile_mark_kernel
+  uint16_t* active = step + TILE;                                  // [TILE] positions whose chain has not left the tile yet
+  uint16_t* cand = active + TILE;                                  // [TILE] positions holding a byte below 7
+  uint16_t* slow = cand + TILE;                                    // [TILE] positions that need the long decode
+  uint8_t* sb = reinterpret_cast<uint8_t*>(slow + TILE);           // [TILE + HALO]
+  uint32_t* counters = reinterpret_cast<uint32_t*>(sb + TILE + HALO);
+  uint32_t &n_active = counters[0], &n_cand = counters[1], &n_slow = counters[2];
+  constexpr uint32_t SLOW = PERR | 0xfeu;
+  constexpr uint32_t NOT_OP = PERR | PPD_ERR_INVALID_OPERATOR;
+  const uint32_t base = blockIdx.x * TILE, end = min(base + TILE, n);
+  stage_tile(sb, w, n, base, threadIdx.x, TE_THREADS);
+  if (threadIdx.x < 3) counters[threadIdx.x] = 0;
+  __syncthreads();
+  const uint8_t* ws = sb - base;
+  // pass 1
+  {
+    static_assert(TILE == 8 * TE_THREADS, "eight positions per thread");
+    const uint32_t o0 = 8 * threadIdx.x;
+    const uint2 W = reinterpret_cast<const uint2*>(sb)[threadIdx.x];
+    if (base + TILE <= end) {
+      const uint4 d = make_uint4(NOT_OP, NOT_OP, NOT_OP, NOT_OP);
+      reinterpret_cast<uint4*>(nxt + o0)[0] = d, reinterpret_cast<uint4*>(nxt + o0)[1] = d;
+    } else {  // the last tile: positions past the end of the stream are never referenced
+#pragma unroll
+      for (uint32_t j = 0; j < 8; j++) nxt[o0 + j] = base + o0 + j < end ? NOT_OP : PERR;
+    }
+    *reinterpret_cast<uint4*>(step + o0) = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+    // bit 8k+7 set <=> byte k of the word is below 7: (b | 0x80) - 7 never borrows from the next byte, and its top bit
+    // is clear exactly when b < 7 or 128 <= b < 135; the second case has the top bit of b set
+    uint32_t m0 = ~(((W.x | 0x80808080u) - 0x07070707u) | W.x) & 0x80808080u;
+    uint32_t m1 = ~(((W.y | 0x80808080u) - 0x07070707u) | W.y) & 0x80808080u;
+    if (base == 0 && threadIdx.x == 0) m0 |= 0x80u;  // byte 0 is the header: it "ends" at 1 whatever it holds
+    while (m0) {
+      const uint32_t o = o0 + (((uint32_t)__ffs(m0) - 1u) >> 3);
+      m0 &= m0 - 1;
+      if (base + o < end) cand[atomicAdd(&n_cand, 1u)] = (uint16_t)o;
+    }
+    while (m1) {
+      const uint32_t o = o0 + 4 + (((uint32_t)__ffs(m1) - 1u) >> 3);
+      m1 &= m1 - 1;
+      if (base + o < end) cand[atomicAdd(&n_cand, 1u)] = (uint16_t)o;
+    }
+  }
+  __syncthreads();
+  // pass 2 (same rules, same order as the round-1 kernel's branch-free classification)
+  {
+    const uint32_t nc = n_cand;
+    for (uint32_t a = threadIdx.x; a < nc; a += TE_THREADS) {
+      const uint32_t o = cand[a], p = base + o;
+      const uint32_t op = ws[p], b1 = ws[p + 1];
+      // opcodes 0 1 2 4 5 start with a CBOR head: an unsigned integer (major 0) for a branch mask, else a byte
+      // string (major 2); additional info above 27 is not accepted.  Error code per opcode from a nibble table.
+      const bool is_uint_head = op == PPD_OP_BRANCH;
+      const uint32_t e_head = (((uint32_t)PPD_ERR_INVALID_BYTE_VECTOR * 0x00100011u + (uint32_t)PPD_ERR_INVALID_BYTES_FOR_TYPE * 0x00010100u) >> (4 * (op & 7u))) & 15u;
+      const bool head_ok = p + 1 < n && (b1 - (is_uint_head ? 0u : 0x40u)) <= 0x1bu;
+      uint32_t r = head_ok ? SLOW : (PERR | e_head);
+      r = op == PPD_OP_HASH ? (n - (p + 1) < 32 ? (PERR | PPD_ERR_INVALID_BYTES_FOR_TYPE) : p + 33) : r;
+      r = op == PPD_OP_EMPTY_ROOT ? p + 1 : r;
+      r = op > PPD_OP_EMPTY_ROOT ? NOT_OP : r;
+      r = p == 0 ? 1u : r;
+      if (r == SLOW) {
+        slow[atomicAdd(&n_slow, 1u)] = (uint16_t)o;
+      } else {
+        nxt[o] = r;
+        if (r < end) {
+          step[o] = (uint16_t)(r - base);
+          active[atomicAdd(&n_active, 1u)] = (uint16_t)o;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  // pass 3
+  {
+    const uint32_t ns = n_slow;
+    for (uint32_t a = threadIdx.x; a < ns; a += TE_THREADS) {
+      const uint32_t o = slow[a];
+      Ins ins;
+      const uint32_t e = decode_ins(ws, n, base + o, ins);
+      const uint32_t r = e ? (PERR | e) : ins.next;
+      nxt[o] = r;
+      if (r < end) {
+        step[o] = (uint16_t)(r - base);
+        active[atomicAdd(&n_active, 1u)] = (uint16_t)o;
+      }
     }
   }
   __syncthreads();
@@ -377,6 +506,36 @@ __global__ void __launch_bounds__(TM_WARPS * 32) tile_mark_kernel(const uint16_t
   for (uint32_t k = lane; k < TILE / 32; k += 32) bitmap[(size_t)t * (TILE / 32) + k] = bits[wi][k];
 }
 
+// The same walk with one THREAD per tile, straight from the global link table (the bitmap is zeroed beforehand and only
+// the words that hold a start are written).  A walk is about 124 dependent 2-byte loads, so a lone launch takes longer
+// than the staged form above, but it issues 40x fewer warp instructions (no 8 KiB staging per tile, 32 walks per
+// warp instead of one), and with other blocks' kernels beside it the parse is bound by issue slots, not by latency.
+__global__ void __launch_bounds__(128) tile_mark_thin_kernel(const uint16_t* __restrict__ step1, uint32_t n_tiles, const uint32_t* __restrict__ tile_entry,
+                                                             uint32_t* __restrict__ bitmap, uint32_t* __restrict__ tile_count) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_tiles) return;
+  const uint32_t cur = tile_entry[t];
+  uint32_t count = 0;
+  if (cur != NONE) {
+    const uint16_t* __restrict__ step = step1 + (size_t)t * TILE;
+    uint32_t* __restrict__ bits = bitmap + (size_t)t * (TILE / 32);
+    uint32_t o = cur - t * TILE;
+    if (cur == 0) o = __ldg(step);  // the header byte is not an instruction
+    uint32_t word = o >> 5, acc = 0;  // starts are visited in increasing order
+    while (o != 0xffffu) {
+      if ((o >> 5) != word) {
+        bits[word] = acc;
+        word = o >> 5, acc = 0;
+      }
+      acc |= 1u << (o & 31);
+      count++;
+      o = __ldg(step + o);
+    }
+    if (acc) bits[word] = acc;
+  }
+  tile_count[t] = count;
+}
+
 __global__ void __launch_bounds__(TILE / 32) ins_scatter_kernel(const uint32_t* __restrict__ bitmap, const uint32_t* __restrict__ tile_base,
                                                                 uint32_t* __restrict__ ins_pos) {
   __shared__ uint32_t wsum[TILE / 32 / 32];
@@ -483,9 +642,7 @@ __device__ __forceinline__ uint32_t pops_of(uint32_t meta) {
 }
 
 // meta = op | flags << 8 | (branch mask & 0xffff) << 16
-__global__ void ins_info_kernel(ParseTree T) {
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i > T.n_ins) return;
+__device__ __forceinline__ void ins_info_one(const ParseTree& T, uint32_t i) {
   if (i == T.n_ins) {
     T.delta[i] = 0;
     return;
@@ -506,6 +663,36 @@ __global__ void ins_info_kernel(ParseTree T) {
   T.pending[i] = o.op == PPD_OP_ACCOUNT_LEAF ? ((o.flags >> 1) & 1u) : pops;
   T.lvlmax[i] = 0;
   T.aux0[i] = NONE;
+}
+__global__ void ins_info_kernel_v1(ParseTree T) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > T.n_ins) return;
+  ins_info_one(T, i);
+}
+// A thread block takes LIST_CHUNK consecutive instructions: the short ones (hashed-out node, branch, empty root) are
+// done in place, the keyed ones (one in twenty: leaf, extension, account leaf, code) are listed and worked off with
+// one per thread, so that the warps in the long decode are full.
+constexpr int LIST_THREADS = 256;
+constexpr uint32_t LIST_CHUNK = 2048;
+__global__ void __launch_bounds__(LIST_THREADS) ins_info_kernel(ParseTree T) {
+  __shared__ uint16_t listed[LIST_CHUNK];
+  __shared__ uint32_t n_listed;
+  const uint32_t chunk0 = blockIdx.x * LIST_CHUNK;
+  if (threadIdx.x == 0) n_listed = 0;
+  __syncthreads();
+#pragma unroll 1
+  for (uint32_t k = threadIdx.x; k < LIST_CHUNK; k += LIST_THREADS) {
+    const uint32_t i = chunk0 + k;
+    if (i > T.n_ins) break;
+    const uint32_t op = i < T.n_ins ? (uint32_t)__ldg(T.wit + T.ins_pos[i]) : (uint32_t)PPD_OP_HASH;
+    if (op == PPD_OP_LEAF || op == PPD_OP_EXTENSION || op == PPD_OP_ACCOUNT_LEAF || op == PPD_OP_CODE)
+      listed[atomicAdd(&n_listed, 1u)] = (uint16_t)k;
+    else
+      ins_info_one(T, i);
+  }
+  __syncthreads();
+  const uint32_t nl = n_listed;
+  for (uint32_t a = threadIdx.x; a < nl; a += LIST_THREADS) ins_info_one(T, chunk0 + listed[a]);
 }
 
 // heights as int16 (+ sentinel), stack underflow check
@@ -537,14 +724,82 @@ __global__ void min64_i16_kernel(const int16_t* __restrict__ in, uint32_t n_in, 
   out[j] = (int16_t)m;
 }
 
+// m0[c] = min of in[8c .. 8c + 7], m1[j] = min of in[64j .. 64j + 63]: one thread per cell of 64, eight 128-bit loads
+// (the arrays are carved at 256-byte boundaries inside one allocation, so a whole cell is always readable)
+__global__ void min8_64_i16_kernel(const int16_t* __restrict__ in, uint32_t n_in, int16_t* __restrict__ m0, int16_t* __restrict__ m1, uint32_t n_m1) {
+  uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n_m1) return;
+  int m = INT16_MAX;
+  uint32_t packed[4];
+#pragma unroll
+  for (uint32_t c = 0; c < 8; c++) {
+    const uint32_t lo = j * 64 + c * 8;
+    int mc = INT16_MAX;
+    if (lo < n_in) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(in + lo));
+      const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (uint32_t q = 0; q < 4; q++) {
+        const int a = (int)(int16_t)(wv[q] & 0xffffu), b = (int)(int16_t)(wv[q] >> 16);
+        if (lo + 2 * q < n_in) mc = min(mc, a);
+        if (lo + 2 * q + 1 < n_in) mc = min(mc, b);
+      }
+    }
+    m = min(m, mc);
+    const uint32_t h = (uint32_t)mc & 0xffffu;
+    packed[c >> 1] = (c & 1) ? (packed[c >> 1] | (h << 16)) : h;
+  }
+  reinterpret_cast<uint4*>(m0)[j] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+  m1[j] = (int16_t)m;
+}
+
+// smallest r > q with h16[r] < thr, over the pyramid with an extra 8-wide level (h16[n_ins] = INT16_MIN ends every
+// scan).  A scan that has to jump a sibling subtree of a few hundred instructions takes at most 7 single steps and
+// 7 steps of eight on either side of its steps of 64, instead of up to 63 single steps on either side.
+__device__ __forceinline__ uint32_t scan_right8(const ParseTree& T, uint32_t q, int thr) {
+  uint32_t p = q + 1;
+  for (;;) {
+    if ((p & 7u) == 0u) {
+      if ((p & 63u) == 0u) {
+        if ((p & 4095u) == 0u) {
+          if ((p & 262143u) == 0u && T.m3[p >> 18] >= thr) {
+            p += 262144u;
+            continue;
+          }
+          if (T.m2[p >> 12] >= thr) {
+            p += 4096u;
+            continue;
+          }
+        }
+        if (T.m1[p >> 6] >= thr) {
+          p += 64u;
+          continue;
+        }
+      }
+      if (T.m0[p >> 3] >= thr) {
+        p += 8u;
+        continue;
+      }
+    }
+    if (T.h16[p] < thr) return p;
+    p++;
+  }
+}
+
 // info = slot (bits 0-3) | role (bits 4-5: 0 child of branch / extension, 1 account code, 2 account storage)
 //        | depth << 8 | in_storage << 16 | storage_nonempty << 17 (account leaves)
+template <bool FINE>
 __global__ void link_kernel16(ParseTree T) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= T.n_ins) return;
-  Pyramid16 P{T.h16, T.m1, T.m2, T.m3};
   int ha = T.h16[i];
-  uint32_t j = scan_right(P, i, ha + 1);  // first j > i with height_after(j) <= height_after(i); n_ins when none
+  uint32_t j;  // first j > i with height_after(j) <= height_after(i); n_ins when none
+  if (FINE) {
+    j = scan_right8(T, i, ha + 1);
+  } else {
+    Pyramid16 P{T.h16, T.m1, T.m2, T.m3};
+    j = scan_right(P, i, ha + 1);
+  }
   T.parent[i] = j;
   uint32_t info = 0;
   if (j < T.n_ins) {
@@ -577,9 +832,7 @@ __global__ void link_kernel16(ParseTree T) {
 }
 
 // depth inside the own trie, trie membership, canonicity, per-instruction sizes
-__global__ void shape_kernel(ParseTree T) {
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i > T.n_ins) return;
+__device__ __forceinline__ void shape_one(const ParseTree& T, uint32_t i) {
   const size_t S = T.cnt_stride;
   if (i == T.n_ins) {
     for (int k = 0; k < PARSE_N_CNT; k++) T.cnt[k * S + i] = 0;
@@ -659,6 +912,32 @@ __global__ void shape_kernel(ParseTree T) {
   T.cnt[PARSE_C_ACCT * S + i] = c_acct;
   T.cnt[PARSE_C_CODE * S + i] = c_code;
 }
+__global__ void shape_kernel_v1(ParseTree T) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > T.n_ins) return;
+  shape_one(T, i);
+}
+// the instructions that walk to the root of their trie (everything but hashed-out nodes, code and empty roots) on a list
+__global__ void __launch_bounds__(LIST_THREADS) shape_kernel(ParseTree T) {
+  __shared__ uint16_t listed[LIST_CHUNK];
+  __shared__ uint32_t n_listed;
+  const uint32_t chunk0 = blockIdx.x * LIST_CHUNK;
+  if (threadIdx.x == 0) n_listed = 0;
+  __syncthreads();
+#pragma unroll 1
+  for (uint32_t k = threadIdx.x; k < LIST_CHUNK; k += LIST_THREADS) {
+    const uint32_t i = chunk0 + k;
+    if (i > T.n_ins) break;
+    const uint32_t op = i < T.n_ins ? (T.meta[i] & 7u) : (uint32_t)PPD_OP_HASH;
+    if (i < T.n_ins && op != PPD_OP_HASH && op != PPD_OP_CODE && op != PPD_OP_EMPTY_ROOT)
+      listed[atomicAdd(&n_listed, 1u)] = (uint16_t)k;
+    else
+      shape_one(T, i);
+  }
+  __syncthreads();
+  const uint32_t nl = n_listed;
+  for (uint32_t a = threadIdx.x; a < nl; a += LIST_THREADS) shape_one(T, chunk0 + listed[a]);
+}
 
 __global__ void totals_kernel(ParseTree T) {
   uint32_t k = threadIdx.x;
@@ -691,7 +970,7 @@ __device__ __forceinline__ void copy_bytes(uint8_t* __restrict__ dst, const uint
   for (uint32_t k = 0; k < n; k++) dst[k] = __ldg(src + k);
 }
 
-__global__ void __launch_bounds__(128) emit_kernel(ParseEmit E) {
+__global__ void __launch_bounds__(128) emit_kernel_v1(ParseEmit E) {
   const ParseTree& T = E.T;
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= T.n_ins) return;
@@ -818,6 +1097,157 @@ __global__ void __launch_bounds__(128) emit_kernel(ParseEmit E) {
   E.nodes[my_id] = NodeRec{dw0(NK_LEAF_ACCOUNT, d, kn), koff, a, 0};
 }
 
+// One instruction in twenty carries a key (leaf, extension, account leaf) and needs its path assembled by a walk up
+// its ancestors; with one instruction per thread those few lanes set every warp's instruction count (round-1 capture:
+// 6 of 32 threads active).  A thread block takes EMIT_CHUNK consecutive instructions: every thread does the short
+// work of its instructions (child slot of the parent branch, hashed-out node, branch record) and lists the keyed
+// ones; the list is then worked off with one keyed instruction per thread.
+constexpr int EMIT_THREADS = 256;
+constexpr uint32_t EMIT_CHUNK = 2048;
+
+__device__ __forceinline__ void emit_keyed(const ParseEmit& E, uint32_t i) {
+  const ParseTree& T = E.T;
+  const size_t S = T.cnt_stride;
+  const uint32_t meta = T.meta[i], op = meta & 7u, info = T.info[i];
+  const uint32_t pos = T.ins_pos[i];
+  const uint32_t my_id = T.scn[PARSE_C_NODE * S + i];
+  Ins o;
+  decode_ins(T.wit, T.n, pos, o);
+  const uint32_t d = (info >> 8) & 255u, kn = T.knib[i], nd = min(d + kn, 64u);
+  // the full path: own key nibbles, then every ancestor's contribution up to the root of the own trie
+  uint8_t pk[36];
+#pragma unroll
+  for (int k = 0; k < 36; k++) pk[k] = 0;
+  if (d + kn <= 64) put_key_nibbles(pk, d, T.wit, o.key_pos, o.key_len);
+  {
+    uint32_t cur = i;
+    for (uint32_t guard = 0; guard < 4096; guard++) {
+      uint32_t j = T.parent[cur];
+      if (j >= T.n_ins) break;
+      uint32_t pm = T.meta[j], pop = pm & 7u;
+      uint32_t pd = (T.info[j] >> 8) & 255u;
+      if (pop == PPD_OP_BRANCH) {
+        if (pd < 64) set_nib(pk, pd, nth_set_bit(pm >> 16, T.info[cur] & 15u));
+      } else if (pop == PPD_OP_EXTENSION) {
+        Ins e;
+        decode_ins(T.wit, T.n, T.ins_pos[j], e);
+        if (pd + T.knib[j] <= 64) put_key_nibbles(pk, pd, T.wit, e.key_pos, e.key_len);
+      } else {
+        break;
+      }
+      cur = j;
+    }
+  }
+  const uint32_t koff = T.scn[PARSE_C_KEY * S + i];
+  {
+    uint8_t* kd = E.key_pool + koff;
+    uint32_t nb = (nd + 1) / 2;
+    for (uint32_t k = 0; k < nb; k++) kd[k] = pk[k];
+    kd[nb] = 0;
+  }
+  if (op == PPD_OP_EXTENSION) {
+    E.nodes[my_id] = NodeRec{dw0(NK_EXT, d, kn), koff, i ? id_of(T, i - 1) : NODE_EMPTY, 0};
+    return;
+  }
+  if (op == PPD_OP_LEAF) {
+    // rlp_str(value), compact_to_partial_trie.rs:119
+    uint32_t voff = T.scn[PARSE_C_VAL * S + i], vl = o.val_len, hl = 0;
+    uint8_t* v = E.val_pool + voff;
+    if (!(vl == 1 && __ldg(T.wit + o.val_pos) < 0x80)) {
+      if (vl < 56) {
+        v[hl++] = (uint8_t)(0x80 + vl);
+      } else {
+        uint32_t k = vl < 256 ? 1 : vl < 65536 ? 2 : vl < (1u << 24) ? 3 : 4;
+        v[hl++] = (uint8_t)(0xb7 + k);
+        for (uint32_t q = k; q-- > 0;) v[hl++] = (uint8_t)(vl >> (8 * q));
+      }
+    }
+    copy_bytes(v + hl, T.wit + o.val_pos, vl);
+    E.nodes[my_id] = NodeRec{dw0(NK_LEAF, d, kn), koff, voff, hl + vl};
+    return;
+  }
+  // account leaf: the record (compact_to_partial_trie.rs:141-165), the storage trie's ROOT node, the host's list entry
+  const uint32_t a = T.scn[PARSE_C_ACCT * S + i];
+  const uint32_t nonempty = (info >> 17) & 1u;
+  uint32_t sroot = NODE_EMPTY, root_node = NODE_EMPTY;
+  if (meta & (2u << 8)) sroot = i ? id_of(T, i - 1) : NODE_EMPTY;
+  if (nonempty) {
+    root_node = my_id + 1;
+    E.nodes[root_node] = NodeRec{dw0(NK_ROOT, 0, 0), 0, sroot, 0};
+  }
+  {
+    uint32_t* r = reinterpret_cast<uint32_t*>(E.accounts + a);
+    uint8_t* rb = reinterpret_cast<uint8_t*>(r);
+    for (int k = 0; k < 36; k++) r[k] = 0;
+    for (int k = 0; k < 8; k++) rb[31 - k] = (uint8_t)(o.nonce >> (8 * k));
+    if (meta & (8u << 8)) copy_bytes(rb + 32 + 32 - o.val_len, T.wit + o.val_pos, o.val_len);
+    for (int k = 0; k < 32; k++) rb[64 + k] = C_EMPTY_TRIE_HASH[k];
+    uint32_t code_idx = NONE;
+    if (meta & (1u << 8)) {
+      uint32_t ci = T.aux0[i];
+      if (ci < T.n_ins) {
+        if ((T.meta[ci] & 7u) == PPD_OP_CODE) {
+          code_idx = T.scn[PARSE_C_CODE * S + ci];
+          const uint8_t* dg = E.code_digest + 32ull * code_idx;
+          for (int k = 0; k < 32; k++) rb[96 + k] = dg[k];
+        } else {
+          copy_bytes(rb + 96, T.wit + T.ins_pos[ci] + 1, 32);
+        }
+      }
+    } else {
+      for (int k = 0; k < 32; k++) rb[96 + k] = C_EMPTY_CODE_HASH[k];
+    }
+    r[32] = root_node;  // storage_src
+    uint32_t* L = E.acct_list + 5ull * a;
+    L[0] = my_id, L[1] = sroot, L[2] = root_node, L[3] = ((meta >> 9) & 1u) | (nonempty << 1), L[4] = code_idx;
+  }
+  E.nodes[my_id] = NodeRec{dw0(NK_LEAF_ACCOUNT, d, kn), koff, a, 0};
+}
+
+__global__ void __launch_bounds__(EMIT_THREADS, 3) emit_kernel(ParseEmit E) {
+  const ParseTree& T = E.T;
+  __shared__ uint16_t keyed[EMIT_CHUNK];
+  __shared__ uint32_t n_keyed;
+  const size_t S = T.cnt_stride;
+  const uint32_t chunk0 = blockIdx.x * EMIT_CHUNK;
+  if (threadIdx.x == 0) n_keyed = 0;
+  __syncthreads();
+#pragma unroll 1
+  for (uint32_t k = threadIdx.x; k < EMIT_CHUNK; k += EMIT_THREADS) {
+    const uint32_t i = chunk0 + k;
+    if (i >= T.n_ins) break;
+    const uint32_t meta = T.meta[i], op = meta & 7u, info = T.info[i];
+    const uint32_t my_id = id_of(T, i);
+    // register with the parent branch
+    {
+      uint32_t j = T.parent[i];
+      if (j >= T.n_ins) T.result[PARSE_R_ROOT_ID] = my_id;
+      if (j < T.n_ins && (T.meta[j] & 7u) == PPD_OP_BRANCH) E.child_pool[T.scn[PARSE_C_CHILD * S + j] + (info & 15u)] = my_id;
+    }
+    if (op == PPD_OP_HASH) {
+      uint32_t* dst = reinterpret_cast<uint32_t*>(E.hash_pool + 32ull * (my_id - HASH_BASE));
+      // 32 bytes at an arbitrary alignment: nine aligned words re-aligned with funnel shifts (the witness
+      // buffer is readable past its end)
+      const uintptr_t a = reinterpret_cast<uintptr_t>(T.wit + T.ins_pos[i] + 1);
+      const uint32_t* q = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
+      const uint32_t sh = (uint32_t)(a & 3) * 8;
+      uint32_t x[9];
+#pragma unroll
+      for (int c = 0; c < 9; c++) x[c] = __ldg(q + c);
+      uint4 lo = make_uint4(__funnelshift_r(x[0], x[1], sh), __funnelshift_r(x[1], x[2], sh), __funnelshift_r(x[2], x[3], sh), __funnelshift_r(x[3], x[4], sh));
+      uint4 hi = make_uint4(__funnelshift_r(x[4], x[5], sh), __funnelshift_r(x[5], x[6], sh), __funnelshift_r(x[6], x[7], sh), __funnelshift_r(x[7], x[8], sh));
+      reinterpret_cast<uint4*>(dst)[0] = lo, reinterpret_cast<uint4*>(dst)[1] = hi;
+    } else if (op == PPD_OP_BRANCH) {
+      E.nodes[my_id] = NodeRec{dw0(NK_BRANCH, 0, 0), T.scn[PARSE_C_CHILD * S + i], meta >> 16, 0};
+    } else if (op == PPD_OP_LEAF || op == PPD_OP_EXTENSION || op == PPD_OP_ACCOUNT_LEAF) {
+      keyed[atomicAdd(&n_keyed, 1u)] = (uint16_t)k;
+    }
+  }
+  __syncthreads();
+  const uint32_t nk = n_keyed;
+  for (uint32_t a = threadIdx.x; a < nk; a += EMIT_THREADS) emit_keyed(E, chunk0 + keyed[a]);
+}
+
 // levels: 1 + the maximum level of what a node reads (host_arena.h constructors), bottom-up
 __global__ void climb_kernel(ParseEmit E) {
   const ParseTree& T = E.T;
@@ -857,6 +1287,13 @@ __global__ void climb_kernel(ParseEmit E) {
 
 inline uint32_t cdiv(uint64_t a, uint32_t b) { return (uint32_t)((a + b - 1) / b); }
 
+// PPD_PARSE_V1=<mask>: the round-1 forms of tile_exit (1) / link (2) / emit (4) / tile_mark (8) / ins_info and shape (16),
+// kept for A/B timing; read per call
+inline bool parse_v1(int bit) {
+  const char* e = getenv("PPD_PARSE_V1");
+  return e && (atoi(e) & bit) != 0;
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------
@@ -873,13 +1310,24 @@ size_t parse_scan_tmp_words(size_t n, uint32_t K) {
 
 uint32_t launch_parse_bounds(const ParseBounds& B, cudaStream_t st) {
   const uint32_t group_bytes = B.group_tiles * TILE;
-  tile_exit_kernel<<<B.n_tiles, TE_THREADS, 0, st>>>(B.wit, B.n, B.exit1, B.step1);
+  if (parse_v1(1)) {
+    tile_exit_kernel_v1<<<B.n_tiles, TE_THREADS, 0, st>>>(B.wit, B.n, B.exit1, B.step1);
+  } else {
+    static const bool once = [] { return cudaFuncSetAttribute(tile_exit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TE_SMEM_BYTES) == cudaSuccess; }();
+    (void)once;
+    tile_exit_kernel<<<B.n_tiles, TE_THREADS, TE_SMEM_BYTES, st>>>(B.wit, B.n, B.exit1, B.step1);
+  }
   group_exit_kernel<<<dim3(TILE / 256, B.n_groups), 256, 0, st>>>(B.exit1, B.n, group_bytes, B.exit2);
   cudaMemsetAsync(B.group_entry, 0xff, 4ull * B.n_groups, st);
   cudaMemsetAsync(B.tile_entry, 0xff, 4ull * B.n_tiles, st);
   top_chain_kernel<<<1, 32, 0, st>>>(B.exit1, B.exit2, B.n, group_bytes, B.group_entry, B.result);
   tile_entry_kernel<<<cdiv(B.n_groups, 64), 64, 0, st>>>(B.exit1, B.group_entry, B.n, B.n_groups, group_bytes, B.tile_entry);
-  tile_mark_kernel<<<cdiv(B.n_tiles, TM_WARPS), TM_WARPS * 32, 0, st>>>(B.step1, B.n, B.n_tiles, B.tile_entry, B.bitmap, B.tile_count);
+  if (parse_v1(8)) {
+    tile_mark_kernel<<<cdiv(B.n_tiles, TM_WARPS), TM_WARPS * 32, 0, st>>>(B.step1, B.n, B.n_tiles, B.tile_entry, B.bitmap, B.tile_count);
+  } else {
+    cudaMemsetAsync(B.bitmap, 0, (size_t)B.n_tiles * (TILE / 8), st);
+    tile_mark_thin_kernel<<<cdiv(B.n_tiles, 128), 128, 0, st>>>(B.step1, B.n_tiles, B.tile_entry, B.bitmap, B.tile_count);
+  }
   cudaMemsetAsync(B.tile_count + B.n_tiles, 0, 4, st);
   uint32_t launches = 5 + mscan(B.tile_count, B.tile_base, B.n_tiles + 1, 0, 1, B.scan_tmp, st);
   cudaMemcpyAsync(B.result + PARSE_R_NINS, B.tile_base + B.n_tiles, 4, cudaMemcpyDeviceToDevice, st);
@@ -892,16 +1340,29 @@ void launch_parse_scatter(const ParseBounds& B, uint32_t* ins_pos, cudaStream_t 
 
 uint32_t launch_parse_tree(const ParseTree& T, cudaStream_t st) {
   const uint32_t n1 = T.n_ins + 1;
-  ins_info_kernel<<<cdiv(n1, 256), 256, 0, st>>>(T);
+  if (parse_v1(16))
+    ins_info_kernel_v1<<<cdiv(n1, 256), 256, 0, st>>>(T);
+  else
+    ins_info_kernel<<<cdiv(n1, LIST_CHUNK), LIST_THREADS, 0, st>>>(T);
   uint32_t launches = 8;  // ins_info, heights, 3 x min64, link, shape, totals
   launches += mscan(T.delta, T.hb, n1, 0, 1, T.scan_tmp, st);
   heights_kernel<<<cdiv(n1, 256), 256, 0, st>>>(T);
   const uint32_t n_m1 = cdiv(n1, 64), n_m2 = cdiv(n_m1, 64), n_m3 = cdiv(n_m2, 64);
-  min64_i16_kernel<<<cdiv(n_m1, 128), 128, 0, st>>>(T.h16, n1, T.m1, n_m1);
+  const bool v1 = parse_v1(2);
+  if (v1)
+    min64_i16_kernel<<<cdiv(n_m1, 128), 128, 0, st>>>(T.h16, n1, T.m1, n_m1);
+  else
+    min8_64_i16_kernel<<<cdiv(n_m1, 128), 128, 0, st>>>(T.h16, n1, T.m0, T.m1, n_m1);
   min64_i16_kernel<<<cdiv(n_m2, 128), 128, 0, st>>>(T.m1, n_m1, T.m2, n_m2);
   min64_i16_kernel<<<cdiv(n_m3, 128), 128, 0, st>>>(T.m2, n_m2, T.m3, n_m3);
-  link_kernel16<<<cdiv(T.n_ins, 256), 256, 0, st>>>(T);
-  shape_kernel<<<cdiv(n1, 256), 256, 0, st>>>(T);
+  if (v1)
+    link_kernel16<false><<<cdiv(T.n_ins, 256), 256, 0, st>>>(T);
+  else
+    link_kernel16<true><<<cdiv(T.n_ins, 256), 256, 0, st>>>(T);
+  if (parse_v1(16))
+    shape_kernel_v1<<<cdiv(n1, 256), 256, 0, st>>>(T);
+  else
+    shape_kernel<<<cdiv(n1, LIST_CHUNK), LIST_THREADS, 0, st>>>(T);
   launches += mscan(T.cnt, T.scn, n1, T.cnt_stride, PARSE_N_CNT, T.scan_tmp, st);
   totals_kernel<<<1, 32, 0, st>>>(T);
   return launches;
@@ -910,7 +1371,10 @@ uint32_t launch_parse_tree(const ParseTree& T, cudaStream_t st) {
 void launch_parse_code_list(const ParseEmit& E, cudaStream_t st) { code_list_kernel<<<cdiv(E.T.n_ins, 256), 256, 0, st>>>(E); }
 
 void launch_parse_emit(const ParseEmit& E, cudaStream_t st) {
-  emit_kernel<<<cdiv(E.T.n_ins, 128), 128, 0, st>>>(E);
+  if (parse_v1(4))
+    emit_kernel_v1<<<cdiv(E.T.n_ins, 128), 128, 0, st>>>(E);
+  else
+    emit_kernel<<<cdiv(E.T.n_ins, EMIT_CHUNK), EMIT_THREADS, 0, st>>>(E);
   climb_kernel<<<cdiv(E.T.n_ins, 256), 256, 0, st>>>(E);
 }
 
