@@ -712,15 +712,50 @@ int ppd_replay_last(ppd_ctx* c, unsigned what, double* gpu_ms_out) {
               ((what & (PPD_REPLAY_TXN | PPD_REPLAY_DUMP)) && L->has_last_txn);
     }
     if (!used) fail(PPD_ERR_BAD_ARGUMENT, "nothing of the requested kind is resident");
-    // all lanes start after ev0 on the main stream; the main stream then waits for every lane
-    CUDA_OK(cudaEventRecord(c->ev0, c->st));
-    for (size_t w = 0; w < n_lanes; w++) {
-      Lane* L = c->lanes[w];
-      CUDA_OK(cudaStreamWaitEvent(L->st, c->ev0, 0));
-      replay_lane(L, what);
-      CUDA_OK(cudaEventRecord(L->ev1, L->st));
-      CUDA_OK(cudaStreamWaitEvent(c->st, L->ev1, 0));
-    }
+    // all lanes start after ev0 on the main stream; the main stream then waits for every lane.  Every lane is queued by
+    // its own host thread, as in the decode itself (a lane's stages are 50-200 launches: queued by ONE thread, 30 lanes
+    // would measure that thread's launch rate -- about 5 us per call -- instead of the device).  PPD_REPLAY_THREADS=1
+    // gives the single-threaded form back.
+    static const unsigned replay_threads = [] {
+      const char* e = getenv("PPD_REPLAY_THREADS");
+      const long v = e ? atol(e) : 0;
+      return (unsigned)(v > 0 ? v : 0);
+    }();
+    const unsigned workers = (unsigned)std::min<size_t>(replay_threads ? replay_threads : std::max(1u, host_threads()), n_lanes);
+    // the threads exist and wait before ev0 is recorded, so that starting them is not inside the timed region
+    std::atomic<unsigned> ready{0};
+    std::atomic<bool> go{false}, failed{false};
+    Fail first{PPD_OK, ""};
+    std::mutex mu;
+    auto body = [&](unsigned t) {
+      try {
+        if (t) {
+          CUDA_OK(cudaSetDevice(c->device));
+          ready.fetch_add(1);
+          while (!go.load(std::memory_order_acquire)) std::this_thread::yield();
+        }
+        for (size_t w = t; w < n_lanes && !failed.load(); w += workers) {
+          Lane* L = c->lanes[w];
+          CUDA_OK(cudaStreamWaitEvent(L->st, c->ev0, 0));
+          replay_lane(L, what);
+          CUDA_OK(cudaEventRecord(L->ev1, L->st));
+        }
+      } catch (const Fail& e) {
+        if (t && !go.load()) ready.fetch_add(1);  // (cudaSetDevice failed before the thread reported in)
+        std::lock_guard<std::mutex> g(mu);
+        if (!failed.exchange(true)) first = e;
+      }
+    };
+    std::vector<std::thread> th;
+    for (unsigned t = 1; t < workers; t++) th.emplace_back(body, t);
+    while (ready.load() + 1 < workers) std::this_thread::yield();
+    cudaError_t e0 = cudaEventRecord(c->ev0, c->st);
+    go.store(true, std::memory_order_release);
+    if (e0 == cudaSuccess) body(0);
+    for (auto& t : th) t.join();
+    CUDA_OK(e0);
+    if (failed.load()) throw first;
+    for (size_t w = 0; w < n_lanes; w++) CUDA_OK(cudaStreamWaitEvent(c->st, c->lanes[w]->ev1, 0));
     CUDA_OK(cudaEventRecord(c->ev1, c->st));
     CUDA_OK(cudaStreamSynchronize(c->st));
     float ms = 0;

@@ -673,7 +673,7 @@ __global__ void ins_info_kernel_v1(ParseTree T) {
 // done in place, the keyed ones (one in twenty: leaf, extension, account leaf, code) are listed and worked off with
 // one per thread, so that the warps in the long decode are full.
 constexpr int LIST_THREADS = 256;
-constexpr uint32_t LIST_CHUNK = 2048;
+constexpr uint32_t LIST_CHUNK = 1024;
 __global__ void __launch_bounds__(LIST_THREADS) ins_info_kernel(ParseTree T) {
   __shared__ uint16_t listed[LIST_CHUNK];
   __shared__ uint32_t n_listed;
@@ -1103,7 +1103,7 @@ __global__ void __launch_bounds__(128) emit_kernel_v1(ParseEmit E) {
 // work of its instructions (child slot of the parent branch, hashed-out node, branch record) and lists the keyed
 // ones; the list is then worked off with one keyed instruction per thread.
 constexpr int EMIT_THREADS = 256;
-constexpr uint32_t EMIT_CHUNK = 2048;
+constexpr uint32_t EMIT_CHUNK = 1024;
 
 __device__ __forceinline__ void emit_keyed(const ParseEmit& E, uint32_t i) {
   const ParseTree& T = E.T;
