@@ -76,6 +76,15 @@ int ppd_keccak256_batch(ppd_ctx* ctx, const uint8_t* data, const uint64_t* offse
  * of every resulting trie (HashedPartialTrie::hash): TrieCompact bytes -> PreImageDump. */
 int ppd_compact_decode(ppd_ctx* ctx, const uint8_t* witness, size_t len, uint8_t** out, size_t* out_len);
 
+/* A Separate{state: Direct, storage: MultipleTries{Direct}} pre-image (trace_protocol.rs:58-108; the DirectPreImage
+ * payload of include/ppd_flat.h) re-spelled as the TrieCompact witness of the same tries, on the host, without a
+ * context: what ppd_block_decode does first with a kind-2 FlatBlock (csrc/host_direct.cu; processed_block_trace.rs:
+ * 130-168 is the reference side, whose storage half is todo!()).  Accounts whose storage trie is not in the payload
+ * appear in the witness with their storage root hashed out.  Structure only, no hashing.  Release with ppd_free.
+ * Returns PPD_ERR_BAD_FLAT_INPUT for a malformed payload, PPD_PANIC_PRE_IMAGE_ACCOUNT_DECODE for a state leaf that is
+ * not an RLP account. */
+int ppd_direct_to_compact(const uint8_t* direct, size_t len, uint8_t** out, size_t* out_len);
+
 /* BlockTrace::into_txn_proof_gen_ir (processed_block_trace.rs:38-50 -> decoding.rs:80-177):
  * FlatBlock -> IrDump (one GenerationInputs per txn, plus dummies / the withdrawal entry). */
 int ppd_block_decode(ppd_ctx* ctx, const uint8_t* flat_block, size_t len, uint8_t** out, size_t* out_len);

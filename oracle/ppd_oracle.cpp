@@ -1132,6 +1132,66 @@ struct Reader {
   }
 };
 
+// DirectPreImage (include/ppd_flat.h): Trie state_trie; u32 n_storage; n x { hashed_addr[32]; Trie }, tries in the
+// pre-order Node form of the IrDump.  trace_protocol.rs:97-99 (TrieDirect(HashedPartialTrie)), :101-108 (MultipleTries).
+static NodeP read_direct_node(Reader& r, int depth) {
+  if (depth > 130) fail(PPD_ERR_BAD_FLAT_INPUT, "direct trie nested deeper than any 64-nibble key allows");
+  switch (r.u8()) {
+    case PPD_NODE_EMPTY:
+      return EMPTY_NODE;
+    case PPD_NODE_HASH: {
+      H256 h;
+      r.raw(h.b, 32);
+      return mk_hash(h);
+    }
+    case PPD_NODE_BRANCH: {
+      std::array<NodeP, 16> ch;
+      for (int i = 0; i < 16; i++) ch[i] = read_direct_node(r, depth + 1);
+      return mk_branch(ch, r.bytes());
+    }
+    case PPD_NODE_EXTENSION: {
+      Nibs k;
+      uint8_t cnt = r.u8();
+      if (cnt > 64) fail(PPD_ERR_BAD_FLAT_INPUT, "direct trie: more than 64 nibbles");
+      for (int i = 0; i < cnt; i++) {
+        uint8_t v = r.u8();
+        if (v > 15) fail(PPD_ERR_BAD_FLAT_INPUT, "direct trie: nibble above 15");
+        k.push(v);
+      }
+      return mk_ext(k, read_direct_node(r, depth + 1));
+    }
+    case PPD_NODE_LEAF: {
+      Nibs k;
+      uint8_t cnt = r.u8();
+      if (cnt > 64) fail(PPD_ERR_BAD_FLAT_INPUT, "direct trie: more than 64 nibbles");
+      for (int i = 0; i < cnt; i++) {
+        uint8_t v = r.u8();
+        if (v > 15) fail(PPD_ERR_BAD_FLAT_INPUT, "direct trie: nibble above 15");
+        k.push(v);
+      }
+      return mk_leaf(k, r.bytes());
+    }
+    default:
+      fail(PPD_ERR_BAD_FLAT_INPUT, "direct trie: unknown node kind");
+  }
+  return EMPTY_NODE;
+}
+// process_separate_trie_pre_images (processed_block_trace.rs:130-141): tries as given, no code mappings
+static PreImage process_direct_pre_image(const uint8_t* p, size_t n) {
+  Reader r{p, n};
+  PreImage pre;
+  pre.version = 1;
+  pre.state = read_direct_node(r, 0);
+  uint32_t ns = r.u32();
+  for (uint32_t i = 0; i < ns; i++) {
+    H256 h;
+    r.raw(h.b, 32);
+    pre.storage[h] = read_direct_node(r, 0);
+  }
+  if (r.pos != r.n) fail(PPD_ERR_BAD_FLAT_INPUT, "bytes after the direct pre-image");
+  return pre;
+}
+
 struct Addr {
   uint8_t b[20];
 };
@@ -1150,7 +1210,8 @@ struct Txn {
   uint64_t gas_used;
 };
 struct Block {
-  Bytes compact;
+  uint32_t pre_image_kind = 0;  // 0 Combined{compact}; 2 Separate{Direct, MultipleTries{Direct}} (include/ppd_flat.h)
+  Bytes compact;                // the TrieCompact bytes, or the DirectPreImage payload
   std::vector<Txn> txns;
   std::map<H256, Bytes> resolved_code;
   std::vector<std::pair<Addr, std::array<uint8_t, 32>>> withdrawals;
@@ -1161,7 +1222,12 @@ static Block read_block(const uint8_t* p, size_t n) {
   Reader r{p, n};
   Block b;
   if (r.u32() != PPD_FLAT_BLOCK_MAGIC || r.u32() != 1) fail(PPD_ERR_BAD_FLAT_INPUT, "bad magic/version");
-  if (r.u32() != 0) fail(PPD_PANIC_UNIMPLEMENTED_PRE_IMAGE, "only Combined{compact} pre-images are implemented by the reference");
+  b.pre_image_kind = r.u32();
+  // processed_block_trace.rs:130-168: Separate{state: Direct} is `t.0`; every other Separate form ends in todo!().
+  // Kind 2 (Direct state trie + a Direct trie per hashed address) is this repo's completion of
+  // process_multiple_storage_tries -- each entry taken as the trie it holds, as process_state_trie does.
+  if (b.pre_image_kind != 0 && b.pre_image_kind != 2)
+    fail(PPD_PANIC_UNIMPLEMENTED_PRE_IMAGE, "pre-image variant the reference leaves as todo!()");
   b.compact = r.bytes();
   uint32_t nt = r.u32();
   for (uint32_t t = 0; t < nt; t++) {
@@ -1457,7 +1523,8 @@ static void apply_withdrawals(const Block& blk, NodeP& state) {
 }
 
 static std::vector<GenInputs> decode_block(const Block& blk) {
-  PreImage pre = process_compact_prestate(blk.compact.data(), blk.compact.size());
+  PreImage pre = blk.pre_image_kind == 2 ? process_direct_pre_image(blk.compact.data(), blk.compact.size())
+                                         : process_compact_prestate(blk.compact.data(), blk.compact.size());
   if (pre.version != 1) fail(PPD_PANIC_INCOMPATIBLE_HEADER_VERSION, "compact header version is not 1");
 
   std::vector<std::pair<H256, Account>> all_accounts;
@@ -1757,6 +1824,24 @@ int oracle_compact_decode(const uint8_t* w, size_t n, uint8_t** out, size_t* out
         g_stats = Stats();
         PreImage pre = process_compact_prestate(w, n);
         return finish(dump_pre_image(pre), out, out_len);
+      },
+      err, err_cap);
+}
+
+// process_compact_prestate -> the same tries as a DirectPreImage payload (include/ppd_flat.h): what a tracer that
+// sends Separate{Direct} pre-images would send for this state.  Test infrastructure for the kind-2 FlatBlock.
+int oracle_compact_to_direct(const uint8_t* w, size_t n, uint8_t** out, size_t* out_len, char* err, size_t err_cap) {
+  return guarded(
+      [&] {
+        PreImage pre = process_compact_prestate(w, n);
+        Writer wr;
+        dump_node(wr, *pre.state);
+        wr.u32((uint32_t)pre.storage.size());
+        for (const auto& s2 : pre.storage) {
+          wr.raw(s2.first.b, 32);
+          dump_node(wr, *s2.second);
+        }
+        return finish(wr.b, out, out_len);
       },
       err, err_cap);
 }

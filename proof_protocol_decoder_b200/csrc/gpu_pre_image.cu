@@ -177,6 +177,7 @@ bool gpu_pre_image(Lane* L, Job& J, BlockJob& b, bool check_version, Slots* slot
     T.parent = c.take<uint32_t>(n_ins);
     T.info = c.take<uint32_t>(n_ins);
     T.aux0 = c.take<uint32_t>(n_ins);
+    T.keyed = c.take<uint32_t>(n_ins);
     T.pending = c.take<uint32_t>(n_ins);
     T.lvlmax = c.take<uint32_t>(n_ins);
     T.cnt = c.take<uint32_t>(PARSE_N_CNT * T.cnt_stride);
@@ -211,6 +212,8 @@ bool gpu_pre_image(Lane* L, Job& J, BlockJob& b, bool check_version, Slots* slot
   // ---- phase C: emit the arena into the lane's buffers ----
   ParseEmit E{};
   E.T = T;
+  E.n_keyed = hr[PARSE_R_NKEYED];
+  if (E.n_keyed > n_ins) return false;
   uint16_t* d_level = nullptr;
   uint8_t* d_code_digest = nullptr;
   auto layout_c = [&](Carve& c) {

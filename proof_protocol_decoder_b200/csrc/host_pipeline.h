@@ -26,6 +26,7 @@
 #include <mutex>
 #include <string>
 #include <thread>
+#include <unordered_set>
 #include <unordered_map>
 #include <vector>
 
@@ -470,6 +471,10 @@ struct IrPlan {
 struct BlockJob {
   // input views
   Span compact;
+  uint32_t pre_image_kind = 0;         // 0 Combined{compact}; 2 Separate{Direct, MultipleTries{Direct}} (host_direct.cu)
+  Span direct;                         // kind 2: the DirectPreImage payload; `compact` then points into compact_owned
+  std::vector<uint8_t> compact_owned;  // kind 2: the pre-image re-spelled as a compact witness
+  std::vector<H256> direct_keep;       // kind 2: the hashed addresses that have a storage trie
   std::vector<TxnV> txns;
   std::unordered_map<H256, Span, H256Hasher> resolved_code;
   std::vector<std::pair<const uint8_t*, const uint8_t*>> withdrawals;
@@ -508,6 +513,9 @@ struct BlockJob {
 };
 
 void read_flat_block(const uint8_t* p, size_t n, BlockJob& b);
+// host_direct.cu: a kind-2 pre-image as a compact witness (b.compact, b.direct_keep); the storage map cut to b.direct_keep
+void direct_to_compact(BlockJob& b);
+void direct_filter_storage(BlockJob& b);
 // ---- minimal RLP helpers (structure only; no hashing): host_txn.cu ----
 uint32_t u256_sig(const uint8_t* be);
 void rlp_str(std::vector<uint8_t>& out, const uint8_t* p, size_t n);

@@ -9,8 +9,14 @@ namespace ppd {
 void read_flat_block(const uint8_t* p, size_t n, BlockJob& b) {
   FlatReader r{p, n};
   if (r.u32() != PPD_FLAT_BLOCK_MAGIC || r.u32() != 1) fail(PPD_ERR_BAD_FLAT_INPUT, "bad magic/version");
-  if (r.u32() != 0) fail(PPD_PANIC_UNIMPLEMENTED_PRE_IMAGE, "only Combined{compact} pre-images are implemented by the reference");
-  b.compact = r.bytes();
+  // processed_block_trace.rs:120-168: Combined{compact}, and Separate{Direct state trie, a Direct trie per hashed address}
+  // (kind 2, host_direct.cu); every other Separate form is todo!() in the reference
+  b.pre_image_kind = r.u32();
+  if (b.pre_image_kind != 0 && b.pre_image_kind != 2) fail(PPD_PANIC_UNIMPLEMENTED_PRE_IMAGE, "pre-image variant the reference leaves as todo!()");
+  if (b.pre_image_kind == 2)
+    b.direct = r.bytes();
+  else
+    b.compact = r.bytes();
   // counts are checked against the bytes that are left before anything is sized by them (a txn is at least 24 bytes,
   // a trace 21, a resolved-code entry 36, a withdrawal 52)
   uint32_t nt = r.u32();

@@ -422,6 +422,13 @@ void decode_one_inner(ppd_ctx* c, Lane* L, const uint8_t* flat, size_t len, uint
     try {
       read_flat_block(flat, len, b);
       pt.lap("read-flat");
+      if (b.pre_image_kind == 2) {
+        // a direct pre-image is re-spelled as a witness on the host; its storage map is by address, which the
+        // device path's by-root join does not express: the host-shaped path takes it
+        if (on_device) continue;
+        direct_to_compact(b);
+        pt.lap("direct");
+      }
       if (on_device) {
         if (gpu_block(c, L, J, flat, len, out, out_len) == GPU_BLOCK_DONE) {
           *status = PPD_OK;
@@ -435,7 +442,10 @@ void decode_one_inner(ppd_ctx* c, Lane* L, const uint8_t* flat, size_t len, uint
       J.kh.run(L);
       pt.lap("keyhash");
       if (!b.pre_image_built) build_pre_image(J, b);
-      if (b.storage_partial) join_storage_by_root(L, J, b);
+      if (b.pre_image_kind == 2)
+        direct_filter_storage(b);
+      else if (b.storage_partial)
+        join_storage_by_root(L, J, b);
       shape_block(J, b);
       pt.lap("shape");
       sweep(L, J, /*refs_to_host=*/!gpu_dump_enabled());

@@ -115,6 +115,7 @@ enum {  // words of ParseBounds::result / ParseTree::result (one 16-word device 
   PARSE_R_HEIGHT = 3,  // entries left on the stack (1 for a well-formed witness)
   PARSE_R_ROOT = 4,    // the instruction left on the stack
   PARSE_R_ROOT_ID = 5, // its arena id (written by the emit kernel)
+  PARSE_R_NKEYED = 6,  // entries of ParseTree::keyed (leaf, extension and account-leaf instructions)
   PARSE_R_TOTALS = 8,  // PARSE_N_CNT totals of the size counters
   PARSE_R_WORDS = 16
 };
@@ -159,6 +160,7 @@ struct ParseTree {
   uint32_t* parent;         // [n_ins]
   uint32_t* info;           // [n_ins]
   uint32_t* aux0;           // [n_ins]
+  uint32_t* keyed;          // [n_ins] the keyed instructions, in no particular order (shape_kernel); result[PARSE_R_NKEYED] of them
   uint32_t *pending, *lvlmax;
   uint32_t *cnt, *scn;      // [PARSE_N_CNT][cnt_stride]
   size_t cnt_stride;        // >= n_ins + 1
@@ -176,6 +178,7 @@ struct ParseEmit {
   uint64_t* code_se;           // [n_code][2] (begin, end) into the witness
   uint32_t* code_list;         // [n_code][2] (pos, len)
   const uint8_t* code_digest;  // [n_code][32]
+  uint32_t n_keyed;            // result[PARSE_R_NKEYED] as the host read it after phase B
 };
 size_t parse_scan_tmp_words(size_t n, uint32_t K);
 uint32_t launch_parse_bounds(const ParseBounds& B, cudaStream_t st);  // the launchers return the number of kernels launched

@@ -664,35 +664,10 @@ __device__ __forceinline__ void ins_info_one(const ParseTree& T, uint32_t i) {
   T.lvlmax[i] = 0;
   T.aux0[i] = NONE;
 }
-__global__ void ins_info_kernel_v1(ParseTree T) {
+__global__ void ins_info_kernel(ParseTree T) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i > T.n_ins) return;
   ins_info_one(T, i);
-}
-// A thread block takes LIST_CHUNK consecutive instructions: the short ones (hashed-out node, branch, empty root) are
-// done in place, the keyed ones (one in twenty: leaf, extension, account leaf, code) are listed and worked off with
-// one per thread, so that the warps in the long decode are full.
-constexpr int LIST_THREADS = 256;
-constexpr uint32_t LIST_CHUNK = 1024;
-__global__ void __launch_bounds__(LIST_THREADS) ins_info_kernel(ParseTree T) {
-  __shared__ uint16_t listed[LIST_CHUNK];
-  __shared__ uint32_t n_listed;
-  const uint32_t chunk0 = blockIdx.x * LIST_CHUNK;
-  if (threadIdx.x == 0) n_listed = 0;
-  __syncthreads();
-#pragma unroll 1
-  for (uint32_t k = threadIdx.x; k < LIST_CHUNK; k += LIST_THREADS) {
-    const uint32_t i = chunk0 + k;
-    if (i > T.n_ins) break;
-    const uint32_t op = i < T.n_ins ? (uint32_t)__ldg(T.wit + T.ins_pos[i]) : (uint32_t)PPD_OP_HASH;
-    if (op == PPD_OP_LEAF || op == PPD_OP_EXTENSION || op == PPD_OP_ACCOUNT_LEAF || op == PPD_OP_CODE)
-      listed[atomicAdd(&n_listed, 1u)] = (uint16_t)k;
-    else
-      ins_info_one(T, i);
-  }
-  __syncthreads();
-  const uint32_t nl = n_listed;
-  for (uint32_t a = threadIdx.x; a < nl; a += LIST_THREADS) ins_info_one(T, chunk0 + listed[a]);
 }
 
 // heights as int16 (+ sentinel), stack underflow check
@@ -912,31 +887,27 @@ __device__ __forceinline__ void shape_one(const ParseTree& T, uint32_t i) {
   T.cnt[PARSE_C_ACCT * S + i] = c_acct;
   T.cnt[PARSE_C_CODE * S + i] = c_code;
 }
-__global__ void shape_kernel_v1(ParseTree T) {
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i > T.n_ins) return;
-  shape_one(T, i);
-}
-// the instructions that walk to the root of their trie (everything but hashed-out nodes, code and empty roots) on a list
-__global__ void __launch_bounds__(LIST_THREADS) shape_kernel(ParseTree T) {
-  __shared__ uint16_t listed[LIST_CHUNK];
-  __shared__ uint32_t n_listed;
-  const uint32_t chunk0 = blockIdx.x * LIST_CHUNK;
-  if (threadIdx.x == 0) n_listed = 0;
+// One thread per instruction; the keyed instructions (leaf, extension, account leaf: the ones whose path the emit
+// phase assembles by a walk up their ancestors) are appended to T.keyed, one global atomic per thread block, so that
+// emit_keyed_kernel runs with full warps.  The list's order is the order thread blocks finish in; nothing depends on it.
+__global__ void __launch_bounds__(256) shape_kernel(ParseTree T) {
+  __shared__ uint32_t n_here, base;
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (threadIdx.x == 0) n_here = 0;
   __syncthreads();
-#pragma unroll 1
-  for (uint32_t k = threadIdx.x; k < LIST_CHUNK; k += LIST_THREADS) {
-    const uint32_t i = chunk0 + k;
-    if (i > T.n_ins) break;
-    const uint32_t op = i < T.n_ins ? (T.meta[i] & 7u) : (uint32_t)PPD_OP_HASH;
-    if (i < T.n_ins && op != PPD_OP_HASH && op != PPD_OP_CODE && op != PPD_OP_EMPTY_ROOT)
-      listed[atomicAdd(&n_listed, 1u)] = (uint16_t)k;
-    else
-      shape_one(T, i);
+  bool keyed = false;
+  if (i <= T.n_ins) {
+    shape_one(T, i);
+    if (i < T.n_ins) {
+      const uint32_t op = T.meta[i] & 7u;
+      keyed = op == PPD_OP_LEAF || op == PPD_OP_EXTENSION || op == PPD_OP_ACCOUNT_LEAF;
+    }
   }
+  const uint32_t at = keyed ? atomicAdd(&n_here, 1u) : 0u;
   __syncthreads();
-  const uint32_t nl = n_listed;
-  for (uint32_t a = threadIdx.x; a < nl; a += LIST_THREADS) shape_one(T, chunk0 + listed[a]);
+  if (threadIdx.x == 0 && n_here) base = atomicAdd(T.result + PARSE_R_NKEYED, n_here);
+  __syncthreads();
+  if (keyed) T.keyed[base + at] = i;
 }
 
 __global__ void totals_kernel(ParseTree T) {
@@ -1099,12 +1070,9 @@ __global__ void __launch_bounds__(128) emit_kernel_v1(ParseEmit E) {
 
 // One instruction in twenty carries a key (leaf, extension, account leaf) and needs its path assembled by a walk up
 // its ancestors; with one instruction per thread those few lanes set every warp's instruction count (round-1 capture:
-// 6 of 32 threads active).  A thread block takes EMIT_CHUNK consecutive instructions: every thread does the short
-// work of its instructions (child slot of the parent branch, hashed-out node, branch record) and lists the keyed
-// ones; the list is then worked off with one keyed instruction per thread.
-constexpr int EMIT_THREADS = 256;
-constexpr uint32_t EMIT_CHUNK = 1024;
-
+// 6 of 32 threads active, 58 M warp instructions).  emit_kernel does the short work of every instruction (child slot
+// of the parent branch, hashed-out node, branch record); emit_keyed_kernel takes the keyed instructions from the
+// list shape_kernel made, one per thread.
 __device__ __forceinline__ void emit_keyed(const ParseEmit& E, uint32_t i) {
   const ParseTree& T = E.T;
   const size_t S = T.cnt_stride;
@@ -1204,48 +1172,40 @@ __device__ __forceinline__ void emit_keyed(const ParseEmit& E, uint32_t i) {
   E.nodes[my_id] = NodeRec{dw0(NK_LEAF_ACCOUNT, d, kn), koff, a, 0};
 }
 
-__global__ void __launch_bounds__(EMIT_THREADS, 3) emit_kernel(ParseEmit E) {
+__global__ void __launch_bounds__(256) emit_kernel(ParseEmit E) {
   const ParseTree& T = E.T;
-  __shared__ uint16_t keyed[EMIT_CHUNK];
-  __shared__ uint32_t n_keyed;
   const size_t S = T.cnt_stride;
-  const uint32_t chunk0 = blockIdx.x * EMIT_CHUNK;
-  if (threadIdx.x == 0) n_keyed = 0;
-  __syncthreads();
-#pragma unroll 1
-  for (uint32_t k = threadIdx.x; k < EMIT_CHUNK; k += EMIT_THREADS) {
-    const uint32_t i = chunk0 + k;
-    if (i >= T.n_ins) break;
-    const uint32_t meta = T.meta[i], op = meta & 7u, info = T.info[i];
-    const uint32_t my_id = id_of(T, i);
-    // register with the parent branch
-    {
-      uint32_t j = T.parent[i];
-      if (j >= T.n_ins) T.result[PARSE_R_ROOT_ID] = my_id;
-      if (j < T.n_ins && (T.meta[j] & 7u) == PPD_OP_BRANCH) E.child_pool[T.scn[PARSE_C_CHILD * S + j] + (info & 15u)] = my_id;
-    }
-    if (op == PPD_OP_HASH) {
-      uint32_t* dst = reinterpret_cast<uint32_t*>(E.hash_pool + 32ull * (my_id - HASH_BASE));
-      // 32 bytes at an arbitrary alignment: nine aligned words re-aligned with funnel shifts (the witness
-      // buffer is readable past its end)
-      const uintptr_t a = reinterpret_cast<uintptr_t>(T.wit + T.ins_pos[i] + 1);
-      const uint32_t* q = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
-      const uint32_t sh = (uint32_t)(a & 3) * 8;
-      uint32_t x[9];
-#pragma unroll
-      for (int c = 0; c < 9; c++) x[c] = __ldg(q + c);
-      uint4 lo = make_uint4(__funnelshift_r(x[0], x[1], sh), __funnelshift_r(x[1], x[2], sh), __funnelshift_r(x[2], x[3], sh), __funnelshift_r(x[3], x[4], sh));
-      uint4 hi = make_uint4(__funnelshift_r(x[4], x[5], sh), __funnelshift_r(x[5], x[6], sh), __funnelshift_r(x[6], x[7], sh), __funnelshift_r(x[7], x[8], sh));
-      reinterpret_cast<uint4*>(dst)[0] = lo, reinterpret_cast<uint4*>(dst)[1] = hi;
-    } else if (op == PPD_OP_BRANCH) {
-      E.nodes[my_id] = NodeRec{dw0(NK_BRANCH, 0, 0), T.scn[PARSE_C_CHILD * S + i], meta >> 16, 0};
-    } else if (op == PPD_OP_LEAF || op == PPD_OP_EXTENSION || op == PPD_OP_ACCOUNT_LEAF) {
-      keyed[atomicAdd(&n_keyed, 1u)] = (uint16_t)k;
-    }
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= T.n_ins) return;
+  const uint32_t meta = T.meta[i], op = meta & 7u, info = T.info[i];
+  const uint32_t my_id = id_of(T, i);
+  // register with the parent branch
+  {
+    uint32_t j = T.parent[i];
+    if (j >= T.n_ins) T.result[PARSE_R_ROOT_ID] = my_id;
+    if (j < T.n_ins && (T.meta[j] & 7u) == PPD_OP_BRANCH) E.child_pool[T.scn[PARSE_C_CHILD * S + j] + (info & 15u)] = my_id;
   }
-  __syncthreads();
-  const uint32_t nk = n_keyed;
-  for (uint32_t a = threadIdx.x; a < nk; a += EMIT_THREADS) emit_keyed(E, chunk0 + keyed[a]);
+  if (op == PPD_OP_HASH) {
+    uint32_t* dst = reinterpret_cast<uint32_t*>(E.hash_pool + 32ull * (my_id - HASH_BASE));
+    // 32 bytes at an arbitrary alignment: nine aligned words re-aligned with funnel shifts (the witness
+    // buffer is readable past its end)
+    const uintptr_t a = reinterpret_cast<uintptr_t>(T.wit + T.ins_pos[i] + 1);
+    const uint32_t* q = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
+    const uint32_t sh = (uint32_t)(a & 3) * 8;
+    uint32_t x[9];
+#pragma unroll
+    for (int c = 0; c < 9; c++) x[c] = __ldg(q + c);
+    uint4 lo = make_uint4(__funnelshift_r(x[0], x[1], sh), __funnelshift_r(x[1], x[2], sh), __funnelshift_r(x[2], x[3], sh), __funnelshift_r(x[3], x[4], sh));
+    uint4 hi = make_uint4(__funnelshift_r(x[4], x[5], sh), __funnelshift_r(x[5], x[6], sh), __funnelshift_r(x[6], x[7], sh), __funnelshift_r(x[7], x[8], sh));
+    reinterpret_cast<uint4*>(dst)[0] = lo, reinterpret_cast<uint4*>(dst)[1] = hi;
+  } else if (op == PPD_OP_BRANCH) {
+    E.nodes[my_id] = NodeRec{dw0(NK_BRANCH, 0, 0), T.scn[PARSE_C_CHILD * S + i], meta >> 16, 0};
+  }
+}
+__global__ void __launch_bounds__(128) emit_keyed_kernel(ParseEmit E) {
+  const uint32_t a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= E.n_keyed) return;
+  emit_keyed(E, E.T.keyed[a]);
 }
 
 // levels: 1 + the maximum level of what a node reads (host_arena.h constructors), bottom-up
@@ -1271,8 +1231,10 @@ __global__ void climb_kernel(ParseEmit E) {
       if (nonempty) E.level[nid + 1] = (uint16_t)min(lv + 1, 65535u);
       lv = nonempty ? lv + 2 : 0;
     } else if (pop == PPD_OP_BRANCH || pop == PPD_OP_EXTENSION) {
-      atomicMax(T.lvlmax + j, lv);
-      __threadfence();
+      if (lv) {  // (lvlmax starts at 0: a level-0 child -- two instructions in three are hashed-out nodes -- has nothing to add)
+        atomicMax(T.lvlmax + j, lv);
+        __threadfence();
+      }
       uint32_t old = atomicSub(T.pending + j, 1u);
       if (old != 1u) break;
       __threadfence();
@@ -1287,8 +1249,8 @@ __global__ void climb_kernel(ParseEmit E) {
 
 inline uint32_t cdiv(uint64_t a, uint32_t b) { return (uint32_t)((a + b - 1) / b); }
 
-// PPD_PARSE_V1=<mask>: the round-1 forms of tile_exit (1) / link (2) / emit (4) / tile_mark (8) / ins_info and shape (16),
-// kept for A/B timing; read per call
+// PPD_PARSE_V1=<mask>: the round-1 forms of tile_exit (1) / link (2) / emit (4) / tile_mark (8), kept for A/B timing;
+// read per call
 inline bool parse_v1(int bit) {
   const char* e = getenv("PPD_PARSE_V1");
   return e && (atoi(e) & bit) != 0;
@@ -1340,10 +1302,7 @@ void launch_parse_scatter(const ParseBounds& B, uint32_t* ins_pos, cudaStream_t 
 
 uint32_t launch_parse_tree(const ParseTree& T, cudaStream_t st) {
   const uint32_t n1 = T.n_ins + 1;
-  if (parse_v1(16))
-    ins_info_kernel_v1<<<cdiv(n1, 256), 256, 0, st>>>(T);
-  else
-    ins_info_kernel<<<cdiv(n1, LIST_CHUNK), LIST_THREADS, 0, st>>>(T);
+  ins_info_kernel<<<cdiv(n1, 256), 256, 0, st>>>(T);
   uint32_t launches = 8;  // ins_info, heights, 3 x min64, link, shape, totals
   launches += mscan(T.delta, T.hb, n1, 0, 1, T.scan_tmp, st);
   heights_kernel<<<cdiv(n1, 256), 256, 0, st>>>(T);
@@ -1359,10 +1318,7 @@ uint32_t launch_parse_tree(const ParseTree& T, cudaStream_t st) {
     link_kernel16<false><<<cdiv(T.n_ins, 256), 256, 0, st>>>(T);
   else
     link_kernel16<true><<<cdiv(T.n_ins, 256), 256, 0, st>>>(T);
-  if (parse_v1(16))
-    shape_kernel_v1<<<cdiv(n1, 256), 256, 0, st>>>(T);
-  else
-    shape_kernel<<<cdiv(n1, LIST_CHUNK), LIST_THREADS, 0, st>>>(T);
+  shape_kernel<<<cdiv(n1, 256), 256, 0, st>>>(T);
   launches += mscan(T.cnt, T.scn, n1, T.cnt_stride, PARSE_N_CNT, T.scan_tmp, st);
   totals_kernel<<<1, 32, 0, st>>>(T);
   return launches;
@@ -1371,10 +1327,12 @@ uint32_t launch_parse_tree(const ParseTree& T, cudaStream_t st) {
 void launch_parse_code_list(const ParseEmit& E, cudaStream_t st) { code_list_kernel<<<cdiv(E.T.n_ins, 256), 256, 0, st>>>(E); }
 
 void launch_parse_emit(const ParseEmit& E, cudaStream_t st) {
-  if (parse_v1(4))
+  if (parse_v1(4)) {
     emit_kernel_v1<<<cdiv(E.T.n_ins, 128), 128, 0, st>>>(E);
-  else
-    emit_kernel<<<cdiv(E.T.n_ins, EMIT_CHUNK), EMIT_THREADS, 0, st>>>(E);
+  } else {
+    emit_kernel<<<cdiv(E.T.n_ins, 256), 256, 0, st>>>(E);
+    if (E.n_keyed) emit_keyed_kernel<<<cdiv(E.n_keyed, 128), 128, 0, st>>>(E);
+  }
   climb_kernel<<<cdiv(E.T.n_ins, 256), 256, 0, st>>>(E);
 }
 

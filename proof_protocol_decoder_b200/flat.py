@@ -20,12 +20,74 @@ def _bytes(b) -> bytes:
     return struct.pack("<I", len(b)) + b
 
 
-def encode_flat_block(compact, txns, resolved_code, withdrawals, checkpoint_state_trie_root, b_meta=b"", b_hashes=b"") -> bytes:
+PRE_IMAGE_COMBINED, PRE_IMAGE_DIRECT = 0, 2
+
+
+def encode_node(node) -> bytes:
+    """A trie in the pre-order Node form of include/ppd_flat.h, from the tuples `parse_ir_dump` gives:
+    ("empty",) | ("hash", h32) | ("branch", [16 nodes], value) | ("extension", nibbles, node) | ("leaf", nibbles, value)."""
+    k = node[0]
+    if k == "empty":
+        return bytes([NODE_EMPTY])
+    if k == "hash":
+        assert len(node[1]) == 32
+        return bytes([NODE_HASH]) + bytes(node[1])
+    if k == "branch":
+        assert len(node[1]) == 16
+        return bytes([NODE_BRANCH]) + b"".join(encode_node(c) for c in node[1]) + _bytes(node[2])
+    if k == "extension":
+        return bytes([NODE_EXTENSION, len(node[1])]) + bytes(node[1]) + encode_node(node[2])
+    if k == "leaf":
+        return bytes([NODE_LEAF, len(node[1])]) + bytes(node[1]) + _bytes(node[2])
+    raise ValueError("bad node %r" % (k,))
+
+
+def encode_direct_pre_image(state_trie, storage_tries) -> bytes:
+    """DirectPreImage payload (pre_image_kind 2): the state trie, then a trie per hashed address, sorted by address.
+    Tries are node tuples (see encode_node) or already encoded bytes."""
+    enc = lambda t: bytes(t) if isinstance(t, (bytes, bytearray, memoryview)) else encode_node(t)  # noqa: E731
+    items = sorted((bytes(h), t) for h, t in (storage_tries.items() if isinstance(storage_tries, dict) else storage_tries))
+    out = [enc(state_trie), struct.pack("<I", len(items))]
+    for h, t in items:
+        assert len(h) == 32
+        out.append(h + enc(t))
+    return b"".join(out)
+
+
+def parse_direct_pre_image(b: bytes):
+    """-> (state trie, {hashed address: trie}) as node tuples"""
+    r = _R(b)
+    state = _node(r)
+    storage = {}
+    for _ in range(r.u32()):
+        h = r.take(32)
+        storage[h] = _node(r)
+    assert r.p == len(b), "trailing bytes in DirectPreImage"
+    return state, storage
+
+
+def with_pre_image(flat_block: bytes, kind: int, payload: bytes) -> bytes:
+    """`flat_block` with its pre-image replaced (kind: PRE_IMAGE_COMBINED with TrieCompact bytes, PRE_IMAGE_DIRECT with
+    a DirectPreImage payload)."""
+    magic, ver, _kind, n = struct.unpack_from("<IIII", flat_block, 0)
+    assert magic == FLAT_BLOCK_MAGIC and ver == 1
+    return struct.pack("<III", magic, ver, kind) + _bytes(payload) + bytes(flat_block[16 + n :])
+
+
+def pre_image_of(flat_block: bytes):
+    """-> (kind, payload) of a FlatBlock"""
+    magic, ver, kind, n = struct.unpack_from("<IIII", flat_block, 0)
+    assert magic == FLAT_BLOCK_MAGIC and ver == 1
+    return kind, bytes(flat_block[16 : 16 + n])
+
+
+def encode_flat_block(compact, txns, resolved_code, withdrawals, checkpoint_state_trie_root, b_meta=b"", b_hashes=b"", pre_image_kind=PRE_IMAGE_COMBINED) -> bytes:
     """txns: list of dicts {traces: [(addr20, trace dict)], byte_code, new_txn_trie_node_byte,
     new_receipt_trie_node_byte, gas_used}; trace dict keys: balance, nonce (int or None),
     storage_read (list of 32-byte keys or None), storage_written (list of (key32, int value) or None),
-    code_read (32-byte hash) | code_write (bytes), self_destructed (bool)."""
-    out = [struct.pack("<III", FLAT_BLOCK_MAGIC, 1, 0), _bytes(compact), struct.pack("<I", len(txns))]
+    code_read (32-byte hash) | code_write (bytes), self_destructed (bool).
+    `compact`: the TrieCompact bytes, or with pre_image_kind=PRE_IMAGE_DIRECT a DirectPreImage payload."""
+    out = [struct.pack("<III", FLAT_BLOCK_MAGIC, 1, pre_image_kind), _bytes(compact), struct.pack("<I", len(txns))]
     for tx in txns:
         out.append(struct.pack("<I", len(tx["traces"])))
         for addr, tr in tx["traces"]:

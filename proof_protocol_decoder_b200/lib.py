@@ -109,6 +109,7 @@ EXPORTS = [
     "ppd_replay_last_hashing",
     "ppd_replay_last_parse",
     "ppd_microbench",
+    "ppd_direct_to_compact",
 ]
 
 
@@ -154,8 +155,23 @@ class PpdLibrary:
         L.ppd_trie_subroot_sorted_leaves_dev.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_uint32, ctypes.c_char_p]
         L.ppd_trie_root_from_children.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_uint32, ctypes.c_char_p]
 
+        L.ppd_direct_to_compact.argtypes = [ctypes.c_void_p, ctypes.c_size_t, u8pp, szp]
+
     def exported(self):
         return [name for name in EXPORTS if hasattr(self.L, name)]
+
+    def direct_to_compact(self, direct: bytes) -> bytes:
+        """ppd_direct_to_compact: a DirectPreImage payload (FlatBlock pre_image_kind 2) as the TrieCompact witness of the
+        same tries.  Host only: needs no context and no device."""
+        out, n = ctypes.POINTER(ctypes.c_uint8)(), ctypes.c_size_t()
+        buf = ctypes.create_string_buffer(bytes(direct), len(direct)) if len(direct) else ctypes.create_string_buffer(1)
+        rc = self.L.ppd_direct_to_compact(buf, len(direct), ctypes.byref(out), ctypes.byref(n))
+        if rc != 0:
+            raise PpdError(rc, "ppd_direct_to_compact")
+        try:
+            return ctypes.string_at(out, n.value)
+        finally:
+            self.L.ppd_free(out)
 
 
 class OwnedBuffer:

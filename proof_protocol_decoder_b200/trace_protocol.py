@@ -78,8 +78,12 @@ class ProcessingMeta:
 
 @dataclass
 class BlockTrace:
-    """trace_protocol.rs:40-48.  `trie_pre_images` is {"combined": {"compact": bytes}}: the only
-    variant the reference implements end to end (processed_block_trace.rs:117-181)."""
+    """trace_protocol.rs:40-48.  `trie_pre_images` is {"combined": {"compact": bytes}} -- the only variant the
+    reference implements end to end (processed_block_trace.rs:117-181) -- or
+    {"separate": {"state": {"direct": trie}, "storage": {"multiple_tries": {hashed address: {"direct": trie}}}}}
+    (trace_protocol.rs:58-108) with tries as node tuples (flat.encode_node) or encoded bytes: FlatBlock kind 2, this
+    repo's completion of the reference's todo!() for a Direct trie per account (csrc/host_direct.cu).  Every other
+    `separate` form is reported as unimplemented, as the reference's todo!() would."""
 
     trie_pre_images: dict
     txn_info: List[TxnInfo] = field(default_factory=list)
@@ -98,9 +102,17 @@ class BlockTrace:
 
     def to_flat(self, p_meta: ProcessingMeta, other_data: OtherBlockData) -> bytes:
         pre = self.trie_pre_images
-        if "combined" not in pre:
-            raise PpdError(45, "only Combined{compact} pre-images are implemented by the reference (todo!() at processed_block_trace.rs:144,161,167)")
-        compact = pre["combined"]["compact"]
+        kind = flat.PRE_IMAGE_COMBINED
+        if "combined" in pre:
+            compact = pre["combined"]["compact"]
+        else:
+            sep = pre.get("separate") or {}
+            state, storage = sep.get("state") or {}, sep.get("storage") or {}
+            tries = storage.get("multiple_tries") if isinstance(storage, dict) else None
+            if not (isinstance(state, dict) and "direct" in state and isinstance(tries, dict) and all(isinstance(t, dict) and "direct" in t for t in tries.values())):
+                raise PpdError(45, "pre-image variant the reference leaves as todo!() (processed_block_trace.rs:144,161,167)")
+            kind = flat.PRE_IMAGE_DIRECT
+            compact = flat.encode_direct_pre_image(state["direct"], {h: t["direct"] for h, t in tries.items()})
         txns, wanted = [], []
         for ti in self.txn_info:
             traces = []
@@ -135,7 +147,8 @@ class BlockTrace:
                 if code is not None:  # None: the caller knows the witness carries this code
                     resolved.append((h, code))
         return flat.encode_flat_block(
-            compact, txns, resolved, other_data.b_data.withdrawals, other_data.checkpoint_state_trie_root, other_data.b_data.b_meta, other_data.b_data.b_hashes
+            compact, txns, resolved, other_data.b_data.withdrawals, other_data.checkpoint_state_trie_root, other_data.b_data.b_meta, other_data.b_data.b_hashes,
+            pre_image_kind=kind,
         )
 
     def into_txn_proof_gen_ir(self, p_meta: ProcessingMeta, other_data: OtherBlockData, ctx: Optional[Context] = None):

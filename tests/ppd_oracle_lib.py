@@ -28,7 +28,7 @@ class Oracle:
         L = ctypes.CDLL(path)
         self.L = L
         u8p = ctypes.POINTER(ctypes.c_uint8)
-        for name in ("oracle_compact_instructions", "oracle_compact_decode", "oracle_block_decode"):
+        for name in ("oracle_compact_instructions", "oracle_compact_decode", "oracle_block_decode", "oracle_compact_to_direct"):
             getattr(L, name).argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.POINTER(u8p), ctypes.POINTER(ctypes.c_size_t), ctypes.c_char_p, ctypes.c_size_t]
             getattr(L, name).restype = ctypes.c_int
         L.oracle_free.argtypes = [ctypes.c_void_p]
@@ -81,6 +81,10 @@ class Oracle:
 
     def block_decode(self, flat: bytes) -> bytes:
         return self._call(self.L.oracle_block_decode, flat)
+
+    def compact_to_direct(self, witness: bytes) -> bytes:
+        """The tries a compact witness decodes to, as a DirectPreImage payload (include/ppd_flat.h, pre_image_kind 2)."""
+        return self._call(self.L.oracle_compact_to_direct, witness)
 
     def trie_root_from_leaves(self, keys, val_off, vals) -> bytes:
         import numpy as np
