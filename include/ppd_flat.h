@@ -9,7 +9,17 @@
  *
  *   u32 magic = PPD_FLAT_BLOCK_MAGIC, u32 version = 1
  *   u32 pre_image_kind      0 = Combined{compact} (the only variant the reference implements end to end)
- *   u32 compact_len, u8 compact[compact_len]                 TrieCompact bytes
+ *                           2 = Separate{state: Direct, storage: MultipleTries{hashed address -> Direct}}
+ *                               (trace_protocol.rs:58-108).  The reference takes the Direct state trie as it is
+ *                               (processed_block_trace.rs:143-148) and leaves the storage half as todo!() (:164-168);
+ *                               kind 2 completes it: every entry is the trie it holds, no code mappings (:139).
+ *                           any other value: PPD_PANIC_UNIMPLEMENTED_PRE_IMAGE (the reference's todo!() variants)
+ *   u32 pre_image_len, u8 pre_image[pre_image_len]
+ *                           kind 0: TrieCompact bytes
+ *                           kind 2: DirectPreImage := Trie state_trie
+ *                                                     u32 n_storage; n x { u8 hashed_addr[32]; Trie }
+ *                                   (Trie as in the IrDump below; state leaves hold rlp(AccountRlp), storage leaves
+ *                                   rlp(value), exactly the bytes the tries hash)
  *   u32 n_txns
  *   n_txns x TxnInfo:
  *     u32 n_traces

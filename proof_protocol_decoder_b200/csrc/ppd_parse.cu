@@ -301,8 +301,9 @@ __global__ void __launch_bounds__(TE_THREADS, 3) tile_exit_kernel_v1(const uint8
 // then the pointer doubling over the positions whose instruction ends inside the tile, as before.
 constexpr uint32_t TE_SMEM_BYTES = 4 * TILE + 4 * 2 * TILE + (TILE + HALO) + 16;
 
-__global__ void __launch_bounds__(TE_THREADS, 3) tile_exit_kernel(const uint8_t* __restrict__ w, uint32_t n, uint32_t* __restrict__ exit1,
-                                                                  uint16_t* __restrict__ step1) {
+template <int MIN_BLOCKS>  // resident thread blocks per SM the register budget is set for (4: 32 registers, a few spilled words in the long decode)
+__global__ void __launch_bounds__(TE_THREADS, MIN_BLOCKS) tile_exit_kernel(const uint8_t* __restrict__ w, uint32_t n, uint32_t* __restrict__ exit1,
+                                                                           uint16_t* __restrict__ step1) {
   extern __shared__ __align__(16) uint8_t te_smem[];
   uint32_t* nxt = reinterpret_cast<uint32_t*>(te_smem);            // [TILE]
   uint16_t* step = reinterpret_cast<uint16_t*>(te_smem + 4 * TILE);  // [TILE] single-step links inside the tile (0xffff: the instruction ends outside), for tile_mark_kernel
@@ -1275,9 +1276,19 @@ uint32_t launch_parse_bounds(const ParseBounds& B, cudaStream_t st) {
   if (parse_v1(1)) {
     tile_exit_kernel_v1<<<B.n_tiles, TE_THREADS, 0, st>>>(B.wit, B.n, B.exit1, B.step1);
   } else {
-    static const bool once = [] { return cudaFuncSetAttribute(tile_exit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TE_SMEM_BYTES) == cudaSuccess; }();
+    static const bool once = [] {
+      return cudaFuncSetAttribute(tile_exit_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TE_SMEM_BYTES) == cudaSuccess &&
+             cudaFuncSetAttribute(tile_exit_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TE_SMEM_BYTES) == cudaSuccess;
+    }();
     (void)once;
-    tile_exit_kernel<<<B.n_tiles, TE_THREADS, TE_SMEM_BYTES, st>>>(B.wit, B.n, B.exit1, B.step1);
+    static const bool occ4 = [] {  // PPD_TILE_EXIT_OCC=4: four resident thread blocks per SM instead of three
+      const char* e = getenv("PPD_TILE_EXIT_OCC");
+      return e && atoi(e) == 4;
+    }();
+    if (occ4)
+      tile_exit_kernel<4><<<B.n_tiles, TE_THREADS, TE_SMEM_BYTES, st>>>(B.wit, B.n, B.exit1, B.step1);
+    else
+      tile_exit_kernel<3><<<B.n_tiles, TE_THREADS, TE_SMEM_BYTES, st>>>(B.wit, B.n, B.exit1, B.step1);
   }
   group_exit_kernel<<<dim3(TILE / 256, B.n_groups), 256, 0, st>>>(B.exit1, B.n, group_bytes, B.exit2);
   cudaMemsetAsync(B.group_entry, 0xff, 4ull * B.n_groups, st);

@@ -210,25 +210,121 @@ def txn_info_to_json(t: TxnInfo) -> dict:
     return {"traces": {"0x" + bytes(a).hex(): txn_trace_to_json(tr) for a, tr in t.traces.items()}, "meta": txn_meta_to_json(t.meta)}
 
 
+# ---- TrieDirect(HashedPartialTrie), trace_protocol.rs:97-99 ------------------------------------------------------
+# The serde form of `HashedPartialTrie` belongs to eth_trie_utils (rev 7fc3c3f5), which is NOT under /root/reference:
+# what follows is RECALLED and unpinned.  A trie is {"node": Node, "hash": null | H256} (the cached hash is ignored on
+# input and written as null); Node is an externally tagged enum with the variant names as written in Rust: "Empty",
+# {"Hash": H256}, {"Branch": {"children": [16 tries], "value": [u8]}}, {"Extension": {"nibbles": Nibbles, "child": trie}},
+# {"Leaf": {"nibbles": Nibbles, "value": [u8]}}; Nibbles is {"count": usize, "packed": U512 as 0x-hex}, the first nibble
+# in the most significant position.  A bare Node (without the {"node": ...} wrapper) and hex strings for byte vectors
+# are accepted on input too.  Parsed tries are the node tuples of flat.encode_node.
+def _vec_u8_from_json(v: Any, what: str) -> bytes:
+    if isinstance(v, str):
+        return byte_string_from_json(v)
+    if not isinstance(v, list) or any(isinstance(x, bool) or not isinstance(x, int) or not 0 <= x < 256 for x in v):
+        raise WireFormatError(f"{what}: expected a sequence of u8")
+    return bytes(v)
+
+
+def nibbles_from_json(v: Any) -> list:
+    d = _struct(v, "Nibbles", ("count", "packed"))
+    count = d["count"]
+    if isinstance(count, bool) or not isinstance(count, int) or not 0 <= count <= 64:
+        raise WireFormatError("Nibbles.count: expected 0..64")
+    if not isinstance(d["packed"], str) or not d["packed"].startswith("0x"):
+        raise WireFormatError("Nibbles.packed: expected a 0x-prefixed hex string")
+    body = d["packed"][2:]
+    if len(body) > 128 or any(ch not in _HEX for ch in body):
+        raise WireFormatError("Nibbles.packed: expected at most 128 hex digits")
+    packed = int(body, 16) if body else 0
+    if packed >> (4 * count):
+        raise WireFormatError("Nibbles.packed: more nibbles than `count`")
+    return [(packed >> (4 * (count - 1 - i))) & 15 for i in range(count)]
+
+
+def nibbles_to_json(nibs) -> dict:
+    packed = 0
+    for n in nibs:
+        packed = (packed << 4) | int(n)
+    return {"count": len(nibs), "packed": hex(packed)}
+
+
+def direct_trie_from_json(v: Any, depth: int = 0):
+    if depth > 140:
+        raise WireFormatError("HashedPartialTrie: nested deeper than any 64-nibble key allows")
+    if isinstance(v, dict) and "node" in v:
+        v = v["node"]
+    if v == "Empty":
+        return ("empty",)
+    tag, body = _enum(v, "Node", ("Empty", "Hash", "Branch", "Extension", "Leaf"))
+    if tag == "Empty":
+        return ("empty",)
+    if tag == "Hash":
+        return ("hash", h256_from_json(body))
+    if tag == "Branch":
+        d = _struct(body, "Node::Branch", ("children", "value"))
+        if not isinstance(d["children"], list) or len(d["children"]) != 16:
+            raise WireFormatError("Node::Branch.children: expected 16 entries")
+        return ("branch", [direct_trie_from_json(c, depth + 1) for c in d["children"]], _vec_u8_from_json(d["value"], "Node::Branch.value"))
+    if tag == "Extension":
+        d = _struct(body, "Node::Extension", ("nibbles", "child"))
+        return ("extension", nibbles_from_json(d["nibbles"]), direct_trie_from_json(d["child"], depth + 1))
+    d = _struct(body, "Node::Leaf", ("nibbles", "value"))
+    return ("leaf", nibbles_from_json(d["nibbles"]), _vec_u8_from_json(d["value"], "Node::Leaf.value"))
+
+
+def direct_trie_to_json(node) -> dict:
+    k = node[0]
+    if k == "empty":
+        n: Any = "Empty"
+    elif k == "hash":
+        n = {"Hash": "0x" + bytes(node[1]).hex()}
+    elif k == "branch":
+        n = {"Branch": {"children": [direct_trie_to_json(c) for c in node[1]], "value": list(bytes(node[2]))}}
+    elif k == "extension":
+        n = {"Extension": {"nibbles": nibbles_to_json(node[1]), "child": direct_trie_to_json(node[2])}}
+    else:
+        n = {"Leaf": {"nibbles": nibbles_to_json(node[1]), "value": list(bytes(node[2]))}}
+    return {"node": n, "hash": None}
+
+
 def pre_images_from_json(v: Any) -> dict:
     """BlockTraceTriePreImages (trace_protocol.rs:50-108).  `combined` is decoded to {"combined": {"compact": bytes}},
-    the form `BlockTrace.to_flat` takes.  `separate` is accepted structurally and kept as parsed JSON: the reference
-    has no working decode path behind it (todo!() at processed_block_trace.rs:144,161,167), so
-    `into_txn_proof_gen_ir` reports it as unimplemented."""
+    the form `BlockTrace.to_flat` takes.  `separate` with a Direct state trie and MultipleTries of Direct tries is decoded
+    to node tuples ({"separate": {"state": {"direct": trie}, "storage": {"multiple_tries": {hashed address: {"direct":
+    trie}}}}}: FlatBlock kind 2).  The other `separate` forms are accepted structurally and kept as parsed JSON: the
+    reference has no decode path behind them (todo!() at processed_block_trace.rs:144,161), so `into_txn_proof_gen_ir`
+    reports them as unimplemented."""
     tag, body = _enum(v, "BlockTraceTriePreImages", ("separate", "combined"))
     if tag == "combined":
         d = _struct(body, "CombinedPreImages", ("compact",))
         return {"combined": {"compact": byte_string_from_json(d["compact"])}}
     d = _struct(body, "SeparateTriePreImages", ("state", "storage"))
-    _enum(d["state"], "SeparateTriePreImage", ("uncompressed", "direct"))
-    _enum(d["storage"], "SeparateStorageTriesPreImage", ("single_trie", "multiple_tries"))
-    return {"separate": d}
+    stag, sbody = _enum(d["state"], "SeparateTriePreImage", ("uncompressed", "direct"))
+    ttag, tbody = _enum(d["storage"], "SeparateStorageTriesPreImage", ("single_trie", "multiple_tries"))
+    if stag != "direct" or ttag != "multiple_tries":
+        return {"separate": d}
+    if not isinstance(tbody, dict):
+        raise WireFormatError("SeparateStorageTriesPreImage::MultipleTries: expected a map")
+    tries = {}
+    for h, t in tbody.items():
+        ktag, kbody = _enum(t, "SeparateTriePreImage", ("uncompressed", "direct"))
+        if ktag != "direct":
+            return {"separate": d}
+        tries[h256_from_json(h)] = {"direct": direct_trie_from_json(kbody)}
+    return {"separate": {"state": {"direct": direct_trie_from_json(sbody)}, "storage": {"multiple_tries": tries}}}
 
 
 def pre_images_to_json(p: dict) -> dict:
     if "combined" in p:
         return {"combined": {"compact": byte_string_to_json(p["combined"]["compact"])}}
-    return {"separate": p["separate"]}
+    sep = p["separate"]
+    state, storage = sep.get("state"), sep.get("storage")
+    if isinstance(state, dict) and isinstance(state.get("direct"), tuple) and isinstance(storage, dict) and isinstance(storage.get("multiple_tries"), dict):
+        return {"separate": {"state": {"direct": direct_trie_to_json(state["direct"])},
+                             "storage": {"multiple_tries": {"0x" + bytes(h).hex(): {"direct": direct_trie_to_json(t["direct"])}
+                                                            for h, t in storage["multiple_tries"].items()}}}}
+    return {"separate": sep}
 
 
 def block_trace_from_json(src: Any) -> BlockTrace:

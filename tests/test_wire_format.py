@@ -138,3 +138,27 @@ def test_random_traces_round_trip():
         assert BlockTrace.from_json(bt.to_json()) == bt
 
     check()
+
+
+def test_direct_pre_image_json_round_trip_unpinned():
+    """Separate{Direct, MultipleTries{Direct}} through the JSON form (the serde shape of HashedPartialTrie is recalled,
+    not pinned: eth_trie_utils is not under /root/reference) into a kind-2 FlatBlock."""
+    from proof_protocol_decoder_b200 import flat
+    from proof_protocol_decoder_b200.trace_protocol import OtherBlockData, ProcessingMeta
+
+    leaf = ("leaf", [1, 2, 3], b"\x05")
+    state = ("branch", [("hash", bytes([7]) * 32), ("extension", [0xa, 0xb], ("branch", [leaf] + [("empty",)] * 14 + [leaf], b""))] + [("empty",)] * 14, b"")
+    bt = BlockTrace(trie_pre_images={"separate": {"state": {"direct": state}, "storage": {"multiple_tries": {bytes([9]) * 32: {"direct": leaf}}}}}, txn_info=[])
+    again = BlockTrace.from_json(bt.to_json())
+    assert again == bt
+    f = again.to_flat(ProcessingMeta(lambda h: None), OtherBlockData())
+    kind, payload = flat.pre_image_of(f)
+    assert kind == flat.PRE_IMAGE_DIRECT and flat.parse_direct_pre_image(payload) == (state, {bytes([9]) * 32: leaf})
+    assert wire.nibbles_from_json({"count": 3, "packed": "0x123"}) == [1, 2, 3]
+    assert wire.nibbles_from_json({"count": 2, "packed": "0x3"}) == [0, 3]
+    for bad in ({"count": 1, "packed": "0x12"}, {"count": 65, "packed": "0x0"}, {"count": 1}):
+        with pytest.raises(wire.WireFormatError):
+            wire.nibbles_from_json(bad)
+    # a bare Node and hex byte vectors are accepted on input
+    assert wire.direct_trie_from_json({"Leaf": {"nibbles": {"count": 1, "packed": "0xf"}, "value": "0x0102"}}) == ("leaf", [15], b"\x01\x02")
+    assert wire.direct_trie_from_json("Empty") == ("empty",)
