@@ -716,7 +716,7 @@ def run_b200(args, rank, world, local_rank):
             "note": "achieved = sum over the step's level launches of (L + 32) bytes per hashed node / device time of the step",
         },
         "parse": {
-            "kernels": "ppd_parse.cu: tile_exit (lists of opcode bytes) / group_exit / top_chain / tile_entry / tile_mark_thin / scans / link (8-wide pyramid level) / shape / emit + emit_keyed / climb (all lanes concurrent, every lane queued by its own host thread)",
+            "kernels": "ppd_parse.cu: tile_exit (lists of opcode bytes) / group_exit / top_chain / tile_entry / tile_mark_thin / scans / link (8-wide pyramid level) / shape / emit + emit_keyed / climb (all lanes concurrent)",
             "witnesses_on_gpu_per_step": int(sum_over_ranks(float(st["witnesses_on_gpu"]))),
             "witness_bytes_per_step": wit_bytes_all,
             "instructions_per_step": wit_ins_all,

@@ -722,16 +722,16 @@ int ppd_replay_last(ppd_ctx* c, unsigned what, double* gpu_ms_out) {
               ((what & (PPD_REPLAY_TXN | PPD_REPLAY_DUMP)) && L->has_last_txn);
     }
     if (!used) fail(PPD_ERR_BAD_ARGUMENT, "nothing of the requested kind is resident");
-    // all lanes start after ev0 on the main stream; the main stream then waits for every lane.  Every lane is queued by
-    // its own host thread, as in the decode itself (a lane's stages are 50-200 launches: queued by ONE thread, 30 lanes
-    // would measure that thread's launch rate -- about 5 us per call -- instead of the device).  PPD_REPLAY_THREADS=1
-    // gives the single-threaded form back.
+    // all lanes start after ev0 on the main stream; the main stream then waits for every lane.  One host thread queues
+    // all lanes by default; PPD_REPLAY_THREADS=<n> spreads the lanes over n threads, as the decode itself does.  Measured
+    // (profiles/r02b_replay_threads.txt): 30 lanes' parse replay 13.4 ms queued by one thread, 13.7 ms by thirty -- the
+    // replays are bound by the device, not by the queueing thread (one thread launches 0.29 M kernels/s, r02b_launch_rate.txt).
     static const unsigned replay_threads = [] {
       const char* e = getenv("PPD_REPLAY_THREADS");
-      const long v = e ? atol(e) : 0;
-      return (unsigned)(v > 0 ? v : 0);
+      const long v = e ? atol(e) : 1;
+      return (unsigned)(v > 0 ? v : 1);
     }();
-    const unsigned workers = (unsigned)std::min<size_t>(replay_threads ? replay_threads : std::max(1u, host_threads()), n_lanes);
+    const unsigned workers = (unsigned)std::min<size_t>(replay_threads, n_lanes);
     // the threads exist and wait before ev0 is recorded, so that starting them is not inside the timed region
     std::atomic<unsigned> ready{0};
     std::atomic<bool> go{false}, failed{false};
