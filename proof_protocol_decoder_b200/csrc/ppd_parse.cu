@@ -12,22 +12,25 @@
 //
 // Phase A: instruction boundaries.  The stream is serial (an instruction's length is known only after
 //   its CBOR heads are read), so every byte position is decoded speculatively: nxt[p] = where the
-//   instruction that would start at p ends.  Per 4 KiB tile (staged in shared memory) the chain
+//   instruction that would start at p ends (only a byte below 7 can start one: those positions are listed and
+//   decoded, every other position gets the "not an opcode" default).  Per 4 KiB tile (staged in shared memory) the chain
 //   p -> nxt[p] is pointer-doubled into exit1[p] = the first position outside the tile that the chain
 //   from p reaches; the single-step links are kept too (step1).  Tiles are grouped (about sqrt(#tiles)
 //   per group); every position of a group's first tile walks exit1 to the end of the group (exit2); one
 //   thread then hops group to group from position 0, the groups' true entries are walked back down to
-//   tile entries, and one warp lane per tile follows step1 from the tile's entry and marks the true
+//   tile entries, and one thread per tile follows step1 from the tile's entry and marks the true
 //   instruction starts in a bitmap.  Counts are scanned and the starts scattered into ins_pos[].
 // Phase B: the stack machine in closed form.  Every instruction pushes one entry and pops `pops`;
 //   height_after = inclusive scan of (1 - pops).  The parent of instruction i is the next instruction
 //   whose height_after is not larger (nearest-smaller-value query on a min-pyramid), and i is its
 //   (height_after(i) - height_after(parent))-th popped entry: the k-th set bit of a branch mask, or the
 //   code / storage slot of an account leaf.  Depths and trie membership come from walking the parent
-//   chain (<= 64 steps); seven per-instruction size counters are scanned together.
-// Phase C: emit.  Every instruction writes its own arena records (node, key, value, hash, child slot,
-//   account record, storage ROOT node); levels are computed by climbing from the leaves with a
-//   pending-children counter per inner node (the last child to arrive continues upwards).
+//   chain (<= 64 steps); seven per-instruction size counters are scanned together; the keyed instructions
+//   (leaf, extension, account leaf) are listed.
+// Phase C: emit.  Every instruction writes its own arena records (child slot, hashed-out node, branch record in
+//   emit_kernel; node, key, value, account record, storage ROOT node of the listed keyed instructions in
+//   emit_keyed_kernel); levels are computed by climbing from the leaves with a pending-children counter per
+//   inner node (the last child to arrive continues upwards).
 #include <cstdint>
 #include <cstdlib>
 
