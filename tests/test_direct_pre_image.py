@@ -333,3 +333,21 @@ def test_drawn_direct_tries_round_trip_through_the_product_transcoder(oracle):
                 assert back_storage.get(h) == t
 
     check()
+
+
+def test_direct_block_through_the_json_wire_form(oracle):
+    """A Combined block's tries as Separate{Direct} JSON (wire.py) -> BlockTrace -> kind-2 FlatBlock: the oracle's IRs equal
+    those of the Combined block (the txn part of the FlatBlock is carried over as it is)."""
+    from proof_protocol_decoder_b200 import wire
+
+    blk = synth.gen_block(31, n_accounts=90, n_txns=3, inline_code_frac=0.0)
+    want = oracle.block_decode(blk.flat)
+    state, storage = flat.parse_direct_pre_image(oracle.compact_to_direct(flat.pre_image_of(blk.flat)[1]))
+    js = wire.pre_images_to_json({"separate": {"state": {"direct": state}, "storage": {"multiple_tries": {h: {"direct": t} for h, t in storage.items()}}}})
+    import json
+
+    pre = wire.pre_images_from_json(json.loads(json.dumps(js)))
+    bt = BlockTrace(trie_pre_images=pre, txn_info=[])
+    kind, payload = flat.pre_image_of(bt.to_flat(ProcessingMeta(lambda h: None), OtherBlockData()))
+    assert kind == flat.PRE_IMAGE_DIRECT
+    assert oracle.block_decode(flat.with_pre_image(blk.flat, kind, payload)) == want
