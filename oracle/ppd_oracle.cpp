@@ -56,6 +56,14 @@ struct Err {
   std::string msg;
 };
 [[noreturn]] static void fail(int code, const std::string& msg) { throw Err{code, msg}; }
+// The payloads of the TraceParsingError variants (decoding.rs:31-49) follow the sentence as "; key=value ..." words: the
+// form the product's ppd_last_error uses, so that a caller can rebuild the reference's error value.
+static std::string hex_str(const uint8_t* p, size_t n) {
+  std::string o;
+  char t[3];
+  for (size_t i = 0; i < n; i++) snprintf(t, sizeof t, "%02x", p[i]), o += t;
+  return o;
+}
 
 // ---------------------------------------------------------------------------------------------
 // Keccak-256 (tiny-keccak 2.0.2 behaviour: rate 136, padding 0x01 .. 0x80, 24 rounds)
@@ -1413,11 +1421,12 @@ static Nibs txn_key(size_t idx) {
 // to zero nibbles (count = ceil(bits/4) = 0): the root is marked and nothing below it.  RECALLED.
 static std::vector<Nibs> dummy_subset_keys() { return {Nibs()}; }
 
-static NodeP subset_wrapped(const NodeP& trie, const std::vector<Nibs>& keys) {
+// create_trie_subset_wrapped (decoding.rs:595-602): the SubsetTrieError becomes MissingKeysCreatingSubPartialTrie(trie_type)
+static NodeP subset_wrapped(const NodeP& trie, const std::vector<Nibs>& keys, const char* trie_type) {
   try {
     return create_trie_subset(trie, keys);
   } catch (const Err& e) {
-    if (e.code == PPD_ERR_MISSING_KEYS_CREATING_SUB_PARTIAL_TRIE) throw;
+    if (e.code == PPD_ERR_MISSING_KEYS_CREATING_SUB_PARTIAL_TRIE) fail(e.code, e.msg + "; trie_type=" + trie_type);
     throw;
   }
 }
@@ -1426,9 +1435,9 @@ static TrieInputs minimal_tries_for_txn(TrieState& cur, const NodesUsedByTxn& no
   TrieInputs ti;
   std::vector<Nibs> state_keys;
   for (const H256& h : nodes.state_accesses) state_keys.push_back(nibs_from_h256(h));
-  ti.state = subset_wrapped(cur.state, state_keys);
-  ti.txn = subset_wrapped(cur.txn, {txn_key(txn_idx)});
-  ti.receipt = subset_wrapped(cur.receipt, {txn_key(txn_idx)});
+  ti.state = subset_wrapped(cur.state, state_keys, "State");
+  ti.txn = subset_wrapped(cur.txn, {txn_key(txn_idx)}, "Txn");
+  ti.receipt = subset_wrapped(cur.receipt, {txn_key(txn_idx)}, "Receipt");
   for (const auto& acc : nodes.storage_accesses) {
     H256 haddr = h256_from_slice_of_nibs(acc.first);
     auto f = cur.storage.find(haddr);
@@ -1437,7 +1446,7 @@ static TrieInputs minimal_tries_for_txn(TrieState& cur, const NodesUsedByTxn& no
       NodeP t = g != nodes.accounts_with_storage_but_no_accesses.end() ? mk_hash(g->second) : EMPTY_NODE;
       f = cur.storage.insert({haddr, t}).first;
     }
-    ti.storage.push_back({haddr, subset_wrapped(f->second, acc.second)});
+    ti.storage.push_back({haddr, subset_wrapped(f->second, acc.second, "Storage")});
   }
   return ti;
 }
@@ -1446,7 +1455,7 @@ static void apply_deltas(TrieState& ts, const ProcessedTxn& tx, size_t txn_idx) 
   for (const auto& sw : tx.nodes.storage_writes) {
     H256 haddr = h256_from_slice_of_nibs(sw.first);
     auto f = ts.storage.find(haddr);
-    if (f == ts.storage.end()) fail(PPD_ERR_MISSING_ACCOUNT_STORAGE_TRIE, "no storage trie for a written account");
+    if (f == ts.storage.end()) fail(PPD_ERR_MISSING_ACCOUNT_STORAGE_TRIE, "no storage trie for a written account; hashed_addr=" + hex_str(haddr.b, 32));
     for (const auto& kv : sw.second) {
       Bytes pre = nibs_bytes_be_minimal(kv.first);
       Nibs slot = nibs_from_h256(hash_bytes(pre));
@@ -1464,10 +1473,10 @@ static void apply_deltas(TrieState& ts, const ProcessedTxn& tx, size_t txn_idx) 
     const Bytes* cur = trie_get(ts.state, k);
     if (!cur) cur = &EMPTY_ACCOUNT;
     Account a;
-    if (!account_decode(cur->data(), cur->size(), a)) fail(PPD_ERR_ACCOUNT_DECODE, "state leaf is not an account");
+    if (!account_decode(cur->data(), cur->size(), a)) fail(PPD_ERR_ACCOUNT_DECODE, "state leaf is not an account; bytes=" + hex_str(cur->data(), cur->size()));
     if (w.storage_trie_change) {
       auto f = ts.storage.find(w.haddr);
-      if (f == ts.storage.end()) fail(PPD_ERR_MISSING_ACCOUNT_STORAGE_TRIE, "no storage trie for a changed account");
+      if (f == ts.storage.end()) fail(PPD_ERR_MISSING_ACCOUNT_STORAGE_TRIE, "no storage trie for a changed account; hashed_addr=" + hex_str(w.haddr.b, 32));
       a.storage_root = trie_hash(f->second);
     }
     if (w.has_balance) memcpy(a.balance, w.balance, 32);
@@ -1476,7 +1485,7 @@ static void apply_deltas(TrieState& ts, const ProcessedTxn& tx, size_t txn_idx) 
     ts.state = trie_insert(ts.state, k, InsertVal{false, account_encode(a), {}});
   }
   for (const H256& h : tx.nodes.self_destructed) {
-    if (!ts.storage.erase(h)) fail(PPD_ERR_MISSING_ACCOUNT_STORAGE_TRIE, "self-destructed account has no storage trie");
+    if (!ts.storage.erase(h)) fail(PPD_ERR_MISSING_ACCOUNT_STORAGE_TRIE, "self-destructed account has no storage trie; hashed_addr=" + hex_str(h.b, 32));
     NodeP d = trie_delete(ts.state, nibs_from_h256(h));
     if (d) ts.state = d;
   }
@@ -1514,9 +1523,9 @@ static void apply_withdrawals(const Block& blk, NodeP& state) {
     H256 h = hash_bytes(w.first.b, 20);
     Nibs k = nibs_from_h256(h);
     const Bytes* cur = trie_get(state, k);
-    if (!cur) fail(PPD_ERR_MISSING_WITHDRAWAL_ACCOUNT, "withdrawal to an account that is not in the state trie");
+    if (!cur) fail(PPD_ERR_MISSING_WITHDRAWAL_ACCOUNT, "withdrawal to an account that is not in the state trie; addr=" + hex_str(w.first.b, 20) + " hashed_addr=" + hex_str(h.b, 32) + " amount=" + hex_str(w.second.data(), 32));
     Account a;
-    if (!account_decode(cur->data(), cur->size(), a)) fail(PPD_ERR_ACCOUNT_DECODE, "withdrawal account does not decode");
+    if (!account_decode(cur->data(), cur->size(), a)) fail(PPD_ERR_ACCOUNT_DECODE, "withdrawal account does not decode; bytes=" + hex_str(cur->data(), cur->size()));
     u256_add(a.balance, w.second.data());
     state = trie_insert(state, k, InsertVal{false, account_encode(a), {}});
   }

@@ -18,6 +18,7 @@
 
 #include "../../include/ppd_status.h"
 #include "arena.h"
+#include "err_detail.h"
 
 namespace ppd {
 
@@ -26,6 +27,7 @@ struct Fail {
   std::string msg;
 };
 [[noreturn]] inline void fail(int code, const char* msg) { throw Fail{code, msg}; }
+[[noreturn]] inline void fail(int code, const std::string& msg) { throw Fail{code, msg}; }
 
 static const uint32_t UNCHANGED = 0xfffffffeu;
 // Hashed-out subtrees (Node::Hash) are not arena nodes: their id is HASH_ID_BASE + index into hash_pool,

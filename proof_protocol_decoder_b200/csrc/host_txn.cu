@@ -247,14 +247,24 @@ void dummy_plan(Job& J, BlockJob& b, IrPlan& p, uint32_t state_root, uint32_t tx
   p.root_receipt = root_node_for(J, b, receipt_root);
 }
 
+// AccountDecode's payload (decoding.rs:604-607): the bytes of the leaf that is not an account.  A pre-image built on the
+// GPU keeps its value pool on the device until an IR is serialised on the host; a value that is not resident here is
+// left out rather than fetched on the error path.
+static std::string leaf_value_detail(const Job& J, uint32_t leaf, const char* what) {
+  const HostArena& A = J.A;
+  const uint32_t off = A.nodes[leaf].a1, n = A.nodes[leaf].a2;
+  const bool resident = (J.pools_on_host || off >= J.dev.vals) && (size_t)off + n <= A.val_pool.size();
+  return resident ? detail_account_decode(what, A.val_pool.data() + off, n) : std::string(what);
+}
+
 void apply_withdrawals(Job& J, BlockJob& b, uint32_t& state_root) {
   HostArena& A = J.A;
   for (size_t i = 0; i < b.withdrawals.size(); i++) {
     const H256& h = J.kh.digest[b.m_withdrawal_addr[i]];
     uint32_t koff = key_from_digest(J, h);
     uint32_t leaf = A.get(state_root, koff, 64);
-    if (leaf == NODE_EMPTY) fail(PPD_ERR_MISSING_WITHDRAWAL_ACCOUNT, "withdrawal to an account that is not in the state trie");
-    if (A.kind(leaf) != NK_LEAF_ACCOUNT) fail(PPD_ERR_ACCOUNT_DECODE, "withdrawal account does not decode");
+    if (leaf == NODE_EMPTY) fail(PPD_ERR_MISSING_WITHDRAWAL_ACCOUNT, detail_missing_withdrawal_account(b.withdrawals[i].first, h.b, b.withdrawals[i].second));
+    if (A.kind(leaf) != NK_LEAF_ACCOUNT) fail(PPD_ERR_ACCOUNT_DECODE, leaf_value_detail(J, leaf, "withdrawal account does not decode"));
     AccountRec rec = A.accounts[A.nodes[leaf].a1];
     u256_add(rec.balance, b.withdrawals[i].second);
     uint32_t r = (uint32_t)A.accounts.size();
@@ -350,7 +360,24 @@ void shape_block(Job& J, BlockJob& b) {
       p.storage_subs.push_back({haddr, sroot});
     }
     p.touched.reserve(marks.size() * 10);
-    A.mark_many(marks.data(), marks.size(), p.touched);
+    try {
+      A.mark_many(marks.data(), marks.size(), p.touched);
+    } catch (const Fail& e) {
+      if (e.code != PPD_ERR_MISSING_KEYS_CREATING_SUB_PARTIAL_TRIE) throw;
+      // the variant's TrieType is that of the first key, in the reference's order (state accesses, the txn index in the
+      // txn and receipt tries, storage slots: decoding.rs:185-209), that runs into a hashed-out node; mark_many walks
+      // the keys interleaved, so the keys are walked again one by one on this (cold) path
+      std::vector<uint32_t> scratch;
+      for (size_t i = 0; i < marks.size(); i++) {
+        try {
+          A.mark(marks[i].root, marks[i].koff, marks[i].klen, scratch);
+        } catch (const Fail&) {
+          const size_t nt = tx.traces.size();
+          fail(e.code, detail_missing_keys(i < nt ? TRIE_STATE : i == nt ? TRIE_TXN : i == nt + 1 ? TRIE_RECEIPT : TRIE_STORAGE));
+        }
+      }
+      throw;
+    }
     // the marking walk of an address also finds its leaf in the pre-txn state: the state writes below read the account
     // from it (other addresses' writes in between only path-copy branches; the leaf's payload stays)
     for (size_t i = 0; i < tx.traces.size() && i < marks.size(); i++) haddr_leaf[i] = marks[i].leaf;
@@ -362,7 +389,7 @@ void shape_block(Job& J, BlockJob& b) {
     for (TraceV& tr : tx.traces) {
       const H256& haddr = J.kh.digest[tr.m_addr];
       auto f = b.storage.find(haddr);
-      if (f == b.storage.end()) fail(PPD_ERR_MISSING_ACCOUNT_STORAGE_TRIE, "no storage trie for a written account");
+      if (f == b.storage.end()) fail(PPD_ERR_MISSING_ACCOUNT_STORAGE_TRIE, detail_missing_storage_trie("no storage trie for a written account", haddr.b));
       for (uint32_t k = 0; k < tr.n_writes; k++) {
         const uint8_t* val = tr.writes + 64 * k + 32;
         uint32_t koff = key_from_digest(J, J.kh.digest[tr.m_writes_min + k]);
@@ -398,7 +425,7 @@ void shape_block(Job& J, BlockJob& b) {
       AccountRec rec;
       const uint32_t leaf = haddr_leaf[i];
       if (leaf != NODE_EMPTY) {
-        if (A.kind(leaf) != NK_LEAF_ACCOUNT) fail(PPD_ERR_ACCOUNT_DECODE, "state leaf is not an account");
+        if (A.kind(leaf) != NK_LEAF_ACCOUNT) fail(PPD_ERR_ACCOUNT_DECODE, leaf_value_detail(J, leaf, "state leaf is not an account"));
         rec = A.accounts[A.nodes[leaf].a1];
       } else {
         memset(&rec, 0, sizeof rec);
@@ -408,7 +435,7 @@ void shape_block(Job& J, BlockJob& b) {
       }
       if (storage_change) {
         auto f = b.storage.find(haddr);
-        if (f == b.storage.end()) fail(PPD_ERR_MISSING_ACCOUNT_STORAGE_TRIE, "no storage trie for a changed account");
+        if (f == b.storage.end()) fail(PPD_ERR_MISSING_ACCOUNT_STORAGE_TRIE, detail_missing_storage_trie("no storage trie for a changed account", haddr.b));
         rec.storage_src = root_node_for(J, b, f->second);
       }
       if (tr.flags & PPD_TR_BALANCE) memcpy(rec.balance, tr.balance, 32);
@@ -428,7 +455,7 @@ void shape_block(Job& J, BlockJob& b) {
     for (size_t i = 0; i < tx.traces.size(); i++) {
       if (!(tx.traces[i].flags & PPD_TR_SELF_DESTRUCTED)) continue;
       const H256& haddr = J.kh.digest[tx.traces[i].m_addr];
-      if (!b.storage.erase(haddr)) fail(PPD_ERR_MISSING_ACCOUNT_STORAGE_TRIE, "self-destructed account has no storage trie");
+      if (!b.storage.erase(haddr)) fail(PPD_ERR_MISSING_ACCOUNT_STORAGE_TRIE, detail_missing_storage_trie("self-destructed account has no storage trie", haddr.b));
       uint32_t r = A.remove(state, haddr_key[i], 64, 0);
       if (r != UNCHANGED) state = r;
     }

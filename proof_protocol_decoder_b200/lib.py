@@ -53,6 +53,14 @@ class PpdError(Exception):
     def __init__(self, code, msg=""):
         super().__init__(f"ppd status {code} ({STATUS_NAMES.get(code, '?')}): {msg}")
         self.code = code
+        self.msg = msg  # ppd_last_error: for 21-25 the sentence is followed by "; key=value ..." (csrc/err_detail.h)
+
+    def payload(self) -> dict:
+        """The payload of a TraceParsingError variant (decoding.rs:31-49) as ppd_last_error spells it: hashed_addr / addr /
+        amount / bytes as hex, trie_type as the reference's variant name."""
+        if "; " not in self.msg:
+            return {}
+        return dict(w.split("=", 1) for w in self.msg.split("; ", 1)[1].split(" ") if "=" in w)
 
 
 class PpdStats(ctypes.Structure):

@@ -14,6 +14,7 @@ class OracleError(Exception):
     def __init__(self, code, msg):
         super().__init__(f"oracle status {code}: {msg}")
         self.code = code
+        self.msg = msg
 
 
 def build(force=False):

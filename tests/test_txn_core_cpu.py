@@ -120,3 +120,51 @@ def test_device_txn_loop_shortened_slot_keys_and_read_write_overlap(txncheck, tm
                     tr["storage_read"] = list(tr.get("storage_read") or []) + [k for k, _ in tr["storage_written"][:2]]
         blocks.append(blk)
     _run(txncheck, tmp_path, blocks)
+
+
+def _error_blocks():
+    """Blocks whose decoding ends in a TraceParsingError variant that carries a payload (decoding.rs:31-49)."""
+    import copy
+
+    from proof_protocol_decoder_b200 import synth
+
+    def base(**kw):
+        return synth.gen_block(55, n_accounts=80, n_txns=3, n_withdrawals=1, **kw)
+
+    cases = []
+    b = base()
+    b.withdrawals = [(bytes(range(20)), 5)]  # MissingWithdrawalAccount(addr, hashed addr, amount)
+    cases.append(("withdrawal_to_missing_account", 25, b.flat))
+    b = base(virtual_depth=3, virtual_accounts_log16=3)
+    b.txns = copy.deepcopy(b.txns)
+    b.txns[0]["traces"].append((bytes([7] * 20), {"balance": 1}))  # MissingKeysCreatingSubPartialTrie(State)
+    cases.append(("touched_account_behind_hash_node", 24, b.flat))
+    return cases
+
+
+@pytest.mark.parametrize("name,code,flat_block", _error_blocks(), ids=[c[0] for c in _error_blocks()])
+def test_host_path_error_payloads_equal_the_oracles(txncheck, oracle, tmp_path, name, code, flat_block):
+    """ppd_last_error's wording for the TraceParsingError statuses carries the variant's payload (csrc/err_detail.h) so
+    that the Rust shim can rebuild the error value: the host path of the product (which reports every block error) and
+    the oracle must spell it the same way."""
+    import re
+
+    from ppd_oracle_lib import OracleError
+
+    with pytest.raises(OracleError) as eo:
+        oracle.block_decode(flat_block)
+    assert eo.value.code == code
+    p = tmp_path / "b.flat"
+    p.write_bytes(flat_block)
+    res = subprocess.run([txncheck, str(p)], capture_output=True, text=True)
+    m = re.search(r": status (\d+) \((.*)\) from the host path", res.stdout)
+    assert m, res.stdout[-2000:] + res.stderr[-2000:]
+    assert int(m.group(1)) == code
+    assert m.group(2) == eo.value.msg
+    sentence, payload = m.group(2).split("; ")
+    words = dict(w.split("=") for w in payload.split(" "))
+    if code == 25:
+        assert words["addr"] == bytes(range(20)).hex() and int(words["amount"], 16) == 5
+        assert bytes.fromhex(words["hashed_addr"]) == oracle.keccak256(bytes(range(20)))
+    else:
+        assert words == {"trie_type": "State"}
