@@ -58,7 +58,10 @@ typedef struct ppd_stats {
 
 int ppd_ctx_create(int device, ppd_ctx** out);
 void ppd_ctx_destroy(ppd_ctx* ctx);
-/* message of the last non-OK status on this context ("" if none) */
+/* message of the last non-OK status on this context ("" if none).  For the TraceParsingError statuses (21-25,
+ * decoding.rs:31-49) the sentence is followed by "; " and the variant's payload as key=value words — hashed_addr=<64 hex>,
+ * trie_type=State|Storage|Receipt|Txn, addr=<40 hex> hashed_addr=<64 hex> amount=<64 hex>, bytes=<hex> (csrc/err_detail.h) —
+ * from which the shim rebuilds the reference's error value (integration/rust/src/b200/status.rs). */
 const char* ppd_last_error(const ppd_ctx* ctx);
 void ppd_last_stats(const ppd_ctx* ctx, ppd_stats* out);
 void ppd_free(void* p);
