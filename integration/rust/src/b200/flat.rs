@@ -102,8 +102,10 @@ pub fn encode_block(bt: &BlockTrace, resolved: &[(H256, Vec<u8>)], other: &Other
     put_u32(&mut o, wd.len() as u32);
     for (a, amt) in wd { o.extend_from_slice(a.as_bytes()); put_u256(&mut o, *amt); }
     o.extend_from_slice(other.checkpoint_state_trie_root.as_bytes());
-    put_bytes(&mut o, &bincode::serialize(&other.b_data.b_meta).unwrap());      // opaque to the library: copied into every IR
-    put_bytes(&mut o, &bincode::serialize(&other.b_data.b_hashes).unwrap());
+    // b_meta / b_hashes are opaque to the library, which copies them into every IR; decode_ir_dump takes both from
+    // `other` instead, so the shim sends them empty (no serialiser needed, and 8 KB less per IR on the way back)
+    put_bytes(&mut o, &[]);
+    put_bytes(&mut o, &[]);
     o
 }
 

@@ -30,7 +30,7 @@ impl BlockTrace {
             .flat_map(|t| t.traces.values())
             .filter_map(|tr| match &tr.code_usage { Some(ContractCodeUsage::Read(h)) => Some(*h), _ => None })
             .collect::<std::collections::BTreeSet<_>>().into_iter()
-            .map(|h| (h, (p_meta.resolve_code_hash_fn)(&h))).collect();
+            .map(|h| (h, (p_meta.resolve_code_hash_fn)(&h))).collect();   // (the field becomes pub(crate): processed_block_trace.rs:188)
         // 2. BlockTrace + resolved code + OtherBlockData -> FlatBlock (include/ppd_flat.h, "input").
         let flat = flat::encode_block(&self, &resolved, &other_data);
         // 3. One call; kernels, copies and host threads are the library's business.
