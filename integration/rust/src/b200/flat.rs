@@ -27,7 +27,7 @@ fn put_u256(o: &mut Vec<u8>, v: U256) { let mut b = [0u8; 32]; v.to_big_endian(&
 
 /// Trie := Node in pre-order (include/ppd_flat.h); the same form `decode_ir_dump` reads back.
 fn put_trie(o: &mut Vec<u8>, t: &HashedPartialTrie) {
-    match &t.node {
+    match &**t {   // PartialTrie: Deref<Target = Node<Self>>
         Node::Empty => o.push(0),
         Node::Hash(h) => { o.push(1); o.extend_from_slice(h.as_bytes()); }
         Node::Branch { children, value } => { o.push(2); for c in children { put_trie(o, c); } put_bytes(o, value); }
@@ -126,15 +126,15 @@ impl<'a> R<'a> {
     /// a Trie blob: nodes in pre-order (0 empty, 1 hash, 2 branch, 3 extension, 4 leaf)
     fn node(&mut self) -> HashedPartialTrie {
         match self.u8() {
-            0 => Node::Empty.into(),
-            1 => Node::Hash(self.h256()).into(),
+            0 => HashedPartialTrie::new(Node::Empty),   // the constructor decoding.rs:577 uses
+            1 => HashedPartialTrie::new(Node::Hash(self.h256())),
             2 => {
                 let children = std::array::from_fn(|_| std::sync::Arc::new(Box::new(self.node())));
                 let value = self.bytes().to_vec();
-                Node::Branch { children, value }.into()
+                HashedPartialTrie::new(Node::Branch { children, value })
             }
-            3 => { let nibbles = self.nibbles(); let child = std::sync::Arc::new(Box::new(self.node())); Node::Extension { nibbles, child }.into() }
-            4 => { let nibbles = self.nibbles(); let value = self.bytes().to_vec(); Node::Leaf { nibbles, value }.into() }
+            3 => { let nibbles = self.nibbles(); let child = std::sync::Arc::new(Box::new(self.node())); HashedPartialTrie::new(Node::Extension { nibbles, child }) }
+            4 => { let nibbles = self.nibbles(); let value = self.bytes().to_vec(); HashedPartialTrie::new(Node::Leaf { nibbles, value }) }
             k => panic!("bad node kind {k} in IrDump"),
         }
     }
