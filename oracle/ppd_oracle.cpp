@@ -1438,6 +1438,9 @@ static TrieInputs minimal_tries_for_txn(TrieState& cur, const NodesUsedByTxn& no
   ti.state = subset_wrapped(cur.state, state_keys, "State");
   ti.txn = subset_wrapped(cur.txn, {txn_key(txn_idx)}, "Txn");
   ti.receipt = subset_wrapped(cur.receipt, {txn_key(txn_idx)}, "Receipt");
+  // decoding.rs:199-203: storage_access_vec is collected (every key through H256::from_slice, the panic site) before
+  // create_minimal_storage_partial_tries cuts the first storage subset
+  for (const auto& acc : nodes.storage_accesses) (void)h256_from_slice_of_nibs(acc.first);
   for (const auto& acc : nodes.storage_accesses) {
     H256 haddr = h256_from_slice_of_nibs(acc.first);
     auto f = cur.storage.find(haddr);

@@ -337,14 +337,15 @@ void shape_block(Job& J, BlockJob& b) {
     marks.push_back({txn_trie, tk, tk_len, NODE_EMPTY});
     marks.push_back({receipt_trie, tk, tk_len, NODE_EMPTY});
     p.storage_subs.reserve(tx.traces.size());
+    // decoding.rs:199-203 converts EVERY trace's hashed address (H256::from_slice of its bytes_be(): a panic when the hash
+    // begins with a zero byte) before the first storage subset is cut, and after the state / txn / receipt subsets: with
+    // such an address among the traces no storage key is marked, and the panic is reported after the marks of the three
+    // other tries
     bool short_haddr = false;
-    for (size_t i = 0; i < tx.traces.size(); i++) {
+    for (size_t i = 0; i < tx.traces.size() && !short_haddr; i++) short_haddr = J.kh.digest[tx.traces[i].m_addr].b[0] == 0;
+    for (size_t i = 0; i < tx.traces.size() && !short_haddr; i++) {
       TraceV& tr = tx.traces[i];
       const H256& haddr = J.kh.digest[tr.m_addr];
-      if (haddr.b[0] == 0) {  // reported after the marks collected so far (they come first in the reference's order)
-        short_haddr = true;
-        break;
-      }
       auto f = b.storage.find(haddr);
       if (f == b.storage.end()) {
         // missing storage trie: Hash(pre-image storage root) when the account had storage in the pre-image
