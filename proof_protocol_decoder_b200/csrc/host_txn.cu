@@ -286,6 +286,30 @@ void shape_block(Job& J, BlockJob& b) {
   uint32_t state = b.state_root, txn_trie = NODE_EMPTY, receipt_trie = NODE_EMPTY;
   uint64_t txn_before = 0, gas_before = 0, gas_after = 0;
 
+  // The reference turns EVERY TxnInfo into its processed form (processed_block_trace.rs:58-66 -> :209-343) before the
+  // first txn enters the loop of decoding.rs:106-153: what can fail there -- a code hash nobody resolves, a receipt that
+  // is neither legacy nor a byte string -- is reported for the first such txn even when an earlier txn fails in the loop.
+  std::vector<H256> written;  // code a trace of the same txn wrote earlier is in the txn's map already (:277-291)
+  for (const TxnV& tx : b.txns) {
+    written.clear();
+    for (const TraceV& tr : tx.traces) {
+      if (tr.flags & PPD_TR_CODE_READ) {
+        if (memcmp(tr.code_read, EMPTY_CODE_HASH, 32) == 0) continue;
+        H256 h;
+        memcpy(h.b, tr.code_read, 32);
+        if (b.pre_code.find(h) == b.pre_code.end() && b.resolved_code.find(h) == b.resolved_code.end() &&
+            std::find(written.begin(), written.end(), h) == written.end())
+          fail(PPD_ERR_UNRESOLVED_CODE_HASH, "code hash not resolvable");
+      } else if (tr.flags & PPD_TR_CODE_WRITE) {
+        written.push_back(J.kh.digest[tr.m_code]);
+      }
+    }
+    RlpItem it;
+    const Span receipt = tx.new_receipt_node;
+    if (!is_legacy_receipt(receipt.p, receipt.n) && (!rlp_item(receipt.p, receipt.n, it) || it.is_list))
+      fail(PPD_PANIC_RECEIPT_DECODE, "receipt is neither legacy nor a byte string");
+  }
+
   for (size_t ti = 0; ti < b.txns.size(); ti++) {
     TxnV& tx = b.txns[ti];
     IrPlan p;
