@@ -198,3 +198,53 @@ def test_host_path_error_payloads_equal_the_oracles(txncheck, oracle, tmp_path, 
         assert bytes.fromhex(words["hashed_addr"]) == oracle.keccak256(bytes(range(20)))
     else:
         assert words == {"trie_type": "State"}
+
+
+def test_host_path_reports_the_fault_the_oracle_reports_when_a_block_has_several(txncheck, oracle, tmp_path):
+    """Blocks with one to three injected faults of different kinds at random txns: which of them is reported is a matter
+    of the reference's ORDER of work (every TxnInfo processed first, then per txn the state / txn / receipt subsets, the
+    H256::from_slice of every trace, the storage subsets, the deltas; withdrawals last).  The product's host path (which
+    reports every block error) and the oracle must pick the same one, with the same words."""
+    import copy
+    import re
+
+    from ppd_oracle_lib import OracleError
+    from proof_protocol_decoder_b200 import synth
+
+    short = next(a for a in (i.to_bytes(20, "big") for i in range(1, 100000)) if oracle.keccak256(a)[0] == 0)
+    rng = np.random.default_rng(5)
+    kinds = ["behind_hash", "bad_receipt", "unresolvable_code", "short_haddr", "missing_withdrawal"]
+    paths, want = [], []
+    for case in range(int(os.environ.get("PPD_FAULT_CASES", "36"))):
+        n_txns = int(rng.integers(2, 6))
+        b = synth.gen_block(700 + case, n_accounts=60, n_txns=n_txns, n_withdrawals=1, virtual_depth=3, virtual_accounts_log16=3, allow_new_accounts=False)
+        b.txns = copy.deepcopy(b.txns)
+        faults = rng.choice(kinds, size=int(rng.integers(1, 4)), replace=False)
+        for k in faults:
+            t = int(rng.integers(0, n_txns))
+            if k == "behind_hash":
+                b.txns[t]["traces"].append((bytes([7] * 20), {"balance": 1}))
+            elif k == "bad_receipt":
+                b.txns[t]["new_receipt_trie_node_byte"] = b"\xc1\x80"
+            elif k == "unresolvable_code":
+                b.txns[t]["traces"].append((bytes([9] * 19 + [t]), {"code_read": bytes([0xAB] * 32)}))
+            elif k == "short_haddr":
+                b.txns[t]["traces"].append((short, {"balance": 1}))
+            else:
+                b.withdrawals = [(bytes(range(20)), 5)]
+        with pytest.raises(OracleError) as eo:
+            oracle.block_decode(b.flat)
+        p = tmp_path / f"f{case}.flat"
+        p.write_bytes(b.flat)
+        paths.append(str(p))
+        want.append((eo.value.code, eo.value.msg, sorted(faults)))
+    res = subprocess.run([txncheck] + paths, capture_output=True, text=True)
+    lines = [ln for ln in res.stdout.splitlines() if ln.strip()]
+    assert len(lines) == len(paths), res.stdout[-2000:] + res.stderr[-2000:]
+    seen = set()
+    for ln, (code, msg, faults) in zip(lines, want):
+        m = re.search(r": status (\d+) \((.*)\) from the host path", ln)
+        assert m, (ln, faults)
+        assert (int(m.group(1)), m.group(2)) == (code, msg), (ln, code, msg, faults)
+        seen.add(code)
+    assert len(seen) >= 4, seen  # the draw must exercise most kinds as the winning fault
