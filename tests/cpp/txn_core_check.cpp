@@ -101,7 +101,19 @@ int check_block(const std::vector<uint8_t>& flatv, const char* name) {
   read_flat_block(flat, flatv.size(), b1);
   collect_messages(J1, b1);
   J1.kh.run(nullptr);
-  shape_block(J1, b1);
+  // a block the host loop fails on (an error the reference reports) must never come out of the device path as a result:
+  // the device side still runs, and has to decline the block or raise a flag (either hands the block to the host path)
+  bool host_failed = false;
+  Fail host_err{PPD_OK, ""};
+  try {
+    shape_block(J1, b1);
+  } catch (const Fail& e) {
+    host_failed = true, host_err = e;
+  }
+  auto handed_over = [&](const char* how) {
+    printf("%s: status %d (%s) from the host path; the device path %s\n", name, host_err.code, host_err.msg.c_str(), how);
+    return 4;
+  };
   // ---- side 2: the pre-image alone, then the device loop on host memory ----
   Job J2;
   J2.reset(1);
@@ -113,6 +125,7 @@ int check_block(const std::vector<uint8_t>& flatv, const char* name) {
   HostArena& A = J2.A;
   TxnTables T;
   if (!txn_tables_phase1(b2, flat, flatv.size(), T)) {
+    if (host_failed) return handed_over("declines the block in phase 1 of its tables");
     printf("%s: not a block the device loop takes: skipped\n", name);
     return 0;
   }
@@ -157,6 +170,7 @@ int check_block(const std::vector<uint8_t>& flatv, const char* name) {
     return c->v->key_pool + c->v->dig_base + 32ull * c->T->traces[t].m_code;
   };
   if (!txn_tables_phase2(b2, flat, B, code_digest, &cd, T)) {
+    if (host_failed) return handed_over("declines the block in phase 2 of its tables");
     printf("%s: phase 2 declined the block (the host path reports its error): skipped\n", name);
     return 0;
   }
@@ -223,6 +237,15 @@ int check_block(const std::vector<uint8_t>& flatv, const char* name) {
   txn::Ctx c{v, 0, 1, &sh_clock};
   for (uint32_t ti = 0; ti < v.n_txns && !cur.flag; ti++) txn::run_txn(c, ti, EMPTY_TRIE_HASH, EMPTY_CODE_HASH);
   txn::run_finish(c, b2.state_root);
+  if (host_failed) {
+    if (cur.flag) {
+      char how[96];
+      snprintf(how, sizeof how, "raises flag %u at txn %u", cur.flag, cur.flag_txn);
+      return handed_over(how);
+    }
+    printf("%s: MISMATCH: the device loop finished a block the host path fails with status %d (%s)\n", name, host_err.code, host_err.msg.c_str());
+    return 1;
+  }
   if (cur.flag) {
     printf("%s: the loop raised flag %u at txn %u (the host path would redo the block)\n", name, cur.flag, cur.flag_txn);
     return 2;
