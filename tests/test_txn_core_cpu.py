@@ -139,11 +139,28 @@ def _error_blocks():
     b.txns = copy.deepcopy(b.txns)
     b.txns[0]["traces"].append((bytes([7] * 20), {"balance": 1}))  # MissingKeysCreatingSubPartialTrie(State)
     cases.append(("touched_account_behind_hash_node", 24, b.flat))
-    # an address whose Keccak begins with a zero byte: H256::from_slice(&bytes_be()) panics (decoding.rs:202) after the
-    # state / txn / receipt subsets and before any storage subset; no payload
+    # MissingKeysCreatingSubPartialTrie(Storage): the storage trie of an account a txn reads a slot of, with the node on
+    # that slot's path hashed out (the tries as direct nodes from the oracle, re-spelled as a witness by the product's
+    # host-only ppd_direct_to_compact)
     import ppd_oracle_lib
+    from proof_protocol_decoder_b200 import flat, lib
 
     orc = ppd_oracle_lib.load()
+    b = synth.gen_block(55, n_accounts=80, n_txns=3, n_withdrawals=1, inline_code_frac=0.0, contract_frac=0.5, slots_hi=40)
+    state, storage = flat.parse_direct_pre_image(orc.compact_to_direct(flat.pre_image_of(b.flat)[1]))
+    addr, tr = next((a, t) for a, t in b.txns[1]["traces"] if t.get("storage_read"))
+    haddr, hslot = orc.keccak256(addr), orc.keccak256(tr["storage_read"][0])
+    root = storage[haddr]
+    if root[0] == "branch":
+        ch = list(root[1])
+        ch[hslot[0] >> 4] = ("hash", bytes([0x5A]) * 32)
+        storage[haddr] = ("branch", ch, root[2])
+    else:
+        storage[haddr] = ("hash", bytes([0x5A]) * 32)
+    wit = lib.load_library().direct_to_compact(flat.encode_direct_pre_image(state, storage))
+    cases.append(("storage_slot_behind_hash_node", 24, flat.with_pre_image(b.flat, flat.PRE_IMAGE_COMBINED, wit)))
+    # an address whose Keccak begins with a zero byte: H256::from_slice(&bytes_be()) panics (decoding.rs:202) after the
+    # state / txn / receipt subsets and before any storage subset; no payload
     short = next(a for a in (i.to_bytes(20, "big") for i in range(1, 100000)) if orc.keccak256(a)[0] == 0)
     b = base()
     b.txns = copy.deepcopy(b.txns)
@@ -197,7 +214,7 @@ def test_host_path_error_payloads_equal_the_oracles(txncheck, oracle, tmp_path, 
         assert words["addr"] == bytes(range(20)).hex() and int(words["amount"], 16) == 5
         assert bytes.fromhex(words["hashed_addr"]) == oracle.keccak256(bytes(range(20)))
     else:
-        assert words == {"trie_type": "State"}
+        assert words == {"trie_type": "Storage" if name.startswith("storage_slot") else "State"}
 
 
 def test_host_path_reports_the_fault_the_oracle_reports_when_a_block_has_several(txncheck, oracle, tmp_path):
