@@ -267,3 +267,66 @@ def test_host_path_reports_the_fault_the_oracle_reports_when_a_block_has_several
         assert (int(m.group(1)), m.group(2)) == (code, msg), (ln, code, msg, faults)
         seen.add(code)
     assert len(seen) >= 4, seen  # the draw must exercise most kinds as the winning fault
+
+
+def _witness_like_storage(oracle, blk, rng):
+    """The block with every storage trie cut down to what a real witness carries: the nodes on the paths of the slots
+    the block's txns read or write, every other subtree hashed out (the generator witnesses storage tries in full).
+    The tries are taken as direct nodes from the oracle, pruned, and re-spelled as a compact witness by the product's
+    host-only ppd_direct_to_compact.  Returns (FlatBlock, number of subtrees hashed out)."""
+    from proof_protocol_decoder_b200 import flat, lib
+
+    def nibs_of(h):
+        return [x for byte in h for x in (byte >> 4, byte & 15)]
+
+    hashed = [0]
+
+    def prune(node, keys):
+        if not keys:
+            if node[0] in ("empty", "hash"):
+                return node
+            hashed[0] += 1
+            return ("hash", bytes(rng.bytes(32)))
+        if node[0] == "branch":
+            return ("branch", [prune(c, [k[1:] for k in keys if k and k[0] == i]) for i, c in enumerate(node[1])], node[2])
+        if node[0] == "extension":
+            n = len(node[1])
+            return ("extension", node[1], prune(node[2], [k[n:] for k in keys if k[:n] == list(node[1])]))
+        return node
+
+    state, storage = flat.parse_direct_pre_image(oracle.compact_to_direct(flat.pre_image_of(blk.flat)[1]))
+    accessed = {}
+    for t in blk.txns:
+        for addr, tr in t["traces"]:
+            ks = accessed.setdefault(oracle.keccak256(addr), [])
+            ks += [nibs_of(oracle.keccak256(s)) for s in tr.get("storage_read") or []]
+            sw = tr.get("storage_written") or {}
+            ks += [nibs_of(oracle.keccak256(s)) for s in (sw.keys() if isinstance(sw, dict) else [x[0] for x in sw])]
+    for h, trie in list(storage.items()):
+        if accessed.get(h):
+            storage[h] = prune(trie, accessed[h])
+    wit = lib.load_library().direct_to_compact(flat.encode_direct_pre_image(state, storage))
+    return flat.with_pre_image(blk.flat, flat.PRE_IMAGE_COMBINED, wit), hashed[0]
+
+
+def test_device_txn_loop_on_witness_like_storage_tries(txncheck, oracle, tmp_path):
+    """Storage tries as mainnet witnesses carry them — hashed siblings next to every touched path — with 60 % of the
+    writes zero (deletes: a branch that loses a child next to hashed-out siblings, extensions that merge): the oracle
+    decodes the block, and the device loop builds the same tries as the host loop, txn by txn."""
+    from proof_protocol_decoder_b200 import synth
+
+    rng = np.random.default_rng(1)
+    paths, total = [], 0
+    for i in range(int(os.environ.get("PPD_WITNESS_LIKE_CASES", "16"))):
+        b = synth.gen_block(900 + i, n_accounts=40, n_txns=int(rng.integers(2, 8)), inline_code_frac=0.0, contract_frac=0.7, slots_lo=4, slots_hi=60,
+                            slot_reads=(0, 4), slot_writes=(0, 6), zero_write_frac=0.6, accounts_per_txn=(2, 6))
+        fb, n_hashed = _witness_like_storage(oracle, b, rng)
+        total += n_hashed
+        oracle.block_decode(fb)  # no error: every touched path is witnessed
+        p = tmp_path / f"w{i}.flat"
+        p.write_bytes(fb)
+        paths.append(str(p))
+    assert total > 20 * len(paths), total  # the pruning did hash subtrees out
+    res = subprocess.run([txncheck] + paths, capture_output=True, text=True)
+    lines = [ln for ln in res.stdout.splitlines() if ln.strip()]
+    assert res.returncode == 0 and len(lines) == len(paths) and all(ln.endswith("identical") for ln in lines), "\n".join(lines[-10:]) + res.stderr[-2000:]
