@@ -150,21 +150,3 @@ def test_storage_tries_are_joined_by_root_hash(ctx, oracle, hashed_last, host_tx
     assert isinstance(want, int) == hashed_last
     got, st = _decode(ctx, fb, host_txn)
     assert got == want
-
-
-@pytest.mark.xfail(strict=False, reason="written after the round's GPU minutes were spent: never run on hardware; the device loop's code is checked against the host loop on the same blocks on the CPU (test_txn_core_cpu.py::test_device_txn_loop_on_witness_like_storage_tries)")
-@pytest.mark.parametrize("host_txn", [False, True])
-def test_witness_like_storage_tries_unverified_on_hardware(ctx, oracle, host_txn):
-    """Storage tries with hashed siblings next to every touched path (what a mainnet witness carries; the generator
-    witnesses them in full), most writes deletes: the product's IR bytes are the oracle's, through both loops."""
-    from proof_protocol_decoder_b200 import synth
-    from test_txn_core_cpu import _witness_like_storage
-
-    rng = np.random.default_rng(1)
-    for i in range(8):
-        b = synth.gen_block(900 + i, n_accounts=40, n_txns=int(rng.integers(2, 8)), inline_code_frac=0.0, contract_frac=0.7, slots_lo=4, slots_hi=60,
-                            slot_reads=(0, 4), slot_writes=(0, 6), zero_write_frac=0.6, accounts_per_txn=(2, 6))
-        fb, n_hashed = _witness_like_storage(oracle, b, rng)
-        assert n_hashed > 0
-        got, _ = _decode(ctx, fb, host_txn)
-        assert got == _oracle(oracle, fb), f"block {i}"

@@ -408,22 +408,6 @@ def test_block_error_statuses_match_oracle(ctx, oracle, name, flat_block):
     assert ctx.block_decode(ok) == oracle.block_decode(ok)
 
 
-@pytest.mark.xfail(strict=False, reason="written after the round's GPU minutes were spent: never run on hardware; the same wording is checked on the CPU by test_host_path_error_payloads_equal_the_oracles")
-def test_block_error_payloads_match_oracle_unverified_on_hardware(ctx, oracle):
-    """ppd_last_error carries the payload of the TraceParsingError variants as the oracle spells it (csrc/err_detail.h)."""
-    from proof_protocol_decoder_b200 import PpdError
-
-    for name, flat_block in _error_cases():
-        with pytest.raises(OracleError) as eo:
-            oracle.block_decode(flat_block)
-        if not 21 <= eo.value.code <= 25:
-            continue
-        with pytest.raises(PpdError) as eg:
-            ctx.block_decode(flat_block)
-        assert eg.value.code == eo.value.code and eg.value.msg == eo.value.msg, name
-        assert eg.value.payload(), name
-
-
 # ---- the witness parse / pre-image arena on the GPU (ppd_parse.cu) against the host builder --------------
 def _both_builders(ctx, fn):
     """fn() with the GPU witness parser, then with the host one (PPD_HOST_PARSE); returns both results and stats."""
